@@ -1,0 +1,208 @@
+"""TEST INFRASTRUCTURE ONLY (oracle).  ctypes front-end of oracle/_ref/libsvref.so — the reference's
+own sources (Code/Source/liner_solver/*.cpp, Code/Source/solver/{fluid,lhsa,nn,fs,...}.cpp) compiled
+unmodified by oracle/Makefile, driven through oracle/ref_harness.cpp.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this
+module.  Nothing under svfsiplus_b200/ does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libsvref.so")
+
+LS_CG, LS_GMRES, LS_NS, LS_BICGS = 798, 797, 796, 795      # L/fils_struct.hpp:70-76
+PREC_FSILS, PREC_RCS = 701, 709                              # S/consts.h:426
+
+_lib = None
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise RuntimeError(f"{LIB_PATH} missing: run `make -C oracle ref` where /root/reference exists")
+        L = C.CDLL(LIB_PATH)
+        L.ref_last_error.restype = C.c_char_p
+        L.ref_asm_create.restype = C.c_void_p
+        L.ref_asm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double]
+        L.ref_asm_destroy.argtypes = [C.c_void_p]
+        L.ref_asm_nnz.argtypes = [C.c_void_p]
+        L.ref_asm_get_csr.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_asm_get_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_asm_fluid.restype = C.c_double
+        L.ref_asm_fluid.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_double] * 5 + [C.c_void_p, C.c_double] + [C.c_void_p] * 6
+        L.ref_rank_create.restype = C.c_void_p
+        L.ref_rank_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_rank_destroy.argtypes = [C.c_void_p]
+        L.ref_rank_add_face.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_ranks_build.argtypes = [C.c_int, C.c_void_p]
+        L.ref_rank_get_info.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.ref_rank_get_req.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_ranks_solve.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_ranks_spmv.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_ranks_commuv.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+class RefAssembly:
+    """One mesh + one equation inside the reference's ComMod (see ref_harness.cpp)."""
+
+    def __init__(self, x, ien, nFs: int = 1, qmTET4: float = -1.0):
+        self.x = _c(x, np.float64)
+        self.ien = _c(ien, np.int32)
+        self.nNo = self.x.shape[0]
+        self.nEl, self.eNoN = self.ien.shape
+        self.h = lib().ref_asm_create(self.nNo, self.nEl, self.eNoN, _p(self.ien), _p(self.x), nFs, qmTET4)
+        if not self.h:
+            raise RuntimeError(lib().ref_last_error().decode())
+        self.nnz = lib().ref_asm_nnz(self.h)
+
+    def close(self):
+        if self.h:
+            lib().ref_asm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def csr(self):
+        rowPtr = np.empty(self.nNo + 1, np.int32)
+        colPtr = np.empty(self.nnz, np.int32)
+        lib().ref_asm_get_csr(self.h, _p(rowPtr), _p(colPtr))
+        return rowPtr, colPtr
+
+    def tables(self):
+        nG = lib().ref_asm_get_tables(self.h, None, None, None)
+        w = np.empty(nG)
+        N = np.empty((nG, self.eNoN))
+        Nx = np.empty((nG, self.eNoN, 3))
+        lib().ref_asm_get_tables(self.h, _p(w), _p(N), _p(Nx))
+        return w, N, Nx
+
+    def fluid(self, Ag, Yg, Bf, *, dt, am, af, gam, rho, mu, f=(0.0, 0.0, 0.0), Kinv=0.0,
+              visc=None, mvMsh=False):
+        """construct_fluid (S/fluid.cpp:464).  Returns R (nNo,4), Val (nnz,16), seconds."""
+        Ag = _c(Ag, np.float64); Yg = _c(Yg, np.float64); Bf = _c(Bf, np.float64)
+        tDof = Ag.shape[1]
+        v = np.array(visc if visc is not None else [0, mu, 0, 0, 0, 0], dtype=np.float64)
+        fv = np.array(f, dtype=np.float64)
+        R = np.empty((self.nNo, 4))
+        Val = np.empty((self.nnz, 16))
+        t = lib().ref_asm_fluid(self.h, tDof, int(mvMsh), dt, am, af, gam, rho, _p(fv), Kinv, _p(v),
+                                _p(Ag), _p(Yg), _p(Bf), _p(R), _p(Val))
+        if t < 0:
+            raise RuntimeError(lib().ref_last_error().decode())
+        return R, Val, t
+
+
+def ls_params(ls_type, relTol, absTol=1e-10, mItr=10, sD=100, gm=(1e-2, 1e-10, 2, 100), cg=(0.2, 1e-10, 500)):
+    return np.array([ls_type, relTol, absTol, mItr, sD, gm[0], gm[1], gm[2], gm[3], cg[0], cg[1], cg[2]], np.float64)
+
+
+OUT_FIELDS = ("suc", "itr", "iNorm", "fNorm", "dB", "callD", "GM_itr", "CG_itr", "Resm", "Resc",
+              "GM_callD", "CG_callD", "wall_s")
+
+
+class RefRanks:
+    """nranks "MPI ranks" (threads) of the reference FSILS: lhs_create + bc_create + solve."""
+
+    def __init__(self, parts):
+        """parts: list of dict(gnNo, gNodes, rowPtr, colPtr, faces=[dict(nodes(local ids), dof, bGrp, val|None)])"""
+        L = lib()
+        self.n = len(parts)
+        self.parts = parts
+        self.hs = []
+        self._keep = []
+        for p in parts:
+            g = _c(p["gNodes"], np.int32); r = _c(p["rowPtr"], np.int32); c = _c(p["colPtr"], np.int32)
+            h = L.ref_rank_create(int(p["gnNo"]), len(g), len(c), _p(g), _p(r), _p(c))
+            for f in p.get("faces", []):
+                nodes = _c(f["nodes"], np.int32)
+                val = None if f.get("val") is None else _c(f["val"], np.float64)
+                L.ref_rank_add_face(h, len(nodes), int(f["dof"]), int(f["bGrp"]), _p(nodes), _p(val))
+            self.hs.append(h)
+        self.harr = (C.c_void_p * self.n)(*self.hs)
+        if L.ref_ranks_build(self.n, self.harr) != 0:
+            raise RuntimeError(L.ref_last_error().decode())
+
+    def close(self):
+        for h in self.hs:
+            lib().ref_rank_destroy(h)
+        self.hs = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self, p):
+        nNo = len(self.parts[p]["gNodes"]); nnz = len(self.parts[p]["colPtr"])
+        info = np.zeros(3, np.int32); mp = np.empty(nNo, np.int32); rp = np.empty((nNo, 2), np.int32)
+        cp = np.empty(nnz, np.int32); dp = np.empty(nNo, np.int32)
+        lib().ref_rank_get_info(self.hs[p], _p(info), _p(mp), _p(rp), _p(cp), _p(dp))
+        reqs = []
+        for i in range(int(info[2])):
+            iP = C.c_int(0)
+            n = lib().ref_rank_get_req(self.hs[p], i, C.byref(iP), None)
+            ptr = np.empty(n, np.int32)
+            lib().ref_rank_get_req(self.hs[p], i, C.byref(iP), _p(ptr))
+            reqs.append((iP.value, ptr))
+        return dict(mynNo=int(info[0]), shnNo=int(info[1]), nReq=int(info[2]), map=mp, rowPtr=rp, colPtr=cp,
+                    diagPtr=dp, reqs=reqs)
+
+    def _ptrs(self, arrs):
+        return (C.c_void_p * self.n)(*[a.ctypes.data for a in arrs])
+
+    def solve(self, dof, ls, prec, R, Val, incL=None, res=None):
+        """fsils_solve (L/solve.cpp:50) on every rank.  R, Val: lists of per-rank arrays (copied).
+        Returns (X list, Val_scaled list, out list[dict])."""
+        Rs = [_c(r, np.float64).copy() for r in R]
+        Vs = [_c(v, np.float64).copy() for v in Val]
+        out = np.zeros((self.n, len(OUT_FIELDS)))
+        incL_a = None if incL is None else _c(incL, np.int32)
+        res_a = None if res is None else _c(res, np.float64)
+        ls = _c(ls, np.float64)
+        rc = lib().ref_ranks_solve(self.n, self.harr, dof, _p(ls), int(prec), self._ptrs(Rs), self._ptrs(Vs),
+                                   _p(incL_a), _p(res_a), _p(out))
+        if rc != 0:
+            raise RuntimeError(lib().ref_last_error().decode())
+        return Rs, Vs, [dict(zip(OUT_FIELDS, o)) for o in out]
+
+    def spmv(self, dof, Val, X, reps=1):
+        Vs = [_c(v, np.float64) for v in Val]
+        Xs = [_c(x, np.float64) for x in X]
+        Ys = [np.zeros_like(x) for x in Xs]
+        secs = C.c_double(0.0)
+        rc = lib().ref_ranks_spmv(self.n, self.harr, dof, self._ptrs(Vs), self._ptrs(Xs), self._ptrs(Ys), reps,
+                                  C.byref(secs))
+        if rc != 0:
+            raise RuntimeError(lib().ref_last_error().decode())
+        return Ys, secs.value
+
+    def commuv(self, dof, V):
+        Vs = [_c(v, np.float64).copy() for v in V]
+        lib().ref_ranks_commuv(self.n, self.harr, dof, self._ptrs(Vs))
+        return Vs

@@ -1,0 +1,407 @@
+// TEST INFRASTRUCTURE ONLY (oracle).  C-ABI harness around the UNMODIFIED reference sources
+// (compiled from where they lie under /root/reference by oracle/Makefile into
+// oracle/_ref/libsvref.so).  It fills the reference's own ComMod / mshType / eqType / FSILS_lhsType
+// objects programmatically from flat arrays (the reference's VTK readers are not available here)
+// and then calls the reference's own functions:
+//
+//   lhsa_ns::lhsa                 Code/Source/solver/lhsa.cpp:153
+//   nn::select_ele                Code/Source/solver/nn.cpp:943
+//   fs::init_fs_msh               Code/Source/solver/fs.cpp:258
+//   fluid::construct_fluid        Code/Source/solver/fluid.cpp:464   (-> do_assem lhsa.cpp:97)
+//   fsils_commu_create            Code/Source/liner_solver/commu.cpp:44
+//   fsils_lhs_create              Code/Source/liner_solver/lhs.cpp:57
+//   fsils_bc_create               Code/Source/liner_solver/bc.cpp:45
+//   fsils_solve                   Code/Source/liner_solver/solve.cpp:50
+//   fsils_spar_mul_vv / commuv    Code/Source/liner_solver/spar_mul.cpp:191, in_commu.cpp:111
+//
+// Nothing in the product (svfsiplus_b200/) links or loads this file; only tests/, smoke() and
+// bench.py's cpu_baseline / --impl reference legs do.
+#include "Simulation.h"
+#include "ComMod.h"
+#include "FsilsLinearAlgebra.h"
+#include "all_fun.h"
+#include "consts.h"
+#include "fluid.h"
+#include "fs.h"
+#include "fsils_api.hpp"
+#include "lhsa.h"
+#include "nn.h"
+#include "spar_mul.h"
+#include "commu.h"
+#include "lhs.h"
+
+#include "mpi.h"
+
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+using namespace fsi_linear_solver;
+
+namespace {
+
+thread_local std::string t_err;
+std::string g_err;
+
+double now_s()
+{
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ----------------------------------------------------------------------------------------------
+// Assembly context: one Simulation (ComMod) with one mesh and one equation.
+// ----------------------------------------------------------------------------------------------
+struct AsmCtx {
+  std::unique_ptr<Simulation> sim;
+  int nnz = 0;
+};
+
+} // namespace
+
+extern "C" {
+
+const char* ref_last_error() { return g_err.c_str(); }
+
+// Create a ComMod with one 3-D mesh of nEl elements with eNoN nodes each (4 = TET4, 8 = HEX8,
+// 10 = TET10), call the reference's select_ele / init_fs_msh / lhsa.  Returns an opaque context.
+void* ref_asm_create(int nNo, int nEl, int eNoN, const int* IEN, const double* x, int nFs, double qmTET4)
+{
+  try {
+    mpistub_set_world(1);
+    mpistub_bind_rank(0);
+    auto ctx = new AsmCtx;
+    ctx->sim.reset(new Simulation());
+    auto& com_mod = ctx->sim->com_mod;
+    com_mod.nsd = 3;
+    com_mod.nsymd = 6;
+    com_mod.tnNo = nNo;
+    com_mod.gtnNo = nNo;
+    com_mod.nMsh = 1;
+    com_mod.msh.resize(1);
+    auto& msh = com_mod.msh[0];
+    msh.name = "msh";
+    msh.nNo = nNo;
+    msh.gnNo = nNo;
+    msh.nEl = nEl;
+    msh.gnEl = nEl;
+    msh.eNoN = eNoN;
+    msh.nFs = nFs;
+    if (qmTET4 > 0.0) msh.qmTET4 = qmTET4;
+    msh.IEN.resize(eNoN, nEl);
+    std::memcpy(msh.IEN.data(), IEN, sizeof(int)*size_t(eNoN)*nEl);
+    msh.gN.resize(nNo);
+    for (int a = 0; a < nNo; a++) msh.gN(a) = a;
+    com_mod.x.resize(3, nNo);
+    std::memcpy(com_mod.x.data(), x, sizeof(double)*3*size_t(nNo));
+
+    nn::select_ele(com_mod, msh);
+    fs::init_fs_msh(com_mod, msh);
+
+    int nnz = 0;
+    lhsa_ns::lhsa(ctx->sim.get(), nnz);
+    ctx->nnz = nnz;
+    com_mod.lhs.nnz = nnz;
+    com_mod.lhs.nNo = nNo;
+    return ctx;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+
+void ref_asm_destroy(void* h) { delete static_cast<AsmCtx*>(h); }
+
+int ref_asm_nnz(void* h) { return static_cast<AsmCtx*>(h)->nnz; }
+
+// rowPtr: nNo+1 ints, colPtr: nnz ints (the reference's lhsa output, S/lhsa.cpp:153).
+void ref_asm_get_csr(void* h, int* rowPtr, int* colPtr)
+{
+  auto& com_mod = static_cast<AsmCtx*>(h)->sim->com_mod;
+  std::memcpy(rowPtr, com_mod.rowPtr.data(), sizeof(int)*com_mod.rowPtr.size());
+  std::memcpy(colPtr, com_mod.colPtr.data(), sizeof(int)*com_mod.colPtr.size());
+}
+
+// Gauss tables chosen by the reference for the mesh (for checking the product's own tables).
+// w: nG, N: eNoN*nG (col-major N(a,g)), Nx: 3*eNoN*nG (Nx(i,a,g)).  Returns nG.
+int ref_asm_get_tables(void* h, double* w, double* N, double* Nx)
+{
+  auto& msh = static_cast<AsmCtx*>(h)->sim->com_mod.msh[0];
+  if (w) std::memcpy(w, msh.w.data(), sizeof(double)*msh.w.size());
+  if (N) std::memcpy(N, msh.N.data(), sizeof(double)*msh.N.size());
+  if (Nx) std::memcpy(Nx, msh.Nx.data(), sizeof(double)*msh.Nx.size());
+  return msh.nG;
+}
+
+// Fluid (Navier-Stokes VMS) assembly through the reference's construct_fluid.
+// visc = {type(0 const,1 Carreau-Yasuda,2 Casson), mu_i, mu_o, lam, a, n}
+// Ag, Yg: tDof x nNo (column-major, i.e. node-contiguous), Bf: 3 x nNo.
+// Outputs R (dof x nNo), Val (dof*dof x nnz).  Returns seconds spent inside construct_fluid, <0 on error.
+double ref_asm_fluid(void* h, int tDof, int mvMsh, double dt, double am, double af, double gam,
+                     double rho, const double* f, double Kinv_darcy, const double* visc,
+                     const double* Ag, const double* Yg, const double* Bf, double* R, double* Val)
+{
+  try {
+    using namespace consts;
+    auto ctx = static_cast<AsmCtx*>(h);
+    auto& com_mod = ctx->sim->com_mod;
+    const int nNo = com_mod.tnNo;
+    const int dof = 4;
+    com_mod.tDof = tDof;
+    com_mod.dof = dof;
+    com_mod.dt = dt;
+    com_mod.mvMsh = (mvMsh != 0);
+    com_mod.cEq = 0;
+    com_mod.nEq = 1;
+    com_mod.eq.resize(1);
+    auto& eq = com_mod.eq[0];
+    eq.phys = EquationType::phys_fluid;
+    eq.dof = dof;
+    eq.s = 0;
+    eq.e = dof - 1;
+    eq.am = am;
+    eq.af = af;
+    eq.gam = gam;
+    eq.nDmn = 1;
+    eq.dmn.resize(1);
+    auto& dmn = eq.dmn[0];
+    dmn.Id = -1;
+    dmn.phys = EquationType::phys_fluid;
+    dmn.prop[PhysicalProperyType::fluid_density] = rho;
+    dmn.prop[PhysicalProperyType::f_x] = f[0];
+    dmn.prop[PhysicalProperyType::f_y] = f[1];
+    dmn.prop[PhysicalProperyType::f_z] = f[2];
+    dmn.prop[PhysicalProperyType::inverse_darcy_permeability] = Kinv_darcy;
+    int vt = int(visc[0]);
+    dmn.fluid_visc.viscType = (vt == 0) ? FluidViscosityModelType::viscType_Const
+                            : (vt == 1) ? FluidViscosityModelType::viscType_CY
+                                        : FluidViscosityModelType::viscType_Cass;
+    dmn.fluid_visc.mu_i = visc[1];
+    dmn.fluid_visc.mu_o = visc[2];
+    dmn.fluid_visc.lam = visc[3];
+    dmn.fluid_visc.a = visc[4];
+    dmn.fluid_visc.n = visc[5];
+    if (!eq.linear_algebra) eq.linear_algebra = new FsilsLinearAlgebra();
+
+    com_mod.Bf.resize(3, nNo);
+    std::memcpy(com_mod.Bf.data(), Bf, sizeof(double)*3*size_t(nNo));
+    Array<double> Ag_a(tDof, nNo), Yg_a(tDof, nNo);
+    std::memcpy(Ag_a.data(), Ag, sizeof(double)*size_t(tDof)*nNo);
+    std::memcpy(Yg_a.data(), Yg, sizeof(double)*size_t(tDof)*nNo);
+
+    // ls_alloc contract (S/ls.cpp:51): R and Val zeroed by resize.
+    com_mod.R.resize(dof, nNo);
+    eq.linear_algebra->alloc(com_mod, eq);
+
+    double t0 = now_s();
+    fluid::construct_fluid(com_mod, com_mod.msh[0], Ag_a, Yg_a);
+    double t1 = now_s();
+
+    std::memcpy(R, com_mod.R.data(), sizeof(double)*size_t(dof)*nNo);
+    std::memcpy(Val, com_mod.Val.data(), sizeof(double)*size_t(dof)*dof*ctx->nnz);
+    return t1 - t0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1.0;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// FSILS: multi-"rank" (thread per rank) lhs_create + bc_create + solve / spmv.
+// ----------------------------------------------------------------------------------------------
+struct RefRank {
+  // inputs
+  int gnNo = 0, nNo = 0, nnz = 0;
+  std::vector<int> gNodes, rowPtr, colPtr;
+  struct Face { int nNo, dof, bGrp; std::vector<int> gNodes; std::vector<double> val; };
+  std::vector<Face> faces;
+  // built
+  FSILS_lhsType lhs;
+  FSILS_commuType commu;
+  bool built = false;
+  std::string err;
+};
+
+void* ref_rank_create(int gnNo, int nNo, int nnz, const int* gNodes, const int* rowPtr, const int* colPtr)
+{
+  auto r = new RefRank;
+  r->gnNo = gnNo; r->nNo = nNo; r->nnz = nnz;
+  r->gNodes.assign(gNodes, gNodes + nNo);
+  r->rowPtr.assign(rowPtr, rowPtr + nNo + 1);
+  r->colPtr.assign(colPtr, colPtr + nnz);
+  return r;
+}
+
+void ref_rank_destroy(void* h) { delete static_cast<RefRank*>(h); }
+
+// bGrp: 0 = Dirichlet, 1 = Neumann (L/fils_struct.hpp:58).  val: dof x nNo or NULL.
+void ref_rank_add_face(void* h, int nNo, int dof, int bGrp, const int* gNodes, const double* val)
+{
+  auto r = static_cast<RefRank*>(h);
+  RefRank::Face f;
+  f.nNo = nNo; f.dof = dof; f.bGrp = bGrp;
+  f.gNodes.assign(gNodes, gNodes + nNo);
+  if (val) f.val.assign(val, val + size_t(dof)*nNo);
+  r->faces.push_back(std::move(f));
+}
+
+static void run_ranks(int nranks, void** hs, const std::function<void(int, RefRank&)>& fn)
+{
+  mpistub_set_world(nranks);
+  std::vector<std::thread> th;
+  for (int p = 0; p < nranks; p++) {
+    th.emplace_back([&, p]() {
+      mpistub_bind_rank(p);
+      auto& r = *static_cast<RefRank*>(hs[p]);
+      try { fn(p, r); } catch (const std::exception& e) { r.err = e.what(); }
+    });
+  }
+  for (auto& t : th) t.join();
+}
+
+static void build_rank(RefRank& r)
+{
+  if (r.built) return;
+  fsils_commu_create(r.commu, MPI_COMM_WORLD);
+  Vector<int> gNodes(r.nNo), rowPtr(r.nNo+1), colPtr(r.nnz);
+  std::memcpy(gNodes.data(), r.gNodes.data(), sizeof(int)*r.nNo);
+  std::memcpy(rowPtr.data(), r.rowPtr.data(), sizeof(int)*(r.nNo+1));
+  std::memcpy(colPtr.data(), r.colPtr.data(), sizeof(int)*r.nnz);
+  int nFaces = int(r.faces.size());
+  fsils_lhs_create(r.lhs, r.commu, r.gnNo, r.nNo, r.nnz, gNodes, rowPtr, colPtr, nFaces);
+  for (int i = 0; i < nFaces; i++) {
+    auto& f = r.faces[i];
+    Vector<int> gN(f.nNo);
+    std::memcpy(gN.data(), f.gNodes.data(), sizeof(int)*f.nNo);
+    BcType bt = f.bGrp == 0 ? BcType::BC_TYPE_Dir : BcType::BC_TYPE_Neu;
+    if (!f.val.empty()) {
+      Array<double> v(f.dof, f.nNo);
+      std::memcpy(v.data(), f.val.data(), sizeof(double)*f.val.size());
+      fsils_bc_create(r.lhs, i, f.nNo, f.dof, bt, gN, v);
+    } else {
+      fsils_bc_create(r.lhs, i, f.nNo, f.dof, bt, gN);
+    }
+  }
+  r.built = true;
+}
+
+// Build lhs (+faces) on all ranks.  Returns 0 on success.
+int ref_ranks_build(int nranks, void** hs)
+{
+  run_ranks(nranks, hs, [](int, RefRank& r) { build_rank(r); });
+  for (int p = 0; p < nranks; p++) {
+    auto& r = *static_cast<RefRank*>(hs[p]);
+    if (!r.err.empty()) { g_err = r.err; return 1; }
+  }
+  return 0;
+}
+
+// Introspection of the reference's lhs (to pin the product's own lhs construction).
+// info = {mynNo, shnNo, nReq}
+void ref_rank_get_info(void* h, int* info, int* map, int* rowPtr2, int* colPtr, int* diagPtr)
+{
+  auto& lhs = static_cast<RefRank*>(h)->lhs;
+  info[0] = lhs.mynNo; info[1] = lhs.shnNo; info[2] = lhs.nReq;
+  if (map) std::memcpy(map, lhs.map.data(), sizeof(int)*lhs.nNo);
+  if (rowPtr2) std::memcpy(rowPtr2, lhs.rowPtr.data(), sizeof(int)*2*lhs.nNo);
+  if (colPtr) std::memcpy(colPtr, lhs.colPtr.data(), sizeof(int)*lhs.nnz);
+  if (diagPtr) std::memcpy(diagPtr, lhs.diagPtr.data(), sizeof(int)*lhs.nNo);
+}
+
+// i-th communication request: returns n, fills iP; ptr may be NULL to query n first.
+int ref_rank_get_req(void* h, int i, int* iP, int* ptr)
+{
+  auto& cs = static_cast<RefRank*>(h)->lhs.cS[i];
+  *iP = cs.iP;
+  if (ptr) std::memcpy(ptr, cs.ptr.data(), sizeof(int)*cs.n);
+  return cs.n;
+}
+
+// ls = {LS_type(795..798), RI.relTol, RI.absTol, RI.mItr, RI.sD, GM.relTol, GM.absTol, GM.mItr, GM.sD,
+//       CG.relTol, CG.absTol, CG.mItr}   (doubles)
+// prec: 701 = PREC_FSILS, 709 = PREC_RCS (S/consts.h:426)
+// Per rank p: Ri[p] (dof x nNo, in: residual, out: solution), Val[p] (dof*dof x nnz, destroyed).
+// incL/res: nFaces (same on all ranks), may be NULL when no faces.
+// out[p*OUTN ..]: {RI.suc, RI.itr, RI.iNorm, RI.fNorm, RI.dB, RI.callD, GM.itr, CG.itr, Resm, Resc, GM.callD, CG.callD, wall_s}
+int ref_ranks_solve(int nranks, void** hs, int dof, const double* ls, int prec, double** Ri, double** Val,
+                    const int* incL, const double* res, double* out)
+{
+  run_ranks(nranks, hs, [&](int p, RefRank& r) {
+    build_rank(r);
+    FSILS_lsType L{};
+    fsils_ls_create(L, static_cast<LinearSolverType>(int(ls[0])));
+    L.RI.relTol = ls[1]; L.RI.absTol = ls[2]; L.RI.mItr = int(ls[3]); L.RI.sD = int(ls[4]);
+    L.GM.relTol = ls[5]; L.GM.absTol = ls[6]; L.GM.mItr = int(ls[7]); L.GM.sD = int(ls[8]);
+    L.CG.relTol = ls[9]; L.CG.absTol = ls[10]; L.CG.mItr = int(ls[11]);
+    L.RI.itr = 0; L.GM.itr = 0; L.CG.itr = 0;
+    L.RI.callD = 0; L.GM.callD = 0; L.CG.callD = 0; L.Resm = 0; L.Resc = 0;
+    L.RI.iNorm = 0; L.RI.fNorm = 0; L.RI.dB = 0; L.RI.suc = false;
+    int nFaces = int(r.faces.size());
+    Array<double> Ri_a(dof, r.nNo), Val_a(dof*dof, r.nnz);
+    std::memcpy(Ri_a.data(), Ri[p], sizeof(double)*size_t(dof)*r.nNo);
+    std::memcpy(Val_a.data(), Val[p], sizeof(double)*size_t(dof)*dof*r.nnz);
+    Vector<int> incL_v(nFaces);
+    Vector<double> res_v(nFaces);
+    for (int i = 0; i < nFaces; i++) { incL_v(i) = incL ? incL[i] : 1; res_v(i) = res ? res[i] : 0.0; }
+    auto pt = static_cast<consts::PreconditionerType>(prec);
+    double t0 = now_s();
+    fsils_solve(r.lhs, L, dof, Ri_a, Val_a, pt, incL_v, res_v);
+    double t1 = now_s();
+    std::memcpy(Ri[p], Ri_a.data(), sizeof(double)*size_t(dof)*r.nNo);
+    std::memcpy(Val[p], Val_a.data(), sizeof(double)*size_t(dof)*dof*r.nnz);
+    double* o = out + 13*p;
+    o[0] = L.RI.suc; o[1] = L.RI.itr; o[2] = L.RI.iNorm; o[3] = L.RI.fNorm; o[4] = L.RI.dB; o[5] = L.RI.callD;
+    o[6] = L.GM.itr; o[7] = L.CG.itr; o[8] = L.Resm; o[9] = L.Resc; o[10] = L.GM.callD; o[11] = L.CG.callD;
+    o[12] = t1 - t0;
+  });
+  for (int p = 0; p < nranks; p++) {
+    auto& r = *static_cast<RefRank*>(hs[p]);
+    if (!r.err.empty()) { g_err = r.err; r.err.clear(); return 1; }
+  }
+  return 0;
+}
+
+// y = K x (+ halo add) through fsils_spar_mul_vv on vectors given in the CALLER's node order
+// (they are permuted by lhs.map on the way in and out, like fsils_solve does).  reps>1 repeats the
+// product for timing; returns seconds per product on rank 0 in *secs.
+int ref_ranks_spmv(int nranks, void** hs, int dof, double** Val, double** X, double** Y, int reps, double* secs)
+{
+  run_ranks(nranks, hs, [&](int p, RefRank& r) {
+    build_rank(r);
+    Array<double> K(dof*dof, r.nnz), U(dof, r.nNo), KU(dof, r.nNo);
+    std::memcpy(K.data(), Val[p], sizeof(double)*size_t(dof)*dof*r.nnz);
+    for (int a = 0; a < r.nNo; a++)
+      for (int i = 0; i < dof; i++) U(i, r.lhs.map(a)) = X[p][i + size_t(a)*dof];
+    double t0 = now_s();
+    for (int k = 0; k < reps; k++)
+      spar_mul::fsils_spar_mul_vv(r.lhs, r.lhs.rowPtr, r.lhs.colPtr, dof, K, U, KU);
+    double t1 = now_s();
+    for (int a = 0; a < r.nNo; a++)
+      for (int i = 0; i < dof; i++) Y[p][i + size_t(a)*dof] = KU(i, r.lhs.map(a));
+    if (p == 0 && secs) *secs = (t1 - t0) / reps;
+  });
+  for (int p = 0; p < nranks; p++) {
+    auto& r = *static_cast<RefRank*>(hs[p]);
+    if (!r.err.empty()) { g_err = r.err; r.err.clear(); return 1; }
+  }
+  return 0;
+}
+
+// In-place halo add of a dof x nNo vector given in the caller's node order (fsils_commuv).
+int ref_ranks_commuv(int nranks, void** hs, int dof, double** V)
+{
+  run_ranks(nranks, hs, [&](int p, RefRank& r) {
+    build_rank(r);
+    Array<double> U(dof, r.nNo);
+    for (int a = 0; a < r.nNo; a++)
+      for (int i = 0; i < dof; i++) U(i, r.lhs.map(a)) = V[p][i + size_t(a)*dof];
+    fsils_commuv(r.lhs, dof, U);
+    for (int a = 0; a < r.nNo; a++)
+      for (int i = 0; i < dof; i++) V[p][i + size_t(a)*dof] = U(i, r.lhs.map(a));
+  });
+  return 0;
+}
+
+} // extern "C"
