@@ -1,0 +1,117 @@
+/* svb200.h — C ABI of the B200 (sm_100a) backend for svMultiPhysics' nonlinear-step hot path:
+ * element assembly into the block-CSR system followed by the FSILS-equivalent Krylov solve.
+ *
+ * This is the drop-in boundary.  The reference's plug-in interface is the C++ class
+ * `LinearAlgebra` (Code/Source/solver/LinearAlgebra.h:39-63: alloc / assemble / check_options /
+ * initialize / set_assembly / set_preconditioner / solve); the thin host class that implements it on
+ * top of this header is svfsiplus_b200/host/B200LinearAlgebra.{h,cpp}, and INTEGRATION.md shows the
+ * four registration lines a maintainer adds.  The shape of the layer follows the reference's own
+ * extern "C" shim for Trilinos (Code/Source/solver/trilinos_impl.h:185-224).
+ *
+ * Conventions: plain pointers and sizes only; every array is HOST memory unless the name says
+ * `_dev`; all indices are 0-based 32-bit ints; all reals are IEEE double.  2-D arrays use the
+ * reference's column-major containers seen from C: R(dof,nNo) = R[i + dof*a] (the dof values of a
+ * node are contiguous), Val(dof*dof,nnz) = Val[i*dof + j + dof*dof*p] = dR_i/du_j of non-zero p
+ * (Code/Source/solver/Array.h:379; block row-major inside, liner_solver/spar_mul.cpp:229-236).
+ * Every function returns 0 on success, non-zero on failure with a message in b200_last_error().
+ * There is no CPU fallback: a call made without a usable CUDA device fails.
+ */
+#ifndef SVB200_H
+#define SVB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_handle b200_handle;
+
+/* Linear solver / preconditioner codes: identical to the reference's enums
+ * (liner_solver/fils_struct.hpp:70-76, solver/consts.h:426-440). */
+enum { B200_LS_BICGS = 795, B200_LS_NS = 796, B200_LS_GMRES = 797, B200_LS_CG = 798 };
+enum { B200_PREC_FSILS = 701, B200_PREC_RCS = 709 };
+enum { B200_BC_DIR = 0, B200_BC_NEU = 1 };                  /* fils_struct.hpp:58 BcType */
+
+/* Inputs of one FSILS_subLsType (fils_struct.hpp:211-257). */
+typedef struct { double relTol, absTol; int mItr, sD; } b200_tol;
+/* Outputs of one FSILS_subLsType. */
+typedef struct { int suc, itr; double iNorm, fNorm, dB, callD; } b200_sub_out;
+/* Outputs of FSILS_lsType (fils_struct.hpp:259-279). */
+typedef struct { b200_sub_out RI, GM, CG; int Resm, Resc; } b200_ls_out;
+
+/* Per-(equation, domain) constants of the fluid element, flattened from eqType/dmnType
+ * (solver/ComMod.h:1021,431; look-ups at solver/fluid.cpp:1727-1737,2142-2200). */
+typedef struct {
+  double dt, am, af, gam;       /* com_mod.dt, eq.am, eq.af, eq.gam */
+  int tDof, mvMsh;              /* com_mod.tDof, com_mod.mvMsh */
+  double rho, f[3], Kinv;       /* fluid_density, f_x..f_z, inverse_darcy_permeability */
+  int viscType;                 /* 0 constant, 1 Carreau-Yasuda, 2 Casson */
+  double mu_i, mu_o, lam, a, n; /* dmn.fluid_visc */
+} b200_fluid_props;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+int  b200_create(b200_handle** h, int device);
+void b200_destroy(b200_handle* h);
+const char* b200_last_error(b200_handle* h);                 /* h may be NULL: last create error */
+int  b200_device_count(void);
+
+/* ---- communicator (replaces FSILS_commuType + MPI, liner_solver/commu.cpp:44) ------------- */
+/* uid: 128 bytes produced on rank 0 and distributed by the caller (MPI_Bcast / torch.distributed). */
+int b200_comm_unique_id(void* uid128);
+int b200_comm_init(b200_handle* h, int rank, int nranks, const void* uid128);
+
+/* ---- structure (replaces fsils_lhs_create liner_solver/lhs.cpp:57; consumes its result) ---- */
+/* rowPtr(nNo+1)/colPtr(nnz): the assembly-order CSR of lhsa (solver/lhsa.cpp:153).  map(nNo):
+ * assembly id -> solver id (lhs.map).  mynNo: rows counted in dots (lhs.mynNo).  Halo lists as in
+ * lhs.cS[i]: req_rank[i] = iP, req_n[i] = n, req_ptr = the ptr arrays concatenated (solver ids). */
+int b200_lhs_create(b200_handle* h, int gnNo, int nNo, int mynNo, int nnz,
+                    const int* rowPtr, const int* colPtr, const int* map,
+                    int nReq, const int* req_rank, const int* req_n, const int* req_ptr, int nFaces);
+/* replaces lhs.face[faIn] as left by fsils_bc_create / fsils_bc_update (liner_solver/bc.cpp:45,171):
+ * glob = solver ids, val(dof,nNo) already halo-summed when the face is shared. */
+int b200_face_set(b200_handle* h, int faIn, int nNo, int dof, int bGrp, const int* glob,
+                  const double* val, int shared);
+
+/* ---- assembly (replaces construct_fluid + do_assem, solver/fluid.cpp:464, lhsa.cpp:97) ------- */
+/* IEN(eNoN,nEl) with assembly node ids, x(3,nNo).  eNoN = 4 (TET4).  qmTET4 <= 0 selects the
+ * default (5+3*sqrt(5))/20 (solver/ComMod.h:1011). */
+int b200_mesh_set(b200_handle* h, int eNoN, int nEl, const int* IEN, const double* x, double qmTET4);
+/* ls_alloc contract (solver/ls.cpp:51-60): after it R(dof,nNo) and Val(dof*dof,nnz) are zero. */
+int b200_zero(b200_handle* h, int dof);
+/* Upload Ag, Yg (tDof,nNo) and Bf (3,nNo; NULL = zero) for the next b200_assemble_fluid. */
+int b200_state_set(b200_handle* h, int tDof, const double* Ag, const double* Yg, const double* Bf);
+/* Whole-mesh fluid assembly on the device into R/Val, using the state uploaded last. */
+int b200_assemble_fluid(b200_handle* h, const b200_fluid_props* p);
+/* LinearAlgebra::assemble for the few boundary-face elements: staged on the host, flushed by one
+ * scatter kernel before the next get/solve.  eqN(d), lK(dof*dof,d,d), lR(dof,d). */
+int b200_assemble_elem(b200_handle* h, int d, const int* eqN, const double* lK, const double* lR);
+/* parity taps / host boundary-condition code (assembly ordering, like com_mod.R / com_mod.Val). */
+int b200_get_R(b200_handle* h, double* R);
+int b200_set_R(b200_handle* h, int dof, const double* R);
+int b200_get_Val(b200_handle* h, double* Val);
+int b200_set_Val(b200_handle* h, int dof, const double* Val);
+/* all_fun::commu(R) (solver/all_fun.cpp:122): overlap-node add of the device R. */
+int b200_commu_R(b200_handle* h);
+
+/* ---- solve (replaces fsils_solve, liner_solver/solve.cpp:50) ------------------------------- */
+/* Consumes the device R/Val (Val is scaled in place like the reference), leaves the solution in the
+ * device R and, when R_out != NULL, copies it to the host (dof,nNo, assembly order).  GM/CG are
+ * read for ls_type == B200_LS_NS only.  incL/res: nFaces entries or NULL. */
+int b200_solve(b200_handle* h, int ls_type, int prec, const b200_tol* RI, const b200_tol* GM,
+               const b200_tol* CG, const int* incL, const double* res, double* R_out, b200_ls_out* out);
+
+/* ---- single-kernel taps used by the parity tests and the roofline bench --------------------- */
+/* y = K x (+ overlap add) with the device Val; x, y host (dof,nNo) in assembly order. */
+int b200_spmv(b200_handle* h, int dof, const double* x, double* y);
+/* Times `reps` launches of the block SpMV on device-resident random x (CUDA events on the launch
+ * stream); returns mean milliseconds per launch. */
+int b200_spmv_bench(b200_handle* h, int dof, int reps, double* ms_per_launch);
+/* Kernel-launch counter (all kernels this handle launched since creation). */
+long long b200_launch_count(b200_handle* h);
+/* Milliseconds spent (CUDA events) in the phases of the last b200_assemble_fluid / b200_solve:
+ * t[0] assembly, t[1] preconditioning, t[2] Krylov, t[3] SpMV share of t[2] (0 unless profiling on). */
+int b200_last_timings(b200_handle* h, double* t4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVB200_H */

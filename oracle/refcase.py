@@ -1,0 +1,47 @@
+"""TEST INFRASTRUCTURE ONLY (oracle).  Runs a svfsiplus_b200.problem case through the compiled
+reference (oracle/_ref/libsvref.so): construct_fluid for R/Val, then fsils_solve."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import ref
+
+
+def _ls_vector(ls):
+    ls_type, RI, GM, CG = ls
+    GM = GM or (1e-2, 1e-10, 2, 100)
+    CG = CG or (0.2, 1e-10, 500, 0)
+    return ref.ls_params(ls_type, RI[0], RI[1], RI[2], RI[3], gm=(GM[0], GM[1], GM[2], GM[3]), cg=(CG[0], CG[1], CG[2]))
+
+
+def reference_assemble(case):
+    m = case["mesh"]
+    ra = ref.RefAssembly(m.x, m.ien)
+    p = dict(case["props"])
+    visc = None
+    if p.get("viscType", 0) != 0:
+        visc = [p["viscType"], p["mu"], p.get("mu_o", 0.0), p.get("lam", 0.0), p.get("a", 0.0), p.get("n", 0.0)]
+    R, Val, secs = ra.fluid(case["Ag"], case["Yg"], case["Bf"], dt=p["dt"], am=p["am"], af=p["af"], gam=p["gam"],
+                            rho=p["rho"], mu=p["mu"], f=p.get("f", (0.0, 0.0, 0.0)), Kinv=p.get("Kinv", 0.0),
+                            visc=visc, mvMsh=p.get("mvMsh", False))
+    rowPtr, colPtr = ra.csr()
+    ra.close()
+    return R, Val, rowPtr, colPtr, secs
+
+
+def reference_solve(case, R, Val, ls, prec=ref.PREC_FSILS):
+    m = case["mesh"]
+    part = dict(gnNo=m.nNo, gNodes=np.arange(m.nNo), rowPtr=case["rowPtr"], colPtr=case["colPtr"],
+                faces=[dict(nodes=f["nodes"], dof=f["dof"], bGrp=f["bGrp"], val=f["val"]) for f in case["faces"]])
+    rr = ref.RefRanks([part])
+    X, Vs, out = rr.solve(R.shape[1], _ls_vector(ls), prec, [R], [Val], case["incL"], case["res"])
+    rr.close()
+    return X[0], out[0]
+
+
+def reference_step(case, ls="NS"):
+    from svfsiplus_b200.problem import LS_SETTINGS
+    ls = LS_SETTINGS[ls] if isinstance(ls, str) else ls
+    R, Val, rowPtr, colPtr, _ = reference_assemble(case)
+    X, out = reference_solve(case, R, Val, ls)
+    return R, Val, X, out

@@ -1,0 +1,261 @@
+"""ctypes binding of the C ABI in include/svb200.h (svfsiplus_b200/libsvb200.so).
+
+This is the Python-side stub of the drop-in boundary, used by the parity tests, bench.py and
+__graft_entry__.smoke().  It mirrors, call for call, what the C++ plug-in class
+svfsiplus_b200/host/B200LinearAlgebra.cpp does inside svMultiPhysics (LinearAlgebra interface,
+Code/Source/solver/LinearAlgebra.h:39-63).  There is no fallback: if the CUDA library is missing or
+no device is present every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvb200.so")
+
+LS_BICGS, LS_NS, LS_GMRES, LS_CG = 795, 796, 797, 798
+PREC_FSILS, PREC_RCS = 701, 709
+BC_DIR, BC_NEU = 0, 1
+
+
+class Tol(C.Structure):
+    _fields_ = [("relTol", C.c_double), ("absTol", C.c_double), ("mItr", C.c_int), ("sD", C.c_int)]
+
+
+class SubOut(C.Structure):
+    _fields_ = [("suc", C.c_int), ("itr", C.c_int), ("iNorm", C.c_double), ("fNorm", C.c_double),
+                ("dB", C.c_double), ("callD", C.c_double)]
+
+
+class LsOut(C.Structure):
+    _fields_ = [("RI", SubOut), ("GM", SubOut), ("CG", SubOut), ("Resm", C.c_int), ("Resc", C.c_int)]
+
+
+class FluidProps(C.Structure):
+    _fields_ = [("dt", C.c_double), ("am", C.c_double), ("af", C.c_double), ("gam", C.c_double),
+                ("tDof", C.c_int), ("mvMsh", C.c_int),
+                ("rho", C.c_double), ("f", C.c_double * 3), ("Kinv", C.c_double),
+                ("viscType", C.c_int),
+                ("mu_i", C.c_double), ("mu_o", C.c_double), ("lam", C.c_double), ("a", C.c_double), ("n", C.c_double)]
+
+
+EXPORTS = [
+    "b200_create", "b200_destroy", "b200_last_error", "b200_device_count", "b200_comm_unique_id", "b200_comm_init",
+    "b200_lhs_create", "b200_face_set", "b200_mesh_set", "b200_zero", "b200_state_set", "b200_assemble_fluid",
+    "b200_assemble_elem", "b200_get_R", "b200_set_R", "b200_get_Val", "b200_set_Val", "b200_commu_R", "b200_solve",
+    "b200_spmv", "b200_spmv_bench", "b200_launch_count", "b200_last_timings",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libsvb200.so (fails loudly when the CUDA extension has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                               "There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        vp, ci, cd = C.c_void_p, C.c_int, C.c_double
+        L.b200_create.argtypes = [C.POINTER(vp), ci]
+        L.b200_destroy.argtypes = [vp]
+        L.b200_destroy.restype = None
+        L.b200_last_error.argtypes = [vp]
+        L.b200_last_error.restype = C.c_char_p
+        L.b200_comm_unique_id.argtypes = [vp]
+        L.b200_comm_init.argtypes = [vp, ci, ci, vp]
+        L.b200_lhs_create.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, ci, vp, vp, vp, ci]
+        L.b200_face_set.argtypes = [vp, ci, ci, ci, ci, vp, vp, ci]
+        L.b200_mesh_set.argtypes = [vp, ci, ci, vp, vp, cd]
+        L.b200_zero.argtypes = [vp, ci]
+        L.b200_state_set.argtypes = [vp, ci, vp, vp, vp]
+        L.b200_assemble_fluid.argtypes = [vp, C.POINTER(FluidProps)]
+        L.b200_assemble_elem.argtypes = [vp, ci, vp, vp, vp]
+        L.b200_get_R.argtypes = [vp, vp]
+        L.b200_set_R.argtypes = [vp, ci, vp]
+        L.b200_get_Val.argtypes = [vp, vp]
+        L.b200_set_Val.argtypes = [vp, ci, vp]
+        L.b200_commu_R.argtypes = [vp]
+        L.b200_solve.argtypes = [vp, ci, ci, C.POINTER(Tol), C.POINTER(Tol), C.POINTER(Tol), vp, vp, vp, C.POINTER(LsOut)]
+        L.b200_spmv.argtypes = [vp, ci, vp, vp]
+        L.b200_spmv_bench.argtypes = [vp, ci, ci, C.POINTER(cd)]
+        L.b200_launch_count.argtypes = [vp]
+        L.b200_launch_count.restype = C.c_longlong
+        L.b200_last_timings.argtypes = [vp, vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))          # raw address (e.g. a pinned torch tensor's data_ptr())
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def fluid_props(*, dt, am, af, gam, rho, mu, tDof=4, mvMsh=False, f=(0.0, 0.0, 0.0), Kinv=0.0,
+                viscType=0, mu_o=0.0, lam=0.0, a=0.0, n=0.0) -> FluidProps:
+    p = FluidProps()
+    p.dt, p.am, p.af, p.gam = dt, am, af, gam
+    p.tDof, p.mvMsh = tDof, int(mvMsh)
+    p.rho, p.Kinv = rho, Kinv
+    p.f[0], p.f[1], p.f[2] = f
+    p.viscType, p.mu_i, p.mu_o, p.lam, p.a, p.n = viscType, mu, mu_o, lam, a, n
+    return p
+
+
+def sub_out_dict(s: SubOut):
+    return dict(suc=bool(s.suc), itr=s.itr, iNorm=s.iNorm, fNorm=s.fNorm, dB=s.dB, callD=s.callD)
+
+
+class Backend:
+    """One handle = one (equation x GPU), like one LinearAlgebra object per equation per MPI rank."""
+
+    def __init__(self, device: int = 0):
+        self.L = lib()
+        self.h = C.c_void_p()
+        if self.L.b200_create(C.byref(self.h), device) != 0:
+            raise RuntimeError("b200_create: " + self.L.b200_last_error(None).decode())
+        self.nNo = 0
+        self.nnz = 0
+        self.dof = 0
+
+    def close(self):
+        if self.h:
+            self.L.b200_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what}: " + self.L.b200_last_error(self.h).decode())
+
+    # -- communicator --------------------------------------------------------------------------
+    def unique_id(self) -> np.ndarray:
+        uid = np.zeros(128, np.uint8)
+        if self.L.b200_comm_unique_id(_p(uid)) != 0:
+            raise RuntimeError("b200_comm_unique_id: " + self.L.b200_last_error(None).decode())
+        return uid
+
+    def comm_init(self, rank, nranks, uid):
+        uid = _c(uid, np.uint8)
+        self._ck(self.L.b200_comm_init(self.h, rank, nranks, _p(uid)), "b200_comm_init")
+
+    # -- structure -----------------------------------------------------------------------------
+    def lhs_create(self, gnNo, rowPtr, colPtr, map=None, mynNo=None, reqs=(), nFaces=0):
+        rowPtr = _c(rowPtr, np.int32); colPtr = _c(colPtr, np.int32)
+        nNo = len(rowPtr) - 1
+        mp = None if map is None else _c(map, np.int32)
+        rr = _c([r[0] for r in reqs], np.int32)
+        rn = _c([len(r[1]) for r in reqs], np.int32)
+        rp = _c(np.concatenate([np.asarray(r[1], np.int32) for r in reqs]) if reqs else np.zeros(0, np.int32), np.int32)
+        self._ck(self.L.b200_lhs_create(self.h, int(gnNo), nNo, int(nNo if mynNo is None else mynNo), len(colPtr),
+                                        _p(rowPtr), _p(colPtr), _p(mp), len(reqs), _p(rr), _p(rn), _p(rp), nFaces),
+                 "b200_lhs_create")
+        self.nNo, self.nnz = nNo, len(colPtr)
+
+    def face_set(self, faIn, glob, dof, bGrp, val=None, shared=False):
+        glob = _c(glob, np.int32)
+        v = None if val is None else _c(val, np.float64)
+        self._ck(self.L.b200_face_set(self.h, faIn, len(glob), dof, bGrp, _p(glob), _p(v), int(shared)), "b200_face_set")
+
+    # -- assembly --------------------------------------------------------------------------------
+    def mesh_set(self, ien, x, qmTET4=-1.0):
+        ien = _c(ien, np.int32); x = _c(x, np.float64)
+        self._ck(self.L.b200_mesh_set(self.h, ien.shape[1], ien.shape[0], _p(ien), _p(x), qmTET4), "b200_mesh_set")
+
+    def zero(self, dof):
+        self._ck(self.L.b200_zero(self.h, dof), "b200_zero")
+        self.dof = dof
+
+    def state_set(self, tDof, Ag, Yg, Bf=None):
+        """Ag/Yg/Bf: numpy arrays or raw host addresses (pinned buffers)."""
+        if isinstance(Ag, np.ndarray):
+            Ag = _c(Ag, np.float64); Yg = _c(Yg, np.float64)
+            Bf = None if Bf is None else _c(Bf, np.float64)
+        self._keep = (Ag, Yg, Bf)
+        self._ck(self.L.b200_state_set(self.h, tDof, _p(Ag), _p(Yg), _p(Bf)), "b200_state_set")
+
+    def assemble_fluid(self, props: FluidProps):
+        self._ck(self.L.b200_assemble_fluid(self.h, C.byref(props)), "b200_assemble_fluid")
+
+    def assemble_elem(self, eqN, lK, lR):
+        eqN = _c(eqN, np.int32); lK = _c(lK, np.float64); lR = _c(lR, np.float64)
+        self._ck(self.L.b200_assemble_elem(self.h, len(eqN), _p(eqN), _p(lK), _p(lR)), "b200_assemble_elem")
+
+    def get_R(self):
+        R = np.empty((self.nNo, self.dof))
+        self._ck(self.L.b200_get_R(self.h, _p(R)), "b200_get_R")
+        return R
+
+    def set_R(self, R):
+        R = _c(R, np.float64)
+        self.dof = R.shape[1]
+        self._ck(self.L.b200_set_R(self.h, self.dof, _p(R)), "b200_set_R")
+
+    def get_Val(self):
+        V = np.empty((self.nnz, self.dof * self.dof))
+        self._ck(self.L.b200_get_Val(self.h, _p(V)), "b200_get_Val")
+        return V
+
+    def set_Val(self, V):
+        V = _c(V, np.float64)
+        dof = int(round(V.shape[1] ** 0.5))
+        self.dof = dof
+        self._ck(self.L.b200_set_Val(self.h, dof, _p(V)), "b200_set_Val")
+
+    def commu_R(self):
+        self._ck(self.L.b200_commu_R(self.h), "b200_commu_R")
+
+    # -- solve -----------------------------------------------------------------------------------
+    def solve(self, ls_type, prec, RI, GM=None, CG=None, incL=None, res=None, out=None, fetch=True):
+        """RI/GM/CG: (relTol, absTol, mItr, sD).  Returns (X or None, info dict).
+        `out`: optional preallocated (nNo, dof) array or raw pinned address for the solution."""
+        def tol(t):
+            return None if t is None else Tol(t[0], t[1], int(t[2]), int(t[3]) if len(t) > 3 else 0)
+        tRI, tGM, tCG = tol(RI), tol(GM), tol(CG)
+        incL_a = None if incL is None else _c(incL, np.int32)
+        res_a = None if res is None else _c(res, np.float64)
+        X = None
+        if fetch:
+            X = out if out is not None else np.empty((self.nNo, self.dof))
+        o = LsOut()
+        self._ck(self.L.b200_solve(self.h, ls_type, prec,
+                                   C.byref(tRI), C.byref(tGM) if tGM else None, C.byref(tCG) if tCG else None,
+                                   _p(incL_a), _p(res_a), _p(X), C.byref(o)), "b200_solve")
+        info = dict(RI=sub_out_dict(o.RI), GM=sub_out_dict(o.GM), CG=sub_out_dict(o.CG), Resm=o.Resm, Resc=o.Resc)
+        return X, info
+
+    # -- taps --------------------------------------------------------------------------------------
+    def spmv(self, x):
+        x = _c(x, np.float64)
+        y = np.empty_like(x)
+        self._ck(self.L.b200_spmv(self.h, x.shape[1], _p(x), _p(y)), "b200_spmv")
+        return y
+
+    def spmv_bench(self, dof, reps=20) -> float:
+        ms = C.c_double(0)
+        self._ck(self.L.b200_spmv_bench(self.h, dof, reps, C.byref(ms)), "b200_spmv_bench")
+        return ms.value
+
+    def launch_count(self) -> int:
+        return int(self.L.b200_launch_count(self.h))
+
+    def timings(self):
+        t = np.zeros(4)
+        self.L.b200_last_timings(self.h, _p(t))
+        return dict(assembly_ms=t[0], precond_ms=t[1], krylov_ms=t[2])

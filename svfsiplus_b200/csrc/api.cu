@@ -1,0 +1,649 @@
+// api.cu — the extern "C" layer declared in include/svb200.h.  Thin: argument checking, uploads,
+// host-side structure preparation (solver-order CSR, transpose map, element colouring) and calls
+// into CudaOps / krylov.hpp / assembly.cuh.  No compute happens on the host.
+#include "svb200.h"
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "assembly.cuh"
+#include "ops_cuda.cuh"
+
+using namespace svb200;
+
+namespace {
+std::string g_create_error;
+}
+
+struct b200_handle {
+  int device = 0;
+  std::unique_ptr<CudaOps> ops;
+  std::string err;
+
+  // assembly-order structure kept for layout conversions and staged-element scatter
+  int nNo = 0, nnz = 0, dof = 0;
+  std::vector<int> h_rowPtrA, h_colA, h_map, h_rowPtrS;
+  bool identity_map = true;
+  int* d_rowPtrA = nullptr;
+  int* d_colA = nullptr;
+  int* d_map = nullptr;
+
+  // system
+  double* R = nullptr;       // dof x nNo, solver ordering
+  double* Val = nullptr;     // dof*dof x nnz, solver layout
+  size_t R_cap = 0, Val_cap = 0;
+  double* stage_d = nullptr; // staging for host<->device conversions
+  size_t stage_cap = 0;
+
+  // mesh
+  int eNoN = 0, nEl = 0, nColors = 0;
+  std::vector<int> color_off;
+  int* d_ien = nullptr;      // colour-sorted
+  int* d_rdest = nullptr;
+  int* d_edest = nullptr;
+  double* d_x = nullptr;
+  int* d_err = nullptr;
+  double qmTET4 = 0.0;
+
+  // state
+  int tDof = 0;
+  double* d_Ag = nullptr;
+  double* d_Yg = nullptr;
+  double* d_Bf = nullptr;
+  size_t state_cap = 0;
+
+  // staged boundary elements
+  struct Staged { int d; std::vector<int> eqN; std::vector<double> lK, lR; };
+  std::vector<Staged> staged;
+
+  // spmv bench vectors
+  double* bx = nullptr;
+  double* by = nullptr;
+
+  ~b200_handle()
+  {
+    cudaFree(d_rowPtrA); cudaFree(d_colA); cudaFree(d_map);
+    cudaFree(R); cudaFree(Val); cudaFree(stage_d);
+    cudaFree(d_ien); cudaFree(d_rdest); cudaFree(d_edest); cudaFree(d_x); cudaFree(d_err);
+    cudaFree(d_Ag); cudaFree(d_Yg); cudaFree(d_Bf);
+    cudaFree(bx); cudaFree(by);
+  }
+};
+
+namespace {
+
+template <class F> int guarded(b200_handle* h, F&& f)
+{
+  if (!h) return 1;
+  try {
+    CU_CHECK(cudaSetDevice(h->device));
+    f();
+    return 0;
+  } catch (const std::exception& e) {
+    h->err = e.what();
+    return 1;
+  }
+}
+
+template <class T> T* upload(const T* src, size_t n, cudaStream_t st)
+{
+  T* d = nullptr;
+  CU_CHECK(cudaMalloc(&d, std::max<size_t>(n, 1)*sizeof(T)));
+  if (n) CU_CHECK(cudaMemcpyAsync(d, src, n*sizeof(T), cudaMemcpyHostToDevice, st));
+  return d;
+}
+
+void ensure(double*& p, size_t& cap, size_t n)
+{
+  if (cap >= n && p) return;
+  if (p) CU_CHECK(cudaFree(p));
+  CU_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1)*sizeof(double)));
+  cap = n;
+}
+
+void ensure_system(b200_handle* h, int dof)
+{
+  ensure(h->R, h->R_cap, size_t(dof)*h->nNo);
+  ensure(h->Val, h->Val_cap, size_t(dof)*dof*h->nnz);
+  h->dof = dof;
+}
+
+// flush LinearAlgebra::assemble contributions staged on the host (one deterministic scatter kernel)
+void flush_staged(b200_handle* h)
+{
+  if (h->staged.empty()) return;
+  auto& ops = *h->ops;
+  const int dof = h->dof, bs = dof*dof;
+  // group by d (number of element nodes); boundary faces of one mesh share d
+  std::vector<int> ds;
+  for (auto& s : h->staged) if (std::find(ds.begin(), ds.end(), s.d) == ds.end()) ds.push_back(s.d);
+  for (int d : ds) {
+    std::vector<int> rows, pos;
+    std::vector<double> lK, lR;
+    int n = 0;
+    for (auto& s : h->staged) {
+      if (s.d != d) continue;
+      n++;
+      for (int a = 0; a < d; a++) rows.push_back(s.eqN[a] < 0 ? -1 : h->h_map[s.eqN[a]]);
+      for (int a = 0; a < d; a++) {
+        for (int b = 0; b < d; b++) {
+          int p = -1;
+          const int A = s.eqN[a], B = s.eqN[b];
+          if (A >= 0 && B >= 0) {
+            const int* beg = h->h_colA.data() + h->h_rowPtrA[A];
+            const int* end = h->h_colA.data() + h->h_rowPtrA[A+1];
+            const int* it = std::lower_bound(beg, end, B);
+            if (it == end || *it != B) throw std::runtime_error("assemble: column not in the sparsity pattern");
+            p = h->h_rowPtrS[h->h_map[A]] + int(it - beg);
+          }
+          pos.push_back(p);
+        }
+      }
+      lK.insert(lK.end(), s.lK.begin(), s.lK.end());
+      lR.insert(lR.end(), s.lR.begin(), s.lR.end());
+    }
+    int* d_rows = upload(rows.data(), rows.size(), ops.st);
+    int* d_pos = upload(pos.data(), pos.size(), ops.st);
+    double* d_lK = upload(lK.data(), lK.size(), ops.st);
+    double* d_lR = upload(lR.data(), lR.size(), ops.st);
+    k_scatter_staged<<<1, 256, 0, ops.st>>>(n, d, dof, d_rows, d_pos, d_lK, d_lR, h->R, h->Val);
+    ops.post();
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+    cudaFree(d_rows); cudaFree(d_pos); cudaFree(d_lK); cudaFree(d_lR);
+    (void)bs;
+  }
+  h->staged.clear();
+}
+
+} // namespace
+
+extern "C" {
+
+int b200_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int b200_create(b200_handle** out, int device)
+{
+  *out = nullptr;
+  try {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) throw std::runtime_error("no CUDA device available: this backend has no CPU fallback");
+    if (device < 0 || device >= n) throw std::runtime_error("invalid device index");
+    auto h = std::make_unique<b200_handle>();
+    h->device = device;
+    h->ops.reset(new CudaOps(device));
+    CU_CHECK(cudaMalloc(&h->d_err, sizeof(int)));
+    CU_CHECK(cudaMemset(h->d_err, 0, sizeof(int)));
+    *out = h.release();
+    return 0;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return 1;
+  }
+}
+
+void b200_destroy(b200_handle* h)
+{
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  delete h;
+}
+
+const char* b200_last_error(b200_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int b200_comm_unique_id(void* uid128)
+{
+  try {
+    Nccl n;
+    n.load();
+    Nccl::UniqueId id;
+    n.check(n.GetUniqueId(&id), "GetUniqueId");
+    std::memcpy(uid128, &id, 128);
+    return 0;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return 1;
+  }
+}
+
+int b200_comm_init(b200_handle* h, int rank, int nranks, const void* uid128)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    ops.rank = rank;
+    ops.nranks = nranks;
+    if (nranks > 1) {
+      ops.nccl.load();
+      Nccl::UniqueId id;
+      std::memcpy(&id, uid128, 128);
+      ops.nccl.check(ops.nccl.CommInitRank(&ops.comm, nranks, id, rank), "CommInitRank");
+    }
+  });
+}
+
+int b200_lhs_create(b200_handle* h, int gnNo, int nNo, int mynNo, int nnz, const int* rowPtr, const int* colPtr,
+                    const int* map, int nReq, const int* req_rank, const int* req_n, const int* req_ptr, int nFaces)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (nNo <= 0 || nnz <= 0) throw std::runtime_error("lhs_create: empty system");
+    if (nReq > 0 && ops.nranks == 1) throw std::runtime_error("lhs_create: halo lists given but no communicator (call b200_comm_init first)");
+    h->nNo = nNo; h->nnz = nnz;
+    h->h_rowPtrA.assign(rowPtr, rowPtr + nNo + 1);
+    h->h_colA.assign(colPtr, colPtr + nnz);
+    h->h_map.resize(nNo);
+    h->identity_map = true;
+    for (int a = 0; a < nNo; a++) {
+      h->h_map[a] = map ? map[a] : a;
+      if (h->h_map[a] != a) h->identity_map = false;
+    }
+    // solver-order CSR: row s = map[a] takes the entries of assembly row a, in the same order,
+    // with mapped column ids (this is what lhs.rowPtr(2,nNo)/lhs.colPtr describe, lhs.cpp:232-256).
+    std::vector<int> inv(nNo);
+    for (int a = 0; a < nNo; a++) inv[h->h_map[a]] = a;
+    std::vector<int>& rpS = h->h_rowPtrS;
+    rpS.assign(nNo + 1, 0);
+    for (int s = 0; s < nNo; s++) rpS[s+1] = rpS[s] + (rowPtr[inv[s]+1] - rowPtr[inv[s]]);
+    std::vector<int> colS(nnz), diag(nNo, -1), tpos(nnz, -1);
+    for (int s = 0; s < nNo; s++) {
+      const int a = inv[s];
+      const int len = rowPtr[a+1] - rowPtr[a];
+      for (int k = 0; k < len; k++) {
+        const int c = h->h_map[colPtr[rowPtr[a] + k]];
+        colS[rpS[s] + k] = c;
+        if (c == s && diag[s] < 0) diag[s] = rpS[s] + k;
+      }
+      if (diag[s] < 0) throw std::runtime_error("lhs_create: a row has no diagonal entry");
+    }
+    // transpose positions (pattern symmetric): entry (s,c) at p <-> entry (c,s).  Columns inside a
+    // row are sorted by ASSEMBLY id, so search in the assembly CSR.
+    for (int a = 0; a < nNo; a++) {
+      const int s = h->h_map[a];
+      for (int k = rowPtr[a]; k < rowPtr[a+1]; k++) {
+        const int b = colPtr[k];
+        const int* beg = colPtr + rowPtr[b];
+        const int* end = colPtr + rowPtr[b+1];
+        const int* it = std::lower_bound(beg, end, a);
+        const int p = rpS[s] + (k - rowPtr[a]);
+        if (it != end && *it == a) tpos[p] = rpS[h->h_map[b]] + int(it - beg);
+        else tpos[p] = p;      // non-symmetric pattern entry: never hit for FE node graphs
+      }
+    }
+    cudaFree(ops.rowPtr); cudaFree(ops.col); cudaFree(ops.diag); cudaFree(ops.tpos);
+    cudaFree(h->d_rowPtrA); cudaFree(h->d_colA); cudaFree(h->d_map);
+    ops.rowPtr = upload(rpS.data(), rpS.size(), ops.st);
+    ops.col = upload(colS.data(), colS.size(), ops.st);
+    ops.diag = upload(diag.data(), diag.size(), ops.st);
+    ops.tpos = upload(tpos.data(), tpos.size(), ops.st);
+    h->d_rowPtrA = upload(h->h_rowPtrA.data(), h->h_rowPtrA.size(), ops.st);
+    h->d_colA = upload(h->h_colA.data(), h->h_colA.size(), ops.st);
+    h->d_map = upload(h->h_map.data(), h->h_map.size(), ops.st);
+    ops.gnNo_ = gnNo; ops.nNo_ = nNo; ops.mynNo_ = mynNo; ops.nnz_ = nnz;
+
+    for (auto& f : ops.faces) { cudaFree(f.glob); cudaFree(f.val); cudaFree(f.valM); }
+    ops.faces.assign(nFaces, DevFace());
+    for (auto& r : ops.reqs) { cudaFree(r.ptr); cudaFree(r.sbuf); cudaFree(r.rbuf); }
+    ops.reqs.assign(nReq, HaloReq());
+    ops.halo_dof_cap = 4;
+    size_t off = 0;
+    for (int i = 0; i < nReq; i++) {
+      auto& r = ops.reqs[i];
+      r.peer = req_rank[i];
+      r.n = req_n[i];
+      r.ptr = upload(req_ptr + off, size_t(r.n), ops.st);
+      CU_CHECK(cudaMalloc(&r.sbuf, sizeof(double)*std::max(1, r.n)*ops.halo_dof_cap));
+      CU_CHECK(cudaMalloc(&r.rbuf, sizeof(double)*std::max(1, r.n)*ops.halo_dof_cap));
+      off += size_t(r.n);
+    }
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+  });
+}
+
+int b200_face_set(b200_handle* h, int faIn, int nNo, int dof, int bGrp, const int* glob, const double* val, int shared)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (faIn < 0) throw std::runtime_error("FSILS: faIn is smaller than zero");
+    if (faIn >= int(ops.faces.size()))
+      throw std::runtime_error("FSILS: faIn is exceeding lhs structure maximum number of faces");
+    auto& f = ops.faces[faIn];
+    cudaFree(f.glob); cudaFree(f.val); cudaFree(f.valM);
+    f = DevFace();
+    f.nNo = nNo; f.dof = dof; f.bGrp = bGrp; f.shared = shared != 0; f.set = true;
+    f.glob = upload(glob, size_t(nNo), ops.st);
+    std::vector<double> z;
+    if (!val) { z.assign(size_t(nNo)*dof, 0.0); val = z.data(); }
+    f.val = upload(val, size_t(nNo)*dof, ops.st);
+    CU_CHECK(cudaMalloc(&f.valM, sizeof(double)*std::max<size_t>(1, size_t(nNo)*dof)));
+    CU_CHECK(cudaMemsetAsync(f.valM, 0, sizeof(double)*std::max<size_t>(1, size_t(nNo)*dof), ops.st));
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+  });
+}
+
+int b200_mesh_set(b200_handle* h, int eNoN, int nEl, const int* IEN, const double* x, double qmTET4)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (eNoN != 4) throw std::runtime_error("mesh_set: only TET4 (eNoN = 4) is built in this round");
+    if (h->nNo == 0) throw std::runtime_error("mesh_set: call b200_lhs_create first");
+    h->eNoN = eNoN; h->nEl = nEl;
+    h->qmTET4 = qmTET4 > 0.0 ? qmTET4 : (5.0 + 3.0*std::sqrt(5.0))/20.0;
+
+    // greedy colouring: no two elements of a colour share a node (deterministic scatter order)
+    const int nNo = h->nNo;
+    constexpr int W = 4;                                  // 256 colours max
+    std::vector<uint64_t> used(size_t(nNo)*W, 0);
+    std::vector<int> color(nEl);
+    int nColors = 0;
+    for (int e = 0; e < nEl; e++) {
+      uint64_t m[W] = {0, 0, 0, 0};
+      for (int a = 0; a < eNoN; a++) {
+        const int A = IEN[size_t(e)*eNoN + a];
+        if (A < 0 || A >= nNo) throw std::runtime_error("mesh_set: IEN entry out of range");
+        for (int w = 0; w < W; w++) m[w] |= used[size_t(A)*W + w];
+      }
+      int c = -1;
+      for (int w = 0; w < W && c < 0; w++) if (~m[w]) c = w*64 + __builtin_ctzll(~m[w]);
+      if (c < 0) throw std::runtime_error("mesh_set: more than 256 colours needed");
+      color[e] = c;
+      nColors = std::max(nColors, c + 1);
+      for (int a = 0; a < eNoN; a++) used[size_t(IEN[size_t(e)*eNoN + a])*W + c/64] |= (uint64_t(1) << (c % 64));
+    }
+    h->nColors = nColors;
+    h->color_off.assign(nColors + 1, 0);
+    for (int e = 0; e < nEl; e++) h->color_off[color[e] + 1]++;
+    for (int c = 0; c < nColors; c++) h->color_off[c+1] += h->color_off[c];
+    std::vector<int> cursor(h->color_off.begin(), h->color_off.end() - 1);
+    std::vector<int> ien_sorted(size_t(nEl)*eNoN);
+    for (int e = 0; e < nEl; e++) {
+      const int dst = cursor[color[e]]++;
+      std::memcpy(&ien_sorted[size_t(dst)*eNoN], &IEN[size_t(e)*eNoN], sizeof(int)*eNoN);
+    }
+
+    cudaFree(h->d_ien); cudaFree(h->d_rdest); cudaFree(h->d_edest); cudaFree(h->d_x);
+    h->d_ien = upload(ien_sorted.data(), ien_sorted.size(), ops.st);
+    h->d_x = upload(x, size_t(nNo)*3, ops.st);
+    CU_CHECK(cudaMalloc(&h->d_rdest, sizeof(int)*size_t(nEl)*eNoN));
+    CU_CHECK(cudaMalloc(&h->d_edest, sizeof(int)*size_t(nEl)*eNoN*eNoN));
+    k_elem_dest<<<CudaOps::grid_for(size_t(nEl)*eNoN, 256, 1), 256, 0, ops.st>>>(nEl, eNoN, h->d_ien, h->d_rowPtrA, h->d_colA,
+                                                                                  h->d_map, ops.rowPtr, h->d_rdest, h->d_edest);
+    ops.post();
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+  });
+}
+
+int b200_zero(b200_handle* h, int dof)
+{
+  return guarded(h, [&] {
+    if (dof < 1 || dof > 4) throw std::runtime_error("zero: dof must be 1..4");
+    ensure_system(h, dof);
+    CU_CHECK(cudaMemsetAsync(h->R, 0, sizeof(double)*size_t(dof)*h->nNo, h->ops->st));
+    CU_CHECK(cudaMemsetAsync(h->Val, 0, sizeof(double)*size_t(dof)*dof*h->nnz, h->ops->st));
+    h->staged.clear();
+  });
+}
+
+int b200_state_set(b200_handle* h, int tDof, const double* Ag, const double* Yg, const double* Bf)
+{
+  return guarded(h, [&] {
+    auto st = h->ops->st;
+    const size_t n = size_t(h->nNo);
+    if (h->state_cap < n*tDof || h->tDof != tDof) {
+      cudaFree(h->d_Ag); cudaFree(h->d_Yg); cudaFree(h->d_Bf);
+      CU_CHECK(cudaMalloc(&h->d_Ag, sizeof(double)*n*tDof));
+      CU_CHECK(cudaMalloc(&h->d_Yg, sizeof(double)*n*tDof));
+      CU_CHECK(cudaMalloc(&h->d_Bf, sizeof(double)*n*3));
+      h->state_cap = n*tDof;
+      h->tDof = tDof;
+    }
+    CU_CHECK(cudaMemcpyAsync(h->d_Ag, Ag, sizeof(double)*n*tDof, cudaMemcpyHostToDevice, st));
+    CU_CHECK(cudaMemcpyAsync(h->d_Yg, Yg, sizeof(double)*n*tDof, cudaMemcpyHostToDevice, st));
+    if (Bf) CU_CHECK(cudaMemcpyAsync(h->d_Bf, Bf, sizeof(double)*n*3, cudaMemcpyHostToDevice, st));
+    else CU_CHECK(cudaMemsetAsync(h->d_Bf, 0, sizeof(double)*n*3, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+int b200_assemble_fluid(b200_handle* h, const b200_fluid_props* p)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (h->nEl == 0) throw std::runtime_error("assemble_fluid: no mesh (b200_mesh_set)");
+    if (!h->d_Ag) throw std::runtime_error("assemble_fluid: no state (b200_state_set)");
+    if (h->dof != 4 || !h->Val) throw std::runtime_error("assemble_fluid: call b200_zero(h, 4) first");
+    if (p->tDof != h->tDof) throw std::runtime_error("assemble_fluid: tDof differs from the uploaded state");
+    if (p->mvMsh && p->tDof < 7) throw std::runtime_error("assemble_fluid: mvMsh needs tDof >= 7");
+    FluidConsts c;
+    c.dt = p->dt; c.am = p->am; c.af = p->af; c.gam = p->gam;
+    c.rho = p->rho; c.f[0] = p->f[0]; c.f[1] = p->f[1]; c.f[2] = p->f[2]; c.Kinv = p->Kinv;
+    c.viscType = p->viscType; c.mu_i = p->mu_i; c.mu_o = p->mu_o; c.lam = p->lam; c.a = p->a; c.n = p->n;
+    c.tDof = p->tDof; c.mvMsh = p->mvMsh;
+    // Gauss rule and shape functions of TET4 (nn_elem_gip.h:501-517, nn_elem_gnn.h:1232-1238)
+    const double s = h->qmTET4, t = (1.0 - s)/3.0;
+    const double xi[4][3] = {{s, t, t}, {t, s, t}, {t, t, s}, {t, t, t}};
+    for (int g = 0; g < 4; g++) {
+      c.w[g] = 1.0/24.0;
+      c.N[g][0] = xi[g][0]; c.N[g][1] = xi[g][1]; c.N[g][2] = xi[g][2];
+      c.N[g][3] = 1.0 - xi[g][0] - xi[g][1] - xi[g][2];
+    }
+    double t0 = wall_s();
+    for (int col = 0; col < h->nColors; col++) {
+      const int e0 = h->color_off[col], e1 = h->color_off[col+1];
+      if (e1 == e0) continue;
+      const int blocks = (e1 - e0 + 127)/128;
+      k_assemble_fluid_tet4<<<blocks, 128, 0, ops.st>>>(e0, e1, c, h->d_ien, h->d_rdest, h->d_edest, h->d_x,
+                                                        h->d_Ag, h->d_Yg, h->d_Bf, h->R, h->Val, h->d_err);
+      ops.post();
+    }
+    int flag = 0;
+    CU_CHECK(cudaMemcpyAsync(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, ops.st));
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+    ops.phase_ms[0] = (wall_s() - t0)*1e3;
+    if (flag != 0) {
+      CU_CHECK(cudaMemset(h->d_err, 0, sizeof(int)));
+      throw std::runtime_error("[construct_fluid] Jacobian for element " + std::to_string(flag - 1) + " is < 0.");
+    }
+  });
+}
+
+int b200_assemble_elem(b200_handle* h, int d, const int* eqN, const double* lK, const double* lR)
+{
+  return guarded(h, [&] {
+    if (h->dof == 0) throw std::runtime_error("assemble: call b200_zero first");
+    b200_handle::Staged s;
+    s.d = d;
+    s.eqN.assign(eqN, eqN + d);
+    s.lK.assign(lK, lK + size_t(h->dof)*h->dof*d*d);
+    s.lR.assign(lR, lR + size_t(h->dof)*d);
+    h->staged.push_back(std::move(s));
+  });
+}
+
+int b200_get_R(b200_handle* h, double* R)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    flush_staged(h);
+    const size_t n = size_t(h->dof)*h->nNo;
+    if (h->identity_map) {
+      CU_CHECK(cudaMemcpyAsync(R, h->R, sizeof(double)*n, cudaMemcpyDeviceToHost, ops.st));
+    } else {
+      ensure(h->stage_d, h->stage_cap, n);
+      k_permute_bwd<<<CudaOps::grid_for(n, 256), 256, 0, ops.st>>>(h->nNo, h->dof, h->d_map, h->R, h->stage_d);
+      ops.post();
+      CU_CHECK(cudaMemcpyAsync(R, h->stage_d, sizeof(double)*n, cudaMemcpyDeviceToHost, ops.st));
+    }
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+  });
+}
+
+int b200_set_R(b200_handle* h, int dof, const double* R)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (h->dof != dof || !h->R) { ensure_system(h, dof); }
+    const size_t n = size_t(dof)*h->nNo;
+    if (h->identity_map) {
+      CU_CHECK(cudaMemcpyAsync(h->R, R, sizeof(double)*n, cudaMemcpyHostToDevice, ops.st));
+    } else {
+      ensure(h->stage_d, h->stage_cap, n);
+      CU_CHECK(cudaMemcpyAsync(h->stage_d, R, sizeof(double)*n, cudaMemcpyHostToDevice, ops.st));
+      k_permute_fwd<<<CudaOps::grid_for(n, 256), 256, 0, ops.st>>>(h->nNo, dof, h->d_map, h->stage_d, h->R);
+      ops.post();
+    }
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+  });
+}
+
+int b200_get_Val(b200_handle* h, double* Val)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    flush_staged(h);
+    const int bs = h->dof*h->dof;
+    const size_t n = size_t(bs)*h->nnz;
+    if (h->identity_map) {
+      CU_CHECK(cudaMemcpyAsync(Val, h->Val, sizeof(double)*n, cudaMemcpyDeviceToHost, ops.st));
+    } else {
+      ensure(h->stage_d, h->stage_cap, n);
+      k_val_rows<<<kSmCount*8, 256, 0, ops.st>>>(h->nNo, bs, h->d_map, h->d_rowPtrA, ops.rowPtr, h->Val, h->stage_d, 0);
+      ops.post();
+      CU_CHECK(cudaMemcpyAsync(Val, h->stage_d, sizeof(double)*n, cudaMemcpyDeviceToHost, ops.st));
+    }
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+  });
+}
+
+int b200_set_Val(b200_handle* h, int dof, const double* Val)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (h->dof != dof || !h->Val) { ensure_system(h, dof); }
+    const int bs = dof*dof;
+    const size_t n = size_t(bs)*h->nnz;
+    if (h->identity_map) {
+      CU_CHECK(cudaMemcpyAsync(h->Val, Val, sizeof(double)*n, cudaMemcpyHostToDevice, ops.st));
+    } else {
+      ensure(h->stage_d, h->stage_cap, n);
+      CU_CHECK(cudaMemcpyAsync(h->stage_d, Val, sizeof(double)*n, cudaMemcpyHostToDevice, ops.st));
+      k_val_rows<<<kSmCount*8, 256, 0, ops.st>>>(h->nNo, bs, h->d_map, h->d_rowPtrA, ops.rowPtr, h->stage_d, h->Val, 1);
+      ops.post();
+    }
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+  });
+}
+
+int b200_commu_R(b200_handle* h)
+{
+  return guarded(h, [&] {
+    flush_staged(h);
+    h->ops->halo_add(h->dof, h->R);
+    CU_CHECK(cudaStreamSynchronize(h->ops->st));
+  });
+}
+
+int b200_solve(b200_handle* h, int ls_type, int prec, const b200_tol* RI, const b200_tol* GM, const b200_tol* CG,
+               const int* incL, const double* res, double* R_out, b200_ls_out* out)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (!h->R || !h->Val || h->dof == 0) throw std::runtime_error("solve: no assembled system");
+    flush_staged(h);
+    Ls ls;
+    ls.LS_type = ls_type;
+    auto set = [](SubLs& s, const b200_tol* t) { if (t) { s.relTol = t->relTol; s.absTol = t->absTol; s.mItr = t->mItr; s.sD = t->sD; } };
+    set(ls.RI, RI); set(ls.GM, GM); set(ls.CG, CG);
+    if (!RI) throw std::runtime_error("solve: RI tolerances are required");
+    if (ls_type == B200_LS_NS && (!GM || !CG)) throw std::runtime_error("solve: NS solver needs GM and CG tolerances");
+    if (ls_type == B200_LS_NS && h->dof < 3) throw std::runtime_error("solve: NS solver needs dof = nsd + 1");
+    if ((ls_type == B200_LS_GMRES || ls_type == B200_LS_NS) && ls.RI.sD <= 0 && ls_type == B200_LS_GMRES)
+      throw std::runtime_error("solve: Krylov space dimension must be positive");
+    ops.phase_ms[1] = ops.phase_ms[2] = ops.phase_ms[3] = 0.0;
+    svb200::solve(ops, ls, h->dof, prec, h->R, h->Val, incL, res);
+    if (R_out) {
+      const size_t n = size_t(h->dof)*h->nNo;
+      if (h->identity_map) {
+        CU_CHECK(cudaMemcpyAsync(R_out, h->R, sizeof(double)*n, cudaMemcpyDeviceToHost, ops.st));
+      } else {
+        ensure(h->stage_d, h->stage_cap, n);
+        k_permute_bwd<<<CudaOps::grid_for(n, 256), 256, 0, ops.st>>>(h->nNo, h->dof, h->d_map, h->R, h->stage_d);
+        ops.post();
+        CU_CHECK(cudaMemcpyAsync(R_out, h->stage_d, sizeof(double)*n, cudaMemcpyDeviceToHost, ops.st));
+      }
+    }
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+    if (out) {
+      auto cp = [](b200_sub_out& o, const SubLs& s) { o.suc = s.suc; o.itr = s.itr; o.iNorm = s.iNorm; o.fNorm = s.fNorm; o.dB = s.dB; o.callD = s.callD; };
+      cp(out->RI, ls.RI); cp(out->GM, ls.GM); cp(out->CG, ls.CG);
+      out->Resm = ls.Resm; out->Resc = ls.Resc;
+    }
+  });
+}
+
+int b200_spmv(b200_handle* h, int dof, const double* x, double* y)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (!h->Val || h->dof != dof) throw std::runtime_error("spmv: no matrix with this dof on the device");
+    const size_t n = size_t(dof)*h->nNo;
+    auto mk = ops.mark();
+    double* xs = ops.vec(n);
+    double* ys = ops.vec(n);
+    double* tmp = ops.vec(n);
+    CU_CHECK(cudaMemcpyAsync(tmp, x, sizeof(double)*n, cudaMemcpyHostToDevice, ops.st));
+    k_permute_fwd<<<CudaOps::grid_for(n, 256), 256, 0, ops.st>>>(h->nNo, dof, h->d_map, tmp, xs); ops.post();
+    ops.spmv_vv(dof, h->Val, xs, ys);
+    k_permute_bwd<<<CudaOps::grid_for(n, 256), 256, 0, ops.st>>>(h->nNo, dof, h->d_map, ys, tmp); ops.post();
+    CU_CHECK(cudaMemcpyAsync(y, tmp, sizeof(double)*n, cudaMemcpyDeviceToHost, ops.st));
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+    ops.release(mk);
+  });
+}
+
+int b200_spmv_bench(b200_handle* h, int dof, int reps, double* ms_per_launch)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (!h->Val || h->dof != dof) throw std::runtime_error("spmv_bench: no matrix with this dof on the device");
+    const size_t n = size_t(dof)*h->nNo;
+    if (!h->bx) {
+      CU_CHECK(cudaMalloc(&h->bx, sizeof(double)*n));
+      CU_CHECK(cudaMalloc(&h->by, sizeof(double)*n));
+      ops.fill(n, 1.0, h->bx);
+    }
+    cudaEvent_t e0, e1;
+    CU_CHECK(cudaEventCreate(&e0));
+    CU_CHECK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; i++) ops.spmv_vv(dof, h->Val, h->bx, h->by);
+    CU_CHECK(cudaEventRecord(e0, ops.st));
+    for (int i = 0; i < reps; i++) ops.spmv_vv(dof, h->Val, h->bx, h->by);
+    CU_CHECK(cudaEventRecord(e1, ops.st));
+    CU_CHECK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_launch = double(ms)/reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  });
+}
+
+long long b200_launch_count(b200_handle* h) { return h ? h->ops->launches : 0; }
+
+int b200_last_timings(b200_handle* h, double* t4)
+{
+  if (!h) return 1;
+  for (int i = 0; i < 4; i++) t4[i] = h->ops->phase_ms[i];
+  return 0;
+}
+
+} // extern "C"

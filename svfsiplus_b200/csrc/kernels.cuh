@@ -1,0 +1,627 @@
+// kernels.cuh — hand-written FP64 kernels for sm_100a: dof-blocked CSR SpMV in the four FSILS
+// shapes, deterministic multi-dot / Gram-Schmidt kernels, Jacobi scaling, depart, halo pack/add,
+// resistance-face rank-1 update.  All kernels are HBM-bound streaming kernels:
+// 256-bit / 128-bit vector loads, one contiguous block row per lane group, streaming cache hints on
+// the matrix (read once per product) and default/evict-last on the gathered vector (re-used from L2).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace svb200 {
+
+constexpr int kSmCount = 148;           // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+constexpr int kRedBlocks = kSmCount*4;  // CTAs of every two-stage reduction
+constexpr int kRedThreads = 256;
+constexpr int kDotJB = 8;               // basis vectors handled per multi-dot launch
+constexpr int kMaxComb = 32;            // vectors per lin_comb launch
+
+// ---- vector memory helpers -------------------------------------------------------------------
+struct d4 { double x, y, z, w; };
+
+// streaming 256-bit load: matrix data is touched once per product -> do not pollute L1, evict first from L2
+__device__ __forceinline__ d4 ld256_stream(const double* p)
+{
+  d4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+// gathered vector entries are re-used by ~15 rows: keep them
+__device__ __forceinline__ d4 ld256_keep(const double* p)
+{
+  d4 v;
+  asm volatile("ld.global.nc.L2::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ d4 ld256(const double* p)
+{
+  d4 v;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st256(double* p, const d4& v)
+{
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
+__device__ __forceinline__ double ld_stream(const double* p)
+{
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream_i(const int* p)
+{
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// =================================================================================================
+// K1  block SpMV  KU = K U   (fsils_spar_mul_vv, liner_solver/spar_mul.cpp:191-260)
+// One group of 4 lanes per row; lane i owns component i of the row: it streams block-row i of every
+// 4x4 block (one 256-bit load), gathers the 4-vector of the column node (one 256-bit load, same
+// address for the 4 lanes -> one sector) and accumulates in the reference's order (blocks left to
+// right, j = 0..3 inside).  A warp therefore reads 8 full 128-byte lines per step and writes 8
+// consecutive 32-byte results.  rowPtr is the standard (nNo+1) CSR pointer in solver ordering.
+// =================================================================================================
+__global__ void __launch_bounds__(256)
+k_spmv_vv4(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
+           const double* __restrict__ K, const double* __restrict__ U, double* __restrict__ KU)
+{
+  const int lane4 = threadIdx.x & 3;
+  const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
+  const int ngroups = (gridDim.x*blockDim.x) >> 2;
+  for (int row = group; row < nNo; row += ngroups) {
+    const int s = __ldg(rowPtr + row);
+    const int e = __ldg(rowPtr + row + 1);
+    double acc = 0.0;
+    int p = s;
+    // 4 blocks in flight per lane (8 x 256-bit loads)
+    for (; p + 4 <= e; p += 4) {
+      const int c0 = ld_stream_i(col + p), c1 = ld_stream_i(col + p + 1), c2 = ld_stream_i(col + p + 2), c3 = ld_stream_i(col + p + 3);
+      const d4 k0 = ld256_stream(K + (size_t(p)*16 + lane4*4));
+      const d4 k1 = ld256_stream(K + (size_t(p+1)*16 + lane4*4));
+      const d4 k2 = ld256_stream(K + (size_t(p+2)*16 + lane4*4));
+      const d4 k3 = ld256_stream(K + (size_t(p+3)*16 + lane4*4));
+      const d4 u0 = ld256_keep(U + size_t(c0)*4);
+      const d4 u1 = ld256_keep(U + size_t(c1)*4);
+      const d4 u2 = ld256_keep(U + size_t(c2)*4);
+      const d4 u3 = ld256_keep(U + size_t(c3)*4);
+      acc = acc + k0.x*u0.x + k0.y*u0.y + k0.z*u0.z + k0.w*u0.w;
+      acc = acc + k1.x*u1.x + k1.y*u1.y + k1.z*u1.z + k1.w*u1.w;
+      acc = acc + k2.x*u2.x + k2.y*u2.y + k2.z*u2.z + k2.w*u2.w;
+      acc = acc + k3.x*u3.x + k3.y*u3.y + k3.z*u3.z + k3.w*u3.w;
+    }
+    for (; p < e; p++) {
+      const int c0 = ld_stream_i(col + p);
+      const d4 k0 = ld256_stream(K + (size_t(p)*16 + lane4*4));
+      const d4 u0 = ld256_keep(U + size_t(c0)*4);
+      acc = acc + k0.x*u0.x + k0.y*u0.y + k0.z*u0.z + k0.w*u0.w;
+    }
+    KU[size_t(row)*4 + lane4] = acc;
+  }
+}
+
+// Generic small-dof variant (dof 1..3; mK of the NS solver is dof 3: 72-byte blocks).  4 lanes per
+// row, lane i < DOF owns component i.
+template <int DOF>
+__global__ void __launch_bounds__(256)
+k_spmv_vv(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
+          const double* __restrict__ K, const double* __restrict__ U, double* __restrict__ KU)
+{
+  const int lane4 = threadIdx.x & 3;
+  const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
+  const int ngroups = (gridDim.x*blockDim.x) >> 2;
+  for (int row = group; row < nNo; row += ngroups) {
+    const int s = __ldg(rowPtr + row);
+    const int e = __ldg(rowPtr + row + 1);
+    if (lane4 < DOF) {
+      double acc = 0.0;
+#pragma unroll 4
+      for (int p = s; p < e; p++) {
+        const int c = __ldg(col + p);
+        const double* k = K + (size_t(p)*DOF*DOF + lane4*DOF);
+        const double* u = U + size_t(c)*DOF;
+        double t = acc;
+#pragma unroll
+        for (int j = 0; j < DOF; j++) t = t + __ldg(k + j)*__ldg(u + j);
+        acc = t;
+      }
+      KU[size_t(row)*DOF + lane4] = acc;
+    }
+  }
+}
+
+// K2a  KU(i) = sum_j K(j) U(col_j)                     (fsils_spar_mul_ss, spar_mul.cpp:46-61)
+// 4 lanes per row striding over the row's entries; fixed-order quad reduction.
+__global__ void __launch_bounds__(256)
+k_spmv_ss(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
+          const double* __restrict__ K, const double* __restrict__ U, double* __restrict__ KU)
+{
+  const int lane4 = threadIdx.x & 3;
+  const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
+  const int ngroups = (gridDim.x*blockDim.x) >> 2;
+  const int nrounds = (nNo + ngroups - 1)/ngroups;
+  for (int r = 0; r < nrounds; r++) {
+    const int row = group + r*ngroups;
+    double acc = 0.0;
+    if (row < nNo) {
+      const int s = __ldg(rowPtr + row);
+      const int e = __ldg(rowPtr + row + 1);
+      for (int p = s + lane4; p < e; p += 4) acc = acc + ld_stream(K + p)*__ldg(U + __ldg(col + p));
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (row < nNo && lane4 == 0) KU[row] = acc;
+  }
+}
+
+// K2b  KU(m,i) = sum_j K(m,j) U(col_j)                 (fsils_spar_mul_sv, spar_mul.cpp:63-127)
+template <int DOF>
+__global__ void __launch_bounds__(256)
+k_spmv_sv(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
+          const double* __restrict__ K, const double* __restrict__ U, double* __restrict__ KU)
+{
+  const int lane4 = threadIdx.x & 3;
+  const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
+  const int ngroups = (gridDim.x*blockDim.x) >> 2;
+  for (int row = group; row < nNo; row += ngroups) {
+    const int s = __ldg(rowPtr + row);
+    const int e = __ldg(rowPtr + row + 1);
+    if (lane4 < DOF) {
+      double acc = 0.0;
+#pragma unroll 4
+      for (int p = s; p < e; p++) acc = acc + ld_stream(K + size_t(p)*DOF + lane4)*__ldg(U + __ldg(col + p));
+      KU[size_t(row)*DOF + lane4] = acc;
+    }
+  }
+}
+
+// K2c  KU(i) = sum_j K(:,j) . U(:,col_j)                (fsils_spar_mul_vs, spar_mul.cpp:129-189)
+template <int DOF>
+__global__ void __launch_bounds__(256)
+k_spmv_vs(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
+          const double* __restrict__ K, const double* __restrict__ U, double* __restrict__ KU)
+{
+  const int lane4 = threadIdx.x & 3;
+  const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
+  const int ngroups = (gridDim.x*blockDim.x) >> 2;
+  const int nrounds = (nNo + ngroups - 1)/ngroups;
+  for (int r = 0; r < nrounds; r++) {
+    const int row = group + r*ngroups;
+    double acc = 0.0;
+    if (row < nNo) {
+      const int s = __ldg(rowPtr + row);
+      const int e = __ldg(rowPtr + row + 1);
+      for (int p = s + lane4; p < e; p += 4) {
+        const int c = __ldg(col + p);
+        double t = 0.0;
+#pragma unroll
+        for (int m = 0; m < DOF; m++) t = t + ld_stream(K + size_t(p)*DOF + m)*__ldg(U + size_t(c)*DOF + m);
+        acc = acc + t;
+      }
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    if (row < nNo && lane4 == 0) KU[row] = acc;
+  }
+}
+
+// =================================================================================================
+// K3  multi-dot: red[slot0 + j] = sum_{idx < n} V_j[idx] * w[idx],  j = 0..cnt-1 (cnt <= kDotJB),
+// V_j = base + j*stride.  (fsils_nc_dot_v inside the Arnoldi loop, liner_solver/gmres.cpp:550-555;
+// dot.cpp:134-175.)  Deterministic: fixed grid, fixed-shape tree inside the CTA, and the last CTA
+// to finish adds the per-CTA partials in CTA order.  One pass over w serves up to 8 basis vectors.
+// =================================================================================================
+__global__ void __launch_bounds__(kRedThreads)
+k_multi_dot(size_t n, const double* __restrict__ base, size_t stride, const double* __restrict__ w, int cnt,
+            double* __restrict__ partial, unsigned int* __restrict__ counter, double* __restrict__ red, int slot0)
+{
+  double acc[kDotJB];
+#pragma unroll
+  for (int j = 0; j < kDotJB; j++) acc[j] = 0.0;
+  const size_t tid = size_t(blockIdx.x)*blockDim.x + threadIdx.x;
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t idx = tid; idx < n; idx += nth) {
+    const double wv = w[idx];
+#pragma unroll
+    for (int j = 0; j < kDotJB; j++) {
+      if (j < cnt) acc[j] = fma(base[size_t(j)*stride + idx], wv, acc[j]);
+    }
+  }
+  __shared__ double sm[kRedThreads/32][kDotJB];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < kDotJB; j++) {
+    double v = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sm[wid][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kDotJB) {
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < kRedThreads/32; k++) v += sm[k][threadIdx.x];
+    partial[size_t(blockIdx.x)*kDotJB + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(counter, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    // warp j sums partial[:, j] : lane-strided serial sums, then a fixed shuffle tree
+    if (wid < cnt) {
+      double v = 0.0;
+      for (unsigned int b = lane; b < gridDim.x; b += 32) v += __ldcg(partial + size_t(b)*kDotJB + wid);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) red[slot0 + wid] = v;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
+}
+
+// K4  classical Gram-Schmidt update + normalisation in one pass
+//   w <- (w - sum_{j<k} h_j u_j) * 1/sqrt|h_k - sum_j h_j^2|,  h = red[slot0 ..]  (already reduced)
+// (omp_sum_v / omp_mul_v calls at liner_solver/gmres.cpp:561-569; same left-to-right order.)
+__global__ void __launch_bounds__(256)
+k_cgs_update_scale(size_t n, int k, const double* __restrict__ base, size_t stride, double* __restrict__ w,
+                   const double* __restrict__ red, int slot0)
+{
+  extern __shared__ double hs[];     // k+1 coefficients
+  for (int j = threadIdx.x; j <= k; j += blockDim.x) hs[j] = red[slot0 + j];
+  __syncthreads();
+  __shared__ double inv;
+  if (threadIdx.x == 0) {
+    double hh = hs[k];
+    for (int j = 0; j < k; j++) hh = __dsub_rn(hh, __dmul_rn(hs[j], hs[j]));
+    inv = 1.0 / sqrt(fabs(hh));
+  }
+  __syncthreads();
+  const double sc = inv;
+  const size_t tid = size_t(blockIdx.x)*blockDim.x + threadIdx.x;
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t idx = tid; idx < n; idx += nth) {
+    double v = w[idx];
+    for (int j = 0; j < k; j++) v = fma(-hs[j], base[size_t(j)*stride + idx], v);
+    w[idx] = sc*v;
+  }
+}
+
+// out = base + sum_j coef[j] * V[j]   (sequential in j; base may be null = 0; out may alias base)
+struct CombArgs { double coef[kMaxComb]; };
+__global__ void __launch_bounds__(256)
+k_lin_comb(size_t n, double* __restrict__ out, const double* base, int k, const double* __restrict__ V, size_t stride, CombArgs a)
+{
+  const size_t tid = size_t(blockIdx.x)*blockDim.x + threadIdx.x;
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t idx = tid; idx < n; idx += nth) {
+    double v = base ? base[idx] : 0.0;
+    for (int j = 0; j < k; j++) v = fma(a.coef[j], V[size_t(j)*stride + idx], v);
+    out[idx] = v;
+  }
+}
+
+// ---- BLAS-1 (omp_la.cpp:39-148) ------------------------------------------------------------------
+__global__ void k_axpy(size_t n, double a, const double* __restrict__ x, double* __restrict__ y)
+{
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) y[i] = fma(a, x[i], y[i]);
+}
+__global__ void k_scal(size_t n, double a, double* __restrict__ x)
+{
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) x[i] = a*x[i];
+}
+__global__ void k_divs(size_t n, double d, double* __restrict__ x)
+{
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) x[i] = x[i]/d;
+}
+__global__ void k_fill(size_t n, double a, double* __restrict__ x)
+{
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) x[i] = a;
+}
+__global__ void k_sub(size_t n, const double* a, const double* b, double* out)     // out = a - b (may alias)
+{
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) out[i] = a[i] - b[i];
+}
+__global__ void k_mul(size_t n, const double* __restrict__ w, double* __restrict__ x)   // x = w (.) x
+{
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) x[i] = w[i]*x[i];
+}
+// out = a*x + b*y    (S = R - alpha V, R = S - omega T of bicgs.cpp:96,103)
+__global__ void k_lin2(size_t n, double* out, double a, const double* x, double b, const double* y)
+{
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) out[i] = fma(b, y[i], a*x[i]);
+}
+// X = X + a P + b S   (bicgs.cpp:102)
+__global__ void k_axpy2(size_t n, double* __restrict__ X, double a, const double* __restrict__ P, double b, const double* __restrict__ S)
+{
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) X[i] = fma(b, S[i], fma(a, P[i], X[i]));
+}
+// P = R + beta (P - omega V)   (bicgs.cpp:113)
+__global__ void k_bicg_p(size_t n, double* __restrict__ P, const double* __restrict__ R, const double* __restrict__ V, double beta, double omega)
+{
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) P[i] = fma(beta, fma(-omega, V[i], P[i]), R[i]);
+}
+
+// ---- permutation by lhs.map (solve.cpp:116-120,188-192) ------------------------------------------
+// out(:, map[a]) = in(:, a)
+__global__ void k_permute_fwd(int nNo, int dof, const int* __restrict__ map, const double* __restrict__ in, double* __restrict__ out)
+{
+  const size_t n = size_t(nNo)*dof;
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) {
+    const int a = int(i / dof), l = int(i % dof);
+    out[size_t(map[a])*dof + l] = in[i];
+  }
+}
+// out(:, a) = in(:, map[a])
+__global__ void k_permute_bwd(int nNo, int dof, const int* __restrict__ map, const double* __restrict__ in, double* __restrict__ out)
+{
+  const size_t n = size_t(nNo)*dof;
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) {
+    const int a = int(i / dof), l = int(i % dof);
+    out[i] = in[size_t(map[a])*dof + l];
+  }
+}
+// Val rows between assembly layout (rows in assembly order) and solver layout (rows in solver order):
+// row a of the assembly CSR [rowPtrA[a], rowPtrA[a+1]) <-> row map[a] of the solver CSR.
+__global__ void k_val_rows(int nNo, int bs, const int* __restrict__ map, const int* __restrict__ rowPtrA,
+                           const int* __restrict__ rowPtrS, const double* __restrict__ src, double* __restrict__ dst, int to_solver)
+{
+  // one warp per row
+  const int warp = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x*blockDim.x) >> 5;
+  for (int a = warp; a < nNo; a += nwarps) {
+    const int sa = rowPtrA[a], len = rowPtrA[a+1] - sa;
+    const int ss = rowPtrS[map[a]];
+    const size_t cnt = size_t(len)*bs;
+    const double* s = to_solver ? src + size_t(sa)*bs : src + size_t(ss)*bs;
+    double* d = to_solver ? dst + size_t(ss)*bs : dst + size_t(sa)*bs;
+    for (size_t i = lane; i < cnt; i += 32) d[i] = s[i];
+  }
+}
+
+// ---- K6 Jacobi (diagonal) preconditioner (liner_solver/precond.cpp:122-256) -----------------------
+__global__ void k_diag_extract(int nNo, int dof, const int* __restrict__ diagPtr, const double* __restrict__ Val, double* __restrict__ W)
+{
+  const size_t n = size_t(nNo)*dof;
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) {
+    const int a = int(i / dof), l = int(i % dof);
+    W[i] = Val[size_t(diagPtr[a])*dof*dof + l*dof + l];
+  }
+}
+__global__ void k_w_invsqrt(size_t n, double* __restrict__ W)
+{
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) {
+    double w = W[i];
+    if (w == 0.0) w = 1.0;
+    W[i] = 1.0 / sqrt(fabs(w));
+  }
+}
+// W(i, glob[a]) *= val(i,a), i < m   (Dirichlet masking, precond.cpp:204-224)
+__global__ void k_face_mask(int fnNo, int m, int fdof, int dof, const int* __restrict__ glob, const double* __restrict__ val, double* __restrict__ W)
+{
+  const int n = fnNo*m;
+  for (int t = blockIdx.x*blockDim.x + threadIdx.x; t < n; t += gridDim.x*blockDim.x) {
+    const int a = t / m, i = t % m;
+    W[size_t(glob[a])*dof + i] *= val[size_t(a)*fdof + i];
+  }
+}
+// valM(i,a) = val(i,a) * W(i, glob[a])   (precond.cpp:245-255)
+__global__ void k_face_valM(int fnNo, int m, int fdof, int dof, const int* __restrict__ glob, const double* __restrict__ val,
+                            const double* __restrict__ W, double* __restrict__ valM)
+{
+  const int n = fnNo*m;
+  for (int t = blockIdx.x*blockDim.x + threadIdx.x; t < n; t += gridDim.x*blockDim.x) {
+    const int a = t / m, i = t % m;
+    valM[size_t(a)*fdof + i] = val[size_t(a)*fdof + i] * W[size_t(glob[a])*dof + i];
+  }
+}
+// Val <- (W_row Val) W_col in ONE read-modify-write pass (the reference makes two: pre_mul :549 then
+// pos_mul :46); each entry is rounded as (v*Wr)*Wc like the reference.  4 lanes per row, lane i owns
+// block-row i (dof 4: one 256-bit load + store).
+template <int DOF>
+__global__ void __launch_bounds__(256)
+k_scale_val(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col, const double* __restrict__ Wr,
+            const double* __restrict__ Wc, double* __restrict__ Val)
+{
+  const int lane4 = threadIdx.x & 3;
+  const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
+  const int ngroups = (gridDim.x*blockDim.x) >> 2;
+  for (int row = group; row < nNo; row += ngroups) {
+    const int s = rowPtr[row], e = rowPtr[row+1];
+    if (lane4 < DOF) {
+      const double wr = Wr[size_t(row)*DOF + lane4];
+      for (int p = s; p < e; p++) {
+        const int c = col[p];
+        double* v = Val + (size_t(p)*DOF*DOF + lane4*DOF);
+        if constexpr (DOF == 4) {
+          d4 k = ld256(v);
+          const d4 wc = ld256(Wc + size_t(c)*4);
+          k.x = (k.x*wr)*wc.x; k.y = (k.y*wr)*wc.y; k.z = (k.z*wr)*wc.z; k.w = (k.w*wr)*wc.w;
+          st256(v, k);
+        } else {
+#pragma unroll
+          for (int j = 0; j < DOF; j++) v[j] = (v[j]*wr)*Wc[size_t(c)*DOF + j];
+        }
+      }
+    }
+  }
+}
+
+// ---- K8 depart (liner_solver/ns_solver.cpp:91-163), nsd = 3 --------------------------------------
+// Splits the scaled 4x4 blocks into mK(9), mG(3), mD(3), mL(1) and builds Gt(:,l) = -mG(:,tpos[l])
+// with the transpose position precomputed once (the reference searches the row each time).
+__global__ void __launch_bounds__(256)
+k_depart3(size_t nnz, const int* __restrict__ tpos, const double* __restrict__ Val, double* __restrict__ Gt,
+          double* __restrict__ mK, double* __restrict__ mG, double* __restrict__ mD, double* __restrict__ mL)
+{
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t p = size_t(blockIdx.x)*blockDim.x + threadIdx.x; p < nnz; p += nth) {
+    const double* v = Val + p*16;
+    const d4 r0 = ld256(v), r1 = ld256(v + 4), r2 = ld256(v + 8), r3 = ld256(v + 12);
+    double* k = mK + p*9;
+    k[0] = r0.x; k[1] = r0.y; k[2] = r0.z;
+    k[3] = r1.x; k[4] = r1.y; k[5] = r1.z;
+    k[6] = r2.x; k[7] = r2.y; k[8] = r2.z;
+    double* g = mG + p*3;
+    g[0] = r0.w; g[1] = r1.w; g[2] = r2.w;
+    double* d = mD + p*3;
+    d[0] = r3.x; d[1] = r3.y; d[2] = r3.z;
+    mL[p] = r3.w;
+    const size_t t = size_t(tpos[p]);
+    const double* vt = Val + t*16;
+    double* gt = Gt + p*3;
+    gt[0] = -vt[3]; gt[1] = -vt[7]; gt[2] = -vt[11];
+  }
+}
+template <int NSD>
+__global__ void k_depart_generic(size_t nnz, const int* __restrict__ tpos, const double* __restrict__ Val, double* __restrict__ Gt,
+                                 double* __restrict__ mK, double* __restrict__ mG, double* __restrict__ mD, double* __restrict__ mL)
+{
+  constexpr int D = NSD + 1;
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t p = size_t(blockIdx.x)*blockDim.x + threadIdx.x; p < nnz; p += nth) {
+    const double* v = Val + p*D*D;
+    for (int i = 0; i < NSD; i++) {
+      for (int j = 0; j < NSD; j++) mK[p*NSD*NSD + i*NSD + j] = v[i*D + j];
+      mG[p*NSD + i] = v[i*D + NSD];
+      mD[p*NSD + i] = v[NSD*D + i];
+    }
+    mL[p] = v[D*D - 1];
+    const double* vt = Val + size_t(tpos[p])*D*D;
+    for (int i = 0; i < NSD; i++) Gt[p*NSD + i] = -vt[i*D + NSD];
+  }
+}
+
+// Ri(dof,nNo) <-> Rm(nsd,nNo), Rc(nNo)   (ns_solver.cpp:201-213, 481-488)
+__global__ void k_split_mc(int nNo, int dof, const double* __restrict__ Ri, double* __restrict__ Rm, double* __restrict__ Rc)
+{
+  const size_t n = size_t(nNo)*dof;
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) {
+    const size_t a = i / dof; const int l = int(i % dof);
+    if (l < dof-1) Rm[a*(dof-1) + l] = Ri[i]; else Rc[a] = Ri[i];
+  }
+}
+__global__ void k_join_mc(int nNo, int dof, const double* __restrict__ Rm, const double* __restrict__ Rc, double* __restrict__ Ri)
+{
+  const size_t n = size_t(nNo)*dof;
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) {
+    const size_t a = i / dof; const int l = int(i % dof);
+    Ri[i] = (l < dof-1) ? Rm[a*(dof-1) + l] : Rc[a];
+  }
+}
+
+// ---- K9 resistance-face rank-1 update (liner_solver/add_bc_mul.cpp:53-121) ------------------------
+// stage 1 (one CTA): out[0] = sum_{a, i<m} valM(i,a) * X(i, glob[a])  over face nodes with glob[a] < lim
+// (lim = nNo for a face owned by one rank, mynNo for a shared face whose dot is completed by an
+// all-reduce).  Fixed-shape tree -> deterministic.
+__global__ void __launch_bounds__(256)
+k_face_dot(int fnNo, int m, int fdof, int dof, int lim, const int* __restrict__ glob, const double* __restrict__ valM,
+           const double* X, double* __restrict__ out)
+{
+  double acc = 0.0;
+  const int n = fnNo*m;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    const int a = t / m, i = t % m;
+    const int Ac = glob[a];
+    if (Ac < lim) {
+      const double xv = X ? X[size_t(Ac)*dof + i] : valM[size_t(a)*fdof + i];
+      acc = fma(valM[size_t(a)*fdof + i], xv, acc);
+    }
+  }
+  __shared__ double sm[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if (lane == 0) sm[wid] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int k = 0; k < 8; k++) v += sm[k];
+    out[0] = v;
+  }
+}
+// stage 2: Y(i, glob[a]) += valM(i,a) * (coef * S)
+__global__ void k_face_axpy(int fnNo, int m, int fdof, int dof, const int* __restrict__ glob, const double* __restrict__ valM,
+                            double coef, const double* __restrict__ S, double* Y)
+{
+  const double s = coef * S[0];
+  const int n = fnNo*m;
+  for (int t = blockIdx.x*blockDim.x + threadIdx.x; t < n; t += gridDim.x*blockDim.x) {
+    const int a = t / m, i = t % m;
+    Y[size_t(glob[a])*dof + i] += valM[size_t(a)*fdof + i]*s;
+  }
+}
+
+// ---- halo exchange (fsils_commuv/commus, liner_solver/in_commu.cpp:49-170) ------------------------
+__global__ void k_halo_pack(int n, int dof, const int* __restrict__ ptr, const double* __restrict__ V, double* __restrict__ buf)
+{
+  const int tot = n*dof;
+  for (int t = blockIdx.x*blockDim.x + threadIdx.x; t < tot; t += gridDim.x*blockDim.x) {
+    const int j = t / dof, l = t % dof;
+    buf[t] = V[size_t(ptr[j])*dof + l];
+  }
+}
+__global__ void k_halo_add(int n, int dof, const int* __restrict__ ptr, const double* __restrict__ buf, double* __restrict__ V)
+{
+  const int tot = n*dof;
+  for (int t = blockIdx.x*blockDim.x + threadIdx.x; t < tot; t += gridDim.x*blockDim.x) {
+    const int j = t / dof, l = t % dof;
+    V[size_t(ptr[j])*dof + l] += buf[t];
+  }
+}
+
+// ---- staged element scatter (LinearAlgebra::assemble path; lhsa.cpp:97-142) -----------------------
+// One CTA walks the staged elements in submission order (deterministic); threads cover the entries
+// of one element.  rows are SOLVER ids; the column search runs on the solver CSR (columns of a row
+// keep the assembly order, i.e. they are sorted by assembly id, so we search linearly).
+__global__ void __launch_bounds__(256)
+k_scatter_staged(int nElem, int d, int dof, const int* __restrict__ rows, const int* __restrict__ pos,
+                 const double* __restrict__ lK, const double* __restrict__ lR, double* __restrict__ R, double* __restrict__ Val)
+{
+  const int bs = dof*dof;
+  for (int e = 0; e < nElem; e++) {
+    const int* er = rows + size_t(e)*d;
+    const int* ep = pos + size_t(e)*d*d;
+    const double* eK = lK + size_t(e)*bs*d*d;
+    const double* eR = lR + size_t(e)*dof*d;
+    for (int t = threadIdx.x; t < d*dof; t += blockDim.x) {
+      const int a = t / dof, i = t % dof;
+      if (er[a] >= 0) R[size_t(er[a])*dof + i] += eR[t];
+    }
+    for (int t = threadIdx.x; t < d*d*bs; t += blockDim.x) {
+      const int ab = t / bs, i = t % bs;      // lK(i,a,b) = eK[i + bs*(a + d*b)]
+      const int a = ab % d, b = ab / d;
+      const int p = ep[a*d + b];
+      if (p >= 0) Val[size_t(p)*bs + i] += eK[t];
+    }
+    __syncthreads();
+  }
+}
+
+} // namespace svb200

@@ -1,0 +1,442 @@
+// ops_cuda.cuh — the device policy behind krylov.hpp: owns the device CSR (solver ordering), a
+// stack arena for Krylov work vectors, the deterministic reduction buffers, the halo lists and the
+// NCCL communicator, and launches the kernels of kernels.cuh on ONE stream.  There is no host
+// implementation of any of these operations in the product.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "krylov.hpp"
+
+namespace svb200 {
+
+#define CU_CHECK(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (call);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + \
+                               __FILE__ + ":" + std::to_string(__LINE__));                    \
+  } while (0)
+
+// ---- NCCL through dlopen (the library torch already loaded, or the system one) -------------------
+struct Nccl {
+  typedef struct { char internal[128]; } UniqueId;
+  typedef void* Comm;
+  void* lib = nullptr;
+  int (*GetUniqueId)(UniqueId*) = nullptr;
+  int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
+  int (*CommDestroy)(Comm) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  static constexpr int kFloat64 = 8, kSum = 0, kInt32 = 2, kMax = 2;
+
+  void load()
+  {
+    if (lib) return;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (auto n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+    if (!lib) throw std::runtime_error("NCCL library not found (libnccl.so.2)");
+    auto sym = [&](const char* s) { void* p = dlsym(lib, s); if (!p) throw std::runtime_error(std::string("NCCL symbol missing: ") + s); return p; };
+    GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(sym("ncclGetUniqueId"));
+    CommInitRank = reinterpret_cast<decltype(CommInitRank)>(sym("ncclCommInitRank"));
+    CommDestroy = reinterpret_cast<decltype(CommDestroy)>(sym("ncclCommDestroy"));
+    AllReduce = reinterpret_cast<decltype(AllReduce)>(sym("ncclAllReduce"));
+    Send = reinterpret_cast<decltype(Send)>(sym("ncclSend"));
+    Recv = reinterpret_cast<decltype(Recv)>(sym("ncclRecv"));
+    GroupStart = reinterpret_cast<decltype(GroupStart)>(sym("ncclGroupStart"));
+    GroupEnd = reinterpret_cast<decltype(GroupEnd)>(sym("ncclGroupEnd"));
+    GetErrorString = reinterpret_cast<decltype(GetErrorString)>(sym("ncclGetErrorString"));
+  }
+  void check(int r, const char* what)
+  {
+    if (r != 0) throw std::runtime_error(std::string("NCCL error in ") + what + ": " + (GetErrorString ? GetErrorString(r) : "?"));
+  }
+};
+
+struct DevFace {               // lhs.face[faIn] (liner_solver/fils_struct.hpp:116-161)
+  int nNo = 0, dof = 0, bGrp = B200_BC_DIR;
+  bool shared = false, inc = true, coupled = false, set = false;
+  double res = 0.0, nS = 0.0;
+  int* glob = nullptr;
+  double* val = nullptr;
+  double* valM = nullptr;
+};
+
+struct HaloReq { int peer = -1, n = 0; int* ptr = nullptr; double* sbuf = nullptr; double* rbuf = nullptr; };
+
+class CudaOps {
+ public:
+  cudaStream_t st = nullptr;
+  long long launches = 0;
+  double phase_ms[4] = {0, 0, 0, 0};
+
+  // structure (solver ordering)
+  int gnNo_ = 0, nNo_ = 0, mynNo_ = 0, nnz_ = 0;
+  int* rowPtr = nullptr;     // nNo+1
+  int* col = nullptr;        // nnz (solver ids, row entries keep the assembly order)
+  int* diag = nullptr;       // nNo
+  int* tpos = nullptr;       // nnz transpose positions
+  std::vector<DevFace> faces;
+  std::vector<HaloReq> reqs;
+  int halo_dof_cap = 0;
+
+  // communicator
+  Nccl nccl;
+  Nccl::Comm comm = nullptr;
+  int rank = 0, nranks = 1;
+
+  // reductions
+  static constexpr int kMaxSlots = 1024;
+  double* red_d = nullptr;
+  double* red_h = nullptr;        // pinned
+  double* partial_d = nullptr;
+  unsigned int* counter_d = nullptr;
+
+  // arena
+  struct Chunk { char* p; size_t cap, top; };
+  std::vector<Chunk> chunks;
+  int cur_chunk = 0;
+  struct Mark { int chunk; size_t top; };
+
+  explicit CudaOps(int device)
+  {
+    CU_CHECK(cudaSetDevice(device));
+    CU_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CU_CHECK(cudaMalloc(&red_d, sizeof(double)*kMaxSlots));
+    CU_CHECK(cudaMallocHost(&red_h, sizeof(double)*kMaxSlots));
+    CU_CHECK(cudaMalloc(&partial_d, sizeof(double)*kRedBlocks*kDotJB));
+    CU_CHECK(cudaMalloc(&counter_d, sizeof(unsigned int)));
+    CU_CHECK(cudaMemset(counter_d, 0, sizeof(unsigned int)));
+  }
+  ~CudaOps()
+  {
+    for (auto& c : chunks) cudaFree(c.p);
+    for (auto& f : faces) { cudaFree(f.glob); cudaFree(f.val); cudaFree(f.valM); }
+    for (auto& r : reqs) { cudaFree(r.ptr); cudaFree(r.sbuf); cudaFree(r.rbuf); }
+    cudaFree(rowPtr); cudaFree(col); cudaFree(diag); cudaFree(tpos);
+    cudaFree(red_d); cudaFreeHost(red_h); cudaFree(partial_d); cudaFree(counter_d);
+    if (comm) nccl.CommDestroy(comm);
+    if (st) cudaStreamDestroy(st);
+  }
+
+  int nNo() const { return nNo_; }
+  int mynNo() const { return mynNo_; }
+  size_t nnz() const { return size_t(nnz_); }
+  bool is_master() const { return rank == 0; }
+
+  // ---- arena ------------------------------------------------------------------------------------
+  Mark mark() const { return Mark{cur_chunk, chunks.empty() ? 0 : chunks[cur_chunk].top}; }
+  void release(Mark m)
+  {
+    if (chunks.empty()) return;
+    for (int c = m.chunk + 1; c < int(chunks.size()); c++) chunks[c].top = 0;
+    cur_chunk = m.chunk;
+    chunks[cur_chunk].top = m.top;
+  }
+  double* vec(size_t n)
+  {
+    const size_t bytes = ((n*sizeof(double) + 255)/256)*256;
+    for (int c = cur_chunk; c < int(chunks.size()); c++) {
+      if (c > cur_chunk && chunks[c].top != 0) continue;
+      if (chunks[c].cap - chunks[c].top >= bytes) {
+        char* p = chunks[c].p + chunks[c].top;
+        chunks[c].top += bytes;
+        cur_chunk = c;
+        return reinterpret_cast<double*>(p);
+      }
+    }
+    Chunk nc;
+    nc.cap = std::max(bytes, size_t(64) << 20);
+    nc.top = bytes;
+    CU_CHECK(cudaMalloc(&nc.p, nc.cap));
+    chunks.push_back(nc);
+    cur_chunk = int(chunks.size()) - 1;
+    return reinterpret_cast<double*>(nc.p);
+  }
+
+  // ---- launch helpers -----------------------------------------------------------------------------
+  static int grid_for(size_t n, int threads, int per_thread = 4)
+  {
+    size_t b = (n + size_t(threads)*per_thread - 1)/(size_t(threads)*per_thread);
+    const size_t cap = size_t(kSmCount)*16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return int(b);
+  }
+  // row-per-4-lanes kernels: enough CTAs to cover all rows, capped at 16 waves of 148 CTAs
+  static int grid_rows(int nNo)
+  {
+    size_t groups_per_block = 256/4;
+    size_t b = (size_t(nNo) + groups_per_block - 1)/groups_per_block;
+    const size_t cap = size_t(kSmCount)*32;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return int(b);
+  }
+  void post() { launches++; }
+
+  // ---- BLAS-1 -------------------------------------------------------------------------------------
+  void zero(size_t n, double* x) { CU_CHECK(cudaMemsetAsync(x, 0, n*sizeof(double), st)); }
+  void copy(size_t n, const double* x, double* y) { CU_CHECK(cudaMemcpyAsync(y, x, n*sizeof(double), cudaMemcpyDeviceToDevice, st)); }
+  void fill(size_t n, double a, double* x) { k_fill<<<grid_for(n, 256), 256, 0, st>>>(n, a, x); post(); }
+  void axpy(size_t n, double a, const double* x, double* y) { k_axpy<<<grid_for(n, 256), 256, 0, st>>>(n, a, x, y); post(); }
+  void scal(size_t n, double a, double* x) { k_scal<<<grid_for(n, 256), 256, 0, st>>>(n, a, x); post(); }
+  void divs(size_t n, double d, double* x) { k_divs<<<grid_for(n, 256), 256, 0, st>>>(n, d, x); post(); }
+  void sub(size_t n, const double* a, const double* b, double* out) { k_sub<<<grid_for(n, 256), 256, 0, st>>>(n, a, b, out); post(); }
+  void mul_inplace(size_t n, const double* w, double* x) { k_mul<<<grid_for(n, 256), 256, 0, st>>>(n, w, x); post(); }
+  void lin2(size_t n, double* out, double a, const double* x, double b, const double* y) { k_lin2<<<grid_for(n, 256), 256, 0, st>>>(n, out, a, x, b, y); post(); }
+  void axpy2(size_t n, double* X, double a, const double* P, double b, const double* S) { k_axpy2<<<grid_for(n, 256), 256, 0, st>>>(n, X, a, P, b, S); post(); }
+  void bicg_p_update(size_t n, double* P, const double* R, const double* V, double beta, double omega) { k_bicg_p<<<grid_for(n, 256), 256, 0, st>>>(n, P, R, V, beta, omega); post(); }
+
+  // out = base + sum_j coef[j] V[(j0+j)*stride], sequential in j (base may be null, out may alias base)
+  void lin_comb(size_t n, double* out, const double* base, int k, const double* V, size_t stride, int j0, const double* coef)
+  {
+    const double* b = base;
+    int done = 0;
+    if (k == 0) { if (base == nullptr) zero(n, out); else if (base != out) copy(n, base, out); return; }
+    while (done < k) {
+      const int m = std::min(kMaxComb, k - done);
+      CombArgs a;
+      for (int j = 0; j < m; j++) a.coef[j] = coef[done + j];
+      k_lin_comb<<<grid_for(n, 256), 256, 0, st>>>(n, out, b, m, V + size_t(j0 + done)*stride, stride, a);
+      post();
+      b = out;
+      done += m;
+    }
+  }
+
+  // ---- reductions ---------------------------------------------------------------------------------
+  // red[slot0 + j] = <base + j*stride, w> over the first mynNo nodes, j < count (local part only)
+  void dots_local(int dof, int count, const double* base, size_t stride, const double* w, int slot0)
+  {
+    if (slot0 + count > kMaxSlots) throw std::runtime_error("reduction slot overflow");
+    const size_t n = size_t(dof)*mynNo_;
+    int done = 0;
+    while (done < count) {
+      const int m = std::min(kDotJB, count - done);
+      k_multi_dot<<<kRedBlocks, kRedThreads, 0, st>>>(n, base + size_t(done)*stride, stride, w, m, partial_d, counter_d, red_d, slot0 + done);
+      post();
+      done += m;
+    }
+  }
+  void reduce_begin(int nslots)
+  {
+    if (nranks > 1) nccl.check(nccl.AllReduce(red_d, red_d, size_t(nslots), Nccl::kFloat64, Nccl::kSum, comm, st), "AllReduce");
+  }
+  void reduce_fetch(int nslots, double* out)
+  {
+    CU_CHECK(cudaMemcpyAsync(red_h, red_d, sizeof(double)*nslots, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    std::memcpy(out, red_h, sizeof(double)*nslots);
+  }
+  double dot(int dof, const double* a, const double* b)
+  {
+    dots_local(dof, 1, a, 0, b, 0);
+    reduce_begin(1);
+    double r;
+    reduce_fetch(1, &r);
+    return r;
+  }
+  double norm(int dof, const double* a) { return std::sqrt(dot(dof, a, a)); }
+
+  void cgs_update_scale(int dof, int k, const double* base, size_t stride, double* w, int slot0)
+  {
+    const size_t n = size_t(dof)*nNo_;
+    k_cgs_update_scale<<<grid_for(n, 256), 256, sizeof(double)*(k+1), st>>>(n, k, base, stride, w, red_d, slot0);
+    post();
+  }
+
+  // ---- SpMV (+ overlap-node add) --------------------------------------------------------------------
+  void spmv_vv(int dof, const double* K, const double* U, double* KU)
+  {
+    const int g = grid_rows(nNo_);
+    switch (dof) {
+      case 4: k_spmv_vv4<<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU); break;
+      case 3: k_spmv_vv<3><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU); break;
+      case 2: k_spmv_vv<2><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU); break;
+      case 1: k_spmv_vv<1><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU); break;
+      default: throw std::runtime_error("spmv_vv: dof > 4 is not a supported FSILS path");
+    }
+    post();
+    halo_add(dof, KU);
+  }
+  void spmv_ss(const double* K, const double* U, double* KU)
+  {
+    k_spmv_ss<<<grid_rows(nNo_), 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
+    post();
+    halo_add(1, KU);
+  }
+  void spmv_sv(int dof, const double* K, const double* U, double* KU)
+  {
+    const int g = grid_rows(nNo_);
+    if (dof == 3) k_spmv_sv<3><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
+    else if (dof == 2) k_spmv_sv<2><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
+    else throw std::runtime_error("spmv_sv: nsd must be 2 or 3");
+    post();
+    halo_add(dof, KU);
+  }
+  void spmv_vs(int dof, const double* K, const double* U, double* KU)
+  {
+    const int g = grid_rows(nNo_);
+    if (dof == 3) k_spmv_vs<3><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
+    else if (dof == 2) k_spmv_vs<2><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
+    else throw std::runtime_error("spmv_vs: nsd must be 2 or 3");
+    post();
+    halo_add(1, KU);
+  }
+
+  // fsils_commuv / fsils_commus: pack -> grouped ncclSend/ncclRecv -> add in request order
+  void halo_add(int dof, double* V)
+  {
+    if (nranks == 1 || reqs.empty()) return;
+    if (dof > halo_dof_cap) throw std::runtime_error("halo buffers too small for dof");
+    for (auto& r : reqs) {
+      k_halo_pack<<<grid_for(size_t(r.n)*dof, 256, 1), 256, 0, st>>>(r.n, dof, r.ptr, V, r.sbuf);
+      post();
+    }
+    nccl.check(nccl.GroupStart(), "GroupStart");
+    for (auto& r : reqs) {
+      nccl.check(nccl.Recv(r.rbuf, size_t(r.n)*dof, Nccl::kFloat64, r.peer, comm, st), "Recv");
+      nccl.check(nccl.Send(r.sbuf, size_t(r.n)*dof, Nccl::kFloat64, r.peer, comm, st), "Send");
+    }
+    nccl.check(nccl.GroupEnd(), "GroupEnd");
+    for (auto& r : reqs) {
+      k_halo_add<<<grid_for(size_t(r.n)*dof, 256, 1), 256, 0, st>>>(r.n, dof, r.ptr, r.rbuf, V);
+      post();
+    }
+  }
+
+  // ---- faces ----------------------------------------------------------------------------------------
+  int n_faces() const { return int(faces.size()); }
+  bool face_coupled(int f) const { return faces[f].coupled; }
+  bool face_inc(int f) const { return faces[f].inc; }
+  int face_bgrp(int f) const { return faces[f].bGrp; }
+  void face_set_inc(int f, bool v) { faces[f].inc = v; }
+  void face_set_coupled(int f, bool c, double res) { faces[f].coupled = c; if (c) faces[f].res = res; }
+
+  // face.nS = ||valM||^2 (ns_solver.cpp:56-87, gmres.cpp:50-85)
+  void bc_pre(int nsd)
+  {
+    int nslot = 0;
+    std::vector<int> which;
+    for (int f = 0; f < n_faces(); f++) {
+      auto& fa = faces[f];
+      if (!fa.coupled) continue;
+      const int m = std::min(fa.dof, nsd);
+      const int lim = fa.shared ? mynNo_ : nNo_;
+      k_face_dot<<<1, 256, 0, st>>>(fa.nNo, m, fa.dof, nsd, lim, fa.glob, fa.valM, nullptr, red_d + nslot);
+      post();
+      which.push_back(f);
+      nslot++;
+    }
+    if (nslot == 0) return;
+    // shared faces complete their norm with an all-reduce; for a face owned by one rank the other
+    // ranks hold no nodes of it (nNo = 0 -> 0 contribution), so one reduction serves both cases
+    // only when every coupled face is shared; otherwise reduce face by face.
+    if (nranks > 1) {
+      for (int k = 0; k < nslot; k++) {
+        if (faces[which[k]].shared)
+          nccl.check(nccl.AllReduce(red_d + k, red_d + k, 1, Nccl::kFloat64, Nccl::kSum, comm, st), "AllReduce");
+      }
+    }
+    std::vector<double> v(nslot);
+    reduce_fetch(nslot, v.data());
+    for (int k = 0; k < nslot; k++) faces[which[k]].nS = v[k];
+  }
+
+  // Y += coef * v (v^T X), v = valM on the face nodes (add_bc_mul.cpp:53-121); X may alias Y
+  void add_bc_mul(int op, int dof, const double* X, double* Y)
+  {
+    for (int f = 0; f < n_faces(); f++) {
+      auto& fa = faces[f];
+      if (!fa.coupled) continue;
+      const double coef = (op == BCOP_ADD) ? fa.res : -fa.res/(1.0 + fa.res*fa.nS);
+      const int m = std::min(fa.dof, dof);
+      const int lim = fa.shared ? mynNo_ : nNo_;
+      double* S = red_d + (kMaxSlots - 1);
+      k_face_dot<<<1, 256, 0, st>>>(fa.nNo, m, fa.dof, dof, lim, fa.glob, fa.valM, X, S);
+      post();
+      if (fa.shared && nranks > 1) nccl.check(nccl.AllReduce(S, S, 1, Nccl::kFloat64, Nccl::kSum, comm, st), "AllReduce");
+      if (fa.nNo > 0) {
+        k_face_axpy<<<grid_for(size_t(fa.nNo)*m, 256, 1), 256, 0, st>>>(fa.nNo, m, fa.dof, dof, fa.glob, fa.valM, coef, S, Y);
+        post();
+      }
+    }
+  }
+
+  // ---- preconditioners --------------------------------------------------------------------------------
+  // precond_diag (precond.cpp:122-256): W = diag -> overlap add -> 0->1 -> 1/sqrt|W| -> Dirichlet mask;
+  // Val <- W Val W (one pass), R <- W R, valM = val W for coupled faces.
+  void precond_diag(int dof, double* Val, double* R, double* W)
+  {
+    const size_t n = size_t(dof)*nNo_;
+    k_diag_extract<<<grid_for(n, 256), 256, 0, st>>>(nNo_, dof, diag, Val, W); post();
+    halo_add(dof, W);
+    k_w_invsqrt<<<grid_for(n, 256), 256, 0, st>>>(n, W); post();
+    for (auto& fa : faces) {
+      if (!fa.inc || fa.bGrp != B200_BC_DIR || fa.nNo == 0) continue;
+      const int m = std::min(fa.dof, dof);
+      k_face_mask<<<grid_for(size_t(fa.nNo)*m, 256, 1), 256, 0, st>>>(fa.nNo, m, fa.dof, dof, fa.glob, fa.val, W); post();
+    }
+    scale_val(dof, W, W, Val);
+    mul_inplace(n, W, R);
+    for (auto& fa : faces) {
+      if (!fa.coupled || fa.nNo == 0) continue;
+      const int m = std::min(fa.dof, dof);
+      k_face_valM<<<grid_for(size_t(fa.nNo)*m, 256, 1), 256, 0, st>>>(fa.nNo, m, fa.dof, dof, fa.glob, fa.val, W, fa.valM); post();
+    }
+  }
+  void scale_val(int dof, const double* Wr, const double* Wc, double* Val)
+  {
+    const int g = grid_rows(nNo_);
+    switch (dof) {
+      case 4: k_scale_val<4><<<g, 256, 0, st>>>(nNo_, rowPtr, col, Wr, Wc, Val); break;
+      case 3: k_scale_val<3><<<g, 256, 0, st>>>(nNo_, rowPtr, col, Wr, Wc, Val); break;
+      case 2: k_scale_val<2><<<g, 256, 0, st>>>(nNo_, rowPtr, col, Wr, Wc, Val); break;
+      case 1: k_scale_val<1><<<g, 256, 0, st>>>(nNo_, rowPtr, col, Wr, Wc, Val); break;
+      default: throw std::runtime_error("scale_val: dof > 4");
+    }
+    post();
+  }
+  void precond_rcs(int, double*, double*, double*, double*)
+  {
+    throw std::runtime_error("row-column-scaling preconditioner (precond_rcs) is not built yet in this round");
+  }
+
+  // ---- NS helpers ---------------------------------------------------------------------------------------
+  void depart(int nsd, const double* Val, double* Gt, double* mK, double* mG, double* mD, double* mL)
+  {
+    const size_t nz = size_t(nnz_);
+    if (nsd == 3) k_depart3<<<grid_for(nz, 256, 1), 256, 0, st>>>(nz, tpos, Val, Gt, mK, mG, mD, mL);
+    else if (nsd == 2) k_depart_generic<2><<<grid_for(nz, 256, 1), 256, 0, st>>>(nz, tpos, Val, Gt, mK, mG, mD, mL);
+    else throw std::runtime_error("FSILS: Not defined nsd for DEPART");
+    post();
+  }
+  void split_mc(int dof, const double* Ri, double* Rm, double* Rc)
+  {
+    k_split_mc<<<grid_for(size_t(nNo_)*dof, 256), 256, 0, st>>>(nNo_, dof, Ri, Rm, Rc); post();
+  }
+  void join_mc(int dof, const double* Rm, const double* Rc, double* Ri)
+  {
+    k_join_mc<<<grid_for(size_t(nNo_)*dof, 256), 256, 0, st>>>(nNo_, dof, Rm, Rc, Ri); post();
+  }
+
+  void phase_mark(int which, double t0)
+  {
+    CU_CHECK(cudaStreamSynchronize(st));
+    phase_ms[which] = (wall_s() - t0)*1e3;
+  }
+};
+
+} // namespace svb200

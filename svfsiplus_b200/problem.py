@@ -1,0 +1,82 @@
+"""Workloads of the hot path: the pipe_RCR_3d Navier-Stokes case on synthetic refined pipes.
+
+Everything the reference reads from tests/cases/fluid/pipe_RCR_3d/solver.xml is restated here as
+data (density 1.06, constant viscosity 0.04, dt 0.005, rho_inf 0.5, <LS type="NS"> tol 1e-3, 15 outer
+iterations, GM 1e-3/10, CG 1e-3/300, absTol 1e-17, Krylov dimension 250, preconditioner fsils; inlet
+and wall Dirichlet, outlet RCR-coupled Neumann).  The mesh is generated (svfsiplus_b200/mesh.py); the
+outlet resistance enters the linear solve as res = gam*dt*r (Code/Source/solver/main.cpp:571-578).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import backend as B
+from . import mesh as M
+
+# <LS> blocks: (ls_type, RI, GM, CG) with tolerances (relTol, absTol, mItr, sD)
+LS_SETTINGS = {
+    # tests/cases/fluid/pipe_RCR_3d/solver.xml:75-87
+    "NS": (B.LS_NS, (1e-3, 1e-17, 15, 250), (1e-3, 1e-17, 10, 250), (1e-3, 1e-17, 300, 0)),
+    # plain GMRES variant of SURVEY.md §8d (the metric names GMRES): same tolerance, restarts of 250
+    "GMRES": (B.LS_GMRES, (1e-3, 1e-17, 4, 250), None, None),
+    "CG": (B.LS_CG, (1e-3, 1e-12, 50, 0), None, None),
+    "BICGS": (B.LS_BICGS, (1e-8, 1e-14, 200, 0), None, None),
+}
+
+
+def pipe_case(nx, ny, nz, *, radius=1.0, length=10.0, jitter=0.1, coupled=True, visc=None):
+    m = M.pipe_mesh(nx, ny, nz, radius=radius, length=length, jitter=jitter)
+    rowPtr, colPtr = M.csr_pattern(m.ien, m.nNo)
+    am, af, gam = M.gen_alpha(0.5)
+    Ag, Yg, Bf = M.pipe_state(m, radius=radius, length=length)
+    dt = 0.005
+    props = dict(dt=dt, am=am, af=af, gam=gam, rho=1.06, mu=0.04)
+    if visc:
+        props.update(visc)
+    out_nodes = m.faces["outlet"]["nodes"]
+    faces = [
+        dict(name="lumen_inlet", nodes=m.faces["inlet"]["nodes"], dof=3, bGrp=B.BC_DIR,
+             val=np.zeros((len(m.faces["inlet"]["nodes"]), 3))),
+        dict(name="lumen_wall", nodes=m.faces["wall"]["nodes"], dof=3, bGrp=B.BC_DIR,
+             val=np.zeros((len(m.faces["wall"]["nodes"]), 3))),
+        dict(name="lumen_outlet", nodes=out_nodes, dof=3, bGrp=B.BC_NEU,
+             val=M.face_normal_integral(m.x, m.faces["outlet"]["tris"], out_nodes)),
+    ]
+    r_out = 121.0 + 1212.0                          # Rp + Rd of the RCR block
+    res = np.array([0.0, 0.0, gam * dt * r_out if coupled else 0.0])
+    incL = np.array([1, 1, 1], np.int32)
+    return dict(mesh=m, rowPtr=rowPtr, colPtr=colPtr, Ag=Ag, Yg=Yg, Bf=Bf, props=props, faces=faces,
+                res=res, incL=incL, name=f"pipe_{nx}x{ny}x{nz}")
+
+
+def setup_backend(case, device=0) -> B.Backend:
+    """Single-rank set-up: what initialize() + fsi_ls_ini + add_eq_linear_algebra do once."""
+    m = case["mesh"]
+    be = B.Backend(device)
+    be.lhs_create(m.nNo, case["rowPtr"], case["colPtr"], nFaces=len(case["faces"]))
+    for i, f in enumerate(case["faces"]):
+        be.face_set(i, f["nodes"], f["dof"], f["bGrp"], f["val"], shared=False)
+    be.mesh_set(m.ien, m.x)
+    return be
+
+
+def assemble(be: B.Backend, case, upload=True):
+    """ls_alloc + global_eq_assem for the fluid equation."""
+    if upload:
+        be.state_set(case["Ag"].shape[1], case["Ag"], case["Yg"], case["Bf"])
+    be.zero(4)
+    p = case["props"]
+    be.assemble_fluid(B.fluid_props(tDof=case["Ag"].shape[1], **p))
+
+
+def newton_linear_step(be: B.Backend, case, ls="NS", want_system=False, upload=True, fetch=True, out=None):
+    """One Newton iteration's hot path: assemble R/Val, then solve.  Returns (X, info[, R, Val])."""
+    assemble(be, case, upload=upload)
+    R = Val = None
+    if want_system:
+        R, Val = be.get_R(), be.get_Val()
+    ls_type, RI, GM, CG = LS_SETTINGS[ls] if isinstance(ls, str) else ls
+    X, info = be.solve(ls_type, B.PREC_FSILS, RI, GM, CG, case["incL"], case["res"], out=out, fetch=fetch)
+    if want_system:
+        return X, info, R, Val
+    return X, info

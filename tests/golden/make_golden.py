@@ -1,0 +1,49 @@
+"""Generates the golden fixtures under tests/golden/ from the COMPILED REFERENCE (oracle/_ref).
+
+Run here (where /root/reference exists and `make -C oracle ref` has been run):
+    python tests/golden/make_golden.py
+The fixtures pin the oracle and the CUDA path to outputs of the reference's own code
+(construct_fluid + fsils_solve) on seeded synthetic inputs; they travel with the repo so the GPU box
+needs neither /root/reference nor the oracle build.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import refcase  # noqa: E402
+from svfsiplus_b200 import problem as P  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    # full system + all four solvers on a tiny pipe
+    case = P.pipe_case(4, 4, 6)
+    R, Val, rowPtr, colPtr, _ = refcase.reference_assemble(case)
+    out = dict(R=R, Val=Val, rowPtr=rowPtr, colPtr=colPtr)
+    for ls in ("NS", "GMRES", "CG", "BICGS"):
+        X, o = refcase.reference_solve(case, R, Val, P.LS_SETTINGS[ls])
+        out[f"X_{ls}"] = X
+        out[f"info_{ls}"] = np.array([o["suc"], o["itr"], o["iNorm"], o["fNorm"], o["GM_itr"], o["CG_itr"]])
+    # non-Newtonian viscosity models + moving-mesh convective velocity (assembly only)
+    for tag, visc in (("cy", dict(viscType=1, mu=0.04, mu_o=0.6, lam=8.2, a=1.23, n=0.64)),
+                      ("cass", dict(viscType=2, mu=0.3, mu_o=0.4, lam=0.5))):
+        c2 = P.pipe_case(4, 4, 6, visc=visc)
+        R2, V2, _, _, _ = refcase.reference_assemble(c2)
+        out[f"R_{tag}"] = R2
+        out[f"Val_{tag}"] = V2
+    np.savez_compressed(os.path.join(HERE, "pipe_4_4_6.npz"), **out)
+
+    case = P.pipe_case(6, 6, 12)
+    R, Val, X, o = refcase.reference_step(case, "NS")
+    np.savez_compressed(os.path.join(HERE, "pipe_6_6_12_ns.npz"), X=X,
+                        info=np.array([o["suc"], o["itr"], o["iNorm"], o["fNorm"], o["GM_itr"], o["CG_itr"]]))
+    print("golden fixtures written")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,59 @@
+"""Shared helpers for the tests."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel_inf(a, b):
+    """norm-wise relative difference max|a-b| / max|b|"""
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def golden(name):
+    return np.load(os.path.join(ROOT, "tests", "golden", name))
+
+
+_hl = None
+
+
+def hostlogic():
+    global _hl
+    if _hl is None:
+        _hl = C.CDLL(os.path.join(ROOT, "tests", "_build", "libhostlogic.so"))
+        _hl.hl_last_error.restype = C.c_char_p
+    return _hl
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def hl_solve(rowPtr, colPtr, dof, R, Val, ls, prec, faces, incL=None, res=None):
+    """krylov.hpp (the product's solver control flow) driven by the TEST-ONLY serial host policy."""
+    L = hostlogic()
+    R = np.ascontiguousarray(R, np.float64).copy()
+    Val = np.ascontiguousarray(Val, np.float64).copy()
+    rowPtr = np.ascontiguousarray(rowPtr, np.int32); colPtr = np.ascontiguousarray(colPtr, np.int32)
+    nF = len(faces)
+    fn = np.array([len(f["nodes"]) for f in faces], np.int32)
+    fd = np.array([f["dof"] for f in faces], np.int32)
+    fb = np.array([f["bGrp"] for f in faces], np.int32)
+    fg = np.concatenate([np.asarray(f["nodes"], np.int32) for f in faces]) if nF else np.zeros(0, np.int32)
+    fv = np.concatenate([np.asarray(f["val"], np.float64).reshape(-1) for f in faces]) if nF else np.zeros(0)
+    out = np.zeros(9)
+    incL_a = None if incL is None else np.ascontiguousarray(incL, np.int32)
+    res_a = None if res is None else np.ascontiguousarray(res, np.float64)
+    ls = np.ascontiguousarray(ls, np.float64)
+    rc = L.hl_solve(len(rowPtr) - 1, len(colPtr), _p(rowPtr), _p(colPtr), dof, _p(R), _p(Val), _p(ls), int(prec), nF,
+                    _p(fn), _p(fd), _p(fb), _p(fg), _p(fv), _p(incL_a), _p(res_a), _p(out))
+    if rc != 0:
+        raise RuntimeError(L.hl_last_error().decode())
+    keys = ["suc", "itr", "iNorm", "fNorm", "dB", "GM_itr", "CG_itr", "Resm", "Resc"]
+    return R, Val, dict(zip(keys, out))
