@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py — Newton-iteration throughput of the nonlinear-step hot path (assembly + FSILS-equivalent
+solve) on the synthetic 10M-tet pipe (P10), one process per GPU.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this framework (CUDA, sm_100a)
+    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU code (oracle/_ref)
+
+A "step" is one Newton iteration's hot path: ls_alloc (zero R/Val) + construct_fluid over the whole
+mesh + fsils_solve with the <LS> block of tests/cases/fluid/pipe_RCR_3d/solver.xml.
+  value : Newton iterations / s, inputs (Ag, Yg, Bf) resident in HBM when the timed region starts
+  e2e   : the same metric through the C ABI with HOST buffers: every step copies Ag/Yg/Bf host->device
+          from pinned memory and the solution device->host inside the timed region
+Timing: CUDA events on the library's launch stream (b200_timer), barrier + device synchronize on both
+sides, max over ranks.  The matrix (3.2 GB at P10) is far larger than L2 (126 MB), so no L2 flush is
+needed between iterations (stated in config.l2).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "NS Newton-iters/s, 10M-tet pipe (assembly+GMRES)"
+UNIT = "Newton-iters/s"
+P10 = (96, 96, 181)
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device=0):
+        self.rows = []
+        self.proc = None
+        self.device = device
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _dist():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def run_reference(args):
+    """The reference's own CPU implementation (compiled from its sources, oracle/_ref) on a bounded
+    sample of the workload.  The reference has no threading; its parallelism is MPI ranks, and no MPI
+    runtime exists on this box, so it runs on ONE core (stated in `cores`)."""
+    rank, world, _ = _dist()
+    if rank != 0:
+        return
+    from oracle import ref, refcase
+    from svfsiplus_b200 import problem as P
+    dims = tuple(args.ref_dims)
+    case = P.pipe_case(*dims)
+    ntet = case["mesh"].nEl
+    scale = ntet / float(6 * P10[0] * P10[1] * P10[2])
+    ls = P.LS_SETTINGS[args.ls]
+    times = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        R, Val, _, _, t_asm = refcase.reference_assemble(case)
+        X, info = refcase.reference_solve(case, R, Val, ls)
+        t1 = time.perf_counter()
+        if i >= args.warmup:
+            times.append(t1 - t0)
+    ms = 1e3 * float(np.mean(times))
+    # Newton iterations per second on the sample, scaled to the P10 unit by the tet ratio (optimistic
+    # for the CPU: Krylov iteration counts grow with refinement)
+    value = (1.0 / (ms * 1e-3)) * scale
+    sample = (f"pipe {dims[0]}x{dims[1]}x{dims[2]} = {ntet} tets ({100*scale:.2f}% of P10), full construct_fluid + "
+              f"fsils_solve ({args.ls}); iters/s on the sample scaled by the tet ratio to the 10M-tet unit")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"P10 pipe 96x96x181 (10,008,576 TET4), NS VMS, LS {args.ls}; reference timed on a bounded sample",
+                   "sample_dims": list(dims), "ls": args.ls, "krylov_itr": int(info["itr"]), "gm_itr": int(info["GM_itr"]),
+                   "cg_itr": int(info["CG_itr"])},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference" if ref.available() else "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline_leg(args, ls_name):
+    """Bounded CPU sample for the `cpu_baseline` object of the GPU arm (rank 0, N=1 only)."""
+    try:
+        from oracle import ref, refcase
+        from svfsiplus_b200 import problem as P
+        if not ref.available():
+            return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "oracle/_ref not present"}
+        dims = tuple(args.ref_dims)
+        case = P.pipe_case(*dims)
+        ntet = case["mesh"].nEl
+        scale = ntet / float(6 * P10[0] * P10[1] * P10[2])
+        t0 = time.perf_counter()
+        R, Val, _, _, t_asm = refcase.reference_assemble(case)
+        X, info = refcase.reference_solve(case, R, Val, P.LS_SETTINGS[ls_name])
+        dt = time.perf_counter() - t0
+        return {"value": (1.0 / dt) * scale, "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": f"pipe {dims[0]}x{dims[1]}x{dims[2]} = {ntet} tets ({100*scale:.2f}% of P10): one full "
+                          f"construct_fluid ({t_asm:.2f} s) + fsils_solve {ls_name} ({info['wall_s']:.2f} s, itr {int(info['itr'])}/"
+                          f"{int(info['GM_itr'])}/{int(info['CG_itr'])}); iters/s scaled by the tet ratio",
+                "assembly_us_per_tet": 1e6 * t_asm / ntet}
+    except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU line
+        return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from svfsiplus_b200 import backend as B
+    from svfsiplus_b200 import problem as P
+
+    rank, world, local = _dist()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+
+    if world > 1:
+        from svfsiplus_b200 import partition as PT
+        dims = PT.weak_dims(P10, world)
+        case, be = PT.setup_distributed_case(dims, rank, world, local, dist)
+    else:
+        dims = tuple(args.dims)
+        case = P.pipe_case(*dims)
+        be = P.setup_backend(case, device=local)
+    nNo_local = be.nNo
+    tDof = case["Ag"].shape[1]
+    ntet_total = 6 * dims[0] * dims[1] * dims[2]
+
+    # pinned host buffers for the end-to-end leg
+    pin = {k: torch.from_numpy(np.ascontiguousarray(case[k])).pin_memory() for k in ("Ag", "Yg", "Bf")}
+    out_pin = torch.empty((nNo_local, 4), dtype=torch.float64).pin_memory()
+    ls_type, RI, GM, CG = P.LS_SETTINGS[args.ls]
+    props = B.fluid_props(tDof=tDof, **case["props"])
+
+    def step_resident():
+        be.zero(4)
+        be.assemble_fluid(props)
+        _, info = be.solve(ls_type, B.PREC_FSILS, RI, GM, CG, case["incL"], case["res"], fetch=False)
+        return info
+
+    def step_e2e():
+        be.state_set(tDof, pin["Ag"].data_ptr(), pin["Yg"].data_ptr(), pin["Bf"].data_ptr())
+        be.zero(4)
+        be.assemble_fluid(props)
+        _, info = be.solve(ls_type, B.PREC_FSILS, RI, GM, CG, case["incL"], case["res"], out=out_pin.data_ptr(), fetch=True)
+        return info
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxreduce(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    be.state_set(tDof, pin["Ag"].data_ptr(), pin["Yg"].data_ptr(), pin["Bf"].data_ptr())
+    info = None
+    for _ in range(args.warmup):
+        info = step_resident()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    be.profile(True)
+    l0 = be.launch_count()
+    barrier()
+    be.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        info = step_resident()
+    dev_ms = be.timer_stop()
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = be.launch_count() - l0
+    prof = be.profile_read()
+    be.profile(False)
+    dev_ms = maxreduce(dev_ms)
+    ms_per_step = dev_ms / args.steps
+
+    # end-to-end leg (same K)
+    step_e2e()
+    barrier()
+    be.timer_start()
+    for _ in range(args.steps):
+        step_e2e()
+    e2e_ms = be.timer_stop()
+    barrier()
+    e2e_ms = maxreduce(e2e_ms) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # dominant kernel class of the timed region -> roofline
+    peak, peak_src = _peaks()
+    tot_k = sum(v["ms"] for v in prof.values())
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    d = prof[dom]
+    achieved = (d["bytes"] / 1e9) / (d["ms"] * 1e-3) if d["ms"] > 0 else 0.0
+    shares = {k: round(v["ms"] / dev_ms, 4) for k, v in prof.items() if v["ms"] > 0}
+    per_class = {k: {"ms_per_launch": v["ms"] / max(v["launches"], 1), "launches_per_step": v["launches"] / args.steps,
+                     "GBps": (v["bytes"] / 1e9) / (v["ms"] * 1e-3) if v["ms"] > 0 else None}
+                 for k, v in prof.items() if v["launches"] > 0}
+    # stand-alone block SpMV (the north-star kernel): CUDA events over 50 back-to-back launches
+    P.assemble(be, case, upload=False)
+    spmv_ms = be.spmv_bench(4, 50)
+    nnz, nNo = be.nnz, be.nNo
+    spmv_bytes = nnz * 132.0 + nNo * 72.0
+    spmv_gbs = spmv_bytes / 1e9 / (spmv_ms * 1e-3)
+
+    scale = ntet_total / float(6 * P10[0] * P10[1] * P10[2])
+    value = (1e3 / ms_per_step) * (scale if world > 1 else 1.0)
+    e2e_value = (1e3 / e2e_ms) * (scale if world > 1 else 1.0)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"pipe {dims[0]}x{dims[1]}x{dims[2]} = {ntet_total} TET4, NS VMS P1-P1, one Newton iteration "
+                               f"(ls_alloc + construct_fluid + fsils_solve LS {args.ls}, pipe_RCR_3d solver.xml parameters)",
+                   "ls": args.ls, "nNo": int(nNo), "nnz_blocks": int(nnz), "parallelism": f"dd{world}",
+                   "l2": "inputs larger than L2 (Val 3.2 GB vs 126 MB L2): no flush between iterations",
+                   "krylov_itr": info["RI"]["itr"], "gm_itr": info["GM"]["itr"], "cg_itr": info["CG"]["itr"],
+                   "suc": info["RI"]["suc"], "wall_ms_per_step": wall_ms / args.steps,
+                   "value_note": "N>1: Newton-iters/s x (total tets / 10,008,576), i.e. 10M-tet-equivalent iterations/s"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((2 * tDof + 3) * nNo_local * 8),
+                "d2h_bytes_per_step": int(4 * nNo_local * 8), "ms_per_step": e2e_ms},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "share_of_step": d["ms"] / dev_ms, "launches": d["launches"],
+                     "bytes_per_launch": d["bytes"] / max(d["launches"], 1)},
+        "kernel_shares": shares, "kernels": per_class, "kernel_time_frac_of_step": tot_k / dev_ms,
+        "spmv": {"kernel": "k_spmv_vv4", "ms": spmv_ms, "bytes": spmv_bytes, "GBps": spmv_gbs, "frac_of_peak": spmv_gbs / peak,
+                 "frac_of_8TBps": spmv_gbs / 8000.0},
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_leg(args, args.ls)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ls", default="NS", choices=["NS", "GMRES", "BICGS"])
+    ap.add_argument("--dims", type=int, nargs=3, default=list(P10), help="pipe hex counts nx ny nz (default P10)")
+    ap.add_argument("--ref-dims", type=int, nargs=3, default=[24, 24, 46], help="bounded CPU sample of the workload")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

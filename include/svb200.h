@@ -107,6 +107,18 @@ int b200_spmv(b200_handle* h, int dof, const double* x, double* y);
 int b200_spmv_bench(b200_handle* h, int dof, int reps, double* ms_per_launch);
 /* Kernel-launch counter (all kernels this handle launched since creation). */
 long long b200_launch_count(b200_handle* h);
+/* Live kernel timing inside a step.  b200_profile(h,1) resets the counters and makes every kernel
+ * class record CUDA-event pairs on the launch stream; b200_profile_read synchronises and returns,
+ * per class, the summed device milliseconds, the ALGORITHMIC bytes (SURVEY.md par. 8d formulas) and the
+ * number of launches.  Classes: 0 spmv_vv dof4, 1 spmv_vv dof<4, 2 spmv_ss, 3 spmv_sv, 4 spmv_vs,
+ * 5 multi_dot, 6 cgs_update_scale, 7 blas1 (axpy/scale/lin_comb/...), 8 scale_val (Jacobi), 9 depart,
+ * 10 assembly (all colours), 11 halo pack/add. */
+#define B200_NUM_KERNEL_CLASSES 12
+int b200_profile(b200_handle* h, int enable);
+int b200_profile_read(b200_handle* h, int max_classes, double* ms, double* bytes, long long* launches);
+/* Device-side stopwatch on the launch stream: b200_timer(h,0,NULL) records the start event,
+ * b200_timer(h,1,&ms) records + synchronises the stop event and returns the elapsed milliseconds. */
+int b200_timer(b200_handle* h, int stop, double* ms);
 /* Milliseconds spent (CUDA events) in the phases of the last b200_assemble_fluid / b200_solve:
  * t[0] assembly, t[1] preconditioning, t[2] Krylov, t[3] SpMV share of t[2] (0 unless profiling on). */
 int b200_last_timings(b200_handle* h, double* t4);

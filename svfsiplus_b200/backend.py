@@ -46,8 +46,12 @@ EXPORTS = [
     "b200_create", "b200_destroy", "b200_last_error", "b200_device_count", "b200_comm_unique_id", "b200_comm_init",
     "b200_lhs_create", "b200_face_set", "b200_mesh_set", "b200_zero", "b200_state_set", "b200_assemble_fluid",
     "b200_assemble_elem", "b200_get_R", "b200_set_R", "b200_get_Val", "b200_set_Val", "b200_commu_R", "b200_solve",
-    "b200_spmv", "b200_spmv_bench", "b200_launch_count", "b200_last_timings",
+    "b200_spmv", "b200_spmv_bench", "b200_launch_count", "b200_last_timings", "b200_profile", "b200_profile_read",
+    "b200_timer",
 ]
+
+KERNEL_CLASSES = ["spmv_vv4", "spmv_vv3", "spmv_ss", "spmv_sv", "spmv_vs", "multi_dot", "cgs_update_scale", "blas1",
+                  "scale_val", "depart", "assembly", "halo"]
 
 _lib = None
 
@@ -86,6 +90,9 @@ def lib():
         L.b200_launch_count.argtypes = [vp]
         L.b200_launch_count.restype = C.c_longlong
         L.b200_last_timings.argtypes = [vp, vp]
+        L.b200_profile.argtypes = [vp, ci]
+        L.b200_profile_read.argtypes = [vp, ci, vp, vp, vp]
+        L.b200_timer.argtypes = [vp, ci, C.POINTER(cd)]
         _lib = L
     return _lib
 
@@ -250,6 +257,23 @@ class Backend:
     def spmv_bench(self, dof, reps=20) -> float:
         ms = C.c_double(0)
         self._ck(self.L.b200_spmv_bench(self.h, dof, reps, C.byref(ms)), "b200_spmv_bench")
+        return ms.value
+
+    def profile(self, enable=True):
+        self._ck(self.L.b200_profile(self.h, int(enable)), "b200_profile")
+
+    def profile_read(self):
+        n = len(KERNEL_CLASSES)
+        ms = np.zeros(n); by = np.zeros(n); ln = np.zeros(n, np.int64)
+        self._ck(self.L.b200_profile_read(self.h, n, _p(ms), _p(by), _p(ln)), "b200_profile_read")
+        return {k: dict(ms=float(ms[i]), bytes=float(by[i]), launches=int(ln[i])) for i, k in enumerate(KERNEL_CLASSES)}
+
+    def timer_start(self):
+        self._ck(self.L.b200_timer(self.h, 0, None), "b200_timer")
+
+    def timer_stop(self) -> float:
+        ms = C.c_double(0)
+        self._ck(self.L.b200_timer(self.h, 1, C.byref(ms)), "b200_timer")
         return ms.value
 
     def launch_count(self) -> int:

@@ -438,6 +438,8 @@ int b200_assemble_fluid(b200_handle* h, const b200_fluid_props* p)
       c.N[g][3] = 1.0 - xi[g][0] - xi[g][1] - xi[g][2];
     }
     double t0 = wall_s();
+    {
+    CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*128.0 + double(h->nNo)*(32.0 + 24.0 + 16.0*p->tDof + 24.0) + double(h->nEl)*(16.0 + 16.0 + 64.0), h->nColors);
     for (int col = 0; col < h->nColors; col++) {
       const int e0 = h->color_off[col], e1 = h->color_off[col+1];
       if (e1 == e0) continue;
@@ -445,6 +447,7 @@ int b200_assemble_fluid(b200_handle* h, const b200_fluid_props* p)
       k_assemble_fluid_tet4<<<blocks, 128, 0, ops.st>>>(e0, e1, c, h->d_ien, h->d_rdest, h->d_edest, h->d_x,
                                                         h->d_Ag, h->d_Yg, h->d_Bf, h->R, h->Val, h->d_err);
       ops.post();
+    }
     }
     int flag = 0;
     CU_CHECK(cudaMemcpyAsync(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, ops.st));
@@ -638,6 +641,43 @@ int b200_spmv_bench(b200_handle* h, int dof, int reps, double* ms_per_launch)
 }
 
 long long b200_launch_count(b200_handle* h) { return h ? h->ops->launches : 0; }
+
+int b200_profile(b200_handle* h, int enable)
+{
+  return guarded(h, [&] {
+    CU_CHECK(cudaStreamSynchronize(h->ops->st));
+    h->ops->profile_reset();
+    h->ops->profiling = enable != 0;
+  });
+}
+
+int b200_profile_read(b200_handle* h, int max_classes, double* ms, double* bytes, long long* launches)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+    ops.profile_resolve();
+    for (int c = 0; c < KC_COUNT && c < max_classes; c++) { ms[c] = ops.cls_ms[c]; bytes[c] = ops.cls_bytes[c]; launches[c] = ops.cls_launches[c]; }
+  });
+}
+
+int b200_timer(b200_handle* h, int stop, double* ms)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    static thread_local cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (!e0) { CU_CHECK(cudaEventCreate(&e0)); CU_CHECK(cudaEventCreate(&e1)); }
+    if (!stop) {
+      CU_CHECK(cudaEventRecord(e0, ops.st));
+    } else {
+      CU_CHECK(cudaEventRecord(e1, ops.st));
+      CU_CHECK(cudaEventSynchronize(e1));
+      float t = 0;
+      CU_CHECK(cudaEventElapsedTime(&t, e0, e1));
+      if (ms) *ms = t;
+    }
+  });
+}
 
 int b200_last_timings(b200_handle* h, double* t4)
 {

@@ -75,11 +75,59 @@ struct DevFace {               // lhs.face[faIn] (liner_solver/fils_struct.hpp:1
 
 struct HaloReq { int peer = -1, n = 0; int* ptr = nullptr; double* sbuf = nullptr; double* rbuf = nullptr; };
 
+// kernel classes for live (CUDA-event) timing inside a step: see b200_profile_read in svb200.h
+enum KClass { KC_SPMV_VV4 = 0, KC_SPMV_VV3, KC_SPMV_SS, KC_SPMV_SV, KC_SPMV_VS, KC_MULTI_DOT, KC_CGS_UPDATE,
+              KC_BLAS1, KC_SCALE_VAL, KC_DEPART, KC_ASSEMBLY, KC_HALO, KC_COUNT };
+
 class CudaOps {
  public:
   cudaStream_t st = nullptr;
   long long launches = 0;
   double phase_ms[4] = {0, 0, 0, 0};
+
+  // ---- live kernel timing: event pairs on the launch stream, resolved after the step ---------------
+  bool profiling = false;
+  struct Span { cudaEvent_t a, b; int cls; };
+  std::vector<Span> spans;
+  size_t span_used = 0;
+  double cls_ms[KC_COUNT] = {0};
+  double cls_bytes[KC_COUNT] = {0};
+  long long cls_launches[KC_COUNT] = {0};
+
+  struct Scope {
+    CudaOps& o; int idx;
+    Scope(CudaOps& o_, int cls, double bytes, int nl = 1) : o(o_), idx(-1)
+    {
+      if (!o.profiling) return;
+      if (o.span_used == o.spans.size()) {
+        Span s; cudaEventCreate(&s.a); cudaEventCreate(&s.b); s.cls = cls; o.spans.push_back(s);
+      }
+      idx = int(o.span_used++);
+      o.spans[idx].cls = cls;
+      o.cls_bytes[cls] += bytes;
+      o.cls_launches[cls] += nl;
+      cudaEventRecord(o.spans[idx].a, o.st);
+    }
+    ~Scope() { if (idx >= 0) cudaEventRecord(o.spans[idx].b, o.st); }
+  };
+  // fold the recorded spans into cls_ms (call after a stream synchronize)
+  void profile_resolve()
+  {
+    for (size_t i = 0; i < span_used; i++) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, spans[i].a, spans[i].b) == cudaSuccess) cls_ms[spans[i].cls] += ms;
+    }
+    span_used = 0;
+  }
+  void profile_reset()
+  {
+    span_used = 0;
+    for (int c = 0; c < KC_COUNT; c++) { cls_ms[c] = 0; cls_bytes[c] = 0; cls_launches[c] = 0; }
+  }
+  // algorithmic bytes (SURVEY.md par. 8d)
+  double bytes_vv(int d) const { return double(nnz_)*(8.0*d*d + 4.0) + double(nNo_)*(16.0*d + 8.0); }
+  double bytes_ss() const { return double(nnz_)*12.0 + double(nNo_)*24.0; }
+  double bytes_svs(int d) const { return double(nnz_)*(8.0*d + 4.0) + double(nNo_)*(8.0*d + 16.0); }
 
   // structure (solver ordering)
   int gnNo_ = 0, nNo_ = 0, mynNo_ = 0, nnz_ = 0;
@@ -122,6 +170,7 @@ class CudaOps {
   ~CudaOps()
   {
     for (auto& c : chunks) cudaFree(c.p);
+    for (auto& sp : spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto& f : faces) { cudaFree(f.glob); cudaFree(f.val); cudaFree(f.valM); }
     for (auto& r : reqs) { cudaFree(r.ptr); cudaFree(r.sbuf); cudaFree(r.rbuf); }
     cudaFree(rowPtr); cudaFree(col); cudaFree(diag); cudaFree(tpos);
@@ -189,15 +238,15 @@ class CudaOps {
   // ---- BLAS-1 -------------------------------------------------------------------------------------
   void zero(size_t n, double* x) { CU_CHECK(cudaMemsetAsync(x, 0, n*sizeof(double), st)); }
   void copy(size_t n, const double* x, double* y) { CU_CHECK(cudaMemcpyAsync(y, x, n*sizeof(double), cudaMemcpyDeviceToDevice, st)); }
-  void fill(size_t n, double a, double* x) { k_fill<<<grid_for(n, 256), 256, 0, st>>>(n, a, x); post(); }
-  void axpy(size_t n, double a, const double* x, double* y) { k_axpy<<<grid_for(n, 256), 256, 0, st>>>(n, a, x, y); post(); }
-  void scal(size_t n, double a, double* x) { k_scal<<<grid_for(n, 256), 256, 0, st>>>(n, a, x); post(); }
-  void divs(size_t n, double d, double* x) { k_divs<<<grid_for(n, 256), 256, 0, st>>>(n, d, x); post(); }
-  void sub(size_t n, const double* a, const double* b, double* out) { k_sub<<<grid_for(n, 256), 256, 0, st>>>(n, a, b, out); post(); }
-  void mul_inplace(size_t n, const double* w, double* x) { k_mul<<<grid_for(n, 256), 256, 0, st>>>(n, w, x); post(); }
-  void lin2(size_t n, double* out, double a, const double* x, double b, const double* y) { k_lin2<<<grid_for(n, 256), 256, 0, st>>>(n, out, a, x, b, y); post(); }
-  void axpy2(size_t n, double* X, double a, const double* P, double b, const double* S) { k_axpy2<<<grid_for(n, 256), 256, 0, st>>>(n, X, a, P, b, S); post(); }
-  void bicg_p_update(size_t n, double* P, const double* R, const double* V, double beta, double omega) { k_bicg_p<<<grid_for(n, 256), 256, 0, st>>>(n, P, R, V, beta, omega); post(); }
+  void fill(size_t n, double a, double* x) { Scope sc(*this, KC_BLAS1, 8.0*n); k_fill<<<grid_for(n, 256), 256, 0, st>>>(n, a, x); post(); }
+  void axpy(size_t n, double a, const double* x, double* y) { Scope sc(*this, KC_BLAS1, 24.0*n); k_axpy<<<grid_for(n, 256), 256, 0, st>>>(n, a, x, y); post(); }
+  void scal(size_t n, double a, double* x) { Scope sc(*this, KC_BLAS1, 16.0*n); k_scal<<<grid_for(n, 256), 256, 0, st>>>(n, a, x); post(); }
+  void divs(size_t n, double d, double* x) { Scope sc(*this, KC_BLAS1, 16.0*n); k_divs<<<grid_for(n, 256), 256, 0, st>>>(n, d, x); post(); }
+  void sub(size_t n, const double* a, const double* b, double* out) { Scope sc(*this, KC_BLAS1, 24.0*n); k_sub<<<grid_for(n, 256), 256, 0, st>>>(n, a, b, out); post(); }
+  void mul_inplace(size_t n, const double* w, double* x) { Scope sc(*this, KC_BLAS1, 24.0*n); k_mul<<<grid_for(n, 256), 256, 0, st>>>(n, w, x); post(); }
+  void lin2(size_t n, double* out, double a, const double* x, double b, const double* y) { Scope sc(*this, KC_BLAS1, 24.0*n); k_lin2<<<grid_for(n, 256), 256, 0, st>>>(n, out, a, x, b, y); post(); }
+  void axpy2(size_t n, double* X, double a, const double* P, double b, const double* S) { Scope sc(*this, KC_BLAS1, 32.0*n); k_axpy2<<<grid_for(n, 256), 256, 0, st>>>(n, X, a, P, b, S); post(); }
+  void bicg_p_update(size_t n, double* P, const double* R, const double* V, double beta, double omega) { Scope sc(*this, KC_BLAS1, 32.0*n); k_bicg_p<<<grid_for(n, 256), 256, 0, st>>>(n, P, R, V, beta, omega); post(); }
 
   // out = base + sum_j coef[j] V[(j0+j)*stride], sequential in j (base may be null, out may alias base)
   void lin_comb(size_t n, double* out, const double* base, int k, const double* V, size_t stride, int j0, const double* coef)
@@ -209,6 +258,7 @@ class CudaOps {
       const int m = std::min(kMaxComb, k - done);
       CombArgs a;
       for (int j = 0; j < m; j++) a.coef[j] = coef[done + j];
+      Scope sc(*this, KC_BLAS1, 8.0*double(n)*(m + 2));
       k_lin_comb<<<grid_for(n, 256), 256, 0, st>>>(n, out, b, m, V + size_t(j0 + done)*stride, stride, a);
       post();
       b = out;
@@ -223,6 +273,7 @@ class CudaOps {
     if (slot0 + count > kMaxSlots) throw std::runtime_error("reduction slot overflow");
     const size_t n = size_t(dof)*mynNo_;
     int done = 0;
+    Scope sc(*this, KC_MULTI_DOT, 8.0*double(n)*(count + (count + kDotJB - 1)/kDotJB), (count + kDotJB - 1)/kDotJB);
     while (done < count) {
       const int m = std::min(kDotJB, count - done);
       k_multi_dot<<<kRedBlocks, kRedThreads, 0, st>>>(n, base + size_t(done)*stride, stride, w, m, partial_d, counter_d, red_d, slot0 + done);
@@ -253,6 +304,7 @@ class CudaOps {
   void cgs_update_scale(int dof, int k, const double* base, size_t stride, double* w, int slot0)
   {
     const size_t n = size_t(dof)*nNo_;
+    Scope sc(*this, KC_CGS_UPDATE, 8.0*double(n)*(k + 2));
     k_cgs_update_scale<<<grid_for(n, 256), 256, sizeof(double)*(k+1), st>>>(n, k, base, stride, w, red_d, slot0);
     post();
   }
@@ -261,6 +313,8 @@ class CudaOps {
   void spmv_vv(int dof, const double* K, const double* U, double* KU)
   {
     const int g = grid_rows(nNo_);
+    {
+    Scope sc(*this, dof == 4 ? KC_SPMV_VV4 : KC_SPMV_VV3, bytes_vv(dof));
     switch (dof) {
       case 4: k_spmv_vv4<<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU); break;
       case 3: k_spmv_vv<3><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU); break;
@@ -269,30 +323,40 @@ class CudaOps {
       default: throw std::runtime_error("spmv_vv: dof > 4 is not a supported FSILS path");
     }
     post();
+    }
     halo_add(dof, KU);
   }
   void spmv_ss(const double* K, const double* U, double* KU)
   {
-    k_spmv_ss<<<grid_rows(nNo_), 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
-    post();
+    {
+      Scope sc(*this, KC_SPMV_SS, bytes_ss());
+      k_spmv_ss<<<grid_rows(nNo_), 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
+      post();
+    }
     halo_add(1, KU);
   }
   void spmv_sv(int dof, const double* K, const double* U, double* KU)
   {
     const int g = grid_rows(nNo_);
-    if (dof == 3) k_spmv_sv<3><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
-    else if (dof == 2) k_spmv_sv<2><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
-    else throw std::runtime_error("spmv_sv: nsd must be 2 or 3");
-    post();
+    {
+      Scope sc(*this, KC_SPMV_SV, bytes_svs(dof));
+      if (dof == 3) k_spmv_sv<3><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
+      else if (dof == 2) k_spmv_sv<2><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
+      else throw std::runtime_error("spmv_sv: nsd must be 2 or 3");
+      post();
+    }
     halo_add(dof, KU);
   }
   void spmv_vs(int dof, const double* K, const double* U, double* KU)
   {
     const int g = grid_rows(nNo_);
-    if (dof == 3) k_spmv_vs<3><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
-    else if (dof == 2) k_spmv_vs<2><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
-    else throw std::runtime_error("spmv_vs: nsd must be 2 or 3");
-    post();
+    {
+      Scope sc(*this, KC_SPMV_VS, bytes_svs(dof));
+      if (dof == 3) k_spmv_vs<3><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
+      else if (dof == 2) k_spmv_vs<2><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
+      else throw std::runtime_error("spmv_vs: nsd must be 2 or 3");
+      post();
+    }
     halo_add(1, KU);
   }
 
@@ -301,6 +365,8 @@ class CudaOps {
   {
     if (nranks == 1 || reqs.empty()) return;
     if (dof > halo_dof_cap) throw std::runtime_error("halo buffers too small for dof");
+    double hb = 0; for (auto& r : reqs) hb += 32.0*r.n*dof;
+    Scope sc(*this, KC_HALO, hb, int(reqs.size())*2);
     for (auto& r : reqs) {
       k_halo_pack<<<grid_for(size_t(r.n)*dof, 256, 1), 256, 0, st>>>(r.n, dof, r.ptr, V, r.sbuf);
       post();
@@ -400,6 +466,7 @@ class CudaOps {
   void scale_val(int dof, const double* Wr, const double* Wc, double* Val)
   {
     const int g = grid_rows(nNo_);
+    Scope sc(*this, KC_SCALE_VAL, double(nnz_)*(16.0*dof*dof + 4.0) + double(nNo_)*(16.0*dof + 8.0));
     switch (dof) {
       case 4: k_scale_val<4><<<g, 256, 0, st>>>(nNo_, rowPtr, col, Wr, Wc, Val); break;
       case 3: k_scale_val<3><<<g, 256, 0, st>>>(nNo_, rowPtr, col, Wr, Wc, Val); break;
@@ -418,6 +485,7 @@ class CudaOps {
   void depart(int nsd, const double* Val, double* Gt, double* mK, double* mG, double* mD, double* mL)
   {
     const size_t nz = size_t(nnz_);
+    Scope sc(*this, KC_DEPART, double(nnz_)*(8.0*(nsd+1)*(nsd+1)*2 + 8.0*nsd + 4.0));
     if (nsd == 3) k_depart3<<<grid_for(nz, 256, 1), 256, 0, st>>>(nz, tpos, Val, Gt, mK, mG, mD, mL);
     else if (nsd == 2) k_depart_generic<2><<<grid_for(nz, 256, 1), 256, 0, st>>>(nz, tpos, Val, Gt, mK, mG, mD, mL);
     else throw std::runtime_error("FSILS: Not defined nsd for DEPART");

@@ -81,9 +81,16 @@ def pipe_mesh(nx: int, ny: int, nz: int, radius: float = 1.0, length: float = 10
     v = np.linspace(-1.0, 1.0, ny + 1)
     w = np.linspace(0.0, length, nz + 1)
     W, V, U = np.meshgrid(w, v, u, indexing="ij")          # node order: x fastest
-    # elliptical square->disc map
-    X = radius * U * np.sqrt(1.0 - 0.5 * V * V)
-    Y = radius * V * np.sqrt(1.0 - 0.5 * U * U)
+    # concentric (Shirley-Chiu) square->disc map: radius = max(|u|,|v|), angle linear along the
+    # square's perimeter.  Unlike the elliptical map its Jacobian stays bounded away from zero at the
+    # four square corners, so the corner cells keep an O(h^2) area.
+    with np.errstate(divide="ignore", invalid="ignore"):
+        a = np.abs(U) >= np.abs(V)
+        r = np.where(a, U, V)
+        phi = np.where(a, (np.pi / 4.0) * np.where(U != 0.0, V / np.where(U == 0.0, 1.0, U), 0.0),
+                       (np.pi / 2.0) - (np.pi / 4.0) * np.where(V != 0.0, U / np.where(V == 0.0, 1.0, V), 0.0))
+    X = radius * r * np.cos(phi)
+    Y = radius * r * np.sin(phi)
     x = np.stack([X.reshape(-1), Y.reshape(-1), W.reshape(-1)], axis=1)
 
     ii = np.arange(nx + 1)
@@ -99,7 +106,7 @@ def pipe_mesh(nx: int, ny: int, nz: int, radius: float = 1.0, length: float = 10
     ien = _kuhn_tets(nx, ny, nz)
     if jitter > 0.0:
         rng = np.random.default_rng(seed)
-        # local spacing: shortest edge of any incident tet, so slivers near the disc "corners" survive
+        # local spacing: shortest edge of any incident tet
         e = ien
         hmin = np.full(x.shape[0], np.inf)
         for a, b in itertools.combinations(range(4), 2):
@@ -107,7 +114,17 @@ def pipe_mesh(nx: int, ny: int, nz: int, radius: float = 1.0, length: float = 10
             np.minimum.at(hmin, e[:, a], d)
             np.minimum.at(hmin, e[:, b], d)
         dx = rng.uniform(-1.0, 1.0, size=x.shape) * (jitter * hmin)[:, None]
-        x[interior] += dx[interior]
+        dx[~interior] = 0.0
+        # thin cells along the map's diagonals must not fold: halve the displacement of the nodes of
+        # any element that loses more than 70% of its volume (or inverts) until none does
+        v0 = tet_volumes(x, ien)
+        for _ in range(12):
+            v = tet_volumes(x + dx, ien)
+            bad = (v * v0 <= 0.0) | (np.abs(v) < 0.3 * np.abs(v0))
+            if not bad.any():
+                break
+            dx[np.unique(ien[bad].reshape(-1))] *= 0.5
+        x = x + dx
     ien = _fix_orientation(x, ien).astype(np.int32)
 
     nid = np.arange(x.shape[0], dtype=np.int32)
