@@ -268,9 +268,8 @@ def run_gpu(args):
                  for k, v in prof.items() if v["launches"] > 0}
     # stand-alone block SpMV (the north-star kernel): CUDA events over 50 back-to-back launches
     P.assemble(be, case, upload=False)
-    spmv_ms = be.spmv_bench(4, 50)
+    spmv_ms, spmv_bytes = be.op_bench("spmv_vv4", reps=50)
     nnz, nNo = be.nnz, be.nNo
-    spmv_bytes = nnz * 132.0 + nNo * 72.0
     spmv_gbs = spmv_bytes / 1e9 / (spmv_ms * 1e-3)
 
     scale = ntet_total / float(6 * P10[0] * P10[1] * P10[2])

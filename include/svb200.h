@@ -102,9 +102,12 @@ int b200_solve(b200_handle* h, int ls_type, int prec, const b200_tol* RI, const 
 /* ---- single-kernel taps used by the parity tests and the roofline bench --------------------- */
 /* y = K x (+ overlap add) with the device Val; x, y host (dof,nNo) in assembly order. */
 int b200_spmv(b200_handle* h, int dof, const double* x, double* y);
-/* Times `reps` launches of the block SpMV on device-resident random x (CUDA events on the launch
- * stream); returns mean milliseconds per launch. */
-int b200_spmv_bench(b200_handle* h, int dof, int reps, double* ms_per_launch);
+/* Stand-alone kernel bench: times `reps` back-to-back launches of ONE kernel class (ids as in
+ * b200_profile_read) on device-resident data with CUDA events on the launch stream, after 3 warm-up
+ * launches; returns mean milliseconds and the ALGORITHMIC bytes per launch.  Needs an assembled dof-4
+ * system.  NS shapes (1-4, 9) run on the departed matrix; 3 / 4 are the two passes of the fused Schur
+ * operator; k = number of basis vectors for multi_dot (5) and cgs_update_scale (6) on dof-3 vectors. */
+int b200_op_bench(b200_handle* h, int op, int k, int reps, double* ms_per_launch, double* bytes_per_launch);
 /* Kernel-launch counter (all kernels this handle launched since creation). */
 long long b200_launch_count(b200_handle* h);
 /* Live kernel timing inside a step.  b200_profile(h,1) resets the counters and makes every kernel

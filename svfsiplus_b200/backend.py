@@ -46,7 +46,7 @@ EXPORTS = [
     "b200_create", "b200_destroy", "b200_last_error", "b200_device_count", "b200_comm_unique_id", "b200_comm_init",
     "b200_lhs_create", "b200_face_set", "b200_mesh_set", "b200_zero", "b200_state_set", "b200_assemble_fluid",
     "b200_assemble_elem", "b200_get_R", "b200_set_R", "b200_get_Val", "b200_set_Val", "b200_commu_R", "b200_solve",
-    "b200_spmv", "b200_spmv_bench", "b200_launch_count", "b200_last_timings", "b200_profile", "b200_profile_read",
+    "b200_spmv", "b200_op_bench", "b200_launch_count", "b200_last_timings", "b200_profile", "b200_profile_read",
     "b200_timer",
 ]
 
@@ -86,7 +86,7 @@ def lib():
         L.b200_commu_R.argtypes = [vp]
         L.b200_solve.argtypes = [vp, ci, ci, C.POINTER(Tol), C.POINTER(Tol), C.POINTER(Tol), vp, vp, vp, C.POINTER(LsOut)]
         L.b200_spmv.argtypes = [vp, ci, vp, vp]
-        L.b200_spmv_bench.argtypes = [vp, ci, ci, C.POINTER(cd)]
+        L.b200_op_bench.argtypes = [vp, ci, ci, ci, C.POINTER(cd), C.POINTER(cd)]
         L.b200_launch_count.argtypes = [vp]
         L.b200_launch_count.restype = C.c_longlong
         L.b200_last_timings.argtypes = [vp, vp]
@@ -254,10 +254,13 @@ class Backend:
         self._ck(self.L.b200_spmv(self.h, x.shape[1], _p(x), _p(y)), "b200_spmv")
         return y
 
-    def spmv_bench(self, dof, reps=20) -> float:
-        ms = C.c_double(0)
-        self._ck(self.L.b200_spmv_bench(self.h, dof, reps, C.byref(ms)), "b200_spmv_bench")
-        return ms.value
+    def op_bench(self, op, k=0, reps=20):
+        """Stand-alone bench of one kernel class (name from KERNEL_CLASSES or id): (ms, bytes) per launch."""
+        if isinstance(op, str):
+            op = KERNEL_CLASSES.index(op)
+        ms = C.c_double(0); by = C.c_double(0)
+        self._ck(self.L.b200_op_bench(self.h, op, k, reps, C.byref(ms), C.byref(by)), "b200_op_bench")
+        return ms.value, by.value
 
     def profile(self, enable=True):
         self._ck(self.L.b200_profile(self.h, int(enable)), "b200_profile")

@@ -61,9 +61,6 @@ struct b200_handle {
   struct Staged { int d; std::vector<int> eqN; std::vector<double> lK, lR; };
   std::vector<Staged> staged;
 
-  // spmv bench vectors
-  double* bx = nullptr;
-  double* by = nullptr;
 
   ~b200_handle()
   {
@@ -71,7 +68,6 @@ struct b200_handle {
     cudaFree(R); cudaFree(Val); cudaFree(stage_d);
     cudaFree(d_ien); cudaFree(d_rdest); cudaFree(d_edest); cudaFree(d_x); cudaFree(d_err);
     cudaFree(d_Ag); cudaFree(d_Yg); cudaFree(d_Bf);
-    cudaFree(bx); cudaFree(by);
   }
 };
 
@@ -614,29 +610,81 @@ int b200_spmv(b200_handle* h, int dof, const double* x, double* y)
   });
 }
 
-int b200_spmv_bench(b200_handle* h, int dof, int reps, double* ms_per_launch)
+int b200_op_bench(b200_handle* h, int op, int k, int reps, double* ms_per_launch, double* bytes_per_launch)
 {
   return guarded(h, [&] {
     auto& ops = *h->ops;
-    if (!h->Val || h->dof != dof) throw std::runtime_error("spmv_bench: no matrix with this dof on the device");
-    const size_t n = size_t(dof)*h->nNo;
-    if (!h->bx) {
-      CU_CHECK(cudaMalloc(&h->bx, sizeof(double)*n));
-      CU_CHECK(cudaMalloc(&h->by, sizeof(double)*n));
-      ops.fill(n, 1.0, h->bx);
+    if (!h->Val || h->dof != 4) throw std::runtime_error("op_bench: needs an assembled dof-4 system on the device");
+    if (reps < 1) throw std::runtime_error("op_bench: reps must be positive");
+    const size_t nNo = size_t(h->nNo), nnz = size_t(h->nnz);
+    auto mk = ops.mark();
+    double *Gt = nullptr, *mK = nullptr, *mG = nullptr, *mD = nullptr, *mL = nullptr;
+    const bool ns_shape = (op == KC_SPMV_VV3 || op == KC_SPMV_SS || op == KC_SPMV_SV || op == KC_SPMV_VS || op == KC_DEPART);
+    if (ns_shape) {
+      Gt = ops.vec(3*nnz); mK = ops.vec(9*nnz); mG = ops.vec(3*nnz); mD = ops.vec(3*nnz); mL = ops.vec(nnz);
+      ops.depart(3, h->Val, Gt, mK, mG, mD, mL);
     }
+    const int kk = std::max(1, k);
+    const size_t n4 = 4*nNo, n3 = 3*nNo;
+    double* x = ops.vec(n4);
+    double* y = ops.vec(n4);
+    double* z = ops.vec(n4);
+    ops.fill(n4, 1.0, x);
+    ops.fill(n4, 0.5, z);
+    double* basis = nullptr;
+    double* valcopy = nullptr;
+    if (op == KC_MULTI_DOT || op == KC_CGS_UPDATE) {
+      basis = ops.vec(n3*(size_t(kk) + 1));
+      ops.fill(n3*(size_t(kk) + 1), 1e-3, basis);
+      ops.fill(size_t(kk) + 1, 1e-6, ops.red_d);
+    }
+    if (op == KC_SCALE_VAL) {
+      valcopy = ops.vec(16*nnz);
+      ops.copy(16*nnz, h->Val, valcopy);
+    }
+    double bytes = 0.0;
+    auto run = [&]() {
+      switch (op) {
+        case KC_SPMV_VV4: ops.spmv_vv(4, h->Val, x, y); bytes = ops.bytes_vv(4); break;
+        case KC_SPMV_VV3: ops.spmv_vv(3, mK, x, y); bytes = ops.bytes_vv(3); break;
+        case KC_SPMV_SS:  ops.spmv_ss(mL, x, y); bytes = ops.bytes_ss(); break;
+        case KC_SPMV_SV:  // pass 1 of the fused Schur operator
+          k_schur_gp<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(h->nNo, ops.rowPtr, ops.col, mG, x, ops.V4); ops.post();
+          bytes = ops.bytes_schur_gp(); break;
+        case KC_SPMV_VS:  // pass 2 of the fused Schur operator
+          k_schur_sp<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(h->nNo, ops.rowPtr, ops.col, ops.GtL, ops.V4, y); ops.post();
+          bytes = ops.bytes_schur_sp(); break;
+        case KC_MULTI_DOT: {
+          const int my = ops.mynNo_; ops.mynNo_ = h->nNo;
+          ops.dots_local(3, kk + 1, basis, n3, basis + n3*size_t(kk), 0);
+          ops.mynNo_ = my;
+          bytes = 8.0*double(n3)*(kk + 2); break; }
+        case KC_CGS_UPDATE: ops.cgs_update_scale(3, kk, basis, n3, basis + n3*size_t(kk), 0); bytes = 8.0*double(n3)*(kk + 2); break;
+        case KC_BLAS1: ops.axpy(n4, 0.25, x, y); bytes = 24.0*double(n4); break;
+        case KC_SCALE_VAL: ops.scale_val(4, z, z, valcopy); bytes = double(nnz)*(16.0*16 + 4.0) + double(nNo)*(16.0*4 + 8.0); break;
+        case KC_DEPART: ops.depart(3, h->Val, Gt, mK, mG, mD, mL); bytes = double(nnz)*(8.0*16*2 + 8.0*3 + 4.0 + 32.0); break;
+        default: throw std::runtime_error("op_bench: this kernel class has no stand-alone bench");
+      }
+    };
+    if (op == KC_SPMV_VS) { k_schur_gp<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(h->nNo, ops.rowPtr, ops.col, mG, x, ops.V4); ops.post(); }
+    const bool prof = ops.profiling;
+    ops.profiling = false;
     cudaEvent_t e0, e1;
     CU_CHECK(cudaEventCreate(&e0));
     CU_CHECK(cudaEventCreate(&e1));
-    for (int i = 0; i < 3; i++) ops.spmv_vv(dof, h->Val, h->bx, h->by);
+    auto mk2 = ops.mark();
+    for (int i = 0; i < 3; i++) { run(); if (op == KC_DEPART) ops.release(mk2); }
     CU_CHECK(cudaEventRecord(e0, ops.st));
-    for (int i = 0; i < reps; i++) ops.spmv_vv(dof, h->Val, h->bx, h->by);
+    for (int i = 0; i < reps; i++) { run(); if (op == KC_DEPART) ops.release(mk2); }
     CU_CHECK(cudaEventRecord(e1, ops.st));
     CU_CHECK(cudaEventSynchronize(e1));
     float ms = 0;
     CU_CHECK(cudaEventElapsedTime(&ms, e0, e1));
-    *ms_per_launch = double(ms)/reps;
+    ops.profiling = prof;
+    if (ms_per_launch) *ms_per_launch = double(ms)/reps;
+    if (bytes_per_launch) *bytes_per_launch = bytes;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ops.release(mk);
   });
 }
 

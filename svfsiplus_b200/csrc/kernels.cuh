@@ -13,7 +13,8 @@ namespace svb200 {
 constexpr int kSmCount = 148;           // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 constexpr int kRedBlocks = kSmCount*4;  // CTAs of every two-stage reduction
 constexpr int kRedThreads = 256;
-constexpr int kDotJB = 8;               // basis vectors handled per multi-dot launch
+constexpr int kDotJB = 8;               // basis vectors per register batch inside the multi-dot kernel
+constexpr int kMaxDots = 256;           // basis vectors per multi-dot launch (partials: kRedBlocks x kMaxDots)
 constexpr int kMaxComb = 32;            // vectors per lin_comb launch
 
 // ---- vector memory helpers -------------------------------------------------------------------
@@ -210,47 +211,135 @@ k_spmv_vs(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
   }
 }
 
+// K2d/K2e  the pressure Schur operator of the NS solver, SP = L P - Gt (G P)  (cgrad.cpp:96-113), as
+// two passes over 32-byte-friendly layouts instead of three SpMVs + an axpy:
+//   pass 1  V4(i) = [ sum_j G(:,j) P(col_j) , P(i) ]        G(3,nnz); P gathered as scalars
+//   pass 2  SP(i) = sum_j L(j) V4(3,col_j) - sum_j Gt(:,j).V4(0:2,col_j)   GtL(4,nnz) = [Gt, L]
+// Pass 2 streams one aligned 256-bit matrix entry and gathers one aligned 256-bit (one-sector) vector
+// entry per non-zero, like the dof-4 block SpMV.  Between the passes the caller halo-adds V4(0:2,:)
+// and applies the resistance-face preconditioner to it (ld = 4).
+// 4 lanes per row striding over the row's entries; fixed-order quad reduction.
+__global__ void __launch_bounds__(256)
+k_schur_gp(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col, const double* __restrict__ G,
+           const double* __restrict__ P, double* __restrict__ V4)
+{
+  const int lane4 = threadIdx.x & 3;
+  const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
+  const int ngroups = (gridDim.x*blockDim.x) >> 2;
+  const int nrounds = (nNo + ngroups - 1)/ngroups;
+  for (int r = 0; r < nrounds; r++) {
+    const int row = group + r*ngroups;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    if (row < nNo) {
+      const int s = __ldg(rowPtr + row);
+      const int e = __ldg(rowPtr + row + 1);
+#pragma unroll 2
+      for (int p = s + lane4; p < e; p += 4) {
+        const double u = __ldg(P + __ldg(col + p));
+        const double* g = G + size_t(p)*3;
+        a0 = fma(__ldg(g), u, a0);
+        a1 = fma(__ldg(g + 1), u, a1);
+        a2 = fma(__ldg(g + 2), u, a2);
+      }
+    }
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 2); a1 += __shfl_xor_sync(0xffffffffu, a1, 2); a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
+    if (row < nNo && lane4 == 0) {
+      d4 o; o.x = a0; o.y = a1; o.z = a2; o.w = __ldg(P + row);
+      st256(V4 + size_t(row)*4, o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_schur_sp(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col, const double* __restrict__ GtL,
+           const double* __restrict__ V4, double* __restrict__ SP)
+{
+  const int lane4 = threadIdx.x & 3;
+  const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
+  const int ngroups = (gridDim.x*blockDim.x) >> 2;
+  const int nrounds = (nNo + ngroups - 1)/ngroups;
+  for (int r = 0; r < nrounds; r++) {
+    const int row = group + r*ngroups;
+    double aL = 0.0, aD = 0.0;
+    if (row < nNo) {
+      const int s = __ldg(rowPtr + row);
+      const int e = __ldg(rowPtr + row + 1);
+#pragma unroll 2
+      for (int p = s + lane4; p < e; p += 4) {
+        const int c = ld_stream_i(col + p);
+        const d4 k = ld256_stream(GtL + size_t(p)*4);
+        const d4 v = ld256_keep(V4 + size_t(c)*4);
+        aL = fma(k.w, v.w, aL);
+        aD = aD + (k.x*v.x + k.y*v.y + k.z*v.z);
+      }
+    }
+    aL += __shfl_xor_sync(0xffffffffu, aL, 1); aD += __shfl_xor_sync(0xffffffffu, aD, 1);
+    aL += __shfl_xor_sync(0xffffffffu, aL, 2); aD += __shfl_xor_sync(0xffffffffu, aD, 2);
+    if (row < nNo && lane4 == 0) SP[row] = aL - aD;
+  }
+}
+
 // =================================================================================================
-// K3  multi-dot: red[slot0 + j] = sum_{idx < n} V_j[idx] * w[idx],  j = 0..cnt-1 (cnt <= kDotJB),
-// V_j = base + j*stride.  (fsils_nc_dot_v inside the Arnoldi loop, liner_solver/gmres.cpp:550-555;
-// dot.cpp:134-175.)  Deterministic: fixed grid, fixed-shape tree inside the CTA, and the last CTA
-// to finish adds the per-CTA partials in CTA order.  One pass over w serves up to 8 basis vectors.
+// K3  multi-dot: red[slot0 + j] = sum_{idx < n} V_j[idx] * w[idx],  j = 0..cnt-1, V_j = base + j*stride.
+// (fsils_nc_dot_v inside the Arnoldi loop, liner_solver/gmres.cpp:550-555; dot.cpp:134-175.)
+// ONE launch serves every basis vector of an Arnoldi step: each CTA owns a contiguous chunk of the
+// index range and walks the vectors in batches of kDotJB, so every V_j is streamed from HBM exactly
+// once and the CTA's chunk of w (<= 70 KB at P10) is re-read from L1/L2, not from HBM.
+// Deterministic: fixed grid and chunking, fixed-shape tree inside the CTA, per-CTA partials added in
+// CTA order by the last CTA to finish.  partial must hold gridDim.x * cnt doubles.
 // =================================================================================================
 __global__ void __launch_bounds__(kRedThreads)
 k_multi_dot(size_t n, const double* __restrict__ base, size_t stride, const double* __restrict__ w, int cnt,
             double* __restrict__ partial, unsigned int* __restrict__ counter, double* __restrict__ red, int slot0)
 {
-  double acc[kDotJB];
-#pragma unroll
-  for (int j = 0; j < kDotJB; j++) acc[j] = 0.0;
-  const size_t tid = size_t(blockIdx.x)*blockDim.x + threadIdx.x;
-  const size_t nth = size_t(gridDim.x)*blockDim.x;
-  for (size_t idx = tid; idx < n; idx += nth) {
-    const double wv = w[idx];
-#pragma unroll
-    for (int j = 0; j < kDotJB; j++) {
-      if (j < cnt) acc[j] = fma(base[size_t(j)*stride + idx], wv, acc[j]);
-    }
-  }
   __shared__ double sm[kRedThreads/32][kDotJB];
   __shared__ bool last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const size_t chunk = ((n + gridDim.x - 1)/gridDim.x + 3) & ~size_t(3);
+  const size_t beg = size_t(blockIdx.x)*chunk;
+  const size_t end = (beg + chunk < n) ? beg + chunk : n;
+
+  for (int j0 = 0; j0 < cnt; j0 += kDotJB) {
+    const int m = (cnt - j0 < kDotJB) ? cnt - j0 : kDotJB;
+    double acc[kDotJB];
 #pragma unroll
-  for (int j = 0; j < kDotJB; j++) {
-    double v = acc[j];
+    for (int j = 0; j < kDotJB; j++) acc[j] = 0.0;
+    const double* vb = base + size_t(j0)*stride;
+    if (m == kDotJB) {
+      for (size_t idx = beg + threadIdx.x; idx < end; idx += kRedThreads) {
+        const double wv = w[idx];
+        double v[kDotJB];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) sm[wid][j] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < kDotJB) {
-    double v = 0.0;
+        for (int j = 0; j < kDotJB; j++) v[j] = ld_stream(vb + size_t(j)*stride + idx);
 #pragma unroll
-    for (int k = 0; k < kRedThreads/32; k++) v += sm[k][threadIdx.x];
-    partial[size_t(blockIdx.x)*kDotJB + threadIdx.x] = v;
+        for (int j = 0; j < kDotJB; j++) acc[j] = fma(v[j], wv, acc[j]);
+      }
+    } else {
+      for (size_t idx = beg + threadIdx.x; idx < end; idx += kRedThreads) {
+        const double wv = w[idx];
+#pragma unroll
+        for (int j = 0; j < kDotJB; j++)
+          if (j < m) acc[j] = fma(ld_stream(vb + size_t(j)*stride + idx), wv, acc[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kDotJB; j++) {
+      double v = acc[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) sm[wid][j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < m) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < kRedThreads/32; k++) v += sm[k][threadIdx.x];
+      partial[size_t(blockIdx.x)*cnt + j0 + threadIdx.x] = v;
+    }
+    __syncthreads();
   }
   __threadfence();
-  __syncthreads();
   if (threadIdx.x == 0) {
     unsigned int t = atomicAdd(counter, 1u);
     last = (t == gridDim.x - 1);
@@ -258,13 +347,14 @@ k_multi_dot(size_t n, const double* __restrict__ base, size_t stride, const doub
   __syncthreads();
   if (last) {
     __threadfence();
-    // warp j sums partial[:, j] : lane-strided serial sums, then a fixed shuffle tree
-    if (wid < cnt) {
+    // warp `wid` sums partial[:, j] for j = wid, wid+8, ...: lane-strided serial sums in CTA order,
+    // then a fixed shuffle tree
+    for (int j = wid; j < cnt; j += kRedThreads/32) {
       double v = 0.0;
-      for (unsigned int b = lane; b < gridDim.x; b += 32) v += __ldcg(partial + size_t(b)*kDotJB + wid);
+      for (unsigned int b = lane; b < gridDim.x; b += 32) v += __ldcg(partial + size_t(b)*cnt + j);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-      if (lane == 0) red[slot0 + wid] = v;
+      if (lane == 0) red[slot0 + j] = v;
     }
     if (threadIdx.x == 0) *counter = 0u;
   }
@@ -476,7 +566,8 @@ k_scale_val(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col
 // with the transpose position precomputed once (the reference searches the row each time).
 __global__ void __launch_bounds__(256)
 k_depart3(size_t nnz, const int* __restrict__ tpos, const double* __restrict__ Val, double* __restrict__ Gt,
-          double* __restrict__ mK, double* __restrict__ mG, double* __restrict__ mD, double* __restrict__ mL)
+          double* __restrict__ mK, double* __restrict__ mG, double* __restrict__ mD, double* __restrict__ mL,
+          double* __restrict__ GtL)
 {
   const size_t nth = size_t(gridDim.x)*blockDim.x;
   for (size_t p = size_t(blockIdx.x)*blockDim.x + threadIdx.x; p < nnz; p += nth) {
@@ -494,7 +585,9 @@ k_depart3(size_t nnz, const int* __restrict__ tpos, const double* __restrict__ V
     const size_t t = size_t(tpos[p]);
     const double* vt = Val + t*16;
     double* gt = Gt + p*3;
-    gt[0] = -vt[3]; gt[1] = -vt[7]; gt[2] = -vt[11];
+    const double g0 = -vt[3], g1 = -vt[7], g2 = -vt[11];
+    gt[0] = g0; gt[1] = g1; gt[2] = g2;
+    if (GtL) { d4 o; o.x = g0; o.y = g1; o.z = g2; o.w = r3.w; st256(GtL + p*4, o); }   // packed [Gt, L] for k_schur_sp
   }
 }
 template <int NSD>
@@ -579,20 +672,21 @@ __global__ void k_face_axpy(int fnNo, int m, int fdof, int dof, const int* __res
 }
 
 // ---- halo exchange (fsils_commuv/commus, liner_solver/in_commu.cpp:49-170) ------------------------
-__global__ void k_halo_pack(int n, int dof, const int* __restrict__ ptr, const double* __restrict__ V, double* __restrict__ buf)
+// ld = leading dimension of V (ld >= dof; V4 of the Schur operator carries 3 components with ld 4)
+__global__ void k_halo_pack(int n, int dof, int ld, const int* __restrict__ ptr, const double* __restrict__ V, double* __restrict__ buf)
 {
   const int tot = n*dof;
   for (int t = blockIdx.x*blockDim.x + threadIdx.x; t < tot; t += gridDim.x*blockDim.x) {
     const int j = t / dof, l = t % dof;
-    buf[t] = V[size_t(ptr[j])*dof + l];
+    buf[t] = V[size_t(ptr[j])*ld + l];
   }
 }
-__global__ void k_halo_add(int n, int dof, const int* __restrict__ ptr, const double* __restrict__ buf, double* __restrict__ V)
+__global__ void k_halo_add(int n, int dof, int ld, const int* __restrict__ ptr, const double* __restrict__ buf, double* __restrict__ V)
 {
   const int tot = n*dof;
   for (int t = blockIdx.x*blockDim.x + threadIdx.x; t < tot; t += gridDim.x*blockDim.x) {
     const int j = t / dof, l = t % dof;
-    V[size_t(ptr[j])*dof + l] += buf[t];
+    V[size_t(ptr[j])*ld + l] += buf[t];
   }
 }
 

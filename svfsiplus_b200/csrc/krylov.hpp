@@ -381,11 +381,7 @@ void schur(Ops& ops, SubLs& ls, int nsd, const double* D, const double* G, const
     last_i = i;
     if (err < eps) { ls.suc = true; break; }
     errO = err;
-    ops.spmv_sv(nsd, G, P, GP);
-    if (coupled) ops.add_bc_mul(BCOP_PRE, nsd, GP, GP);
-    ops.spmv_vs(nsd, D, GP, DGP);
-    ops.spmv_ss(L, P, SP);
-    ops.axpy(nn, -1.0, DGP, SP);
+    ops.schur_op(nsd, D, G, L, P, GP, DGP, SP, coupled);     // SP = L P - D (G P [+ PRE])
     double alpha = errO / ops.dot(1, P, SP);
     ops.axpy(nn, alpha, P, X);
     ops.axpy(nn, -alpha, SP, R);

@@ -163,7 +163,7 @@ class CudaOps {
     CU_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     CU_CHECK(cudaMalloc(&red_d, sizeof(double)*kMaxSlots));
     CU_CHECK(cudaMallocHost(&red_h, sizeof(double)*kMaxSlots));
-    CU_CHECK(cudaMalloc(&partial_d, sizeof(double)*kRedBlocks*kDotJB));
+    CU_CHECK(cudaMalloc(&partial_d, sizeof(double)*kRedBlocks*kMaxDots));
     CU_CHECK(cudaMalloc(&counter_d, sizeof(unsigned int)));
     CU_CHECK(cudaMemset(counter_d, 0, sizeof(unsigned int)));
   }
@@ -273,10 +273,12 @@ class CudaOps {
     if (slot0 + count > kMaxSlots) throw std::runtime_error("reduction slot overflow");
     const size_t n = size_t(dof)*mynNo_;
     int done = 0;
-    Scope sc(*this, KC_MULTI_DOT, 8.0*double(n)*(count + (count + kDotJB - 1)/kDotJB), (count + kDotJB - 1)/kDotJB);
     while (done < count) {
-      const int m = std::min(kDotJB, count - done);
-      k_multi_dot<<<kRedBlocks, kRedThreads, 0, st>>>(n, base + size_t(done)*stride, stride, w, m, partial_d, counter_d, red_d, slot0 + done);
+      const int m = std::min(kMaxDots, count - done);
+      Scope sc(*this, KC_MULTI_DOT, 8.0*double(n)*(m + 1));
+      // enough CTAs to fill the machine, never more than one per 1024 entries (tiny systems)
+      const int g = int(std::min<size_t>(size_t(kRedBlocks), (n + 1023)/1024 + 1));
+      k_multi_dot<<<g, kRedThreads, 0, st>>>(n, base + size_t(done)*stride, stride, w, m, partial_d, counter_d, red_d, slot0 + done);
       post();
       done += m;
     }
@@ -361,14 +363,15 @@ class CudaOps {
   }
 
   // fsils_commuv / fsils_commus: pack -> grouped ncclSend/ncclRecv -> add in request order
-  void halo_add(int dof, double* V)
+  void halo_add(int dof, double* V, int ld = 0)
   {
     if (nranks == 1 || reqs.empty()) return;
+    if (ld == 0) ld = dof;
     if (dof > halo_dof_cap) throw std::runtime_error("halo buffers too small for dof");
     double hb = 0; for (auto& r : reqs) hb += 32.0*r.n*dof;
     Scope sc(*this, KC_HALO, hb, int(reqs.size())*2);
     for (auto& r : reqs) {
-      k_halo_pack<<<grid_for(size_t(r.n)*dof, 256, 1), 256, 0, st>>>(r.n, dof, r.ptr, V, r.sbuf);
+      k_halo_pack<<<grid_for(size_t(r.n)*dof, 256, 1), 256, 0, st>>>(r.n, dof, ld, r.ptr, V, r.sbuf);
       post();
     }
     nccl.check(nccl.GroupStart(), "GroupStart");
@@ -378,7 +381,7 @@ class CudaOps {
     }
     nccl.check(nccl.GroupEnd(), "GroupEnd");
     for (auto& r : reqs) {
-      k_halo_add<<<grid_for(size_t(r.n)*dof, 256, 1), 256, 0, st>>>(r.n, dof, r.ptr, r.rbuf, V);
+      k_halo_add<<<grid_for(size_t(r.n)*dof, 256, 1), 256, 0, st>>>(r.n, dof, ld, r.ptr, r.rbuf, V);
       post();
     }
   }
@@ -422,8 +425,10 @@ class CudaOps {
   }
 
   // Y += coef * v (v^T X), v = valM on the face nodes (add_bc_mul.cpp:53-121); X may alias Y
-  void add_bc_mul(int op, int dof, const double* X, double* Y)
+  // (ld: leading dimension of X and Y when it differs from dof)
+  void add_bc_mul(int op, int dof, const double* X, double* Y, int ld = 0)
   {
+    if (ld == 0) ld = dof;
     for (int f = 0; f < n_faces(); f++) {
       auto& fa = faces[f];
       if (!fa.coupled) continue;
@@ -431,11 +436,11 @@ class CudaOps {
       const int m = std::min(fa.dof, dof);
       const int lim = fa.shared ? mynNo_ : nNo_;
       double* S = red_d + (kMaxSlots - 1);
-      k_face_dot<<<1, 256, 0, st>>>(fa.nNo, m, fa.dof, dof, lim, fa.glob, fa.valM, X, S);
+      k_face_dot<<<1, 256, 0, st>>>(fa.nNo, m, fa.dof, ld, lim, fa.glob, fa.valM, X, S);
       post();
       if (fa.shared && nranks > 1) nccl.check(nccl.AllReduce(S, S, 1, Nccl::kFloat64, Nccl::kSum, comm, st), "AllReduce");
       if (fa.nNo > 0) {
-        k_face_axpy<<<grid_for(size_t(fa.nNo)*m, 256, 1), 256, 0, st>>>(fa.nNo, m, fa.dof, dof, fa.glob, fa.valM, coef, S, Y);
+        k_face_axpy<<<grid_for(size_t(fa.nNo)*m, 256, 1), 256, 0, st>>>(fa.nNo, m, fa.dof, ld, fa.glob, fa.valM, coef, S, Y);
         post();
       }
     }
@@ -482,14 +487,57 @@ class CudaOps {
   }
 
   // ---- NS helpers ---------------------------------------------------------------------------------------
+  // packed copies made by depart for the fused Schur operator (valid until the arena mark of the
+  // NS solve is released): GtL(4,nnz) = [Gt, L], V4(4,nNo) = [G P, P]
+  const double* packed_Gt = nullptr;
+  double* GtL = nullptr;
+  double* V4 = nullptr;
+
   void depart(int nsd, const double* Val, double* Gt, double* mK, double* mG, double* mD, double* mL)
   {
     const size_t nz = size_t(nnz_);
-    Scope sc(*this, KC_DEPART, double(nnz_)*(8.0*(nsd+1)*(nsd+1)*2 + 8.0*nsd + 4.0));
-    if (nsd == 3) k_depart3<<<grid_for(nz, 256, 1), 256, 0, st>>>(nz, tpos, Val, Gt, mK, mG, mD, mL);
+    packed_Gt = nullptr; GtL = nullptr; V4 = nullptr;
+    if (nsd == 3) {
+      GtL = vec(4*nz);
+      V4 = vec(4*size_t(nNo_));
+      packed_Gt = Gt;
+    }
+    Scope sc(*this, KC_DEPART, double(nnz_)*(8.0*(nsd+1)*(nsd+1)*2 + 8.0*nsd + 4.0 + (nsd == 3 ? 32.0 : 0.0)));
+    if (nsd == 3) k_depart3<<<grid_for(nz, 256, 1), 256, 0, st>>>(nz, tpos, Val, Gt, mK, mG, mD, mL, GtL);
     else if (nsd == 2) k_depart_generic<2><<<grid_for(nz, 256, 1), 256, 0, st>>>(nz, tpos, Val, Gt, mK, mG, mD, mL);
     else throw std::runtime_error("FSILS: Not defined nsd for DEPART");
     post();
+  }
+  double bytes_schur_gp() const { return double(nnz_)*28.0 + double(nNo_)*(8.0 + 8.0 + 32.0 + 8.0); }
+  double bytes_schur_sp() const { return double(nnz_)*36.0 + double(nNo_)*(32.0 + 8.0 + 8.0); }
+
+  // SP = L P - Gt (G P), with the resistance preconditioner applied to G P when a face is coupled
+  // (cgrad.cpp:96-113).  GP, DGP: caller work vectors used by the unfused path only.
+  void schur_op(int nsd, const double* Gt, const double* G, const double* L, const double* P, double* GP, double* DGP,
+                double* SP, bool coupled)
+  {
+    if (nsd == 3 && Gt == packed_Gt && GtL) {
+      const int g = grid_rows(nNo_);
+      {
+        Scope sc(*this, KC_SPMV_SV, bytes_schur_gp());
+        k_schur_gp<<<g, 256, 0, st>>>(nNo_, rowPtr, col, G, P, V4);
+        post();
+      }
+      halo_add(3, V4, 4);
+      if (coupled) add_bc_mul(BCOP_PRE, 3, V4, V4, 4);
+      {
+        Scope sc(*this, KC_SPMV_VS, bytes_schur_sp());
+        k_schur_sp<<<g, 256, 0, st>>>(nNo_, rowPtr, col, GtL, V4, SP);
+        post();
+      }
+      halo_add(1, SP);
+      return;
+    }
+    spmv_sv(nsd, G, P, GP);
+    if (coupled) add_bc_mul(BCOP_PRE, nsd, GP, GP);
+    spmv_vs(nsd, Gt, GP, DGP);
+    spmv_ss(L, P, SP);
+    axpy(size_t(nNo_), -1.0, DGP, SP);
   }
   void split_mc(int dof, const double* Ri, double* Rm, double* Rc)
   {

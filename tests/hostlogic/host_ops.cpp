@@ -108,6 +108,15 @@ struct HostOps {
       KU[r] = a;
     }
   }
+  void schur_op(int nsd, const double* Gt, const double* G, const double* L, const double* P, double* GP, double* DGP,
+                double* SP, bool coupled)
+  {
+    spmv_sv(nsd, G, P, GP);
+    if (coupled) add_bc_mul(svb200::BCOP_PRE, nsd, GP, GP);
+    spmv_vs(nsd, Gt, GP, DGP);
+    spmv_ss(L, P, SP);
+    axpy(size_t(nNo_), -1.0, DGP, SP);
+  }
   int n_faces() const { return int(faces.size()); }
   bool face_coupled(int f) const { return faces[f].coupled; }
   bool face_inc(int f) const { return faces[f].inc; }

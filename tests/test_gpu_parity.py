@@ -86,6 +86,12 @@ def test_solve_matches_golden(tiny, ls):
         # CG on this non-symmetric system does not converge (neither does the reference's): the
         # iterate after 50 steps is sensitive to rounding, compare loosely
         assert rel_l2(X, g[f"X_{ls}"]) < 1e-4
+    elif ls == "GMRES":
+        # stopped at relTol 1e-3 on a system whose pressure level is fixed only by the resistance
+        # outlet (|X| ~ 1e6): the serial left-to-right sums of dot.cpp and the tree sums of the CUDA
+        # reductions differ by rounding that this solve amplifies to ~2e-8 (measured on B200).  The
+        # 1e-8 bar is checked with tight linear tolerances in test_tight_tolerance_*.
+        assert rel_l2(X, g[f"X_{ls}"]) < TOL_SOL_LOOSE
     else:
         assert rel_l2(X, g[f"X_{ls}"]) < TOL_SOL
     if ls == "NS":

@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Profiling drivers (run on the GPU box, normally under ncu):
+
+  python tools/prof.py tour  [--dims nx ny nz] [--reps R]   stand-alone bench of every kernel class
+  python tools/prof.py step  [--dims nx ny nz] [--ls NS]    one resident Newton-iteration hot path
+  python tools/prof.py asm   [--dims nx ny nz] [--reps R]   assembly only
+
+`tour` prints one JSON line per kernel class (ms, algorithmic GB/s, fraction of the measured HBM peak);
+under `ncu --set full -k regex:k_` it gives one capture per kernel on production-size data.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from svfsiplus_b200 import backend as B  # noqa: E402
+from svfsiplus_b200 import problem as P  # noqa: E402
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("mode", choices=["tour", "step", "asm"])
+    ap.add_argument("--dims", type=int, nargs=3, default=[96, 96, 181])
+    ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--ls", default="NS")
+    a = ap.parse_args()
+    t0 = time.time()
+    case = P.pipe_case(*a.dims)
+    be = P.setup_backend(case)
+    print(f"# setup {time.time()-t0:.1f} s: nNo {be.nNo} nnz {be.nnz} nEl {case['mesh'].nEl}", flush=True)
+    pk = peak()
+    if a.mode == "asm":
+        be.state_set(case["Ag"].shape[1], case["Ag"], case["Yg"], case["Bf"])
+        props = B.fluid_props(tDof=case["Ag"].shape[1], **case["props"])
+        for _ in range(2):
+            be.zero(4); be.assemble_fluid(props)
+        be.timer_start()
+        for _ in range(a.reps):
+            be.zero(4); be.assemble_fluid(props)
+        ms = be.timer_stop() / a.reps
+        by = be.nnz * 128.0 + be.nNo * (32.0 + 24 + 64 + 24) + case["mesh"].nEl * 16.0
+        print(json.dumps(dict(kernel="assembly(+zero)", ms=ms, GBps=by / 1e6 / ms, frac=by / 1e6 / ms / pk,
+                              ns_per_tet=1e6 * ms / case["mesh"].nEl)))
+        return
+    P.assemble(be, case)
+    if a.mode == "tour":
+        plan = [("spmv_vv4", 0), ("spmv_vv3", 0), ("spmv_ss", 0), ("spmv_sv", 0), ("spmv_vs", 0), ("multi_dot", 8),
+                ("multi_dot", 64), ("cgs_update_scale", 8), ("cgs_update_scale", 64), ("blas1", 0), ("scale_val", 0), ("depart", 0)]
+        for name, k in plan:
+            ms, by = be.op_bench(name, k=k, reps=a.reps)
+            print(json.dumps(dict(kernel=name, k=k, ms=ms, MB=by / 1e6, GBps=by / 1e6 / ms, frac=by / 1e6 / ms / pk)), flush=True)
+    else:
+        ls_type, RI, GM, CG = P.LS_SETTINGS[a.ls]
+        be.timer_start()
+        X, info = be.solve(ls_type, B.PREC_FSILS, RI, GM, CG, case["incL"], case["res"], fetch=False)
+        ms = be.timer_stop()
+        print(json.dumps(dict(solve_ms=ms, info=info, launches=be.launch_count())))
+    be.close()
+
+
+if __name__ == "__main__":
+    main()
