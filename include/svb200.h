@@ -87,6 +87,8 @@ int b200_assemble_elem(b200_handle* h, int d, const int* eqN, const double* lK, 
 /* parity taps / host boundary-condition code (assembly ordering, like com_mod.R / com_mod.Val). */
 int b200_get_R(b200_handle* h, double* R);
 int b200_set_R(b200_handle* h, int dof, const double* R);
+/* device R += host R (what host boundary-condition code added to com_mod.R since ls_alloc). */
+int b200_add_R(b200_handle* h, int dof, const double* R);
 int b200_get_Val(b200_handle* h, double* Val);
 int b200_set_Val(b200_handle* h, int dof, const double* Val);
 /* all_fun::commu(R) (solver/all_fun.cpp:122): overlap-node add of the device R. */
@@ -104,7 +106,7 @@ int b200_solve(b200_handle* h, int ls_type, int prec, const b200_tol* RI, const 
 int b200_spmv(b200_handle* h, int dof, const double* x, double* y);
 /* Stand-alone kernel bench: times `reps` back-to-back launches of ONE kernel class (ids as in
  * b200_profile_read) on device-resident data with CUDA events on the launch stream, after 3 warm-up
- * launches; returns mean milliseconds and the ALGORITHMIC bytes per launch.  Needs an assembled dof-4
+ * launches (none when reps == 1, for profiler captures); returns mean milliseconds and the ALGORITHMIC bytes per launch.  Needs an assembled dof-4
  * system.  NS shapes (1-4, 9) run on the departed matrix; 3 / 4 are the two passes of the fused Schur
  * operator; k = number of basis vectors for multi_dot (5) and cgs_update_scale (6) on dof-3 vectors. */
 int b200_op_bench(b200_handle* h, int op, int k, int reps, double* ms_per_launch, double* bytes_per_launch);

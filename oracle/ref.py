@@ -18,11 +18,69 @@ LIB_PATH = os.path.join(_HERE, "_ref", "libsvref.so")
 LS_CG, LS_GMRES, LS_NS, LS_BICGS = 798, 797, 796, 795      # L/fils_struct.hpp:70-76
 PREC_FSILS, PREC_RCS = 701, 709                              # S/consts.h:426
 
+DROPIN_PATH = os.path.join(_HERE, "_ref", "libsvdropin.so")
+
 _lib = None
+_dropin = None
 
 
 def available() -> bool:
     return os.path.exists(LIB_PATH)
+
+
+def dropin_available() -> bool:
+    return os.path.exists(DROPIN_PATH)
+
+
+def dropin_lib():
+    """The reference objects + the B200LinearAlgebra plug-in class linked against libsvb200.so."""
+    global _dropin
+    if _dropin is None:
+        if not dropin_available():
+            raise RuntimeError(f"{DROPIN_PATH} missing: run `make -C oracle ref` after building libsvb200.so")
+        L = C.CDLL(DROPIN_PATH)
+        L.ref_last_error.restype = C.c_char_p
+        L.ref_asm_create.restype = C.c_void_p
+        L.ref_asm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double]
+        L.ref_asm_destroy.argtypes = [C.c_void_p]
+        L.ref_dropin_fluid_step.argtypes = ([C.c_void_p, C.c_int, C.c_int] + [C.c_double] * 5 + [C.c_void_p, C.c_double]
+                                            + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 8)
+        _dropin = L
+    return _dropin
+
+
+def dropin_fluid_step(case, ls, mode):
+    """One Newton-iteration hot path through the reference's own ComMod/eqType with
+    eq.linear_algebra = B200LinearAlgebra.  mode 0: reference host assembly + device solve,
+    mode 1: device assembly + device solve.  Returns (X (nNo,4), info dict)."""
+    L = dropin_lib()
+    m = case["mesh"]
+    x = _c(m.x, np.float64); ien = _c(m.ien, np.int32)
+    h = L.ref_asm_create(m.nNo, m.nEl, ien.shape[1], _p(ien), _p(x), 1, -1.0)
+    if not h:
+        raise RuntimeError(L.ref_last_error().decode())
+    try:
+        p = case["props"]
+        Ag = _c(case["Ag"], np.float64); Yg = _c(case["Yg"], np.float64); Bf = _c(case["Bf"], np.float64)
+        visc = np.array([p.get("viscType", 0), p["mu"], p.get("mu_o", 0.0), p.get("lam", 0.0), p.get("a", 0.0),
+                         p.get("n", 0.0)], np.float64)
+        fv = np.array(p.get("f", (0.0, 0.0, 0.0)), np.float64)
+        faces = case["faces"]
+        f_info = np.array([[len(f["nodes"]), f["dof"], f["bGrp"]] for f in faces], np.int32).reshape(-1)
+        f_nodes = np.concatenate([np.asarray(f["nodes"], np.int32) for f in faces])
+        f_val = np.concatenate([np.asarray(f["val"], np.float64).reshape(-1) for f in faces])
+        X = np.empty((m.nNo, 4)); out = np.zeros(9)
+        ls = _c(ls, np.float64)
+        incL = _c(case["incL"], np.int32); res = _c(case["res"], np.float64)
+        rc = L.ref_dropin_fluid_step(h, int(mode), Ag.shape[1], p["dt"], p["am"], p["af"], p["gam"], p["rho"], _p(fv),
+                                     p.get("Kinv", 0.0), _p(visc), _p(Ag), _p(Yg), _p(Bf), len(faces), _p(f_info),
+                                     _p(f_nodes), _p(f_val), _p(ls), _p(incL), _p(res), _p(X), _p(out))
+        if rc != 0:
+            raise RuntimeError(L.ref_last_error().decode())
+    finally:
+        L.ref_asm_destroy(h)
+    keys = ("suc", "itr", "iNorm", "fNorm", "GM_itr", "CG_itr", "Resm", "Resc", "device_assembly")
+    return X, dict(zip(keys, out))
 
 
 def lib():

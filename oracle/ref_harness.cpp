@@ -29,6 +29,10 @@
 #include "spar_mul.h"
 #include "commu.h"
 #include "lhs.h"
+#include "ls.h"
+#ifdef WITH_B200_DROPIN
+#include "B200LinearAlgebra.h"
+#endif
 
 #include "mpi.h"
 
@@ -135,6 +139,59 @@ int ref_asm_get_tables(void* h, double* w, double* N, double* Nx)
   return msh.nG;
 }
 
+} // extern "C"
+
+namespace {
+// Fill ComMod / eqType / dmnType for one Navier-Stokes equation on the context's mesh.
+// visc = {type(0 const,1 Carreau-Yasuda,2 Casson), mu_i, mu_o, lam, a, n}
+void configure_fluid(AsmCtx* ctx, int tDof, int mvMsh, double dt, double am, double af, double gam,
+                     double rho, const double* f, double Kinv_darcy, const double* visc, const double* Bf)
+{
+  using namespace consts;
+  auto& com_mod = ctx->sim->com_mod;
+  const int nNo = com_mod.tnNo;
+  const int dof = 4;
+  com_mod.tDof = tDof;
+  com_mod.dof = dof;
+  com_mod.dt = dt;
+  com_mod.mvMsh = (mvMsh != 0);
+  com_mod.cEq = 0;
+  com_mod.nEq = 1;
+  if (com_mod.eq.size() != 1) com_mod.eq.resize(1);
+  auto& eq = com_mod.eq[0];
+  eq.phys = EquationType::phys_fluid;
+  eq.dof = dof;
+  eq.s = 0;
+  eq.e = dof - 1;
+  eq.am = am;
+  eq.af = af;
+  eq.gam = gam;
+  eq.nDmn = 1;
+  if (eq.dmn.size() != 1) eq.dmn.resize(1);
+  auto& dmn = eq.dmn[0];
+  dmn.Id = -1;
+  dmn.phys = EquationType::phys_fluid;
+  dmn.prop[PhysicalProperyType::fluid_density] = rho;
+  dmn.prop[PhysicalProperyType::f_x] = f[0];
+  dmn.prop[PhysicalProperyType::f_y] = f[1];
+  dmn.prop[PhysicalProperyType::f_z] = f[2];
+  dmn.prop[PhysicalProperyType::inverse_darcy_permeability] = Kinv_darcy;
+  int vt = int(visc[0]);
+  dmn.fluid_visc.viscType = (vt == 0) ? FluidViscosityModelType::viscType_Const
+                          : (vt == 1) ? FluidViscosityModelType::viscType_CY
+                                      : FluidViscosityModelType::viscType_Cass;
+  dmn.fluid_visc.mu_i = visc[1];
+  dmn.fluid_visc.mu_o = visc[2];
+  dmn.fluid_visc.lam = visc[3];
+  dmn.fluid_visc.a = visc[4];
+  dmn.fluid_visc.n = visc[5];
+  com_mod.Bf.resize(3, nNo);
+  std::memcpy(com_mod.Bf.data(), Bf, sizeof(double)*3*size_t(nNo));
+}
+} // namespace
+
+extern "C" {
+
 // Fluid (Navier-Stokes VMS) assembly through the reference's construct_fluid.
 // visc = {type(0 const,1 Carreau-Yasuda,2 Casson), mu_i, mu_o, lam, a, n}
 // Ag, Yg: tDof x nNo (column-major, i.e. node-contiguous), Bf: 3 x nNo.
@@ -149,44 +206,10 @@ double ref_asm_fluid(void* h, int tDof, int mvMsh, double dt, double am, double 
     auto& com_mod = ctx->sim->com_mod;
     const int nNo = com_mod.tnNo;
     const int dof = 4;
-    com_mod.tDof = tDof;
-    com_mod.dof = dof;
-    com_mod.dt = dt;
-    com_mod.mvMsh = (mvMsh != 0);
-    com_mod.cEq = 0;
-    com_mod.nEq = 1;
-    com_mod.eq.resize(1);
+    configure_fluid(ctx, tDof, mvMsh, dt, am, af, gam, rho, f, Kinv_darcy, visc, Bf);
     auto& eq = com_mod.eq[0];
-    eq.phys = EquationType::phys_fluid;
-    eq.dof = dof;
-    eq.s = 0;
-    eq.e = dof - 1;
-    eq.am = am;
-    eq.af = af;
-    eq.gam = gam;
-    eq.nDmn = 1;
-    eq.dmn.resize(1);
-    auto& dmn = eq.dmn[0];
-    dmn.Id = -1;
-    dmn.phys = EquationType::phys_fluid;
-    dmn.prop[PhysicalProperyType::fluid_density] = rho;
-    dmn.prop[PhysicalProperyType::f_x] = f[0];
-    dmn.prop[PhysicalProperyType::f_y] = f[1];
-    dmn.prop[PhysicalProperyType::f_z] = f[2];
-    dmn.prop[PhysicalProperyType::inverse_darcy_permeability] = Kinv_darcy;
-    int vt = int(visc[0]);
-    dmn.fluid_visc.viscType = (vt == 0) ? FluidViscosityModelType::viscType_Const
-                            : (vt == 1) ? FluidViscosityModelType::viscType_CY
-                                        : FluidViscosityModelType::viscType_Cass;
-    dmn.fluid_visc.mu_i = visc[1];
-    dmn.fluid_visc.mu_o = visc[2];
-    dmn.fluid_visc.lam = visc[3];
-    dmn.fluid_visc.a = visc[4];
-    dmn.fluid_visc.n = visc[5];
     if (!eq.linear_algebra) eq.linear_algebra = new FsilsLinearAlgebra();
 
-    com_mod.Bf.resize(3, nNo);
-    std::memcpy(com_mod.Bf.data(), Bf, sizeof(double)*3*size_t(nNo));
     Array<double> Ag_a(tDof, nNo), Yg_a(tDof, nNo);
     std::memcpy(Ag_a.data(), Ag, sizeof(double)*size_t(tDof)*nNo);
     std::memcpy(Yg_a.data(), Yg, sizeof(double)*size_t(tDof)*nNo);
@@ -403,5 +426,91 @@ int ref_ranks_commuv(int nranks, void** hs, int dof, double** V)
   });
   return 0;
 }
+
+#ifdef WITH_B200_DROPIN
+// ----------------------------------------------------------------------------------------------
+// Drop-in test: one Newton-iteration hot path driven the way the reference drives a LinearAlgebra
+// plug-in (main.cpp:68-77, 480-600): the reference's own ComMod / eqType / FSILS_lhsType objects,
+// ls_ns::ls_alloc -> global assembly -> ls_ns::ls_solve, with eq.linear_algebra = B200LinearAlgebra
+// (svfsiplus_b200/host).  mode 0: host assembly by the reference's construct_fluid (do_assem) +
+// device solve; mode 1: device assembly (assemble_mesh) + device solve.
+// faces: nFaces x {nNo, dof, bGrp}; nodes/vals concatenated.  ls as in ref_ranks_solve.
+// out = {RI.suc, RI.itr, RI.iNorm, RI.fNorm, GM.itr, CG.itr, Resm, Resc, used_device_assembly}
+// ----------------------------------------------------------------------------------------------
+int ref_dropin_fluid_step(void* h, int mode, int tDof, double dt, double am, double af, double gam, double rho,
+                          const double* f, double Kinv_darcy, const double* visc,
+                          const double* Ag, const double* Yg, const double* Bf,
+                          int nFaces, const int* f_info, const int* f_nodes, const double* f_val,
+                          const double* ls, const int* incL, const double* res, double* X, double* out)
+{
+  try {
+    using namespace consts;
+    mpistub_set_world(1);
+    mpistub_bind_rank(0);
+    auto ctx = static_cast<AsmCtx*>(h);
+    auto& com_mod = ctx->sim->com_mod;
+    const int nNo = com_mod.tnNo;
+    const int dof = 4;
+    configure_fluid(ctx, tDof, 0, dt, am, af, gam, rho, f, Kinv_darcy, visc, Bf);
+    auto& eq = com_mod.eq[0];
+
+    // what initialize() / fsi_ls_ini (baf_ini.cpp:689) leave behind: com_mod.lhs and its faces
+    auto& lhs = com_mod.lhs;
+    lhs = FSILS_lhsType();
+    fsils_commu_create(lhs.commu, MPI_COMM_WORLD);
+    Vector<int> gNodes(nNo);
+    for (int a = 0; a < nNo; a++) gNodes(a) = a;
+    fsils_lhs_create(lhs, lhs.commu, nNo, nNo, ctx->nnz, gNodes, com_mod.rowPtr, com_mod.colPtr, nFaces);
+    size_t on = 0, ov = 0;
+    for (int i = 0; i < nFaces; i++) {
+      const int fn = f_info[3*i], fd = f_info[3*i+1], fb = f_info[3*i+2];
+      Vector<int> gN(fn);
+      std::memcpy(gN.data(), f_nodes + on, sizeof(int)*fn);
+      Array<double> v(fd, fn);
+      std::memcpy(v.data(), f_val + ov, sizeof(double)*size_t(fd)*fn);
+      fsils_bc_create(lhs, i, fn, fd, fb == 0 ? BcType::BC_TYPE_Dir : BcType::BC_TYPE_Neu, gN, v);
+      on += fn; ov += size_t(fd)*fn;
+    }
+
+    // read_files.cpp:2046-2075 + add_eq_linear_algebra (main.cpp:68-77)
+    fsils_ls_create(eq.FSILS, static_cast<LinearSolverType>(int(ls[0])));
+    eq.FSILS.RI.relTol = ls[1]; eq.FSILS.RI.absTol = ls[2]; eq.FSILS.RI.mItr = int(ls[3]); eq.FSILS.RI.sD = int(ls[4]);
+    eq.FSILS.GM.relTol = ls[5]; eq.FSILS.GM.absTol = ls[6]; eq.FSILS.GM.mItr = int(ls[7]); eq.FSILS.GM.sD = int(ls[8]);
+    eq.FSILS.CG.relTol = ls[9]; eq.FSILS.CG.absTol = ls[10]; eq.FSILS.CG.mItr = int(ls[11]);
+    eq.linear_algebra_preconditioner = PreconditionerType::PREC_FSILS;
+    delete eq.linear_algebra;
+    auto* la = new B200LinearAlgebra();
+    eq.linear_algebra = la;
+    la->check_options(PreconditionerType::PREC_FSILS, mode == 1 ? B200_LINEAR_ALGEBRA_TYPE : LinearAlgebraType::fsils);
+    la->set_preconditioner(eq.linear_algebra_preconditioner);
+    la->initialize(com_mod, eq);
+    la->set_assembly(mode == 1 ? B200_LINEAR_ALGEBRA_TYPE : LinearAlgebraType::fsils);
+
+    Array<double> Ag_a(tDof, nNo), Yg_a(tDof, nNo), Dg_a(tDof, nNo);
+    std::memcpy(Ag_a.data(), Ag, sizeof(double)*size_t(tDof)*nNo);
+    std::memcpy(Yg_a.data(), Yg, sizeof(double)*size_t(tDof)*nNo);
+
+    // one Newton iteration (main.cpp iterate_solution): ls_alloc, global_eq_assem, ls_solve
+    ls_ns::ls_alloc(com_mod, eq);
+    bool on_device = la->assemble_mesh(com_mod, com_mod.msh[0], Ag_a, Yg_a, Dg_a);   // the global_eq_assem hook
+    if (!on_device) fluid::construct_fluid(com_mod, com_mod.msh[0], Ag_a, Yg_a);
+    Vector<int> incL_v(nFaces);
+    Vector<double> res_v(nFaces);
+    for (int i = 0; i < nFaces; i++) { incL_v(i) = incL ? incL[i] : 1; res_v(i) = res ? res[i] : 0.0; }
+    ls_ns::ls_solve(com_mod, eq, incL_v, res_v);
+
+    std::memcpy(X, com_mod.R.data(), sizeof(double)*size_t(dof)*nNo);
+    auto& L = eq.FSILS;
+    out[0] = L.RI.suc; out[1] = L.RI.itr; out[2] = L.RI.iNorm; out[3] = L.RI.fNorm;
+    out[4] = L.GM.itr; out[5] = L.CG.itr; out[6] = L.Resm; out[7] = L.Resc; out[8] = on_device ? 1.0 : 0.0;
+    delete eq.linear_algebra;
+    eq.linear_algebra = nullptr;
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+#endif
 
 } // extern "C"

@@ -45,7 +45,7 @@ class FluidProps(C.Structure):
 EXPORTS = [
     "b200_create", "b200_destroy", "b200_last_error", "b200_device_count", "b200_comm_unique_id", "b200_comm_init",
     "b200_lhs_create", "b200_face_set", "b200_mesh_set", "b200_zero", "b200_state_set", "b200_assemble_fluid",
-    "b200_assemble_elem", "b200_get_R", "b200_set_R", "b200_get_Val", "b200_set_Val", "b200_commu_R", "b200_solve",
+    "b200_assemble_elem", "b200_get_R", "b200_set_R", "b200_add_R", "b200_get_Val", "b200_set_Val", "b200_commu_R", "b200_solve",
     "b200_spmv", "b200_op_bench", "b200_launch_count", "b200_last_timings", "b200_profile", "b200_profile_read",
     "b200_timer",
 ]
@@ -81,6 +81,7 @@ def lib():
         L.b200_assemble_elem.argtypes = [vp, ci, vp, vp, vp]
         L.b200_get_R.argtypes = [vp, vp]
         L.b200_set_R.argtypes = [vp, ci, vp]
+        L.b200_add_R.argtypes = [vp, ci, vp]
         L.b200_get_Val.argtypes = [vp, vp]
         L.b200_set_Val.argtypes = [vp, ci, vp]
         L.b200_commu_R.argtypes = [vp]
@@ -213,6 +214,10 @@ class Backend:
         R = _c(R, np.float64)
         self.dof = R.shape[1]
         self._ck(self.L.b200_set_R(self.h, self.dof, _p(R)), "b200_set_R")
+
+    def add_R(self, R):
+        R = _c(R, np.float64)
+        self._ck(self.L.b200_add_R(self.h, R.shape[1], _p(R)), "b200_add_R")
 
     def get_Val(self):
         V = np.empty((self.nnz, self.dof * self.dof))

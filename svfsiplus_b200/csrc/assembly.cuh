@@ -12,11 +12,13 @@
 // constants and only N_a(g), u, tauM, tauC, tauB, u' vary with the Gauss point.  Those exact zeros
 // are dropped, every other term is evaluated in the reference's order.
 //
-// Scatter is deterministic: elements are greedily coloured so that no two elements of a colour
-// share a node; one launch per colour, plain (non-atomic) 256-bit read-modify-writes of whole
-// 128-byte Val blocks at precomputed positions (the reference's per-entry binary search,
-// lhsa.cpp:121-133, is done once at mesh_set time).  Every Val entry therefore receives its
-// contributions in colour order, independent of scheduling.
+// Scatter is deterministic AND in the reference's order: no colours, no atomics, no read-modify-write.
+// Every element writes its 16 tangent blocks and 4 residual rows into a staging buffer at slots that
+// were sorted once (mesh_set) by destination and, inside a destination, by ascending element number;
+// a second streaming kernel then sums each destination's contiguous run of contributions left to
+// right, i.e. in exactly the order in which do_assem (lhsa.cpp:97-142) adds them while construct_fluid
+// walks e = 0..nEl-1, and writes every Val block / R row once.  Traffic: 2 KB written + 2 KB read per
+// element (HBM streaming, full sectors) instead of 16 scattered 128-byte read-modify-writes.
 #pragma once
 
 #include "kernels.cuh"
@@ -63,18 +65,18 @@ __device__ __forceinline__ void viscosity(const FluidConsts& c, double& gamma, d
   }
 }
 
-// elements [e0, e1) of the colour-sorted element list
+// one thread per element, elements in mesh order
 __global__ void __launch_bounds__(128)
-k_assemble_fluid_tet4(int e0, int e1, FluidConsts c,
-                      const int* __restrict__ ien,      // 4 x nEl (colour-sorted), assembly node ids
-                      const int* __restrict__ rdest,    // 4 x nEl solver row of each element node
-                      const int* __restrict__ edest,    // 16 x nEl position (in blocks) of (a,b) in the solver-layout Val
+k_assemble_fluid_tet4(int nEl, FluidConsts c,
+                      const int* __restrict__ ien,      // 4 x nEl, assembly node ids
+                      const int* __restrict__ rslot,    // 4 x nEl staging slot (32-byte rows) of lR(:,a)
+                      const int* __restrict__ kslot,    // 16 x nEl staging slot (128-byte blocks) of lK(:,a,b)
                       const double* __restrict__ x,     // 3 x nNo
                       const double* __restrict__ Ag, const double* __restrict__ Yg, const double* __restrict__ Bf,
-                      double* __restrict__ R, double* __restrict__ Val, int* __restrict__ err_flag)
+                      double* __restrict__ stageR, double* __restrict__ stageK, int* __restrict__ err_flag)
 {
-  const int e = e0 + blockIdx.x*blockDim.x + threadIdx.x;
-  if (e >= e1) return;
+  const int e = blockIdx.x*blockDim.x + threadIdx.x;
+  if (e >= nEl) return;
 
   int nd[4];
   {
@@ -295,16 +297,14 @@ k_assemble_fluid_tet4(int e0, int e1, FluidConsts c,
     tauM_g[g] = tauM; tauC_g[g] = tauC; tauB_g[g] = tauB;
   }
 
-  // ---- residual scatter (lhsa.cpp:109-111); nodes of one colour are disjoint ------------------------
+  // ---- residual rows to their staging slots (summed in element order by k_sum_segments) -------------
   {
-    const int4 rd = *reinterpret_cast<const int4*>(rdest + size_t(e)*4);
+    const int4 rd = *reinterpret_cast<const int4*>(rslot + size_t(e)*4);
     const int rr[4] = {rd.x, rd.y, rd.z, rd.w};
 #pragma unroll
     for (int a = 0; a < 4; a++) {
-      double* r = R + size_t(rr[a])*4;
-      d4 v = ld256(r);
-      v.x += lR[a][0]; v.y += lR[a][1]; v.z += lR[a][2]; v.w += lR[a][3];
-      st256(r, v);
+      d4 v; v.x = lR[a][0]; v.y = lR[a][1]; v.z = lR[a][2]; v.w = lR[a][3];
+      st256_stream(stageR + size_t(rr[a])*4, v);
     }
   }
 
@@ -313,7 +313,7 @@ k_assemble_fluid_tet4(int e0, int e1, FluidConsts c,
   // so that no array is indexed dynamically (which would push it to local memory).
 #pragma unroll 1
   for (int a = 0; a < 4; a++) {
-    const int4 ed = *reinterpret_cast<const int4*>(edest + size_t(e)*16 + a*4);
+    const int4 ed = *reinterpret_cast<const int4*>(kslot + size_t(e)*16 + a*4);
     const int pos[4] = {ed.x, ed.y, ed.z, ed.w};
     double Nxa[3], esNxa[3], uNxa[4], upNxa[4], Na_g[4];
 #pragma unroll
@@ -379,15 +379,87 @@ k_assemble_fluid_tet4(int e0, int e1, FluidConsts c,
         kb[3][3] = kb[3][3] + wl*tauM*NxNx;
       }
 
-      // ---- do_assem: Val(:,ptr) += lK(:,a,b) (lhsa.cpp:136-138), whole 128-byte block ---------------
-      double* v = Val + size_t(pos[b])*16;
+      // ---- lK(:,a,b) to its staging slot, whole 128-byte block ----------------------------------------
+      double* v = stageK + size_t(pos[b])*16;
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        d4 t = ld256(v + 4*i);
-        t.x += kb[i][0]; t.y += kb[i][1]; t.z += kb[i][2]; t.w += kb[i][3];
-        st256(v + 4*i, t);
+        d4 t; t.x = kb[i][0]; t.y = kb[i][1]; t.z = kb[i][2]; t.w = kb[i][3];
+        st256_stream(v + 4*i, t);
       }
     }
+  }
+}
+
+// do_assem (lhsa.cpp:97-142) as an ordered segmented sum: destination d (a Val block when W = 4 lanes
+// of 32 bytes, an R row when W = 1) owns the contiguous staging run [seg[d], seg[d+1]), ordered by
+// ascending element; out(:,d) (+)= sum of the run, left to right.  ASSIGN: out is known to be zero
+// (ls_alloc just ran), so it is neither read nor was it memset.  W lanes per destination, one 256-bit
+// row each: a warp streams 32/W consecutive runs, i.e. one contiguous piece of the staging buffer.
+template <int W, bool ASSIGN>
+__global__ void __launch_bounds__(256)
+k_sum_segments(size_t nDest, const int* __restrict__ seg, const double* __restrict__ stage, double* __restrict__ out)
+{
+  const size_t t = size_t(blockIdx.x)*blockDim.x + threadIdx.x;
+  const size_t d = t / W;
+  const int l = int(t % W);
+  if (d >= nDest) return;
+  const int s = __ldg(seg + d), e = __ldg(seg + d + 1);
+  d4 acc;
+  if (ASSIGN) { acc.x = acc.y = acc.z = acc.w = 0.0; }
+  else acc = ld256(out + (d*W + l)*4);
+  int q = s;
+  for (; q + 4 <= e; q += 4) {
+    const d4 v0 = ld256_stream(stage + (size_t(q)*W + l)*4);
+    const d4 v1 = ld256_stream(stage + (size_t(q+1)*W + l)*4);
+    const d4 v2 = ld256_stream(stage + (size_t(q+2)*W + l)*4);
+    const d4 v3 = ld256_stream(stage + (size_t(q+3)*W + l)*4);
+    acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+    acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+    acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+    acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+  }
+  for (; q < e; q++) {
+    const d4 v = ld256_stream(stage + (size_t(q)*W + l)*4);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  st256(out + (d*W + l)*4, acc);
+}
+
+// ---- one-time slot construction (mesh_set) --------------------------------------------------------
+// key[i] = destination of item i (i = e*16 + a*4 + b for blocks, e*4 + a for rows); items of one
+// destination are ranked by ascending i, so that the run of a destination is in element order.
+__global__ void k_slot_count(size_t nItems, const int* __restrict__ key, int* __restrict__ cnt, int* __restrict__ bad)
+{
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < nItems; i += nth) {
+    const int k = key[i];
+    if (k < 0) { atomicExch(bad, 1); continue; }
+    atomicAdd(cnt + k, 1);
+  }
+}
+__global__ void k_slot_fill(size_t nItems, const int* __restrict__ key, const int* __restrict__ seg, int* __restrict__ cursor,
+                            int* __restrict__ items)
+{
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < nItems; i += nth) {
+    const int k = key[i];
+    if (k < 0) continue;
+    items[seg[k] + atomicAdd(cursor + k, 1)] = int(i);
+  }
+}
+// one thread per destination: insertion-sort its (short) item list, then publish the slots
+__global__ void k_slot_rank(size_t nDest, const int* __restrict__ seg, int* __restrict__ items, int* __restrict__ slot)
+{
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t d = size_t(blockIdx.x)*blockDim.x + threadIdx.x; d < nDest; d += nth) {
+    const int s = seg[d], e = seg[d+1];
+    for (int i = s + 1; i < e; i++) {
+      const int v = items[i];
+      int j = i - 1;
+      while (j >= s && items[j] > v) { items[j+1] = items[j]; j--; }
+      items[j+1] = v;
+    }
+    for (int i = s; i < e; i++) slot[items[i]] = i;
   }
 }
 

@@ -47,6 +47,11 @@ __device__ __forceinline__ void st256(double* p, const d4& v)
 {
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
 }
+// staging data is written once and read once by another kernel: keep it out of L1, evict first from L2
+__device__ __forceinline__ void st256_stream(double* p, const d4& v)
+{
+  asm volatile("st.global.L1::no_allocate.L2::evict_first.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(p), "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w) : "memory");
+}
 __device__ __forceinline__ double ld_stream(const double* p)
 {
   double v;
@@ -133,6 +138,40 @@ k_spmv_vv(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
       }
       KU[size_t(row)*DOF + lane4] = acc;
     }
+  }
+}
+
+// dof-3 variant with all four lanes busy (mK of the NS solver, 72-byte blocks): lane l takes the blocks
+// p = s+l, s+l+4, ... of the row (whole 3x3 block + the 3-vector of its column), the quad then adds
+// its partial 3-vectors in a fixed order.  Per step a quad streams 288 contiguous bytes.
+__global__ void __launch_bounds__(256)
+k_spmv_vv3s(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
+            const double* __restrict__ K, const double* __restrict__ U, double* __restrict__ KU)
+{
+  const int lane4 = threadIdx.x & 3;
+  const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
+  const int ngroups = (gridDim.x*blockDim.x) >> 2;
+  const int nrounds = (nNo + ngroups - 1)/ngroups;
+  for (int r = 0; r < nrounds; r++) {
+    const int row = group + r*ngroups;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    if (row < nNo) {
+      const int s = __ldg(rowPtr + row);
+      const int e = __ldg(rowPtr + row + 1);
+#pragma unroll 2
+      for (int p = s + lane4; p < e; p += 4) {
+        const int c = __ldg(col + p);
+        const double* k = K + size_t(p)*9;
+        const double* u = U + size_t(c)*3;
+        const double u0 = __ldg(u), u1 = __ldg(u + 1), u2 = __ldg(u + 2);
+        a0 = a0 + (__ldg(k)*u0 + __ldg(k + 1)*u1 + __ldg(k + 2)*u2);
+        a1 = a1 + (__ldg(k + 3)*u0 + __ldg(k + 4)*u1 + __ldg(k + 5)*u2);
+        a2 = a2 + (__ldg(k + 6)*u0 + __ldg(k + 7)*u1 + __ldg(k + 8)*u2);
+      }
+    }
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 2); a1 += __shfl_xor_sync(0xffffffffu, a1, 2); a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
+    if (row < nNo && lane4 < 3) KU[size_t(row)*3 + lane4] = (lane4 == 0) ? a0 : (lane4 == 1) ? a1 : a2;
   }
 }
 
@@ -382,7 +421,16 @@ k_cgs_update_scale(size_t n, int k, const double* __restrict__ base, size_t stri
   const size_t nth = size_t(gridDim.x)*blockDim.x;
   for (size_t idx = tid; idx < n; idx += nth) {
     double v = w[idx];
-    for (int j = 0; j < k; j++) v = fma(-hs[j], base[size_t(j)*stride + idx], v);
+    int j = 0;
+    // 8 independent streaming loads in flight, then the updates in the reference's order (j ascending)
+    for (; j + 8 <= k; j += 8) {
+      double b[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) b[u] = ld_stream(base + size_t(j + u)*stride + idx);
+#pragma unroll
+      for (int u = 0; u < 8; u++) v = fma(-hs[j + u], b[u], v);
+    }
+    for (; j < k; j++) v = fma(-hs[j], ld_stream(base + size_t(j)*stride + idx), v);
     w[idx] = sc*v;
   }
 }
@@ -630,24 +678,31 @@ __global__ void k_join_mc(int nNo, int dof, const double* __restrict__ Rm, const
 }
 
 // ---- K9 resistance-face rank-1 update (liner_solver/add_bc_mul.cpp:53-121) ------------------------
-// stage 1 (one CTA): out[0] = sum_{a, i<m} valM(i,a) * X(i, glob[a])  over face nodes with glob[a] < lim
+// stage 1: out[0] = sum_{a, i<m} valM(i,a) * X(i, glob[a])  over face nodes with glob[a] < lim
 // (lim = nNo for a face owned by one rank, mynNo for a shared face whose dot is completed by an
-// all-reduce).  Fixed-shape tree -> deterministic.
+// all-reduce).  Up to kFaceBlocks CTAs over contiguous chunks of the face, fixed-shape tree inside a
+// CTA, partials added in CTA order by the last CTA -> deterministic.  ld = leading dimension of X.
+constexpr int kFaceBlocks = 64;
 __global__ void __launch_bounds__(256)
-k_face_dot(int fnNo, int m, int fdof, int dof, int lim, const int* __restrict__ glob, const double* __restrict__ valM,
-           const double* X, double* __restrict__ out)
+k_face_dot(int fnNo, int m, int fdof, int ld, int lim, const int* __restrict__ glob, const double* __restrict__ valM,
+           const double* X, double* __restrict__ partial, unsigned int* __restrict__ counter, double* __restrict__ out)
 {
-  double acc = 0.0;
   const int n = fnNo*m;
-  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+  const int chunk = (n + gridDim.x - 1)/gridDim.x;
+  const int beg = blockIdx.x*chunk;
+  const int end = min(n, beg + chunk);
+  double acc = 0.0;
+  for (int t = beg + threadIdx.x; t < end; t += blockDim.x) {
     const int a = t / m, i = t % m;
     const int Ac = glob[a];
     if (Ac < lim) {
-      const double xv = X ? X[size_t(Ac)*dof + i] : valM[size_t(a)*fdof + i];
-      acc = fma(valM[size_t(a)*fdof + i], xv, acc);
+      const double vm = valM[size_t(a)*fdof + i];
+      const double xv = X ? X[size_t(Ac)*ld + i] : vm;
+      acc = fma(vm, xv, acc);
     }
   }
   __shared__ double sm[8];
+  __shared__ bool last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
@@ -656,7 +711,20 @@ k_face_dot(int fnNo, int m, int fdof, int dof, int lim, const int* __restrict__ 
   if (threadIdx.x == 0) {
     double v = 0.0;
     for (int k = 0; k < 8; k++) v += sm[k];
+    if (gridDim.x == 1) { out[0] = v; last = false; }
+    else {
+      partial[blockIdx.x] = v;
+      __threadfence();
+      last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double v = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; b++) v += __ldcg(partial + b);
     out[0] = v;
+    *counter = 0u;
   }
 }
 // stage 2: Y(i, glob[a]) += valM(i,a) * (coef * S)

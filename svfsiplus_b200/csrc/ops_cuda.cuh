@@ -149,7 +149,8 @@ class CudaOps {
   double* red_d = nullptr;
   double* red_h = nullptr;        // pinned
   double* partial_d = nullptr;
-  unsigned int* counter_d = nullptr;
+  unsigned int* counter_d = nullptr;   // [0] multi-dot, [1] face dot
+  double* face_partial_d = nullptr;
 
   // arena
   struct Chunk { char* p; size_t cap, top; };
@@ -164,8 +165,9 @@ class CudaOps {
     CU_CHECK(cudaMalloc(&red_d, sizeof(double)*kMaxSlots));
     CU_CHECK(cudaMallocHost(&red_h, sizeof(double)*kMaxSlots));
     CU_CHECK(cudaMalloc(&partial_d, sizeof(double)*kRedBlocks*kMaxDots));
-    CU_CHECK(cudaMalloc(&counter_d, sizeof(unsigned int)));
-    CU_CHECK(cudaMemset(counter_d, 0, sizeof(unsigned int)));
+    CU_CHECK(cudaMalloc(&counter_d, 2*sizeof(unsigned int)));
+    CU_CHECK(cudaMemset(counter_d, 0, 2*sizeof(unsigned int)));
+    CU_CHECK(cudaMalloc(&face_partial_d, sizeof(double)*kFaceBlocks));
   }
   ~CudaOps()
   {
@@ -174,7 +176,7 @@ class CudaOps {
     for (auto& f : faces) { cudaFree(f.glob); cudaFree(f.val); cudaFree(f.valM); }
     for (auto& r : reqs) { cudaFree(r.ptr); cudaFree(r.sbuf); cudaFree(r.rbuf); }
     cudaFree(rowPtr); cudaFree(col); cudaFree(diag); cudaFree(tpos);
-    cudaFree(red_d); cudaFreeHost(red_h); cudaFree(partial_d); cudaFree(counter_d);
+    cudaFree(red_d); cudaFreeHost(red_h); cudaFree(partial_d); cudaFree(counter_d); cudaFree(face_partial_d);
     if (comm) nccl.CommDestroy(comm);
     if (st) cudaStreamDestroy(st);
   }
@@ -311,6 +313,7 @@ class CudaOps {
     post();
   }
 
+  int variant_vv3 = 0;       // 0: lane = component, 1: lanes stride over the row's blocks (A/B by op_bench)
   // ---- SpMV (+ overlap-node add) --------------------------------------------------------------------
   void spmv_vv(int dof, const double* K, const double* U, double* KU)
   {
@@ -319,7 +322,9 @@ class CudaOps {
     Scope sc(*this, dof == 4 ? KC_SPMV_VV4 : KC_SPMV_VV3, bytes_vv(dof));
     switch (dof) {
       case 4: k_spmv_vv4<<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU); break;
-      case 3: k_spmv_vv<3><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU); break;
+      case 3: if (variant_vv3 == 1) k_spmv_vv3s<<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
+              else k_spmv_vv<3><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
+              break;
       case 2: k_spmv_vv<2><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU); break;
       case 1: k_spmv_vv<1><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU); break;
       default: throw std::runtime_error("spmv_vv: dof > 4 is not a supported FSILS path");
@@ -394,6 +399,13 @@ class CudaOps {
   void face_set_inc(int f, bool v) { faces[f].inc = v; }
   void face_set_coupled(int f, bool c, double res) { faces[f].coupled = c; if (c) faces[f].res = res; }
 
+  void face_dot(const DevFace& fa, int m, int ld, int lim, const double* X, double* out)
+  {
+    const int n = fa.nNo*m;
+    const int g = std::max(1, std::min(kFaceBlocks, (n + 511)/512));
+    k_face_dot<<<g, 256, 0, st>>>(fa.nNo, m, fa.dof, ld, lim, fa.glob, fa.valM, X, face_partial_d, counter_d + 1, out);
+    post();
+  }
   // face.nS = ||valM||^2 (ns_solver.cpp:56-87, gmres.cpp:50-85)
   void bc_pre(int nsd)
   {
@@ -404,8 +416,7 @@ class CudaOps {
       if (!fa.coupled) continue;
       const int m = std::min(fa.dof, nsd);
       const int lim = fa.shared ? mynNo_ : nNo_;
-      k_face_dot<<<1, 256, 0, st>>>(fa.nNo, m, fa.dof, nsd, lim, fa.glob, fa.valM, nullptr, red_d + nslot);
-      post();
+      face_dot(fa, m, nsd, lim, nullptr, red_d + nslot);
       which.push_back(f);
       nslot++;
     }
@@ -436,8 +447,7 @@ class CudaOps {
       const int m = std::min(fa.dof, dof);
       const int lim = fa.shared ? mynNo_ : nNo_;
       double* S = red_d + (kMaxSlots - 1);
-      k_face_dot<<<1, 256, 0, st>>>(fa.nNo, m, fa.dof, ld, lim, fa.glob, fa.valM, X, S);
-      post();
+      face_dot(fa, m, ld, lim, X, S);
       if (fa.shared && nranks > 1) nccl.check(nccl.AllReduce(S, S, 1, Nccl::kFloat64, Nccl::kSum, comm, st), "AllReduce");
       if (fa.nNo > 0) {
         k_face_axpy<<<grid_for(size_t(fa.nNo)*m, 256, 1), 256, 0, st>>>(fa.nNo, m, fa.dof, ld, fa.glob, fa.valM, coef, S, Y);

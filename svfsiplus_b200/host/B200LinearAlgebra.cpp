@@ -1,0 +1,209 @@
+// B200LinearAlgebra.cpp — see B200LinearAlgebra.h.  Thin: it only translates the reference's
+// containers (ComMod, eqType, FSILS_lhsType; all column-major, Array.h:379) into the flat arrays of
+// the C ABI (include/svb200.h) and converts status codes into the std::runtime_error exceptions the
+// reference's virtuals use.  No numerical work happens here.
+#include "B200LinearAlgebra.h"
+
+#include "svb200.h"
+#include "lhsa.h"
+
+#include <stdexcept>
+#include <vector>
+
+std::set<consts::LinearAlgebraType> B200LinearAlgebra::valid_assemblers = {
+  consts::LinearAlgebraType::none,
+  consts::LinearAlgebraType::fsils,
+  B200_LINEAR_ALGEBRA_TYPE,
+};
+
+B200LinearAlgebra::B200LinearAlgebra()
+{
+  interface_type = B200_LINEAR_ALGEBRA_TYPE;
+  assembly_type = consts::LinearAlgebraType::fsils;
+  preconditioner_type = consts::PreconditionerType::PREC_FSILS;
+}
+
+B200LinearAlgebra::~B200LinearAlgebra()
+{
+  if (h_) b200_destroy(h_);
+}
+
+void B200LinearAlgebra::check(int rc, const char* what)
+{
+  if (rc != 0) {
+    throw std::runtime_error(std::string("[B200LinearAlgebra] ") + what + ": " + b200_last_error(h_));
+  }
+}
+
+void B200LinearAlgebra::check_options(const consts::PreconditionerType prec_cond_type,
+    const consts::LinearAlgebraType assembly_type)
+{
+  std::string error_msg;
+  if (valid_assemblers.count(assembly_type) == 0) {
+    error_msg = "b200 linear algebra can't use '" + LinearAlgebra::type_to_name.at(assembly_type) + "' for assembly.";
+  }
+  // the backend implements the FSILS preconditioners (diagonal 'fsils' and row-column scaling 'rcs')
+  if (consts::fsils_preconditioners.count(prec_cond_type) == 0) {
+    error_msg = "b200 linear algebra can't use '" + consts::preconditioner_type_to_name.at(prec_cond_type) +
+        "' for a preconditioner.";
+  }
+  if (error_msg != "") {
+    throw std::runtime_error("[svFSIplus] ERROR: " + error_msg);
+  }
+}
+
+void B200LinearAlgebra::set_assembly(consts::LinearAlgebraType atype)
+{
+  if (atype == consts::LinearAlgebraType::none) {
+    return;
+  }
+  if (valid_assemblers.count(atype) == 0) {
+    throw std::runtime_error("[B200LinearAlgebra] ERROR: Can't set b200 linear algebra to use '" +
+        LinearAlgebra::type_to_name.at(atype) + "' for assembly.");
+  }
+  assembly_type = atype;
+  device_assembly_ = (atype == B200_LINEAR_ALGEBRA_TYPE);
+}
+
+void B200LinearAlgebra::set_preconditioner(consts::PreconditionerType prec_type)
+{
+  if (consts::fsils_preconditioners.count(prec_type) == 0) {
+    throw std::runtime_error("[B200LinearAlgebra] ERROR: b200 linear algebra can't use '" +
+        consts::preconditioner_type_to_name.at(prec_type) + "' for a preconditioner.");
+  }
+  preconditioner_type = prec_type;
+}
+
+/// Called once per equation by add_eq_linear_algebra (main.cpp:68-77), after com_mod.lhs, rowPtr,
+/// colPtr and the faces exist.  The device handle is created here, not in the constructor.
+void B200LinearAlgebra::initialize(ComMod& com_mod, eqType& lEq)
+{
+  if (h_) return;
+  if (b200_create(&h_, device_) != 0) {
+    throw std::runtime_error(std::string("[B200LinearAlgebra] ") + b200_last_error(nullptr));
+  }
+  upload_structure(com_mod);
+}
+
+/// CSR pattern (lhsa, lhsa.cpp:153), node map, halo lists and faces (fsils_lhs_create lhs.cpp:57,
+/// fsils_bc_create bc.cpp:45) -> device, once.
+void B200LinearAlgebra::upload_structure(ComMod& com_mod)
+{
+  auto& lhs = com_mod.lhs;
+  const int nNo = lhs.nNo;
+  std::vector<int> req_rank, req_n, req_ptr;
+  for (int i = 0; i < lhs.nReq; i++) {
+    req_rank.push_back(lhs.cS[i].iP);
+    req_n.push_back(lhs.cS[i].n);
+    for (int j = 0; j < lhs.cS[i].n; j++) req_ptr.push_back(lhs.cS[i].ptr(j));
+  }
+  check(b200_lhs_create(h_, lhs.gnNo, nNo, lhs.mynNo, lhs.nnz, com_mod.rowPtr.data(), com_mod.colPtr.data(),
+                        lhs.map.data(), lhs.nReq, req_rank.data(), req_n.data(), req_ptr.data(), lhs.nFaces),
+        "b200_lhs_create");
+  structure_uploaded_ = true;
+  update_faces(com_mod);
+}
+
+void B200LinearAlgebra::update_faces(ComMod& com_mod)
+{
+  auto& lhs = com_mod.lhs;
+  for (int f = 0; f < lhs.nFaces; f++) {
+    auto& face = lhs.face[f];      // (fsils_bc_create never raises face.foC in the C++ reference: upload every slot)
+    const int bGrp = (face.bGrp == fsi_linear_solver::BcType::BC_TYPE_Dir) ? B200_BC_DIR : B200_BC_NEU;
+    check(b200_face_set(h_, f, face.nNo, face.dof, bGrp, face.glob.data(), face.val.data(), face.sharedFlag ? 1 : 0),
+          "b200_face_set");
+  }
+}
+
+/// ls_alloc contract (ls.cpp:51-60): afterwards the system is zero.
+void B200LinearAlgebra::alloc(ComMod& com_mod, eqType& lEq)
+{
+  const int dof = com_mod.dof;
+  if (!device_assembly_) {
+    com_mod.Val.resize(dof*dof, com_mod.lhs.nnz);      // host assembly target, exactly like FsilsLinearAlgebra::alloc
+  }
+  check(b200_zero(h_, dof), "b200_zero");
+  any_device_contribution_ = false;
+}
+
+/// Per-element entry (boundary faces and any physics without a device kernel).
+void B200LinearAlgebra::assemble(ComMod& com_mod, const int num_elem_nodes, const Vector<int>& eqN,
+    const Array3<double>& lK, const Array<double>& lR)
+{
+  if (!device_assembly_) {
+    lhsa_ns::do_assem(com_mod, num_elem_nodes, eqN, lK, lR);
+    return;
+  }
+  check(b200_assemble_elem(h_, num_elem_nodes, eqN.data(), lK.data(), lR.data()), "b200_assemble_elem");
+  any_device_contribution_ = true;
+}
+
+void B200LinearAlgebra::upload_mesh(ComMod& com_mod, const mshType& lM)
+{
+  // IEN holds assembly (local) node ids already (ComMod.h:893); x is com_mod.x (3 x tnNo)
+  check(b200_mesh_set(h_, lM.eNoN, lM.nEl, lM.IEN.data(), com_mod.x.data(), lM.qmTET4), "b200_mesh_set");
+  mesh_uploaded_ = &lM;
+}
+
+bool B200LinearAlgebra::assemble_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag,
+    const Array<double>& Yg, const Array<double>& Dg)
+{
+  using namespace consts;
+  if (!device_assembly_) return false;
+  auto& eq = com_mod.eq[com_mod.cEq];
+  // device kernels available in this round: Navier-Stokes VMS on linear tetrahedra, one fluid domain
+  if (eq.phys != EquationType::phys_fluid || lM.eType != ElementType::TET4 || eq.nDmn != 1 || lM.nFs != 1) return false;
+  if (com_mod.nsd != 3 || com_mod.dof != 4) return false;
+  if (mesh_uploaded_ != &lM) upload_mesh(com_mod, lM);
+
+  const auto& dmn = eq.dmn[0];
+  b200_fluid_props p;
+  p.dt = com_mod.dt; p.am = eq.am; p.af = eq.af; p.gam = eq.gam;
+  p.tDof = com_mod.tDof; p.mvMsh = com_mod.mvMsh ? 1 : 0;
+  p.rho = dmn.prop.at(PhysicalProperyType::fluid_density);
+  p.f[0] = dmn.prop.at(PhysicalProperyType::f_x);
+  p.f[1] = dmn.prop.at(PhysicalProperyType::f_y);
+  p.f[2] = dmn.prop.at(PhysicalProperyType::f_z);
+  p.Kinv = dmn.prop.at(PhysicalProperyType::inverse_darcy_permeability);
+  switch (dmn.fluid_visc.viscType) {
+    case FluidViscosityModelType::viscType_Const: p.viscType = 0; break;
+    case FluidViscosityModelType::viscType_CY:    p.viscType = 1; break;
+    case FluidViscosityModelType::viscType_Cass:  p.viscType = 2; break;
+    default: return false;
+  }
+  p.mu_i = dmn.fluid_visc.mu_i; p.mu_o = dmn.fluid_visc.mu_o; p.lam = dmn.fluid_visc.lam;
+  p.a = dmn.fluid_visc.a; p.n = dmn.fluid_visc.n;
+
+  check(b200_state_set(h_, com_mod.tDof, Ag.data(), Yg.data(), com_mod.Bf.data()), "b200_state_set");
+  check(b200_assemble_fluid(h_, &p), "b200_assemble_fluid");
+  any_device_contribution_ = true;
+  return true;
+}
+
+/// ls_solve (ls.cpp:69-82) -> fsils_solve (solve.cpp:50) on the device.  On return com_mod.R holds
+/// the solution, like FsilsLinearAlgebra::solve.
+void B200LinearAlgebra::solve(ComMod& com_mod, eqType& lEq, const Vector<int>& incL, const Vector<double>& res)
+{
+  const int dof = com_mod.dof;
+  auto& ls = lEq.FSILS;
+  if (device_assembly_) {
+    // host code may have added to com_mod.R since ls_alloc (it starts from zero): fold it in
+    check(b200_add_R(h_, dof, com_mod.R.data()), "b200_add_R");
+  } else {
+    check(b200_set_R(h_, dof, com_mod.R.data()), "b200_set_R");
+    check(b200_set_Val(h_, dof, com_mod.Val.data()), "b200_set_Val");
+  }
+  b200_tol RI{ls.RI.relTol, ls.RI.absTol, ls.RI.mItr, ls.RI.sD};
+  b200_tol GM{ls.GM.relTol, ls.GM.absTol, ls.GM.mItr, ls.GM.sD};
+  b200_tol CG{ls.CG.relTol, ls.CG.absTol, ls.CG.mItr, ls.CG.sD};
+  const int prec = (lEq.linear_algebra_preconditioner == consts::PreconditionerType::PREC_RCS) ? B200_PREC_RCS : B200_PREC_FSILS;
+  b200_ls_out out;
+  check(b200_solve(h_, static_cast<int>(ls.LS_type), prec, &RI, &GM, &CG,
+                   incL.size() ? incL.data() : nullptr, res.size() ? res.data() : nullptr, com_mod.R.data(), &out),
+        "b200_solve");
+  auto put = [](fsi_linear_solver::FSILS_subLsType& s, const b200_sub_out& o) {
+    s.suc = o.suc != 0; s.itr = o.itr; s.iNorm = o.iNorm; s.fNorm = o.fNorm; s.dB = o.dB; s.callD = o.callD;
+  };
+  put(ls.RI, out.RI); put(ls.GM, out.GM); put(ls.CG, out.CG);
+  ls.Resm = out.Resm; ls.Resc = out.Resc;
+}

@@ -1,0 +1,72 @@
+// B200LinearAlgebra — the plug-in class that exposes the CUDA backend (include/svb200.h) to
+// svMultiPhysics through the reference's own LinearAlgebra interface
+// (Code/Source/solver/LinearAlgebra.h:39-63), beside FsilsLinearAlgebra / PetscLinearAlgebra /
+// TrilinosLinearAlgebra.  This file is compiled INSIDE the reference's source tree (it includes the
+// reference's headers); INTEGRATION.md lists the registration lines.  oracle/Makefile compiles it
+// against the unmodified reference headers to prove that it builds and tests/test_dropin.py drives it
+// through the reference's own ComMod / eqType / FSILS_lhsType objects.
+//
+// Two modes, chosen by <Linear_algebra type="b200"> <Assembly> :
+//   assembly "fsils" (or none)  the reference assembles on the host (do_assem into com_mod.R / com_mod.Val);
+//                               solve() uploads both, solves on the GPU, returns the solution in com_mod.R.
+//   assembly "b200"             global_eq_assem calls assemble_mesh(): whole-mesh element assembly on the
+//                               GPU; assemble() (boundary elements) is staged and flushed by one scatter
+//                               kernel; anything host code added to com_mod.R meanwhile is added on upload.
+#ifndef B200_LINEAR_ALGEBRA_H
+#define B200_LINEAR_ALGEBRA_H
+
+#include "LinearAlgebra.h"
+
+#include <set>
+#include <string>
+
+struct b200_handle;
+
+// A maintainer adds `b200` to consts::LinearAlgebraType (consts.h:503); until then the class can be
+// compiled against the unmodified header by defining the enumerator value on the command line.
+#ifndef B200_LINEAR_ALGEBRA_TYPE
+#define B200_LINEAR_ALGEBRA_TYPE consts::LinearAlgebraType::b200
+#endif
+
+class B200LinearAlgebra : public virtual LinearAlgebra {
+  public:
+    B200LinearAlgebra();          // cheap, no CUDA context: Parameters.cpp:2444 instantiates it at parse time
+    ~B200LinearAlgebra();
+
+    virtual void alloc(ComMod& com_mod, eqType& lEq);
+    virtual void assemble(ComMod& com_mod, const int num_elem_nodes, const Vector<int>& eqN,
+        const Array3<double>& lK, const Array<double>& lR);
+    virtual void check_options(const consts::PreconditionerType prec_cond_type, const consts::LinearAlgebraType assembly_type);
+    virtual void initialize(ComMod& com_mod, eqType& lEq);
+    virtual void solve(ComMod& com_mod, eqType& lEq, const Vector<int>& incL, const Vector<double>& res);
+    virtual void set_assembly(consts::LinearAlgebraType atype);
+    virtual void set_preconditioner(consts::PreconditionerType prec_type);
+
+    /// Whole-mesh element assembly on the device; called by eq_assem::global_eq_assem instead of
+    /// construct_fluid when device assembly is selected.  Returns false when this physics / element
+    /// type has no device kernel yet (the caller then falls back to the reference's construct_* with
+    /// per-element assemble()).
+    bool assemble_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag, const Array<double>& Yg,
+        const Array<double>& Dg);
+
+    /// fsils_bc_update counterpart: re-upload the face vectors (moving meshes, follower loads).
+    void update_faces(ComMod& com_mod);
+
+    bool device_assembly() const { return device_assembly_; }
+    void set_device(int device) { device_ = device; }
+
+  private:
+    void check(int rc, const char* what);
+    void upload_structure(ComMod& com_mod);
+    void upload_mesh(ComMod& com_mod, const mshType& lM);
+
+    b200_handle* h_ = nullptr;
+    int device_ = 0;
+    bool device_assembly_ = false;
+    bool structure_uploaded_ = false;
+    const mshType* mesh_uploaded_ = nullptr;
+    bool any_device_contribution_ = false;
+    static std::set<consts::LinearAlgebraType> valid_assemblers;
+};
+
+#endif

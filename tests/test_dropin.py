@@ -1,0 +1,45 @@
+"""Drop-in boundary test (`-m gpu`): the plug-in class svfsiplus_b200/host/B200LinearAlgebra.cpp, compiled
+against the UNMODIFIED reference headers, is driven through the reference's own objects (ComMod, eqType,
+FSILS_lhsType built by fsils_lhs_create / fsils_bc_create) and the reference's own call sequence
+ls_alloc -> global assembly -> ls_solve (Code/Source/solver/ls.cpp:51-82), and compared with the
+reference's FsilsLinearAlgebra path on the same inputs."""
+import numpy as np
+import pytest
+
+from util import rel_l2
+
+from svfsiplus_b200 import problem as P
+
+pytestmark = pytest.mark.gpu
+
+
+def _need():
+    from oracle import ref
+    if not (ref.available() and ref.dropin_available()):
+        pytest.skip("oracle/_ref (libsvref.so + libsvdropin.so) not present on this box")
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("ls", ["NS", "GMRES"])
+def test_plugin_class_matches_fsils_backend(mode, ls):
+    _need()
+    from oracle import ref, refcase
+    case = P.pipe_case(8, 8, 16)
+    lsv = refcase._ls_vector(P.LS_SETTINGS[ls])
+    X, info = ref.dropin_fluid_step(case, lsv, mode)
+    assert int(info["device_assembly"]) == mode
+    Rr, Vr, Xr, oref = refcase.reference_step(case, ls)
+    assert rel_l2(X, Xr) < 1e-5          # production tolerance 1e-3 solve, see test_gpu_parity.TOL_SOL_LOOSE
+    assert abs(int(info["itr"]) - int(oref["itr"])) <= 1
+    assert bool(info["suc"]) == bool(oref["suc"])
+
+
+def test_plugin_class_tight_solve():
+    _need()
+    from oracle import ref, refcase
+    from svfsiplus_b200 import backend as B
+    case = P.pipe_case(8, 8, 16)
+    ls = (B.LS_GMRES, (1e-11, 1e-30, 10, 300), None, None)
+    X, info = ref.dropin_fluid_step(case, refcase._ls_vector(ls), 1)
+    Rr, Vr, Xr, oref = refcase.reference_step(case, ls)
+    assert rel_l2(X, Xr) < 1e-6        # cond x 1e-11, see test_gpu_parity.test_tight_tolerance_solution
