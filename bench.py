@@ -193,6 +193,8 @@ def run_gpu(args):
     def step_resident():
         be.zero(4)
         be.assemble_fluid(props)
+        if world > 1:
+            be.commu_R()
         _, info = be.solve(ls_type, B.PREC_FSILS, RI, GM, CG, case["incL"], case["res"], fetch=False)
         return info
 
@@ -200,6 +202,8 @@ def run_gpu(args):
         be.state_set(tDof, pin["Ag"].data_ptr(), pin["Yg"].data_ptr(), pin["Bf"].data_ptr())
         be.zero(4)
         be.assemble_fluid(props)
+        if world > 1:
+            be.commu_R()
         _, info = be.solve(ls_type, B.PREC_FSILS, RI, GM, CG, case["incL"], case["res"], out=out_pin.data_ptr(), fetch=True)
         return info
 

@@ -125,6 +125,14 @@ def sub_out_dict(s: SubOut):
     return dict(suc=bool(s.suc), itr=s.itr, iNorm=s.iNorm, fNorm=s.fNorm, dB=s.dB, callD=s.callD)
 
 
+def unique_id() -> np.ndarray:
+    """128-byte NCCL unique id, made on rank 0 and distributed by the caller (torch.distributed / MPI_Bcast)."""
+    uid = np.zeros(128, np.uint8)
+    if lib().b200_comm_unique_id(_p(uid)) != 0:
+        raise RuntimeError("b200_comm_unique_id: " + lib().b200_last_error(None).decode())
+    return uid
+
+
 class Backend:
     """One handle = one (equation x GPU), like one LinearAlgebra object per equation per MPI rank."""
 
@@ -154,10 +162,7 @@ class Backend:
 
     # -- communicator --------------------------------------------------------------------------
     def unique_id(self) -> np.ndarray:
-        uid = np.zeros(128, np.uint8)
-        if self.L.b200_comm_unique_id(_p(uid)) != 0:
-            raise RuntimeError("b200_comm_unique_id: " + self.L.b200_last_error(None).decode())
-        return uid
+        return unique_id()
 
     def comm_init(self, rank, nranks, uid):
         uid = _c(uid, np.uint8)

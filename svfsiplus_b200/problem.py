@@ -67,6 +67,8 @@ def assemble(be: B.Backend, case, upload=True):
     be.zero(4)
     p = case["props"]
     be.assemble_fluid(B.fluid_props(tDof=case["Ag"].shape[1], **p))
+    if case.get("nranks", 1) > 1:
+        be.commu_R()                  # all_fun::commu(R), main.cpp:513
 
 
 def newton_linear_step(be: B.Backend, case, ls="NS", want_system=False, upload=True, fetch=True, out=None):

@@ -1,0 +1,129 @@
+"""Host logic of the multi-GPU path on CPU: the slab partition, the numpy restatement of
+fsils_lhs_create's node reordering and overlap lists against the COMPILED REFERENCE run with
+threads-as-ranks (oracle/_ref), and the same set-up under torch.distributed (gloo, world_size 2)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import needs_ref
+from util import ROOT
+
+from svfsiplus_b200 import partition as PT
+from svfsiplus_b200 import problem as P
+
+
+@pytest.mark.parametrize("nparts", [2, 3, 4])
+def test_split_covers_mesh(nparts):
+    case = P.pipe_case(4, 4, 9)
+    parts = PT.split_case(case, nparts)
+    m = case["mesh"]
+    assert sum(p["mesh"].nEl for p in parts) == m.nEl
+    seen = np.zeros(m.nNo, int)
+    for p in parts:
+        seen[p["gNodes"]] += 1
+        assert (p["mesh"].x == m.x[p["gNodes"]]).all()
+        # local connectivity points at the same global nodes
+        assert (np.sort(np.unique(p["gNodes"][p["mesh"].ien])) == np.sort(p["gNodes"])).all()
+    assert (seen >= 1).all() and (seen <= 2).all()       # slabs: interface planes are held twice
+
+
+@needs_ref
+@pytest.mark.parametrize("nparts", [2, 3, 4])
+def test_lhs_layout_equals_reference_fsils_lhs_create(nparts):
+    from oracle import ref
+    case = P.pipe_case(4, 4, 9)
+    parts = PT.split_case(case, nparts)
+    rr = ref.RefRanks([dict(gnNo=p["gnNo"], gNodes=p["gNodes"], rowPtr=p["rowPtr"], colPtr=p["colPtr"], faces=[])
+                       for p in parts])
+    allg = [p["gNodes"] for p in parts]
+    for r in range(nparts):
+        info = rr.info(r)
+        lay = PT.lhs_layout(r, allg, parts[r]["gnNo"])
+        assert lay["mynNo"] == info["mynNo"] and lay["shnNo"] == info["shnNo"]
+        assert (lay["map"] == info["map"]).all()
+        assert len(lay["reqs"]) == info["nReq"]
+        for (pa, ptra), (pb, ptrb) in zip(lay["reqs"], info["reqs"]):
+            assert pa == pb and (ptra == ptrb).all()
+    rr.close()
+
+
+@needs_ref
+def test_lhs_layout_equals_reference_irregular_partition():
+    """A partition that is NOT slabs (round-robin blocks of elements): more than two owners per node."""
+    from oracle import ref
+    case = P.pipe_case(3, 3, 5)
+    m = case["mesh"]
+    part = (np.arange(m.nEl) // 7) % 3
+    parts = PT.split_case(case, 3, part.astype(np.int32))
+    rr = ref.RefRanks([dict(gnNo=p["gnNo"], gNodes=p["gNodes"], rowPtr=p["rowPtr"], colPtr=p["colPtr"], faces=[])
+                       for p in parts])
+    allg = [p["gNodes"] for p in parts]
+    for r in range(3):
+        info = rr.info(r)
+        lay = PT.lhs_layout(r, allg, parts[r]["gnNo"])
+        assert lay["mynNo"] == info["mynNo"] and lay["shnNo"] == info["shnNo"]
+        assert (lay["map"] == info["map"]).all()
+        assert [q[0] for q in lay["reqs"]] == [q[0] for q in info["reqs"]]
+        for (pa, ptra), (pb, ptrb) in zip(lay["reqs"], info["reqs"]):
+            assert (ptra == ptrb).all()
+    rr.close()
+
+
+def test_local_slab_case_matches_neighbours():
+    """Rank-local generation (bench --gpus N): interface planes agree between neighbours."""
+    dims = (4, 4, 8)
+    a, ga = PT.local_slab_case(dims, 0, 2)
+    b, gb = PT.local_slab_case(dims, 1, 2)
+    plane = 25
+    assert (a["gNodes"][-plane:] == b["gNodes"][:plane]).all()
+    assert np.array_equal(a["mesh"].x[-plane:], b["mesh"].x[:plane])
+    assert np.array_equal(a["Yg"][-plane:], b["Yg"][:plane]) and np.array_equal(a["Ag"][-plane:], b["Ag"][:plane])
+    la = PT.lhs_layout(0, ga, a["gnNo"]); lb = PT.lhs_layout(1, gb, b["gnNo"])
+    assert la["mynNo"] == a["mesh"].nNo - plane and lb["shnNo"] == plane and lb["mynNo"] == b["mesh"].nNo
+    # the two ends of a request list name the same global nodes in the same order
+    inv_a = np.empty(a["mesh"].nNo, int); inv_a[la["map"]] = np.arange(a["mesh"].nNo)
+    inv_b = np.empty(b["mesh"].nNo, int); inv_b[lb["map"]] = np.arange(b["mesh"].nNo)
+    assert (a["gNodes"][inv_a[la["reqs"][0][1]]] == b["gNodes"][inv_b[lb["reqs"][0][1]]]).all()
+
+
+GLOO_WORKER = r"""
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from svfsiplus_b200 import partition as PT, problem as P
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+case = P.pipe_case(4, 4, 9)
+part = PT.split_case(case, world)[rank]
+# what a multi-process run does: every rank contributes its node list, all ranks derive their layout
+lst = [None] * world
+dist.all_gather_object(lst, part["gNodes"])
+lay = PT.lhs_layout(rank, lst, part["gnNo"])
+# consistency across ranks: each pair of request lists has equal length and names the same global nodes
+inv = np.empty(len(part["gNodes"]), int); inv[lay["map"]] = np.arange(len(part["gNodes"]))
+mine = {peer: part["gNodes"][inv[ptr]] for peer, ptr in lay["reqs"]}
+allm = [None] * world
+dist.all_gather_object(allm, mine)
+for peer, g in mine.items():
+    assert (allm[peer][rank] == g).all()
+owned = torch.tensor([lay["mynNo"]], dtype=torch.int64)
+dist.all_reduce(owned)
+assert int(owned) == case["mesh"].nNo, (int(owned), case["mesh"].nNo)     # every global node is counted once
+if rank == 0:
+    print("GLOO_OK")
+dist.destroy_process_group()
+"""
+
+
+def test_layout_under_gloo_world_size_2(tmp_path):
+    w = tmp_path / "worker.py"
+    w.write_text(GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(w), ROOT],
+                       capture_output=True, text=True, timeout=600, env=env)
+    assert "GLOO_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
