@@ -117,7 +117,7 @@ long long b200_launch_count(b200_handle* h);
  * per class, the summed device milliseconds, the ALGORITHMIC bytes (SURVEY.md par. 8d formulas) and the
  * number of launches.  Classes: 0 spmv_vv dof4, 1 spmv_vv dof<4, 2 spmv_ss, 3 spmv_sv, 4 spmv_vs,
  * 5 multi_dot, 6 cgs_update_scale, 7 blas1 (axpy/scale/lin_comb/...), 8 scale_val (Jacobi), 9 depart,
- * 10 assembly (all colours), 11 halo pack/add. */
+ * 10 assembly (all colours), 11 halo pack/add.  enable: 0 off, 1 every class, 2 + c only class c. */
 #define B200_NUM_KERNEL_CLASSES 12
 int b200_profile(b200_handle* h, int enable);
 int b200_profile_read(b200_handle* h, int max_classes, double* ms, double* bytes, long long* launches);

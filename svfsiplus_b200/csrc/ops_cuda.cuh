@@ -87,6 +87,7 @@ class CudaOps {
 
   // ---- live kernel timing: event pairs on the launch stream, resolved after the step ---------------
   bool profiling = false;
+  unsigned profile_mask = 0xffffffffu;      // kernel classes that record events while profiling
   struct Span { cudaEvent_t a, b; int cls; };
   std::vector<Span> spans;
   size_t span_used = 0;
@@ -98,7 +99,7 @@ class CudaOps {
     CudaOps& o; int idx;
     Scope(CudaOps& o_, int cls, double bytes, int nl = 1) : o(o_), idx(-1)
     {
-      if (!o.profiling) return;
+      if (!o.profiling || !((o.profile_mask >> cls) & 1u)) return;
       if (o.span_used == o.spans.size()) {
         Span s; cudaEventCreate(&s.a); cudaEventCreate(&s.b); s.cls = cls; o.spans.push_back(s);
       }

@@ -79,8 +79,21 @@ void B200LinearAlgebra::set_preconditioner(consts::PreconditionerType prec_type)
 void B200LinearAlgebra::initialize(ComMod& com_mod, eqType& lEq)
 {
   if (h_) return;
+  // one rank per GPU: rank r of the solver's communicator drives device r mod (devices on this node)
+  if (device_ < 0) {
+    const int n = b200_device_count();
+    device_ = (n > 0) ? com_mod.cm.idcm() % n : 0;
+  }
   if (b200_create(&h_, device_) != 0) {
     throw std::runtime_error(std::string("[B200LinearAlgebra] ") + b200_last_error(nullptr));
+  }
+  // multi-rank: rank 0 creates the NCCL id, the solver's own communicator distributes it
+  const int nranks = com_mod.cm.np();
+  if (nranks > 1) {
+    char uid[128];
+    if (com_mod.cm.idcm() == 0) check(b200_comm_unique_id(uid), "b200_comm_unique_id");
+    MPI_Bcast(uid, 128, MPI_CHAR, 0, com_mod.cm.com());
+    check(b200_comm_init(h_, com_mod.cm.idcm(), nranks, uid), "b200_comm_init");
   }
   upload_structure(com_mod);
 }

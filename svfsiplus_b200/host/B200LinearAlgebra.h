@@ -61,7 +61,7 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
     void upload_mesh(ComMod& com_mod, const mshType& lM);
 
     b200_handle* h_ = nullptr;
-    int device_ = 0;
+    int device_ = -1;         // -1: rank mod device count, chosen in initialize()
     bool device_assembly_ = false;
     bool structure_uploaded_ = false;
     const mshType* mesh_uploaded_ = nullptr;
