@@ -39,9 +39,9 @@ def reference_solve(case, R, Val, ls, prec=ref.PREC_FSILS):
     return X[0], out[0]
 
 
-def reference_step(case, ls="NS"):
+def reference_step(case, ls="NS", prec=ref.PREC_FSILS):
     from svfsiplus_b200.problem import LS_SETTINGS
     ls = LS_SETTINGS[ls] if isinstance(ls, str) else ls
     R, Val, rowPtr, colPtr, _ = reference_assemble(case)
-    X, out = reference_solve(case, R, Val, ls)
+    X, out = reference_solve(case, R, Val, ls, prec)
     return R, Val, X, out

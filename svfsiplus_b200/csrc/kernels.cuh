@@ -609,6 +609,105 @@ k_scale_val(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col
   }
 }
 
+// ---- K7 row-and-column-scaling preconditioner (liner_solver/precond.cpp:266-540) ------------------
+// Wr <- 1 where Wr > 0.5, 0 elsewhere, with the reference's arithmetic (:305-307): after the overlap
+// add a Dirichlet mask shared by several ranks can exceed 1.
+__global__ void k_rcs_renorm(size_t n, double* __restrict__ W)
+{
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) {
+    double w = W[i] - 0.5;
+    w = w / fabs(w);
+    W[i] = (w + fabs(w)) * 0.5;
+  }
+}
+// unit diagonal on the killed rows: Val(ii,d) = Wr(i)*(Val(ii,d) - 1) + 1   (:321-366)
+__global__ void k_rcs_unit_diag(int nNo, int dof, const int* __restrict__ diagPtr, const double* __restrict__ Wr, double* __restrict__ Val)
+{
+  const size_t n = size_t(nNo)*dof;
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t t = size_t(blockIdx.x)*blockDim.x + threadIdx.x; t < n; t += nth) {
+    const int a = int(t / dof), i = int(t % dof);
+    double* v = Val + (size_t(diagPtr[a])*dof*dof + i*dof + i);
+    *v = Wr[t]*(*v - 1.0) + 1.0;
+  }
+}
+// max is exact and order-independent, so an atomic max on the bit pattern of a non-negative double
+// is deterministic
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v)
+{
+  atomicMax(reinterpret_cast<unsigned long long*>(addr), static_cast<unsigned long long>(__double_as_longlong(v)));
+}
+// One sweep's norms (:384-510): Wr(i,row) = max_j,p |Val(i,j,p)| over the row's blocks,
+// Wc(j,col_p) = max_i |Val(i,j,p)|.  Quad per row, lane i owns block-row i; the column maxima of a
+// block are first reduced across the quad (lane j ends up with column j), then ONE atomic per lane.
+// Wc must be zero on entry.
+template <int DOF>
+__global__ void __launch_bounds__(256)
+k_rcs_norms(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col, const double* __restrict__ Val,
+            double* __restrict__ Wr, double* __restrict__ Wc)
+{
+  const int lane4 = threadIdx.x & 3;
+  const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
+  const int ngroups = (gridDim.x*blockDim.x) >> 2;
+  const int nrounds = (nNo + ngroups - 1)/ngroups;
+  for (int r = 0; r < nrounds; r++) {
+    const int row = group + r*ngroups;
+    const bool live = row < nNo;
+    const int s = live ? rowPtr[row] : 0, e = live ? rowPtr[row+1] : 0;
+    // all four lanes of a quad walk the same row, so the shuffles below are uniform inside the quad;
+    // quads of one warp may have different lengths -> pad to the warp's longest row
+    int len = e - s;
+    int wl = len;
+#pragma unroll
+    for (int o = 16; o >= 4; o >>= 1) wl = max(wl, __shfl_xor_sync(0xffffffffu, wl, o));
+    double rmax = 0.0;
+    for (int k = 0; k < wl; k++) {
+      const int p = s + k;
+      const bool on = k < len;
+      double v[4] = {0.0, 0.0, 0.0, 0.0};
+      if (on && lane4 < DOF) {
+#pragma unroll
+        for (int j = 0; j < DOF; j++) v[j] = fabs(Val[size_t(p)*DOF*DOF + lane4*DOF + j]);
+      }
+#pragma unroll
+      for (int j = 0; j < DOF; j++) rmax = fmax(rmax, v[j]);
+      // column maxima across the quad
+      double mine = 0.0;
+#pragma unroll
+      for (int j = 0; j < DOF; j++) {
+        double m = v[j];
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        if (lane4 == j) mine = m;
+      }
+      if (on && lane4 < DOF) atomic_max_nonneg(Wc + size_t(col[p])*DOF + lane4, mine);
+    }
+    if (live && lane4 < DOF) Wr[size_t(row)*DOF + lane4] = rmax;
+  }
+}
+// out[0] = max(out[0], max_i |1 - W[i]|)  (:514); out must be zero on entry
+__global__ void __launch_bounds__(256)
+k_rcs_dev1(size_t n, const double* __restrict__ W, double* __restrict__ out)
+{
+  double m = 0.0;
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) m = fmax(m, fabs(1.0 - W[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomic_max_nonneg(out, m);
+}
+// W = 1/sqrt(W); Wacc *= W   (:518-527)
+__global__ void k_rcs_invsqrt_accum(size_t n, double* __restrict__ W, double* __restrict__ Wacc)
+{
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) {
+    const double w = 1.0 / sqrt(W[i]);
+    W[i] = w;
+    Wacc[i] = Wacc[i] * w;
+  }
+}
+
 // ---- K8 depart (liner_solver/ns_solver.cpp:91-163), nsd = 3 --------------------------------------
 // Splits the scaled 4x4 blocks into mK(9), mG(3), mD(3), mL(1) and builds Gt(:,l) = -mG(:,tpos[l])
 // with the transpose position precomputed once (the reference searches the row each time).

@@ -492,9 +492,73 @@ class CudaOps {
     }
     post();
   }
-  void precond_rcs(int, double*, double*, double*, double*)
+  // precond_rcs (precond.cpp:266-540): Dirichlet rows/columns killed and given a unit diagonal, then up
+  // to 10 sweeps of row / column max-norm scaling.  W1 (row) and W2 (column) accumulate the scalings;
+  // R <- W1 R at the end, the caller multiplies the solution by W2.  Like the reference it never
+  // touches face.valM (a coupled face therefore contributes nothing under this preconditioner).
+  void precond_rcs(int dof, double* Val, double* R, double* W1, double* W2)
   {
-    throw std::runtime_error("row-column-scaling preconditioner (precond_rcs) is not built yet in this round");
+    if (dof < 1 || dof > 4) throw std::runtime_error("precond_rcs: dof > 4");
+    const size_t n = size_t(dof)*nNo_;
+    auto mk = mark();
+    double* Wr = vec(n);
+    double* Wc = vec(n);
+    fill(n, 1.0, W1);
+    fill(n, 1.0, W2);
+    fill(n, 1.0, Wr);
+    for (auto& fa : faces) {
+      if (!fa.inc || fa.bGrp != B200_BC_DIR || fa.nNo == 0) continue;
+      const int m = std::min(fa.dof, dof);
+      k_face_mask<<<grid_for(size_t(fa.nNo)*m, 256, 1), 256, 0, st>>>(fa.nNo, m, fa.dof, dof, fa.glob, fa.val, Wr); post();
+    }
+    halo_add(dof, Wr);
+    k_rcs_renorm<<<grid_for(n, 256), 256, 0, st>>>(n, Wr); post();
+    scale_val(dof, Wr, Wr, Val);                      // pre_mul + pos_mul in one pass, same rounding
+    mul_inplace(n, Wr, R);
+    k_rcs_unit_diag<<<grid_for(n, 256), 256, 0, st>>>(nNo_, dof, diag, Wr, Val); post();
+
+    const int maxiter = 10;
+    const double tol = 2.0;
+    int iter = 0;
+    bool flag = true;
+    const int g = grid_rows(nNo_);
+    while (flag) {
+      zero(n, Wc);
+      iter++;
+      if (iter >= maxiter) flag = false;     // (the reference prints a warning here)
+      {
+        Scope sc(*this, KC_SCALE_VAL, double(nnz_)*(8.0*dof*dof + 4.0) + double(nNo_)*(16.0*dof + 8.0));
+        switch (dof) {
+          case 4: k_rcs_norms<4><<<g, 256, 0, st>>>(nNo_, rowPtr, col, Val, Wr, Wc); break;
+          case 3: k_rcs_norms<3><<<g, 256, 0, st>>>(nNo_, rowPtr, col, Val, Wr, Wc); break;
+          case 2: k_rcs_norms<2><<<g, 256, 0, st>>>(nNo_, rowPtr, col, Val, Wr, Wc); break;
+          default: k_rcs_norms<1><<<g, 256, 0, st>>>(nNo_, rowPtr, col, Val, Wr, Wc); break;
+        }
+        post();
+      }
+      halo_add(dof, Wr);
+      halo_add(dof, Wc);
+      zero(2, red_d);
+      k_rcs_dev1<<<grid_for(n, 256), 256, 0, st>>>(n, Wr, red_d); post();
+      k_rcs_dev1<<<grid_for(n, 256), 256, 0, st>>>(n, Wc, red_d + 1); post();
+      double dev[2];
+      reduce_fetch(2, dev);
+      // NaN-safe like the reference's `max(...) < tol` (a NaN keeps the flag)
+      if ((dev[0] < tol) && (dev[1] < tol)) flag = false;
+      k_rcs_invsqrt_accum<<<grid_for(n, 256), 256, 0, st>>>(n, Wr, W1); post();
+      k_rcs_invsqrt_accum<<<grid_for(n, 256), 256, 0, st>>>(n, Wc, W2); post();
+      scale_val(dof, Wr, Wc, Val);
+      if (nranks > 1) {
+        // MPI_Allgather of the flags + any() (:529-534)
+        fill(1, flag ? 1.0 : 0.0, red_d);
+        nccl.check(nccl.AllReduce(red_d, red_d, 1, Nccl::kFloat64, Nccl::kMax, comm, st), "AllReduce");
+        double f;
+        reduce_fetch(1, &f);
+        flag = f > 0.5;
+      }
+    }
+    mul_inplace(n, W1, R);
+    release(mk);
   }
 
   // ---- NS helpers ---------------------------------------------------------------------------------------

@@ -71,14 +71,15 @@ def assemble(be: B.Backend, case, upload=True):
         be.commu_R()                  # all_fun::commu(R), main.cpp:513
 
 
-def newton_linear_step(be: B.Backend, case, ls="NS", want_system=False, upload=True, fetch=True, out=None):
+def newton_linear_step(be: B.Backend, case, ls="NS", want_system=False, upload=True, fetch=True, out=None,
+                       prec=B.PREC_FSILS):
     """One Newton iteration's hot path: assemble R/Val, then solve.  Returns (X, info[, R, Val])."""
     assemble(be, case, upload=upload)
     R = Val = None
     if want_system:
         R, Val = be.get_R(), be.get_Val()
     ls_type, RI, GM, CG = LS_SETTINGS[ls] if isinstance(ls, str) else ls
-    X, info = be.solve(ls_type, B.PREC_FSILS, RI, GM, CG, case["incL"], case["res"], out=out, fetch=fetch)
+    X, info = be.solve(ls_type, prec, RI, GM, CG, case["incL"], case["res"], out=out, fetch=fetch)
     if want_system:
         return X, info, R, Val
     return X, info
