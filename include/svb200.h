@@ -48,11 +48,37 @@ typedef struct {
   double mu_i, mu_o, lam, a, n; /* dmn.fluid_visc */
 } b200_fluid_props;
 
+/* Per-(equation, domain) constants of the displacement-based solid element, flattened from eqType /
+ * dmnType / stModelType (solver/sv_struct.cpp:576-594, solver/ComMod.h:345-388).  s = eq.s, the row of
+ * the equation's first unknown inside Ag/Yg/Dg(tDof,nNo).  isoType: 0 neo-Hookean (C10 = mu/2),
+ * 1 St.Venant-Kirchhoff (C10 = lambda, C01 = mu), 2 modified StVK (C10 = kappa, C01 = mu);
+ * volType: 0 none, 1 Quad, 2 ST91, 3 M94 (solver/mat_models.cpp:1626-1645). */
+typedef struct {
+  double dt, am, af, gam, beta;
+  int tDof, s;
+  double rho, dmp, f[3];
+  int isoType, volType;
+  double C10, C01, Kpen;
+} b200_struct_props;
+
+/* Linear elasticity (solver/l_elas.cpp:274-390).  mesh_mode != 0: the ALE mesh-motion equation
+ * (solver/mesh.cpp:42-160): reference configuration x + Do(s..s+2), displacement Dg - Do, Gauss weights
+ * without the Jacobian, no body force. */
+typedef struct {
+  double dt, am, af, beta;
+  int tDof, s, mesh_mode;
+  double rho, elM, nu, f[3];
+} b200_lelas_props;
+
 /* ---- life cycle ------------------------------------------------------------------------- */
 int  b200_create(b200_handle** h, int device);
 void b200_destroy(b200_handle* h);
 const char* b200_last_error(b200_handle* h);                 /* h may be NULL: last create error */
 int  b200_device_count(void);
+/* Gauss rule and shape functions the element kernels use for eNoN = 4 (TET4) / 8 (HEX8): w[nG],
+ * N[nG][eNoN], Nxi[nG][eNoN][3]; returns nG (what nn::select_ele leaves in lM.w / lM.N / lM.Nx,
+ * solver/nn_elem_gip.h:40,501; nn_elem_gnn.h:732,1232).  Host-only, needs no device. */
+int  b200_elem_tables(int eNoN, double qmTET4, double* w, double* N, double* Nxi);
 
 /* ---- communicator (replaces FSILS_commuType + MPI, liner_solver/commu.cpp:44) ------------- */
 /* uid: 128 bytes produced on rank 0 and distributed by the caller (MPI_Bcast / torch.distributed). */
@@ -72,8 +98,8 @@ int b200_face_set(b200_handle* h, int faIn, int nNo, int dof, int bGrp, const in
                   const double* val, int shared);
 
 /* ---- assembly (replaces construct_fluid + do_assem, solver/fluid.cpp:464, lhsa.cpp:97) ------- */
-/* IEN(eNoN,nEl) with assembly node ids, x(3,nNo).  eNoN = 4 (TET4).  qmTET4 <= 0 selects the
- * default (5+3*sqrt(5))/20 (solver/ComMod.h:1011). */
+/* IEN(eNoN,nEl) with assembly node ids, x(3,nNo).  eNoN = 4 (TET4) or 8 (HEX8, the reference's node
+ * order, nn_elem_gnn.h:732).  qmTET4 <= 0 selects the default (5+3*sqrt(5))/20 (solver/ComMod.h:1011). */
 int b200_mesh_set(b200_handle* h, int eNoN, int nEl, const int* IEN, const double* x, double qmTET4);
 /* ls_alloc contract (solver/ls.cpp:51-60): after it R(dof,nNo) and Val(dof*dof,nnz) are zero. */
 int b200_zero(b200_handle* h, int dof);
@@ -81,6 +107,13 @@ int b200_zero(b200_handle* h, int dof);
 int b200_state_set(b200_handle* h, int tDof, const double* Ag, const double* Yg, const double* Bf);
 /* Whole-mesh fluid assembly on the device into R/Val, using the state uploaded last. */
 int b200_assemble_fluid(b200_handle* h, const b200_fluid_props* p);
+/* Upload Dg (tDof,nNo) and, for the mesh equation, Do (tDof,nNo; NULL otherwise). */
+int b200_disp_set(b200_handle* h, int tDof, const double* Dg, const double* Do);
+/* Whole-mesh solid assembly into R/Val (dof 3; b200_zero(h,3) first): replaces construct_dsolid +
+ * struct_3d_carray + get_pk2cc (solver/sv_struct.cpp:213,552; mat_models_carray.h:182) ... */
+int b200_assemble_struct(b200_handle* h, const b200_struct_props* p);
+/* ... and construct_l_elas / construct_mesh + l_elas_3d (solver/l_elas.cpp:58,274; mesh.cpp:42). */
+int b200_assemble_lelas(b200_handle* h, const b200_lelas_props* p);
 /* LinearAlgebra::assemble for the few boundary-face elements: staged on the host, flushed by one
  * scatter kernel before the next get/solve.  eqN(d), lK(dof*dof,d,d), lR(dof,d). */
 int b200_assemble_elem(b200_handle* h, int d, const int* eqN, const double* lK, const double* lR);

@@ -98,6 +98,8 @@ def lib():
         L.ref_asm_get_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_asm_fluid.restype = C.c_double
         L.ref_asm_fluid.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_double] * 5 + [C.c_void_p, C.c_double] + [C.c_void_p] * 6
+        L.ref_asm_solid.restype = C.c_double
+        L.ref_asm_solid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
         L.ref_rank_create.restype = C.c_void_p
         L.ref_rank_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_rank_destroy.argtypes = [C.c_void_p]
@@ -170,6 +172,27 @@ class RefAssembly:
         Val = np.empty((self.nnz, 16))
         t = lib().ref_asm_fluid(self.h, tDof, int(mvMsh), dt, am, af, gam, rho, _p(fv), Kinv, _p(v),
                                 _p(Ag), _p(Yg), _p(Bf), _p(R), _p(Val))
+        if t < 0:
+            raise RuntimeError(lib().ref_last_error().decode())
+        return R, Val, t
+
+
+    ISO = {"nHook": 0, "StVK": 1, "mStVK": 2}
+    VOL = {None: 0, "Quad": 1, "ST91": 2, "M94": 3}
+
+    def solid(self, kind, Ag, Yg, Dg, Bf, *, dt, am, af, gam, beta, rho, dmp=0.0, f=(0.0, 0.0, 0.0), iso="nHook",
+              vol="ST91", C10=0.0, C01=0.0, Kpen=0.0, elM=0.0, nu=0.0, s=0, Do=None):
+        """kind "struct": construct_dsolid (S/sv_struct.cpp:213); "lelas": construct_l_elas (S/l_elas.cpp:58).
+        Returns R (nNo,3), Val (nnz,9), seconds."""
+        Ag = _c(Ag, np.float64); Yg = _c(Yg, np.float64); Dg = _c(Dg, np.float64); Bf = _c(Bf, np.float64)
+        tDof = Ag.shape[1]
+        par = np.array([dt, am, af, gam, beta, rho, dmp, f[0], f[1], f[2], self.ISO[iso], self.VOL[vol], C10, C01, Kpen,
+                        elM, nu], np.float64)
+        R = np.empty((self.nNo, 3))
+        Val = np.empty((self.nnz, 9))
+        Do = None if Do is None else _c(Do, np.float64)
+        t = lib().ref_asm_solid(self.h, {"struct": 0, "lelas": 1, "mesh": 2}[kind], tDof, int(s), _p(par), _p(Ag), _p(Yg),
+                                _p(Dg), _p(Do), _p(Bf), _p(R), _p(Val))
         if t < 0:
             raise RuntimeError(lib().ref_last_error().decode())
         return R, Val, t

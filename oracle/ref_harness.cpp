@@ -23,6 +23,9 @@
 #include "consts.h"
 #include "fluid.h"
 #include "fs.h"
+#include "l_elas.h"
+#include "mesh.h"
+#include "sv_struct.h"
 #include "fsils_api.hpp"
 #include "lhsa.h"
 #include "nn.h"
@@ -220,6 +223,85 @@ double ref_asm_fluid(void* h, int tDof, int mvMsh, double dt, double am, double 
 
     double t0 = now_s();
     fluid::construct_fluid(com_mod, com_mod.msh[0], Ag_a, Yg_a);
+    double t1 = now_s();
+
+    std::memcpy(R, com_mod.R.data(), sizeof(double)*size_t(dof)*nNo);
+    std::memcpy(Val, com_mod.Val.data(), sizeof(double)*size_t(dof)*dof*ctx->nnz);
+    return t1 - t0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1.0;
+  }
+}
+
+// Solid assembly through the reference's construct_dsolid (S/sv_struct.cpp:213 -> struct_3d_carray :552 ->
+// get_pk2cc<3> S/mat_models_carray.h:182) or construct_l_elas (S/l_elas.cpp:58 -> l_elas_3d :274).
+// kind 0: struct, 1: lElas, 2: mesh (construct_mesh S/mesh.cpp:42; needs Do and eq.s = s).  par = {dt, am, af, gam, beta, rho, dmp, fx, fy, fz,
+//   iso (0 nHook, 1 StVK, 2 mStVK), vol (0 none, 1 Quad, 2 ST91, 3 M94), C10, C01, Kpen, elM, nu}
+// Ag, Yg, Dg: tDof x nNo (eq.s = 0, dof = 3).  Outputs R (3 x nNo), Val (9 x nnz).
+double ref_asm_solid(void* h, int kind, int tDof, int s, const double* par, const double* Ag, const double* Yg,
+                     const double* Dg, const double* Do, const double* Bf, double* R, double* Val)
+{
+  try {
+    using namespace consts;
+    auto ctx = static_cast<AsmCtx*>(h);
+    auto& com_mod = ctx->sim->com_mod;
+    const int nNo = com_mod.tnNo;
+    const int dof = 3;
+    com_mod.tDof = tDof;
+    com_mod.dof = dof;
+    com_mod.dt = par[0];
+    com_mod.mvMsh = false;
+    com_mod.cEq = 0;
+    com_mod.nEq = 1;
+    if (com_mod.eq.size() != 1) com_mod.eq.resize(1);
+    auto& eq = com_mod.eq[0];
+    eq.phys = (kind == 0) ? EquationType::phys_struct : (kind == 1) ? EquationType::phys_lElas : EquationType::phys_mesh;
+    eq.dof = dof;
+    eq.s = s;
+    eq.e = s + dof - 1;
+    if (kind == 2) {
+      com_mod.Do.resize(tDof, nNo);
+      std::memcpy(com_mod.Do.data(), Do, sizeof(double)*size_t(tDof)*nNo);
+    }
+    eq.am = par[1]; eq.af = par[2]; eq.gam = par[3]; eq.beta = par[4];
+    eq.nDmn = 1;
+    if (eq.dmn.size() != 1) eq.dmn.resize(1);
+    auto& dmn = eq.dmn[0];
+    dmn.Id = -1;
+    dmn.phys = eq.phys;
+    dmn.prop[PhysicalProperyType::solid_density] = par[5];
+    dmn.prop[PhysicalProperyType::damping] = par[6];
+    dmn.prop[PhysicalProperyType::f_x] = par[7];
+    dmn.prop[PhysicalProperyType::f_y] = par[8];
+    dmn.prop[PhysicalProperyType::f_z] = par[9];
+    dmn.prop[PhysicalProperyType::elasticity_modulus] = par[15];
+    dmn.prop[PhysicalProperyType::poisson_ratio] = par[16];
+    const int iso = int(par[10]), vol = int(par[11]);
+    dmn.stM.isoType = (iso == 0) ? ConstitutiveModelType::stIso_nHook
+                    : (iso == 1) ? ConstitutiveModelType::stIso_StVK : ConstitutiveModelType::stIso_mStVK;
+    dmn.stM.volType = (vol == 1) ? ConstitutiveModelType::stVol_Quad
+                    : (vol == 2) ? ConstitutiveModelType::stVol_ST91
+                    : (vol == 3) ? ConstitutiveModelType::stVol_M94 : ConstitutiveModelType::stIso_NA;
+    dmn.stM.C10 = par[12];
+    dmn.stM.C01 = par[13];
+    dmn.stM.Kpen = par[14];
+    com_mod.Bf.resize(3, nNo);
+    std::memcpy(com_mod.Bf.data(), Bf, sizeof(double)*3*size_t(nNo));
+    if (!eq.linear_algebra) eq.linear_algebra = new FsilsLinearAlgebra();
+
+    Array<double> Ag_a(tDof, nNo), Yg_a(tDof, nNo), Dg_a(tDof, nNo);
+    std::memcpy(Ag_a.data(), Ag, sizeof(double)*size_t(tDof)*nNo);
+    std::memcpy(Yg_a.data(), Yg, sizeof(double)*size_t(tDof)*nNo);
+    std::memcpy(Dg_a.data(), Dg, sizeof(double)*size_t(tDof)*nNo);
+
+    com_mod.R.resize(dof, nNo);
+    eq.linear_algebra->alloc(com_mod, eq);
+
+    double t0 = now_s();
+    if (kind == 0) struct_ns::construct_dsolid(com_mod, ctx->sim->cep_mod, com_mod.msh[0], Ag_a, Yg_a, Dg_a);
+    else if (kind == 1) l_elas::construct_l_elas(com_mod, com_mod.msh[0], Ag_a, Dg_a);
+    else mesh::construct_mesh(com_mod, ctx->sim->cep_mod, com_mod.msh[0], Ag_a, Dg_a);
     double t1 = now_s();
 
     std::memcpy(R, com_mod.R.data(), sizeof(double)*size_t(dof)*nNo);

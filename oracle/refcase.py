@@ -45,3 +45,23 @@ def reference_step(case, ls="NS", prec=ref.PREC_FSILS):
     R, Val, rowPtr, colPtr, _ = reference_assemble(case)
     X, out = reference_solve(case, R, Val, ls, prec)
     return R, Val, X, out
+
+
+def reference_assemble_solid(case):
+    """construct_dsolid / construct_l_elas on a svfsiplus_b200.problem.block_case."""
+    m = case["mesh"]
+    ra = ref.RefAssembly(m.x, m.ien)
+    p = dict(case["props"])
+    R, Val, secs = ra.solid(case["kind"], case["Ag"], case["Yg"], case["Dg"], case["Bf"], Do=case.get("Do"), **p)
+    rowPtr, colPtr = ra.csr()
+    tabs = ra.tables()
+    ra.close()
+    return R, Val, rowPtr, colPtr, secs, tabs
+
+
+def reference_solid_step(case, ls, prec=ref.PREC_FSILS):
+    from svfsiplus_b200.problem import LS_SETTINGS
+    ls = LS_SETTINGS[ls] if isinstance(ls, str) else ls
+    R, Val, rowPtr, colPtr, _, _ = reference_assemble_solid(case)
+    X, out = reference_solve(case, R, Val, ls, prec)
+    return R, Val, X, out

@@ -42,9 +42,27 @@ class FluidProps(C.Structure):
                 ("mu_i", C.c_double), ("mu_o", C.c_double), ("lam", C.c_double), ("a", C.c_double), ("n", C.c_double)]
 
 
+class StructProps(C.Structure):
+    _fields_ = [("dt", C.c_double), ("am", C.c_double), ("af", C.c_double), ("gam", C.c_double), ("beta", C.c_double),
+                ("tDof", C.c_int), ("s", C.c_int),
+                ("rho", C.c_double), ("dmp", C.c_double), ("f", C.c_double * 3),
+                ("isoType", C.c_int), ("volType", C.c_int),
+                ("C10", C.c_double), ("C01", C.c_double), ("Kpen", C.c_double)]
+
+
+class LelasProps(C.Structure):
+    _fields_ = [("dt", C.c_double), ("am", C.c_double), ("af", C.c_double), ("beta", C.c_double),
+                ("tDof", C.c_int), ("s", C.c_int), ("mesh_mode", C.c_int),
+                ("rho", C.c_double), ("elM", C.c_double), ("nu", C.c_double), ("f", C.c_double * 3)]
+
+
+ISO_TYPES = {"nHook": 0, "StVK": 1, "mStVK": 2}
+VOL_TYPES = {None: 0, "Quad": 1, "ST91": 2, "M94": 3}
+
 EXPORTS = [
-    "b200_create", "b200_destroy", "b200_last_error", "b200_device_count", "b200_comm_unique_id", "b200_comm_init",
+    "b200_create", "b200_destroy", "b200_last_error", "b200_device_count", "b200_elem_tables", "b200_comm_unique_id", "b200_comm_init",
     "b200_lhs_create", "b200_face_set", "b200_mesh_set", "b200_zero", "b200_state_set", "b200_assemble_fluid",
+    "b200_disp_set", "b200_assemble_struct", "b200_assemble_lelas",
     "b200_assemble_elem", "b200_get_R", "b200_set_R", "b200_add_R", "b200_get_Val", "b200_set_Val", "b200_commu_R", "b200_solve",
     "b200_spmv", "b200_op_bench", "b200_launch_count", "b200_last_timings", "b200_profile", "b200_profile_read",
     "b200_timer",
@@ -70,6 +88,7 @@ def lib():
         L.b200_destroy.restype = None
         L.b200_last_error.argtypes = [vp]
         L.b200_last_error.restype = C.c_char_p
+        L.b200_elem_tables.argtypes = [ci, cd, vp, vp, vp]
         L.b200_comm_unique_id.argtypes = [vp]
         L.b200_comm_init.argtypes = [vp, ci, ci, vp]
         L.b200_lhs_create.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, ci, vp, vp, vp, ci]
@@ -78,6 +97,9 @@ def lib():
         L.b200_zero.argtypes = [vp, ci]
         L.b200_state_set.argtypes = [vp, ci, vp, vp, vp]
         L.b200_assemble_fluid.argtypes = [vp, C.POINTER(FluidProps)]
+        L.b200_disp_set.argtypes = [vp, ci, vp, vp]
+        L.b200_assemble_struct.argtypes = [vp, C.POINTER(StructProps)]
+        L.b200_assemble_lelas.argtypes = [vp, C.POINTER(LelasProps)]
         L.b200_assemble_elem.argtypes = [vp, ci, vp, vp, vp]
         L.b200_get_R.argtypes = [vp, vp]
         L.b200_set_R.argtypes = [vp, ci, vp]
@@ -119,6 +141,36 @@ def fluid_props(*, dt, am, af, gam, rho, mu, tDof=4, mvMsh=False, f=(0.0, 0.0, 0
     p.f[0], p.f[1], p.f[2] = f
     p.viscType, p.mu_i, p.mu_o, p.lam, p.a, p.n = viscType, mu, mu_o, lam, a, n
     return p
+
+
+def struct_props(*, dt, am, af, gam, beta, rho, tDof=3, s=0, dmp=0.0, f=(0.0, 0.0, 0.0), iso="nHook", vol="ST91",
+                 C10=0.0, C01=0.0, Kpen=0.0) -> StructProps:
+    p = StructProps()
+    p.dt, p.am, p.af, p.gam, p.beta = dt, am, af, gam, beta
+    p.tDof, p.s = tDof, s
+    p.rho, p.dmp = rho, dmp
+    p.f[0], p.f[1], p.f[2] = f
+    p.isoType, p.volType = ISO_TYPES[iso], VOL_TYPES[vol]
+    p.C10, p.C01, p.Kpen = C10, C01, Kpen
+    return p
+
+
+def lelas_props(*, dt, am, af, beta, rho, elM, nu, tDof=3, s=0, f=(0.0, 0.0, 0.0), mesh_mode=False, **_ignored) -> LelasProps:
+    p = LelasProps()
+    p.dt, p.am, p.af, p.beta = dt, am, af, beta
+    p.tDof, p.s, p.mesh_mode = tDof, s, int(mesh_mode)
+    p.rho, p.elM, p.nu = rho, elM, nu
+    p.f[0], p.f[1], p.f[2] = f
+    return p
+
+
+def elem_tables(eNoN, qmTET4=-1.0):
+    """(w[nG], N[nG,eNoN], Nxi[nG,eNoN,3]) of the element kernels; host-only."""
+    nG = {4: 4, 8: 8}[eNoN]
+    w = np.zeros(nG); N = np.zeros((nG, eNoN)); Nxi = np.zeros((nG, eNoN, 3))
+    if lib().b200_elem_tables(eNoN, qmTET4, _p(w), _p(N), _p(Nxi)) != nG:
+        raise RuntimeError("b200_elem_tables failed")
+    return w, N, Nxi
 
 
 def sub_out_dict(s: SubOut):
@@ -205,6 +257,17 @@ class Backend:
 
     def assemble_fluid(self, props: FluidProps):
         self._ck(self.L.b200_assemble_fluid(self.h, C.byref(props)), "b200_assemble_fluid")
+
+    def disp_set(self, tDof, Dg, Do=None):
+        Dg = _c(Dg, np.float64)
+        Do = None if Do is None else _c(Do, np.float64)
+        self._ck(self.L.b200_disp_set(self.h, tDof, _p(Dg), _p(Do)), "b200_disp_set")
+
+    def assemble_struct(self, props: StructProps):
+        self._ck(self.L.b200_assemble_struct(self.h, C.byref(props)), "b200_assemble_struct")
+
+    def assemble_lelas(self, props: LelasProps):
+        self._ck(self.L.b200_assemble_lelas(self.h, C.byref(props)), "b200_assemble_lelas")
 
     def assemble_elem(self, eqN, lK, lR):
         eqN = _c(eqN, np.int32); lK = _c(lK, np.float64); lR = _c(lR, np.float64)

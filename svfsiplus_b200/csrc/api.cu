@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "assembly.cuh"
+#include "assembly_solid.cuh"
 #include "ops_cuda.cuh"
 
 using namespace svb200;
@@ -49,6 +50,9 @@ struct b200_handle {
   int* d_kseg = nullptr;     // nnz+1             staging run of every Val block
   double* stageR = nullptr;  // dof x eNoN x nEl
   double* stageK = nullptr;  // dof^2 x eNoN^2 x nEl
+  size_t stageR_cap = 0, stageK_cap = 0;
+  double* d_tab = nullptr;   // packed Gauss tables of the mesh's element type (w, N, dN/dxi)
+  ElemTables tab;
   double* d_x = nullptr;
   int* d_err = nullptr;
   double qmTET4 = 0.0;
@@ -60,7 +64,9 @@ struct b200_handle {
   double* d_Ag = nullptr;
   double* d_Yg = nullptr;
   double* d_Bf = nullptr;
-  size_t state_cap = 0;
+  double* d_Dg = nullptr;
+  double* d_Do = nullptr;
+  size_t state_cap = 0, disp_cap = 0;
 
   // staged boundary elements
   struct Staged { int d; std::vector<int> eqN; std::vector<double> lK, lR; };
@@ -73,7 +79,7 @@ struct b200_handle {
     cudaFree(R); cudaFree(Val); cudaFree(stage_d);
     cudaFree(d_ien); cudaFree(d_rslot); cudaFree(d_kslot); cudaFree(d_rseg); cudaFree(d_kseg);
     cudaFree(stageR); cudaFree(stageK); cudaFree(d_x); cudaFree(d_err);
-    cudaFree(d_Ag); cudaFree(d_Yg); cudaFree(d_Bf);
+    cudaFree(d_Ag); cudaFree(d_Yg); cudaFree(d_Bf); cudaFree(d_Dg); cudaFree(d_Do); cudaFree(d_tab);
   }
 };
 
@@ -155,6 +161,129 @@ void build_slots(b200_handle* h, size_t nItems, const int* d_key, size_t nDest, 
   cudaFree(cnt); cudaFree(items); cudaFree(bad);
 }
 
+// Gauss rule and shape functions of the mesh's element type: what nn::select_ele + get_gip + get_gnn leave
+// in lM.w / lM.N / lM.Nx (nn_elem_gip.h:40-66 HEX8, :501-517 TET4; nn_elem_gnn.h:732-786 HEX8, :1232-1250 TET4).
+void fill_tables(ElemTables& t, int eNoN, double qmTET4)
+{
+  std::memset(&t, 0, sizeof(t));
+  t.eNoN = eNoN;
+  if (eNoN == 4) {
+    t.nG = 4;
+    const double s = qmTET4, r = (1.0 - s)/3.0;
+    const double xi[4][3] = {{s, r, r}, {r, s, r}, {r, r, s}, {r, r, r}};
+    for (int g = 0; g < 4; g++) {
+      t.w[g] = 1.0/24.0;
+      t.N[g][0] = xi[g][0]; t.N[g][1] = xi[g][1]; t.N[g][2] = xi[g][2];
+      t.N[g][3] = 1.0 - xi[g][0] - xi[g][1] - xi[g][2];
+      const double d[4][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {-1, -1, -1}};
+      for (int a = 0; a < 4; a++) for (int i = 0; i < 3; i++) t.Nxi[g][a][i] = d[a][i];
+    }
+  } else {
+    t.nG = 8;
+    const double s = 1.0/std::sqrt(3.0), m = -1.0/std::sqrt(3.0);
+    const double xi[8][3] = {{m, m, m}, {s, m, m}, {s, s, m}, {m, s, m}, {m, m, s}, {s, m, s}, {s, s, s}, {m, s, s}};
+    for (int g = 0; g < 8; g++) {
+      t.w[g] = 1.0;
+      const double lx = 1.0 - xi[g][0], ly = 1.0 - xi[g][1], lz = 1.0 - xi[g][2];
+      const double ux = 1.0 + xi[g][0], uy = 1.0 + xi[g][1], uz = 1.0 + xi[g][2];
+      const double N[8] = {lx*ly*lz/8.0, ux*ly*lz/8.0, ux*uy*lz/8.0, lx*uy*lz/8.0, lx*ly*uz/8.0, ux*ly*uz/8.0, ux*uy*uz/8.0, lx*uy*uz/8.0};
+      const double D[8][3] = {{-ly*lz/8.0, -lx*lz/8.0, -lx*ly/8.0}, { ly*lz/8.0, -ux*lz/8.0, -ux*ly/8.0},
+                              { uy*lz/8.0,  ux*lz/8.0, -ux*uy/8.0}, {-uy*lz/8.0,  lx*lz/8.0, -lx*uy/8.0},
+                              {-ly*uz/8.0, -lx*uz/8.0,  lx*ly/8.0}, { ly*uz/8.0, -ux*uz/8.0,  ux*ly/8.0},
+                              { uy*uz/8.0,  ux*uz/8.0,  ux*uy/8.0}, {-uy*uz/8.0,  lx*uz/8.0,  lx*uy/8.0}};
+      for (int a = 0; a < 8; a++) { t.N[g][a] = N[a]; for (int i = 0; i < 3; i++) t.Nxi[g][a][i] = D[a][i]; }
+    }
+  }
+}
+
+void build_tables(b200_handle* h)
+{
+  ElemTables& t = h->tab;
+  fill_tables(t, h->eNoN, h->qmTET4);
+  // packed device copy: w[nG], N[nG][eNoN], Nxi[nG][eNoN][3]
+  std::vector<double> pk;
+  for (int g = 0; g < t.nG; g++) pk.push_back(t.w[g]);
+  for (int g = 0; g < t.nG; g++) for (int a = 0; a < t.eNoN; a++) pk.push_back(t.N[g][a]);
+  for (int g = 0; g < t.nG; g++) for (int a = 0; a < t.eNoN; a++) for (int i = 0; i < 3; i++) pk.push_back(t.Nxi[g][a][i]);
+  cudaFree(h->d_tab);
+  h->d_tab = upload(pk.data(), pk.size(), h->ops->st);
+  CU_CHECK(cudaStreamSynchronize(h->ops->st));
+}
+
+// staging buffers of the ordered scatter: dof x eNoN x nEl rows and dof^2 x eNoN^2 x nEl blocks
+void ensure_stage(b200_handle* h, int dof)
+{
+  ensure(h->stageR, h->stageR_cap, size_t(dof)*h->eNoN*size_t(h->nEl) + 4);
+  ensure(h->stageK, h->stageK_cap, size_t(dof)*dof*h->eNoN*h->eNoN*size_t(h->nEl) + 4);
+}
+
+// shared tail of the whole-mesh assemblies: ordered run sums into R / Val, error flag, phase time
+void finish_assembly(b200_handle* h, int dof, double t0, const char* who)
+{
+  auto& ops = *h->ops;
+  const int bs = dof*dof;
+  if (dof == 4) {
+    const size_t tR = size_t(h->nNo), tK = size_t(h->nnz)*4;
+    if (h->R_is_zero) k_sum_segments<1, true><<<unsigned((tR + 255)/256), 256, 0, ops.st>>>(size_t(h->nNo), h->d_rseg, h->stageR, h->R);
+    else k_sum_segments<1, false><<<unsigned((tR + 255)/256), 256, 0, ops.st>>>(size_t(h->nNo), h->d_rseg, h->stageR, h->R);
+    ops.post();
+    if (h->Val_is_zero) k_sum_segments<4, true><<<unsigned((tK + 255)/256), 256, 0, ops.st>>>(size_t(h->nnz), h->d_kseg, h->stageK, h->Val);
+    else k_sum_segments<4, false><<<unsigned((tK + 255)/256), 256, 0, ops.st>>>(size_t(h->nnz), h->d_kseg, h->stageK, h->Val);
+    ops.post();
+  } else {
+    const size_t tR = size_t(h->nNo)*dof, tK = size_t(h->nnz)*bs;
+    if (h->R_is_zero) k_sum_run<true><<<unsigned((tR + 255)/256), 256, 0, ops.st>>>(size_t(h->nNo), dof, h->d_rseg, h->stageR, h->R);
+    else k_sum_run<false><<<unsigned((tR + 255)/256), 256, 0, ops.st>>>(size_t(h->nNo), dof, h->d_rseg, h->stageR, h->R);
+    ops.post();
+    if (h->Val_is_zero) k_sum_run<true><<<unsigned((tK + 255)/256), 256, 0, ops.st>>>(size_t(h->nnz), bs, h->d_kseg, h->stageK, h->Val);
+    else k_sum_run<false><<<unsigned((tK + 255)/256), 256, 0, ops.st>>>(size_t(h->nnz), bs, h->d_kseg, h->stageK, h->Val);
+    ops.post();
+  }
+  h->R_is_zero = h->Val_is_zero = false;
+  int flag = 0;
+  CU_CHECK(cudaMemcpyAsync(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, ops.st));
+  CU_CHECK(cudaStreamSynchronize(ops.st));
+  ops.phase_ms[0] = (wall_s() - t0)*1e3;
+  if (flag != 0) {
+    CU_CHECK(cudaMemset(h->d_err, 0, sizeof(int)));
+    throw std::runtime_error(std::string("[") + who + "] Jacobian for element " + std::to_string(flag - 1) + " is < 0.");
+  }
+}
+
+template <int ENON, int NG, int EPB, int APT>
+void launch_solid(b200_handle* h, const SolidConsts& c)
+{
+  auto& ops = *h->ops;
+  constexpr int TABN = NG + NG*ENON + NG*ENON*3;
+  const size_t smem = sizeof(double)*(size_t((TABN + 3) & ~3) + size_t(EPB)*NG*solid_rec(ENON));
+  auto kern = k_assemble_solid<ENON, NG, EPB, APT>;
+  CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  kern<<<(h->nEl + EPB - 1)/EPB, EPB*NG, smem, ops.st>>>(h->nEl, c, h->d_tab, h->d_ien, h->d_rslot, h->d_kslot, h->d_x,
+                                                         h->d_Ag, h->d_Yg, h->d_Dg, h->d_Do, h->d_Bf, h->stageR, h->stageK, h->d_err);
+  CU_CHECK(cudaGetLastError());
+  ops.post();
+}
+
+void assemble_solid(b200_handle* h, const SolidConsts& c, const char* who)
+{
+  auto& ops = *h->ops;
+  if (h->nEl == 0) throw std::runtime_error(std::string(who) + ": no mesh (b200_mesh_set)");
+  if (!h->d_Ag || !h->d_Dg) throw std::runtime_error(std::string(who) + ": no state (b200_state_set + b200_disp_set)");
+  if (c.kind == 2 && !h->d_Do) throw std::runtime_error(std::string(who) + ": the mesh equation needs Do (b200_disp_set)");
+  if (h->dof != 3 || !h->Val) throw std::runtime_error(std::string(who) + ": call b200_zero(h, 3) first");
+  if (c.tDof != h->tDof) throw std::runtime_error(std::string(who) + ": tDof differs from the uploaded state");
+  if (c.s < 0 || c.s + 3 > c.tDof) throw std::runtime_error(std::string(who) + ": equation offset outside the state");
+  ensure_stage(h, 3);
+  const double t0 = wall_s();
+  {
+    // algorithmic bytes: Val and R written once, nodal fields and IEN read once
+    CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*72.0 + double(h->nNo)*(24.0 + 24.0 + 24.0*3 + 24.0) + double(h->nEl)*4.0*h->eNoN, 3);
+    if (h->eNoN == 4) launch_solid<4, 4, 32, 1>(h, c);
+    else launch_solid<8, 8, 16, 2>(h, c);
+  }
+  finish_assembly(h, 3, t0, who);
+}
+
 // flush LinearAlgebra::assemble contributions staged on the host (one deterministic scatter kernel)
 void flush_staged(b200_handle* h)
 {
@@ -206,6 +335,21 @@ void flush_staged(b200_handle* h)
 } // namespace
 
 extern "C" {
+
+int b200_elem_tables(int eNoN, double qmTET4, double* w, double* N, double* Nxi)
+{
+  if (eNoN != 4 && eNoN != 8) return -1;
+  ElemTables t;
+  fill_tables(t, eNoN, qmTET4 > 0.0 ? qmTET4 : (5.0 + 3.0*std::sqrt(5.0))/20.0);
+  for (int g = 0; g < t.nG; g++) {
+    if (w) w[g] = t.w[g];
+    for (int a = 0; a < eNoN; a++) {
+      if (N) N[g*eNoN + a] = t.N[g][a];
+      if (Nxi) for (int i = 0; i < 3; i++) Nxi[(g*eNoN + a)*3 + i] = t.Nxi[g][a][i];
+    }
+  }
+  return t.nG;
+}
 
 int b200_device_count(void)
 {
@@ -378,10 +522,11 @@ int b200_mesh_set(b200_handle* h, int eNoN, int nEl, const int* IEN, const doubl
 {
   return guarded(h, [&] {
     auto& ops = *h->ops;
-    if (eNoN != 4) throw std::runtime_error("mesh_set: only TET4 (eNoN = 4) is built in this round");
+    if (eNoN != 4 && eNoN != 8) throw std::runtime_error("mesh_set: element type not supported (TET4 and HEX8 are)");
     if (h->nNo == 0) throw std::runtime_error("mesh_set: call b200_lhs_create first");
     h->eNoN = eNoN; h->nEl = nEl;
     h->qmTET4 = qmTET4 > 0.0 ? qmTET4 : (5.0 + 3.0*std::sqrt(5.0))/20.0;
+    build_tables(h);
 
     const int nNo = h->nNo;
     for (size_t i = 0; i < size_t(nEl)*eNoN; i++)
@@ -391,6 +536,7 @@ int b200_mesh_set(b200_handle* h, int eNoN, int nEl, const int* IEN, const doubl
     cudaFree(h->d_ien); cudaFree(h->d_rslot); cudaFree(h->d_kslot); cudaFree(h->d_rseg); cudaFree(h->d_kseg);
     cudaFree(h->stageR); cudaFree(h->stageK); cudaFree(h->d_x);
     h->d_ien = h->d_rslot = h->d_kslot = h->d_rseg = h->d_kseg = nullptr; h->stageR = h->stageK = nullptr; h->d_x = nullptr;
+    h->stageR_cap = h->stageK_cap = 0;
     h->d_ien = upload(IEN, size_t(nEl)*eNoN, ops.st);
     h->d_x = upload(x, size_t(nNo)*3, ops.st);
     // destination of every element row / block in the solver layout (the reference's per-entry binary
@@ -406,8 +552,6 @@ int b200_mesh_set(b200_handle* h, int eNoN, int nEl, const int* IEN, const doubl
       build_slots(h, size_t(nEl)*eNoN*eNoN, edest, size_t(h->nnz), &h->d_kslot, &h->d_kseg);
     } catch (...) { cudaFree(rdest); cudaFree(edest); throw; }
     cudaFree(rdest); cudaFree(edest);
-    CU_CHECK(cudaMalloc(&h->stageR, sizeof(double)*4*size_t(nEl)*eNoN));
-    CU_CHECK(cudaMalloc(&h->stageK, sizeof(double)*16*size_t(nEl)*eNoN*eNoN));
     CU_CHECK(cudaStreamSynchronize(ops.st));
   });
 }
@@ -465,6 +609,8 @@ int b200_assemble_fluid(b200_handle* h, const b200_fluid_props* p)
       c.N[g][0] = xi[g][0]; c.N[g][1] = xi[g][1]; c.N[g][2] = xi[g][2];
       c.N[g][3] = 1.0 - xi[g][0] - xi[g][1] - xi[g][2];
     }
+    if (h->eNoN != 4) throw std::runtime_error("assemble_fluid: the fluid kernel is built for TET4 meshes");
+    ensure_stage(h, 4);
     double t0 = wall_s();
     {
       // algorithmic bytes (SURVEY.md par. 8d): Val and R written once, nodal fields and IEN read once
@@ -472,23 +618,57 @@ int b200_assemble_fluid(b200_handle* h, const b200_fluid_props* p)
       k_assemble_fluid_tet4<<<(h->nEl + 127)/128, 128, 0, ops.st>>>(h->nEl, c, h->d_ien, h->d_rslot, h->d_kslot, h->d_x,
                                                                   h->d_Ag, h->d_Yg, h->d_Bf, h->stageR, h->stageK, h->d_err);
       ops.post();
-      const size_t tR = size_t(h->nNo), tK = size_t(h->nnz)*4;
-      if (h->R_is_zero) k_sum_segments<1, true><<<unsigned((tR + 255)/256), 256, 0, ops.st>>>(size_t(h->nNo), h->d_rseg, h->stageR, h->R);
-      else k_sum_segments<1, false><<<unsigned((tR + 255)/256), 256, 0, ops.st>>>(size_t(h->nNo), h->d_rseg, h->stageR, h->R);
-      ops.post();
-      if (h->Val_is_zero) k_sum_segments<4, true><<<unsigned((tK + 255)/256), 256, 0, ops.st>>>(size_t(h->nnz), h->d_kseg, h->stageK, h->Val);
-      else k_sum_segments<4, false><<<unsigned((tK + 255)/256), 256, 0, ops.st>>>(size_t(h->nnz), h->d_kseg, h->stageK, h->Val);
-      ops.post();
-      h->R_is_zero = h->Val_is_zero = false;
     }
-    int flag = 0;
-    CU_CHECK(cudaMemcpyAsync(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, ops.st));
-    CU_CHECK(cudaStreamSynchronize(ops.st));
-    ops.phase_ms[0] = (wall_s() - t0)*1e3;
-    if (flag != 0) {
-      CU_CHECK(cudaMemset(h->d_err, 0, sizeof(int)));
-      throw std::runtime_error("[construct_fluid] Jacobian for element " + std::to_string(flag - 1) + " is < 0.");
+    finish_assembly(h, 4, t0, "construct_fluid");
+  });
+}
+
+int b200_disp_set(b200_handle* h, int tDof, const double* Dg, const double* Do)
+{
+  return guarded(h, [&] {
+    auto st = h->ops->st;
+    const size_t n = size_t(h->nNo);
+    if (!Dg) throw std::runtime_error("disp_set: Dg is required");
+    if (h->disp_cap < n*tDof) {
+      cudaFree(h->d_Dg); cudaFree(h->d_Do);
+      h->d_Dg = h->d_Do = nullptr;
+      CU_CHECK(cudaMalloc(&h->d_Dg, sizeof(double)*n*tDof));
+      h->disp_cap = n*tDof;
     }
+    CU_CHECK(cudaMemcpyAsync(h->d_Dg, Dg, sizeof(double)*n*tDof, cudaMemcpyHostToDevice, st));
+    if (Do) {
+      if (!h->d_Do) CU_CHECK(cudaMalloc(&h->d_Do, sizeof(double)*h->disp_cap));
+      CU_CHECK(cudaMemcpyAsync(h->d_Do, Do, sizeof(double)*n*tDof, cudaMemcpyHostToDevice, st));
+    }
+    CU_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+int b200_assemble_struct(b200_handle* h, const b200_struct_props* p)
+{
+  return guarded(h, [&] {
+    if (p->isoType < 0 || p->isoType > 2) throw std::runtime_error("assemble_struct: constitutive model has no device kernel");
+    if (p->volType < 0 || p->volType > 3) throw std::runtime_error("assemble_struct: dilational penalty model not defined");
+    SolidConsts c;
+    std::memset(&c, 0, sizeof(c));
+    c.dt = p->dt; c.am = p->am; c.af = p->af; c.gam = p->gam; c.beta = p->beta;
+    c.rho = p->rho; c.dmp = p->dmp; c.f[0] = p->f[0]; c.f[1] = p->f[1]; c.f[2] = p->f[2];
+    c.iso = p->isoType; c.vol = p->volType; c.C10 = p->C10; c.C01 = p->C01; c.Kpen = p->Kpen;
+    c.tDof = p->tDof; c.s = p->s; c.kind = 0;
+    assemble_solid(h, c, "construct_dsolid");
+  });
+}
+
+int b200_assemble_lelas(b200_handle* h, const b200_lelas_props* p)
+{
+  return guarded(h, [&] {
+    SolidConsts c;
+    std::memset(&c, 0, sizeof(c));
+    c.dt = p->dt; c.am = p->am; c.af = p->af; c.beta = p->beta;
+    c.rho = p->rho; c.f[0] = p->f[0]; c.f[1] = p->f[1]; c.f[2] = p->f[2];
+    c.elM = p->elM; c.nu = p->nu;
+    c.tDof = p->tDof; c.s = p->s; c.kind = p->mesh_mode ? 2 : 1;
+    assemble_solid(h, c, p->mesh_mode ? "construct_mesh" : "construct_l_elas");
   });
 }
 

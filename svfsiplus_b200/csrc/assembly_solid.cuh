@@ -1,0 +1,453 @@
+// assembly_solid.cuh — K11: whole-mesh assembly of the displacement-based solid equations
+//   struct   construct_dsolid + struct_3d_carray + get_pk2cc<3> + gnn + do_assem
+//            (Code/Source/solver/sv_struct.cpp:213-362, 552-846; mat_models_carray.h:182-1359;
+//             mat_models.cpp:1626-1645; nn.cpp:455-541; lhsa.cpp:97-142)
+//   lElas    construct_l_elas + l_elas_3d                     (l_elas.cpp:58-170, 274-390)
+//   mesh     construct_mesh (ALE mesh motion: l_elas_3d on the step-start configuration, weights
+//            WITHOUT the Jacobian)                            (mesh.cpp:42-160)
+// for TET4 (4 Gauss points, constant gradients) and HEX8 (8 Gauss points, gnn per point), dof = 3.
+//
+// Design: a CTA owns EPB consecutive elements and works in three phases on shared memory.
+//   phase 1  one thread per (element, Gauss point): gather, Jacobian, shape gradients (gnn), F, the
+//            constitutive law (S, 6x6 Voigt Dm), P = F S, inertia/body-force vector; the per-point
+//            record (<= 73 doubles) goes to shared memory.
+//   phase R  one thread per (element, a): residual rows, Gauss points summed in the reference's order.
+//   phase 2  the eNoN x eNoN tangent blocks: a warp covers whole elements (HEX8: 32 lanes = 8 b x 4
+//            pairs of a; TET4: 16 lanes per element), so F, S, Dm of a Gauss point are shared-memory
+//            broadcasts; each lane forms Dm*Bm_b once per Gauss point and reuses it for its a's.
+// The Gauss tables (w, N, dN/dxi) are staged in shared memory at kernel start.
+// Scatter: the same destination-sorted staging as the fluid kernel (assembly.cuh): blocks / rows are
+// written to precomputed slots and k_sum_run adds each destination's run in element order, i.e. in
+// do_assem's order.  No atomics, bitwise reproducible.
+#pragma once
+
+#include "assembly.cuh"
+
+namespace svb200 {
+
+struct ElemTables {            // lM.w, lM.N, lM.Nx of the reference (nn_elem_gip.h, nn_elem_gnn.h)
+  int eNoN, nG;
+  double w[8];
+  double N[8][8];              // [g][a]
+  double Nxi[8][8][3];         // [g][a][i]
+};
+
+struct SolidConsts {
+  double dt, am, af, gam, beta;
+  double rho, dmp, f[3];
+  int iso, vol;                // iso: 0 nHook, 1 StVK, 2 mStVK; vol: 0 none, 1 Quad, 2 ST91, 3 M94
+  double C10, C01, Kpen;
+  double elM, nu;              // lElas / mesh
+  int tDof, s;                 // row offset of this equation's unknowns in Ag/Yg/Dg (eq.s)
+  int kind;                    // 0 struct, 1 lElas, 2 mesh
+};
+
+enum { SREC_W = 0, SREC_F = 1, SREC_S = 10, SREC_DM = 16, SREC_UD = 37, SREC_P = 40, SREC_NX = 49 };
+__host__ __device__ constexpr int solid_rec(int eNoN) { return SREC_NX + 3*eNoN; }
+
+// index of (I,J), I <= J, in the packed upper triangle of the 6x6 Voigt matrix
+__device__ __forceinline__ int dm_idx(int I, int J) { return I*6 - (I*(I-1))/2 + (J - I); }
+
+// get_pk2cc<3> for the isotropic laws without fibres / active stress, + get_svol_p.
+// Outputs S (sym: 00 11 22 01 12 20) and the upper triangle of Dm (Voigt order 00 11 22 01 12 20).
+__device__ void pk2cc_iso(const SolidConsts& c, const double F[3][3], double* __restrict__ S6, double* __restrict__ Dm21)
+{
+  // mat_det<3> (mat_fun_carray.h:92-122): cofactor expansion along the first row
+  const double J = ((0.0 + 1.0*F[0][0]*(F[1][1]*F[2][2] - F[1][2]*F[2][1]))
+                    + (-1.0)*F[0][1]*(F[1][0]*F[2][2] - F[1][2]*F[2][0]))
+                    + 1.0*F[0][2]*(F[1][0]*F[2][1] - F[1][1]*F[2][0]);
+  const double nd = 3.0;
+  const double J2d = pow(J, -2.0/nd);
+  double C[3][3], Ci[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) C[i][j] = (0.0 + F[0][i]*F[0][j]) + F[1][i]*F[1][j] + F[2][i]*F[2][j];
+  {
+    const double d = ((0.0 + C[0][0]*(C[1][1]*C[2][2] - C[1][2]*C[2][1]))
+                      - C[0][1]*(C[1][0]*C[2][2] - C[1][2]*C[2][0]))
+                      + C[0][2]*(C[1][0]*C[2][1] - C[1][1]*C[2][0]);
+    Ci[0][0] = (C[1][1]*C[2][2] - C[1][2]*C[2][1]) / d;
+    Ci[0][1] = (C[0][2]*C[2][1] - C[0][1]*C[2][2]) / d;
+    Ci[0][2] = (C[0][1]*C[1][2] - C[0][2]*C[1][1]) / d;
+    Ci[1][0] = (C[1][2]*C[2][0] - C[1][0]*C[2][2]) / d;
+    Ci[1][1] = (C[0][0]*C[2][2] - C[0][2]*C[2][0]) / d;
+    Ci[1][2] = (C[0][2]*C[1][0] - C[0][0]*C[1][2]) / d;
+    Ci[2][0] = (C[1][0]*C[2][1] - C[1][1]*C[2][0]) / d;
+    Ci[2][1] = (C[0][1]*C[2][0] - C[0][0]*C[2][1]) / d;
+    Ci[2][2] = (C[0][0]*C[1][1] - C[0][1]*C[1][0]) / d;
+  }
+  const double trC = C[0][0] + C[1][1] + C[2][2];
+  const double Inv1 = J2d*trC;
+  double p = 0.0, pl = 0.0;
+  if (!is_zero_d(c.Kpen)) {                     // get_svol_p (mat_models.cpp:1626-1645)
+    if (c.vol == 1)      { p = c.Kpen*(J - 1.0);        pl = c.Kpen*(2.0*J - 1.0); }
+    else if (c.vol == 2) { p = 0.5*c.Kpen*(J - 1.0/J);  pl = c.Kpen*J; }
+    else if (c.vol == 3) { p = c.Kpen*(1.0 - 1.0/J);    pl = c.Kpen; }
+  }
+  const int vi[6] = {0, 1, 2, 0, 1, 2}, vj[6] = {0, 1, 2, 1, 2, 0};
+  double S[3][3];
+  if (c.iso == 0) {
+    // neo-Hookean (mat_models_carray.h:370-434)
+    const double g1 = 2.0*c.C10;
+    const double r1 = g1*Inv1/nd;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) S[i][j] = J2d*((i == j) ? g1 : 0.0) - r1*Ci[i][j];
+    const double c2 = 2.0*(r1 - p*J), c3 = pl*J - 2.0*r1/nd;
+#pragma unroll
+    for (int I = 0; I < 6; I++)
+#pragma unroll
+      for (int Jv = I; Jv < 6; Jv++) {
+        const int i = vi[I], j = vj[I], k = vi[Jv], l = vj[Jv];
+        double cc = (-2.0/nd)*(Ci[i][j]*S[k][l] + S[i][j]*Ci[k][l]);
+        cc += c2*(0.5*(Ci[i][k]*Ci[j][l] + Ci[i][l]*Ci[j][k])) + c3*(Ci[i][j]*Ci[k][l]);
+        Dm21[dm_idx(I, Jv)] = cc;
+      }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) S[i][j] += p*J*Ci[i][j];
+  } else if (c.iso == 1) {
+    // St. Venant-Kirchhoff (:302-322): C10 = lambda, C01 = mu
+    const double g1 = c.C10, g2 = c.C01*2.0;
+    double E[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) E[i][j] = 0.5*(C[i][j] - ((i == j) ? 1.0 : 0.0));
+    const double trE = E[0][0] + E[1][1] + E[2][2];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) S[i][j] = g1*trE*((i == j) ? 1.0 : 0.0) + g2*E[i][j];
+#pragma unroll
+    for (int I = 0; I < 6; I++)
+#pragma unroll
+      for (int Jv = I; Jv < 6; Jv++) {
+        const int i = vi[I], j = vj[I], k = vi[Jv], l = vj[Jv];
+        const double idp = ((i == j) && (k == l)) ? 1.0 : 0.0;
+        const double ids = (((i == k) && (j == l)) ? 0.5 : 0.0) + (((i == l) && (j == k)) ? 0.5 : 0.0);
+        Dm21[dm_idx(I, Jv)] = g1*idp + g2*ids;
+      }
+  } else {
+    // modified St. Venant-Kirchhoff (:326-356): C10 = kappa, C01 = mu
+    const double g1 = c.C10, g2 = c.C01;
+    const double lJ = log(J);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) S[i][j] = g1*lJ*Ci[i][j] + g2*(C[i][j] - ((i == j) ? 1.0 : 0.0));
+#pragma unroll
+    for (int I = 0; I < 6; I++)
+#pragma unroll
+      for (int Jv = I; Jv < 6; Jv++) {
+        const int i = vi[I], j = vj[I], k = vi[Jv], l = vj[Jv];
+        const double ids = (((i == k) && (j == l)) ? 0.5 : 0.0) + (((i == l) && (j == k)) ? 0.5 : 0.0);
+        const double sym = 0.5*(Ci[i][k]*Ci[j][l] + Ci[i][l]*Ci[j][k]);
+        Dm21[dm_idx(I, Jv)] = g1*(-2.0*lJ*sym + Ci[i][j]*Ci[k][l]) + 2.0*g2*ids;
+      }
+  }
+  S6[0] = S[0][0]; S6[1] = S[1][1]; S6[2] = S[2][2]; S6[3] = S[0][1]; S6[4] = S[1][2]; S6[5] = S[2][0];
+}
+
+// ENON nodes, NG Gauss points, EPB elements per CTA, APT a-indices per lane in phase 2.
+// blockDim.x = EPB*NG.  Dynamic shared memory: tables + EPB*NG records.
+template <int ENON, int NG, int EPB, int APT>
+__global__ void __launch_bounds__(EPB*NG)
+k_assemble_solid(int nEl, SolidConsts c, const double* __restrict__ tab,      // packed: w[NG], N[NG][ENON], Nxi[NG][ENON][3]
+                 const int* __restrict__ ien, const int* __restrict__ rslot, const int* __restrict__ kslot,
+                 const double* __restrict__ x, const double* __restrict__ Ag, const double* __restrict__ Yg,
+                 const double* __restrict__ Dg, const double* __restrict__ Do, const double* __restrict__ Bf,
+                 double* __restrict__ stageR, double* __restrict__ stageK, int* __restrict__ err_flag)
+{
+  constexpr int REC = solid_rec(ENON);
+  constexpr int NT = EPB*NG;
+  constexpr int TABN = NG + NG*ENON + NG*ENON*3;
+  extern __shared__ double sm[];
+  double* s_w = sm;
+  double* s_N = sm + NG;                 // [g][a]
+  double* s_Nxi = s_N + NG*ENON;         // [g][a][3]
+  double* s_rec = sm + ((TABN + 3) & ~3);
+  for (int i = threadIdx.x; i < TABN; i += NT) sm[i] = tab[i];
+  __syncthreads();
+
+  const int e0 = blockIdx.x*EPB;
+  const int tD = c.tDof, s0 = c.s;
+
+  // ---------------- phase 1: one thread per (element, Gauss point) --------------------------------
+  {
+    const int el = threadIdx.x / NG, g = threadIdx.x % NG;
+    const int e = e0 + el;
+    double* rec = s_rec + size_t(threadIdx.x)*REC;
+    if (e < nEl) {
+      int nd[ENON];
+#pragma unroll
+      for (int a = 0; a < ENON; a++) nd[a] = ien[size_t(e)*ENON + a];
+      // nn::gnn (nn.cpp:505-540).  For lShpF elements (TET4) the reference evaluates it at g = 0 only;
+      // the gradients are constant, so evaluating it per point gives the same numbers.
+      double xXi[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+      for (int a = 0; a < ENON; a++) {
+        double xa[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          xa[i] = x[size_t(nd[a])*3 + i];
+          if (c.kind == 2) xa[i] = xa[i] + Do[size_t(nd[a])*tD + s0 + i];     // mesh.cpp:117-122
+        }
+        const double* nxi = s_Nxi + (g*ENON + a)*3;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          xXi[i][0] = xXi[i][0] + xa[i]*nxi[0];
+          xXi[i][1] = xXi[i][1] + xa[i]*nxi[1];
+          xXi[i][2] = xXi[i][2] + xa[i]*nxi[2];
+        }
+      }
+      const double Jac = xXi[0][0]*xXi[1][1]*xXi[2][2] + xXi[0][1]*xXi[1][2]*xXi[2][0] + xXi[0][2]*xXi[1][0]*xXi[2][1]
+                       - xXi[0][0]*xXi[1][2]*xXi[2][1] - xXi[0][1]*xXi[1][0]*xXi[2][2] - xXi[0][2]*xXi[1][1]*xXi[2][0];
+      if (is_zero_d(Jac)) atomicExch(err_flag, e + 1);
+      double xiX[3][3];
+      xiX[0][0] = (xXi[1][1]*xXi[2][2] - xXi[1][2]*xXi[2][1])/Jac;
+      xiX[0][1] = (xXi[2][1]*xXi[0][2] - xXi[2][2]*xXi[0][1])/Jac;
+      xiX[0][2] = (xXi[0][1]*xXi[1][2] - xXi[0][2]*xXi[1][1])/Jac;
+      xiX[1][0] = (xXi[1][2]*xXi[2][0] - xXi[1][0]*xXi[2][2])/Jac;
+      xiX[1][1] = (xXi[2][2]*xXi[0][0] - xXi[2][0]*xXi[0][2])/Jac;
+      xiX[1][2] = (xXi[0][2]*xXi[1][0] - xXi[0][0]*xXi[1][2])/Jac;
+      xiX[2][0] = (xXi[1][0]*xXi[2][1] - xXi[1][1]*xXi[2][0])/Jac;
+      xiX[2][1] = (xXi[2][0]*xXi[0][1] - xXi[2][1]*xXi[0][0])/Jac;
+      xiX[2][2] = (xXi[0][0]*xXi[1][1] - xXi[0][1]*xXi[1][0])/Jac;
+
+      // struct / lElas integrate with w*Jac, the mesh equation with w alone (mesh.cpp:141)
+      rec[SREC_W] = (c.kind == 2) ? s_w[g] : s_w[g]*Jac;
+
+      double F[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+      double ed[6] = {0, 0, 0, 0, 0, 0};
+      double ud[3];
+      if (c.kind == 0) { ud[0] = -c.rho*c.f[0]; ud[1] = -c.rho*c.f[1]; ud[2] = -c.rho*c.f[2]; }
+      else { ud[0] = -c.f[0]; ud[1] = -c.f[1]; ud[2] = -c.f[2]; }
+#pragma unroll
+      for (int a = 0; a < ENON; a++) {
+        const double* nxi = s_Nxi + (g*ENON + a)*3;
+        double nx[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          nx[i] = ((0.0 + nxi[0]*xiX[0][i]) + nxi[1]*xiX[1][i]) + nxi[2]*xiX[2][i];
+          rec[SREC_NX + a*3 + i] = nx[i];
+        }
+        const double Na = s_N[g*ENON + a];
+        const size_t A = size_t(nd[a]);
+        double al[3], dl[3], yl[3], bl[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          al[i] = Ag[A*tD + s0 + i];
+          dl[i] = Dg[A*tD + s0 + i];
+          if (c.kind == 2) { dl[i] = dl[i] - Do[A*tD + s0 + i]; bl[i] = 0.0; yl[i] = 0.0; }
+          else { bl[i] = Bf[A*3 + i]; yl[i] = (c.kind == 0) ? Yg[A*tD + s0 + i] : 0.0; }
+        }
+        if (c.kind == 0) {
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            ud[i] += Na*(c.rho*(al[i] - bl[i]) + c.dmp*yl[i]);
+            F[i][0] += nx[0]*dl[i];
+            F[i][1] += nx[1]*dl[i];
+            F[i][2] += nx[2]*dl[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 3; i++) ud[i] = ud[i] + Na*(al[i] - bl[i]);
+          ed[0] = ed[0] + nx[0]*dl[0];
+          ed[1] = ed[1] + nx[1]*dl[1];
+          ed[2] = ed[2] + nx[2]*dl[2];
+          ed[3] = ed[3] + nx[1]*dl[0] + nx[0]*dl[1];
+          ed[4] = ed[4] + nx[2]*dl[1] + nx[1]*dl[2];
+          ed[5] = ed[5] + nx[0]*dl[2] + nx[2]*dl[0];
+        }
+      }
+      rec[SREC_UD] = ud[0]; rec[SREC_UD + 1] = ud[1]; rec[SREC_UD + 2] = ud[2];
+      if (c.kind == 0) {
+        double S6[6];
+        pk2cc_iso(c, F, S6, rec + SREC_DM);
+#pragma unroll
+        for (int i = 0; i < 6; i++) rec[SREC_S + i] = S6[i];
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 3; j++) rec[SREC_F + i*3 + j] = F[i][j];
+        // P = F S (mat_mul<3>)
+        const double S[3][3] = {{S6[0], S6[3], S6[5]}, {S6[3], S6[1], S6[4]}, {S6[5], S6[4], S6[2]}};
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 3; j++) rec[SREC_P + i*3 + j] = ((0.0 + F[i][0]*S[0][j]) + F[i][1]*S[1][j]) + F[i][2]*S[2][j];
+      } else {
+        // l_elas_3d (l_elas.cpp:300-360)
+        const double lambda = c.elM*c.nu / (1.0 + c.nu) / (1.0 - 2.0*c.nu);
+        const double mu = c.elM*0.5 / (1.0 + c.nu);
+        const double divD = lambda*(ed[0] + ed[1] + ed[2]);
+        rec[SREC_S + 0] = divD + 2.0*mu*ed[0];
+        rec[SREC_S + 1] = divD + 2.0*mu*ed[1];
+        rec[SREC_S + 2] = divD + 2.0*mu*ed[2];
+        rec[SREC_S + 3] = mu*ed[3];
+        rec[SREC_S + 4] = mu*ed[4];
+        rec[SREC_S + 5] = mu*ed[5];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase R: residual rows, one thread per (element, a) ------------------------------
+  for (int item = threadIdx.x; item < EPB*ENON; item += NT) {
+    const int el = item / ENON, a = item % ENON;
+    const int e = e0 + el;
+    if (e >= nEl) continue;
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+    for (int g = 0; g < NG; g++) {
+      const double* rec = s_rec + size_t(el*NG + g)*REC;
+      const double w = rec[SREC_W];
+      const double Na = s_N[g*ENON + a];
+      const double n0 = rec[SREC_NX + a*3], n1 = rec[SREC_NX + a*3 + 1], n2 = rec[SREC_NX + a*3 + 2];
+      if (c.kind == 0) {
+        const double* P = rec + SREC_P;
+        r0 = r0 + w*(Na*rec[SREC_UD]     + n0*P[0] + n1*P[1] + n2*P[2]);
+        r1 = r1 + w*(Na*rec[SREC_UD + 1] + n0*P[3] + n1*P[4] + n2*P[5]);
+        r2 = r2 + w*(Na*rec[SREC_UD + 2] + n0*P[6] + n1*P[7] + n2*P[8]);
+      } else {
+        const double* S = rec + SREC_S;
+        r0 = r0 + w*(c.rho*Na*rec[SREC_UD]     + n0*S[0] + n1*S[3] + n2*S[5]);
+        r1 = r1 + w*(c.rho*Na*rec[SREC_UD + 1] + n0*S[3] + n1*S[1] + n2*S[4]);
+        r2 = r2 + w*(c.rho*Na*rec[SREC_UD + 2] + n0*S[5] + n1*S[4] + n2*S[2]);
+      }
+    }
+    double* out = stageR + size_t(rslot[size_t(e)*ENON + a])*3;
+    out[0] = r0; out[1] = r1; out[2] = r2;
+  }
+
+  // ---------------- phase 2: tangent blocks ------------------------------------------------------------
+  constexpr int AGN = ENON/APT;            // a-groups per b
+  constexpr int IPE = ENON*AGN;            // lanes per element
+  const double afu = c.af*c.beta*c.dt*c.dt;
+  for (int item = threadIdx.x; item < EPB*IPE; item += NT) {
+    const int el = item / IPE, r = item % IPE;
+    const int b = r % ENON, a0 = (r / ENON)*APT;
+    const int e = e0 + el;
+    if (e >= nEl) continue;
+    double acc[APT][9];
+#pragma unroll
+    for (int q = 0; q < APT; q++)
+#pragma unroll
+      for (int i = 0; i < 9; i++) acc[q][i] = 0.0;
+
+    if (c.kind == 0) {
+      const double amd = c.am*c.rho + c.af*c.gam*c.dt*c.dmp;
+      for (int g = 0; g < NG; g++) {
+        const double* rec = s_rec + size_t(el*NG + g)*REC;
+        const double w = rec[SREC_W];
+        const double* F = rec + SREC_F;
+        const double* S = rec + SREC_S;
+        const double* Dm = rec + SREC_DM;
+        const double nb0 = rec[SREC_NX + b*3], nb1 = rec[SREC_NX + b*3 + 1], nb2 = rec[SREC_NX + b*3 + 2];
+        const double Nb = s_N[g*ENON + b];
+        // Bm(:,:,b) (sv_struct.cpp:716-742) and DBm = Dm Bm_b (mat_mul6x3)
+        double Bb[6][3], DB[6][3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+          Bb[0][j] = nb0*F[j*3 + 0];
+          Bb[1][j] = nb1*F[j*3 + 1];
+          Bb[2][j] = nb2*F[j*3 + 2];
+          Bb[3][j] = nb0*F[j*3 + 1] + F[j*3 + 0]*nb1;
+          Bb[4][j] = nb1*F[j*3 + 2] + F[j*3 + 1]*nb2;
+          Bb[5][j] = nb2*F[j*3 + 0] + F[j*3 + 2]*nb0;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+          for (int j = 0; j < 3; j++) {
+            double sum = 0.0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) sum += Dm[(i <= k) ? dm_idx(i, k) : dm_idx(k, i)]*Bb[k][j];
+            DB[i][j] = sum;
+          }
+#pragma unroll
+        for (int q = 0; q < APT; q++) {
+          const int a = a0 + q;
+          const double na0 = rec[SREC_NX + a*3], na1 = rec[SREC_NX + a*3 + 1], na2 = rec[SREC_NX + a*3 + 2];
+          const double Na = s_N[g*ENON + a];
+          // geometric stiffness (sv_struct.cpp:753-757): S is exactly symmetric
+          const double NxSNx = na0*S[0]*nb0 + na1*S[3]*nb0 + na2*S[5]*nb0 + na0*S[3]*nb1 + na1*S[1]*nb1
+                             + na2*S[4]*nb1 + na0*S[5]*nb2 + na1*S[4]*nb2 + na2*S[2]*nb2;
+          const double T1 = amd*Na*Nb + afu*NxSNx;
+          double Ba[6][3];
+#pragma unroll
+          for (int j = 0; j < 3; j++) {
+            Ba[0][j] = na0*F[j*3 + 0];
+            Ba[1][j] = na1*F[j*3 + 1];
+            Ba[2][j] = na2*F[j*3 + 2];
+            Ba[3][j] = na0*F[j*3 + 1] + F[j*3 + 0]*na1;
+            Ba[4][j] = na1*F[j*3 + 2] + F[j*3 + 1]*na2;
+            Ba[5][j] = na2*F[j*3 + 0] + F[j*3 + 2]*na0;
+          }
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+              const double BDB = Ba[0][i]*DB[0][j] + Ba[1][i]*DB[1][j] + Ba[2][i]*DB[2][j]
+                               + Ba[3][i]*DB[3][j] + Ba[4][i]*DB[4][j] + Ba[5][i]*DB[5][j];
+              acc[q][i*3 + j] = acc[q][i*3 + j] + w*(((i == j) ? T1 : 0.0) + afu*BDB);
+            }
+        }
+      }
+    } else {
+      // l_elas_3d tangent (l_elas.cpp:362-386)
+      const double lambda = c.elM*c.nu / (1.0 + c.nu) / (1.0 - 2.0*c.nu);
+      const double mu = c.elM*0.5 / (1.0 + c.nu);
+      const double lDm = lambda/mu;
+      const double amd = c.am/afu*c.rho;
+      for (int g = 0; g < NG; g++) {
+        const double* rec = s_rec + size_t(el*NG + g)*REC;
+        const double wl = rec[SREC_W]*afu*mu;
+        const double nb[3] = {rec[SREC_NX + b*3], rec[SREC_NX + b*3 + 1], rec[SREC_NX + b*3 + 2]};
+        const double Nb = s_N[g*ENON + b];
+#pragma unroll
+        for (int q = 0; q < APT; q++) {
+          const int a = a0 + q;
+          const double na[3] = {rec[SREC_NX + a*3], rec[SREC_NX + a*3 + 1], rec[SREC_NX + a*3 + 2]};
+          const double Na = s_N[g*ENON + a];
+          const double NxdNx = na[0]*nb[0] + na[1]*nb[1] + na[2]*nb[2];
+          const double T1 = amd*Na*Nb/mu + NxdNx;
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+              const double t = (i == j) ? (T1 + (1.0 + lDm)*na[i]*nb[i]) : (lDm*na[i]*nb[j] + na[j]*nb[i]);
+              acc[q][i*3 + j] = acc[q][i*3 + j] + wl*t;
+            }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < APT; q++) {
+      double* out = stageK + size_t(kslot[(size_t(e)*ENON + (a0 + q))*ENON + b])*9;
+#pragma unroll
+      for (int i = 0; i < 9; i++) out[i] = acc[q][i];
+    }
+  }
+}
+
+// Ordered run sum for arbitrary block sizes (dof 3: 9-double blocks, 3-double rows): one thread per
+// destination double, runs walked left to right (element order) -> do_assem's order.
+template <bool ASSIGN>
+__global__ void __launch_bounds__(256)
+k_sum_run(size_t nDest, int bs, const int* __restrict__ seg, const double* __restrict__ stage, double* __restrict__ out)
+{
+  const size_t t = size_t(blockIdx.x)*blockDim.x + threadIdx.x;
+  const size_t d = t / bs;
+  const int l = int(t % bs);
+  if (d >= nDest) return;
+  const int s = __ldg(seg + d), e = __ldg(seg + d + 1);
+  double acc = ASSIGN ? 0.0 : out[t];
+  for (int q = s; q < e; q++) acc += ld_stream(stage + size_t(q)*bs + l);
+  out[t] = acc;
+}
+
+} // namespace svb200

@@ -159,14 +159,32 @@ void B200LinearAlgebra::upload_mesh(ComMod& com_mod, const mshType& lM)
 }
 
 bool B200LinearAlgebra::assemble_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag,
-    const Array<double>& Yg, const Array<double>& Dg)
+    const Array<double>& Yg, const Array<double>& Dg, const CepMod* cep_mod)
 {
   using namespace consts;
   if (!device_assembly_) return false;
   auto& eq = com_mod.eq[com_mod.cEq];
-  // device kernels available in this round: Navier-Stokes VMS on linear tetrahedra, one fluid domain
-  if (eq.phys != EquationType::phys_fluid || lM.eType != ElementType::TET4 || eq.nDmn != 1 || lM.nFs != 1) return false;
-  if (com_mod.nsd != 3 || com_mod.dof != 4) return false;
+  // one domain, one function space, 3-D; anything else falls back to the reference's construct_*
+  if (eq.nDmn != 1 || lM.nFs != 1 || com_mod.nsd != 3) return false;
+  switch (eq.phys) {
+    case EquationType::phys_fluid:
+      return assemble_fluid_mesh(com_mod, lM, Ag, Yg);
+    case EquationType::phys_struct:
+    case EquationType::phys_lElas:
+    case EquationType::phys_mesh:
+      return assemble_solid_mesh(com_mod, lM, Ag, Yg, Dg, cep_mod);
+    default:
+      return false;
+  }
+}
+
+bool B200LinearAlgebra::assemble_fluid_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag,
+    const Array<double>& Yg)
+{
+  using namespace consts;
+  auto& eq = com_mod.eq[com_mod.cEq];
+  // device kernel: Navier-Stokes VMS on linear tetrahedra
+  if (lM.eType != ElementType::TET4 || com_mod.dof != 4) return false;
   if (mesh_uploaded_ != &lM) upload_mesh(com_mod, lM);
 
   const auto& dmn = eq.dmn[0];
@@ -189,6 +207,65 @@ bool B200LinearAlgebra::assemble_mesh(ComMod& com_mod, const mshType& lM, const 
 
   check(b200_state_set(h_, com_mod.tDof, Ag.data(), Yg.data(), com_mod.Bf.data()), "b200_state_set");
   check(b200_assemble_fluid(h_, &p), "b200_assemble_fluid");
+  any_device_contribution_ = true;
+  return true;
+}
+
+/// struct (construct_dsolid, sv_struct.cpp:213), lElas (construct_l_elas, l_elas.cpp:58) and the ALE mesh
+/// equation (construct_mesh, mesh.cpp:42) on TET4 / HEX8.  Features without a device kernel (fibre
+/// stress, solid viscosity, prestress, electromechanics, anisotropic laws) return false.
+bool B200LinearAlgebra::assemble_solid_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag,
+    const Array<double>& Yg, const Array<double>& Dg, const CepMod* cep_mod)
+{
+  using namespace consts;
+  auto& eq = com_mod.eq[com_mod.cEq];
+  if ((lM.eType != ElementType::TET4 && lM.eType != ElementType::HEX8) || com_mod.dof != 3) return false;
+  if (com_mod.pS0.size() != 0 || com_mod.pstEq) return false;
+  if (cep_mod && (cep_mod->cem.cpld || cep_mod->cem.aStress || cep_mod->cem.aStrain)) return false;
+  const auto& dmn = eq.dmn[0];
+
+  b200_struct_props sp{};
+  b200_lelas_props lp{};
+  const bool is_struct = (eq.phys == EquationType::phys_struct);
+  if (is_struct) {
+    const auto& stM = dmn.stM;
+    if (stM.Tf.fType != 0 || dmn.solid_visc.viscType != SolidViscosityModelType::viscType_NA) return false;
+    switch (stM.isoType) {
+      case ConstitutiveModelType::stIso_nHook: sp.isoType = 0; break;
+      case ConstitutiveModelType::stIso_StVK:  sp.isoType = 1; break;
+      case ConstitutiveModelType::stIso_mStVK: sp.isoType = 2; break;
+      default: return false;
+    }
+    switch (stM.volType) {
+      case ConstitutiveModelType::stVol_Quad: sp.volType = 1; break;
+      case ConstitutiveModelType::stVol_ST91: sp.volType = 2; break;
+      case ConstitutiveModelType::stVol_M94:  sp.volType = 3; break;
+      default: sp.volType = 0; break;
+    }
+    sp.dt = com_mod.dt; sp.am = eq.am; sp.af = eq.af; sp.gam = eq.gam; sp.beta = eq.beta;
+    sp.tDof = com_mod.tDof; sp.s = eq.s;
+    sp.rho = dmn.prop.at(PhysicalProperyType::solid_density);
+    sp.dmp = dmn.prop.at(PhysicalProperyType::damping);
+    sp.f[0] = dmn.prop.at(PhysicalProperyType::f_x);
+    sp.f[1] = dmn.prop.at(PhysicalProperyType::f_y);
+    sp.f[2] = dmn.prop.at(PhysicalProperyType::f_z);
+    sp.C10 = stM.C10; sp.C01 = stM.C01; sp.Kpen = stM.Kpen;
+  } else {
+    lp.dt = com_mod.dt; lp.am = eq.am; lp.af = eq.af; lp.beta = eq.beta;
+    lp.tDof = com_mod.tDof; lp.s = eq.s;
+    lp.mesh_mode = (eq.phys == EquationType::phys_mesh) ? 1 : 0;
+    lp.rho = dmn.prop.at(PhysicalProperyType::solid_density);
+    lp.elM = dmn.prop.at(PhysicalProperyType::elasticity_modulus);
+    lp.nu = dmn.prop.at(PhysicalProperyType::poisson_ratio);
+    lp.f[0] = dmn.prop.at(PhysicalProperyType::f_x);
+    lp.f[1] = dmn.prop.at(PhysicalProperyType::f_y);
+    lp.f[2] = dmn.prop.at(PhysicalProperyType::f_z);
+  }
+  if (mesh_uploaded_ != &lM) upload_mesh(com_mod, lM);
+  check(b200_state_set(h_, com_mod.tDof, Ag.data(), Yg.data(), com_mod.Bf.data()), "b200_state_set");
+  check(b200_disp_set(h_, com_mod.tDof, Dg.data(), lp.mesh_mode && !is_struct ? com_mod.Do.data() : nullptr), "b200_disp_set");
+  if (is_struct) check(b200_assemble_struct(h_, &sp), "b200_assemble_struct");
+  else check(b200_assemble_lelas(h_, &lp), "b200_assemble_lelas");
   any_device_contribution_ = true;
   return true;
 }

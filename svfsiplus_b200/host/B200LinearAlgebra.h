@@ -16,6 +16,7 @@
 #define B200_LINEAR_ALGEBRA_H
 
 #include "LinearAlgebra.h"
+#include "CepMod.h"
 
 #include <set>
 #include <string>
@@ -47,7 +48,7 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
     /// type has no device kernel yet (the caller then falls back to the reference's construct_* with
     /// per-element assemble()).
     bool assemble_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag, const Array<double>& Yg,
-        const Array<double>& Dg);
+        const Array<double>& Dg, const CepMod* cep_mod = nullptr);
 
     /// fsils_bc_update counterpart: re-upload the face vectors (moving meshes, follower loads).
     void update_faces(ComMod& com_mod);
@@ -59,6 +60,9 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
     void check(int rc, const char* what);
     void upload_structure(ComMod& com_mod);
     void upload_mesh(ComMod& com_mod, const mshType& lM);
+    bool assemble_fluid_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag, const Array<double>& Yg);
+    bool assemble_solid_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag, const Array<double>& Yg,
+        const Array<double>& Dg, const CepMod* cep_mod);
 
     b200_handle* h_ = nullptr;
     int device_ = -1;         // -1: rank mod device count, chosen in initialize()

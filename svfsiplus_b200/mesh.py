@@ -142,6 +142,60 @@ def pipe_mesh(nx: int, ny: int, nz: int, radius: float = 1.0, length: float = 10
     return Mesh(x=np.ascontiguousarray(x), ien=np.ascontiguousarray(ien), faces=faces, shape=(nx, ny, nz))
 
 
+def block_mesh(n: int, elem: str = "hex", length: float = 1.0, jitter: float = 0.1, seed: int = 4321) -> Mesh:
+    """Cube [0,L]^3 of n^3 HEX8 (reference node order, nn_elem_gnn.h:732: bottom face counter-clockwise, then the
+    top face) or its 6-tet Kuhn split; interior nodes jittered by jitter*h*U(-1,1).  Faces X0..Z1 = node lists."""
+    h = length / n
+    g = np.arange(n + 1) * h
+    Z, Y, X = np.meshgrid(g, g, g, indexing="ij")            # node id = i + (n+1) j + (n+1)^2 k
+    x = np.stack([X.reshape(-1), Y.reshape(-1), Z.reshape(-1)], axis=1)
+    rng = np.random.default_rng(seed)
+    interior = np.all((x > 1e-12) & (x < length - 1e-12), axis=1)
+    x[interior] += jitter * h * rng.uniform(-1.0, 1.0, size=(int(interior.sum()), 3))
+    if elem == "hex":
+        sx, sy, sz = 1, n + 1, (n + 1) ** 2
+        i, j, k = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+        base = (i * sx + j * sy + k * sz).transpose(2, 1, 0).reshape(-1).astype(np.int64)
+        off = [0, sx, sx + sy, sy, sz, sx + sz, sx + sy + sz, sy + sz]
+        ien = np.stack([base + o for o in off], axis=1).astype(np.int32)
+    elif elem == "tet":
+        ien = _fix_orientation(x, _kuhn_tets(n, n, n)).astype(np.int32)
+    else:
+        raise ValueError(elem)
+    nid = np.arange(x.shape[0], dtype=np.int32)
+    faces = {}
+    for ax, nm in enumerate("XYZ"):
+        faces[nm + "0"] = dict(nodes=nid[np.abs(x[:, ax]) < 1e-12], tris=None)
+        faces[nm + "1"] = dict(nodes=nid[np.abs(x[:, ax] - length) < 1e-12], tris=None)
+    return Mesh(x=np.ascontiguousarray(x), ien=np.ascontiguousarray(ien), faces=faces, shape=(n, n, n))
+
+
+def block_state(mesh: Mesh, length: float = 1.0, amp: float = 0.05, noise: float = 0.01, seed: int = 2026, tDof: int = 3, s: int = 0):
+    """Displacement state of SURVEY.md par. 8d for the solid block: d = amp*L*sin field + noise, Ag/Yg random."""
+    x = mesh.x
+    n = x.shape[0]
+    rng = np.random.default_rng(seed)
+    k = np.pi / length
+    Dg = np.zeros((n, tDof)); Ag = np.zeros((n, tDof)); Yg = np.zeros((n, tDof))
+    Dg[:, s + 0] = amp * length * np.sin(k * x[:, 0]) * np.cos(k * x[:, 1])
+    Dg[:, s + 1] = amp * length * np.sin(k * x[:, 1]) * np.cos(k * x[:, 2])
+    Dg[:, s + 2] = -amp * length * np.sin(k * x[:, 2]) * np.cos(k * x[:, 0])
+    Dg[:, s:s + 3] += noise * amp * length * rng.standard_normal((n, 3))
+    Yg[:, s:s + 3] = 0.1 * rng.standard_normal((n, 3))
+    Ag[:, s:s + 3] = 10.0 * rng.standard_normal((n, 3))
+    Bf = 0.5 * rng.standard_normal((n, 3))
+    return Ag, Yg, Dg, Bf
+
+
+def gen_alpha2(ro_inf: float = 0.5):
+    """Generalised-alpha constants for a second-order (solid) equation (S/initialize.cpp:424-463)."""
+    am = (2.0 - ro_inf) / (1.0 + ro_inf)
+    af = 1.0 / (1.0 + ro_inf)
+    beta = 0.25 * (1.0 + am - af) ** 2
+    gam = 0.5 + am - af
+    return am, af, gam, beta
+
+
 def csr_pattern(ien: np.ndarray, nNo: int):
     """Node-graph CSR with sorted columns and the diagonal present.
 

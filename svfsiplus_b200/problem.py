@@ -21,6 +21,10 @@ LS_SETTINGS = {
     "GMRES": (B.LS_GMRES, (1e-3, 1e-17, 4, 250), None, None),
     "CG": (B.LS_CG, (1e-3, 1e-12, 50, 0), None, None),
     "BICGS": (B.LS_BICGS, (1e-8, 1e-14, 200, 0), None, None),
+    # tests/cases/struct/block_compression/solver.xml: <LS type="BICG"> tol 1e-12, 600 iterations
+    "BICGS_STRUCT": (B.LS_BICGS, (1e-12, 1e-10, 600, 0), None, None),
+    "GMRES_STRUCT": (B.LS_GMRES, (1e-9, 1e-10, 10, 100), None, None),
+    "CG_MESH": (B.LS_CG, (1e-10, 1e-14, 400, 0), None, None),
 }
 
 
@@ -83,3 +87,73 @@ def newton_linear_step(be: B.Backend, case, ls="NS", want_system=False, upload=T
     if want_system:
         return X, info, R, Val
     return X, info
+
+
+# ---------------------------------------------------------------------------------------------------
+# solid block (tests/cases/struct/block_compression/solver.xml: neo-Hookean, E 240.56596e6, nu 0.5, ST91
+# penalty 4e9, density 1000, dt 1e-4, rho_inf 0.5; X0/Y0/Z0 Dirichlet in one direction each)
+# ---------------------------------------------------------------------------------------------------
+def block_case(n, elem="hex", kind="struct", iso="nHook", vol="ST91", jitter=0.1):
+    m = M.block_mesh(n, elem=elem, jitter=jitter)
+    rowPtr, colPtr = M.csr_pattern(m.ien, m.nNo)
+    am, af, gam, beta = M.gen_alpha2(0.5)
+    Ag, Yg, Dg, Bf = M.block_state(m)
+    E, nu = 240.56596e6, 0.5
+    mu = 0.5 * E / (1.0 + nu)
+    dt = 1e-4
+    if kind == "struct":
+        if iso == "nHook":
+            C10, C01 = 0.5 * mu, 0.0
+        elif iso == "StVK":                      # C10 = lambda, C01 = mu (nu 0.3 keeps lambda finite)
+            C10, C01 = E * 0.3 / (1.3 * 0.4), 0.5 * E / 1.3
+        else:                                    # mStVK: C10 = kappa, C01 = mu
+            C10, C01 = E / (3.0 * 0.4), 0.5 * E / 1.3
+        props = dict(dt=dt, am=am, af=af, gam=gam, beta=beta, rho=1000.0, dmp=0.0, f=(0.0, 0.0, 0.0), iso=iso, vol=vol,
+                     C10=C10, C01=C01, Kpen=4.0e9 if vol else 0.0)
+    elif kind == "lelas":
+        props = dict(dt=dt, am=am, af=af, gam=gam, beta=beta, rho=1000.0, elM=E, nu=0.3, f=(0.0, 0.0, -9.81))
+    else:
+        # ALE mesh-motion equation as the FSI case configures it: unknowns in rows 4..6 of a tDof = 7 state
+        # (fluid/struct velocity-pressure first), unit modulus, reference configuration x + Do
+        props = dict(dt=dt, am=am, af=af, gam=gam, beta=beta, rho=0.0, elM=1.0, nu=0.3, f=(0.0, 0.0, 0.0), s=4)
+        A7, Y7, D7, _ = M.block_state(m, tDof=7, s=4)
+        rng = np.random.default_rng(77)
+        Do = np.zeros_like(D7)
+        Do[:, 4:7] = 0.5 * D7[:, 4:7] + 0.002 * rng.standard_normal((m.nNo, 3))
+        Ag, Yg, Dg = A7, Y7, D7
+    faces = []
+    for ax, nm in enumerate(("X0", "Y0", "Z0")):
+        nodes = m.faces[nm]["nodes"]
+        val = np.ones((len(nodes), 3))
+        val[:, ax] = 0.0
+        faces.append(dict(name=nm, nodes=nodes, dof=3, bGrp=B.BC_DIR, val=val))
+    case = dict(mesh=m, rowPtr=rowPtr, colPtr=colPtr, Ag=Ag, Yg=Yg, Dg=Dg, Bf=Bf, props=props, faces=faces, kind=kind,
+                res=np.zeros(len(faces)), incL=np.ones(len(faces), np.int32), name=f"block_{elem}_{n}_{kind}")
+    if kind == "mesh":
+        case["Do"] = Do
+    return case
+
+
+def assemble_solid(be: B.Backend, case, upload=True):
+    """ls_alloc + global_eq_assem for a struct / lElas equation (dof 3)."""
+    tDof = case["Ag"].shape[1]
+    if upload:
+        be.state_set(tDof, case["Ag"], case["Yg"], case["Bf"])
+        be.disp_set(tDof, case["Dg"], case.get("Do"))
+    be.zero(3)
+    if case["kind"] == "struct":
+        be.assemble_struct(B.struct_props(tDof=tDof, **case["props"]))
+    else:
+        be.assemble_lelas(B.lelas_props(tDof=tDof, mesh_mode=(case["kind"] == "mesh"), **case["props"]))
+    if case.get("nranks", 1) > 1:
+        be.commu_R()
+
+
+def solid_linear_step(be: B.Backend, case, ls="BICGS_STRUCT", want_system=False, prec=B.PREC_FSILS):
+    assemble_solid(be, case)
+    R = Val = None
+    if want_system:
+        R, Val = be.get_R(), be.get_Val()
+    ls_type, RI, GM, CG = LS_SETTINGS[ls] if isinstance(ls, str) else ls
+    X, info = be.solve(ls_type, prec, RI, GM, CG, case["incL"], case["res"])
+    return (X, info, R, Val) if want_system else (X, info)

@@ -42,6 +42,18 @@ def main():
     R, Val, X, o = refcase.reference_step(case, "NS")
     np.savez_compressed(os.path.join(HERE, "pipe_6_6_12_ns.npz"), X=X,
                         info=np.array([o["suc"], o["itr"], o["iNorm"], o["fNorm"], o["GM_itr"], o["CG_itr"]]))
+    # solid equations on a 3^3 block: struct (three laws), lElas, mesh; TET4 and HEX8
+    out = {}
+    for elem in ("tet", "hex"):
+        for kind, iso, vol in (("struct", "nHook", "ST91"), ("struct", "nHook", "M94"), ("struct", "StVK", None),
+                               ("struct", "mStVK", None), ("lelas", None, None), ("mesh", None, None)):
+            c = P.block_case(3, elem=elem, kind=kind, iso=iso or "nHook", vol=vol)
+            R, Val, _, _, _, tabs = refcase.reference_assemble_solid(c)
+            tag = f"{elem}_{kind}_{iso}_{vol}"
+            out[f"R_{tag}"] = R
+            out[f"Val_{tag}"] = Val
+        out[f"w_{elem}"], out[f"N_{elem}"], out[f"Nx_{elem}"] = tabs
+    np.savez_compressed(os.path.join(HERE, "block_3_solid.npz"), **out)
     print("golden fixtures written")
 
 

@@ -8,7 +8,7 @@ import re
 import numpy as np
 import pytest
 
-from conftest import needs_ref
+from conftest import have_ref, needs_ref
 from util import ROOT, golden, hl_solve, rel_inf, rel_l2
 
 from svfsiplus_b200 import mesh as M
@@ -129,3 +129,28 @@ def test_no_cpu_fallback_without_device():
         pytest.skip("a GPU is present")
     with pytest.raises(RuntimeError, match="no CUDA device"):
         B.Backend(0)
+
+
+@pytest.mark.parametrize("elem,eNoN", [("tet", 4), ("hex", 8)])
+def test_gauss_tables_equal_reference(elem, eNoN):
+    """The element kernels' Gauss rule / shape tables (host code of the product, no device needed) against
+    what the reference's select_ele leaves in lM.w / lM.N / lM.Nx (stored in the golden fixture)."""
+    from svfsiplus_b200 import backend as B
+    g = golden("block_3_solid.npz")
+    w, N, Nxi = B.elem_tables(eNoN)
+    assert np.array_equal(w, g[f"w_{elem}"])
+    assert np.abs(N - g[f"N_{elem}"]).max() < 1e-15
+    assert np.abs(Nxi - g[f"Nx_{elem}"]).max() < 1e-15
+
+
+def test_oracle_reproduces_solid_golden():
+    if not have_ref():
+        pytest.skip("compiled reference not available")
+    from oracle import refcase
+    g = golden("block_3_solid.npz")
+    for elem in ("tet", "hex"):
+        for kind, iso, vol in (("struct", "nHook", "ST91"), ("lelas", None, None), ("mesh", None, None)):
+            c = P.block_case(3, elem=elem, kind=kind, iso=iso or "nHook", vol=vol)
+            R, Val, *_ = refcase.reference_assemble_solid(c)
+            tag = f"{elem}_{kind}_{iso}_{vol}"
+            assert np.array_equal(R, g[f"R_{tag}"]) and np.array_equal(Val, g[f"Val_{tag}"])
