@@ -114,6 +114,13 @@ int b200_disp_set(b200_handle* h, int tDof, const double* Dg, const double* Do);
 int b200_assemble_struct(b200_handle* h, const b200_struct_props* p);
 /* ... and construct_l_elas / construct_mesh + l_elas_3d (solver/l_elas.cpp:58,274; mesh.cpp:42). */
 int b200_assemble_lelas(b200_handle* h, const b200_lelas_props* p);
+/* FSI equation (solver/fsi.cpp:42-334: one element loop with a per-element domain switch).  elem_dmn[e] =
+ * index of the equation domain element e belongs to (all_fun::domain, solver/all_fun.cpp:149), uploaded once;
+ * the device keeps one element list per domain, so each domain is one divergence-free launch. */
+int b200_mesh_domains(b200_handle* h, int nDmn, const int* elem_dmn);
+/* dmn_kind[d]: 0 fluid (fluid_3d_m/c on the ALE configuration x + Dg(4:6), mvMsh), 1 struct (struct_3d into the
+ * 3x3 corner of the dof-4 blocks).  fluid[d] / solid[d] are read for the domains of that kind (dof 4; TET4). */
+int b200_assemble_fsi(b200_handle* h, int nDmn, const int* dmn_kind, const b200_fluid_props* fluid, const b200_struct_props* solid);
 /* LinearAlgebra::assemble for the few boundary-face elements: staged on the host, flushed by one
  * scatter kernel before the next get/solve.  eqN(d), lK(dof*dof,d,d), lR(dof,d). */
 int b200_assemble_elem(b200_handle* h, int d, const int* eqN, const double* lK, const double* lR);

@@ -100,6 +100,8 @@ def lib():
         L.ref_asm_fluid.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_double] * 5 + [C.c_void_p, C.c_double] + [C.c_void_p] * 6
         L.ref_asm_solid.restype = C.c_double
         L.ref_asm_solid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
+        L.ref_asm_fsi.restype = C.c_double
+        L.ref_asm_fsi.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 5 + [C.c_void_p] * 9
         L.ref_rank_create.restype = C.c_void_p
         L.ref_rank_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_rank_destroy.argtypes = [C.c_void_p]
@@ -193,6 +195,26 @@ class RefAssembly:
         Do = None if Do is None else _c(Do, np.float64)
         t = lib().ref_asm_solid(self.h, {"struct": 0, "lelas": 1, "mesh": 2}[kind], tDof, int(s), _p(par), _p(Ag), _p(Yg),
                                 _p(Dg), _p(Do), _p(Bf), _p(R), _p(Val))
+        if t < 0:
+            raise RuntimeError(lib().ref_last_error().decode())
+        return R, Val, t
+
+
+    def fsi(self, elem_dmn, Ag, Yg, Dg, Bf, *, dt, am, af, gam, beta, fluid, solid):
+        """construct_fsi (S/fsi.cpp:42) with domain 0 = fluid, 1 = struct.  fluid: dict(rho, mu, f, viscType...);
+        solid: dict(rho, dmp, f, iso, vol, C10, C01, Kpen).  Returns R (nNo,4), Val (nnz,16), seconds."""
+        Ag = _c(Ag, np.float64); Yg = _c(Yg, np.float64); Dg = _c(Dg, np.float64); Bf = _c(Bf, np.float64)
+        ed = _c(elem_dmn, np.int32)
+        ff = fluid.get("f", (0.0, 0.0, 0.0)); sf = solid.get("f", (0.0, 0.0, 0.0))
+        fpar = np.array([fluid["rho"], ff[0], ff[1], ff[2], fluid.get("viscType", 0), fluid["mu"], fluid.get("mu_o", 0.0),
+                         fluid.get("lam", 0.0), fluid.get("a", 0.0), fluid.get("n", 0.0)], np.float64)
+        spar = np.array([dt, am, af, gam, beta, solid["rho"], solid.get("dmp", 0.0), sf[0], sf[1], sf[2],
+                         self.ISO[solid.get("iso", "nHook")], self.VOL[solid.get("vol", "ST91")], solid["C10"],
+                         solid.get("C01", 0.0), solid.get("Kpen", 0.0), 0.0, 0.0], np.float64)
+        R = np.empty((self.nNo, 4))
+        Val = np.empty((self.nnz, 16))
+        t = lib().ref_asm_fsi(self.h, Ag.shape[1], dt, am, af, gam, beta, _p(fpar), _p(spar), _p(ed), _p(Ag), _p(Yg), _p(Dg),
+                              _p(Bf), _p(R), _p(Val))
         if t < 0:
             raise RuntimeError(lib().ref_last_error().decode())
         return R, Val, t

@@ -23,6 +23,8 @@
 #include "consts.h"
 #include "fluid.h"
 #include "fs.h"
+#include "mat_fun.h"
+#include "fsi.h"
 #include "l_elas.h"
 #include "mesh.h"
 #include "sv_struct.h"
@@ -106,6 +108,7 @@ void* ref_asm_create(int nNo, int nEl, int eNoN, const int* IEN, const double* x
 
     nn::select_ele(com_mod, msh);
     fs::init_fs_msh(com_mod, msh);
+    mat_fun::ten_init(3);            // what initialize() does once (S/initialize.cpp:547)
 
     int nnz = 0;
     lhsa_ns::lhsa(ctx->sim.get(), nnz);
@@ -304,6 +307,90 @@ double ref_asm_solid(void* h, int kind, int tDof, int s, const double* par, cons
     else mesh::construct_mesh(com_mod, ctx->sim->cep_mod, com_mod.msh[0], Ag_a, Dg_a);
     double t1 = now_s();
 
+    std::memcpy(R, com_mod.R.data(), sizeof(double)*size_t(dof)*nNo);
+    std::memcpy(Val, com_mod.Val.data(), sizeof(double)*size_t(dof)*dof*ctx->nnz);
+    return t1 - t0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1.0;
+  }
+}
+
+// FSI equation through the reference's construct_fsi (S/fsi.cpp:42): domain 0 = fluid (Id 0), domain 1 =
+// struct (Id 1); elem_dmn[e] in {0,1} becomes the bit mask lM.eId.  tDof = 7 (FSI unknowns 0..3, mesh 4..6).
+// fpar = {rho, fx, fy, fz, visc type, mu_i, mu_o, lam, a, n};  spar as in ref_asm_solid (struct).
+double ref_asm_fsi(void* h, int tDof, double dt, double am, double af, double gam, double beta, const double* fpar,
+                   const double* spar, const int* elem_dmn, const double* Ag, const double* Yg, const double* Dg,
+                   const double* Bf, double* R, double* Val)
+{
+  try {
+    using namespace consts;
+    auto ctx = static_cast<AsmCtx*>(h);
+    auto& com_mod = ctx->sim->com_mod;
+    auto& msh = com_mod.msh[0];
+    const int nNo = com_mod.tnNo;
+    const int dof = 4;
+    com_mod.tDof = tDof;
+    com_mod.dof = dof;
+    com_mod.dt = dt;
+    com_mod.mvMsh = true;
+    com_mod.cEq = 0;
+    com_mod.nEq = 1;
+    if (com_mod.eq.size() != 1) com_mod.eq.resize(1);
+    auto& eq = com_mod.eq[0];
+    eq.phys = EquationType::phys_FSI;
+    eq.dof = dof; eq.s = 0; eq.e = dof - 1;
+    eq.am = am; eq.af = af; eq.gam = gam; eq.beta = beta;
+    eq.nDmn = 2;
+    if (eq.dmn.size() != 2) eq.dmn.resize(2);
+    {
+      auto& dmn = eq.dmn[0];
+      dmn.Id = 0;
+      dmn.phys = EquationType::phys_fluid;
+      dmn.prop[PhysicalProperyType::fluid_density] = fpar[0];
+      dmn.prop[PhysicalProperyType::f_x] = fpar[1];
+      dmn.prop[PhysicalProperyType::f_y] = fpar[2];
+      dmn.prop[PhysicalProperyType::f_z] = fpar[3];
+      dmn.prop[PhysicalProperyType::inverse_darcy_permeability] = 0.0;
+      const int vt = int(fpar[4]);
+      dmn.fluid_visc.viscType = (vt == 0) ? FluidViscosityModelType::viscType_Const
+                              : (vt == 1) ? FluidViscosityModelType::viscType_CY : FluidViscosityModelType::viscType_Cass;
+      dmn.fluid_visc.mu_i = fpar[5]; dmn.fluid_visc.mu_o = fpar[6]; dmn.fluid_visc.lam = fpar[7];
+      dmn.fluid_visc.a = fpar[8]; dmn.fluid_visc.n = fpar[9];
+    }
+    {
+      auto& dmn = eq.dmn[1];
+      dmn.Id = 1;
+      dmn.phys = EquationType::phys_struct;
+      dmn.prop[PhysicalProperyType::solid_density] = spar[5];
+      dmn.prop[PhysicalProperyType::damping] = spar[6];
+      dmn.prop[PhysicalProperyType::f_x] = spar[7];
+      dmn.prop[PhysicalProperyType::f_y] = spar[8];
+      dmn.prop[PhysicalProperyType::f_z] = spar[9];
+      const int iso = int(spar[10]), vol = int(spar[11]);
+      dmn.stM.isoType = (iso == 0) ? ConstitutiveModelType::stIso_nHook
+                      : (iso == 1) ? ConstitutiveModelType::stIso_StVK : ConstitutiveModelType::stIso_mStVK;
+      dmn.stM.volType = (vol == 1) ? ConstitutiveModelType::stVol_Quad
+                      : (vol == 2) ? ConstitutiveModelType::stVol_ST91
+                      : (vol == 3) ? ConstitutiveModelType::stVol_M94 : ConstitutiveModelType::stIso_NA;
+      dmn.stM.C10 = spar[12]; dmn.stM.C01 = spar[13]; dmn.stM.Kpen = spar[14];
+    }
+    msh.eId.resize(msh.nEl);
+    for (int e = 0; e < msh.nEl; e++) msh.eId(e) = 1 << elem_dmn[e];
+    com_mod.Bf.resize(3, nNo);
+    std::memcpy(com_mod.Bf.data(), Bf, sizeof(double)*3*size_t(nNo));
+    if (!eq.linear_algebra) eq.linear_algebra = new FsilsLinearAlgebra();
+
+    Array<double> Ag_a(tDof, nNo), Yg_a(tDof, nNo), Dg_a(tDof, nNo);
+    std::memcpy(Ag_a.data(), Ag, sizeof(double)*size_t(tDof)*nNo);
+    std::memcpy(Yg_a.data(), Yg, sizeof(double)*size_t(tDof)*nNo);
+    std::memcpy(Dg_a.data(), Dg, sizeof(double)*size_t(tDof)*nNo);
+
+    com_mod.R.resize(dof, nNo);
+    eq.linear_algebra->alloc(com_mod, eq);
+    double t0 = now_s();
+    fsi::construct_fsi(com_mod, ctx->sim->cep_mod, msh, Ag_a, Yg_a, Dg_a);
+    double t1 = now_s();
     std::memcpy(R, com_mod.R.data(), sizeof(double)*size_t(dof)*nNo);
     std::memcpy(Val, com_mod.Val.data(), sizeof(double)*size_t(dof)*dof*ctx->nnz);
     return t1 - t0;

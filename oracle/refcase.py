@@ -65,3 +65,21 @@ def reference_solid_step(case, ls, prec=ref.PREC_FSILS):
     R, Val, rowPtr, colPtr, _, _ = reference_assemble_solid(case)
     X, out = reference_solve(case, R, Val, ls, prec)
     return R, Val, X, out
+
+
+def reference_assemble_fsi(case):
+    m = case["mesh"]
+    ra = ref.RefAssembly(m.x, m.ien)
+    t = case["time"]
+    R, Val, secs = ra.fsi(case["elem_dmn"], case["Ag"], case["Yg"], case["Dg"], case["Bf"], dt=t["dt"], am=t["am"], af=t["af"],
+                          gam=t["gam"], beta=t["beta"], fluid=case["fluid"], solid=case["solid"])
+    ra.close()
+    return R, Val, secs
+
+
+def reference_fsi_step(case, ls, prec=ref.PREC_FSILS):
+    from svfsiplus_b200.problem import LS_SETTINGS
+    ls = LS_SETTINGS[ls] if isinstance(ls, str) else ls
+    R, Val, _ = reference_assemble_fsi(case)
+    X, out = reference_solve(case, R, Val, ls, prec)
+    return R, Val, X, out

@@ -62,7 +62,7 @@ VOL_TYPES = {None: 0, "Quad": 1, "ST91": 2, "M94": 3}
 EXPORTS = [
     "b200_create", "b200_destroy", "b200_last_error", "b200_device_count", "b200_elem_tables", "b200_comm_unique_id", "b200_comm_init",
     "b200_lhs_create", "b200_face_set", "b200_mesh_set", "b200_zero", "b200_state_set", "b200_assemble_fluid",
-    "b200_disp_set", "b200_assemble_struct", "b200_assemble_lelas",
+    "b200_disp_set", "b200_assemble_struct", "b200_assemble_lelas", "b200_mesh_domains", "b200_assemble_fsi",
     "b200_assemble_elem", "b200_get_R", "b200_set_R", "b200_add_R", "b200_get_Val", "b200_set_Val", "b200_commu_R", "b200_solve",
     "b200_spmv", "b200_op_bench", "b200_launch_count", "b200_last_timings", "b200_profile", "b200_profile_read",
     "b200_timer",
@@ -100,6 +100,8 @@ def lib():
         L.b200_disp_set.argtypes = [vp, ci, vp, vp]
         L.b200_assemble_struct.argtypes = [vp, C.POINTER(StructProps)]
         L.b200_assemble_lelas.argtypes = [vp, C.POINTER(LelasProps)]
+        L.b200_mesh_domains.argtypes = [vp, ci, vp]
+        L.b200_assemble_fsi.argtypes = [vp, ci, vp, C.POINTER(FluidProps), C.POINTER(StructProps)]
         L.b200_assemble_elem.argtypes = [vp, ci, vp, vp, vp]
         L.b200_get_R.argtypes = [vp, vp]
         L.b200_set_R.argtypes = [vp, ci, vp]
@@ -268,6 +270,18 @@ class Backend:
 
     def assemble_lelas(self, props: LelasProps):
         self._ck(self.L.b200_assemble_lelas(self.h, C.byref(props)), "b200_assemble_lelas")
+
+    def mesh_domains(self, nDmn, elem_dmn):
+        ed = _c(elem_dmn, np.int32)
+        self._ck(self.L.b200_mesh_domains(self.h, nDmn, _p(ed)), "b200_mesh_domains")
+
+    def assemble_fsi(self, kinds, fluid_props_list, struct_props_list):
+        """kinds[d] in {0 fluid, 1 struct}; *_props_list[d] = props of domain d (None where not that kind)."""
+        n = len(kinds)
+        k = _c(kinds, np.int32)
+        fl = (FluidProps * n)(*[p if p is not None else FluidProps() for p in fluid_props_list])
+        st = (StructProps * n)(*[p if p is not None else StructProps() for p in struct_props_list])
+        self._ck(self.L.b200_assemble_fsi(self.h, n, _p(k), fl, st), "b200_assemble_fsi")
 
     def assemble_elem(self, eqN, lK, lR):
         eqN = _c(eqN, np.int32); lK = _c(lK, np.float64); lR = _c(lR, np.float64)

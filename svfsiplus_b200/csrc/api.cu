@@ -51,6 +51,8 @@ struct b200_handle {
   double* stageR = nullptr;  // dof x eNoN x nEl
   double* stageK = nullptr;  // dof^2 x eNoN^2 x nEl
   size_t stageR_cap = 0, stageK_cap = 0;
+  std::vector<int*> d_dmn_elems;      // per FSI domain: element list (ascending element ids)
+  std::vector<int> dmn_count;
   double* d_tab = nullptr;   // packed Gauss tables of the mesh's element type (w, N, dN/dxi)
   ElemTables tab;
   double* d_x = nullptr;
@@ -80,6 +82,7 @@ struct b200_handle {
     cudaFree(d_ien); cudaFree(d_rslot); cudaFree(d_kslot); cudaFree(d_rseg); cudaFree(d_kseg);
     cudaFree(stageR); cudaFree(stageK); cudaFree(d_x); cudaFree(d_err);
     cudaFree(d_Ag); cudaFree(d_Yg); cudaFree(d_Bf); cudaFree(d_Dg); cudaFree(d_Do); cudaFree(d_tab);
+    for (auto p : d_dmn_elems) cudaFree(p);
   }
 };
 
@@ -250,18 +253,46 @@ void finish_assembly(b200_handle* h, int dof, double t0, const char* who)
   }
 }
 
-template <int ENON, int NG, int EPB, int APT>
-void launch_solid(b200_handle* h, const SolidConsts& c)
+template <int ENON, int NG, int EPB, int APT, int ODOF>
+void launch_solid(b200_handle* h, const SolidConsts& c, int nList, const int* d_elist)
 {
   auto& ops = *h->ops;
+  if (nList == 0) return;
   constexpr int TABN = NG + NG*ENON + NG*ENON*3;
   const size_t smem = sizeof(double)*(size_t((TABN + 3) & ~3) + size_t(EPB)*NG*solid_rec(ENON));
-  auto kern = k_assemble_solid<ENON, NG, EPB, APT>;
+  auto kern = k_assemble_solid<ENON, NG, EPB, APT, ODOF>;
   CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-  kern<<<(h->nEl + EPB - 1)/EPB, EPB*NG, smem, ops.st>>>(h->nEl, c, h->d_tab, h->d_ien, h->d_rslot, h->d_kslot, h->d_x,
-                                                         h->d_Ag, h->d_Yg, h->d_Dg, h->d_Do, h->d_Bf, h->stageR, h->stageK, h->d_err);
+  kern<<<(nList + EPB - 1)/EPB, EPB*NG, smem, ops.st>>>(nList, d_elist, c, h->d_tab, h->d_ien, h->d_rslot, h->d_kslot, h->d_x,
+                                                        h->d_Ag, h->d_Yg, h->d_Dg, h->d_Do, h->d_Bf, h->stageR, h->stageK, h->d_err);
   CU_CHECK(cudaGetLastError());
   ops.post();
+}
+
+FluidConsts fluid_consts(b200_handle* h, const b200_fluid_props* p)
+{
+  FluidConsts c;
+  c.dt = p->dt; c.am = p->am; c.af = p->af; c.gam = p->gam;
+  c.rho = p->rho; c.f[0] = p->f[0]; c.f[1] = p->f[1]; c.f[2] = p->f[2]; c.Kinv = p->Kinv;
+  c.viscType = p->viscType; c.mu_i = p->mu_i; c.mu_o = p->mu_o; c.lam = p->lam; c.a = p->a; c.n = p->n;
+  c.tDof = p->tDof; c.mvMsh = p->mvMsh;
+  for (int g = 0; g < 4; g++) {
+    c.w[g] = h->tab.w[g];
+    for (int a = 0; a < 4; a++) c.N[g][a] = h->tab.N[g][a];
+  }
+  return c;
+}
+
+SolidConsts struct_consts(const b200_struct_props* p)
+{
+  if (p->isoType < 0 || p->isoType > 2) throw std::runtime_error("assemble_struct: constitutive model has no device kernel");
+  if (p->volType < 0 || p->volType > 3) throw std::runtime_error("assemble_struct: dilational penalty model not defined");
+  SolidConsts c;
+  std::memset(&c, 0, sizeof(c));
+  c.dt = p->dt; c.am = p->am; c.af = p->af; c.gam = p->gam; c.beta = p->beta;
+  c.rho = p->rho; c.dmp = p->dmp; c.f[0] = p->f[0]; c.f[1] = p->f[1]; c.f[2] = p->f[2];
+  c.iso = p->isoType; c.vol = p->volType; c.C10 = p->C10; c.C01 = p->C01; c.Kpen = p->Kpen;
+  c.tDof = p->tDof; c.s = p->s; c.kind = 0;
+  return c;
 }
 
 void assemble_solid(b200_handle* h, const SolidConsts& c, const char* who)
@@ -278,8 +309,8 @@ void assemble_solid(b200_handle* h, const SolidConsts& c, const char* who)
   {
     // algorithmic bytes: Val and R written once, nodal fields and IEN read once
     CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*72.0 + double(h->nNo)*(24.0 + 24.0 + 24.0*3 + 24.0) + double(h->nEl)*4.0*h->eNoN, 3);
-    if (h->eNoN == 4) launch_solid<4, 4, 32, 1>(h, c);
-    else launch_solid<8, 8, 16, 2>(h, c);
+    if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 3>(h, c, h->nEl, nullptr);
+    else launch_solid<8, 8, 16, 2, 3>(h, c, h->nEl, nullptr);
   }
   finish_assembly(h, 3, t0, who);
 }
@@ -596,26 +627,14 @@ int b200_assemble_fluid(b200_handle* h, const b200_fluid_props* p)
     if (h->dof != 4 || !h->Val) throw std::runtime_error("assemble_fluid: call b200_zero(h, 4) first");
     if (p->tDof != h->tDof) throw std::runtime_error("assemble_fluid: tDof differs from the uploaded state");
     if (p->mvMsh && p->tDof < 7) throw std::runtime_error("assemble_fluid: mvMsh needs tDof >= 7");
-    FluidConsts c;
-    c.dt = p->dt; c.am = p->am; c.af = p->af; c.gam = p->gam;
-    c.rho = p->rho; c.f[0] = p->f[0]; c.f[1] = p->f[1]; c.f[2] = p->f[2]; c.Kinv = p->Kinv;
-    c.viscType = p->viscType; c.mu_i = p->mu_i; c.mu_o = p->mu_o; c.lam = p->lam; c.a = p->a; c.n = p->n;
-    c.tDof = p->tDof; c.mvMsh = p->mvMsh;
-    // Gauss rule and shape functions of TET4 (nn_elem_gip.h:501-517, nn_elem_gnn.h:1232-1238)
-    const double s = h->qmTET4, t = (1.0 - s)/3.0;
-    const double xi[4][3] = {{s, t, t}, {t, s, t}, {t, t, s}, {t, t, t}};
-    for (int g = 0; g < 4; g++) {
-      c.w[g] = 1.0/24.0;
-      c.N[g][0] = xi[g][0]; c.N[g][1] = xi[g][1]; c.N[g][2] = xi[g][2];
-      c.N[g][3] = 1.0 - xi[g][0] - xi[g][1] - xi[g][2];
-    }
     if (h->eNoN != 4) throw std::runtime_error("assemble_fluid: the fluid kernel is built for TET4 meshes");
+    const FluidConsts c = fluid_consts(h, p);
     ensure_stage(h, 4);
     double t0 = wall_s();
     {
       // algorithmic bytes (SURVEY.md par. 8d): Val and R written once, nodal fields and IEN read once
       CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*128.0 + double(h->nNo)*(32.0 + 24.0 + 16.0*p->tDof + 24.0) + double(h->nEl)*16.0, 3);
-      k_assemble_fluid_tet4<<<(h->nEl + 127)/128, 128, 0, ops.st>>>(h->nEl, c, h->d_ien, h->d_rslot, h->d_kslot, h->d_x,
+      k_assemble_fluid_tet4<<<(h->nEl + 127)/128, 128, 0, ops.st>>>(h->nEl, nullptr, nullptr, c, h->d_ien, h->d_rslot, h->d_kslot, h->d_x,
                                                                   h->d_Ag, h->d_Yg, h->d_Bf, h->stageR, h->stageK, h->d_err);
       ops.post();
     }
@@ -647,14 +666,7 @@ int b200_disp_set(b200_handle* h, int tDof, const double* Dg, const double* Do)
 int b200_assemble_struct(b200_handle* h, const b200_struct_props* p)
 {
   return guarded(h, [&] {
-    if (p->isoType < 0 || p->isoType > 2) throw std::runtime_error("assemble_struct: constitutive model has no device kernel");
-    if (p->volType < 0 || p->volType > 3) throw std::runtime_error("assemble_struct: dilational penalty model not defined");
-    SolidConsts c;
-    std::memset(&c, 0, sizeof(c));
-    c.dt = p->dt; c.am = p->am; c.af = p->af; c.gam = p->gam; c.beta = p->beta;
-    c.rho = p->rho; c.dmp = p->dmp; c.f[0] = p->f[0]; c.f[1] = p->f[1]; c.f[2] = p->f[2];
-    c.iso = p->isoType; c.vol = p->volType; c.C10 = p->C10; c.C01 = p->C01; c.Kpen = p->Kpen;
-    c.tDof = p->tDof; c.s = p->s; c.kind = 0;
+    const SolidConsts c = struct_consts(p);
     assemble_solid(h, c, "construct_dsolid");
   });
 }
@@ -669,6 +681,68 @@ int b200_assemble_lelas(b200_handle* h, const b200_lelas_props* p)
     c.elM = p->elM; c.nu = p->nu;
     c.tDof = p->tDof; c.s = p->s; c.kind = p->mesh_mode ? 2 : 1;
     assemble_solid(h, c, p->mesh_mode ? "construct_mesh" : "construct_l_elas");
+  });
+}
+
+int b200_mesh_domains(b200_handle* h, int nDmn, const int* elem_dmn)
+{
+  return guarded(h, [&] {
+    if (h->nEl == 0) throw std::runtime_error("mesh_domains: no mesh (b200_mesh_set)");
+    if (nDmn < 1) throw std::runtime_error("mesh_domains: nDmn must be positive");
+    for (auto p : h->d_dmn_elems) cudaFree(p);
+    h->d_dmn_elems.assign(nDmn, nullptr);
+    h->dmn_count.assign(nDmn, 0);
+    std::vector<std::vector<int>> lists(nDmn);
+    for (int e = 0; e < h->nEl; e++) {
+      const int d = elem_dmn[e];
+      if (d < -1 || d >= nDmn) throw std::runtime_error("mesh_domains: domain index out of range");
+      if (d >= 0) lists[d].push_back(e);          // -1: element belongs to no domain of this equation
+    }
+    for (int d = 0; d < nDmn; d++) {
+      h->dmn_count[d] = int(lists[d].size());
+      h->d_dmn_elems[d] = upload(lists[d].data(), lists[d].size(), h->ops->st);
+    }
+    CU_CHECK(cudaStreamSynchronize(h->ops->st));
+  });
+}
+
+int b200_assemble_fsi(b200_handle* h, int nDmn, const int* dmn_kind, const b200_fluid_props* fluid, const b200_struct_props* solid)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (h->nEl == 0) throw std::runtime_error("assemble_fsi: no mesh (b200_mesh_set)");
+    if (int(h->d_dmn_elems.size()) != nDmn) throw std::runtime_error("assemble_fsi: call b200_mesh_domains with the same nDmn first");
+    if (!h->d_Ag || !h->d_Dg) throw std::runtime_error("assemble_fsi: no state (b200_state_set + b200_disp_set)");
+    if (h->dof != 4 || !h->Val) throw std::runtime_error("assemble_fsi: call b200_zero(h, 4) first");
+    if (h->eNoN != 4) throw std::runtime_error("assemble_fsi: built for TET4 meshes (the fluid kernel)");
+    int covered = 0;
+    for (int d = 0; d < nDmn; d++) covered += h->dmn_count[d];
+    if (covered != h->nEl) throw std::runtime_error("assemble_fsi: every element must belong to a fluid or struct domain");
+    ensure_stage(h, 4);
+    const double t0 = wall_s();
+    {
+      CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*128.0 + double(h->nNo)*(32.0 + 24.0 + 24.0*h->tDof + 24.0) + double(h->nEl)*16.0, 2 + nDmn);
+      for (int d = 0; d < nDmn; d++) {
+        const int n = h->dmn_count[d];
+        if (n == 0) continue;
+        if (dmn_kind[d] == 0) {
+          // fluid domain: current configuration x + d_mesh, plain Navier-Stokes (permeability term off), fsi.cpp:157-163,220
+          if (fluid[d].tDof != h->tDof || fluid[d].tDof < 7) throw std::runtime_error("assemble_fsi: the fluid domain needs tDof >= 7 (mesh displacement in rows 4..6)");
+          FluidConsts c = fluid_consts(h, &fluid[d]);
+          c.Kinv = 0.0;
+          k_assemble_fluid_tet4<<<(n + 127)/128, 128, 0, ops.st>>>(n, h->d_dmn_elems[d], h->d_Dg, c, h->d_ien, h->d_rslot, h->d_kslot, h->d_x,
+                                                                 h->d_Ag, h->d_Yg, h->d_Bf, h->stageR, h->stageK, h->d_err);
+          ops.post();
+        } else if (dmn_kind[d] == 1) {
+          if (solid[d].tDof != h->tDof) throw std::runtime_error("assemble_fsi: tDof differs from the uploaded state");
+          const SolidConsts c = struct_consts(&solid[d]);
+          launch_solid<4, 4, 32, 1, 4>(h, c, n, h->d_dmn_elems[d]);
+        } else {
+          throw std::runtime_error("assemble_fsi: domain physics has no device kernel (fluid and struct have)");
+        }
+      }
+    }
+    finish_assembly(h, 4, t0, "construct_fsi");
   });
 }
 

@@ -66,8 +66,10 @@ __device__ __forceinline__ void viscosity(const FluidConsts& c, double& gamma, d
 }
 
 // one thread per element, elements in mesh order
+// elist != nullptr: the kernel covers the nEl elements elist[0..nEl) (the fluid domain of an FSI equation);
+// Dmesh != nullptr: the element lives on the ALE-displaced configuration x + Dg(4:6) (fsi.cpp:157-163).
 __global__ void __launch_bounds__(128)
-k_assemble_fluid_tet4(int nEl, FluidConsts c,
+k_assemble_fluid_tet4(int nEl, const int* __restrict__ elist, const double* __restrict__ Dmesh, FluidConsts c,
                       const int* __restrict__ ien,      // 4 x nEl, assembly node ids
                       const int* __restrict__ rslot,    // 4 x nEl staging slot (32-byte rows) of lR(:,a)
                       const int* __restrict__ kslot,    // 16 x nEl staging slot (128-byte blocks) of lK(:,a,b)
@@ -75,8 +77,9 @@ k_assemble_fluid_tet4(int nEl, FluidConsts c,
                       const double* __restrict__ Ag, const double* __restrict__ Yg, const double* __restrict__ Bf,
                       double* __restrict__ stageR, double* __restrict__ stageK, int* __restrict__ err_flag)
 {
-  const int e = blockIdx.x*blockDim.x + threadIdx.x;
-  if (e >= nEl) return;
+  const int ei = blockIdx.x*blockDim.x + threadIdx.x;
+  if (ei >= nEl) return;
+  const int e = elist ? elist[ei] : ei;
 
   int nd[4];
   {
@@ -93,6 +96,7 @@ k_assemble_fluid_tet4(int nEl, FluidConsts c,
 #pragma unroll
     for (int i = 0; i < 3; i++) {
       xl[a][i] = x[A*3 + i];
+      if (Dmesh) xl[a][i] = xl[a][i] + Dmesh[A*tD + 4 + i];
       bl[a][i] = Bf[A*3 + i];
       al[a][i] = Ag[A*tD + i];
       yl[a][i] = Yg[A*tD + i];

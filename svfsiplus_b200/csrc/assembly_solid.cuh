@@ -154,9 +154,12 @@ __device__ void pk2cc_iso(const SolidConsts& c, const double F[3][3], double* __
 
 // ENON nodes, NG Gauss points, EPB elements per CTA, APT a-indices per lane in phase 2.
 // blockDim.x = EPB*NG.  Dynamic shared memory: tables + EPB*NG records.
-template <int ENON, int NG, int EPB, int APT>
+// ODOF: block size of the system the element is scattered into (3: struct/lElas/mesh equations; 4: the FSI
+// equation, where struct_3d fills the 3x3 corner of lK(dof*dof,a,b) and leaves the pressure row/column zero,
+// fsi.cpp:225).  elist != nullptr: the kernel covers the nEl elements elist[0..nEl) (one FSI domain).
+template <int ENON, int NG, int EPB, int APT, int ODOF>
 __global__ void __launch_bounds__(EPB*NG)
-k_assemble_solid(int nEl, SolidConsts c, const double* __restrict__ tab,      // packed: w[NG], N[NG][ENON], Nxi[NG][ENON][3]
+k_assemble_solid(int nEl, const int* __restrict__ elist, SolidConsts c, const double* __restrict__ tab,      // packed: w[NG], N[NG][ENON], Nxi[NG][ENON][3]
                  const int* __restrict__ ien, const int* __restrict__ rslot, const int* __restrict__ kslot,
                  const double* __restrict__ x, const double* __restrict__ Ag, const double* __restrict__ Yg,
                  const double* __restrict__ Dg, const double* __restrict__ Do, const double* __restrict__ Bf,
@@ -179,9 +182,10 @@ k_assemble_solid(int nEl, SolidConsts c, const double* __restrict__ tab,      //
   // ---------------- phase 1: one thread per (element, Gauss point) --------------------------------
   {
     const int el = threadIdx.x / NG, g = threadIdx.x % NG;
-    const int e = e0 + el;
+    const int live = (e0 + el) < nEl;
+    const int e = live ? (elist ? elist[e0 + el] : e0 + el) : 0;
     double* rec = s_rec + size_t(threadIdx.x)*REC;
-    if (e < nEl) {
+    if (live) {
       int nd[ENON];
 #pragma unroll
       for (int a = 0; a < ENON; a++) nd[a] = ien[size_t(e)*ENON + a];
@@ -299,8 +303,8 @@ k_assemble_solid(int nEl, SolidConsts c, const double* __restrict__ tab,      //
   // ---------------- phase R: residual rows, one thread per (element, a) ------------------------------
   for (int item = threadIdx.x; item < EPB*ENON; item += NT) {
     const int el = item / ENON, a = item % ENON;
-    const int e = e0 + el;
-    if (e >= nEl) continue;
+    if (e0 + el >= nEl) continue;
+    const int e = elist ? elist[e0 + el] : e0 + el;
     double r0 = 0.0, r1 = 0.0, r2 = 0.0;
     for (int g = 0; g < NG; g++) {
       const double* rec = s_rec + size_t(el*NG + g)*REC;
@@ -319,8 +323,9 @@ k_assemble_solid(int nEl, SolidConsts c, const double* __restrict__ tab,      //
         r2 = r2 + w*(c.rho*Na*rec[SREC_UD + 2] + n0*S[5] + n1*S[4] + n2*S[2]);
       }
     }
-    double* out = stageR + size_t(rslot[size_t(e)*ENON + a])*3;
+    double* out = stageR + size_t(rslot[size_t(e)*ENON + a])*ODOF;
     out[0] = r0; out[1] = r1; out[2] = r2;
+    if (ODOF == 4) out[3] = 0.0;
   }
 
   // ---------------- phase 2: tangent blocks ------------------------------------------------------------
@@ -330,8 +335,8 @@ k_assemble_solid(int nEl, SolidConsts c, const double* __restrict__ tab,      //
   for (int item = threadIdx.x; item < EPB*IPE; item += NT) {
     const int el = item / IPE, r = item % IPE;
     const int b = r % ENON, a0 = (r / ENON)*APT;
-    const int e = e0 + el;
-    if (e >= nEl) continue;
+    if (e0 + el >= nEl) continue;
+    const int e = elist ? elist[e0 + el] : e0 + el;
     double acc[APT][9];
 #pragma unroll
     for (int q = 0; q < APT; q++)
@@ -427,9 +432,18 @@ k_assemble_solid(int nEl, SolidConsts c, const double* __restrict__ tab,      //
     }
 #pragma unroll
     for (int q = 0; q < APT; q++) {
-      double* out = stageK + size_t(kslot[(size_t(e)*ENON + (a0 + q))*ENON + b])*9;
+      double* out = stageK + size_t(kslot[(size_t(e)*ENON + (a0 + q))*ENON + b])*(ODOF*ODOF);
+      if (ODOF == 3) {
 #pragma unroll
-      for (int i = 0; i < 9; i++) out[i] = acc[q][i];
+        for (int i = 0; i < 9; i++) out[i] = acc[q][i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          d4 t;
+          t.x = (i < 3) ? acc[q][i*3] : 0.0; t.y = (i < 3) ? acc[q][i*3 + 1] : 0.0; t.z = (i < 3) ? acc[q][i*3 + 2] : 0.0; t.w = 0.0;
+          st256_stream(out + 4*i, t);
+        }
+      }
     }
   }
 }

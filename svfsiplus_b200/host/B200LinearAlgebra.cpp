@@ -6,6 +6,7 @@
 
 #include "svb200.h"
 #include "lhsa.h"
+#include "all_fun.h"
 
 #include <stdexcept>
 #include <vector>
@@ -164,8 +165,10 @@ bool B200LinearAlgebra::assemble_mesh(ComMod& com_mod, const mshType& lM, const 
   using namespace consts;
   if (!device_assembly_) return false;
   auto& eq = com_mod.eq[com_mod.cEq];
-  // one domain, one function space, 3-D; anything else falls back to the reference's construct_*
-  if (eq.nDmn != 1 || lM.nFs != 1 || com_mod.nsd != 3) return false;
+  // one function space, 3-D; anything else falls back to the reference's construct_*
+  if (lM.nFs != 1 || com_mod.nsd != 3) return false;
+  if (eq.phys == EquationType::phys_FSI) return assemble_fsi_mesh(com_mod, lM, Ag, Yg, Dg, cep_mod);
+  if (eq.nDmn != 1) return false;
   switch (eq.phys) {
     case EquationType::phys_fluid:
       return assemble_fluid_mesh(com_mod, lM, Ag, Yg);
@@ -187,8 +190,18 @@ bool B200LinearAlgebra::assemble_fluid_mesh(ComMod& com_mod, const mshType& lM, 
   if (lM.eType != ElementType::TET4 || com_mod.dof != 4) return false;
   if (mesh_uploaded_ != &lM) upload_mesh(com_mod, lM);
 
-  const auto& dmn = eq.dmn[0];
   b200_fluid_props p;
+  if (!fill_fluid_props(com_mod, eq, eq.dmn[0], p)) return false;
+
+  check(b200_state_set(h_, com_mod.tDof, Ag.data(), Yg.data(), com_mod.Bf.data()), "b200_state_set");
+  check(b200_assemble_fluid(h_, &p), "b200_assemble_fluid");
+  any_device_contribution_ = true;
+  return true;
+}
+
+bool B200LinearAlgebra::fill_fluid_props(ComMod& com_mod, const eqType& eq, const dmnType& dmn, b200_fluid_props& p)
+{
+  using namespace consts;
   p.dt = com_mod.dt; p.am = eq.am; p.af = eq.af; p.gam = eq.gam;
   p.tDof = com_mod.tDof; p.mvMsh = com_mod.mvMsh ? 1 : 0;
   p.rho = dmn.prop.at(PhysicalProperyType::fluid_density);
@@ -204,9 +217,71 @@ bool B200LinearAlgebra::assemble_fluid_mesh(ComMod& com_mod, const mshType& lM, 
   }
   p.mu_i = dmn.fluid_visc.mu_i; p.mu_o = dmn.fluid_visc.mu_o; p.lam = dmn.fluid_visc.lam;
   p.a = dmn.fluid_visc.a; p.n = dmn.fluid_visc.n;
+  return true;
+}
 
+bool B200LinearAlgebra::fill_struct_props(ComMod& com_mod, const eqType& eq, const dmnType& dmn, b200_struct_props& sp)
+{
+  using namespace consts;
+  const auto& stM = dmn.stM;
+  if (stM.Tf.fType != 0 || dmn.solid_visc.viscType != SolidViscosityModelType::viscType_NA) return false;
+  switch (stM.isoType) {
+    case ConstitutiveModelType::stIso_nHook: sp.isoType = 0; break;
+    case ConstitutiveModelType::stIso_StVK:  sp.isoType = 1; break;
+    case ConstitutiveModelType::stIso_mStVK: sp.isoType = 2; break;
+    default: return false;
+  }
+  switch (stM.volType) {
+    case ConstitutiveModelType::stVol_Quad: sp.volType = 1; break;
+    case ConstitutiveModelType::stVol_ST91: sp.volType = 2; break;
+    case ConstitutiveModelType::stVol_M94:  sp.volType = 3; break;
+    default: sp.volType = 0; break;
+  }
+  sp.dt = com_mod.dt; sp.am = eq.am; sp.af = eq.af; sp.gam = eq.gam; sp.beta = eq.beta;
+  sp.tDof = com_mod.tDof; sp.s = eq.s;
+  sp.rho = dmn.prop.at(PhysicalProperyType::solid_density);
+  sp.dmp = dmn.prop.at(PhysicalProperyType::damping);
+  sp.f[0] = dmn.prop.at(PhysicalProperyType::f_x);
+  sp.f[1] = dmn.prop.at(PhysicalProperyType::f_y);
+  sp.f[2] = dmn.prop.at(PhysicalProperyType::f_z);
+  sp.C10 = stM.C10; sp.C01 = stM.C01; sp.Kpen = stM.Kpen;
+  return true;
+}
+
+/// FSI equation (construct_fsi, fsi.cpp:42): fluid and struct domains of one TET4 mesh in one dof-4 system.
+bool B200LinearAlgebra::assemble_fsi_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag,
+    const Array<double>& Yg, const Array<double>& Dg, const CepMod* cep_mod)
+{
+  using namespace consts;
+  auto& eq = com_mod.eq[com_mod.cEq];
+  if (lM.eType != ElementType::TET4 || com_mod.dof != 4 || !com_mod.mvMsh) return false;
+  if (com_mod.pS0.size() != 0 || com_mod.pstEq) return false;
+  if (cep_mod && (cep_mod->cem.cpld || cep_mod->cem.aStress || cep_mod->cem.aStrain)) return false;
+  const int nDmn = eq.nDmn;
+  std::vector<int> kinds(nDmn, -1);
+  std::vector<b200_fluid_props> fl(nDmn);
+  std::vector<b200_struct_props> st(nDmn);
+  for (int d = 0; d < nDmn; d++) {
+    if (eq.dmn[d].phys == EquationType::phys_fluid) {
+      kinds[d] = 0;
+      if (!fill_fluid_props(com_mod, eq, eq.dmn[d], fl[d])) return false;
+    } else if (eq.dmn[d].phys == EquationType::phys_struct) {
+      kinds[d] = 1;
+      if (!fill_struct_props(com_mod, eq, eq.dmn[d], st[d])) return false;
+    } else {
+      return false;
+    }
+  }
+  if (mesh_uploaded_ != &lM) upload_mesh(com_mod, lM);
+  if (domains_uploaded_ != &lM) {
+    std::vector<int> elem_dmn(lM.nEl);
+    for (int e = 0; e < lM.nEl; e++) elem_dmn[e] = all_fun::domain(com_mod, lM, com_mod.cEq, e);
+    check(b200_mesh_domains(h_, nDmn, elem_dmn.data()), "b200_mesh_domains");
+    domains_uploaded_ = &lM;
+  }
   check(b200_state_set(h_, com_mod.tDof, Ag.data(), Yg.data(), com_mod.Bf.data()), "b200_state_set");
-  check(b200_assemble_fluid(h_, &p), "b200_assemble_fluid");
+  check(b200_disp_set(h_, com_mod.tDof, Dg.data(), nullptr), "b200_disp_set");
+  check(b200_assemble_fsi(h_, nDmn, kinds.data(), fl.data(), st.data()), "b200_assemble_fsi");
   any_device_contribution_ = true;
   return true;
 }
@@ -228,28 +303,7 @@ bool B200LinearAlgebra::assemble_solid_mesh(ComMod& com_mod, const mshType& lM, 
   b200_lelas_props lp{};
   const bool is_struct = (eq.phys == EquationType::phys_struct);
   if (is_struct) {
-    const auto& stM = dmn.stM;
-    if (stM.Tf.fType != 0 || dmn.solid_visc.viscType != SolidViscosityModelType::viscType_NA) return false;
-    switch (stM.isoType) {
-      case ConstitutiveModelType::stIso_nHook: sp.isoType = 0; break;
-      case ConstitutiveModelType::stIso_StVK:  sp.isoType = 1; break;
-      case ConstitutiveModelType::stIso_mStVK: sp.isoType = 2; break;
-      default: return false;
-    }
-    switch (stM.volType) {
-      case ConstitutiveModelType::stVol_Quad: sp.volType = 1; break;
-      case ConstitutiveModelType::stVol_ST91: sp.volType = 2; break;
-      case ConstitutiveModelType::stVol_M94:  sp.volType = 3; break;
-      default: sp.volType = 0; break;
-    }
-    sp.dt = com_mod.dt; sp.am = eq.am; sp.af = eq.af; sp.gam = eq.gam; sp.beta = eq.beta;
-    sp.tDof = com_mod.tDof; sp.s = eq.s;
-    sp.rho = dmn.prop.at(PhysicalProperyType::solid_density);
-    sp.dmp = dmn.prop.at(PhysicalProperyType::damping);
-    sp.f[0] = dmn.prop.at(PhysicalProperyType::f_x);
-    sp.f[1] = dmn.prop.at(PhysicalProperyType::f_y);
-    sp.f[2] = dmn.prop.at(PhysicalProperyType::f_z);
-    sp.C10 = stM.C10; sp.C01 = stM.C01; sp.Kpen = stM.Kpen;
+    if (!fill_struct_props(com_mod, eq, dmn, sp)) return false;
   } else {
     lp.dt = com_mod.dt; lp.am = eq.am; lp.af = eq.af; lp.beta = eq.beta;
     lp.tDof = com_mod.tDof; lp.s = eq.s;

@@ -21,7 +21,7 @@
 #include <set>
 #include <string>
 
-struct b200_handle;
+#include "svb200.h"
 
 // A maintainer adds `b200` to consts::LinearAlgebraType (consts.h:503); until then the class can be
 // compiled against the unmodified header by defining the enumerator value on the command line.
@@ -61,6 +61,10 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
     void upload_structure(ComMod& com_mod);
     void upload_mesh(ComMod& com_mod, const mshType& lM);
     bool assemble_fluid_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag, const Array<double>& Yg);
+    bool assemble_fsi_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag, const Array<double>& Yg,
+        const Array<double>& Dg, const CepMod* cep_mod);
+    bool fill_fluid_props(ComMod& com_mod, const eqType& eq, const dmnType& dmn, b200_fluid_props& p);
+    bool fill_struct_props(ComMod& com_mod, const eqType& eq, const dmnType& dmn, b200_struct_props& p);
     bool assemble_solid_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag, const Array<double>& Yg,
         const Array<double>& Dg, const CepMod* cep_mod);
 
@@ -69,6 +73,7 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
     bool device_assembly_ = false;
     bool structure_uploaded_ = false;
     const mshType* mesh_uploaded_ = nullptr;
+    const mshType* domains_uploaded_ = nullptr;
     bool any_device_contribution_ = false;
     static std::set<consts::LinearAlgebraType> valid_assemblers;
 };

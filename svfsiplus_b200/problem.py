@@ -24,6 +24,9 @@ LS_SETTINGS = {
     # tests/cases/struct/block_compression/solver.xml: <LS type="BICG"> tol 1e-12, 600 iterations
     "BICGS_STRUCT": (B.LS_BICGS, (1e-12, 1e-10, 600, 0), None, None),
     "GMRES_STRUCT": (B.LS_GMRES, (1e-9, 1e-10, 10, 100), None, None),
+    "GMRES_STRUCT_LOOSE": (B.LS_GMRES, (1e-4, 1e-10, 10, 100), None, None),
+    # tests/cases/fsi/pipe_3d/solver.xml: FSI equation <LS type="GMRES"> tol 1e-12, 100 iterations, Krylov dim 50
+    "GMRES_FSI": (B.LS_GMRES, (1e-12, 1e-10, 100, 50), None, None),
     "CG_MESH": (B.LS_CG, (1e-10, 1e-14, 400, 0), None, None),
 }
 
@@ -156,4 +159,63 @@ def solid_linear_step(be: B.Backend, case, ls="BICGS_STRUCT", want_system=False,
         R, Val = be.get_R(), be.get_Val()
     ls_type, RI, GM, CG = LS_SETTINGS[ls] if isinstance(ls, str) else ls
     X, info = be.solve(ls_type, prec, RI, GM, CG, case["incL"], case["res"])
+    return (X, info, R, Val) if want_system else (X, info)
+
+
+# ---------------------------------------------------------------------------------------------------
+# FSI pipe (tests/cases/fsi/pipe_3d/solver.xml): lumen = fluid domain, outer shell of the same structured
+# pipe = struct domain (neo-Hookean wall), one dof-4 matrix, tDof = 7 (FSI unknowns 0..3, mesh 4..6)
+# ---------------------------------------------------------------------------------------------------
+def fsi_case(nx, ny, nz, *, wall_from=0.8, radius=1.0, length=10.0):
+    m = M.pipe_mesh(nx, ny, nz, radius=radius, length=length)
+    rowPtr, colPtr = M.csr_pattern(m.ien, m.nNo)
+    am, af, gam = M.gen_alpha(0.5)                 # FSI is a first-order equation (initialize.cpp:424-433)
+    beta = 0.25 * (1.0 + am - af) ** 2
+    dt = 1e-4
+    cen = m.x[m.ien].mean(axis=1)
+    r = np.sqrt(cen[:, 0] ** 2 + cen[:, 1] ** 2)
+    elem_dmn = (r > wall_from * radius).astype(np.int32)       # 0 fluid (lumen), 1 struct (wall)
+    n = m.nNo
+    A4, Y4, Bf = M.pipe_state(m, radius=radius, length=length)
+    rng = np.random.default_rng(99)
+    Ag = np.zeros((n, 7)); Yg = np.zeros((n, 7)); Dg = np.zeros((n, 7))
+    Ag[:, :4] = A4; Yg[:, :4] = Y4
+    h = 2.0 * radius / nx
+    Dg[:, 0:3] = 0.02 * h * rng.standard_normal((n, 3))         # solid displacement (used in the wall)
+    Dg[:, 4:7] = 0.05 * h * rng.standard_normal((n, 3))         # mesh displacement (used in the lumen)
+    Yg[:, 4:7] = 0.5 * rng.standard_normal((n, 3))              # mesh velocity
+    Ag[:, 4:7] = rng.standard_normal((n, 3))
+    Bf = 0.1 * rng.standard_normal((n, 3))
+    E, nu = 1.0e7, 0.3
+    mu = 0.5 * E / (1.0 + nu)
+    fluid = dict(rho=1.0, mu=0.04)
+    solid = dict(rho=1.0, dmp=0.0, iso="nHook", vol="ST91", C10=0.5 * mu, C01=0.0, Kpen=E / (3.0 * (1.0 - 2.0 * nu)))
+    faces = [
+        dict(name="inlet", nodes=m.faces["inlet"]["nodes"], dof=3, bGrp=B.BC_DIR, val=np.zeros((len(m.faces["inlet"]["nodes"]), 3))),
+        dict(name="outlet", nodes=m.faces["outlet"]["nodes"], dof=3, bGrp=B.BC_DIR, val=np.zeros((len(m.faces["outlet"]["nodes"]), 3))),
+    ]
+    return dict(mesh=m, rowPtr=rowPtr, colPtr=colPtr, Ag=Ag, Yg=Yg, Dg=Dg, Bf=Bf, elem_dmn=elem_dmn, fluid=fluid, solid=solid,
+                time=dict(dt=dt, am=am, af=af, gam=gam, beta=beta), faces=faces, res=np.zeros(2), incL=np.ones(2, np.int32),
+                kind="fsi", name=f"fsi_{nx}x{ny}x{nz}")
+
+
+def assemble_fsi(be: B.Backend, case, upload=True):
+    t = case["time"]
+    if upload:
+        be.state_set(7, case["Ag"], case["Yg"], case["Bf"])
+        be.disp_set(7, case["Dg"])
+        be.mesh_domains(2, case["elem_dmn"])
+    be.zero(4)
+    fp = B.fluid_props(tDof=7, mvMsh=True, dt=t["dt"], am=t["am"], af=t["af"], gam=t["gam"], **case["fluid"])
+    sp = B.struct_props(tDof=7, s=0, dt=t["dt"], am=t["am"], af=t["af"], gam=t["gam"], beta=t["beta"], **case["solid"])
+    be.assemble_fsi([0, 1], [fp, None], [None, sp])
+
+
+def fsi_linear_step(be: B.Backend, case, ls="GMRES_FSI", want_system=False):
+    assemble_fsi(be, case)
+    R = Val = None
+    if want_system:
+        R, Val = be.get_R(), be.get_Val()
+    ls_type, RI, GM, CG = LS_SETTINGS[ls] if isinstance(ls, str) else ls
+    X, info = be.solve(ls_type, B.PREC_FSILS, RI, GM, CG, case["incL"], case["res"])
     return (X, info, R, Val) if want_system else (X, info)

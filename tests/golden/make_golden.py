@@ -54,6 +54,10 @@ def main():
             out[f"Val_{tag}"] = Val
         out[f"w_{elem}"], out[f"N_{elem}"], out[f"Nx_{elem}"] = tabs
     np.savez_compressed(os.path.join(HERE, "block_3_solid.npz"), **out)
+    # FSI equation (construct_fsi): fluid lumen + struct wall on one dof-4 matrix
+    c = P.fsi_case(4, 4, 4)
+    R, Val, _ = refcase.reference_assemble_fsi(c)
+    np.savez_compressed(os.path.join(HERE, "fsi_4_4_4.npz"), R=R, Val=Val, elem_dmn=c["elem_dmn"])
     print("golden fixtures written")
 
 
