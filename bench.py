@@ -270,6 +270,12 @@ def run_gpu(args):
     e2e_ms = maxreduce(e2e_ms) / args.steps
     clocks = sampler.stop() if rank == 0 else None
 
+    # stand-alone block SpMV (the north-star kernel): CUDA events over 50 back-to-back launches.  Collective
+    # for N > 1 (assembly is followed by commu(R), every product by its overlap add): ALL ranks run it.
+    P.assemble(be, case, upload=False)
+    spmv_ms, spmv_bytes = be.op_bench("spmv_vv4", reps=50)
+    barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -284,9 +290,6 @@ def run_gpu(args):
     per_class = {k: {"ms_per_launch": v["ms"] / max(v["launches"], 1), "launches_per_step": v["launches"] / args.prof_steps,
                      "GBps": (v["bytes"] / 1e9) / (v["ms"] * 1e-3) if v["ms"] > 0 else None}
                  for k, v in prof.items() if v["launches"] > 0}
-    # stand-alone block SpMV (the north-star kernel): CUDA events over 50 back-to-back launches
-    P.assemble(be, case, upload=False)
-    spmv_ms, spmv_bytes = be.op_bench("spmv_vv4", reps=50)
     nnz, nNo = be.nnz, be.nNo
     spmv_gbs = spmv_bytes / 1e9 / (spmv_ms * 1e-3)
 

@@ -963,10 +963,14 @@ int b200_op_bench(b200_handle* h, int op, int k, int reps, double* ms_per_launch
         case KC_SPMV_VV3: { const int v0 = ops.variant_vv3; ops.variant_vv3 = k; ops.spmv_vv(3, mK, x, y); ops.variant_vv3 = v0; bytes = ops.bytes_vv(3); break; }
         case KC_SPMV_SS:  ops.spmv_ss(mL, x, y); bytes = ops.bytes_ss(); break;
         case KC_SPMV_SV:  // pass 1 of the fused Schur operator
-          k_schur_gp<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(h->nNo, ops.rowPtr, ops.col, mG, x, ops.V4); ops.post();
+          if (k == 1) k_schur_gp4<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(nullptr, h->nNo, ops.rowPtr, ops.col, mG, x, ops.V4);
+          else k_schur_gp<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(nullptr, h->nNo, ops.rowPtr, ops.col, mG, x, ops.V4);
+          ops.post();
           bytes = ops.bytes_schur_gp(); break;
         case KC_SPMV_VS:  // pass 2 of the fused Schur operator
-          k_schur_sp<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(h->nNo, ops.rowPtr, ops.col, ops.GtL, ops.V4, y); ops.post();
+          if (k == 1) k_schur_sp4<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(nullptr, h->nNo, ops.rowPtr, ops.col, ops.GtL, ops.V4, y);
+          else k_schur_sp<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(nullptr, h->nNo, ops.rowPtr, ops.col, ops.GtL, ops.V4, y);
+          ops.post();
           bytes = ops.bytes_schur_sp(); break;
         case KC_MULTI_DOT: {
           const int my = ops.mynNo_; ops.mynNo_ = h->nNo;
@@ -980,7 +984,7 @@ int b200_op_bench(b200_handle* h, int op, int k, int reps, double* ms_per_launch
         default: throw std::runtime_error("op_bench: this kernel class has no stand-alone bench");
       }
     };
-    if (op == KC_SPMV_VS) { k_schur_gp<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(h->nNo, ops.rowPtr, ops.col, mG, x, ops.V4); ops.post(); }
+    if (op == KC_SPMV_VS) { k_schur_gp<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(nullptr, h->nNo, ops.rowPtr, ops.col, mG, x, ops.V4); ops.post(); }
     const bool prof = ops.profiling;
     ops.profiling = false;
     cudaEvent_t e0, e1;

@@ -74,9 +74,10 @@ __device__ __forceinline__ int ld_stream_i(const int* p)
 // consecutive 32-byte results.  rowPtr is the standard (nNo+1) CSR pointer in solver ordering.
 // =================================================================================================
 __global__ void __launch_bounds__(256)
-k_spmv_vv4(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
+k_spmv_vv4(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
            const double* __restrict__ K, const double* __restrict__ U, double* __restrict__ KU)
 {
+  if (skip && *skip) return;
   const int lane4 = threadIdx.x & 3;
   const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
   const int ngroups = (gridDim.x*blockDim.x) >> 2;
@@ -115,9 +116,10 @@ k_spmv_vv4(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
 // row, lane i < DOF owns component i.
 template <int DOF>
 __global__ void __launch_bounds__(256)
-k_spmv_vv(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
+k_spmv_vv(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
           const double* __restrict__ K, const double* __restrict__ U, double* __restrict__ KU)
 {
+  if (skip && *skip) return;
   const int lane4 = threadIdx.x & 3;
   const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
   const int ngroups = (gridDim.x*blockDim.x) >> 2;
@@ -145,9 +147,10 @@ k_spmv_vv(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
 // p = s+l, s+l+4, ... of the row (whole 3x3 block + the 3-vector of its column), the quad then adds
 // its partial 3-vectors in a fixed order.  Per step a quad streams 288 contiguous bytes.
 __global__ void __launch_bounds__(256)
-k_spmv_vv3s(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
+k_spmv_vv3s(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
             const double* __restrict__ K, const double* __restrict__ U, double* __restrict__ KU)
 {
+  if (skip && *skip) return;
   const int lane4 = threadIdx.x & 3;
   const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
   const int ngroups = (gridDim.x*blockDim.x) >> 2;
@@ -178,9 +181,10 @@ k_spmv_vv3s(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col
 // K2a  KU(i) = sum_j K(j) U(col_j)                     (fsils_spar_mul_ss, spar_mul.cpp:46-61)
 // 4 lanes per row striding over the row's entries; fixed-order quad reduction.
 __global__ void __launch_bounds__(256)
-k_spmv_ss(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
+k_spmv_ss(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
           const double* __restrict__ K, const double* __restrict__ U, double* __restrict__ KU)
 {
+  if (skip && *skip) return;
   const int lane4 = threadIdx.x & 3;
   const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
   const int ngroups = (gridDim.x*blockDim.x) >> 2;
@@ -202,9 +206,10 @@ k_spmv_ss(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
 // K2b  KU(m,i) = sum_j K(m,j) U(col_j)                 (fsils_spar_mul_sv, spar_mul.cpp:63-127)
 template <int DOF>
 __global__ void __launch_bounds__(256)
-k_spmv_sv(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
+k_spmv_sv(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
           const double* __restrict__ K, const double* __restrict__ U, double* __restrict__ KU)
 {
+  if (skip && *skip) return;
   const int lane4 = threadIdx.x & 3;
   const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
   const int ngroups = (gridDim.x*blockDim.x) >> 2;
@@ -223,9 +228,10 @@ k_spmv_sv(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
 // K2c  KU(i) = sum_j K(:,j) . U(:,col_j)                (fsils_spar_mul_vs, spar_mul.cpp:129-189)
 template <int DOF>
 __global__ void __launch_bounds__(256)
-k_spmv_vs(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
+k_spmv_vs(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
           const double* __restrict__ K, const double* __restrict__ U, double* __restrict__ KU)
 {
+  if (skip && *skip) return;
   const int lane4 = threadIdx.x & 3;
   const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
   const int ngroups = (gridDim.x*blockDim.x) >> 2;
@@ -259,9 +265,10 @@ k_spmv_vs(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
 // and applies the resistance-face preconditioner to it (ld = 4).
 // 4 lanes per row striding over the row's entries; fixed-order quad reduction.
 __global__ void __launch_bounds__(256)
-k_schur_gp(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col, const double* __restrict__ G,
+k_schur_gp(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col, const double* __restrict__ G,
            const double* __restrict__ P, double* __restrict__ V4)
 {
+  if (skip && *skip) return;
   const int lane4 = threadIdx.x & 3;
   const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
   const int ngroups = (gridDim.x*blockDim.x) >> 2;
@@ -291,9 +298,10 @@ k_schur_gp(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
 }
 
 __global__ void __launch_bounds__(256)
-k_schur_sp(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col, const double* __restrict__ GtL,
+k_schur_sp(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col, const double* __restrict__ GtL,
            const double* __restrict__ V4, double* __restrict__ SP)
 {
+  if (skip && *skip) return;
   const int lane4 = threadIdx.x & 3;
   const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
   const int ngroups = (gridDim.x*blockDim.x) >> 2;
@@ -319,6 +327,88 @@ k_schur_sp(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
   }
 }
 
+// Variants of the two Schur passes with four entries in flight per lane (rows of <= 16 entries take one
+// trip): 4 x (index -> matrix entry + gathered vector entry) independent chains per thread instead of two.
+__global__ void __launch_bounds__(256)
+k_schur_gp4(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col, const double* __restrict__ G,
+            const double* __restrict__ P, double* __restrict__ V4)
+{
+  if (skip && *skip) return;
+  const int lane4 = threadIdx.x & 3;
+  const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
+  const int ngroups = (gridDim.x*blockDim.x) >> 2;
+  const int nrounds = (nNo + ngroups - 1)/ngroups;
+  for (int r = 0; r < nrounds; r++) {
+    const int row = group + r*ngroups;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    if (row < nNo) {
+      const int s = __ldg(rowPtr + row);
+      const int e = __ldg(rowPtr + row + 1);
+      for (int base = s + lane4; base < e; base += 16) {
+        int c[4];
+        double u[4], g0[4], g1[4], g2[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const int p = base + 4*q; c[q] = (p < e) ? ld_stream_i(col + p) : -1; }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int p = base + 4*q;
+          const bool on = c[q] >= 0;
+          const double* g = G + size_t(on ? p : s)*3;
+          g0[q] = on ? ld_stream(g) : 0.0; g1[q] = on ? ld_stream(g + 1) : 0.0; g2[q] = on ? ld_stream(g + 2) : 0.0;
+          u[q] = on ? __ldg(P + c[q]) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) { a0 = fma(g0[q], u[q], a0); a1 = fma(g1[q], u[q], a1); a2 = fma(g2[q], u[q], a2); }
+      }
+    }
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 2); a1 += __shfl_xor_sync(0xffffffffu, a1, 2); a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
+    if (row < nNo && lane4 == 0) {
+      d4 o; o.x = a0; o.y = a1; o.z = a2; o.w = __ldg(P + row);
+      st256(V4 + size_t(row)*4, o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_schur_sp4(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col, const double* __restrict__ GtL,
+            const double* __restrict__ V4, double* __restrict__ SP)
+{
+  if (skip && *skip) return;
+  const int lane4 = threadIdx.x & 3;
+  const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
+  const int ngroups = (gridDim.x*blockDim.x) >> 2;
+  const int nrounds = (nNo + ngroups - 1)/ngroups;
+  for (int r = 0; r < nrounds; r++) {
+    const int row = group + r*ngroups;
+    double aL = 0.0, aD = 0.0;
+    if (row < nNo) {
+      const int s = __ldg(rowPtr + row);
+      const int e = __ldg(rowPtr + row + 1);
+      for (int base = s + lane4; base < e; base += 16) {
+        int c[4];
+        d4 k[4], v[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const int p = base + 4*q; c[q] = (p < e) ? ld_stream_i(col + p) : -1; }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const int p = base + 4*q;
+          if (c[q] >= 0) { k[q] = ld256_stream(GtL + size_t(p)*4); v[q] = ld256_keep(V4 + size_t(c[q])*4); }
+          else { k[q].x = k[q].y = k[q].z = k[q].w = 0.0; v[q] = k[q]; }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          aL = fma(k[q].w, v[q].w, aL);
+          aD = aD + (k[q].x*v[q].x + k[q].y*v[q].y + k[q].z*v[q].z);
+        }
+      }
+    }
+    aL += __shfl_xor_sync(0xffffffffu, aL, 1); aD += __shfl_xor_sync(0xffffffffu, aD, 1);
+    aL += __shfl_xor_sync(0xffffffffu, aL, 2); aD += __shfl_xor_sync(0xffffffffu, aD, 2);
+    if (row < nNo && lane4 == 0) SP[row] = aL - aD;
+  }
+}
+
 // =================================================================================================
 // K3  multi-dot: red[slot0 + j] = sum_{idx < n} V_j[idx] * w[idx],  j = 0..cnt-1, V_j = base + j*stride.
 // (fsils_nc_dot_v inside the Arnoldi loop, liner_solver/gmres.cpp:550-555; dot.cpp:134-175.)
@@ -329,9 +419,10 @@ k_schur_sp(int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
 // CTA order by the last CTA to finish.  partial must hold gridDim.x * cnt doubles.
 // =================================================================================================
 __global__ void __launch_bounds__(kRedThreads)
-k_multi_dot(size_t n, const double* __restrict__ base, size_t stride, const double* __restrict__ w, int cnt,
+k_multi_dot(const int* __restrict__ skip, size_t n, const double* __restrict__ base, size_t stride, const double* __restrict__ w, int cnt,
             double* __restrict__ partial, unsigned int* __restrict__ counter, double* __restrict__ red, int slot0)
 {
+  if (skip && *skip) return;
   __shared__ double sm[kRedThreads/32][kDotJB];
   __shared__ bool last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -497,6 +588,80 @@ __global__ void k_bicg_p(size_t n, double* __restrict__ P, const double* __restr
 {
   const size_t nth = size_t(gridDim.x)*blockDim.x;
   for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) P[i] = fma(beta, fma(-omega, V[i], P[i]), R[i]);
+}
+
+// ---- device-resident CG iteration of the Schur / vector CG solvers (cgrad.cpp:50-160, 166-246) ----------
+// The scalars of the iteration (err, errO, alpha) live on the device, so that the host can enqueue
+// iterations back to back and only polls the state every few iterations; once `done` is set every
+// kernel of the remaining (already enqueued) iterations returns at once.
+struct CgState { double err, errO, eps; int done, suc, last_i, pad; };
+
+// top of iteration i:  last_i = i; if (err < eps) { suc; break; }  errO = err;
+__global__ void k_cg_head(CgState* st, int i)
+{
+  if (st->done) return;
+  st->last_i = i;
+  if (st->err < st->eps) { st->done = 1; st->suc = 1; }
+  else st->errO = st->err;
+}
+// alpha = errO / <P,SP>;  X += alpha P;  R -= alpha SP;  red[slot] = sum_{idx < nOwn} R^2  (local part)
+// Same two-stage deterministic reduction as k_multi_dot.
+__global__ void __launch_bounds__(kRedThreads)
+k_cg_update(size_t n, size_t nOwn, const CgState* __restrict__ st, const double* __restrict__ red_dot,
+            const double* __restrict__ P, const double* __restrict__ SP, double* __restrict__ X, double* __restrict__ R,
+            double* __restrict__ partial, unsigned int* __restrict__ counter, double* __restrict__ red_out)
+{
+  if (st->done) return;
+  __shared__ double sm[kRedThreads/32];
+  __shared__ bool last;
+  const double alpha = st->errO / red_dot[0];
+  const size_t chunk = ((n + gridDim.x - 1)/gridDim.x + 3) & ~size_t(3);
+  const size_t beg = size_t(blockIdx.x)*chunk;
+  const size_t end = (beg + chunk < n) ? beg + chunk : n;
+  double acc = 0.0;
+  for (size_t idx = beg + threadIdx.x; idx < end; idx += kRedThreads) {
+    X[idx] = fma(alpha, P[idx], X[idx]);
+    const double r = fma(-alpha, SP[idx], R[idx]);
+    R[idx] = r;
+    if (idx < nOwn) acc = fma(r, r, acc);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if (lane == 0) sm[wid] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+#pragma unroll
+    for (int k = 0; k < kRedThreads/32; k++) v += sm[k];
+    partial[blockIdx.x] = v;
+    __threadfence();
+    last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && wid == 0) {
+    __threadfence();
+    double v = 0.0;
+    for (unsigned int b = lane; b < gridDim.x; b += 32) v += __ldcg(partial + b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) { red_out[0] = v; *counter = 0u; }
+  }
+}
+// err = (sqrt(red))^2;  P = (err/errO) * (P + (errO/err) R);  state.err = err   (cgrad.cpp:222-227)
+__global__ void __launch_bounds__(256)
+k_cg_pupdate(size_t n, CgState* st, const double* __restrict__ red_rr, const double* __restrict__ R, double* __restrict__ P)
+{
+  if (st->done) return;
+  const double errO = st->errO;
+  double err = sqrt(red_rr[0]);
+  err = err*err;
+  const double a = errO/err, b = err/errO;
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  for (size_t i = size_t(blockIdx.x)*blockDim.x + threadIdx.x; i < n; i += nth) P[i] = b*fma(a, R[i], P[i]);
+  // every CTA has read st->errO / red_rr before this store can matter: the only reader of st->err is
+  // the next iteration's k_cg_head, ordered after this kernel by the stream
+  if (blockIdx.x == 0 && threadIdx.x == 0) st->err = err;
 }
 
 // ---- permutation by lhs.map (solve.cpp:116-120,188-192) ------------------------------------------

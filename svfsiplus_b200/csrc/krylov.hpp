@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <limits>
 #include <stdexcept>
+#include <type_traits>
 #include <vector>
 
 #include "svb200.h"
@@ -142,6 +143,10 @@ struct Hessenberg {
     }
   }
 };
+
+// Policies that keep the CG scalars on the device (CudaOps) expose cg_device(); the serial test policy does not.
+template <class T, class = void> struct has_cg_device : std::false_type {};
+template <class T> struct has_cg_device<T, std::void_t<decltype(&T::cg_batch)>> : std::true_type {};
 
 template <class Ops> inline bool any_coupled(Ops& ops)
 {
@@ -330,6 +335,9 @@ void cgrad_v(Ops& ops, SubLs& ls, int dof, const double* K, double* R)
   ops.copy(n, R, P);
   int last_i = 0;
 
+  if constexpr (has_cg_device<Ops>::value) {
+    ops.cg_device(ls, dof, R, X, P, KP, [&](const double* p, double* kp) { ops.spmv_vv(dof, K, p, kp); }, last_i, err, errO);
+  } else {
   for (int i = 0; i < ls.mItr; i++) {
     last_i = i;
     if (err < eps) { ls.suc = true; break; }
@@ -342,6 +350,7 @@ void cgrad_v(Ops& ops, SubLs& ls, int dof, const double* K, double* R)
     err = err*err;
     ops.axpy(n, errO/err, R, P);      // P = P + (errO/err) R
     ops.scal(n, err/errO, P);         // P = (err/errO) P
+  }
   }
   ops.copy(n, X, R);
   ls.itr = last_i;
@@ -377,6 +386,10 @@ void schur(Ops& ops, SubLs& ls, int nsd, const double* D, const double* G, const
   ops.copy(nn, R, P);
   int last_i = 0;
 
+  if constexpr (has_cg_device<Ops>::value) {
+    ops.cg_device(ls, 1, R, X, P, SP, [&](const double* p, double* sp) { ops.schur_op(nsd, D, G, L, p, GP, DGP, sp, coupled); },
+                  last_i, err, errO);
+  } else {
   for (int i = 0; i < ls.mItr; i++) {
     last_i = i;
     if (err < eps) { ls.suc = true; break; }
@@ -389,6 +402,7 @@ void schur(Ops& ops, SubLs& ls, int nsd, const double* D, const double* G, const
     err = err*err;
     ops.axpy(nn, errO/err, R, P);
     ops.scal(nn, err/errO, P);
+  }
   }
   ops.copy(nn, X, R);
   ls.fNorm = std::sqrt(err);

@@ -152,6 +152,11 @@ class CudaOps {
   double* partial_d = nullptr;
   unsigned int* counter_d = nullptr;   // [0] multi-dot, [1] face dot
   double* face_partial_d = nullptr;
+  CgState* cg_d = nullptr;             // device-resident CG scalars
+  CgState* cg_h = nullptr;             // pinned: [0..1] polling slots, [2] initial / final state
+  cudaEvent_t cg_ev[2] = {nullptr, nullptr};
+  int cg_batch = 8;
+  const int* skip_flag = nullptr;      // != null inside a device-resident loop: heavy kernels return at once when set
 
   // arena
   struct Chunk { char* p; size_t cap, top; };
@@ -169,6 +174,10 @@ class CudaOps {
     CU_CHECK(cudaMalloc(&counter_d, 2*sizeof(unsigned int)));
     CU_CHECK(cudaMemset(counter_d, 0, 2*sizeof(unsigned int)));
     CU_CHECK(cudaMalloc(&face_partial_d, sizeof(double)*kFaceBlocks));
+    CU_CHECK(cudaMalloc(&cg_d, sizeof(CgState)));
+    CU_CHECK(cudaMallocHost(&cg_h, 3*sizeof(CgState)));
+    CU_CHECK(cudaEventCreateWithFlags(&cg_ev[0], cudaEventDisableTiming));
+    CU_CHECK(cudaEventCreateWithFlags(&cg_ev[1], cudaEventDisableTiming));
   }
   ~CudaOps()
   {
@@ -177,6 +186,9 @@ class CudaOps {
     for (auto& f : faces) { cudaFree(f.glob); cudaFree(f.val); cudaFree(f.valM); }
     for (auto& r : reqs) { cudaFree(r.ptr); cudaFree(r.sbuf); cudaFree(r.rbuf); }
     cudaFree(rowPtr); cudaFree(col); cudaFree(diag); cudaFree(tpos);
+    cudaFree(cg_d); cudaFreeHost(cg_h);
+    if (cg_ev[0]) cudaEventDestroy(cg_ev[0]);
+    if (cg_ev[1]) cudaEventDestroy(cg_ev[1]);
     cudaFree(red_d); cudaFreeHost(red_h); cudaFree(partial_d); cudaFree(counter_d); cudaFree(face_partial_d);
     if (comm) nccl.CommDestroy(comm);
     if (st) cudaStreamDestroy(st);
@@ -281,7 +293,7 @@ class CudaOps {
       Scope sc(*this, KC_MULTI_DOT, 8.0*double(n)*(m + 1));
       // enough CTAs to fill the machine, never more than one per 1024 entries (tiny systems)
       const int g = int(std::min<size_t>(size_t(kRedBlocks), (n + 1023)/1024 + 1));
-      k_multi_dot<<<g, kRedThreads, 0, st>>>(n, base + size_t(done)*stride, stride, w, m, partial_d, counter_d, red_d, slot0 + done);
+      k_multi_dot<<<g, kRedThreads, 0, st>>>(skip_flag, n, base + size_t(done)*stride, stride, w, m, partial_d, counter_d, red_d, slot0 + done);
       post();
       done += m;
     }
@@ -314,6 +326,9 @@ class CudaOps {
     post();
   }
 
+  // entries in flight per lane in the two Schur passes (A/B on B200, profiles/r01_tour_b.jsonl): pass 1 is
+  // fastest with two (0.151 vs 0.163 ms at P10), pass 2 with four (0.193 vs 0.217 ms)
+  int variant_gp = 0, variant_sp = 1;
   int variant_vv3 = 0;       // 0: lane = component, 1: lanes stride over the row's blocks (A/B by op_bench)
   // ---- SpMV (+ overlap-node add) --------------------------------------------------------------------
   void spmv_vv(int dof, const double* K, const double* U, double* KU)
@@ -322,12 +337,12 @@ class CudaOps {
     {
     Scope sc(*this, dof == 4 ? KC_SPMV_VV4 : KC_SPMV_VV3, bytes_vv(dof));
     switch (dof) {
-      case 4: k_spmv_vv4<<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU); break;
-      case 3: if (variant_vv3 == 1) k_spmv_vv3s<<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
-              else k_spmv_vv<3><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
+      case 4: k_spmv_vv4<<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU); break;
+      case 3: if (variant_vv3 == 1) k_spmv_vv3s<<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU);
+              else k_spmv_vv<3><<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU);
               break;
-      case 2: k_spmv_vv<2><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU); break;
-      case 1: k_spmv_vv<1><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU); break;
+      case 2: k_spmv_vv<2><<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU); break;
+      case 1: k_spmv_vv<1><<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU); break;
       default: throw std::runtime_error("spmv_vv: dof > 4 is not a supported FSILS path");
     }
     post();
@@ -338,7 +353,7 @@ class CudaOps {
   {
     {
       Scope sc(*this, KC_SPMV_SS, bytes_ss());
-      k_spmv_ss<<<grid_rows(nNo_), 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
+      k_spmv_ss<<<grid_rows(nNo_), 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU);
       post();
     }
     halo_add(1, KU);
@@ -348,8 +363,8 @@ class CudaOps {
     const int g = grid_rows(nNo_);
     {
       Scope sc(*this, KC_SPMV_SV, bytes_svs(dof));
-      if (dof == 3) k_spmv_sv<3><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
-      else if (dof == 2) k_spmv_sv<2><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
+      if (dof == 3) k_spmv_sv<3><<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU);
+      else if (dof == 2) k_spmv_sv<2><<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU);
       else throw std::runtime_error("spmv_sv: nsd must be 2 or 3");
       post();
     }
@@ -360,8 +375,8 @@ class CudaOps {
     const int g = grid_rows(nNo_);
     {
       Scope sc(*this, KC_SPMV_VS, bytes_svs(dof));
-      if (dof == 3) k_spmv_vs<3><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
-      else if (dof == 2) k_spmv_vs<2><<<g, 256, 0, st>>>(nNo_, rowPtr, col, K, U, KU);
+      if (dof == 3) k_spmv_vs<3><<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU);
+      else if (dof == 2) k_spmv_vs<2><<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU);
       else throw std::runtime_error("spmv_vs: nsd must be 2 or 3");
       post();
     }
@@ -595,14 +610,16 @@ class CudaOps {
       const int g = grid_rows(nNo_);
       {
         Scope sc(*this, KC_SPMV_SV, bytes_schur_gp());
-        k_schur_gp<<<g, 256, 0, st>>>(nNo_, rowPtr, col, G, P, V4);
+        if (variant_gp == 1) k_schur_gp4<<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, G, P, V4);
+        else k_schur_gp<<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, G, P, V4);
         post();
       }
       halo_add(3, V4, 4);
       if (coupled) add_bc_mul(BCOP_PRE, 3, V4, V4, 4);
       {
         Scope sc(*this, KC_SPMV_VS, bytes_schur_sp());
-        k_schur_sp<<<g, 256, 0, st>>>(nNo_, rowPtr, col, GtL, V4, SP);
+        if (variant_sp == 1) k_schur_sp4<<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, GtL, V4, SP);
+        else k_schur_sp<<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, GtL, V4, SP);
         post();
       }
       halo_add(1, SP);
@@ -614,6 +631,62 @@ class CudaOps {
     spmv_ss(L, P, SP);
     axpy(size_t(nNo_), -1.0, DGP, SP);
   }
+  // ---- device-resident CG loops --------------------------------------------------------------------------
+  // Generic driver: `apply(P, SP)` enqueues SP = A P (with its overlap adds); the scalars stay on the device
+  // (k_cg_head / k_cg_update / k_cg_pupdate) and the host polls the state every cg_batch iterations, one batch
+  // behind, so the stream never drains.  Same arithmetic as the host-driven loop of krylov.hpp.
+  template <class Apply>
+  void cg_device(SubLs& ls, int dof, double* R, double* X, double* P, double* SP, Apply&& apply, int& last_i, double& err, double& errO)
+  {
+    const size_t n = size_t(dof)*nNo_, nOwn = size_t(dof)*mynNo_;
+    CgState init;
+    init.err = err; init.errO = errO; init.eps = std::pow(std::max(ls.absTol, ls.relTol*ls.iNorm), 2.0);
+    init.done = 0; init.suc = 0; init.last_i = 0; init.pad = 0;
+    cg_h[2] = init;
+    CU_CHECK(cudaMemcpyAsync(cg_d, &cg_h[2], sizeof(CgState), cudaMemcpyHostToDevice, st));
+    const int g = int(std::min<size_t>(size_t(kRedBlocks), (n + 1023)/1024 + 1));
+    int enq = 0, slot = 0, pending = -1;
+    bool stop = (ls.mItr <= 0);
+    skip_flag = &cg_d->done;
+    while (!stop) {
+      const int nb = std::min(cg_batch, ls.mItr - enq);
+      for (int k = 0; k < nb; k++) {
+        k_cg_head<<<1, 1, 0, st>>>(cg_d, enq + k); post();
+        apply(P, SP);
+        dots_local(dof, 1, P, 0, SP, 0);
+        reduce_begin(1);
+        {
+          Scope sc(*this, KC_BLAS1, 48.0*double(n));
+          k_cg_update<<<g, kRedThreads, 0, st>>>(n, nOwn, cg_d, red_d, P, SP, X, R, partial_d, counter_d, red_d + 1); post();
+        }
+        if (nranks > 1) nccl.check(nccl.AllReduce(red_d + 1, red_d + 1, 1, Nccl::kFloat64, Nccl::kSum, comm, st), "AllReduce");
+        {
+          Scope sc(*this, KC_BLAS1, 24.0*double(n));
+          k_cg_pupdate<<<grid_for(n, 256), 256, 0, st>>>(n, cg_d, red_d + 1, R, P); post();
+        }
+      }
+      enq += nb;
+      CU_CHECK(cudaMemcpyAsync(&cg_h[slot], cg_d, sizeof(CgState), cudaMemcpyDeviceToHost, st));
+      CU_CHECK(cudaEventRecord(cg_ev[slot], st));
+      if (pending >= 0) {
+        CU_CHECK(cudaEventSynchronize(cg_ev[pending]));
+        if (cg_h[pending].done) stop = true;
+      }
+      pending = slot; slot ^= 1;
+      if (enq >= ls.mItr) stop = true;
+    }
+    // the reference leaves the loop with last_i = mItr - 1 when it never converges; a final head would only
+    // matter for the `suc` flag of an iterate that converged in the very last iteration, which the reference
+    // does not report either (it tests at the top of an iteration)
+    skip_flag = nullptr;
+    CU_CHECK(cudaMemcpyAsync(&cg_h[2], cg_d, sizeof(CgState), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    ls.suc = cg_h[2].suc != 0;
+    last_i = cg_h[2].last_i;
+    err = cg_h[2].err;
+    errO = cg_h[2].errO;
+  }
+
   void split_mc(int dof, const double* Ri, double* Rm, double* Rc)
   {
     k_split_mc<<<grid_for(size_t(nNo_)*dof, 256), 256, 0, st>>>(nNo_, dof, Ri, Rm, Rc); post();

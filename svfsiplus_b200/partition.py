@@ -178,9 +178,12 @@ def face_shared_flags(parts):
 # weak-scaling workload generated rank-locally (bench.py --gpus N)
 # ------------------------------------------------------------------------------------------------
 def weak_dims(base_dims, world):
-    """N GPUs: the pipe keeps its cross-section and gets N times the layers (same tets per GPU)."""
+    """N GPUs: the SAME pipe refined to N times the tets (BASELINE.json configs[2]: "same pipe refined to ~80M
+    tets" on 8 GPUs), every direction scaled by N^(1/3): N = 8 gives 192 x 192 x 362 = 80 068 608 TET4 exactly,
+    N = 2 -> 121 x 121 x 228 (20.0 M), N = 4 -> 152 x 152 x 287 (39.8 M).  Cut into z-slabs of whole layers."""
     nx, ny, nz = base_dims
-    return (nx, ny, nz * world)
+    f = float(world) ** (1.0 / 3.0)
+    return (int(round(nx * f)), int(round(ny * f)), int(round(nz * f)))
 
 
 def local_slab_case(dims, rank, world, *, radius=1.0, length=10.0):

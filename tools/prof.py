@@ -53,7 +53,7 @@ def main():
         return
     P.assemble(be, case)
     if a.mode == "tour":
-        plan = [("spmv_vv4", 0), ("spmv_vv3", 0), ("spmv_vv3", 1), ("spmv_ss", 0), ("spmv_sv", 0), ("spmv_vs", 0), ("multi_dot", 8),
+        plan = [("spmv_vv4", 0), ("spmv_vv3", 0), ("spmv_vv3", 1), ("spmv_ss", 0), ("spmv_sv", 0), ("spmv_sv", 1), ("spmv_vs", 0), ("spmv_vs", 1), ("multi_dot", 8),
                 ("multi_dot", 64), ("cgs_update_scale", 8), ("cgs_update_scale", 64), ("blas1", 0), ("scale_val", 0), ("depart", 0)]
         for name, k in plan:
             ms, by = be.op_bench(name, k=k, reps=a.reps)
