@@ -174,7 +174,7 @@ def run_gpu(args):
 
     if world > 1:
         from svfsiplus_b200 import partition as PT
-        dims = PT.weak_dims(P10, world)
+        dims = PT.weak_dims(tuple(args.dims), world)      # default --dims = P10 -> configs[2] at N = 8
         case, be = PT.setup_distributed_case(dims, rank, world, local, dist)
     else:
         dims = tuple(args.dims)

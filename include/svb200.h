@@ -70,6 +70,17 @@ typedef struct {
   double rho, elM, nu, f[3];
 } b200_lelas_props;
 
+/* Mixed velocity-pressure solid (ustruct; solver/ustruct.cpp:1158-1575, 632-876).  elM, nu, ctM, ctC feed
+ * get_tau (solver/mat_models.cpp:1655); Kpen, volType feed g_vol_pen (:1696).  isoType 0 = neo-Hookean. */
+typedef struct {
+  double dt, am, af, gam;
+  int tDof, s;
+  double rho, f[3];
+  double elM, nu, ctM, ctC;
+  int isoType, volType;
+  double C10, Kpen;
+} b200_ustruct_props;
+
 /* ---- life cycle ------------------------------------------------------------------------- */
 int  b200_create(b200_handle** h, int device);
 void b200_destroy(b200_handle* h);
@@ -114,6 +125,14 @@ int b200_disp_set(b200_handle* h, int tDof, const double* Dg, const double* Do);
 int b200_assemble_struct(b200_handle* h, const b200_struct_props* p);
 /* ... and construct_l_elas / construct_mesh + l_elas_3d (solver/l_elas.cpp:58,274; mesh.cpp:42). */
 int b200_assemble_lelas(b200_handle* h, const b200_lelas_props* p);
+/* ustruct equation (dof 4; b200_zero(h,4) first): replaces construct_usolid + ustruct_3d_m/c + ustruct_do_assem
+ * (solver/ustruct.cpp:216,1158,632,1579) for equal-order TET4/HEX8 with idMap = identity; also fills the device
+ * copy of com_mod.Kd(12,nnz). */
+int b200_assemble_ustruct(b200_handle* h, const b200_ustruct_props* p);
+/* ustruct_r (solver/ustruct.cpp:1726): R -= ami * Kd * (amg*Ad - Yg(s:s+2)) + overlap add; the caller invokes it on
+ * the first Newton iteration only (eq.itr <= 1), like the reference.  Ad(3,nNo) host, assembly order. */
+int b200_ustruct_r(b200_handle* h, double amg, double ami, int s, const double* Ad);
+int b200_get_Kd(b200_handle* h, double* Kd);      /* parity tap: Kd(12,nnz), assembly layout */
 /* FSI equation (solver/fsi.cpp:42-334: one element loop with a per-element domain switch).  elem_dmn[e] =
  * index of the equation domain element e belongs to (all_fun::domain, solver/all_fun.cpp:149), uploaded once;
  * the device keeps one element list per domain, so each domain is one divergence-free launch. */

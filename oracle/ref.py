@@ -102,6 +102,8 @@ def lib():
         L.ref_asm_solid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
         L.ref_asm_fsi.restype = C.c_double
         L.ref_asm_fsi.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 5 + [C.c_void_p] * 9
+        L.ref_asm_ustruct.restype = C.c_double
+        L.ref_asm_ustruct.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 9
         L.ref_rank_create.restype = C.c_void_p
         L.ref_rank_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_rank_destroy.argtypes = [C.c_void_p]
@@ -218,6 +220,20 @@ class RefAssembly:
         if t < 0:
             raise RuntimeError(lib().ref_last_error().decode())
         return R, Val, t
+
+
+    def ustruct(self, Ag, Yg, Dg, Bf, *, dt, am, af, gam, rho, elM, nu, ctM, ctC, vol, C10, Kpen, f=(0.0, 0.0, 0.0), Ad=None,
+                **_ignored):
+        """construct_usolid (S/ustruct.cpp:216) [+ ustruct_r when Ad is given].  Returns R (nNo,4), Val (nnz,16),
+        Kd (nnz,12), seconds."""
+        Ag = _c(Ag, np.float64); Yg = _c(Yg, np.float64); Dg = _c(Dg, np.float64); Bf = _c(Bf, np.float64)
+        Ad = None if Ad is None else _c(Ad, np.float64)
+        par = np.array([dt, am, af, gam, rho, f[0], f[1], f[2], elM, nu, ctM, ctC, self.VOL[vol], C10, Kpen], np.float64)
+        R = np.empty((self.nNo, 4)); Val = np.empty((self.nnz, 16)); Kd = np.empty((self.nnz, 12))
+        t = lib().ref_asm_ustruct(self.h, Ag.shape[1], _p(par), _p(Ag), _p(Yg), _p(Dg), _p(Bf), _p(Ad), _p(R), _p(Val), _p(Kd))
+        if t < 0:
+            raise RuntimeError(lib().ref_last_error().decode())
+        return R, Val, Kd, t
 
 
 def ls_params(ls_type, relTol, absTol=1e-10, mItr=10, sD=100, gm=(1e-2, 1e-10, 2, 100), cg=(0.2, 1e-10, 500)):

@@ -28,6 +28,7 @@
 #include "l_elas.h"
 #include "mesh.h"
 #include "sv_struct.h"
+#include "ustruct.h"
 #include "fsils_api.hpp"
 #include "lhsa.h"
 #include "nn.h"
@@ -393,6 +394,82 @@ double ref_asm_fsi(void* h, int tDof, double dt, double am, double af, double ga
     double t1 = now_s();
     std::memcpy(R, com_mod.R.data(), sizeof(double)*size_t(dof)*nNo);
     std::memcpy(Val, com_mod.Val.data(), sizeof(double)*size_t(dof)*dof*ctx->nnz);
+    return t1 - t0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1.0;
+  }
+}
+
+// ustruct equation through the reference's construct_usolid (S/ustruct.cpp:216) and, when Ad != NULL,
+// ustruct_r (S/ustruct.cpp:1726, first Newton iteration).  par = {dt, am, af, gam, rho, fx, fy, fz, elM, nu,
+// ctM, ctC, vol (0 none,1 Quad,2 ST91,3 M94), C10, Kpen}.  tDof = 4, eq.s = 0.
+// Outputs R (4 x nNo), Val (16 x nnz), Kd (12 x nnz).
+double ref_asm_ustruct(void* h, int tDof, const double* par, const double* Ag, const double* Yg, const double* Dg,
+                       const double* Bf, const double* Ad, double* R, double* Val, double* Kd)
+{
+  try {
+    using namespace consts;
+    auto ctx = static_cast<AsmCtx*>(h);
+    auto& com_mod = ctx->sim->com_mod;
+    const int nNo = com_mod.tnNo;
+    const int dof = 4;
+    com_mod.tDof = tDof;
+    com_mod.dof = dof;
+    com_mod.dt = par[0];
+    com_mod.mvMsh = false;
+    com_mod.cEq = 0;
+    com_mod.nEq = 1;
+    if (com_mod.eq.size() != 1) com_mod.eq.resize(1);
+    auto& eq = com_mod.eq[0];
+    eq.phys = EquationType::phys_ustruct;
+    eq.dof = dof; eq.s = 0; eq.e = dof - 1;
+    eq.am = par[1]; eq.af = par[2]; eq.gam = par[3];
+    eq.itr = 1;
+    eq.nDmn = 1;
+    if (eq.dmn.size() != 1) eq.dmn.resize(1);
+    auto& dmn = eq.dmn[0];
+    dmn.Id = -1;
+    dmn.phys = EquationType::phys_ustruct;
+    dmn.prop[PhysicalProperyType::solid_density] = par[4];
+    dmn.prop[PhysicalProperyType::f_x] = par[5];
+    dmn.prop[PhysicalProperyType::f_y] = par[6];
+    dmn.prop[PhysicalProperyType::f_z] = par[7];
+    dmn.prop[PhysicalProperyType::elasticity_modulus] = par[8];
+    dmn.prop[PhysicalProperyType::poisson_ratio] = par[9];
+    dmn.prop[PhysicalProperyType::ctau_M] = par[10];
+    dmn.prop[PhysicalProperyType::ctau_C] = par[11];
+    const int vol = int(par[12]);
+    dmn.stM.isoType = ConstitutiveModelType::stIso_nHook;
+    dmn.stM.volType = (vol == 1) ? ConstitutiveModelType::stVol_Quad
+                    : (vol == 2) ? ConstitutiveModelType::stVol_ST91
+                    : (vol == 3) ? ConstitutiveModelType::stVol_M94 : ConstitutiveModelType::stIso_NA;
+    dmn.stM.C10 = par[13];
+    dmn.stM.Kpen = par[14];
+    com_mod.Bf.resize(3, nNo);
+    std::memcpy(com_mod.Bf.data(), Bf, sizeof(double)*3*size_t(nNo));
+    if (!eq.linear_algebra) eq.linear_algebra = new FsilsLinearAlgebra();
+
+    Array<double> Ag_a(tDof, nNo), Yg_a(tDof, nNo), Dg_a(tDof, nNo);
+    std::memcpy(Ag_a.data(), Ag, sizeof(double)*size_t(tDof)*nNo);
+    std::memcpy(Yg_a.data(), Yg, sizeof(double)*size_t(tDof)*nNo);
+    std::memcpy(Dg_a.data(), Dg, sizeof(double)*size_t(tDof)*nNo);
+
+    com_mod.R.resize(dof, nNo);
+    eq.linear_algebra->alloc(com_mod, eq);
+    com_mod.Kd.resize(12, ctx->nnz);        // S/initialize.cpp:595; zeroed every Newton iteration (S/main.cpp:412)
+    double t0 = now_s();
+    ustruct::construct_usolid(com_mod, ctx->sim->cep_mod, com_mod.msh[0], Ag_a, Yg_a, Dg_a);
+    double t1 = now_s();
+    if (Ad) {
+      com_mod.Ad.resize(3, nNo);
+      std::memcpy(com_mod.Ad.data(), Ad, sizeof(double)*3*size_t(nNo));
+      com_mod.Rd.resize(3, nNo);
+      ustruct::ustruct_r(com_mod, Yg_a);
+    }
+    std::memcpy(R, com_mod.R.data(), sizeof(double)*size_t(dof)*nNo);
+    std::memcpy(Val, com_mod.Val.data(), sizeof(double)*size_t(dof)*dof*ctx->nnz);
+    std::memcpy(Kd, com_mod.Kd.data(), sizeof(double)*size_t(12)*ctx->nnz);
     return t1 - t0;
   } catch (const std::exception& e) {
     g_err = e.what();

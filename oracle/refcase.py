@@ -83,3 +83,19 @@ def reference_fsi_step(case, ls, prec=ref.PREC_FSILS):
     R, Val, _ = reference_assemble_fsi(case)
     X, out = reference_solve(case, R, Val, ls, prec)
     return R, Val, X, out
+
+
+def reference_assemble_ustruct(case, with_r=False):
+    m = case["mesh"]
+    ra = ref.RefAssembly(m.x, m.ien)
+    R, Val, Kd, secs = ra.ustruct(case["Ag"], case["Yg"], case["Dg"], case["Bf"], Ad=case["Ad"] if with_r else None, **case["props"])
+    ra.close()
+    return R, Val, Kd, secs
+
+
+def reference_ustruct_step(case, ls, with_r=True, prec=ref.PREC_FSILS):
+    from svfsiplus_b200.problem import LS_SETTINGS
+    ls = LS_SETTINGS[ls] if isinstance(ls, str) else ls
+    R, Val, Kd, _ = reference_assemble_ustruct(case, with_r=with_r)
+    X, out = reference_solve(case, R, Val, ls, prec)
+    return R, Val, Kd, X, out

@@ -56,6 +56,15 @@ class LelasProps(C.Structure):
                 ("rho", C.c_double), ("elM", C.c_double), ("nu", C.c_double), ("f", C.c_double * 3)]
 
 
+class UstructProps(C.Structure):
+    _fields_ = [("dt", C.c_double), ("am", C.c_double), ("af", C.c_double), ("gam", C.c_double),
+                ("tDof", C.c_int), ("s", C.c_int),
+                ("rho", C.c_double), ("f", C.c_double * 3),
+                ("elM", C.c_double), ("nu", C.c_double), ("ctM", C.c_double), ("ctC", C.c_double),
+                ("isoType", C.c_int), ("volType", C.c_int),
+                ("C10", C.c_double), ("Kpen", C.c_double)]
+
+
 ISO_TYPES = {"nHook": 0, "StVK": 1, "mStVK": 2}
 VOL_TYPES = {None: 0, "Quad": 1, "ST91": 2, "M94": 3}
 
@@ -63,6 +72,7 @@ EXPORTS = [
     "b200_create", "b200_destroy", "b200_last_error", "b200_device_count", "b200_elem_tables", "b200_comm_unique_id", "b200_comm_init",
     "b200_lhs_create", "b200_face_set", "b200_mesh_set", "b200_zero", "b200_state_set", "b200_assemble_fluid",
     "b200_disp_set", "b200_assemble_struct", "b200_assemble_lelas", "b200_mesh_domains", "b200_assemble_fsi",
+    "b200_assemble_ustruct", "b200_ustruct_r", "b200_get_Kd",
     "b200_assemble_elem", "b200_get_R", "b200_set_R", "b200_add_R", "b200_get_Val", "b200_set_Val", "b200_commu_R", "b200_solve",
     "b200_spmv", "b200_op_bench", "b200_launch_count", "b200_last_timings", "b200_profile", "b200_profile_read",
     "b200_timer",
@@ -100,6 +110,9 @@ def lib():
         L.b200_disp_set.argtypes = [vp, ci, vp, vp]
         L.b200_assemble_struct.argtypes = [vp, C.POINTER(StructProps)]
         L.b200_assemble_lelas.argtypes = [vp, C.POINTER(LelasProps)]
+        L.b200_assemble_ustruct.argtypes = [vp, C.POINTER(UstructProps)]
+        L.b200_ustruct_r.argtypes = [vp, cd, cd, ci, vp]
+        L.b200_get_Kd.argtypes = [vp, vp]
         L.b200_mesh_domains.argtypes = [vp, ci, vp]
         L.b200_assemble_fsi.argtypes = [vp, ci, vp, C.POINTER(FluidProps), C.POINTER(StructProps)]
         L.b200_assemble_elem.argtypes = [vp, ci, vp, vp, vp]
@@ -163,6 +176,19 @@ def lelas_props(*, dt, am, af, beta, rho, elM, nu, tDof=3, s=0, f=(0.0, 0.0, 0.0
     p.tDof, p.s, p.mesh_mode = tDof, s, int(mesh_mode)
     p.rho, p.elM, p.nu = rho, elM, nu
     p.f[0], p.f[1], p.f[2] = f
+    return p
+
+
+def ustruct_props(*, dt, am, af, gam, rho, elM, nu, ctM, ctC, vol, C10, Kpen, tDof=4, s=0, f=(0.0, 0.0, 0.0), iso="nHook",
+                  **_ignored) -> UstructProps:
+    p = UstructProps()
+    p.dt, p.am, p.af, p.gam = dt, am, af, gam
+    p.tDof, p.s = tDof, s
+    p.rho = rho
+    p.f[0], p.f[1], p.f[2] = f
+    p.elM, p.nu, p.ctM, p.ctC = elM, nu, ctM, ctC
+    p.isoType, p.volType = ISO_TYPES[iso], VOL_TYPES[vol]
+    p.C10, p.Kpen = C10, Kpen
     return p
 
 
@@ -270,6 +296,18 @@ class Backend:
 
     def assemble_lelas(self, props: LelasProps):
         self._ck(self.L.b200_assemble_lelas(self.h, C.byref(props)), "b200_assemble_lelas")
+
+    def assemble_ustruct(self, props: UstructProps):
+        self._ck(self.L.b200_assemble_ustruct(self.h, C.byref(props)), "b200_assemble_ustruct")
+
+    def ustruct_r(self, amg, ami, s, Ad):
+        Ad = _c(Ad, np.float64)
+        self._ck(self.L.b200_ustruct_r(self.h, amg, ami, s, _p(Ad)), "b200_ustruct_r")
+
+    def get_Kd(self):
+        Kd = np.empty((self.nnz, 12))
+        self._ck(self.L.b200_get_Kd(self.h, _p(Kd)), "b200_get_Kd")
+        return Kd
 
     def mesh_domains(self, nDmn, elem_dmn):
         ed = _c(elem_dmn, np.int32)

@@ -13,6 +13,7 @@
 
 #include "assembly.cuh"
 #include "assembly_solid.cuh"
+#include "assembly_ustruct.cuh"
 #include "ops_cuda.cuh"
 
 using namespace svb200;
@@ -51,6 +52,9 @@ struct b200_handle {
   double* stageR = nullptr;  // dof x eNoN x nEl
   double* stageK = nullptr;  // dof^2 x eNoN^2 x nEl
   size_t stageR_cap = 0, stageK_cap = 0;
+  double* Kd = nullptr;      // ustruct: displacement tangent, 12 x nnz, solver layout (com_mod.Kd)
+  double* stageKd = nullptr; // 12 x eNoN^2 x nEl
+  size_t Kd_cap = 0, stageKd_cap = 0;
   std::vector<int*> d_dmn_elems;      // per FSI domain: element list (ascending element ids)
   std::vector<int> dmn_count;
   double* d_tab = nullptr;   // packed Gauss tables of the mesh's element type (w, N, dN/dxi)
@@ -83,6 +87,7 @@ struct b200_handle {
     cudaFree(stageR); cudaFree(stageK); cudaFree(d_x); cudaFree(d_err);
     cudaFree(d_Ag); cudaFree(d_Yg); cudaFree(d_Bf); cudaFree(d_Dg); cudaFree(d_Do); cudaFree(d_tab);
     for (auto p : d_dmn_elems) cudaFree(p);
+    cudaFree(Kd); cudaFree(stageKd);
   }
 };
 
@@ -264,6 +269,20 @@ void launch_solid(b200_handle* h, const SolidConsts& c, int nList, const int* d_
   CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   kern<<<(nList + EPB - 1)/EPB, EPB*NG, smem, ops.st>>>(nList, d_elist, c, h->d_tab, h->d_ien, h->d_rslot, h->d_kslot, h->d_x,
                                                         h->d_Ag, h->d_Yg, h->d_Dg, h->d_Do, h->d_Bf, h->stageR, h->stageK, h->d_err);
+  CU_CHECK(cudaGetLastError());
+  ops.post();
+}
+
+template <int ENON, int NG, int EPB, int APT>
+void launch_ustruct(b200_handle* h, const UstructConsts& c)
+{
+  auto& ops = *h->ops;
+  constexpr int TABN = NG + NG*ENON + NG*ENON*3;
+  const size_t smem = sizeof(double)*(size_t((TABN + 3) & ~3) + size_t(EPB)*NG*ustruct_rec(ENON));
+  auto kern = k_assemble_ustruct<ENON, NG, EPB, APT>;
+  CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  kern<<<(h->nEl + EPB - 1)/EPB, EPB*NG, smem, ops.st>>>(h->nEl, c, h->d_tab, h->d_ien, h->d_rslot, h->d_kslot, h->d_x,
+                                                         h->d_Ag, h->d_Yg, h->d_Dg, h->d_Bf, h->stageR, h->stageK, h->stageKd, h->d_err);
   CU_CHECK(cudaGetLastError());
   ops.post();
 }
@@ -681,6 +700,81 @@ int b200_assemble_lelas(b200_handle* h, const b200_lelas_props* p)
     c.elM = p->elM; c.nu = p->nu;
     c.tDof = p->tDof; c.s = p->s; c.kind = p->mesh_mode ? 2 : 1;
     assemble_solid(h, c, p->mesh_mode ? "construct_mesh" : "construct_l_elas");
+  });
+}
+
+int b200_assemble_ustruct(b200_handle* h, const b200_ustruct_props* p)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (h->nEl == 0) throw std::runtime_error("assemble_ustruct: no mesh (b200_mesh_set)");
+    if (!h->d_Ag || !h->d_Dg) throw std::runtime_error("assemble_ustruct: no state (b200_state_set + b200_disp_set)");
+    if (h->dof != 4 || !h->Val) throw std::runtime_error("assemble_ustruct: call b200_zero(h, 4) first");
+    if (p->tDof != h->tDof) throw std::runtime_error("assemble_ustruct: tDof differs from the uploaded state");
+    if (p->s < 0 || p->s + 4 > p->tDof) throw std::runtime_error("assemble_ustruct: equation offset outside the state");
+    if (p->isoType != 0) throw std::runtime_error("assemble_ustruct: constitutive model has no device kernel (neo-Hookean has)");
+    if (p->volType < 0 || p->volType > 3) throw std::runtime_error("assemble_ustruct: dilational penalty model not defined");
+    UstructConsts c;
+    std::memset(&c, 0, sizeof(c));
+    c.dt = p->dt; c.am = p->am; c.af = p->af; c.gam = p->gam;
+    c.rho0 = p->rho; c.f[0] = p->f[0]; c.f[1] = p->f[1]; c.f[2] = p->f[2];
+    c.elM = p->elM; c.nu = p->nu; c.ctM = p->ctM; c.ctC = p->ctC;
+    c.iso = p->isoType; c.vol = p->volType; c.C10 = p->C10; c.Kpen = p->Kpen;
+    c.tDof = p->tDof; c.s = p->s;
+    ensure_stage(h, 4);
+    ensure(h->stageKd, h->stageKd_cap, size_t(12)*h->eNoN*h->eNoN*size_t(h->nEl) + 4);
+    ensure(h->Kd, h->Kd_cap, size_t(12)*h->nnz);
+    const double t0 = wall_s();
+    {
+      CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*(128.0 + 96.0) + double(h->nNo)*(32.0 + 24.0 + 24.0*h->tDof + 24.0) + double(h->nEl)*4.0*h->eNoN, 4);
+      if (h->eNoN == 4) launch_ustruct<4, 4, 16, 1>(h, c);
+      else launch_ustruct<8, 8, 8, 2>(h, c);
+      // Kd is rebuilt (assigned) by every assembly: ls_alloc zeroes com_mod.Kd too (ls.cpp:51-60)
+      const size_t tK = size_t(h->nnz)*12;
+      k_sum_run<true><<<unsigned((tK + 255)/256), 256, 0, ops.st>>>(size_t(h->nnz), 12, h->d_kseg, h->stageKd, h->Kd);
+      ops.post();
+    }
+    finish_assembly(h, 4, t0, "construct_usolid");
+  });
+}
+
+int b200_ustruct_r(b200_handle* h, double amg, double ami, int s, const double* Ad)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (!h->Kd || h->dof != 4 || !h->R) throw std::runtime_error("ustruct_r: no assembled ustruct system");
+    if (!h->d_Yg) throw std::runtime_error("ustruct_r: no state (b200_state_set)");
+    flush_staged(h);
+    const size_t n3 = size_t(h->nNo)*3, n4 = size_t(h->nNo)*4;
+    auto mk = ops.mark();
+    double* ad = ops.vec(n3);
+    double* rd = ops.vec(n3);
+    double* ku = ops.vec(n4);
+    CU_CHECK(cudaMemcpyAsync(ad, Ad, sizeof(double)*n3, cudaMemcpyHostToDevice, ops.st));
+    k_ustruct_rd<<<CudaOps::grid_for(n3, 256), 256, 0, ops.st>>>(h->nNo, h->tDof, s, amg, h->d_map, ad, h->d_Yg, rd); ops.post();
+    k_spmv_kd<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(h->nNo, ops.rowPtr, ops.col, h->Kd, rd, ku); ops.post();
+    ops.halo_add(4, ku);                       // all_fun::commu(KU)
+    ops.axpy(n4, -ami, ku, h->R);
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+    ops.release(mk);
+  });
+}
+
+int b200_get_Kd(b200_handle* h, double* Kd)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (!h->Kd) throw std::runtime_error("get_Kd: no ustruct system on the device");
+    const size_t n = size_t(12)*h->nnz;
+    if (h->identity_map) {
+      CU_CHECK(cudaMemcpyAsync(Kd, h->Kd, sizeof(double)*n, cudaMemcpyDeviceToHost, ops.st));
+    } else {
+      ensure(h->stage_d, h->stage_cap, n);
+      k_val_rows<<<kSmCount*8, 256, 0, ops.st>>>(h->nNo, 12, h->d_map, h->d_rowPtrA, ops.rowPtr, h->Kd, h->stage_d, 0);
+      ops.post();
+      CU_CHECK(cudaMemcpyAsync(Kd, h->stage_d, sizeof(double)*n, cudaMemcpyDeviceToHost, ops.st));
+    }
+    CU_CHECK(cudaStreamSynchronize(ops.st));
   });
 }
 

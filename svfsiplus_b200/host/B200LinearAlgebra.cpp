@@ -138,6 +138,7 @@ void B200LinearAlgebra::alloc(ComMod& com_mod, eqType& lEq)
   }
   check(b200_zero(h_, dof), "b200_zero");
   any_device_contribution_ = false;
+  ustruct_on_device_ = false;
 }
 
 /// Per-element entry (boundary faces and any physics without a device kernel).
@@ -176,6 +177,8 @@ bool B200LinearAlgebra::assemble_mesh(ComMod& com_mod, const mshType& lM, const 
     case EquationType::phys_lElas:
     case EquationType::phys_mesh:
       return assemble_solid_mesh(com_mod, lM, Ag, Yg, Dg, cep_mod);
+    case EquationType::phys_ustruct:
+      return assemble_ustruct_mesh(com_mod, lM, Ag, Yg, Dg, cep_mod);
     default:
       return false;
   }
@@ -283,6 +286,58 @@ bool B200LinearAlgebra::assemble_fsi_mesh(ComMod& com_mod, const mshType& lM, co
   check(b200_disp_set(h_, com_mod.tDof, Dg.data(), nullptr), "b200_disp_set");
   check(b200_assemble_fsi(h_, nDmn, kinds.data(), fl.data(), st.data()), "b200_assemble_fsi");
   any_device_contribution_ = true;
+  return true;
+}
+
+/// ustruct (construct_usolid, ustruct.cpp:216) on equal-order TET4 / HEX8 with idMap = identity.
+bool B200LinearAlgebra::assemble_ustruct_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag,
+    const Array<double>& Yg, const Array<double>& Dg, const CepMod* cep_mod)
+{
+  using namespace consts;
+  auto& eq = com_mod.eq[com_mod.cEq];
+  if ((lM.eType != ElementType::TET4 && lM.eType != ElementType::HEX8) || com_mod.dof != 4) return false;
+  if (cep_mod && (cep_mod->cem.cpld || cep_mod->cem.aStress || cep_mod->cem.aStrain)) return false;
+  for (int a = 0; a < com_mod.tnNo; a++) if (com_mod.idMap(a) != a) return false;      // undeformed-Neumann faces
+  const auto& dmn = eq.dmn[0];
+  const auto& stM = dmn.stM;
+  if (stM.isoType != ConstitutiveModelType::stIso_nHook) return false;
+  if (stM.Tf.fType != 0 || dmn.solid_visc.viscType != SolidViscosityModelType::viscType_NA) return false;
+  b200_ustruct_props p{};
+  p.dt = com_mod.dt; p.am = eq.am; p.af = eq.af; p.gam = eq.gam;
+  p.tDof = com_mod.tDof; p.s = eq.s;
+  p.rho = dmn.prop.at(PhysicalProperyType::solid_density);
+  p.f[0] = dmn.prop.at(PhysicalProperyType::f_x);
+  p.f[1] = dmn.prop.at(PhysicalProperyType::f_y);
+  p.f[2] = dmn.prop.at(PhysicalProperyType::f_z);
+  p.elM = dmn.prop.at(PhysicalProperyType::elasticity_modulus);
+  p.nu = dmn.prop.at(PhysicalProperyType::poisson_ratio);
+  p.ctM = dmn.prop.at(PhysicalProperyType::ctau_M);
+  p.ctC = dmn.prop.at(PhysicalProperyType::ctau_C);
+  p.isoType = 0;
+  switch (stM.volType) {
+    case ConstitutiveModelType::stVol_Quad: p.volType = 1; break;
+    case ConstitutiveModelType::stVol_ST91: p.volType = 2; break;
+    case ConstitutiveModelType::stVol_M94:  p.volType = 3; break;
+    default: p.volType = 0; break;
+  }
+  p.C10 = stM.C10; p.Kpen = stM.Kpen;
+  if (mesh_uploaded_ != &lM) upload_mesh(com_mod, lM);
+  check(b200_state_set(h_, com_mod.tDof, Ag.data(), Yg.data(), com_mod.Bf.data()), "b200_state_set");
+  check(b200_disp_set(h_, com_mod.tDof, Dg.data(), nullptr), "b200_disp_set");
+  check(b200_assemble_ustruct(h_, &p), "b200_assemble_ustruct");
+  any_device_contribution_ = true;
+  ustruct_on_device_ = true;
+  return true;
+}
+
+bool B200LinearAlgebra::ustruct_r(ComMod& com_mod, const Array<double>& Yg)
+{
+  if (!device_assembly_ || !ustruct_on_device_) return false;
+  const auto& eq = com_mod.eq[com_mod.cEq];
+  if (eq.itr > 1) { com_mod.Rd = 0.0; return true; }
+  const double amg = (eq.gam - eq.am) / (eq.gam - 1.0);
+  const double ami = 1.0 / eq.am;
+  check(b200_ustruct_r(h_, amg, ami, eq.s, com_mod.Ad.data()), "b200_ustruct_r");
   return true;
 }
 

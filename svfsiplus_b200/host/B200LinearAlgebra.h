@@ -50,6 +50,11 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
     bool assemble_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag, const Array<double>& Yg,
         const Array<double>& Dg, const CepMod* cep_mod = nullptr);
 
+    /// ustruct_r counterpart (ustruct.cpp:1726; called from main.cpp:526 on the first Newton iteration): the
+    /// displacement tangent Kd lives on the device when the ustruct equation was assembled there.  Returns false
+    /// when the system was assembled on the host (the caller then runs the reference's ustruct_r).
+    bool ustruct_r(ComMod& com_mod, const Array<double>& Yg);
+
     /// fsils_bc_update counterpart: re-upload the face vectors (moving meshes, follower loads).
     void update_faces(ComMod& com_mod);
 
@@ -65,6 +70,8 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
         const Array<double>& Dg, const CepMod* cep_mod);
     bool fill_fluid_props(ComMod& com_mod, const eqType& eq, const dmnType& dmn, b200_fluid_props& p);
     bool fill_struct_props(ComMod& com_mod, const eqType& eq, const dmnType& dmn, b200_struct_props& p);
+    bool assemble_ustruct_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag, const Array<double>& Yg,
+        const Array<double>& Dg, const CepMod* cep_mod);
     bool assemble_solid_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag, const Array<double>& Yg,
         const Array<double>& Dg, const CepMod* cep_mod);
 
@@ -75,6 +82,7 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
     const mshType* mesh_uploaded_ = nullptr;
     const mshType* domains_uploaded_ = nullptr;
     bool any_device_contribution_ = false;
+    bool ustruct_on_device_ = false;
     static std::set<consts::LinearAlgebraType> valid_assemblers;
 };
 

@@ -27,6 +27,9 @@ LS_SETTINGS = {
     "GMRES_STRUCT_LOOSE": (B.LS_GMRES, (1e-4, 1e-10, 10, 100), None, None),
     # tests/cases/fsi/pipe_3d/solver.xml: FSI equation <LS type="GMRES"> tol 1e-12, 100 iterations, Krylov dim 50
     "GMRES_FSI": (B.LS_GMRES, (1e-12, 1e-10, 100, 50), None, None),
+    # tests/cases/ustruct/block_compression/P1P1_VMS/solver.xml: <LS type="GMRES"> tol 1e-12 (Krylov dim capped here)
+    "GMRES_USTRUCT": (B.LS_GMRES, (1e-8, 1e-10, 10, 200), None, None),
+    "GMRES_USTRUCT_LOOSE": (B.LS_GMRES, (1e-3, 1e-10, 10, 200), None, None),
     "CG_MESH": (B.LS_CG, (1e-10, 1e-14, 400, 0), None, None),
 }
 
@@ -219,3 +222,57 @@ def fsi_linear_step(be: B.Backend, case, ls="GMRES_FSI", want_system=False):
     ls_type, RI, GM, CG = LS_SETTINGS[ls] if isinstance(ls, str) else ls
     X, info = be.solve(ls_type, B.PREC_FSILS, RI, GM, CG, case["incL"], case["res"])
     return (X, info, R, Val) if want_system else (X, info)
+
+
+# ---------------------------------------------------------------------------------------------------
+# ustruct block (tests/cases/ustruct/block_compression/P1P1_VMS/solver.xml: neo-Hookean, E 240.56596e6,
+# nu 0.4999999, ST91, density 1e-3, stabilisation coefficients 1e-3, first-order generalised-alpha)
+# ---------------------------------------------------------------------------------------------------
+def ustruct_case(n, elem="tet", vol="ST91"):
+    m = M.block_mesh(n, elem=elem)
+    rowPtr, colPtr = M.csr_pattern(m.ien, m.nNo)
+    am, af, gam = M.gen_alpha(0.5)
+    E, nu = 240.56596e6, 0.4999999
+    mu = 0.5 * E / (1.0 + nu)
+    kap = E / (3.0 * (1.0 - 2.0 * nu))
+    dt = 1e-3
+    A3, Y3, D3, Bf = M.block_state(m)
+    rng = np.random.default_rng(515)
+    nN = m.nNo
+    Ag = np.zeros((nN, 4)); Yg = np.zeros((nN, 4)); Dg = np.zeros((nN, 4))
+    Ag[:, :3] = A3; Yg[:, :3] = 0.1 * Y3; Dg[:, :3] = 0.2 * D3
+    Yg[:, 3] = 1.0e3 * rng.standard_normal(nN)        # pressure
+    Ag[:, 3] = 1.0e4 * rng.standard_normal(nN)        # pressure rate
+    Ad = rng.standard_normal((nN, 3))                 # displacement-equation acceleration (com_mod.Ad)
+    # stabilisation coefficients 0.1 instead of the XML's 1e-3: on this random (non-equilibrium) state the Jacobian with
+    # 1e-3 needs ~1600 GMRES iterations in the reference itself, with 0.1 about 200
+    props = dict(dt=dt, am=am, af=af, gam=gam, rho=1e-3, elM=E, nu=nu, ctM=0.1, ctC=0.1, vol=vol, C10=0.5 * mu, Kpen=kap,
+                 f=(0.0, 0.0, -9.81))
+    faces = []
+    for ax, nm in enumerate(("X0", "Y0", "Z0")):
+        nodes = m.faces[nm]["nodes"]
+        val = np.ones((len(nodes), 3))
+        val[:, ax] = 0.0
+        faces.append(dict(name=nm, nodes=nodes, dof=3, bGrp=B.BC_DIR, val=val))
+    return dict(mesh=m, rowPtr=rowPtr, colPtr=colPtr, Ag=Ag, Yg=Yg, Dg=Dg, Bf=Bf, Ad=Ad, props=props, faces=faces, kind="ustruct",
+                res=np.zeros(len(faces)), incL=np.ones(len(faces), np.int32), name=f"ustruct_{elem}_{n}")
+
+
+def assemble_ustruct(be: B.Backend, case, upload=True, with_r=False):
+    if upload:
+        be.state_set(4, case["Ag"], case["Yg"], case["Bf"])
+        be.disp_set(4, case["Dg"])
+    be.zero(4)
+    p = case["props"]
+    be.assemble_ustruct(B.ustruct_props(tDof=4, **p))
+    if with_r:                                         # main.cpp:526, first Newton iteration
+        amg = (p["gam"] - p["am"]) / (p["gam"] - 1.0)
+        be.ustruct_r(amg, 1.0 / p["am"], 0, case["Ad"])
+
+
+def ustruct_linear_step(be: B.Backend, case, ls="GMRES_USTRUCT", with_r=True):
+    assemble_ustruct(be, case, with_r=with_r)
+    R, Val, Kd = be.get_R(), be.get_Val(), be.get_Kd()
+    ls_type, RI, GM, CG = LS_SETTINGS[ls] if isinstance(ls, str) else ls
+    X, info = be.solve(ls_type, B.PREC_FSILS, RI, GM, CG, case["incL"], case["res"])
+    return X, info, R, Val, Kd

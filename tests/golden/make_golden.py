@@ -58,6 +58,15 @@ def main():
     c = P.fsi_case(4, 4, 4)
     R, Val, _ = refcase.reference_assemble_fsi(c)
     np.savez_compressed(os.path.join(HERE, "fsi_4_4_4.npz"), R=R, Val=Val, elem_dmn=c["elem_dmn"])
+    # ustruct equation (construct_usolid + ustruct_r): R, Val, Kd
+    out = {}
+    for elem in ("tet", "hex"):
+        for vol in ("ST91", "M94", "Quad"):
+            c = P.ustruct_case(3, elem=elem, vol=vol)
+            R, Val, Kd, _ = refcase.reference_assemble_ustruct(c, with_r=False)
+            Rr, _, _, _ = refcase.reference_assemble_ustruct(c, with_r=True)
+            out[f"R_{elem}_{vol}"] = R; out[f"Val_{elem}_{vol}"] = Val; out[f"Kd_{elem}_{vol}"] = Kd; out[f"Rr_{elem}_{vol}"] = Rr
+    np.savez_compressed(os.path.join(HERE, "ustruct_3.npz"), **out)
     print("golden fixtures written")
 
 

@@ -139,6 +139,47 @@ def test_fsi_step_matches_reference():
     be.close()
 
 
+@pytest.mark.parametrize("elem", ["tet", "hex"])
+@pytest.mark.parametrize("vol", ["ST91", "M94", "Quad"])
+def test_ustruct_assembly_matches_golden(elem, vol):
+    """construct_usolid + ustruct_do_assem (R, Val, Kd) and ustruct_r (R after the first-iteration correction)."""
+    g = golden("ustruct_3.npz")
+    case = P.ustruct_case(3, elem=elem, vol=vol)
+    be = _setup(case)
+    P.assemble_ustruct(be, case)
+    R, Val, Kd = be.get_R(), be.get_Val(), be.get_Kd()
+    assert rel_inf(R, g[f"R_{elem}_{vol}"]) < TOL_ASM
+    assert rel_inf(Val, g[f"Val_{elem}_{vol}"]) < TOL_ASM
+    assert rel_inf(Kd, g[f"Kd_{elem}_{vol}"]) < TOL_ASM
+    P.assemble_ustruct(be, case, upload=False, with_r=True)
+    assert rel_inf(be.get_R(), g[f"Rr_{elem}_{vol}"]) < TOL_ASM
+    be.close()
+
+
+@pytest.mark.parametrize("elem,n", [("tet", 6), ("hex", 6)])
+@pytest.mark.parametrize("ls", ["GMRES_USTRUCT", "GMRES_USTRUCT_LOOSE"])
+def test_ustruct_step_matches_reference(elem, n, ls):
+    """One Newton iteration of the ustruct block: assembly + ustruct_r + GMRES."""
+    if not _ref_available():
+        pytest.skip("oracle/_ref not present on this box")
+    from oracle import refcase
+    case = P.ustruct_case(n, elem=elem)
+    be = _setup(case)
+    X, info, R, Val, Kd = P.ustruct_linear_step(be, case, ls=ls)
+    Rr, Vr, Kdr, Xr, oref = refcase.reference_ustruct_step(case, ls)
+    assert rel_inf(R, Rr) < TOL_ASM and rel_inf(Val, Vr) < TOL_ASM and rel_inf(Kd, Kdr) < TOL_ASM
+    assert bool(info["RI"]["suc"]) == (oref["suc"] == 1.0)
+    if ls == "GMRES_USTRUCT_LOOSE":
+        assert abs(info["RI"]["itr"] - int(oref["itr"])) <= max(1, 0.02 * oref["itr"])
+        assert rel_l2(X, Xr) < 1e-2          # two iterates that both stop at a 1e-3 residual
+    else:
+        # eight orders with classical Gram-Schmidt on a saddle-point system: count governed by rounding (see
+        # test_struct_step_matches_reference); converged on both sides, not slower, same solution to cond x 1e-8
+        assert info["RI"]["itr"] <= int(oref["itr"]) * 1.05 + 1
+        assert rel_l2(X, Xr) < 1e-4
+    be.close()
+
+
 def test_struct_large_block_properties():
     """64^3 HEX8 (262 144 elements, SURVEY par. 8d): size-independent properties of the hyperelastic tangent.
     (a) total-Lagrangian hyperelastic tangent + mass is symmetric: block (a,b) = block (b,a)^T;
