@@ -327,6 +327,9 @@ def run_gpu(args):
 
 
 def main():
+    # NCCL prints a "NCCL version ..." banner to STDOUT at NCCL_DEBUG=VERSION/WARN; stdout must carry one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+        os.environ["NCCL_DEBUG"] = "NONE"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

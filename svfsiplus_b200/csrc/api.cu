@@ -543,6 +543,21 @@ int b200_lhs_create(b200_handle* h, int gnNo, int nNo, int mynNo, int nnz, const
       CU_CHECK(cudaMalloc(&r.rbuf, sizeof(double)*std::max(1, r.n)*ops.halo_dof_cap));
       off += size_t(r.n);
     }
+    // rows that take part in an overlap exchange: [0, ovA) and [ovB, nNo) in the FSILS ordering (lhs.cpp:160-230)
+    ops.overlap_ok = false; ops.ovA = 0; ops.ovB = nNo;
+    if (nReq > 0) {
+      std::vector<char> mark(nNo, 0);
+      size_t tot = 0;
+      for (int i = 0; i < nReq; i++) tot += size_t(req_n[i]);
+      bool in_range = true;
+      for (size_t k = 0; k < tot; k++) { const int r = req_ptr[k]; if (r < 0 || r >= nNo) { in_range = false; break; } mark[r] = 1; }
+      if (!in_range) throw std::runtime_error("lhs_create: overlap list entry out of range");
+      int a = 0; while (a < nNo && mark[a]) a++;
+      int b = nNo; while (b > a && mark[b-1]) b--;
+      bool ok = true;
+      for (int r = a; r < b; r++) if (mark[r]) { ok = false; break; }
+      ops.ovA = a; ops.ovB = b; ops.overlap_ok = ok && (b > a);
+    }
     CU_CHECK(cudaStreamSynchronize(ops.st));
   });
 }
@@ -1057,8 +1072,8 @@ int b200_op_bench(b200_handle* h, int op, int k, int reps, double* ms_per_launch
         case KC_SPMV_VV3: { const int v0 = ops.variant_vv3; ops.variant_vv3 = k; ops.spmv_vv(3, mK, x, y); ops.variant_vv3 = v0; bytes = ops.bytes_vv(3); break; }
         case KC_SPMV_SS:  ops.spmv_ss(mL, x, y); bytes = ops.bytes_ss(); break;
         case KC_SPMV_SV:  // pass 1 of the fused Schur operator
-          if (k == 1) k_schur_gp4<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(nullptr, h->nNo, ops.rowPtr, ops.col, mG, x, ops.V4);
-          else k_schur_gp<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(nullptr, h->nNo, ops.rowPtr, ops.col, mG, x, ops.V4);
+          if (k == 1) k_schur_gp4<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(nullptr, h->nNo, ops.rowPtr, ops.col, mG, x, x, ops.V4);
+          else k_schur_gp<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(nullptr, h->nNo, ops.rowPtr, ops.col, mG, x, x, ops.V4);
           ops.post();
           bytes = ops.bytes_schur_gp(); break;
         case KC_SPMV_VS:  // pass 2 of the fused Schur operator
@@ -1078,7 +1093,7 @@ int b200_op_bench(b200_handle* h, int op, int k, int reps, double* ms_per_launch
         default: throw std::runtime_error("op_bench: this kernel class has no stand-alone bench");
       }
     };
-    if (op == KC_SPMV_VS) { k_schur_gp<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(nullptr, h->nNo, ops.rowPtr, ops.col, mG, x, ops.V4); ops.post(); }
+    if (op == KC_SPMV_VS) { k_schur_gp<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(nullptr, h->nNo, ops.rowPtr, ops.col, mG, x, x, ops.V4); ops.post(); }
     const bool prof = ops.profiling;
     ops.profiling = false;
     cudaEvent_t e0, e1;

@@ -266,7 +266,7 @@ k_spmv_vs(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr,
 // 4 lanes per row striding over the row's entries; fixed-order quad reduction.
 __global__ void __launch_bounds__(256)
 k_schur_gp(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col, const double* __restrict__ G,
-           const double* __restrict__ P, double* __restrict__ V4)
+           const double* __restrict__ P, const double* __restrict__ Pown, double* __restrict__ V4)
 {
   if (skip && *skip) return;
   const int lane4 = threadIdx.x & 3;
@@ -291,7 +291,7 @@ k_schur_gp(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr
     a0 += __shfl_xor_sync(0xffffffffu, a0, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
     a0 += __shfl_xor_sync(0xffffffffu, a0, 2); a1 += __shfl_xor_sync(0xffffffffu, a1, 2); a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
     if (row < nNo && lane4 == 0) {
-      d4 o; o.x = a0; o.y = a1; o.z = a2; o.w = __ldg(P + row);
+      d4 o; o.x = a0; o.y = a1; o.z = a2; o.w = __ldg(Pown + row);
       st256(V4 + size_t(row)*4, o);
     }
   }
@@ -331,7 +331,7 @@ k_schur_sp(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr
 // trip): 4 x (index -> matrix entry + gathered vector entry) independent chains per thread instead of two.
 __global__ void __launch_bounds__(256)
 k_schur_gp4(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col, const double* __restrict__ G,
-            const double* __restrict__ P, double* __restrict__ V4)
+            const double* __restrict__ P, const double* __restrict__ Pown, double* __restrict__ V4)
 {
   if (skip && *skip) return;
   const int lane4 = threadIdx.x & 3;
@@ -364,7 +364,7 @@ k_schur_gp4(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPt
     a0 += __shfl_xor_sync(0xffffffffu, a0, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
     a0 += __shfl_xor_sync(0xffffffffu, a0, 2); a1 += __shfl_xor_sync(0xffffffffu, a1, 2); a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
     if (row < nNo && lane4 == 0) {
-      d4 o; o.x = a0; o.y = a1; o.z = a2; o.w = __ldg(P + row);
+      d4 o; o.x = a0; o.y = a1; o.z = a2; o.w = __ldg(Pown + row);
       st256(V4 + size_t(row)*4, o);
     }
   }

@@ -140,6 +140,13 @@ class CudaOps {
   std::vector<HaloReq> reqs;
   int halo_dof_cap = 0;
 
+  // overlap of the halo exchange with the interior rows: in the FSILS ordering the rows that appear in an
+  // overlap list are [0, ovA) (shared with lower ranks) and [ovB, nNo) (shared with higher ranks)
+  cudaStream_t st2 = nullptr;          // communication stream (highest priority)
+  cudaEvent_t ev_b = nullptr, ev_c = nullptr;
+  int ovA = 0, ovB = 0;
+  bool overlap_ok = false;
+
   // communicator
   Nccl nccl;
   Nccl::Comm comm = nullptr;
@@ -168,6 +175,13 @@ class CudaOps {
   {
     CU_CHECK(cudaSetDevice(device));
     CU_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    {
+      int lo = 0, hi = 0;
+      CU_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CU_CHECK(cudaStreamCreateWithPriority(&st2, cudaStreamNonBlocking, hi));
+      CU_CHECK(cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming));
+      CU_CHECK(cudaEventCreateWithFlags(&ev_c, cudaEventDisableTiming));
+    }
     CU_CHECK(cudaMalloc(&red_d, sizeof(double)*kMaxSlots));
     CU_CHECK(cudaMallocHost(&red_h, sizeof(double)*kMaxSlots));
     CU_CHECK(cudaMalloc(&partial_d, sizeof(double)*kRedBlocks*kMaxDots));
@@ -191,6 +205,9 @@ class CudaOps {
     if (cg_ev[1]) cudaEventDestroy(cg_ev[1]);
     cudaFree(red_d); cudaFreeHost(red_h); cudaFree(partial_d); cudaFree(counter_d); cudaFree(face_partial_d);
     if (comm) nccl.CommDestroy(comm);
+    if (ev_b) cudaEventDestroy(ev_b);
+    if (ev_c) cudaEventDestroy(ev_c);
+    if (st2) cudaStreamDestroy(st2);
     if (st) cudaStreamDestroy(st);
   }
 
@@ -330,81 +347,107 @@ class CudaOps {
   // fastest with two (0.151 vs 0.163 ms at P10), pass 2 with four (0.193 vs 0.217 ms)
   int variant_gp = 0, variant_sp = 1;
   int variant_vv3 = 0;       // 0: lane = component, 1: lanes stride over the row's blocks (A/B by op_bench)
+
   // ---- SpMV (+ overlap-node add) --------------------------------------------------------------------
+  // Every product is launched on row ranges: launch(r0, r1) computes rows [r0, r1).  With more than one rank the
+  // boundary rows go first, their exchange (pack -> ncclSend/ncclRecv) runs on the communication stream while the
+  // interior rows are computed, and the received contributions are added in request order afterwards.
+  template <class Launch>
+  void rows_then_halo(int dof, double* out, int ld, Launch&& launch)
+  {
+    if (nranks == 1 || reqs.empty()) { launch(0, nNo_); return; }
+    if (!overlap_ok) { launch(0, nNo_); halo_add(dof, out, ld); return; }
+    if (ovA > 0) launch(0, ovA);
+    if (ovB < nNo_) launch(ovB, nNo_);
+    CU_CHECK(cudaEventRecord(ev_b, st));
+    CU_CHECK(cudaStreamWaitEvent(st2, ev_b, 0));
+    halo_exchange(dof, out, ld ? ld : dof, st2);
+    CU_CHECK(cudaEventRecord(ev_c, st2));
+    if (ovB > ovA) launch(ovA, ovB);
+    CU_CHECK(cudaStreamWaitEvent(st, ev_c, 0));
+    halo_accumulate(dof, out, ld ? ld : dof);
+  }
+
   void spmv_vv(int dof, const double* K, const double* U, double* KU)
   {
-    const int g = grid_rows(nNo_);
-    {
+    if (dof < 1 || dof > 4) throw std::runtime_error("spmv_vv: dof > 4 is not a supported FSILS path");
     Scope sc(*this, dof == 4 ? KC_SPMV_VV4 : KC_SPMV_VV3, bytes_vv(dof));
-    switch (dof) {
-      case 4: k_spmv_vv4<<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU); break;
-      case 3: if (variant_vv3 == 1) k_spmv_vv3s<<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU);
-              else k_spmv_vv<3><<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU);
-              break;
-      case 2: k_spmv_vv<2><<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU); break;
-      case 1: k_spmv_vv<1><<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU); break;
-      default: throw std::runtime_error("spmv_vv: dof > 4 is not a supported FSILS path");
-    }
-    post();
-    }
-    halo_add(dof, KU);
+    rows_then_halo(dof, KU, dof, [&](int r0, int r1) {
+      const int n = r1 - r0, g = grid_rows(n);
+      const int* rp = rowPtr + r0;
+      double* out = KU + size_t(r0)*dof;
+      switch (dof) {
+        case 4: k_spmv_vv4<<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out); break;
+        case 3: if (variant_vv3 == 1) k_spmv_vv3s<<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out);
+                else k_spmv_vv<3><<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out);
+                break;
+        case 2: k_spmv_vv<2><<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out); break;
+        default: k_spmv_vv<1><<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out); break;
+      }
+      post();
+    });
   }
   void spmv_ss(const double* K, const double* U, double* KU)
   {
-    {
-      Scope sc(*this, KC_SPMV_SS, bytes_ss());
-      k_spmv_ss<<<grid_rows(nNo_), 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU);
+    Scope sc(*this, KC_SPMV_SS, bytes_ss());
+    rows_then_halo(1, KU, 1, [&](int r0, int r1) {
+      k_spmv_ss<<<grid_rows(r1 - r0), 256, 0, st>>>(skip_flag, r1 - r0, rowPtr + r0, col, K, U, KU + r0);
       post();
-    }
-    halo_add(1, KU);
+    });
   }
   void spmv_sv(int dof, const double* K, const double* U, double* KU)
   {
-    const int g = grid_rows(nNo_);
-    {
-      Scope sc(*this, KC_SPMV_SV, bytes_svs(dof));
-      if (dof == 3) k_spmv_sv<3><<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU);
-      else if (dof == 2) k_spmv_sv<2><<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU);
-      else throw std::runtime_error("spmv_sv: nsd must be 2 or 3");
+    if (dof != 2 && dof != 3) throw std::runtime_error("spmv_sv: nsd must be 2 or 3");
+    Scope sc(*this, KC_SPMV_SV, bytes_svs(dof));
+    rows_then_halo(dof, KU, dof, [&](int r0, int r1) {
+      const int n = r1 - r0, g = grid_rows(n);
+      if (dof == 3) k_spmv_sv<3><<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, K, U, KU + size_t(r0)*3);
+      else k_spmv_sv<2><<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, K, U, KU + size_t(r0)*2);
       post();
-    }
-    halo_add(dof, KU);
+    });
   }
   void spmv_vs(int dof, const double* K, const double* U, double* KU)
   {
-    const int g = grid_rows(nNo_);
-    {
-      Scope sc(*this, KC_SPMV_VS, bytes_svs(dof));
-      if (dof == 3) k_spmv_vs<3><<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU);
-      else if (dof == 2) k_spmv_vs<2><<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, K, U, KU);
-      else throw std::runtime_error("spmv_vs: nsd must be 2 or 3");
+    if (dof != 2 && dof != 3) throw std::runtime_error("spmv_vs: nsd must be 2 or 3");
+    Scope sc(*this, KC_SPMV_VS, bytes_svs(dof));
+    rows_then_halo(1, KU, 1, [&](int r0, int r1) {
+      const int n = r1 - r0, g = grid_rows(n);
+      if (dof == 3) k_spmv_vs<3><<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, K, U, KU + r0);
+      else k_spmv_vs<2><<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, K, U, KU + r0);
       post();
-    }
-    halo_add(1, KU);
+    });
   }
 
   // fsils_commuv / fsils_commus: pack -> grouped ncclSend/ncclRecv -> add in request order
-  void halo_add(int dof, double* V, int ld = 0)
+  void halo_exchange(int dof, const double* V, int ld, cudaStream_t s)
   {
-    if (nranks == 1 || reqs.empty()) return;
-    if (ld == 0) ld = dof;
     if (dof > halo_dof_cap) throw std::runtime_error("halo buffers too small for dof");
-    double hb = 0; for (auto& r : reqs) hb += 32.0*r.n*dof;
-    Scope sc(*this, KC_HALO, hb, int(reqs.size())*2);
     for (auto& r : reqs) {
-      k_halo_pack<<<grid_for(size_t(r.n)*dof, 256, 1), 256, 0, st>>>(r.n, dof, ld, r.ptr, V, r.sbuf);
+      k_halo_pack<<<grid_for(size_t(r.n)*dof, 256, 1), 256, 0, s>>>(r.n, dof, ld, r.ptr, V, r.sbuf);
       post();
     }
     nccl.check(nccl.GroupStart(), "GroupStart");
     for (auto& r : reqs) {
-      nccl.check(nccl.Recv(r.rbuf, size_t(r.n)*dof, Nccl::kFloat64, r.peer, comm, st), "Recv");
-      nccl.check(nccl.Send(r.sbuf, size_t(r.n)*dof, Nccl::kFloat64, r.peer, comm, st), "Send");
+      nccl.check(nccl.Recv(r.rbuf, size_t(r.n)*dof, Nccl::kFloat64, r.peer, comm, s), "Recv");
+      nccl.check(nccl.Send(r.sbuf, size_t(r.n)*dof, Nccl::kFloat64, r.peer, comm, s), "Send");
     }
     nccl.check(nccl.GroupEnd(), "GroupEnd");
+  }
+  void halo_accumulate(int dof, double* V, int ld)
+  {
     for (auto& r : reqs) {
       k_halo_add<<<grid_for(size_t(r.n)*dof, 256, 1), 256, 0, st>>>(r.n, dof, ld, r.ptr, r.rbuf, V);
       post();
     }
+  }
+  void halo_add(int dof, double* V, int ld = 0)
+  {
+    if (nranks == 1 || reqs.empty()) return;
+    if (ld == 0) ld = dof;
+    double hb = 0; for (auto& r : reqs) hb += 32.0*r.n*dof;
+    Scope sc(*this, KC_HALO, hb, int(reqs.size())*2);
+    halo_exchange(dof, V, ld, st);
+    halo_accumulate(dof, V, ld);
   }
 
   // ---- faces ----------------------------------------------------------------------------------------
@@ -607,22 +650,25 @@ class CudaOps {
                 double* SP, bool coupled)
   {
     if (nsd == 3 && Gt == packed_Gt && GtL) {
-      const int g = grid_rows(nNo_);
       {
         Scope sc(*this, KC_SPMV_SV, bytes_schur_gp());
-        if (variant_gp == 1) k_schur_gp4<<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, G, P, V4);
-        else k_schur_gp<<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, G, P, V4);
-        post();
+        rows_then_halo(3, V4, 4, [&](int r0, int r1) {
+          const int n = r1 - r0, g = grid_rows(n);
+          if (variant_gp == 1) k_schur_gp4<<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, G, P, P + r0, V4 + size_t(r0)*4);
+          else k_schur_gp<<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, G, P, P + r0, V4 + size_t(r0)*4);
+          post();
+        });
       }
-      halo_add(3, V4, 4);
       if (coupled) add_bc_mul(BCOP_PRE, 3, V4, V4, 4);
       {
         Scope sc(*this, KC_SPMV_VS, bytes_schur_sp());
-        if (variant_sp == 1) k_schur_sp4<<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, GtL, V4, SP);
-        else k_schur_sp<<<g, 256, 0, st>>>(skip_flag, nNo_, rowPtr, col, GtL, V4, SP);
-        post();
+        rows_then_halo(1, SP, 1, [&](int r0, int r1) {
+          const int n = r1 - r0, g = grid_rows(n);
+          if (variant_sp == 1) k_schur_sp4<<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, GtL, V4, SP + r0);
+          else k_schur_sp<<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, GtL, V4, SP + r0);
+          post();
+        });
       }
-      halo_add(1, SP);
       return;
     }
     spmv_sv(nsd, G, P, GP);
