@@ -45,8 +45,45 @@ def dropin_lib():
         L.ref_asm_destroy.argtypes = [C.c_void_p]
         L.ref_dropin_fluid_step.argtypes = ([C.c_void_p, C.c_int, C.c_int] + [C.c_double] * 5 + [C.c_void_p, C.c_double]
                                             + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 8)
+        L.ref_dropin_solid_step.argtypes = ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_int]
+                                            + [C.c_void_p] * 8)
         _dropin = L
     return _dropin
+
+
+def dropin_solid_step(case, ls, mode):
+    """Like dropin_fluid_step for a svfsiplus_b200.problem.block_case (struct / lelas / mesh, dof 3)."""
+    L = dropin_lib()
+    m = case["mesh"]
+    x = _c(m.x, np.float64); ien = _c(m.ien, np.int32)
+    h = L.ref_asm_create(m.nNo, m.nEl, ien.shape[1], _p(ien), _p(x), 1, -1.0)
+    if not h:
+        raise RuntimeError(L.ref_last_error().decode())
+    try:
+        p = case["props"]
+        f = p.get("f", (0.0, 0.0, 0.0))
+        par = np.array([p["dt"], p["am"], p["af"], p["gam"], p["beta"], p["rho"], p.get("dmp", 0.0), f[0], f[1], f[2],
+                        RefAssembly.ISO[p.get("iso", "nHook")], RefAssembly.VOL[p.get("vol")], p.get("C10", 0.0), p.get("C01", 0.0),
+                        p.get("Kpen", 0.0), p.get("elM", 0.0), p.get("nu", 0.0)], np.float64)
+        Ag = _c(case["Ag"], np.float64); Yg = _c(case["Yg"], np.float64); Dg = _c(case["Dg"], np.float64)
+        Bf = _c(case["Bf"], np.float64)
+        Do = None if case.get("Do") is None else _c(case["Do"], np.float64)
+        faces = case["faces"]
+        f_info = np.array([[len(fa["nodes"]), fa["dof"], fa["bGrp"]] for fa in faces], np.int32).reshape(-1)
+        f_nodes = np.concatenate([np.asarray(fa["nodes"], np.int32) for fa in faces])
+        f_val = np.concatenate([np.asarray(fa["val"], np.float64).reshape(-1) for fa in faces])
+        X = np.empty((m.nNo, 3)); out = np.zeros(9)
+        ls = _c(ls, np.float64)
+        incL = _c(case["incL"], np.int32); res = _c(case["res"], np.float64)
+        kind = {"struct": 0, "lelas": 1, "mesh": 2}[case["kind"]]
+        rc = L.ref_dropin_solid_step(h, int(mode), kind, Ag.shape[1], int(p.get("s", 0)), _p(par), _p(Ag), _p(Yg), _p(Dg), _p(Do),
+                                     _p(Bf), len(faces), _p(f_info), _p(f_nodes), _p(f_val), _p(ls), _p(incL), _p(res), _p(X), _p(out))
+        if rc != 0:
+            raise RuntimeError(L.ref_last_error().decode())
+    finally:
+        L.ref_asm_destroy(h)
+    keys = ("suc", "itr", "iNorm", "fNorm", "GM_itr", "CG_itr", "Resm", "Resc", "device_assembly")
+    return X, dict(zip(keys, out))
 
 
 def dropin_fluid_step(case, ls, mode):

@@ -238,19 +238,15 @@ double ref_asm_fluid(void* h, int tDof, int mvMsh, double dt, double am, double 
   }
 }
 
-// Solid assembly through the reference's construct_dsolid (S/sv_struct.cpp:213 -> struct_3d_carray :552 ->
-// get_pk2cc<3> S/mat_models_carray.h:182) or construct_l_elas (S/l_elas.cpp:58 -> l_elas_3d :274).
-// kind 0: struct, 1: lElas, 2: mesh (construct_mesh S/mesh.cpp:42; needs Do and eq.s = s).  par = {dt, am, af, gam, beta, rho, dmp, fx, fy, fz,
-//   iso (0 nHook, 1 StVK, 2 mStVK), vol (0 none, 1 Quad, 2 ST91, 3 M94), C10, C01, Kpen, elM, nu}
-// Ag, Yg, Dg: tDof x nNo (eq.s = 0, dof = 3).  Outputs R (3 x nNo), Val (9 x nnz).
-double ref_asm_solid(void* h, int kind, int tDof, int s, const double* par, const double* Ag, const double* Yg,
-                     const double* Dg, const double* Do, const double* Bf, double* R, double* Val)
+} // extern "C"
+
+namespace {
+// Fill ComMod / eqType / dmnType for one struct (kind 0), lElas (1) or mesh (2) equation; par as in ref_asm_solid.
+void configure_solid(AsmCtx* ctx, int kind, int tDof, int s, const double* par, const double* Do, const double* Bf)
 {
-  try {
-    using namespace consts;
-    auto ctx = static_cast<AsmCtx*>(h);
-    auto& com_mod = ctx->sim->com_mod;
-    const int nNo = com_mod.tnNo;
+  using namespace consts;
+  auto& com_mod = ctx->sim->com_mod;
+  const int nNo = com_mod.tnNo;
     const int dof = 3;
     com_mod.tDof = tDof;
     com_mod.dof = dof;
@@ -292,6 +288,27 @@ double ref_asm_solid(void* h, int kind, int tDof, int s, const double* par, cons
     dmn.stM.Kpen = par[14];
     com_mod.Bf.resize(3, nNo);
     std::memcpy(com_mod.Bf.data(), Bf, sizeof(double)*3*size_t(nNo));
+}
+} // namespace
+
+extern "C" {
+
+// Solid assembly through the reference's construct_dsolid (S/sv_struct.cpp:213 -> struct_3d_carray :552 ->
+// get_pk2cc<3> S/mat_models_carray.h:182) or construct_l_elas (S/l_elas.cpp:58 -> l_elas_3d :274).
+// kind 0: struct, 1: lElas, 2: mesh (construct_mesh S/mesh.cpp:42; needs Do and eq.s = s).  par = {dt, am, af, gam, beta, rho, dmp, fx, fy, fz,
+//   iso (0 nHook, 1 StVK, 2 mStVK), vol (0 none, 1 Quad, 2 ST91, 3 M94), C10, C01, Kpen, elM, nu}
+// Ag, Yg, Dg: tDof x nNo (eq.s = 0, dof = 3).  Outputs R (3 x nNo), Val (9 x nnz).
+double ref_asm_solid(void* h, int kind, int tDof, int s, const double* par, const double* Ag, const double* Yg,
+                     const double* Dg, const double* Do, const double* Bf, double* R, double* Val)
+{
+  try {
+    using namespace consts;
+    auto ctx = static_cast<AsmCtx*>(h);
+    auto& com_mod = ctx->sim->com_mod;
+    const int nNo = com_mod.tnNo;
+    const int dof = 3;
+    configure_solid(ctx, kind, tDof, s, par, Do, Bf);
+    auto& eq = com_mod.eq[0];
     if (!eq.linear_algebra) eq.linear_algebra = new FsilsLinearAlgebra();
 
     Array<double> Ag_a(tDof, nNo), Yg_a(tDof, nNo), Dg_a(tDof, nNo);
@@ -683,6 +700,76 @@ int ref_ranks_commuv(int nranks, void** hs, int dof, double** V)
 // faces: nFaces x {nNo, dof, bGrp}; nodes/vals concatenated.  ls as in ref_ranks_solve.
 // out = {RI.suc, RI.itr, RI.iNorm, RI.fNorm, GM.itr, CG.itr, Resm, Resc, used_device_assembly}
 // ----------------------------------------------------------------------------------------------
+} // extern "C"
+
+namespace {
+// Shared tail of the drop-in steps: what initialize() / fsi_ls_ini leave behind (com_mod.lhs + faces), the <LS> block,
+// eq.linear_algebra = B200LinearAlgebra, then one Newton iteration (ls_alloc, global_eq_assem hook, ls_solve).
+template <class HostAssembly>
+void dropin_newton_iteration(AsmCtx* ctx, int dof, int mode, int tDof, const double* Ag, const double* Yg, const double* Dg,
+                             int nFaces, const int* f_info, const int* f_nodes, const double* f_val,
+                             const double* ls, const int* incL, const double* res, double* X, double* out,
+                             HostAssembly&& host_assembly)
+{
+  using namespace consts;
+  auto& com_mod = ctx->sim->com_mod;
+  const int nNo = com_mod.tnNo;
+  auto& eq = com_mod.eq[0];
+  auto& lhs = com_mod.lhs;
+  lhs = FSILS_lhsType();
+  fsils_commu_create(lhs.commu, MPI_COMM_WORLD);
+  Vector<int> gNodes(nNo);
+  for (int a = 0; a < nNo; a++) gNodes(a) = a;
+  fsils_lhs_create(lhs, lhs.commu, nNo, nNo, ctx->nnz, gNodes, com_mod.rowPtr, com_mod.colPtr, nFaces);
+  size_t on = 0, ov = 0;
+  for (int i = 0; i < nFaces; i++) {
+    const int fn = f_info[3*i], fd = f_info[3*i+1], fb = f_info[3*i+2];
+    Vector<int> gN(fn);
+    std::memcpy(gN.data(), f_nodes + on, sizeof(int)*fn);
+    Array<double> v(fd, fn);
+    std::memcpy(v.data(), f_val + ov, sizeof(double)*size_t(fd)*fn);
+    fsils_bc_create(lhs, i, fn, fd, fb == 0 ? BcType::BC_TYPE_Dir : BcType::BC_TYPE_Neu, gN, v);
+    on += fn; ov += size_t(fd)*fn;
+  }
+  // read_files.cpp:2046-2075 + add_eq_linear_algebra (main.cpp:68-77)
+  fsils_ls_create(eq.FSILS, static_cast<LinearSolverType>(int(ls[0])));
+  eq.FSILS.RI.relTol = ls[1]; eq.FSILS.RI.absTol = ls[2]; eq.FSILS.RI.mItr = int(ls[3]); eq.FSILS.RI.sD = int(ls[4]);
+  eq.FSILS.GM.relTol = ls[5]; eq.FSILS.GM.absTol = ls[6]; eq.FSILS.GM.mItr = int(ls[7]); eq.FSILS.GM.sD = int(ls[8]);
+  eq.FSILS.CG.relTol = ls[9]; eq.FSILS.CG.absTol = ls[10]; eq.FSILS.CG.mItr = int(ls[11]);
+  eq.linear_algebra_preconditioner = PreconditionerType::PREC_FSILS;
+  delete eq.linear_algebra;
+  auto* la = new B200LinearAlgebra();
+  eq.linear_algebra = la;
+  la->check_options(PreconditionerType::PREC_FSILS, mode == 1 ? B200_LINEAR_ALGEBRA_TYPE : LinearAlgebraType::fsils);
+  la->set_preconditioner(eq.linear_algebra_preconditioner);
+  la->initialize(com_mod, eq);
+  la->set_assembly(mode == 1 ? B200_LINEAR_ALGEBRA_TYPE : LinearAlgebraType::fsils);
+
+  Array<double> Ag_a(tDof, nNo), Yg_a(tDof, nNo), Dg_a(tDof, nNo);
+  std::memcpy(Ag_a.data(), Ag, sizeof(double)*size_t(tDof)*nNo);
+  std::memcpy(Yg_a.data(), Yg, sizeof(double)*size_t(tDof)*nNo);
+  if (Dg) std::memcpy(Dg_a.data(), Dg, sizeof(double)*size_t(tDof)*nNo);
+
+  // one Newton iteration (main.cpp iterate_solution): ls_alloc, global_eq_assem, ls_solve
+  ls_ns::ls_alloc(com_mod, eq);
+  bool on_device = la->assemble_mesh(com_mod, com_mod.msh[0], Ag_a, Yg_a, Dg_a, &ctx->sim->cep_mod);   // the global_eq_assem hook
+  if (!on_device) host_assembly(Ag_a, Yg_a, Dg_a);
+  Vector<int> incL_v(nFaces);
+  Vector<double> res_v(nFaces);
+  for (int i = 0; i < nFaces; i++) { incL_v(i) = incL ? incL[i] : 1; res_v(i) = res ? res[i] : 0.0; }
+  ls_ns::ls_solve(com_mod, eq, incL_v, res_v);
+
+  std::memcpy(X, com_mod.R.data(), sizeof(double)*size_t(dof)*nNo);
+  auto& L = eq.FSILS;
+  out[0] = L.RI.suc; out[1] = L.RI.itr; out[2] = L.RI.iNorm; out[3] = L.RI.fNorm;
+  out[4] = L.GM.itr; out[5] = L.CG.itr; out[6] = L.Resm; out[7] = L.Resc; out[8] = on_device ? 1.0 : 0.0;
+  delete eq.linear_algebra;
+  eq.linear_algebra = nullptr;
+}
+} // namespace
+
+extern "C" {
+
 int ref_dropin_fluid_step(void* h, int mode, int tDof, double dt, double am, double af, double gam, double rho,
                           const double* f, double Kinv_darcy, const double* visc,
                           const double* Ag, const double* Yg, const double* Bf,
@@ -690,67 +777,38 @@ int ref_dropin_fluid_step(void* h, int mode, int tDof, double dt, double am, dou
                           const double* ls, const int* incL, const double* res, double* X, double* out)
 {
   try {
-    using namespace consts;
     mpistub_set_world(1);
     mpistub_bind_rank(0);
     auto ctx = static_cast<AsmCtx*>(h);
     auto& com_mod = ctx->sim->com_mod;
-    const int nNo = com_mod.tnNo;
-    const int dof = 4;
     configure_fluid(ctx, tDof, 0, dt, am, af, gam, rho, f, Kinv_darcy, visc, Bf);
-    auto& eq = com_mod.eq[0];
+    dropin_newton_iteration(ctx, 4, mode, tDof, Ag, Yg, nullptr, nFaces, f_info, f_nodes, f_val, ls, incL, res, X, out,
+                            [&](Array<double>& A, Array<double>& Y, Array<double>&) { fluid::construct_fluid(com_mod, com_mod.msh[0], A, Y); });
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
 
-    // what initialize() / fsi_ls_ini (baf_ini.cpp:689) leave behind: com_mod.lhs and its faces
-    auto& lhs = com_mod.lhs;
-    lhs = FSILS_lhsType();
-    fsils_commu_create(lhs.commu, MPI_COMM_WORLD);
-    Vector<int> gNodes(nNo);
-    for (int a = 0; a < nNo; a++) gNodes(a) = a;
-    fsils_lhs_create(lhs, lhs.commu, nNo, nNo, ctx->nnz, gNodes, com_mod.rowPtr, com_mod.colPtr, nFaces);
-    size_t on = 0, ov = 0;
-    for (int i = 0; i < nFaces; i++) {
-      const int fn = f_info[3*i], fd = f_info[3*i+1], fb = f_info[3*i+2];
-      Vector<int> gN(fn);
-      std::memcpy(gN.data(), f_nodes + on, sizeof(int)*fn);
-      Array<double> v(fd, fn);
-      std::memcpy(v.data(), f_val + ov, sizeof(double)*size_t(fd)*fn);
-      fsils_bc_create(lhs, i, fn, fd, fb == 0 ? BcType::BC_TYPE_Dir : BcType::BC_TYPE_Neu, gN, v);
-      on += fn; ov += size_t(fd)*fn;
-    }
-
-    // read_files.cpp:2046-2075 + add_eq_linear_algebra (main.cpp:68-77)
-    fsils_ls_create(eq.FSILS, static_cast<LinearSolverType>(int(ls[0])));
-    eq.FSILS.RI.relTol = ls[1]; eq.FSILS.RI.absTol = ls[2]; eq.FSILS.RI.mItr = int(ls[3]); eq.FSILS.RI.sD = int(ls[4]);
-    eq.FSILS.GM.relTol = ls[5]; eq.FSILS.GM.absTol = ls[6]; eq.FSILS.GM.mItr = int(ls[7]); eq.FSILS.GM.sD = int(ls[8]);
-    eq.FSILS.CG.relTol = ls[9]; eq.FSILS.CG.absTol = ls[10]; eq.FSILS.CG.mItr = int(ls[11]);
-    eq.linear_algebra_preconditioner = PreconditionerType::PREC_FSILS;
-    delete eq.linear_algebra;
-    auto* la = new B200LinearAlgebra();
-    eq.linear_algebra = la;
-    la->check_options(PreconditionerType::PREC_FSILS, mode == 1 ? B200_LINEAR_ALGEBRA_TYPE : LinearAlgebraType::fsils);
-    la->set_preconditioner(eq.linear_algebra_preconditioner);
-    la->initialize(com_mod, eq);
-    la->set_assembly(mode == 1 ? B200_LINEAR_ALGEBRA_TYPE : LinearAlgebraType::fsils);
-
-    Array<double> Ag_a(tDof, nNo), Yg_a(tDof, nNo), Dg_a(tDof, nNo);
-    std::memcpy(Ag_a.data(), Ag, sizeof(double)*size_t(tDof)*nNo);
-    std::memcpy(Yg_a.data(), Yg, sizeof(double)*size_t(tDof)*nNo);
-
-    // one Newton iteration (main.cpp iterate_solution): ls_alloc, global_eq_assem, ls_solve
-    ls_ns::ls_alloc(com_mod, eq);
-    bool on_device = la->assemble_mesh(com_mod, com_mod.msh[0], Ag_a, Yg_a, Dg_a);   // the global_eq_assem hook
-    if (!on_device) fluid::construct_fluid(com_mod, com_mod.msh[0], Ag_a, Yg_a);
-    Vector<int> incL_v(nFaces);
-    Vector<double> res_v(nFaces);
-    for (int i = 0; i < nFaces; i++) { incL_v(i) = incL ? incL[i] : 1; res_v(i) = res ? res[i] : 0.0; }
-    ls_ns::ls_solve(com_mod, eq, incL_v, res_v);
-
-    std::memcpy(X, com_mod.R.data(), sizeof(double)*size_t(dof)*nNo);
-    auto& L = eq.FSILS;
-    out[0] = L.RI.suc; out[1] = L.RI.itr; out[2] = L.RI.iNorm; out[3] = L.RI.fNorm;
-    out[4] = L.GM.itr; out[5] = L.CG.itr; out[6] = L.Resm; out[7] = L.Resc; out[8] = on_device ? 1.0 : 0.0;
-    delete eq.linear_algebra;
-    eq.linear_algebra = nullptr;
+// Same for a struct (kind 0) / lElas (1) / mesh (2) equation; par, s, Do as in ref_asm_solid.
+int ref_dropin_solid_step(void* h, int mode, int kind, int tDof, int s, const double* par,
+                          const double* Ag, const double* Yg, const double* Dg, const double* Do, const double* Bf,
+                          int nFaces, const int* f_info, const int* f_nodes, const double* f_val,
+                          const double* ls, const int* incL, const double* res, double* X, double* out)
+{
+  try {
+    mpistub_set_world(1);
+    mpistub_bind_rank(0);
+    auto ctx = static_cast<AsmCtx*>(h);
+    auto& com_mod = ctx->sim->com_mod;
+    configure_solid(ctx, kind, tDof, s, par, Do, Bf);
+    dropin_newton_iteration(ctx, 3, mode, tDof, Ag, Yg, Dg, nFaces, f_info, f_nodes, f_val, ls, incL, res, X, out,
+                            [&](Array<double>& A, Array<double>& Y, Array<double>& D) {
+                              if (kind == 0) struct_ns::construct_dsolid(com_mod, ctx->sim->cep_mod, com_mod.msh[0], A, Y, D);
+                              else if (kind == 1) l_elas::construct_l_elas(com_mod, com_mod.msh[0], A, D);
+                              else mesh::construct_mesh(com_mod, ctx->sim->cep_mod, com_mod.msh[0], A, D);
+                            });
     return 0;
   } catch (const std::exception& e) {
     g_err = e.what();

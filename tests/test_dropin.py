@@ -43,3 +43,20 @@ def test_plugin_class_tight_solve():
     X, info = ref.dropin_fluid_step(case, refcase._ls_vector(ls), 1)
     Rr, Vr, Xr, oref = refcase.reference_step(case, ls)
     assert rel_l2(X, Xr) < 1e-6        # cond x 1e-11, see test_gpu_parity.test_tight_tolerance_solution
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("elem,kind,ls", [("hex", "struct", "BICGS_STRUCT"), ("tet", "struct", "BICGS_STRUCT"),
+                                          ("tet", "lelas", "GMRES_STRUCT_LOOSE")])
+def test_plugin_class_solid_equations(mode, elem, kind, ls):
+    """struct / lElas through the reference's own ComMod with eq.linear_algebra = B200LinearAlgebra: host assembly +
+    device solve (mode 0) and device assembly through assemble_mesh (mode 1), against the FsilsLinearAlgebra path."""
+    _need()
+    from oracle import ref, refcase
+    case = P.block_case(6, elem=elem, kind=kind)
+    X, info = ref.dropin_solid_step(case, refcase._ls_vector(P.LS_SETTINGS[ls]), mode)
+    assert int(info["device_assembly"]) == mode
+    Rr, Vr, Xr, oref = refcase.reference_solid_step(case, ls)
+    assert bool(info["suc"]) == bool(oref["suc"])
+    assert rel_l2(X, Xr) < (1e-8 if ls.startswith("BICGS") else 1e-2)
+    assert abs(int(info["itr"]) - int(oref["itr"])) <= max(1, 0.02 * oref["itr"])

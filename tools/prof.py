@@ -28,11 +28,26 @@ def peak():
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["tour", "step", "asm"])
+    ap.add_argument("mode", choices=["tour", "step", "asm", "solid"])
     ap.add_argument("--dims", type=int, nargs=3, default=[96, 96, 181])
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--ls", default="NS")
     a = ap.parse_args()
+    if a.mode == "solid":
+        # K11 element kernels on production-size blocks: struct HEX8 100^3 (1.0 M hex), struct / ustruct TET4 60^3 x 6
+        for name, case, asm in (("struct_hex8_100", P.block_case(100, elem="hex", kind="struct"), P.assemble_solid),
+                                ("struct_tet4_60", P.block_case(60, elem="tet", kind="struct"), P.assemble_solid),
+                                ("ustruct_tet4_60", P.ustruct_case(60, elem="tet"), P.assemble_ustruct)):
+            be = P.setup_backend(case)
+            asm(be, case)
+            be.timer_start()
+            for _ in range(a.reps):
+                asm(be, case, upload=False)
+            ms = be.timer_stop() / a.reps
+            nEl = case["mesh"].nEl
+            print(json.dumps(dict(kernel=name, nEl=nEl, ms=ms, ns_per_elem=1e6 * ms / nEl, nnz=be.nnz)), flush=True)
+            be.close()
+        return
     t0 = time.time()
     case = P.pipe_case(*a.dims)
     be = P.setup_backend(case)
