@@ -51,7 +51,8 @@ typedef struct {
 /* Per-(equation, domain) constants of the displacement-based solid element, flattened from eqType /
  * dmnType / stModelType (solver/sv_struct.cpp:576-594, solver/ComMod.h:345-388).  s = eq.s, the row of
  * the equation's first unknown inside Ag/Yg/Dg(tDof,nNo).  isoType: 0 neo-Hookean (C10 = mu/2),
- * 1 St.Venant-Kirchhoff (C10 = lambda, C01 = mu), 2 modified StVK (C10 = kappa, C01 = mu);
+ * 1 St.Venant-Kirchhoff (C10 = lambda, C01 = mu), 2 modified StVK (C10 = kappa, C01 = mu), 3 Holzapfel-Ogden
+ * (solver/mat_models_carray.h:905-1135; needs b200_mesh_fibers);
  * volType: 0 none, 1 Quad, 2 ST91, 3 M94 (solver/mat_models.cpp:1626-1645). */
 typedef struct {
   double dt, am, af, gam, beta;
@@ -59,6 +60,7 @@ typedef struct {
   double rho, dmp, f[3];
   int isoType, volType;
   double C10, C01, Kpen;
+  double a, b, aff, bff, ass, bss, afs, bfs, khs;   /* isoType 3 (Holzapfel-Ogden): stModelType a..bfs, khs */
 } b200_struct_props;
 
 /* Linear elasticity (solver/l_elas.cpp:274-390).  mesh_mode != 0: the ALE mesh-motion equation
@@ -133,6 +135,8 @@ int b200_assemble_ustruct(b200_handle* h, const b200_ustruct_props* p);
  * the first Newton iteration only (eq.itr <= 1), like the reference.  Ad(3,nNo) host, assembly order. */
 int b200_ustruct_r(b200_handle* h, double amg, double ami, int s, const double* Ad);
 int b200_get_Kd(b200_handle* h, double* Kd);      /* parity tap: Kd(12,nnz), assembly layout */
+/* lM.fN for nFn = 2: fN(6,nEl) = fibre and sheet direction of every element (solver/ComMod.h:975). */
+int b200_mesh_fibers(b200_handle* h, int nFn, const double* fN);
 /* FSI equation (solver/fsi.cpp:42-334: one element loop with a per-element domain switch).  elem_dmn[e] =
  * index of the equation domain element e belongs to (all_fun::domain, solver/all_fun.cpp:149), uploaded once;
  * the device keeps one element list per domain, so each domain is one divergence-free launch. */

@@ -64,7 +64,7 @@ def dropin_solid_step(case, ls, mode):
         f = p.get("f", (0.0, 0.0, 0.0))
         par = np.array([p["dt"], p["am"], p["af"], p["gam"], p["beta"], p["rho"], p.get("dmp", 0.0), f[0], f[1], f[2],
                         RefAssembly.ISO[p.get("iso", "nHook")], RefAssembly.VOL[p.get("vol")], p.get("C10", 0.0), p.get("C01", 0.0),
-                        p.get("Kpen", 0.0), p.get("elM", 0.0), p.get("nu", 0.0)], np.float64)
+                        p.get("Kpen", 0.0), p.get("elM", 0.0), p.get("nu", 0.0)] + [0.0] * 8 + [100.0], np.float64)
         Ag = _c(case["Ag"], np.float64); Yg = _c(case["Yg"], np.float64); Dg = _c(case["Dg"], np.float64)
         Bf = _c(case["Bf"], np.float64)
         Do = None if case.get("Do") is None else _c(case["Do"], np.float64)
@@ -135,6 +135,7 @@ def lib():
         L.ref_asm_get_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_asm_fluid.restype = C.c_double
         L.ref_asm_fluid.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_double] * 5 + [C.c_void_p, C.c_double] + [C.c_void_p] * 6
+        L.ref_asm_set_fibers.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ref_asm_solid.restype = C.c_double
         L.ref_asm_solid.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
         L.ref_asm_fsi.restype = C.c_double
@@ -218,17 +219,27 @@ class RefAssembly:
         return R, Val, t
 
 
-    ISO = {"nHook": 0, "StVK": 1, "mStVK": 2}
+    ISO = {"nHook": 0, "StVK": 1, "mStVK": 2, "HO": 3}
+    HO_KEYS = ("a", "b", "aff", "bff", "ass", "bss", "afs", "bfs", "khs")
+
+    def set_fibers(self, fN):
+        """lM.fN: (nEl, 6) fibre + sheet directions, or None."""
+        if fN is None:
+            lib().ref_asm_set_fibers(self.h, 0, None)
+        else:
+            fN = _c(fN, np.float64)
+            lib().ref_asm_set_fibers(self.h, 2, _p(fN))
     VOL = {None: 0, "Quad": 1, "ST91": 2, "M94": 3}
 
     def solid(self, kind, Ag, Yg, Dg, Bf, *, dt, am, af, gam, beta, rho, dmp=0.0, f=(0.0, 0.0, 0.0), iso="nHook",
-              vol="ST91", C10=0.0, C01=0.0, Kpen=0.0, elM=0.0, nu=0.0, s=0, Do=None):
+              vol="ST91", C10=0.0, C01=0.0, Kpen=0.0, elM=0.0, nu=0.0, s=0, Do=None, ho=None):
         """kind "struct": construct_dsolid (S/sv_struct.cpp:213); "lelas": construct_l_elas (S/l_elas.cpp:58).
         Returns R (nNo,3), Val (nnz,9), seconds."""
         Ag = _c(Ag, np.float64); Yg = _c(Yg, np.float64); Dg = _c(Dg, np.float64); Bf = _c(Bf, np.float64)
         tDof = Ag.shape[1]
+        ho = ho or {}
         par = np.array([dt, am, af, gam, beta, rho, dmp, f[0], f[1], f[2], self.ISO[iso], self.VOL[vol], C10, C01, Kpen,
-                        elM, nu], np.float64)
+                        elM, nu] + [ho.get(k, 100.0 if k == "khs" else 0.0) for k in self.HO_KEYS], np.float64)
         R = np.empty((self.nNo, 3))
         Val = np.empty((self.nnz, 9))
         Do = None if Do is None else _c(Do, np.float64)
@@ -249,7 +260,7 @@ class RefAssembly:
                          fluid.get("lam", 0.0), fluid.get("a", 0.0), fluid.get("n", 0.0)], np.float64)
         spar = np.array([dt, am, af, gam, beta, solid["rho"], solid.get("dmp", 0.0), sf[0], sf[1], sf[2],
                          self.ISO[solid.get("iso", "nHook")], self.VOL[solid.get("vol", "ST91")], solid["C10"],
-                         solid.get("C01", 0.0), solid.get("Kpen", 0.0), 0.0, 0.0], np.float64)
+                         solid.get("C01", 0.0), solid.get("Kpen", 0.0), 0.0, 0.0] + [0.0] * 8 + [100.0], np.float64)
         R = np.empty((self.nNo, 4))
         Val = np.empty((self.nnz, 16))
         t = lib().ref_asm_fsi(self.h, Ag.shape[1], dt, am, af, gam, beta, _p(fpar), _p(spar), _p(ed), _p(Ag), _p(Yg), _p(Dg),

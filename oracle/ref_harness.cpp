@@ -125,6 +125,16 @@ void* ref_asm_create(int nNo, int nEl, int eNoN, const int* IEN, const double* x
 
 void ref_asm_destroy(void* h) { delete static_cast<AsmCtx*>(h); }
 
+// lM.fN(nsd*nFn, nEl) / lM.nFn: fibre directions per element (fN == NULL clears them).
+void ref_asm_set_fibers(void* h, int nFn, const double* fN)
+{
+  auto& msh = static_cast<AsmCtx*>(h)->sim->com_mod.msh[0];
+  if (!fN) { msh.nFn = 0; msh.fN.resize(0, 0); return; }
+  msh.nFn = nFn;
+  msh.fN.resize(3*nFn, msh.nEl);
+  std::memcpy(msh.fN.data(), fN, sizeof(double)*size_t(3*nFn)*msh.nEl);
+}
+
 int ref_asm_nnz(void* h) { return static_cast<AsmCtx*>(h)->nnz; }
 
 // rowPtr: nNo+1 ints, colPtr: nnz ints (the reference's lhsa output, S/lhsa.cpp:153).
@@ -279,13 +289,17 @@ void configure_solid(AsmCtx* ctx, int kind, int tDof, int s, const double* par, 
     dmn.prop[PhysicalProperyType::poisson_ratio] = par[16];
     const int iso = int(par[10]), vol = int(par[11]);
     dmn.stM.isoType = (iso == 0) ? ConstitutiveModelType::stIso_nHook
-                    : (iso == 1) ? ConstitutiveModelType::stIso_StVK : ConstitutiveModelType::stIso_mStVK;
+                    : (iso == 1) ? ConstitutiveModelType::stIso_StVK
+                    : (iso == 2) ? ConstitutiveModelType::stIso_mStVK : ConstitutiveModelType::stIso_HO;
     dmn.stM.volType = (vol == 1) ? ConstitutiveModelType::stVol_Quad
                     : (vol == 2) ? ConstitutiveModelType::stVol_ST91
                     : (vol == 3) ? ConstitutiveModelType::stVol_M94 : ConstitutiveModelType::stIso_NA;
     dmn.stM.C10 = par[12];
     dmn.stM.C01 = par[13];
     dmn.stM.Kpen = par[14];
+    // Holzapfel-Ogden parameters (par[17..25]) and the mesh's fibre / sheet directions
+    dmn.stM.a = par[17]; dmn.stM.b = par[18]; dmn.stM.aff = par[19]; dmn.stM.bff = par[20];
+    dmn.stM.ass = par[21]; dmn.stM.bss = par[22]; dmn.stM.afs = par[23]; dmn.stM.bfs = par[24]; dmn.stM.khs = par[25];
     com_mod.Bf.resize(3, nNo);
     std::memcpy(com_mod.Bf.data(), Bf, sizeof(double)*3*size_t(nNo));
 }

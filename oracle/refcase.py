@@ -52,6 +52,7 @@ def reference_assemble_solid(case):
     m = case["mesh"]
     ra = ref.RefAssembly(m.x, m.ien)
     p = dict(case["props"])
+    ra.set_fibers(case.get("fN"))
     R, Val, secs = ra.solid(case["kind"], case["Ag"], case["Yg"], case["Dg"], case["Bf"], Do=case.get("Do"), **p)
     rowPtr, colPtr = ra.csr()
     tabs = ra.tables()

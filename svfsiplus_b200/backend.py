@@ -47,7 +47,9 @@ class StructProps(C.Structure):
                 ("tDof", C.c_int), ("s", C.c_int),
                 ("rho", C.c_double), ("dmp", C.c_double), ("f", C.c_double * 3),
                 ("isoType", C.c_int), ("volType", C.c_int),
-                ("C10", C.c_double), ("C01", C.c_double), ("Kpen", C.c_double)]
+                ("C10", C.c_double), ("C01", C.c_double), ("Kpen", C.c_double),
+                ("a", C.c_double), ("b", C.c_double), ("aff", C.c_double), ("bff", C.c_double), ("ass", C.c_double),
+                ("bss", C.c_double), ("afs", C.c_double), ("bfs", C.c_double), ("khs", C.c_double)]
 
 
 class LelasProps(C.Structure):
@@ -65,13 +67,13 @@ class UstructProps(C.Structure):
                 ("C10", C.c_double), ("Kpen", C.c_double)]
 
 
-ISO_TYPES = {"nHook": 0, "StVK": 1, "mStVK": 2}
+ISO_TYPES = {"nHook": 0, "StVK": 1, "mStVK": 2, "HO": 3}
 VOL_TYPES = {None: 0, "Quad": 1, "ST91": 2, "M94": 3}
 
 EXPORTS = [
     "b200_create", "b200_destroy", "b200_last_error", "b200_device_count", "b200_elem_tables", "b200_comm_unique_id", "b200_comm_init",
     "b200_lhs_create", "b200_face_set", "b200_mesh_set", "b200_zero", "b200_state_set", "b200_assemble_fluid",
-    "b200_disp_set", "b200_assemble_struct", "b200_assemble_lelas", "b200_mesh_domains", "b200_assemble_fsi",
+    "b200_disp_set", "b200_assemble_struct", "b200_assemble_lelas", "b200_mesh_domains", "b200_mesh_fibers", "b200_assemble_fsi",
     "b200_assemble_ustruct", "b200_ustruct_r", "b200_get_Kd",
     "b200_assemble_elem", "b200_get_R", "b200_set_R", "b200_add_R", "b200_get_Val", "b200_set_Val", "b200_commu_R", "b200_solve",
     "b200_spmv", "b200_op_bench", "b200_launch_count", "b200_last_timings", "b200_profile", "b200_profile_read",
@@ -114,6 +116,7 @@ def lib():
         L.b200_ustruct_r.argtypes = [vp, cd, cd, ci, vp]
         L.b200_get_Kd.argtypes = [vp, vp]
         L.b200_mesh_domains.argtypes = [vp, ci, vp]
+        L.b200_mesh_fibers.argtypes = [vp, ci, vp]
         L.b200_assemble_fsi.argtypes = [vp, ci, vp, C.POINTER(FluidProps), C.POINTER(StructProps)]
         L.b200_assemble_elem.argtypes = [vp, ci, vp, vp, vp]
         L.b200_get_R.argtypes = [vp, vp]
@@ -159,7 +162,7 @@ def fluid_props(*, dt, am, af, gam, rho, mu, tDof=4, mvMsh=False, f=(0.0, 0.0, 0
 
 
 def struct_props(*, dt, am, af, gam, beta, rho, tDof=3, s=0, dmp=0.0, f=(0.0, 0.0, 0.0), iso="nHook", vol="ST91",
-                 C10=0.0, C01=0.0, Kpen=0.0) -> StructProps:
+                 C10=0.0, C01=0.0, Kpen=0.0, ho=None) -> StructProps:
     p = StructProps()
     p.dt, p.am, p.af, p.gam, p.beta = dt, am, af, gam, beta
     p.tDof, p.s = tDof, s
@@ -167,6 +170,9 @@ def struct_props(*, dt, am, af, gam, beta, rho, tDof=3, s=0, dmp=0.0, f=(0.0, 0.
     p.f[0], p.f[1], p.f[2] = f
     p.isoType, p.volType = ISO_TYPES[iso], VOL_TYPES[vol]
     p.C10, p.C01, p.Kpen = C10, C01, Kpen
+    p.khs = 100.0
+    for k, v in (ho or {}).items():
+        setattr(p, k, v)
     return p
 
 
@@ -308,6 +314,10 @@ class Backend:
         Kd = np.empty((self.nnz, 12))
         self._ck(self.L.b200_get_Kd(self.h, _p(Kd)), "b200_get_Kd")
         return Kd
+
+    def mesh_fibers(self, fN):
+        fN = _c(fN, np.float64)
+        self._ck(self.L.b200_mesh_fibers(self.h, 2, _p(fN)), "b200_mesh_fibers")
 
     def mesh_domains(self, nDmn, elem_dmn):
         ed = _c(elem_dmn, np.int32)

@@ -57,6 +57,7 @@ struct b200_handle {
   size_t Kd_cap = 0, stageKd_cap = 0;
   std::vector<int*> d_dmn_elems;      // per FSI domain: element list (ascending element ids)
   std::vector<int> dmn_count;
+  double* d_fN = nullptr;    // 6 x nEl fibre + sheet directions (lM.fN with nFn = 2)
   double* d_tab = nullptr;   // packed Gauss tables of the mesh's element type (w, N, dN/dxi)
   ElemTables tab;
   double* d_x = nullptr;
@@ -87,7 +88,7 @@ struct b200_handle {
     cudaFree(stageR); cudaFree(stageK); cudaFree(d_x); cudaFree(d_err);
     cudaFree(d_Ag); cudaFree(d_Yg); cudaFree(d_Bf); cudaFree(d_Dg); cudaFree(d_Do); cudaFree(d_tab);
     for (auto p : d_dmn_elems) cudaFree(p);
-    cudaFree(Kd); cudaFree(stageKd);
+    cudaFree(Kd); cudaFree(stageKd); cudaFree(d_fN);
   }
 };
 
@@ -268,7 +269,7 @@ void launch_solid(b200_handle* h, const SolidConsts& c, int nList, const int* d_
   auto kern = k_assemble_solid<ENON, NG, EPB, APT, ODOF>;
   CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   kern<<<(nList + EPB - 1)/EPB, EPB*NG, smem, ops.st>>>(nList, d_elist, c, h->d_tab, h->d_ien, h->d_rslot, h->d_kslot, h->d_x,
-                                                        h->d_Ag, h->d_Yg, h->d_Dg, h->d_Do, h->d_Bf, h->stageR, h->stageK, h->d_err);
+                                                        h->d_Ag, h->d_Yg, h->d_Dg, h->d_Do, h->d_Bf, h->d_fN, h->stageR, h->stageK, h->d_err);
   CU_CHECK(cudaGetLastError());
   ops.post();
 }
@@ -303,13 +304,15 @@ FluidConsts fluid_consts(b200_handle* h, const b200_fluid_props* p)
 
 SolidConsts struct_consts(const b200_struct_props* p)
 {
-  if (p->isoType < 0 || p->isoType > 2) throw std::runtime_error("assemble_struct: constitutive model has no device kernel");
+  if (p->isoType < 0 || p->isoType > 3) throw std::runtime_error("assemble_struct: constitutive model has no device kernel");
   if (p->volType < 0 || p->volType > 3) throw std::runtime_error("assemble_struct: dilational penalty model not defined");
   SolidConsts c;
   std::memset(&c, 0, sizeof(c));
   c.dt = p->dt; c.am = p->am; c.af = p->af; c.gam = p->gam; c.beta = p->beta;
   c.rho = p->rho; c.dmp = p->dmp; c.f[0] = p->f[0]; c.f[1] = p->f[1]; c.f[2] = p->f[2];
   c.iso = p->isoType; c.vol = p->volType; c.C10 = p->C10; c.C01 = p->C01; c.Kpen = p->Kpen;
+  c.ho_a = p->a; c.ho_b = p->b; c.ho_aff = p->aff; c.ho_bff = p->bff; c.ho_ass = p->ass; c.ho_bss = p->bss;
+  c.ho_afs = p->afs; c.ho_bfs = p->bfs; c.ho_khs = p->khs;
   c.tDof = p->tDof; c.s = p->s; c.kind = 0;
   return c;
 }
@@ -323,6 +326,7 @@ void assemble_solid(b200_handle* h, const SolidConsts& c, const char* who)
   if (h->dof != 3 || !h->Val) throw std::runtime_error(std::string(who) + ": call b200_zero(h, 3) first");
   if (c.tDof != h->tDof) throw std::runtime_error(std::string(who) + ": tDof differs from the uploaded state");
   if (c.s < 0 || c.s + 3 > c.tDof) throw std::runtime_error(std::string(who) + ": equation offset outside the state");
+  if (c.kind == 0 && c.iso == 3 && !h->d_fN) throw std::runtime_error(std::string(who) + ": the Holzapfel-Ogden law needs fibre directions (b200_mesh_fibers)");
   ensure_stage(h, 3);
   const double t0 = wall_s();
   {
@@ -790,6 +794,17 @@ int b200_get_Kd(b200_handle* h, double* Kd)
       CU_CHECK(cudaMemcpyAsync(Kd, h->stage_d, sizeof(double)*n, cudaMemcpyDeviceToHost, ops.st));
     }
     CU_CHECK(cudaStreamSynchronize(ops.st));
+  });
+}
+
+int b200_mesh_fibers(b200_handle* h, int nFn, const double* fN)
+{
+  return guarded(h, [&] {
+    if (h->nEl == 0) throw std::runtime_error("mesh_fibers: no mesh (b200_mesh_set)");
+    if (nFn != 2) throw std::runtime_error("mesh_fibers: two fibre families (fibre, sheet) are expected");
+    cudaFree(h->d_fN);
+    h->d_fN = upload(fN, size_t(6)*h->nEl, h->ops->st);
+    CU_CHECK(cudaStreamSynchronize(h->ops->st));
   });
 }
 

@@ -35,8 +35,9 @@ struct ElemTables {            // lM.w, lM.N, lM.Nx of the reference (nn_elem_gi
 struct SolidConsts {
   double dt, am, af, gam, beta;
   double rho, dmp, f[3];
-  int iso, vol;                // iso: 0 nHook, 1 StVK, 2 mStVK; vol: 0 none, 1 Quad, 2 ST91, 3 M94
+  int iso, vol;                // iso: 0 nHook, 1 StVK, 2 mStVK, 3 Holzapfel-Ogden; vol: 0 none, 1 Quad, 2 ST91, 3 M94
   double C10, C01, Kpen;
+  double ho_a, ho_b, ho_aff, ho_bff, ho_ass, ho_bss, ho_afs, ho_bfs, ho_khs;   // stModelType a..bfs, khs
   double elM, nu;              // lElas / mesh
   int tDof, s;                 // row offset of this equation's unknowns in Ag/Yg/Dg (eq.s)
   int kind;                    // 0 struct, 1 lElas, 2 mesh
@@ -50,7 +51,9 @@ __device__ __forceinline__ int dm_idx(int I, int J) { return I*6 - (I*(I-1))/2 +
 
 // get_pk2cc<3> for the isotropic laws without fibres / active stress, + get_svol_p.
 // Outputs S (sym: 00 11 22 01 12 20) and the upper triangle of Dm (Voigt order 00 11 22 01 12 20).
-__device__ void pk2cc_iso(const SolidConsts& c, const double F[3][3], double* __restrict__ S6, double* __restrict__ Dm21)
+// fl: the element's fibre (fl[0..2]) and sheet (fl[3..5]) directions, read by the Holzapfel-Ogden law only.
+__device__ void pk2cc_iso(const SolidConsts& c, const double F[3][3], const double* __restrict__ fl,
+                          double* __restrict__ S6, double* __restrict__ Dm21)
 {
   // mat_det<3> (mat_fun_carray.h:92-122): cofactor expansion along the first row
   const double J = ((0.0 + 1.0*F[0][0]*(F[1][1]*F[2][2] - F[1][2]*F[2][1]))
@@ -131,6 +134,96 @@ __device__ void pk2cc_iso(const SolidConsts& c, const double F[3][3], double* __
         const double ids = (((i == k) && (j == l)) ? 0.5 : 0.0) + (((i == l) && (j == k)) ? 0.5 : 0.0);
         Dm21[dm_idx(I, Jv)] = g1*idp + g2*ids;
       }
+  } else if (c.iso == 3) {
+    // Holzapfel-Ogden (mat_models_carray.h:905-1135).  The reference builds CCb = sum_k g_k H_k (x) H_k and
+    // projects it with PP = Ids - (1/3) Ci (x) C from both sides (two 81 x 9 contractions).  For symmetric H_k,
+    // PP : H_k = H_k - (1/3)(C : H_k) Ci, so the projected tensor is sum_k g_k Hd_k (x) Hd_k: same numbers up to
+    // rounding, 4 rank-one terms instead of the dense contractions.
+    const double J4d = J2d*J2d;
+    const double f0[3] = {fl[0], fl[1], fl[2]}, s0[3] = {fl[3], fl[4], fl[5]};
+    double Cf[3], Cs[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      Cf[i] = C[i][0]*f0[0] + C[i][1]*f0[1] + C[i][2]*f0[2];
+      Cs[i] = C[i][0]*s0[0] + C[i][1]*s0[1] + C[i][2]*s0[2];
+    }
+    const double Inv4 = J2d*(f0[0]*Cf[0] + f0[1]*Cf[1] + f0[2]*Cf[2]);
+    const double Inv6 = J2d*(s0[0]*Cs[0] + s0[1]*Cs[1] + s0[2]*Cs[2]);
+    const double Inv8 = J2d*(f0[0]*Cs[0] + f0[1]*Cs[1] + f0[2]*Cs[2]);
+    const double Eff = Inv4 - 1.0, Ess = Inv6 - 1.0, Efs = Inv8;
+    const double k = c.ho_khs;
+    const double of = 1.0/(exp(k*Eff) + 1.0), os = 1.0/(exp(k*Ess) + 1.0);
+    const double c4f = 1.0 - of, c4s = 1.0 - os;
+    const double dc4f = k*(of - of*of), dc4s = k*(os - os*os);
+    const double ddc4f = k*k*(-of + 3.0*of*of - 2.0*of*of*of), ddc4s = k*k*(-os + 3.0*os*os - 2.0*os*os*os);
+    // stress coefficients
+    double g1 = c.ho_a*exp(c.ho_b*(Inv1 - 3.0));
+    double g2 = 2.0*c.ho_afs*exp(c.ho_bfs*Efs*Efs);
+    const double rexpf = exp(c.ho_bff*Eff*Eff), rexps = exp(c.ho_bss*Ess*Ess);
+    double gff = c4f*Eff*rexpf; gff = gff + (0.5*dc4f/c.ho_bff)*(rexpf - 1.0); gff = 2.0*c.ho_aff*gff + 0.0;
+    double gss = c4s*Ess*rexps; gss = gss + (0.5*dc4s/c.ho_bss)*(rexps - 1.0); gss = 2.0*c.ho_ass*gss + 0.0;
+    double H[4][3][3];          // Idm, Hfs, Hff, Hss
+    double Sb[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        H[0][i][j] = (i == j) ? 1.0 : 0.0;
+        H[1][i][j] = 0.5*(f0[i]*s0[j] + f0[j]*s0[i]);
+        H[2][i][j] = f0[i]*f0[j];
+        H[3][i][j] = s0[i]*s0[j];
+        Sb[i][j] = g1*H[0][i][j] + g2*Efs*H[1][i][j];
+        Sb[i][j] += gff*H[2][i][j];
+        Sb[i][j] += gss*H[3][i][j];
+      }
+    // stiffness coefficients
+    double gk[4];
+    gk[0] = g1*2.0*J4d*c.ho_b;
+    gk[1] = g2*2.0*J4d*(1.0 + 2.0*c.ho_bfs*Efs*Efs);
+    {
+      double t = c4f*(1.0 + 2.0*c.ho_bff*Eff*Eff); t = (t + 2.0*dc4f*Eff)*rexpf; t = t + (0.5*ddc4f/c.ho_bff)*(rexpf - 1.0);
+      gk[2] = 4.0*J4d*c.ho_aff*t;
+      double u = c4s*(1.0 + 2.0*c.ho_bss*Ess*Ess); u = (u + 2.0*dc4s*Ess)*rexps; u = u + (0.5*ddc4s/c.ho_bss)*(rexps - 1.0);
+      gk[3] = 4.0*J4d*c.ho_ass*u;
+    }
+    double CSb = 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int i = 0; i < 3; i++) CSb = CSb + C[i][j]*Sb[i][j];
+    const double r1 = J2d*CSb/nd;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) S[i][j] = J2d*Sb[i][j] - r1*Ci[i][j];
+    // projected dyads Hd_k = H_k - (1/3)(C : H_k) Ci
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      double ch = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) ch += C[i][j]*H[q][i][j];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) H[q][i][j] = H[q][i][j] - (1.0/nd)*ch*Ci[i][j];
+    }
+    const double c2 = 2.0*(r1 - p*J), c3 = pl*J - 2.0*r1/nd;
+#pragma unroll
+    for (int I = 0; I < 6; I++)
+#pragma unroll
+      for (int Jv = I; Jv < 6; Jv++) {
+        const int i = vi[I], j = vj[I], kk = vi[Jv], l = vj[Jv];
+        double cc = gk[0]*H[0][i][j]*H[0][kk][l] + gk[1]*H[1][i][j]*H[1][kk][l] + gk[2]*H[2][i][j]*H[2][kk][l] + gk[3]*H[3][i][j]*H[3][kk][l];
+        cc -= (2.0/nd)*(Ci[i][j]*S[kk][l] + S[i][j]*Ci[kk][l]);
+        cc += c2*(0.5*(Ci[i][kk]*Ci[j][l] + Ci[i][l]*Ci[j][kk])) + c3*(Ci[i][j]*Ci[kk][l]);
+        Dm21[dm_idx(I, Jv)] = cc;
+      }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) S[i][j] += p*J*Ci[i][j];
   } else {
     // modified St. Venant-Kirchhoff (:326-356): C10 = kappa, C01 = mu
     const double g1 = c.C10, g2 = c.C01;
@@ -163,6 +256,7 @@ k_assemble_solid(int nEl, const int* __restrict__ elist, SolidConsts c, const do
                  const int* __restrict__ ien, const int* __restrict__ rslot, const int* __restrict__ kslot,
                  const double* __restrict__ x, const double* __restrict__ Ag, const double* __restrict__ Yg,
                  const double* __restrict__ Dg, const double* __restrict__ Do, const double* __restrict__ Bf,
+                 const double* __restrict__ fN,      // 6 x nEl fibre + sheet directions (Holzapfel-Ogden) or null
                  double* __restrict__ stageR, double* __restrict__ stageK, int* __restrict__ err_flag)
 {
   constexpr int REC = solid_rec(ENON);
@@ -271,7 +365,12 @@ k_assemble_solid(int nEl, const int* __restrict__ elist, SolidConsts c, const do
       rec[SREC_UD] = ud[0]; rec[SREC_UD + 1] = ud[1]; rec[SREC_UD + 2] = ud[2];
       if (c.kind == 0) {
         double S6[6];
-        pk2cc_iso(c, F, S6, rec + SREC_DM);
+        double fl[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (fN) {
+#pragma unroll
+          for (int i = 0; i < 6; i++) fl[i] = fN[size_t(e)*6 + i];
+        }
+        pk2cc_iso(c, F, fl, S6, rec + SREC_DM);
 #pragma unroll
         for (int i = 0; i < 6; i++) rec[SREC_S + i] = S6[i];
 #pragma unroll

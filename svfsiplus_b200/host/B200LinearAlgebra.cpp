@@ -157,6 +157,9 @@ void B200LinearAlgebra::upload_mesh(ComMod& com_mod, const mshType& lM)
 {
   // IEN holds assembly (local) node ids already (ComMod.h:893); x is com_mod.x (3 x tnNo)
   check(b200_mesh_set(h_, lM.eNoN, lM.nEl, lM.IEN.data(), com_mod.x.data(), lM.qmTET4), "b200_mesh_set");
+  if (lM.nFn == 2 && lM.fN.size() != 0) {
+    check(b200_mesh_fibers(h_, 2, lM.fN.data()), "b200_mesh_fibers");      // fN(nsd*nFn, nEl), ComMod.h:975
+  }
   mesh_uploaded_ = &lM;
 }
 
@@ -232,8 +235,11 @@ bool B200LinearAlgebra::fill_struct_props(ComMod& com_mod, const eqType& eq, con
     case ConstitutiveModelType::stIso_nHook: sp.isoType = 0; break;
     case ConstitutiveModelType::stIso_StVK:  sp.isoType = 1; break;
     case ConstitutiveModelType::stIso_mStVK: sp.isoType = 2; break;
+    case ConstitutiveModelType::stIso_HO:    sp.isoType = 3; break;      // needs lM.fN with two families (upload_mesh)
     default: return false;
   }
+  sp.a = stM.a; sp.b = stM.b; sp.aff = stM.aff; sp.bff = stM.bff; sp.ass = stM.ass; sp.bss = stM.bss;
+  sp.afs = stM.afs; sp.bfs = stM.bfs; sp.khs = stM.khs;
   switch (stM.volType) {
     case ConstitutiveModelType::stVol_Quad: sp.volType = 1; break;
     case ConstitutiveModelType::stVol_ST91: sp.volType = 2; break;
@@ -359,6 +365,7 @@ bool B200LinearAlgebra::assemble_solid_mesh(ComMod& com_mod, const mshType& lM, 
   const bool is_struct = (eq.phys == EquationType::phys_struct);
   if (is_struct) {
     if (!fill_struct_props(com_mod, eq, dmn, sp)) return false;
+    if (sp.isoType == 3 && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
   } else {
     lp.dt = com_mod.dt; lp.am = eq.am; lp.af = eq.af; lp.beta = eq.beta;
     lp.tDof = com_mod.tDof; lp.s = eq.s;

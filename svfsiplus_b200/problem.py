@@ -110,12 +110,17 @@ def block_case(n, elem="hex", kind="struct", iso="nHook", vol="ST91", jitter=0.1
     if kind == "struct":
         if iso == "nHook":
             C10, C01 = 0.5 * mu, 0.0
+        elif iso == "HO":                        # Holzapfel-Ogden myocardium (parameters of tests/cases/struct/LV_* style, cgs)
+            C10, C01 = 0.0, 0.0
         elif iso == "StVK":                      # C10 = lambda, C01 = mu (nu 0.3 keeps lambda finite)
             C10, C01 = E * 0.3 / (1.3 * 0.4), 0.5 * E / 1.3
         else:                                    # mStVK: C10 = kappa, C01 = mu
             C10, C01 = E / (3.0 * 0.4), 0.5 * E / 1.3
         props = dict(dt=dt, am=am, af=af, gam=gam, beta=beta, rho=1000.0, dmp=0.0, f=(0.0, 0.0, 0.0), iso=iso, vol=vol,
                      C10=C10, C01=C01, Kpen=4.0e9 if vol else 0.0)
+        if iso == "HO":
+            props["ho"] = dict(a=590.0, b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12, afs=2160.0, bfs=11.436, khs=100.0)
+            props["Kpen"] = 1.0e6
     elif kind == "lelas":
         props = dict(dt=dt, am=am, af=af, gam=gam, beta=beta, rho=1000.0, elM=E, nu=0.3, f=(0.0, 0.0, -9.81))
     else:
@@ -135,6 +140,14 @@ def block_case(n, elem="hex", kind="struct", iso="nHook", vol="ST91", jitter=0.1
         faces.append(dict(name=nm, nodes=nodes, dof=3, bGrp=B.BC_DIR, val=val))
     case = dict(mesh=m, rowPtr=rowPtr, colPtr=colPtr, Ag=Ag, Yg=Yg, Dg=Dg, Bf=Bf, props=props, faces=faces, kind=kind,
                 res=np.zeros(len(faces)), incL=np.ones(len(faces), np.int32), name=f"block_{elem}_{n}_{kind}")
+    if kind == "struct" and iso == "HO":
+        # fibre / sheet directions rotating through the block (unit, orthogonal), one pair per element
+        cen = m.x[m.ien].mean(axis=1)
+        th = 0.5 * np.pi * cen[:, 2] + 0.3 * cen[:, 0]
+        fN = np.zeros((m.nEl, 6))
+        fN[:, 0], fN[:, 1] = np.cos(th), np.sin(th)
+        fN[:, 3], fN[:, 4] = -np.sin(th), np.cos(th)
+        case["fN"] = fN
     if kind == "mesh":
         case["Do"] = Do
     return case
@@ -146,6 +159,8 @@ def assemble_solid(be: B.Backend, case, upload=True):
     if upload:
         be.state_set(tDof, case["Ag"], case["Yg"], case["Bf"])
         be.disp_set(tDof, case["Dg"], case.get("Do"))
+    if upload and case.get("fN") is not None:
+        be.mesh_fibers(case["fN"])
     be.zero(3)
     if case["kind"] == "struct":
         be.assemble_struct(B.struct_props(tDof=tDof, **case["props"]))

@@ -46,7 +46,7 @@ def main():
     out = {}
     for elem in ("tet", "hex"):
         for kind, iso, vol in (("struct", "nHook", "ST91"), ("struct", "nHook", "M94"), ("struct", "StVK", None),
-                               ("struct", "mStVK", None), ("lelas", None, None), ("mesh", None, None)):
+                               ("struct", "mStVK", None), ("struct", "HO", "ST91"), ("lelas", None, None), ("mesh", None, None)):
             c = P.block_case(3, elem=elem, kind=kind, iso=iso or "nHook", vol=vol)
             R, Val, _, _, _, tabs = refcase.reference_assemble_solid(c)
             tag = f"{elem}_{kind}_{iso}_{vol}"

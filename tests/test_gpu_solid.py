@@ -19,6 +19,7 @@ pytestmark = pytest.mark.gpu
 
 TOL_ASM = 1e-12
 CONFIGS = [("struct", "nHook", "ST91"), ("struct", "nHook", "M94"), ("struct", "StVK", None), ("struct", "mStVK", None),
+           ("struct", "HO", "ST91"),
            ("lelas", None, None), ("mesh", None, None)]
 
 
@@ -47,7 +48,8 @@ def test_solid_assembly_matches_golden(elem, kind, iso, vol):
 
 
 @pytest.mark.parametrize("elem,n", [("tet", 10), ("hex", 10)])
-@pytest.mark.parametrize("kind,iso,vol", [("struct", "nHook", "ST91"), ("lelas", None, None), ("mesh", None, None)])
+@pytest.mark.parametrize("kind,iso,vol", [("struct", "nHook", "ST91"), ("struct", "HO", "ST91"), ("lelas", None, None),
+                                          ("mesh", None, None)])
 def test_solid_assembly_matches_reference(elem, n, kind, iso, vol):
     if not _ref_available():
         pytest.skip("oracle/_ref not present on this box")
