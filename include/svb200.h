@@ -73,7 +73,8 @@ typedef struct {
 } b200_lelas_props;
 
 /* Mixed velocity-pressure solid (ustruct; solver/ustruct.cpp:1158-1575, 632-876).  elM, nu, ctM, ctC feed
- * get_tau (solver/mat_models.cpp:1655); Kpen, volType feed g_vol_pen (:1696).  isoType 0 = neo-Hookean. */
+ * get_tau (solver/mat_models.cpp:1655); Kpen, volType feed g_vol_pen (:1696).  isoType 0 = neo-Hookean,
+ * 3 = Holzapfel-Ogden (needs b200_mesh_fibers). */
 typedef struct {
   double dt, am, af, gam;
   int tDof, s;
@@ -81,6 +82,7 @@ typedef struct {
   double elM, nu, ctM, ctC;
   int isoType, volType;
   double C10, Kpen;
+  double a, b, aff, bff, ass, bss, afs, bfs, khs;   /* isoType 3 (Holzapfel-Ogden) */
 } b200_ustruct_props;
 
 /* ---- life cycle ------------------------------------------------------------------------- */

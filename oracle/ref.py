@@ -271,12 +271,14 @@ class RefAssembly:
 
 
     def ustruct(self, Ag, Yg, Dg, Bf, *, dt, am, af, gam, rho, elM, nu, ctM, ctC, vol, C10, Kpen, f=(0.0, 0.0, 0.0), Ad=None,
-                **_ignored):
+                iso="nHook", ho=None, **_ignored):
         """construct_usolid (S/ustruct.cpp:216) [+ ustruct_r when Ad is given].  Returns R (nNo,4), Val (nnz,16),
         Kd (nnz,12), seconds."""
         Ag = _c(Ag, np.float64); Yg = _c(Yg, np.float64); Dg = _c(Dg, np.float64); Bf = _c(Bf, np.float64)
         Ad = None if Ad is None else _c(Ad, np.float64)
-        par = np.array([dt, am, af, gam, rho, f[0], f[1], f[2], elM, nu, ctM, ctC, self.VOL[vol], C10, Kpen], np.float64)
+        ho = ho or {}
+        par = np.array([dt, am, af, gam, rho, f[0], f[1], f[2], elM, nu, ctM, ctC, self.VOL[vol], C10, Kpen, self.ISO[iso]]
+                       + [ho.get(k, 100.0 if k == "khs" else 0.0) for k in self.HO_KEYS], np.float64)
         R = np.empty((self.nNo, 4)); Val = np.empty((self.nnz, 16)); Kd = np.empty((self.nnz, 12))
         t = lib().ref_asm_ustruct(self.h, Ag.shape[1], _p(par), _p(Ag), _p(Yg), _p(Dg), _p(Bf), _p(Ad), _p(R), _p(Val), _p(Kd))
         if t < 0:

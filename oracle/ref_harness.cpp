@@ -434,7 +434,8 @@ double ref_asm_fsi(void* h, int tDof, double dt, double am, double af, double ga
 
 // ustruct equation through the reference's construct_usolid (S/ustruct.cpp:216) and, when Ad != NULL,
 // ustruct_r (S/ustruct.cpp:1726, first Newton iteration).  par = {dt, am, af, gam, rho, fx, fy, fz, elM, nu,
-// ctM, ctC, vol (0 none,1 Quad,2 ST91,3 M94), C10, Kpen}.  tDof = 4, eq.s = 0.
+// ctM, ctC, vol (0 none,1 Quad,2 ST91,3 M94), C10, Kpen, iso (0 nHook, 3 HO), a, b, aff, bff, ass, bss, afs, bfs, khs}.
+// tDof = 4, eq.s = 0.  Fibres: ref_asm_set_fibers.
 // Outputs R (4 x nNo), Val (16 x nnz), Kd (12 x nnz).
 double ref_asm_ustruct(void* h, int tDof, const double* par, const double* Ag, const double* Yg, const double* Dg,
                        const double* Bf, const double* Ad, double* R, double* Val, double* Kd)
@@ -471,12 +472,14 @@ double ref_asm_ustruct(void* h, int tDof, const double* par, const double* Ag, c
     dmn.prop[PhysicalProperyType::ctau_M] = par[10];
     dmn.prop[PhysicalProperyType::ctau_C] = par[11];
     const int vol = int(par[12]);
-    dmn.stM.isoType = ConstitutiveModelType::stIso_nHook;
+    dmn.stM.isoType = (int(par[15]) == 3) ? ConstitutiveModelType::stIso_HO : ConstitutiveModelType::stIso_nHook;
     dmn.stM.volType = (vol == 1) ? ConstitutiveModelType::stVol_Quad
                     : (vol == 2) ? ConstitutiveModelType::stVol_ST91
                     : (vol == 3) ? ConstitutiveModelType::stVol_M94 : ConstitutiveModelType::stIso_NA;
     dmn.stM.C10 = par[13];
     dmn.stM.Kpen = par[14];
+    dmn.stM.a = par[16]; dmn.stM.b = par[17]; dmn.stM.aff = par[18]; dmn.stM.bff = par[19];
+    dmn.stM.ass = par[20]; dmn.stM.bss = par[21]; dmn.stM.afs = par[22]; dmn.stM.bfs = par[23]; dmn.stM.khs = par[24];
     com_mod.Bf.resize(3, nNo);
     std::memcpy(com_mod.Bf.data(), Bf, sizeof(double)*3*size_t(nNo));
     if (!eq.linear_algebra) eq.linear_algebra = new FsilsLinearAlgebra();

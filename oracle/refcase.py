@@ -89,6 +89,7 @@ def reference_fsi_step(case, ls, prec=ref.PREC_FSILS):
 def reference_assemble_ustruct(case, with_r=False):
     m = case["mesh"]
     ra = ref.RefAssembly(m.x, m.ien)
+    ra.set_fibers(case.get("fN"))
     R, Val, Kd, secs = ra.ustruct(case["Ag"], case["Yg"], case["Dg"], case["Bf"], Ad=case["Ad"] if with_r else None, **case["props"])
     ra.close()
     return R, Val, Kd, secs

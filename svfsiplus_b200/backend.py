@@ -64,7 +64,9 @@ class UstructProps(C.Structure):
                 ("rho", C.c_double), ("f", C.c_double * 3),
                 ("elM", C.c_double), ("nu", C.c_double), ("ctM", C.c_double), ("ctC", C.c_double),
                 ("isoType", C.c_int), ("volType", C.c_int),
-                ("C10", C.c_double), ("Kpen", C.c_double)]
+                ("C10", C.c_double), ("Kpen", C.c_double),
+                ("a", C.c_double), ("b", C.c_double), ("aff", C.c_double), ("bff", C.c_double), ("ass", C.c_double),
+                ("bss", C.c_double), ("afs", C.c_double), ("bfs", C.c_double), ("khs", C.c_double)]
 
 
 ISO_TYPES = {"nHook": 0, "StVK": 1, "mStVK": 2, "HO": 3}
@@ -186,7 +188,7 @@ def lelas_props(*, dt, am, af, beta, rho, elM, nu, tDof=3, s=0, f=(0.0, 0.0, 0.0
 
 
 def ustruct_props(*, dt, am, af, gam, rho, elM, nu, ctM, ctC, vol, C10, Kpen, tDof=4, s=0, f=(0.0, 0.0, 0.0), iso="nHook",
-                  **_ignored) -> UstructProps:
+                  ho=None, **_ignored) -> UstructProps:
     p = UstructProps()
     p.dt, p.am, p.af, p.gam = dt, am, af, gam
     p.tDof, p.s = tDof, s
@@ -195,6 +197,9 @@ def ustruct_props(*, dt, am, af, gam, rho, elM, nu, ctM, ctC, vol, C10, Kpen, tD
     p.elM, p.nu, p.ctM, p.ctC = elM, nu, ctM, ctC
     p.isoType, p.volType = ISO_TYPES[iso], VOL_TYPES[vol]
     p.C10, p.Kpen = C10, Kpen
+    p.khs = 100.0
+    for k, v in (ho or {}).items():
+        setattr(p, k, v)
     return p
 
 

@@ -283,7 +283,7 @@ void launch_ustruct(b200_handle* h, const UstructConsts& c)
   auto kern = k_assemble_ustruct<ENON, NG, EPB, APT>;
   CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   kern<<<(h->nEl + EPB - 1)/EPB, EPB*NG, smem, ops.st>>>(h->nEl, c, h->d_tab, h->d_ien, h->d_rslot, h->d_kslot, h->d_x,
-                                                         h->d_Ag, h->d_Yg, h->d_Dg, h->d_Bf, h->stageR, h->stageK, h->stageKd, h->d_err);
+                                                         h->d_Ag, h->d_Yg, h->d_Dg, h->d_Bf, h->d_fN, h->stageR, h->stageK, h->stageKd, h->d_err);
   CU_CHECK(cudaGetLastError());
   ops.post();
 }
@@ -731,7 +731,8 @@ int b200_assemble_ustruct(b200_handle* h, const b200_ustruct_props* p)
     if (h->dof != 4 || !h->Val) throw std::runtime_error("assemble_ustruct: call b200_zero(h, 4) first");
     if (p->tDof != h->tDof) throw std::runtime_error("assemble_ustruct: tDof differs from the uploaded state");
     if (p->s < 0 || p->s + 4 > p->tDof) throw std::runtime_error("assemble_ustruct: equation offset outside the state");
-    if (p->isoType != 0) throw std::runtime_error("assemble_ustruct: constitutive model has no device kernel (neo-Hookean has)");
+    if (p->isoType != 0 && p->isoType != 3) throw std::runtime_error("assemble_ustruct: constitutive model has no device kernel (neo-Hookean and Holzapfel-Ogden have)");
+    if (p->isoType == 3 && !h->d_fN) throw std::runtime_error("assemble_ustruct: the Holzapfel-Ogden law needs fibre directions (b200_mesh_fibers)");
     if (p->volType < 0 || p->volType > 3) throw std::runtime_error("assemble_ustruct: dilational penalty model not defined");
     UstructConsts c;
     std::memset(&c, 0, sizeof(c));
@@ -739,6 +740,7 @@ int b200_assemble_ustruct(b200_handle* h, const b200_ustruct_props* p)
     c.rho0 = p->rho; c.f[0] = p->f[0]; c.f[1] = p->f[1]; c.f[2] = p->f[2];
     c.elM = p->elM; c.nu = p->nu; c.ctM = p->ctM; c.ctC = p->ctC;
     c.iso = p->isoType; c.vol = p->volType; c.C10 = p->C10; c.Kpen = p->Kpen;
+    c.ho = HoParams{p->a, p->b, p->aff, p->bff, p->ass, p->bss, p->afs, p->bfs, p->khs};
     c.tDof = p->tDof; c.s = p->s;
     ensure_stage(h, 4);
     ensure(h->stageKd, h->stageKd_cap, size_t(12)*h->eNoN*h->eNoN*size_t(h->nEl) + 4);

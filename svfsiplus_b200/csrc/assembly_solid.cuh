@@ -49,6 +49,86 @@ __host__ __device__ constexpr int solid_rec(int eNoN) { return SREC_NX + 3*eNoN;
 // index of (I,J), I <= J, in the packed upper triangle of the 6x6 Voigt matrix
 __device__ __forceinline__ int dm_idx(int I, int J) { return I*6 - (I*(I-1))/2 + (J - I); }
 
+struct HoParams { double a, b, aff, bff, ass, bss, afs, bfs, khs; };
+
+// Isochoric part of the Holzapfel-Ogden law (mat_models_carray.h:905-1060, mat_models.cpp:866-935): isochoric
+// stress S = J2d Sb - r1 Ci, r1, and the projected rank-one factors of the isochoric tangent
+//   PP : (sum_k g_k H_k (x) H_k) : PP^T = sum_k g_k Hd_k (x) Hd_k,   Hd_k = H_k - (1/3)(C : H_k) Ci
+// (the reference forms CCb and contracts it with PP = Ids - (1/3) Ci (x) C from both sides; for symmetric H_k
+// this is the same tensor up to rounding).  H_0 = I, H_1 = sym(f (x) s), H_2 = f (x) f, H_3 = s (x) s.
+__device__ void ho_isochoric(const HoParams& h, const double C[3][3], const double Ci[3][3], double J2d, double Inv1,
+                             const double* __restrict__ fl, double S[3][3], double& r1, double gk[4], double H[4][3][3])
+{
+  const double nd = 3.0;
+  const double J4d = J2d*J2d;
+  const double f0[3] = {fl[0], fl[1], fl[2]}, s0[3] = {fl[3], fl[4], fl[5]};
+  double Cf[3], Cs[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    Cf[i] = C[i][0]*f0[0] + C[i][1]*f0[1] + C[i][2]*f0[2];
+    Cs[i] = C[i][0]*s0[0] + C[i][1]*s0[1] + C[i][2]*s0[2];
+  }
+  const double Inv4 = J2d*(f0[0]*Cf[0] + f0[1]*Cf[1] + f0[2]*Cf[2]);
+  const double Inv6 = J2d*(s0[0]*Cs[0] + s0[1]*Cs[1] + s0[2]*Cs[2]);
+  const double Inv8 = J2d*(f0[0]*Cs[0] + f0[1]*Cs[1] + f0[2]*Cs[2]);
+  const double Eff = Inv4 - 1.0, Ess = Inv6 - 1.0, Efs = Inv8;
+  const double k = h.khs;
+  const double of = 1.0/(exp(k*Eff) + 1.0), os = 1.0/(exp(k*Ess) + 1.0);
+  const double c4f = 1.0 - of, c4s = 1.0 - os;
+  const double dc4f = k*(of - of*of), dc4s = k*(os - os*os);
+  const double ddc4f = k*k*(-of + 3.0*of*of - 2.0*of*of*of), ddc4s = k*k*(-os + 3.0*os*os - 2.0*os*os*os);
+  // stress coefficients
+  const double g1 = h.a*exp(h.b*(Inv1 - 3.0));
+  const double g2 = 2.0*h.afs*exp(h.bfs*Efs*Efs);
+  const double rexpf = exp(h.bff*Eff*Eff), rexps = exp(h.bss*Ess*Ess);
+  double gff = c4f*Eff*rexpf; gff = gff + (0.5*dc4f/h.bff)*(rexpf - 1.0); gff = 2.0*h.aff*gff + 0.0;
+  double gss = c4s*Ess*rexps; gss = gss + (0.5*dc4s/h.bss)*(rexps - 1.0); gss = 2.0*h.ass*gss + 0.0;
+  double Sb[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      H[0][i][j] = (i == j) ? 1.0 : 0.0;
+      H[1][i][j] = 0.5*(f0[i]*s0[j] + f0[j]*s0[i]);
+      H[2][i][j] = f0[i]*f0[j];
+      H[3][i][j] = s0[i]*s0[j];
+      Sb[i][j] = g1*H[0][i][j] + g2*Efs*H[1][i][j];
+      Sb[i][j] += gff*H[2][i][j];
+      Sb[i][j] += gss*H[3][i][j];
+    }
+  // stiffness coefficients
+  gk[0] = g1*2.0*J4d*h.b;
+  gk[1] = g2*2.0*J4d*(1.0 + 2.0*h.bfs*Efs*Efs);
+  {
+    double t = c4f*(1.0 + 2.0*h.bff*Eff*Eff); t = (t + 2.0*dc4f*Eff)*rexpf; t = t + (0.5*ddc4f/h.bff)*(rexpf - 1.0);
+    gk[2] = 4.0*J4d*h.aff*t;
+    double u = c4s*(1.0 + 2.0*h.bss*Ess*Ess); u = (u + 2.0*dc4s*Ess)*rexps; u = u + (0.5*ddc4s/h.bss)*(rexps - 1.0);
+    gk[3] = 4.0*J4d*h.ass*u;
+  }
+  double CSb = 0.0;
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+#pragma unroll
+    for (int i = 0; i < 3; i++) CSb = CSb + C[i][j]*Sb[i][j];
+  r1 = J2d*CSb/nd;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) S[i][j] = J2d*Sb[i][j] - r1*Ci[i][j];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    double ch = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) ch += C[i][j]*H[q][i][j];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) H[q][i][j] = H[q][i][j] - (1.0/nd)*ch*Ci[i][j];
+  }
+}
+
 // get_pk2cc<3> for the isotropic laws without fibres / active stress, + get_svol_p.
 // Outputs S (sym: 00 11 22 01 12 20) and the upper triangle of Dm (Voigt order 00 11 22 01 12 20).
 // fl: the element's fibre (fl[0..2]) and sheet (fl[3..5]) directions, read by the Holzapfel-Ogden law only.
@@ -135,80 +215,10 @@ __device__ void pk2cc_iso(const SolidConsts& c, const double F[3][3], const doub
         Dm21[dm_idx(I, Jv)] = g1*idp + g2*ids;
       }
   } else if (c.iso == 3) {
-    // Holzapfel-Ogden (mat_models_carray.h:905-1135).  The reference builds CCb = sum_k g_k H_k (x) H_k and
-    // projects it with PP = Ids - (1/3) Ci (x) C from both sides (two 81 x 9 contractions).  For symmetric H_k,
-    // PP : H_k = H_k - (1/3)(C : H_k) Ci, so the projected tensor is sum_k g_k Hd_k (x) Hd_k: same numbers up to
-    // rounding, 4 rank-one terms instead of the dense contractions.
-    const double J4d = J2d*J2d;
-    const double f0[3] = {fl[0], fl[1], fl[2]}, s0[3] = {fl[3], fl[4], fl[5]};
-    double Cf[3], Cs[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      Cf[i] = C[i][0]*f0[0] + C[i][1]*f0[1] + C[i][2]*f0[2];
-      Cs[i] = C[i][0]*s0[0] + C[i][1]*s0[1] + C[i][2]*s0[2];
-    }
-    const double Inv4 = J2d*(f0[0]*Cf[0] + f0[1]*Cf[1] + f0[2]*Cf[2]);
-    const double Inv6 = J2d*(s0[0]*Cs[0] + s0[1]*Cs[1] + s0[2]*Cs[2]);
-    const double Inv8 = J2d*(f0[0]*Cs[0] + f0[1]*Cs[1] + f0[2]*Cs[2]);
-    const double Eff = Inv4 - 1.0, Ess = Inv6 - 1.0, Efs = Inv8;
-    const double k = c.ho_khs;
-    const double of = 1.0/(exp(k*Eff) + 1.0), os = 1.0/(exp(k*Ess) + 1.0);
-    const double c4f = 1.0 - of, c4s = 1.0 - os;
-    const double dc4f = k*(of - of*of), dc4s = k*(os - os*os);
-    const double ddc4f = k*k*(-of + 3.0*of*of - 2.0*of*of*of), ddc4s = k*k*(-os + 3.0*os*os - 2.0*os*os*os);
-    // stress coefficients
-    double g1 = c.ho_a*exp(c.ho_b*(Inv1 - 3.0));
-    double g2 = 2.0*c.ho_afs*exp(c.ho_bfs*Efs*Efs);
-    const double rexpf = exp(c.ho_bff*Eff*Eff), rexps = exp(c.ho_bss*Ess*Ess);
-    double gff = c4f*Eff*rexpf; gff = gff + (0.5*dc4f/c.ho_bff)*(rexpf - 1.0); gff = 2.0*c.ho_aff*gff + 0.0;
-    double gss = c4s*Ess*rexps; gss = gss + (0.5*dc4s/c.ho_bss)*(rexps - 1.0); gss = 2.0*c.ho_ass*gss + 0.0;
-    double H[4][3][3];          // Idm, Hfs, Hff, Hss
-    double Sb[3][3];
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-      for (int j = 0; j < 3; j++) {
-        H[0][i][j] = (i == j) ? 1.0 : 0.0;
-        H[1][i][j] = 0.5*(f0[i]*s0[j] + f0[j]*s0[i]);
-        H[2][i][j] = f0[i]*f0[j];
-        H[3][i][j] = s0[i]*s0[j];
-        Sb[i][j] = g1*H[0][i][j] + g2*Efs*H[1][i][j];
-        Sb[i][j] += gff*H[2][i][j];
-        Sb[i][j] += gss*H[3][i][j];
-      }
-    // stiffness coefficients
-    double gk[4];
-    gk[0] = g1*2.0*J4d*c.ho_b;
-    gk[1] = g2*2.0*J4d*(1.0 + 2.0*c.ho_bfs*Efs*Efs);
-    {
-      double t = c4f*(1.0 + 2.0*c.ho_bff*Eff*Eff); t = (t + 2.0*dc4f*Eff)*rexpf; t = t + (0.5*ddc4f/c.ho_bff)*(rexpf - 1.0);
-      gk[2] = 4.0*J4d*c.ho_aff*t;
-      double u = c4s*(1.0 + 2.0*c.ho_bss*Ess*Ess); u = (u + 2.0*dc4s*Ess)*rexps; u = u + (0.5*ddc4s/c.ho_bss)*(rexps - 1.0);
-      gk[3] = 4.0*J4d*c.ho_ass*u;
-    }
-    double CSb = 0.0;
-#pragma unroll
-    for (int j = 0; j < 3; j++)
-#pragma unroll
-      for (int i = 0; i < 3; i++) CSb = CSb + C[i][j]*Sb[i][j];
-    const double r1 = J2d*CSb/nd;
-#pragma unroll
-    for (int i = 0; i < 3; i++)
-#pragma unroll
-      for (int j = 0; j < 3; j++) S[i][j] = J2d*Sb[i][j] - r1*Ci[i][j];
-    // projected dyads Hd_k = H_k - (1/3)(C : H_k) Ci
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      double ch = 0.0;
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) ch += C[i][j]*H[q][i][j];
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) H[q][i][j] = H[q][i][j] - (1.0/nd)*ch*Ci[i][j];
-    }
+    // Holzapfel-Ogden (mat_models_carray.h:905-1135), see ho_isochoric
+    const HoParams hp = {c.ho_a, c.ho_b, c.ho_aff, c.ho_bff, c.ho_ass, c.ho_bss, c.ho_afs, c.ho_bfs, c.ho_khs};
+    double r1, gk[4], H[4][3][3];
+    ho_isochoric(hp, C, Ci, J2d, Inv1, fl, S, r1, gk, H);
     const double c2 = 2.0*(r1 - p*J), c3 = pl*J - 2.0*r1/nd;
 #pragma unroll
     for (int I = 0; I < 6; I++)

@@ -20,8 +20,9 @@ struct UstructConsts {
   double dt, am, af, gam;        // eq.am, eq.af, eq.gam
   double rho0, f[3];
   double elM, nu, ctM, ctC;      // get_tau inputs
-  int iso, vol;                  // iso: 0 nHook; vol: 0 none, 1 Quad, 2 ST91, 3 M94
+  int iso, vol;                  // iso: 0 nHook, 3 Holzapfel-Ogden; vol: 0 none, 1 Quad, 2 ST91, 3 M94
   double C10, Kpen;
+  HoParams ho;
   int tDof, s;
 };
 
@@ -36,8 +37,8 @@ __global__ void __launch_bounds__(EPB*NG)
 k_assemble_ustruct(int nEl, UstructConsts c, const double* __restrict__ tab, const int* __restrict__ ien,
                    const int* __restrict__ rslot, const int* __restrict__ kslot, const double* __restrict__ x,
                    const double* __restrict__ Ag, const double* __restrict__ Yg, const double* __restrict__ Dg,
-                   const double* __restrict__ Bf, double* __restrict__ stageR, double* __restrict__ stageK,
-                   double* __restrict__ stageKd, int* __restrict__ err_flag)
+                   const double* __restrict__ Bf, const double* __restrict__ fN, double* __restrict__ stageR,
+                   double* __restrict__ stageK, double* __restrict__ stageKd, int* __restrict__ err_flag)
 {
   constexpr int REC = ustruct_rec(ENON);
   constexpr int NT = EPB*NG;
@@ -161,22 +162,41 @@ k_assemble_ustruct(int nEl, UstructConsts c, const double* __restrict__ tab, con
         Ci[2][1] = (C[0][1]*C[2][0] - C[0][0]*C[2][1]) / d;
         Ci[2][2] = (C[0][0]*C[1][1] - C[0][1]*C[1][0]) / d;
         const double Inv1 = J2d*(C[0][0] + C[1][1] + C[2][2]);
-        const double g1 = 2.0*c.C10;
-        const double r1 = g1*Inv1/nd3;
         double S[3][3];
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-          for (int j = 0; j < 3; j++) S[i][j] = J2d*((i == j) ? g1 : 0.0) - r1*Ci[i][j];
         const int vi[6] = {0, 1, 2, 0, 1, 2}, vj[6] = {0, 1, 2, 1, 2, 0};
+        if (c.iso == 3) {
+          // Holzapfel-Ogden, deviatoric form (mat_models.cpp:866-935)
+          double fl[6];
 #pragma unroll
-        for (int I = 0; I < 6; I++)
+          for (int i = 0; i < 6; i++) fl[i] = fN[size_t(e)*6 + i];
+          double r1, gk[4], H[4][3][3];
+          ho_isochoric(c.ho, C, Ci, J2d, Inv1, fl, S, r1, gk, H);
 #pragma unroll
-          for (int Jv = I; Jv < 6; Jv++) {
-            const int i = vi[I], j = vj[I], k = vi[Jv], l = vj[Jv];
-            const double sym = 0.5*(Ci[i][k]*Ci[j][l] + Ci[i][l]*Ci[j][k]);
-            rec[UR_DM + dm_idx(I, Jv)] = 2.0*r1*(sym - 1.0/nd3*(Ci[i][j]*Ci[k][l])) - 2.0/nd3*(Ci[i][j]*S[k][l] + S[i][j]*Ci[k][l]);
-          }
+          for (int I = 0; I < 6; I++)
+#pragma unroll
+            for (int Jv = I; Jv < 6; Jv++) {
+              const int i = vi[I], j = vj[I], k = vi[Jv], l = vj[Jv];
+              const double sym = 0.5*(Ci[i][k]*Ci[j][l] + Ci[i][l]*Ci[j][k]);
+              double cc = gk[0]*H[0][i][j]*H[0][k][l] + gk[1]*H[1][i][j]*H[1][k][l] + gk[2]*H[2][i][j]*H[2][k][l] + gk[3]*H[3][i][j]*H[3][k][l];
+              cc += 2.0*r1*(sym - 1.0/nd3*(Ci[i][j]*Ci[k][l])) - 2.0/nd3*(Ci[i][j]*S[k][l] + S[i][j]*Ci[k][l]);
+              rec[UR_DM + dm_idx(I, Jv)] = cc;
+            }
+        } else {
+          const double g1 = 2.0*c.C10;
+          const double r1 = g1*Inv1/nd3;
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) S[i][j] = J2d*((i == j) ? g1 : 0.0) - r1*Ci[i][j];
+#pragma unroll
+          for (int I = 0; I < 6; I++)
+#pragma unroll
+            for (int Jv = I; Jv < 6; Jv++) {
+              const int i = vi[I], j = vj[I], k = vi[Jv], l = vj[Jv];
+              const double sym = 0.5*(Ci[i][k]*Ci[j][l] + Ci[i][l]*Ci[j][k]);
+              rec[UR_DM + dm_idx(I, Jv)] = 2.0*r1*(sym - 1.0/nd3*(Ci[i][j]*Ci[k][l])) - 2.0/nd3*(Ci[i][j]*S[k][l] + S[i][j]*Ci[k][l]);
+            }
+        }
         S6[0] = S[0][0]; S6[1] = S[1][1]; S6[2] = S[2][2]; S6[3] = S[0][1]; S6[4] = S[1][2]; S6[5] = S[2][0];
 #pragma unroll
         for (int i = 0; i < 6; i++) rec[UR_S + i] = S6[i];

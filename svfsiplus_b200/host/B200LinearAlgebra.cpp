@@ -306,7 +306,9 @@ bool B200LinearAlgebra::assemble_ustruct_mesh(ComMod& com_mod, const mshType& lM
   for (int a = 0; a < com_mod.tnNo; a++) if (com_mod.idMap(a) != a) return false;      // undeformed-Neumann faces
   const auto& dmn = eq.dmn[0];
   const auto& stM = dmn.stM;
-  if (stM.isoType != ConstitutiveModelType::stIso_nHook) return false;
+  const bool ho = (stM.isoType == ConstitutiveModelType::stIso_HO);
+  if (stM.isoType != ConstitutiveModelType::stIso_nHook && !ho) return false;
+  if (ho && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
   if (stM.Tf.fType != 0 || dmn.solid_visc.viscType != SolidViscosityModelType::viscType_NA) return false;
   b200_ustruct_props p{};
   p.dt = com_mod.dt; p.am = eq.am; p.af = eq.af; p.gam = eq.gam;
@@ -319,7 +321,9 @@ bool B200LinearAlgebra::assemble_ustruct_mesh(ComMod& com_mod, const mshType& lM
   p.nu = dmn.prop.at(PhysicalProperyType::poisson_ratio);
   p.ctM = dmn.prop.at(PhysicalProperyType::ctau_M);
   p.ctC = dmn.prop.at(PhysicalProperyType::ctau_C);
-  p.isoType = 0;
+  p.isoType = ho ? 3 : 0;
+  p.a = stM.a; p.b = stM.b; p.aff = stM.aff; p.bff = stM.bff; p.ass = stM.ass; p.bss = stM.bss;
+  p.afs = stM.afs; p.bfs = stM.bfs; p.khs = stM.khs;
   switch (stM.volType) {
     case ConstitutiveModelType::stVol_Quad: p.volType = 1; break;
     case ConstitutiveModelType::stVol_ST91: p.volType = 2; break;

@@ -243,7 +243,7 @@ def fsi_linear_step(be: B.Backend, case, ls="GMRES_FSI", want_system=False):
 # ustruct block (tests/cases/ustruct/block_compression/P1P1_VMS/solver.xml: neo-Hookean, E 240.56596e6,
 # nu 0.4999999, ST91, density 1e-3, stabilisation coefficients 1e-3, first-order generalised-alpha)
 # ---------------------------------------------------------------------------------------------------
-def ustruct_case(n, elem="tet", vol="ST91"):
+def ustruct_case(n, elem="tet", vol="ST91", iso="nHook"):
     m = M.block_mesh(n, elem=elem)
     rowPtr, colPtr = M.csr_pattern(m.ien, m.nNo)
     am, af, gam = M.gen_alpha(0.5)
@@ -269,14 +269,26 @@ def ustruct_case(n, elem="tet", vol="ST91"):
         val = np.ones((len(nodes), 3))
         val[:, ax] = 0.0
         faces.append(dict(name=nm, nodes=nodes, dof=3, bGrp=B.BC_DIR, val=val))
-    return dict(mesh=m, rowPtr=rowPtr, colPtr=colPtr, Ag=Ag, Yg=Yg, Dg=Dg, Bf=Bf, Ad=Ad, props=props, faces=faces, kind="ustruct",
+    case = dict(mesh=m, rowPtr=rowPtr, colPtr=colPtr, Ag=Ag, Yg=Yg, Dg=Dg, Bf=Bf, Ad=Ad, props=props, faces=faces, kind="ustruct",
                 res=np.zeros(len(faces)), incL=np.ones(len(faces), np.int32), name=f"ustruct_{elem}_{n}")
+    if iso == "HO":
+        props["iso"] = "HO"
+        props["ho"] = dict(a=590.0, b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12, afs=2160.0, bfs=11.436, khs=100.0)
+        cen = m.x[m.ien].mean(axis=1)
+        th = 0.5 * np.pi * cen[:, 2] + 0.3 * cen[:, 0]
+        fN = np.zeros((m.nEl, 6))
+        fN[:, 0], fN[:, 1] = np.cos(th), np.sin(th)
+        fN[:, 3], fN[:, 4] = -np.sin(th), np.cos(th)
+        case["fN"] = fN
+    return case
 
 
 def assemble_ustruct(be: B.Backend, case, upload=True, with_r=False):
     if upload:
         be.state_set(4, case["Ag"], case["Yg"], case["Bf"])
         be.disp_set(4, case["Dg"])
+        if case.get("fN") is not None:
+            be.mesh_fibers(case["fN"])
     be.zero(4)
     p = case["props"]
     be.assemble_ustruct(B.ustruct_props(tDof=4, **p))

@@ -66,6 +66,9 @@ def main():
             R, Val, Kd, _ = refcase.reference_assemble_ustruct(c, with_r=False)
             Rr, _, _, _ = refcase.reference_assemble_ustruct(c, with_r=True)
             out[f"R_{elem}_{vol}"] = R; out[f"Val_{elem}_{vol}"] = Val; out[f"Kd_{elem}_{vol}"] = Kd; out[f"Rr_{elem}_{vol}"] = Rr
+        c = P.ustruct_case(3, elem=elem, iso="HO")
+        R, Val, Kd, _ = refcase.reference_assemble_ustruct(c, with_r=False)
+        out[f"R_{elem}_HO"] = R; out[f"Val_{elem}_HO"] = Val; out[f"Kd_{elem}_HO"] = Kd
     np.savez_compressed(os.path.join(HERE, "ustruct_3.npz"), **out)
     print("golden fixtures written")
 

@@ -158,6 +158,18 @@ def test_ustruct_assembly_matches_golden(elem, vol):
     be.close()
 
 
+@pytest.mark.parametrize("elem", ["tet", "hex"])
+def test_ustruct_holzapfel_ogden_matches_golden(elem):
+    g = golden("ustruct_3.npz")
+    case = P.ustruct_case(3, elem=elem, iso="HO")
+    be = _setup(case)
+    P.assemble_ustruct(be, case)
+    assert rel_inf(be.get_R(), g[f"R_{elem}_HO"]) < TOL_ASM
+    assert rel_inf(be.get_Val(), g[f"Val_{elem}_HO"]) < TOL_ASM
+    assert rel_inf(be.get_Kd(), g[f"Kd_{elem}_HO"]) < TOL_ASM
+    be.close()
+
+
 @pytest.mark.parametrize("elem,n", [("tet", 6), ("hex", 6)])
 @pytest.mark.parametrize("ls", ["GMRES_USTRUCT", "GMRES_USTRUCT_LOOSE"])
 def test_ustruct_step_matches_reference(elem, n, ls):
