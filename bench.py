@@ -34,6 +34,12 @@ UNIT = "Newton-iters/s"
 P10 = (96, 96, 181)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at P10 on one GPU, from the `ncu --set full` capture
+# profiles/r01_tour_c_ncu_raw.csv (same kernels, same data set-up as the bench)
+NCU_TRAFFIC_P10 = {"spmv_vv4": 3.5201e9 + 0.0319e9, "spmv_vv3": 2.0842e9 + 0.0425e9, "spmv_sv": 0.7326e9 + 0.0516e9,
+                   "spmv_vs": 1.0476e9 + 0.0084e9, "multi_dot": None, "cgs_update_scale": None}
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -93,44 +99,60 @@ def _dist():
     return rank, world, local
 
 
-def run_reference(args):
-    """The reference's own CPU implementation (compiled from its sources, oracle/_ref) on a bounded
-    sample of the workload.  The reference has no threading; its parallelism is MPI ranks, and no MPI
-    runtime exists on this box, so it runs on ONE core (stated in `cores`)."""
-    rank, world, _ = _dist()
-    if rank != 0:
-        return
+def _ref_ranks(args, dims):
+    """Ranks (= host threads) of the reference arm: its parallelism is MPI ranks; no MPI runtime exists on the box,
+    so the ranks are threads of the in-process MPI stand-in (oracle/mpi_stub).  At least two hex layers per rank."""
+    if args.ref_ranks > 0:
+        return args.ref_ranks
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except Exception:
+        ncpu = os.cpu_count() or 1
+    return max(1, min(ncpu, 16, dims[2] // 2))
+
+
+def _reference_sample(args, ls_name):
     from oracle import ref, refcase
     from svfsiplus_b200 import problem as P
     dims = tuple(args.ref_dims)
     case = P.pipe_case(*dims)
     ntet = case["mesh"].nEl
     scale = ntet / float(6 * P10[0] * P10[1] * P10[2])
-    ls = P.LS_SETTINGS[args.ls]
+    nr = _ref_ranks(args, dims)
+    r = refcase.reference_step_ranks(case, ls_name, nr)
+    return case, dims, ntet, scale, nr, r
+
+
+def _sample_text(dims, ntet, scale, nr, r, ls_name):
+    return (f"pipe {dims[0]}x{dims[1]}x{dims[2]} = {ntet} tets ({100*scale:.2f}% of P10) on {nr} rank(s) = host threads of the "
+            f"in-process MPI stand-in: construct_fluid ({r['asm_s']:.2f} s, slowest rank) + commu + fsils_solve {ls_name} "
+            f"({r['solve_s']:.2f} s, itr {r['itr']}/{r['GM_itr']}/{r['CG_itr']}); iters/s scaled by the tet ratio to the 10M-tet unit "
+            f"(optimistic for the CPU: Krylov counts grow with refinement)")
+
+
+def run_reference(args):
+    """The reference's own CPU implementation (compiled from its sources, oracle/_ref) on a bounded sample of the
+    workload, on as many host threads as it can use (one rank per thread, see _ref_ranks)."""
+    rank, world, _ = _dist()
+    if rank != 0:
+        return
+    from oracle import ref
     times = []
-    info = None
+    r = None
     for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        R, Val, _, _, t_asm = refcase.reference_assemble(case)
-        X, info = refcase.reference_solve(case, R, Val, ls)
-        t1 = time.perf_counter()
+        case, dims, ntet, scale, nr, r = _reference_sample(args, args.ls)
         if i >= args.warmup:
-            times.append(t1 - t0)
+            times.append(r["wall_s"])
     ms = 1e3 * float(np.mean(times))
-    # Newton iterations per second on the sample, scaled to the P10 unit by the tet ratio (optimistic
-    # for the CPU: Krylov iteration counts grow with refinement)
     value = (1.0 / (ms * 1e-3)) * scale
-    sample = (f"pipe {dims[0]}x{dims[1]}x{dims[2]} = {ntet} tets ({100*scale:.2f}% of P10), full construct_fluid + "
-              f"fsils_solve ({args.ls}); iters/s on the sample scaled by the tet ratio to the 10M-tet unit")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"P10 pipe 96x96x181 (10,008,576 TET4), NS VMS, LS {args.ls}; reference timed on a bounded sample",
-                   "sample_dims": list(dims), "ls": args.ls, "krylov_itr": int(info["itr"]), "gm_itr": int(info["GM_itr"]),
-                   "cg_itr": int(info["CG_itr"])},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference" if ref.available() else "port",
-                         "sample": sample},
+                   "sample_dims": list(dims), "ls": args.ls, "krylov_itr": r["itr"], "gm_itr": r["GM_itr"], "cg_itr": r["CG_itr"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nr, "kind": "reference" if ref.available() else "port",
+                         "sample": _sample_text(dims, ntet, scale, nr, r, args.ls)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -140,23 +162,13 @@ def run_reference(args):
 def cpu_baseline_leg(args, ls_name):
     """Bounded CPU sample for the `cpu_baseline` object of the GPU arm (rank 0, N=1 only)."""
     try:
-        from oracle import ref, refcase
-        from svfsiplus_b200 import problem as P
+        from oracle import ref
         if not ref.available():
             return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "oracle/_ref not present"}
-        dims = tuple(args.ref_dims)
-        case = P.pipe_case(*dims)
-        ntet = case["mesh"].nEl
-        scale = ntet / float(6 * P10[0] * P10[1] * P10[2])
-        t0 = time.perf_counter()
-        R, Val, _, _, t_asm = refcase.reference_assemble(case)
-        X, info = refcase.reference_solve(case, R, Val, P.LS_SETTINGS[ls_name])
-        dt = time.perf_counter() - t0
-        return {"value": (1.0 / dt) * scale, "unit": UNIT, "cores": 1, "kind": "reference",
-                "sample": f"pipe {dims[0]}x{dims[1]}x{dims[2]} = {ntet} tets ({100*scale:.2f}% of P10): one full "
-                          f"construct_fluid ({t_asm:.2f} s) + fsils_solve {ls_name} ({info['wall_s']:.2f} s, itr {int(info['itr'])}/"
-                          f"{int(info['GM_itr'])}/{int(info['CG_itr'])}); iters/s scaled by the tet ratio",
-                "assembly_us_per_tet": 1e6 * t_asm / ntet}
+        case, dims, ntet, scale, nr, r = _reference_sample(args, ls_name)
+        return {"value": (1.0 / r["wall_s"]) * scale, "unit": UNIT, "cores": nr, "kind": "reference",
+                "sample": _sample_text(dims, ntet, scale, nr, r, ls_name),
+                "assembly_us_per_tet_per_rank": 1e6 * r["asm_s"] * nr / ntet}
     except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU line
         return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
 
@@ -311,7 +323,9 @@ def run_gpu(args):
                 "d2h_bytes_per_step": int(4 * nNo_local * 8), "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak,
+                     "traffic": (NCU_TRAFFIC_P10.get(dom) if (world == 1 and tuple(dims) == P10) else None),
+                     "traffic_source": "ncu --set full, profiles/r01_tour_c_ncu_raw.csv (per launch)", "peak_source": peak_src,
                      "share_of_step": d["ms"] / dev_ms, "launches": d["launches"],
                      "bytes_per_launch": d["bytes"] / max(d["launches"], 1)},
         "kernel_shares": shares, "kernels": per_class, "kernel_time_frac_of_step": tot_k / prof_ms, "profiled_ms_per_step": prof_ms / args.prof_steps,
@@ -337,7 +351,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ls", default="NS", choices=["NS", "GMRES", "BICGS"])
     ap.add_argument("--dims", type=int, nargs=3, default=list(P10), help="pipe hex counts nx ny nz (default P10)")
-    ap.add_argument("--ref-dims", type=int, nargs=3, default=[24, 24, 46], help="bounded CPU sample of the workload")
+    ap.add_argument("--ref-dims", type=int, nargs=3, default=[24, 24, 48], help="bounded CPU sample of the workload")
+    ap.add_argument("--ref-ranks", type=int, default=0, help="ranks (threads) of the reference arm; 0 = min(host cores, 16, layers/2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prof-steps", type=int, default=1, help="extra steps run with per-kernel CUDA events (shares, roofline)")
     args = ap.parse_args()

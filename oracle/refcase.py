@@ -101,3 +101,44 @@ def reference_ustruct_step(case, ls, with_r=True, prec=ref.PREC_FSILS):
     R, Val, Kd, _ = reference_assemble_ustruct(case, with_r=with_r)
     X, out = reference_solve(case, R, Val, ls, prec)
     return R, Val, Kd, X, out
+
+
+def reference_step_ranks(case, ls, nranks):
+    """One Newton-iteration hot path of the reference on `nranks` ranks of the in-process MPI stand-in (threads as
+    ranks, oracle/mpi_stub): the case is cut into z-slabs like a partitioned run, every rank assembles its own
+    elements (construct_fluid; no communication), then commu(R) + fsils_solve run on all ranks together.
+    Returns dict(asm_s = slowest rank's construct_fluid, solve_s, wall_s, itr, GM_itr, CG_itr, nranks)."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    from svfsiplus_b200 import partition as PT
+    from svfsiplus_b200.problem import LS_SETTINGS
+    ls = LS_SETTINGS[ls] if isinstance(ls, str) else ls
+    if nranks <= 1:
+        t0 = time.perf_counter()
+        R, Val, _, _, t_asm = reference_assemble(case)
+        X, out = reference_solve(case, R, Val, ls)
+        return dict(asm_s=t_asm, solve_s=float(out["wall_s"]), wall_s=time.perf_counter() - t0, itr=int(out["itr"]),
+                    GM_itr=int(out["GM_itr"]), CG_itr=int(out["CG_itr"]), nranks=1)
+    parts = PT.split_case(case, nranks)
+    # Assembly: one PROCESS per rank (like MPI ranks).  Threads would share the reference's static allocation
+    # counters (Array<T>::num_allocated) and glibc arenas, which serialises its many per-element heap allocations.
+    # The time of a rank is the time inside its own construct_fluid; the slowest rank counts.
+    try:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(nranks) as pool:
+            asm = pool.map(reference_assemble, parts)
+    except Exception:
+        with ThreadPoolExecutor(nranks) as ex:
+            asm = list(ex.map(reference_assemble, parts))
+    t0, t1 = 0.0, max(a[4] for a in asm)
+    rr = ref.RefRanks([dict(gnNo=p["gnNo"], gNodes=p["gNodes"], rowPtr=p["rowPtr"], colPtr=p["colPtr"],
+                            faces=[dict(nodes=f["nodes"], dof=f["dof"], bGrp=f["bGrp"], val=f["val"]) for f in p["faces"]])
+                       for p in parts])
+    t2 = time.perf_counter()
+    Rs = rr.commuv(4, [a[0] for a in asm])
+    Xs, _, outs = rr.solve(4, _ls_vector(ls), ref.PREC_FSILS, Rs, [a[1] for a in asm], case["incL"], case["res"])
+    t3 = time.perf_counter()
+    rr.close()
+    # lhs_create / bc_create (t1..t2) is one-time set-up in the reference, not part of a Newton iteration
+    return dict(asm_s=t1 - t0, solve_s=t3 - t2, wall_s=(t1 - t0) + (t3 - t2), itr=int(outs[0]["itr"]),
+                GM_itr=int(outs[0]["GM_itr"]), CG_itr=int(outs[0]["CG_itr"]), nranks=nranks)
