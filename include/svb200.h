@@ -90,9 +90,9 @@ int  b200_create(b200_handle** h, int device);
 void b200_destroy(b200_handle* h);
 const char* b200_last_error(b200_handle* h);                 /* h may be NULL: last create error */
 int  b200_device_count(void);
-/* Gauss rule and shape functions the element kernels use for eNoN = 4 (TET4) / 8 (HEX8): w[nG],
- * N[nG][eNoN], Nxi[nG][eNoN][3]; returns nG (what nn::select_ele leaves in lM.w / lM.N / lM.Nx,
- * solver/nn_elem_gip.h:40,501; nn_elem_gnn.h:732,1232).  Host-only, needs no device. */
+/* Gauss rule and shape functions the element kernels use for eNoN = 4 (TET4) / 8 (HEX8) / 10 (TET10): w[nG],
+ * N[nG][eNoN], Nxi[nG][eNoN][3]; returns nG = 4 / 8 / 15 (what nn::select_ele leaves in lM.w / lM.N / lM.Nx,
+ * solver/nn_elem_gip.h:40,501,520; nn_elem_gnn.h:732,1232,1256).  Host-only, needs no device. */
 int  b200_elem_tables(int eNoN, double qmTET4, double* w, double* N, double* Nxi);
 
 /* ---- communicator (replaces FSILS_commuType + MPI, liner_solver/commu.cpp:44) ------------- */
@@ -113,14 +113,17 @@ int b200_face_set(b200_handle* h, int faIn, int nNo, int dof, int bGrp, const in
                   const double* val, int shared);
 
 /* ---- assembly (replaces construct_fluid + do_assem, solver/fluid.cpp:464, lhsa.cpp:97) ------- */
-/* IEN(eNoN,nEl) with assembly node ids, x(3,nNo).  eNoN = 4 (TET4) or 8 (HEX8, the reference's node
- * order, nn_elem_gnn.h:732).  qmTET4 <= 0 selects the default (5+3*sqrt(5))/20 (solver/ComMod.h:1011). */
+/* IEN(eNoN,nEl) with assembly node ids, x(3,nNo).  eNoN = 4 (TET4), 8 (HEX8, the reference's node
+ * order, nn_elem_gnn.h:732) or 10 (TET10, nn_elem_gnn.h:1256; fluid equation only).  qmTET4 <= 0 selects the
+ * default (5+3*sqrt(5))/20 (solver/ComMod.h:1011). */
 int b200_mesh_set(b200_handle* h, int eNoN, int nEl, const int* IEN, const double* x, double qmTET4);
 /* ls_alloc contract (solver/ls.cpp:51-60): after it R(dof,nNo) and Val(dof*dof,nnz) are zero. */
 int b200_zero(b200_handle* h, int dof);
 /* Upload Ag, Yg (tDof,nNo) and Bf (3,nNo; NULL = zero) for the next b200_assemble_fluid. */
 int b200_state_set(b200_handle* h, int tDof, const double* Ag, const double* Yg, const double* Bf);
-/* Whole-mesh fluid assembly on the device into R/Val, using the state uploaded last. */
+/* Whole-mesh fluid assembly on the device into R/Val, using the state uploaded last: TET4 (constant gradients),
+ * HEX8 (nn::gnn per Gauss point) and TET10 (gnn + gn_nxx second derivatives, solver/nn.cpp:455,809), one function
+ * space (VMS-stabilised equal order, lM.nFs = 1). */
 int b200_assemble_fluid(b200_handle* h, const b200_fluid_props* p);
 /* Upload Dg (tDof,nNo) and, for the mesh equation, Do (tDof,nNo; NULL otherwise). */
 int b200_disp_set(b200_handle* h, int tDof, const double* Dg, const double* Do);
@@ -144,7 +147,7 @@ int b200_mesh_fibers(b200_handle* h, int nFn, const double* fN);
  * the device keeps one element list per domain, so each domain is one divergence-free launch. */
 int b200_mesh_domains(b200_handle* h, int nDmn, const int* elem_dmn);
 /* dmn_kind[d]: 0 fluid (fluid_3d_m/c on the ALE configuration x + Dg(4:6), mvMsh), 1 struct (struct_3d into the
- * 3x3 corner of the dof-4 blocks).  fluid[d] / solid[d] are read for the domains of that kind (dof 4; TET4). */
+ * 3x3 corner of the dof-4 blocks).  fluid[d] / solid[d] are read for the domains of that kind (dof 4; TET4, HEX8). */
 int b200_assemble_fsi(b200_handle* h, int nDmn, const int* dmn_kind, const b200_fluid_props* fluid, const b200_struct_props* solid);
 /* LinearAlgebra::assemble for the few boundary-face elements: staged on the host, flushed by one
  * scatter kernel before the next get/solve.  eqN(d), lK(dof*dof,d,d), lR(dof,d). */

@@ -14,6 +14,7 @@
 #include "assembly.cuh"
 #include "assembly_solid.cuh"
 #include "assembly_ustruct.cuh"
+#include "assembly_fluid_gen.cuh"
 #include "ops_cuda.cuh"
 
 using namespace svb200;
@@ -170,50 +171,11 @@ void build_slots(b200_handle* h, size_t nItems, const int* d_key, size_t nDest, 
   cudaFree(cnt); cudaFree(items); cudaFree(bad);
 }
 
-// Gauss rule and shape functions of the mesh's element type: what nn::select_ele + get_gip + get_gnn leave
-// in lM.w / lM.N / lM.Nx (nn_elem_gip.h:40-66 HEX8, :501-517 TET4; nn_elem_gnn.h:732-786 HEX8, :1232-1250 TET4).
-void fill_tables(ElemTables& t, int eNoN, double qmTET4)
-{
-  std::memset(&t, 0, sizeof(t));
-  t.eNoN = eNoN;
-  if (eNoN == 4) {
-    t.nG = 4;
-    const double s = qmTET4, r = (1.0 - s)/3.0;
-    const double xi[4][3] = {{s, r, r}, {r, s, r}, {r, r, s}, {r, r, r}};
-    for (int g = 0; g < 4; g++) {
-      t.w[g] = 1.0/24.0;
-      t.N[g][0] = xi[g][0]; t.N[g][1] = xi[g][1]; t.N[g][2] = xi[g][2];
-      t.N[g][3] = 1.0 - xi[g][0] - xi[g][1] - xi[g][2];
-      const double d[4][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {-1, -1, -1}};
-      for (int a = 0; a < 4; a++) for (int i = 0; i < 3; i++) t.Nxi[g][a][i] = d[a][i];
-    }
-  } else {
-    t.nG = 8;
-    const double s = 1.0/std::sqrt(3.0), m = -1.0/std::sqrt(3.0);
-    const double xi[8][3] = {{m, m, m}, {s, m, m}, {s, s, m}, {m, s, m}, {m, m, s}, {s, m, s}, {s, s, s}, {m, s, s}};
-    for (int g = 0; g < 8; g++) {
-      t.w[g] = 1.0;
-      const double lx = 1.0 - xi[g][0], ly = 1.0 - xi[g][1], lz = 1.0 - xi[g][2];
-      const double ux = 1.0 + xi[g][0], uy = 1.0 + xi[g][1], uz = 1.0 + xi[g][2];
-      const double N[8] = {lx*ly*lz/8.0, ux*ly*lz/8.0, ux*uy*lz/8.0, lx*uy*lz/8.0, lx*ly*uz/8.0, ux*ly*uz/8.0, ux*uy*uz/8.0, lx*uy*uz/8.0};
-      const double D[8][3] = {{-ly*lz/8.0, -lx*lz/8.0, -lx*ly/8.0}, { ly*lz/8.0, -ux*lz/8.0, -ux*ly/8.0},
-                              { uy*lz/8.0,  ux*lz/8.0, -ux*uy/8.0}, {-uy*lz/8.0,  lx*lz/8.0, -lx*uy/8.0},
-                              {-ly*uz/8.0, -lx*uz/8.0,  lx*ly/8.0}, { ly*uz/8.0, -ux*uz/8.0,  ux*ly/8.0},
-                              { uy*uz/8.0,  ux*uz/8.0,  ux*uy/8.0}, {-uy*uz/8.0,  lx*uz/8.0,  lx*uy/8.0}};
-      for (int a = 0; a < 8; a++) { t.N[g][a] = N[a]; for (int i = 0; i < 3; i++) t.Nxi[g][a][i] = D[a][i]; }
-    }
-  }
-}
-
 void build_tables(b200_handle* h)
 {
   ElemTables& t = h->tab;
   fill_tables(t, h->eNoN, h->qmTET4);
-  // packed device copy: w[nG], N[nG][eNoN], Nxi[nG][eNoN][3]
-  std::vector<double> pk;
-  for (int g = 0; g < t.nG; g++) pk.push_back(t.w[g]);
-  for (int g = 0; g < t.nG; g++) for (int a = 0; a < t.eNoN; a++) pk.push_back(t.N[g][a]);
-  for (int g = 0; g < t.nG; g++) for (int a = 0; a < t.eNoN; a++) for (int i = 0; i < 3; i++) pk.push_back(t.Nxi[g][a][i]);
+  const std::vector<double> pk = pack_tables(t);
   cudaFree(h->d_tab);
   h->d_tab = upload(pk.data(), pk.size(), h->ops->st);
   CU_CHECK(cudaStreamSynchronize(h->ops->st));
@@ -302,6 +264,41 @@ FluidConsts fluid_consts(b200_handle* h, const b200_fluid_props* p)
   return c;
 }
 
+// elements per CTA of the generic fluid kernel: 8 x 8 x 129 doubles = 66 KB (HEX8), 4 x 15 x 209 doubles = 100 KB (TET10)
+constexpr int FLUID_EPB_HEX8 = 8, FLUID_EPB_TET10 = 4;
+
+// K10 for HEX8 / TET10 (assembly_fluid_gen.cuh); d_elist / Dmesh as in the TET4 kernel
+template <int ENON, int NG, int EPB, bool NXX>
+void launch_fluid_gen(b200_handle* h, const FluidConsts& c, int nList, const int* d_elist, const double* Dmesh)
+{
+  auto& ops = *h->ops;
+  if (nList == 0) return;
+  constexpr int TABN = fluid_gen_tabn<ENON, NG, NXX>();
+  const size_t smem = sizeof(double)*(size_t((TABN + 3) & ~3) + size_t(EPB)*NG*FluidRec<ENON, NXX>::SIZE);
+  auto kern = k_assemble_fluid_gen<ENON, NG, EPB, NXX>;
+  CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+  kern<<<(nList + EPB - 1)/EPB, EPB*NG, smem, ops.st>>>(nList, d_elist, Dmesh, c, h->d_tab, h->d_ien, h->d_rslot, h->d_kslot, h->d_x,
+                                                        h->d_Ag, h->d_Yg, h->d_Bf, h->stageR, h->stageK, h->d_err);
+  CU_CHECK(cudaGetLastError());
+  ops.post();
+}
+
+// whole-mesh (or one FSI domain's) fluid assembly launch for the mesh's element type
+void launch_fluid(b200_handle* h, const FluidConsts& c, int nList, const int* d_elist, const double* Dmesh)
+{
+  auto& ops = *h->ops;
+  if (nList == 0) return;
+  if (h->eNoN == 4) {
+    k_assemble_fluid_tet4<<<(nList + 127)/128, 128, 0, ops.st>>>(nList, d_elist, Dmesh, c, h->d_ien, h->d_rslot, h->d_kslot, h->d_x,
+                                                               h->d_Ag, h->d_Yg, h->d_Bf, h->stageR, h->stageK, h->d_err);
+    ops.post();
+  } else if (h->eNoN == 8) {
+    launch_fluid_gen<8, 8, FLUID_EPB_HEX8, false>(h, c, nList, d_elist, Dmesh);
+  } else {
+    launch_fluid_gen<10, 15, FLUID_EPB_TET10, true>(h, c, nList, d_elist, Dmesh);
+  }
+}
+
 SolidConsts struct_consts(const b200_struct_props* p)
 {
   if (p->isoType < 0 || p->isoType > 3) throw std::runtime_error("assemble_struct: constitutive model has no device kernel");
@@ -333,7 +330,8 @@ void assemble_solid(b200_handle* h, const SolidConsts& c, const char* who)
     // algorithmic bytes: Val and R written once, nodal fields and IEN read once
     CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*72.0 + double(h->nNo)*(24.0 + 24.0 + 24.0*3 + 24.0) + double(h->nEl)*4.0*h->eNoN, 3);
     if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 3>(h, c, h->nEl, nullptr);
-    else launch_solid<8, 8, 16, 2, 3>(h, c, h->nEl, nullptr);
+    else if (h->eNoN == 8) launch_solid<8, 8, 16, 2, 3>(h, c, h->nEl, nullptr);
+    else throw std::runtime_error(std::string(who) + ": the solid kernels are built for TET4 and HEX8 meshes");
   }
   finish_assembly(h, 3, t0, who);
 }
@@ -392,7 +390,7 @@ extern "C" {
 
 int b200_elem_tables(int eNoN, double qmTET4, double* w, double* N, double* Nxi)
 {
-  if (eNoN != 4 && eNoN != 8) return -1;
+  if (!elem_supported(eNoN)) return -1;
   ElemTables t;
   fill_tables(t, eNoN, qmTET4 > 0.0 ? qmTET4 : (5.0 + 3.0*std::sqrt(5.0))/20.0);
   for (int g = 0; g < t.nG; g++) {
@@ -591,7 +589,7 @@ int b200_mesh_set(b200_handle* h, int eNoN, int nEl, const int* IEN, const doubl
 {
   return guarded(h, [&] {
     auto& ops = *h->ops;
-    if (eNoN != 4 && eNoN != 8) throw std::runtime_error("mesh_set: element type not supported (TET4 and HEX8 are)");
+    if (!elem_supported(eNoN)) throw std::runtime_error("mesh_set: element type not supported (TET4, HEX8 and TET10 are)");
     if (h->nNo == 0) throw std::runtime_error("mesh_set: call b200_lhs_create first");
     h->eNoN = eNoN; h->nEl = nEl;
     h->qmTET4 = qmTET4 > 0.0 ? qmTET4 : (5.0 + 3.0*std::sqrt(5.0))/20.0;
@@ -665,16 +663,13 @@ int b200_assemble_fluid(b200_handle* h, const b200_fluid_props* p)
     if (h->dof != 4 || !h->Val) throw std::runtime_error("assemble_fluid: call b200_zero(h, 4) first");
     if (p->tDof != h->tDof) throw std::runtime_error("assemble_fluid: tDof differs from the uploaded state");
     if (p->mvMsh && p->tDof < 7) throw std::runtime_error("assemble_fluid: mvMsh needs tDof >= 7");
-    if (h->eNoN != 4) throw std::runtime_error("assemble_fluid: the fluid kernel is built for TET4 meshes");
     const FluidConsts c = fluid_consts(h, p);
     ensure_stage(h, 4);
     double t0 = wall_s();
     {
       // algorithmic bytes (SURVEY.md par. 8d): Val and R written once, nodal fields and IEN read once
-      CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*128.0 + double(h->nNo)*(32.0 + 24.0 + 16.0*p->tDof + 24.0) + double(h->nEl)*16.0, 3);
-      k_assemble_fluid_tet4<<<(h->nEl + 127)/128, 128, 0, ops.st>>>(h->nEl, nullptr, nullptr, c, h->d_ien, h->d_rslot, h->d_kslot, h->d_x,
-                                                                  h->d_Ag, h->d_Yg, h->d_Bf, h->stageR, h->stageK, h->d_err);
-      ops.post();
+      CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*128.0 + double(h->nNo)*(32.0 + 24.0 + 16.0*p->tDof + 24.0) + double(h->nEl)*4.0*h->eNoN, 3);
+      launch_fluid(h, c, h->nEl, nullptr, nullptr);
     }
     finish_assembly(h, 4, t0, "construct_fluid");
   });
@@ -840,14 +835,14 @@ int b200_assemble_fsi(b200_handle* h, int nDmn, const int* dmn_kind, const b200_
     if (int(h->d_dmn_elems.size()) != nDmn) throw std::runtime_error("assemble_fsi: call b200_mesh_domains with the same nDmn first");
     if (!h->d_Ag || !h->d_Dg) throw std::runtime_error("assemble_fsi: no state (b200_state_set + b200_disp_set)");
     if (h->dof != 4 || !h->Val) throw std::runtime_error("assemble_fsi: call b200_zero(h, 4) first");
-    if (h->eNoN != 4) throw std::runtime_error("assemble_fsi: built for TET4 meshes (the fluid kernel)");
+    if (h->eNoN != 4 && h->eNoN != 8) throw std::runtime_error("assemble_fsi: built for TET4 and HEX8 meshes (the struct kernel)");
     int covered = 0;
     for (int d = 0; d < nDmn; d++) covered += h->dmn_count[d];
     if (covered != h->nEl) throw std::runtime_error("assemble_fsi: every element must belong to a fluid or struct domain");
     ensure_stage(h, 4);
     const double t0 = wall_s();
     {
-      CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*128.0 + double(h->nNo)*(32.0 + 24.0 + 24.0*h->tDof + 24.0) + double(h->nEl)*16.0, 2 + nDmn);
+      CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*128.0 + double(h->nNo)*(32.0 + 24.0 + 24.0*h->tDof + 24.0) + double(h->nEl)*4.0*h->eNoN, 2 + nDmn);
       for (int d = 0; d < nDmn; d++) {
         const int n = h->dmn_count[d];
         if (n == 0) continue;
@@ -856,13 +851,12 @@ int b200_assemble_fsi(b200_handle* h, int nDmn, const int* dmn_kind, const b200_
           if (fluid[d].tDof != h->tDof || fluid[d].tDof < 7) throw std::runtime_error("assemble_fsi: the fluid domain needs tDof >= 7 (mesh displacement in rows 4..6)");
           FluidConsts c = fluid_consts(h, &fluid[d]);
           c.Kinv = 0.0;
-          k_assemble_fluid_tet4<<<(n + 127)/128, 128, 0, ops.st>>>(n, h->d_dmn_elems[d], h->d_Dg, c, h->d_ien, h->d_rslot, h->d_kslot, h->d_x,
-                                                                 h->d_Ag, h->d_Yg, h->d_Bf, h->stageR, h->stageK, h->d_err);
-          ops.post();
+          launch_fluid(h, c, n, h->d_dmn_elems[d], h->d_Dg);
         } else if (dmn_kind[d] == 1) {
           if (solid[d].tDof != h->tDof) throw std::runtime_error("assemble_fsi: tDof differs from the uploaded state");
           const SolidConsts c = struct_consts(&solid[d]);
-          launch_solid<4, 4, 32, 1, 4>(h, c, n, h->d_dmn_elems[d]);
+          if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 4>(h, c, n, h->d_dmn_elems[d]);
+          else launch_solid<8, 8, 16, 2, 4>(h, c, n, h->d_dmn_elems[d]);
         } else {
           throw std::runtime_error("assemble_fsi: domain physics has no device kernel (fluid and struct have)");
         }

@@ -22,48 +22,9 @@
 #pragma once
 
 #include "kernels.cuh"
+#include "fluid_elem.hpp"      // FluidConsts, is_zero_d, viscosity (host/device shared)
 
 namespace svb200 {
-
-struct FluidConsts {
-  double dt, am, af, gam;
-  double rho, f[3], Kinv;
-  int viscType;
-  double mu_i, mu_o, lam, a, n;
-  int tDof, mvMsh;
-  double w[4];          // Gauss weights (nn_elem_gip.h:501-517)
-  double N[4][4];       // N[g][a]       (nn_elem_gnn.h:1232-1238)
-};
-
-// utils::is_zero(a) with b = 0 (solver/utils.cpp:170-190): relative test against eps.
-__device__ __forceinline__ bool is_zero_d(double v)
-{
-  const double eps = 2.220446049250313e-16;
-  const double a = fabs(v);
-  const double nrm = fmax(a, eps);
-  return (a/nrm) < 10.0*eps;
-}
-
-// fluid::get_viscosity (solver/fluid.cpp:2142-2200)
-__device__ __forceinline__ void viscosity(const FluidConsts& c, double& gamma, double& mu, double& mu_g)
-{
-  if (c.viscType == 0) {
-    mu = c.mu_i; mu_g = 0.0;
-  } else if (c.viscType == 1) {
-    double T1 = 1.0 + pow(c.lam*gamma, c.a);
-    double T2 = pow(T1, (c.n - 1.0)/c.a);
-    mu = c.mu_i + (c.mu_o - c.mu_i)*T2;
-    T1 = T2/T1;
-    T2 = pow(c.lam, c.a) * pow(gamma, c.a - 1.0) * T1;
-    mu_g = (c.mu_o - c.mu_i)*(c.n - 1.0)*T2;
-  } else {
-    double mu_o = c.mu_o;
-    if (gamma < c.lam) { mu_o = mu_o/sqrt(c.lam); gamma = c.lam; }
-    else               { mu_o = mu_o/sqrt(gamma); }
-    mu = (c.mu_i + mu_o)*(c.mu_i + mu_o);
-    mu_g = 2.0*mu_o*(mu_o + c.mu_i)/gamma;
-  }
-}
 
 // one thread per element, elements in mesh order
 // elist != nullptr: the kernel covers the nEl elements elist[0..nEl) (the fluid domain of an FSI equation);

@@ -22,15 +22,9 @@
 #pragma once
 
 #include "assembly.cuh"
+#include "elem_tables.hpp"
 
 namespace svb200 {
-
-struct ElemTables {            // lM.w, lM.N, lM.Nx of the reference (nn_elem_gip.h, nn_elem_gnn.h)
-  int eNoN, nG;
-  double w[8];
-  double N[8][8];              // [g][a]
-  double Nxi[8][8][3];         // [g][a][i]
-};
 
 struct SolidConsts {
   double dt, am, af, gam, beta;

@@ -142,9 +142,10 @@ def pipe_mesh(nx: int, ny: int, nz: int, radius: float = 1.0, length: float = 10
     return Mesh(x=np.ascontiguousarray(x), ien=np.ascontiguousarray(ien), faces=faces, shape=(nx, ny, nz))
 
 
-def block_mesh(n: int, elem: str = "hex", length: float = 1.0, jitter: float = 0.1, seed: int = 4321) -> Mesh:
+def block_mesh(n: int, elem: str = "hex", length: float = 1.0, jitter: float = 0.1, seed: int = 4321, curve: float = 0.03) -> Mesh:
     """Cube [0,L]^3 of n^3 HEX8 (reference node order, nn_elem_gnn.h:732: bottom face counter-clockwise, then the
-    top face) or its 6-tet Kuhn split; interior nodes jittered by jitter*h*U(-1,1).  Faces X0..Z1 = node lists."""
+    top face), its 6-tet Kuhn split ("tet") or the quadratic version of that split ("tet10"); interior nodes jittered
+    by jitter*h*U(-1,1).  Faces X0..Z1 = node lists."""
     h = length / n
     g = np.arange(n + 1) * h
     Z, Y, X = np.meshgrid(g, g, g, indexing="ij")            # node id = i + (n+1) j + (n+1)^2 k
@@ -160,6 +161,21 @@ def block_mesh(n: int, elem: str = "hex", length: float = 1.0, jitter: float = 0
         ien = np.stack([base + o for o in off], axis=1).astype(np.int32)
     elif elem == "tet":
         ien = _fix_orientation(x, _kuhn_tets(n, n, n)).astype(np.int32)
+    elif elem == "tet10":
+        # quadratic tets: the Kuhn split + one node per edge in the reference's order (nn_elem_gnn.h:1256-1268:
+        # nodes 4..9 sit on the edges 0-1, 1-2, 0-2, 0-3, 1-3, 2-3); mid-edge nodes of interior edges are moved off
+        # the chord by curve*h*U(-1,1), so the elements are genuinely curved (xXi2 != 0 in gn_nxx)
+        t4 = _fix_orientation(x, _kuhn_tets(n, n, n)).astype(np.int64)
+        pairs = [(0, 1), (1, 2), (0, 2), (0, 3), (1, 3), (2, 3)]
+        nv = x.shape[0]
+        ek = np.stack([np.minimum(t4[:, a], t4[:, b]) * nv + np.maximum(t4[:, a], t4[:, b]) for a, b in pairs], axis=1)
+        uniq, inv = np.unique(ek.reshape(-1), return_inverse=True)
+        ea, eb = uniq // nv, uniq % nv
+        xm = 0.5 * (x[ea] + x[eb])
+        inner = interior[ea] | interior[eb]
+        xm[inner] += curve * h * rng.uniform(-1.0, 1.0, size=(int(inner.sum()), 3))
+        x = np.concatenate([x, xm])
+        ien = np.concatenate([t4, nv + inv.reshape(-1, 6)], axis=1).astype(np.int32)
     else:
         raise ValueError(elem)
     nid = np.arange(x.shape[0], dtype=np.int32)

@@ -59,6 +59,39 @@ def pipe_case(nx, ny, nz, *, radius=1.0, length=10.0, jitter=0.1, coupled=True, 
                 res=res, incL=incL, name=f"pipe_{nx}x{ny}x{nz}")
 
 
+def fluid_block_case(n, elem="hex", *, visc=None, Kinv=0.0, mvMsh=False):
+    """Navier-Stokes on the unit block meshed with HEX8 ("hex"), TET10 ("tet10", curved edges) or TET4 ("tet"):
+    the element types of SURVEY.md par. 8 rows A4/A5 beyond the linear tet.  Fluid parameters of pipe_RCR_3d; a
+    smooth swirling velocity + noise, body force and (optionally) Darcy permeability so every term of fluid_3d_m/c is
+    exercised.  Walls X0, X1, Y0, Y1 and the inflow Z0 are Dirichlet, Z1 is a traction-free outflow."""
+    m = M.block_mesh(n, elem=elem)
+    rowPtr, colPtr = M.csr_pattern(m.ien, m.nNo)
+    am, af, gam = M.gen_alpha(0.5)
+    x = m.x
+    nN = m.nNo
+    tDof = 7 if mvMsh else 4
+    rng = np.random.default_rng(3030)
+    Yg = np.zeros((nN, tDof)); Ag = np.zeros((nN, tDof))
+    Yg[:, 0] = 5.0 * np.sin(np.pi * x[:, 1]) * np.cos(np.pi * x[:, 2])
+    Yg[:, 1] = -5.0 * np.sin(np.pi * x[:, 0]) * np.cos(np.pi * x[:, 2])
+    Yg[:, 2] = 20.0 * x[:, 0] * (1.0 - x[:, 0]) * x[:, 1] * (1.0 - x[:, 1])
+    Yg[:, :3] += 0.2 * rng.standard_normal((nN, 3))
+    Yg[:, 3] = 100.0 * (1.0 - x[:, 2]) + rng.standard_normal(nN)
+    Ag[:, :4] = 10.0 * rng.standard_normal((nN, 4))
+    if mvMsh:
+        Yg[:, 4:7] = 0.5 * rng.standard_normal((nN, 3))
+    Bf = 0.5 * rng.standard_normal((nN, 3))
+    props = dict(dt=0.005, am=am, af=af, gam=gam, rho=1.06, mu=0.04, f=(0.3, -0.2, 0.1), Kinv=Kinv, mvMsh=mvMsh)
+    if visc:
+        props.update(visc)
+    faces = []
+    for nm in ("X0", "X1", "Y0", "Y1", "Z0"):
+        nodes = m.faces[nm]["nodes"]
+        faces.append(dict(name=nm, nodes=nodes, dof=3, bGrp=B.BC_DIR, val=np.zeros((len(nodes), 3))))
+    return dict(mesh=m, rowPtr=rowPtr, colPtr=colPtr, Ag=Ag, Yg=Yg, Bf=Bf, props=props, faces=faces,
+                res=np.zeros(len(faces)), incL=np.ones(len(faces), np.int32), name=f"fluid_block_{elem}_{n}")
+
+
 def setup_backend(case, device=0) -> B.Backend:
     """Single-rank set-up: what initialize() + fsi_ls_ini + add_eq_linear_algebra do once."""
     m = case["mesh"]
@@ -215,6 +248,33 @@ def fsi_case(nx, ny, nz, *, wall_from=0.8, radius=1.0, length=10.0):
     return dict(mesh=m, rowPtr=rowPtr, colPtr=colPtr, Ag=Ag, Yg=Yg, Dg=Dg, Bf=Bf, elem_dmn=elem_dmn, fluid=fluid, solid=solid,
                 time=dict(dt=dt, am=am, af=af, gam=gam, beta=beta), faces=faces, res=np.zeros(2), incL=np.ones(2, np.int32),
                 kind="fsi", name=f"fsi_{nx}x{ny}x{nz}")
+
+
+def fsi_block_case(n, elem="hex"):
+    """construct_fsi on the unit block (HEX8 or TET4): x < 0.5 is the fluid domain on the ALE configuration, the rest
+    a neo-Hookean struct domain; same unknown layout as fsi_case (tDof 7)."""
+    m = M.block_mesh(n, elem=elem)
+    rowPtr, colPtr = M.csr_pattern(m.ien, m.nNo)
+    am, af, gam = M.gen_alpha(0.5)
+    beta = 0.25 * (1.0 + am - af) ** 2
+    cen = m.x[m.ien].mean(axis=1)
+    elem_dmn = (cen[:, 0] > 0.5).astype(np.int32)
+    base = fluid_block_case(n, elem=elem, mvMsh=True)
+    nN = m.nNo
+    h = 1.0 / n
+    rng = np.random.default_rng(98)
+    Dg = np.zeros((nN, 7))
+    Dg[:, 0:3] = 0.02 * h * rng.standard_normal((nN, 3))
+    Dg[:, 4:7] = 0.05 * h * rng.standard_normal((nN, 3))
+    E, nu = 1.0e7, 0.3
+    mu = 0.5 * E / (1.0 + nu)
+    fluid = dict(rho=1.0, mu=0.04)
+    solid = dict(rho=1.0, dmp=0.0, iso="nHook", vol="ST91", C10=0.5 * mu, C01=0.0, Kpen=E / (3.0 * (1.0 - 2.0 * nu)))
+    faces = [dict(name=nm, nodes=m.faces[nm]["nodes"], dof=3, bGrp=B.BC_DIR, val=np.zeros((len(m.faces[nm]["nodes"]), 3)))
+             for nm in ("Z0", "Z1")]
+    return dict(mesh=m, rowPtr=rowPtr, colPtr=colPtr, Ag=base["Ag"], Yg=base["Yg"], Dg=Dg, Bf=base["Bf"], elem_dmn=elem_dmn,
+                fluid=fluid, solid=solid, time=dict(dt=1e-4, am=am, af=af, gam=gam, beta=beta), faces=faces, res=np.zeros(2),
+                incL=np.ones(2, np.int32), kind="fsi", name=f"fsi_block_{elem}_{n}")
 
 
 def assemble_fsi(be: B.Backend, case, upload=True):

@@ -13,6 +13,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from oracle import refcase  # noqa: E402
 from svfsiplus_b200 import problem as P  # noqa: E402
@@ -70,6 +71,20 @@ def main():
         R, Val, Kd, _ = refcase.reference_assemble_ustruct(c, with_r=False)
         out[f"R_{elem}_HO"] = R; out[f"Val_{elem}_HO"] = Val; out[f"Kd_{elem}_HO"] = Kd
     np.savez_compressed(os.path.join(HERE, "ustruct_3.npz"), **out)
+    # generic fluid element (HEX8, TET10 with curved edges): assembly for every branch + one tight GMRES step
+    import test_fluid_elements as T
+    from svfsiplus_b200 import backend as B
+    out = {}
+    for tag, elem, n, kw in T.GOLDEN_CASES:
+        R, Val, _, _, _ = refcase.reference_assemble(P.fluid_block_case(n, elem=elem, **kw))
+        out[f"R_{tag}"] = R; out[f"Val_{tag}"] = Val
+    for tag, elem, n in (("hex", "hex", 6), ("tet10", "tet10", 3)):
+        R, Val, X, o = refcase.reference_step(P.fluid_block_case(n, elem=elem), (B.LS_GMRES, (1e-10, 1e-14, 10, 150), None, None))
+        out[f"X_step_{tag}"] = X
+        out[f"info_step_{tag}"] = np.array([o["suc"], o["itr"], o["iNorm"], o["fNorm"]])
+    R, Val, _ = refcase.reference_assemble_fsi(P.fsi_block_case(4, elem="hex"))
+    out["R_fsi_hex"] = R; out["Val_fsi_hex"] = Val
+    np.savez_compressed(os.path.join(HERE, "fluid_block.npz"), **out)
     print("golden fixtures written")
 
 

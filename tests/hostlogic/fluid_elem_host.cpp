@@ -1,0 +1,100 @@
+// tests/hostlogic/fluid_elem_host.cpp — TEST-ONLY host instantiation of svfsiplus_b200/csrc/fluid_elem.hpp.
+// It lets the CPU test-suite (`-m "not gpu"`) check the Gauss-point arithmetic of the generic fluid element (HEX8,
+// TET10: gnn, gn_nxx, fluid_3d_m, fluid_3d_c) against the compiled reference without a GPU.  It walks the elements
+// serially and adds lR / lK straight into R / Val in element order (what do_assem does, lhsa.cpp:97-142).  It is
+// never built into, loaded by, or reachable from the product library (libsvb200.so runs the same header on the
+// device through assembly_fluid_gen.cuh).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "elem_tables.hpp"
+#include "fluid_elem.hpp"
+
+using namespace svb200;
+
+namespace {
+
+template <int N, int NG, bool NXX>
+int assemble(int nEl, const int* ien, const double* x, const double* Dmesh, const FluidConsts& c, const ElemTables& t,
+             const double* Ag, const double* Yg, const double* Bf, const int* rowPtr, const int* colPtr, double* R, double* Val)
+{
+  typedef FluidRec<N, NXX> L;
+  std::vector<double> Ntab(NG*N), Nxi(NG*N*3), Nxi2(NG*N*6);
+  for (int g = 0; g < NG; g++)
+    for (int a = 0; a < N; a++) {
+      Ntab[g*N + a] = t.N[g][a];
+      for (int i = 0; i < 3; i++) Nxi[(g*N + a)*3 + i] = t.Nxi[g][a][i];
+      for (int k = 0; k < 6; k++) Nxi2[(g*N + a)*6 + k] = t.Nxi2[g][a][k];
+    }
+  std::vector<double> recs(static_cast<size_t>(NG)*L::SIZE);
+  for (int e = 0; e < nEl; e++) {
+    const int* nd = ien + size_t(e)*N;
+    for (int g = 0; g < NG; g++)
+      if (!fluid_geom<N, NXX>(nd, x, Dmesh, c.tDof, t.w[g], &Nxi[g*N*3], NXX ? &Nxi2[g*N*6] : nullptr, &recs[size_t(g)*L::SIZE]))
+        return e + 1;
+    for (int g = 0; g < NG; g++)
+      fluid_point<N, NXX>(c, nd, Ag, Yg, Bf, &Ntab[g*N], &recs[size_t(g)*L::SIZE], &recs[size_t(NG - 1)*L::SIZE]);
+    for (int a = 0; a < N; a++) {
+      double r[4];
+      fluid_res_row<N, NG, NXX>(c, recs.data(), Ntab.data(), a, r);
+      for (int i = 0; i < 4; i++) R[size_t(nd[a])*4 + i] += r[i];
+      const int* beg = colPtr + rowPtr[nd[a]];
+      const int* end = colPtr + rowPtr[nd[a] + 1];
+      for (int b = 0; b < N; b++) {
+        double kb[16];
+        fluid_tan_block<N, NG, NXX>(c, recs.data(), Ntab.data(), a, b, kb);
+        const int* it = std::lower_bound(beg, end, nd[b]);
+        if (it == end || *it != nd[b]) return -(e + 1);
+        double* v = Val + size_t(it - colPtr)*16;
+        for (int i = 0; i < 16; i++) v[i] += kb[i];
+      }
+    }
+  }
+  return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+// par = {dt, am, af, gam, rho, f0, f1, f2, Kinv, viscType, mu_i, mu_o, lam, a, n, tDof, mvMsh}.
+// Dmesh: Dg(tDof,nNo) for the ALE configuration or NULL.  R(4,nNo), Val(16,nnz) must be zero on entry.
+// Returns 0, e+1 when element e has a zero Jacobian, -(e+1) when a column is missing from the pattern, -1000000 for
+// an unsupported element.
+int host_fluid_assemble(int eNoN, int nEl, const int* ien, const double* x, const double* Dmesh, const double* par, double qmTET4,
+                        const double* Ag, const double* Yg, const double* Bf, const int* rowPtr, const int* colPtr,
+                        double* R, double* Val)
+{
+  FluidConsts c;
+  std::memset(&c, 0, sizeof(c));
+  c.dt = par[0]; c.am = par[1]; c.af = par[2]; c.gam = par[3]; c.rho = par[4];
+  c.f[0] = par[5]; c.f[1] = par[6]; c.f[2] = par[7]; c.Kinv = par[8];
+  c.viscType = int(par[9]); c.mu_i = par[10]; c.mu_o = par[11]; c.lam = par[12]; c.a = par[13]; c.n = par[14];
+  c.tDof = int(par[15]); c.mvMsh = int(par[16]);
+  ElemTables t;
+  if (!elem_supported(eNoN)) return -1000000;
+  fill_tables(t, eNoN, qmTET4 > 0.0 ? qmTET4 : (5.0 + 3.0*std::sqrt(5.0))/20.0);
+  if (eNoN == 4) return assemble<4, 4, false>(nEl, ien, x, Dmesh, c, t, Ag, Yg, Bf, rowPtr, colPtr, R, Val);
+  if (eNoN == 8) return assemble<8, 8, false>(nEl, ien, x, Dmesh, c, t, Ag, Yg, Bf, rowPtr, colPtr, R, Val);
+  return assemble<10, 15, true>(nEl, ien, x, Dmesh, c, t, Ag, Yg, Bf, rowPtr, colPtr, R, Val);
+}
+
+// the tables themselves (checked against what the reference's select_ele leaves in lM): returns nG
+int host_elem_tables(int eNoN, double qmTET4, double* w, double* N, double* Nxi, double* Nxi2)
+{
+  if (!elem_supported(eNoN)) return -1;
+  ElemTables t;
+  fill_tables(t, eNoN, qmTET4 > 0.0 ? qmTET4 : (5.0 + 3.0*std::sqrt(5.0))/20.0);
+  for (int g = 0; g < t.nG; g++) {
+    if (w) w[g] = t.w[g];
+    for (int a = 0; a < eNoN; a++) {
+      if (N) N[g*eNoN + a] = t.N[g][a];
+      if (Nxi) for (int i = 0; i < 3; i++) Nxi[(g*eNoN + a)*3 + i] = t.Nxi[g][a][i];
+      if (Nxi2) for (int k = 0; k < 6; k++) Nxi2[(g*eNoN + a)*6 + k] = t.Nxi2[g][a][k];
+    }
+  }
+  return t.nG;
+}
+
+}

@@ -57,3 +57,37 @@ def hl_solve(rowPtr, colPtr, dof, R, Val, ls, prec, faces, incL=None, res=None):
         raise RuntimeError(L.hl_last_error().decode())
     keys = ["suc", "itr", "iNorm", "fNorm", "dB", "GM_itr", "CG_itr", "Resm", "Resc"]
     return R, Val, dict(zip(keys, out))
+
+
+_eh = None
+
+
+def elemhost():
+    global _eh
+    if _eh is None:
+        _eh = C.CDLL(os.path.join(ROOT, "tests", "_build", "libelemhost.so"))
+        _eh.host_fluid_assemble.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_double] + [C.c_void_p] * 7
+        _eh.host_elem_tables.argtypes = [C.c_int, C.c_double] + [C.c_void_p] * 4
+    return _eh
+
+
+def host_fluid_assemble(case):
+    """fluid_elem.hpp (the product's Gauss-point arithmetic) run serially on the host by the TEST-ONLY harness
+    tests/hostlogic/fluid_elem_host.cpp on a svfsiplus_b200.problem fluid case.  Returns R (nNo,4), Val (nnz,16)."""
+    L = elemhost()
+    m = case["mesh"]
+    p = case["props"]
+    tD = case["Ag"].shape[1]
+    f = p.get("f", (0.0, 0.0, 0.0))
+    par = np.array([p["dt"], p["am"], p["af"], p["gam"], p["rho"], f[0], f[1], f[2], p.get("Kinv", 0.0), p.get("viscType", 0),
+                    p["mu"], p.get("mu_o", 0.0), p.get("lam", 0.0), p.get("a", 0.0), p.get("n", 0.0), tD,
+                    int(p.get("mvMsh", False))], np.float64)
+    ien = np.ascontiguousarray(m.ien, np.int32); x = np.ascontiguousarray(m.x, np.float64)
+    Ag = np.ascontiguousarray(case["Ag"]); Yg = np.ascontiguousarray(case["Yg"]); Bf = np.ascontiguousarray(case["Bf"])
+    rp = np.ascontiguousarray(case["rowPtr"], np.int32); cp = np.ascontiguousarray(case["colPtr"], np.int32)
+    R = np.zeros((m.nNo, 4)); Val = np.zeros((len(cp), 16))
+    rc = L.host_fluid_assemble(ien.shape[1], m.nEl, _p(ien), _p(x), None, _p(par), -1.0, _p(Ag), _p(Yg), _p(Bf), _p(rp), _p(cp),
+                               _p(R), _p(Val))
+    if rc != 0:
+        raise RuntimeError(f"host_fluid_assemble: rc {rc}")
+    return R, Val

@@ -4,6 +4,8 @@
   python tools/prof.py tour  [--dims nx ny nz] [--reps R]   stand-alone bench of every kernel class
   python tools/prof.py step  [--dims nx ny nz] [--ls NS]    one resident Newton-iteration hot path
   python tools/prof.py asm   [--dims nx ny nz] [--reps R]   assembly only
+  python tools/prof.py solid [--reps R]                     K11 solid element kernels on production-size blocks
+  python tools/prof.py fluidgen [--reps R]                  K10 generic fluid element (HEX8 100^3, TET10 6 x 32^3)
 
 `tour` prints one JSON line per kernel class (ms, algorithmic GB/s, fraction of the measured HBM peak);
 under `ncu --set full -k regex:k_` it gives one capture per kernel on production-size data.
@@ -28,7 +30,7 @@ def peak():
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["tour", "step", "asm", "solid"])
+    ap.add_argument("mode", choices=["tour", "step", "asm", "solid", "fluidgen"])
     ap.add_argument("--dims", type=int, nargs=3, default=[96, 96, 181])
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--ls", default="NS")
@@ -46,6 +48,21 @@ def main():
             ms = be.timer_stop() / a.reps
             nEl = case["mesh"].nEl
             print(json.dumps(dict(kernel=name, nEl=nEl, ms=ms, ns_per_elem=1e6 * ms / nEl, nnz=be.nnz)), flush=True)
+            be.close()
+        return
+    if a.mode == "fluidgen":
+        for name, case in (("fluid_hex8_100", P.fluid_block_case(100, elem="hex")), ("fluid_tet10_32", P.fluid_block_case(32, elem="tet10"))):
+            be = P.setup_backend(case)
+            P.assemble(be, case)
+            if a.reps > 1:
+                P.assemble(be, case, upload=False)
+            be.timer_start()
+            for _ in range(a.reps):
+                P.assemble(be, case, upload=False)
+            ms = be.timer_stop() / a.reps
+            nEl = case["mesh"].nEl
+            print(json.dumps(dict(kernel=name, nEl=nEl, nNo=be.nNo, nnz=be.nnz, ms=ms, ns_per_elem=1e6 * ms / nEl,
+                                  val_write_GBps=be.nnz * 128.0 / 1e6 / ms)), flush=True)
             be.close()
         return
     t0 = time.time()
