@@ -119,7 +119,8 @@ int b200_face_set(b200_handle* h, int faIn, int nNo, int dof, int bGrp, const in
 int b200_mesh_set(b200_handle* h, int eNoN, int nEl, const int* IEN, const double* x, double qmTET4);
 /* ls_alloc contract (solver/ls.cpp:51-60): after it R(dof,nNo) and Val(dof*dof,nnz) are zero. */
 int b200_zero(b200_handle* h, int dof);
-/* Upload Ag, Yg (tDof,nNo) and Bf (3,nNo; NULL = zero) for the next b200_assemble_fluid. */
+/* Upload Ag, Yg (tDof,nNo) and Bf (3,nNo; NULL = zero) for the next b200_assemble_fluid.  Ag = Yg = NULL keeps the
+ * device copies (written by b200_pici) and uploads Bf only. */
 int b200_state_set(b200_handle* h, int tDof, const double* Ag, const double* Yg, const double* Bf);
 /* Whole-mesh fluid assembly on the device into R/Val, using the state uploaded last: TET4 (constant gradients),
  * HEX8 (nn::gnn per Gauss point) and TET10 (gnn + gn_nxx second derivatives, solver/nn.cpp:455,809), one function
@@ -161,6 +162,30 @@ int b200_get_Val(b200_handle* h, double* Val);
 int b200_set_Val(b200_handle* h, int dof, const double* Val);
 /* all_fun::commu(R) (solver/all_fun.cpp:122): overlap-node add of the device R. */
 int b200_commu_R(b200_handle* h);
+
+/* ---- time integrator on the device (replaces pic::picp / pici / picc, solver/pic.cpp:591,486,74) ---------- */
+/* With the generalised-alpha state resident on the device a Newton iteration needs no upload of Ag/Yg/Dg and no
+ * download of the solution: b200_pici writes the state the assembly kernels read (what b200_state_set / b200_disp_set
+ * upload otherwise), b200_picc consumes the device R left by b200_solve.  Arrays are (tDof,nNo) in assembly order like
+ * com_mod.Ao..Dn; Ad is com_mod.Ad(3,nNo).  kind = what picc does for the equation (pic.cpp:116-160): 0 the general
+ * update of An, Yn, Dn (every equation when !sstEq; the mesh equation under sstEq), 1 ustruct / FSI under sstEq (An,
+ * Yn from R; Ad, Dn through Rd), 2 nothing (any other equation under sstEq). */
+typedef struct { int s, e; double am, af, gam, beta; int kind; } b200_pic_eq;
+enum { B200_PIC_AO = 0, B200_PIC_YO, B200_PIC_DO, B200_PIC_AN, B200_PIC_YN, B200_PIC_DN, B200_PIC_AD,
+       B200_PIC_AG, B200_PIC_YG, B200_PIC_DG };
+/* dFlag, sstEq: com_mod.dFlag / com_mod.sstEq (they select the displacement predictor, pic.cpp:690-712). */
+int b200_pic_init(b200_handle* h, int tDof, int nEq, const b200_pic_eq* eqs, int dFlag, int sstEq);
+int b200_pic_set(b200_handle* h, int which, const double* a);        /* upload one array */
+int b200_pic_get(b200_handle* h, int which, double* a);              /* download one array */
+/* set_bc_dir (solver/set_bc.cpp:794) on the device copy: arr[idx[k]] = val[k], idx = i + tDof*a. */
+int b200_pic_scatter(b200_handle* h, int which, int n, const int* idx, const double* val);
+int b200_picp(b200_handle* h, double dt);                            /* predictor, every equation */
+int b200_pici(b200_handle* h);                                       /* Ag, Yg, Dg of every equation */
+/* corrector for equation iEq from the device solution; first_itr: eq.itr == 1 (ustruct_r's Rd, kind 1 only). */
+int b200_picc(b200_handle* h, int iEq, double dt, int first_itr);
+/* FSI tail of picc (pic.cpp:166-181): on the listed solid-domain nodes copy rows [0,cnt) of An/Yn/Dn to [s2,s2+cnt). */
+int b200_pic_copy_rows(b200_handle* h, int n, const int* nodes, int s2, int cnt);
+int b200_pic_advance(b200_handle* h);                                /* end of time step: Ao = An, Yo = Yn, Do = Dn */
 
 /* ---- solve (replaces fsils_solve, liner_solver/solve.cpp:50) ------------------------------- */
 /* Consumes the device R/Val (Val is scaled in place like the reference), leaves the solution in the

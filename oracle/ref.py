@@ -153,6 +153,7 @@ def lib():
                                       C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_ranks_spmv.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_ranks_commuv.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_pic.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_double] + [C.c_void_p] * 12
         _lib = L
     return _lib
 
@@ -375,3 +376,23 @@ class RefRanks:
         Vs = [_c(v, np.float64).copy() for v in V]
         lib().ref_ranks_commuv(self.n, self.harr, dof, self._ptrs(Vs))
         return Vs
+
+
+PHYS = dict(fluid=0, struct=1, lElas=2, ustruct=3, FSI=4, mesh=5)
+
+
+def pic(op, state, eqs, *, dt, cEq=0, dFlag=False, sstEq=False, R=None, Rd=None):
+    """The reference's pic::picp / pici / picc (S/pic.cpp:591,486,74) on host arrays.  op: "p", "i" or "c".
+    state: dict with Ao, Yo, Do, An, Yn, Dn (nNo,tDof), Ad (nNo,3), Ag, Yg, Dg; modified copies are returned.
+    eqs: list of dict(s, e, am, af, gam, beta, phys, itr)."""
+    st = {k: _c(v, np.float64).copy() for k, v in state.items()}
+    nNo, tDof = st["Ao"].shape
+    par = np.array([[q["s"], q["e"], q["am"], q["af"], q["gam"], q.get("beta", 0.0), PHYS[q["phys"]], q.get("itr", 1)] for q in eqs],
+                   np.float64)
+    Ra = None if R is None else _c(R, np.float64)
+    Rda = None if Rd is None else _c(Rd, np.float64)
+    rc = lib().ref_pic({"p": 0, "i": 1, "c": 2}[op], nNo, tDof, len(eqs), cEq, _p(par), int(dFlag), int(sstEq), dt,
+                       *[_p(st[k]) for k in ("Ao", "Yo", "Do", "An", "Yn", "Dn", "Ad", "Ag", "Yg", "Dg")], _p(Ra), _p(Rda))
+    if rc != 0:
+        raise RuntimeError(lib().ref_last_error().decode())
+    return st

@@ -13,6 +13,7 @@
 //   fsils_bc_create               Code/Source/liner_solver/bc.cpp:45
 //   fsils_solve                   Code/Source/liner_solver/solve.cpp:50
 //   fsils_spar_mul_vv / commuv    Code/Source/liner_solver/spar_mul.cpp:191, in_commu.cpp:111
+//   pic::picp / pici / picc       Code/Source/solver/pic.cpp:591, 486, 74
 //
 // Nothing in the product (svfsiplus_b200/) links or loads this file; only tests/, smoke() and
 // bench.py's cpu_baseline / --impl reference legs do.
@@ -36,6 +37,7 @@
 #include "commu.h"
 #include "lhs.h"
 #include "ls.h"
+#include "pic.h"
 #ifdef WITH_B200_DROPIN
 #include "B200LinearAlgebra.h"
 #endif
@@ -833,5 +835,72 @@ int ref_dropin_solid_step(void* h, int mode, int kind, int tDof, int s, const do
   }
 }
 #endif
+
+} // extern "C"
+
+// ----------------------------------------------------------------------------------------------
+// Generalised-alpha time integrator: the reference's own pic::picp / pici / picc on caller arrays.
+// ----------------------------------------------------------------------------------------------
+extern "C" {
+
+// op: 0 picp, 1 pici, 2 picc (for equation cEq).  eqpar[8*i..] = {s, e, am, af, gam, beta, phys, itr} of equation i with
+// phys 0 fluid, 1 struct, 2 lElas, 3 ustruct, 5 mesh.  State arrays are (tDof, tnNo), Ad and Rd (3, tnNo), R (dof, tnNo).
+int ref_pic(int op, int tnNo, int tDof, int nEq, int cEq, const double* eqpar, int dFlag, int sstEq, double dt,
+            double* Ao, double* Yo, double* Do, double* An, double* Yn, double* Dn, double* Ad, double* Ag, double* Yg, double* Dg,
+            const double* R, const double* Rd)
+{
+  try {
+    using namespace consts;
+    mpistub_set_world(1);
+    mpistub_bind_rank(0);
+    Simulation sim;
+    auto& com_mod = sim.com_mod;
+    com_mod.nsd = 3;
+    com_mod.tnNo = tnNo;
+    com_mod.tDof = tDof;
+    com_mod.dt = dt;
+    com_mod.nMsh = 0;
+    com_mod.nEq = nEq;
+    com_mod.cEq = cEq;
+    com_mod.dFlag = (dFlag != 0);
+    com_mod.sstEq = (sstEq != 0);
+    com_mod.pstEq = false;
+    com_mod.eq.resize(nEq);
+    const EquationType phys_of[6] = {EquationType::phys_fluid, EquationType::phys_struct, EquationType::phys_lElas,
+                                     EquationType::phys_ustruct, EquationType::phys_FSI, EquationType::phys_mesh};
+    for (int i = 0; i < nEq; i++) {
+      auto& eq = com_mod.eq[i];
+      const double* q = eqpar + 8*i;
+      eq.s = int(q[0]); eq.e = int(q[1]); eq.am = q[2]; eq.af = q[3]; eq.gam = q[4]; eq.beta = q[5];
+      eq.phys = phys_of[int(q[6])];
+      eq.itr = int(q[7]);
+      eq.dof = eq.e - eq.s + 1;
+      eq.coupled = true; eq.ok = false; eq.minItr = 1; eq.maxItr = 100; eq.tol = 1e-30; eq.iNorm = 1.0; eq.pNorm = 1.0;
+      eq.FSILS.RI.iNorm = 1.0;
+    }
+    auto load = [&](Array<double>& A, const double* src, int nr) { A.resize(nr, tnNo); if (src) std::memcpy(A.data(), src, sizeof(double)*size_t(nr)*tnNo); };
+    load(com_mod.Ao, Ao, tDof); load(com_mod.Yo, Yo, tDof); load(com_mod.Do, Do, tDof);
+    load(com_mod.An, An, tDof); load(com_mod.Yn, Yn, tDof); load(com_mod.Dn, Dn, tDof);
+    load(com_mod.Ad, Ad, 3);
+    Array<double> Ag_a, Yg_a, Dg_a;
+    load(Ag_a, Ag, tDof); load(Yg_a, Yg, tDof); load(Dg_a, Dg, tDof);
+    if (op == 2) {
+      const int dof = com_mod.eq[cEq].dof;
+      com_mod.dof = dof;
+      load(com_mod.R, R, dof);
+      load(com_mod.Rd, Rd, 3);
+    }
+    if (op == 0) pic::picp(&sim);
+    else if (op == 1) pic::pici(&sim, Ag_a, Yg_a, Dg_a);
+    else pic::picc(&sim);
+    auto store = [&](double* dst, const Array<double>& A) { if (dst) std::memcpy(dst, A.data(), sizeof(double)*A.size()); };
+    store(An, com_mod.An); store(Yn, com_mod.Yn); store(Dn, com_mod.Dn); store(Ad, com_mod.Ad);
+    store(Ag, Ag_a); store(Yg, Yg_a); store(Dg, Dg_a);
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
 
 } // extern "C"

@@ -20,6 +20,11 @@ void construct_cep(ComMod&, CepMod&, const mshType&, const Array<double>&, const
 { throw std::runtime_error("[oracle] cep::construct_cep is outside the hot path"); }
 }
 
+namespace cep_ion {
+void cep_integ(Simulation*, const int, const int, const Array<double>&)
+{ throw std::runtime_error("[oracle] cep_ion::cep_integ is outside the hot path"); }
+}
+
 extern "C" {
 
 // A (n x n, column-major, lda) = P L U in place; ipiv 1-based.

@@ -69,6 +69,13 @@ class UstructProps(C.Structure):
                 ("bss", C.c_double), ("afs", C.c_double), ("bfs", C.c_double), ("khs", C.c_double)]
 
 
+class PicEq(C.Structure):
+    _fields_ = [("s", C.c_int), ("e", C.c_int), ("am", C.c_double), ("af", C.c_double), ("gam", C.c_double),
+                ("beta", C.c_double), ("kind", C.c_int)]
+
+
+PIC = dict(Ao=0, Yo=1, Do=2, An=3, Yn=4, Dn=5, Ad=6, Ag=7, Yg=8, Dg=9)
+
 ISO_TYPES = {"nHook": 0, "StVK": 1, "mStVK": 2, "HO": 3}
 VOL_TYPES = {None: 0, "Quad": 1, "ST91": 2, "M94": 3}
 
@@ -80,6 +87,8 @@ EXPORTS = [
     "b200_assemble_elem", "b200_get_R", "b200_set_R", "b200_add_R", "b200_get_Val", "b200_set_Val", "b200_commu_R", "b200_solve",
     "b200_spmv", "b200_op_bench", "b200_launch_count", "b200_last_timings", "b200_profile", "b200_profile_read",
     "b200_timer",
+    "b200_pic_init", "b200_pic_set", "b200_pic_get", "b200_pic_scatter", "b200_picp", "b200_pici", "b200_picc",
+    "b200_pic_copy_rows", "b200_pic_advance",
 ]
 
 KERNEL_CLASSES = ["spmv_vv4", "spmv_vv3", "spmv_ss", "spmv_sv", "spmv_vs", "multi_dot", "cgs_update_scale", "blas1",
@@ -136,6 +145,15 @@ def lib():
         L.b200_profile.argtypes = [vp, ci]
         L.b200_profile_read.argtypes = [vp, ci, vp, vp, vp]
         L.b200_timer.argtypes = [vp, ci, C.POINTER(cd)]
+        L.b200_pic_init.argtypes = [vp, ci, ci, C.POINTER(PicEq), ci, ci]
+        L.b200_pic_set.argtypes = [vp, ci, vp]
+        L.b200_pic_get.argtypes = [vp, ci, vp]
+        L.b200_pic_scatter.argtypes = [vp, ci, ci, vp, vp]
+        L.b200_picp.argtypes = [vp, cd]
+        L.b200_pici.argtypes = [vp]
+        L.b200_picc.argtypes = [vp, ci, cd, ci]
+        L.b200_pic_copy_rows.argtypes = [vp, ci, vp, ci, ci]
+        L.b200_pic_advance.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -386,6 +404,45 @@ class Backend:
                                    _p(incL_a), _p(res_a), _p(X), C.byref(o)), "b200_solve")
         info = dict(RI=sub_out_dict(o.RI), GM=sub_out_dict(o.GM), CG=sub_out_dict(o.CG), Resm=o.Resm, Resc=o.Resc)
         return X, info
+
+    # -- time integrator on the device (pic::picp / pici / picc) ---------------------------------------
+    def pic_init(self, tDof, eqs, dFlag=False, sstEq=False):
+        """eqs: list of dict(s, e, am, af, gam, beta, kind)."""
+        arr = (PicEq * len(eqs))()
+        for i, q in enumerate(eqs):
+            arr[i].s, arr[i].e, arr[i].kind = int(q["s"]), int(q["e"]), int(q.get("kind", 0))
+            arr[i].am, arr[i].af, arr[i].gam, arr[i].beta = q["am"], q["af"], q["gam"], q.get("beta", 0.0)
+        self._ck(self.L.b200_pic_init(self.h, tDof, len(eqs), arr, int(dFlag), int(sstEq)), "b200_pic_init")
+        self.pic_tDof = tDof
+
+    def pic_set(self, which, a):
+        a = _c(a, np.float64)
+        self._ck(self.L.b200_pic_set(self.h, PIC[which], _p(a)), "b200_pic_set")
+
+    def pic_get(self, which):
+        a = np.empty((self.nNo, 3 if which == "Ad" else self.pic_tDof))
+        self._ck(self.L.b200_pic_get(self.h, PIC[which], _p(a)), "b200_pic_get")
+        return a
+
+    def pic_scatter(self, which, idx, val):
+        idx = _c(idx, np.int32); val = _c(val, np.float64)
+        self._ck(self.L.b200_pic_scatter(self.h, PIC[which], len(idx), _p(idx), _p(val)), "b200_pic_scatter")
+
+    def picp(self, dt):
+        self._ck(self.L.b200_picp(self.h, dt), "b200_picp")
+
+    def pici(self):
+        self._ck(self.L.b200_pici(self.h), "b200_pici")
+
+    def picc(self, iEq, dt, first_itr=False):
+        self._ck(self.L.b200_picc(self.h, iEq, dt, int(first_itr)), "b200_picc")
+
+    def pic_copy_rows(self, nodes, s2, cnt):
+        nodes = _c(nodes, np.int32)
+        self._ck(self.L.b200_pic_copy_rows(self.h, len(nodes), _p(nodes), s2, cnt), "b200_pic_copy_rows")
+
+    def pic_advance(self):
+        self._ck(self.L.b200_pic_advance(self.h), "b200_pic_advance")
 
     # -- taps --------------------------------------------------------------------------------------
     def spmv(self, x):

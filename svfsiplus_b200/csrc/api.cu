@@ -15,6 +15,7 @@
 #include "assembly_solid.cuh"
 #include "assembly_ustruct.cuh"
 #include "assembly_fluid_gen.cuh"
+#include "pic.cuh"
 #include "ops_cuda.cuh"
 
 using namespace svb200;
@@ -76,6 +77,11 @@ struct b200_handle {
   double* d_Do = nullptr;
   size_t state_cap = 0, disp_cap = 0;
 
+  // time integrator (pic.cuh): Ao Yo Do An Yn Dn (tDof x nNo) and Ad (3 x nNo), assembly order
+  double* pic_arr[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int pic_tDof = 0, pic_dFlag = 0, pic_sstEq = 0;
+  std::vector<b200_pic_eq> pic_eqs;
+
   // staged boundary elements
   struct Staged { int d; std::vector<int> eqN; std::vector<double> lK, lR; };
   std::vector<Staged> staged;
@@ -90,6 +96,7 @@ struct b200_handle {
     cudaFree(d_Ag); cudaFree(d_Yg); cudaFree(d_Bf); cudaFree(d_Dg); cudaFree(d_Do); cudaFree(d_tab);
     for (auto p : d_dmn_elems) cudaFree(p);
     cudaFree(Kd); cudaFree(stageKd); cudaFree(d_fN);
+    for (auto p : pic_arr) cudaFree(p);
   }
 };
 
@@ -633,21 +640,45 @@ int b200_zero(b200_handle* h, int dof)
   });
 }
 
+namespace {
+// device copies of Ag / Yg (tDof x nNo) and Bf (3 x nNo)
+void ensure_state(b200_handle* h, int tDof)
+{
+  const size_t n = size_t(h->nNo);
+  if (h->state_cap < n*tDof || h->tDof != tDof) {
+    cudaFree(h->d_Ag); cudaFree(h->d_Yg); cudaFree(h->d_Bf);
+    CU_CHECK(cudaMalloc(&h->d_Ag, sizeof(double)*n*tDof));
+    CU_CHECK(cudaMalloc(&h->d_Yg, sizeof(double)*n*tDof));
+    CU_CHECK(cudaMalloc(&h->d_Bf, sizeof(double)*n*3));
+    CU_CHECK(cudaMemsetAsync(h->d_Bf, 0, sizeof(double)*n*3, h->ops->st));
+    h->state_cap = n*tDof;
+    h->tDof = tDof;
+  }
+}
+void ensure_disp(b200_handle* h, int tDof)
+{
+  const size_t n = size_t(h->nNo);
+  if (h->disp_cap < n*tDof) {
+    cudaFree(h->d_Dg); cudaFree(h->d_Do);
+    h->d_Dg = h->d_Do = nullptr;
+    CU_CHECK(cudaMalloc(&h->d_Dg, sizeof(double)*n*tDof));
+    h->disp_cap = n*tDof;
+  }
+}
+} // namespace
+
 int b200_state_set(b200_handle* h, int tDof, const double* Ag, const double* Yg, const double* Bf)
 {
   return guarded(h, [&] {
     auto st = h->ops->st;
     const size_t n = size_t(h->nNo);
-    if (h->state_cap < n*tDof || h->tDof != tDof) {
-      cudaFree(h->d_Ag); cudaFree(h->d_Yg); cudaFree(h->d_Bf);
-      CU_CHECK(cudaMalloc(&h->d_Ag, sizeof(double)*n*tDof));
-      CU_CHECK(cudaMalloc(&h->d_Yg, sizeof(double)*n*tDof));
-      CU_CHECK(cudaMalloc(&h->d_Bf, sizeof(double)*n*3));
-      h->state_cap = n*tDof;
-      h->tDof = tDof;
+    if ((Ag == nullptr) != (Yg == nullptr)) throw std::runtime_error("state_set: Ag and Yg must both be given or both be NULL");
+    if (!Ag && (!h->d_Ag || h->tDof != tDof)) throw std::runtime_error("state_set: no device state to keep (b200_pici first)");
+    ensure_state(h, tDof);
+    if (Ag) {
+      CU_CHECK(cudaMemcpyAsync(h->d_Ag, Ag, sizeof(double)*n*tDof, cudaMemcpyHostToDevice, st));
+      CU_CHECK(cudaMemcpyAsync(h->d_Yg, Yg, sizeof(double)*n*tDof, cudaMemcpyHostToDevice, st));
     }
-    CU_CHECK(cudaMemcpyAsync(h->d_Ag, Ag, sizeof(double)*n*tDof, cudaMemcpyHostToDevice, st));
-    CU_CHECK(cudaMemcpyAsync(h->d_Yg, Yg, sizeof(double)*n*tDof, cudaMemcpyHostToDevice, st));
     if (Bf) CU_CHECK(cudaMemcpyAsync(h->d_Bf, Bf, sizeof(double)*n*3, cudaMemcpyHostToDevice, st));
     else CU_CHECK(cudaMemsetAsync(h->d_Bf, 0, sizeof(double)*n*3, st));
     CU_CHECK(cudaStreamSynchronize(st));
@@ -681,12 +712,7 @@ int b200_disp_set(b200_handle* h, int tDof, const double* Dg, const double* Do)
     auto st = h->ops->st;
     const size_t n = size_t(h->nNo);
     if (!Dg) throw std::runtime_error("disp_set: Dg is required");
-    if (h->disp_cap < n*tDof) {
-      cudaFree(h->d_Dg); cudaFree(h->d_Do);
-      h->d_Dg = h->d_Do = nullptr;
-      CU_CHECK(cudaMalloc(&h->d_Dg, sizeof(double)*n*tDof));
-      h->disp_cap = n*tDof;
-    }
+    ensure_disp(h, tDof);
     CU_CHECK(cudaMemcpyAsync(h->d_Dg, Dg, sizeof(double)*n*tDof, cudaMemcpyHostToDevice, st));
     if (Do) {
       if (!h->d_Do) CU_CHECK(cudaMalloc(&h->d_Do, sizeof(double)*h->disp_cap));
@@ -981,6 +1007,187 @@ int b200_commu_R(b200_handle* h)
     flush_staged(h);
     h->ops->halo_add(h->dof, h->R);
     CU_CHECK(cudaStreamSynchronize(h->ops->st));
+  });
+}
+
+// ---- time integrator on the device (pic.cuh) ------------------------------------------------------------------
+namespace {
+double* pic_array(b200_handle* h, int which, size_t& len)
+{
+  if (h->pic_tDof == 0) throw std::runtime_error("pic: call b200_pic_init first");
+  const size_t n = size_t(h->nNo);
+  if (which >= B200_PIC_AO && which <= B200_PIC_DN) { len = n*h->pic_tDof; return h->pic_arr[which]; }
+  if (which == B200_PIC_AD) { len = n*3; return h->pic_arr[6]; }
+  len = n*h->pic_tDof;
+  if (which == B200_PIC_AG) return h->d_Ag;
+  if (which == B200_PIC_YG) return h->d_Yg;
+  if (which == B200_PIC_DG) return h->d_Dg;
+  throw std::runtime_error("pic: unknown array id");
+}
+} // namespace
+
+int b200_pic_init(b200_handle* h, int tDof, int nEq, const b200_pic_eq* eqs, int dFlag, int sstEq)
+{
+  return guarded(h, [&] {
+    if (h->nNo == 0) throw std::runtime_error("pic_init: call b200_lhs_create first");
+    if (tDof < 1 || nEq < 1) throw std::runtime_error("pic_init: tDof and nEq must be positive");
+    for (int i = 0; i < nEq; i++) {
+      if (eqs[i].s < 0 || eqs[i].e < eqs[i].s || eqs[i].e >= tDof) throw std::runtime_error("pic_init: equation rows outside the state");
+      if (eqs[i].kind < 0 || eqs[i].kind > 2) throw std::runtime_error("pic_init: kind must be 0, 1 or 2");
+      if (eqs[i].kind == 1 && eqs[i].e - eqs[i].s != 3) throw std::runtime_error("pic_init: a ustruct / FSI equation has nsd + 1 = 4 unknowns");
+    }
+    auto st = h->ops->st;
+    const size_t n = size_t(h->nNo);
+    for (auto& p : h->pic_arr) { cudaFree(p); p = nullptr; }
+    for (int k = 0; k < 7; k++) {
+      const size_t len = (k == 6) ? n*3 : n*tDof;
+      CU_CHECK(cudaMalloc(&h->pic_arr[k], sizeof(double)*len));
+      CU_CHECK(cudaMemsetAsync(h->pic_arr[k], 0, sizeof(double)*len, st));
+    }
+    h->pic_tDof = tDof; h->pic_dFlag = dFlag; h->pic_sstEq = sstEq;
+    h->pic_eqs.assign(eqs, eqs + nEq);
+    ensure_state(h, tDof);
+    ensure_disp(h, tDof);
+    CU_CHECK(cudaMemsetAsync(h->d_Ag, 0, sizeof(double)*n*tDof, st));
+    CU_CHECK(cudaMemsetAsync(h->d_Yg, 0, sizeof(double)*n*tDof, st));
+    CU_CHECK(cudaMemsetAsync(h->d_Dg, 0, sizeof(double)*n*tDof, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+  });
+}
+
+int b200_pic_set(b200_handle* h, int which, const double* a)
+{
+  return guarded(h, [&] {
+    size_t len = 0;
+    double* d = pic_array(h, which, len);
+    CU_CHECK(cudaMemcpyAsync(d, a, sizeof(double)*len, cudaMemcpyHostToDevice, h->ops->st));
+    CU_CHECK(cudaStreamSynchronize(h->ops->st));
+  });
+}
+
+int b200_pic_get(b200_handle* h, int which, double* a)
+{
+  return guarded(h, [&] {
+    size_t len = 0;
+    double* d = pic_array(h, which, len);
+    CU_CHECK(cudaMemcpyAsync(a, d, sizeof(double)*len, cudaMemcpyDeviceToHost, h->ops->st));
+    CU_CHECK(cudaStreamSynchronize(h->ops->st));
+  });
+}
+
+int b200_pic_scatter(b200_handle* h, int which, int n, const int* idx, const double* val)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    size_t len = 0;
+    double* d = pic_array(h, which, len);
+    if (n <= 0) return;
+    for (int k = 0; k < n; k++) if (idx[k] < 0 || size_t(idx[k]) >= len) throw std::runtime_error("pic_scatter: index outside the array");
+    int* d_idx = upload(idx, size_t(n), ops.st);
+    double* d_val = upload(val, size_t(n), ops.st);
+    k_pic_scatter<<<CudaOps::grid_for(size_t(n), 256, 1), 256, 0, ops.st>>>(n, d_idx, d_val, d); ops.post();
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+    cudaFree(d_idx); cudaFree(d_val);
+  });
+}
+
+int b200_picp(b200_handle* h, double dt)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (h->pic_tDof == 0) throw std::runtime_error("picp: call b200_pic_init first");
+    const int tD = h->pic_tDof;
+    double** A = h->pic_arr;
+    for (const auto& q : h->pic_eqs) {
+      const double coefA = (q.gam - 1.0)/q.gam;                               // pic.cpp:679
+      const double coefD = dt*dt*(0.5*q.gam - q.beta)/(q.gam - 1.0);          // pic.cpp:697,710
+      // displacement predictor (pic.cpp:690-712): 0 Dn = Do, 1 Newmark formula, 2 rows left alone
+      int dmode = 0;
+      if (h->pic_dFlag) {
+        if (!h->pic_sstEq) dmode = 1;
+        else dmode = (q.kind == 1) ? 0 : (q.kind == 0) ? 1 : 2;
+      }
+      const size_t n = size_t(h->nNo)*(q.e - q.s + 1);
+      k_picp<<<CudaOps::grid_for(n, 256), 256, 0, ops.st>>>(h->nNo, tD, q.s, q.e, coefA, dmode, dt, coefD, A[0], A[1], A[2], A[3], A[4], A[5]);
+      ops.post();
+      if (h->pic_dFlag && h->pic_sstEq && q.kind == 1) ops.scal(size_t(h->nNo)*3, coefA, A[6]);      // Ad = Ad*coef, pic.cpp:704
+    }
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+  });
+}
+
+int b200_pici(b200_handle* h)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (h->pic_tDof == 0) throw std::runtime_error("pici: call b200_pic_init first");
+    const int tD = h->pic_tDof;
+    double** A = h->pic_arr;
+    ensure_state(h, tD);
+    ensure_disp(h, tD);
+    for (const auto& q : h->pic_eqs) {
+      const size_t n = size_t(h->nNo)*(q.e - q.s + 1);
+      k_pici<<<CudaOps::grid_for(n, 256), 256, 0, ops.st>>>(h->nNo, tD, q.s, q.e, 1.0 - q.am, q.am, 1.0 - q.af, q.af,
+                                                           A[0], A[3], A[1], A[4], A[2], A[5], h->d_Ag, h->d_Yg, h->d_Dg);
+      ops.post();
+    }
+    // the mesh equation assembles on the step-start configuration x + Do (mesh.cpp:117-122): keep the device Do current
+    if (!h->d_Do) CU_CHECK(cudaMalloc(&h->d_Do, sizeof(double)*h->disp_cap));
+    CU_CHECK(cudaMemcpyAsync(h->d_Do, A[2], sizeof(double)*size_t(h->nNo)*tD, cudaMemcpyDeviceToDevice, ops.st));
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+  });
+}
+
+int b200_picc(b200_handle* h, int iEq, double dt, int first_itr)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (h->pic_tDof == 0) throw std::runtime_error("picc: call b200_pic_init first");
+    if (iEq < 0 || iEq >= int(h->pic_eqs.size())) throw std::runtime_error("picc: no such equation");
+    const auto& q = h->pic_eqs[iEq];
+    const int dof = q.e - q.s + 1;
+    if (!h->R || h->dof != dof) throw std::runtime_error("picc: the device R does not hold a solution of this equation");
+    const int tD = h->pic_tDof;
+    double** A = h->pic_arr;
+    const double c0 = q.gam*dt, c1 = q.beta*dt*dt, c2 = 1.0/q.am, c3 = q.af*c0*c2;      // pic.cpp:107-111
+    const int grid = CudaOps::grid_for(size_t(h->nNo), 256, 1);
+    if (q.kind == 0) {
+      k_picc<<<grid, 256, 0, ops.st>>>(h->nNo, tD, q.s, dof, c0, c1, h->d_map, h->R, A[3], A[4], A[5]); ops.post();
+    } else if (q.kind == 1) {
+      const double amg = (q.gam - q.am)/(q.gam - 1.0);                                   // ustruct.cpp:1746
+      k_picc_ustruct<<<grid, 256, 0, ops.st>>>(h->nNo, tD, q.s, dof, c0, c2, c3, first_itr, amg, h->d_map, h->R, h->d_Yg,
+                                               A[3], A[4], A[5], A[6]);
+      ops.post();
+    }
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+  });
+}
+
+int b200_pic_copy_rows(b200_handle* h, int n, const int* nodes, int s2, int cnt)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (h->pic_tDof == 0) throw std::runtime_error("pic_copy_rows: call b200_pic_init first");
+    if (n <= 0 || cnt <= 0) return;
+    if (s2 < cnt || s2 + cnt > h->pic_tDof) throw std::runtime_error("pic_copy_rows: rows outside the state or overlapping");
+    for (int k = 0; k < n; k++) if (nodes[k] < 0 || nodes[k] >= h->nNo) throw std::runtime_error("pic_copy_rows: node out of range");
+    int* d_nodes = upload(nodes, size_t(n), ops.st);
+    double** A = h->pic_arr;
+    k_pic_copy_rows<<<CudaOps::grid_for(size_t(n)*cnt, 256, 1), 256, 0, ops.st>>>(n, h->pic_tDof, s2, cnt, d_nodes, A[3], A[4], A[5]);
+    ops.post();
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+    cudaFree(d_nodes);
+  });
+}
+
+int b200_pic_advance(b200_handle* h)
+{
+  return guarded(h, [&] {
+    auto st = h->ops->st;
+    if (h->pic_tDof == 0) throw std::runtime_error("pic_advance: call b200_pic_init first");
+    const size_t bytes = sizeof(double)*size_t(h->nNo)*h->pic_tDof;
+    for (int k = 0; k < 3; k++) CU_CHECK(cudaMemcpyAsync(h->pic_arr[k], h->pic_arr[3 + k], bytes, cudaMemcpyDeviceToDevice, st));
+    CU_CHECK(cudaStreamSynchronize(st));
   });
 }
 

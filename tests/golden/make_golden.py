@@ -79,10 +79,9 @@ def main():
         R, Val, _, _, _ = refcase.reference_assemble(P.fluid_block_case(n, elem=elem, **kw))
         out[f"R_{tag}"] = R; out[f"Val_{tag}"] = Val
     for tag, elem, n in (("hex", "hex", 6), ("tet10", "tet10", 3)):
-        for key, ls in (("step", T.LS_TIGHT), ("loose", T.LS_LOOSE)):
-            R, Val, X, o = refcase.reference_step(P.fluid_block_case(n, elem=elem), ls)
-            out[f"X_{key}_{tag}"] = X
-            out[f"info_{key}_{tag}"] = np.array([o["suc"], o["itr"], o["iNorm"], o["fNorm"]])
+        R, Val, X, o = refcase.reference_step(P.fluid_block_case(n, elem=elem), T.LS_STEP)
+        out[f"X_step_{tag}"] = X
+        out[f"info_step_{tag}"] = np.array([o["suc"], o["itr"], o["iNorm"], o["fNorm"]])
     R, Val, _ = refcase.reference_assemble_fsi(P.fsi_block_case(4, elem="hex"))
     out["R_fsi_hex"] = R; out["Val_fsi_hex"] = Val
     np.savez_compressed(os.path.join(HERE, "fluid_block.npz"), **out)
