@@ -114,7 +114,7 @@ int b200_face_set(b200_handle* h, int faIn, int nNo, int dof, int bGrp, const in
 
 /* ---- assembly (replaces construct_fluid + do_assem, solver/fluid.cpp:464, lhsa.cpp:97) ------- */
 /* IEN(eNoN,nEl) with assembly node ids, x(3,nNo).  eNoN = 4 (TET4), 8 (HEX8, the reference's node
- * order, nn_elem_gnn.h:732) or 10 (TET10, nn_elem_gnn.h:1256; fluid equation only).  qmTET4 <= 0 selects the
+ * order, nn_elem_gnn.h:732) or 10 (TET10, nn_elem_gnn.h:1256; every equation but FSI).  qmTET4 <= 0 selects the
  * default (5+3*sqrt(5))/20 (solver/ComMod.h:1011). */
 int b200_mesh_set(b200_handle* h, int eNoN, int nEl, const int* IEN, const double* x, double qmTET4);
 /* ls_alloc contract (solver/ls.cpp:51-60): after it R(dof,nNo) and Val(dof*dof,nnz) are zero. */
@@ -134,7 +134,7 @@ int b200_assemble_struct(b200_handle* h, const b200_struct_props* p);
 /* ... and construct_l_elas / construct_mesh + l_elas_3d (solver/l_elas.cpp:58,274; mesh.cpp:42). */
 int b200_assemble_lelas(b200_handle* h, const b200_lelas_props* p);
 /* ustruct equation (dof 4; b200_zero(h,4) first): replaces construct_usolid + ustruct_3d_m/c + ustruct_do_assem
- * (solver/ustruct.cpp:216,1158,632,1579) for equal-order TET4/HEX8 with idMap = identity; also fills the device
+ * (solver/ustruct.cpp:216,1158,632,1579) for equal-order TET4/HEX8/TET10 with idMap = identity; also fills the device
  * copy of com_mod.Kd(12,nnz). */
 int b200_assemble_ustruct(b200_handle* h, const b200_ustruct_props* p);
 /* ustruct_r (solver/ustruct.cpp:1726): R -= ami * Kd * (amg*Ad - Yg(s:s+2)) + overlap add; the caller invokes it on

@@ -338,7 +338,7 @@ void assemble_solid(b200_handle* h, const SolidConsts& c, const char* who)
     CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*72.0 + double(h->nNo)*(24.0 + 24.0 + 24.0*3 + 24.0) + double(h->nEl)*4.0*h->eNoN, 3);
     if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 3>(h, c, h->nEl, nullptr);
     else if (h->eNoN == 8) launch_solid<8, 8, 16, 2, 3>(h, c, h->nEl, nullptr);
-    else throw std::runtime_error(std::string(who) + ": the solid kernels are built for TET4 and HEX8 meshes");
+    else launch_solid<10, 15, 8, 2, 3>(h, c, h->nEl, nullptr);       // TET10: 15 Gauss points, gnn per point
   }
   finish_assembly(h, 3, t0, who);
 }
@@ -770,7 +770,8 @@ int b200_assemble_ustruct(b200_handle* h, const b200_ustruct_props* p)
     {
       CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*(128.0 + 96.0) + double(h->nNo)*(32.0 + 24.0 + 24.0*h->tDof + 24.0) + double(h->nEl)*4.0*h->eNoN, 4);
       if (h->eNoN == 4) launch_ustruct<4, 4, 16, 1>(h, c);
-      else launch_ustruct<8, 8, 8, 2>(h, c);
+      else if (h->eNoN == 8) launch_ustruct<8, 8, 8, 2>(h, c);
+      else launch_ustruct<10, 15, 4, 2>(h, c);                         // TET10, one function space
       // Kd is rebuilt (assigned) by every assembly: ls_alloc zeroes com_mod.Kd too (ls.cpp:51-60)
       const size_t tK = size_t(h->nnz)*12;
       k_sum_run<true><<<unsigned((tK + 255)/256), 256, 0, ops.st>>>(size_t(h->nnz), 12, h->d_kseg, h->stageKd, h->Kd);

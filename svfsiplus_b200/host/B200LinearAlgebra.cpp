@@ -295,13 +295,13 @@ bool B200LinearAlgebra::assemble_fsi_mesh(ComMod& com_mod, const mshType& lM, co
   return true;
 }
 
-/// ustruct (construct_usolid, ustruct.cpp:216) on equal-order TET4 / HEX8 with idMap = identity.
+/// ustruct (construct_usolid, ustruct.cpp:216) on equal-order TET4 / HEX8 / TET10 with idMap = identity.
 bool B200LinearAlgebra::assemble_ustruct_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag,
     const Array<double>& Yg, const Array<double>& Dg, const CepMod* cep_mod)
 {
   using namespace consts;
   auto& eq = com_mod.eq[com_mod.cEq];
-  if ((lM.eType != ElementType::TET4 && lM.eType != ElementType::HEX8) || com_mod.dof != 4) return false;
+  if ((lM.eType != ElementType::TET4 && lM.eType != ElementType::HEX8 && lM.eType != ElementType::TET10) || com_mod.dof != 4) return false;
   if (cep_mod && (cep_mod->cem.cpld || cep_mod->cem.aStress || cep_mod->cem.aStrain)) return false;
   for (int a = 0; a < com_mod.tnNo; a++) if (com_mod.idMap(a) != a) return false;      // undeformed-Neumann faces
   const auto& dmn = eq.dmn[0];
@@ -359,7 +359,7 @@ bool B200LinearAlgebra::assemble_solid_mesh(ComMod& com_mod, const mshType& lM, 
 {
   using namespace consts;
   auto& eq = com_mod.eq[com_mod.cEq];
-  if ((lM.eType != ElementType::TET4 && lM.eType != ElementType::HEX8) || com_mod.dof != 3) return false;
+  if ((lM.eType != ElementType::TET4 && lM.eType != ElementType::HEX8 && lM.eType != ElementType::TET10) || com_mod.dof != 3) return false;
   if (com_mod.pS0.size() != 0 || com_mod.pstEq) return false;
   if (cep_mod && (cep_mod->cem.cpld || cep_mod->cem.aStress || cep_mod->cem.aStrain)) return false;
   const auto& dmn = eq.dmn[0];

@@ -85,6 +85,18 @@ def main():
     R, Val, _ = refcase.reference_assemble_fsi(P.fsi_block_case(4, elem="hex"))
     out["R_fsi_hex"] = R; out["Val_fsi_hex"] = Val
     np.savez_compressed(os.path.join(HERE, "fluid_block.npz"), **out)
+    # solid equations on curved TET10 (15 Gauss points)
+    import test_tet10_solids as T10
+    out = {}
+    for kind, iso, vol in T10.SOLID:
+        R, Val, _, _, _, _ = refcase.reference_assemble_solid(T10._solid_case(kind, iso, vol))
+        out[f"R_{kind}_{iso}_{vol}"] = R; out[f"Val_{kind}_{iso}_{vol}"] = Val
+    for iso in ("nHook", "HO"):
+        c = P.ustruct_case(2, elem="tet10", iso=iso)
+        R, Val, Kd, _ = refcase.reference_assemble_ustruct(c, with_r=False)
+        Rr, _, _, _ = refcase.reference_assemble_ustruct(c, with_r=True)
+        out[f"uR_{iso}"] = R; out[f"uVal_{iso}"] = Val; out[f"uKd_{iso}"] = Kd; out[f"uRr_{iso}"] = Rr
+    np.savez_compressed(os.path.join(HERE, "block_tet10.npz"), **out)
     print("golden fixtures written")
 
 

@@ -1,0 +1,54 @@
+"""Displacement-based and mixed solid equations on quadratic tetrahedra (TET10, 15 Gauss points, curved edges): the K11
+kernels k_assemble_solid / k_assemble_ustruct instantiated for 10 nodes, through the C ABI, against the compiled reference
+(construct_dsolid, construct_l_elas, construct_mesh, construct_usolid on the same mesh) at 1e-12."""
+import numpy as np
+import pytest
+
+from conftest import needs_ref
+from util import golden, rel_inf
+
+from svfsiplus_b200 import problem as P
+
+TOL_ASM = 1e-12
+SOLID = [("struct", "nHook", "ST91"), ("struct", "HO", "ST91"), ("struct", "mStVK", None), ("lelas", None, None), ("mesh", None, None)]
+
+
+def _solid_case(kind, iso, vol):
+    return P.block_case(2, elem="tet10", kind=kind, iso=iso or "nHook", vol=vol)
+
+
+@needs_ref
+def test_oracle_reproduces_tet10_fixtures():
+    from oracle import refcase
+    g = golden("block_tet10.npz")
+    for kind, iso, vol in SOLID:
+        R, Val, _, _, _, _ = refcase.reference_assemble_solid(_solid_case(kind, iso, vol))
+        assert np.array_equal(R, g[f"R_{kind}_{iso}_{vol}"]) and np.array_equal(Val, g[f"Val_{kind}_{iso}_{vol}"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,iso,vol", SOLID)
+def test_tet10_solid_assembly_matches_golden(kind, iso, vol):
+    g = golden("block_tet10.npz")
+    case = _solid_case(kind, iso, vol)
+    be = P.setup_backend(case)
+    P.assemble_solid(be, case)
+    assert rel_inf(be.get_R(), g[f"R_{kind}_{iso}_{vol}"]) < TOL_ASM
+    assert rel_inf(be.get_Val(), g[f"Val_{kind}_{iso}_{vol}"]) < TOL_ASM
+    be.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("iso", ["nHook", "HO"])
+def test_tet10_ustruct_assembly_matches_golden(iso):
+    """construct_usolid + ustruct_do_assem (R, Val, Kd) and ustruct_r on equal-order TET10."""
+    g = golden("block_tet10.npz")
+    case = P.ustruct_case(2, elem="tet10", iso=iso)
+    be = P.setup_backend(case)
+    P.assemble_ustruct(be, case)
+    assert rel_inf(be.get_R(), g[f"uR_{iso}"]) < TOL_ASM
+    assert rel_inf(be.get_Val(), g[f"uVal_{iso}"]) < TOL_ASM
+    assert rel_inf(be.get_Kd(), g[f"uKd_{iso}"]) < TOL_ASM
+    P.assemble_ustruct(be, case, upload=False, with_r=True)
+    assert rel_inf(be.get_R(), g[f"uRr_{iso}"]) < TOL_ASM
+    be.close()
