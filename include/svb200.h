@@ -150,6 +150,18 @@ int b200_mesh_domains(b200_handle* h, int nDmn, const int* elem_dmn);
 /* dmn_kind[d]: 0 fluid (fluid_3d_m/c on the ALE configuration x + Dg(4:6), mvMsh), 1 struct (struct_3d into the
  * 3x3 corner of the dof-4 blocks).  fluid[d] / solid[d] are read for the domains of that kind (dof 4; TET4, HEX8). */
 int b200_assemble_fsi(b200_handle* h, int nDmn, const int* dmn_kind, const b200_fluid_props* fluid, const b200_struct_props* solid);
+/* Boundary-face (Neumann) assembly on the device: replaces b_assem_neu_bc + gnnb + b_fluid / b_l_elas
+ * (solver/eq_assem.cpp:58-170, nn.cpp:552-755, fluid.cpp:46-133, l_elas.cpp:48-59) and with them the per-element
+ * LinearAlgebra::assemble calls of set_bc_neu_l.  b200_face_mesh_set: lFa.IEN(eNoNb,nElb) with assembly node ids and
+ * lFa.gE(nElb) (parent element of every face element), eNoNb = 3 (TRI3), 4 (QUD4) or 6 (TRI6), uploaded once per face
+ * (index faIn as in b200_face_set).  b200_assemble_bneu adds the face's contribution to the device R / Val AFTER the
+ * volume assembly, face elements in order (do_assem's order): kind 0 = b_fluid (traction h n + backflow stabilisation,
+ * residual + tangent; dof 4), kind 1 = b_l_elas (traction, residual only; dof 3 or 4).  hg(nNo): the nodal Neumann
+ * values set_bc_neu_l passes (read on the face nodes only); the velocity comes from the device Yg (b200_state_set /
+ * b200_pici), the moving-mesh geometry from Do (b200_disp_set). */
+typedef struct { double dt, af, gam; int tDof, mvMsh; double rho, bfs; } b200_bneu_props;
+int b200_face_mesh_set(b200_handle* h, int faIn, int eNoNb, int nElb, const int* IENb, const int* gE);
+int b200_assemble_bneu(b200_handle* h, int faIn, int kind, const b200_bneu_props* p, const double* hg);
 /* LinearAlgebra::assemble for the few boundary-face elements: staged on the host, flushed by one
  * scatter kernel before the next get/solve.  eqN(d), lK(dof*dof,d,d), lR(dof,d). */
 int b200_assemble_elem(b200_handle* h, int d, const int* eqN, const double* lK, const double* lR);

@@ -45,6 +45,8 @@ def dropin_lib():
         L.ref_asm_destroy.argtypes = [C.c_void_p]
         L.ref_dropin_fluid_step.argtypes = ([C.c_void_p, C.c_int, C.c_int] + [C.c_double] * 5 + [C.c_void_p, C.c_double]
                                             + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 8)
+        L.ref_dropin_fluid_face_step.argtypes = ([C.c_void_p, C.c_int, C.c_int] + [C.c_double] * 6 + [C.c_void_p] * 4 + [C.c_int]
+                                                 + [C.c_void_p] * 3 + [C.c_int, C.c_int] + [C.c_void_p] * 8)
         L.ref_dropin_solid_step.argtypes = ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 6 + [C.c_int]
                                             + [C.c_void_p] * 8)
         _dropin = L
@@ -83,6 +85,37 @@ def dropin_solid_step(case, ls, mode):
     finally:
         L.ref_asm_destroy(h)
     keys = ("suc", "itr", "iNorm", "fNorm", "GM_itr", "CG_itr", "Resm", "Resc", "device_assembly")
+    return X, dict(zip(keys, out))
+
+
+def dropin_fluid_face_step(case, ls, mode, IENb, gE, hg, bfs=0.2):
+    """dropin_fluid_step with one Neumann face assembled after the volume (set_bc_neu_l hook).  info["face_on_device"]."""
+    L = dropin_lib()
+    m = case["mesh"]
+    x = _c(m.x, np.float64); ien = _c(m.ien, np.int32)
+    h = L.ref_asm_create(m.nNo, m.nEl, ien.shape[1], _p(ien), _p(x), 1, -1.0)
+    if not h:
+        raise RuntimeError(L.ref_last_error().decode())
+    try:
+        p = case["props"]
+        Ag = _c(case["Ag"], np.float64); Yg = _c(case["Yg"], np.float64); Bf = _c(case["Bf"], np.float64)
+        visc = np.array([0, p["mu"], 0.0, 0.0, 0.0, 0.0], np.float64)
+        faces = case["faces"]
+        f_info = np.array([[len(f["nodes"]), f["dof"], f["bGrp"]] for f in faces], np.int32).reshape(-1)
+        f_nodes = np.concatenate([np.asarray(f["nodes"], np.int32) for f in faces])
+        f_val = np.concatenate([np.asarray(f["val"], np.float64).reshape(-1) for f in faces])
+        X = np.empty((m.nNo, 4)); out = np.zeros(10)
+        ls = _c(ls, np.float64)
+        incL = _c(case["incL"], np.int32); res = _c(case["res"], np.float64)
+        IENb = _c(IENb, np.int32); gE = _c(gE, np.int32); hg = _c(hg, np.float64)
+        rc = L.ref_dropin_fluid_face_step(h, int(mode), Ag.shape[1], p["dt"], p["am"], p["af"], p["gam"], p["rho"], bfs, _p(visc),
+                                          _p(Ag), _p(Yg), _p(Bf), len(faces), _p(f_info), _p(f_nodes), _p(f_val),
+                                          IENb.shape[1], IENb.shape[0], _p(IENb), _p(gE), _p(hg), _p(ls), _p(incL), _p(res), _p(X), _p(out))
+        if rc != 0:
+            raise RuntimeError(L.ref_last_error().decode())
+    finally:
+        L.ref_asm_destroy(h)
+    keys = ("suc", "itr", "iNorm", "fNorm", "GM_itr", "CG_itr", "Resm", "Resc", "device_assembly", "face_on_device")
     return X, dict(zip(keys, out))
 
 
@@ -153,6 +186,7 @@ def lib():
                                       C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_ranks_spmv.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_ranks_commuv.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_asm_bneu.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
         L.ref_pic.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_double] + [C.c_void_p] * 12
         _lib = L
     return _lib
@@ -219,6 +253,20 @@ class RefAssembly:
             raise RuntimeError(lib().ref_last_error().decode())
         return R, Val, t
 
+
+    def bneu(self, kind, IENb, gE, hg, Yg, *, dt, af, gam, rho=0.0, bfs=0.0, mvMsh=False, Do=None):
+        """b_assem_neu_bc (S/eq_assem.cpp:58) on one face: kind "fluid" (b_fluid, dof 4) or "solid" (b_l_elas, dof 3).
+        Returns the face's contribution alone: R (nNo,dof), Val (nnz,dof*dof)."""
+        IENb = _c(IENb, np.int32); gE = _c(gE, np.int32); hg = _c(hg, np.float64); Yg = _c(Yg, np.float64)
+        Do = None if Do is None else _c(Do, np.float64)
+        dof = 4 if kind == "fluid" else 3
+        par = np.array([dt, af, gam, rho, bfs, Yg.shape[1], int(mvMsh)], np.float64)
+        R = np.empty((self.nNo, dof)); Val = np.empty((self.nnz, dof * dof))
+        rc = lib().ref_asm_bneu(self.h, 0 if kind == "fluid" else 1, IENb.shape[1], IENb.shape[0], _p(IENb), _p(gE), _p(par), _p(hg),
+                                _p(Yg), _p(Do), _p(R), _p(Val))
+        if rc != 0:
+            raise RuntimeError(lib().ref_last_error().decode())
+        return R, Val
 
     ISO = {"nHook": 0, "StVK": 1, "mStVK": 2, "HO": 3}
     HO_KEYS = ("a", "b", "aff", "bff", "ass", "bss", "afs", "bfs", "khs")

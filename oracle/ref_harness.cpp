@@ -14,6 +14,7 @@
 //   fsils_solve                   Code/Source/liner_solver/solve.cpp:50
 //   fsils_spar_mul_vv / commuv    Code/Source/liner_solver/spar_mul.cpp:191, in_commu.cpp:111
 //   pic::picp / pici / picc       Code/Source/solver/pic.cpp:591, 486, 74
+//   nn::select_eleb, eq_assem::b_assem_neu_bc   Code/Source/solver/nn.cpp:997, eq_assem.cpp:58
 //
 // Nothing in the product (svfsiplus_b200/) links or loads this file; only tests/, smoke() and
 // bench.py's cpu_baseline / --impl reference legs do.
@@ -38,6 +39,7 @@
 #include "lhs.h"
 #include "ls.h"
 #include "pic.h"
+#include "eq_assem.h"
 #ifdef WITH_B200_DROPIN
 #include "B200LinearAlgebra.h"
 #endif
@@ -45,6 +47,7 @@
 #include "mpi.h"
 
 #include <chrono>
+#include <functional>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -728,7 +731,8 @@ template <class HostAssembly>
 void dropin_newton_iteration(AsmCtx* ctx, int dof, int mode, int tDof, const double* Ag, const double* Yg, const double* Dg,
                              int nFaces, const int* f_info, const int* f_nodes, const double* f_val,
                              const double* ls, const int* incL, const double* res, double* X, double* out,
-                             HostAssembly&& host_assembly)
+                             HostAssembly&& host_assembly,
+                             const std::function<void(B200LinearAlgebra*, Array<double>&)>& after_assembly = nullptr)
 {
   using namespace consts;
   auto& com_mod = ctx->sim->com_mod;
@@ -773,6 +777,7 @@ void dropin_newton_iteration(AsmCtx* ctx, int dof, int mode, int tDof, const dou
   ls_ns::ls_alloc(com_mod, eq);
   bool on_device = la->assemble_mesh(com_mod, com_mod.msh[0], Ag_a, Yg_a, Dg_a, &ctx->sim->cep_mod);   // the global_eq_assem hook
   if (!on_device) host_assembly(Ag_a, Yg_a, Dg_a);
+  if (after_assembly) after_assembly(la, Yg_a);        // set_bc_neu (main.cpp:478) with the set_bc_neu_l hook
   Vector<int> incL_v(nFaces);
   Vector<double> res_v(nFaces);
   for (int i = 0; i < nFaces; i++) { incL_v(i) = incL ? incL[i] : 1; res_v(i) = res ? res[i] : 0.0; }
@@ -803,6 +808,50 @@ int ref_dropin_fluid_step(void* h, int mode, int tDof, double dt, double am, dou
     configure_fluid(ctx, tDof, 0, dt, am, af, gam, rho, f, Kinv_darcy, visc, Bf);
     dropin_newton_iteration(ctx, 4, mode, tDof, Ag, Yg, nullptr, nFaces, f_info, f_nodes, f_val, ls, incL, res, X, out,
                             [&](Array<double>& A, Array<double>& Y, Array<double>&) { fluid::construct_fluid(com_mod, com_mod.msh[0], A, Y); });
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+// Fluid step with one Neumann face (lFa.IEN, lFa.gE, nodal values hg) assembled after the volume: through
+// B200LinearAlgebra::assemble_face when it takes the face, else through the reference's b_assem_neu_bc + assemble().
+// out[8]: device volume assembly, out[9] (when out has 10 entries): 1 if the face went to the device.
+int ref_dropin_fluid_face_step(void* h, int mode, int tDof, double dt, double am, double af, double gam, double rho, double bfs,
+                               const double* visc, const double* Ag, const double* Yg, const double* Bf,
+                               int nFaces, const int* f_info, const int* f_nodes, const double* f_val,
+                               int eNoNb, int nElb, const int* IENb, const int* gE, const double* hg,
+                               const double* ls, const int* incL, const double* res, double* X, double* out)
+{
+  try {
+    mpistub_set_world(1);
+    mpistub_bind_rank(0);
+    auto ctx = static_cast<AsmCtx*>(h);
+    auto& com_mod = ctx->sim->com_mod;
+    const double f[3] = {0.0, 0.0, 0.0};
+    configure_fluid(ctx, tDof, 0, dt, am, af, gam, rho, f, 0.0, visc, Bf);
+    com_mod.eq[0].dmn[0].prop[consts::PhysicalProperyType::backflow_stab] = bfs;
+    auto& msh = com_mod.msh[0];
+    msh.nFa = 1;
+    msh.fa.resize(1);
+    auto& fa = msh.fa[0];
+    fa.name = "face"; fa.iM = 0; fa.eNoN = eNoNb; fa.nEl = nElb;
+    fa.IEN.resize(eNoNb, nElb);
+    std::memcpy(fa.IEN.data(), IENb, sizeof(int)*size_t(eNoNb)*nElb);
+    fa.gE.resize(nElb);
+    std::memcpy(fa.gE.data(), gE, sizeof(int)*size_t(nElb));
+    nn::select_eleb(ctx->sim.get(), msh, fa);
+    Vector<double> hg_v(com_mod.tnNo);
+    std::memcpy(hg_v.data(), hg, sizeof(double)*size_t(com_mod.tnNo));
+    double face_on_device = 0.0;
+    dropin_newton_iteration(ctx, 4, mode, tDof, Ag, Yg, nullptr, nFaces, f_info, f_nodes, f_val, ls, incL, res, X, out,
+                            [&](Array<double>& A, Array<double>& Y, Array<double>&) { fluid::construct_fluid(com_mod, com_mod.msh[0], A, Y); },
+                            [&](B200LinearAlgebra* la, Array<double>& Y) {
+                              if (la->assemble_face(com_mod, fa, hg_v, Y)) face_on_device = 1.0;
+                              else eq_assem::b_assem_neu_bc(com_mod, fa, hg_v, Y);
+                            });
+    out[9] = face_on_device;
     return 0;
   } catch (const std::exception& e) {
     g_err = e.what();
@@ -896,6 +945,78 @@ int ref_pic(int op, int tnNo, int tDof, int nEq, int cEq, const double* eqpar, i
     auto store = [&](double* dst, const Array<double>& A) { if (dst) std::memcpy(dst, A.data(), sizeof(double)*A.size()); };
     store(An, com_mod.An); store(Yn, com_mod.Yn); store(Dn, com_mod.Dn); store(Ad, com_mod.Ad);
     store(Ag, Ag_a); store(Yg, Yg_a); store(Dg, Dg_a);
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+} // extern "C"
+
+// ----------------------------------------------------------------------------------------------
+// Boundary-face (Neumann) assembly: the reference's b_assem_neu_bc (+ gnnb, b_fluid / b_l_elas) on one face.
+// ----------------------------------------------------------------------------------------------
+extern "C" {
+
+// kind 0: fluid equation (dof 4, b_fluid), 1: struct equation (dof 3, b_l_elas).
+// par = {dt, af, gam, rho, bfs, tDof, mvMsh}.  IENb(eNoNb,nElb), gE(nElb); hg(nNo); Yg, Do (tDof,nNo; Do may be NULL).
+// Outputs the face's contribution alone: R (dof,nNo), Val (dof*dof,nnz).
+int ref_asm_bneu(void* h, int kind, int eNoNb, int nElb, const int* IENb, const int* gE, const double* par, const double* hg,
+                 const double* Yg, const double* Do, double* R, double* Val)
+{
+  try {
+    using namespace consts;
+    auto ctx = static_cast<AsmCtx*>(h);
+    auto& com_mod = ctx->sim->com_mod;
+    const int nNo = com_mod.tnNo;
+    const int tDof = int(par[5]);
+    const int dof = (kind == 0) ? 4 : 3;
+    if (kind == 0) {
+      const double f[3] = {0.0, 0.0, 0.0};
+      const double visc[6] = {0.0, 0.04, 0.0, 0.0, 0.0, 0.0};
+      std::vector<double> Bf(size_t(3)*nNo, 0.0);
+      configure_fluid(ctx, tDof, int(par[6]), par[0], 1.0, par[1], par[2], par[3], f, 0.0, visc, Bf.data());
+      com_mod.eq[0].dmn[0].prop[PhysicalProperyType::backflow_stab] = par[4];
+    } else {
+      com_mod.tDof = tDof; com_mod.dof = dof; com_mod.dt = par[0]; com_mod.mvMsh = false;
+      com_mod.cEq = 0; com_mod.nEq = 1;
+      if (com_mod.eq.size() != 1) com_mod.eq.resize(1);
+      auto& eq = com_mod.eq[0];
+      eq.phys = EquationType::phys_struct; eq.dof = dof; eq.s = 0; eq.e = dof - 1; eq.af = par[1]; eq.gam = par[2];
+      eq.nDmn = 1;
+      if (eq.dmn.size() != 1) eq.dmn.resize(1);
+      eq.dmn[0].Id = -1;
+      eq.dmn[0].phys = EquationType::phys_struct;
+    }
+    auto& eq = com_mod.eq[0];
+    if (!eq.linear_algebra) eq.linear_algebra = new FsilsLinearAlgebra();
+    auto& msh = com_mod.msh[0];
+    msh.nFa = 1;
+    msh.fa.resize(1);
+    auto& fa = msh.fa[0];
+    fa.name = "face";
+    fa.iM = 0;
+    fa.eNoN = eNoNb;
+    fa.nEl = nElb;
+    fa.IEN.resize(eNoNb, nElb);
+    std::memcpy(fa.IEN.data(), IENb, sizeof(int)*size_t(eNoNb)*nElb);
+    fa.gE.resize(nElb);
+    std::memcpy(fa.gE.data(), gE, sizeof(int)*size_t(nElb));
+    nn::select_eleb(ctx->sim.get(), msh, fa);
+    if (Do) {
+      com_mod.Do.resize(tDof, nNo);
+      std::memcpy(com_mod.Do.data(), Do, sizeof(double)*size_t(tDof)*nNo);
+    }
+    Vector<double> hg_v(nNo);
+    std::memcpy(hg_v.data(), hg, sizeof(double)*size_t(nNo));
+    Array<double> Yg_a(tDof, nNo);
+    std::memcpy(Yg_a.data(), Yg, sizeof(double)*size_t(tDof)*nNo);
+    com_mod.R.resize(dof, nNo);
+    eq.linear_algebra->alloc(com_mod, eq);
+    eq_assem::b_assem_neu_bc(com_mod, fa, hg_v, Yg_a);
+    std::memcpy(R, com_mod.R.data(), sizeof(double)*size_t(dof)*nNo);
+    std::memcpy(Val, com_mod.Val.data(), sizeof(double)*size_t(dof)*dof*ctx->nnz);
     return 0;
   } catch (const std::exception& e) {
     g_err = e.what();

@@ -69,6 +69,11 @@ class UstructProps(C.Structure):
                 ("bss", C.c_double), ("afs", C.c_double), ("bfs", C.c_double), ("khs", C.c_double)]
 
 
+class BneuProps(C.Structure):
+    _fields_ = [("dt", C.c_double), ("af", C.c_double), ("gam", C.c_double), ("tDof", C.c_int), ("mvMsh", C.c_int),
+                ("rho", C.c_double), ("bfs", C.c_double)]
+
+
 class PicEq(C.Structure):
     _fields_ = [("s", C.c_int), ("e", C.c_int), ("am", C.c_double), ("af", C.c_double), ("gam", C.c_double),
                 ("beta", C.c_double), ("kind", C.c_int)]
@@ -88,7 +93,7 @@ EXPORTS = [
     "b200_spmv", "b200_op_bench", "b200_launch_count", "b200_last_timings", "b200_profile", "b200_profile_read",
     "b200_timer",
     "b200_pic_init", "b200_pic_set", "b200_pic_get", "b200_pic_scatter", "b200_picp", "b200_pici", "b200_picc",
-    "b200_pic_copy_rows", "b200_pic_advance",
+    "b200_pic_copy_rows", "b200_pic_advance", "b200_face_mesh_set", "b200_assemble_bneu",
 ]
 
 KERNEL_CLASSES = ["spmv_vv4", "spmv_vv3", "spmv_ss", "spmv_sv", "spmv_vs", "multi_dot", "cgs_update_scale", "blas1",
@@ -154,6 +159,8 @@ def lib():
         L.b200_picc.argtypes = [vp, ci, cd, ci]
         L.b200_pic_copy_rows.argtypes = [vp, ci, vp, ci, ci]
         L.b200_pic_advance.argtypes = [vp]
+        L.b200_face_mesh_set.argtypes = [vp, ci, ci, ci, vp, vp]
+        L.b200_assemble_bneu.argtypes = [vp, ci, ci, C.POINTER(BneuProps), vp]
         _lib = L
     return _lib
 
@@ -404,6 +411,18 @@ class Backend:
                                    _p(incL_a), _p(res_a), _p(X), C.byref(o)), "b200_solve")
         info = dict(RI=sub_out_dict(o.RI), GM=sub_out_dict(o.GM), CG=sub_out_dict(o.CG), Resm=o.Resm, Resc=o.Resc)
         return X, info
+
+    # -- boundary-face (Neumann) assembly (b_assem_neu_bc) ---------------------------------------------
+    def face_mesh_set(self, faIn, IENb, gE):
+        IENb = _c(IENb, np.int32); gE = _c(gE, np.int32)
+        self._ck(self.L.b200_face_mesh_set(self.h, faIn, IENb.shape[1], IENb.shape[0], _p(IENb), _p(gE)), "b200_face_mesh_set")
+
+    def assemble_bneu(self, faIn, kind, hg, *, dt=0.0, af=0.0, gam=0.0, tDof=4, mvMsh=False, rho=0.0, bfs=0.0):
+        """kind "fluid" (b_fluid) or "solid" (b_l_elas); hg: nodal Neumann values (nNo,)."""
+        p = BneuProps()
+        p.dt, p.af, p.gam, p.tDof, p.mvMsh, p.rho, p.bfs = dt, af, gam, tDof, int(mvMsh), rho, bfs
+        hg = _c(hg, np.float64)
+        self._ck(self.L.b200_assemble_bneu(self.h, faIn, {"fluid": 0, "solid": 1}[kind], C.byref(p), _p(hg)), "b200_assemble_bneu")
 
     # -- time integrator on the device (pic::picp / pici / picc) ---------------------------------------
     def pic_init(self, tDof, eqs, dFlag=False, sstEq=False):

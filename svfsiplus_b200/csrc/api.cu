@@ -16,6 +16,7 @@
 #include "assembly_ustruct.cuh"
 #include "assembly_fluid_gen.cuh"
 #include "pic.cuh"
+#include "assembly_face.cuh"
 #include "ops_cuda.cuh"
 
 using namespace svb200;
@@ -77,6 +78,22 @@ struct b200_handle {
   double* d_Do = nullptr;
   size_t state_cap = 0, disp_cap = 0;
 
+  // boundary-face meshes (assembly_face.cuh), indexed like lhs.face[]
+  struct FaceMesh {
+    int eNoNb = 0, nElb = 0, nUR = 0, nUK = 0;
+    int *ienb = nullptr, *inode = nullptr, *rslot = nullptr, *kslot = nullptr;
+    int *udestR = nullptr, *usegR = nullptr, *udestK = nullptr, *usegK = nullptr;
+    double *tab = nullptr, *stageR = nullptr, *stageT = nullptr, *hg = nullptr;
+    std::vector<int> nodes;          // unique face nodes (assembly ids), for the compact upload of hg
+    void release()
+    {
+      cudaFree(ienb); cudaFree(inode); cudaFree(rslot); cudaFree(kslot); cudaFree(udestR); cudaFree(usegR); cudaFree(udestK);
+      cudaFree(usegK); cudaFree(tab); cudaFree(stageR); cudaFree(stageT); cudaFree(hg);
+      *this = FaceMesh();
+    }
+  };
+  std::vector<FaceMesh> fmesh;
+
   // time integrator (pic.cuh): Ao Yo Do An Yn Dn (tDof x nNo) and Ad (3 x nNo), assembly order
   double* pic_arr[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int pic_tDof = 0, pic_dFlag = 0, pic_sstEq = 0;
@@ -97,6 +114,7 @@ struct b200_handle {
     for (auto p : d_dmn_elems) cudaFree(p);
     cudaFree(Kd); cudaFree(stageKd); cudaFree(d_fN);
     for (auto p : pic_arr) cudaFree(p);
+    for (auto& f : fmesh) f.release();
   }
 };
 
@@ -1008,6 +1026,158 @@ int b200_commu_R(b200_handle* h)
     flush_staged(h);
     h->ops->halo_add(h->dof, h->R);
     CU_CHECK(cudaStreamSynchronize(h->ops->st));
+  });
+}
+
+// ---- boundary-face (Neumann) assembly on the device (assembly_face.cuh) -----------------------------------------------
+extern "C++" {
+namespace {
+// compact ordered-run structure of a face: items keyed by destination, runs in item (= face element) order
+void face_runs(const std::vector<int>& key, std::vector<int>& slot, std::vector<int>& udest, std::vector<int>& useg)
+{
+  const size_t n = key.size();
+  std::vector<int> order(n);
+  for (size_t i = 0; i < n; i++) order[i] = int(i);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+  slot.assign(n, 0); udest.clear(); useg.clear();
+  for (size_t q = 0; q < n; q++) {
+    const int it = order[q];
+    if (q == 0 || key[it] != key[order[q - 1]]) { udest.push_back(key[it]); useg.push_back(int(q)); }
+    slot[it] = int(q);
+  }
+  useg.push_back(int(n));
+}
+
+template <int NB, int NG>
+void launch_bneu(b200_handle* h, b200_handle::FaceMesh& f, const BneuConsts& c)
+{
+  auto& ops = *h->ops;
+  k_bneu_elem<NB, NG><<<(f.nElb + 127)/128, 128, 0, ops.st>>>(f.nElb, c, f.tab, f.ienb, f.inode, f.rslot, f.kslot, h->d_x, h->d_Do, f.hg,
+                                                             h->d_Yg, f.stageR, f.stageT);
+  CU_CHECK(cudaGetLastError());
+  ops.post();
+}
+} // namespace
+} // extern "C++"
+
+int b200_face_mesh_set(b200_handle* h, int faIn, int eNoNb, int nElb, const int* IENb, const int* gE)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (h->nEl == 0) throw std::runtime_error("face_mesh_set: call b200_mesh_set first");
+    if (faIn < 0) throw std::runtime_error("face_mesh_set: negative face index");
+    if (!face_supported(eNoNb)) throw std::runtime_error("face_mesh_set: face element type not supported (TRI3, QUD4 and TRI6 are)");
+    if (nElb < 0) throw std::runtime_error("face_mesh_set: negative element count");
+    if (faIn >= int(h->fmesh.size())) h->fmesh.resize(faIn + 1);
+    auto& f = h->fmesh[faIn];
+    f.release();
+    f.eNoNb = eNoNb; f.nElb = nElb;
+    if (nElb == 0) return;
+    const int eNoN = h->eNoN;
+    for (int e = 0; e < nElb; e++) {
+      if (gE[e] < 0 || gE[e] >= h->nEl) throw std::runtime_error("face_mesh_set: gE entry outside the mesh");
+      for (int a = 0; a < eNoNb; a++)
+        if (IENb[size_t(e)*eNoNb + a] < 0 || IENb[size_t(e)*eNoNb + a] >= h->nNo) throw std::runtime_error("face_mesh_set: face IEN entry out of range");
+    }
+    // parents' connectivity -> gnnb's ptr(eNoNb): the first parent node (in parent order) that is not a face node
+    int* d_gE = upload(gE, size_t(nElb), ops.st);
+    int* d_par = nullptr;
+    CU_CHECK(cudaMalloc(&d_par, sizeof(int)*size_t(nElb)*eNoN));
+    k_gather_ien<<<CudaOps::grid_for(size_t(nElb)*eNoN, 256, 1), 256, 0, ops.st>>>(nElb, eNoN, d_gE, h->d_ien, d_par); ops.post();
+    std::vector<int> par(size_t(nElb)*eNoN);
+    CU_CHECK(cudaMemcpyAsync(par.data(), d_par, sizeof(int)*par.size(), cudaMemcpyDeviceToHost, ops.st));
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+    cudaFree(d_gE); cudaFree(d_par);
+    std::vector<int> inode(nElb);
+    for (int e = 0; e < nElb; e++) {
+      const int* fn = IENb + size_t(e)*eNoNb;
+      const int* pn = par.data() + size_t(e)*eNoN;
+      int found = -1;
+      for (int a = 0; a < eNoNb; a++)
+        if (std::find(pn, pn + eNoN, fn[a]) == pn + eNoN)
+          throw std::runtime_error("[svFSIplus::gnnb] The face node " + std::to_string(fn[a]) + " could not be matched to a node in the volume mesh.");
+      for (int b = 0; b < eNoN && found < 0; b++)
+        if (std::find(fn, fn + eNoNb, pn[b]) == fn + eNoNb) found = pn[b];
+      if (found < 0) throw std::runtime_error("face_mesh_set: parent element has no node off the face");
+      inode[e] = found;
+    }
+    // destinations in the solver layout (what do_assem searches for, lhsa.cpp:121-133) and their ordered runs
+    std::vector<int> rkey(size_t(nElb)*eNoNb), kkey(size_t(nElb)*eNoNb*eNoNb);
+    for (int e = 0; e < nElb; e++) {
+      for (int a = 0; a < eNoNb; a++) {
+        const int A = IENb[size_t(e)*eNoNb + a];
+        const int rowS = h->h_map[A];
+        rkey[size_t(e)*eNoNb + a] = rowS;
+        const int* beg = h->h_colA.data() + h->h_rowPtrA[A];
+        const int* end = h->h_colA.data() + h->h_rowPtrA[A + 1];
+        for (int b = 0; b < eNoNb; b++) {
+          const int B = IENb[size_t(e)*eNoNb + b];
+          const int* it = std::lower_bound(beg, end, B);
+          if (it == end || *it != B) throw std::runtime_error("face_mesh_set: column not in the sparsity pattern");
+          kkey[(size_t(e)*eNoNb + a)*eNoNb + b] = h->h_rowPtrS[rowS] + int(it - beg);
+        }
+      }
+    }
+    std::vector<int> rslot, kslot, udR, usR, udK, usK;
+    face_runs(rkey, rslot, udR, usR);
+    face_runs(kkey, kslot, udK, usK);
+    f.nUR = int(udR.size()); f.nUK = int(udK.size());
+    f.ienb = upload(IENb, size_t(nElb)*eNoNb, ops.st);
+    f.inode = upload(inode.data(), inode.size(), ops.st);
+    f.rslot = upload(rslot.data(), rslot.size(), ops.st);
+    f.kslot = upload(kslot.data(), kslot.size(), ops.st);
+    f.udestR = upload(udR.data(), udR.size(), ops.st); f.usegR = upload(usR.data(), usR.size(), ops.st);
+    f.udestK = upload(udK.data(), udK.size(), ops.st); f.usegK = upload(usK.data(), usK.size(), ops.st);
+    FaceTables t;
+    fill_face_tables(t, eNoNb, 2.0/3.0);                 // faceType::qmTRI3 default, ComMod.h:611
+    std::vector<double> pk;
+    for (int g = 0; g < t.nG; g++) pk.push_back(t.w[g]);
+    for (int g = 0; g < t.nG; g++) for (int a = 0; a < eNoNb; a++) pk.push_back(t.N[g][a]);
+    for (int g = 0; g < t.nG; g++) for (int a = 0; a < eNoNb; a++) { pk.push_back(t.Nx[g][a][0]); pk.push_back(t.Nx[g][a][1]); }
+    f.tab = upload(pk.data(), pk.size(), ops.st);
+    CU_CHECK(cudaMalloc(&f.stageR, sizeof(double)*rslot.size()*3));
+    CU_CHECK(cudaMalloc(&f.stageT, sizeof(double)*kslot.size()));
+    CU_CHECK(cudaMalloc(&f.hg, sizeof(double)*size_t(h->nNo)));
+    CU_CHECK(cudaMemsetAsync(f.hg, 0, sizeof(double)*size_t(h->nNo), ops.st));
+    f.nodes.assign(IENb, IENb + size_t(nElb)*eNoNb);
+    std::sort(f.nodes.begin(), f.nodes.end());
+    f.nodes.erase(std::unique(f.nodes.begin(), f.nodes.end()), f.nodes.end());
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+  });
+}
+
+int b200_assemble_bneu(b200_handle* h, int faIn, int kind, const b200_bneu_props* p, const double* hg)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (faIn < 0 || faIn >= int(h->fmesh.size()) || h->fmesh[faIn].eNoNb == 0) throw std::runtime_error("assemble_bneu: no face mesh (b200_face_mesh_set)");
+    auto& f = h->fmesh[faIn];
+    if (f.nElb == 0) return;
+    if (kind != 0 && kind != 1) throw std::runtime_error("assemble_bneu: kind must be 0 (b_fluid) or 1 (b_l_elas)");
+    if (h->dof < 3 || !h->Val) throw std::runtime_error("assemble_bneu: call b200_zero first (dof 3 or 4)");
+    if (kind == 0 && h->dof != 4) throw std::runtime_error("assemble_bneu: b_fluid needs a dof-4 system");
+    if (kind == 0 && (!h->d_Yg || p->tDof != h->tDof)) throw std::runtime_error("assemble_bneu: no state (b200_state_set / b200_pici) or tDof differs");
+    if (p->mvMsh && (!h->d_Do || p->tDof < 7)) throw std::runtime_error("assemble_bneu: a moving mesh needs Do (b200_disp_set) and tDof >= 7");
+    flush_staged(h);                      // also materialises the deferred ls_alloc zeroing
+    BneuConsts c;
+    c.dt = p->dt; c.af = p->af; c.gam = p->gam; c.tDof = p->tDof; c.mvMsh = p->mvMsh; c.rho = p->rho; c.bfs = p->bfs;
+    c.kind = kind; c.dof = h->dof;
+    // nodal Neumann values of the face nodes (set_bc_neu_l fills hg on the face only, set_bc.cpp)
+    {
+      std::vector<double> hv(f.nodes.size());
+      for (size_t i = 0; i < hv.size(); i++) hv[i] = hg[f.nodes[i]];
+      int* d_idx = upload(f.nodes.data(), f.nodes.size(), ops.st);
+      double* d_val = upload(hv.data(), hv.size(), ops.st);
+      k_pic_scatter<<<CudaOps::grid_for(hv.size(), 256, 1), 256, 0, ops.st>>>(int(hv.size()), d_idx, d_val, f.hg); ops.post();
+      CU_CHECK(cudaStreamSynchronize(ops.st));
+      cudaFree(d_idx); cudaFree(d_val);
+    }
+    if (f.eNoNb == 3) launch_bneu<3, 3>(h, f, c);
+    else if (f.eNoNb == 4) launch_bneu<4, 4>(h, f, c);
+    else launch_bneu<6, 7>(h, f, c);
+    k_bneu_sum_R<<<(f.nUR + 127)/128, 128, 0, ops.st>>>(f.nUR, h->dof, f.udestR, f.usegR, f.stageR, h->R); ops.post();
+    if (kind == 0) { k_bneu_sum_K<<<(f.nUK + 127)/128, 128, 0, ops.st>>>(f.nUK, f.udestK, f.usegK, f.stageT, h->Val); ops.post(); }
+    CU_CHECK(cudaStreamSynchronize(ops.st));
   });
 }
 

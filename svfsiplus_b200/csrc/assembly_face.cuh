@@ -1,0 +1,82 @@
+// assembly_face.cuh — boundary-face (Neumann) assembly on the device: b_assem_neu_bc + gnnb + b_fluid / b_l_elas
+// (Code/Source/solver/eq_assem.cpp:58-170, nn.cpp:552-755, fluid.cpp:46-133, l_elas.cpp:48-59) for TRI3, QUD4 and TRI6
+// faces.  SURVEY.md par. 8(f) row 1: replaces the per-element LinearAlgebra::assemble calls of the boundary code (host
+// staging list + upload every Newton iteration).  The arithmetic is face_elem.hpp (host/device shared).
+//
+// Faces are small (1e3..1e5 elements): one thread per face element; the element's rows / diagonal tangent scalars go
+// to a face-private staging buffer whose slots were sorted at b200_face_mesh_set by destination and, inside a
+// destination, by face element; a second kernel walks every touched destination once and adds its run onto R / Val in
+// that order -- the order in which do_assem adds the face elements after the volume assembly.  No atomics.
+#pragma once
+
+#include "kernels.cuh"
+#include "face_elem.hpp"
+
+namespace svb200 {
+
+template <int NB, int NG>
+__global__ void __launch_bounds__(128)
+k_bneu_elem(int nElb, BneuConsts c, const double* __restrict__ tab,     // packed: w[NG], N[NG][NB], Nx[NG][NB][2]
+            const int* __restrict__ ienb, const int* __restrict__ inode, const int* __restrict__ rslot, const int* __restrict__ kslot,
+            const double* __restrict__ x, const double* __restrict__ Do, const double* __restrict__ hg, const double* __restrict__ Yg,
+            double* __restrict__ stageR, double* __restrict__ stageT)
+{
+  __shared__ double s_tab[NG + NG*NB + NG*NB*2];
+  for (int i = threadIdx.x; i < NG + NG*NB + NG*NB*2; i += blockDim.x) s_tab[i] = tab[i];
+  __syncthreads();
+  const int e = blockIdx.x*blockDim.x + threadIdx.x;
+  if (e >= nElb) return;
+  int nd[NB];
+#pragma unroll
+  for (int a = 0; a < NB; a++) nd[a] = ienb[size_t(e)*NB + a];
+  double lR[NB*3], lKd[NB*NB];
+  face_element<NB, NG>(c, nd, inode[e], x, Do, hg, Yg, s_tab, s_tab + NG, s_tab + NG + NG*NB, lR, lKd);
+#pragma unroll
+  for (int a = 0; a < NB; a++) {
+    double* o = stageR + size_t(rslot[size_t(e)*NB + a])*3;
+    o[0] = lR[a*3]; o[1] = lR[a*3 + 1]; o[2] = lR[a*3 + 2];
+  }
+  if (c.kind == 0) {
+#pragma unroll
+    for (int q = 0; q < NB*NB; q++) stageT[kslot[size_t(e)*NB*NB + q]] = lKd[q];
+  }
+}
+
+// R(0:2, row) += run of staged rows, in face-element order.  One thread per touched row.
+__global__ void k_bneu_sum_R(int nU, int dof, const int* __restrict__ udest, const int* __restrict__ useg, const double* __restrict__ stageR,
+                             double* __restrict__ R)
+{
+  const int t = blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= nU) return;
+  double* r = R + size_t(udest[t])*dof;
+  double a0 = r[0], a1 = r[1], a2 = r[2];
+  for (int q = useg[t]; q < useg[t + 1]; q++) {
+    a0 += stageR[size_t(q)*3]; a1 += stageR[size_t(q)*3 + 1]; a2 += stageR[size_t(q)*3 + 2];
+  }
+  r[0] = a0; r[1] = a1; r[2] = a2;
+}
+
+// Val(0, 5, 10; block) += run of staged scalars (the three equal diagonal entries b_fluid adds), in face-element order.
+__global__ void k_bneu_sum_K(int nU, const int* __restrict__ udest, const int* __restrict__ useg, const double* __restrict__ stageT,
+                             double* __restrict__ Val)
+{
+  const int t = blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= nU) return;
+  double* v = Val + size_t(udest[t])*16;
+  double a0 = v[0], a1 = v[5], a2 = v[10];
+  for (int q = useg[t]; q < useg[t + 1]; q++) {
+    const double s = stageT[q];
+    a0 += s; a1 += s; a2 += s;
+  }
+  v[0] = a0; v[5] = a1; v[10] = a2;
+}
+
+// rows of IEN for a list of elements (face parents), to find the interior node on the host
+__global__ void k_gather_ien(int n, int eNoN, const int* __restrict__ gE, const int* __restrict__ ien, int* __restrict__ out)
+{
+  const int tot = n*eNoN;
+  for (int t = blockIdx.x*blockDim.x + threadIdx.x; t < tot; t += gridDim.x*blockDim.x)
+    out[t] = ien[size_t(gE[t / eNoN])*eNoN + (t % eNoN)];
+}
+
+} // namespace svb200

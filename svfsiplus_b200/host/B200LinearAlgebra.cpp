@@ -295,6 +295,43 @@ bool B200LinearAlgebra::assemble_fsi_mesh(ComMod& com_mod, const mshType& lM, co
   return true;
 }
 
+/// Neumann face on the device (b_assem_neu_bc, eq_assem.cpp:58): b_fluid for fluid domains, b_l_elas for the solid-type ones.
+bool B200LinearAlgebra::assemble_face(ComMod& com_mod, const faceType& lFa, const Vector<double>& hg, const Array<double>& Yg)
+{
+  using namespace consts;
+  if (!device_assembly_ || !any_device_contribution_ || com_mod.nsd != 3) return false;
+  auto& eq = com_mod.eq[com_mod.cEq];
+  const auto& msh = com_mod.msh[lFa.iM];
+  if (eq.nDmn != 1 || msh.lShl || mesh_uploaded_ != &msh) return false;
+  if (lFa.eType != ElementType::TRI3 && lFa.eType != ElementType::QUD4 && lFa.eType != ElementType::TRI6) return false;
+  if (lFa.eType == ElementType::TRI3 && lFa.qmTRI3 != 2.0/3.0) return false;       // device tables use the default rule
+  int kind;
+  switch (eq.dmn[0].phys) {
+    case EquationType::phys_fluid: kind = 0; break;
+    case EquationType::phys_lElas: case EquationType::phys_struct: case EquationType::phys_ustruct:
+    case EquationType::phys_mesh: case EquationType::phys_stokes: kind = 1; break;
+    default: return false;
+  }
+  if (kind == 0 && com_mod.dof != 4) return false;
+  if (com_mod.mvMsh) return false;      // moving-mesh faces need com_mod.Do on the device: FSI faces stay on the host path
+  auto it = face_meshes_.find(&lFa);
+  if (it == face_meshes_.end()) {
+    const int slot = int(face_meshes_.size());
+    check(b200_face_mesh_set(h_, slot, lFa.eNoN, lFa.nEl, lFa.IEN.data(), lFa.gE.data()), "b200_face_mesh_set");
+    it = face_meshes_.emplace(&lFa, slot).first;
+  }
+  b200_bneu_props p;
+  p.dt = com_mod.dt; p.af = eq.af; p.gam = eq.gam; p.tDof = com_mod.tDof; p.mvMsh = 0;
+  p.rho = 0.0; p.bfs = 0.0;
+  if (kind == 0) {
+    p.rho = eq.dmn[0].prop.at(PhysicalProperyType::fluid_density);
+    p.bfs = eq.dmn[0].prop.at(PhysicalProperyType::backflow_stab);
+  }
+  (void)Yg;      // the device holds the Yg uploaded for the volume assembly of this iteration
+  check(b200_assemble_bneu(h_, it->second, kind, &p, hg.data()), "b200_assemble_bneu");
+  return true;
+}
+
 /// ustruct (construct_usolid, ustruct.cpp:216) on equal-order TET4 / HEX8 / TET10 with idMap = identity.
 bool B200LinearAlgebra::assemble_ustruct_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag,
     const Array<double>& Yg, const Array<double>& Dg, const CepMod* cep_mod)

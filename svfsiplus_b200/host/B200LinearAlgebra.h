@@ -18,6 +18,7 @@
 #include "LinearAlgebra.h"
 #include "CepMod.h"
 
+#include <map>
 #include <set>
 #include <string>
 
@@ -55,6 +56,12 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
     /// when the system was assembled on the host (the caller then runs the reference's ustruct_r).
     bool ustruct_r(ComMod& com_mod, const Array<double>& Yg);
 
+    /// b_assem_neu_bc counterpart (eq_assem.cpp:58; called from set_bc::set_bc_neu_l, set_bc.cpp:1449): the Neumann
+    /// face is assembled on the device on top of the volume assembly of this Newton iteration.  Returns false when the
+    /// face / physics has no device kernel or the volume was assembled on the host (the caller then runs the
+    /// reference's b_assem_neu_bc with per-element assemble()).
+    bool assemble_face(ComMod& com_mod, const faceType& lFa, const Vector<double>& hg, const Array<double>& Yg);
+
     /// fsils_bc_update counterpart: re-upload the face vectors (moving meshes, follower loads).
     void update_faces(ComMod& com_mod);
 
@@ -83,6 +90,7 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
     const mshType* domains_uploaded_ = nullptr;
     bool any_device_contribution_ = false;
     bool ustruct_on_device_ = false;
+    std::map<const faceType*, int> face_meshes_;      // faces whose connectivity is on the device -> slot
     static std::set<consts::LinearAlgebraType> valid_assemblers;
 };
 

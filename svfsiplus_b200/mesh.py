@@ -186,6 +186,37 @@ def block_mesh(n: int, elem: str = "hex", length: float = 1.0, jitter: float = 0
     return Mesh(x=np.ascontiguousarray(x), ien=np.ascontiguousarray(ien), faces=faces, shape=(n, n, n))
 
 
+# local faces of the volume elements, in an order that is a valid face element of the reference (nn_elem_gnn.h:1536-1610:
+# QUD4 nodes cyclic; TRI6 = corners 0,1,2 then the mid-edge nodes of 0-1, 1-2, 0-2)
+_TET_FACES = [(0, 1, 2), (0, 1, 3), (1, 2, 3), (0, 2, 3)]
+_TET10_MID = {(0, 1): 4, (1, 2): 5, (0, 2): 6, (0, 3): 7, (1, 3): 8, (2, 3): 9}
+_HEX_FACES = [(0, 1, 2, 3), (4, 5, 6, 7), (0, 1, 5, 4), (1, 2, 6, 5), (2, 3, 7, 6), (3, 0, 4, 7)]
+
+
+def face_elements(mesh: Mesh, on_face: np.ndarray):
+    """Boundary-face mesh of the nodes flagged by ``on_face`` (bool per node): every local face of a volume element whose
+    nodes are all flagged.  Returns (IENb (nElb, eNoNb) int32, gE (nElb,) int32) = lFa.IEN and lFa.gE of the reference
+    (ComMod.h faceType): TRI3 for TET4, QUD4 for HEX8, TRI6 for TET10."""
+    ien = mesh.ien
+    eNoN = ien.shape[1]
+    if eNoN == 8:
+        loc = [list(f) for f in _HEX_FACES]
+    elif eNoN == 4:
+        loc = [list(f) for f in _TET_FACES]
+    else:
+        mid = lambda a, b: _TET10_MID[(min(a, b), max(a, b))]
+        loc = [[i, j, k, mid(i, j), mid(j, k), mid(i, k)] for i, j, k in _TET_FACES]
+    out_i, out_e = [], []
+    for f in loc:
+        nodes = ien[:, f]
+        sel = np.nonzero(on_face[nodes].all(axis=1))[0]
+        out_i.append(nodes[sel]); out_e.append(sel)
+    IENb = np.concatenate(out_i).astype(np.int32)
+    gE = np.concatenate(out_e).astype(np.int32)
+    order = np.argsort(gE, kind="stable")                  # face elements in the order of their parents
+    return np.ascontiguousarray(IENb[order]), np.ascontiguousarray(gE[order])
+
+
 def block_state(mesh: Mesh, length: float = 1.0, amp: float = 0.05, noise: float = 0.01, seed: int = 2026, tDof: int = 3, s: int = 0):
     """Displacement state of SURVEY.md par. 8d for the solid block: d = amp*L*sin field + noise, Ag/Yg random."""
     x = mesh.x

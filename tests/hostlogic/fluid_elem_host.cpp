@@ -10,6 +10,7 @@
 
 #include "elem_tables.hpp"
 #include "fluid_elem.hpp"
+#include "face_elem.hpp"
 
 using namespace svb200;
 
@@ -78,6 +79,53 @@ int host_fluid_assemble(int eNoN, int nEl, const int* ien, const double* x, cons
   if (eNoN == 4) return assemble<4, 4, false>(nEl, ien, x, Dmesh, c, t, Ag, Yg, Bf, rowPtr, colPtr, R, Val);
   if (eNoN == 8) return assemble<8, 8, false>(nEl, ien, x, Dmesh, c, t, Ag, Yg, Bf, rowPtr, colPtr, R, Val);
   return assemble<10, 15, true>(nEl, ien, x, Dmesh, c, t, Ag, Yg, Bf, rowPtr, colPtr, R, Val);
+}
+
+// Boundary-face assembly (face_elem.hpp): b_assem_neu_bc on one face, serial, face elements in order.
+// par = {dt, af, gam, rho, bfs, tDof, mvMsh}; kind 0 b_fluid (dof 4), 1 b_l_elas (dof 3).  ien: the volume mesh (eNoN x nEl).
+// R(dof,nNo), Val(dof*dof,nnz) must be zero on entry.
+int host_bneu_assemble(int kind, int eNoN, const int* ien, int eNoNb, int nElb, const int* IENb, const int* gE, const double* par,
+                       const double* x, const double* Do, const double* hg, const double* Yg, const int* rowPtr, const int* colPtr,
+                       double* R, double* Val)
+{
+  if (!face_supported(eNoNb)) return -1000000;
+  BneuConsts c;
+  c.dt = par[0]; c.af = par[1]; c.gam = par[2]; c.rho = par[3]; c.bfs = par[4]; c.tDof = int(par[5]); c.mvMsh = int(par[6]);
+  c.kind = kind; c.dof = (kind == 0) ? 4 : 3;
+  FaceTables t;
+  fill_face_tables(t, eNoNb, 2.0/3.0);
+  std::vector<double> N(t.nG*eNoNb), Nx(t.nG*eNoNb*2);
+  for (int g = 0; g < t.nG; g++)
+    for (int a = 0; a < eNoNb; a++) {
+      N[g*eNoNb + a] = t.N[g][a];
+      Nx[(g*eNoNb + a)*2] = t.Nx[g][a][0]; Nx[(g*eNoNb + a)*2 + 1] = t.Nx[g][a][1];
+    }
+  const int dof = c.dof;
+  for (int e = 0; e < nElb; e++) {
+    const int* nd = IENb + size_t(e)*eNoNb;
+    const int* pn = ien + size_t(gE[e])*eNoN;
+    int inode = -1;
+    for (int b = 0; b < eNoN && inode < 0; b++)
+      if (std::find(nd, nd + eNoNb, pn[b]) == nd + eNoNb) inode = pn[b];
+    if (inode < 0) return e + 1;
+    double lR[18], lKd[36];
+    if (eNoNb == 3) face_element<3, 3>(c, nd, inode, x, Do, hg, Yg, t.w, N.data(), Nx.data(), lR, lKd);
+    else if (eNoNb == 4) face_element<4, 4>(c, nd, inode, x, Do, hg, Yg, t.w, N.data(), Nx.data(), lR, lKd);
+    else face_element<6, 7>(c, nd, inode, x, Do, hg, Yg, t.w, N.data(), Nx.data(), lR, lKd);
+    for (int a = 0; a < eNoNb; a++) {
+      for (int i = 0; i < 3; i++) R[size_t(nd[a])*dof + i] += lR[a*3 + i];
+      if (kind != 0) continue;
+      const int* beg = colPtr + rowPtr[nd[a]];
+      const int* end = colPtr + rowPtr[nd[a] + 1];
+      for (int b = 0; b < eNoNb; b++) {
+        const int* it = std::lower_bound(beg, end, nd[b]);
+        if (it == end || *it != nd[b]) return -(e + 1);
+        double* v = Val + size_t(it - colPtr)*16;
+        v[0] += lKd[a*eNoNb + b]; v[5] += lKd[a*eNoNb + b]; v[10] += lKd[a*eNoNb + b];
+      }
+    }
+  }
+  return 0;
 }
 
 // the tables themselves (checked against what the reference's select_ele leaves in lM): returns nG

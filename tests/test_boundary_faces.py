@@ -1,0 +1,132 @@
+"""Boundary-face (Neumann) assembly (SURVEY.md par. 8(f) row 1): b_assem_neu_bc + gnnb + b_fluid / b_l_elas
+(Code/Source/solver/eq_assem.cpp:58, nn.cpp:552, fluid.cpp:46, l_elas.cpp:48) on TRI3 / QUD4 / TRI6 faces.
+
+CPU: the host/device-shared arithmetic (csrc/face_elem.hpp) against the compiled reference, bit for bit.
+GPU: b200_face_mesh_set + b200_assemble_bneu through the C ABI against the reference at 1e-12, alone and on top of a
+volume assembly, with a moving mesh, and the size-independent property sum_a R_a = -area * n for a unit traction."""
+import numpy as np
+import pytest
+
+from conftest import needs_ref
+from util import golden, host_bneu_assemble, rel_inf
+
+from svfsiplus_b200 import mesh as M
+from svfsiplus_b200 import problem as P
+
+TIME = dict(dt=0.005, af=0.6, gam=0.7)
+ELEMS = [("tet", 3), ("hex", 3), ("tet10", 2)]
+
+
+def _setup(elem, n, mvMsh=False, seed=0):
+    case = P.fluid_block_case(n, elem=elem, mvMsh=mvMsh)
+    m = case["mesh"]
+    on = np.abs(m.x[:, 2]) < 1e-12                             # Z0: the flow enters there, so the backflow term is active
+    IENb, gE = M.face_elements(m, on)
+    rng = np.random.default_rng(seed)
+    hg = np.where(on, 50.0 + 10.0 * rng.standard_normal(m.nNo), 0.0)
+    Do = None
+    if mvMsh:
+        Do = np.zeros((m.nNo, 7))
+        Do[:, 4:7] = 0.03 / n * rng.standard_normal((m.nNo, 3))
+    return case, IENb, gE, hg, Do
+
+
+def _ref_face(case, kind, IENb, gE, hg, Do, mvMsh):
+    from oracle import ref
+    m = case["mesh"]
+    ra = ref.RefAssembly(m.x, m.ien)
+    Yg = case["Yg"] if kind == "fluid" else case["Yg"][:, :3]
+    R, Val = ra.bneu(kind, IENb, gE, hg, Yg, rho=1.06, bfs=0.2, mvMsh=mvMsh, Do=Do, **TIME)
+    ra.close()
+    return R, Val
+
+
+# ---------------------------------------------------------------------------------------------- CPU
+@pytest.mark.parametrize("elem,n", ELEMS)
+@pytest.mark.parametrize("kind,mvMsh", [("fluid", False), ("fluid", True), ("solid", False)])
+@needs_ref
+def test_host_face_element_matches_reference_bitwise(elem, n, kind, mvMsh):
+    case, IENb, gE, hg, Do = _setup(elem, n, mvMsh)
+    Rr, Vr = _ref_face(case, kind, IENb, gE, hg, Do, mvMsh)
+    Yg = case["Yg"] if kind == "fluid" else case["Yg"][:, :3]
+    R, Val = host_bneu_assemble(kind, case["mesh"], IENb, gE, hg, Yg, case["rowPtr"], case["colPtr"], rho=1.06, bfs=0.2,
+                                mvMsh=mvMsh, Do=Do, **TIME)
+    assert np.abs(Rr).max() > 0 and (kind == "solid" or np.abs(Vr).max() > 0)
+    assert np.array_equal(R, Rr) and np.array_equal(Val, Vr)
+
+
+@pytest.mark.parametrize("elem,n", ELEMS)
+def test_host_face_element_matches_golden(elem, n):
+    g = golden("boundary_faces.npz")
+    for kind, mvMsh in (("fluid", False), ("fluid", True), ("solid", False)):
+        case, IENb, gE, hg, Do = _setup(elem, n, mvMsh)
+        Yg = case["Yg"] if kind == "fluid" else case["Yg"][:, :3]
+        R, Val = host_bneu_assemble(kind, case["mesh"], IENb, gE, hg, Yg, case["rowPtr"], case["colPtr"], rho=1.06, bfs=0.2,
+                                    mvMsh=mvMsh, Do=Do, **TIME)
+        tag = f"{elem}_{kind}_{int(mvMsh)}"
+        assert rel_inf(R, g[f"R_{tag}"]) < 1e-14 and rel_inf(Val, g[f"Val_{tag}"]) < 1e-14
+
+
+# ---------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("elem,n", ELEMS)
+@pytest.mark.parametrize("kind,mvMsh", [("fluid", False), ("fluid", True), ("solid", False)])
+def test_gpu_face_assembly_matches_golden(elem, n, kind, mvMsh):
+    g = golden("boundary_faces.npz")
+    case, IENb, gE, hg, Do = _setup(elem, n, mvMsh)
+    be = P.setup_backend(case)
+    be.face_mesh_set(5, IENb, gE)
+    tDof = case["Yg"].shape[1]
+    if kind == "fluid":
+        be.state_set(tDof, case["Ag"], case["Yg"], case["Bf"])
+        if mvMsh:
+            be.disp_set(tDof, np.zeros_like(Do), Do)
+        be.zero(4)
+    else:
+        be.zero(3)
+    be.assemble_bneu(5, kind, hg, tDof=tDof, mvMsh=mvMsh, rho=1.06, bfs=0.2, **TIME)
+    tag = f"{elem}_{kind}_{int(mvMsh)}"
+    assert rel_inf(be.get_R(), g[f"R_{tag}"]) < 1e-12
+    if kind == "fluid":
+        assert rel_inf(be.get_Val(), g[f"Val_{tag}"]) < 1e-12
+    else:
+        assert np.abs(be.get_Val()).max() == 0.0
+    be.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("elem,n", ELEMS)
+def test_gpu_face_on_top_of_volume_assembly(elem, n):
+    """Volume assembly, then the face: R / Val equal the reference's construct_fluid followed by b_assem_neu_bc."""
+    g = golden("boundary_faces.npz")
+    gv = golden("fluid_block.npz")
+    case, IENb, gE, hg, Do = _setup(elem, n)
+    be = P.setup_backend(case)
+    be.face_mesh_set(0, IENb, gE)
+    P.assemble(be, case)
+    R0, V0 = be.get_R(), be.get_Val()
+    be.assemble_bneu(0, "fluid", hg, tDof=4, rho=1.06, bfs=0.2, **TIME)
+    R, Val = be.get_R(), be.get_Val()
+    tag = f"{elem}_fluid_0"
+    assert rel_inf(R - R0, g[f"R_{tag}"]) < 1e-10            # differences of assembled numbers: rounding of the larger terms
+    assert rel_inf(R, R0 + g[f"R_{tag}"]) < 1e-12 and rel_inf(Val, V0 + g[f"Val_{tag}"]) < 1e-12
+    if elem in ("hex", "tet10") and n == {"hex": 3, "tet10": 2}[elem]:
+        key = "hex" if elem == "hex" else "tet10"
+        assert rel_inf(R0, gv[f"R_{key}"]) < 1e-12
+    be.close()
+
+
+@pytest.mark.gpu
+def test_gpu_unit_traction_integrates_to_area_normal():
+    """Size-independent property on a large face (200 x 200 x 2 triangles): sum_a R(:,a) = -|face| n for h = 1."""
+    m = M.block_mesh(20, "tet")
+    case = P.fluid_block_case(20, elem="tet")
+    on = np.abs(m.x[:, 0]) < 1e-12                             # X0, outward normal (-1, 0, 0)
+    IENb, gE = M.face_elements(case["mesh"], on)
+    be = P.setup_backend(case)
+    be.face_mesh_set(1, IENb, gE)
+    be.zero(3)
+    be.assemble_bneu(1, "solid", np.ones(case["mesh"].nNo), tDof=3, **TIME)
+    s = be.get_R().sum(axis=0)
+    assert np.allclose(s, [1.0, 0.0, 0.0], atol=1e-13)
+    be.close()

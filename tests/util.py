@@ -68,6 +68,7 @@ def elemhost():
         _eh = C.CDLL(os.path.join(ROOT, "tests", "_build", "libelemhost.so"))
         _eh.host_fluid_assemble.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_double] + [C.c_void_p] * 7
         _eh.host_elem_tables.argtypes = [C.c_int, C.c_double] + [C.c_void_p] * 4
+        _eh.host_bneu_assemble.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 11
     return _eh
 
 
@@ -90,4 +91,22 @@ def host_fluid_assemble(case):
                                _p(R), _p(Val))
     if rc != 0:
         raise RuntimeError(f"host_fluid_assemble: rc {rc}")
+    return R, Val
+
+
+def host_bneu_assemble(kind, mesh, IENb, gE, hg, Yg, rowPtr, colPtr, *, dt, af, gam, rho=0.0, bfs=0.0, mvMsh=False, Do=None):
+    """face_elem.hpp (b_assem_neu_bc + gnnb + b_fluid / b_l_elas) run serially on the host by the TEST-ONLY harness."""
+    L = elemhost()
+    dof = 4 if kind == "fluid" else 3
+    ien = np.ascontiguousarray(mesh.ien, np.int32); x = np.ascontiguousarray(mesh.x, np.float64)
+    IENb = np.ascontiguousarray(IENb, np.int32); gE = np.ascontiguousarray(gE, np.int32)
+    hg = np.ascontiguousarray(hg, np.float64); Yg = np.ascontiguousarray(Yg, np.float64)
+    Do = None if Do is None else np.ascontiguousarray(Do, np.float64)
+    rp = np.ascontiguousarray(rowPtr, np.int32); cp = np.ascontiguousarray(colPtr, np.int32)
+    par = np.array([dt, af, gam, rho, bfs, Yg.shape[1], int(mvMsh)], np.float64)
+    R = np.zeros((mesh.nNo, dof)); Val = np.zeros((len(cp), dof * dof))
+    rc = L.host_bneu_assemble(0 if kind == "fluid" else 1, ien.shape[1], _p(ien), IENb.shape[1], IENb.shape[0], _p(IENb), _p(gE),
+                              _p(par), _p(x), _p(Do), _p(hg), _p(Yg), _p(rp), _p(cp), _p(R), _p(Val))
+    if rc != 0:
+        raise RuntimeError(f"host_bneu_assemble: rc {rc}")
     return R, Val
