@@ -147,6 +147,12 @@ int b200_mesh_fibers(b200_handle* h, int nFn, const double* fN);
  * index of the equation domain element e belongs to (all_fun::domain, solver/all_fun.cpp:149), uploaded once;
  * the device keeps one element list per domain, so each domain is one divergence-free launch. */
 int b200_mesh_domains(b200_handle* h, int nDmn, const int* elem_dmn);
+/* Equations with several domains of ONE physics (eq.nDmn > 1, each eq.dmn[d] with its own properties; the element loop
+ * of construct_fluid / construct_dsolid picks them per element, solver/fluid.cpp:531, sv_struct.cpp:261): p[d] are the
+ * properties of domain d, the element lists come from b200_mesh_domains.  dof 4 / dof 3 systems as in the single-domain
+ * calls. */
+int b200_assemble_fluid_dmn(b200_handle* h, int nDmn, const b200_fluid_props* p);
+int b200_assemble_struct_dmn(b200_handle* h, int nDmn, const b200_struct_props* p);
 /* dmn_kind[d]: 0 fluid (fluid_3d_m/c on the ALE configuration x + Dg(4:6), mvMsh), 1 struct (struct_3d into the
  * 3x3 corner of the dof-4 blocks).  fluid[d] / solid[d] are read for the domains of that kind (dof 4; TET4, HEX8). */
 int b200_assemble_fsi(b200_handle* h, int nDmn, const int* dmn_kind, const b200_fluid_props* fluid, const b200_struct_props* solid);

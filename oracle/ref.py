@@ -186,6 +186,8 @@ def lib():
                                       C.c_void_p, C.c_void_p, C.c_void_p]
         L.ref_ranks_spmv.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_ranks_commuv.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.ref_asm_domains.restype = C.c_double
+        L.ref_asm_domains.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 6
         L.ref_asm_bneu.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
         L.ref_pic.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_double] + [C.c_void_p] * 12
         _lib = L
@@ -253,6 +255,45 @@ class RefAssembly:
             raise RuntimeError(lib().ref_last_error().decode())
         return R, Val, t
 
+
+    def struct_domains(self, elem_dmn, props, Ag, Yg, Dg, Bf):
+        """construct_dsolid with eq.nDmn = len(props) struct domains; props: list of dicts as for solid()."""
+        Ag = _c(Ag, np.float64); Yg = _c(Yg, np.float64); Dg = _c(Dg, np.float64); Bf = _c(Bf, np.float64)
+        rows = []
+        for p in props:
+            f = p.get("f", (0.0, 0.0, 0.0)); ho = p.get("ho") or {}
+            rows.append([p["dt"], p["am"], p["af"], p["gam"], p["beta"], p["rho"], p.get("dmp", 0.0), f[0], f[1], f[2],
+                         self.ISO[p.get("iso", "nHook")], self.VOL[p.get("vol")], p.get("C10", 0.0), p.get("C01", 0.0), p.get("Kpen", 0.0),
+                         0.0, 0.0] + [ho.get(k, 100.0 if k == "khs" else 0.0) for k in self.HO_KEYS])
+        par = np.array(rows, np.float64)
+        ed = _c(elem_dmn, np.int32)
+        # construct_dsolid reads the properties of com_mod.cDmn for every element (a copy where construct_fluid takes a
+        # reference, see ref_harness.cpp): assemble one domain at a time and add, which is what the loop intends
+        R = np.zeros((self.nNo, 3)); Val = np.zeros((self.nnz, 9))
+        for d in range(len(props)):
+            Rd = np.empty((self.nNo, 3)); Vd = np.empty((self.nnz, 9))
+            t = lib().ref_asm_domains(self.h, 0, Ag.shape[1], len(props), par.shape[1], _p(par), _p(ed), d, _p(Ag), _p(Yg), _p(Dg), _p(Bf),
+                                      _p(Rd), _p(Vd))
+            if t < 0:
+                raise RuntimeError(lib().ref_last_error().decode())
+            R += Rd; Val += Vd
+        return R, Val
+
+    def fluid_domains(self, elem_dmn, props, Ag, Yg, Bf):
+        """construct_fluid with eq.nDmn = len(props) fluid domains; props: list of dicts(dt, am, af, gam, rho, mu, f, Kinv, viscType...)."""
+        Ag = _c(Ag, np.float64); Yg = _c(Yg, np.float64); Bf = _c(Bf, np.float64)
+        rows = []
+        for p in props:
+            f = p.get("f", (0.0, 0.0, 0.0))
+            rows.append([p["dt"], p["am"], p["af"], p["gam"], p["rho"], f[0], f[1], f[2], p.get("Kinv", 0.0), p.get("viscType", 0), p["mu"],
+                         p.get("mu_o", 0.0), p.get("lam", 0.0), p.get("a", 0.0), p.get("n", 0.0), 0.0, 0.0])
+        par = np.array(rows, np.float64)
+        ed = _c(elem_dmn, np.int32)
+        R = np.empty((self.nNo, 4)); Val = np.empty((self.nnz, 16))
+        t = lib().ref_asm_domains(self.h, 3, Ag.shape[1], len(props), par.shape[1], _p(par), _p(ed), -1, _p(Ag), _p(Yg), None, _p(Bf), _p(R), _p(Val))
+        if t < 0:
+            raise RuntimeError(lib().ref_last_error().decode())
+        return R, Val
 
     def bneu(self, kind, IENb, gE, hg, Yg, *, dt, af, gam, rho=0.0, bfs=0.0, mvMsh=False, Do=None):
         """b_assem_neu_bc (S/eq_assem.cpp:58) on one face: kind "fluid" (b_fluid, dof 4) or "solid" (b_l_elas, dof 3).

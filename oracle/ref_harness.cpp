@@ -353,6 +353,65 @@ double ref_asm_solid(void* h, int kind, int tDof, int s, const double* par, cons
   }
 }
 
+// Multi-domain struct (kind 0, dof 3) or fluid (kind 3, dof 4) equation: nDmn domains of the same physics with their own
+// properties (eq.dmn[d], Id = d), elem_dmn[e] = domain of element e (lM.eId = 1 << d, S/all_fun.cpp:149).
+// struct: par (nDmn x 26) rows as in ref_asm_solid; fluid: par (nDmn x 17) rows = {dt, am, af, gam, rho, fx, fy, fz, Kinv,
+// viscType, mu_i, mu_o, lam, a, n, 0, 0}.
+//
+// only_dmn >= 0 (struct): construct_dsolid keeps a COPY of com_mod.cDmn (S/sv_struct.cpp:229 `auto cDmn`, where
+// construct_fluid takes a reference, S/fluid.cpp:491), so struct_3d_carray reads the properties of whatever domain
+// com_mod.cDmn was left at, for every element.  To obtain what the element loop evidently intends, the harness assembles
+// one domain at a time: domain only_dmn keeps phys_struct (the others are skipped by the phys test :265) and
+// com_mod.cDmn = only_dmn; the caller adds the per-domain results.
+double ref_asm_domains(void* h, int kind, int tDof, int nDmn, int npar, const double* par, const int* elem_dmn, int only_dmn,
+                       const double* Ag, const double* Yg, const double* Dg, const double* Bf, double* R, double* Val)
+{
+  try {
+    using namespace consts;
+    auto ctx = static_cast<AsmCtx*>(h);
+    auto& com_mod = ctx->sim->com_mod;
+    auto& msh = com_mod.msh[0];
+    const int nNo = com_mod.tnNo;
+    const int dof = (kind == 0) ? 3 : 4;
+    std::vector<dmnType> dm;
+    for (int d = 0; d < nDmn; d++) {
+      const double* q = par + size_t(d)*npar;
+      if (kind == 0) configure_solid(ctx, 0, tDof, 0, q, nullptr, Bf);
+      else configure_fluid(ctx, tDof, 0, q[0], q[1], q[2], q[3], q[4], q + 5, q[8], q + 9, Bf);
+      dm.push_back(com_mod.eq[0].dmn[0]);
+      dm.back().Id = d;
+    }
+    auto& eq = com_mod.eq[0];
+    eq.nDmn = nDmn;
+    eq.dmn = dm;
+    if (only_dmn >= 0) {
+      for (int d = 0; d < nDmn; d++) if (d != only_dmn) eq.dmn[d].phys = EquationType::phys_lElas;
+      com_mod.cDmn = only_dmn;
+    }
+    msh.eId.resize(msh.nEl);
+    for (int e = 0; e < msh.nEl; e++) msh.eId(e) = 1 << elem_dmn[e];
+    if (!eq.linear_algebra) eq.linear_algebra = new FsilsLinearAlgebra();
+    Array<double> Ag_a(tDof, nNo), Yg_a(tDof, nNo), Dg_a(tDof, nNo);
+    std::memcpy(Ag_a.data(), Ag, sizeof(double)*size_t(tDof)*nNo);
+    std::memcpy(Yg_a.data(), Yg, sizeof(double)*size_t(tDof)*nNo);
+    if (Dg) std::memcpy(Dg_a.data(), Dg, sizeof(double)*size_t(tDof)*nNo);
+    com_mod.R.resize(dof, nNo);
+    eq.linear_algebra->alloc(com_mod, eq);
+    double t0 = now_s();
+    if (kind == 0) struct_ns::construct_dsolid(com_mod, ctx->sim->cep_mod, msh, Ag_a, Yg_a, Dg_a);
+    else fluid::construct_fluid(com_mod, msh, Ag_a, Yg_a);
+    double t1 = now_s();
+    std::memcpy(R, com_mod.R.data(), sizeof(double)*size_t(dof)*nNo);
+    std::memcpy(Val, com_mod.Val.data(), sizeof(double)*size_t(dof)*dof*ctx->nnz);
+    // leave a single-domain equation behind for the calls that follow on this context
+    eq.nDmn = 1; eq.dmn.resize(1); eq.dmn[0].Id = -1; msh.eId.resize(0); com_mod.cDmn = 0;
+    return t1 - t0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1.0;
+  }
+}
+
 // FSI equation through the reference's construct_fsi (S/fsi.cpp:42): domain 0 = fluid (Id 0), domain 1 =
 // struct (Id 1); elem_dmn[e] in {0,1} becomes the bit mask lM.eId.  tDof = 7 (FSI unknowns 0..3, mesh 4..6).
 // fpar = {rho, fx, fy, fz, visc type, mu_i, mu_o, lam, a, n};  spar as in ref_asm_solid (struct).

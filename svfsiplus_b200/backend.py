@@ -94,6 +94,7 @@ EXPORTS = [
     "b200_timer",
     "b200_pic_init", "b200_pic_set", "b200_pic_get", "b200_pic_scatter", "b200_picp", "b200_pici", "b200_picc",
     "b200_pic_copy_rows", "b200_pic_advance", "b200_face_mesh_set", "b200_assemble_bneu",
+    "b200_assemble_fluid_dmn", "b200_assemble_struct_dmn",
 ]
 
 KERNEL_CLASSES = ["spmv_vv4", "spmv_vv3", "spmv_ss", "spmv_sv", "spmv_vs", "multi_dot", "cgs_update_scale", "blas1",
@@ -159,6 +160,8 @@ def lib():
         L.b200_picc.argtypes = [vp, ci, cd, ci]
         L.b200_pic_copy_rows.argtypes = [vp, ci, vp, ci, ci]
         L.b200_pic_advance.argtypes = [vp]
+        L.b200_assemble_fluid_dmn.argtypes = [vp, ci, C.POINTER(FluidProps)]
+        L.b200_assemble_struct_dmn.argtypes = [vp, ci, C.POINTER(StructProps)]
         L.b200_face_mesh_set.argtypes = [vp, ci, ci, ci, vp, vp]
         L.b200_assemble_bneu.argtypes = [vp, ci, ci, C.POINTER(BneuProps), vp]
         _lib = L
@@ -411,6 +414,14 @@ class Backend:
                                    _p(incL_a), _p(res_a), _p(X), C.byref(o)), "b200_solve")
         info = dict(RI=sub_out_dict(o.RI), GM=sub_out_dict(o.GM), CG=sub_out_dict(o.CG), Resm=o.Resm, Resc=o.Resc)
         return X, info
+
+    def assemble_fluid_dmn(self, props):
+        arr = (FluidProps * len(props))(*props)
+        self._ck(self.L.b200_assemble_fluid_dmn(self.h, len(props), arr), "b200_assemble_fluid_dmn")
+
+    def assemble_struct_dmn(self, props):
+        arr = (StructProps * len(props))(*props)
+        self._ck(self.L.b200_assemble_struct_dmn(self.h, len(props), arr), "b200_assemble_struct_dmn")
 
     # -- boundary-face (Neumann) assembly (b_assem_neu_bc) ---------------------------------------------
     def face_mesh_set(self, faIn, IENb, gE):

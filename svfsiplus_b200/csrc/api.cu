@@ -911,6 +911,64 @@ int b200_assemble_fsi(b200_handle* h, int nDmn, const int* dmn_kind, const b200_
   });
 }
 
+int b200_assemble_fluid_dmn(b200_handle* h, int nDmn, const b200_fluid_props* p)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (h->nEl == 0) throw std::runtime_error("assemble_fluid_dmn: no mesh (b200_mesh_set)");
+    if (int(h->d_dmn_elems.size()) != nDmn) throw std::runtime_error("assemble_fluid_dmn: call b200_mesh_domains with the same number of domains first");
+    if (!h->d_Ag) throw std::runtime_error("assemble_fluid_dmn: no state (b200_state_set)");
+    if (h->dof != 4 || !h->Val) throw std::runtime_error("assemble_fluid_dmn: call b200_zero(h, 4) first");
+    int covered = 0;
+    for (int d = 0; d < nDmn; d++) {
+      covered += h->dmn_count[d];
+      if (p[d].tDof != h->tDof) throw std::runtime_error("assemble_fluid_dmn: tDof differs from the uploaded state");
+      if (p[d].mvMsh && p[d].tDof < 7) throw std::runtime_error("assemble_fluid_dmn: mvMsh needs tDof >= 7");
+    }
+    if (covered != h->nEl) throw std::runtime_error("assemble_fluid_dmn: every element must belong to a domain");
+    ensure_stage(h, 4);
+    const double t0 = wall_s();
+    {
+      CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*128.0 + double(h->nNo)*(32.0 + 24.0 + 16.0*h->tDof + 24.0) + double(h->nEl)*4.0*h->eNoN, 2 + nDmn);
+      for (int d = 0; d < nDmn; d++) launch_fluid(h, fluid_consts(h, &p[d]), h->dmn_count[d], h->d_dmn_elems[d], nullptr);
+    }
+    finish_assembly(h, 4, t0, "construct_fluid");
+  });
+}
+
+int b200_assemble_struct_dmn(b200_handle* h, int nDmn, const b200_struct_props* p)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (h->nEl == 0) throw std::runtime_error("assemble_struct_dmn: no mesh (b200_mesh_set)");
+    if (int(h->d_dmn_elems.size()) != nDmn) throw std::runtime_error("assemble_struct_dmn: call b200_mesh_domains with the same number of domains first");
+    if (!h->d_Ag || !h->d_Dg) throw std::runtime_error("assemble_struct_dmn: no state (b200_state_set + b200_disp_set)");
+    if (h->dof != 3 || !h->Val) throw std::runtime_error("assemble_struct_dmn: call b200_zero(h, 3) first");
+    int covered = 0;
+    std::vector<SolidConsts> cs;
+    for (int d = 0; d < nDmn; d++) {
+      covered += h->dmn_count[d];
+      cs.push_back(struct_consts(&p[d]));
+      if (cs[d].tDof != h->tDof) throw std::runtime_error("assemble_struct_dmn: tDof differs from the uploaded state");
+      if (cs[d].s < 0 || cs[d].s + 3 > cs[d].tDof) throw std::runtime_error("assemble_struct_dmn: equation offset outside the state");
+      if (cs[d].iso == 3 && !h->d_fN) throw std::runtime_error("assemble_struct_dmn: the Holzapfel-Ogden law needs fibre directions (b200_mesh_fibers)");
+    }
+    if (covered != h->nEl) throw std::runtime_error("assemble_struct_dmn: every element must belong to a domain");
+    ensure_stage(h, 3);
+    const double t0 = wall_s();
+    {
+      CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*72.0 + double(h->nNo)*(24.0 + 24.0 + 24.0*3 + 24.0) + double(h->nEl)*4.0*h->eNoN, 2 + nDmn);
+      for (int d = 0; d < nDmn; d++) {
+        const int n = h->dmn_count[d];
+        if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 3>(h, cs[d], n, h->d_dmn_elems[d]);
+        else if (h->eNoN == 8) launch_solid<8, 8, 16, 2, 3>(h, cs[d], n, h->d_dmn_elems[d]);
+        else launch_solid<10, 15, 8, 2, 3>(h, cs[d], n, h->d_dmn_elems[d]);
+      }
+    }
+    finish_assembly(h, 3, t0, "construct_dsolid");
+  });
+}
+
 int b200_assemble_elem(b200_handle* h, int d, const int* eqN, const double* lK, const double* lR)
 {
   return guarded(h, [&] {

@@ -172,7 +172,7 @@ bool B200LinearAlgebra::assemble_mesh(ComMod& com_mod, const mshType& lM, const 
   // one function space, 3-D; anything else falls back to the reference's construct_*
   if (lM.nFs != 1 || com_mod.nsd != 3) return false;
   if (eq.phys == EquationType::phys_FSI) return assemble_fsi_mesh(com_mod, lM, Ag, Yg, Dg, cep_mod);
-  if (eq.nDmn != 1) return false;
+  if (eq.nDmn != 1) return assemble_domains_mesh(com_mod, lM, Ag, Yg, Dg, cep_mod);
   switch (eq.phys) {
     case EquationType::phys_fluid:
       return assemble_fluid_mesh(com_mod, lM, Ag, Yg);
@@ -423,6 +423,53 @@ bool B200LinearAlgebra::assemble_solid_mesh(ComMod& com_mod, const mshType& lM, 
   check(b200_disp_set(h_, com_mod.tDof, Dg.data(), lp.mesh_mode && !is_struct ? com_mod.Do.data() : nullptr), "b200_disp_set");
   if (is_struct) check(b200_assemble_struct(h_, &sp), "b200_assemble_struct");
   else check(b200_assemble_lelas(h_, &lp), "b200_assemble_lelas");
+  any_device_contribution_ = true;
+  return true;
+}
+
+/// Fluid or struct equation with several domains of that one physics (eq.nDmn > 1): one launch per domain over the
+/// domain's element list.  Every element takes the properties of its own domain (all_fun::domain), which is what
+/// construct_fluid does; construct_dsolid reads them through a stale copy of com_mod.cDmn (sv_struct.cpp:229) -- that
+/// defect is not reproduced.
+bool B200LinearAlgebra::assemble_domains_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag,
+    const Array<double>& Yg, const Array<double>& Dg, const CepMod* cep_mod)
+{
+  using namespace consts;
+  auto& eq = com_mod.eq[com_mod.cEq];
+  if (lM.eType != ElementType::TET4 && lM.eType != ElementType::HEX8 && lM.eType != ElementType::TET10) return false;
+  const int nDmn = eq.nDmn;
+  const bool fluid = (eq.phys == EquationType::phys_fluid);
+  if (!fluid && eq.phys != EquationType::phys_struct) return false;
+  if (com_mod.dof != (fluid ? 4 : 3)) return false;
+  std::vector<b200_fluid_props> fl(nDmn);
+  std::vector<b200_struct_props> st(nDmn);
+  for (int d = 0; d < nDmn; d++) {
+    if (eq.dmn[d].phys != eq.phys) return false;
+    if (fluid) {
+      if (!fill_fluid_props(com_mod, eq, eq.dmn[d], fl[d])) return false;
+    } else {
+      if (!fill_struct_props(com_mod, eq, eq.dmn[d], st[d])) return false;
+      if (st[d].isoType == 3 && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
+    }
+  }
+  if (!fluid) {
+    if (com_mod.pS0.size() != 0 || com_mod.pstEq) return false;
+    if (cep_mod && (cep_mod->cem.cpld || cep_mod->cem.aStress || cep_mod->cem.aStrain)) return false;
+  }
+  if (mesh_uploaded_ != &lM) upload_mesh(com_mod, lM);
+  if (domains_uploaded_ != &lM) {
+    std::vector<int> elem_dmn(lM.nEl);
+    for (int e = 0; e < lM.nEl; e++) elem_dmn[e] = all_fun::domain(com_mod, lM, com_mod.cEq, e);
+    check(b200_mesh_domains(h_, nDmn, elem_dmn.data()), "b200_mesh_domains");
+    domains_uploaded_ = &lM;
+  }
+  check(b200_state_set(h_, com_mod.tDof, Ag.data(), Yg.data(), com_mod.Bf.data()), "b200_state_set");
+  if (fluid) {
+    check(b200_assemble_fluid_dmn(h_, nDmn, fl.data()), "b200_assemble_fluid_dmn");
+  } else {
+    check(b200_disp_set(h_, com_mod.tDof, Dg.data(), nullptr), "b200_disp_set");
+    check(b200_assemble_struct_dmn(h_, nDmn, st.data()), "b200_assemble_struct_dmn");
+  }
   any_device_contribution_ = true;
   return true;
 }

@@ -81,6 +81,8 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
         const Array<double>& Dg, const CepMod* cep_mod);
     bool assemble_solid_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag, const Array<double>& Yg,
         const Array<double>& Dg, const CepMod* cep_mod);
+    bool assemble_domains_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag, const Array<double>& Yg,
+        const Array<double>& Dg, const CepMod* cep_mod);
 
     b200_handle* h_ = nullptr;
     int device_ = -1;         // -1: rank mod device count, chosen in initialize()
