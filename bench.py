@@ -190,8 +190,10 @@ def run_gpu(args):
         case, be = PT.setup_distributed_case(dims, rank, world, local, dist)
     else:
         dims = tuple(args.dims)
-        case = P.pipe_case(*dims)
-        be = P.setup_backend(case, device=local)
+        from svfsiplus_b200 import backend as B
+        be = B.Backend(local)
+        case = P.pipe_case(*dims, pattern=lambda n, ien: be.pattern(n, [ien]))       # lhsa on the device (b200_pattern_*)
+        be = P.setup_backend(case, device=local, be=be)
     nNo_local = be.nNo
     tDof = case["Ag"].shape[1]
     ntet_total = 6 * dims[0] * dims[1] * dims[2]

@@ -112,6 +112,17 @@ int b200_lhs_create(b200_handle* h, int gnNo, int nNo, int mynNo, int nnz,
 int b200_face_set(b200_handle* h, int faIn, int nNo, int dof, int bGrp, const int* glob,
                   const double* val, int shared);
 
+/* ---- pattern (replaces lhsa_ns::lhsa, solver/lhsa.cpp:153, for idMap = identity, no shells) ------------------------- */
+/* Device-side construction of the block-CSR pattern from the connectivity of every mesh of the equation system:
+ * b200_pattern_begin(h, tnNo); b200_pattern_add_mesh(...) once per mesh (IEN(eNoN,nEl), assembly node ids);
+ * b200_pattern_finish returns nnz; b200_pattern_get copies rowPtr(tnNo+1) / colPtr(nnz) to the host: sorted columns,
+ * diagonal present, 0-based -- integer for integer what lhsa leaves in com_mod.rowPtr / colPtr.  Independent of
+ * b200_lhs_create (it produces that call's inputs). */
+int b200_pattern_begin(b200_handle* h, int tnNo);
+int b200_pattern_add_mesh(b200_handle* h, int eNoN, int nEl, const int* IEN);
+int b200_pattern_finish(b200_handle* h, int* nnz);
+int b200_pattern_get(b200_handle* h, int* rowPtr, int* colPtr);
+
 /* ---- assembly (replaces construct_fluid + do_assem, solver/fluid.cpp:464, lhsa.cpp:97) ------- */
 /* IEN(eNoN,nEl) with assembly node ids, x(3,nNo).  eNoN = 4 (TET4), 8 (HEX8, the reference's node
  * order, nn_elem_gnn.h:732) or 10 (TET10, nn_elem_gnn.h:1256; every equation but FSI).  qmTET4 <= 0 selects the

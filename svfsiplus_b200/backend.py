@@ -95,6 +95,7 @@ EXPORTS = [
     "b200_pic_init", "b200_pic_set", "b200_pic_get", "b200_pic_scatter", "b200_picp", "b200_pici", "b200_picc",
     "b200_pic_copy_rows", "b200_pic_advance", "b200_face_mesh_set", "b200_assemble_bneu",
     "b200_assemble_fluid_dmn", "b200_assemble_struct_dmn",
+    "b200_pattern_begin", "b200_pattern_add_mesh", "b200_pattern_finish", "b200_pattern_get",
 ]
 
 KERNEL_CLASSES = ["spmv_vv4", "spmv_vv3", "spmv_ss", "spmv_sv", "spmv_vs", "multi_dot", "cgs_update_scale", "blas1",
@@ -160,6 +161,10 @@ def lib():
         L.b200_picc.argtypes = [vp, ci, cd, ci]
         L.b200_pic_copy_rows.argtypes = [vp, ci, vp, ci, ci]
         L.b200_pic_advance.argtypes = [vp]
+        L.b200_pattern_begin.argtypes = [vp, ci]
+        L.b200_pattern_add_mesh.argtypes = [vp, ci, ci, vp]
+        L.b200_pattern_finish.argtypes = [vp, C.POINTER(ci)]
+        L.b200_pattern_get.argtypes = [vp, vp, vp]
         L.b200_assemble_fluid_dmn.argtypes = [vp, ci, C.POINTER(FluidProps)]
         L.b200_assemble_struct_dmn.argtypes = [vp, ci, C.POINTER(StructProps)]
         L.b200_face_mesh_set.argtypes = [vp, ci, ci, ci, vp, vp]
@@ -414,6 +419,18 @@ class Backend:
                                    _p(incL_a), _p(res_a), _p(X), C.byref(o)), "b200_solve")
         info = dict(RI=sub_out_dict(o.RI), GM=sub_out_dict(o.GM), CG=sub_out_dict(o.CG), Resm=o.Resm, Resc=o.Resc)
         return X, info
+
+    def pattern(self, tnNo, meshes):
+        """lhsa on the device: meshes = list of IEN arrays (nEl, eNoN).  Returns rowPtr (tnNo+1), colPtr (nnz)."""
+        self._ck(self.L.b200_pattern_begin(self.h, tnNo), "b200_pattern_begin")
+        for ien in meshes:
+            ien = _c(ien, np.int32)
+            self._ck(self.L.b200_pattern_add_mesh(self.h, ien.shape[1], ien.shape[0], _p(ien)), "b200_pattern_add_mesh")
+        nnz = C.c_int(0)
+        self._ck(self.L.b200_pattern_finish(self.h, C.byref(nnz)), "b200_pattern_finish")
+        rowPtr = np.empty(tnNo + 1, np.int32); colPtr = np.empty(nnz.value, np.int32)
+        self._ck(self.L.b200_pattern_get(self.h, _p(rowPtr), _p(colPtr)), "b200_pattern_get")
+        return rowPtr, colPtr
 
     def assemble_fluid_dmn(self, props):
         arr = (FluidProps * len(props))(*props)

@@ -17,6 +17,7 @@
 #include "assembly_fluid_gen.cuh"
 #include "pic.cuh"
 #include "assembly_face.cuh"
+#include "pattern.cuh"
 #include "ops_cuda.cuh"
 
 using namespace svb200;
@@ -94,6 +95,12 @@ struct b200_handle {
   };
   std::vector<FaceMesh> fmesh;
 
+  // pattern construction (pattern.cuh)
+  int pat_nNo = 0, pat_bits = 0;
+  size_t pat_nkeys = 0, pat_cap = 0, pat_nnz = 0;
+  unsigned long long* pat_keys = nullptr;
+  int *pat_rowPtr = nullptr, *pat_colPtr = nullptr;
+
   // time integrator (pic.cuh): Ao Yo Do An Yn Dn (tDof x nNo) and Ad (3 x nNo), assembly order
   double* pic_arr[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int pic_tDof = 0, pic_dFlag = 0, pic_sstEq = 0;
@@ -115,6 +122,7 @@ struct b200_handle {
     cudaFree(Kd); cudaFree(stageKd); cudaFree(d_fN);
     for (auto p : pic_arr) cudaFree(p);
     for (auto& f : fmesh) f.release();
+    cudaFree(pat_keys); cudaFree(pat_rowPtr); cudaFree(pat_colPtr);
   }
 };
 
@@ -1084,6 +1092,94 @@ int b200_commu_R(b200_handle* h)
     flush_staged(h);
     h->ops->halo_add(h->dof, h->R);
     CU_CHECK(cudaStreamSynchronize(h->ops->st));
+  });
+}
+
+// ---- pattern construction on the device (pattern.cuh) ---------------------------------------------------------------
+int b200_pattern_begin(b200_handle* h, int tnNo)
+{
+  return guarded(h, [&] {
+    if (tnNo < 1) throw std::runtime_error("pattern_begin: tnNo must be positive");
+    h->pat_nNo = tnNo; h->pat_nkeys = 0; h->pat_nnz = 0;
+    h->pat_bits = 1;
+    while ((1ll << h->pat_bits) < (long long)tnNo) h->pat_bits++;
+    cudaFree(h->pat_rowPtr); cudaFree(h->pat_colPtr);
+    h->pat_rowPtr = h->pat_colPtr = nullptr;
+  });
+}
+
+int b200_pattern_add_mesh(b200_handle* h, int eNoN, int nEl, const int* IEN)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (h->pat_nNo == 0) throw std::runtime_error("pattern_add_mesh: call b200_pattern_begin first");
+    if (eNoN < 1 || nEl < 0) throw std::runtime_error("pattern_add_mesh: bad element counts");
+    for (size_t i = 0; i < size_t(nEl)*eNoN; i++)
+      if (IEN[i] < 0 || IEN[i] >= h->pat_nNo) throw std::runtime_error("pattern_add_mesh: IEN entry out of range");
+    const size_t add = size_t(nEl)*eNoN*eNoN;
+    if (h->pat_nkeys + add > h->pat_cap) {
+      unsigned long long* nk = nullptr;
+      const size_t cap = h->pat_nkeys + add;
+      CU_CHECK(cudaMalloc(&nk, sizeof(unsigned long long)*std::max<size_t>(cap, 1)));
+      if (h->pat_nkeys) CU_CHECK(cudaMemcpyAsync(nk, h->pat_keys, sizeof(unsigned long long)*h->pat_nkeys, cudaMemcpyDeviceToDevice, ops.st));
+      CU_CHECK(cudaStreamSynchronize(ops.st));
+      cudaFree(h->pat_keys);
+      h->pat_keys = nk; h->pat_cap = cap;
+    }
+    int* d_ien = upload(IEN, size_t(nEl)*eNoN, ops.st);
+    k_pattern_keys<<<CudaOps::grid_for(add, 256, 4), 256, 0, ops.st>>>(size_t(nEl), eNoN, h->pat_bits, d_ien, h->pat_keys + h->pat_nkeys); ops.post();
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+    cudaFree(d_ien);
+    h->pat_nkeys += add;
+  });
+}
+
+int b200_pattern_finish(b200_handle* h, int* nnz)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (h->pat_nNo == 0 || h->pat_nkeys == 0) throw std::runtime_error("pattern_finish: no mesh added");
+    const size_t n = h->pat_nkeys;
+    if (n > 2147483647ULL) throw std::runtime_error("pattern_finish: more than 2^31 element pairs on one device");
+    const int bits = h->pat_bits;
+    unsigned long long *alt = nullptr, *uniq = nullptr;
+    size_t* d_num = nullptr;
+    CU_CHECK(cudaMalloc(&alt, sizeof(unsigned long long)*n));
+    CU_CHECK(cudaMalloc(&d_num, sizeof(size_t)));
+    cub::DoubleBuffer<unsigned long long> db(h->pat_keys, alt);
+    void* tmp = nullptr; size_t tmp_bytes = 0;
+    CU_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, db, int(n), 0, 2*bits, ops.st));
+    CU_CHECK(cudaMalloc(&tmp, tmp_bytes));
+    CU_CHECK(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, db, int(n), 0, 2*bits, ops.st));
+    cudaStreamSynchronize(ops.st);
+    cudaFree(tmp); tmp = nullptr; tmp_bytes = 0;
+    unsigned long long* sorted = db.Current();
+    uniq = (sorted == h->pat_keys) ? alt : h->pat_keys;           // the other buffer receives the unique keys
+    CU_CHECK(cub::DeviceSelect::Unique(nullptr, tmp_bytes, sorted, uniq, d_num, int(n), ops.st));
+    CU_CHECK(cudaMalloc(&tmp, tmp_bytes));
+    CU_CHECK(cub::DeviceSelect::Unique(tmp, tmp_bytes, sorted, uniq, d_num, int(n), ops.st));
+    size_t num = 0;
+    CU_CHECK(cudaMemcpyAsync(&num, d_num, sizeof(size_t), cudaMemcpyDeviceToHost, ops.st));
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+    cudaFree(tmp); cudaFree(d_num);
+    h->pat_nnz = num;
+    CU_CHECK(cudaMalloc(&h->pat_rowPtr, sizeof(int)*(size_t(h->pat_nNo) + 1)));
+    CU_CHECK(cudaMalloc(&h->pat_colPtr, sizeof(int)*std::max<size_t>(num, 1)));
+    k_pattern_csr<<<CudaOps::grid_for(num + h->pat_nNo + 1, 256, 4), 256, 0, ops.st>>>(h->pat_nNo, bits, num, uniq, h->pat_rowPtr, h->pat_colPtr);
+    ops.post();
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+    cudaFree(alt); cudaFree(h->pat_keys);
+    h->pat_keys = nullptr; h->pat_cap = 0; h->pat_nkeys = 0;
+    *nnz = int(num);
+  });
+}
+
+int b200_pattern_get(b200_handle* h, int* rowPtr, int* colPtr)
+{
+  return guarded(h, [&] {
+    if (!h->pat_rowPtr) throw std::runtime_error("pattern_get: call b200_pattern_finish first");
+    CU_CHECK(cudaMemcpy(rowPtr, h->pat_rowPtr, sizeof(int)*(size_t(h->pat_nNo) + 1), cudaMemcpyDeviceToHost));
+    CU_CHECK(cudaMemcpy(colPtr, h->pat_colPtr, sizeof(int)*h->pat_nnz, cudaMemcpyDeviceToHost));
   });
 }
 

@@ -150,10 +150,11 @@ def lhs_layout(rank: int, all_gnodes: list[np.ndarray], gnNo: int):
 # ------------------------------------------------------------------------------------------------
 # backend set-up of one rank
 # ------------------------------------------------------------------------------------------------
-def setup_rank_backend(part, layout, device, uid=None):
+def setup_rank_backend(part, layout, device, uid=None, be=None):
     """What initialize() + fsils_lhs_create + fsils_bc_create + add_eq_linear_algebra do on one rank."""
     from . import backend as B
-    be = B.Backend(device)
+    if be is None:
+        be = B.Backend(device)
     if part["nranks"] > 1:
         be.comm_init(part["rank"], part["nranks"], uid)
     m = part["mesh"]
@@ -186,13 +187,15 @@ def weak_dims(base_dims, world):
     return (int(round(nx * f)), int(round(ny * f)), int(round(nz * f)))
 
 
-def local_slab_case(dims, rank, world, *, radius=1.0, length=10.0):
+def local_slab_case(dims, rank, world, *, radius=1.0, length=10.0, pattern=None):
     """The rank's z-slab of the global pipe `dims`, generated without ever building the global mesh.
 
     Node (i,j,k) has global id k*(nx+1)*(ny+1) + j*(nx+1) + i.  The global pipe's jitter is not
     reproduced (it would need the global random stream): the slab is jittered on its own with a
     rank-dependent seed and the two interface planes are left unjittered so that neighbours agree.
     Returns a per-rank case like split_case's plus `all_gnodes` (analytic, no communication needed).
+    pattern: optional callable (nNo, ien) -> (rowPtr, colPtr), e.g. the device-side lhsa (Backend.pattern); the host
+    construction (numpy) takes ~30 s at 10 M tets.
     """
     from . import backend as B
     nx, ny, nz = dims
@@ -204,7 +207,7 @@ def local_slab_case(dims, rank, world, *, radius=1.0, length=10.0):
     m.x[:, 2] += k0 * dz
     m.shape = (nx, ny, nz)
     gN = (np.arange(m.nNo, dtype=np.int64) + k0 * plane).astype(np.int32)
-    rowPtr, colPtr = M.csr_pattern(m.ien, m.nNo)
+    rowPtr, colPtr = pattern(m.nNo, m.ien) if pattern else M.csr_pattern(m.ien, m.nNo)
     am, af, gam = M.gen_alpha(0.5)
     Ag, Yg, Bf = M.pipe_state(m, radius=radius, length=length, seed_y=2024 + rank, seed_a=2025 + rank)
     # interface planes must carry identical state on both owners: take them from a plane-keyed stream
@@ -241,7 +244,8 @@ def setup_distributed_case(dims, rank, world, local_device, dist=None):
     """bench.py entry: rank-local slab, FSILS layout, NCCL communicator bootstrapped over torch.distributed."""
     import torch
     from . import backend as B
-    part, all_gnodes = local_slab_case(dims, rank, world)
+    be = B.Backend(local_device)
+    part, all_gnodes = local_slab_case(dims, rank, world, pattern=lambda n, ien: be.pattern(n, [ien]))     # lhsa on the device
     layout = lhs_layout(rank, all_gnodes, part["gnNo"])
     uid = None
     if world > 1:
@@ -251,5 +255,5 @@ def setup_distributed_case(dims, rank, world, local_device, dist=None):
         t = t.cuda() if dist.get_backend() == "nccl" else t
         dist.broadcast(t, src=0)
         uid = t.cpu().numpy()
-    be = setup_rank_backend(part, layout, local_device, uid)
+    be = setup_rank_backend(part, layout, local_device, uid, be=be)
     return part, be

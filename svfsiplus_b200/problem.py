@@ -34,9 +34,11 @@ LS_SETTINGS = {
 }
 
 
-def pipe_case(nx, ny, nz, *, radius=1.0, length=10.0, jitter=0.1, coupled=True, visc=None):
+def pipe_case(nx, ny, nz, *, radius=1.0, length=10.0, jitter=0.1, coupled=True, visc=None, pattern=None):
+    """pattern: optional callable (nNo, ien) -> (rowPtr, colPtr), e.g. the device-side lhsa (Backend.pattern); default is
+    the host construction M.csr_pattern (~30 s at 10 M tets)."""
     m = M.pipe_mesh(nx, ny, nz, radius=radius, length=length, jitter=jitter)
-    rowPtr, colPtr = M.csr_pattern(m.ien, m.nNo)
+    rowPtr, colPtr = pattern(m.nNo, m.ien) if pattern else M.csr_pattern(m.ien, m.nNo)
     am, af, gam = M.gen_alpha(0.5)
     Ag, Yg, Bf = M.pipe_state(m, radius=radius, length=length)
     dt = 0.005
@@ -92,10 +94,11 @@ def fluid_block_case(n, elem="hex", *, visc=None, Kinv=0.0, mvMsh=False):
                 res=np.zeros(len(faces)), incL=np.ones(len(faces), np.int32), name=f"fluid_block_{elem}_{n}")
 
 
-def setup_backend(case, device=0) -> B.Backend:
+def setup_backend(case, device=0, be=None) -> B.Backend:
     """Single-rank set-up: what initialize() + fsi_ls_ini + add_eq_linear_algebra do once."""
     m = case["mesh"]
-    be = B.Backend(device)
+    if be is None:
+        be = B.Backend(device)
     be.lhs_create(m.nNo, case["rowPtr"], case["colPtr"], nFaces=len(case["faces"]))
     for i, f in enumerate(case["faces"]):
         be.face_set(i, f["nodes"], f["dof"], f["bGrp"], f["val"], shared=False)
