@@ -188,6 +188,8 @@ def lib():
         L.ref_ranks_commuv.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.ref_asm_domains.restype = C.c_double
         L.ref_asm_domains.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 6
+        L.ref_face_integ.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_asm_bneu.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
         L.ref_pic.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_double] + [C.c_void_p] * 12
         _lib = L
@@ -294,6 +296,19 @@ class RefAssembly:
         if t < 0:
             raise RuntimeError(lib().ref_last_error().decode())
         return R, Val
+
+    def face_integ(self, IENb, gE, s, l=0, u=None, geo=0, D=None):
+        """all_fun::integ (S/all_fun.cpp:858) over one face: rows l..u of s (nNo, nrows); s None = the face area."""
+        IENb = _c(IENb, np.int32); gE = _c(gE, np.int32)
+        sa = None if s is None else _c(s, np.float64)
+        Da = None if D is None else _c(D, np.float64)
+        u = l if u is None else u
+        out = C.c_double(0.0)
+        rc = lib().ref_face_integ(self.h, IENb.shape[1], IENb.shape[0], _p(IENb), _p(gE), 0 if sa is None else sa.shape[1], _p(sa), l, u,
+                                  geo, 0 if Da is None else Da.shape[1], _p(Da), C.byref(out))
+        if rc != 0:
+            raise RuntimeError(lib().ref_last_error().decode())
+        return out.value
 
     def bneu(self, kind, IENb, gE, hg, Yg, *, dt, af, gam, rho=0.0, bfs=0.0, mvMsh=False, Do=None):
         """b_assem_neu_bc (S/eq_assem.cpp:58) on one face: kind "fluid" (b_fluid, dof 4) or "solid" (b_l_elas, dof 3).

@@ -47,6 +47,7 @@
 #include "mpi.h"
 
 #include <chrono>
+#include <optional>
 #include <functional>
 #include <cstring>
 #include <memory>
@@ -1017,6 +1018,55 @@ int ref_pic(int op, int tnNo, int tDof, int nEq, int cEq, const double* eqpar, i
 // Boundary-face (Neumann) assembly: the reference's b_assem_neu_bc (+ gnnb, b_fluid / b_l_elas) on one face.
 // ----------------------------------------------------------------------------------------------
 extern "C" {
+
+// all_fun::integ over one face (S/all_fun.cpp:561,724,858): rows l..u of s(nrows,nNo).  s == NULL: integrand 1 (area).
+// geo: 0 reference, 1 old time step (x + Do(0:2)), 2 new (x + Dn(0:2)), 3 moving mesh (x + Do(4:6)); D(tDofD,nNo).
+int ref_face_integ(void* h, int eNoNb, int nElb, const int* IENb, const int* gE, int nrows, const double* s, int l, int u,
+                   int geo, int tDofD, const double* D, double* result)
+{
+  try {
+    using namespace consts;
+    auto ctx = static_cast<AsmCtx*>(h);
+    auto& com_mod = ctx->sim->com_mod;
+    const int nNo = com_mod.tnNo;
+    auto& msh = com_mod.msh[0];
+    msh.nFa = 1;
+    msh.fa.resize(1);
+    auto& fa = msh.fa[0];
+    fa.name = "face"; fa.iM = 0; fa.eNoN = eNoNb; fa.nEl = nElb;
+    fa.IEN.resize(eNoNb, nElb);
+    std::memcpy(fa.IEN.data(), IENb, sizeof(int)*size_t(eNoNb)*nElb);
+    fa.gE.resize(nElb);
+    std::memcpy(fa.gE.data(), gE, sizeof(int)*size_t(nElb));
+    nn::select_eleb(ctx->sim.get(), msh, fa);
+    fs::init_fs_face(com_mod, msh, fa);
+    com_mod.mvMsh = (geo == 3);
+    auto cfg = MechanicalConfigurationType::reference;
+    if (geo == 1 || geo == 3) {
+      com_mod.Do.resize(tDofD, nNo);
+      std::memcpy(com_mod.Do.data(), D, sizeof(double)*size_t(tDofD)*nNo);
+      if (geo == 1) cfg = MechanicalConfigurationType::old_timestep;
+    } else if (geo == 2) {
+      com_mod.Dn.resize(tDofD, nNo);
+      std::memcpy(com_mod.Dn.data(), D, sizeof(double)*size_t(tDofD)*nNo);
+      cfg = MechanicalConfigurationType::new_timestep;
+    }
+    if (!s) {
+      Vector<double> one(nNo);
+      one = 1.0;
+      *result = all_fun::integ(com_mod, ctx->sim->cm_mod, fa, one, false, cfg);
+    } else {
+      Array<double> sa(nrows, nNo);
+      std::memcpy(sa.data(), s, sizeof(double)*size_t(nrows)*nNo);
+      *result = all_fun::integ(com_mod, ctx->sim->cm_mod, fa, sa, l, std::optional<int>(u), false, cfg);
+    }
+    com_mod.mvMsh = false;
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
 
 // kind 0: fluid equation (dof 4, b_fluid), 1: struct equation (dof 3, b_l_elas).
 // par = {dt, af, gam, rho, bfs, tDof, mvMsh}.  IENb(eNoNb,nElb), gE(nElb); hg(nNo); Yg, Do (tDof,nNo; Do may be NULL).

@@ -95,7 +95,7 @@ EXPORTS = [
     "b200_pic_init", "b200_pic_set", "b200_pic_get", "b200_pic_scatter", "b200_picp", "b200_pici", "b200_picc",
     "b200_pic_copy_rows", "b200_pic_advance", "b200_face_mesh_set", "b200_assemble_bneu",
     "b200_assemble_fluid_dmn", "b200_assemble_struct_dmn",
-    "b200_pattern_begin", "b200_pattern_add_mesh", "b200_pattern_finish", "b200_pattern_get",
+    "b200_face_integ", "b200_pattern_begin", "b200_pattern_add_mesh", "b200_pattern_finish", "b200_pattern_get",
 ]
 
 KERNEL_CLASSES = ["spmv_vv4", "spmv_vv3", "spmv_ss", "spmv_sv", "spmv_vs", "multi_dot", "cgs_update_scale", "blas1",
@@ -168,6 +168,7 @@ def lib():
         L.b200_assemble_fluid_dmn.argtypes = [vp, ci, C.POINTER(FluidProps)]
         L.b200_assemble_struct_dmn.argtypes = [vp, ci, C.POINTER(StructProps)]
         L.b200_face_mesh_set.argtypes = [vp, ci, ci, ci, vp, vp]
+        L.b200_face_integ.argtypes = [vp, ci, ci, ci, ci, ci, C.POINTER(cd)]
         L.b200_assemble_bneu.argtypes = [vp, ci, ci, C.POINTER(BneuProps), vp]
         _lib = L
     return _lib
@@ -444,6 +445,13 @@ class Backend:
     def face_mesh_set(self, faIn, IENb, gE):
         IENb = _c(IENb, np.int32); gE = _c(gE, np.int32)
         self._ck(self.L.b200_face_mesh_set(self.h, faIn, IENb.shape[1], IENb.shape[0], _p(IENb), _p(gE)), "b200_face_mesh_set")
+
+    def face_integ(self, faIn, which, l=0, u=None, geo=0):
+        """all_fun::integ over face faIn of rows l..u of a device array ("Yn", "Yo", ... or None for the area)."""
+        out = C.c_double(0.0)
+        u = l if u is None else u
+        self._ck(self.L.b200_face_integ(self.h, faIn, -1 if which is None else PIC[which], l, u, geo, C.byref(out)), "b200_face_integ")
+        return out.value
 
     def assemble_bneu(self, faIn, kind, hg, *, dt=0.0, af=0.0, gam=0.0, tDof=4, mvMsh=False, rho=0.0, bfs=0.0):
         """kind "fluid" (b_fluid) or "solid" (b_l_elas); hg: nodal Neumann values (nNo,)."""

@@ -1300,6 +1300,70 @@ int b200_face_mesh_set(b200_handle* h, int faIn, int eNoNb, int nElb, const int*
   });
 }
 
+namespace {
+double* pic_array(b200_handle* h, int which, size_t& len);        // defined with the time integrator below
+}
+extern "C++" {
+namespace {
+template <int NB, int NG>
+void launch_face_integ(b200_handle* h, b200_handle::FaceMesh& f, const double* geo, int gtD, int goff, const double* s, int stD,
+                       int l, int nrow, double* terms, double* d_out)
+{
+  auto& ops = *h->ops;
+  k_face_integ_terms<NB, NG><<<(f.nElb + 127)/128, 128, 0, ops.st>>>(f.nElb, f.tab, f.ienb, f.inode, h->d_x, geo, gtD, goff, s, stD, l, nrow, terms);
+  CU_CHECK(cudaGetLastError());
+  ops.post();
+  k_face_integ_sum<<<1, 32, 0, ops.st>>>(size_t(f.nElb)*NG, terms, d_out);
+  ops.post();
+}
+} // namespace
+} // extern "C++"
+
+int b200_face_integ(b200_handle* h, int faIn, int which, int l, int u, int geo, double* result)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (faIn < 0 || faIn >= int(h->fmesh.size()) || h->fmesh[faIn].eNoNb == 0) throw std::runtime_error("face_integ: no face mesh (b200_face_mesh_set)");
+    auto& f = h->fmesh[faIn];
+    *result = 0.0;
+    if (f.nElb == 0) return;
+    const double* s = nullptr;
+    int stD = 1;
+    if (which >= 0) {
+      size_t len = 0;
+      s = pic_array(h, which, len);
+      stD = (which == B200_PIC_AD) ? 3 : h->pic_tDof;
+      if (!s) throw std::runtime_error("face_integ: the array is not on the device");
+      if (l < 0 || u < l || u >= stD) throw std::runtime_error("face_integ: rows outside the array");
+    } else {
+      l = u = 0;
+    }
+    const int nrow = u - l + 1;
+    if (nrow != 1 && nrow != 3) throw std::runtime_error("Unexpected dof in integ");
+    const double* g = nullptr;
+    int gtD = 0, goff = 0;
+    if (geo != 0) {
+      if (h->pic_tDof == 0) throw std::runtime_error("face_integ: a displaced configuration needs the time-integrator arrays (b200_pic_init)");
+      gtD = h->pic_tDof;
+      if (geo == 1) { g = h->pic_arr[2]; goff = 0; }
+      else if (geo == 2) { g = h->pic_arr[5]; goff = 0; }
+      else if (geo == 3) { g = h->pic_arr[2]; goff = 4; }
+      else throw std::runtime_error("face_integ: geo must be 0..3");
+      if (goff + 3 > gtD) throw std::runtime_error("face_integ: the configuration rows are outside the state");
+    }
+    const int NG = (f.eNoNb == 3) ? 3 : (f.eNoNb == 4) ? 4 : 7;
+    double *terms = nullptr, *d_out = nullptr;
+    CU_CHECK(cudaMalloc(&terms, sizeof(double)*(size_t(f.nElb)*NG + 1)));
+    d_out = terms + size_t(f.nElb)*NG;
+    if (f.eNoNb == 3) launch_face_integ<3, 3>(h, f, g, gtD, goff, s, stD, l, nrow, terms, d_out);
+    else if (f.eNoNb == 4) launch_face_integ<4, 4>(h, f, g, gtD, goff, s, stD, l, nrow, terms, d_out);
+    else launch_face_integ<6, 7>(h, f, g, gtD, goff, s, stD, l, nrow, terms, d_out);
+    CU_CHECK(cudaMemcpyAsync(result, d_out, sizeof(double), cudaMemcpyDeviceToHost, ops.st));
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+    cudaFree(terms);
+  });
+}
+
 int b200_assemble_bneu(b200_handle* h, int faIn, int kind, const b200_bneu_props* p, const double* hg)
 {
   return guarded(h, [&] {

@@ -71,6 +71,36 @@ __global__ void k_bneu_sum_K(int nU, const int* __restrict__ udest, const int* _
   v[0] = a0; v[5] = a1; v[10] = a2;
 }
 
+// all_fun::integ: one thread per face element writes its NG terms; k_face_integ_sum adds them serially in (element,
+// Gauss point) order -- the reference's running sum, bit for bit (faces are small: <= 1e5 elements).
+template <int NB, int NG>
+__global__ void __launch_bounds__(128)
+k_face_integ_terms(int nElb, const double* __restrict__ tab, const int* __restrict__ ienb, const int* __restrict__ inode,
+                   const double* __restrict__ x, const double* __restrict__ geo, int gtD, int goff, const double* __restrict__ s,
+                   int stD, int l, int nrow, double* __restrict__ terms)
+{
+  __shared__ double s_tab[NG + NG*NB + NG*NB*2];
+  for (int i = threadIdx.x; i < NG + NG*NB + NG*NB*2; i += blockDim.x) s_tab[i] = tab[i];
+  __syncthreads();
+  const int e = blockIdx.x*blockDim.x + threadIdx.x;
+  if (e >= nElb) return;
+  int nd[NB];
+#pragma unroll
+  for (int a = 0; a < NB; a++) nd[a] = ienb[size_t(e)*NB + a];
+  double t[NG];
+  face_integ_terms<NB, NG>(nd, inode[e], x, geo, gtD, goff, s, stD, l, nrow, s_tab, s_tab + NG, s_tab + NG + NG*NB, t);
+#pragma unroll
+  for (int g = 0; g < NG; g++) terms[size_t(e)*NG + g] = t[g];
+}
+
+__global__ void k_face_integ_sum(size_t n, const double* __restrict__ terms, double* __restrict__ out)
+{
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double r = 0.0;
+  for (size_t i = 0; i < n; i++) r = r + terms[i];
+  *out = r;
+}
+
 // rows of IEN for a list of elements (face parents), to find the interior node on the host
 __global__ void k_gather_ien(int n, int eNoN, const int* __restrict__ gE, const int* __restrict__ ien, int* __restrict__ out)
 {

@@ -173,4 +173,57 @@ SVB_HD_NOINL void face_element(const BneuConsts& c, const int* nd, int inode, co
   }
 }
 
+// all_fun::integ over a face (Code/Source/solver/all_fun.cpp:561-722 scalar, :724-856 vector flux): the terms one face
+// element adds to the running sum, one per Gauss point, in the reference's order.
+//   vector (nrow == 3): w(g) * sum_a sum_i N(a,g) s(l+i, Ac) n(i)        n = gnnb's area-weighted normal (not normalised)
+//   scalar (nrow == 1): |n| * w(g) * sum_a s(l, Ac) N(a,g)               s == null: integrand 1 (the face area)
+// geo != null: geometry x + geo(goff : goff+3, node) (gnnb: Do(4:6) when the mesh moves, Do / Dn(0:2) for the old / new
+// configuration, nn.cpp:609-640).
+template <int NB, int NG>
+SVB_HD_NOINL void face_integ_terms(const int* nd, int inode, const double* x, const double* geo, int gtD, int goff,
+                                   const double* s, int stD, int l, int nrow, const double* wtab, const double* Ntab,
+                                   const double* Nxtab, double* terms)
+{
+  double lX[NB][3], xin[3];
+  for (int a = 0; a < NB; a++) {
+    const size_t A = size_t(nd[a]);
+    for (int i = 0; i < 3; i++) {
+      lX[a][i] = x[A*3 + i];
+      if (geo) lX[a][i] = lX[a][i] + geo[A*gtD + goff + i];
+    }
+  }
+  for (int i = 0; i < 3; i++) {
+    xin[i] = x[size_t(inode)*3 + i];
+    if (geo) xin[i] = xin[i] + geo[size_t(inode)*gtD + goff + i];
+  }
+  for (int g = 0; g < NG; g++) {
+    double xXi[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    for (int a = 0; a < NB; a++)
+      for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 3; j++) xXi[j][i] = xXi[j][i] + Nxtab[(g*NB + a)*2 + i]*lX[a][j];
+    double n[3];
+    n[0] = xXi[1][0]*xXi[2][1] - xXi[2][0]*xXi[1][1];
+    n[1] = xXi[2][0]*xXi[0][1] - xXi[0][0]*xXi[2][1];
+    n[2] = xXi[0][0]*xXi[1][1] - xXi[1][0]*xXi[0][1];
+    double dotv = 0.0;
+    for (int i = 0; i < 3; i++) dotv += n[i]*(lX[0][i] - xin[i]);
+    if (dotv < 0.0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+    const double* N = Ntab + g*NB;
+    double sHat = 0.0;
+    if (nrow == 3) {
+      for (int a = 0; a < NB; a++) {
+        const size_t A = size_t(nd[a]);
+        for (int i = 0; i < 3; i++) sHat = sHat + N[a]*s[A*stD + l + i]*n[i];
+      }
+      terms[g] = wtab[g]*sHat;
+    } else {
+      double nn = 0.0;
+      for (int i = 0; i < 3; i++) nn += n[i]*n[i];
+      const double Jac = sqrt(nn);
+      for (int a = 0; a < NB; a++) sHat = sHat + (s ? s[size_t(nd[a])*stD + l] : 1.0)*N[a];
+      terms[g] = Jac*wtab[g]*sHat;
+    }
+  }
+}
+
 } // namespace svb200

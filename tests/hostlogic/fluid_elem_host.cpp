@@ -128,6 +128,34 @@ int host_bneu_assemble(int kind, int eNoN, const int* ien, int eNoNb, int nElb, 
   return 0;
 }
 
+// all_fun::integ over one face (face_integ_terms), the running sum in (element, Gauss point) order.
+double host_face_integ(int eNoN, const int* ien, int eNoNb, int nElb, const int* IENb, const int* gE, const double* x,
+                       const double* geo, int gtD, int goff, const double* s, int stD, int l, int nrow)
+{
+  FaceTables t;
+  fill_face_tables(t, eNoNb, 2.0/3.0);
+  std::vector<double> N(t.nG*eNoNb), Nx(t.nG*eNoNb*2);
+  for (int g = 0; g < t.nG; g++)
+    for (int a = 0; a < eNoNb; a++) {
+      N[g*eNoNb + a] = t.N[g][a];
+      Nx[(g*eNoNb + a)*2] = t.Nx[g][a][0]; Nx[(g*eNoNb + a)*2 + 1] = t.Nx[g][a][1];
+    }
+  double result = 0.0;
+  for (int e = 0; e < nElb; e++) {
+    const int* nd = IENb + size_t(e)*eNoNb;
+    const int* pn = ien + size_t(gE[e])*eNoN;
+    int inode = -1;
+    for (int b = 0; b < eNoN && inode < 0; b++)
+      if (std::find(nd, nd + eNoNb, pn[b]) == nd + eNoNb) inode = pn[b];
+    double terms[7];
+    if (eNoNb == 3) face_integ_terms<3, 3>(nd, inode, x, geo, gtD, goff, s, stD, l, nrow, t.w, N.data(), Nx.data(), terms);
+    else if (eNoNb == 4) face_integ_terms<4, 4>(nd, inode, x, geo, gtD, goff, s, stD, l, nrow, t.w, N.data(), Nx.data(), terms);
+    else face_integ_terms<6, 7>(nd, inode, x, geo, gtD, goff, s, stD, l, nrow, t.w, N.data(), Nx.data(), terms);
+    for (int g = 0; g < t.nG; g++) result = result + terms[g];
+  }
+  return result;
+}
+
 // the tables themselves (checked against what the reference's select_ele leaves in lM): returns nG
 int host_elem_tables(int eNoN, double qmTET4, double* w, double* N, double* Nxi, double* Nxi2)
 {

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from conftest import needs_ref
-from util import golden, host_bneu_assemble, rel_inf
+from util import golden, host_bneu_assemble, host_face_integ, rel_inf
 
 from svfsiplus_b200 import mesh as M
 from svfsiplus_b200 import problem as P
@@ -65,6 +65,63 @@ def test_host_face_element_matches_golden(elem, n):
                                     mvMsh=mvMsh, Do=Do, **TIME)
         tag = f"{elem}_{kind}_{int(mvMsh)}"
         assert rel_inf(R, g[f"R_{tag}"]) < 1e-14 and rel_inf(Val, g[f"Val_{tag}"]) < 1e-14
+
+
+def _integ_inputs(elem, n):
+    case, IENb, gE, hg, _ = _setup(elem, n)
+    m = case["mesh"]
+    rng = np.random.default_rng(12)
+    Y = np.zeros((m.nNo, 7)); Y[:, :4] = case["Yg"]
+    D = np.zeros((m.nNo, 7))
+    D[:, 0:3] = 0.02 / n * rng.standard_normal((m.nNo, 3))
+    D[:, 4:7] = 0.03 / n * rng.standard_normal((m.nNo, 3))
+    return case, IENb, gE, Y, D
+
+
+# (name, source rows l..u, geo, offset of the configuration rows): flux on the reference / old / new / moving configurations,
+# pressure integral, area
+INTEG = [("flux", 0, 2, 0, 0), ("flux_old", 0, 2, 1, 0), ("flux_new", 0, 2, 2, 0), ("flux_mv", 0, 2, 3, 4), ("pressure", 3, 3, 0, 0),
+         ("area", None, None, 0, 0), ("area_mv", None, None, 3, 4)]
+
+
+@pytest.mark.parametrize("elem,n", ELEMS)
+@needs_ref
+def test_host_face_integrals_match_reference_bitwise(elem, n):
+    """all_fun::integ (all_fun.cpp:561,724,858): flux of the velocity, pressure integral and area of a face."""
+    from oracle import ref
+    case, IENb, gE, Y, D = _integ_inputs(elem, n)
+    m = case["mesh"]
+    ra = ref.RefAssembly(m.x, m.ien)
+    for name, l, u, geo, goff in INTEG:
+        want = ra.face_integ(IENb, gE, None if l is None else Y, 0 if l is None else l, u, geo=geo, D=D if geo else None)
+        got = host_face_integ(m, IENb, gE, None if l is None else Y, 0 if l is None else l, u, geo=D if geo else None, goff=goff)
+        assert got == want and want != 0.0, (name, got, want)
+    assert abs(ra.face_integ(IENb, gE, None) - 1.0) < 1e-12          # Z0 of the unit block (boundary nodes are not jittered)
+    ra.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("elem,n", ELEMS)
+def test_gpu_face_integrals_bitwise(elem, n):
+    """b200_face_integ on the device-resident time-integrator arrays: equal to the host run of the same arithmetic (which the
+    CPU suite pins to the reference bit for bit) and to the reference itself where it travelled."""
+    case, IENb, gE, Y, D = _integ_inputs(elem, n)
+    m = case["mesh"]
+    be = P.setup_backend(case)
+    be.face_mesh_set(2, IENb, gE)
+    be.pic_init(7, [dict(s=0, e=3, am=1.0, af=1.0, gam=1.0, beta=0.25), dict(s=4, e=6, am=1.0, af=1.0, gam=1.0, beta=0.25)], dFlag=True)
+    be.pic_set("Yn", Y)
+    from oracle import ref
+    ra = ref.RefAssembly(m.x, m.ien) if ref.available() else None
+    for name, l, u, geo, goff in INTEG:
+        be.pic_set("Do", D if geo in (1, 3) else np.zeros_like(D))
+        be.pic_set("Dn", D if geo == 2 else np.zeros_like(D))
+        got = be.face_integ(2, None if l is None else "Yn", 0 if l is None else l, u, geo=geo)
+        host = host_face_integ(m, IENb, gE, None if l is None else Y, 0 if l is None else l, u, geo=D if geo else None, goff=goff)
+        assert got == host, (name, got, host)
+        if ra is not None:
+            assert got == ra.face_integ(IENb, gE, None if l is None else Y, 0 if l is None else l, u, geo=geo, D=D if geo else None), name
+    be.close()
 
 
 # ---------------------------------------------------------------------------------------------- GPU

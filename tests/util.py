@@ -68,6 +68,9 @@ def elemhost():
         _eh = C.CDLL(os.path.join(ROOT, "tests", "_build", "libelemhost.so"))
         _eh.host_fluid_assemble.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_double] + [C.c_void_p] * 7
         _eh.host_elem_tables.argtypes = [C.c_int, C.c_double] + [C.c_void_p] * 4
+        _eh.host_face_integ.restype = C.c_double
+        _eh.host_face_integ.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
         _eh.host_bneu_assemble.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 11
     return _eh
 
@@ -110,3 +113,15 @@ def host_bneu_assemble(kind, mesh, IENb, gE, hg, Yg, rowPtr, colPtr, *, dt, af, 
     if rc != 0:
         raise RuntimeError(f"host_bneu_assemble: rc {rc}")
     return R, Val
+
+
+def host_face_integ(mesh, IENb, gE, s, l=0, u=None, geo=None, goff=0):
+    """face_elem.hpp face_integ_terms summed serially on the host (TEST-ONLY harness).  s (nNo, nrows) or None (area)."""
+    L = elemhost()
+    ien = np.ascontiguousarray(mesh.ien, np.int32); x = np.ascontiguousarray(mesh.x, np.float64)
+    IENb = np.ascontiguousarray(IENb, np.int32); gE = np.ascontiguousarray(gE, np.int32)
+    sa = None if s is None else np.ascontiguousarray(s, np.float64)
+    ga = None if geo is None else np.ascontiguousarray(geo, np.float64)
+    u = l if u is None else u
+    return L.host_face_integ(ien.shape[1], _p(ien), IENb.shape[1], IENb.shape[0], _p(IENb), _p(gE), _p(x), _p(ga),
+                             0 if ga is None else ga.shape[1], goff, _p(sa), 1 if sa is None else sa.shape[1], l, u - l + 1)
