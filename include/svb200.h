@@ -186,6 +186,12 @@ int b200_face_mesh_set(b200_handle* h, int faIn, int eNoNb, int nElb, const int*
  * run this is the rank's part; the caller reduces it like cm.reduce does. */
 int b200_face_integ(b200_handle* h, int faIn, int which, int l, int u, int geo, double* result);
 int b200_assemble_bneu(b200_handle* h, int faIn, int kind, const b200_bneu_props* p, const double* hg);
+/* eq_assem::fsi_ls_upd (solver/eq_assem.cpp:316-371) + fsils_bc_update (liner_solver/bc.cpp:171): recompute the vector
+ * val(i,a) = int N_a n_i dGamma of the coupled Neumann face lsFace (index of b200_face_set, dof 3) from the face mesh
+ * faIn on the configuration geo (as in b200_face_integ; the reference uses 2 = new time step), halo-summed when the face
+ * is shared between ranks.  The face vectors of the linear solve then follow the moving mesh without a host round trip. */
+int b200_face_normal_update(b200_handle* h, int faIn, int lsFace, int geo);
+int b200_face_get_val(b200_handle* h, int lsFace, double* val);            /* parity tap: lhs.face[lsFace].val(dof,nNo) */
 /* LinearAlgebra::assemble for the few boundary-face elements: staged on the host, flushed by one
  * scatter kernel before the next get/solve.  eqN(d), lK(dof*dof,d,d), lR(dof,d). */
 int b200_assemble_elem(b200_handle* h, int d, const int* eqN, const double* lK, const double* lR);

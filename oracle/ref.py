@@ -190,6 +190,8 @@ def lib():
         L.ref_asm_domains.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 6
         L.ref_face_integ.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_fsi_ls_upd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p]
         L.ref_asm_bneu.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
         L.ref_pic.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_double] + [C.c_void_p] * 12
         _lib = L
@@ -309,6 +311,15 @@ class RefAssembly:
         if rc != 0:
             raise RuntimeError(lib().ref_last_error().decode())
         return out.value
+
+    def fsi_ls_upd(self, IENb, gE, gN, D, mvMsh=False):
+        """eq_assem::fsi_ls_upd (S/eq_assem.cpp:316): val (nNoFace, 3) = int N_a n dGamma on x + Dn(0:2) or, moving mesh, x + Do(4:6)."""
+        IENb = _c(IENb, np.int32); gE = _c(gE, np.int32); gN = _c(gN, np.int32); D = _c(D, np.float64)
+        val = np.empty((len(gN), 3))
+        rc = lib().ref_fsi_ls_upd(self.h, IENb.shape[1], IENb.shape[0], _p(IENb), _p(gE), len(gN), _p(gN), int(mvMsh), D.shape[1], _p(D), _p(val))
+        if rc != 0:
+            raise RuntimeError(lib().ref_last_error().decode())
+        return val
 
     def bneu(self, kind, IENb, gE, hg, Yg, *, dt, af, gam, rho=0.0, bfs=0.0, mvMsh=False, Do=None):
         """b_assem_neu_bc (S/eq_assem.cpp:58) on one face: kind "fluid" (b_fluid, dof 4) or "solid" (b_l_elas, dof 3).

@@ -1068,6 +1068,54 @@ int ref_face_integ(void* h, int eNoNb, int nElb, const int* IENb, const int* gE,
   }
 }
 
+// eq_assem::fsi_ls_upd (S/eq_assem.cpp:316) + fsils_bc_update: the face vector val(3,nNoFace) = int N_a n dGamma of a Neumann
+// face on the new-time-step configuration x + Dn(0:2) (mvMsh = 0) or the moving mesh x + Do(4:6) (mvMsh = 1).
+// gN(nNoFace): the face's node list (lFa.gN).  The lhs is built here (1 rank) with that one face.
+int ref_fsi_ls_upd(void* h, int eNoNb, int nElb, const int* IENb, const int* gE, int nNoFace, const int* gN, int mvMsh, int tDofD,
+                   const double* D, double* val)
+{
+  try {
+    using namespace consts;
+    mpistub_set_world(1);
+    mpistub_bind_rank(0);
+    auto ctx = static_cast<AsmCtx*>(h);
+    auto& com_mod = ctx->sim->com_mod;
+    const int nNo = com_mod.tnNo;
+    auto& msh = com_mod.msh[0];
+    msh.nFa = 1;
+    msh.fa.resize(1);
+    auto& fa = msh.fa[0];
+    fa.name = "face"; fa.iM = 0; fa.eNoN = eNoNb; fa.nEl = nElb; fa.nNo = nNoFace;
+    fa.IEN.resize(eNoNb, nElb);
+    std::memcpy(fa.IEN.data(), IENb, sizeof(int)*size_t(eNoNb)*nElb);
+    fa.gE.resize(nElb);
+    std::memcpy(fa.gE.data(), gE, sizeof(int)*size_t(nElb));
+    fa.gN.resize(nNoFace);
+    std::memcpy(fa.gN.data(), gN, sizeof(int)*size_t(nNoFace));
+    nn::select_eleb(ctx->sim.get(), msh, fa);
+    com_mod.mvMsh = (mvMsh != 0);
+    if (mvMsh) { com_mod.Do.resize(tDofD, nNo); std::memcpy(com_mod.Do.data(), D, sizeof(double)*size_t(tDofD)*nNo); }
+    else { com_mod.Dn.resize(tDofD, nNo); std::memcpy(com_mod.Dn.data(), D, sizeof(double)*size_t(tDofD)*nNo); }
+    auto& lhs = com_mod.lhs;
+    lhs = FSILS_lhsType();
+    fsils_commu_create(lhs.commu, MPI_COMM_WORLD);
+    Vector<int> gNodes(nNo);
+    for (int a = 0; a < nNo; a++) gNodes(a) = a;
+    fsils_lhs_create(lhs, lhs.commu, nNo, nNo, ctx->nnz, gNodes, com_mod.rowPtr, com_mod.colPtr, 1);
+    Array<double> v0(3, nNoFace);
+    fsils_bc_create(lhs, 0, nNoFace, 3, BcType::BC_TYPE_Neu, fa.gN, v0);
+    bcType lBc;
+    lBc.lsPtr = 0;
+    eq_assem::fsi_ls_upd(com_mod, lBc, fa);
+    std::memcpy(val, lhs.face[0].val.data(), sizeof(double)*size_t(3)*nNoFace);
+    com_mod.mvMsh = false;
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
 // kind 0: fluid equation (dof 4, b_fluid), 1: struct equation (dof 3, b_l_elas).
 // par = {dt, af, gam, rho, bfs, tDof, mvMsh}.  IENb(eNoNb,nElb), gE(nElb); hg(nNo); Yg, Do (tDof,nNo; Do may be NULL).
 // Outputs the face's contribution alone: R (dof,nNo), Val (dof*dof,nnz).

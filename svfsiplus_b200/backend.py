@@ -95,7 +95,7 @@ EXPORTS = [
     "b200_pic_init", "b200_pic_set", "b200_pic_get", "b200_pic_scatter", "b200_picp", "b200_pici", "b200_picc",
     "b200_pic_copy_rows", "b200_pic_advance", "b200_face_mesh_set", "b200_assemble_bneu",
     "b200_assemble_fluid_dmn", "b200_assemble_struct_dmn",
-    "b200_face_integ", "b200_pattern_begin", "b200_pattern_add_mesh", "b200_pattern_finish", "b200_pattern_get",
+    "b200_face_integ", "b200_face_normal_update", "b200_face_get_val", "b200_pattern_begin", "b200_pattern_add_mesh", "b200_pattern_finish", "b200_pattern_get",
 ]
 
 KERNEL_CLASSES = ["spmv_vv4", "spmv_vv3", "spmv_ss", "spmv_sv", "spmv_vs", "multi_dot", "cgs_update_scale", "blas1",
@@ -169,6 +169,8 @@ def lib():
         L.b200_assemble_struct_dmn.argtypes = [vp, ci, C.POINTER(StructProps)]
         L.b200_face_mesh_set.argtypes = [vp, ci, ci, ci, vp, vp]
         L.b200_face_integ.argtypes = [vp, ci, ci, ci, ci, ci, C.POINTER(cd)]
+        L.b200_face_normal_update.argtypes = [vp, ci, ci, ci]
+        L.b200_face_get_val.argtypes = [vp, ci, vp]
         L.b200_assemble_bneu.argtypes = [vp, ci, ci, C.POINTER(BneuProps), vp]
         _lib = L
     return _lib
@@ -452,6 +454,15 @@ class Backend:
         u = l if u is None else u
         self._ck(self.L.b200_face_integ(self.h, faIn, -1 if which is None else PIC[which], l, u, geo, C.byref(out)), "b200_face_integ")
         return out.value
+
+    def face_normal_update(self, faIn, lsFace, geo=2):
+        """fsi_ls_upd: recompute the face vector of linear-solver face lsFace from face mesh faIn (geo as in face_integ)."""
+        self._ck(self.L.b200_face_normal_update(self.h, faIn, lsFace, geo), "b200_face_normal_update")
+
+    def face_get_val(self, lsFace, nNoFace, dof=3):
+        val = np.empty((nNoFace, dof))
+        self._ck(self.L.b200_face_get_val(self.h, lsFace, _p(val)), "b200_face_get_val")
+        return val
 
     def assemble_bneu(self, faIn, kind, hg, *, dt=0.0, af=0.0, gam=0.0, tDof=4, mvMsh=False, rho=0.0, bfs=0.0):
         """kind "fluid" (b_fluid) or "solid" (b_l_elas); hg: nodal Neumann values (nNo,)."""

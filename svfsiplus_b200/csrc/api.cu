@@ -1364,6 +1364,72 @@ int b200_face_integ(b200_handle* h, int faIn, int which, int l, int u, int geo, 
   });
 }
 
+extern "C++" {
+namespace {
+template <int NB, int NG>
+void launch_face_nrm(b200_handle* h, b200_handle::FaceMesh& f, const double* geo, int gtD, int goff, double* stage, double* buf)
+{
+  auto& ops = *h->ops;
+  k_face_nrm_elem<NB, NG><<<(f.nElb + 127)/128, 128, 0, ops.st>>>(f.nElb, f.tab, f.ienb, f.inode, f.rslot, h->d_x, geo, gtD, goff, stage);
+  CU_CHECK(cudaGetLastError());
+  ops.post();
+  k_face_nrm_sum<<<(f.nUR + 127)/128, 128, 0, ops.st>>>(f.nUR, NG, f.udestR, f.usegR, stage, buf);
+  ops.post();
+}
+} // namespace
+} // extern "C++"
+
+int b200_face_normal_update(b200_handle* h, int faIn, int lsFace, int geo)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (faIn < 0 || faIn >= int(h->fmesh.size()) || h->fmesh[faIn].eNoNb == 0) throw std::runtime_error("face_normal_update: no face mesh (b200_face_mesh_set)");
+    if (lsFace < 0 || lsFace >= int(ops.faces.size()) || !ops.faces[lsFace].set) throw std::runtime_error("face_normal_update: no such linear-solver face (b200_face_set)");
+    auto& f = h->fmesh[faIn];
+    auto& lf = ops.faces[lsFace];
+    if (lf.dof != 3) throw std::runtime_error("face_normal_update: the face vector must have nsd = 3 components");
+    const double* g = nullptr;
+    int gtD = 0, goff = 0;
+    if (geo != 0) {
+      if (h->pic_tDof == 0) throw std::runtime_error("face_normal_update: a displaced configuration needs the time-integrator arrays (b200_pic_init)");
+      gtD = h->pic_tDof;
+      if (geo == 1) { g = h->pic_arr[2]; goff = 0; }
+      else if (geo == 2) { g = h->pic_arr[5]; goff = 0; }
+      else if (geo == 3) { g = h->pic_arr[2]; goff = 4; }
+      else throw std::runtime_error("face_normal_update: geo must be 0..3");
+      if (goff + 3 > gtD) throw std::runtime_error("face_normal_update: the configuration rows are outside the state");
+    }
+    const auto m = ops.mark();
+    const size_t n3 = size_t(h->nNo)*3;
+    double* buf = ops.vec(n3);
+    ops.zero(n3, buf);
+    if (f.nElb > 0) {
+      const int NG = (f.eNoNb == 3) ? 3 : (f.eNoNb == 4) ? 4 : 7;
+      double* stage = nullptr;
+      CU_CHECK(cudaMalloc(&stage, sizeof(double)*size_t(f.nElb)*f.eNoNb*NG*3));
+      if (f.eNoNb == 3) launch_face_nrm<3, 3>(h, f, g, gtD, goff, stage, buf);
+      else if (f.eNoNb == 4) launch_face_nrm<4, 4>(h, f, g, gtD, goff, stage, buf);
+      else launch_face_nrm<6, 7>(h, f, g, gtD, goff, stage, buf);
+      CU_CHECK(cudaStreamSynchronize(ops.st));
+      cudaFree(stage);
+    }
+    if (lf.shared) ops.halo_add(3, buf);                     // fsils_bc_update: commuv of the nodal vector (bc.cpp:185-207)
+    if (lf.nNo > 0) { k_face_gather3<<<CudaOps::grid_for(size_t(lf.nNo)*3, 256, 1), 256, 0, ops.st>>>(lf.nNo, lf.glob, buf, lf.val); ops.post(); }
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+    ops.release(m);
+  });
+}
+
+int b200_face_get_val(b200_handle* h, int lsFace, double* val)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (lsFace < 0 || lsFace >= int(ops.faces.size()) || !ops.faces[lsFace].set) throw std::runtime_error("face_get_val: no such face");
+    auto& lf = ops.faces[lsFace];
+    CU_CHECK(cudaMemcpy(val, lf.val, sizeof(double)*size_t(lf.nNo)*lf.dof, cudaMemcpyDeviceToHost));
+  });
+}
+
 int b200_assemble_bneu(b200_handle* h, int faIn, int kind, const b200_bneu_props* p, const double* hg)
 {
   return guarded(h, [&] {

@@ -101,6 +101,54 @@ __global__ void k_face_integ_sum(size_t n, const double* __restrict__ terms, dou
   *out = r;
 }
 
+// fsi_ls_upd: sV(i, node) = int N_a n_i dGamma.  Per face element the NB x NG x 3 terms go to the element's row slots;
+// k_face_nrm_sum adds every node's run in (element, Gauss point) order into a nodal buffer (solver ordering).
+template <int NB, int NG>
+__global__ void __launch_bounds__(128)
+k_face_nrm_elem(int nElb, const double* __restrict__ tab, const int* __restrict__ ienb, const int* __restrict__ inode,
+                const int* __restrict__ rslot, const double* __restrict__ x, const double* __restrict__ geo, int gtD, int goff,
+                double* __restrict__ stage)
+{
+  __shared__ double s_tab[NG + NG*NB + NG*NB*2];
+  for (int i = threadIdx.x; i < NG + NG*NB + NG*NB*2; i += blockDim.x) s_tab[i] = tab[i];
+  __syncthreads();
+  const int e = blockIdx.x*blockDim.x + threadIdx.x;
+  if (e >= nElb) return;
+  int nd[NB];
+#pragma unroll
+  for (int a = 0; a < NB; a++) nd[a] = ienb[size_t(e)*NB + a];
+  double t[NB*NG*3];
+  face_normal_terms<NB, NG>(nd, inode[e], x, geo, gtD, goff, s_tab, s_tab + NG, s_tab + NG + NG*NB, t);
+#pragma unroll
+  for (int a = 0; a < NB; a++) {
+    double* o = stage + size_t(rslot[size_t(e)*NB + a])*(NG*3);
+#pragma unroll
+    for (int q = 0; q < NG*3; q++) o[q] = t[a*NG*3 + q];
+  }
+}
+
+__global__ void k_face_nrm_sum(int nU, int ng, const int* __restrict__ udest, const int* __restrict__ useg, const double* __restrict__ stage,
+                               double* __restrict__ buf)
+{
+  const int t = blockIdx.x*blockDim.x + threadIdx.x;
+  if (t >= nU) return;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+  for (int q = useg[t]; q < useg[t + 1]; q++)
+    for (int g = 0; g < ng; g++) {
+      const double* s = stage + (size_t(q)*ng + g)*3;
+      a0 = a0 + s[0]; a1 = a1 + s[1]; a2 = a2 + s[2];
+    }
+  double* o = buf + size_t(udest[t])*3;
+  o[0] = a0; o[1] = a1; o[2] = a2;
+}
+
+// lhs.face val(0:2, a) = buf(0:2, glob[a])
+__global__ void k_face_gather3(int fnNo, const int* __restrict__ glob, const double* __restrict__ buf, double* __restrict__ val)
+{
+  const int n = fnNo*3;
+  for (int t = blockIdx.x*blockDim.x + threadIdx.x; t < n; t += gridDim.x*blockDim.x) val[t] = buf[size_t(glob[t/3])*3 + t % 3];
+}
+
 // rows of IEN for a list of elements (face parents), to find the interior node on the host
 __global__ void k_gather_ien(int n, int eNoN, const int* __restrict__ gE, const int* __restrict__ ien, int* __restrict__ out)
 {

@@ -226,4 +226,40 @@ SVB_HD_NOINL void face_integ_terms(const int* nd, int inode, const double* x, co
   }
 }
 
+// eq_assem::fsi_ls_upd (Code/Source/solver/eq_assem.cpp:316-371): the terms N(a,g) w(g) n(i) one face element adds to
+// sV(i, node a) = int N_a n_i dGamma on the configuration `geo` (new time step there; gnnb's area-weighted normal).
+// out[(a*NG + g)*3 + i]; the caller adds them per node in (element, Gauss point) order.
+template <int NB, int NG>
+SVB_HD_NOINL void face_normal_terms(const int* nd, int inode, const double* x, const double* geo, int gtD, int goff,
+                                    const double* wtab, const double* Ntab, const double* Nxtab, double* out)
+{
+  double lX[NB][3], xin[3];
+  for (int a = 0; a < NB; a++) {
+    const size_t A = size_t(nd[a]);
+    for (int i = 0; i < 3; i++) {
+      lX[a][i] = x[A*3 + i];
+      if (geo) lX[a][i] = lX[a][i] + geo[A*gtD + goff + i];
+    }
+  }
+  for (int i = 0; i < 3; i++) {
+    xin[i] = x[size_t(inode)*3 + i];
+    if (geo) xin[i] = xin[i] + geo[size_t(inode)*gtD + goff + i];
+  }
+  for (int g = 0; g < NG; g++) {
+    double xXi[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    for (int a = 0; a < NB; a++)
+      for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 3; j++) xXi[j][i] = xXi[j][i] + Nxtab[(g*NB + a)*2 + i]*lX[a][j];
+    double n[3];
+    n[0] = xXi[1][0]*xXi[2][1] - xXi[2][0]*xXi[1][1];
+    n[1] = xXi[2][0]*xXi[0][1] - xXi[0][0]*xXi[2][1];
+    n[2] = xXi[0][0]*xXi[1][1] - xXi[1][0]*xXi[0][1];
+    double dotv = 0.0;
+    for (int i = 0; i < 3; i++) dotv += n[i]*(lX[0][i] - xin[i]);
+    if (dotv < 0.0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+    for (int a = 0; a < NB; a++)
+      for (int i = 0; i < 3; i++) out[(a*NG + g)*3 + i] = Ntab[g*NB + a]*wtab[g]*n[i];
+  }
+}
+
 } // namespace svb200

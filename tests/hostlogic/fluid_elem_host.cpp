@@ -156,6 +156,36 @@ double host_face_integ(int eNoN, const int* ien, int eNoNb, int nElb, const int*
   return result;
 }
 
+// fsi_ls_upd (face_normal_terms): sV(3,nNo) accumulated per node in (element, Gauss point) order; sV must be zero on entry.
+int host_face_normals(int eNoN, const int* ien, int eNoNb, int nElb, const int* IENb, const int* gE, const double* x,
+                      const double* geo, int gtD, int goff, double* sV)
+{
+  FaceTables t;
+  fill_face_tables(t, eNoNb, 2.0/3.0);
+  std::vector<double> N(t.nG*eNoNb), Nx(t.nG*eNoNb*2);
+  for (int g = 0; g < t.nG; g++)
+    for (int a = 0; a < eNoNb; a++) {
+      N[g*eNoNb + a] = t.N[g][a];
+      Nx[(g*eNoNb + a)*2] = t.Nx[g][a][0]; Nx[(g*eNoNb + a)*2 + 1] = t.Nx[g][a][1];
+    }
+  for (int e = 0; e < nElb; e++) {
+    const int* nd = IENb + size_t(e)*eNoNb;
+    const int* pn = ien + size_t(gE[e])*eNoN;
+    int inode = -1;
+    for (int b = 0; b < eNoN && inode < 0; b++)
+      if (std::find(nd, nd + eNoNb, pn[b]) == nd + eNoNb) inode = pn[b];
+    if (inode < 0) return e + 1;
+    double out[6*7*3];
+    if (eNoNb == 3) face_normal_terms<3, 3>(nd, inode, x, geo, gtD, goff, t.w, N.data(), Nx.data(), out);
+    else if (eNoNb == 4) face_normal_terms<4, 4>(nd, inode, x, geo, gtD, goff, t.w, N.data(), Nx.data(), out);
+    else face_normal_terms<6, 7>(nd, inode, x, geo, gtD, goff, t.w, N.data(), Nx.data(), out);
+    for (int g = 0; g < t.nG; g++)
+      for (int a = 0; a < eNoNb; a++)
+        for (int i = 0; i < 3; i++) sV[size_t(nd[a])*3 + i] = sV[size_t(nd[a])*3 + i] + out[(a*t.nG + g)*3 + i];
+  }
+  return 0;
+}
+
 // the tables themselves (checked against what the reference's select_ele leaves in lM): returns nG
 int host_elem_tables(int eNoN, double qmTET4, double* w, double* N, double* Nxi, double* Nxi2)
 {

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from conftest import needs_ref
-from util import golden, host_bneu_assemble, host_face_integ, rel_inf
+from util import golden, host_bneu_assemble, host_face_integ, host_face_normals, rel_inf
 
 from svfsiplus_b200 import mesh as M
 from svfsiplus_b200 import problem as P
@@ -121,6 +121,49 @@ def test_gpu_face_integrals_bitwise(elem, n):
         assert got == host, (name, got, host)
         if ra is not None:
             assert got == ra.face_integ(IENb, gE, None if l is None else Y, 0 if l is None else l, u, geo=geo, D=D if geo else None), name
+    be.close()
+
+
+@pytest.mark.parametrize("elem,n", ELEMS)
+@pytest.mark.parametrize("mvMsh", [False, True])
+@needs_ref
+def test_host_face_normals_match_reference_bitwise(elem, n, mvMsh):
+    """fsi_ls_upd (eq_assem.cpp:316): val = int N_a n dGamma on the new-time-step / moving-mesh configuration."""
+    from oracle import ref
+    case, IENb, gE, Y, D = _integ_inputs(elem, n)
+    m = case["mesh"]
+    gN = np.unique(IENb)
+    ra = ref.RefAssembly(m.x, m.ien)
+    want = ra.fsi_ls_upd(IENb, gE, gN, D, mvMsh=mvMsh)
+    ra.close()
+    got = host_face_normals(m, IENb, gE, geo=D, goff=4 if mvMsh else 0)
+    assert np.abs(want).max() > 0 and np.array_equal(got[gN], want)
+    off = np.ones(m.nNo, bool); off[gN] = False
+    assert np.abs(got[off]).max() == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("elem,n", ELEMS)
+@pytest.mark.parametrize("geo", [2, 3])
+def test_gpu_face_normal_update_bitwise(elem, n, geo):
+    """b200_face_normal_update: the coupled face's vector follows the moving configuration on the device."""
+    case, IENb, gE, Y, D = _integ_inputs(elem, n)
+    m = case["mesh"]
+    gN = np.unique(IENb)
+    be = P.setup_backend(case)                                   # faces 0..4 of the case are Dirichlet
+    be.face_set(4, gN, 3, 1, np.zeros((len(gN), 3)), shared=False)      # turn slot 4 into the Neumann face Z0
+    be.face_mesh_set(0, IENb, gE)
+    be.pic_init(7, [dict(s=0, e=3, am=1.0, af=1.0, gam=1.0, beta=0.25), dict(s=4, e=6, am=1.0, af=1.0, gam=1.0, beta=0.25)], dFlag=True)
+    be.pic_set("Dn" if geo == 2 else "Do", D)
+    be.face_normal_update(0, 4, geo=geo)
+    got = be.face_get_val(4, len(gN))
+    host = host_face_normals(m, IENb, gE, geo=D, goff=4 if geo == 3 else 0)[gN]
+    assert np.array_equal(got, host)
+    from oracle import ref
+    if ref.available():
+        ra = ref.RefAssembly(m.x, m.ien)
+        assert np.array_equal(got, ra.fsi_ls_upd(IENb, gE, gN, D, mvMsh=(geo == 3)))
+        ra.close()
     be.close()
 
 

@@ -71,6 +71,8 @@ def elemhost():
         _eh.host_face_integ.restype = C.c_double
         _eh.host_face_integ.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                         C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _eh.host_face_normals.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_int, C.c_void_p]
         _eh.host_bneu_assemble.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 11
     return _eh
 
@@ -125,3 +127,17 @@ def host_face_integ(mesh, IENb, gE, s, l=0, u=None, geo=None, goff=0):
     u = l if u is None else u
     return L.host_face_integ(ien.shape[1], _p(ien), IENb.shape[1], IENb.shape[0], _p(IENb), _p(gE), _p(x), _p(ga),
                              0 if ga is None else ga.shape[1], goff, _p(sa), 1 if sa is None else sa.shape[1], l, u - l + 1)
+
+
+def host_face_normals(mesh, IENb, gE, geo=None, goff=0):
+    """face_elem.hpp face_normal_terms (fsi_ls_upd) accumulated on the host: sV (nNo, 3)."""
+    L = elemhost()
+    ien = np.ascontiguousarray(mesh.ien, np.int32); x = np.ascontiguousarray(mesh.x, np.float64)
+    IENb = np.ascontiguousarray(IENb, np.int32); gE = np.ascontiguousarray(gE, np.int32)
+    ga = None if geo is None else np.ascontiguousarray(geo, np.float64)
+    sV = np.zeros((mesh.nNo, 3))
+    rc = L.host_face_normals(ien.shape[1], _p(ien), IENb.shape[1], IENb.shape[0], _p(IENb), _p(gE), _p(x), _p(ga),
+                             0 if ga is None else ga.shape[1], goff, _p(sV))
+    if rc != 0:
+        raise RuntimeError(f"host_face_normals: rc {rc}")
+    return sV
