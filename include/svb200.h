@@ -61,6 +61,8 @@ typedef struct {
   int isoType, volType;
   double C10, C01, Kpen;
   double a, b, aff, bff, ass, bss, afs, bfs, khs;   /* isoType 3 (Holzapfel-Ogden): stModelType a..bfs, khs */
+  double Tfa, Tsa;   /* fibre-reinforcement / active stress along the fibre and sheet directions: what get_fib_stress returns
+                        for stM.Tf at this time, and Tfa*Tf.eta_s (mat_models_carray.h:222-225); laws 0 and 3, needs fibres */
 } b200_struct_props;
 
 /* Linear elasticity (solver/l_elas.cpp:274-390).  mesh_mode != 0: the ALE mesh-motion equation
@@ -83,6 +85,7 @@ typedef struct {
   int isoType, volType;
   double C10, Kpen;
   double a, b, aff, bff, ass, bss, afs, bfs, khs;   /* isoType 3 (Holzapfel-Ogden) */
+  double Tfa, Tsa;   /* fibre / sheet reinforcement stress as in the struct properties above; mat_models.cpp:682-684 */
 } b200_ustruct_props;
 
 /* ---- life cycle ------------------------------------------------------------------------- */

@@ -306,6 +306,10 @@ void configure_solid(AsmCtx* ctx, int kind, int tDof, int s, const double* par, 
     // Holzapfel-Ogden parameters (par[17..25]) and the mesh's fibre / sheet directions
     dmn.stM.a = par[17]; dmn.stM.b = par[18]; dmn.stM.aff = par[19]; dmn.stM.bff = par[20];
     dmn.stM.ass = par[21]; dmn.stM.bss = par[22]; dmn.stM.afs = par[23]; dmn.stM.bfs = par[24]; dmn.stM.khs = par[25];
+    // steady fibre-reinforcement stress (get_fib_stress, S/mat_models.cpp:126): par[26] = Tf.g, par[27] = Tf.eta_s
+    dmn.stM.Tf.fType = (par[26] != 0.0) ? utils::ibset(0, iBC_std) : 0;
+    dmn.stM.Tf.g = par[26];
+    dmn.stM.Tf.eta_s = par[27];
     com_mod.Bf.resize(3, nNo);
     std::memcpy(com_mod.Bf.data(), Bf, sizeof(double)*3*size_t(nNo));
 }
@@ -545,6 +549,9 @@ double ref_asm_ustruct(void* h, int tDof, const double* par, const double* Ag, c
     dmn.stM.Kpen = par[14];
     dmn.stM.a = par[16]; dmn.stM.b = par[17]; dmn.stM.aff = par[18]; dmn.stM.bff = par[19];
     dmn.stM.ass = par[20]; dmn.stM.bss = par[21]; dmn.stM.afs = par[22]; dmn.stM.bfs = par[23]; dmn.stM.khs = par[24];
+    dmn.stM.Tf.fType = (par[25] != 0.0) ? utils::ibset(0, iBC_std) : 0;        // par[25] = Tf.g, par[26] = Tf.eta_s
+    dmn.stM.Tf.g = par[25];
+    dmn.stM.Tf.eta_s = par[26];
     com_mod.Bf.resize(3, nNo);
     std::memcpy(com_mod.Bf.data(), Bf, sizeof(double)*3*size_t(nNo));
     if (!eq.linear_algebra) eq.linear_algebra = new FsilsLinearAlgebra();

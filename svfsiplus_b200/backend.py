@@ -49,7 +49,8 @@ class StructProps(C.Structure):
                 ("isoType", C.c_int), ("volType", C.c_int),
                 ("C10", C.c_double), ("C01", C.c_double), ("Kpen", C.c_double),
                 ("a", C.c_double), ("b", C.c_double), ("aff", C.c_double), ("bff", C.c_double), ("ass", C.c_double),
-                ("bss", C.c_double), ("afs", C.c_double), ("bfs", C.c_double), ("khs", C.c_double)]
+                ("bss", C.c_double), ("afs", C.c_double), ("bfs", C.c_double), ("khs", C.c_double),
+                ("Tfa", C.c_double), ("Tsa", C.c_double)]
 
 
 class LelasProps(C.Structure):
@@ -66,7 +67,8 @@ class UstructProps(C.Structure):
                 ("isoType", C.c_int), ("volType", C.c_int),
                 ("C10", C.c_double), ("Kpen", C.c_double),
                 ("a", C.c_double), ("b", C.c_double), ("aff", C.c_double), ("bff", C.c_double), ("ass", C.c_double),
-                ("bss", C.c_double), ("afs", C.c_double), ("bfs", C.c_double), ("khs", C.c_double)]
+                ("bss", C.c_double), ("afs", C.c_double), ("bfs", C.c_double), ("khs", C.c_double),
+                ("Tfa", C.c_double), ("Tsa", C.c_double)]
 
 
 class BneuProps(C.Structure):
@@ -200,7 +202,7 @@ def fluid_props(*, dt, am, af, gam, rho, mu, tDof=4, mvMsh=False, f=(0.0, 0.0, 0
 
 
 def struct_props(*, dt, am, af, gam, beta, rho, tDof=3, s=0, dmp=0.0, f=(0.0, 0.0, 0.0), iso="nHook", vol="ST91",
-                 C10=0.0, C01=0.0, Kpen=0.0, ho=None) -> StructProps:
+                 C10=0.0, C01=0.0, Kpen=0.0, ho=None, Tfa=0.0, eta_s=0.0) -> StructProps:
     p = StructProps()
     p.dt, p.am, p.af, p.gam, p.beta = dt, am, af, gam, beta
     p.tDof, p.s = tDof, s
@@ -208,6 +210,7 @@ def struct_props(*, dt, am, af, gam, beta, rho, tDof=3, s=0, dmp=0.0, f=(0.0, 0.
     p.f[0], p.f[1], p.f[2] = f
     p.isoType, p.volType = ISO_TYPES[iso], VOL_TYPES[vol]
     p.C10, p.C01, p.Kpen = C10, C01, Kpen
+    p.Tfa, p.Tsa = Tfa, Tfa * eta_s
     p.khs = 100.0
     for k, v in (ho or {}).items():
         setattr(p, k, v)
@@ -224,7 +227,7 @@ def lelas_props(*, dt, am, af, beta, rho, elM, nu, tDof=3, s=0, f=(0.0, 0.0, 0.0
 
 
 def ustruct_props(*, dt, am, af, gam, rho, elM, nu, ctM, ctC, vol, C10, Kpen, tDof=4, s=0, f=(0.0, 0.0, 0.0), iso="nHook",
-                  ho=None, **_ignored) -> UstructProps:
+                  ho=None, Tfa=0.0, eta_s=0.0, **_ignored) -> UstructProps:
     p = UstructProps()
     p.dt, p.am, p.af, p.gam = dt, am, af, gam
     p.tDof, p.s = tDof, s
@@ -233,6 +236,7 @@ def ustruct_props(*, dt, am, af, gam, rho, elM, nu, ctM, ctC, vol, C10, Kpen, tD
     p.elM, p.nu, p.ctM, p.ctC = elM, nu, ctM, ctC
     p.isoType, p.volType = ISO_TYPES[iso], VOL_TYPES[vol]
     p.C10, p.Kpen = C10, Kpen
+    p.Tfa, p.Tsa = Tfa, Tfa * eta_s
     p.khs = 100.0
     for k, v in (ho or {}).items():
         setattr(p, k, v)

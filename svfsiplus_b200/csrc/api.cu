@@ -343,6 +343,7 @@ SolidConsts struct_consts(const b200_struct_props* p)
   c.iso = p->isoType; c.vol = p->volType; c.C10 = p->C10; c.C01 = p->C01; c.Kpen = p->Kpen;
   c.ho_a = p->a; c.ho_b = p->b; c.ho_aff = p->aff; c.ho_bff = p->bff; c.ho_ass = p->ass; c.ho_bss = p->bss;
   c.ho_afs = p->afs; c.ho_bfs = p->bfs; c.ho_khs = p->khs;
+  c.Tfa = p->Tfa; c.Tsa = p->Tsa;
   c.tDof = p->tDof; c.s = p->s; c.kind = 0;
   return c;
 }
@@ -787,7 +788,7 @@ int b200_assemble_ustruct(b200_handle* h, const b200_ustruct_props* p)
     c.rho0 = p->rho; c.f[0] = p->f[0]; c.f[1] = p->f[1]; c.f[2] = p->f[2];
     c.elM = p->elM; c.nu = p->nu; c.ctM = p->ctM; c.ctC = p->ctC;
     c.iso = p->isoType; c.vol = p->volType; c.C10 = p->C10; c.Kpen = p->Kpen;
-    c.ho = HoParams{p->a, p->b, p->aff, p->bff, p->ass, p->bss, p->afs, p->bfs, p->khs};
+    c.ho = HoParams{p->a, p->b, p->aff, p->bff, p->ass, p->bss, p->afs, p->bfs, p->khs, p->Tfa, p->Tsa};
     c.tDof = p->tDof; c.s = p->s;
     ensure_stage(h, 4);
     ensure(h->stageKd, h->stageKd_cap, size_t(12)*h->eNoN*h->eNoN*size_t(h->nEl) + 4);

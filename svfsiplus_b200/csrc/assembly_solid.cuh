@@ -32,6 +32,7 @@ struct SolidConsts {
   int iso, vol;                // iso: 0 nHook, 1 StVK, 2 mStVK, 3 Holzapfel-Ogden; vol: 0 none, 1 Quad, 2 ST91, 3 M94
   double C10, C01, Kpen;
   double ho_a, ho_b, ho_aff, ho_bff, ho_ass, ho_bss, ho_afs, ho_bfs, ho_khs;   // stModelType a..bfs, khs
+  double Tfa, Tsa;             // fibre / sheet reinforcement stress (get_fib_stress, mat_models_carray.h:222-225)
   double elM, nu;              // lElas / mesh
   int tDof, s;                 // row offset of this equation's unknowns in Ag/Yg/Dg (eq.s)
   int kind;                    // 0 struct, 1 lElas, 2 mesh
@@ -43,7 +44,7 @@ __host__ __device__ constexpr int solid_rec(int eNoN) { return SREC_NX + 3*eNoN;
 // index of (I,J), I <= J, in the packed upper triangle of the 6x6 Voigt matrix
 __device__ __forceinline__ int dm_idx(int I, int J) { return I*6 - (I*(I-1))/2 + (J - I); }
 
-struct HoParams { double a, b, aff, bff, ass, bss, afs, bfs, khs; };
+struct HoParams { double a, b, aff, bff, ass, bss, afs, bfs, khs, Tfa, Tsa; };
 
 // Isochoric part of the Holzapfel-Ogden law (mat_models_carray.h:905-1060, mat_models.cpp:866-935): isochoric
 // stress S = J2d Sb - r1 Ci, r1, and the projected rank-one factors of the isochoric tangent
@@ -75,8 +76,8 @@ __device__ void ho_isochoric(const HoParams& h, const double C[3][3], const doub
   const double g1 = h.a*exp(h.b*(Inv1 - 3.0));
   const double g2 = 2.0*h.afs*exp(h.bfs*Efs*Efs);
   const double rexpf = exp(h.bff*Eff*Eff), rexps = exp(h.bss*Ess*Ess);
-  double gff = c4f*Eff*rexpf; gff = gff + (0.5*dc4f/h.bff)*(rexpf - 1.0); gff = 2.0*h.aff*gff + 0.0;
-  double gss = c4s*Ess*rexps; gss = gss + (0.5*dc4s/h.bss)*(rexps - 1.0); gss = 2.0*h.ass*gss + 0.0;
+  double gff = c4f*Eff*rexpf; gff = gff + (0.5*dc4f/h.bff)*(rexpf - 1.0); gff = 2.0*h.aff*gff + h.Tfa;
+  double gss = c4s*Ess*rexps; gss = gss + (0.5*dc4s/h.bss)*(rexps - 1.0); gss = 2.0*h.ass*gss + h.Tsa;
   double Sb[3][3];
 #pragma unroll
   for (int i = 0; i < 3; i++)
@@ -171,7 +172,11 @@ __device__ void pk2cc_iso(const SolidConsts& c, const double F[3][3], const doub
 #pragma unroll
     for (int i = 0; i < 3; i++)
 #pragma unroll
-      for (int j = 0; j < 3; j++) S[i][j] = J2d*((i == j) ? g1 : 0.0) - r1*Ci[i][j];
+      for (int j = 0; j < 3; j++) {
+        // Sb = g1 I + Tfa f (x) f (mat_models_carray.h:371-388); without fibres f = 0
+        const double Sb = ((i == j) ? g1 : 0.0) + c.Tfa*(fl[i]*fl[j]);
+        S[i][j] = J2d*Sb - r1*Ci[i][j];
+      }
     const double c2 = 2.0*(r1 - p*J), c3 = pl*J - 2.0*r1/nd;
 #pragma unroll
     for (int I = 0; I < 6; I++)
@@ -210,7 +215,7 @@ __device__ void pk2cc_iso(const SolidConsts& c, const double F[3][3], const doub
       }
   } else if (c.iso == 3) {
     // Holzapfel-Ogden (mat_models_carray.h:905-1135), see ho_isochoric
-    const HoParams hp = {c.ho_a, c.ho_b, c.ho_aff, c.ho_bff, c.ho_ass, c.ho_bss, c.ho_afs, c.ho_bfs, c.ho_khs};
+    const HoParams hp = {c.ho_a, c.ho_b, c.ho_aff, c.ho_bff, c.ho_ass, c.ho_bss, c.ho_afs, c.ho_bfs, c.ho_khs, c.Tfa, c.Tsa};
     double r1, gk[4], H[4][3][3];
     ho_isochoric(hp, C, Ci, J2d, Inv1, fl, S, r1, gk, H);
     const double c2 = 2.0*(r1 - p*J), c3 = pl*J - 2.0*r1/nd;

@@ -184,10 +184,13 @@ k_assemble_ustruct(int nEl, UstructConsts c, const double* __restrict__ tab, con
         } else {
           const double g1 = 2.0*c.C10;
           const double r1 = g1*Inv1/nd3;
+          // Sb = g1 I + Tfa f (x) f (mat_models.cpp:699-704); without fibres f = 0
+          double f0[3] = {0.0, 0.0, 0.0};
+          if (fN) { f0[0] = fN[size_t(e)*6]; f0[1] = fN[size_t(e)*6 + 1]; f0[2] = fN[size_t(e)*6 + 2]; }
 #pragma unroll
           for (int i = 0; i < 3; i++)
 #pragma unroll
-            for (int j = 0; j < 3; j++) S[i][j] = J2d*((i == j) ? g1 : 0.0) - r1*Ci[i][j];
+            for (int j = 0; j < 3; j++) S[i][j] = J2d*(((i == j) ? g1 : 0.0) + c.ho.Tfa*(f0[i]*f0[j])) - r1*Ci[i][j];
 #pragma unroll
           for (int I = 0; I < 6; I++)
 #pragma unroll

@@ -7,6 +7,8 @@
 #include "svb200.h"
 #include "lhsa.h"
 #include "all_fun.h"
+#include "fft.h"
+#include "utils.h"
 
 #include <stdexcept>
 #include <vector>
@@ -226,11 +228,29 @@ bool B200LinearAlgebra::fill_fluid_props(ComMod& com_mod, const eqType& eq, cons
   return true;
 }
 
+/// mat_models::get_fib_stress (mat_models.cpp:126-139) + the cross-fibre factor (mat_models_carray.h:225): the fibre
+/// reinforcement stress of this time step, steady (Tf.g) or interpolated from the Fourier series (Tf.gt).
+void B200LinearAlgebra::fibre_stress(const ComMod& com_mod, const fibStrsType& Tf, double& Tfa, double& Tsa)
+{
+  using namespace consts;
+  Tfa = 0.0;
+  if (utils::btest(Tf.fType, iBC_std)) {
+    Tfa = Tf.g;
+  } else if (utils::btest(Tf.fType, iBC_ustd)) {
+    Vector<double> gv(1), tv(1);
+    ifft(com_mod, Tf.gt, gv, tv);
+    Tfa = gv[0];
+  }
+  Tsa = Tfa*Tf.eta_s;
+}
+
 bool B200LinearAlgebra::fill_struct_props(ComMod& com_mod, const eqType& eq, const dmnType& dmn, b200_struct_props& sp)
 {
   using namespace consts;
   const auto& stM = dmn.stM;
-  if (stM.Tf.fType != 0 || dmn.solid_visc.viscType != SolidViscosityModelType::viscType_NA) return false;
+  if (dmn.solid_visc.viscType != SolidViscosityModelType::viscType_NA) return false;
+  fibre_stress(com_mod, stM.Tf, sp.Tfa, sp.Tsa);
+  if (sp.Tfa != 0.0 && stM.isoType != ConstitutiveModelType::stIso_nHook && stM.isoType != ConstitutiveModelType::stIso_HO) return false;
   switch (stM.isoType) {
     case ConstitutiveModelType::stIso_nHook: sp.isoType = 0; break;
     case ConstitutiveModelType::stIso_StVK:  sp.isoType = 1; break;
@@ -277,6 +297,7 @@ bool B200LinearAlgebra::assemble_fsi_mesh(ComMod& com_mod, const mshType& lM, co
     } else if (eq.dmn[d].phys == EquationType::phys_struct) {
       kinds[d] = 1;
       if (!fill_struct_props(com_mod, eq, eq.dmn[d], st[d])) return false;
+      if ((st[d].isoType == 3 || st[d].Tfa != 0.0) && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
     } else {
       return false;
     }
@@ -346,8 +367,10 @@ bool B200LinearAlgebra::assemble_ustruct_mesh(ComMod& com_mod, const mshType& lM
   const bool ho = (stM.isoType == ConstitutiveModelType::stIso_HO);
   if (stM.isoType != ConstitutiveModelType::stIso_nHook && !ho) return false;
   if (ho && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
-  if (stM.Tf.fType != 0 || dmn.solid_visc.viscType != SolidViscosityModelType::viscType_NA) return false;
+  if (dmn.solid_visc.viscType != SolidViscosityModelType::viscType_NA) return false;
   b200_ustruct_props p{};
+  fibre_stress(com_mod, stM.Tf, p.Tfa, p.Tsa);
+  if (p.Tfa != 0.0 && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
   p.dt = com_mod.dt; p.am = eq.am; p.af = eq.af; p.gam = eq.gam;
   p.tDof = com_mod.tDof; p.s = eq.s;
   p.rho = dmn.prop.at(PhysicalProperyType::solid_density);
@@ -406,7 +429,7 @@ bool B200LinearAlgebra::assemble_solid_mesh(ComMod& com_mod, const mshType& lM, 
   const bool is_struct = (eq.phys == EquationType::phys_struct);
   if (is_struct) {
     if (!fill_struct_props(com_mod, eq, dmn, sp)) return false;
-    if (sp.isoType == 3 && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
+    if ((sp.isoType == 3 || sp.Tfa != 0.0) && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
   } else {
     lp.dt = com_mod.dt; lp.am = eq.am; lp.af = eq.af; lp.beta = eq.beta;
     lp.tDof = com_mod.tDof; lp.s = eq.s;
@@ -449,7 +472,7 @@ bool B200LinearAlgebra::assemble_domains_mesh(ComMod& com_mod, const mshType& lM
       if (!fill_fluid_props(com_mod, eq, eq.dmn[d], fl[d])) return false;
     } else {
       if (!fill_struct_props(com_mod, eq, eq.dmn[d], st[d])) return false;
-      if (st[d].isoType == 3 && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
+      if ((st[d].isoType == 3 || st[d].Tfa != 0.0) && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
     }
   }
   if (!fluid) {

@@ -77,6 +77,7 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
         const Array<double>& Dg, const CepMod* cep_mod);
     bool fill_fluid_props(ComMod& com_mod, const eqType& eq, const dmnType& dmn, b200_fluid_props& p);
     bool fill_struct_props(ComMod& com_mod, const eqType& eq, const dmnType& dmn, b200_struct_props& p);
+    static void fibre_stress(const ComMod& com_mod, const fibStrsType& Tf, double& Tfa, double& Tsa);
     bool assemble_ustruct_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag, const Array<double>& Yg,
         const Array<double>& Dg, const CepMod* cep_mod);
     bool assemble_solid_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag, const Array<double>& Yg,

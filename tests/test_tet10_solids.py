@@ -52,3 +52,61 @@ def test_tet10_ustruct_assembly_matches_golden(iso):
     P.assemble_ustruct(be, case, upload=False, with_r=True)
     assert rel_inf(be.get_R(), g[f"uRr_{iso}"]) < TOL_ASM
     be.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fibre-reinforcement / active stress (stM.Tf: get_fib_stress, mat_models.cpp:126; Tfa along the fibre, Tfa*eta_s along the
+# sheet direction; mat_models_carray.h:222-225, 386, 984, 1015; mat_models.cpp:682-684, 704, 914, 929)
+# ---------------------------------------------------------------------------------------------------------------------
+ACTIVE = [("struct", "hex", "HO"), ("struct", "tet", "nHook"), ("struct", "tet10", "HO"), ("ustruct", "tet", "HO"), ("ustruct", "hex", "nHook")]
+
+
+def _active_case(eq, elem, iso):
+    n = 2 if elem == "tet10" else 3
+    if eq == "struct":
+        case = P.block_case(n, elem=elem, kind="struct", iso="HO", vol="ST91")      # brings fibre directions
+        if iso == "nHook":
+            E = 240.56596e6
+            case["props"].update(iso="nHook", C10=0.25 * E / 1.5, Kpen=4.0e9)
+            case["props"].pop("ho")
+        case["props"].update(Tfa=3.0e4, eta_s=0.4)
+    else:
+        case = P.ustruct_case(n, elem=elem, iso="HO")
+        if iso == "nHook":
+            case["props"].pop("ho"); case["props"]["iso"] = "nHook"
+        case["props"].update(Tfa=2.0e4, eta_s=0.3)
+    return case
+
+
+@needs_ref
+def test_oracle_reproduces_active_stress_fixtures():
+    from oracle import refcase
+    g = golden("active_stress.npz")
+    for eq, elem, iso in ACTIVE:
+        case = _active_case(eq, elem, iso)
+        if eq == "struct":
+            R, Val, _, _, _, _ = refcase.reference_assemble_solid(case)
+            zero = dict(case); zero["props"] = dict(case["props"], Tfa=0.0)
+            R0, _, _, _, _, _ = refcase.reference_assemble_solid(zero)
+        else:
+            R, Val, Kd, _ = refcase.reference_assemble_ustruct(case)
+            zero = dict(case); zero["props"] = dict(case["props"], Tfa=0.0)
+            R0, _, _, _ = refcase.reference_assemble_ustruct(zero)
+        assert np.array_equal(R, g[f"R_{eq}_{elem}_{iso}"]) and np.array_equal(Val, g[f"Val_{eq}_{elem}_{iso}"])
+        assert rel_inf(R0, R) > 1e-6, (eq, elem, iso)           # the fibre stress matters
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("eq,elem,iso", ACTIVE)
+def test_active_fibre_stress_matches_golden(eq, elem, iso):
+    g = golden("active_stress.npz")
+    case = _active_case(eq, elem, iso)
+    be = P.setup_backend(case)
+    if eq == "struct":
+        P.assemble_solid(be, case)
+    else:
+        P.assemble_ustruct(be, case)
+        assert rel_inf(be.get_Kd(), g[f"Kd_{eq}_{elem}_{iso}"]) < TOL_ASM
+    assert rel_inf(be.get_R(), g[f"R_{eq}_{elem}_{iso}"]) < TOL_ASM
+    assert rel_inf(be.get_Val(), g[f"Val_{eq}_{elem}_{iso}"]) < TOL_ASM
+    be.close()
