@@ -52,7 +52,7 @@ typedef struct {
  * dmnType / stModelType (solver/sv_struct.cpp:576-594, solver/ComMod.h:345-388).  s = eq.s, the row of
  * the equation's first unknown inside Ag/Yg/Dg(tDof,nNo).  isoType: 0 neo-Hookean (C10 = mu/2),
  * 1 St.Venant-Kirchhoff (C10 = lambda, C01 = mu), 2 modified StVK (C10 = kappa, C01 = mu), 3 Holzapfel-Ogden
- * (solver/mat_models_carray.h:905-1135; needs b200_mesh_fibers);
+ * (solver/mat_models_carray.h:905-1135; needs b200_mesh_fibers), 4 Mooney-Rivlin (C10, C01; :438-540);
  * volType: 0 none, 1 Quad, 2 ST91, 3 M94 (solver/mat_models.cpp:1626-1645). */
 typedef struct {
   double dt, am, af, gam, beta;

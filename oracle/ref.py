@@ -192,6 +192,7 @@ def lib():
                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_fsi_ls_upd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p]
+        L.ref_pk2cc.argtypes = [C.c_void_p] * 6
         L.ref_asm_bneu.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
         L.ref_pic.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_double] + [C.c_void_p] * 12
         _lib = L
@@ -335,7 +336,19 @@ class RefAssembly:
             raise RuntimeError(lib().ref_last_error().decode())
         return R, Val
 
-    ISO = {"nHook": 0, "StVK": 1, "mStVK": 2, "HO": 3}
+    def pk2cc(self, F, fl, *, iso="nHook", vol="ST91", C10=0.0, C01=0.0, Kpen=0.0, ho=None, Tfa=0.0, eta_s=0.0):
+        """mat_models_carray::get_pk2cc<3> (S/mat_models_carray.h:182): S (3,3) and Dm (6,6) at the deformation gradient F."""
+        ho = ho or {}
+        par = np.array([0.0] * 10 + [self.ISO[iso], self.VOL[vol], C10, C01, Kpen, 0.0, 0.0]
+                       + [ho.get(k, 100.0 if k == "khs" else 0.0) for k in self.HO_KEYS] + [Tfa, eta_s], np.float64)
+        F = _c(F, np.float64); fl = _c(fl, np.float64)
+        S = np.empty((3, 3)); Dm = np.empty((6, 6))
+        rc = lib().ref_pk2cc(self.h, _p(par), _p(F), _p(fl), _p(S), _p(Dm))
+        if rc != 0:
+            raise RuntimeError(lib().ref_last_error().decode())
+        return S, Dm
+
+    ISO = {"nHook": 0, "StVK": 1, "mStVK": 2, "HO": 3, "MR": 4}
     HO_KEYS = ("a", "b", "aff", "bff", "ass", "bss", "afs", "bfs", "khs")
 
     def set_fibers(self, fN):

@@ -26,6 +26,8 @@
 #include "fluid.h"
 #include "fs.h"
 #include "mat_fun.h"
+#include "mat_models.h"
+#include "mat_models_carray.h"
 #include "fsi.h"
 #include "l_elas.h"
 #include "mesh.h"
@@ -296,7 +298,8 @@ void configure_solid(AsmCtx* ctx, int kind, int tDof, int s, const double* par, 
     const int iso = int(par[10]), vol = int(par[11]);
     dmn.stM.isoType = (iso == 0) ? ConstitutiveModelType::stIso_nHook
                     : (iso == 1) ? ConstitutiveModelType::stIso_StVK
-                    : (iso == 2) ? ConstitutiveModelType::stIso_mStVK : ConstitutiveModelType::stIso_HO;
+                    : (iso == 2) ? ConstitutiveModelType::stIso_mStVK
+                    : (iso == 4) ? ConstitutiveModelType::stIso_MR : ConstitutiveModelType::stIso_HO;
     dmn.stM.volType = (vol == 1) ? ConstitutiveModelType::stVol_Quad
                     : (vol == 2) ? ConstitutiveModelType::stVol_ST91
                     : (vol == 3) ? ConstitutiveModelType::stVol_M94 : ConstitutiveModelType::stIso_NA;
@@ -1116,6 +1119,30 @@ int ref_fsi_ls_upd(void* h, int eNoNb, int nElb, const int* IENb, const int* gE,
     eq_assem::fsi_ls_upd(com_mod, lBc, fa);
     std::memcpy(val, lhs.face[0].val.data(), sizeof(double)*size_t(3)*nNoFace);
     com_mod.mvMsh = false;
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+// mat_models_carray::get_pk2cc<3> (S/mat_models_carray.h:182) at one deformation gradient.  par as in ref_asm_solid (28
+// entries); F(3,3) row-major; fl = fibre and sheet directions (6).  Outputs S(3,3) and Dm(6,6) row-major.
+int ref_pk2cc(void* h, const double* par, const double* F9, const double* fl6, double* S9, double* Dm36)
+{
+  try {
+    auto ctx = static_cast<AsmCtx*>(h);
+    auto& com_mod = ctx->sim->com_mod;
+    std::vector<double> Bf(size_t(3)*com_mod.tnNo, 0.0);
+    configure_solid(ctx, 0, 3, 0, par, nullptr, Bf.data());
+    double F[3][3], S[3][3], Dm[6][6];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) F[i][j] = F9[i*3 + j];
+    Array<double> fl(3, 2);
+    for (int i = 0; i < 3; i++) { fl(i, 0) = fl6[i]; fl(i, 1) = fl6[3 + i]; }
+    mat_fun_carray::ten_init(3);                 // struct_3d_carray does this before every call (S/sv_struct.cpp:654)
+    mat_models_carray::get_pk2cc<3>(com_mod, ctx->sim->cep_mod, com_mod.eq[0].dmn[0], F, 2, fl, 0.0, S, Dm);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) S9[i*3 + j] = S[i][j];
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) Dm36[i*6 + j] = Dm[i][j];
     return 0;
   } catch (const std::exception& e) {
     g_err = e.what();

@@ -334,7 +334,7 @@ void launch_fluid(b200_handle* h, const FluidConsts& c, int nList, const int* d_
 
 SolidConsts struct_consts(const b200_struct_props* p)
 {
-  if (p->isoType < 0 || p->isoType > 3) throw std::runtime_error("assemble_struct: constitutive model has no device kernel");
+  if (p->isoType < 0 || p->isoType > 4) throw std::runtime_error("assemble_struct: constitutive model has no device kernel");
   if (p->volType < 0 || p->volType > 3) throw std::runtime_error("assemble_struct: dilational penalty model not defined");
   SolidConsts c;
   std::memset(&c, 0, sizeof(c));

@@ -1,0 +1,281 @@
+// solid_law.hpp — constitutive laws of the displacement-based and mixed solid elements, host/device shared like
+// fluid_elem.hpp: 2nd Piola-Kirchhoff stress S and the Voigt elasticity matrix Dm from the deformation gradient.
+// Replaces mat_models_carray::get_pk2cc<3> (Code/Source/solver/mat_models_carray.h:182-1380; neo-Hookean :370-434,
+// Mooney-Rivlin :438-540, St.Venant-Kirchhoff :302-322, modified StVK :326-356, Holzapfel-Ogden :905-1135) with
+// get_svol_p (mat_models.cpp:1626-1645) and the fibre reinforcement stress (mat_models_carray.h:222-225).
+// tests/hostlogic/fluid_elem_host.cpp instantiates the same source on the CPU (test tree only) and
+// tests/test_solid_laws.py compares it with the compiled reference's get_pk2cc on random deformation gradients.
+#pragma once
+
+#include "fluid_elem.hpp"      // SVB_HD, is_zero_d
+
+namespace svb200 {
+
+struct SolidConsts {
+  double dt, am, af, gam, beta;
+  double rho, dmp, f[3];
+  int iso, vol;                // iso: 0 nHook, 1 StVK, 2 mStVK, 3 Holzapfel-Ogden, 4 Mooney-Rivlin; vol: 0 none, 1 Quad, 2 ST91, 3 M94
+  double C10, C01, Kpen;
+  double ho_a, ho_b, ho_aff, ho_bff, ho_ass, ho_bss, ho_afs, ho_bfs, ho_khs;   // stModelType a..bfs, khs
+  double Tfa, Tsa;             // fibre / sheet reinforcement stress (get_fib_stress, mat_models_carray.h:222-225)
+  double elM, nu;              // lElas / mesh
+  int tDof, s;                 // row offset of this equation's unknowns in Ag/Yg/Dg (eq.s)
+  int kind;                    // 0 struct, 1 lElas, 2 mesh
+};
+
+// index of (I,J), I <= J, in the packed upper triangle of the 6x6 Voigt matrix
+SVB_HD int dm_idx(int I, int J) { return I*6 - (I*(I-1))/2 + (J - I); }
+
+struct HoParams { double a, b, aff, bff, ass, bss, afs, bfs, khs, Tfa, Tsa; };
+
+// Isochoric part of the Holzapfel-Ogden law (mat_models_carray.h:905-1060, mat_models.cpp:866-935): isochoric
+// stress S = J2d Sb - r1 Ci, r1, and the projected rank-one factors of the isochoric tangent
+//   PP : (sum_k g_k H_k (x) H_k) : PP^T = sum_k g_k Hd_k (x) Hd_k,   Hd_k = H_k - (1/3)(C : H_k) Ci
+// (the reference forms CCb and contracts it with PP = Ids - (1/3) Ci (x) C from both sides; for symmetric H_k
+// this is the same tensor up to rounding).  H_0 = I, H_1 = sym(f (x) s), H_2 = f (x) f, H_3 = s (x) s.
+SVB_HD_NOINL void ho_isochoric(const HoParams& h, const double C[3][3], const double Ci[3][3], double J2d, double Inv1,
+                             const double* fl, double S[3][3], double& r1, double gk[4], double H[4][3][3])
+{
+  const double nd = 3.0;
+  const double J4d = J2d*J2d;
+  const double f0[3] = {fl[0], fl[1], fl[2]}, s0[3] = {fl[3], fl[4], fl[5]};
+  double Cf[3], Cs[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    Cf[i] = C[i][0]*f0[0] + C[i][1]*f0[1] + C[i][2]*f0[2];
+    Cs[i] = C[i][0]*s0[0] + C[i][1]*s0[1] + C[i][2]*s0[2];
+  }
+  const double Inv4 = J2d*(f0[0]*Cf[0] + f0[1]*Cf[1] + f0[2]*Cf[2]);
+  const double Inv6 = J2d*(s0[0]*Cs[0] + s0[1]*Cs[1] + s0[2]*Cs[2]);
+  const double Inv8 = J2d*(f0[0]*Cs[0] + f0[1]*Cs[1] + f0[2]*Cs[2]);
+  const double Eff = Inv4 - 1.0, Ess = Inv6 - 1.0, Efs = Inv8;
+  const double k = h.khs;
+  const double of = 1.0/(exp(k*Eff) + 1.0), os = 1.0/(exp(k*Ess) + 1.0);
+  const double c4f = 1.0 - of, c4s = 1.0 - os;
+  const double dc4f = k*(of - of*of), dc4s = k*(os - os*os);
+  const double ddc4f = k*k*(-of + 3.0*of*of - 2.0*of*of*of), ddc4s = k*k*(-os + 3.0*os*os - 2.0*os*os*os);
+  // stress coefficients
+  const double g1 = h.a*exp(h.b*(Inv1 - 3.0));
+  const double g2 = 2.0*h.afs*exp(h.bfs*Efs*Efs);
+  const double rexpf = exp(h.bff*Eff*Eff), rexps = exp(h.bss*Ess*Ess);
+  double gff = c4f*Eff*rexpf; gff = gff + (0.5*dc4f/h.bff)*(rexpf - 1.0); gff = 2.0*h.aff*gff + h.Tfa;
+  double gss = c4s*Ess*rexps; gss = gss + (0.5*dc4s/h.bss)*(rexps - 1.0); gss = 2.0*h.ass*gss + h.Tsa;
+  double Sb[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      H[0][i][j] = (i == j) ? 1.0 : 0.0;
+      H[1][i][j] = 0.5*(f0[i]*s0[j] + f0[j]*s0[i]);
+      H[2][i][j] = f0[i]*f0[j];
+      H[3][i][j] = s0[i]*s0[j];
+      Sb[i][j] = g1*H[0][i][j] + g2*Efs*H[1][i][j];
+      Sb[i][j] += gff*H[2][i][j];
+      Sb[i][j] += gss*H[3][i][j];
+    }
+  // stiffness coefficients
+  gk[0] = g1*2.0*J4d*h.b;
+  gk[1] = g2*2.0*J4d*(1.0 + 2.0*h.bfs*Efs*Efs);
+  {
+    double t = c4f*(1.0 + 2.0*h.bff*Eff*Eff); t = (t + 2.0*dc4f*Eff)*rexpf; t = t + (0.5*ddc4f/h.bff)*(rexpf - 1.0);
+    gk[2] = 4.0*J4d*h.aff*t;
+    double u = c4s*(1.0 + 2.0*h.bss*Ess*Ess); u = (u + 2.0*dc4s*Ess)*rexps; u = u + (0.5*ddc4s/h.bss)*(rexps - 1.0);
+    gk[3] = 4.0*J4d*h.ass*u;
+  }
+  double CSb = 0.0;
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+#pragma unroll
+    for (int i = 0; i < 3; i++) CSb = CSb + C[i][j]*Sb[i][j];
+  r1 = J2d*CSb/nd;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) S[i][j] = J2d*Sb[i][j] - r1*Ci[i][j];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    double ch = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) ch += C[i][j]*H[q][i][j];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) H[q][i][j] = H[q][i][j] - (1.0/nd)*ch*Ci[i][j];
+  }
+}
+
+// get_pk2cc<3> for the isotropic laws without fibres / active stress, + get_svol_p.
+// Outputs S (sym: 00 11 22 01 12 20) and the upper triangle of Dm (Voigt order 00 11 22 01 12 20).
+// fl: the element's fibre (fl[0..2]) and sheet (fl[3..5]) directions, read by the Holzapfel-Ogden law only.
+SVB_HD_NOINL void pk2cc_iso(const SolidConsts& c, const double F[3][3], const double* fl,
+                          double* S6, double* Dm21)
+{
+  // mat_det<3> (mat_fun_carray.h:92-122): cofactor expansion along the first row
+  const double J = ((0.0 + 1.0*F[0][0]*(F[1][1]*F[2][2] - F[1][2]*F[2][1]))
+                    + (-1.0)*F[0][1]*(F[1][0]*F[2][2] - F[1][2]*F[2][0]))
+                    + 1.0*F[0][2]*(F[1][0]*F[2][1] - F[1][1]*F[2][0]);
+  const double nd = 3.0;
+  const double J2d = pow(J, -2.0/nd);
+  double C[3][3], Ci[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) C[i][j] = (0.0 + F[0][i]*F[0][j]) + F[1][i]*F[1][j] + F[2][i]*F[2][j];
+  {
+    const double d = ((0.0 + C[0][0]*(C[1][1]*C[2][2] - C[1][2]*C[2][1]))
+                      - C[0][1]*(C[1][0]*C[2][2] - C[1][2]*C[2][0]))
+                      + C[0][2]*(C[1][0]*C[2][1] - C[1][1]*C[2][0]);
+    Ci[0][0] = (C[1][1]*C[2][2] - C[1][2]*C[2][1]) / d;
+    Ci[0][1] = (C[0][2]*C[2][1] - C[0][1]*C[2][2]) / d;
+    Ci[0][2] = (C[0][1]*C[1][2] - C[0][2]*C[1][1]) / d;
+    Ci[1][0] = (C[1][2]*C[2][0] - C[1][0]*C[2][2]) / d;
+    Ci[1][1] = (C[0][0]*C[2][2] - C[0][2]*C[2][0]) / d;
+    Ci[1][2] = (C[0][2]*C[1][0] - C[0][0]*C[1][2]) / d;
+    Ci[2][0] = (C[1][0]*C[2][1] - C[1][1]*C[2][0]) / d;
+    Ci[2][1] = (C[0][1]*C[2][0] - C[0][0]*C[2][1]) / d;
+    Ci[2][2] = (C[0][0]*C[1][1] - C[0][1]*C[1][0]) / d;
+  }
+  const double trC = C[0][0] + C[1][1] + C[2][2];
+  const double Inv1 = J2d*trC;
+  double p = 0.0, pl = 0.0;
+  if (!is_zero_d(c.Kpen)) {                     // get_svol_p (mat_models.cpp:1626-1645)
+    if (c.vol == 1)      { p = c.Kpen*(J - 1.0);        pl = c.Kpen*(2.0*J - 1.0); }
+    else if (c.vol == 2) { p = 0.5*c.Kpen*(J - 1.0/J);  pl = c.Kpen*J; }
+    else if (c.vol == 3) { p = c.Kpen*(1.0 - 1.0/J);    pl = c.Kpen; }
+  }
+  const int vi[6] = {0, 1, 2, 0, 1, 2}, vj[6] = {0, 1, 2, 1, 2, 0};
+  double S[3][3];
+  if (c.iso == 0) {
+    // neo-Hookean (mat_models_carray.h:370-434)
+    const double g1 = 2.0*c.C10;
+    const double r1 = g1*Inv1/nd;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        // Sb = g1 I + Tfa f (x) f (mat_models_carray.h:371-388); without fibres f = 0
+        const double Sb = ((i == j) ? g1 : 0.0) + c.Tfa*(fl[i]*fl[j]);
+        S[i][j] = J2d*Sb - r1*Ci[i][j];
+      }
+    const double c2 = 2.0*(r1 - p*J), c3 = pl*J - 2.0*r1/nd;
+#pragma unroll
+    for (int I = 0; I < 6; I++)
+#pragma unroll
+      for (int Jv = I; Jv < 6; Jv++) {
+        const int i = vi[I], j = vj[I], k = vi[Jv], l = vj[Jv];
+        double cc = (-2.0/nd)*(Ci[i][j]*S[k][l] + S[i][j]*Ci[k][l]);
+        cc += c2*(0.5*(Ci[i][k]*Ci[j][l] + Ci[i][l]*Ci[j][k])) + c3*(Ci[i][j]*Ci[k][l]);
+        Dm21[dm_idx(I, Jv)] = cc;
+      }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) S[i][j] += p*J*Ci[i][j];
+  } else if (c.iso == 1) {
+    // St. Venant-Kirchhoff (:302-322): C10 = lambda, C01 = mu
+    const double g1 = c.C10, g2 = c.C01*2.0;
+    double E[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) E[i][j] = 0.5*(C[i][j] - ((i == j) ? 1.0 : 0.0));
+    const double trE = E[0][0] + E[1][1] + E[2][2];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) S[i][j] = g1*trE*((i == j) ? 1.0 : 0.0) + g2*E[i][j];
+#pragma unroll
+    for (int I = 0; I < 6; I++)
+#pragma unroll
+      for (int Jv = I; Jv < 6; Jv++) {
+        const int i = vi[I], j = vj[I], k = vi[Jv], l = vj[Jv];
+        const double idp = ((i == j) && (k == l)) ? 1.0 : 0.0;
+        const double ids = (((i == k) && (j == l)) ? 0.5 : 0.0) + (((i == l) && (j == k)) ? 0.5 : 0.0);
+        Dm21[dm_idx(I, Jv)] = g1*idp + g2*ids;
+      }
+  } else if (c.iso == 3) {
+    // Holzapfel-Ogden (mat_models_carray.h:905-1135), see ho_isochoric
+    const HoParams hp = {c.ho_a, c.ho_b, c.ho_aff, c.ho_bff, c.ho_ass, c.ho_bss, c.ho_afs, c.ho_bfs, c.ho_khs, c.Tfa, c.Tsa};
+    double r1, gk[4], H[4][3][3];
+    ho_isochoric(hp, C, Ci, J2d, Inv1, fl, S, r1, gk, H);
+    const double c2 = 2.0*(r1 - p*J), c3 = pl*J - 2.0*r1/nd;
+#pragma unroll
+    for (int I = 0; I < 6; I++)
+#pragma unroll
+      for (int Jv = I; Jv < 6; Jv++) {
+        const int i = vi[I], j = vj[I], kk = vi[Jv], l = vj[Jv];
+        double cc = gk[0]*H[0][i][j]*H[0][kk][l] + gk[1]*H[1][i][j]*H[1][kk][l] + gk[2]*H[2][i][j]*H[2][kk][l] + gk[3]*H[3][i][j]*H[3][kk][l];
+        cc -= (2.0/nd)*(Ci[i][j]*S[kk][l] + S[i][j]*Ci[kk][l]);
+        cc += c2*(0.5*(Ci[i][kk]*Ci[j][l] + Ci[i][l]*Ci[j][kk])) + c3*(Ci[i][j]*Ci[kk][l]);
+        Dm21[dm_idx(I, Jv)] = cc;
+      }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) S[i][j] += p*J*Ci[i][j];
+  } else if (c.iso == 4) {
+    // Mooney-Rivlin (:438-540): Sb = g1 I + g2 J2d C (+ Tfa f (x) f), CCb = gk (I (x) I - Ids); the isochoric tangent
+    // PP : CCb : PP^T in closed form with PP = Ids - (1/3) Ci (x) C:
+    //   PP : (I (x) I) : PP^T = Hd (x) Hd,  Hd = I - (1/3) tr(C) Ci
+    //   PP : Ids : PP^T       = Ids - (1/3)(C (x) Ci + Ci (x) C) + (1/9)(C : C) Ci (x) Ci
+    const double J4d = J2d*J2d;
+    const double g1 = 2.0*(c.C10 + Inv1*c.C01), g2 = -2.0*c.C01;
+    double Sb[3][3], Hd[3][3];
+    double CSb = 0.0, CC2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        Sb[i][j] = (((i == j) ? g1 : 0.0) + g2*J2d*C[i][j]) + c.Tfa*(fl[i]*fl[j]);
+        Hd[i][j] = ((i == j) ? 1.0 : 0.0) - (1.0/nd)*trC*Ci[i][j];
+      }
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int i = 0; i < 3; i++) { CSb = CSb + C[i][j]*Sb[i][j]; CC2 = CC2 + C[i][j]*C[i][j]; }
+    const double gk = 4.0*J4d*c.C01;
+    const double r1 = J2d*CSb/nd;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) S[i][j] = J2d*Sb[i][j] - r1*Ci[i][j];
+    const double c2 = 2.0*(r1 - p*J), c3 = pl*J - 2.0*r1/nd;
+#pragma unroll
+    for (int I = 0; I < 6; I++)
+#pragma unroll
+      for (int Jv = I; Jv < 6; Jv++) {
+        const int i = vi[I], j = vj[I], k = vi[Jv], l = vj[Jv];
+        const double ids = (((i == k) && (j == l)) ? 0.5 : 0.0) + (((i == l) && (j == k)) ? 0.5 : 0.0);
+        double cc = gk*(Hd[i][j]*Hd[k][l] - (ids - (1.0/nd)*(C[i][j]*Ci[k][l] + Ci[i][j]*C[k][l]) + (1.0/(nd*nd))*CC2*(Ci[i][j]*Ci[k][l])));
+        cc -= (2.0/nd)*(Ci[i][j]*S[k][l] + S[i][j]*Ci[k][l]);
+        cc += c2*(0.5*(Ci[i][k]*Ci[j][l] + Ci[i][l]*Ci[j][k])) + c3*(Ci[i][j]*Ci[k][l]);
+        Dm21[dm_idx(I, Jv)] = cc;
+      }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) S[i][j] += p*J*Ci[i][j];
+  } else {
+    // modified St. Venant-Kirchhoff (:326-356): C10 = kappa, C01 = mu
+    const double g1 = c.C10, g2 = c.C01;
+    const double lJ = log(J);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) S[i][j] = g1*lJ*Ci[i][j] + g2*(C[i][j] - ((i == j) ? 1.0 : 0.0));
+#pragma unroll
+    for (int I = 0; I < 6; I++)
+#pragma unroll
+      for (int Jv = I; Jv < 6; Jv++) {
+        const int i = vi[I], j = vj[I], k = vi[Jv], l = vj[Jv];
+        const double ids = (((i == k) && (j == l)) ? 0.5 : 0.0) + (((i == l) && (j == k)) ? 0.5 : 0.0);
+        const double sym = 0.5*(Ci[i][k]*Ci[j][l] + Ci[i][l]*Ci[j][k]);
+        Dm21[dm_idx(I, Jv)] = g1*(-2.0*lJ*sym + Ci[i][j]*Ci[k][l]) + 2.0*g2*ids;
+      }
+  }
+  S6[0] = S[0][0]; S6[1] = S[1][1]; S6[2] = S[2][2]; S6[3] = S[0][1]; S6[4] = S[1][2]; S6[5] = S[2][0];
+}
+
+} // namespace svb200

@@ -250,12 +250,14 @@ bool B200LinearAlgebra::fill_struct_props(ComMod& com_mod, const eqType& eq, con
   const auto& stM = dmn.stM;
   if (dmn.solid_visc.viscType != SolidViscosityModelType::viscType_NA) return false;
   fibre_stress(com_mod, stM.Tf, sp.Tfa, sp.Tsa);
-  if (sp.Tfa != 0.0 && stM.isoType != ConstitutiveModelType::stIso_nHook && stM.isoType != ConstitutiveModelType::stIso_HO) return false;
+  if (sp.Tfa != 0.0 && stM.isoType != ConstitutiveModelType::stIso_nHook && stM.isoType != ConstitutiveModelType::stIso_HO &&
+      stM.isoType != ConstitutiveModelType::stIso_MR) return false;
   switch (stM.isoType) {
     case ConstitutiveModelType::stIso_nHook: sp.isoType = 0; break;
     case ConstitutiveModelType::stIso_StVK:  sp.isoType = 1; break;
     case ConstitutiveModelType::stIso_mStVK: sp.isoType = 2; break;
     case ConstitutiveModelType::stIso_HO:    sp.isoType = 3; break;      // needs lM.fN with two families (upload_mesh)
+    case ConstitutiveModelType::stIso_MR:    sp.isoType = 4; break;
     default: return false;
   }
   sp.a = stM.a; sp.b = stM.b; sp.aff = stM.aff; sp.bff = stM.bff; sp.ass = stM.ass; sp.bss = stM.bss;

@@ -148,6 +148,8 @@ def block_case(n, elem="hex", kind="struct", iso="nHook", vol="ST91", jitter=0.1
             C10, C01 = 0.5 * mu, 0.0
         elif iso == "HO":                        # Holzapfel-Ogden myocardium (parameters of tests/cases/struct/LV_* style, cgs)
             C10, C01 = 0.0, 0.0
+        elif iso == "MR":                        # Mooney-Rivlin: C10 + C01 = mu / 2
+            C10, C01 = 0.3 * mu, 0.2 * mu
         elif iso == "StVK":                      # C10 = lambda, C01 = mu (nu 0.3 keeps lambda finite)
             C10, C01 = E * 0.3 / (1.3 * 0.4), 0.5 * E / 1.3
         else:                                    # mStVK: C10 = kappa, C01 = mu

@@ -1,0 +1,52 @@
+"""Constitutive laws of the solid elements (csrc/solid_law.hpp, the source the device kernels compile) on the host against
+the compiled reference's mat_models_carray::get_pk2cc<3> (Code/Source/solver/mat_models_carray.h:182) at random deformation
+gradients: 2nd Piola-Kirchhoff stress and the Voigt elasticity matrix, every law x penalty x fibre stress combination."""
+import numpy as np
+import pytest
+
+from conftest import needs_ref
+from util import host_pk2cc
+
+from svfsiplus_b200 import mesh as M
+
+E = 240.56596e6
+MU = 0.5 * E / 1.5
+HO = dict(a=590.0, b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12, afs=2160.0, bfs=11.436, khs=100.0)
+LAWS = [
+    ("nHook", "ST91", dict(C10=0.5 * MU, Kpen=4.0e9)),
+    ("nHook", "M94", dict(C10=0.5 * MU, Kpen=4.0e9, Tfa=3.0e4, eta_s=0.4)),
+    ("nHook", "Quad", dict(C10=0.5 * MU, Kpen=1.0e8)),
+    ("StVK", None, dict(C10=E * 0.3 / (1.3 * 0.4), C01=0.5 * E / 1.3)),
+    ("mStVK", None, dict(C10=E / 1.2, C01=0.5 * E / 1.3)),
+    ("HO", "ST91", dict(Kpen=1.0e6, ho=HO)),
+    ("HO", "M94", dict(Kpen=1.0e6, ho=HO, Tfa=2.0e4, eta_s=0.3)),
+    ("MR", "ST91", dict(C10=0.3 * MU, C01=0.2 * MU, Kpen=4.0e9)),
+    ("MR", None, dict(C10=0.3 * MU, C01=0.2 * MU)),
+    ("MR", "M94", dict(C10=0.3 * MU, C01=0.2 * MU, Kpen=1.0e8, Tfa=3.0e4, eta_s=0.4)),
+]
+VOIGT = [(0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (2, 0)]
+
+
+@pytest.mark.parametrize("iso,vol,kw", LAWS, ids=[f"{l[0]}-{l[1]}-{'Tf' if 'Tfa' in l[2] else '0'}" for l in LAWS])
+@needs_ref
+def test_law_matches_reference_get_pk2cc(iso, vol, kw):
+    from oracle import ref
+    m = M.block_mesh(1, "tet")
+    ra = ref.RefAssembly(m.x, m.ien)
+    rng = np.random.default_rng(42)
+    th = 0.7
+    fl = np.array([np.cos(th), np.sin(th), 0.0, -np.sin(th), np.cos(th), 0.0])
+    worst = 0.0
+    for _ in range(20):
+        F = np.eye(3) + 0.15 * rng.standard_normal((3, 3))
+        if np.linalg.det(F) < 0.3:
+            continue
+        S, Dm = ra.pk2cc(F, fl, iso=iso, vol=vol, **kw)
+        S6, Dm21 = host_pk2cc(F, fl, iso=iso, vol=vol, **kw)
+        Sr = np.array([S[i, j] for i, j in VOIGT])
+        Dr = np.array([Dm[I, J] for I in range(6) for J in range(I, 6)])
+        worst = max(worst, np.abs(S6 - Sr).max() / np.abs(Sr).max(), np.abs(Dm21 - Dr).max() / np.abs(Dr).max())
+        assert np.allclose(Dm, Dm.T, rtol=1e-10, atol=1e-10 * np.abs(Dm).max())          # the reference's Dm is symmetric
+    ra.close()
+    # the isochoric projections are evaluated in closed form here and by generic fourth-order contractions there
+    assert worst < 1e-12, worst

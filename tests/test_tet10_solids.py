@@ -110,3 +110,27 @@ def test_active_fibre_stress_matches_golden(eq, elem, iso):
     assert rel_inf(be.get_R(), g[f"R_{eq}_{elem}_{iso}"]) < TOL_ASM
     assert rel_inf(be.get_Val(), g[f"Val_{eq}_{elem}_{iso}"]) < TOL_ASM
     be.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Mooney-Rivlin law (mat_models_carray.h:438-540; the law itself is pinned on the CPU in tests/test_solid_laws.py)
+# ---------------------------------------------------------------------------------------------------------------------
+@needs_ref
+def test_oracle_reproduces_mooney_rivlin_fixtures():
+    from oracle import refcase
+    g = golden("active_stress.npz")
+    for elem in ("tet", "hex", "tet10"):
+        R, Val, _, _, _, _ = refcase.reference_assemble_solid(P.block_case(2 if elem == "tet10" else 3, elem=elem, kind="struct", iso="MR", vol="ST91"))
+        assert np.array_equal(R, g[f"R_MR_{elem}"]) and np.array_equal(Val, g[f"Val_MR_{elem}"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("elem", ["tet", "hex", "tet10"])
+def test_mooney_rivlin_assembly_matches_golden(elem):
+    g = golden("active_stress.npz")
+    case = P.block_case(2 if elem == "tet10" else 3, elem=elem, kind="struct", iso="MR", vol="ST91")
+    be = P.setup_backend(case)
+    P.assemble_solid(be, case)
+    assert rel_inf(be.get_R(), g[f"R_MR_{elem}"]) < TOL_ASM
+    assert rel_inf(be.get_Val(), g[f"Val_MR_{elem}"]) < TOL_ASM
+    be.close()
