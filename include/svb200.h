@@ -185,7 +185,7 @@ int b200_face_mesh_set(b200_handle* h, int faIn, int eNoNb, int nElb, const int*
  * B200_PIC_* id (Yo, Yn, ... of the time integrator; Ag/Yg/Dg state) or -1 for the integrand 1 (the face area).
  * u - l + 1 == 3: flux  sum w N s.n  with the area-weighted normal; l == u: scalar  sum |n| w N s.  geo: configuration of the
  * normals as in gnnb (nn.cpp:609-640): 0 reference x, 1 x + Do(0:2) (old time step), 2 x + Dn(0:2) (new), 3 moving mesh
- * x + Do(4:6).  The sum runs serially over (element, Gauss point) like the reference's: bit-identical.  In a multi-rank
+ * x + Do(4:6).  The sum runs serially over (element, Gauss point), the reference's order.  In a multi-rank
  * run this is the rank's part; the caller reduces it like cm.reduce does. */
 int b200_face_integ(b200_handle* h, int faIn, int which, int l, int u, int geo, double* result);
 int b200_assemble_bneu(b200_handle* h, int faIn, int kind, const b200_bneu_props* p, const double* hg);

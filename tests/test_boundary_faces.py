@@ -102,9 +102,10 @@ def test_host_face_integrals_match_reference_bitwise(elem, n):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("elem,n", ELEMS)
-def test_gpu_face_integrals_bitwise(elem, n):
-    """b200_face_integ on the device-resident time-integrator arrays: equal to the host run of the same arithmetic (which the
-    CPU suite pins to the reference bit for bit) and to the reference itself where it travelled."""
+def test_gpu_face_integrals(elem, n):
+    """b200_face_integ on the device-resident time-integrator arrays against the host run of the same arithmetic (which the
+    CPU suite pins to the reference bit for bit) and the reference itself where it travelled: 1e-13 (the device contracts
+    a*b + c into FMAs, the host build does not; the running sum has the reference's order on both)."""
     case, IENb, gE, Y, D = _integ_inputs(elem, n)
     m = case["mesh"]
     be = P.setup_backend(case)
@@ -118,9 +119,10 @@ def test_gpu_face_integrals_bitwise(elem, n):
         be.pic_set("Dn", D if geo == 2 else np.zeros_like(D))
         got = be.face_integ(2, None if l is None else "Yn", 0 if l is None else l, u, geo=geo)
         host = host_face_integ(m, IENb, gE, None if l is None else Y, 0 if l is None else l, u, geo=D if geo else None, goff=goff)
-        assert got == host, (name, got, host)
+        assert abs(got - host) <= 1e-13 * abs(host), (name, got, host)
         if ra is not None:
-            assert got == ra.face_integ(IENb, gE, None if l is None else Y, 0 if l is None else l, u, geo=geo, D=D if geo else None), name
+            want = ra.face_integ(IENb, gE, None if l is None else Y, 0 if l is None else l, u, geo=geo, D=D if geo else None)
+            assert abs(got - want) <= 1e-13 * abs(want), (name, got, want)
     be.close()
 
 
@@ -145,7 +147,7 @@ def test_host_face_normals_match_reference_bitwise(elem, n, mvMsh):
 @pytest.mark.gpu
 @pytest.mark.parametrize("elem,n", ELEMS)
 @pytest.mark.parametrize("geo", [2, 3])
-def test_gpu_face_normal_update_bitwise(elem, n, geo):
+def test_gpu_face_normal_update(elem, n, geo):
     """b200_face_normal_update: the coupled face's vector follows the moving configuration on the device."""
     case, IENb, gE, Y, D = _integ_inputs(elem, n)
     m = case["mesh"]
@@ -158,11 +160,11 @@ def test_gpu_face_normal_update_bitwise(elem, n, geo):
     be.face_normal_update(0, 4, geo=geo)
     got = be.face_get_val(4, len(gN))
     host = host_face_normals(m, IENb, gE, geo=D, goff=4 if geo == 3 else 0)[gN]
-    assert np.array_equal(got, host)
+    assert rel_inf(got, host) < 1e-13                     # FMA contraction on the device, none in the host build
     from oracle import ref
     if ref.available():
         ra = ref.RefAssembly(m.x, m.ien)
-        assert np.array_equal(got, ra.fsi_ls_upd(IENb, gE, gN, D, mvMsh=(geo == 3)))
+        assert rel_inf(got, ra.fsi_ls_upd(IENb, gE, gN, D, mvMsh=(geo == 3))) < 1e-13
         ra.close()
     be.close()
 
