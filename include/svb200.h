@@ -52,7 +52,8 @@ typedef struct {
  * dmnType / stModelType (solver/sv_struct.cpp:576-594, solver/ComMod.h:345-388).  s = eq.s, the row of
  * the equation's first unknown inside Ag/Yg/Dg(tDof,nNo).  isoType: 0 neo-Hookean (C10 = mu/2),
  * 1 St.Venant-Kirchhoff (C10 = lambda, C01 = mu), 2 modified StVK (C10 = kappa, C01 = mu), 3 Holzapfel-Ogden
- * (solver/mat_models_carray.h:905-1135; needs b200_mesh_fibers), 4 Mooney-Rivlin (C10, C01; :438-540);
+ * (solver/mat_models_carray.h:905-1135; needs b200_mesh_fibers), 4 Mooney-Rivlin (C10, C01; :438-540),
+ * 5 Holzapfel-Gasser-Ogden (:544-688; needs b200_mesh_fibers);
  * volType: 0 none, 1 Quad, 2 ST91, 3 M94 (solver/mat_models.cpp:1626-1645). */
 typedef struct {
   double dt, am, af, gam, beta;
@@ -62,7 +63,8 @@ typedef struct {
   double C10, C01, Kpen;
   double a, b, aff, bff, ass, bss, afs, bfs, khs;   /* isoType 3 (Holzapfel-Ogden): stModelType a..bfs, khs */
   double Tfa, Tsa;   /* fibre-reinforcement / active stress along the fibre and sheet directions: what get_fib_stress returns
-                        for stM.Tf at this time, and Tfa*Tf.eta_s (mat_models_carray.h:222-225); laws 0 and 3, needs fibres */
+                        for stM.Tf at this time, and Tfa*Tf.eta_s (mat_models_carray.h:222-225); laws 0, 3, 4, 5, needs fibres */
+  double kap;        /* isoType 5 (Holzapfel-Gasser-Ogden): fibre dispersion stM.kap; C10, aff, bff, ass, bss as in the XML */
 } b200_struct_props;
 
 /* Linear elasticity (solver/l_elas.cpp:274-390).  mesh_mode != 0: the ALE mesh-motion equation

@@ -66,7 +66,7 @@ def dropin_solid_step(case, ls, mode):
         f = p.get("f", (0.0, 0.0, 0.0))
         par = np.array([p["dt"], p["am"], p["af"], p["gam"], p["beta"], p["rho"], p.get("dmp", 0.0), f[0], f[1], f[2],
                         RefAssembly.ISO[p.get("iso", "nHook")], RefAssembly.VOL[p.get("vol")], p.get("C10", 0.0), p.get("C01", 0.0),
-                        p.get("Kpen", 0.0), p.get("elM", 0.0), p.get("nu", 0.0)] + [0.0] * 8 + [100.0, 0.0, 0.0], np.float64)
+                        p.get("Kpen", 0.0), p.get("elM", 0.0), p.get("nu", 0.0)] + [0.0] * 8 + [100.0, 0.0, 0.0, 0.0], np.float64)
         Ag = _c(case["Ag"], np.float64); Yg = _c(case["Yg"], np.float64); Dg = _c(case["Dg"], np.float64)
         Bf = _c(case["Bf"], np.float64)
         Do = None if case.get("Do") is None else _c(case["Do"], np.float64)
@@ -269,7 +269,7 @@ class RefAssembly:
             f = p.get("f", (0.0, 0.0, 0.0)); ho = p.get("ho") or {}
             rows.append([p["dt"], p["am"], p["af"], p["gam"], p["beta"], p["rho"], p.get("dmp", 0.0), f[0], f[1], f[2],
                          self.ISO[p.get("iso", "nHook")], self.VOL[p.get("vol")], p.get("C10", 0.0), p.get("C01", 0.0), p.get("Kpen", 0.0),
-                         0.0, 0.0] + [ho.get(k, 100.0 if k == "khs" else 0.0) for k in self.HO_KEYS] + [p.get("Tfa", 0.0), p.get("eta_s", 0.0)])
+                         0.0, 0.0] + [ho.get(k, 100.0 if k == "khs" else 0.0) for k in self.HO_KEYS] + [p.get("Tfa", 0.0), p.get("eta_s", 0.0), p.get("kap", 0.0)])
         par = np.array(rows, np.float64)
         ed = _c(elem_dmn, np.int32)
         # construct_dsolid reads the properties of com_mod.cDmn for every element (a copy where construct_fluid takes a
@@ -336,11 +336,11 @@ class RefAssembly:
             raise RuntimeError(lib().ref_last_error().decode())
         return R, Val
 
-    def pk2cc(self, F, fl, *, iso="nHook", vol="ST91", C10=0.0, C01=0.0, Kpen=0.0, ho=None, Tfa=0.0, eta_s=0.0):
+    def pk2cc(self, F, fl, *, iso="nHook", vol="ST91", C10=0.0, C01=0.0, Kpen=0.0, ho=None, Tfa=0.0, eta_s=0.0, kap=0.0):
         """mat_models_carray::get_pk2cc<3> (S/mat_models_carray.h:182): S (3,3) and Dm (6,6) at the deformation gradient F."""
         ho = ho or {}
         par = np.array([0.0] * 10 + [self.ISO[iso], self.VOL[vol], C10, C01, Kpen, 0.0, 0.0]
-                       + [ho.get(k, 100.0 if k == "khs" else 0.0) for k in self.HO_KEYS] + [Tfa, eta_s], np.float64)
+                       + [ho.get(k, 100.0 if k == "khs" else 0.0) for k in self.HO_KEYS] + [Tfa, eta_s, kap], np.float64)
         F = _c(F, np.float64); fl = _c(fl, np.float64)
         S = np.empty((3, 3)); Dm = np.empty((6, 6))
         rc = lib().ref_pk2cc(self.h, _p(par), _p(F), _p(fl), _p(S), _p(Dm))
@@ -348,7 +348,7 @@ class RefAssembly:
             raise RuntimeError(lib().ref_last_error().decode())
         return S, Dm
 
-    ISO = {"nHook": 0, "StVK": 1, "mStVK": 2, "HO": 3, "MR": 4}
+    ISO = {"nHook": 0, "StVK": 1, "mStVK": 2, "HO": 3, "MR": 4, "HGO": 5}
     HO_KEYS = ("a", "b", "aff", "bff", "ass", "bss", "afs", "bfs", "khs")
 
     def set_fibers(self, fN):
@@ -361,14 +361,14 @@ class RefAssembly:
     VOL = {None: 0, "Quad": 1, "ST91": 2, "M94": 3}
 
     def solid(self, kind, Ag, Yg, Dg, Bf, *, dt, am, af, gam, beta, rho, dmp=0.0, f=(0.0, 0.0, 0.0), iso="nHook",
-              vol="ST91", C10=0.0, C01=0.0, Kpen=0.0, elM=0.0, nu=0.0, s=0, Do=None, ho=None, Tfa=0.0, eta_s=0.0):
+              vol="ST91", C10=0.0, C01=0.0, Kpen=0.0, elM=0.0, nu=0.0, s=0, Do=None, ho=None, Tfa=0.0, eta_s=0.0, kap=0.0):
         """kind "struct": construct_dsolid (S/sv_struct.cpp:213); "lelas": construct_l_elas (S/l_elas.cpp:58).
         Returns R (nNo,3), Val (nnz,9), seconds."""
         Ag = _c(Ag, np.float64); Yg = _c(Yg, np.float64); Dg = _c(Dg, np.float64); Bf = _c(Bf, np.float64)
         tDof = Ag.shape[1]
         ho = ho or {}
         par = np.array([dt, am, af, gam, beta, rho, dmp, f[0], f[1], f[2], self.ISO[iso], self.VOL[vol], C10, C01, Kpen,
-                        elM, nu] + [ho.get(k, 100.0 if k == "khs" else 0.0) for k in self.HO_KEYS] + [Tfa, eta_s], np.float64)
+                        elM, nu] + [ho.get(k, 100.0 if k == "khs" else 0.0) for k in self.HO_KEYS] + [Tfa, eta_s, kap], np.float64)
         R = np.empty((self.nNo, 3))
         Val = np.empty((self.nnz, 9))
         Do = None if Do is None else _c(Do, np.float64)
@@ -389,7 +389,7 @@ class RefAssembly:
                          fluid.get("lam", 0.0), fluid.get("a", 0.0), fluid.get("n", 0.0)], np.float64)
         spar = np.array([dt, am, af, gam, beta, solid["rho"], solid.get("dmp", 0.0), sf[0], sf[1], sf[2],
                          self.ISO[solid.get("iso", "nHook")], self.VOL[solid.get("vol", "ST91")], solid["C10"],
-                         solid.get("C01", 0.0), solid.get("Kpen", 0.0), 0.0, 0.0] + [0.0] * 8 + [100.0, 0.0, 0.0], np.float64)
+                         solid.get("C01", 0.0), solid.get("Kpen", 0.0), 0.0, 0.0] + [0.0] * 8 + [100.0, 0.0, 0.0, 0.0], np.float64)
         R = np.empty((self.nNo, 4))
         Val = np.empty((self.nnz, 16))
         t = lib().ref_asm_fsi(self.h, Ag.shape[1], dt, am, af, gam, beta, _p(fpar), _p(spar), _p(ed), _p(Ag), _p(Yg), _p(Dg),

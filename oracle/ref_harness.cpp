@@ -299,7 +299,8 @@ void configure_solid(AsmCtx* ctx, int kind, int tDof, int s, const double* par, 
     dmn.stM.isoType = (iso == 0) ? ConstitutiveModelType::stIso_nHook
                     : (iso == 1) ? ConstitutiveModelType::stIso_StVK
                     : (iso == 2) ? ConstitutiveModelType::stIso_mStVK
-                    : (iso == 4) ? ConstitutiveModelType::stIso_MR : ConstitutiveModelType::stIso_HO;
+                    : (iso == 4) ? ConstitutiveModelType::stIso_MR
+                    : (iso == 5) ? ConstitutiveModelType::stIso_HGO : ConstitutiveModelType::stIso_HO;
     dmn.stM.volType = (vol == 1) ? ConstitutiveModelType::stVol_Quad
                     : (vol == 2) ? ConstitutiveModelType::stVol_ST91
                     : (vol == 3) ? ConstitutiveModelType::stVol_M94 : ConstitutiveModelType::stIso_NA;
@@ -313,6 +314,7 @@ void configure_solid(AsmCtx* ctx, int kind, int tDof, int s, const double* par, 
     dmn.stM.Tf.fType = (par[26] != 0.0) ? utils::ibset(0, iBC_std) : 0;
     dmn.stM.Tf.g = par[26];
     dmn.stM.Tf.eta_s = par[27];
+    dmn.stM.kap = par[28];                        // HGO fibre dispersion
     com_mod.Bf.resize(3, nNo);
     std::memcpy(com_mod.Bf.data(), Bf, sizeof(double)*3*size_t(nNo));
 }

@@ -1,7 +1,7 @@
 // solid_law.hpp — constitutive laws of the displacement-based and mixed solid elements, host/device shared like
 // fluid_elem.hpp: 2nd Piola-Kirchhoff stress S and the Voigt elasticity matrix Dm from the deformation gradient.
 // Replaces mat_models_carray::get_pk2cc<3> (Code/Source/solver/mat_models_carray.h:182-1380; neo-Hookean :370-434,
-// Mooney-Rivlin :438-540, St.Venant-Kirchhoff :302-322, modified StVK :326-356, Holzapfel-Ogden :905-1135) with
+// Mooney-Rivlin :438-540, Holzapfel-Gasser-Ogden :544-688, St.Venant-Kirchhoff :302-322, modified StVK :326-356, Holzapfel-Ogden :905-1135) with
 // get_svol_p (mat_models.cpp:1626-1645) and the fibre reinforcement stress (mat_models_carray.h:222-225).
 // tests/hostlogic/fluid_elem_host.cpp instantiates the same source on the CPU (test tree only) and
 // tests/test_solid_laws.py compares it with the compiled reference's get_pk2cc on random deformation gradients.
@@ -14,10 +14,11 @@ namespace svb200 {
 struct SolidConsts {
   double dt, am, af, gam, beta;
   double rho, dmp, f[3];
-  int iso, vol;                // iso: 0 nHook, 1 StVK, 2 mStVK, 3 Holzapfel-Ogden, 4 Mooney-Rivlin; vol: 0 none, 1 Quad, 2 ST91, 3 M94
+  int iso, vol;                // iso: 0 nHook, 1 StVK, 2 mStVK, 3 Holzapfel-Ogden, 4 Mooney-Rivlin, 5 HGO; vol: 0 none, 1 Quad, 2 ST91, 3 M94
   double C10, C01, Kpen;
   double ho_a, ho_b, ho_aff, ho_bff, ho_ass, ho_bss, ho_afs, ho_bfs, ho_khs;   // stModelType a..bfs, khs
   double Tfa, Tsa;             // fibre / sheet reinforcement stress (get_fib_stress, mat_models_carray.h:222-225)
+  double kap;                  // HGO fibre dispersion (stM.kap)
   double elM, nu;              // lElas / mesh
   int tDof, s;                 // row offset of this equation's unknowns in Ag/Yg/Dg (eq.s)
   int kind;                    // 0 struct, 1 lElas, 2 mesh
@@ -249,6 +250,65 @@ SVB_HD_NOINL void pk2cc_iso(const SolidConsts& c, const double F[3][3], const do
         const int i = vi[I], j = vj[I], k = vi[Jv], l = vj[Jv];
         const double ids = (((i == k) && (j == l)) ? 0.5 : 0.0) + (((i == l) && (j == k)) ? 0.5 : 0.0);
         double cc = gk*(Hd[i][j]*Hd[k][l] - (ids - (1.0/nd)*(C[i][j]*Ci[k][l] + Ci[i][j]*C[k][l]) + (1.0/(nd*nd))*CC2*(Ci[i][j]*Ci[k][l])));
+        cc -= (2.0/nd)*(Ci[i][j]*S[k][l] + S[i][j]*Ci[k][l]);
+        cc += c2*(0.5*(Ci[i][k]*Ci[j][l] + Ci[i][l]*Ci[j][k])) + c3*(Ci[i][j]*Ci[k][l]);
+        Dm21[dm_idx(I, Jv)] = cc;
+      }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) S[i][j] += p*J*Ci[i][j];
+  } else if (c.iso == 5) {
+    // Holzapfel-Gasser-Ogden with fibre dispersion kap (:544-688): two families H = kap I + (1 - 3 kap) f (x) f, exponential
+    // terms in E = kap Inv1 + (1 - 3 kap) Inv4 - 1; C10 = the isotropic modulus, aff / bff / ass / bss the fibre parameters.
+    // Isochoric tangent PP : (k1 Hf (x) Hf + k2 Hs (x) Hs) : PP^T through the projected factors Hd = H - (1/3)(C : H) Ci.
+    const double J4d = J2d*J2d, kap = c.kap;
+    const double f0[3] = {fl[0], fl[1], fl[2]}, s0[3] = {fl[3], fl[4], fl[5]};
+    double Cf[3], Cs[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      Cf[i] = C[i][0]*f0[0] + C[i][1]*f0[1] + C[i][2]*f0[2];
+      Cs[i] = C[i][0]*s0[0] + C[i][1]*s0[1] + C[i][2]*s0[2];
+    }
+    const double Inv4 = J2d*(f0[0]*Cf[0] + f0[1]*Cf[1] + f0[2]*Cf[2]);
+    const double Inv6 = J2d*(s0[0]*Cs[0] + s0[1]*Cs[1] + s0[2]*Cs[2]);
+    const double Eff = kap*Inv1 + (1.0 - 3.0*kap)*Inv4 - 1.0;
+    const double Ess = kap*Inv1 + (1.0 - 3.0*kap)*Inv6 - 1.0;
+    const double ef = exp(c.ho_bff*Eff*Eff), es = exp(c.ho_bss*Ess*Ess);
+    const double g1 = c.C10, g2 = c.ho_aff*Eff*ef, g3 = c.ho_ass*Ess*es;
+    const double k1 = 4.0*J4d*(c.ho_aff*(1.0 + 2.0*c.ho_bff*Eff*Eff)*ef);
+    const double k2 = 4.0*J4d*(c.ho_ass*(1.0 + 2.0*c.ho_bss*Ess*Ess)*es);
+    double Hf[3][3], Hs[3][3], Sb[3][3];
+    double CSb = 0.0, CHf = 0.0, CHs = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const double d = (i == j) ? 1.0 : 0.0;
+        Hf[i][j] = kap*d + (1.0 - 3.0*kap)*(f0[i]*f0[j]);
+        Hs[i][j] = kap*d + (1.0 - 3.0*kap)*(s0[i]*s0[j]);
+        Sb[i][j] = 2.0*(g1*d + g2*Hf[i][j] + g3*Hs[i][j]) + c.Tfa*(f0[i]*f0[j]);
+      }
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int i = 0; i < 3; i++) { CSb = CSb + C[i][j]*Sb[i][j]; CHf = CHf + C[i][j]*Hf[i][j]; CHs = CHs + C[i][j]*Hs[i][j]; }
+    const double r1 = J2d*CSb/nd;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        S[i][j] = J2d*Sb[i][j] - r1*Ci[i][j];
+        Hf[i][j] = Hf[i][j] - (1.0/nd)*CHf*Ci[i][j];
+        Hs[i][j] = Hs[i][j] - (1.0/nd)*CHs*Ci[i][j];
+      }
+    const double c2 = 2.0*(r1 - p*J), c3 = pl*J - 2.0*r1/nd;
+#pragma unroll
+    for (int I = 0; I < 6; I++)
+#pragma unroll
+      for (int Jv = I; Jv < 6; Jv++) {
+        const int i = vi[I], j = vj[I], k = vi[Jv], l = vj[Jv];
+        double cc = k1*Hf[i][j]*Hf[k][l] + k2*Hs[i][j]*Hs[k][l];
         cc -= (2.0/nd)*(Ci[i][j]*S[k][l] + S[i][j]*Ci[k][l]);
         cc += c2*(0.5*(Ci[i][k]*Ci[j][l] + Ci[i][l]*Ci[j][k])) + c3*(Ci[i][j]*Ci[k][l]);
         Dm21[dm_idx(I, Jv)] = cc;

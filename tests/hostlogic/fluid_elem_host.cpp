@@ -187,7 +187,7 @@ int host_face_normals(int eNoN, const int* ien, int eNoNb, int nElb, const int* 
   return 0;
 }
 
-// get_pk2cc<3> (solid_law.hpp): par = {iso, vol, C10, C01, Kpen, a, b, aff, bff, ass, bss, afs, bfs, khs, Tfa, Tsa};
+// get_pk2cc<3> (solid_law.hpp): par = {iso, vol, C10, C01, Kpen, a, b, aff, bff, ass, bss, afs, bfs, khs, Tfa, Tsa, kap};
 // F row-major 3x3, fl = fibre + sheet directions; outputs S (00 11 22 01 12 20) and the 21 upper-triangle entries of Dm.
 void host_pk2cc(const double* par, const double* F9, const double* fl6, double* S6, double* Dm21)
 {
@@ -195,7 +195,7 @@ void host_pk2cc(const double* par, const double* F9, const double* fl6, double* 
   std::memset(&c, 0, sizeof(c));
   c.iso = int(par[0]); c.vol = int(par[1]); c.C10 = par[2]; c.C01 = par[3]; c.Kpen = par[4];
   c.ho_a = par[5]; c.ho_b = par[6]; c.ho_aff = par[7]; c.ho_bff = par[8]; c.ho_ass = par[9]; c.ho_bss = par[10];
-  c.ho_afs = par[11]; c.ho_bfs = par[12]; c.ho_khs = par[13]; c.Tfa = par[14]; c.Tsa = par[15];
+  c.ho_afs = par[11]; c.ho_bfs = par[12]; c.ho_khs = par[13]; c.Tfa = par[14]; c.Tsa = par[15]; c.kap = par[16];
   double F[3][3];
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) F[i][j] = F9[i*3 + j];
   pk2cc_iso(c, F, fl6, S6, Dm21);

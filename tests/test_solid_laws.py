@@ -23,6 +23,8 @@ LAWS = [
     ("MR", "ST91", dict(C10=0.3 * MU, C01=0.2 * MU, Kpen=4.0e9)),
     ("MR", None, dict(C10=0.3 * MU, C01=0.2 * MU)),
     ("MR", "M94", dict(C10=0.3 * MU, C01=0.2 * MU, Kpen=1.0e8, Tfa=3.0e4, eta_s=0.4)),
+    ("HGO", "ST91", dict(C10=0.5 * MU, Kpen=4.0e9, kap=0.226, ho=dict(aff=9.96e5, bff=524.6, ass=9.96e5, bss=524.6))),
+    ("HGO", "Quad", dict(C10=0.5 * MU, Kpen=1.0e8, kap=0.0, ho=dict(aff=2.0e6, bff=20.0, ass=1.0e6, bss=10.0), Tfa=3.0e4, eta_s=0.4)),
 ]
 VOIGT = [(0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (2, 0)]
 

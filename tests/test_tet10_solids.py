@@ -113,24 +113,32 @@ def test_active_fibre_stress_matches_golden(eq, elem, iso):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# Mooney-Rivlin law (mat_models_carray.h:438-540; the law itself is pinned on the CPU in tests/test_solid_laws.py)
+# Mooney-Rivlin and Holzapfel-Gasser-Ogden laws (mat_models_carray.h:438-540, 544-688; the laws themselves are pinned on the CPU
+# in tests/test_solid_laws.py)
 # ---------------------------------------------------------------------------------------------------------------------
+NEW_LAWS = [(iso, elem) for iso in ("MR", "HGO") for elem in ("tet", "hex", "tet10")]
+
+
+def _law_case(iso, elem):
+    return P.block_case(2 if elem == "tet10" else 3, elem=elem, kind="struct", iso=iso, vol="ST91")
+
+
 @needs_ref
-def test_oracle_reproduces_mooney_rivlin_fixtures():
+def test_oracle_reproduces_new_law_fixtures():
     from oracle import refcase
     g = golden("active_stress.npz")
-    for elem in ("tet", "hex", "tet10"):
-        R, Val, _, _, _, _ = refcase.reference_assemble_solid(P.block_case(2 if elem == "tet10" else 3, elem=elem, kind="struct", iso="MR", vol="ST91"))
-        assert np.array_equal(R, g[f"R_MR_{elem}"]) and np.array_equal(Val, g[f"Val_MR_{elem}"])
+    for iso, elem in NEW_LAWS:
+        R, Val, _, _, _, _ = refcase.reference_assemble_solid(_law_case(iso, elem))
+        assert np.array_equal(R, g[f"R_{iso}_{elem}"]) and np.array_equal(Val, g[f"Val_{iso}_{elem}"])
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("elem", ["tet", "hex", "tet10"])
-def test_mooney_rivlin_assembly_matches_golden(elem):
+@pytest.mark.parametrize("iso,elem", NEW_LAWS)
+def test_new_law_assembly_matches_golden(iso, elem):
     g = golden("active_stress.npz")
-    case = P.block_case(2 if elem == "tet10" else 3, elem=elem, kind="struct", iso="MR", vol="ST91")
+    case = _law_case(iso, elem)
     be = P.setup_backend(case)
     P.assemble_solid(be, case)
-    assert rel_inf(be.get_R(), g[f"R_MR_{elem}"]) < TOL_ASM
-    assert rel_inf(be.get_Val(), g[f"Val_MR_{elem}"]) < TOL_ASM
+    assert rel_inf(be.get_R(), g[f"R_{iso}_{elem}"]) < TOL_ASM
+    assert rel_inf(be.get_Val(), g[f"Val_{iso}_{elem}"]) < TOL_ASM
     be.close()

@@ -145,13 +145,13 @@ def host_face_normals(mesh, IENb, gE, geo=None, goff=0):
     return sV
 
 
-def host_pk2cc(F, fl, *, iso, vol, C10=0.0, C01=0.0, Kpen=0.0, ho=None, Tfa=0.0, eta_s=0.0):
+def host_pk2cc(F, fl, *, iso, vol, C10=0.0, C01=0.0, Kpen=0.0, ho=None, Tfa=0.0, eta_s=0.0, kap=0.0):
     """solid_law.hpp pk2cc_iso on the host (TEST-ONLY harness): S (6: 00 11 22 01 12 20), Dm upper triangle (21)."""
     L = elemhost()
     ho = ho or {}
     keys = ("a", "b", "aff", "bff", "ass", "bss", "afs", "bfs", "khs")
-    par = np.array([{"nHook": 0, "StVK": 1, "mStVK": 2, "HO": 3, "MR": 4}[iso], {None: 0, "Quad": 1, "ST91": 2, "M94": 3}[vol], C10, C01, Kpen]
-                   + [ho.get(k, 100.0 if k == "khs" else 0.0) for k in keys] + [Tfa, Tfa * eta_s], np.float64)
+    par = np.array([{"nHook": 0, "StVK": 1, "mStVK": 2, "HO": 3, "MR": 4, "HGO": 5}[iso], {None: 0, "Quad": 1, "ST91": 2, "M94": 3}[vol], C10, C01, Kpen]
+                   + [ho.get(k, 100.0 if k == "khs" else 0.0) for k in keys] + [Tfa, Tfa * eta_s, kap], np.float64)
     F = np.ascontiguousarray(F, np.float64); fl = np.ascontiguousarray(fl, np.float64)
     S6 = np.empty(6); Dm21 = np.empty(21)
     L.host_pk2cc(_p(par), _p(F), _p(fl), _p(S6), _p(Dm21))
