@@ -53,7 +53,7 @@ typedef struct {
  * the equation's first unknown inside Ag/Yg/Dg(tDof,nNo).  isoType: 0 neo-Hookean (C10 = mu/2),
  * 1 St.Venant-Kirchhoff (C10 = lambda, C01 = mu), 2 modified StVK (C10 = kappa, C01 = mu), 3 Holzapfel-Ogden
  * (solver/mat_models_carray.h:905-1135; needs b200_mesh_fibers), 4 Mooney-Rivlin (C10, C01; :438-540),
- * 5 Holzapfel-Gasser-Ogden (:544-688; needs b200_mesh_fibers);
+ * 5 Holzapfel-Gasser-Ogden (:544-688; needs b200_mesh_fibers), 6 Guccione (C10, bff, bss, bfs; :692-903; needs b200_mesh_fibers);
  * volType: 0 none, 1 Quad, 2 ST91, 3 M94 (solver/mat_models.cpp:1626-1645). */
 typedef struct {
   double dt, am, af, gam, beta;

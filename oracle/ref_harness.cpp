@@ -300,7 +300,8 @@ void configure_solid(AsmCtx* ctx, int kind, int tDof, int s, const double* par, 
                     : (iso == 1) ? ConstitutiveModelType::stIso_StVK
                     : (iso == 2) ? ConstitutiveModelType::stIso_mStVK
                     : (iso == 4) ? ConstitutiveModelType::stIso_MR
-                    : (iso == 5) ? ConstitutiveModelType::stIso_HGO : ConstitutiveModelType::stIso_HO;
+                    : (iso == 5) ? ConstitutiveModelType::stIso_HGO
+                    : (iso == 6) ? ConstitutiveModelType::stIso_Gucci : ConstitutiveModelType::stIso_HO;
     dmn.stM.volType = (vol == 1) ? ConstitutiveModelType::stVol_Quad
                     : (vol == 2) ? ConstitutiveModelType::stVol_ST91
                     : (vol == 3) ? ConstitutiveModelType::stVol_M94 : ConstitutiveModelType::stIso_NA;

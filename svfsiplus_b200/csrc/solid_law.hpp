@@ -1,7 +1,7 @@
 // solid_law.hpp — constitutive laws of the displacement-based and mixed solid elements, host/device shared like
 // fluid_elem.hpp: 2nd Piola-Kirchhoff stress S and the Voigt elasticity matrix Dm from the deformation gradient.
 // Replaces mat_models_carray::get_pk2cc<3> (Code/Source/solver/mat_models_carray.h:182-1380; neo-Hookean :370-434,
-// Mooney-Rivlin :438-540, Holzapfel-Gasser-Ogden :544-688, St.Venant-Kirchhoff :302-322, modified StVK :326-356, Holzapfel-Ogden :905-1135) with
+// Mooney-Rivlin :438-540, Holzapfel-Gasser-Ogden :544-688, Guccione :692-903, St.Venant-Kirchhoff :302-322, modified StVK :326-356, Holzapfel-Ogden :905-1135) with
 // get_svol_p (mat_models.cpp:1626-1645) and the fibre reinforcement stress (mat_models_carray.h:222-225).
 // tests/hostlogic/fluid_elem_host.cpp instantiates the same source on the CPU (test tree only) and
 // tests/test_solid_laws.py compares it with the compiled reference's get_pk2cc on random deformation gradients.
@@ -14,7 +14,7 @@ namespace svb200 {
 struct SolidConsts {
   double dt, am, af, gam, beta;
   double rho, dmp, f[3];
-  int iso, vol;                // iso: 0 nHook, 1 StVK, 2 mStVK, 3 Holzapfel-Ogden, 4 Mooney-Rivlin, 5 HGO; vol: 0 none, 1 Quad, 2 ST91, 3 M94
+  int iso, vol;                // iso: 0 nHook, 1 StVK, 2 mStVK, 3 Holzapfel-Ogden, 4 Mooney-Rivlin, 5 HGO, 6 Guccione; vol: 0 none, 1 Quad, 2 ST91, 3 M94
   double C10, C01, Kpen;
   double ho_a, ho_b, ho_aff, ho_bff, ho_ass, ho_bss, ho_afs, ho_bfs, ho_khs;   // stModelType a..bfs, khs
   double Tfa, Tsa;             // fibre / sheet reinforcement stress (get_fib_stress, mat_models_carray.h:222-225)
@@ -309,6 +309,95 @@ SVB_HD_NOINL void pk2cc_iso(const SolidConsts& c, const double F[3][3], const do
       for (int Jv = I; Jv < 6; Jv++) {
         const int i = vi[I], j = vj[I], k = vi[Jv], l = vj[Jv];
         double cc = k1*Hf[i][j]*Hf[k][l] + k2*Hs[i][j]*Hs[k][l];
+        cc -= (2.0/nd)*(Ci[i][j]*S[k][l] + S[i][j]*Ci[k][l]);
+        cc += c2*(0.5*(Ci[i][k]*Ci[j][l] + Ci[i][l]*Ci[j][k])) + c3*(Ci[i][j]*Ci[k][l]);
+        Dm21[dm_idx(I, Jv)] = cc;
+      }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) S[i][j] += p*J*Ci[i][j];
+  } else if (c.iso == 6) {
+    // Guccione (1995), transversely isotropic in the local frame (f, s, f x s) (:692-903): Q quadratic in the isochoric
+    // Green strain E* of that frame, W = C10/2 (exp Q - 1); parameters C10, bff, bss, bfs.  Isochoric tangent
+    //   CCb = r2 J4d (2 Sq (x) Sq + bff M0 (x) M0 + bss (M1 (x) M1 + M2 (x) M2 + 2 M4 (x) M4) + 2 bfs (M3 (x) M3 + M5 (x) M5)),
+    // seven rank-one terms, projected through Hd = H - (1/3)(C : H) Ci like the Holzapfel-Ogden law.
+    const double J4d = J2d*J2d;
+    const double g1 = c.ho_bff, g2 = c.ho_bss, g3 = c.ho_bfs;
+    const double f0[3] = {fl[0], fl[1], fl[2]}, s0[3] = {fl[3], fl[4], fl[5]};
+    const double n0[3] = {f0[1]*s0[2] - f0[2]*s0[1], f0[2]*s0[0] - f0[0]*s0[2], f0[0]*s0[1] - f0[1]*s0[0]};
+    double Rm[3][3], Eb[3][3], E1[3][3], Es[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { Rm[i][0] = f0[i]; Rm[i][1] = s0[i]; Rm[i][2] = n0[i]; }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) Eb[i][j] = 0.50*(J2d*C[i][j] - ((i == j) ? 1.0 : 0.0));
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) E1[i][j] = ((0.0 + Eb[i][0]*Rm[0][j]) + Eb[i][1]*Rm[1][j]) + Eb[i][2]*Rm[2][j];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) Es[i][j] = ((0.0 + Rm[0][i]*E1[0][j]) + Rm[1][i]*E1[1][j]) + Rm[2][i]*E1[2][j];
+    const double QQ = g1*Es[0][0]*Es[0][0]
+                    + g2*(Es[1][1]*Es[1][1] + Es[2][2]*Es[2][2] + Es[1][2]*Es[1][2] + Es[2][1]*Es[2][1])
+                    + g3*(Es[0][1]*Es[0][1] + Es[1][0]*Es[1][0] + Es[0][2]*Es[0][2] + Es[2][0]*Es[2][0]);
+    double r2 = c.C10*exp(QQ);
+    // H[0] = Sq (the stress direction before the exp factor), H[1..6] = M0..M5
+    double H[7][3][3];
+    const int pa[6] = {0, 1, 2, 0, 1, 2}, pb[6] = {0, 1, 2, 1, 2, 0};
+#pragma unroll
+    for (int q = 0; q < 6; q++)
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+          H[1 + q][i][j] = (q < 3) ? Rm[i][pa[q]]*Rm[j][pa[q]] : 0.5*(Rm[i][pa[q]]*Rm[j][pb[q]] + Rm[j][pa[q]]*Rm[i][pb[q]]);
+    double Sb[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        H[0][i][j] = g1*Es[0][0]*H[1][i][j]
+                   + g2*(Es[1][1]*H[2][i][j] + Es[2][2]*H[3][i][j] + 2.0*Es[1][2]*H[5][i][j])
+                   + 2.0*g3*(Es[0][1]*H[4][i][j] + Es[0][2]*H[6][i][j]);
+        Sb[i][j] = H[0][i][j]*r2 + c.Tfa*(f0[i]*f0[j]);
+      }
+    double CSb = 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int i = 0; i < 3; i++) CSb = CSb + C[i][j]*Sb[i][j];
+    const double r1 = J2d*CSb/nd;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) S[i][j] = J2d*Sb[i][j] - r1*Ci[i][j];
+    r2 = r2*J4d;
+    const double wk[7] = {2.0*r2, g1*r2, g2*r2, g2*r2, 2.0*g3*r2, 2.0*g2*r2, 2.0*g3*r2};
+#pragma unroll
+    for (int q = 0; q < 7; q++) {
+      double ch = 0.0;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) ch += C[i][j]*H[q][i][j];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) H[q][i][j] = H[q][i][j] - (1.0/nd)*ch*Ci[i][j];
+    }
+    const double c2 = 2.0*(r1 - p*J), c3 = pl*J - 2.0*r1/nd;
+#pragma unroll
+    for (int I = 0; I < 6; I++)
+#pragma unroll
+      for (int Jv = I; Jv < 6; Jv++) {
+        const int i = vi[I], j = vj[I], k = vi[Jv], l = vj[Jv];
+        double cc = 0.0;
+#pragma unroll
+        for (int q = 0; q < 7; q++) cc += wk[q]*H[q][i][j]*H[q][k][l];
         cc -= (2.0/nd)*(Ci[i][j]*S[k][l] + S[i][j]*Ci[k][l]);
         cc += c2*(0.5*(Ci[i][k]*Ci[j][l] + Ci[i][l]*Ci[j][k])) + c3*(Ci[i][j]*Ci[k][l]);
         Dm21[dm_idx(I, Jv)] = cc;

@@ -251,7 +251,8 @@ bool B200LinearAlgebra::fill_struct_props(ComMod& com_mod, const eqType& eq, con
   if (dmn.solid_visc.viscType != SolidViscosityModelType::viscType_NA) return false;
   fibre_stress(com_mod, stM.Tf, sp.Tfa, sp.Tsa);
   if (sp.Tfa != 0.0 && stM.isoType != ConstitutiveModelType::stIso_nHook && stM.isoType != ConstitutiveModelType::stIso_HO &&
-      stM.isoType != ConstitutiveModelType::stIso_MR && stM.isoType != ConstitutiveModelType::stIso_HGO) return false;
+      stM.isoType != ConstitutiveModelType::stIso_MR && stM.isoType != ConstitutiveModelType::stIso_HGO &&
+      stM.isoType != ConstitutiveModelType::stIso_Gucci) return false;
   switch (stM.isoType) {
     case ConstitutiveModelType::stIso_nHook: sp.isoType = 0; break;
     case ConstitutiveModelType::stIso_StVK:  sp.isoType = 1; break;
@@ -259,6 +260,7 @@ bool B200LinearAlgebra::fill_struct_props(ComMod& com_mod, const eqType& eq, con
     case ConstitutiveModelType::stIso_HO:    sp.isoType = 3; break;      // needs lM.fN with two families (upload_mesh)
     case ConstitutiveModelType::stIso_MR:    sp.isoType = 4; break;
     case ConstitutiveModelType::stIso_HGO:   sp.isoType = 5; sp.kap = stM.kap; break;   // two fibre families (upload_mesh)
+    case ConstitutiveModelType::stIso_Gucci: sp.isoType = 6; break;                     // fibre + sheet frame (upload_mesh)
     default: return false;
   }
   sp.a = stM.a; sp.b = stM.b; sp.aff = stM.aff; sp.bff = stM.bff; sp.ass = stM.ass; sp.bss = stM.bss;
@@ -300,7 +302,7 @@ bool B200LinearAlgebra::assemble_fsi_mesh(ComMod& com_mod, const mshType& lM, co
     } else if (eq.dmn[d].phys == EquationType::phys_struct) {
       kinds[d] = 1;
       if (!fill_struct_props(com_mod, eq, eq.dmn[d], st[d])) return false;
-      if ((st[d].isoType == 3 || st[d].isoType == 5 || st[d].Tfa != 0.0) && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
+      if ((st[d].isoType == 3 || st[d].isoType == 5 || st[d].isoType == 6 || st[d].Tfa != 0.0) && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
     } else {
       return false;
     }
@@ -432,7 +434,7 @@ bool B200LinearAlgebra::assemble_solid_mesh(ComMod& com_mod, const mshType& lM, 
   const bool is_struct = (eq.phys == EquationType::phys_struct);
   if (is_struct) {
     if (!fill_struct_props(com_mod, eq, dmn, sp)) return false;
-    if ((sp.isoType == 3 || sp.isoType == 5 || sp.Tfa != 0.0) && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
+    if ((sp.isoType == 3 || sp.isoType == 5 || sp.isoType == 6 || sp.Tfa != 0.0) && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
   } else {
     lp.dt = com_mod.dt; lp.am = eq.am; lp.af = eq.af; lp.beta = eq.beta;
     lp.tDof = com_mod.tDof; lp.s = eq.s;
@@ -475,7 +477,7 @@ bool B200LinearAlgebra::assemble_domains_mesh(ComMod& com_mod, const mshType& lM
       if (!fill_fluid_props(com_mod, eq, eq.dmn[d], fl[d])) return false;
     } else {
       if (!fill_struct_props(com_mod, eq, eq.dmn[d], st[d])) return false;
-      if ((st[d].isoType == 3 || st[d].isoType == 5 || st[d].Tfa != 0.0) && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
+      if ((st[d].isoType == 3 || st[d].isoType == 5 || st[d].isoType == 6 || st[d].Tfa != 0.0) && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
     }
   }
   if (!fluid) {

@@ -146,7 +146,7 @@ def block_case(n, elem="hex", kind="struct", iso="nHook", vol="ST91", jitter=0.1
     if kind == "struct":
         if iso == "nHook":
             C10, C01 = 0.5 * mu, 0.0
-        elif iso in ("HO", "HGO"):               # Holzapfel-Ogden myocardium (parameters of tests/cases/struct/LV_* style, cgs)
+        elif iso in ("HO", "HGO", "Gucci"):      # Holzapfel-Ogden myocardium (parameters of tests/cases/struct/LV_* style, cgs)
             C10, C01 = 0.0, 0.0
         elif iso == "MR":                        # Mooney-Rivlin: C10 + C01 = mu / 2
             C10, C01 = 0.3 * mu, 0.2 * mu
@@ -159,6 +159,8 @@ def block_case(n, elem="hex", kind="struct", iso="nHook", vol="ST91", jitter=0.1
         if iso == "HO":
             props["ho"] = dict(a=590.0, b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12, afs=2160.0, bfs=11.436, khs=100.0)
             props["Kpen"] = 1.0e6
+        if iso == "Gucci":                       # Guccione myocardium: C10 and the three exponents
+            props.update(C10=880.0, Kpen=1.0e6, ho=dict(bff=8.0, bss=6.0, bfs=12.0))
         if iso == "HGO":                         # arterial-wall style parameters: two dispersed fibre families
             props.update(C10=0.5 * mu, kap=0.226, ho=dict(aff=9.96e5, bff=524.6, ass=9.96e5, bss=524.6))
     elif kind == "lelas":
@@ -180,7 +182,7 @@ def block_case(n, elem="hex", kind="struct", iso="nHook", vol="ST91", jitter=0.1
         faces.append(dict(name=nm, nodes=nodes, dof=3, bGrp=B.BC_DIR, val=val))
     case = dict(mesh=m, rowPtr=rowPtr, colPtr=colPtr, Ag=Ag, Yg=Yg, Dg=Dg, Bf=Bf, props=props, faces=faces, kind=kind,
                 res=np.zeros(len(faces)), incL=np.ones(len(faces), np.int32), name=f"block_{elem}_{n}_{kind}")
-    if kind == "struct" and iso in ("HO", "HGO"):
+    if kind == "struct" and iso in ("HO", "HGO", "Gucci"):
         # fibre / sheet directions rotating through the block (unit, orthogonal), one pair per element
         cen = m.x[m.ien].mean(axis=1)
         th = 0.5 * np.pi * cen[:, 2] + 0.3 * cen[:, 0]

@@ -113,10 +113,10 @@ def test_active_fibre_stress_matches_golden(eq, elem, iso):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# Mooney-Rivlin and Holzapfel-Gasser-Ogden laws (mat_models_carray.h:438-540, 544-688; the laws themselves are pinned on the CPU
+# Mooney-Rivlin, Holzapfel-Gasser-Ogden and Guccione laws (mat_models_carray.h:438-540, 544-688, 692-903; the laws themselves are pinned on the CPU
 # in tests/test_solid_laws.py)
 # ---------------------------------------------------------------------------------------------------------------------
-NEW_LAWS = [(iso, elem) for iso in ("MR", "HGO") for elem in ("tet", "hex", "tet10")]
+NEW_LAWS = [(iso, elem) for iso in ("MR", "HGO", "Gucci") for elem in ("tet", "hex", "tet10")]
 
 
 def _law_case(iso, elem):
