@@ -77,8 +77,9 @@ typedef struct {
 } b200_lelas_props;
 
 /* Mixed velocity-pressure solid (ustruct; solver/ustruct.cpp:1158-1575, 632-876).  elM, nu, ctM, ctC feed
- * get_tau (solver/mat_models.cpp:1655); Kpen, volType feed g_vol_pen (:1696).  isoType 0 = neo-Hookean,
- * 3 = Holzapfel-Ogden (needs b200_mesh_fibers). */
+ * get_tau (solver/mat_models.cpp:1655); Kpen, volType feed g_vol_pen (:1696).  isoType as in the struct properties, the
+ * laws with an isochoric split (get_pk2cc_dev, mat_models.cpp:630): 0 neo-Hookean, 3 Holzapfel-Ogden, 4 Mooney-Rivlin,
+ * 5 Holzapfel-Gasser-Ogden, 6 Guccione (3, 5, 6 need b200_mesh_fibers). */
 typedef struct {
   double dt, am, af, gam;
   int tDof, s;
@@ -88,6 +89,7 @@ typedef struct {
   double C10, Kpen;
   double a, b, aff, bff, ass, bss, afs, bfs, khs;   /* isoType 3 (Holzapfel-Ogden) */
   double Tfa, Tsa;   /* fibre / sheet reinforcement stress as in the struct properties above; mat_models.cpp:682-684 */
+  double C01, kap;   /* isoType 4 (Mooney-Rivlin) second modulus; isoType 5 (HGO) fibre dispersion */
 } b200_ustruct_props;
 
 /* ---- life cycle ------------------------------------------------------------------------- */

@@ -193,6 +193,7 @@ def lib():
         L.ref_fsi_ls_upd.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p]
         L.ref_pk2cc.argtypes = [C.c_void_p] * 6
+        L.ref_pk2cc_dev.argtypes = [C.c_void_p] * 6
         L.ref_asm_bneu.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
         L.ref_pic.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_double] + [C.c_void_p] * 12
         _lib = L
@@ -336,14 +337,15 @@ class RefAssembly:
             raise RuntimeError(lib().ref_last_error().decode())
         return R, Val
 
-    def pk2cc(self, F, fl, *, iso="nHook", vol="ST91", C10=0.0, C01=0.0, Kpen=0.0, ho=None, Tfa=0.0, eta_s=0.0, kap=0.0):
-        """mat_models_carray::get_pk2cc<3> (S/mat_models_carray.h:182): S (3,3) and Dm (6,6) at the deformation gradient F."""
+    def pk2cc(self, F, fl, *, iso="nHook", vol="ST91", C10=0.0, C01=0.0, Kpen=0.0, ho=None, Tfa=0.0, eta_s=0.0, kap=0.0, dev=False):
+        """mat_models_carray::get_pk2cc<3> (S/mat_models_carray.h:182) or, dev=True, mat_models::get_pk2cc_dev (S/mat_models.cpp:630,
+        the ustruct form without volumetric terms): S (3,3) and Dm (6,6) at the deformation gradient F."""
         ho = ho or {}
         par = np.array([0.0] * 10 + [self.ISO[iso], self.VOL[vol], C10, C01, Kpen, 0.0, 0.0]
                        + [ho.get(k, 100.0 if k == "khs" else 0.0) for k in self.HO_KEYS] + [Tfa, eta_s, kap], np.float64)
         F = _c(F, np.float64); fl = _c(fl, np.float64)
         S = np.empty((3, 3)); Dm = np.empty((6, 6))
-        rc = lib().ref_pk2cc(self.h, _p(par), _p(F), _p(fl), _p(S), _p(Dm))
+        rc = (lib().ref_pk2cc_dev if dev else lib().ref_pk2cc)(self.h, _p(par), _p(F), _p(fl), _p(S), _p(Dm))
         if rc != 0:
             raise RuntimeError(lib().ref_last_error().decode())
         return S, Dm
@@ -400,14 +402,14 @@ class RefAssembly:
 
 
     def ustruct(self, Ag, Yg, Dg, Bf, *, dt, am, af, gam, rho, elM, nu, ctM, ctC, vol, C10, Kpen, f=(0.0, 0.0, 0.0), Ad=None,
-                iso="nHook", ho=None, Tfa=0.0, eta_s=0.0, **_ignored):
+                iso="nHook", ho=None, Tfa=0.0, eta_s=0.0, C01=0.0, kap=0.0, **_ignored):
         """construct_usolid (S/ustruct.cpp:216) [+ ustruct_r when Ad is given].  Returns R (nNo,4), Val (nnz,16),
         Kd (nnz,12), seconds."""
         Ag = _c(Ag, np.float64); Yg = _c(Yg, np.float64); Dg = _c(Dg, np.float64); Bf = _c(Bf, np.float64)
         Ad = None if Ad is None else _c(Ad, np.float64)
         ho = ho or {}
         par = np.array([dt, am, af, gam, rho, f[0], f[1], f[2], elM, nu, ctM, ctC, self.VOL[vol], C10, Kpen, self.ISO[iso]]
-                       + [ho.get(k, 100.0 if k == "khs" else 0.0) for k in self.HO_KEYS] + [Tfa, eta_s], np.float64)
+                       + [ho.get(k, 100.0 if k == "khs" else 0.0) for k in self.HO_KEYS] + [Tfa, eta_s, C01, kap], np.float64)
         R = np.empty((self.nNo, 4)); Val = np.empty((self.nnz, 16)); Kd = np.empty((self.nnz, 12))
         t = lib().ref_asm_ustruct(self.h, Ag.shape[1], _p(par), _p(Ag), _p(Yg), _p(Dg), _p(Bf), _p(Ad), _p(R), _p(Val), _p(Kd))
         if t < 0:

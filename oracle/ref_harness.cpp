@@ -547,7 +547,12 @@ double ref_asm_ustruct(void* h, int tDof, const double* par, const double* Ag, c
     dmn.prop[PhysicalProperyType::ctau_M] = par[10];
     dmn.prop[PhysicalProperyType::ctau_C] = par[11];
     const int vol = int(par[12]);
-    dmn.stM.isoType = (int(par[15]) == 3) ? ConstitutiveModelType::stIso_HO : ConstitutiveModelType::stIso_nHook;
+    {
+      const int iso = int(par[15]);
+      dmn.stM.isoType = (iso == 3) ? ConstitutiveModelType::stIso_HO : (iso == 4) ? ConstitutiveModelType::stIso_MR
+                      : (iso == 5) ? ConstitutiveModelType::stIso_HGO : (iso == 6) ? ConstitutiveModelType::stIso_Gucci
+                      : ConstitutiveModelType::stIso_nHook;
+    }
     dmn.stM.volType = (vol == 1) ? ConstitutiveModelType::stVol_Quad
                     : (vol == 2) ? ConstitutiveModelType::stVol_ST91
                     : (vol == 3) ? ConstitutiveModelType::stVol_M94 : ConstitutiveModelType::stIso_NA;
@@ -558,6 +563,8 @@ double ref_asm_ustruct(void* h, int tDof, const double* par, const double* Ag, c
     dmn.stM.Tf.fType = (par[25] != 0.0) ? utils::ibset(0, iBC_std) : 0;        // par[25] = Tf.g, par[26] = Tf.eta_s
     dmn.stM.Tf.g = par[25];
     dmn.stM.Tf.eta_s = par[26];
+    dmn.stM.C01 = par[27];                        // Mooney-Rivlin
+    dmn.stM.kap = par[28];                        // HGO
     com_mod.Bf.resize(3, nNo);
     std::memcpy(com_mod.Bf.data(), Bf, sizeof(double)*3*size_t(nNo));
     if (!eq.linear_algebra) eq.linear_algebra = new FsilsLinearAlgebra();
@@ -1146,6 +1153,30 @@ int ref_pk2cc(void* h, const double* par, const double* F9, const double* fl6, d
     mat_models_carray::get_pk2cc<3>(com_mod, ctx->sim->cep_mod, com_mod.eq[0].dmn[0], F, 2, fl, 0.0, S, Dm);
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) S9[i*3 + j] = S[i][j];
     for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) Dm36[i*6 + j] = Dm[i][j];
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+// mat_models::get_pk2cc_dev (S/mat_models.cpp:630; the ustruct form: deviatoric S, isochoric Dm) at one deformation gradient.
+// Arguments as ref_pk2cc.
+int ref_pk2cc_dev(void* h, const double* par, const double* F9, const double* fl6, double* S9, double* Dm36)
+{
+  try {
+    auto ctx = static_cast<AsmCtx*>(h);
+    auto& com_mod = ctx->sim->com_mod;
+    std::vector<double> Bf(size_t(3)*com_mod.tnNo, 0.0);
+    configure_solid(ctx, 0, 3, 0, par, nullptr, Bf.data());
+    Array<double> F(3, 3), S(3, 3), Dm(6, 6), fl(3, 2);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) F(i, j) = F9[i*3 + j];
+    for (int i = 0; i < 3; i++) { fl(i, 0) = fl6[i]; fl(i, 1) = fl6[3 + i]; }
+    double Ja = 0.0;
+    mat_fun::ten_init(3);
+    mat_models::get_pk2cc_dev(com_mod, ctx->sim->cep_mod, com_mod.eq[0].dmn[0], F, 2, fl, 0.0, S, Dm, Ja);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) S9[i*3 + j] = S(i, j);
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) Dm36[i*6 + j] = Dm(i, j);
     return 0;
   } catch (const std::exception& e) {
     g_err = e.what();

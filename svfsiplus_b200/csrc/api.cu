@@ -779,8 +779,8 @@ int b200_assemble_ustruct(b200_handle* h, const b200_ustruct_props* p)
     if (h->dof != 4 || !h->Val) throw std::runtime_error("assemble_ustruct: call b200_zero(h, 4) first");
     if (p->tDof != h->tDof) throw std::runtime_error("assemble_ustruct: tDof differs from the uploaded state");
     if (p->s < 0 || p->s + 4 > p->tDof) throw std::runtime_error("assemble_ustruct: equation offset outside the state");
-    if (p->isoType != 0 && p->isoType != 3) throw std::runtime_error("assemble_ustruct: constitutive model has no device kernel (neo-Hookean and Holzapfel-Ogden have)");
-    if (p->isoType == 3 && !h->d_fN) throw std::runtime_error("assemble_ustruct: the Holzapfel-Ogden law needs fibre directions (b200_mesh_fibers)");
+    if (p->isoType != 0 && (p->isoType < 3 || p->isoType > 6)) throw std::runtime_error("assemble_ustruct: constitutive model has no isochoric split (neo-Hookean, Holzapfel-Ogden, Mooney-Rivlin, HGO and Guccione have)");
+    if ((p->isoType == 3 || p->isoType == 5 || p->isoType == 6) && !h->d_fN) throw std::runtime_error("assemble_ustruct: the fibre-based laws need fibre directions (b200_mesh_fibers)");
     if (p->volType < 0 || p->volType > 3) throw std::runtime_error("assemble_ustruct: dilational penalty model not defined");
     UstructConsts c;
     std::memset(&c, 0, sizeof(c));
@@ -788,7 +788,10 @@ int b200_assemble_ustruct(b200_handle* h, const b200_ustruct_props* p)
     c.rho0 = p->rho; c.f[0] = p->f[0]; c.f[1] = p->f[1]; c.f[2] = p->f[2];
     c.elM = p->elM; c.nu = p->nu; c.ctM = p->ctM; c.ctC = p->ctC;
     c.iso = p->isoType; c.vol = p->volType; c.C10 = p->C10; c.Kpen = p->Kpen;
-    c.ho = HoParams{p->a, p->b, p->aff, p->bff, p->ass, p->bss, p->afs, p->bfs, p->khs, p->Tfa, p->Tsa};
+    c.law.iso = p->isoType; c.law.vol = 0; c.law.C10 = p->C10; c.law.C01 = p->C01; c.law.Kpen = 0.0;
+    c.law.ho_a = p->a; c.law.ho_b = p->b; c.law.ho_aff = p->aff; c.law.ho_bff = p->bff; c.law.ho_ass = p->ass; c.law.ho_bss = p->bss;
+    c.law.ho_afs = p->afs; c.law.ho_bfs = p->bfs; c.law.ho_khs = p->khs;
+    c.law.Tfa = p->Tfa; c.law.Tsa = p->Tsa; c.law.kap = p->kap;
     c.tDof = p->tDof; c.s = p->s;
     ensure_stage(h, 4);
     ensure(h->stageKd, h->stageKd_cap, size_t(12)*h->eNoN*h->eNoN*size_t(h->nEl) + 4);

@@ -20,9 +20,9 @@ struct UstructConsts {
   double dt, am, af, gam;        // eq.am, eq.af, eq.gam
   double rho0, f[3];
   double elM, nu, ctM, ctC;      // get_tau inputs
-  int iso, vol;                  // iso: 0 nHook, 3 Holzapfel-Ogden; vol: 0 none, 1 Quad, 2 ST91, 3 M94
+  int iso, vol;                  // iso as in SolidConsts (isochoric laws: 0, 3, 4, 5, 6); vol: 0 none, 1 Quad, 2 ST91, 3 M94
   double C10, Kpen;
-  HoParams ho;
+  SolidConsts law;               // the isochoric law for pk2cc_iso: Kpen = 0, vol = 0 (get_pk2cc_dev has no volumetric part)
   int tDof, s;
 };
 
@@ -140,70 +140,20 @@ k_assemble_ustruct(int nEl, UstructConsts c, const double* __restrict__ tab, con
 #pragma unroll
         for (int j = 0; j < 3; j++) rec[UR_F + i*3 + j] = F[i][j];
 
-      // get_pk2cc_dev, neo-Hookean (mat_models.cpp:694-708): deviatoric S and isochoric CC
+      // get_pk2cc_dev (mat_models.cpp:630-1000): deviatoric S and isochoric CC = the law of solid_law.hpp without its
+      // volumetric terms (c.law has Kpen = 0, so p = pl = 0 there: c2 = 2 r1, c3 = -2 r1 / nd)
       double S6[6];
       {
-        const double nd3 = 3.0;
-        const double J2d = pow(J, -2.0/nd3);
-        double C[3][3], Ci[3][3];
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-#pragma unroll
-          for (int j = 0; j < 3; j++) C[i][j] = (0.0 + F[0][i]*F[0][j]) + F[1][i]*F[1][j] + F[2][i]*F[2][j];
-        const double d = C[0][0]*C[1][1]*C[2][2] + C[0][1]*C[1][2]*C[2][0] + C[0][2]*C[1][0]*C[2][1]
-                       - C[0][0]*C[1][2]*C[2][1] - C[0][1]*C[1][0]*C[2][2] - C[0][2]*C[1][1]*C[2][0];
-        Ci[0][0] = (C[1][1]*C[2][2] - C[1][2]*C[2][1]) / d;
-        Ci[0][1] = (C[0][2]*C[2][1] - C[0][1]*C[2][2]) / d;
-        Ci[0][2] = (C[0][1]*C[1][2] - C[0][2]*C[1][1]) / d;
-        Ci[1][0] = (C[1][2]*C[2][0] - C[1][0]*C[2][2]) / d;
-        Ci[1][1] = (C[0][0]*C[2][2] - C[0][2]*C[2][0]) / d;
-        Ci[1][2] = (C[0][2]*C[1][0] - C[0][0]*C[1][2]) / d;
-        Ci[2][0] = (C[1][0]*C[2][1] - C[1][1]*C[2][0]) / d;
-        Ci[2][1] = (C[0][1]*C[2][0] - C[0][0]*C[2][1]) / d;
-        Ci[2][2] = (C[0][0]*C[1][1] - C[0][1]*C[1][0]) / d;
-        const double Inv1 = J2d*(C[0][0] + C[1][1] + C[2][2]);
-        double S[3][3];
-        const int vi[6] = {0, 1, 2, 0, 1, 2}, vj[6] = {0, 1, 2, 1, 2, 0};
-        if (c.iso == 3) {
-          // Holzapfel-Ogden, deviatoric form (mat_models.cpp:866-935)
-          double fl[6];
+        double fl[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (fN) {
 #pragma unroll
           for (int i = 0; i < 6; i++) fl[i] = fN[size_t(e)*6 + i];
-          double r1, gk[4], H[4][3][3];
-          ho_isochoric(c.ho, C, Ci, J2d, Inv1, fl, S, r1, gk, H);
-#pragma unroll
-          for (int I = 0; I < 6; I++)
-#pragma unroll
-            for (int Jv = I; Jv < 6; Jv++) {
-              const int i = vi[I], j = vj[I], k = vi[Jv], l = vj[Jv];
-              const double sym = 0.5*(Ci[i][k]*Ci[j][l] + Ci[i][l]*Ci[j][k]);
-              double cc = gk[0]*H[0][i][j]*H[0][k][l] + gk[1]*H[1][i][j]*H[1][k][l] + gk[2]*H[2][i][j]*H[2][k][l] + gk[3]*H[3][i][j]*H[3][k][l];
-              cc += 2.0*r1*(sym - 1.0/nd3*(Ci[i][j]*Ci[k][l])) - 2.0/nd3*(Ci[i][j]*S[k][l] + S[i][j]*Ci[k][l]);
-              rec[UR_DM + dm_idx(I, Jv)] = cc;
-            }
-        } else {
-          const double g1 = 2.0*c.C10;
-          const double r1 = g1*Inv1/nd3;
-          // Sb = g1 I + Tfa f (x) f (mat_models.cpp:699-704); without fibres f = 0
-          double f0[3] = {0.0, 0.0, 0.0};
-          if (fN) { f0[0] = fN[size_t(e)*6]; f0[1] = fN[size_t(e)*6 + 1]; f0[2] = fN[size_t(e)*6 + 2]; }
-#pragma unroll
-          for (int i = 0; i < 3; i++)
-#pragma unroll
-            for (int j = 0; j < 3; j++) S[i][j] = J2d*(((i == j) ? g1 : 0.0) + c.ho.Tfa*(f0[i]*f0[j])) - r1*Ci[i][j];
-#pragma unroll
-          for (int I = 0; I < 6; I++)
-#pragma unroll
-            for (int Jv = I; Jv < 6; Jv++) {
-              const int i = vi[I], j = vj[I], k = vi[Jv], l = vj[Jv];
-              const double sym = 0.5*(Ci[i][k]*Ci[j][l] + Ci[i][l]*Ci[j][k]);
-              rec[UR_DM + dm_idx(I, Jv)] = 2.0*r1*(sym - 1.0/nd3*(Ci[i][j]*Ci[k][l])) - 2.0/nd3*(Ci[i][j]*S[k][l] + S[i][j]*Ci[k][l]);
-            }
         }
-        S6[0] = S[0][0]; S6[1] = S[1][1]; S6[2] = S[2][2]; S6[3] = S[0][1]; S6[4] = S[1][2]; S6[5] = S[2][0];
+        pk2cc_iso(c.law, F, fl, S6, rec + UR_DM);
 #pragma unroll
         for (int i = 0; i < 6; i++) rec[UR_S + i] = S6[i];
         // Pdev = F Siso
+        const double S[3][3] = {{S6[0], S6[3], S6[5]}, {S6[3], S6[1], S6[4]}, {S6[5], S6[4], S6[2]}};
 #pragma unroll
         for (int i = 0; i < 3; i++)
 #pragma unroll

@@ -369,9 +369,16 @@ bool B200LinearAlgebra::assemble_ustruct_mesh(ComMod& com_mod, const mshType& lM
   for (int a = 0; a < com_mod.tnNo; a++) if (com_mod.idMap(a) != a) return false;      // undeformed-Neumann faces
   const auto& dmn = eq.dmn[0];
   const auto& stM = dmn.stM;
-  const bool ho = (stM.isoType == ConstitutiveModelType::stIso_HO);
-  if (stM.isoType != ConstitutiveModelType::stIso_nHook && !ho) return false;
-  if (ho && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
+  int iso;
+  switch (stM.isoType) {                       // the laws of get_pk2cc_dev with a device kernel
+    case ConstitutiveModelType::stIso_nHook: iso = 0; break;
+    case ConstitutiveModelType::stIso_HO:    iso = 3; break;
+    case ConstitutiveModelType::stIso_MR:    iso = 4; break;
+    case ConstitutiveModelType::stIso_HGO:   iso = 5; break;
+    case ConstitutiveModelType::stIso_Gucci: iso = 6; break;
+    default: return false;
+  }
+  if ((iso == 3 || iso == 5 || iso == 6) && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
   if (dmn.solid_visc.viscType != SolidViscosityModelType::viscType_NA) return false;
   b200_ustruct_props p{};
   fibre_stress(com_mod, stM.Tf, p.Tfa, p.Tsa);
@@ -386,7 +393,8 @@ bool B200LinearAlgebra::assemble_ustruct_mesh(ComMod& com_mod, const mshType& lM
   p.nu = dmn.prop.at(PhysicalProperyType::poisson_ratio);
   p.ctM = dmn.prop.at(PhysicalProperyType::ctau_M);
   p.ctC = dmn.prop.at(PhysicalProperyType::ctau_C);
-  p.isoType = ho ? 3 : 0;
+  p.isoType = iso;
+  p.C01 = stM.C01; p.kap = stM.kap;
   p.a = stM.a; p.b = stM.b; p.aff = stM.aff; p.bff = stM.bff; p.ass = stM.ass; p.bss = stM.bss;
   p.afs = stM.afs; p.bfs = stM.bfs; p.khs = stM.khs;
   switch (stM.volType) {

@@ -340,15 +340,23 @@ def ustruct_case(n, elem="tet", vol="ST91", iso="nHook"):
         faces.append(dict(name=nm, nodes=nodes, dof=3, bGrp=B.BC_DIR, val=val))
     case = dict(mesh=m, rowPtr=rowPtr, colPtr=colPtr, Ag=Ag, Yg=Yg, Dg=Dg, Bf=Bf, Ad=Ad, props=props, faces=faces, kind="ustruct",
                 res=np.zeros(len(faces)), incL=np.ones(len(faces), np.int32), name=f"ustruct_{elem}_{n}")
-    if iso == "HO":
-        props["iso"] = "HO"
-        props["ho"] = dict(a=590.0, b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12, afs=2160.0, bfs=11.436, khs=100.0)
-        cen = m.x[m.ien].mean(axis=1)
-        th = 0.5 * np.pi * cen[:, 2] + 0.3 * cen[:, 0]
-        fN = np.zeros((m.nEl, 6))
-        fN[:, 0], fN[:, 1] = np.cos(th), np.sin(th)
-        fN[:, 3], fN[:, 4] = -np.sin(th), np.cos(th)
-        case["fN"] = fN
+    if iso != "nHook":
+        props["iso"] = iso
+        if iso == "HO":
+            props["ho"] = dict(a=590.0, b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12, afs=2160.0, bfs=11.436, khs=100.0)
+        elif iso == "MR":
+            props.update(C10=0.3 * mu, C01=0.2 * mu)
+        elif iso == "HGO":
+            props.update(kap=0.226, ho=dict(aff=9.96e5, bff=524.6, ass=9.96e5, bss=524.6))
+        elif iso == "Gucci":
+            props.update(C10=880.0, ho=dict(bff=8.0, bss=6.0, bfs=12.0))
+        if iso != "MR":                          # fibre / sheet directions rotating through the block
+            cen = m.x[m.ien].mean(axis=1)
+            th = 0.5 * np.pi * cen[:, 2] + 0.3 * cen[:, 0]
+            fN = np.zeros((m.nEl, 6))
+            fN[:, 0], fN[:, 1] = np.cos(th), np.sin(th)
+            fN[:, 3], fN[:, 4] = -np.sin(th), np.cos(th)
+            case["fN"] = fN
     return case
 
 

@@ -54,3 +54,31 @@ def test_law_matches_reference_get_pk2cc(iso, vol, kw):
     ra.close()
     # the isochoric projections are evaluated in closed form here and by generic fourth-order contractions there
     assert worst < 1e-12, worst
+
+
+DEV_LAWS = [l for l in LAWS if l[0] not in ("StVK", "mStVK")]
+
+
+@pytest.mark.parametrize("iso,vol,kw", DEV_LAWS, ids=[f"{l[0]}-{'Tf' if 'Tfa' in l[2] else '0'}-{i}" for i, l in enumerate(DEV_LAWS)])
+@needs_ref
+def test_law_matches_reference_get_pk2cc_dev(iso, vol, kw):
+    """The ustruct kernels evaluate the same law with Kpen = 0: it must equal mat_models::get_pk2cc_dev (mat_models.cpp:630)."""
+    from oracle import ref
+    m = M.block_mesh(1, "tet")
+    ra = ref.RefAssembly(m.x, m.ien)
+    rng = np.random.default_rng(43)
+    th = 0.4
+    fl = np.array([np.cos(th), 0.0, np.sin(th), 0.0, 1.0, 0.0])
+    kw = dict(kw, Kpen=0.0)
+    worst = 0.0
+    for _ in range(12):
+        F = np.eye(3) + 0.15 * rng.standard_normal((3, 3))
+        if np.linalg.det(F) < 0.3:
+            continue
+        S, Dm = ra.pk2cc(F, fl, iso=iso, vol=None, dev=True, **kw)
+        S6, Dm21 = host_pk2cc(F, fl, iso=iso, vol=None, **kw)
+        Sr = np.array([S[i, j] for i, j in VOIGT])
+        Dr = np.array([Dm[I, J] for I in range(6) for J in range(I, 6)])
+        worst = max(worst, np.abs(S6 - Sr).max() / np.abs(Sr).max(), np.abs(Dm21 - Dr).max() / np.abs(Dr).max())
+    ra.close()
+    assert worst < 1e-12, worst

@@ -142,3 +142,29 @@ def test_new_law_assembly_matches_golden(iso, elem):
     assert rel_inf(be.get_R(), g[f"R_{iso}_{elem}"]) < TOL_ASM
     assert rel_inf(be.get_Val(), g[f"Val_{iso}_{elem}"]) < TOL_ASM
     be.close()
+
+
+# the same laws in the mixed (ustruct) formulation: get_pk2cc_dev (mat_models.cpp:630) = the law without volumetric terms
+USTRUCT_LAWS = [("MR", "tet"), ("HGO", "hex"), ("Gucci", "tet"), ("Gucci", "tet10")]
+
+
+@needs_ref
+def test_oracle_reproduces_ustruct_law_fixtures():
+    from oracle import refcase
+    g = golden("active_stress.npz")
+    for iso, elem in USTRUCT_LAWS:
+        R, Val, Kd, _ = refcase.reference_assemble_ustruct(P.ustruct_case(2 if elem == "tet10" else 3, elem=elem, iso=iso))
+        assert np.array_equal(R, g[f"uR_{iso}_{elem}"]) and np.array_equal(Val, g[f"uVal_{iso}_{elem}"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("iso,elem", USTRUCT_LAWS)
+def test_ustruct_law_assembly_matches_golden(iso, elem):
+    g = golden("active_stress.npz")
+    case = P.ustruct_case(2 if elem == "tet10" else 3, elem=elem, iso=iso)
+    be = P.setup_backend(case)
+    P.assemble_ustruct(be, case)
+    assert rel_inf(be.get_R(), g[f"uR_{iso}_{elem}"]) < TOL_ASM
+    assert rel_inf(be.get_Val(), g[f"uVal_{iso}_{elem}"]) < TOL_ASM
+    assert rel_inf(be.get_Kd(), g[f"uKd_{iso}_{elem}"]) < TOL_ASM
+    be.close()
