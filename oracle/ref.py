@@ -194,6 +194,7 @@ def lib():
                                      C.c_void_p, C.c_void_p]
         L.ref_pk2cc.argtypes = [C.c_void_p] * 6
         L.ref_pk2cc_dev.argtypes = [C.c_void_p] * 6
+        L.ref_asm_bfolw.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7
         L.ref_asm_bneu.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
         L.ref_pic.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_double] + [C.c_void_p] * 12
         _lib = L
@@ -322,6 +323,16 @@ class RefAssembly:
         if rc != 0:
             raise RuntimeError(lib().ref_last_error().decode())
         return val
+
+    def bfolw(self, IENb, gE, hg, Dg, *, dt, af, beta):
+        """eq_assem::b_neu_folw_p (S/eq_assem.cpp:186): follower pressure load on a struct face.  Returns R (nNo,3), Val (nnz,9)."""
+        IENb = _c(IENb, np.int32); gE = _c(gE, np.int32); hg = _c(hg, np.float64); Dg = _c(Dg, np.float64)
+        par = np.array([dt, af, beta, Dg.shape[1]], np.float64)
+        R = np.empty((self.nNo, 3)); Val = np.empty((self.nnz, 9))
+        rc = lib().ref_asm_bfolw(self.h, IENb.shape[1], IENb.shape[0], _p(IENb), _p(gE), _p(par), _p(hg), _p(Dg), _p(R), _p(Val))
+        if rc != 0:
+            raise RuntimeError(lib().ref_last_error().decode())
+        return R, Val
 
     def bneu(self, kind, IENb, gE, hg, Yg, *, dt, af, gam, rho=0.0, bfs=0.0, mvMsh=False, Do=None):
         """b_assem_neu_bc (S/eq_assem.cpp:58) on one face: kind "fluid" (b_fluid, dof 4) or "solid" (b_l_elas, dof 3).

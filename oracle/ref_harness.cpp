@@ -1184,6 +1184,56 @@ int ref_pk2cc_dev(void* h, const double* par, const double* F9, const double* fl
   }
 }
 
+// Follower pressure load on one face of a struct equation (dof 3): eq_assem::b_neu_folw_p (S/eq_assem.cpp:186; get_nnx,
+// gnn, gnnb, struct_ns::b_struct_3d).  par = {dt, af, beta, tDof}.  Outputs the face's contribution alone.
+int ref_asm_bfolw(void* h, int eNoNb, int nElb, const int* IENb, const int* gE, const double* par, const double* hg,
+                  const double* Dg, double* R, double* Val)
+{
+  try {
+    using namespace consts;
+    auto ctx = static_cast<AsmCtx*>(h);
+    auto& com_mod = ctx->sim->com_mod;
+    const int nNo = com_mod.tnNo;
+    const int tDof = int(par[3]);
+    const int dof = 3;
+    com_mod.tDof = tDof; com_mod.dof = dof; com_mod.dt = par[0]; com_mod.mvMsh = false;
+    com_mod.cEq = 0; com_mod.nEq = 1;
+    if (com_mod.eq.size() != 1) com_mod.eq.resize(1);
+    auto& eq = com_mod.eq[0];
+    eq.phys = EquationType::phys_struct; eq.dof = dof; eq.s = 0; eq.e = dof - 1; eq.af = par[1]; eq.beta = par[2];
+    eq.nDmn = 1;
+    if (eq.dmn.size() != 1) eq.dmn.resize(1);
+    eq.dmn[0].Id = -1;
+    eq.dmn[0].phys = EquationType::phys_struct;
+    if (!eq.linear_algebra) eq.linear_algebra = new FsilsLinearAlgebra();
+    auto& msh = com_mod.msh[0];
+    msh.nFa = 1;
+    msh.fa.resize(1);
+    auto& fa = msh.fa[0];
+    fa.name = "face"; fa.iM = 0; fa.eNoN = eNoNb; fa.nEl = nElb;
+    fa.IEN.resize(eNoNb, nElb);
+    std::memcpy(fa.IEN.data(), IENb, sizeof(int)*size_t(eNoNb)*nElb);
+    fa.gE.resize(nElb);
+    std::memcpy(fa.gE.data(), gE, sizeof(int)*size_t(nElb));
+    nn::select_eleb(ctx->sim.get(), msh, fa);
+    Vector<double> hg_v(nNo);
+    std::memcpy(hg_v.data(), hg, sizeof(double)*size_t(nNo));
+    Array<double> Dg_a(tDof, nNo);
+    std::memcpy(Dg_a.data(), Dg, sizeof(double)*size_t(tDof)*nNo);
+    com_mod.R.resize(dof, nNo);
+    eq.linear_algebra->alloc(com_mod, eq);
+    bcType lBc;
+    lBc.flwP = true;
+    eq_assem::b_neu_folw_p(com_mod, lBc, fa, hg_v, Dg_a);
+    std::memcpy(R, com_mod.R.data(), sizeof(double)*size_t(dof)*nNo);
+    std::memcpy(Val, com_mod.Val.data(), sizeof(double)*size_t(dof)*dof*ctx->nnz);
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
 // kind 0: fluid equation (dof 4, b_fluid), 1: struct equation (dof 3, b_l_elas).
 // par = {dt, af, gam, rho, bfs, tDof, mvMsh}.  IENb(eNoNb,nElb), gE(nElb); hg(nNo); Yg, Do (tDof,nNo; Do may be NULL).
 // Outputs the face's contribution alone: R (dof,nNo), Val (dof*dof,nnz).

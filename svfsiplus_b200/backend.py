@@ -76,6 +76,10 @@ class BneuProps(C.Structure):
                 ("rho", C.c_double), ("bfs", C.c_double)]
 
 
+class BfolwProps(C.Structure):
+    _fields_ = [("dt", C.c_double), ("af", C.c_double), ("beta", C.c_double), ("tDof", C.c_int), ("s", C.c_int)]
+
+
 class PicEq(C.Structure):
     _fields_ = [("s", C.c_int), ("e", C.c_int), ("am", C.c_double), ("af", C.c_double), ("gam", C.c_double),
                 ("beta", C.c_double), ("kind", C.c_int)]
@@ -97,7 +101,7 @@ EXPORTS = [
     "b200_pic_init", "b200_pic_set", "b200_pic_get", "b200_pic_scatter", "b200_picp", "b200_pici", "b200_picc",
     "b200_pic_copy_rows", "b200_pic_advance", "b200_face_mesh_set", "b200_assemble_bneu",
     "b200_assemble_fluid_dmn", "b200_assemble_struct_dmn",
-    "b200_face_integ", "b200_face_normal_update", "b200_face_get_val", "b200_pattern_begin", "b200_pattern_add_mesh", "b200_pattern_finish", "b200_pattern_get",
+    "b200_assemble_bfolw", "b200_face_integ", "b200_face_normal_update", "b200_face_get_val", "b200_pattern_begin", "b200_pattern_add_mesh", "b200_pattern_finish", "b200_pattern_get",
 ]
 
 KERNEL_CLASSES = ["spmv_vv4", "spmv_vv3", "spmv_ss", "spmv_sv", "spmv_vs", "multi_dot", "cgs_update_scale", "blas1",
@@ -173,6 +177,7 @@ def lib():
         L.b200_face_integ.argtypes = [vp, ci, ci, ci, ci, ci, C.POINTER(cd)]
         L.b200_face_normal_update.argtypes = [vp, ci, ci, ci]
         L.b200_face_get_val.argtypes = [vp, ci, vp]
+        L.b200_assemble_bfolw.argtypes = [vp, ci, C.POINTER(BfolwProps), vp]
         L.b200_assemble_bneu.argtypes = [vp, ci, ci, C.POINTER(BneuProps), vp]
         _lib = L
     return _lib
@@ -451,6 +456,13 @@ class Backend:
     def face_mesh_set(self, faIn, IENb, gE):
         IENb = _c(IENb, np.int32); gE = _c(gE, np.int32)
         self._ck(self.L.b200_face_mesh_set(self.h, faIn, IENb.shape[1], IENb.shape[0], _p(IENb), _p(gE)), "b200_face_mesh_set")
+
+    def assemble_bfolw(self, faIn, hg, *, dt, af, beta, tDof=3, s=0):
+        """b_neu_folw_p: follower pressure load on a struct face (dof 3)."""
+        p = BfolwProps()
+        p.dt, p.af, p.beta, p.tDof, p.s = dt, af, beta, tDof, s
+        hg = _c(hg, np.float64)
+        self._ck(self.L.b200_assemble_bfolw(self.h, faIn, C.byref(p), _p(hg)), "b200_assemble_bfolw")
 
     def face_integ(self, faIn, which, l=0, u=None, geo=0):
         """all_fun::integ over face faIn of rows l..u of a device array ("Yn", "Yo", ... or None for the area)."""

@@ -86,10 +86,17 @@ struct b200_handle {
     int *udestR = nullptr, *usegR = nullptr, *udestK = nullptr, *usegK = nullptr;
     double *tab = nullptr, *stageR = nullptr, *stageT = nullptr, *hg = nullptr;
     std::vector<int> nodes;          // unique face nodes (assembly ids), for the compact upload of hg
+    // follower pressure (b_neu_folw_p): parents' connectivity and the ordered runs of the parent rows / parent-pair blocks
+    std::vector<int> h_parent, pnodes;
+    int nPUR = 0, nPUK = 0;
+    int *parent = nullptr, *prslot = nullptr, *pkslot = nullptr, *pudestR = nullptr, *pusegR = nullptr, *pudestK = nullptr, *pusegK = nullptr;
+    double *pstageR = nullptr, *pstageK = nullptr;
     void release()
     {
       cudaFree(ienb); cudaFree(inode); cudaFree(rslot); cudaFree(kslot); cudaFree(udestR); cudaFree(usegR); cudaFree(udestK);
       cudaFree(usegK); cudaFree(tab); cudaFree(stageR); cudaFree(stageT); cudaFree(hg);
+      cudaFree(parent); cudaFree(prslot); cudaFree(pkslot); cudaFree(pudestR); cudaFree(pusegR); cudaFree(pudestK); cudaFree(pusegK);
+      cudaFree(pstageR); cudaFree(pstageK);
       *this = FaceMesh();
     }
   };
@@ -1297,6 +1304,7 @@ int b200_face_mesh_set(b200_handle* h, int faIn, int eNoNb, int nElb, const int*
     CU_CHECK(cudaMalloc(&f.stageT, sizeof(double)*kslot.size()));
     CU_CHECK(cudaMalloc(&f.hg, sizeof(double)*size_t(h->nNo)));
     CU_CHECK(cudaMemsetAsync(f.hg, 0, sizeof(double)*size_t(h->nNo), ops.st));
+    f.h_parent = par;
     f.nodes.assign(IENb, IENb + size_t(nElb)*eNoNb);
     std::sort(f.nodes.begin(), f.nodes.end());
     f.nodes.erase(std::unique(f.nodes.begin(), f.nodes.end()), f.nodes.end());
@@ -1382,6 +1390,93 @@ void launch_face_nrm(b200_handle* h, b200_handle::FaceMesh& f, const double* geo
 }
 } // namespace
 } // extern "C++"
+
+extern "C++" {
+namespace {
+template <int NP, int NB, int NG>
+void launch_bfolw(b200_handle* h, b200_handle::FaceMesh& f, const FolwConsts& c)
+{
+  auto& ops = *h->ops;
+  k_bfolw_elem<NP, NB, NG><<<(f.nElb + 63)/64, 64, 0, ops.st>>>(f.nElb, c, f.tab, f.ienb, f.parent, f.inode, f.prslot, f.pkslot, h->d_x,
+                                                              h->d_Dg, f.hg, f.pstageR, f.pstageK, h->d_err);
+  CU_CHECK(cudaGetLastError());
+  ops.post();
+}
+} // namespace
+} // extern "C++"
+
+int b200_assemble_bfolw(b200_handle* h, int faIn, const b200_bfolw_props* p, const double* hg)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (faIn < 0 || faIn >= int(h->fmesh.size()) || h->fmesh[faIn].eNoNb == 0) throw std::runtime_error("assemble_bfolw: no face mesh (b200_face_mesh_set)");
+    auto& f = h->fmesh[faIn];
+    if (f.nElb == 0) return;
+    if (h->dof != 3 || !h->Val) throw std::runtime_error("assemble_bfolw: the follower pressure load acts on a struct equation: call b200_zero(h, 3) first");
+    if (!h->d_Dg || p->tDof != h->tDof) throw std::runtime_error("assemble_bfolw: no displacement state (b200_disp_set / b200_pici) or tDof differs");
+    if (p->s < 0 || p->s + 3 > p->tDof) throw std::runtime_error("assemble_bfolw: equation offset outside the state");
+    const int NP = h->eNoN, NB = f.eNoNb;
+    if (!((NP == 4 && NB == 3) || (NP == 8 && NB == 4) || (NP == 10 && NB == 6))) throw std::runtime_error("assemble_bfolw: face / parent element pair not supported");
+    flush_staged(h);
+    if (!f.parent) {
+      // ordered runs of the parents' rows and parent-pair blocks (do_assem's destinations for the eNoN x eNoN element matrix)
+      const int nElb = f.nElb;
+      std::vector<int> rkey(size_t(nElb)*NP), kkey(size_t(nElb)*NP*NP);
+      for (int e = 0; e < nElb; e++) {
+        const int* pn = f.h_parent.data() + size_t(e)*NP;
+        for (int a = 0; a < NP; a++) {
+          const int A = pn[a], rowS = h->h_map[A];
+          rkey[size_t(e)*NP + a] = rowS;
+          const int* beg = h->h_colA.data() + h->h_rowPtrA[A];
+          const int* end = h->h_colA.data() + h->h_rowPtrA[A + 1];
+          for (int b = 0; b < NP; b++) {
+            const int* it = std::lower_bound(beg, end, pn[b]);
+            if (it == end || *it != pn[b]) throw std::runtime_error("assemble_bfolw: column not in the sparsity pattern");
+            kkey[(size_t(e)*NP + a)*NP + b] = h->h_rowPtrS[rowS] + int(it - beg);
+          }
+        }
+      }
+      std::vector<int> rslot, kslot, udR, usR, udK, usK;
+      face_runs(rkey, rslot, udR, usR);
+      face_runs(kkey, kslot, udK, usK);
+      f.nPUR = int(udR.size()); f.nPUK = int(udK.size());
+      f.parent = upload(f.h_parent.data(), f.h_parent.size(), ops.st);
+      f.prslot = upload(rslot.data(), rslot.size(), ops.st); f.pkslot = upload(kslot.data(), kslot.size(), ops.st);
+      f.pudestR = upload(udR.data(), udR.size(), ops.st); f.pusegR = upload(usR.data(), usR.size(), ops.st);
+      f.pudestK = upload(udK.data(), udK.size(), ops.st); f.pusegK = upload(usK.data(), usK.size(), ops.st);
+      CU_CHECK(cudaMalloc(&f.pstageR, sizeof(double)*rslot.size()*3));
+      CU_CHECK(cudaMalloc(&f.pstageK, sizeof(double)*kslot.size()*6));
+      f.pnodes = f.h_parent;
+      std::sort(f.pnodes.begin(), f.pnodes.end());
+      f.pnodes.erase(std::unique(f.pnodes.begin(), f.pnodes.end()), f.pnodes.end());
+    }
+    // hg on the parents' nodes (b_struct_3d interpolates it with the parent's shape functions)
+    {
+      std::vector<double> hv(f.pnodes.size());
+      for (size_t i = 0; i < hv.size(); i++) hv[i] = hg[f.pnodes[i]];
+      int* d_idx = upload(f.pnodes.data(), f.pnodes.size(), ops.st);
+      double* d_val = upload(hv.data(), hv.size(), ops.st);
+      k_pic_scatter<<<CudaOps::grid_for(hv.size(), 256, 1), 256, 0, ops.st>>>(int(hv.size()), d_idx, d_val, f.hg); ops.post();
+      CU_CHECK(cudaStreamSynchronize(ops.st));
+      cudaFree(d_idx); cudaFree(d_val);
+    }
+    FolwConsts c;
+    c.dt = p->dt; c.af = p->af; c.beta = p->beta; c.tDof = p->tDof; c.s = p->s;
+    fill_folw_parent(c, h->tab);
+    if (NP == 4) launch_bfolw<4, 3, 3>(h, f, c);
+    else if (NP == 8) launch_bfolw<8, 4, 4>(h, f, c);
+    else launch_bfolw<10, 6, 7>(h, f, c);
+    k_bneu_sum_R<<<(f.nPUR + 127)/128, 128, 0, ops.st>>>(f.nPUR, 3, f.pudestR, f.pusegR, f.pstageR, h->R); ops.post();
+    k_bfolw_sum_K<<<(f.nPUK + 127)/128, 128, 0, ops.st>>>(f.nPUK, f.pudestK, f.pusegK, f.pstageK, h->Val); ops.post();
+    int flag = 0;
+    CU_CHECK(cudaMemcpyAsync(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, ops.st));
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+    if (flag != 0) {
+      CU_CHECK(cudaMemset(h->d_err, 0, sizeof(int)));
+      throw std::runtime_error("Error in computing shape functions");
+    }
+  });
+}
 
 int b200_face_normal_update(b200_handle* h, int faIn, int lsFace, int geo)
 {

@@ -22,6 +22,7 @@ struct ElemTables {            // lM.w, lM.N, lM.Nx, lM.fs[0].Nxx
   double N[MAXG][MAXN];        // [g][a]
   double Nxi[MAXG][MAXN][3];   // [g][a][i]
   double Nxi2[MAXG][MAXN][6];  // [g][a][k], k = (00, 11, 22, 01, 12, 02)
+  double xi[MAXG][3];          // lM.xi: parametric coordinates of the Gauss points
 };
 
 inline bool elem_supported(int eNoN) { return eNoN == 4 || eNoN == 8 || eNoN == 10; }
@@ -37,6 +38,7 @@ inline void fill_tables(ElemTables& t, int eNoN, double qmTET4)
     const double xi[4][3] = {{s, r, r}, {r, s, r}, {r, r, s}, {r, r, r}};
     for (int g = 0; g < 4; g++) {
       t.w[g] = 1.0/24.0;
+      for (int i = 0; i < 3; i++) t.xi[g][i] = xi[g][i];
       t.N[g][0] = xi[g][0]; t.N[g][1] = xi[g][1]; t.N[g][2] = xi[g][2];
       t.N[g][3] = 1.0 - xi[g][0] - xi[g][1] - xi[g][2];
       const double d[4][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {-1, -1, -1}};
@@ -48,6 +50,7 @@ inline void fill_tables(ElemTables& t, int eNoN, double qmTET4)
     const double xi[8][3] = {{m, m, m}, {s, m, m}, {s, s, m}, {m, s, m}, {m, m, s}, {s, m, s}, {s, s, s}, {m, s, s}};
     for (int g = 0; g < 8; g++) {
       t.w[g] = 1.0;
+      for (int i = 0; i < 3; i++) t.xi[g][i] = xi[g][i];
       const double lx = 1.0 - xi[g][0], ly = 1.0 - xi[g][1], lz = 1.0 - xi[g][2];
       const double ux = 1.0 + xi[g][0], uy = 1.0 + xi[g][1], uz = 1.0 + xi[g][2];
       const double N[8] = {lx*ly*lz/8.0, ux*ly*lz/8.0, ux*uy*lz/8.0, lx*uy*lz/8.0, lx*ly*uz/8.0, ux*ly*uz/8.0, ux*uy*uz/8.0, lx*uy*uz/8.0};
@@ -91,6 +94,7 @@ inline void fill_tables(ElemTables& t, int eNoN, double qmTET4)
                               {ze, en, ze, fn, fn, ze}, {ze, ze, en, ze, fn, fn}};
     for (int g = 0; g < 15; g++) {
       t.w[g] = wt[g];
+      for (int i = 0; i < 3; i++) t.xi[g][i] = xi[g][i];
       const double x0 = xi[g][0], x1 = xi[g][1], x2 = xi[g][2];
       const double s = 1.0 - x0 - x1 - x2;
       double* N = t.N[g];

@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include "fluid_elem.hpp"
+#include "elem_tables.hpp"
 
 namespace svb200 {
 
@@ -260,6 +261,241 @@ SVB_HD_NOINL void face_normal_terms(const int* nd, int inode, const double* x, c
     for (int a = 0; a < NB; a++)
       for (int i = 0; i < 3; i++) out[(a*NG + g)*3 + i] = Ntab[g*NB + a]*wtab[g]*n[i];
   }
+}
+
+// ---- follower pressure load on a struct face: eq_assem::b_neu_folw_p + nn::get_nnx / get_xi + struct_ns::b_struct_3d -----
+// (Code/Source/solver/eq_assem.cpp:186-303, nn.cpp:314-440, sv_struct.cpp:116-210).  The pressure h acts along the CURRENT
+// normal: Nanson's formula da n = J dA F^-T N with F from the parent element's displacement, so the face integral needs
+// the parent's shape functions at the face Gauss point (found by a Newton inverse map) and has a tangent.
+
+// parent-element shape functions and their parametric derivatives at xi (nn_elem_gnn.h:40, 547, 572)
+template <int NP>
+SVB_HD void parent_shape(const double xi[3], double* N, double* Nxi /*[a*3 + k]*/)
+{
+  if (NP == 4) {
+    N[0] = xi[0]; N[1] = xi[1]; N[2] = xi[2]; N[3] = 1.0 - xi[0] - xi[1] - xi[2];
+    const double d[4][3] = {{1.0, 0.0, 0.0}, {0.0, 1.0, 0.0}, {0.0, 0.0, 1.0}, {-1.0, -1.0, -1.0}};
+    for (int a = 0; a < 4; a++) for (int k = 0; k < 3; k++) Nxi[a*3 + k] = d[a][k];
+  } else if (NP == 8) {
+    const double lx = 1.0 - xi[0], ly = 1.0 - xi[1], lz = 1.0 - xi[2], ux = 1.0 + xi[0], uy = 1.0 + xi[1], uz = 1.0 + xi[2];
+    N[0] = lx*ly*lz/8.0; N[1] = ux*ly*lz/8.0; N[2] = ux*uy*lz/8.0; N[3] = lx*uy*lz/8.0;
+    N[4] = lx*ly*uz/8.0; N[5] = ux*ly*uz/8.0; N[6] = ux*uy*uz/8.0; N[7] = lx*uy*uz/8.0;
+    const double d[8][3] = {{-ly*lz/8.0, -lx*lz/8.0, -lx*ly/8.0}, { ly*lz/8.0, -ux*lz/8.0, -ux*ly/8.0},
+                            { uy*lz/8.0,  ux*lz/8.0, -ux*uy/8.0}, {-uy*lz/8.0,  lx*lz/8.0, -lx*uy/8.0},
+                            {-ly*uz/8.0, -lx*uz/8.0,  lx*ly/8.0}, { ly*uz/8.0, -ux*uz/8.0,  ux*ly/8.0},
+                            { uy*uz/8.0,  ux*uz/8.0,  ux*uy/8.0}, {-uy*uz/8.0,  lx*uz/8.0,  lx*uy/8.0}};
+    for (int a = 0; a < 8; a++) for (int k = 0; k < 3; k++) Nxi[a*3 + k] = d[a][k];
+  } else {
+    const double x0 = xi[0], x1 = xi[1], x2 = xi[2], s = 1.0 - x0 - x1 - x2;
+    N[0] = x0*(2.0*x0 - 1.0); N[1] = x1*(2.0*x1 - 1.0); N[2] = x2*(2.0*x2 - 1.0); N[3] = s*(2.0*s - 1.0);
+    N[4] = 4.0*x0*x1; N[5] = 4.0*x1*x2; N[6] = 4.0*x0*x2; N[7] = 4.0*x0*s; N[8] = 4.0*x1*s; N[9] = 4.0*x2*s;
+    const double d[10][3] = {{4.0*x0 - 1.0, 0.0, 0.0}, {0.0, 4.0*x1 - 1.0, 0.0}, {0.0, 0.0, 4.0*x2 - 1.0},
+                             {1.0 - 4.0*s, 1.0 - 4.0*s, 1.0 - 4.0*s}, {4.0*x1, 4.0*x0, 0.0}, {0.0, 4.0*x2, 4.0*x1},
+                             {4.0*x2, 0.0, 4.0*x0}, {4.0*(s - x0), -4.0*x0, -4.0*x0}, {-4.0*x1, 4.0*(s - x1), -4.0*x1},
+                             {-4.0*x2, -4.0*x2, 4.0*(s - x2)}};
+    for (int a = 0; a < 10; a++) for (int k = 0; k < 3; k++) Nxi[a*3 + k] = d[a][k];
+  }
+}
+
+// mat_fun::mat_det / mat_inv for nd = 3 (mat_fun.cpp:65-95, 158-174)
+SVB_HD double det3(const double A[3][3])
+{
+  double D = 0.0;
+  D = D + 1.0*A[0][0]*(A[1][1]*A[2][2] - A[1][2]*A[2][1]);
+  D = D + (-1.0)*A[0][1]*(A[1][0]*A[2][2] - A[1][2]*A[2][0]);
+  D = D + 1.0*A[0][2]*(A[1][0]*A[2][1] - A[1][1]*A[2][0]);
+  return D;
+}
+SVB_HD void inv3(const double A[3][3], double Ai[3][3])
+{
+  const double d = det3(A);
+  Ai[0][0] = (A[1][1]*A[2][2] - A[1][2]*A[2][1])/d;
+  Ai[0][1] = (A[0][2]*A[2][1] - A[0][1]*A[2][2])/d;
+  Ai[0][2] = (A[0][1]*A[1][2] - A[0][2]*A[1][1])/d;
+  Ai[1][0] = (A[1][2]*A[2][0] - A[1][0]*A[2][2])/d;
+  Ai[1][1] = (A[0][0]*A[2][2] - A[0][2]*A[2][0])/d;
+  Ai[1][2] = (A[0][2]*A[1][0] - A[0][0]*A[1][2])/d;
+  Ai[2][0] = (A[1][0]*A[2][1] - A[1][1]*A[2][0])/d;
+  Ai[2][1] = (A[0][1]*A[2][0] - A[0][0]*A[2][1])/d;
+  Ai[2][2] = (A[0][0]*A[1][1] - A[0][1]*A[1][0])/d;
+}
+
+struct FolwConsts {
+  double dt, af, beta;      // com_mod.dt, eq.af, eq.beta
+  int tDof, s;              // state width and eq.s (rows of the displacement in Dg)
+  double xi0[3];            // mean of the parent's Gauss points: start of the Newton inverse map (eq_assem.cpp:249-253)
+  double xib[2][3];         // bounds of the parent's parametric coordinates (+- 1e-4, nn.cpp:186-293)
+  double Nb_lo_c, Nb_hi_c;  // bounds of the corner / (TET10) mid-edge shape functions
+  double Nb_lo_m, Nb_hi_m;
+};
+
+// parent-element data of FolwConsts: what select_ele / get_nn_bnds leave in lM.xi, lM.xib, lM.Nb (host only)
+inline void fill_folw_parent(FolwConsts& c, const ElemTables& t)
+{
+  double xi0[3] = {0.0, 0.0, 0.0};
+  for (int g = 0; g < t.nG; g++) for (int i = 0; i < 3; i++) xi0[i] = xi0[i] + t.xi[g][i];
+  for (int i = 0; i < 3; i++) c.xi0[i] = xi0[i]/static_cast<double>(t.nG);
+  const double tol = 1.0E-4;
+  const bool tet = (t.eNoN == 4 || t.eNoN == 10);
+  for (int i = 0; i < 3; i++) { c.xib[0][i] = (tet ? 0.0 : -1.0) - tol; c.xib[1][i] = 1.0 + tol; }
+  c.Nb_lo_c = ((t.eNoN == 10) ? -0.125 : 0.0) - tol; c.Nb_hi_c = 1.0 + tol;
+  c.Nb_lo_m = 0.0 - tol; c.Nb_hi_m = 4.0 + tol;
+}
+
+// One face element with NB nodes / NG Gauss points of a parent with NP nodes.  pn[NP]: parent nodes (assembly ids), nd[NB]: face
+// nodes, inode: a parent node off the face.  Outputs lR[a*3 + i] (a over the PARENT nodes) and lK6[(a*NP + b)*6 + q] = the six
+// off-diagonal entries (0,1), (1,0), (0,2), (2,0), (1,2), (2,1) of the 3x3 block (a,b); the diagonal stays zero.
+// Returns 0, or 1 when the inverse map fails (the reference throws "Error in computing shape functions", nn.cpp:362).
+template <int NP, int NB, int NG>
+SVB_HD_NOINL int face_follower_element(const FolwConsts& c, const int* pn, const int* nd, int inode, const double* x, const double* Dg,
+                                       const double* hg, const double* wtab, const double* Ntab, const double* Nxtab,
+                                       double* lR, double* lK6)
+{
+  const int tD = c.tDof;
+  double xl[NP][3], dl[NP][3], hl[NP];
+  for (int a = 0; a < NP; a++) {
+    const size_t A = size_t(pn[a]);
+    hl[a] = hg[A];
+    for (int i = 0; i < 3; i++) { xl[a][i] = x[A*3 + i]; dl[a][i] = Dg[A*tD + c.s + i]; }
+  }
+  double xf[NB][3], xin[3];
+  for (int a = 0; a < NB; a++) for (int i = 0; i < 3; i++) xf[a][i] = x[size_t(nd[a])*3 + i];
+  for (int i = 0; i < 3; i++) xin[i] = x[size_t(inode)*3 + i];
+  for (int q = 0; q < NP*3; q++) lR[q] = 0.0;
+  for (int q = 0; q < NP*NP*6; q++) lK6[q] = 0.0;
+  const double afl = c.af*c.beta*c.dt*c.dt;
+  int fail = 0;
+  for (int g = 0; g < NG; g++) {
+    // physical position of the face Gauss point
+    double xp[3] = {0.0, 0.0, 0.0};
+    for (int a = 0; a < NB; a++)
+      for (int i = 0; i < 3; i++) xp[i] = xp[i] + xf[a][i]*Ntab[g*NB + a];
+    // nn::get_xi: Newton inverse map into the parent (nn.cpp:369-440)
+    double xi[3] = {c.xi0[0], c.xi0[1], c.xi0[2]};
+    double N[NP], Nxi[NP*3];
+    bool conv = false;
+    int itr = 0;
+    while (true) {
+      itr = itr + 1;
+      parent_shape<NP>(xi, N, Nxi);
+      double xK[3] = {0.0, 0.0, 0.0}, rK[3];
+      for (int i = 0; i < 3; i++) {
+        for (int a = 0; a < NP; a++) xK[i] = xK[i] + N[a]*xl[a][i];
+        rK[i] = xK[i] - xp[i];
+      }
+      double rmsA = 0.0, rmsR = 0.0;
+      for (int i = 0; i < 3; i++) {
+        rmsA = rmsA + rK[i]*rK[i];
+        const double q = rK[i]/(xK[i] + 2.220446049250313e-16);
+        rmsR = rmsR + q*q;
+      }
+      rmsA = sqrt(rmsA/3.0);
+      rmsR = sqrt(rmsR/3.0);
+      const bool l1 = itr > 5, l2 = rmsA <= 1.0e-12, l3 = rmsR <= 1.0e-6;
+      if (l1 || l2 || l3) { conv = l2 || l3; break; }
+      double Am[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, Ai[3][3];
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+          for (int a = 0; a < NP; a++) Am[i][j] = Am[i][j] + xl[a][i]*Nxi[a*3 + j];
+      inv3(Am, Ai);
+      double dx[3];
+      for (int i = 0; i < 3; i++) dx[i] = ((0.0 + Ai[i][0]*rK[0]) + Ai[i][1]*rK[1]) + Ai[i][2]*rK[2];
+      for (int i = 0; i < 3; i++) xi[i] = xi[i] - dx[i];
+    }
+    // nn::get_nnx checks (nn.cpp:333-364)
+    {
+      int j = 0;
+      for (int i = 0; i < 3; i++) if (xi[i] >= c.xib[0][i] && xi[i] <= c.xib[1][i]) j++;
+      const bool l2 = (j == 3);
+      parent_shape<NP>(xi, N, Nxi);
+      j = 0;
+      double rt = 0.0;
+      for (int a = 0; a < NP; a++) {
+        rt = rt + N[a];
+        const double lo = (NP == 10 && a >= 4) ? c.Nb_lo_m : c.Nb_lo_c, hi = (NP == 10 && a >= 4) ? c.Nb_hi_m : c.Nb_hi_c;
+        if (N[a] > lo && N[a] < hi) j++;
+      }
+      const bool l3 = (j == NP), l4 = (rt >= 0.9999) && (rt <= 1.0001);
+      if (!(conv && l2 && l3 && l4)) fail = 1;
+    }
+    // nn::gnn on the parent at xi: dN/dX in the reference configuration
+    double Nx[NP][3];
+    {
+      double xXi[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      for (int a = 0; a < NP; a++)
+        for (int i = 0; i < 3; i++) {
+          xXi[i][0] = xXi[i][0] + xl[a][i]*Nxi[a*3 + 0];
+          xXi[i][1] = xXi[i][1] + xl[a][i]*Nxi[a*3 + 1];
+          xXi[i][2] = xXi[i][2] + xl[a][i]*Nxi[a*3 + 2];
+        }
+      const double Jp = xXi[0][0]*xXi[1][1]*xXi[2][2] + xXi[0][1]*xXi[1][2]*xXi[2][0] + xXi[0][2]*xXi[1][0]*xXi[2][1]
+                      - xXi[0][0]*xXi[1][2]*xXi[2][1] - xXi[0][1]*xXi[1][0]*xXi[2][2] - xXi[0][2]*xXi[1][1]*xXi[2][0];
+      double xiX[3][3];
+      xiX[0][0] = (xXi[1][1]*xXi[2][2] - xXi[1][2]*xXi[2][1])/Jp;
+      xiX[0][1] = (xXi[2][1]*xXi[0][2] - xXi[2][2]*xXi[0][1])/Jp;
+      xiX[0][2] = (xXi[0][1]*xXi[1][2] - xXi[0][2]*xXi[1][1])/Jp;
+      xiX[1][0] = (xXi[1][2]*xXi[2][0] - xXi[1][0]*xXi[2][2])/Jp;
+      xiX[1][1] = (xXi[2][2]*xXi[0][0] - xXi[2][0]*xXi[0][2])/Jp;
+      xiX[1][2] = (xXi[0][2]*xXi[1][0] - xXi[0][0]*xXi[1][2])/Jp;
+      xiX[2][0] = (xXi[1][0]*xXi[2][1] - xXi[1][1]*xXi[2][0])/Jp;
+      xiX[2][1] = (xXi[2][0]*xXi[0][1] - xXi[2][1]*xXi[0][0])/Jp;
+      xiX[2][2] = (xXi[0][0]*xXi[1][1] - xXi[0][1]*xXi[1][0])/Jp;
+      for (int a = 0; a < NP; a++)
+        for (int i = 0; i < 3; i++)
+          Nx[a][i] = ((0.0 + Nxi[a*3 + 0]*xiX[0][i]) + Nxi[a*3 + 1]*xiX[1][i]) + Nxi[a*3 + 2]*xiX[2][i];
+    }
+    // nn::gnnb: reference-configuration normal of the face
+    double nV[3];
+    {
+      double xXi[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+      for (int a = 0; a < NB; a++)
+        for (int i = 0; i < 2; i++)
+          for (int j = 0; j < 3; j++) xXi[j][i] = xXi[j][i] + Nxtab[(g*NB + a)*2 + i]*xf[a][j];
+      nV[0] = xXi[1][0]*xXi[2][1] - xXi[2][0]*xXi[1][1];
+      nV[1] = xXi[2][0]*xXi[0][1] - xXi[0][0]*xXi[2][1];
+      nV[2] = xXi[0][0]*xXi[1][1] - xXi[1][0]*xXi[0][1];
+      double dotv = 0.0;
+      for (int i = 0; i < 3; i++) dotv += nV[i]*(xf[0][i] - xin[i]);
+      if (dotv < 0.0) { nV[0] = -nV[0]; nV[1] = -nV[1]; nV[2] = -nV[2]; }
+    }
+    double nn = 0.0;
+    for (int i = 0; i < 3; i++) nn += nV[i]*nV[i];
+    const double Jac = sqrt(nn);
+    for (int i = 0; i < 3; i++) nV[i] = nV[i]/Jac;
+    const double w = wtab[g]*Jac;
+    // struct_ns::b_struct_3d (sv_struct.cpp:116-210)
+    double F[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    double h = 0.0;
+    for (int a = 0; a < NP; a++) {
+      h = h + N[a]*hl[a];
+      for (int i = 0; i < 3; i++) {
+        F[i][0] = F[i][0] + Nx[a][0]*dl[a][i];
+        F[i][1] = F[i][1] + Nx[a][1]*dl[a][i];
+        F[i][2] = F[i][2] + Nx[a][2]*dl[a][i];
+      }
+    }
+    const double JF = det3(F);
+    double Fi[3][3];
+    inv3(F, Fi);
+    double NxFi[NP][3], nFi[3];
+    for (int a = 0; a < NP; a++)
+      for (int i = 0; i < 3; i++) NxFi[a][i] = Nx[a][0]*Fi[0][i] + Nx[a][1]*Fi[1][i] + Nx[a][2]*Fi[2][i];
+    for (int i = 0; i < 3; i++) nFi[i] = nV[0]*Fi[0][i] + nV[1]*Fi[1][i] + nV[2]*Fi[2][i];
+    const double wl = w*JF*h;
+    for (int a = 0; a < NP; a++) {
+      for (int i = 0; i < 3; i++) lR[a*3 + i] = lR[a*3 + i] - wl*N[a]*nFi[i];
+      for (int b = 0; b < NP; b++) {
+        double* k6 = lK6 + (a*NP + b)*6;
+        double Ku = wl*afl*N[a]*(nFi[1]*NxFi[b][0] - nFi[0]*NxFi[b][1]);
+        k6[0] = k6[0] + Ku; k6[1] = k6[1] - Ku;
+        Ku = wl*afl*N[a]*(nFi[2]*NxFi[b][0] - nFi[0]*NxFi[b][2]);
+        k6[2] = k6[2] + Ku; k6[3] = k6[3] - Ku;
+        Ku = wl*afl*N[a]*(nFi[2]*NxFi[b][1] - nFi[1]*NxFi[b][2]);
+        k6[4] = k6[4] + Ku; k6[5] = k6[5] - Ku;
+      }
+    }
+  }
+  return fail;
 }
 
 } // namespace svb200

@@ -201,6 +201,64 @@ void host_pk2cc(const double* par, const double* F9, const double* fl6, double* 
   pk2cc_iso(c, F, fl6, S6, Dm21);
 }
 
+// Follower pressure load (face_follower_element): b_neu_folw_p on one face of a struct equation (dof 3), serial.
+// par = {dt, af, beta, tDof, s}.  R(3,nNo), Val(9,nnz) must be zero on entry.
+extern "C++" {
+namespace {
+template <int NP, int NB, int NG>
+int bfolw(const FolwConsts& c, const FaceTables& ft, const double* N, const double* Nx, const int* ien, int nElb, const int* IENb,
+          const int* gE, const double* x, const double* Dg, const double* hg, const int* rowPtr, const int* colPtr, double* R, double* Val)
+{
+  std::vector<double> lR(NP*3), lK6(NP*NP*6);
+  for (int e = 0; e < nElb; e++) {
+    const int* nd = IENb + size_t(e)*NB;
+    const int* pn = ien + size_t(gE[e])*NP;
+    int inode = -1;
+    for (int b = 0; b < NP && inode < 0; b++)
+      if (std::find(nd, nd + NB, pn[b]) == nd + NB) inode = pn[b];
+    if (inode < 0) return e + 1;
+    if (face_follower_element<NP, NB, NG>(c, pn, nd, inode, x, Dg, hg, ft.w, N, Nx, lR.data(), lK6.data()) != 0) return -(e + 1);
+    for (int a = 0; a < NP; a++) {
+      for (int i = 0; i < 3; i++) R[size_t(pn[a])*3 + i] += lR[a*3 + i];
+      const int* beg = colPtr + rowPtr[pn[a]];
+      const int* end = colPtr + rowPtr[pn[a] + 1];
+      for (int b = 0; b < NP; b++) {
+        const int* it = std::lower_bound(beg, end, pn[b]);
+        if (it == end || *it != pn[b]) return -1000000;
+        double* v = Val + size_t(it - colPtr)*9;
+        const double* k6 = &lK6[(a*NP + b)*6];
+        v[1] += k6[0]; v[3] += k6[1]; v[2] += k6[2]; v[6] += k6[3]; v[5] += k6[4]; v[7] += k6[5];
+      }
+    }
+  }
+  return 0;
+}
+} // namespace
+} // extern "C++"
+
+int host_bfolw_assemble(int eNoN, const int* ien, int eNoNb, int nElb, const int* IENb, const int* gE, const double* par,
+                        const double* x, const double* Dg, const double* hg, const int* rowPtr, const int* colPtr, double* R, double* Val)
+{
+  if (!face_supported(eNoNb) || !elem_supported(eNoN)) return -1000001;
+  FolwConsts c;
+  c.dt = par[0]; c.af = par[1]; c.beta = par[2]; c.tDof = int(par[3]); c.s = int(par[4]);
+  ElemTables et;
+  fill_tables(et, eNoN, (5.0 + 3.0*std::sqrt(5.0))/20.0);
+  fill_folw_parent(c, et);
+  FaceTables t;
+  fill_face_tables(t, eNoNb, 2.0/3.0);
+  std::vector<double> N(t.nG*eNoNb), Nx(t.nG*eNoNb*2);
+  for (int g = 0; g < t.nG; g++)
+    for (int a = 0; a < eNoNb; a++) {
+      N[g*eNoNb + a] = t.N[g][a];
+      Nx[(g*eNoNb + a)*2] = t.Nx[g][a][0]; Nx[(g*eNoNb + a)*2 + 1] = t.Nx[g][a][1];
+    }
+  if (eNoN == 4 && eNoNb == 3) return bfolw<4, 3, 3>(c, t, N.data(), Nx.data(), ien, nElb, IENb, gE, x, Dg, hg, rowPtr, colPtr, R, Val);
+  if (eNoN == 8 && eNoNb == 4) return bfolw<8, 4, 4>(c, t, N.data(), Nx.data(), ien, nElb, IENb, gE, x, Dg, hg, rowPtr, colPtr, R, Val);
+  if (eNoN == 10 && eNoNb == 6) return bfolw<10, 6, 7>(c, t, N.data(), Nx.data(), ien, nElb, IENb, gE, x, Dg, hg, rowPtr, colPtr, R, Val);
+  return -1000002;
+}
+
 // the tables themselves (checked against what the reference's select_ele leaves in lM): returns nG
 int host_elem_tables(int eNoN, double qmTET4, double* w, double* N, double* Nxi, double* Nxi2)
 {

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from conftest import needs_ref
-from util import golden, host_bneu_assemble, host_face_integ, host_face_normals, rel_inf
+from util import golden, host_bfolw_assemble, host_bneu_assemble, host_face_integ, host_face_normals, rel_inf
 
 from svfsiplus_b200 import mesh as M
 from svfsiplus_b200 import problem as P
@@ -231,4 +231,65 @@ def test_gpu_unit_traction_integrates_to_area_normal():
     be.assemble_bneu(1, "solid", np.ones(case["mesh"].nNo), tDof=3, **TIME)
     s = be.get_R().sum(axis=0)
     assert np.allclose(s, [1.0, 0.0, 0.0], atol=1e-13)
+    be.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# follower pressure load on a struct face (lBc.flwP): b_neu_folw_p + get_nnx / get_xi + b_struct_3d
+# (eq_assem.cpp:186, nn.cpp:314-440, sv_struct.cpp:116)
+# ---------------------------------------------------------------------------------------------------------------------
+def _folw_setup(elem, n):
+    case = P.block_case(n, elem=elem, kind="struct")
+    m = case["mesh"]
+    on = np.abs(m.x[:, 2] - 1.0) < 1e-12
+    IENb, gE = M.face_elements(m, on)
+    rng = np.random.default_rng(3)
+    hg = np.where(on, 1.0e4 * (1.0 + 0.1 * rng.standard_normal(m.nNo)), 0.0)
+    return case, IENb, gE, hg
+
+
+@pytest.mark.parametrize("elem,n", ELEMS)
+@needs_ref
+def test_host_follower_pressure_matches_reference_bitwise(elem, n):
+    from oracle import ref
+    case, IENb, gE, hg = _folw_setup(elem, n)
+    m, p = case["mesh"], case["props"]
+    ra = ref.RefAssembly(m.x, m.ien)
+    Rr, Vr = ra.bfolw(IENb, gE, hg, case["Dg"], dt=p["dt"], af=p["af"], beta=p["beta"])
+    ra.close()
+    R, Val = host_bfolw_assemble(m, IENb, gE, hg, case["Dg"], case["rowPtr"], case["colPtr"], dt=p["dt"], af=p["af"], beta=p["beta"])
+    assert np.abs(Rr).max() > 0 and np.abs(Vr).max() > 0
+    assert np.array_equal(R, Rr) and np.array_equal(Val, Vr)
+    # the load follows the deformation: the tangent is not symmetric and vanishes on the diagonal entries of every block
+    assert np.abs(Vr[:, [0, 4, 8]]).max() == 0.0
+
+
+@pytest.mark.parametrize("elem,n", ELEMS)
+def test_host_follower_pressure_matches_golden(elem, n):
+    g = golden("boundary_faces.npz")
+    case, IENb, gE, hg = _folw_setup(elem, n)
+    m, p = case["mesh"], case["props"]
+    R, Val = host_bfolw_assemble(m, IENb, gE, hg, case["Dg"], case["rowPtr"], case["colPtr"], dt=p["dt"], af=p["af"], beta=p["beta"])
+    assert rel_inf(R, g[f"R_folw_{elem}"]) < 1e-14 and rel_inf(Val, g[f"Val_folw_{elem}"]) < 1e-14
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("elem,n", ELEMS)
+def test_gpu_follower_pressure_matches_golden(elem, n):
+    g = golden("boundary_faces.npz")
+    case, IENb, gE, hg = _folw_setup(elem, n)
+    p = case["props"]
+    be = P.setup_backend(case)
+    be.face_mesh_set(3, IENb, gE)
+    be.state_set(3, case["Ag"], case["Yg"], case["Bf"])
+    be.disp_set(3, case["Dg"])
+    be.zero(3)
+    be.assemble_bfolw(3, hg, dt=p["dt"], af=p["af"], beta=p["beta"])
+    assert rel_inf(be.get_R(), g[f"R_folw_{elem}"]) < 1e-12
+    assert rel_inf(be.get_Val(), g[f"Val_folw_{elem}"]) < 1e-12
+    # on top of the volume assembly: the sum, and a second call adds the same amount again (do_assem accumulates)
+    P.assemble_solid(be, case)
+    R0, V0 = be.get_R(), be.get_Val()
+    be.assemble_bfolw(3, hg, dt=p["dt"], af=p["af"], beta=p["beta"])
+    assert rel_inf(be.get_R(), R0 + g[f"R_folw_{elem}"]) < 1e-12 and rel_inf(be.get_Val(), V0 + g[f"Val_folw_{elem}"]) < 1e-12
     be.close()

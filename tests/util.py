@@ -75,6 +75,7 @@ def elemhost():
                                           C.c_int, C.c_void_p]
         _eh.host_pk2cc.argtypes = [C.c_void_p] * 5
         _eh.host_pk2cc.restype = None
+        _eh.host_bfolw_assemble.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 10
         _eh.host_bneu_assemble.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 11
     return _eh
 
@@ -156,3 +157,19 @@ def host_pk2cc(F, fl, *, iso, vol, C10=0.0, C01=0.0, Kpen=0.0, ho=None, Tfa=0.0,
     S6 = np.empty(6); Dm21 = np.empty(21)
     L.host_pk2cc(_p(par), _p(F), _p(fl), _p(S6), _p(Dm21))
     return S6, Dm21
+
+
+def host_bfolw_assemble(mesh, IENb, gE, hg, Dg, rowPtr, colPtr, *, dt, af, beta, s=0):
+    """face_elem.hpp face_follower_element (b_neu_folw_p: follower pressure on a struct face) run serially on the host."""
+    L = elemhost()
+    ien = np.ascontiguousarray(mesh.ien, np.int32); x = np.ascontiguousarray(mesh.x, np.float64)
+    IENb = np.ascontiguousarray(IENb, np.int32); gE = np.ascontiguousarray(gE, np.int32)
+    hg = np.ascontiguousarray(hg, np.float64); Dg = np.ascontiguousarray(Dg, np.float64)
+    rp = np.ascontiguousarray(rowPtr, np.int32); cp = np.ascontiguousarray(colPtr, np.int32)
+    par = np.array([dt, af, beta, Dg.shape[1], s], np.float64)
+    R = np.zeros((mesh.nNo, 3)); Val = np.zeros((len(cp), 9))
+    rc = L.host_bfolw_assemble(ien.shape[1], _p(ien), IENb.shape[1], IENb.shape[0], _p(IENb), _p(gE), _p(par), _p(x), _p(Dg), _p(hg),
+                               _p(rp), _p(cp), _p(R), _p(Val))
+    if rc != 0:
+        raise RuntimeError(f"host_bfolw_assemble: rc {rc}")
+    return R, Val
