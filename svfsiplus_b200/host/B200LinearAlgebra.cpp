@@ -358,6 +358,31 @@ bool B200LinearAlgebra::assemble_face(ComMod& com_mod, const faceType& lFa, cons
   return true;
 }
 
+/// Follower pressure load on the device (b_neu_folw_p, eq_assem.cpp:186) for a single-domain struct equation.
+bool B200LinearAlgebra::assemble_follower_face(ComMod& com_mod, const faceType& lFa, const Vector<double>& hg, const Array<double>& Dg)
+{
+  using namespace consts;
+  if (!device_assembly_ || !any_device_contribution_ || com_mod.nsd != 3 || com_mod.dof != 3 || com_mod.mvMsh) return false;
+  auto& eq = com_mod.eq[com_mod.cEq];
+  const auto& msh = com_mod.msh[lFa.iM];
+  if (eq.nDmn != 1 || eq.dmn[0].phys != EquationType::phys_struct || msh.lShl || mesh_uploaded_ != &msh) return false;
+  const bool pair_ok = (msh.eType == ElementType::TET4 && lFa.eType == ElementType::TRI3) ||
+                       (msh.eType == ElementType::HEX8 && lFa.eType == ElementType::QUD4) ||
+                       (msh.eType == ElementType::TET10 && lFa.eType == ElementType::TRI6);
+  if (!pair_ok || (lFa.eType == ElementType::TRI3 && lFa.qmTRI3 != 2.0/3.0)) return false;
+  auto it = face_meshes_.find(&lFa);
+  if (it == face_meshes_.end()) {
+    const int slot = int(face_meshes_.size());
+    check(b200_face_mesh_set(h_, slot, lFa.eNoN, lFa.nEl, lFa.IEN.data(), lFa.gE.data()), "b200_face_mesh_set");
+    it = face_meshes_.emplace(&lFa, slot).first;
+  }
+  b200_bfolw_props p;
+  p.dt = com_mod.dt; p.af = eq.af; p.beta = eq.beta; p.tDof = com_mod.tDof; p.s = eq.s;
+  (void)Dg;      // the device holds the Dg uploaded for the volume assembly of this iteration
+  check(b200_assemble_bfolw(h_, it->second, &p, hg.data()), "b200_assemble_bfolw");
+  return true;
+}
+
 /// ustruct (construct_usolid, ustruct.cpp:216) on equal-order TET4 / HEX8 / TET10 with idMap = identity.
 bool B200LinearAlgebra::assemble_ustruct_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag,
     const Array<double>& Yg, const Array<double>& Dg, const CepMod* cep_mod)

@@ -62,6 +62,10 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
     /// reference's b_assem_neu_bc with per-element assemble()).
     bool assemble_face(ComMod& com_mod, const faceType& lFa, const Vector<double>& hg, const Array<double>& Yg);
 
+    /// b_neu_folw_p counterpart (eq_assem.cpp:186; called from set_bc_neu_l when lBc.flwP, set_bc.cpp:1446): follower
+    /// pressure load on a struct face, on top of the device volume assembly.  Same fall-back rule as assemble_face.
+    bool assemble_follower_face(ComMod& com_mod, const faceType& lFa, const Vector<double>& hg, const Array<double>& Dg);
+
     /// fsils_bc_update counterpart: re-upload the face vectors (moving meshes, follower loads).
     void update_faces(ComMod& com_mod);
 
