@@ -132,7 +132,7 @@ int b200_pattern_get(b200_handle* h, int* rowPtr, int* colPtr);
 
 /* ---- assembly (replaces construct_fluid + do_assem, solver/fluid.cpp:464, lhsa.cpp:97) ------- */
 /* IEN(eNoN,nEl) with assembly node ids, x(3,nNo).  eNoN = 4 (TET4), 8 (HEX8, the reference's node
- * order, nn_elem_gnn.h:732) or 10 (TET10, nn_elem_gnn.h:1256; every equation but FSI).  qmTET4 <= 0 selects the
+ * order, nn_elem_gnn.h:732) or 10 (TET10, nn_elem_gnn.h:1256).  qmTET4 <= 0 selects the
  * default (5+3*sqrt(5))/20 (solver/ComMod.h:1011). */
 int b200_mesh_set(b200_handle* h, int eNoN, int nEl, const int* IEN, const double* x, double qmTET4);
 /* ls_alloc contract (solver/ls.cpp:51-60): after it R(dof,nNo) and Val(dof*dof,nnz) are zero. */
@@ -172,7 +172,7 @@ int b200_mesh_domains(b200_handle* h, int nDmn, const int* elem_dmn);
 int b200_assemble_fluid_dmn(b200_handle* h, int nDmn, const b200_fluid_props* p);
 int b200_assemble_struct_dmn(b200_handle* h, int nDmn, const b200_struct_props* p);
 /* dmn_kind[d]: 0 fluid (fluid_3d_m/c on the ALE configuration x + Dg(4:6), mvMsh), 1 struct (struct_3d into the
- * 3x3 corner of the dof-4 blocks).  fluid[d] / solid[d] are read for the domains of that kind (dof 4; TET4, HEX8). */
+ * 3x3 corner of the dof-4 blocks).  fluid[d] / solid[d] are read for the domains of that kind (dof 4; TET4, HEX8, TET10). */
 int b200_assemble_fsi(b200_handle* h, int nDmn, const int* dmn_kind, const b200_fluid_props* fluid, const b200_struct_props* solid);
 /* Boundary-face (Neumann) assembly on the device: replaces b_assem_neu_bc + gnnb + b_fluid / b_l_elas
  * (solver/eq_assem.cpp:58-170, nn.cpp:552-755, fluid.cpp:46-133, l_elas.cpp:48-59) and with them the per-element

@@ -899,7 +899,6 @@ int b200_assemble_fsi(b200_handle* h, int nDmn, const int* dmn_kind, const b200_
     if (int(h->d_dmn_elems.size()) != nDmn) throw std::runtime_error("assemble_fsi: call b200_mesh_domains with the same nDmn first");
     if (!h->d_Ag || !h->d_Dg) throw std::runtime_error("assemble_fsi: no state (b200_state_set + b200_disp_set)");
     if (h->dof != 4 || !h->Val) throw std::runtime_error("assemble_fsi: call b200_zero(h, 4) first");
-    if (h->eNoN != 4 && h->eNoN != 8) throw std::runtime_error("assemble_fsi: built for TET4 and HEX8 meshes (the struct kernel)");
     int covered = 0;
     for (int d = 0; d < nDmn; d++) covered += h->dmn_count[d];
     if (covered != h->nEl) throw std::runtime_error("assemble_fsi: every element must belong to a fluid or struct domain");
@@ -920,7 +919,8 @@ int b200_assemble_fsi(b200_handle* h, int nDmn, const int* dmn_kind, const b200_
           if (solid[d].tDof != h->tDof) throw std::runtime_error("assemble_fsi: tDof differs from the uploaded state");
           const SolidConsts c = struct_consts(&solid[d]);
           if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 4>(h, c, n, h->d_dmn_elems[d]);
-          else launch_solid<8, 8, 16, 2, 4>(h, c, n, h->d_dmn_elems[d]);
+          else if (h->eNoN == 8) launch_solid<8, 8, 16, 2, 4>(h, c, n, h->d_dmn_elems[d]);
+          else launch_solid<10, 15, 8, 2, 4>(h, c, n, h->d_dmn_elems[d]);
         } else {
           throw std::runtime_error("assemble_fsi: domain physics has no device kernel (fluid and struct have)");
         }

@@ -282,13 +282,13 @@ bool B200LinearAlgebra::fill_struct_props(ComMod& com_mod, const eqType& eq, con
   return true;
 }
 
-/// FSI equation (construct_fsi, fsi.cpp:42): fluid and struct domains of one TET4 / HEX8 mesh in one dof-4 system.
+/// FSI equation (construct_fsi, fsi.cpp:42): fluid and struct domains of one TET4 / HEX8 / TET10 mesh in one dof-4 system.
 bool B200LinearAlgebra::assemble_fsi_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag,
     const Array<double>& Yg, const Array<double>& Dg, const CepMod* cep_mod)
 {
   using namespace consts;
   auto& eq = com_mod.eq[com_mod.cEq];
-  if ((lM.eType != ElementType::TET4 && lM.eType != ElementType::HEX8) || com_mod.dof != 4 || !com_mod.mvMsh) return false;
+  if ((lM.eType != ElementType::TET4 && lM.eType != ElementType::HEX8 && lM.eType != ElementType::TET10) || com_mod.dof != 4 || !com_mod.mvMsh) return false;
   if (com_mod.pS0.size() != 0 || com_mod.pstEq) return false;
   if (cep_mod && (cep_mod->cem.cpld || cep_mod->cem.aStress || cep_mod->cem.aStrain)) return false;
   const int nDmn = eq.nDmn;

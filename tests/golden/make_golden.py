@@ -82,8 +82,9 @@ def main():
         R, Val, X, o = refcase.reference_step(P.fluid_block_case(n, elem=elem), T.LS_STEP)
         out[f"X_step_{tag}"] = X
         out[f"info_step_{tag}"] = np.array([o["suc"], o["itr"], o["iNorm"], o["fNorm"]])
-    R, Val, _ = refcase.reference_assemble_fsi(P.fsi_block_case(4, elem="hex"))
-    out["R_fsi_hex"] = R; out["Val_fsi_hex"] = Val
+    for elem, n in (("hex", 4), ("tet10", 2)):
+        R, Val, _ = refcase.reference_assemble_fsi(P.fsi_block_case(n, elem=elem))
+        out[f"R_fsi_{elem}"] = R; out[f"Val_fsi_{elem}"] = Val
     np.savez_compressed(os.path.join(HERE, "fluid_block.npz"), **out)
     # solid equations on curved TET10 (15 Gauss points)
     import test_tet10_solids as T10

@@ -139,14 +139,15 @@ def test_gpu_linear_step_matches_golden(tag, elem, n):
 
 
 @pytest.mark.gpu
-def test_gpu_fsi_hex8_matches_golden():
-    """construct_fsi (fsi.cpp:42) on HEX8: generic fluid kernel on the ALE configuration + struct kernel, one matrix."""
+@pytest.mark.parametrize("elem,n", [("hex", 4), ("tet10", 2)])
+def test_gpu_fsi_matches_golden(elem, n):
+    """construct_fsi (fsi.cpp:42) on HEX8 / TET10: generic fluid kernel on the ALE configuration + struct kernel, one matrix."""
     g = golden("fluid_block.npz")
-    case = P.fsi_block_case(4, elem="hex")
+    case = P.fsi_block_case(n, elem=elem)
     be = P.setup_backend(case)
     P.assemble_fsi(be, case)
-    assert rel_inf(be.get_R(), g["R_fsi_hex"]) < TOL_ASM
-    assert rel_inf(be.get_Val(), g["Val_fsi_hex"]) < TOL_ASM
+    assert rel_inf(be.get_R(), g[f"R_fsi_{elem}"]) < TOL_ASM
+    assert rel_inf(be.get_Val(), g[f"Val_fsi_{elem}"]) < TOL_ASM
     be.close()
 
 
