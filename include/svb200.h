@@ -193,12 +193,14 @@ int b200_face_mesh_set(b200_handle* h, int faIn, int eNoNb, int nElb, const int*
  * run this is the rank's part; the caller reduces it like cm.reduce does. */
 int b200_face_integ(b200_handle* h, int faIn, int which, int l, int u, int geo, double* result);
 int b200_assemble_bneu(b200_handle* h, int faIn, int kind, const b200_bneu_props* p, const double* hg);
-/* Follower pressure load on a struct face (lBc.flwP): replaces eq_assem::b_neu_folw_p (solver/eq_assem.cpp:186-303) with
- * nn::get_nnx / get_xi (Newton inverse map of the face Gauss points into the parent element, nn.cpp:314-440), gnn, gnnb and
- * struct_ns::b_struct_3d (Nanson's formula; residual and tangent, sv_struct.cpp:116-210).  dof-3 system, displacement from
- * the device Dg (b200_disp_set / b200_pici), rows s..s+2; parents TET4 / HEX8 / TET10.  Fails like the reference when the
- * inverse map does not converge ("Error in computing shape functions"). */
-typedef struct { double dt, af, beta; int tDof, s; } b200_bfolw_props;
+/* Follower pressure load on a struct or ustruct face (lBc.flwP): replaces eq_assem::b_neu_folw_p (solver/eq_assem.cpp:186-303)
+ * with nn::get_nnx / get_xi (Newton inverse map of the face Gauss points into the parent element, nn.cpp:314-440), gnn, gnnb
+ * and struct_ns::b_struct_3d (Nanson's formula; residual and tangent, sv_struct.cpp:116-210; dof-3 system, tangent factor
+ * af*beta*dt^2) or, ustruct != 0, ustruct::b_ustruct_3d + ustruct_do_assem (ustruct.cpp:132-211, 1579: dof-4 system, the
+ * tangent goes to Kd and, scaled by af*gam*dt/am, to the velocity block of Val).  Displacement from the device Dg
+ * (b200_disp_set / b200_pici), rows s..s+2; parents TET4 / HEX8 / TET10.  Fails like the reference when the inverse map
+ * does not converge ("Error in computing shape functions"). */
+typedef struct { double dt, af, beta; int tDof, s; int ustruct; double am, gam; } b200_bfolw_props;
 int b200_assemble_bfolw(b200_handle* h, int faIn, const b200_bfolw_props* p, const double* hg);
 /* eq_assem::fsi_ls_upd (solver/eq_assem.cpp:316-371) + fsils_bc_update (liner_solver/bc.cpp:171): recompute the vector
  * val(i,a) = int N_a n_i dGamma of the coupled Neumann face lsFace (index of b200_face_set, dof 3) from the face mesh

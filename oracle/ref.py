@@ -194,7 +194,7 @@ def lib():
                                      C.c_void_p, C.c_void_p]
         L.ref_pk2cc.argtypes = [C.c_void_p] * 6
         L.ref_pk2cc_dev.argtypes = [C.c_void_p] * 6
-        L.ref_asm_bfolw.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 7
+        L.ref_asm_bfolw.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8
         L.ref_asm_bneu.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
         L.ref_pic.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_double] + [C.c_void_p] * 12
         _lib = L
@@ -324,15 +324,17 @@ class RefAssembly:
             raise RuntimeError(lib().ref_last_error().decode())
         return val
 
-    def bfolw(self, IENb, gE, hg, Dg, *, dt, af, beta):
-        """eq_assem::b_neu_folw_p (S/eq_assem.cpp:186): follower pressure load on a struct face.  Returns R (nNo,3), Val (nnz,9)."""
+    def bfolw(self, IENb, gE, hg, Dg, *, dt, af, beta=0.0, ustruct=False, am=1.0, gam=0.0):
+        """eq_assem::b_neu_folw_p (S/eq_assem.cpp:186): follower pressure load on a struct face -> R (nNo,3), Val (nnz,9), or on a
+        ustruct face -> R (nNo,4), Val (nnz,16), Kd (nnz,12)."""
         IENb = _c(IENb, np.int32); gE = _c(gE, np.int32); hg = _c(hg, np.float64); Dg = _c(Dg, np.float64)
-        par = np.array([dt, af, beta, Dg.shape[1]], np.float64)
-        R = np.empty((self.nNo, 3)); Val = np.empty((self.nnz, 9))
-        rc = lib().ref_asm_bfolw(self.h, IENb.shape[1], IENb.shape[0], _p(IENb), _p(gE), _p(par), _p(hg), _p(Dg), _p(R), _p(Val))
+        par = np.array([dt, af, beta, Dg.shape[1], float(ustruct), am, gam], np.float64)
+        dof = 4 if ustruct else 3
+        R = np.empty((self.nNo, dof)); Val = np.empty((self.nnz, dof * dof)); Kd = np.empty((self.nnz, 12))
+        rc = lib().ref_asm_bfolw(self.h, IENb.shape[1], IENb.shape[0], _p(IENb), _p(gE), _p(par), _p(hg), _p(Dg), _p(R), _p(Val), _p(Kd))
         if rc != 0:
             raise RuntimeError(lib().ref_last_error().decode())
-        return R, Val
+        return (R, Val, Kd) if ustruct else (R, Val)
 
     def bneu(self, kind, IENb, gE, hg, Yg, *, dt, af, gam, rho=0.0, bfs=0.0, mvMsh=False, Do=None):
         """b_assem_neu_bc (S/eq_assem.cpp:58) on one face: kind "fluid" (b_fluid, dof 4) or "solid" (b_l_elas, dof 3).

@@ -1184,10 +1184,11 @@ int ref_pk2cc_dev(void* h, const double* par, const double* F9, const double* fl
   }
 }
 
-// Follower pressure load on one face of a struct equation (dof 3): eq_assem::b_neu_folw_p (S/eq_assem.cpp:186; get_nnx,
-// gnn, gnnb, struct_ns::b_struct_3d).  par = {dt, af, beta, tDof}.  Outputs the face's contribution alone.
+// Follower pressure load on one face of a struct or ustruct equation: eq_assem::b_neu_folw_p (S/eq_assem.cpp:186; get_nnx,
+// gnn, gnnb, struct_ns::b_struct_3d / ustruct::b_ustruct_3d + ustruct_do_assem).  par = {dt, af, beta, tDof, ustruct, am, gam}.
+// Outputs the face's contribution alone: struct R(3,nNo), Val(9,nnz); ustruct R(4,nNo), Val(16,nnz), Kd(12,nnz).
 int ref_asm_bfolw(void* h, int eNoNb, int nElb, const int* IENb, const int* gE, const double* par, const double* hg,
-                  const double* Dg, double* R, double* Val)
+                  const double* Dg, double* R, double* Val, double* Kd)
 {
   try {
     using namespace consts;
@@ -1195,16 +1196,19 @@ int ref_asm_bfolw(void* h, int eNoNb, int nElb, const int* IENb, const int* gE, 
     auto& com_mod = ctx->sim->com_mod;
     const int nNo = com_mod.tnNo;
     const int tDof = int(par[3]);
-    const int dof = 3;
+    const bool us = par[4] != 0.0;
+    const int dof = us ? 4 : 3;
+    const auto phys = us ? EquationType::phys_ustruct : EquationType::phys_struct;
     com_mod.tDof = tDof; com_mod.dof = dof; com_mod.dt = par[0]; com_mod.mvMsh = false;
     com_mod.cEq = 0; com_mod.nEq = 1;
     if (com_mod.eq.size() != 1) com_mod.eq.resize(1);
     auto& eq = com_mod.eq[0];
-    eq.phys = EquationType::phys_struct; eq.dof = dof; eq.s = 0; eq.e = dof - 1; eq.af = par[1]; eq.beta = par[2];
+    eq.phys = phys; eq.dof = dof; eq.s = 0; eq.e = dof - 1; eq.af = par[1]; eq.beta = par[2]; eq.am = par[5]; eq.gam = par[6];
     eq.nDmn = 1;
     if (eq.dmn.size() != 1) eq.dmn.resize(1);
     eq.dmn[0].Id = -1;
-    eq.dmn[0].phys = EquationType::phys_struct;
+    eq.dmn[0].phys = phys;
+    if (us) { com_mod.Kd.resize(12, ctx->nnz); com_mod.Kd = 0.0; }
     if (!eq.linear_algebra) eq.linear_algebra = new FsilsLinearAlgebra();
     auto& msh = com_mod.msh[0];
     msh.nFa = 1;
@@ -1227,6 +1231,7 @@ int ref_asm_bfolw(void* h, int eNoNb, int nElb, const int* IENb, const int* gE, 
     eq_assem::b_neu_folw_p(com_mod, lBc, fa, hg_v, Dg_a);
     std::memcpy(R, com_mod.R.data(), sizeof(double)*size_t(dof)*nNo);
     std::memcpy(Val, com_mod.Val.data(), sizeof(double)*size_t(dof)*dof*ctx->nnz);
+    if (us && Kd) std::memcpy(Kd, com_mod.Kd.data(), sizeof(double)*size_t(12)*ctx->nnz);
     return 0;
   } catch (const std::exception& e) {
     g_err = e.what();

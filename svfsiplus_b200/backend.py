@@ -77,7 +77,8 @@ class BneuProps(C.Structure):
 
 
 class BfolwProps(C.Structure):
-    _fields_ = [("dt", C.c_double), ("af", C.c_double), ("beta", C.c_double), ("tDof", C.c_int), ("s", C.c_int)]
+    _fields_ = [("dt", C.c_double), ("af", C.c_double), ("beta", C.c_double), ("tDof", C.c_int), ("s", C.c_int),
+                ("ustruct", C.c_int), ("am", C.c_double), ("gam", C.c_double)]
 
 
 class PicEq(C.Structure):
@@ -457,10 +458,11 @@ class Backend:
         IENb = _c(IENb, np.int32); gE = _c(gE, np.int32)
         self._ck(self.L.b200_face_mesh_set(self.h, faIn, IENb.shape[1], IENb.shape[0], _p(IENb), _p(gE)), "b200_face_mesh_set")
 
-    def assemble_bfolw(self, faIn, hg, *, dt, af, beta, tDof=3, s=0):
-        """b_neu_folw_p: follower pressure load on a struct face (dof 3)."""
+    def assemble_bfolw(self, faIn, hg, *, dt, af, beta=0.0, tDof=3, s=0, ustruct=False, am=1.0, gam=0.0):
+        """b_neu_folw_p: follower pressure load on a struct (dof 3) or ustruct (dof 4, + Kd) face."""
         p = BfolwProps()
         p.dt, p.af, p.beta, p.tDof, p.s = dt, af, beta, tDof, s
+        p.ustruct, p.am, p.gam = int(ustruct), am, gam
         hg = _c(hg, np.float64)
         self._ck(self.L.b200_assemble_bfolw(self.h, faIn, C.byref(p), _p(hg)), "b200_assemble_bfolw")
 

@@ -90,13 +90,13 @@ struct b200_handle {
     std::vector<int> h_parent, pnodes;
     int nPUR = 0, nPUK = 0;
     int *parent = nullptr, *prslot = nullptr, *pkslot = nullptr, *pudestR = nullptr, *pusegR = nullptr, *pudestK = nullptr, *pusegK = nullptr;
-    double *pstageR = nullptr, *pstageK = nullptr;
+    double *pstageR = nullptr, *pstageK = nullptr, *pstageKm = nullptr;
     void release()
     {
       cudaFree(ienb); cudaFree(inode); cudaFree(rslot); cudaFree(kslot); cudaFree(udestR); cudaFree(usegR); cudaFree(udestK);
       cudaFree(usegK); cudaFree(tab); cudaFree(stageR); cudaFree(stageT); cudaFree(hg);
       cudaFree(parent); cudaFree(prslot); cudaFree(pkslot); cudaFree(pudestR); cudaFree(pusegR); cudaFree(pudestK); cudaFree(pusegK);
-      cudaFree(pstageR); cudaFree(pstageK);
+      cudaFree(pstageR); cudaFree(pstageK); cudaFree(pstageKm);
       *this = FaceMesh();
     }
   };
@@ -1394,11 +1394,11 @@ void launch_face_nrm(b200_handle* h, b200_handle::FaceMesh& f, const double* geo
 extern "C++" {
 namespace {
 template <int NP, int NB, int NG>
-void launch_bfolw(b200_handle* h, b200_handle::FaceMesh& f, const FolwConsts& c)
+void launch_bfolw(b200_handle* h, b200_handle::FaceMesh& f, const FolwConsts& c, bool ustruct)
 {
   auto& ops = *h->ops;
   k_bfolw_elem<NP, NB, NG><<<(f.nElb + 63)/64, 64, 0, ops.st>>>(f.nElb, c, f.tab, f.ienb, f.parent, f.inode, f.prslot, f.pkslot, h->d_x,
-                                                              h->d_Dg, f.hg, f.pstageR, f.pstageK, h->d_err);
+                                                              h->d_Dg, f.hg, f.pstageR, f.pstageK, ustruct ? f.pstageKm : nullptr, h->d_err);
   CU_CHECK(cudaGetLastError());
   ops.post();
 }
@@ -1412,7 +1412,9 @@ int b200_assemble_bfolw(b200_handle* h, int faIn, const b200_bfolw_props* p, con
     if (faIn < 0 || faIn >= int(h->fmesh.size()) || h->fmesh[faIn].eNoNb == 0) throw std::runtime_error("assemble_bfolw: no face mesh (b200_face_mesh_set)");
     auto& f = h->fmesh[faIn];
     if (f.nElb == 0) return;
-    if (h->dof != 3 || !h->Val) throw std::runtime_error("assemble_bfolw: the follower pressure load acts on a struct equation: call b200_zero(h, 3) first");
+    const bool us = p->ustruct != 0;
+    if (h->dof != (us ? 4 : 3) || !h->Val) throw std::runtime_error("assemble_bfolw: call b200_zero first (dof 3 for struct, 4 for ustruct)");
+    if (us && !h->Kd) throw std::runtime_error("assemble_bfolw: no device Kd (b200_assemble_ustruct builds it)");
     if (!h->d_Dg || p->tDof != h->tDof) throw std::runtime_error("assemble_bfolw: no displacement state (b200_disp_set / b200_pici) or tDof differs");
     if (p->s < 0 || p->s + 3 > p->tDof) throw std::runtime_error("assemble_bfolw: equation offset outside the state");
     const int NP = h->eNoN, NB = f.eNoNb;
@@ -1446,6 +1448,7 @@ int b200_assemble_bfolw(b200_handle* h, int faIn, const b200_bfolw_props* p, con
       f.pudestK = upload(udK.data(), udK.size(), ops.st); f.pusegK = upload(usK.data(), usK.size(), ops.st);
       CU_CHECK(cudaMalloc(&f.pstageR, sizeof(double)*rslot.size()*3));
       CU_CHECK(cudaMalloc(&f.pstageK, sizeof(double)*kslot.size()*6));
+      CU_CHECK(cudaMalloc(&f.pstageKm, sizeof(double)*kslot.size()*6));
       f.pnodes = f.h_parent;
       std::sort(f.pnodes.begin(), f.pnodes.end());
       f.pnodes.erase(std::unique(f.pnodes.begin(), f.pnodes.end()), f.pnodes.end());
@@ -1461,13 +1464,22 @@ int b200_assemble_bfolw(b200_handle* h, int faIn, const b200_bfolw_props* p, con
       cudaFree(d_idx); cudaFree(d_val);
     }
     FolwConsts c;
-    c.dt = p->dt; c.af = p->af; c.beta = p->beta; c.tDof = p->tDof; c.s = p->s;
+    c.afl = us ? p->af*p->gam*p->dt : p->af*p->beta*p->dt*p->dt;       // ustruct.cpp:140 / sv_struct.cpp:131
+    c.afm = us ? c.afl/p->am : 0.0;                                     // ustruct.cpp:141
+    c.tDof = p->tDof; c.s = p->s;
     fill_folw_parent(c, h->tab);
-    if (NP == 4) launch_bfolw<4, 3, 3>(h, f, c);
-    else if (NP == 8) launch_bfolw<8, 4, 4>(h, f, c);
-    else launch_bfolw<10, 6, 7>(h, f, c);
-    k_bneu_sum_R<<<(f.nPUR + 127)/128, 128, 0, ops.st>>>(f.nPUR, 3, f.pudestR, f.pusegR, f.pstageR, h->R); ops.post();
-    k_bfolw_sum_K<<<(f.nPUK + 127)/128, 128, 0, ops.st>>>(f.nPUK, f.pudestK, f.pusegK, f.pstageK, h->Val); ops.post();
+    if (NP == 4) launch_bfolw<4, 3, 3>(h, f, c, us);
+    else if (NP == 8) launch_bfolw<8, 4, 4>(h, f, c, us);
+    else launch_bfolw<10, 6, 7>(h, f, c, us);
+    const Idx6 i3 = {{1, 3, 2, 6, 5, 7}}, i4 = {{1, 4, 2, 8, 6, 9}};
+    const int gK = (f.nPUK + 127)/128;
+    k_bneu_sum_R<<<(f.nPUR + 127)/128, 128, 0, ops.st>>>(f.nPUR, h->dof, f.pudestR, f.pusegR, f.pstageR, h->R); ops.post();
+    if (!us) {
+      k_bfolw_sum_K<<<gK, 128, 0, ops.st>>>(f.nPUK, 9, i3, f.pudestK, f.pusegK, f.pstageK, h->Val); ops.post();
+    } else {
+      k_bfolw_sum_K<<<gK, 128, 0, ops.st>>>(f.nPUK, 12, i3, f.pudestK, f.pusegK, f.pstageK, h->Kd); ops.post();
+      k_bfolw_sum_K<<<gK, 128, 0, ops.st>>>(f.nPUK, 16, i4, f.pudestK, f.pusegK, f.pstageKm, h->Val); ops.post();
+    }
     int flag = 0;
     CU_CHECK(cudaMemcpyAsync(&flag, h->d_err, sizeof(int), cudaMemcpyDeviceToHost, ops.st));
     CU_CHECK(cudaStreamSynchronize(ops.st));

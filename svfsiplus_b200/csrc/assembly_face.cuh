@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(64)
 k_bfolw_elem(int nElb, FolwConsts c, const double* __restrict__ tab, const int* __restrict__ ienb, const int* __restrict__ parent,
              const int* __restrict__ inode, const int* __restrict__ rslot, const int* __restrict__ kslot, const double* __restrict__ x,
              const double* __restrict__ Dg, const double* __restrict__ hg, double* __restrict__ stageR, double* __restrict__ stageK,
+             double* __restrict__ stageKm,      // ustruct: the afm-scaled copy for the velocity block of Val; null for struct
              int* __restrict__ err_flag)
 {
   __shared__ double s_tab[NG + NG*NB + NG*NB*2];
@@ -169,32 +170,36 @@ k_bfolw_elem(int nElb, FolwConsts c, const double* __restrict__ tab, const int* 
   for (int a = 0; a < NB; a++) nd[a] = ienb[size_t(e)*NB + a];
 #pragma unroll
   for (int a = 0; a < NP; a++) pn[a] = parent[size_t(e)*NP + a];
-  double lR[NP*3], lK6[NP*NP*6];
-  if (face_follower_element<NP, NB, NG>(c, pn, nd, inode[e], x, Dg, hg, s_tab, s_tab + NG, s_tab + NG + NG*NB, lR, lK6) != 0)
+  double lR[NP*3], lK6[NP*NP*6], lK6m[NP*NP*6];
+  if (face_follower_element<NP, NB, NG>(c, pn, nd, inode[e], x, Dg, hg, s_tab, s_tab + NG, s_tab + NG + NG*NB, lR, lK6,
+                                        stageKm ? lK6m : nullptr) != 0)
     atomicExch(err_flag, e + 1);
   for (int a = 0; a < NP; a++) {
     double* o = stageR + size_t(rslot[size_t(e)*NP + a])*3;
     o[0] = lR[a*3]; o[1] = lR[a*3 + 1]; o[2] = lR[a*3 + 2];
   }
   for (int q = 0; q < NP*NP; q++) {
-    double* o = stageK + size_t(kslot[size_t(e)*NP*NP + q])*6;
-    for (int i = 0; i < 6; i++) o[i] = lK6[q*6 + i];
+    const size_t sl = size_t(kslot[size_t(e)*NP*NP + q])*6;
+    for (int i = 0; i < 6; i++) stageK[sl + i] = lK6[q*6 + i];
+    if (stageKm) for (int i = 0; i < 6; i++) stageKm[sl + i] = lK6m[q*6 + i];
   }
 }
 
-// Val(dof 3 block) += run of staged off-diagonal entries: (0,1), (1,0), (0,2), (2,0), (1,2), (2,1)
-__global__ void k_bfolw_sum_K(int nU, const int* __restrict__ udest, const int* __restrict__ useg, const double* __restrict__ stageK,
-                              double* __restrict__ Val)
+// out(block of bs doubles) += run of the six staged off-diagonal entries (0,1), (1,0), (0,2), (2,0), (1,2), (2,1), whose positions
+// inside the block are idx: {1,3,2,6,5,7} in a 3x3 block (struct Val, ustruct Kd), {1,4,2,8,6,9} in a 4x4 block (ustruct Val).
+struct Idx6 { int i[6]; };
+__global__ void k_bfolw_sum_K(int nU, int bs, Idx6 idx, const int* __restrict__ udest, const int* __restrict__ useg,
+                              const double* __restrict__ stageK, double* __restrict__ out)
 {
   const int t = blockIdx.x*blockDim.x + threadIdx.x;
   if (t >= nU) return;
-  double* v = Val + size_t(udest[t])*9;
-  double a0 = v[1], a1 = v[3], a2 = v[2], a3 = v[6], a4 = v[5], a5 = v[7];
+  double* v = out + size_t(udest[t])*bs;
+  double a0 = v[idx.i[0]], a1 = v[idx.i[1]], a2 = v[idx.i[2]], a3 = v[idx.i[3]], a4 = v[idx.i[4]], a5 = v[idx.i[5]];
   for (int q = useg[t]; q < useg[t + 1]; q++) {
     const double* s = stageK + size_t(q)*6;
     a0 += s[0]; a1 += s[1]; a2 += s[2]; a3 += s[3]; a4 += s[4]; a5 += s[5];
   }
-  v[1] = a0; v[3] = a1; v[2] = a2; v[6] = a3; v[5] = a4; v[7] = a5;
+  v[idx.i[0]] = a0; v[idx.i[1]] = a1; v[idx.i[2]] = a2; v[idx.i[3]] = a3; v[idx.i[4]] = a4; v[idx.i[5]] = a5;
 }
 
 // rows of IEN for a list of elements (face parents), to find the interior node on the host

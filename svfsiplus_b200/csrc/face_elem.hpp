@@ -321,7 +321,8 @@ SVB_HD void inv3(const double A[3][3], double Ai[3][3])
 }
 
 struct FolwConsts {
-  double dt, af, beta;      // com_mod.dt, eq.af, eq.beta
+  double afl;               // tangent factor: struct eq.af*eq.beta*dt*dt (sv_struct.cpp:131), ustruct eq.af*eq.gam*dt (ustruct.cpp:140)
+  double afm;               // ustruct only: afl / eq.am, the factor of the velocity-block copy of the tangent (ustruct.cpp:141)
   int tDof, s;              // state width and eq.s (rows of the displacement in Dg)
   double xi0[3];            // mean of the parent's Gauss points: start of the Newton inverse map (eq_assem.cpp:249-253)
   double xib[2][3];         // bounds of the parent's parametric coordinates (+- 1e-4, nn.cpp:186-293)
@@ -344,12 +345,14 @@ inline void fill_folw_parent(FolwConsts& c, const ElemTables& t)
 
 // One face element with NB nodes / NG Gauss points of a parent with NP nodes.  pn[NP]: parent nodes (assembly ids), nd[NB]: face
 // nodes, inode: a parent node off the face.  Outputs lR[a*3 + i] (a over the PARENT nodes) and lK6[(a*NP + b)*6 + q] = the six
-// off-diagonal entries (0,1), (1,0), (0,2), (2,0), (1,2), (2,1) of the 3x3 block (a,b); the diagonal stays zero.
+// off-diagonal entries (0,1), (1,0), (0,2), (2,0), (1,2), (2,1) of the 3x3 block (a,b); the diagonal stays zero.  For the
+// struct equation that is lK (b_struct_3d); for ustruct it is lKd and lK6m != null receives the velocity-block entries
+// afm*Ku of lK (b_ustruct_3d, ustruct.cpp:132-211).
 // Returns 0, or 1 when the inverse map fails (the reference throws "Error in computing shape functions", nn.cpp:362).
 template <int NP, int NB, int NG>
 SVB_HD_NOINL int face_follower_element(const FolwConsts& c, const int* pn, const int* nd, int inode, const double* x, const double* Dg,
                                        const double* hg, const double* wtab, const double* Ntab, const double* Nxtab,
-                                       double* lR, double* lK6)
+                                       double* lR, double* lK6, double* lK6m)
 {
   const int tD = c.tDof;
   double xl[NP][3], dl[NP][3], hl[NP];
@@ -363,7 +366,8 @@ SVB_HD_NOINL int face_follower_element(const FolwConsts& c, const int* pn, const
   for (int i = 0; i < 3; i++) xin[i] = x[size_t(inode)*3 + i];
   for (int q = 0; q < NP*3; q++) lR[q] = 0.0;
   for (int q = 0; q < NP*NP*6; q++) lK6[q] = 0.0;
-  const double afl = c.af*c.beta*c.dt*c.dt;
+  if (lK6m) for (int q = 0; q < NP*NP*6; q++) lK6m[q] = 0.0;
+  const double afl = c.afl, afm = c.afm;
   int fail = 0;
   for (int g = 0; g < NG; g++) {
     // physical position of the face Gauss point
@@ -486,12 +490,16 @@ SVB_HD_NOINL int face_follower_element(const FolwConsts& c, const int* pn, const
       for (int i = 0; i < 3; i++) lR[a*3 + i] = lR[a*3 + i] - wl*N[a]*nFi[i];
       for (int b = 0; b < NP; b++) {
         double* k6 = lK6 + (a*NP + b)*6;
+        double* m6 = lK6m ? lK6m + (a*NP + b)*6 : nullptr;
         double Ku = wl*afl*N[a]*(nFi[1]*NxFi[b][0] - nFi[0]*NxFi[b][1]);
         k6[0] = k6[0] + Ku; k6[1] = k6[1] - Ku;
+        if (m6) { m6[0] = m6[0] + afm*Ku; m6[1] = m6[1] - afm*Ku; }
         Ku = wl*afl*N[a]*(nFi[2]*NxFi[b][0] - nFi[0]*NxFi[b][2]);
         k6[2] = k6[2] + Ku; k6[3] = k6[3] - Ku;
+        if (m6) { m6[2] = m6[2] + afm*Ku; m6[3] = m6[3] - afm*Ku; }
         Ku = wl*afl*N[a]*(nFi[2]*NxFi[b][1] - nFi[1]*NxFi[b][2]);
         k6[4] = k6[4] + Ku; k6[5] = k6[5] - Ku;
+        if (m6) { m6[4] = m6[4] + afm*Ku; m6[5] = m6[5] - afm*Ku; }
       }
     }
   }

@@ -358,14 +358,17 @@ bool B200LinearAlgebra::assemble_face(ComMod& com_mod, const faceType& lFa, cons
   return true;
 }
 
-/// Follower pressure load on the device (b_neu_folw_p, eq_assem.cpp:186) for a single-domain struct equation.
+/// Follower pressure load on the device (b_neu_folw_p, eq_assem.cpp:186) for a single-domain struct or ustruct equation.
 bool B200LinearAlgebra::assemble_follower_face(ComMod& com_mod, const faceType& lFa, const Vector<double>& hg, const Array<double>& Dg)
 {
   using namespace consts;
-  if (!device_assembly_ || !any_device_contribution_ || com_mod.nsd != 3 || com_mod.dof != 3 || com_mod.mvMsh) return false;
+  if (!device_assembly_ || !any_device_contribution_ || com_mod.nsd != 3 || com_mod.mvMsh) return false;
   auto& eq = com_mod.eq[com_mod.cEq];
   const auto& msh = com_mod.msh[lFa.iM];
-  if (eq.nDmn != 1 || eq.dmn[0].phys != EquationType::phys_struct || msh.lShl || mesh_uploaded_ != &msh) return false;
+  if (eq.nDmn != 1 || msh.lShl || mesh_uploaded_ != &msh) return false;
+  const bool us = (eq.dmn[0].phys == EquationType::phys_ustruct);
+  if (!us && eq.dmn[0].phys != EquationType::phys_struct) return false;
+  if (com_mod.dof != (us ? 4 : 3) || (us && !ustruct_on_device_)) return false;
   const bool pair_ok = (msh.eType == ElementType::TET4 && lFa.eType == ElementType::TRI3) ||
                        (msh.eType == ElementType::HEX8 && lFa.eType == ElementType::QUD4) ||
                        (msh.eType == ElementType::TET10 && lFa.eType == ElementType::TRI6);
@@ -378,6 +381,7 @@ bool B200LinearAlgebra::assemble_follower_face(ComMod& com_mod, const faceType& 
   }
   b200_bfolw_props p;
   p.dt = com_mod.dt; p.af = eq.af; p.beta = eq.beta; p.tDof = com_mod.tDof; p.s = eq.s;
+  p.ustruct = us ? 1 : 0; p.am = eq.am; p.gam = eq.gam;
   (void)Dg;      // the device holds the Dg uploaded for the volume assembly of this iteration
   check(b200_assemble_bfolw(h_, it->second, &p, hg.data()), "b200_assemble_bfolw");
   return true;

@@ -201,15 +201,17 @@ void host_pk2cc(const double* par, const double* F9, const double* fl6, double* 
   pk2cc_iso(c, F, fl6, S6, Dm21);
 }
 
-// Follower pressure load (face_follower_element): b_neu_folw_p on one face of a struct equation (dof 3), serial.
-// par = {dt, af, beta, tDof, s}.  R(3,nNo), Val(9,nnz) must be zero on entry.
+// Follower pressure load (face_follower_element): b_neu_folw_p on one face, serial.  par = {afl, afm, tDof, s, ustruct}.
+// struct (ustruct = 0): R(3,nNo), Val(9,nnz); ustruct: R(4,nNo), Val(16,nnz), Kd(12,nnz).  All zero on entry.
 extern "C++" {
 namespace {
 template <int NP, int NB, int NG>
-int bfolw(const FolwConsts& c, const FaceTables& ft, const double* N, const double* Nx, const int* ien, int nElb, const int* IENb,
-          const int* gE, const double* x, const double* Dg, const double* hg, const int* rowPtr, const int* colPtr, double* R, double* Val)
+int bfolw(const FolwConsts& c, bool ustruct, const FaceTables& ft, const double* N, const double* Nx, const int* ien, int nElb, const int* IENb,
+          const int* gE, const double* x, const double* Dg, const double* hg, const int* rowPtr, const int* colPtr, double* R, double* Val,
+          double* Kd)
 {
-  std::vector<double> lR(NP*3), lK6(NP*NP*6);
+  std::vector<double> lR(NP*3), lK6(NP*NP*6), lK6m(NP*NP*6);
+  const int dof = ustruct ? 4 : 3;
   for (int e = 0; e < nElb; e++) {
     const int* nd = IENb + size_t(e)*NB;
     const int* pn = ien + size_t(gE[e])*NP;
@@ -217,17 +219,26 @@ int bfolw(const FolwConsts& c, const FaceTables& ft, const double* N, const doub
     for (int b = 0; b < NP && inode < 0; b++)
       if (std::find(nd, nd + NB, pn[b]) == nd + NB) inode = pn[b];
     if (inode < 0) return e + 1;
-    if (face_follower_element<NP, NB, NG>(c, pn, nd, inode, x, Dg, hg, ft.w, N, Nx, lR.data(), lK6.data()) != 0) return -(e + 1);
+    if (face_follower_element<NP, NB, NG>(c, pn, nd, inode, x, Dg, hg, ft.w, N, Nx, lR.data(), lK6.data(), ustruct ? lK6m.data() : nullptr) != 0)
+      return -(e + 1);
     for (int a = 0; a < NP; a++) {
-      for (int i = 0; i < 3; i++) R[size_t(pn[a])*3 + i] += lR[a*3 + i];
+      for (int i = 0; i < 3; i++) R[size_t(pn[a])*dof + i] += lR[a*3 + i];
       const int* beg = colPtr + rowPtr[pn[a]];
       const int* end = colPtr + rowPtr[pn[a] + 1];
       for (int b = 0; b < NP; b++) {
         const int* it = std::lower_bound(beg, end, pn[b]);
         if (it == end || *it != pn[b]) return -1000000;
-        double* v = Val + size_t(it - colPtr)*9;
         const double* k6 = &lK6[(a*NP + b)*6];
-        v[1] += k6[0]; v[3] += k6[1]; v[2] += k6[2]; v[6] += k6[3]; v[5] += k6[4]; v[7] += k6[5];
+        if (!ustruct) {
+          double* v = Val + size_t(it - colPtr)*9;
+          v[1] += k6[0]; v[3] += k6[1]; v[2] += k6[2]; v[6] += k6[3]; v[5] += k6[4]; v[7] += k6[5];
+        } else {
+          double* kd = Kd + size_t(it - colPtr)*12;
+          kd[1] += k6[0]; kd[3] += k6[1]; kd[2] += k6[2]; kd[6] += k6[3]; kd[5] += k6[4]; kd[7] += k6[5];
+          const double* m6 = &lK6m[(a*NP + b)*6];
+          double* v = Val + size_t(it - colPtr)*16;
+          v[1] += m6[0]; v[4] += m6[1]; v[2] += m6[2]; v[8] += m6[3]; v[6] += m6[4]; v[9] += m6[5];
+        }
       }
     }
   }
@@ -237,11 +248,13 @@ int bfolw(const FolwConsts& c, const FaceTables& ft, const double* N, const doub
 } // extern "C++"
 
 int host_bfolw_assemble(int eNoN, const int* ien, int eNoNb, int nElb, const int* IENb, const int* gE, const double* par,
-                        const double* x, const double* Dg, const double* hg, const int* rowPtr, const int* colPtr, double* R, double* Val)
+                        const double* x, const double* Dg, const double* hg, const int* rowPtr, const int* colPtr, double* R, double* Val,
+                        double* Kd)
 {
   if (!face_supported(eNoNb) || !elem_supported(eNoN)) return -1000001;
   FolwConsts c;
-  c.dt = par[0]; c.af = par[1]; c.beta = par[2]; c.tDof = int(par[3]); c.s = int(par[4]);
+  c.afl = par[0]; c.afm = par[1]; c.tDof = int(par[2]); c.s = int(par[3]);
+  const bool us = par[4] != 0.0;
   ElemTables et;
   fill_tables(et, eNoN, (5.0 + 3.0*std::sqrt(5.0))/20.0);
   fill_folw_parent(c, et);
@@ -253,9 +266,9 @@ int host_bfolw_assemble(int eNoN, const int* ien, int eNoNb, int nElb, const int
       N[g*eNoNb + a] = t.N[g][a];
       Nx[(g*eNoNb + a)*2] = t.Nx[g][a][0]; Nx[(g*eNoNb + a)*2 + 1] = t.Nx[g][a][1];
     }
-  if (eNoN == 4 && eNoNb == 3) return bfolw<4, 3, 3>(c, t, N.data(), Nx.data(), ien, nElb, IENb, gE, x, Dg, hg, rowPtr, colPtr, R, Val);
-  if (eNoN == 8 && eNoNb == 4) return bfolw<8, 4, 4>(c, t, N.data(), Nx.data(), ien, nElb, IENb, gE, x, Dg, hg, rowPtr, colPtr, R, Val);
-  if (eNoN == 10 && eNoNb == 6) return bfolw<10, 6, 7>(c, t, N.data(), Nx.data(), ien, nElb, IENb, gE, x, Dg, hg, rowPtr, colPtr, R, Val);
+  if (eNoN == 4 && eNoNb == 3) return bfolw<4, 3, 3>(c, us, t, N.data(), Nx.data(), ien, nElb, IENb, gE, x, Dg, hg, rowPtr, colPtr, R, Val, Kd);
+  if (eNoN == 8 && eNoNb == 4) return bfolw<8, 4, 4>(c, us, t, N.data(), Nx.data(), ien, nElb, IENb, gE, x, Dg, hg, rowPtr, colPtr, R, Val, Kd);
+  if (eNoN == 10 && eNoNb == 6) return bfolw<10, 6, 7>(c, us, t, N.data(), Nx.data(), ien, nElb, IENb, gE, x, Dg, hg, rowPtr, colPtr, R, Val, Kd);
   return -1000002;
 }
 

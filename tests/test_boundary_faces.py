@@ -293,3 +293,54 @@ def test_gpu_follower_pressure_matches_golden(elem, n):
     be.assemble_bfolw(3, hg, dt=p["dt"], af=p["af"], beta=p["beta"])
     assert rel_inf(be.get_R(), R0 + g[f"R_folw_{elem}"]) < 1e-12 and rel_inf(be.get_Val(), V0 + g[f"Val_folw_{elem}"]) < 1e-12
     be.close()
+
+
+def _folw_ustruct_setup(elem, n):
+    case = P.ustruct_case(n, elem=elem)
+    m = case["mesh"]
+    on = np.abs(m.x[:, 2] - 1.0) < 1e-12
+    IENb, gE = M.face_elements(m, on)
+    rng = np.random.default_rng(3)
+    hg = np.where(on, 1.0e4 * (1.0 + 0.1 * rng.standard_normal(m.nNo)), 0.0)
+    return case, IENb, gE, hg
+
+
+@pytest.mark.parametrize("elem,n", ELEMS)
+@needs_ref
+def test_host_ustruct_follower_pressure_matches_reference_bitwise(elem, n):
+    """b_ustruct_3d + ustruct_do_assem (ustruct.cpp:132, 1579): R, the velocity block of Val and Kd."""
+    from oracle import ref
+    case, IENb, gE, hg = _folw_ustruct_setup(elem, n)
+    m, p = case["mesh"], case["props"]
+    kw = dict(dt=p["dt"], af=p["af"], ustruct=True, am=p["am"], gam=p["gam"])
+    ra = ref.RefAssembly(m.x, m.ien)
+    Rr, Vr, Kr = ra.bfolw(IENb, gE, hg, case["Dg"], **kw)
+    ra.close()
+    R, Val, Kd = host_bfolw_assemble(m, IENb, gE, hg, case["Dg"], case["rowPtr"], case["colPtr"], **kw)
+    assert np.abs(Rr).max() > 0 and np.abs(Vr).max() > 0 and np.abs(Kr).max() > 0
+    assert np.array_equal(R, Rr) and np.array_equal(Val, Vr) and np.array_equal(Kd, Kr)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("elem,n", ELEMS)
+def test_gpu_ustruct_follower_pressure(elem, n):
+    """On top of the ustruct volume assembly: R, Val and Kd grow by what the host run of the same arithmetic gives
+    (pinned bit for bit to the reference on the CPU) -- and by the reference itself where it travelled."""
+    case, IENb, gE, hg = _folw_ustruct_setup(elem, n)
+    m, p = case["mesh"], case["props"]
+    kw = dict(dt=p["dt"], af=p["af"], ustruct=True, am=p["am"], gam=p["gam"])
+    Rh, Vh, Kh = host_bfolw_assemble(m, IENb, gE, hg, case["Dg"], case["rowPtr"], case["colPtr"], **kw)
+    be = P.setup_backend(case)
+    be.face_mesh_set(0, IENb, gE)
+    P.assemble_ustruct(be, case)
+    R0, V0, K0 = be.get_R(), be.get_Val(), be.get_Kd()
+    be.assemble_bfolw(0, hg, tDof=4, **kw)
+    assert rel_inf(be.get_R(), R0 + Rh) < 1e-12 and rel_inf(be.get_Val(), V0 + Vh) < 1e-12 and rel_inf(be.get_Kd(), K0 + Kh) < 1e-12
+    assert rel_inf(be.get_Kd() - K0, Kh) < 1e-9              # the face's own share of Kd (difference of assembled numbers)
+    from oracle import ref
+    if ref.available():
+        ra = ref.RefAssembly(m.x, m.ien)
+        Rr, Vr, Kr = ra.bfolw(IENb, gE, hg, case["Dg"], **kw)
+        ra.close()
+        assert np.array_equal(Rh, Rr) and np.array_equal(Kh, Kr)
+    be.close()

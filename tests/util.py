@@ -75,7 +75,7 @@ def elemhost():
                                           C.c_int, C.c_void_p]
         _eh.host_pk2cc.argtypes = [C.c_void_p] * 5
         _eh.host_pk2cc.restype = None
-        _eh.host_bfolw_assemble.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 10
+        _eh.host_bfolw_assemble.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 11
         _eh.host_bneu_assemble.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 11
     return _eh
 
@@ -159,17 +159,21 @@ def host_pk2cc(F, fl, *, iso, vol, C10=0.0, C01=0.0, Kpen=0.0, ho=None, Tfa=0.0,
     return S6, Dm21
 
 
-def host_bfolw_assemble(mesh, IENb, gE, hg, Dg, rowPtr, colPtr, *, dt, af, beta, s=0):
-    """face_elem.hpp face_follower_element (b_neu_folw_p: follower pressure on a struct face) run serially on the host."""
+def host_bfolw_assemble(mesh, IENb, gE, hg, Dg, rowPtr, colPtr, *, dt, af, beta=0.0, s=0, ustruct=False, am=1.0, gam=0.0):
+    """face_elem.hpp face_follower_element (b_neu_folw_p: follower pressure on a struct / ustruct face) run serially on the host.
+    Returns (R, Val) for struct, (R, Val, Kd) for ustruct."""
     L = elemhost()
     ien = np.ascontiguousarray(mesh.ien, np.int32); x = np.ascontiguousarray(mesh.x, np.float64)
     IENb = np.ascontiguousarray(IENb, np.int32); gE = np.ascontiguousarray(gE, np.int32)
     hg = np.ascontiguousarray(hg, np.float64); Dg = np.ascontiguousarray(Dg, np.float64)
     rp = np.ascontiguousarray(rowPtr, np.int32); cp = np.ascontiguousarray(colPtr, np.int32)
-    par = np.array([dt, af, beta, Dg.shape[1], s], np.float64)
-    R = np.zeros((mesh.nNo, 3)); Val = np.zeros((len(cp), 9))
+    afl = af * gam * dt if ustruct else af * beta * dt * dt
+    afm = afl / am if ustruct else 0.0
+    par = np.array([afl, afm, Dg.shape[1], s, float(ustruct)], np.float64)
+    dof = 4 if ustruct else 3
+    R = np.zeros((mesh.nNo, dof)); Val = np.zeros((len(cp), dof * dof)); Kd = np.zeros((len(cp), 12))
     rc = L.host_bfolw_assemble(ien.shape[1], _p(ien), IENb.shape[1], IENb.shape[0], _p(IENb), _p(gE), _p(par), _p(x), _p(Dg), _p(hg),
-                               _p(rp), _p(cp), _p(R), _p(Val))
+                               _p(rp), _p(cp), _p(R), _p(Val), _p(Kd))
     if rc != 0:
         raise RuntimeError(f"host_bfolw_assemble: rc {rc}")
-    return R, Val
+    return (R, Val, Kd) if ustruct else (R, Val)
