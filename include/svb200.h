@@ -53,7 +53,8 @@ typedef struct {
  * the equation's first unknown inside Ag/Yg/Dg(tDof,nNo).  isoType: 0 neo-Hookean (C10 = mu/2),
  * 1 St.Venant-Kirchhoff (C10 = lambda, C01 = mu), 2 modified StVK (C10 = kappa, C01 = mu), 3 Holzapfel-Ogden
  * (solver/mat_models_carray.h:905-1135; needs b200_mesh_fibers), 4 Mooney-Rivlin (C10, C01; :438-540),
- * 5 Holzapfel-Gasser-Ogden (:544-688; needs b200_mesh_fibers), 6 Guccione (C10, bff, bss, bfs; :692-903; needs b200_mesh_fibers);
+ * 5 Holzapfel-Gasser-Ogden (:544-688; needs b200_mesh_fibers), 6 Guccione (C10, bff, bss, bfs; :692-903; needs b200_mesh_fibers),
+ * 7 Holzapfel-Ogden with modified anisotropy (HO-ma, full fibre invariants; :1137-1353; needs b200_mesh_fibers);
  * volType: 0 none, 1 Quad, 2 ST91, 3 M94 (solver/mat_models.cpp:1626-1645). */
 typedef struct {
   double dt, am, af, gam, beta;
@@ -79,7 +80,7 @@ typedef struct {
 /* Mixed velocity-pressure solid (ustruct; solver/ustruct.cpp:1158-1575, 632-876).  elM, nu, ctM, ctC feed
  * get_tau (solver/mat_models.cpp:1655); Kpen, volType feed g_vol_pen (:1696).  isoType as in the struct properties, the
  * laws with an isochoric split (get_pk2cc_dev, mat_models.cpp:630): 0 neo-Hookean, 3 Holzapfel-Ogden, 4 Mooney-Rivlin,
- * 5 Holzapfel-Gasser-Ogden, 6 Guccione (3, 5, 6 need b200_mesh_fibers). */
+ * 5 Holzapfel-Gasser-Ogden, 6 Guccione, 7 HO-ma (3, 5, 6, 7 need b200_mesh_fibers). */
 typedef struct {
   double dt, am, af, gam;
   int tDof, s;

@@ -363,7 +363,7 @@ class RefAssembly:
             raise RuntimeError(lib().ref_last_error().decode())
         return S, Dm
 
-    ISO = {"nHook": 0, "StVK": 1, "mStVK": 2, "HO": 3, "MR": 4, "HGO": 5, "Gucci": 6}
+    ISO = {"nHook": 0, "StVK": 1, "mStVK": 2, "HO": 3, "MR": 4, "HGO": 5, "Gucci": 6, "HO_ma": 7}
     HO_KEYS = ("a", "b", "aff", "bff", "ass", "bss", "afs", "bfs", "khs")
 
     def set_fibers(self, fN):

@@ -301,7 +301,8 @@ void configure_solid(AsmCtx* ctx, int kind, int tDof, int s, const double* par, 
                     : (iso == 2) ? ConstitutiveModelType::stIso_mStVK
                     : (iso == 4) ? ConstitutiveModelType::stIso_MR
                     : (iso == 5) ? ConstitutiveModelType::stIso_HGO
-                    : (iso == 6) ? ConstitutiveModelType::stIso_Gucci : ConstitutiveModelType::stIso_HO;
+                    : (iso == 6) ? ConstitutiveModelType::stIso_Gucci
+                    : (iso == 7) ? ConstitutiveModelType::stIso_HO_ma : ConstitutiveModelType::stIso_HO;
     dmn.stM.volType = (vol == 1) ? ConstitutiveModelType::stVol_Quad
                     : (vol == 2) ? ConstitutiveModelType::stVol_ST91
                     : (vol == 3) ? ConstitutiveModelType::stVol_M94 : ConstitutiveModelType::stIso_NA;
@@ -551,7 +552,7 @@ double ref_asm_ustruct(void* h, int tDof, const double* par, const double* Ag, c
       const int iso = int(par[15]);
       dmn.stM.isoType = (iso == 3) ? ConstitutiveModelType::stIso_HO : (iso == 4) ? ConstitutiveModelType::stIso_MR
                       : (iso == 5) ? ConstitutiveModelType::stIso_HGO : (iso == 6) ? ConstitutiveModelType::stIso_Gucci
-                      : ConstitutiveModelType::stIso_nHook;
+                      : (iso == 7) ? ConstitutiveModelType::stIso_HO_ma : ConstitutiveModelType::stIso_nHook;
     }
     dmn.stM.volType = (vol == 1) ? ConstitutiveModelType::stVol_Quad
                     : (vol == 2) ? ConstitutiveModelType::stVol_ST91

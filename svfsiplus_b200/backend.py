@@ -88,7 +88,7 @@ class PicEq(C.Structure):
 
 PIC = dict(Ao=0, Yo=1, Do=2, An=3, Yn=4, Dn=5, Ad=6, Ag=7, Yg=8, Dg=9)
 
-ISO_TYPES = {"nHook": 0, "StVK": 1, "mStVK": 2, "HO": 3, "MR": 4, "HGO": 5, "Gucci": 6}
+ISO_TYPES = {"nHook": 0, "StVK": 1, "mStVK": 2, "HO": 3, "MR": 4, "HGO": 5, "Gucci": 6, "HO_ma": 7}
 VOL_TYPES = {None: 0, "Quad": 1, "ST91": 2, "M94": 3}
 
 EXPORTS = [

@@ -341,7 +341,7 @@ void launch_fluid(b200_handle* h, const FluidConsts& c, int nList, const int* d_
 
 SolidConsts struct_consts(const b200_struct_props* p)
 {
-  if (p->isoType < 0 || p->isoType > 6) throw std::runtime_error("assemble_struct: constitutive model has no device kernel");
+  if (p->isoType < 0 || p->isoType > 7) throw std::runtime_error("assemble_struct: constitutive model has no device kernel");
   if (p->volType < 0 || p->volType > 3) throw std::runtime_error("assemble_struct: dilational penalty model not defined");
   SolidConsts c;
   std::memset(&c, 0, sizeof(c));
@@ -364,7 +364,7 @@ void assemble_solid(b200_handle* h, const SolidConsts& c, const char* who)
   if (h->dof != 3 || !h->Val) throw std::runtime_error(std::string(who) + ": call b200_zero(h, 3) first");
   if (c.tDof != h->tDof) throw std::runtime_error(std::string(who) + ": tDof differs from the uploaded state");
   if (c.s < 0 || c.s + 3 > c.tDof) throw std::runtime_error(std::string(who) + ": equation offset outside the state");
-  if (c.kind == 0 && (c.iso == 3 || c.iso == 5 || c.iso == 6) && !h->d_fN) throw std::runtime_error(std::string(who) + ": the Holzapfel-Ogden laws need fibre directions (b200_mesh_fibers)");
+  if (c.kind == 0 && (c.iso == 3 || c.iso == 5 || c.iso == 6 || c.iso == 7) && !h->d_fN) throw std::runtime_error(std::string(who) + ": the Holzapfel-Ogden laws need fibre directions (b200_mesh_fibers)");
   ensure_stage(h, 3);
   const double t0 = wall_s();
   {
@@ -786,8 +786,8 @@ int b200_assemble_ustruct(b200_handle* h, const b200_ustruct_props* p)
     if (h->dof != 4 || !h->Val) throw std::runtime_error("assemble_ustruct: call b200_zero(h, 4) first");
     if (p->tDof != h->tDof) throw std::runtime_error("assemble_ustruct: tDof differs from the uploaded state");
     if (p->s < 0 || p->s + 4 > p->tDof) throw std::runtime_error("assemble_ustruct: equation offset outside the state");
-    if (p->isoType != 0 && (p->isoType < 3 || p->isoType > 6)) throw std::runtime_error("assemble_ustruct: constitutive model has no isochoric split (neo-Hookean, Holzapfel-Ogden, Mooney-Rivlin, HGO and Guccione have)");
-    if ((p->isoType == 3 || p->isoType == 5 || p->isoType == 6) && !h->d_fN) throw std::runtime_error("assemble_ustruct: the fibre-based laws need fibre directions (b200_mesh_fibers)");
+    if (p->isoType != 0 && (p->isoType < 3 || p->isoType > 7)) throw std::runtime_error("assemble_ustruct: constitutive model has no isochoric split (neo-Hookean, Holzapfel-Ogden, HO-ma, Mooney-Rivlin, HGO and Guccione have)");
+    if ((p->isoType == 3 || p->isoType == 5 || p->isoType == 6 || p->isoType == 7) && !h->d_fN) throw std::runtime_error("assemble_ustruct: the fibre-based laws need fibre directions (b200_mesh_fibers)");
     if (p->volType < 0 || p->volType > 3) throw std::runtime_error("assemble_ustruct: dilational penalty model not defined");
     UstructConsts c;
     std::memset(&c, 0, sizeof(c));
@@ -970,7 +970,7 @@ int b200_assemble_struct_dmn(b200_handle* h, int nDmn, const b200_struct_props* 
       cs.push_back(struct_consts(&p[d]));
       if (cs[d].tDof != h->tDof) throw std::runtime_error("assemble_struct_dmn: tDof differs from the uploaded state");
       if (cs[d].s < 0 || cs[d].s + 3 > cs[d].tDof) throw std::runtime_error("assemble_struct_dmn: equation offset outside the state");
-      if ((cs[d].iso == 3 || cs[d].iso == 5 || cs[d].iso == 6) && !h->d_fN) throw std::runtime_error("assemble_struct_dmn: the Holzapfel-Ogden law needs fibre directions (b200_mesh_fibers)");
+      if ((cs[d].iso == 3 || cs[d].iso == 5 || cs[d].iso == 6 || cs[d].iso == 7) && !h->d_fN) throw std::runtime_error("assemble_struct_dmn: the Holzapfel-Ogden law needs fibre directions (b200_mesh_fibers)");
     }
     if (covered != h->nEl) throw std::runtime_error("assemble_struct_dmn: every element must belong to a domain");
     ensure_stage(h, 3);

@@ -1,7 +1,7 @@
 // solid_law.hpp — constitutive laws of the displacement-based and mixed solid elements, host/device shared like
 // fluid_elem.hpp: 2nd Piola-Kirchhoff stress S and the Voigt elasticity matrix Dm from the deformation gradient.
 // Replaces mat_models_carray::get_pk2cc<3> (Code/Source/solver/mat_models_carray.h:182-1380; neo-Hookean :370-434,
-// Mooney-Rivlin :438-540, Holzapfel-Gasser-Ogden :544-688, Guccione :692-903, St.Venant-Kirchhoff :302-322, modified StVK :326-356, Holzapfel-Ogden :905-1135) with
+// Mooney-Rivlin :438-540, Holzapfel-Gasser-Ogden :544-688, Guccione :692-903, St.Venant-Kirchhoff :302-322, modified StVK :326-356, Holzapfel-Ogden :905-1135, HO-ma :1137-1353) with
 // get_svol_p (mat_models.cpp:1626-1645) and the fibre reinforcement stress (mat_models_carray.h:222-225).
 // tests/hostlogic/fluid_elem_host.cpp instantiates the same source on the CPU (test tree only) and
 // tests/test_solid_laws.py compares it with the compiled reference's get_pk2cc on random deformation gradients.
@@ -14,7 +14,7 @@ namespace svb200 {
 struct SolidConsts {
   double dt, am, af, gam, beta;
   double rho, dmp, f[3];
-  int iso, vol;                // iso: 0 nHook, 1 StVK, 2 mStVK, 3 Holzapfel-Ogden, 4 Mooney-Rivlin, 5 HGO, 6 Guccione; vol: 0 none, 1 Quad, 2 ST91, 3 M94
+  int iso, vol;                // iso: 0 nHook, 1 StVK, 2 mStVK, 3 Holzapfel-Ogden, 4 Mooney-Rivlin, 5 HGO, 6 Guccione, 7 Holzapfel-Ogden modified anisotropy (HO-ma); vol: 0 none, 1 Quad, 2 ST91, 3 M94
   double C10, C01, Kpen;
   double ho_a, ho_b, ho_aff, ho_bff, ho_ass, ho_bss, ho_afs, ho_bfs, ho_khs;   // stModelType a..bfs, khs
   double Tfa, Tsa;             // fibre / sheet reinforcement stress (get_fib_stress, mat_models_carray.h:222-225)
@@ -26,6 +26,18 @@ struct SolidConsts {
 
 // index of (I,J), I <= J, in the packed upper triangle of the 6x6 Voigt matrix
 SVB_HD int dm_idx(int I, int J) { return I*6 - (I*(I-1))/2 + (J - I); }
+
+// x^3 of the smoothed-Heaviside derivatives: the reference calls pow(x, 3) (correctly rounded in glibc), and the expression
+// -x + 3x^2 - 2x^3 cancels to ~1 - x for compressed fibres (x -> 1), so the host instantiation calls pow as well to stay
+// within rounding of the reference there; the device multiplies (CUDA's pow is not correctly rounded either way).
+SVB_HD double cube_d(double x)
+{
+#ifdef __CUDA_ARCH__
+  return x*x*x;
+#else
+  return pow(x, 3.0);
+#endif
+}
 
 struct HoParams { double a, b, aff, bff, ass, bss, afs, bfs, khs, Tfa, Tsa; };
 
@@ -54,7 +66,7 @@ SVB_HD_NOINL void ho_isochoric(const HoParams& h, const double C[3][3], const do
   const double of = 1.0/(exp(k*Eff) + 1.0), os = 1.0/(exp(k*Ess) + 1.0);
   const double c4f = 1.0 - of, c4s = 1.0 - os;
   const double dc4f = k*(of - of*of), dc4s = k*(os - os*os);
-  const double ddc4f = k*k*(-of + 3.0*of*of - 2.0*of*of*of), ddc4s = k*k*(-os + 3.0*os*os - 2.0*os*os*os);
+  const double ddc4f = k*k*(-of + 3.0*(of*of) - 2.0*cube_d(of)), ddc4s = k*k*(-os + 3.0*(os*os) - 2.0*cube_d(os));
   // stress coefficients
   const double g1 = h.a*exp(h.b*(Inv1 - 3.0));
   const double g2 = 2.0*h.afs*exp(h.bfs*Efs*Efs);
@@ -406,6 +418,70 @@ SVB_HD_NOINL void pk2cc_iso(const SolidConsts& c, const double F[3][3], const do
     for (int i = 0; i < 3; i++)
 #pragma unroll
       for (int j = 0; j < 3; j++) S[i][j] += p*J*Ci[i][j];
+  } else if (c.iso == 7) {
+    // Holzapfel-Ogden with modified anisotropy (HO-ma; mat_models_carray.h:1137-1353, mat_models.cpp:513-610 / :963-1054 for
+    // the mixed form): the isotropic exponential term is split isochorically (projected rank-one factor Hd = I - (1/3) tr(C) Ci,
+    // like the neo-Hookean part of the HO law), the fibre / sheet / fibre-sheet terms use the FULL invariants
+    // Inv4 = f.Cf, Inv6 = s.Cs, Inv8 = f.Cs and enter S and CC unprojected, after the volumetric terms.
+    const double J4d = J2d*J2d;
+    const double f0[3] = {fl[0], fl[1], fl[2]}, s0[3] = {fl[3], fl[4], fl[5]};
+    double Cf[3], Cs[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      Cf[i] = C[i][0]*f0[0] + C[i][1]*f0[1] + C[i][2]*f0[2];
+      Cs[i] = C[i][0]*s0[0] + C[i][1]*s0[1] + C[i][2]*s0[2];
+    }
+    const double Eff = (f0[0]*Cf[0] + f0[1]*Cf[1] + f0[2]*Cf[2]) - 1.0;
+    const double Ess = (s0[0]*Cs[0] + s0[1]*Cs[1] + s0[2]*Cs[2]) - 1.0;
+    const double Efs = f0[0]*Cs[0] + f0[1]*Cs[1] + f0[2]*Cs[2];
+    const double k = c.ho_khs;
+    const double of = 1.0/(exp(k*Eff) + 1.0), os = 1.0/(exp(k*Ess) + 1.0);
+    const double c4f = 1.0 - of, c4s = 1.0 - os;
+    const double dc4f = k*(of - of*of), dc4s = k*(os - os*os);
+    const double ddc4f = k*k*(-of + 3.0*(of*of) - 2.0*cube_d(of)), ddc4s = k*k*(-os + 3.0*(os*os) - 2.0*cube_d(os));
+    const double g1 = c.ho_a*exp(c.ho_b*(Inv1 - 3.0));
+    const double r1 = J2d/nd*(g1*trC);
+    const double gk0 = g1*2.0*J4d*c.ho_b;
+    double Hd[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const double d = (i == j) ? 1.0 : 0.0;
+        S[i][j] = J2d*(g1*d) - r1*Ci[i][j];
+        Hd[i][j] = d - (1.0/nd)*trC*Ci[i][j];
+      }
+    // anisotropic coefficients (stress: s_fs, s_ff, s_ss; stiffness: k_fs, k_ff, k_ss)
+    const double efs = 2.0*c.ho_afs*exp(c.ho_bfs*Efs*Efs);
+    const double s_fs = efs*Efs, k_fs = efs*2.0*(1.0 + 2.0*c.ho_bfs*Efs*Efs);
+    const double rexpf = exp(c.ho_bff*Eff*Eff), rexps = exp(c.ho_bss*Ess*Ess);
+    double s_ff = c4f*Eff*rexpf; s_ff = s_ff + (0.5*dc4f/c.ho_bff)*(rexpf - 1.0); s_ff = (2.0*c.ho_aff*s_ff) + c.Tfa;
+    double k_ff = c4f*(1.0 + (2.0*c.ho_bff*Eff*Eff)); k_ff = (k_ff + (2.0*dc4f*Eff))*rexpf; k_ff = k_ff + (0.5*ddc4f/c.ho_bff)*(rexpf - 1.0); k_ff = 4.0*c.ho_aff*k_ff;
+    double s_ss = c4s*Ess*rexps; s_ss = s_ss + (0.5*dc4s/c.ho_bss)*(rexps - 1.0); s_ss = 2.0*c.ho_ass*s_ss + c.Tsa;
+    double k_ss = c4s*(1.0 + (2.0*c.ho_bss*Ess*Ess)); k_ss = (k_ss + (2.0*dc4s*Ess))*rexps; k_ss = k_ss + (0.5*ddc4s/c.ho_bss)*(rexps - 1.0); k_ss = 4.0*c.ho_ass*k_ss;
+    const double c2 = 2.0*(r1 - p*J), c3 = pl*J - 2.0*r1/nd;
+#pragma unroll
+    for (int I = 0; I < 6; I++)
+#pragma unroll
+      for (int Jv = I; Jv < 6; Jv++) {
+        const int i = vi[I], j = vj[I], kk = vi[Jv], l = vj[Jv];
+        double cc = gk0*Hd[i][j]*Hd[kk][l];
+        cc -= (2.0/nd)*(Ci[i][j]*S[kk][l] + S[i][j]*Ci[kk][l]);                 // S: the isotropic isochoric stress only
+        cc += c2*(0.5*(Ci[i][kk]*Ci[j][l] + Ci[i][l]*Ci[j][kk])) + c3*(Ci[i][j]*Ci[kk][l]);
+        cc += k_fs*((0.5*(f0[i]*s0[j] + f0[j]*s0[i]))*(0.5*(f0[kk]*s0[l] + f0[l]*s0[kk])));
+        cc += k_ff*((f0[i]*f0[j])*(f0[kk]*f0[l]));
+        cc += k_ss*((s0[i]*s0[j])*(s0[kk]*s0[l]));
+        Dm21[dm_idx(I, Jv)] = cc;
+      }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        S[i][j] += p*J*Ci[i][j];
+        S[i][j] += s_fs*(0.5*(f0[i]*s0[j] + f0[j]*s0[i]));
+        S[i][j] += s_ff*(f0[i]*f0[j]);
+        S[i][j] += s_ss*(s0[i]*s0[j]);
+      }
   } else {
     // modified St. Venant-Kirchhoff (:326-356): C10 = kappa, C01 = mu
     const double g1 = c.C10, g2 = c.C01;

@@ -252,7 +252,7 @@ bool B200LinearAlgebra::fill_struct_props(ComMod& com_mod, const eqType& eq, con
   fibre_stress(com_mod, stM.Tf, sp.Tfa, sp.Tsa);
   if (sp.Tfa != 0.0 && stM.isoType != ConstitutiveModelType::stIso_nHook && stM.isoType != ConstitutiveModelType::stIso_HO &&
       stM.isoType != ConstitutiveModelType::stIso_MR && stM.isoType != ConstitutiveModelType::stIso_HGO &&
-      stM.isoType != ConstitutiveModelType::stIso_Gucci) return false;
+      stM.isoType != ConstitutiveModelType::stIso_Gucci && stM.isoType != ConstitutiveModelType::stIso_HO_ma) return false;
   switch (stM.isoType) {
     case ConstitutiveModelType::stIso_nHook: sp.isoType = 0; break;
     case ConstitutiveModelType::stIso_StVK:  sp.isoType = 1; break;
@@ -261,6 +261,7 @@ bool B200LinearAlgebra::fill_struct_props(ComMod& com_mod, const eqType& eq, con
     case ConstitutiveModelType::stIso_MR:    sp.isoType = 4; break;
     case ConstitutiveModelType::stIso_HGO:   sp.isoType = 5; sp.kap = stM.kap; break;   // two fibre families (upload_mesh)
     case ConstitutiveModelType::stIso_Gucci: sp.isoType = 6; break;                     // fibre + sheet frame (upload_mesh)
+    case ConstitutiveModelType::stIso_HO_ma: sp.isoType = 7; break;                     // HO with full fibre invariants (upload_mesh)
     default: return false;
   }
   sp.a = stM.a; sp.b = stM.b; sp.aff = stM.aff; sp.bff = stM.bff; sp.ass = stM.ass; sp.bss = stM.bss;
@@ -302,7 +303,7 @@ bool B200LinearAlgebra::assemble_fsi_mesh(ComMod& com_mod, const mshType& lM, co
     } else if (eq.dmn[d].phys == EquationType::phys_struct) {
       kinds[d] = 1;
       if (!fill_struct_props(com_mod, eq, eq.dmn[d], st[d])) return false;
-      if ((st[d].isoType == 3 || st[d].isoType == 5 || st[d].isoType == 6 || st[d].Tfa != 0.0) && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
+      if ((st[d].isoType == 3 || st[d].isoType == 5 || st[d].isoType == 6 || st[d].isoType == 7 || st[d].Tfa != 0.0) && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
     } else {
       return false;
     }
@@ -405,9 +406,10 @@ bool B200LinearAlgebra::assemble_ustruct_mesh(ComMod& com_mod, const mshType& lM
     case ConstitutiveModelType::stIso_MR:    iso = 4; break;
     case ConstitutiveModelType::stIso_HGO:   iso = 5; break;
     case ConstitutiveModelType::stIso_Gucci: iso = 6; break;
+    case ConstitutiveModelType::stIso_HO_ma: iso = 7; break;
     default: return false;
   }
-  if ((iso == 3 || iso == 5 || iso == 6) && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
+  if ((iso == 3 || iso == 5 || iso == 6 || iso == 7) && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
   if (dmn.solid_visc.viscType != SolidViscosityModelType::viscType_NA) return false;
   b200_ustruct_props p{};
   fibre_stress(com_mod, stM.Tf, p.Tfa, p.Tsa);
@@ -471,7 +473,7 @@ bool B200LinearAlgebra::assemble_solid_mesh(ComMod& com_mod, const mshType& lM, 
   const bool is_struct = (eq.phys == EquationType::phys_struct);
   if (is_struct) {
     if (!fill_struct_props(com_mod, eq, dmn, sp)) return false;
-    if ((sp.isoType == 3 || sp.isoType == 5 || sp.isoType == 6 || sp.Tfa != 0.0) && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
+    if ((sp.isoType == 3 || sp.isoType == 5 || sp.isoType == 6 || sp.isoType == 7 || sp.Tfa != 0.0) && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
   } else {
     lp.dt = com_mod.dt; lp.am = eq.am; lp.af = eq.af; lp.beta = eq.beta;
     lp.tDof = com_mod.tDof; lp.s = eq.s;
@@ -514,7 +516,7 @@ bool B200LinearAlgebra::assemble_domains_mesh(ComMod& com_mod, const mshType& lM
       if (!fill_fluid_props(com_mod, eq, eq.dmn[d], fl[d])) return false;
     } else {
       if (!fill_struct_props(com_mod, eq, eq.dmn[d], st[d])) return false;
-      if ((st[d].isoType == 3 || st[d].isoType == 5 || st[d].isoType == 6 || st[d].Tfa != 0.0) && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
+      if ((st[d].isoType == 3 || st[d].isoType == 5 || st[d].isoType == 6 || st[d].isoType == 7 || st[d].Tfa != 0.0) && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
     }
   }
   if (!fluid) {

@@ -146,7 +146,7 @@ def block_case(n, elem="hex", kind="struct", iso="nHook", vol="ST91", jitter=0.1
     if kind == "struct":
         if iso == "nHook":
             C10, C01 = 0.5 * mu, 0.0
-        elif iso in ("HO", "HGO", "Gucci"):      # Holzapfel-Ogden myocardium (parameters of tests/cases/struct/LV_* style, cgs)
+        elif iso in ("HO", "HO_ma", "HGO", "Gucci"):      # Holzapfel-Ogden myocardium (parameters of tests/cases/struct/LV_* style, cgs)
             C10, C01 = 0.0, 0.0
         elif iso == "MR":                        # Mooney-Rivlin: C10 + C01 = mu / 2
             C10, C01 = 0.3 * mu, 0.2 * mu
@@ -156,7 +156,7 @@ def block_case(n, elem="hex", kind="struct", iso="nHook", vol="ST91", jitter=0.1
             C10, C01 = E / (3.0 * 0.4), 0.5 * E / 1.3
         props = dict(dt=dt, am=am, af=af, gam=gam, beta=beta, rho=1000.0, dmp=0.0, f=(0.0, 0.0, 0.0), iso=iso, vol=vol,
                      C10=C10, C01=C01, Kpen=4.0e9 if vol else 0.0)
-        if iso == "HO":
+        if iso in ("HO", "HO_ma"):
             props["ho"] = dict(a=590.0, b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12, afs=2160.0, bfs=11.436, khs=100.0)
             props["Kpen"] = 1.0e6
         if iso == "Gucci":                       # Guccione myocardium: C10 and the three exponents
@@ -182,7 +182,7 @@ def block_case(n, elem="hex", kind="struct", iso="nHook", vol="ST91", jitter=0.1
         faces.append(dict(name=nm, nodes=nodes, dof=3, bGrp=B.BC_DIR, val=val))
     case = dict(mesh=m, rowPtr=rowPtr, colPtr=colPtr, Ag=Ag, Yg=Yg, Dg=Dg, Bf=Bf, props=props, faces=faces, kind=kind,
                 res=np.zeros(len(faces)), incL=np.ones(len(faces), np.int32), name=f"block_{elem}_{n}_{kind}")
-    if kind == "struct" and iso in ("HO", "HGO", "Gucci"):
+    if kind == "struct" and iso in ("HO", "HO_ma", "HGO", "Gucci"):
         # fibre / sheet directions rotating through the block (unit, orthogonal), one pair per element
         cen = m.x[m.ien].mean(axis=1)
         th = 0.5 * np.pi * cen[:, 2] + 0.3 * cen[:, 0]
@@ -342,7 +342,7 @@ def ustruct_case(n, elem="tet", vol="ST91", iso="nHook"):
                 res=np.zeros(len(faces)), incL=np.ones(len(faces), np.int32), name=f"ustruct_{elem}_{n}")
     if iso != "nHook":
         props["iso"] = iso
-        if iso == "HO":
+        if iso in ("HO", "HO_ma"):
             props["ho"] = dict(a=590.0, b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12, afs=2160.0, bfs=11.436, khs=100.0)
         elif iso == "MR":
             props.update(C10=0.3 * mu, C01=0.2 * mu)

@@ -1,0 +1,40 @@
+"""Golden fixtures for the features added late in round 1 (after the round's GPU budget was spent), generated from the
+COMPILED REFERENCE (oracle/_ref) like make_golden.py:
+    python tests/golden/make_golden_late.py
+Writes tests/golden/late_additions.npz; the GPU tests that read it live in tests/test_zz_late_additions.py (sorted last so a
+failure there cannot mask the suites that were green on the B200)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import refcase  # noqa: E402
+from svfsiplus_b200 import problem as P  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    out = {}
+    # Holzapfel-Ogden with modified anisotropy (stIso_HO_ma): struct (get_pk2cc<3>) and ustruct (get_pk2cc_dev)
+    for elem in ("tet", "hex"):
+        c = P.block_case(3, elem=elem, kind="struct", iso="HO_ma", vol="ST91")
+        R, Val, *_ = refcase.reference_assemble_solid(c)
+        out[f"R_{elem}_struct_HO_ma"] = R
+        out[f"Val_{elem}_struct_HO_ma"] = Val
+        c = P.ustruct_case(3, elem=elem, iso="HO_ma")
+        R, Val, Kd, _ = refcase.reference_assemble_ustruct(c)
+        out[f"R_{elem}_ustruct_HO_ma"] = R
+        out[f"Val_{elem}_ustruct_HO_ma"] = Val
+        out[f"Kd_{elem}_ustruct_HO_ma"] = Kd
+    np.savez_compressed(os.path.join(HERE, "late_additions.npz"), **out)
+    for k, v in out.items():
+        print(k, v.shape, float(np.abs(v).max()))
+
+
+if __name__ == "__main__":
+    main()

@@ -26,6 +26,9 @@ LAWS = [
     ("HGO", "ST91", dict(C10=0.5 * MU, Kpen=4.0e9, kap=0.226, ho=dict(aff=9.96e5, bff=524.6, ass=9.96e5, bss=524.6))),
     ("Gucci", "ST91", dict(C10=880.0, Kpen=1.0e6, ho=dict(bff=8.0, bss=6.0, bfs=12.0))),
     ("Gucci", "M94", dict(C10=2000.0, Kpen=1.0e5, ho=dict(bff=18.5, bss=3.58, bfs=1.63), Tfa=500.0, eta_s=0.4)),
+    ("HO_ma", "ST91", dict(Kpen=1.0e6, ho=HO)),
+    ("HO_ma", "M94", dict(Kpen=1.0e6, ho=HO, Tfa=2.0e4, eta_s=0.3)),
+    ("HO_ma", "Quad", dict(Kpen=1.0e5, ho=dict(HO, khs=20.0))),
     ("HGO", "Quad", dict(C10=0.5 * MU, Kpen=1.0e8, kap=0.0, ho=dict(aff=2.0e6, bff=20.0, ass=1.0e6, bss=10.0), Tfa=3.0e4, eta_s=0.4)),
 ]
 VOIGT = [(0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (2, 0)]

@@ -1,0 +1,40 @@
+"""GPU parity of the features added after the round's GPU budget was spent (they were checked on the CPU through the
+host/device-shared headers and the compiled reference, not yet on a B200).  The file name sorts last on purpose: the
+driver runs `pytest -x`, and a failure here must not mask the suites that were green on the device.
+
+Tolerances as everywhere (BASELINE.json north_star): assembled R / Val / Kd <= 1e-12 relative (max-norm)."""
+import numpy as np
+import pytest
+
+from util import golden, rel_inf
+
+from svfsiplus_b200 import problem as P
+
+pytestmark = pytest.mark.gpu
+
+TOL_ASM = 1e-12
+
+
+@pytest.mark.parametrize("elem", ["tet", "hex"])
+def test_struct_ho_ma_matches_golden(elem):
+    """stIso_HO_ma in struct_3d (mat_models_carray.h:1137-1353)."""
+    g = golden("late_additions.npz")
+    case = P.block_case(3, elem=elem, kind="struct", iso="HO_ma", vol="ST91")
+    be = P.setup_backend(case)
+    P.assemble_solid(be, case)
+    assert rel_inf(be.get_R(), g[f"R_{elem}_struct_HO_ma"]) < TOL_ASM
+    assert rel_inf(be.get_Val(), g[f"Val_{elem}_struct_HO_ma"]) < TOL_ASM
+    be.close()
+
+
+@pytest.mark.parametrize("elem", ["tet", "hex"])
+def test_ustruct_ho_ma_matches_golden(elem):
+    """stIso_HO_ma in ustruct_3d_m / _c (get_pk2cc_dev, mat_models.cpp:963-1054)."""
+    g = golden("late_additions.npz")
+    case = P.ustruct_case(3, elem=elem, iso="HO_ma")
+    be = P.setup_backend(case)
+    P.assemble_ustruct(be, case)
+    assert rel_inf(be.get_R(), g[f"R_{elem}_ustruct_HO_ma"]) < TOL_ASM
+    assert rel_inf(be.get_Val(), g[f"Val_{elem}_ustruct_HO_ma"]) < TOL_ASM
+    assert rel_inf(be.get_Kd(), g[f"Kd_{elem}_ustruct_HO_ma"]) < TOL_ASM
+    be.close()

@@ -151,7 +151,7 @@ def host_pk2cc(F, fl, *, iso, vol, C10=0.0, C01=0.0, Kpen=0.0, ho=None, Tfa=0.0,
     L = elemhost()
     ho = ho or {}
     keys = ("a", "b", "aff", "bff", "ass", "bss", "afs", "bfs", "khs")
-    par = np.array([{"nHook": 0, "StVK": 1, "mStVK": 2, "HO": 3, "MR": 4, "HGO": 5, "Gucci": 6}[iso], {None: 0, "Quad": 1, "ST91": 2, "M94": 3}[vol], C10, C01, Kpen]
+    par = np.array([{"nHook": 0, "StVK": 1, "mStVK": 2, "HO": 3, "MR": 4, "HGO": 5, "Gucci": 6, "HO_ma": 7}[iso], {None: 0, "Quad": 1, "ST91": 2, "M94": 3}[vol], C10, C01, Kpen]
                    + [ho.get(k, 100.0 if k == "khs" else 0.0) for k in keys] + [Tfa, Tfa * eta_s, kap], np.float64)
     F = np.ascontiguousarray(F, np.float64); fl = np.ascontiguousarray(fl, np.float64)
     S6 = np.empty(6); Dm21 = np.empty(21)
