@@ -197,6 +197,9 @@ def lib():
         L.ref_asm_bfolw.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8
         L.ref_asm_bneu.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
         L.ref_pic.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_double] + [C.c_void_p] * 12
+        L.ref_io_write_restart.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_io_history.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int] + [C.c_double] * 7 + [C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -539,3 +542,29 @@ def pic(op, state, eqs, *, dt, cEq=0, dFlag=False, sstEq=False, R=None, Rd=None)
     if rc != 0:
         raise RuntimeError(lib().ref_last_error().decode())
     return st
+
+
+def io_write_restart(stem, *, stamp, cTS, time, iNorm, xn, Yn, An, Dn=None, Ad=None, pS0=None):
+    """output::write_restart (S/output.cpp:202-345) for one rank; arrays (tnNo, tDof) row-major = the solver's column-major buffers.
+    Returns the record length the reference computes (S/initialize.cpp:505-513).  The file is <stem>_NNN.bin."""
+    f64 = lambda a: None if a is None else np.ascontiguousarray(a, np.float64)
+    st = np.ascontiguousarray(stamp, np.int32)
+    iNorm, xn, Yn, An, Dn, Ad, pS0 = map(f64, (iNorm, xn, Yn, An, Dn, Ad, pS0))
+    recLn = C.c_longlong()
+    rc = lib().ref_io_write_restart(os.fsencode(stem), _p(st), int(cTS), float(time), iNorm.size, _p(iNorm), xn.size, _p(xn),
+                                    Yn.shape[1], Yn.shape[0], _p(Yn), _p(An), None if Dn is None else _p(Dn),
+                                    0 if Ad is None else Ad.shape[1], None if Ad is None else _p(Ad),
+                                    0 if pS0 is None else pS0.shape[1], None if pS0 is None else _p(pS0), C.byref(recLn))
+    if rc != 0:
+        raise RuntimeError(lib().ref_last_error().decode())
+    return recLn.value
+
+
+def io_history(path, *, nEq, sym, cTS, itr, saved, elapsed, eq_iNorm, eq_pNorm, ri_iNorm, ri_fNorm, ri_dB, ri_callD, ri_itr, ri_suc):
+    """output::output_result (S/output.cpp:46-180): header block + one line into `path`; returns the file's text."""
+    rc = lib().ref_io_history(os.fsencode(path), nEq, sym.encode(), cTS, itr, int(saved), elapsed, eq_iNorm, eq_pNorm, ri_iNorm, ri_fNorm,
+                              ri_dB, ri_callD, ri_itr, int(ri_suc))
+    if rc != 0:
+        raise RuntimeError(lib().ref_last_error().decode())
+    with open(path) as f:
+        return f.read()

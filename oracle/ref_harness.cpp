@@ -42,6 +42,7 @@
 #include "ls.h"
 #include "pic.h"
 #include "eq_assem.h"
+#include "output.h"
 #ifdef WITH_B200_DROPIN
 #include "B200LinearAlgebra.h"
 #endif
@@ -1298,6 +1299,101 @@ int ref_asm_bneu(void* h, int kind, int eNoNb, int nElb, const int* IENb, const 
     eq_assem::b_assem_neu_bc(com_mod, fa, hg_v, Yg_a);
     std::memcpy(R, com_mod.R.data(), sizeof(double)*size_t(dof)*nNo);
     std::memcpy(Val, com_mod.Val.data(), sizeof(double)*size_t(dof)*dof*ctx->nnz);
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+// output::write_restart (S/output.cpp:202-345) on a bare Simulation: one rank, file <stem>_NNN.bin (+ the hard link
+// <stem>_last.bin the reference makes).  Arrays as the solver holds them (column-major (tDof, tnNo)).  Dn / Ad / pS0 may be null.
+int ref_io_write_restart(const char* stem, const int* stamp7, int cTS, double time, int nEq, const double* iNorm, int nXn, const double* xn,
+                         int tDof, int tnNo, const double* Yn, const double* An, const double* Dn, int nsd, const double* Ad,
+                         int nsymd, const double* pS0, long long* recLn_out)
+{
+  try {
+    mpistub_set_world(1);
+    mpistub_bind_rank(0);
+    Simulation sim;
+    auto& com_mod = sim.com_mod;
+    com_mod.stFileName = stem;
+    com_mod.stFileRepl = false;
+    for (int i = 0; i < 7; i++) com_mod.stamp[i] = stamp7[i];
+    com_mod.cTS = cTS;
+    com_mod.time = time;
+    com_mod.nEq = nEq;
+    com_mod.eq.resize(nEq);
+    for (int i = 0; i < nEq; i++) com_mod.eq[i].iNorm = iNorm[i];
+    com_mod.cplBC.nX = nXn;
+    com_mod.cplBC.xn.resize(nXn);
+    std::memcpy(com_mod.cplBC.xn.data(), xn, sizeof(double)*size_t(nXn));
+    com_mod.tDof = tDof;
+    com_mod.tnNo = tnNo;
+    com_mod.nsd = 3;
+    com_mod.nsymd = 6;
+    com_mod.Yn.resize(tDof, tnNo);
+    com_mod.An.resize(tDof, tnNo);
+    std::memcpy(com_mod.Yn.data(), Yn, sizeof(double)*size_t(tDof)*tnNo);
+    std::memcpy(com_mod.An.data(), An, sizeof(double)*size_t(tDof)*tnNo);
+    com_mod.ibFlag = false;
+    com_mod.dFlag = Dn != nullptr;
+    com_mod.sstEq = Ad != nullptr;
+    com_mod.pstEq = pS0 != nullptr;
+    sim.cep_mod.cepEq = false;
+    if (Dn) { com_mod.Dn.resize(tDof, tnNo); std::memcpy(com_mod.Dn.data(), Dn, sizeof(double)*size_t(tDof)*tnNo); }
+    if (Ad) { com_mod.Ad.resize(nsd, tnNo); std::memcpy(com_mod.Ad.data(), Ad, sizeof(double)*size_t(nsd)*tnNo); }
+    if (pS0) { com_mod.pS0.resize(nsymd, tnNo); std::memcpy(com_mod.pS0.data(), pS0, sizeof(double)*size_t(nsymd)*tnNo); }
+    // the record length exactly as S/initialize.cpp:505-513 computes it
+    int i = 2*tDof;
+    if (com_mod.dFlag) i = 3*tDof;
+    if (com_mod.pstEq) i = i + com_mod.nsymd;
+    if (com_mod.sstEq) i = i + com_mod.nsd;
+    i = sizeof(int)*(1 + com_mod.stamp.size()) + sizeof(double)*(2 + com_mod.nEq + com_mod.cplBC.nX + i*com_mod.tnNo);
+    com_mod.recLn = i;
+    *recLn_out = i;
+    std::array<double,3> timeP = {utils::cput(), 0.0, 0.0};
+    output::write_restart(&sim, timeP);
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+// output::output_result (S/output.cpp:46-180) into the history file `path`: the header block (co = 1) followed by one line
+// (co = 2, or 3 when saved) for an equation with the given norms.  The reference takes the elapsed time from the wall clock:
+// timeP[0] is set so that the line is written `elapsed` seconds "after the start" (the millisecond jitter stays below the four
+// printed digits for the values the test uses).
+int ref_io_history(const char* path, int nEq, const char* sym, int cTS, int itr, int saved, double elapsed, double eq_iNorm, double eq_pNorm,
+                   double ri_iNorm, double ri_fNorm, double ri_dB, double ri_callD, int ri_itr, int ri_suc)
+{
+  try {
+    mpistub_set_world(1);
+    mpistub_bind_rank(0);
+    Simulation sim;
+    sim.logger.initialize(path, false);
+    auto& com_mod = sim.com_mod;
+    com_mod.nEq = nEq;
+    com_mod.eq.resize(nEq);
+    com_mod.cTS = cTS;
+    auto& eq = com_mod.eq[0];
+    eq.sym = sym;
+    eq.itr = itr;
+    eq.maxItr = 1000;
+    eq.iNorm = eq_iNorm;
+    eq.pNorm = eq_pNorm;
+    eq.FSILS.RI.iNorm = ri_iNorm;
+    eq.FSILS.RI.fNorm = ri_fNorm;
+    eq.FSILS.RI.dB = ri_dB;
+    eq.FSILS.RI.callD = ri_callD;
+    eq.FSILS.RI.itr = ri_itr;
+    eq.FSILS.RI.suc = ri_suc != 0;
+    std::array<double,3> timeP = {utils::cput(), 0.0, 0.0};
+    output::output_result(&sim, timeP, 1, 0);          // header; leaves timeP[0] = cput() - timeP[0] ~ 0
+    timeP[0] = utils::cput() - elapsed;
+    timeP[1] = 0.0;
+    output::output_result(&sim, timeP, saved ? 3 : 2, 0);
     return 0;
   } catch (const std::exception& e) {
     g_err = e.what();

@@ -1,0 +1,216 @@
+"""ctypes front-end of the VTK-free I/O library (include/svb200_io.h -> svfsiplus_b200/libsvb200io.so, host/sv_io.cpp).
+
+Mirrors what the reference does with VtkData / vtk_xml.cpp / output.cpp (file:line in the header): read a .vtu / .vtp mesh,
+write a result file, write / read restart records, format history lines.  Test and tooling front-end only: numpy in, numpy
+out; every byte of format logic is in the C++ library."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+POINT_DATA, CELL_DATA = 0, 1
+ASCII, BINARY, APPENDED_RAW, APPENDED_BASE64 = 0, 1, 2, 3
+VTK_TYPE = {"LINE": 3, "TRI3": 5, "QUD4": 9, "TET4": 10, "HEX8": 12, "WEDGE": 13, "TRI6": 22, "QUD8": 23, "TET10": 24, "HEX20": 25,
+            "QUD9": 28, "HEX27": 29}
+
+
+class Restart(C.Structure):
+    _fields_ = [("stamp", C.c_int * 7), ("cTS", C.c_int), ("time", C.c_double), ("cpu_time", C.c_double),
+                ("nEq", C.c_int), ("iNorm", C.c_void_p), ("nXn", C.c_int), ("xn", C.c_void_p),
+                ("tDof", C.c_int), ("tnNo", C.c_int), ("Yn", C.c_void_p), ("An", C.c_void_p),
+                ("dFlag", C.c_int), ("Dn", C.c_void_p), ("trailing_Dn", C.c_int),
+                ("sstEq", C.c_int), ("nsd", C.c_int), ("Ad", C.c_void_p),
+                ("pstEq", C.c_int), ("nsymd", C.c_int), ("pS0", C.c_void_p)]
+
+
+class History(C.Structure):
+    _fields_ = [("sym", C.c_char_p), ("cTS", C.c_int), ("itr", C.c_int), ("saved", C.c_int),
+                ("elapsed", C.c_double), ("since_last", C.c_double), ("eq_iNorm", C.c_double), ("eq_pNorm", C.c_double),
+                ("ri_iNorm", C.c_double), ("ri_fNorm", C.c_double), ("ri_dB", C.c_double), ("ri_callD", C.c_double),
+                ("ri_itr", C.c_int), ("ri_suc", C.c_int)]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libsvb200io.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing: run `python __graft_entry__.py` (build()) first")
+        L = C.CDLL(path)
+        L.b200io_last_error.restype = C.c_char_p
+        L.b200io_vtk_new.restype = C.c_void_p
+        L.b200io_vtk_array_name.restype = C.c_char_p
+        L.b200io_restart_record_bytes.restype = C.c_longlong
+        for name, args in {
+            "b200io_vtk_read": [C.c_char_p, C.c_void_p], "b200io_vtk_is_polydata": [C.c_void_p], "b200io_vtk_num_points": [C.c_void_p],
+            "b200io_vtk_num_cells": [C.c_void_p], "b200io_vtk_nodes_per_cell": [C.c_void_p], "b200io_vtk_points": [C.c_void_p, C.c_void_p],
+            "b200io_vtk_connectivity": [C.c_void_p, C.c_void_p], "b200io_vtk_cell_types": [C.c_void_p, C.c_void_p],
+            "b200io_vtk_num_arrays": [C.c_void_p, C.c_int], "b200io_vtk_array_name": [C.c_void_p, C.c_int, C.c_int],
+            "b200io_vtk_array_info": [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p],
+            "b200io_vtk_array_f64": [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p], "b200io_vtk_array_i32": [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p],
+            "b200io_vtk_free": [C.c_void_p], "b200io_vtk_new": [C.c_int], "b200io_vtk_set_points": [C.c_void_p, C.c_int, C.c_void_p],
+            "b200io_vtk_set_cells": [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int],
+            "b200io_vtk_add_array_f64": [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_void_p],
+            "b200io_vtk_add_array_i32": [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_void_p],
+            "b200io_vtk_write": [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int],
+            "b200io_restart_record_bytes": [C.c_void_p], "b200io_restart_write": [C.c_char_p, C.c_int, C.c_longlong, C.c_void_p, C.c_int],
+            "b200io_restart_read": [C.c_char_p, C.c_int, C.c_longlong, C.c_void_p], "b200io_restart_name": [C.c_char_p, C.c_int, C.c_char_p, C.c_int],
+            "b200io_history_header": [C.c_int, C.c_char_p, C.c_int], "b200io_history_line": [C.c_void_p, C.c_char_p, C.c_int],
+        }.items():
+            getattr(L, name).argtypes = args
+        _LIB = L
+    return _LIB
+
+
+class IoError(RuntimeError):
+    pass
+
+
+def _ck(rc):
+    if rc != 0:
+        raise IoError(lib().b200io_last_error().decode())
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def read_vtk(path):
+    """read_vtu / read_vtp (vtk_xml.cpp:568, :438): dict(x (nNo,3), ien (nEl,eNoN) or the ragged pair (conn, offsets), types, point_data, cell_data)."""
+    L = lib()
+    h = C.c_void_p()
+    _ck(L.b200io_vtk_read(os.fsencode(path), C.byref(h)))
+    try:
+        nNo, nEl, eNoN = L.b200io_vtk_num_points(h), L.b200io_vtk_num_cells(h), L.b200io_vtk_nodes_per_cell(h)
+        out = dict(polydata=bool(L.b200io_vtk_is_polydata(h)), nNo=nNo, nEl=nEl, eNoN=eNoN)
+        x = np.zeros((nNo, 3))
+        _ck(L.b200io_vtk_points(h, _p(x)))
+        out["x"] = x
+        if eNoN > 0:
+            ien = np.zeros((nEl, eNoN), np.int32)
+            _ck(L.b200io_vtk_connectivity(h, _p(ien)))
+            out["ien"] = ien
+        types = np.zeros(nEl, np.uint8)
+        if nEl:
+            _ck(L.b200io_vtk_cell_types(h, _p(types)))
+        out["types"] = types
+        for where, key in ((POINT_DATA, "point_data"), (CELL_DATA, "cell_data")):
+            d = {}
+            for i in range(L.b200io_vtk_num_arrays(h, where)):
+                name = L.b200io_vtk_array_name(h, where, i)
+                nc, nt, isint = C.c_int(), C.c_int(), C.c_int()
+                assert L.b200io_vtk_array_info(h, where, name, C.byref(nc), C.byref(nt), C.byref(isint)) == 0
+                a = np.zeros((nt.value, nc.value), np.int32 if isint.value else np.float64)
+                _ck((L.b200io_vtk_array_i32 if isint.value else L.b200io_vtk_array_f64)(h, where, name, _p(a)))
+                d[name.decode()] = a[:, 0] if nc.value == 1 else a
+            out[key] = d
+        return out
+    finally:
+        L.b200io_vtk_free(h)
+
+
+def write_vtk(path, x, ien, vtk_type, point_data=None, cell_data=None, *, polydata=False, mode=APPENDED_RAW, compress=True, header64=True):
+    """write_vtu / write_vtp / write_vtus (vtk_xml.cpp:855, :827, :913): one element type, named point / cell arrays."""
+    L = lib()
+    x = np.ascontiguousarray(x, np.float64)
+    ien = np.ascontiguousarray(ien, np.int32)
+    h = C.c_void_p(L.b200io_vtk_new(int(polydata)))
+    try:
+        _ck(L.b200io_vtk_set_points(h, x.shape[0], _p(x)))
+        _ck(L.b200io_vtk_set_cells(h, ien.shape[0], ien.shape[1] if ien.ndim == 2 else 1, _p(ien), int(vtk_type)))
+        for where, d in ((POINT_DATA, point_data or {}), (CELL_DATA, cell_data or {})):
+            for name, a in d.items():
+                a = np.asarray(a)
+                nt = a.shape[0]
+                nc = 1 if a.ndim == 1 else a.shape[1]
+                if np.issubdtype(a.dtype, np.integer):
+                    a = np.ascontiguousarray(a, np.int32)
+                    _ck(L.b200io_vtk_add_array_i32(h, where, name.encode(), nc, nt, _p(a)))
+                else:
+                    a = np.ascontiguousarray(a, np.float64)
+                    _ck(L.b200io_vtk_add_array_f64(h, where, name.encode(), nc, nt, _p(a)))
+        _ck(L.b200io_vtk_write(h, os.fsencode(path), mode, int(compress), int(header64)))
+    finally:
+        L.b200io_vtk_free(h)
+
+
+def _restart_struct(keep, *, stamp, cTS, time, cpu_time, iNorm, xn, Yn, An, Dn=None, Ad=None, pS0=None, trailing_Dn=True):
+    r = Restart()
+    r.stamp[:] = [int(v) for v in stamp]
+    r.cTS, r.time, r.cpu_time = int(cTS), float(time), float(cpu_time)
+
+    def put(a):
+        a = np.ascontiguousarray(a, np.float64)
+        keep.append(a)
+        return a, a.ctypes.data
+
+    a, r.iNorm = put(iNorm); r.nEq = a.size
+    a, r.xn = put(xn); r.nXn = a.size
+    a, r.Yn = put(Yn); r.tnNo, r.tDof = a.shape
+    a, r.An = put(An)
+    r.dFlag = int(Dn is not None)
+    if Dn is not None:
+        _, r.Dn = put(Dn)
+    r.trailing_Dn = int(trailing_Dn)
+    r.sstEq = int(Ad is not None)
+    if Ad is not None:
+        a, r.Ad = put(Ad); r.nsd = a.shape[1]
+    r.pstEq = int(pS0 is not None)
+    if pS0 is not None:
+        a, r.pS0 = put(pS0); r.nsymd = a.shape[1]
+    return r
+
+
+def restart_record_bytes(**kw):
+    keep = []
+    r = _restart_struct(keep, **kw)
+    return int(lib().b200io_restart_record_bytes(C.byref(r)))
+
+
+def write_restart(path, rank, recLn, create=True, **kw):
+    """output::write_restart (output.cpp:202-345).  Arrays are (tnNo, tDof) row-major = the solver's (tDof, tnNo) column-major."""
+    keep = []
+    r = _restart_struct(keep, **kw)
+    _ck(lib().b200io_restart_write(os.fsencode(path), rank, recLn, C.byref(r), int(create)))
+
+
+def read_restart(path, rank, recLn, *, nEq, nXn, tDof, tnNo, dFlag=False, nsd=0, nsymd=0):
+    """init_from_bin (initialize.cpp:81-230): returns dict(stamp, cTS, time, cpu_time, iNorm, xn, Yn, An[, Dn][, Ad][, pS0])."""
+    kw = dict(stamp=[0]*7, cTS=0, time=0.0, cpu_time=0.0, iNorm=np.zeros(nEq), xn=np.zeros(nXn), Yn=np.zeros((tnNo, tDof)), An=np.zeros((tnNo, tDof)))
+    if dFlag:
+        kw["Dn"] = np.zeros((tnNo, tDof))
+    if nsd:
+        kw["Ad"] = np.zeros((tnNo, nsd))
+    if nsymd:
+        kw["pS0"] = np.zeros((tnNo, nsymd))
+    keep = []
+    r = _restart_struct(keep, **kw)
+    _ck(lib().b200io_restart_read(os.fsencode(path), rank, recLn, C.byref(r)))
+    names = ["iNorm", "xn", "Yn", "An"] + (["Dn"] if dFlag else []) + (["Ad"] if nsd else []) + (["pS0"] if nsymd else [])
+    out = dict(zip(names, keep))
+    out.update(stamp=list(r.stamp), cTS=r.cTS, time=r.time, cpu_time=r.cpu_time)
+    return out
+
+
+def restart_name(stem, cTS):
+    buf = C.create_string_buffer(4096)
+    lib().b200io_restart_name(os.fsencode(stem), cTS, buf, len(buf))
+    return buf.value.decode()
+
+
+def history_header(nEq):
+    buf = C.create_string_buffer(1024)
+    lib().b200io_history_header(nEq, buf, len(buf))
+    return buf.value.decode()
+
+
+def history_line(sym, cTS, itr, *, saved=False, elapsed, since_last, eq_iNorm, eq_pNorm, ri_iNorm, ri_fNorm, ri_dB, ri_callD, ri_itr, ri_suc):
+    h = History(sym.encode(), cTS, itr, int(saved), elapsed, since_last, eq_iNorm, eq_pNorm, ri_iNorm, ri_fNorm, ri_dB, ri_callD, ri_itr, int(ri_suc))
+    buf = C.create_string_buffer(1024)
+    lib().b200io_history_line(C.byref(h), buf, len(buf))
+    return buf.value.decode()

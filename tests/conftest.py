@@ -20,6 +20,7 @@ def _native_built():
     import shutil
     if shutil.which("nvcc"):
         g.build_cuda()
+    g.build_io()
     g.build_hostlogic()
     try:
         g.build_oracle()

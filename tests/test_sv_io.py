@@ -1,0 +1,396 @@
+"""VTK-free I/O (include/svb200_io.h, svfsiplus_b200/host/sv_io.cpp), CPU only.
+
+* VTK XML: round trips through every data mode the VTK writers have, an INDEPENDENT decoder / encoder written here from the
+  published format (xml.etree + base64 + zlib) on both sides of the library, a hand-written ascii PolyData file in the
+  layout vtkXMLPolyDataWriter produces, and the error paths.  The reference itself reads and writes these files through the
+  VTK library (VtkData.cpp), which is not installed here: against the reference this part is unpinned.
+* restart records and history lines: byte / character identical to the reference's own output.cpp compiled into oracle/_ref.
+"""
+import base64
+import os
+import re
+import struct
+import xml.etree.ElementTree as ET
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, needs_ref
+
+from svfsiplus_b200 import mesh as M
+from svfsiplus_b200 import sv_io as IO
+
+NP_TYPE = {"Int8": "i1", "UInt8": "u1", "Int16": "<i2", "UInt16": "<u2", "Int32": "<i4", "UInt32": "<u4", "Int64": "<i8", "UInt64": "<u8",
+           "Float32": "<f4", "Float64": "<f8"}
+
+
+def _mesh(kind="tet"):
+    m = M.block_mesh(3, kind)
+    rng = np.random.default_rng(7)
+    pd = {"Velocity": rng.standard_normal((m.nNo, 3)), "Pressure": rng.standard_normal(m.nNo) * 1e5,
+          "GlobalNodeID": np.arange(1, m.nNo + 1, dtype=np.int32)}
+    cd = {"Domain_ID": rng.integers(0, 3, m.nEl).astype(np.int32), "GlobalElementID": np.arange(1, m.nEl + 1, dtype=np.int32),
+          "Jacobian": rng.standard_normal(m.nEl)}
+    return m, pd, cd
+
+
+def _check(r, m, pd, cd, vtk_type):
+    assert r["nNo"] == m.nNo and r["nEl"] == m.nEl and r["eNoN"] == m.ien.shape[1]
+    assert np.array_equal(r["x"], m.x)
+    assert np.array_equal(r["ien"], m.ien)
+    assert (r["types"] == vtk_type).all()
+    for src, got in ((pd, r["point_data"]), (cd, r["cell_data"])):
+        assert list(got) == list(src)                       # order kept
+        for k, v in src.items():
+            assert got[k].dtype == (np.int32 if np.issubdtype(v.dtype, np.integer) else np.float64)
+            assert np.array_equal(got[k], v), k
+
+
+@pytest.mark.parametrize("header64", [False, True])
+@pytest.mark.parametrize("compress", [False, True])
+@pytest.mark.parametrize("mode", [IO.ASCII, IO.BINARY, IO.APPENDED_RAW, IO.APPENDED_BASE64])
+def test_vtu_round_trip_every_mode(tmp_path, mode, compress, header64):
+    m, pd, cd = _mesh("tet")
+    path = tmp_path / "mesh.vtu"
+    IO.write_vtk(path, m.x, m.ien, IO.VTK_TYPE["TET4"], pd, cd, mode=mode, compress=compress, header64=header64)
+    _check(IO.read_vtk(path), m, pd, cd, 10)
+
+
+def test_hex_and_large_arrays_cross_compression_blocks(tmp_path):
+    """more than one 32 KiB zlib block per array, last block partial"""
+    m = M.block_mesh(12, "hex")
+    rng = np.random.default_rng(3)
+    pd = {"Displacement": rng.standard_normal((m.nNo, 3))}
+    path = tmp_path / "hex.vtu"
+    IO.write_vtk(path, m.x, m.ien, IO.VTK_TYPE["HEX8"], pd, {}, mode=IO.APPENDED_RAW, compress=True)
+    assert m.x.nbytes > 32768
+    r = IO.read_vtk(path)
+    _check(r, m, pd, {}, 12)
+    assert os.path.getsize(path) < m.ien.astype(np.int64).nbytes          # the connectivity compresses well
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# independent restatement of the VTK XML binary conventions (decoder and encoder), from the format description only
+# ---------------------------------------------------------------------------------------------------------------------------
+def _py_decode_block(raw, hfmt, compressed):
+    hs = struct.calcsize(hfmt)
+    if not compressed:
+        (n,) = struct.unpack_from(hfmt, raw, 0)
+        return raw[hs:hs + n]
+    nb, us, ps = struct.unpack_from("<3" + hfmt[-1], raw, 0)
+    cs = struct.unpack_from(f"<{nb}" + hfmt[-1], raw, 3 * hs)
+    off = (3 + nb) * hs
+    out = b""
+    for c in cs:
+        out += zlib.decompress(raw[off:off + c])
+        off += c
+    assert len(out) == (nb - 1) * us + (ps or us) if nb else True
+    return out
+
+
+def _py_b64_pieces(text):
+    """decode a run of separately padded base64 pieces"""
+    text = "".join(text.split())
+    out = b""
+    for i in range(0, len(text), 4):
+        out += base64.b64decode(text[i:i + 4])
+    return out
+
+
+def _py_read_inline(path):
+    root = ET.parse(path).getroot()
+    hfmt = "<Q" if root.get("header_type") == "UInt64" else "<I"
+    comp = root.get("compressor") is not None
+    arrays = {}
+    for da in root.iter("DataArray"):
+        assert da.get("format") == "binary"
+        raw = _py_decode_block(_py_b64_pieces(da.text), hfmt, comp)
+        arrays[da.get("Name")] = np.frombuffer(raw, NP_TYPE[da.get("type")])
+    return root, arrays
+
+
+@pytest.mark.parametrize("compress", [False, True])
+def test_written_file_decodes_with_independent_parser(tmp_path, compress):
+    m, pd, cd = _mesh("tet")
+    path = tmp_path / "w.vtu"
+    IO.write_vtk(path, m.x, m.ien, 10, pd, cd, mode=IO.BINARY, compress=compress, header64=False)
+    root, arr = _py_read_inline(path)
+    assert root.tag == "VTKFile" and root.get("type") == "UnstructuredGrid" and root.get("byte_order") == "LittleEndian"
+    piece = root.find("UnstructuredGrid/Piece")
+    assert int(piece.get("NumberOfPoints")) == m.nNo and int(piece.get("NumberOfCells")) == m.nEl
+    assert np.array_equal(arr["Points"].reshape(-1, 3), m.x)
+    assert np.array_equal(arr["connectivity"].reshape(-1, 4), m.ien)
+    assert np.array_equal(arr["offsets"], 4 * np.arange(1, m.nEl + 1))
+    assert (arr["types"] == 10).all()
+    assert np.array_equal(arr["Velocity"].reshape(-1, 3), pd["Velocity"])
+    assert np.array_equal(arr["Domain_ID"], cd["Domain_ID"])
+
+
+def _py_block(data, hfmt, compressed, bs=1000):
+    """header bytes, payload bytes (VTK encodes them separately)"""
+    if not compressed:
+        return struct.pack(hfmt, len(data)), data
+    blocks = [data[i:i + bs] for i in range(0, len(data), bs)]
+    comp = [zlib.compress(b) for b in blocks]
+    last = len(blocks[-1]) if blocks else 0
+    hdr = struct.pack("<3" + hfmt[-1], len(blocks), bs, 0 if last == bs else last) + b"".join(struct.pack(hfmt, len(c)) for c in comp)
+    return hdr, b"".join(comp)
+
+
+def _py_write(path, m, pd, cd, *, appended, compressed, hfmt, f32_points=False, i32_conn=False):
+    """a VTU in the conventions of vtkXMLUnstructuredGridWriter: CellData / PointData first, separately encoded header and payload"""
+    app = ""
+    items = []
+
+    def da(name, a, ncomp):
+        nonlocal app
+        tname = {v: k for k, v in NP_TYPE.items()}[a.dtype.str if a.dtype.itemsize > 1 else a.dtype.str[1:]]
+        hdr, pl = _py_block(a.tobytes(), hfmt, compressed)
+        enc = base64.b64encode(hdr).decode() + base64.b64encode(pl).decode()
+        if appended:
+            s = f'<DataArray type="{tname}" Name="{name}" NumberOfComponents="{ncomp}" format="appended" RangeMin="0" RangeMax="1" offset="{len(app)}"/>\n'
+            app += enc
+        else:
+            s = f'<DataArray type="{tname}" Name="{name}" NumberOfComponents="{ncomp}" format="binary">\n{enc}\n</DataArray>\n'
+        return s
+
+    x = m.x.astype("<f4") if f32_points else m.x
+    conn = m.ien.astype("<i4" if i32_conn else "<i8").ravel()
+    offs = (m.ien.shape[1] * np.arange(1, m.nEl + 1)).astype(conn.dtype)
+    body = "<PointData Scalars=\"Pressure\">\n" + "".join(da(k, np.ascontiguousarray(v), 1 if v.ndim == 1 else v.shape[1]) for k, v in pd.items()) + "</PointData>\n"
+    body += "<CellData>\n" + "".join(da(k, np.ascontiguousarray(v), 1) for k, v in cd.items()) + "</CellData>\n"
+    body += "<Points>\n" + da("Points", x, 3) + "</Points>\n"
+    body += "<Cells>\n" + da("connectivity", conn, 1) + da("offsets", offs, 1) + da("types", np.full(m.nEl, 10, "u1"), 1) + "</Cells>\n"
+    head = f'<?xml version="1.0"?>\n<!-- written by the test -->\n<VTKFile type="UnstructuredGrid" version="0.1" byte_order="LittleEndian" header_type="{"UInt64" if hfmt == "<Q" else "UInt32"}"'
+    head += ' compressor="vtkZLibDataCompressor">\n' if compressed else ">\n"
+    txt = head + f'<UnstructuredGrid>\n<Piece NumberOfPoints="{m.nNo}" NumberOfCells="{m.nEl}">\n' + body + "</Piece>\n</UnstructuredGrid>\n"
+    if appended:
+        txt += '<AppendedData encoding="base64">\n   _' + app + "\n</AppendedData>\n"
+    txt += "</VTKFile>\n"
+    with open(path, "w") as f:
+        f.write(txt)
+    return x
+
+
+@pytest.mark.parametrize("hfmt", ["<I", "<Q"])
+@pytest.mark.parametrize("compressed", [False, True])
+@pytest.mark.parametrize("appended", [False, True])
+def test_reads_files_in_vtk_writer_conventions(tmp_path, appended, compressed, hfmt):
+    m, pd, cd = _mesh("tet")
+    path = tmp_path / "vtkstyle.vtu"
+    x = _py_write(path, m, pd, cd, appended=appended, compressed=compressed, hfmt=hfmt, f32_points=True, i32_conn=(hfmt == "<I"))
+    r = IO.read_vtk(path)
+    assert np.array_equal(r["x"], x.astype(np.float64))                  # Float32 points widened exactly
+    assert np.array_equal(r["ien"], m.ien)
+    for k, v in pd.items():
+        assert np.array_equal(r["point_data"][k], v)
+    for k, v in cd.items():
+        assert np.array_equal(r["cell_data"][k], v)
+
+
+VTP_ASCII = """<?xml version="1.0"?>
+<VTKFile type="PolyData" version="0.1" byte_order="LittleEndian" header_type="UInt32" compressor="vtkZLibDataCompressor">
+  <PolyData>
+    <Piece NumberOfPoints="5" NumberOfVerts="0" NumberOfLines="0" NumberOfStrips="0" NumberOfPolys="3">
+      <PointData Scalars="GlobalNodeID">
+        <DataArray type="Int32" Name="GlobalNodeID" format="ascii" RangeMin="3" RangeMax="42">
+          3 7 11 40 42
+        </DataArray>
+      </PointData>
+      <CellData Scalars="GlobalElementID">
+        <DataArray type="Int32" Name="GlobalElementID" format="ascii">
+          101 102 103
+        </DataArray>
+        <DataArray type="Int32" Name="ModelFaceID" format="ascii">
+          2 2 2
+        </DataArray>
+      </CellData>
+      <Points>
+        <DataArray type="Float32" Name="Points" NumberOfComponents="3" format="ascii" RangeMin="0" RangeMax="1.5">
+          0 0 0 1 0 0 0 1 0
+          1 1 0 0.5 0.5 1e-1
+        </DataArray>
+      </Points>
+      <Verts>
+        <DataArray type="Int64" Name="connectivity" format="ascii"> </DataArray>
+        <DataArray type="Int64" Name="offsets" format="ascii"> </DataArray>
+      </Verts>
+      <Lines>
+        <DataArray type="Int64" Name="connectivity" format="ascii"> </DataArray>
+        <DataArray type="Int64" Name="offsets" format="ascii"> </DataArray>
+      </Lines>
+      <Strips>
+        <DataArray type="Int64" Name="connectivity" format="ascii"> </DataArray>
+        <DataArray type="Int64" Name="offsets" format="ascii"> </DataArray>
+      </Strips>
+      <Polys>
+        <DataArray type="Int64" Name="connectivity" format="ascii" RangeMin="0" RangeMax="4">
+          0 1 4 1 3 4
+          3 2 4
+        </DataArray>
+        <DataArray type="Int64" Name="offsets" format="ascii" RangeMin="3" RangeMax="9">
+          3 6 9
+        </DataArray>
+      </Polys>
+    </Piece>
+  </PolyData>
+</VTKFile>
+"""
+
+
+def test_reads_ascii_polydata_face_like_the_reference_does(tmp_path):
+    """read_vtp (vtk_xml.cpp:438-506): points, triangle connectivity, GlobalNodeID, GlobalElementID"""
+    path = tmp_path / "face.vtp"
+    path.write_text(VTP_ASCII)
+    r = IO.read_vtk(path)
+    assert r["polydata"] and r["nNo"] == 5 and r["nEl"] == 3 and r["eNoN"] == 3
+    assert np.array_equal(r["ien"], [[0, 1, 4], [1, 3, 4], [3, 2, 4]])
+    assert (r["types"] == 5).all()
+    assert np.array_equal(r["point_data"]["GlobalNodeID"], [3, 7, 11, 40, 42])
+    assert np.array_equal(r["cell_data"]["GlobalElementID"], [101, 102, 103])
+    assert r["x"][4].tolist() == [0.5, 0.5, float(np.float32(0.1))]
+
+
+def test_vtp_round_trip(tmp_path):
+    m = M.block_mesh(3, "tet")
+    nodes = m.faces["Z0"]["nodes"]
+    on = np.zeros(m.nNo, bool)
+    on[nodes] = True
+    IENb, gE = M.face_elements(m, on)
+    loc = -np.ones(m.nNo, np.int64)
+    loc[nodes] = np.arange(len(nodes))
+    tri = loc[IENb].astype(np.int32)
+    path = tmp_path / "z0.vtp"
+    IO.write_vtk(path, m.x[nodes], tri, 5, {"GlobalNodeID": (nodes + 1).astype(np.int32)},
+                 {"GlobalElementID": (gE + 1).astype(np.int32)}, polydata=True, mode=IO.APPENDED_BASE64, compress=True, header64=False)
+    r = IO.read_vtk(path)
+    assert r["polydata"] and np.array_equal(r["ien"], tri) and np.array_equal(r["x"], m.x[nodes])
+    assert np.array_equal(r["point_data"]["GlobalNodeID"], nodes + 1)
+    assert np.array_equal(r["cell_data"]["GlobalElementID"], gE + 1)
+
+
+def test_errors_are_reported_not_swallowed(tmp_path):
+    with pytest.raises(IO.IoError, match="cannot open"):
+        IO.read_vtk(tmp_path / "missing.vtu")
+    p = tmp_path / "big.vtu"
+    p.write_text('<VTKFile type="UnstructuredGrid" byte_order="BigEndian"><UnstructuredGrid><Piece NumberOfPoints="0" NumberOfCells="0"/></UnstructuredGrid></VTKFile>')
+    with pytest.raises(IO.IoError, match="BigEndian"):
+        IO.read_vtk(p)
+    p.write_text('<VTKFile type="ImageData"><ImageData/></VTKFile>')
+    with pytest.raises(IO.IoError, match="not supported"):
+        IO.read_vtk(p)
+    p.write_text('<VTKFile type="UnstructuredGrid" compressor="vtkLZ4DataCompressor"><UnstructuredGrid/></VTKFile>')
+    with pytest.raises(IO.IoError, match="zlib only"):
+        IO.read_vtk(p)
+    m, pd, cd = _mesh("tet")
+    good = tmp_path / "good.vtu"
+    IO.write_vtk(good, m.x, m.ien, 10, pd, cd, mode=IO.BINARY, compress=False, header64=False)
+    txt = good.read_text()
+    # cut the base64 payload of the first array short
+    i = txt.index("format=\"binary\">") + len("format=\"binary\">")
+    j = txt.index("</DataArray>", i)
+    bad = tmp_path / "bad.vtu"
+    bad.write_text(txt[:i] + txt[i:j][: (j - i) // 2 // 4 * 4] + txt[j:])
+    with pytest.raises(IO.IoError, match="shorter than its header|truncated"):
+        IO.read_vtk(bad)
+    # connectivity pointing outside the points
+    IO.write_vtk(good, m.x, m.ien, 10, mode=IO.ASCII)
+    txt = good.read_text().replace(f'NumberOfPoints="{m.nNo}"', f'NumberOfPoints="{m.nNo - 1}"')
+    bad.write_text(txt)
+    with pytest.raises(IO.IoError):
+        IO.read_vtk(bad)
+    with pytest.raises(IO.IoError, match="does not exist"):
+        IO.write_vtk(bad, m.x[:5], m.ien, 10)
+    with pytest.raises(IO.IoError, match="tuple count"):
+        IO.write_vtk(bad, m.x, m.ien, 10, {"P": np.zeros(3)})
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "svb200_io.h")).read()
+    names = sorted(set(re.findall(r"\b(b200io_\w+)\s*\(", hdr)))
+    assert len(names) >= 25
+    L = IO.lib()
+    for n in names:
+        assert hasattr(L, n), n
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# restart records and history lines against the reference's own output.cpp
+# ---------------------------------------------------------------------------------------------------------------------------
+def _restart_state(tnNo=37, tDof=4, nEq=2, nXn=3, seed=5):
+    rng = np.random.default_rng(seed)
+    return dict(stamp=[1, nEq, 1, tnNo, nXn, tDof, 0], cTS=12, time=0.06, iNorm=rng.random(nEq), xn=rng.standard_normal(nXn),
+                Yn=rng.standard_normal((tnNo, tDof)), An=rng.standard_normal((tnNo, tDof)))
+
+
+@needs_ref
+@pytest.mark.parametrize("flags", ["fluid", "struct", "ustruct", "prestress", "ustruct+prestress"])
+def test_restart_record_is_byte_identical_to_the_reference(tmp_path, flags):
+    from oracle import ref
+    st = _restart_state()
+    rng = np.random.default_rng(11)
+    tnNo, tDof = st["Yn"].shape
+    extra = {}
+    if flags != "fluid":
+        extra["Dn"] = rng.standard_normal((tnNo, tDof))
+        st["stamp"][6] = 1
+    if "ustruct" in flags:
+        extra["Ad"] = rng.standard_normal((tnNo, 3))
+    if "prestress" in flags:
+        extra["pS0"] = rng.standard_normal((tnNo, 6))
+    recLn = ref.io_write_restart(str(tmp_path / "ref"), **st, **extra)
+    ref_file = tmp_path / IO.restart_name("ref", st["cTS"])
+    assert ref_file.name == "ref_012.bin" and ref_file.exists()
+    blob = ref_file.read_bytes()
+    # the reference stamps the CPU time since the start of the run into the header: take it from its file
+    cpu_time = struct.unpack_from("<d", blob, 8 * 4 + 8)[0]
+    assert IO.restart_record_bytes(cpu_time=0.0, **st, **extra) == recLn
+    mine = tmp_path / "mine.bin"
+    IO.write_restart(mine, 0, recLn, cpu_time=cpu_time, **st, **extra)
+    assert mine.read_bytes() == blob
+    if flags == "struct":
+        assert len(blob) == recLn + tnNo * tDof * 8           # the reference's trailing second copy of Dn
+        IO.write_restart(mine, 0, recLn, cpu_time=cpu_time, trailing_Dn=False, **st, **extra)
+        assert mine.read_bytes() == blob[:recLn]
+    else:
+        assert len(blob) == recLn
+    # and the reference's file reads back
+    r = IO.read_restart(ref_file, 0, recLn, nEq=2, nXn=3, tDof=tDof, tnNo=tnNo, dFlag="Dn" in extra, nsd=3 if "Ad" in extra else 0,
+                        nsymd=6 if "pS0" in extra else 0)
+    assert r["stamp"] == st["stamp"] and r["cTS"] == 12 and r["time"] == 0.06
+    for k in ("iNorm", "xn", "Yn", "An"):
+        assert np.array_equal(r[k], st[k])
+    for k, v in extra.items():
+        assert np.array_equal(r[k], v)
+
+
+def test_restart_records_of_several_ranks(tmp_path):
+    path = tmp_path / "multi.bin"
+    sts = [_restart_state(tnNo=n, seed=n) for n in (20, 31, 26)]
+    for s in sts:
+        s["stamp"][0] = 3
+    recLn = max(IO.restart_record_bytes(cpu_time=0.0, **s) for s in sts)          # MPI_MAX of initialize.cpp:520
+    for rank in (2, 0, 1):                                                           # any order
+        IO.write_restart(path, rank, recLn, create=(rank == 2), cpu_time=1.5, **sts[rank])
+    for rank, s in enumerate(sts):
+        r = IO.read_restart(path, rank, recLn, nEq=2, nXn=3, tDof=4, tnNo=s["Yn"].shape[0])
+        assert np.array_equal(r["Yn"], s["Yn"]) and np.array_equal(r["An"], s["An"]) and r["cpu_time"] == 1.5
+    assert IO.restart_name("results/stFile", 7).endswith("stFile_007.bin") and IO.restart_name("s", 1500) == "s_1500.bin"
+    with pytest.raises(IO.IoError, match="shorter"):
+        IO.read_restart(path, 5, recLn, nEq=2, nXn=3, tDof=4, tnNo=20)
+
+
+@needs_ref
+@pytest.mark.parametrize("case", [
+    dict(nEq=1, sym="NS", cTS=3, itr=2, saved=False, eq_iNorm=4.2e3, eq_pNorm=0.37, ri_iNorm=1.9, ri_fNorm=3.1e-4, ri_dB=-38.4, ri_callD=30.0, ri_itr=7, ri_suc=True),
+    dict(nEq=2, sym="ST", cTS=120, itr=11, saved=True, eq_iNorm=1.0e-3, eq_pNorm=2.0e-9, ri_iNorm=8.0e-4, ri_fNorm=7.9e-4, ri_dB=-0.6, ri_callD=500.0, ri_itr=600, ri_suc=False),
+    dict(nEq=1, sym="MS", cTS=1, itr=1, saved=False, eq_iNorm=0.0, eq_pNorm=1.0, ri_iNorm=0.0, ri_fNorm=0.0, ri_dB=0.0, ri_callD=0.0, ri_itr=0, ri_suc=True),
+])
+def test_history_line_is_character_identical_to_the_reference(tmp_path, case):
+    from oracle import ref
+    elapsed = 123.42
+    text = ref.io_history(str(tmp_path / "histor.dat"), elapsed=elapsed, **case)
+    kw = {k: v for k, v in case.items() if k not in ("nEq", "sym", "cTS", "itr")}
+    mine = IO.history_header(case["nEq"]) + IO.history_line(case["sym"], case["cTS"], case["itr"], elapsed=elapsed, since_last=elapsed, **kw)
+    assert mine == text
