@@ -120,6 +120,21 @@ int b200_lhs_create(b200_handle* h, int gnNo, int nNo, int mynNo, int nnz,
 int b200_face_set(b200_handle* h, int faIn, int nNo, int dof, int bGrp, const int* glob,
                   const double* val, int shared);
 
+/* ---- partition layout (replaces the renumbering of fsils_lhs_create, liner_solver/lhs.cpp:57-376) -------------------- */
+/* Host-side, needs no device and no handle.  Input: every rank's global node ids in that rank's local (assembly) order --
+ * what the MPI_Allgatherv at lhs.cpp:156 collects.  Output for `rank`: map (local assembly id -> solver id: nodes shared
+ * with lower ranks first, interior, nodes shared with higher ranks last), mynNo, shnNo and one overlap list per neighbour
+ * (solver ids, ordered as the higher rank of the pair walks its renumbered nodes) -- the map / mynNo / request arguments of
+ * b200_lhs_create, integer for integer what the reference leaves in lhs.map / lhs.mynNo / lhs.shnNo / lhs.cS[].ptr.
+ * Errors: non-zero return, text from b200_last_error(NULL). */
+typedef struct b200_layout b200_layout;
+int b200_lhs_layout_create(int rank, int nRanks, int gnNo, const int* counts, const int* const* gnodes, b200_layout** out);
+int b200_lhs_layout_sizes(const b200_layout* lay, int* nNo, int* mynNo, int* shnNo, int* nReq);
+int b200_lhs_layout_map(const b200_layout* lay, int* map /* nNo */);
+/* i-th neighbour (ascending rank): peer, list length, and -- when ptr is not NULL -- the list */
+int b200_lhs_layout_req(const b200_layout* lay, int i, int* peer, int* n, int* ptr);
+void b200_lhs_layout_free(b200_layout* lay);
+
 /* ---- pattern (replaces lhsa_ns::lhsa, solver/lhsa.cpp:153, for idMap = identity, no shells) ------------------------- */
 /* Device-side construction of the block-CSR pattern from the connectivity of every mesh of the equation system:
  * b200_pattern_begin(h, tnNo); b200_pattern_add_mesh(...) once per mesh (IEN(eNoN,nEl), assembly node ids);

@@ -129,6 +129,12 @@ def lib():
         L.b200_comm_unique_id.argtypes = [vp]
         L.b200_comm_init.argtypes = [vp, ci, ci, vp]
         L.b200_lhs_create.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, ci, vp, vp, vp, ci]
+        L.b200_lhs_layout_create.argtypes = [ci, ci, ci, vp, vp, C.POINTER(vp)]
+        L.b200_lhs_layout_sizes.argtypes = [vp, vp, vp, vp, vp]
+        L.b200_lhs_layout_map.argtypes = [vp, vp]
+        L.b200_lhs_layout_req.argtypes = [vp, ci, vp, vp, vp]
+        L.b200_lhs_layout_free.argtypes = [vp]
+        L.b200_lhs_layout_free.restype = None
         L.b200_face_set.argtypes = [vp, ci, ci, ci, ci, vp, vp, ci]
         L.b200_mesh_set.argtypes = [vp, ci, ci, vp, vp, cd]
         L.b200_zero.argtypes = [vp, ci]
@@ -268,6 +274,33 @@ def unique_id() -> np.ndarray:
     if lib().b200_comm_unique_id(_p(uid)) != 0:
         raise RuntimeError("b200_comm_unique_id: " + lib().b200_last_error(None).decode())
     return uid
+
+
+def lhs_layout(rank: int, all_gnodes, gnNo: int):
+    """fsils_lhs_create's renumbering and overlap lists through the C ABI (b200_lhs_layout_*, csrc/lhs_layout.hpp; host side,
+    needs no device): dict(map, mynNo, shnNo, reqs=[(peer, solver ids)]) for `rank` from every rank's global node list."""
+    L = lib()
+    lists = [_c(g, np.int32) for g in all_gnodes]
+    counts = _c([len(g) for g in lists], np.int32)
+    ptrs = (C.c_void_p * len(lists))(*[g.ctypes.data for g in lists])
+    h = C.c_void_p()
+    if L.b200_lhs_layout_create(int(rank), len(lists), int(gnNo), _p(counts), ptrs, C.byref(h)) != 0:
+        raise RuntimeError("b200_lhs_layout_create: " + L.b200_last_error(None).decode())
+    try:
+        nNo, mynNo, shnNo, nReq = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        L.b200_lhs_layout_sizes(h, C.byref(nNo), C.byref(mynNo), C.byref(shnNo), C.byref(nReq))
+        mp = np.zeros(nNo.value, np.int32)
+        L.b200_lhs_layout_map(h, _p(mp))
+        reqs = []
+        for i in range(nReq.value):
+            peer, n = C.c_int(), C.c_int()
+            L.b200_lhs_layout_req(h, i, C.byref(peer), C.byref(n), None)
+            ptr = np.zeros(n.value, np.int32)
+            L.b200_lhs_layout_req(h, i, None, None, _p(ptr))
+            reqs.append((peer.value, ptr))
+        return dict(map=mp, mynNo=mynNo.value, shnNo=shnNo.value, reqs=reqs)
+    finally:
+        L.b200_lhs_layout_free(h)
 
 
 class Backend:

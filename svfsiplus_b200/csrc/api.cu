@@ -18,6 +18,7 @@
 #include "pic.cuh"
 #include "assembly_face.cuh"
 #include "pattern.cuh"
+#include "lhs_layout.hpp"
 #include "ops_cuda.cuh"
 
 using namespace svb200;
@@ -1105,6 +1106,51 @@ int b200_commu_R(b200_handle* h)
     CU_CHECK(cudaStreamSynchronize(h->ops->st));
   });
 }
+
+// ---- fsils_lhs_create's renumbering and overlap lists, host side (lhs_layout.hpp) ------------------------------------
+struct b200_layout { svb200::LhsLayout L; };
+
+int b200_lhs_layout_create(int rank, int nRanks, int gnNo, const int* counts, const int* const* gnodes, b200_layout** out)
+{
+  try {
+    if (!counts || !gnodes || !out) throw std::runtime_error("lhs_layout: null argument");
+    auto lay = std::make_unique<b200_layout>();
+    lay->L = svb200::lhs_layout(rank, nRanks, gnNo, counts, gnodes);
+    *out = lay.release();
+    return 0;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return 1;
+  }
+}
+
+int b200_lhs_layout_sizes(const b200_layout* lay, int* nNo, int* mynNo, int* shnNo, int* nReq)
+{
+  if (!lay) return 1;
+  if (nNo) *nNo = lay->L.nNo;
+  if (mynNo) *mynNo = lay->L.mynNo;
+  if (shnNo) *shnNo = lay->L.shnNo;
+  if (nReq) *nReq = int(lay->L.reqs.size());
+  return 0;
+}
+
+int b200_lhs_layout_map(const b200_layout* lay, int* map)
+{
+  if (!lay || !map) return 1;
+  std::copy(lay->L.map.begin(), lay->L.map.end(), map);
+  return 0;
+}
+
+int b200_lhs_layout_req(const b200_layout* lay, int i, int* peer, int* n, int* ptr)
+{
+  if (!lay || i < 0 || i >= int(lay->L.reqs.size())) return 1;
+  if (peer) *peer = lay->L.reqs[i].first;
+  if (n) *n = int(lay->L.reqs[i].second.size());
+  if (ptr) std::copy(lay->L.reqs[i].second.begin(), lay->L.reqs[i].second.end(), ptr);
+  return 0;
+}
+
+void b200_lhs_layout_free(b200_layout* lay) { delete lay; }
 
 // ---- pattern construction on the device (pattern.cuh) ---------------------------------------------------------------
 int b200_pattern_begin(b200_handle* h, int tnNo)

@@ -1,0 +1,106 @@
+// lhs_layout.hpp — node renumbering and overlap lists of a partitioned linear system, host side (no device needed).
+// Replaces the part of fsils_lhs_create that is not a plain copy (Code/Source/liner_solver/lhs.cpp:57-376): given every
+// rank's global node list in local order (what the MPI_Allgatherv at lhs.cpp:156 collects), rank r's solver ordering is
+//   [ nodes shared with LOWER ranks | interior nodes | nodes shared with HIGHER ranks ]
+// built by walking the other ranks from the highest id down (lhs.cpp:171-224): a node of r that rank i also holds and that
+// no earlier rank claimed goes to the front block (i < r, in rank i's local order) or to the back block (i > r, written from
+// the END backwards, lhs.cpp:198-199); interior nodes keep their relative order.  mynNo = nNo - |back block| (rows this rank
+// counts in dot products), shnNo = |front block|.  The overlap list of a pair is ordered as the HIGHER rank of the pair walks
+// its renumbered node list (lhs.cpp:304-360).  Integer for integer what the reference leaves in lhs.map / lhs.cS[].ptr
+// (tests/test_partition.py, against the compiled reference on threads-as-ranks).
+//
+// Cost: O(gnNo + sum of all node lists) per renumbered list, one list for the rank itself and one per higher rank it shares
+// nodes with; two gnNo-sized int tables at a time (54 MB each at 13.5 M global nodes).
+#pragma once
+
+#include <cstdint>
+#include <stdexcept>
+#include <utility>
+#include <vector>
+
+namespace svb200 {
+
+struct LhsLayout {
+  int nNo = 0, mynNo = 0, shnNo = 0;
+  std::vector<int> map;                                    // local assembly id -> solver id
+  std::vector<std::pair<int, std::vector<int>>> reqs;      // (peer rank, solver ids), ascending peer
+};
+
+namespace detail {
+
+// renumbered global node list of rank r (lhs.cpp:171-224); gtl is scratch of size gnNo
+inline void renumbered_list(int r, int nT, int gnNo, const int* counts, const int* const* gnodes, std::vector<int>& gtl,
+                            std::vector<int>& ltg, int& shnNo, int& mynNo)
+{
+  const int n = counts[r];
+  const int* g = gnodes[r];
+  gtl.assign(size_t(gnNo), -1);
+  for (int a = 0; a < n; a++) {
+    if (g[a] < 0 || g[a] >= gnNo) throw std::runtime_error("lhs_layout: global node id outside [0, gnNo)");
+    if (gtl[g[a]] != -1) throw std::runtime_error("lhs_layout: a rank lists a global node twice");
+    gtl[g[a]] = a;
+  }
+  std::vector<char> taken(size_t(n), 0);
+  std::vector<int> low, high;
+  for (int i = nT - 1; i >= 0; i--) {
+    if (i == r) continue;
+    std::vector<int>& dst = (i < r) ? low : high;
+    const int* gi = gnodes[i];
+    for (int b = 0; b < counts[i]; b++) {
+      const int v = gi[b];
+      if (v < 0 || v >= gnNo) throw std::runtime_error("lhs_layout: global node id outside [0, gnNo)");
+      const int a = gtl[v];
+      if (a >= 0 && !taken[a]) { taken[a] = 1; dst.push_back(v); }
+    }
+  }
+  ltg.clear();
+  ltg.reserve(size_t(n));
+  ltg.insert(ltg.end(), low.begin(), low.end());
+  for (int a = 0; a < n; a++) if (!taken[a]) ltg.push_back(g[a]);
+  ltg.insert(ltg.end(), high.rbegin(), high.rend());
+  shnNo = int(low.size());
+  mynNo = n - int(high.size());
+}
+
+} // namespace detail
+
+inline LhsLayout lhs_layout(int rank, int nT, int gnNo, const int* counts, const int* const* gnodes)
+{
+  if (nT < 1 || rank < 0 || rank >= nT || gnNo < 0) throw std::runtime_error("lhs_layout: bad rank / size arguments");
+  LhsLayout L;
+  const int n = counts[rank];
+  L.nNo = n;
+  L.map.resize(size_t(n));
+  if (nT == 1) {                                           // lhs.cpp:96-121
+    for (int a = 0; a < n; a++) L.map[a] = a;
+    L.mynNo = n;
+    return L;
+  }
+  std::vector<int> gtl, ltg;
+  detail::renumbered_list(rank, nT, gnNo, counts, gnodes, gtl, ltg, L.shnNo, L.mynNo);
+  std::vector<int> pos(size_t(gnNo), -1);                  // global id -> solver id on this rank
+  for (int k = 0; k < n; k++) pos[ltg[k]] = k;
+  for (int a = 0; a < n; a++) L.map[a] = pos[gnodes[rank][a]];
+  std::vector<int> ltg_hi;
+  for (int i = 0; i < nT; i++) {
+    if (i == rank) continue;
+    bool common = false;
+    for (int b = 0; b < counts[i] && !common; b++) common = pos[gnodes[i][b]] >= 0;
+    if (!common) continue;                                 // lhs.cpp:300-302
+    std::vector<int> ptr;
+    if (i < rank) {
+      // this rank is the higher one of the pair: its own renumbered order, restricted to the peer's nodes
+      gtl.assign(size_t(gnNo), -1);
+      for (int b = 0; b < counts[i]; b++) gtl[gnodes[i][b]] = b;
+      for (int k = 0; k < n; k++) if (gtl[ltg[k]] >= 0) ptr.push_back(k);
+    } else {
+      int sh, my;
+      detail::renumbered_list(i, nT, gnNo, counts, gnodes, gtl, ltg_hi, sh, my);
+      for (int v : ltg_hi) if (pos[v] >= 0) ptr.push_back(pos[v]);
+    }
+    L.reqs.emplace_back(i, std::move(ptr));
+  }
+  return L;
+}
+
+} // namespace svb200

@@ -316,31 +316,44 @@ bool B200LinearAlgebra::assemble_fsi_mesh(ComMod& com_mod, const mshType& lM, co
     domains_uploaded_ = &lM;
   }
   check(b200_state_set(h_, com_mod.tDof, Ag.data(), Yg.data(), com_mod.Bf.data()), "b200_state_set");
-  check(b200_disp_set(h_, com_mod.tDof, Dg.data(), nullptr), "b200_disp_set");
+  // Do: the old mesh displacement the moving-mesh Neumann faces of this equation are evaluated on (assemble_face)
+  const bool have_do = com_mod.Do.size() != 0 && com_mod.Do.nrows() == com_mod.tDof;
+  check(b200_disp_set(h_, com_mod.tDof, Dg.data(), have_do ? com_mod.Do.data() : nullptr), "b200_disp_set");
+  do_uploaded_ = have_do;
   check(b200_assemble_fsi(h_, nDmn, kinds.data(), fl.data(), st.data()), "b200_assemble_fsi");
   any_device_contribution_ = true;
   return true;
 }
 
 /// Neumann face on the device (b_assem_neu_bc, eq_assem.cpp:58): b_fluid for fluid domains, b_l_elas for the solid-type ones.
+/// Equations with several domains (FSI: fluid lumen + struct wall) are taken when every element of the face lies in ONE domain
+/// (all_fun::domain of the parent element, all_fun.cpp:149-175) - the reference switches physics per face element, a face
+/// that straddles domains stays on the host path.  Moving meshes (com_mod.mvMsh, gnnb on x + Do(nsd+1..), nn.cpp:609-640)
+/// use the Do that assemble_mesh uploaded with this iteration's state.
 bool B200LinearAlgebra::assemble_face(ComMod& com_mod, const faceType& lFa, const Vector<double>& hg, const Array<double>& Yg)
 {
   using namespace consts;
   if (!device_assembly_ || !any_device_contribution_ || com_mod.nsd != 3) return false;
   auto& eq = com_mod.eq[com_mod.cEq];
   const auto& msh = com_mod.msh[lFa.iM];
-  if (eq.nDmn != 1 || msh.lShl || mesh_uploaded_ != &msh) return false;
+  if (msh.lShl || mesh_uploaded_ != &msh) return false;
   if (lFa.eType != ElementType::TRI3 && lFa.eType != ElementType::QUD4 && lFa.eType != ElementType::TRI6) return false;
   if (lFa.eType == ElementType::TRI3 && lFa.qmTRI3 != 2.0/3.0) return false;       // device tables use the default rule
+  int iDmn = 0;
+  if (eq.nDmn != 1) {
+    if (lFa.nEl == 0) return false;
+    iDmn = all_fun::domain(com_mod, msh, com_mod.cEq, lFa.gE(0));
+    for (int e = 1; e < lFa.nEl; e++) if (all_fun::domain(com_mod, msh, com_mod.cEq, lFa.gE(e)) != iDmn) return false;
+  }
   int kind;
-  switch (eq.dmn[0].phys) {
+  switch (eq.dmn[iDmn].phys) {
     case EquationType::phys_fluid: kind = 0; break;
     case EquationType::phys_lElas: case EquationType::phys_struct: case EquationType::phys_ustruct:
     case EquationType::phys_mesh: case EquationType::phys_stokes: kind = 1; break;
     default: return false;
   }
   if (kind == 0 && com_mod.dof != 4) return false;
-  if (com_mod.mvMsh) return false;      // moving-mesh faces need com_mod.Do on the device: FSI faces stay on the host path
+  if (com_mod.mvMsh && (!do_uploaded_ || com_mod.tDof < 2*com_mod.nsd + 1)) return false;
   auto it = face_meshes_.find(&lFa);
   if (it == face_meshes_.end()) {
     const int slot = int(face_meshes_.size());
@@ -348,11 +361,11 @@ bool B200LinearAlgebra::assemble_face(ComMod& com_mod, const faceType& lFa, cons
     it = face_meshes_.emplace(&lFa, slot).first;
   }
   b200_bneu_props p;
-  p.dt = com_mod.dt; p.af = eq.af; p.gam = eq.gam; p.tDof = com_mod.tDof; p.mvMsh = 0;
+  p.dt = com_mod.dt; p.af = eq.af; p.gam = eq.gam; p.tDof = com_mod.tDof; p.mvMsh = com_mod.mvMsh ? 1 : 0;
   p.rho = 0.0; p.bfs = 0.0;
   if (kind == 0) {
-    p.rho = eq.dmn[0].prop.at(PhysicalProperyType::fluid_density);
-    p.bfs = eq.dmn[0].prop.at(PhysicalProperyType::backflow_stab);
+    p.rho = eq.dmn[iDmn].prop.at(PhysicalProperyType::fluid_density);
+    p.bfs = eq.dmn[iDmn].prop.at(PhysicalProperyType::backflow_stab);
   }
   (void)Yg;      // the device holds the Yg uploaded for the volume assembly of this iteration
   check(b200_assemble_bneu(h_, it->second, kind, &p, hg.data()), "b200_assemble_bneu");

@@ -9,8 +9,9 @@ different: a pipe is cut into z-slabs of whole hex layers (contiguous element ra
 which is what a graph partitioner returns for this geometry up to rounding.  ParMETIS output depends
 on the rank count anyway and only changes summation order.
 
-`lhs_layout` is a numpy restatement of fsils_lhs_create's ordering and is pinned bit-for-bit against
-the compiled reference run on threads-as-ranks (tests/test_partition.py).
+`lhs_layout` (native, csrc/lhs_layout.hpp behind the C ABI) and `lhs_layout_numpy` (an independent numpy restatement)
+reproduce fsils_lhs_create's ordering; both are pinned integer for integer against the compiled reference run on
+threads-as-ranks (tests/test_partition.py).
 """
 from __future__ import annotations
 
@@ -82,6 +83,14 @@ def split_case(case, nparts: int, part: np.ndarray | None = None):
 # fsils_lhs_create: node reordering + overlap lists
 # ------------------------------------------------------------------------------------------------
 def lhs_layout(rank: int, all_gnodes: list[np.ndarray], gnNo: int):
+    """fsils_lhs_create's node ordering and overlap lists for `rank`: the product's native implementation behind the C ABI
+    (b200_lhs_layout_*, csrc/lhs_layout.hpp).  `lhs_layout_numpy` below is the independent numpy restatement the tests
+    compare it with (both are pinned against the compiled reference)."""
+    from . import backend as B
+    return B.lhs_layout(rank, all_gnodes, gnNo)
+
+
+def lhs_layout_numpy(rank: int, all_gnodes: list[np.ndarray], gnNo: int):
     """The part of fsils_lhs_create (lhs.cpp:57-376) that is not a plain copy: for rank `rank`, given
     every rank's global node list in local order (the MPI_Allgatherv at lhs.cpp:156), return
 

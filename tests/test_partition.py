@@ -41,12 +41,13 @@ def test_lhs_layout_equals_reference_fsils_lhs_create(nparts):
     allg = [p["gNodes"] for p in parts]
     for r in range(nparts):
         info = rr.info(r)
-        lay = PT.lhs_layout(r, allg, parts[r]["gnNo"])
-        assert lay["mynNo"] == info["mynNo"] and lay["shnNo"] == info["shnNo"]
-        assert (lay["map"] == info["map"]).all()
-        assert len(lay["reqs"]) == info["nReq"]
-        for (pa, ptra), (pb, ptrb) in zip(lay["reqs"], info["reqs"]):
-            assert pa == pb and (ptra == ptrb).all()
+        for impl in (PT.lhs_layout, PT.lhs_layout_numpy):        # native (C ABI) and the numpy restatement
+            lay = impl(r, allg, parts[r]["gnNo"])
+            assert lay["mynNo"] == info["mynNo"] and lay["shnNo"] == info["shnNo"]
+            assert (lay["map"] == info["map"]).all()
+            assert len(lay["reqs"]) == info["nReq"]
+            for (pa, ptra), (pb, ptrb) in zip(lay["reqs"], info["reqs"]):
+                assert pa == pb and (ptra == ptrb).all()
     rr.close()
 
 
@@ -63,13 +64,63 @@ def test_lhs_layout_equals_reference_irregular_partition():
     allg = [p["gNodes"] for p in parts]
     for r in range(3):
         info = rr.info(r)
-        lay = PT.lhs_layout(r, allg, parts[r]["gnNo"])
-        assert lay["mynNo"] == info["mynNo"] and lay["shnNo"] == info["shnNo"]
-        assert (lay["map"] == info["map"]).all()
-        assert [q[0] for q in lay["reqs"]] == [q[0] for q in info["reqs"]]
-        for (pa, ptra), (pb, ptrb) in zip(lay["reqs"], info["reqs"]):
-            assert (ptra == ptrb).all()
+        for impl in (PT.lhs_layout, PT.lhs_layout_numpy):
+            lay = impl(r, allg, parts[r]["gnNo"])
+            assert lay["mynNo"] == info["mynNo"] and lay["shnNo"] == info["shnNo"]
+            assert (lay["map"] == info["map"]).all()
+            assert [q[0] for q in lay["reqs"]] == [q[0] for q in info["reqs"]]
+            for (pa, ptra), (pb, ptrb) in zip(lay["reqs"], info["reqs"]):
+                assert (ptra == ptrb).all()
     rr.close()
+
+
+@pytest.mark.parametrize("nparts,seed", [(1, 0), (2, 1), (5, 2), (8, 3)])
+def test_native_layout_equals_numpy_restatement_random_partitions(nparts, seed):
+    """Random element -> rank maps (many owners per node, ranks without common nodes, local orders shuffled): the native
+    implementation behind the C ABI and the numpy restatement agree integer for integer; the map is a permutation and the
+    overlap lists of a pair name the same global nodes in the same order on both sides."""
+    rng = np.random.default_rng(seed)
+    case = P.pipe_case(4, 4, 8)
+    m = case["mesh"]
+    # blocks of consecutive elements so that distant ranks share nothing
+    part = np.minimum((np.arange(m.nEl) * nparts) // m.nEl + rng.integers(0, 2, m.nEl), nparts - 1).astype(np.int32)
+    allg = []
+    for r in range(nparts):
+        g = np.unique(m.ien[part == r]).astype(np.int32)
+        rng.shuffle(g)                                        # local order is arbitrary
+        allg.append(g)
+    lays = []
+    for r in range(nparts):
+        a = PT.lhs_layout(r, allg, m.nNo)
+        b = PT.lhs_layout_numpy(r, allg, m.nNo)
+        assert a["mynNo"] == b["mynNo"] and a["shnNo"] == b["shnNo"] and (a["map"] == b["map"]).all()
+        assert [q[0] for q in a["reqs"]] == [q[0] for q in b["reqs"]]
+        for (_, pa), (_, pb) in zip(a["reqs"], b["reqs"]):
+            assert (pa == pb).all()
+        assert sorted(a["map"].tolist()) == list(range(len(allg[r])))
+        lays.append(a)
+    # every node is counted by exactly one rank's [0, mynNo)
+    owners = np.zeros(m.nNo, int)
+    for r, lay in enumerate(lays):
+        inv = np.empty(len(allg[r]), np.int64)
+        inv[lay["map"]] = allg[r]
+        owners[inv[:lay["mynNo"]]] += 1
+        for peer, ptr in lay["reqs"]:
+            back = dict(lays[peer]["reqs"])[r]
+            inv_p = np.empty(len(allg[peer]), np.int64)
+            inv_p[lays[peer]["map"]] = allg[peer]
+            assert (inv[ptr] == inv_p[back]).all()
+    held = np.zeros(m.nNo, bool)
+    for g in allg:
+        held[g] = True
+    assert (owners[held] == 1).all()
+
+
+def test_native_layout_reports_bad_input():
+    with pytest.raises(RuntimeError, match="outside"):
+        PT.lhs_layout(0, [np.array([0, 1, 7], np.int32), np.array([1, 2], np.int32)], 5)
+    with pytest.raises(RuntimeError, match="twice"):
+        PT.lhs_layout(0, [np.array([0, 1, 1], np.int32), np.array([1, 2], np.int32)], 5)
 
 
 def test_local_slab_case_matches_neighbours():

@@ -85,3 +85,20 @@ def test_law_matches_reference_get_pk2cc_dev(iso, vol, kw):
         worst = max(worst, np.abs(S6 - Sr).max() / np.abs(Sr).max(), np.abs(Dm21 - Dr).max() / np.abs(Dr).max())
     ra.close()
     assert worst < 1e-12, worst
+
+
+@needs_ref
+def test_oracle_reproduces_late_addition_fixtures():
+    """tests/golden/late_additions.npz (make_golden_late.py) is what the compiled reference gives today."""
+    from oracle import refcase
+    from util import golden
+    from svfsiplus_b200 import problem as P
+    g = golden("late_additions.npz")
+    for elem in ("tet", "hex"):
+        c = P.block_case(3, elem=elem, kind="struct", iso="HO_ma", vol="ST91")
+        R, Val, *_ = refcase.reference_assemble_solid(c)
+        assert np.array_equal(R, g[f"R_{elem}_struct_HO_ma"]) and np.array_equal(Val, g[f"Val_{elem}_struct_HO_ma"])
+        c = P.ustruct_case(3, elem=elem, iso="HO_ma")
+        R, Val, Kd, _ = refcase.reference_assemble_ustruct(c)
+        assert np.array_equal(R, g[f"R_{elem}_ustruct_HO_ma"]) and np.array_equal(Val, g[f"Val_{elem}_ustruct_HO_ma"])
+        assert np.array_equal(Kd, g[f"Kd_{elem}_ustruct_HO_ma"])
