@@ -103,6 +103,7 @@ EXPORTS = [
     "b200_pic_copy_rows", "b200_pic_advance", "b200_face_mesh_set", "b200_assemble_bneu",
     "b200_assemble_fluid_dmn", "b200_assemble_struct_dmn",
     "b200_assemble_bfolw", "b200_face_integ", "b200_face_normal_update", "b200_face_get_val", "b200_pattern_begin", "b200_pattern_add_mesh", "b200_pattern_finish", "b200_pattern_get",
+    "b200_lhs_layout_create", "b200_lhs_layout_sizes", "b200_lhs_layout_map", "b200_lhs_layout_req", "b200_lhs_layout_free",
 ]
 
 KERNEL_CLASSES = ["spmv_vv4", "spmv_vv3", "spmv_ss", "spmv_sv", "spmv_vs", "multi_dot", "cgs_update_scale", "blas1",
