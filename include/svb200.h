@@ -66,6 +66,9 @@ typedef struct {
   double Tfa, Tsa;   /* fibre-reinforcement / active stress along the fibre and sheet directions: what get_fib_stress returns
                         for stM.Tf at this time, and Tfa*Tf.eta_s (mat_models_carray.h:222-225); laws 0, 3, 4, 5, needs fibres */
   double kap;        /* isoType 5 (Holzapfel-Gasser-Ogden): fibre dispersion stM.kap; C10, aff, bff, ass, bss as in the XML */
+  int viscType;      /* solid viscosity (dmn.solid_visc, mat_models_carray.h:1383-1590): 0 none, 1 Newtonian, 2 pseudo-potential;
+                        single-domain struct equations only (b200_assemble_struct) */
+  double visc_mu;
 } b200_struct_props;
 
 /* Linear elasticity (solver/l_elas.cpp:274-390).  mesh_mode != 0: the ALE mesh-motion equation

@@ -197,6 +197,9 @@ def lib():
         L.ref_asm_bfolw.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 8
         L.ref_asm_bneu.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8
         L.ref_pic.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_double] + [C.c_void_p] * 12
+        L.ref_asm_set_visc.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.ref_asm_set_visc.restype = None
+        L.ref_visc.argtypes = [C.c_int, C.c_double, C.c_int] + [C.c_void_p] * 6
         L.ref_io_write_restart.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_io_history.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int] + [C.c_double] * 7 + [C.c_int, C.c_int]
@@ -379,7 +382,8 @@ class RefAssembly:
     VOL = {None: 0, "Quad": 1, "ST91": 2, "M94": 3}
 
     def solid(self, kind, Ag, Yg, Dg, Bf, *, dt, am, af, gam, beta, rho, dmp=0.0, f=(0.0, 0.0, 0.0), iso="nHook",
-              vol="ST91", C10=0.0, C01=0.0, Kpen=0.0, elM=0.0, nu=0.0, s=0, Do=None, ho=None, Tfa=0.0, eta_s=0.0, kap=0.0):
+              vol="ST91", C10=0.0, C01=0.0, Kpen=0.0, elM=0.0, nu=0.0, s=0, Do=None, ho=None, Tfa=0.0, eta_s=0.0, kap=0.0,
+              visc=None, visc_mu=0.0):
         """kind "struct": construct_dsolid (S/sv_struct.cpp:213); "lelas": construct_l_elas (S/l_elas.cpp:58).
         Returns R (nNo,3), Val (nnz,9), seconds."""
         Ag = _c(Ag, np.float64); Yg = _c(Yg, np.float64); Dg = _c(Dg, np.float64); Bf = _c(Bf, np.float64)
@@ -390,6 +394,7 @@ class RefAssembly:
         R = np.empty((self.nNo, 3))
         Val = np.empty((self.nnz, 9))
         Do = None if Do is None else _c(Do, np.float64)
+        lib().ref_asm_set_visc(self.h, {None: 0, "newt": 1, "pot": 2}[visc], float(visc_mu))      # dmn.solid_visc
         t = lib().ref_asm_solid(self.h, {"struct": 0, "lelas": 1, "mesh": 2}[kind], tDof, int(s), _p(par), _p(Ag), _p(Yg),
                                 _p(Dg), _p(Do), _p(Bf), _p(R), _p(Val))
         if t < 0:
@@ -568,3 +573,15 @@ def io_history(path, *, nEq, sym, cTS, itr, saved, elapsed, eq_iNorm, eq_pNorm, 
         raise RuntimeError(lib().ref_last_error().decode())
     with open(path) as f:
         return f.read()
+
+
+def visc(model, mu, Nx, vx, F):
+    """mat_models_carray::get_visc_stress_and_tangent<3> (S/mat_models_carray.h:1578): model "newt" | "pot"; Nx (eNoN, 3).
+    Returns Svis (3,3), Kvis_u, Kvis_v as (eNoN_a, eNoN_b, 3, 3)."""
+    Nx = np.ascontiguousarray(Nx, np.float64); vx = np.ascontiguousarray(vx, np.float64); F = np.ascontiguousarray(F, np.float64)
+    n = Nx.shape[0]
+    S = np.zeros((3, 3)); Ku = np.zeros((n, n, 9)); Kv = np.zeros((n, n, 9))       # Array3(9, a, b): memory order [b][a][ii]
+    rc = lib().ref_visc({"newt": 1, "pot": 2}[model], float(mu), n, _p(Nx), _p(vx), _p(F), _p(S), _p(Ku), _p(Kv))
+    if rc != 0:
+        raise RuntimeError(lib().ref_last_error().decode())
+    return S, Ku.transpose(1, 0, 2).reshape(n, n, 3, 3), Kv.transpose(1, 0, 2).reshape(n, n, 3, 3)

@@ -76,6 +76,8 @@ double now_s()
 struct AsmCtx {
   std::unique_ptr<Simulation> sim;
   int nnz = 0;
+  int visc_model = 0;        // solid viscosity applied by ref_asm_solid: 0 none, 1 Newtonian, 2 potential (ref_asm_set_visc)
+  double visc_mu = 0.0;
 };
 
 } // namespace
@@ -325,6 +327,14 @@ void configure_solid(AsmCtx* ctx, int kind, int tDof, int s, const double* par, 
 
 extern "C" {
 
+// Solid viscosity of the next ref_asm_solid calls (dmn.solid_visc): model 0 none, 1 Newtonian, 2 potential.
+void ref_asm_set_visc(void* h, int model, double mu)
+{
+  auto ctx = static_cast<AsmCtx*>(h);
+  ctx->visc_model = model;
+  ctx->visc_mu = mu;
+}
+
 // Solid assembly through the reference's construct_dsolid (S/sv_struct.cpp:213 -> struct_3d_carray :552 ->
 // get_pk2cc<3> S/mat_models_carray.h:182) or construct_l_elas (S/l_elas.cpp:58 -> l_elas_3d :274).
 // kind 0: struct, 1: lElas, 2: mesh (construct_mesh S/mesh.cpp:42; needs Do and eq.s = s).  par = {dt, am, af, gam, beta, rho, dmp, fx, fy, fz,
@@ -341,6 +351,9 @@ double ref_asm_solid(void* h, int kind, int tDof, int s, const double* par, cons
     const int dof = 3;
     configure_solid(ctx, kind, tDof, s, par, Do, Bf);
     auto& eq = com_mod.eq[0];
+    eq.dmn[0].solid_visc.viscType = (ctx->visc_model == 1) ? SolidViscosityModelType::viscType_Newtonian
+                                  : (ctx->visc_model == 2) ? SolidViscosityModelType::viscType_Potential : SolidViscosityModelType::viscType_NA;
+    eq.dmn[0].solid_visc.mu = ctx->visc_mu;
     if (!eq.linear_algebra) eq.linear_algebra = new FsilsLinearAlgebra();
 
     Array<double> Ag_a(tDof, nNo), Yg_a(tDof, nNo), Dg_a(tDof, nNo);
@@ -1394,6 +1407,31 @@ int ref_io_history(const char* path, int nEq, const char* sym, int cTS, int itr,
     timeP[0] = utils::cput() - elapsed;
     timeP[1] = 0.0;
     output::output_result(&sim, timeP, saved ? 3 : 2, 0);
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+// mat_models_carray::get_visc_stress_and_tangent<3> (S/mat_models_carray.h:1578) at one Gauss point: model 1 Newtonian, 2 potential.
+// Nx (3 x eNoN, column-major), vx / F row-major 3x3.  Outputs Svis (3x3 row-major), Kvis_u / Kvis_v (9 x eNoN x eNoN, Array3 layout).
+int ref_visc(int model, double mu, int eNoN, const double* Nx, const double* vx9, const double* F9, double* Svis9, double* Ku, double* Kv)
+{
+  try {
+    dmnType dmn;
+    dmn.solid_visc.viscType = (model == 1) ? consts::SolidViscosityModelType::viscType_Newtonian : consts::SolidViscosityModelType::viscType_Potential;
+    dmn.solid_visc.mu = mu;
+    Array<double> Nx_a(3, eNoN);
+    std::memcpy(Nx_a.data(), Nx, sizeof(double)*3*size_t(eNoN));
+    double vx[3][3], F[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { vx[i][j] = vx9[i*3 + j]; F[i][j] = F9[i*3 + j]; }
+    Array<double> Svis(3, 3);
+    Array3<double> Kvis_u(9, eNoN, eNoN), Kvis_v(9, eNoN, eNoN);
+    mat_models_carray::get_visc_stress_and_tangent<3>(dmn, eNoN, Nx_a, vx, F, Svis, Kvis_u, Kvis_v);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Svis9[i*3 + j] = Svis(i, j);
+    std::memcpy(Ku, Kvis_u.data(), sizeof(double)*9*size_t(eNoN)*eNoN);
+    std::memcpy(Kv, Kvis_v.data(), sizeof(double)*9*size_t(eNoN)*eNoN);
     return 0;
   } catch (const std::exception& e) {
     g_err = e.what();

@@ -50,7 +50,8 @@ class StructProps(C.Structure):
                 ("C10", C.c_double), ("C01", C.c_double), ("Kpen", C.c_double),
                 ("a", C.c_double), ("b", C.c_double), ("aff", C.c_double), ("bff", C.c_double), ("ass", C.c_double),
                 ("bss", C.c_double), ("afs", C.c_double), ("bfs", C.c_double), ("khs", C.c_double),
-                ("Tfa", C.c_double), ("Tsa", C.c_double), ("kap", C.c_double)]
+                ("Tfa", C.c_double), ("Tsa", C.c_double), ("kap", C.c_double),
+                ("viscType", C.c_int), ("visc_mu", C.c_double)]
 
 
 class LelasProps(C.Structure):
@@ -215,7 +216,7 @@ def fluid_props(*, dt, am, af, gam, rho, mu, tDof=4, mvMsh=False, f=(0.0, 0.0, 0
 
 
 def struct_props(*, dt, am, af, gam, beta, rho, tDof=3, s=0, dmp=0.0, f=(0.0, 0.0, 0.0), iso="nHook", vol="ST91",
-                 C10=0.0, C01=0.0, Kpen=0.0, ho=None, Tfa=0.0, eta_s=0.0, kap=0.0) -> StructProps:
+                 C10=0.0, C01=0.0, Kpen=0.0, ho=None, Tfa=0.0, eta_s=0.0, kap=0.0, visc=None, visc_mu=0.0) -> StructProps:
     p = StructProps()
     p.dt, p.am, p.af, p.gam, p.beta = dt, am, af, gam, beta
     p.tDof, p.s = tDof, s
@@ -224,6 +225,7 @@ def struct_props(*, dt, am, af, gam, beta, rho, tDof=3, s=0, dmp=0.0, f=(0.0, 0.
     p.isoType, p.volType = ISO_TYPES[iso], VOL_TYPES[vol]
     p.C10, p.C01, p.Kpen = C10, C01, Kpen
     p.Tfa, p.Tsa, p.kap = Tfa, Tfa * eta_s, kap
+    p.viscType, p.visc_mu = {None: 0, "newt": 1, "pot": 2}[visc], visc_mu
     p.khs = 100.0
     for k, v in (ho or {}).items():
         setattr(p, k, v)

@@ -262,14 +262,14 @@ void finish_assembly(b200_handle* h, int dof, double t0, const char* who)
   }
 }
 
-template <int ENON, int NG, int EPB, int APT, int ODOF>
+template <int ENON, int NG, int EPB, int APT, int ODOF, bool VISC = false>
 void launch_solid(b200_handle* h, const SolidConsts& c, int nList, const int* d_elist)
 {
   auto& ops = *h->ops;
   if (nList == 0) return;
   constexpr int TABN = NG + NG*ENON + NG*ENON*3;
-  const size_t smem = sizeof(double)*(size_t((TABN + 3) & ~3) + size_t(EPB)*NG*solid_rec(ENON));
-  auto kern = k_assemble_solid<ENON, NG, EPB, APT, ODOF>;
+  const size_t smem = sizeof(double)*(size_t((TABN + 3) & ~3) + size_t(EPB)*NG*(solid_rec(ENON) + (VISC ? VISC_REC : 0)));
+  auto kern = k_assemble_solid<ENON, NG, EPB, APT, ODOF, VISC>;
   CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   kern<<<(nList + EPB - 1)/EPB, EPB*NG, smem, ops.st>>>(nList, d_elist, c, h->d_tab, h->d_ien, h->d_rslot, h->d_kslot, h->d_x,
                                                         h->d_Ag, h->d_Yg, h->d_Dg, h->d_Do, h->d_Bf, h->d_fN, h->stageR, h->stageK, h->d_err);
@@ -353,6 +353,8 @@ SolidConsts struct_consts(const b200_struct_props* p)
   c.ho_afs = p->afs; c.ho_bfs = p->bfs; c.ho_khs = p->khs;
   c.Tfa = p->Tfa; c.Tsa = p->Tsa; c.kap = p->kap;
   c.tDof = p->tDof; c.s = p->s; c.kind = 0;
+  if (p->viscType < 0 || p->viscType > 2) throw std::runtime_error("assemble_struct: solid viscosity model not defined (0 none, 1 Newtonian, 2 potential)");
+  c.viscType = p->viscType; c.visc_mu = p->visc_mu;
   return c;
 }
 
@@ -371,7 +373,14 @@ void assemble_solid(b200_handle* h, const SolidConsts& c, const char* who)
   {
     // algorithmic bytes: Val and R written once, nodal fields and IEN read once
     CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*72.0 + double(h->nNo)*(24.0 + 24.0 + 24.0*3 + 24.0) + double(h->nEl)*4.0*h->eNoN, 3);
-    if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 3>(h, c, h->nEl, nullptr);
+    if (c.kind == 0 && c.viscType != 0) {
+      // solid viscosity: the instantiation with the longer Gauss-point record (reads Yg for dv/dX)
+      if (!h->d_Yg) throw std::runtime_error(std::string(who) + ": solid viscosity needs the velocity state (b200_state_set)");
+      if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 3, true>(h, c, h->nEl, nullptr);
+      else if (h->eNoN == 8) launch_solid<8, 8, 16, 2, 3, true>(h, c, h->nEl, nullptr);
+      else launch_solid<10, 15, 8, 2, 3, true>(h, c, h->nEl, nullptr);
+    }
+    else if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 3>(h, c, h->nEl, nullptr);
     else if (h->eNoN == 8) launch_solid<8, 8, 16, 2, 3>(h, c, h->nEl, nullptr);
     else launch_solid<10, 15, 8, 2, 3>(h, c, h->nEl, nullptr);       // TET10: 15 Gauss points, gnn per point
   }
@@ -919,6 +928,7 @@ int b200_assemble_fsi(b200_handle* h, int nDmn, const int* dmn_kind, const b200_
         } else if (dmn_kind[d] == 1) {
           if (solid[d].tDof != h->tDof) throw std::runtime_error("assemble_fsi: tDof differs from the uploaded state");
           const SolidConsts c = struct_consts(&solid[d]);
+          if (c.viscType != 0) throw std::runtime_error("assemble_fsi: solid viscosity has a device kernel for single-domain struct equations only");
           if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 4>(h, c, n, h->d_dmn_elems[d]);
           else if (h->eNoN == 8) launch_solid<8, 8, 16, 2, 4>(h, c, n, h->d_dmn_elems[d]);
           else launch_solid<10, 15, 8, 2, 4>(h, c, n, h->d_dmn_elems[d]);
@@ -969,6 +979,7 @@ int b200_assemble_struct_dmn(b200_handle* h, int nDmn, const b200_struct_props* 
     for (int d = 0; d < nDmn; d++) {
       covered += h->dmn_count[d];
       cs.push_back(struct_consts(&p[d]));
+      if (cs[d].viscType != 0) throw std::runtime_error("assemble_struct_dmn: solid viscosity has a device kernel for single-domain struct equations only");
       if (cs[d].tDof != h->tDof) throw std::runtime_error("assemble_struct_dmn: tDof differs from the uploaded state");
       if (cs[d].s < 0 || cs[d].s + 3 > cs[d].tDof) throw std::runtime_error("assemble_struct_dmn: equation offset outside the state");
       if ((cs[d].iso == 3 || cs[d].iso == 5 || cs[d].iso == 6 || cs[d].iso == 7) && !h->d_fN) throw std::runtime_error("assemble_struct_dmn: the Holzapfel-Ogden law needs fibre directions (b200_mesh_fibers)");

@@ -35,7 +35,10 @@ __host__ __device__ constexpr int solid_rec(int eNoN) { return SREC_NX + 3*eNoN;
 // ODOF: block size of the system the element is scattered into (3: struct/lElas/mesh equations; 4: the FSI
 // equation, where struct_3d fills the 3x3 corner of lK(dof*dof,a,b) and leaves the pressure row/column zero,
 // fsi.cpp:225).  elist != nullptr: the kernel covers the nEl elements elist[0..nEl) (one FSI domain).
-template <int ENON, int NG, int EPB, int APT, int ODOF>
+// VISC: solid viscosity (dmn.solid_visc, struct only): the record grows by VISC_REC doubles per Gauss point (visc_point's matrices)
+// and phase 2 adds afu*Kvis_u + afv*Kvis_v (sv_struct.cpp:666-675, 771-842); a separate instantiation, so that the inviscid
+// kernel keeps its record size and occupancy.
+template <int ENON, int NG, int EPB, int APT, int ODOF, bool VISC = false>
 __global__ void __launch_bounds__(EPB*NG)
 k_assemble_solid(int nEl, const int* __restrict__ elist, SolidConsts c, const double* __restrict__ tab,      // packed: w[NG], N[NG][ENON], Nxi[NG][ENON][3]
                  const int* __restrict__ ien, const int* __restrict__ rslot, const int* __restrict__ kslot,
@@ -44,7 +47,8 @@ k_assemble_solid(int nEl, const int* __restrict__ elist, SolidConsts c, const do
                  const double* __restrict__ fN,      // 6 x nEl fibre + sheet directions (Holzapfel-Ogden) or null
                  double* __restrict__ stageR, double* __restrict__ stageK, int* __restrict__ err_flag)
 {
-  constexpr int REC = solid_rec(ENON);
+  constexpr int REC = solid_rec(ENON) + (VISC ? VISC_REC : 0);
+  constexpr int SREC_V = solid_rec(ENON);      // visc_point's record (VISC only)
   constexpr int NT = EPB*NG;
   constexpr int TABN = NG + NG*ENON + NG*ENON*3;
   extern __shared__ double sm[];
@@ -105,6 +109,7 @@ k_assemble_solid(int nEl, const int* __restrict__ elist, SolidConsts c, const do
       rec[SREC_W] = (c.kind == 2) ? s_w[g] : s_w[g]*Jac;
 
       double F[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+      double vx[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};      // dv/dX (sv_struct.cpp:617-626), VISC only
       double ed[6] = {0, 0, 0, 0, 0, 0};
       double ud[3];
       if (c.kind == 0) { ud[0] = -c.rho*c.f[0]; ud[1] = -c.rho*c.f[1]; ud[2] = -c.rho*c.f[2]; }
@@ -135,6 +140,7 @@ k_assemble_solid(int nEl, const int* __restrict__ elist, SolidConsts c, const do
             F[i][0] += nx[0]*dl[i];
             F[i][1] += nx[1]*dl[i];
             F[i][2] += nx[2]*dl[i];
+            if (VISC) { vx[i][0] += nx[0]*yl[i]; vx[i][1] += nx[1]*yl[i]; vx[i][2] += nx[2]*yl[i]; }
           }
         } else {
 #pragma unroll
@@ -156,6 +162,13 @@ k_assemble_solid(int nEl, const int* __restrict__ elist, SolidConsts c, const do
           for (int i = 0; i < 6; i++) fl[i] = fN[size_t(e)*6 + i];
         }
         pk2cc_iso(c, F, fl, S6, rec + SREC_DM);
+        if (VISC) {
+          // elastic + viscous stress (sv_struct.cpp:666-675); the record keeps the six entries 00 11 22 01 12 20 the reference
+          // copies into pSl - its Newtonian Svis is symmetric up to rounding only
+          double Sv[3][3];
+          visc_point(c.viscType, c.visc_mu, F, vx, Sv, rec + SREC_V);
+          S6[0] += Sv[0][0]; S6[1] += Sv[1][1]; S6[2] += Sv[2][2]; S6[3] += Sv[0][1]; S6[4] += Sv[1][2]; S6[5] += Sv[2][0];
+        }
 #pragma unroll
         for (int i = 0; i < 6; i++) rec[SREC_S + i] = S6[i];
 #pragma unroll
@@ -216,6 +229,7 @@ k_assemble_solid(int nEl, const int* __restrict__ elist, SolidConsts c, const do
   constexpr int AGN = ENON/APT;            // a-groups per b
   constexpr int IPE = ENON*AGN;            // lanes per element
   const double afu = c.af*c.beta*c.dt*c.dt;
+  const double afv = c.af*c.gam*c.dt;
   for (int item = threadIdx.x; item < EPB*IPE; item += NT) {
     const int el = item / IPE, r = item % IPE;
     const int b = r % ENON, a0 = (r / ENON)*APT;
@@ -266,6 +280,11 @@ k_assemble_solid(int nEl, const int* __restrict__ elist, SolidConsts c, const do
           const double NxSNx = na0*S[0]*nb0 + na1*S[3]*nb0 + na2*S[5]*nb0 + na0*S[3]*nb1 + na1*S[1]*nb1
                              + na2*S[4]*nb1 + na0*S[5]*nb2 + na1*S[4]*nb2 + na2*S[2]*nb2;
           const double T1 = amd*Na*Nb + afu*NxSNx;
+          double Ku[9], Kv[9];
+          if (VISC) {
+            const double na[3] = {na0, na1, na2}, nb[3] = {nb0, nb1, nb2};
+            visc_pair(c.viscType, c.visc_mu, rec + SREC_V, F, na, nb, Ku, Kv);
+          }
           double Ba[6][3];
 #pragma unroll
           for (int j = 0; j < 3; j++) {
@@ -282,7 +301,8 @@ k_assemble_solid(int nEl, const int* __restrict__ elist, SolidConsts c, const do
             for (int j = 0; j < 3; j++) {
               const double BDB = Ba[0][i]*DB[0][j] + Ba[1][i]*DB[1][j] + Ba[2][i]*DB[2][j]
                                + Ba[3][i]*DB[3][j] + Ba[4][i]*DB[4][j] + Ba[5][i]*DB[5][j];
-              acc[q][i*3 + j] = acc[q][i*3 + j] + w*(((i == j) ? T1 : 0.0) + afu*BDB);
+              if (VISC) acc[q][i*3 + j] = acc[q][i*3 + j] + w*(((i == j) ? T1 : 0.0) + afu*(BDB + Ku[i*3 + j]) + afv*Kv[i*3 + j]);
+              else acc[q][i*3 + j] = acc[q][i*3 + j] + w*(((i == j) ? T1 : 0.0) + afu*BDB);
             }
         }
       }

@@ -22,6 +22,8 @@ struct SolidConsts {
   double elM, nu;              // lElas / mesh
   int tDof, s;                 // row offset of this equation's unknowns in Ag/Yg/Dg (eq.s)
   int kind;                    // 0 struct, 1 lElas, 2 mesh
+  int viscType;                // solid viscosity: 0 none, 1 Newtonian, 2 pseudo-potential (dmn.solid_visc)
+  double visc_mu;
 };
 
 // index of (I,J), I <= J, in the packed upper triangle of the 6x6 Voigt matrix
@@ -501,6 +503,139 @@ SVB_HD_NOINL void pk2cc_iso(const SolidConsts& c, const double F[3][3], const do
       }
   }
   S6[0] = S[0][0]; S6[1] = S[1][1]; S6[2] = S[2][2]; S6[3] = S[0][1]; S6[4] = S[1][2]; S6[5] = S[2][0];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Solid viscosity (mat_models_carray.h:1383-1590, get_visc_stress_and_tangent<3>): viscous 2nd Piola-Kirchhoff stress of a
+// Gauss point and its tangent contributions per node pair.  model 1: Newtonian (viscType_Newtonian, :1470-1560: pull-back of
+// the deviatoric Cauchy stress 2 mu d_dev), model 2: pseudo-potential (viscType_Potential, :1383-1450: S = mu sym(F^T dv/dX)).
+// visc_point fills Svis and a record v[VISC_REC] of the point's matrices; visc_pair forms Kvis_u / Kvis_v (row-major 3x3,
+// entry i*3+j) of the pair (a, b) from the record and the two nodes' reference gradients.  Sums run in the reference's order.
+// ---------------------------------------------------------------------------------------------------------------------------
+enum { VISC_REC = 28 };
+
+SVB_HD void mm3(const double* A, const double* B, double* R)          // mat_mul<3>, row-major 3x3
+{
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double sum = 0.0;
+#pragma unroll
+      for (int k = 0; k < 3; k++) sum += A[i*3 + k]*B[k*3 + j];
+      R[i*3 + j] = sum;
+    }
+}
+
+SVB_HD_NOINL void visc_point(int model, double mu, const double F[3][3], const double vx[3][3], double Svis[3][3], double* v)
+{
+  double Fm[9], Vm[9], Ft[9], Vt[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) { Fm[i*3 + j] = F[i][j]; Vm[i*3 + j] = vx[i][j]; Ft[j*3 + i] = F[i][j]; Vt[j*3 + i] = vx[i][j]; }
+  if (model == 2) {
+    // v[0..8] = F vx^T, v[9..17] = F F^T, v[18..26] = vx
+    double FtV[9];
+    mm3(Fm, Ft, v + 9);
+    mm3(Ft, Vm, FtV);
+    mm3(Fm, Vt, v);
+#pragma unroll
+    for (int i = 0; i < 9; i++) v[18 + i] = Vm[i];
+    v[27] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) Svis[i][j] = mu*(0.5*(FtV[i*3 + j] + FtV[j*3 + i]));
+  } else {
+    // v[0..8] = F^-1, v[9..17] = d_dev, v[18..26] = vx F^-1, v[27] = J
+    const double J = ((0.0 + 1.0*F[0][0]*(F[1][1]*F[2][2] - F[1][2]*F[2][1]))
+                      + (-1.0)*F[0][1]*(F[1][0]*F[2][2] - F[1][2]*F[2][0]))
+                      + 1.0*F[0][2]*(F[1][0]*F[2][1] - F[1][1]*F[2][0]);
+    double* Fi = v;
+    Fi[0] = (F[1][1]*F[2][2] - F[1][2]*F[2][1]) / J;
+    Fi[1] = (F[0][2]*F[2][1] - F[0][1]*F[2][2]) / J;
+    Fi[2] = (F[0][1]*F[1][2] - F[0][2]*F[1][1]) / J;
+    Fi[3] = (F[1][2]*F[2][0] - F[1][0]*F[2][2]) / J;
+    Fi[4] = (F[0][0]*F[2][2] - F[0][2]*F[2][0]) / J;
+    Fi[5] = (F[0][2]*F[1][0] - F[0][0]*F[1][2]) / J;
+    Fi[6] = (F[1][0]*F[2][1] - F[1][1]*F[2][0]) / J;
+    Fi[7] = (F[0][1]*F[2][0] - F[0][0]*F[2][1]) / J;
+    Fi[8] = (F[0][0]*F[1][1] - F[0][1]*F[1][0]) / J;
+    double* vF = v + 18;
+    mm3(Vm, Fi, vF);
+    double sy[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) sy[i*3 + j] = 0.5*(vF[i*3 + j] + vF[j*3 + i]);
+    const double tr = ((0.0 + sy[0]) + sy[4]) + sy[8];
+    double* dd = v + 9;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) dd[i*3 + j] = sy[i*3 + j] - (tr/3.0)*((i == j) ? 1.0 : 0.0);
+    v[27] = J;
+    double Fit[9], dFit[9], X[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) Fit[j*3 + i] = Fi[i*3 + j];
+    mm3(dd, Fit, dFit);
+    mm3(Fi, dFit, X);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) Svis[i][j] = 2.0*mu*J*X[i*3 + j];
+  }
+}
+
+SVB_HD void visc_pair(int model, double mu, const double* v, const double* Fm /* row-major F */, const double* na, const double* nb,
+                      double* Ku, double* Kv)
+{
+  if (model == 2) {
+    const double* FVt = v; const double* FFt = v + 9; const double* Vm = v + 18;
+    double FNa[3], FNb[3], VNa[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      FNa[i] = ((0.0 + Fm[i*3]*na[0]) + Fm[i*3 + 1]*na[1]) + Fm[i*3 + 2]*na[2];
+      FNb[i] = ((0.0 + Fm[i*3]*nb[0]) + Fm[i*3 + 1]*nb[1]) + Fm[i*3 + 2]*nb[2];
+      VNa[i] = ((0.0 + Vm[i*3]*na[0]) + Vm[i*3 + 1]*na[1]) + Vm[i*3 + 2]*na[2];
+    }
+    const double NN = ((0.0 + na[0]*nb[0]) + na[1]*nb[1]) + na[2]*nb[2];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        Ku[i*3 + j] = 0.5*mu*(FNb[i]*VNa[j] + NN*FVt[i*3 + j]);
+        Kv[i*3 + j] = 0.5*mu*(NN*FFt[i*3 + j] + FNb[i]*FNa[j]);
+      }
+  } else {
+    const double* Fi = v; const double* dd = v + 9; const double* vF = v + 18;
+    const double J = v[27];
+    double NFa[3], NFb[3], dNa[3], dNb[3], vNa[3], vNb[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      NFa[i] = ((0.0 + na[0]*Fi[i]) + na[1]*Fi[3 + i]) + na[2]*Fi[6 + i];
+      NFb[i] = ((0.0 + nb[0]*Fi[i]) + nb[1]*Fi[3 + i]) + nb[2]*Fi[6 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      dNa[i] = ((0.0 + dd[i*3]*NFa[0]) + dd[i*3 + 1]*NFa[1]) + dd[i*3 + 2]*NFa[2];
+      dNb[i] = ((0.0 + dd[i*3]*NFb[0]) + dd[i*3 + 1]*NFb[1]) + dd[i*3 + 2]*NFb[2];
+      vNa[i] = ((0.0 + vF[i]*NFa[0]) + vF[3 + i]*NFa[1]) + vF[6 + i]*NFa[2];
+      vNb[i] = ((0.0 + vF[i]*NFb[0]) + vF[3 + i]*NFb[1]) + vF[6 + i]*NFb[2];
+    }
+    const double NN = ((0.0 + NFa[0]*NFb[0]) + NFa[1]*NFb[1]) + NFa[2]*NFb[2];
+    const double r2d = 2.0/3.0;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        Ku[i*3 + j] = mu*J*(2.0*(dNa[i]*NFb[j] - dNb[i]*NFa[j]) - (NN*vF[i*3 + j] + NFb[i]*vNa[j] - r2d*NFa[i]*vNb[j]));
+        Kv[i*3 + j] = mu*J*(NN*((i == j) ? 1.0 : 0.0) + NFb[i]*NFa[j] - r2d*NFa[i]*NFb[j]);
+      }
+  }
 }
 
 } // namespace svb200

@@ -135,7 +135,7 @@ def newton_linear_step(be: B.Backend, case, ls="NS", want_system=False, upload=T
 # solid block (tests/cases/struct/block_compression/solver.xml: neo-Hookean, E 240.56596e6, nu 0.5, ST91
 # penalty 4e9, density 1000, dt 1e-4, rho_inf 0.5; X0/Y0/Z0 Dirichlet in one direction each)
 # ---------------------------------------------------------------------------------------------------
-def block_case(n, elem="hex", kind="struct", iso="nHook", vol="ST91", jitter=0.1):
+def block_case(n, elem="hex", kind="struct", iso="nHook", vol="ST91", jitter=0.1, visc=None, visc_mu=0.0):
     m = M.block_mesh(n, elem=elem, jitter=jitter)
     rowPtr, colPtr = M.csr_pattern(m.ien, m.nNo)
     am, af, gam, beta = M.gen_alpha2(0.5)
@@ -159,6 +159,8 @@ def block_case(n, elem="hex", kind="struct", iso="nHook", vol="ST91", jitter=0.1
         if iso in ("HO", "HO_ma"):
             props["ho"] = dict(a=590.0, b=8.023, aff=184720.0, bff=16.026, ass=24810.0, bss=11.12, afs=2160.0, bfs=11.436, khs=100.0)
             props["Kpen"] = 1.0e6
+        if visc:                                 # solid viscosity (tests/cases/struct/tensile_adventitia_*_viscosity: mu 50)
+            props.update(visc=visc, visc_mu=visc_mu)
         if iso == "Gucci":                       # Guccione myocardium: C10 and the three exponents
             props.update(C10=880.0, Kpen=1.0e6, ho=dict(bff=8.0, bss=6.0, bfs=12.0))
         if iso == "HGO":                         # arterial-wall style parameters: two dispersed fibre families

@@ -31,6 +31,13 @@ def main():
         out[f"R_{elem}_ustruct_HO_ma"] = R
         out[f"Val_{elem}_ustruct_HO_ma"] = Val
         out[f"Kd_{elem}_ustruct_HO_ma"] = Kd
+    # solid viscosity (dmn.solid_visc: Newtonian and pseudo-potential models) in struct_3d
+    for elem, n in (("tet", 3), ("hex", 3), ("tet10", 2)):
+        for visc in ("newt", "pot"):
+            c = P.block_case(n, elem=elem, kind="struct", iso="nHook", vol="ST91", visc=visc, visc_mu=5.0e4)
+            R, Val, *_ = refcase.reference_assemble_solid(c)
+            out[f"R_{elem}_struct_visc_{visc}"] = R
+            out[f"Val_{elem}_struct_visc_{visc}"] = Val
     np.savez_compressed(os.path.join(HERE, "late_additions.npz"), **out)
     for k, v in out.items():
         print(k, v.shape, float(np.abs(v).max()))

@@ -201,6 +201,19 @@ void host_pk2cc(const double* par, const double* F9, const double* fl6, double* 
   pk2cc_iso(c, F, fl6, S6, Dm21);
 }
 
+// Solid viscosity (solid_law.hpp visc_point + visc_pair): model 1 Newtonian, 2 potential; Nx (eNoN x 3, node-major); outputs
+// Svis (3x3 row-major) and Ku / Kv as [a][b][9].
+void host_visc(int model, double mu, int eNoN, const double* Nx, const double* vx9, const double* F9, double* Svis9, double* Ku, double* Kv)
+{
+  double F[3][3], vx[3][3], S[3][3], v[VISC_REC];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { F[i][j] = F9[i*3 + j]; vx[i][j] = vx9[i*3 + j]; }
+  visc_point(model, mu, F, vx, S, v);
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Svis9[i*3 + j] = S[i][j];
+  for (int a = 0; a < eNoN; a++)
+    for (int b = 0; b < eNoN; b++)
+      visc_pair(model, mu, v, F9, Nx + a*3, Nx + b*3, Ku + (size_t(a)*eNoN + b)*9, Kv + (size_t(a)*eNoN + b)*9);
+}
+
 // Follower pressure load (face_follower_element): b_neu_folw_p on one face, serial.  par = {afl, afm, tDof, s, ustruct}.
 // struct (ustruct = 0): R(3,nNo), Val(9,nnz); ustruct: R(4,nNo), Val(16,nnz), Kd(12,nnz).  All zero on entry.
 extern "C++" {

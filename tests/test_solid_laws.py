@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from conftest import needs_ref
-from util import host_pk2cc
+from util import host_pk2cc, host_visc
 
 from svfsiplus_b200 import mesh as M
 
@@ -102,3 +102,88 @@ def test_oracle_reproduces_late_addition_fixtures():
         R, Val, Kd, _ = refcase.reference_assemble_ustruct(c)
         assert np.array_equal(R, g[f"R_{elem}_ustruct_HO_ma"]) and np.array_equal(Val, g[f"Val_{elem}_ustruct_HO_ma"])
         assert np.array_equal(Kd, g[f"Kd_{elem}_ustruct_HO_ma"])
+    for elem, n in (("tet", 3), ("hex", 3), ("tet10", 2)):
+        for visc in ("newt", "pot"):
+            c = P.block_case(n, elem=elem, kind="struct", iso="nHook", vol="ST91", visc=visc, visc_mu=5.0e4)
+            R, Val, *_ = refcase.reference_assemble_solid(c)
+            assert np.array_equal(R, g[f"R_{elem}_struct_visc_{visc}"]) and np.array_equal(Val, g[f"Val_{elem}_struct_visc_{visc}"])
+
+
+@needs_ref
+@pytest.mark.parametrize("model", ["newt", "pot"])
+@pytest.mark.parametrize("eNoN", [4, 8, 10])
+def test_solid_viscosity_matches_reference_bitwise(model, eNoN):
+    """visc_point / visc_pair (solid_law.hpp) against get_visc_stress_and_tangent<3> (mat_models_carray.h:1578): the viscous
+    stress and both tangent arrays of every node pair, bit for bit (same sums in the same order, no FMA contraction)."""
+    from oracle import ref
+    rng = np.random.default_rng(99 + eNoN)
+    for _ in range(6):
+        F = np.eye(3) + 0.2 * rng.standard_normal((3, 3))
+        if np.linalg.det(F) < 0.3:
+            continue
+        vx = 5.0 * rng.standard_normal((3, 3))
+        Nx = rng.standard_normal((eNoN, 3))
+        Sr, Kur, Kvr = ref.visc(model, 50.0, Nx, vx, F)
+        S, Ku, Kv = host_visc(model, 50.0, Nx, vx, F)
+        assert np.array_equal(S, Sr)
+        assert np.array_equal(Ku, Kur) and np.array_equal(Kv, Kvr)
+
+
+@needs_ref
+@pytest.mark.parametrize("visc", ["newt", "pot"])
+@pytest.mark.parametrize("elem", ["tet", "hex"])
+def test_struct_viscosity_element_restated_in_numpy_matches_reference(elem, visc):
+    """The arithmetic k_assemble_solid<..., VISC = true> performs (dv/dX per Gauss point, S = S_el + Svis, P = F S, the residual
+    row, T1 + afu (BtDB + Kvis_u) + afv Kvis_v per node pair), restated element by element in numpy on top of the SAME
+    host/device-shared point functions (pk2cc_iso, visc_point, visc_pair), against construct_dsolid of the compiled reference.
+    Pins the way the viscous terms enter the element (index conventions, afu / afv, pair order) without a GPU."""
+    from oracle import refcase
+    from svfsiplus_b200 import backend as B
+    from svfsiplus_b200 import problem as P
+    c = P.block_case(2, elem=elem, kind="struct", iso="nHook", vol="ST91", visc=visc, visc_mu=5.0e4)
+    Rr, Vr, rowPtr, colPtr, *_ = refcase.reference_assemble_solid(c)
+    m, pr = c["mesh"], c["props"]
+    eNoN = m.ien.shape[1]
+    w, N, Nxi = B.elem_tables(eNoN)
+    dt, am, af, gam, beta, rho, dmp = (pr[k] for k in ("dt", "am", "af", "gam", "beta", "rho", "dmp"))
+    afu, afv, amd = af * beta * dt * dt, af * gam * dt, am * rho + af * gam * dt * dmp
+    R = np.zeros_like(Rr)
+    Val = np.zeros_like(Vr)
+    pos = {}
+    for A in range(m.nNo):
+        for p in range(rowPtr[A], rowPtr[A + 1]):
+            pos[(A, colPtr[p])] = p
+    VO = [(0, 0), (1, 1), (2, 2), (0, 1), (1, 2), (2, 0)]
+    for e in range(m.nEl):
+        nd = m.ien[e]
+        xl, al, yl, dl, bl = m.x[nd], c["Ag"][nd], c["Yg"][nd], c["Dg"][nd], c["Bf"][nd]
+        for g in range(len(w)):
+            xXi = xl.T @ Nxi[g]                                   # dx/dxi
+            Jac = np.linalg.det(xXi)
+            Nx = Nxi[g] @ np.linalg.inv(xXi)                     # (a, 3): dN/dX
+            F = np.eye(3) + dl.T @ Nx
+            vx = yl.T @ Nx
+            ud = -rho * np.asarray(pr["f"]) + N[g] @ (rho * (al - bl) + dmp * yl)
+            S6, Dm21 = host_pk2cc(F, np.zeros(6), iso="nHook", vol="ST91", C10=pr["C10"], Kpen=pr["Kpen"])
+            Sv, Ku, Kv = host_visc(visc, pr["visc_mu"], Nx, vx, F)
+            S = np.zeros((3, 3)); Dm = np.zeros((6, 6))
+            for k, (i, j) in enumerate(VO):
+                S[i, j] = S[j, i] = S6[k] + Sv[i, j]             # the six entries the kernel keeps
+            it = iter(Dm21)
+            for I in range(6):
+                for J in range(I, 6):
+                    Dm[I, J] = Dm[J, I] = next(it)
+            Pk = F @ S
+            wj = w[g] * Jac
+            Bm = np.zeros((eNoN, 6, 3))
+            for a in range(eNoN):
+                for k, (i, j) in enumerate(VO):
+                    Bm[a, k] = Nx[a, i] * F[:, i] if i == j else Nx[a, i] * F[:, j] + F[:, i] * Nx[a, j]
+            for a in range(eNoN):
+                R[nd[a]] += wj * (N[g, a] * ud + Pk @ Nx[a])
+                for b in range(eNoN):
+                    T1 = amd * N[g, a] * N[g, b] + afu * (Nx[a] @ S @ Nx[b])
+                    K = wj * (T1 * np.eye(3) + afu * (Bm[a].T @ Dm @ Bm[b] + Ku[a, b]) + afv * Kv[a, b])
+                    Val[pos[(nd[a], nd[b])]] += K.reshape(9)
+    assert np.abs(R - Rr).max() / np.abs(Rr).max() < 1e-12
+    assert np.abs(Val - Vr).max() / np.abs(Vr).max() < 1e-12

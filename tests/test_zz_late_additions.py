@@ -38,3 +38,24 @@ def test_ustruct_ho_ma_matches_golden(elem):
     assert rel_inf(be.get_Val(), g[f"Val_{elem}_ustruct_HO_ma"]) < TOL_ASM
     assert rel_inf(be.get_Kd(), g[f"Kd_{elem}_ustruct_HO_ma"]) < TOL_ASM
     be.close()
+
+
+@pytest.mark.parametrize("visc", ["newt", "pot"])
+@pytest.mark.parametrize("elem,n", [("tet", 3), ("hex", 3), ("tet10", 2)])
+def test_struct_solid_viscosity_matches_golden(elem, n, visc):
+    """dmn.solid_visc (get_visc_stress_and_tangent<3>, mat_models_carray.h:1578) in struct_3d: the viscous stress in the
+    residual and afu*Kvis_u + afv*Kvis_v in the tangent (sv_struct.cpp:666-675, 771-842)."""
+    g = golden("late_additions.npz")
+    case = P.block_case(n, elem=elem, kind="struct", iso="nHook", vol="ST91", visc=visc, visc_mu=5.0e4)
+    be = P.setup_backend(case)
+    P.assemble_solid(be, case)
+    R, Val = be.get_R(), be.get_Val()
+    assert rel_inf(R, g[f"R_{elem}_struct_visc_{visc}"]) < TOL_ASM
+    assert rel_inf(Val, g[f"Val_{elem}_struct_visc_{visc}"]) < TOL_ASM
+    # the inviscid kernel is a different instantiation: the viscous terms must be visible
+    g0 = golden("block_3_solid.npz") if n == 3 else None
+    if g0 is not None:
+        assert rel_inf(Val, g0[f"Val_{elem}_struct_nHook_ST91"]) > 1e-2
+    P.assemble_solid(be, case, upload=False)
+    assert np.array_equal(R, be.get_R()) and np.array_equal(Val, be.get_Val())
+    be.close()

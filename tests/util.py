@@ -159,6 +159,18 @@ def host_pk2cc(F, fl, *, iso, vol, C10=0.0, C01=0.0, Kpen=0.0, ho=None, Tfa=0.0,
     return S6, Dm21
 
 
+def host_visc(model, mu, Nx, vx, F):
+    """solid_law.hpp visc_point + visc_pair on the host (TEST-ONLY harness): Svis (3,3), Kvis_u, Kvis_v (a, b, 3, 3)."""
+    import ctypes as C
+    L = elemhost()
+    L.host_visc.argtypes = [C.c_int, C.c_double, C.c_int] + [C.c_void_p] * 6
+    Nx = np.ascontiguousarray(Nx, np.float64); vx = np.ascontiguousarray(vx, np.float64); F = np.ascontiguousarray(F, np.float64)
+    n = Nx.shape[0]
+    S = np.zeros((3, 3)); Ku = np.zeros((n, n, 3, 3)); Kv = np.zeros((n, n, 3, 3))
+    L.host_visc({"newt": 1, "pot": 2}[model], float(mu), n, _p(Nx), _p(vx), _p(F), _p(S), _p(Ku), _p(Kv))
+    return S, Ku, Kv
+
+
 def host_bfolw_assemble(mesh, IENb, gE, hg, Dg, rowPtr, colPtr, *, dt, af, beta=0.0, s=0, ustruct=False, am=1.0, gam=0.0):
     """face_elem.hpp face_follower_element (b_neu_folw_p: follower pressure on a struct / ustruct face) run serially on the host.
     Returns (R, Val) for struct, (R, Val, Kd) for ustruct."""
