@@ -94,6 +94,8 @@ typedef struct {
   double a, b, aff, bff, ass, bss, afs, bfs, khs;   /* isoType 3 (Holzapfel-Ogden) */
   double Tfa, Tsa;   /* fibre / sheet reinforcement stress as in the struct properties above; mat_models.cpp:682-684 */
   double C01, kap;   /* isoType 4 (Mooney-Rivlin) second modulus; isoType 5 (HGO) fibre dispersion */
+  int viscType;      /* solid viscosity as in the struct properties (ustruct.cpp:1275-1302): 0 none, 1 Newtonian, 2 potential */
+  double visc_mu;
 } b200_ustruct_props;
 
 /* ---- life cycle ------------------------------------------------------------------------- */

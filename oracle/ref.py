@@ -423,7 +423,7 @@ class RefAssembly:
 
 
     def ustruct(self, Ag, Yg, Dg, Bf, *, dt, am, af, gam, rho, elM, nu, ctM, ctC, vol, C10, Kpen, f=(0.0, 0.0, 0.0), Ad=None,
-                iso="nHook", ho=None, Tfa=0.0, eta_s=0.0, C01=0.0, kap=0.0, **_ignored):
+                iso="nHook", ho=None, Tfa=0.0, eta_s=0.0, C01=0.0, kap=0.0, visc=None, visc_mu=0.0, **_ignored):
         """construct_usolid (S/ustruct.cpp:216) [+ ustruct_r when Ad is given].  Returns R (nNo,4), Val (nnz,16),
         Kd (nnz,12), seconds."""
         Ag = _c(Ag, np.float64); Yg = _c(Yg, np.float64); Dg = _c(Dg, np.float64); Bf = _c(Bf, np.float64)
@@ -432,6 +432,7 @@ class RefAssembly:
         par = np.array([dt, am, af, gam, rho, f[0], f[1], f[2], elM, nu, ctM, ctC, self.VOL[vol], C10, Kpen, self.ISO[iso]]
                        + [ho.get(k, 100.0 if k == "khs" else 0.0) for k in self.HO_KEYS] + [Tfa, eta_s, C01, kap], np.float64)
         R = np.empty((self.nNo, 4)); Val = np.empty((self.nnz, 16)); Kd = np.empty((self.nnz, 12))
+        lib().ref_asm_set_visc(self.h, {None: 0, "newt": 1, "pot": 2}[visc], float(visc_mu))      # dmn.solid_visc
         t = lib().ref_asm_ustruct(self.h, Ag.shape[1], _p(par), _p(Ag), _p(Yg), _p(Dg), _p(Bf), _p(Ad), _p(R), _p(Val), _p(Kd))
         if t < 0:
             raise RuntimeError(lib().ref_last_error().decode())

@@ -553,6 +553,9 @@ double ref_asm_ustruct(void* h, int tDof, const double* par, const double* Ag, c
     auto& dmn = eq.dmn[0];
     dmn.Id = -1;
     dmn.phys = EquationType::phys_ustruct;
+    dmn.solid_visc.viscType = (ctx->visc_model == 1) ? SolidViscosityModelType::viscType_Newtonian
+                            : (ctx->visc_model == 2) ? SolidViscosityModelType::viscType_Potential : SolidViscosityModelType::viscType_NA;
+    dmn.solid_visc.mu = ctx->visc_mu;
     dmn.prop[PhysicalProperyType::solid_density] = par[4];
     dmn.prop[PhysicalProperyType::f_x] = par[5];
     dmn.prop[PhysicalProperyType::f_y] = par[6];

@@ -69,7 +69,8 @@ class UstructProps(C.Structure):
                 ("C10", C.c_double), ("Kpen", C.c_double),
                 ("a", C.c_double), ("b", C.c_double), ("aff", C.c_double), ("bff", C.c_double), ("ass", C.c_double),
                 ("bss", C.c_double), ("afs", C.c_double), ("bfs", C.c_double), ("khs", C.c_double),
-                ("Tfa", C.c_double), ("Tsa", C.c_double), ("C01", C.c_double), ("kap", C.c_double)]
+                ("Tfa", C.c_double), ("Tsa", C.c_double), ("C01", C.c_double), ("kap", C.c_double),
+                ("viscType", C.c_int), ("visc_mu", C.c_double)]
 
 
 class BneuProps(C.Structure):
@@ -242,7 +243,7 @@ def lelas_props(*, dt, am, af, beta, rho, elM, nu, tDof=3, s=0, f=(0.0, 0.0, 0.0
 
 
 def ustruct_props(*, dt, am, af, gam, rho, elM, nu, ctM, ctC, vol, C10, Kpen, tDof=4, s=0, f=(0.0, 0.0, 0.0), iso="nHook",
-                  ho=None, Tfa=0.0, eta_s=0.0, C01=0.0, kap=0.0, **_ignored) -> UstructProps:
+                  ho=None, Tfa=0.0, eta_s=0.0, C01=0.0, kap=0.0, visc=None, visc_mu=0.0, **_ignored) -> UstructProps:
     p = UstructProps()
     p.dt, p.am, p.af, p.gam = dt, am, af, gam
     p.tDof, p.s = tDof, s
@@ -252,6 +253,7 @@ def ustruct_props(*, dt, am, af, gam, rho, elM, nu, ctM, ctC, vol, C10, Kpen, tD
     p.isoType, p.volType = ISO_TYPES[iso], VOL_TYPES[vol]
     p.C10, p.Kpen = C10, Kpen
     p.Tfa, p.Tsa, p.C01, p.kap = Tfa, Tfa * eta_s, C01, kap
+    p.viscType, p.visc_mu = {None: 0, "newt": 1, "pot": 2}[visc], visc_mu
     p.khs = 100.0
     for k, v in (ho or {}).items():
         setattr(p, k, v)

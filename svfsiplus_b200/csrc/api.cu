@@ -277,13 +277,13 @@ void launch_solid(b200_handle* h, const SolidConsts& c, int nList, const int* d_
   ops.post();
 }
 
-template <int ENON, int NG, int EPB, int APT>
+template <int ENON, int NG, int EPB, int APT, bool VISC = false>
 void launch_ustruct(b200_handle* h, const UstructConsts& c)
 {
   auto& ops = *h->ops;
   constexpr int TABN = NG + NG*ENON + NG*ENON*3;
-  const size_t smem = sizeof(double)*(size_t((TABN + 3) & ~3) + size_t(EPB)*NG*ustruct_rec(ENON));
-  auto kern = k_assemble_ustruct<ENON, NG, EPB, APT>;
+  const size_t smem = sizeof(double)*(size_t((TABN + 3) & ~3) + size_t(EPB)*NG*(ustruct_rec(ENON) + (VISC ? VISC_REC : 0)));
+  auto kern = k_assemble_ustruct<ENON, NG, EPB, APT, VISC>;
   CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   kern<<<(h->nEl + EPB - 1)/EPB, EPB*NG, smem, ops.st>>>(h->nEl, c, h->d_tab, h->d_ien, h->d_rslot, h->d_kslot, h->d_x,
                                                          h->d_Ag, h->d_Yg, h->d_Dg, h->d_Bf, h->d_fN, h->stageR, h->stageK, h->stageKd, h->d_err);
@@ -809,6 +809,8 @@ int b200_assemble_ustruct(b200_handle* h, const b200_ustruct_props* p)
     c.law.ho_a = p->a; c.law.ho_b = p->b; c.law.ho_aff = p->aff; c.law.ho_bff = p->bff; c.law.ho_ass = p->ass; c.law.ho_bss = p->bss;
     c.law.ho_afs = p->afs; c.law.ho_bfs = p->bfs; c.law.ho_khs = p->khs;
     c.law.Tfa = p->Tfa; c.law.Tsa = p->Tsa; c.law.kap = p->kap;
+    if (p->viscType < 0 || p->viscType > 2) throw std::runtime_error("assemble_ustruct: solid viscosity model not defined (0 none, 1 Newtonian, 2 potential)");
+    c.law.viscType = p->viscType; c.law.visc_mu = p->visc_mu;
     c.tDof = p->tDof; c.s = p->s;
     ensure_stage(h, 4);
     ensure(h->stageKd, h->stageKd_cap, size_t(12)*h->eNoN*h->eNoN*size_t(h->nEl) + 4);
@@ -816,7 +818,12 @@ int b200_assemble_ustruct(b200_handle* h, const b200_ustruct_props* p)
     const double t0 = wall_s();
     {
       CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*(128.0 + 96.0) + double(h->nNo)*(32.0 + 24.0 + 24.0*h->tDof + 24.0) + double(h->nEl)*4.0*h->eNoN, 4);
-      if (h->eNoN == 4) launch_ustruct<4, 4, 16, 1>(h, c);
+      if (c.law.viscType != 0) {                                        // solid viscosity: the longer Gauss-point record
+        if (h->eNoN == 4) launch_ustruct<4, 4, 16, 1, true>(h, c);
+        else if (h->eNoN == 8) launch_ustruct<8, 8, 8, 2, true>(h, c);
+        else launch_ustruct<10, 15, 4, 2, true>(h, c);
+      }
+      else if (h->eNoN == 4) launch_ustruct<4, 4, 16, 1>(h, c);
       else if (h->eNoN == 8) launch_ustruct<8, 8, 8, 2>(h, c);
       else launch_ustruct<10, 15, 4, 2>(h, c);                         // TET10, one function space
       // Kd is rebuilt (assigned) by every assembly: ls_alloc zeroes com_mod.Kd too (ls.cpp:51-60)

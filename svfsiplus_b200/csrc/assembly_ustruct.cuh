@@ -32,7 +32,9 @@ enum { UR_W = 0, UR_J = 1, UR_F = 2, UR_S = 11, UR_DM = 17, UR_P = 38, UR_VD = 4
        UR_NX = 74 };
 __host__ __device__ constexpr int ustruct_rec(int eNoN) { return UR_NX + 6*eNoN; }   // + Nx[a][3], NxFi[a][3]
 
-template <int ENON, int NG, int EPB, int APT>
+// VISC: solid viscosity (dmn.solid_visc; ustruct.cpp:1275-1302, 1406-1550): Siso += Svis, Ku += Kvis_u, Tv = af Kvis_v - a separate
+// instantiation with VISC_REC more doubles per Gauss-point record (visc_point's matrices), like k_assemble_solid.
+template <int ENON, int NG, int EPB, int APT, bool VISC = false>
 __global__ void __launch_bounds__(EPB*NG)
 k_assemble_ustruct(int nEl, UstructConsts c, const double* __restrict__ tab, const int* __restrict__ ien,
                    const int* __restrict__ rslot, const int* __restrict__ kslot, const double* __restrict__ x,
@@ -40,7 +42,8 @@ k_assemble_ustruct(int nEl, UstructConsts c, const double* __restrict__ tab, con
                    const double* __restrict__ Bf, const double* __restrict__ fN, double* __restrict__ stageR,
                    double* __restrict__ stageK, double* __restrict__ stageKd, int* __restrict__ err_flag)
 {
-  constexpr int REC = ustruct_rec(ENON);
+  constexpr int REC = ustruct_rec(ENON) + (VISC ? VISC_REC : 0);
+  constexpr int UR_V = ustruct_rec(ENON);      // visc_point's record (VISC only)
   constexpr int NT = EPB*NG;
   constexpr int TABN = NG + NG*ENON + NG*ENON*3;
   extern __shared__ double sm[];
@@ -150,6 +153,12 @@ k_assemble_ustruct(int nEl, UstructConsts c, const double* __restrict__ tab, con
           for (int i = 0; i < 6; i++) fl[i] = fN[size_t(e)*6 + i];
         }
         pk2cc_iso(c.law, F, fl, S6, rec + UR_DM);
+        if (VISC) {
+          // total isochoric stress = elastic + viscous (ustruct.cpp:1279, 1302); six entries kept, as in k_assemble_solid
+          double Sv[3][3];
+          visc_point(c.law.viscType, c.law.visc_mu, F, vx, Sv, rec + UR_V);
+          S6[0] += Sv[0][0]; S6[1] += Sv[1][1]; S6[2] += Sv[2][2]; S6[3] += Sv[0][1]; S6[4] += Sv[1][2]; S6[5] += Sv[2][0];
+        }
 #pragma unroll
         for (int i = 0; i < 6; i++) rec[UR_S + i] = S6[i];
         // Pdev = F Siso
@@ -312,6 +321,8 @@ k_assemble_ustruct(int nEl, UstructConsts c, const double* __restrict__ tab, con
           Ba[4][j] = nxa[1]*F[j*3 + 2] + F[j*3 + 1]*nxa[2];
           Ba[5][j] = nxa[2]*F[j*3 + 0] + F[j*3 + 2]*nxa[0];
         }
+        double Kvu[9], Kvv[9];
+        if (VISC) visc_pair(c.law.viscType, c.law.visc_mu, rec + UR_V, F, nxa, nxb, Kvu, Kvv);
         // A block (ustruct.cpp:1398-1538)
 #pragma unroll
         for (int i = 0; i < 3; i++)
@@ -323,16 +334,16 @@ k_assemble_ustruct(int nEl, UstructConsts c, const double* __restrict__ tab, con
             const double T2 = -tauC*J*nfa[i]*VxNxb[j];
             double Ku, T2k;
             if (i == j) {
-              Ku = w*af*(T1 + T2 + BtDB + NxSNx + 0.0);
+              Ku = w*af*(T1 + T2 + BtDB + NxSNx + (VISC ? Kvu[i*3 + j] : 0.0));
               const double T1k = am*J*rho*Na*Nb;
               T2k = T1k + af*J*tauC*rho*nfa[i]*nfb[i];
             } else {
               const double T3 = J*rCl*(nfa[i]*nfb[j] - nfa[j]*nfb[i]);
-              Ku = w*af*(T1 + T2 + T3 + BtDB + 0.0);
+              Ku = w*af*(T1 + T2 + T3 + BtDB + (VISC ? Kvu[i*3 + j] : 0.0));
               T2k = af*J*tauC*rho*nfa[i]*nfb[j];
             }
             Kd[q][i*3 + j] = Kd[q][i*3 + j] + Ku;
-            K[q][i*4 + j] = K[q][i*4 + j] + w*(T2k + 0.0) + afm*Ku;
+            K[q][i*4 + j] = K[q][i*4 + j] + w*(T2k + (VISC ? af*Kvv[i*3 + j] : 0.0)) + afm*Ku;
           }
         // B block (ustruct.cpp:1555-1573)
 #pragma unroll

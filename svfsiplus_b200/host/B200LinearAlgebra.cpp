@@ -431,8 +431,14 @@ bool B200LinearAlgebra::assemble_ustruct_mesh(ComMod& com_mod, const mshType& lM
     default: return false;
   }
   if ((iso == 3 || iso == 5 || iso == 6 || iso == 7) && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
-  if (dmn.solid_visc.viscType != SolidViscosityModelType::viscType_NA) return false;
   b200_ustruct_props p{};
+  switch (dmn.solid_visc.viscType) {             // solid viscosity (ustruct.cpp:1275-1302)
+    case SolidViscosityModelType::viscType_NA:        p.viscType = 0; break;
+    case SolidViscosityModelType::viscType_Newtonian: p.viscType = 1; break;
+    case SolidViscosityModelType::viscType_Potential: p.viscType = 2; break;
+    default: return false;
+  }
+  p.visc_mu = dmn.solid_visc.mu;
   fibre_stress(com_mod, stM.Tf, p.Tfa, p.Tsa);
   if (p.Tfa != 0.0 && (lM.nFn != 2 || lM.fN.size() == 0)) return false;
   p.dt = com_mod.dt; p.am = eq.am; p.af = eq.af; p.gam = eq.gam;

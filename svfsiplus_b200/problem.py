@@ -314,7 +314,7 @@ def fsi_linear_step(be: B.Backend, case, ls="GMRES_FSI", want_system=False):
 # ustruct block (tests/cases/ustruct/block_compression/P1P1_VMS/solver.xml: neo-Hookean, E 240.56596e6,
 # nu 0.4999999, ST91, density 1e-3, stabilisation coefficients 1e-3, first-order generalised-alpha)
 # ---------------------------------------------------------------------------------------------------
-def ustruct_case(n, elem="tet", vol="ST91", iso="nHook"):
+def ustruct_case(n, elem="tet", vol="ST91", iso="nHook", visc=None, visc_mu=0.0):
     m = M.block_mesh(n, elem=elem)
     rowPtr, colPtr = M.csr_pattern(m.ien, m.nNo)
     am, af, gam = M.gen_alpha(0.5)
@@ -342,6 +342,8 @@ def ustruct_case(n, elem="tet", vol="ST91", iso="nHook"):
         faces.append(dict(name=nm, nodes=nodes, dof=3, bGrp=B.BC_DIR, val=val))
     case = dict(mesh=m, rowPtr=rowPtr, colPtr=colPtr, Ag=Ag, Yg=Yg, Dg=Dg, Bf=Bf, Ad=Ad, props=props, faces=faces, kind="ustruct",
                 res=np.zeros(len(faces)), incL=np.ones(len(faces), np.int32), name=f"ustruct_{elem}_{n}")
+    if visc:                                     # solid viscosity (tests/cases/ustruct/tensile_adventitia_*_viscosity)
+        props.update(visc=visc, visc_mu=visc_mu)
     if iso != "nHook":
         props["iso"] = iso
         if iso in ("HO", "HO_ma"):

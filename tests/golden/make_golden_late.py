@@ -38,6 +38,14 @@ def main():
             R, Val, *_ = refcase.reference_assemble_solid(c)
             out[f"R_{elem}_struct_visc_{visc}"] = R
             out[f"Val_{elem}_struct_visc_{visc}"] = Val
+    # ... and in ustruct_3d_m (Siso + Svis, Kvis_u in Ku, af Kvis_v)
+    for elem, n in (("tet", 3), ("hex", 3), ("tet10", 2)):
+        for visc in ("newt", "pot"):
+            c = P.ustruct_case(n, elem=elem, visc=visc, visc_mu=5.0e4)
+            R, Val, Kd, _ = refcase.reference_assemble_ustruct(c)
+            out[f"R_{elem}_ustruct_visc_{visc}"] = R
+            out[f"Val_{elem}_ustruct_visc_{visc}"] = Val
+            out[f"Kd_{elem}_ustruct_visc_{visc}"] = Kd
     np.savez_compressed(os.path.join(HERE, "late_additions.npz"), **out)
     for k, v in out.items():
         print(k, v.shape, float(np.abs(v).max()))

@@ -107,6 +107,10 @@ def test_oracle_reproduces_late_addition_fixtures():
             c = P.block_case(n, elem=elem, kind="struct", iso="nHook", vol="ST91", visc=visc, visc_mu=5.0e4)
             R, Val, *_ = refcase.reference_assemble_solid(c)
             assert np.array_equal(R, g[f"R_{elem}_struct_visc_{visc}"]) and np.array_equal(Val, g[f"Val_{elem}_struct_visc_{visc}"])
+            c = P.ustruct_case(n, elem=elem, visc=visc, visc_mu=5.0e4)
+            R, Val, Kd, _ = refcase.reference_assemble_ustruct(c)
+            assert np.array_equal(R, g[f"R_{elem}_ustruct_visc_{visc}"]) and np.array_equal(Val, g[f"Val_{elem}_ustruct_visc_{visc}"])
+            assert np.array_equal(Kd, g[f"Kd_{elem}_ustruct_visc_{visc}"])
 
 
 @needs_ref
@@ -187,3 +191,51 @@ def test_struct_viscosity_element_restated_in_numpy_matches_reference(elem, visc
                     Val[pos[(nd[a], nd[b])]] += K.reshape(9)
     assert np.abs(R - Rr).max() / np.abs(Rr).max() < 1e-12
     assert np.abs(Val - Vr).max() / np.abs(Vr).max() < 1e-12
+
+
+@needs_ref
+@pytest.mark.parametrize("visc", ["newt", "pot"])
+@pytest.mark.parametrize("elem", ["tet", "hex"])
+def test_ustruct_viscosity_terms_restated_in_numpy_match_reference(elem, visc):
+    """What k_assemble_ustruct<..., VISC = true> adds to the inviscid element (ustruct.cpp:1275-1302, 1406-1550):
+        Siso += Svis   ->  dR_a = w F Svis Nx_a,   dKd_ab = w af (Kvis_u(a,b) + (Nx_a . Svis Nx_b) I),
+        dK_ab  = w af Kvis_v(a,b) + (af/am) dKd_ab          (af = eq.af eq.gam dt)
+    rebuilt in numpy from the host/device-shared visc_point / visc_pair, against the DIFFERENCE of two runs of the compiled
+    reference's construct_usolid (with and without dmn.solid_visc)."""
+    from oracle import refcase
+    from svfsiplus_b200 import backend as B
+    from svfsiplus_b200 import problem as P
+    c1 = P.ustruct_case(2, elem=elem, visc=visc, visc_mu=5.0e4)
+    c0 = P.ustruct_case(2, elem=elem)
+    R1, V1, K1, _ = refcase.reference_assemble_ustruct(c1)
+    R0, V0, K0, _ = refcase.reference_assemble_ustruct(c0)
+    m, pr = c1["mesh"], c1["props"]
+    rowPtr, colPtr = c1["rowPtr"], c1["colPtr"]
+    eNoN = m.ien.shape[1]
+    w, N, Nxi = B.elem_tables(eNoN)
+    af = pr["af"] * pr["gam"] * pr["dt"]
+    afm = af / pr["am"]
+    dR = np.zeros_like(R0); dV = np.zeros_like(V0); dK = np.zeros_like(K0)
+    pos = {(A, colPtr[p]): p for A in range(m.nNo) for p in range(rowPtr[A], rowPtr[A + 1])}
+    for e in range(m.nEl):
+        nd = m.ien[e]
+        xl, yl, dl = m.x[nd], c1["Yg"][nd][:, :3], c1["Dg"][nd][:, :3]
+        for g in range(len(w)):
+            xXi = xl.T @ Nxi[g]
+            Nx = Nxi[g] @ np.linalg.inv(xXi)
+            wj = w[g] * np.linalg.det(xXi)
+            F = np.eye(3) + dl.T @ Nx
+            vx = yl.T @ Nx
+            Sv, Ku, Kv = host_visc(visc, pr["visc_mu"], Nx, vx, F)
+            Sv = 0.5 * (Sv + Sv.T)
+            Pv = F @ Sv
+            for a in range(eNoN):
+                dR[nd[a], :3] += wj * (Pv @ Nx[a])
+                for b in range(eNoN):
+                    kd = wj * af * (Ku[a, b] + (Nx[a] @ Sv @ Nx[b]) * np.eye(3))
+                    p = pos[(nd[a], nd[b])]
+                    dK[p].reshape(4, 3)[:3] += kd
+                    dV[p].reshape(4, 4)[:3, :3] += wj * af * Kv[a, b] + afm * kd
+    for got, want, ref0 in ((dR, R1 - R0, R1), (dV, V1 - V0, V1), (dK, K1 - K0, K1)):
+        assert np.abs(got - want).max() / np.abs(ref0).max() < 1e-12
+        assert np.abs(want).max() > 0

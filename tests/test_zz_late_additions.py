@@ -59,3 +59,17 @@ def test_struct_solid_viscosity_matches_golden(elem, n, visc):
     P.assemble_solid(be, case, upload=False)
     assert np.array_equal(R, be.get_R()) and np.array_equal(Val, be.get_Val())
     be.close()
+
+
+@pytest.mark.parametrize("visc", ["newt", "pot"])
+@pytest.mark.parametrize("elem,n", [("tet", 3), ("hex", 3), ("tet10", 2)])
+def test_ustruct_solid_viscosity_matches_golden(elem, n, visc):
+    """dmn.solid_visc in ustruct_3d_m (ustruct.cpp:1275-1302, 1406-1550): Siso + Svis, Kvis_u in Ku (lK and lKd), af Kvis_v."""
+    g = golden("late_additions.npz")
+    case = P.ustruct_case(n, elem=elem, visc=visc, visc_mu=5.0e4)
+    be = P.setup_backend(case)
+    P.assemble_ustruct(be, case)
+    assert rel_inf(be.get_R(), g[f"R_{elem}_ustruct_visc_{visc}"]) < TOL_ASM
+    assert rel_inf(be.get_Val(), g[f"Val_{elem}_ustruct_visc_{visc}"]) < TOL_ASM
+    assert rel_inf(be.get_Kd(), g[f"Kd_{elem}_ustruct_visc_{visc}"]) < TOL_ASM
+    be.close()
