@@ -935,7 +935,7 @@ int b200_assemble_fsi(b200_handle* h, int nDmn, const int* dmn_kind, const b200_
         } else if (dmn_kind[d] == 1) {
           if (solid[d].tDof != h->tDof) throw std::runtime_error("assemble_fsi: tDof differs from the uploaded state");
           const SolidConsts c = struct_consts(&solid[d]);
-          if (c.viscType != 0) throw std::runtime_error("assemble_fsi: solid viscosity has a device kernel for single-domain struct equations only");
+          if (c.viscType != 0) throw std::runtime_error("assemble_fsi: solid viscosity has a device kernel for struct equations only, not inside the FSI equation");
           if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 4>(h, c, n, h->d_dmn_elems[d]);
           else if (h->eNoN == 8) launch_solid<8, 8, 16, 2, 4>(h, c, n, h->d_dmn_elems[d]);
           else launch_solid<10, 15, 8, 2, 4>(h, c, n, h->d_dmn_elems[d]);
@@ -986,7 +986,6 @@ int b200_assemble_struct_dmn(b200_handle* h, int nDmn, const b200_struct_props* 
     for (int d = 0; d < nDmn; d++) {
       covered += h->dmn_count[d];
       cs.push_back(struct_consts(&p[d]));
-      if (cs[d].viscType != 0) throw std::runtime_error("assemble_struct_dmn: solid viscosity has a device kernel for single-domain struct equations only");
       if (cs[d].tDof != h->tDof) throw std::runtime_error("assemble_struct_dmn: tDof differs from the uploaded state");
       if (cs[d].s < 0 || cs[d].s + 3 > cs[d].tDof) throw std::runtime_error("assemble_struct_dmn: equation offset outside the state");
       if ((cs[d].iso == 3 || cs[d].iso == 5 || cs[d].iso == 6 || cs[d].iso == 7) && !h->d_fN) throw std::runtime_error("assemble_struct_dmn: the Holzapfel-Ogden law needs fibre directions (b200_mesh_fibers)");
@@ -998,7 +997,12 @@ int b200_assemble_struct_dmn(b200_handle* h, int nDmn, const b200_struct_props* 
       CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*72.0 + double(h->nNo)*(24.0 + 24.0 + 24.0*3 + 24.0) + double(h->nEl)*4.0*h->eNoN, 2 + nDmn);
       for (int d = 0; d < nDmn; d++) {
         const int n = h->dmn_count[d];
-        if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 3>(h, cs[d], n, h->d_dmn_elems[d]);
+        if (cs[d].viscType != 0) {                      // a domain with solid viscosity: the longer Gauss-point record
+          if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 3, true>(h, cs[d], n, h->d_dmn_elems[d]);
+          else if (h->eNoN == 8) launch_solid<8, 8, 16, 2, 3, true>(h, cs[d], n, h->d_dmn_elems[d]);
+          else launch_solid<10, 15, 8, 2, 3, true>(h, cs[d], n, h->d_dmn_elems[d]);
+        }
+        else if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 3>(h, cs[d], n, h->d_dmn_elems[d]);
         else if (h->eNoN == 8) launch_solid<8, 8, 16, 2, 3>(h, cs[d], n, h->d_dmn_elems[d]);
         else launch_solid<10, 15, 8, 2, 3>(h, cs[d], n, h->d_dmn_elems[d]);
       }

@@ -248,7 +248,7 @@ bool B200LinearAlgebra::fill_struct_props(ComMod& com_mod, const eqType& eq, con
 {
   using namespace consts;
   const auto& stM = dmn.stM;
-  // solid viscosity (get_visc_stress_and_tangent, mat_models_carray.h:1578): device kernel for single-domain struct equations
+  // solid viscosity (get_visc_stress_and_tangent, mat_models_carray.h:1578): device kernel for struct equations (any number of domains)
   switch (dmn.solid_visc.viscType) {
     case SolidViscosityModelType::viscType_NA:        sp.viscType = 0; break;
     case SolidViscosityModelType::viscType_Newtonian: sp.viscType = 1; break;
@@ -256,7 +256,7 @@ bool B200LinearAlgebra::fill_struct_props(ComMod& com_mod, const eqType& eq, con
     default: return false;
   }
   sp.visc_mu = dmn.solid_visc.mu;
-  if (sp.viscType != 0 && (eq.nDmn != 1 || eq.phys != EquationType::phys_struct)) return false;
+  if (sp.viscType != 0 && eq.phys != EquationType::phys_struct) return false;      // not inside the FSI equation
   fibre_stress(com_mod, stM.Tf, sp.Tfa, sp.Tsa);
   if (sp.Tfa != 0.0 && stM.isoType != ConstitutiveModelType::stIso_nHook && stM.isoType != ConstitutiveModelType::stIso_HO &&
       stM.isoType != ConstitutiveModelType::stIso_MR && stM.isoType != ConstitutiveModelType::stIso_HGO &&
