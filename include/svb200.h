@@ -139,6 +139,10 @@ int b200_lhs_layout_map(const b200_layout* lay, int* map /* nNo */);
 /* i-th neighbour (ascending rank): peer, list length, and -- when ptr is not NULL -- the list */
 int b200_lhs_layout_req(const b200_layout* lay, int i, int* peer, int* n, int* ptr);
 void b200_lhs_layout_free(b200_layout* lay);
+/* Element -> rank map by recursive coordinate bisection of the element centroids (3 x nEl): the stand-in for the reference's
+ * ParMETIS call (solver/distribute.cpp:1683-1700) on meshes that are not generated slab by slab.  Balanced to one element,
+ * deterministic, parts numbered along the cuts.  Host-side, no device. */
+int b200_partition_rcb(int nEl, const double* centroids, int nParts, int* part /* nEl */);
 
 /* ---- pattern (replaces lhsa_ns::lhsa, solver/lhsa.cpp:153, for idMap = identity, no shells) ------------------------- */
 /* Device-side construction of the block-CSR pattern from the connectivity of every mesh of the equation system:

@@ -106,6 +106,7 @@ EXPORTS = [
     "b200_assemble_fluid_dmn", "b200_assemble_struct_dmn",
     "b200_assemble_bfolw", "b200_face_integ", "b200_face_normal_update", "b200_face_get_val", "b200_pattern_begin", "b200_pattern_add_mesh", "b200_pattern_finish", "b200_pattern_get",
     "b200_lhs_layout_create", "b200_lhs_layout_sizes", "b200_lhs_layout_map", "b200_lhs_layout_req", "b200_lhs_layout_free",
+    "b200_partition_rcb",
 ]
 
 KERNEL_CLASSES = ["spmv_vv4", "spmv_vv3", "spmv_ss", "spmv_sv", "spmv_vs", "multi_dot", "cgs_update_scale", "blas1",
@@ -138,6 +139,7 @@ def lib():
         L.b200_lhs_layout_req.argtypes = [vp, ci, vp, vp, vp]
         L.b200_lhs_layout_free.argtypes = [vp]
         L.b200_lhs_layout_free.restype = None
+        L.b200_partition_rcb.argtypes = [ci, vp, ci, vp]
         L.b200_face_set.argtypes = [vp, ci, ci, ci, ci, vp, vp, ci]
         L.b200_mesh_set.argtypes = [vp, ci, ci, vp, vp, cd]
         L.b200_zero.argtypes = [vp, ci]
@@ -279,6 +281,15 @@ def unique_id() -> np.ndarray:
     if lib().b200_comm_unique_id(_p(uid)) != 0:
         raise RuntimeError("b200_comm_unique_id: " + lib().b200_last_error(None).decode())
     return uid
+
+
+def partition_rcb(centroids, nparts: int) -> np.ndarray:
+    """Element -> rank map by recursive coordinate bisection (b200_partition_rcb; host side, no device)."""
+    c = _c(centroids, np.float64)
+    part = np.zeros(c.shape[0], np.int32)
+    if lib().b200_partition_rcb(c.shape[0], _p(c), int(nparts), _p(part)) != 0:
+        raise RuntimeError("b200_partition_rcb: " + lib().b200_last_error(None).decode())
+    return part
 
 
 def lhs_layout(rank: int, all_gnodes, gnNo: int):

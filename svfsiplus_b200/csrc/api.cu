@@ -1174,6 +1174,17 @@ int b200_lhs_layout_req(const b200_layout* lay, int i, int* peer, int* n, int* p
 
 void b200_lhs_layout_free(b200_layout* lay) { delete lay; }
 
+int b200_partition_rcb(int nEl, const double* centroids, int nParts, int* part)
+{
+  try {
+    svb200::partition_rcb(nEl, centroids, nParts, part);
+    return 0;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return 1;
+  }
+}
+
 // ---- pattern construction on the device (pattern.cuh) ---------------------------------------------------------------
 int b200_pattern_begin(b200_handle* h, int tnNo)
 {

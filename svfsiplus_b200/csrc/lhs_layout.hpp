@@ -104,3 +104,54 @@ inline LhsLayout lhs_layout(int rank, int nT, int gnNo, const int* counts, const
 }
 
 } // namespace svb200
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Element partition by recursive coordinate bisection of the element centroids.  The reference partitions the dual graph
+// with ParMETIS (Code/Source/solver/distribute.cpp:1683-1700, SPLIT.c) - a third-party library whose output depends on the
+// rank count and only changes summation order downstream; this is the stand-in for meshes that are not generated slab by
+// slab: balanced to one element, deterministic (ties broken by element id), O(n log P), no graph needed.  Parts are numbered
+// along the cuts, so neighbouring ranks are neighbouring parts for elongated domains (a pipe is cut across its axis).
+// ---------------------------------------------------------------------------------------------------------------------------
+#include <algorithm>
+#include <numeric>
+
+namespace svb200 {
+
+namespace detail {
+
+inline void rcb(const double* c, int* idx, int n, int p0, int np, int* part)
+{
+  if (np == 1 || n == 0) {
+    for (int i = 0; i < n; i++) part[idx[i]] = p0;
+    return;
+  }
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int i = 0; i < n; i++)
+    for (int d = 0; d < 3; d++) {
+      const double v = c[size_t(idx[i])*3 + d];
+      lo[d] = std::min(lo[d], v); hi[d] = std::max(hi[d], v);
+    }
+  int ax = 0;
+  for (int d = 1; d < 3; d++) if (hi[d] - lo[d] > hi[ax] - lo[ax]) ax = d;
+  const int npL = np/2;
+  const int nL = int((long long)n*npL/np);
+  auto less = [c, ax](int a, int b) {
+    const double va = c[size_t(a)*3 + ax], vb = c[size_t(b)*3 + ax];
+    return va < vb || (va == vb && a < b);
+  };
+  std::nth_element(idx, idx + nL, idx + n, less);
+  rcb(c, idx, nL, p0, npL, part);
+  rcb(c, idx + nL, n - nL, p0 + npL, np - npL, part);
+}
+
+} // namespace detail
+
+inline void partition_rcb(int nEl, const double* centroids, int nParts, int* part)
+{
+  if (nEl < 0 || nParts < 1 || (nEl && (!centroids || !part))) throw std::runtime_error("partition_rcb: bad arguments");
+  std::vector<int> idx(size_t(nEl), 0);
+  std::iota(idx.begin(), idx.end(), 0);
+  detail::rcb(centroids, idx.data(), nEl, 0, nParts, part);
+}
+
+} // namespace svb200

@@ -34,6 +34,13 @@ def slab_ranges(nz: int, nparts: int):
     return out
 
 
+def element_partition_rcb(mesh: M.Mesh, nparts: int) -> np.ndarray:
+    """part[e] for ANY mesh: recursive coordinate bisection of the element centroids (native, b200_partition_rcb) - the
+    stand-in for the reference's ParMETIS call (distribute.cpp:1683) where the mesh is not generated slab by slab."""
+    from . import backend as B
+    return B.partition_rcb(mesh.x[mesh.ien].mean(axis=1), nparts)
+
+
 def element_partition(mesh: M.Mesh, nparts: int) -> np.ndarray:
     """part[e] for the generator's element order (6 tets per hex, hexes x-fastest then y then z)."""
     nx, ny, nz = mesh.shape

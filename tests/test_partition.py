@@ -178,3 +178,44 @@ def test_layout_under_gloo_world_size_2(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29611", str(w), ROOT],
                        capture_output=True, text=True, timeout=600, env=env)
     assert "GLOO_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("nparts", [1, 2, 3, 5, 8])
+def test_rcb_partition_is_balanced_deterministic_and_cuts_the_pipe_across_its_axis(nparts):
+    case = P.pipe_case(4, 4, 12)
+    m = case["mesh"]
+    part = PT.element_partition_rcb(m, nparts)
+    assert part.min() == 0 and part.max() == nparts - 1
+    counts = np.bincount(part, minlength=nparts)
+    assert counts.max() - counts.min() <= 1 and counts.sum() == m.nEl
+    assert np.array_equal(part, PT.element_partition_rcb(m, nparts))
+    # the pipe is ten times longer than wide: every cut is across z, parts are ordered along the axis
+    zc = m.x[m.ien].mean(axis=1)[:, 2]
+    for p in range(nparts - 1):
+        assert zc[part == p].max() <= zc[part == p + 1].min()
+
+
+@needs_ref
+def test_rcb_partition_layout_equals_reference_fsils_lhs_create():
+    """An RCB partition of a block (cuts in several directions, nodes with up to four owners) through split_case and the native
+    layout against the reference's fsils_lhs_create on threads-as-ranks."""
+    from oracle import ref
+    from svfsiplus_b200 import mesh as M
+    case = P.pipe_case(5, 5, 5)
+    m = case["mesh"]
+    # make the domain cube-like so that RCB cuts along different axes
+    m2 = M.Mesh(x=m.x * np.array([1.0, 1.0, 0.2]), ien=m.ien, faces=m.faces, shape=m.shape)
+    part = PT.element_partition_rcb(m2, 4)
+    zc, xc = m2.x[m2.ien].mean(axis=1)[:, 2], m2.x[m2.ien].mean(axis=1)[:, 0]
+    assert len({(zc[part == p].mean() > zc.mean(), xc[part == p].mean() > xc.mean()) for p in range(4)}) >= 3      # not slabs
+    parts = PT.split_case(case, 4, part)
+    rr = ref.RefRanks([dict(gnNo=p["gnNo"], gNodes=p["gNodes"], rowPtr=p["rowPtr"], colPtr=p["colPtr"], faces=[]) for p in parts])
+    allg = [p["gNodes"] for p in parts]
+    for r in range(4):
+        info = rr.info(r)
+        lay = PT.lhs_layout(r, allg, parts[r]["gnNo"])
+        assert lay["mynNo"] == info["mynNo"] and lay["shnNo"] == info["shnNo"] and (lay["map"] == info["map"]).all()
+        assert [q[0] for q in lay["reqs"]] == [q[0] for q in info["reqs"]]
+        for (_, pa), (_, pb) in zip(lay["reqs"], info["reqs"]):
+            assert (pa == pb).all()
+    rr.close()
