@@ -144,6 +144,15 @@ void b200_lhs_layout_free(b200_layout* lay);
  * deterministic, parts numbered along the cuts.  Host-side, no device. */
 int b200_partition_rcb(int nEl, const double* centroids, int nParts, int* part /* nEl */);
 
+/* ---- prestress (com_mod.pS0 / pSn / pSa of the struct equation; solver/sv_struct.cpp:262-345, 646-700) ------------------ */
+/* b200_prestress_set uploads the nodal prestress pS0(6,nNo) (rows 00 11 22 01 12 20, assembly node order; NULL: none) that
+ * the next struct assemblies add to the 2nd Piola-Kirchhoff stress, and switches the pstEq accumulations on or off: with
+ * pstEq != 0 every struct assembly also forms pSn(:,A) = sum w N_a pSl and pSa(A) = sum w N_a (pSl = the stress before the
+ * prestress is added), which b200_prestress_get copies out - what construct_dsolid leaves in com_mod.pSn / pSa for pic::picc
+ * (pic.cpp:208-219) to normalise.  Both start from zero at every assembly, as pic::pici zeroes them (pic.cpp:571). */
+int b200_prestress_set(b200_handle* h, const double* pS0, int pstEq);
+int b200_prestress_get(b200_handle* h, double* pSn /* 6 x nNo */, double* pSa /* nNo */);
+
 /* ---- pattern (replaces lhsa_ns::lhsa, solver/lhsa.cpp:153, for idMap = identity, no shells) ------------------------- */
 /* Device-side construction of the block-CSR pattern from the connectivity of every mesh of the equation system:
  * b200_pattern_begin(h, tnNo); b200_pattern_add_mesh(...) once per mesh (IEN(eNoN,nEl), assembly node ids);

@@ -199,6 +199,10 @@ def lib():
         L.ref_pic.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_int, C.c_double] + [C.c_void_p] * 12
         L.ref_asm_set_visc.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.ref_asm_set_visc.restype = None
+        L.ref_asm_set_prestress.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.ref_asm_set_prestress.restype = None
+        L.ref_asm_get_prestress.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ref_asm_get_prestress.restype = None
         L.ref_visc.argtypes = [C.c_int, C.c_double, C.c_int] + [C.c_void_p] * 6
         L.ref_io_write_restart.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -383,7 +387,7 @@ class RefAssembly:
 
     def solid(self, kind, Ag, Yg, Dg, Bf, *, dt, am, af, gam, beta, rho, dmp=0.0, f=(0.0, 0.0, 0.0), iso="nHook",
               vol="ST91", C10=0.0, C01=0.0, Kpen=0.0, elM=0.0, nu=0.0, s=0, Do=None, ho=None, Tfa=0.0, eta_s=0.0, kap=0.0,
-              visc=None, visc_mu=0.0):
+              visc=None, visc_mu=0.0, pS0=None, pstEq=False):
         """kind "struct": construct_dsolid (S/sv_struct.cpp:213); "lelas": construct_l_elas (S/l_elas.cpp:58).
         Returns R (nNo,3), Val (nnz,9), seconds."""
         Ag = _c(Ag, np.float64); Yg = _c(Yg, np.float64); Dg = _c(Dg, np.float64); Bf = _c(Bf, np.float64)
@@ -395,10 +399,16 @@ class RefAssembly:
         Val = np.empty((self.nnz, 9))
         Do = None if Do is None else _c(Do, np.float64)
         lib().ref_asm_set_visc(self.h, {None: 0, "newt": 1, "pot": 2}[visc], float(visc_mu))      # dmn.solid_visc
+        pS0 = None if pS0 is None else _c(pS0, np.float64)
+        lib().ref_asm_set_prestress(self.h, None if pS0 is None else _p(pS0), int(pstEq))             # com_mod.pS0 / pstEq
         t = lib().ref_asm_solid(self.h, {"struct": 0, "lelas": 1, "mesh": 2}[kind], tDof, int(s), _p(par), _p(Ag), _p(Yg),
                                 _p(Dg), _p(Do), _p(Bf), _p(R), _p(Val))
         if t < 0:
             raise RuntimeError(lib().ref_last_error().decode())
+        self.pSn = self.pSa = None
+        if pstEq:
+            self.pSn = np.empty((self.nNo, 6)); self.pSa = np.empty(self.nNo)
+            lib().ref_asm_get_prestress(self.h, _p(self.pSn), _p(self.pSa))
         return R, Val, t
 
 

@@ -78,6 +78,8 @@ struct AsmCtx {
   int nnz = 0;
   int visc_model = 0;        // solid viscosity applied by ref_asm_solid: 0 none, 1 Newtonian, 2 potential (ref_asm_set_visc)
   double visc_mu = 0.0;
+  std::vector<double> pS0;   // nodal prestress (6 x nNo) applied by ref_asm_solid, empty = none (ref_asm_set_prestress)
+  bool pstEq = false;
 };
 
 } // namespace
@@ -335,6 +337,23 @@ void ref_asm_set_visc(void* h, int model, double mu)
   ctx->visc_mu = mu;
 }
 
+// Prestress of the next ref_asm_solid calls: pS0 (6 x nNo, or null for none), pstEq switches the pSn / pSa accumulations on.
+void ref_asm_set_prestress(void* h, const double* pS0, int pstEq)
+{
+  auto ctx = static_cast<AsmCtx*>(h);
+  const int nNo = ctx->sim->com_mod.tnNo;
+  if (pS0) ctx->pS0.assign(pS0, pS0 + size_t(6)*nNo); else ctx->pS0.clear();
+  ctx->pstEq = pstEq != 0;
+}
+
+// com_mod.pSn (6 x nNo) and com_mod.pSa (nNo) after a ref_asm_solid with pstEq.
+void ref_asm_get_prestress(void* h, double* pSn, double* pSa)
+{
+  auto& com_mod = static_cast<AsmCtx*>(h)->sim->com_mod;
+  std::memcpy(pSn, com_mod.pSn.data(), sizeof(double)*6*size_t(com_mod.tnNo));
+  std::memcpy(pSa, com_mod.pSa.data(), sizeof(double)*size_t(com_mod.tnNo));
+}
+
 // Solid assembly through the reference's construct_dsolid (S/sv_struct.cpp:213 -> struct_3d_carray :552 ->
 // get_pk2cc<3> S/mat_models_carray.h:182) or construct_l_elas (S/l_elas.cpp:58 -> l_elas_3d :274).
 // kind 0: struct, 1: lElas, 2: mesh (construct_mesh S/mesh.cpp:42; needs Do and eq.s = s).  par = {dt, am, af, gam, beta, rho, dmp, fx, fy, fz,
@@ -354,6 +373,11 @@ double ref_asm_solid(void* h, int kind, int tDof, int s, const double* par, cons
     eq.dmn[0].solid_visc.viscType = (ctx->visc_model == 1) ? SolidViscosityModelType::viscType_Newtonian
                                   : (ctx->visc_model == 2) ? SolidViscosityModelType::viscType_Potential : SolidViscosityModelType::viscType_NA;
     eq.dmn[0].solid_visc.mu = ctx->visc_mu;
+    // prestress (S/sv_struct.cpp:232-235, 333-343): com_mod.pS0 read by struct_3d, pSn / pSa accumulated when pstEq
+    com_mod.pstEq = ctx->pstEq;
+    if (ctx->pS0.empty()) com_mod.pS0.clear();
+    else { com_mod.pS0.resize(6, nNo); std::memcpy(com_mod.pS0.data(), ctx->pS0.data(), sizeof(double)*6*size_t(nNo)); }
+    if (ctx->pstEq) { com_mod.pSn.resize(6, nNo); com_mod.pSa.resize(nNo); com_mod.pSn = 0.0; com_mod.pSa = 0.0; }
     if (!eq.linear_algebra) eq.linear_algebra = new FsilsLinearAlgebra();
 
     Array<double> Ag_a(tDof, nNo), Yg_a(tDof, nNo), Dg_a(tDof, nNo);

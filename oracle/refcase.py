@@ -53,9 +53,11 @@ def reference_assemble_solid(case):
     ra = ref.RefAssembly(m.x, m.ien)
     p = dict(case["props"])
     ra.set_fibers(case.get("fN"))
-    R, Val, secs = ra.solid(case["kind"], case["Ag"], case["Yg"], case["Dg"], case["Bf"], Do=case.get("Do"), **p)
+    R, Val, secs = ra.solid(case["kind"], case["Ag"], case["Yg"], case["Dg"], case["Bf"], Do=case.get("Do"),
+                            pS0=case.get("pS0"), pstEq=case.get("pstEq", False), **p)
     rowPtr, colPtr = ra.csr()
     tabs = ra.tables()
+    case["_ref_pSn"], case["_ref_pSa"] = ra.pSn, ra.pSa          # com_mod.pSn / pSa when the case has pstEq
     ra.close()
     return R, Val, rowPtr, colPtr, secs, tabs
 

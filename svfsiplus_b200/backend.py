@@ -106,7 +106,7 @@ EXPORTS = [
     "b200_assemble_fluid_dmn", "b200_assemble_struct_dmn",
     "b200_assemble_bfolw", "b200_face_integ", "b200_face_normal_update", "b200_face_get_val", "b200_pattern_begin", "b200_pattern_add_mesh", "b200_pattern_finish", "b200_pattern_get",
     "b200_lhs_layout_create", "b200_lhs_layout_sizes", "b200_lhs_layout_map", "b200_lhs_layout_req", "b200_lhs_layout_free",
-    "b200_partition_rcb",
+    "b200_partition_rcb", "b200_prestress_set", "b200_prestress_get",
 ]
 
 KERNEL_CLASSES = ["spmv_vv4", "spmv_vv3", "spmv_ss", "spmv_sv", "spmv_vs", "multi_dot", "cgs_update_scale", "blas1",
@@ -140,6 +140,8 @@ def lib():
         L.b200_lhs_layout_free.argtypes = [vp]
         L.b200_lhs_layout_free.restype = None
         L.b200_partition_rcb.argtypes = [ci, vp, ci, vp]
+        L.b200_prestress_set.argtypes = [vp, vp, ci]
+        L.b200_prestress_get.argtypes = [vp, vp, vp]
         L.b200_face_set.argtypes = [vp, ci, ci, ci, ci, vp, vp, ci]
         L.b200_mesh_set.argtypes = [vp, ci, ci, vp, vp, cd]
         L.b200_zero.argtypes = [vp, ci]
@@ -399,6 +401,16 @@ class Backend:
 
     def assemble_struct(self, props: StructProps):
         self._ck(self.L.b200_assemble_struct(self.h, C.byref(props)), "b200_assemble_struct")
+
+    def prestress_set(self, pS0=None, pstEq=False):
+        """com_mod.pS0 (nNo, 6) for the next struct assemblies (None: no prestress); pstEq: also accumulate pSn / pSa."""
+        a = None if pS0 is None else _c(pS0, np.float64)
+        self._ck(self.L.b200_prestress_set(self.h, _p(a), int(pstEq)), "b200_prestress_set")
+
+    def prestress_get(self):
+        pSn = np.zeros((self.nNo, 6)); pSa = np.zeros(self.nNo)
+        self._ck(self.L.b200_prestress_get(self.h, _p(pSn), _p(pSa)), "b200_prestress_get")
+        return pSn, pSa
 
     def assemble_lelas(self, props: LelasProps):
         self._ck(self.L.b200_assemble_lelas(self.h, C.byref(props)), "b200_assemble_lelas")

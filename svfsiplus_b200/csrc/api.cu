@@ -63,6 +63,13 @@ struct b200_handle {
   std::vector<int*> d_dmn_elems;      // per FSI domain: element list (ascending element ids)
   std::vector<int> dmn_count;
   double* d_fN = nullptr;    // 6 x nEl fibre + sheet directions (lM.fN with nFn = 2)
+  // prestress (com_mod.pS0 / pSn / pSa): nodal prestress in assembly order, per-slot staging of the pstEq accumulations and
+  // their ordered sums [pSn(0..5), pSa] per node in solver order
+  double* d_pS0 = nullptr;
+  double* stageP = nullptr;
+  double* d_pS7 = nullptr;
+  size_t pS0_cap = 0, stageP_cap = 0, pS7_cap = 0;
+  bool pstEq = false, pS7_valid = false;
   double* d_tab = nullptr;   // packed Gauss tables of the mesh's element type (w, N, dN/dxi)
   ElemTables tab;
   double* d_x = nullptr;
@@ -128,6 +135,7 @@ struct b200_handle {
     cudaFree(d_Ag); cudaFree(d_Yg); cudaFree(d_Bf); cudaFree(d_Dg); cudaFree(d_Do); cudaFree(d_tab);
     for (auto p : d_dmn_elems) cudaFree(p);
     cudaFree(Kd); cudaFree(stageKd); cudaFree(d_fN);
+    cudaFree(d_pS0); cudaFree(stageP); cudaFree(d_pS7);
     for (auto p : pic_arr) cudaFree(p);
     for (auto& f : fmesh) f.release();
     cudaFree(pat_keys); cudaFree(pat_rowPtr); cudaFree(pat_colPtr);
@@ -268,13 +276,35 @@ void launch_solid(b200_handle* h, const SolidConsts& c, int nList, const int* d_
   auto& ops = *h->ops;
   if (nList == 0) return;
   constexpr int TABN = NG + NG*ENON + NG*ENON*3;
-  const size_t smem = sizeof(double)*(size_t((TABN + 3) & ~3) + size_t(EPB)*NG*(solid_rec(ENON) + (VISC ? VISC_REC : 0)));
+  const size_t smem = sizeof(double)*(size_t((TABN + 3) & ~3) + size_t(EPB)*NG*(solid_rec(ENON) + (VISC ? VISC_REC + 6 : 0)));
   auto kern = k_assemble_solid<ENON, NG, EPB, APT, ODOF, VISC>;
   CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   kern<<<(nList + EPB - 1)/EPB, EPB*NG, smem, ops.st>>>(nList, d_elist, c, h->d_tab, h->d_ien, h->d_rslot, h->d_kslot, h->d_x,
-                                                        h->d_Ag, h->d_Yg, h->d_Dg, h->d_Do, h->d_Bf, h->d_fN, h->stageR, h->stageK, h->d_err);
+                                                        h->d_Ag, h->d_Yg, h->d_Dg, h->d_Do, h->d_Bf, h->d_fN, h->stageR, h->stageK, h->d_err,
+                                                        VISC ? h->d_pS0 : nullptr, (VISC && h->pstEq && c.kind == 0) ? h->stageP : nullptr);
   CU_CHECK(cudaGetLastError());
   ops.post();
+}
+
+// struct assemblies that need the extended element: solid viscosity or prestress
+bool struct_extended(const b200_handle* h, const SolidConsts& c) { return c.kind == 0 && (c.viscType != 0 || h->d_pS0 || h->pstEq); }
+
+// pstEq: staging of the pSn / pSa accumulations before, their ordered per-node sums after the element kernels
+void prestress_begin(b200_handle* h)
+{
+  h->pS7_valid = false;
+  if (!h->pstEq) return;
+  ensure(h->stageP, h->stageP_cap, size_t(7)*h->eNoN*size_t(h->nEl) + 4);
+  ensure(h->d_pS7, h->pS7_cap, size_t(7)*h->nNo);
+}
+void prestress_finish(b200_handle* h)
+{
+  if (!h->pstEq) return;
+  auto& ops = *h->ops;
+  const size_t t = size_t(h->nNo)*7;
+  k_sum_run<true><<<unsigned((t + 255)/256), 256, 0, ops.st>>>(size_t(h->nNo), 7, h->d_rseg, h->stageP, h->d_pS7);
+  ops.post();
+  h->pS7_valid = true;
 }
 
 template <int ENON, int NG, int EPB, int APT, bool VISC = false>
@@ -373,9 +403,10 @@ void assemble_solid(b200_handle* h, const SolidConsts& c, const char* who)
   {
     // algorithmic bytes: Val and R written once, nodal fields and IEN read once
     CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*72.0 + double(h->nNo)*(24.0 + 24.0 + 24.0*3 + 24.0) + double(h->nEl)*4.0*h->eNoN, 3);
-    if (c.kind == 0 && c.viscType != 0) {
-      // solid viscosity: the instantiation with the longer Gauss-point record (reads Yg for dv/dX)
+    if (struct_extended(h, c)) {
+      // solid viscosity / prestress: the instantiation with the longer Gauss-point record (viscosity reads Yg for dv/dX)
       if (!h->d_Yg) throw std::runtime_error(std::string(who) + ": solid viscosity needs the velocity state (b200_state_set)");
+      prestress_begin(h);
       if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 3, true>(h, c, h->nEl, nullptr);
       else if (h->eNoN == 8) launch_solid<8, 8, 16, 2, 3, true>(h, c, h->nEl, nullptr);
       else launch_solid<10, 15, 8, 2, 3, true>(h, c, h->nEl, nullptr);
@@ -384,6 +415,7 @@ void assemble_solid(b200_handle* h, const SolidConsts& c, const char* who)
     else if (h->eNoN == 8) launch_solid<8, 8, 16, 2, 3>(h, c, h->nEl, nullptr);
     else launch_solid<10, 15, 8, 2, 3>(h, c, h->nEl, nullptr);       // TET10: 15 Gauss points, gnn per point
   }
+  if (struct_extended(h, c)) prestress_finish(h);
   finish_assembly(h, 3, t0, who);
 }
 
@@ -935,7 +967,7 @@ int b200_assemble_fsi(b200_handle* h, int nDmn, const int* dmn_kind, const b200_
         } else if (dmn_kind[d] == 1) {
           if (solid[d].tDof != h->tDof) throw std::runtime_error("assemble_fsi: tDof differs from the uploaded state");
           const SolidConsts c = struct_consts(&solid[d]);
-          if (c.viscType != 0) throw std::runtime_error("assemble_fsi: solid viscosity has a device kernel for struct equations only, not inside the FSI equation");
+          if (c.viscType != 0 || h->d_pS0 || h->pstEq) throw std::runtime_error("assemble_fsi: solid viscosity and prestress have a device kernel for struct equations only, not inside the FSI equation");
           if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 4>(h, c, n, h->d_dmn_elems[d]);
           else if (h->eNoN == 8) launch_solid<8, 8, 16, 2, 4>(h, c, n, h->d_dmn_elems[d]);
           else launch_solid<10, 15, 8, 2, 4>(h, c, n, h->d_dmn_elems[d]);
@@ -992,12 +1024,13 @@ int b200_assemble_struct_dmn(b200_handle* h, int nDmn, const b200_struct_props* 
     }
     if (covered != h->nEl) throw std::runtime_error("assemble_struct_dmn: every element must belong to a domain");
     ensure_stage(h, 3);
+    prestress_begin(h);
     const double t0 = wall_s();
     {
       CudaOps::Scope sc(ops, KC_ASSEMBLY, double(h->nnz)*72.0 + double(h->nNo)*(24.0 + 24.0 + 24.0*3 + 24.0) + double(h->nEl)*4.0*h->eNoN, 2 + nDmn);
       for (int d = 0; d < nDmn; d++) {
         const int n = h->dmn_count[d];
-        if (cs[d].viscType != 0) {                      // a domain with solid viscosity: the longer Gauss-point record
+        if (struct_extended(h, cs[d])) {                // solid viscosity / prestress: the longer Gauss-point record
           if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 3, true>(h, cs[d], n, h->d_dmn_elems[d]);
           else if (h->eNoN == 8) launch_solid<8, 8, 16, 2, 3, true>(h, cs[d], n, h->d_dmn_elems[d]);
           else launch_solid<10, 15, 8, 2, 3, true>(h, cs[d], n, h->d_dmn_elems[d]);
@@ -1007,7 +1040,51 @@ int b200_assemble_struct_dmn(b200_handle* h, int nDmn, const b200_struct_props* 
         else launch_solid<10, 15, 8, 2, 3>(h, cs[d], n, h->d_dmn_elems[d]);
       }
     }
+    prestress_finish(h);
     finish_assembly(h, 3, t0, "construct_dsolid");
+  });
+}
+
+// ---- prestress (com_mod.pS0 / pSn / pSa) ------------------------------------------------------------------------------
+int b200_prestress_set(b200_handle* h, const double* pS0, int pstEq)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (h->nNo == 0) throw std::runtime_error("prestress_set: no structure (b200_lhs_create)");
+    h->pstEq = pstEq != 0;
+    h->pS7_valid = false;
+    if (!pS0) {
+      if (h->d_pS0) { CU_CHECK(cudaFree(h->d_pS0)); h->d_pS0 = nullptr; h->pS0_cap = 0; }
+      return;
+    }
+    const size_t n = size_t(6)*h->nNo;
+    ensure(h->d_pS0, h->pS0_cap, n);
+    CU_CHECK(cudaMemcpyAsync(h->d_pS0, pS0, sizeof(double)*n, cudaMemcpyHostToDevice, ops.st));
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+  });
+}
+
+int b200_prestress_get(b200_handle* h, double* pSn, double* pSa)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    if (!h->pS7_valid) throw std::runtime_error("prestress_get: no struct assembly with pstEq since b200_prestress_set");
+    if (!pSn || !pSa) throw std::runtime_error("prestress_get: null output");
+    const size_t n = size_t(7)*h->nNo;
+    std::vector<double> tmp(n);
+    if (h->identity_map) {
+      CU_CHECK(cudaMemcpyAsync(tmp.data(), h->d_pS7, sizeof(double)*n, cudaMemcpyDeviceToHost, ops.st));
+    } else {
+      ensure(h->stage_d, h->stage_cap, n);
+      k_permute_bwd<<<CudaOps::grid_for(n, 256), 256, 0, ops.st>>>(h->nNo, 7, h->d_map, h->d_pS7, h->stage_d);
+      ops.post();
+      CU_CHECK(cudaMemcpyAsync(tmp.data(), h->stage_d, sizeof(double)*n, cudaMemcpyDeviceToHost, ops.st));
+    }
+    CU_CHECK(cudaStreamSynchronize(ops.st));
+    for (int a = 0; a < h->nNo; a++) {
+      for (int i = 0; i < 6; i++) pSn[size_t(a)*6 + i] = tmp[size_t(a)*7 + i];
+      pSa[a] = tmp[size_t(a)*7 + 6];
+    }
   });
 }
 

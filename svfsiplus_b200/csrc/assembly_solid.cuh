@@ -35,9 +35,11 @@ __host__ __device__ constexpr int solid_rec(int eNoN) { return SREC_NX + 3*eNoN;
 // ODOF: block size of the system the element is scattered into (3: struct/lElas/mesh equations; 4: the FSI
 // equation, where struct_3d fills the 3x3 corner of lK(dof*dof,a,b) and leaves the pressure row/column zero,
 // fsi.cpp:225).  elist != nullptr: the kernel covers the nEl elements elist[0..nEl) (one FSI domain).
-// VISC: solid viscosity (dmn.solid_visc, struct only): the record grows by VISC_REC doubles per Gauss point (visc_point's matrices)
-// and phase 2 adds afu*Kvis_u + afv*Kvis_v (sv_struct.cpp:666-675, 771-842); a separate instantiation, so that the inviscid
-// kernel keeps its record size and occupancy.
+// VISC: the extended struct element - solid viscosity (dmn.solid_visc: the record grows by VISC_REC doubles per Gauss point,
+// visc_point's matrices, and phase 2 adds afu*Kvis_u + afv*Kvis_v; sv_struct.cpp:666-675, 771-842) and prestress (pS0 != null:
+// S += S0 interpolated from the nodal prestress; stageP != null: the pstEq accumulations pSn += w N_a pSl, pSa += w N_a of
+// construct_dsolid, sv_struct.cpp:646-700, 333-343; 6 more doubles per record for pSl).  A separate instantiation, so that the
+// plain kernel keeps its record size and occupancy; inside it c.viscType / pS0 / stageP select at run time.
 template <int ENON, int NG, int EPB, int APT, int ODOF, bool VISC = false>
 __global__ void __launch_bounds__(EPB*NG)
 k_assemble_solid(int nEl, const int* __restrict__ elist, SolidConsts c, const double* __restrict__ tab,      // packed: w[NG], N[NG][ENON], Nxi[NG][ENON][3]
@@ -45,10 +47,13 @@ k_assemble_solid(int nEl, const int* __restrict__ elist, SolidConsts c, const do
                  const double* __restrict__ x, const double* __restrict__ Ag, const double* __restrict__ Yg,
                  const double* __restrict__ Dg, const double* __restrict__ Do, const double* __restrict__ Bf,
                  const double* __restrict__ fN,      // 6 x nEl fibre + sheet directions (Holzapfel-Ogden) or null
-                 double* __restrict__ stageR, double* __restrict__ stageK, int* __restrict__ err_flag)
+                 double* __restrict__ stageR, double* __restrict__ stageK, int* __restrict__ err_flag,
+                 const double* __restrict__ pS0 = nullptr,      // 6 x nNo nodal prestress (VISC instantiation only) or null
+                 double* __restrict__ stageP = nullptr)         // 7 doubles per (element, a) slot: pSn contribution + pSa, or null
 {
-  constexpr int REC = solid_rec(ENON) + (VISC ? VISC_REC : 0);
+  constexpr int REC = solid_rec(ENON) + (VISC ? VISC_REC + 6 : 0);
   constexpr int SREC_V = solid_rec(ENON);      // visc_point's record (VISC only)
+  constexpr int SREC_PS = SREC_V + VISC_REC;   // pSl: the stress before the prestress is added (VISC only)
   constexpr int NT = EPB*NG;
   constexpr int TABN = NG + NG*ENON + NG*ENON*3;
   extern __shared__ double sm[];
@@ -140,7 +145,7 @@ k_assemble_solid(int nEl, const int* __restrict__ elist, SolidConsts c, const do
             F[i][0] += nx[0]*dl[i];
             F[i][1] += nx[1]*dl[i];
             F[i][2] += nx[2]*dl[i];
-            if (VISC) { vx[i][0] += nx[0]*yl[i]; vx[i][1] += nx[1]*yl[i]; vx[i][2] += nx[2]*yl[i]; }
+            if (VISC && c.viscType != 0) { vx[i][0] += nx[0]*yl[i]; vx[i][1] += nx[1]*yl[i]; vx[i][2] += nx[2]*yl[i]; }
           }
         } else {
 #pragma unroll
@@ -162,12 +167,28 @@ k_assemble_solid(int nEl, const int* __restrict__ elist, SolidConsts c, const do
           for (int i = 0; i < 6; i++) fl[i] = fN[size_t(e)*6 + i];
         }
         pk2cc_iso(c, F, fl, S6, rec + SREC_DM);
-        if (VISC) {
+        if (VISC && c.viscType != 0) {
           // elastic + viscous stress (sv_struct.cpp:666-675); the record keeps the six entries 00 11 22 01 12 20 the reference
           // copies into pSl - its Newtonian Svis is symmetric up to rounding only
           double Sv[3][3];
           visc_point(c.viscType, c.visc_mu, F, vx, Sv, rec + SREC_V);
           S6[0] += Sv[0][0]; S6[1] += Sv[1][1]; S6[2] += Sv[2][2]; S6[3] += Sv[0][1]; S6[4] += Sv[1][2]; S6[5] += Sv[2][0];
+        }
+        if (VISC) {
+          // prestress (sv_struct.cpp:683-700): pSl = S before S0 is added; S0 = sum_a N_a pS0(:,a), rows 00 11 22 01 12 20
+#pragma unroll
+          for (int i = 0; i < 6; i++) rec[SREC_PS + i] = S6[i];
+          if (pS0) {
+            double S0[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int a = 0; a < ENON; a++) {
+              const double Na = s_N[g*ENON + a];
+#pragma unroll
+              for (int i = 0; i < 6; i++) S0[i] += Na*pS0[size_t(nd[a])*6 + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 6; i++) S6[i] += S0[i];
+          }
         }
 #pragma unroll
         for (int i = 0; i < 6; i++) rec[SREC_S + i] = S6[i];
@@ -223,6 +244,20 @@ k_assemble_solid(int nEl, const int* __restrict__ elist, SolidConsts c, const do
     double* out = stageR + size_t(rslot[size_t(e)*ENON + a])*ODOF;
     out[0] = r0; out[1] = r1; out[2] = r2;
     if (ODOF == 4) out[3] = 0.0;
+    if (VISC && stageP && c.kind == 0) {
+      // pstEq (sv_struct.cpp:333-343): this element's share of pSn(:,Ac) and pSa(Ac)
+      double ps[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+      for (int g = 0; g < NG; g++) {
+        const double* rec = s_rec + size_t(el*NG + g)*REC;
+        const double wN = rec[SREC_W]*s_N[g*ENON + a];
+#pragma unroll
+        for (int i = 0; i < 6; i++) ps[i] = ps[i] + wN*rec[SREC_PS + i];
+        ps[6] = ps[6] + wN;
+      }
+      double* po = stageP + size_t(rslot[size_t(e)*ENON + a])*7;
+#pragma unroll
+      for (int i = 0; i < 7; i++) po[i] = ps[i];
+    }
   }
 
   // ---------------- phase 2: tangent blocks ------------------------------------------------------------
@@ -282,8 +317,13 @@ k_assemble_solid(int nEl, const int* __restrict__ elist, SolidConsts c, const do
           const double T1 = amd*Na*Nb + afu*NxSNx;
           double Ku[9], Kv[9];
           if (VISC) {
-            const double na[3] = {na0, na1, na2}, nb[3] = {nb0, nb1, nb2};
-            visc_pair(c.viscType, c.visc_mu, rec + SREC_V, F, na, nb, Ku, Kv);
+            if (c.viscType != 0) {
+              const double na[3] = {na0, na1, na2}, nb[3] = {nb0, nb1, nb2};
+              visc_pair(c.viscType, c.visc_mu, rec + SREC_V, F, na, nb, Ku, Kv);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 9; i++) { Ku[i] = 0.0; Kv[i] = 0.0; }
+            }
           }
           double Ba[6][3];
 #pragma unroll

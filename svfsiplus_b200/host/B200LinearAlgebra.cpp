@@ -491,7 +491,9 @@ bool B200LinearAlgebra::assemble_solid_mesh(ComMod& com_mod, const mshType& lM, 
   using namespace consts;
   auto& eq = com_mod.eq[com_mod.cEq];
   if ((lM.eType != ElementType::TET4 && lM.eType != ElementType::HEX8 && lM.eType != ElementType::TET10) || com_mod.dof != 3) return false;
-  if (com_mod.pS0.size() != 0 || com_mod.pstEq) return false;
+  // prestress (com_mod.pS0 / pstEq, sv_struct.cpp:232-235): device kernel for the struct equation; lElas / mesh never read it
+  const bool prestress = (eq.phys == EquationType::phys_struct) && (com_mod.pS0.size() != 0 || com_mod.pstEq);
+  if (prestress && com_mod.pS0.size() != 0 && (com_mod.pS0.nrows() != 6 || com_mod.pS0.ncols() != com_mod.tnNo)) return false;
   if (cep_mod && (cep_mod->cem.cpld || cep_mod->cem.aStress || cep_mod->cem.aStrain)) return false;
   const auto& dmn = eq.dmn[0];
 
@@ -515,7 +517,23 @@ bool B200LinearAlgebra::assemble_solid_mesh(ComMod& com_mod, const mshType& lM, 
   if (mesh_uploaded_ != &lM) upload_mesh(com_mod, lM);
   check(b200_state_set(h_, com_mod.tDof, Ag.data(), Yg.data(), com_mod.Bf.data()), "b200_state_set");
   check(b200_disp_set(h_, com_mod.tDof, Dg.data(), lp.mesh_mode && !is_struct ? com_mod.Do.data() : nullptr), "b200_disp_set");
-  if (is_struct) check(b200_assemble_struct(h_, &sp), "b200_assemble_struct");
+  if (is_struct) {
+    if (prestress || prestress_on_device_) {
+      check(b200_prestress_set(h_, com_mod.pS0.size() != 0 ? com_mod.pS0.data() : nullptr, com_mod.pstEq ? 1 : 0), "b200_prestress_set");
+      prestress_on_device_ = prestress;
+    }
+    check(b200_assemble_struct(h_, &sp), "b200_assemble_struct");
+    if (prestress && com_mod.pstEq) {
+      // construct_dsolid adds this mesh's share to com_mod.pSn / pSa (sv_struct.cpp:333-343); pic::picc normalises them
+      Array<double> pSn(6, com_mod.tnNo);
+      Vector<double> pSa(com_mod.tnNo);
+      check(b200_prestress_get(h_, pSn.data(), pSa.data()), "b200_prestress_get");
+      for (int a = 0; a < com_mod.tnNo; a++) {
+        com_mod.pSa(a) += pSa(a);
+        for (int i = 0; i < 6; i++) com_mod.pSn(i,a) += pSn(i,a);
+      }
+    }
+  }
   else check(b200_assemble_lelas(h_, &lp), "b200_assemble_lelas");
   any_device_contribution_ = true;
   return true;

@@ -97,6 +97,7 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
     const mshType* domains_uploaded_ = nullptr;
     bool any_device_contribution_ = false;
     bool ustruct_on_device_ = false;
+    bool prestress_on_device_ = false;    // a prestress field / pstEq was set on the handle (cleared when it disappears)
     bool do_uploaded_ = false;            // com_mod.Do is on the device (moving-mesh Neumann faces)
     std::map<const faceType*, int> face_meshes_;      // faces whose connectivity is on the device -> slot
     static std::set<consts::LinearAlgebraType> valid_assemblers;

@@ -135,7 +135,7 @@ def newton_linear_step(be: B.Backend, case, ls="NS", want_system=False, upload=T
 # solid block (tests/cases/struct/block_compression/solver.xml: neo-Hookean, E 240.56596e6, nu 0.5, ST91
 # penalty 4e9, density 1000, dt 1e-4, rho_inf 0.5; X0/Y0/Z0 Dirichlet in one direction each)
 # ---------------------------------------------------------------------------------------------------
-def block_case(n, elem="hex", kind="struct", iso="nHook", vol="ST91", jitter=0.1, visc=None, visc_mu=0.0):
+def block_case(n, elem="hex", kind="struct", iso="nHook", vol="ST91", jitter=0.1, visc=None, visc_mu=0.0, prestress=False):
     m = M.block_mesh(n, elem=elem, jitter=jitter)
     rowPtr, colPtr = M.csr_pattern(m.ien, m.nNo)
     am, af, gam, beta = M.gen_alpha2(0.5)
@@ -194,6 +194,12 @@ def block_case(n, elem="hex", kind="struct", iso="nHook", vol="ST91", jitter=0.1
         case["fN"] = fN
     if kind == "mesh":
         case["Do"] = Do
+    if prestress:
+        # a prestress field of the size of the elastic stresses of this state (symmetric tensor per node, rows 00 11 22 01 12 20)
+        # and the pstEq accumulations switched on (com_mod.pS0 / pstEq, sv_struct.cpp:232-235)
+        rng = np.random.default_rng(3131)
+        case["pS0"] = 2.0e6 * rng.standard_normal((m.nNo, 6))
+        case["pstEq"] = True
     return case
 
 
@@ -205,6 +211,8 @@ def assemble_solid(be: B.Backend, case, upload=True):
         be.disp_set(tDof, case["Dg"], case.get("Do"))
     if upload and case.get("fN") is not None:
         be.mesh_fibers(case["fN"])
+    if upload and (case.get("pS0") is not None or case.get("pstEq")):
+        be.prestress_set(case.get("pS0"), case.get("pstEq", False))          # com_mod.pS0 / pstEq
     be.zero(3)
     if case["kind"] == "struct":
         be.assemble_struct(B.struct_props(tDof=tDof, **case["props"]))

@@ -38,6 +38,13 @@ def main():
             R, Val, *_ = refcase.reference_assemble_solid(c)
             out[f"R_{elem}_struct_visc_{visc}"] = R
             out[f"Val_{elem}_struct_visc_{visc}"] = Val
+    # prestress: S += S0 from the nodal com_mod.pS0, and the pstEq accumulations pSn / pSa (with and without viscosity)
+    for elem, n in (("tet", 3), ("hex", 3), ("tet10", 2)):
+        for visc in (None, "pot"):
+            c = P.block_case(n, elem=elem, kind="struct", iso="nHook", vol="ST91", visc=visc, visc_mu=5.0e4, prestress=True)
+            R, Val, *_ = refcase.reference_assemble_solid(c)
+            tag = f"{elem}_struct_pst_{visc}"
+            out[f"R_{tag}"], out[f"Val_{tag}"], out[f"pSn_{tag}"], out[f"pSa_{tag}"] = R, Val, c["_ref_pSn"], c["_ref_pSa"]
     # ... and in ustruct_3d_m (Siso + Svis, Kvis_u in Ku, af Kvis_v)
     for elem, n in (("tet", 3), ("hex", 3), ("tet10", 2)):
         for visc in ("newt", "pot"):

@@ -107,6 +107,12 @@ def test_oracle_reproduces_late_addition_fixtures():
             c = P.block_case(n, elem=elem, kind="struct", iso="nHook", vol="ST91", visc=visc, visc_mu=5.0e4)
             R, Val, *_ = refcase.reference_assemble_solid(c)
             assert np.array_equal(R, g[f"R_{elem}_struct_visc_{visc}"]) and np.array_equal(Val, g[f"Val_{elem}_struct_visc_{visc}"])
+            for v2 in ((None, "pot") if visc == "pot" else ()):
+                c = P.block_case(n, elem=elem, kind="struct", iso="nHook", vol="ST91", visc=v2, visc_mu=5.0e4, prestress=True)
+                R, Val, *_ = refcase.reference_assemble_solid(c)
+                tag = f"{elem}_struct_pst_{v2}"
+                assert np.array_equal(R, g[f"R_{tag}"]) and np.array_equal(Val, g[f"Val_{tag}"])
+                assert np.array_equal(c["_ref_pSn"], g[f"pSn_{tag}"]) and np.array_equal(c["_ref_pSa"], g[f"pSa_{tag}"])
             c = P.ustruct_case(n, elem=elem, visc=visc, visc_mu=5.0e4)
             R, Val, Kd, _ = refcase.reference_assemble_ustruct(c)
             assert np.array_equal(R, g[f"R_{elem}_ustruct_visc_{visc}"]) and np.array_equal(Val, g[f"Val_{elem}_ustruct_visc_{visc}"])
@@ -134,17 +140,18 @@ def test_solid_viscosity_matches_reference_bitwise(model, eNoN):
 
 
 @needs_ref
-@pytest.mark.parametrize("visc", ["newt", "pot"])
+@pytest.mark.parametrize("visc,prestress", [("newt", False), ("pot", False), (None, True), ("pot", True)])
 @pytest.mark.parametrize("elem", ["tet", "hex"])
-def test_struct_viscosity_element_restated_in_numpy_matches_reference(elem, visc):
-    """The arithmetic k_assemble_solid<..., VISC = true> performs (dv/dX per Gauss point, S = S_el + Svis, P = F S, the residual
-    row, T1 + afu (BtDB + Kvis_u) + afv Kvis_v per node pair), restated element by element in numpy on top of the SAME
+def test_struct_extended_element_restated_in_numpy_matches_reference(elem, visc, prestress):
+    """The arithmetic k_assemble_solid<..., VISC = true> performs (dv/dX per Gauss point, S = S_el + Svis, pSl = S, S += S0 from the
+    nodal prestress, P = F S, the residual row, T1 + afu (BtDB + Kvis_u) + afv Kvis_v per node pair, and the pstEq sums
+    pSn += w N_a pSl, pSa += w N_a), restated element by element in numpy on top of the SAME
     host/device-shared point functions (pk2cc_iso, visc_point, visc_pair), against construct_dsolid of the compiled reference.
     Pins the way the viscous terms enter the element (index conventions, afu / afv, pair order) without a GPU."""
     from oracle import refcase
     from svfsiplus_b200 import backend as B
     from svfsiplus_b200 import problem as P
-    c = P.block_case(2, elem=elem, kind="struct", iso="nHook", vol="ST91", visc=visc, visc_mu=5.0e4)
+    c = P.block_case(2, elem=elem, kind="struct", iso="nHook", vol="ST91", visc=visc, visc_mu=5.0e4, prestress=prestress)
     Rr, Vr, rowPtr, colPtr, *_ = refcase.reference_assemble_solid(c)
     m, pr = c["mesh"], c["props"]
     eNoN = m.ien.shape[1]
@@ -153,6 +160,7 @@ def test_struct_viscosity_element_restated_in_numpy_matches_reference(elem, visc
     afu, afv, amd = af * beta * dt * dt, af * gam * dt, am * rho + af * gam * dt * dmp
     R = np.zeros_like(Rr)
     Val = np.zeros_like(Vr)
+    pSn = np.zeros((m.nNo, 6)); pSa = np.zeros(m.nNo)
     pos = {}
     for A in range(m.nNo):
         for p in range(rowPtr[A], rowPtr[A + 1]):
@@ -169,10 +177,21 @@ def test_struct_viscosity_element_restated_in_numpy_matches_reference(elem, visc
             vx = yl.T @ Nx
             ud = -rho * np.asarray(pr["f"]) + N[g] @ (rho * (al - bl) + dmp * yl)
             S6, Dm21 = host_pk2cc(F, np.zeros(6), iso="nHook", vol="ST91", C10=pr["C10"], Kpen=pr["Kpen"])
-            Sv, Ku, Kv = host_visc(visc, pr["visc_mu"], Nx, vx, F)
+            if visc:
+                Sv, Ku, Kv = host_visc(visc, pr["visc_mu"], Nx, vx, F)
+            else:
+                Sv, Ku, Kv = np.zeros((3, 3)), np.zeros((eNoN, eNoN, 3, 3)), np.zeros((eNoN, eNoN, 3, 3))
             S = np.zeros((3, 3)); Dm = np.zeros((6, 6))
             for k, (i, j) in enumerate(VO):
                 S[i, j] = S[j, i] = S6[k] + Sv[i, j]             # the six entries the kernel keeps
+            wj = w[g] * Jac
+            if prestress:
+                pSl = np.array([S[i, j] for i, j in VO])
+                pSn[nd] += wj * np.outer(N[g], pSl)
+                pSa[nd] += wj * N[g]
+                S0 = N[g] @ c["pS0"][nd]
+                for k, (i, j) in enumerate(VO):
+                    S[i, j] = S[j, i] = S[i, j] + S0[k]
             it = iter(Dm21)
             for I in range(6):
                 for J in range(I, 6):
@@ -191,6 +210,9 @@ def test_struct_viscosity_element_restated_in_numpy_matches_reference(elem, visc
                     Val[pos[(nd[a], nd[b])]] += K.reshape(9)
     assert np.abs(R - Rr).max() / np.abs(Rr).max() < 1e-12
     assert np.abs(Val - Vr).max() / np.abs(Vr).max() < 1e-12
+    if prestress:
+        assert np.abs(pSn - c["_ref_pSn"]).max() / np.abs(c["_ref_pSn"]).max() < 1e-12
+        assert np.abs(pSa - c["_ref_pSa"]).max() / np.abs(c["_ref_pSa"]).max() < 1e-12
 
 
 @needs_ref

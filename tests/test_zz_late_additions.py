@@ -74,3 +74,29 @@ def test_ustruct_solid_viscosity_matches_golden(elem, n, visc):
     assert rel_inf(be.get_Val(), g[f"Val_{elem}_ustruct_visc_{visc}"]) < TOL_ASM
     assert rel_inf(be.get_Kd(), g[f"Kd_{elem}_ustruct_visc_{visc}"]) < TOL_ASM
     be.close()
+
+
+@pytest.mark.parametrize("visc", [None, "pot"])
+@pytest.mark.parametrize("elem,n", [("tet", 3), ("hex", 3), ("tet10", 2)])
+def test_struct_prestress_matches_golden(elem, n, visc):
+    """com_mod.pS0 / pstEq in construct_dsolid + struct_3d (sv_struct.cpp:262-345, 646-700): S += S0 interpolated from the nodal
+    prestress, and the accumulations pSn(:,A) += w N_a pSl, pSa(A) += w N_a, with and without solid viscosity."""
+    g = golden("late_additions.npz")
+    case = P.block_case(n, elem=elem, kind="struct", iso="nHook", vol="ST91", visc=visc, visc_mu=5.0e4, prestress=True)
+    be = P.setup_backend(case)
+    P.assemble_solid(be, case)
+    tag = f"{elem}_struct_pst_{visc}"
+    assert rel_inf(be.get_R(), g[f"R_{tag}"]) < TOL_ASM
+    assert rel_inf(be.get_Val(), g[f"Val_{tag}"]) < TOL_ASM
+    pSn, pSa = be.prestress_get()
+    assert rel_inf(pSn, g[f"pSn_{tag}"]) < TOL_ASM
+    assert rel_inf(pSa, g[f"pSa_{tag}"]) < TOL_ASM
+    # switching the prestress off again gives the plain element back
+    be.prestress_set(None, False)
+    P.assemble_solid(be, dict(case, pS0=None, pstEq=False), upload=False)
+    g0 = golden("late_additions.npz")[f"R_{elem}_struct_visc_pot"] if visc else (golden("block_3_solid.npz")[f"R_{elem}_struct_nHook_ST91"] if n == 3 else None)
+    if g0 is not None:
+        assert rel_inf(be.get_R(), g0) < TOL_ASM
+    with pytest.raises(RuntimeError, match="prestress_get"):
+        be.prestress_get()
+    be.close()
