@@ -12,6 +12,7 @@ from conftest import have_ref, needs_ref
 from util import ROOT, golden, hl_solve, rel_inf, rel_l2
 
 from svfsiplus_b200 import mesh as M
+from svfsiplus_b200 import backend as B
 from svfsiplus_b200 import problem as P
 
 
@@ -154,3 +155,105 @@ def test_oracle_reproduces_solid_golden():
             R, Val, *_ = refcase.reference_assemble_solid(c)
             tag = f"{elem}_{kind}_{iso}_{vol}"
             assert np.array_equal(R, g[f"R_{tag}"]) and np.array_equal(Val, g[f"Val_{tag}"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# edge cases of the solver control flow (csrc/krylov.hpp, the header the device instantiates with CudaOps) against fsils_solve
+# ---------------------------------------------------------------------------------------------------------------------------
+EDGE_LS = {
+    # restarts: Krylov dimension 5, up to 40 outer iterations
+    "gmres_restarts": (B.LS_GMRES, (1e-6, 1e-17, 40, 5), None, None),
+    # iteration limit reached before the tolerance: suc = false, the iterate so far is returned
+    "gmres_not_converged": (B.LS_GMRES, (1e-14, 1e-30, 1, 3), None, None),
+    "cg_not_converged": (B.LS_CG, (1e-14, 1e-30, 3, 0), None, None),
+    "bicgs_not_converged": (B.LS_BICGS, (1e-14, 1e-30, 2, 0), None, None),
+    # absolute tolerance above the initial norm: immediate return
+    "gmres_abstol": (B.LS_GMRES, (1e-3, 1e30, 4, 50), None, None),
+    "bicgs_abstol": (B.LS_BICGS, (1e-3, 1e30, 50, 0), None, None),
+    "cg_abstol": (B.LS_CG, (1e-3, 1e30, 50, 0), None, None),
+    # NS block solver: one outer iteration, tight and loose inner solves, tiny inner Krylov spaces (the last two make the
+    # reference give up: its exception text must come out of the product's control flow as well)
+    "ns_one_outer": (B.LS_NS, (1e-3, 1e-17, 1, 250), (1e-3, 1e-17, 10, 250), (1e-3, 1e-17, 300, 0)),
+    "ns_tight_inner": (B.LS_NS, (1e-5, 1e-17, 8, 250), (1e-6, 1e-17, 20, 30), (1e-6, 1e-17, 500, 0)),
+    "ns_small_inner_space": (B.LS_NS, (1e-3, 1e-17, 10, 250), (1e-2, 1e-17, 3, 4), (1e-1, 1e-17, 5, 0)),
+    "ns_outer_space_of_five": (B.LS_NS, (1e-6, 1e-17, 40, 5), None, None),
+}
+
+
+def _both(case, R, Val, ls):
+    """(X, info) or the exception text, from the reference and from the product's control flow on the host policy."""
+    from oracle import refcase
+    g = golden("pipe_4_4_6.npz")
+    out = []
+    for who in ("ref", "host"):
+        try:
+            if who == "ref":
+                X, o = refcase.reference_solve(case, R, Val, ls)
+            else:
+                X, _, o = hl_solve(g["rowPtr"], g["colPtr"], 4, R, Val, refcase._ls_vector(ls), 701, case["faces"], case["incL"], case["res"])
+            out.append((X, o, None))
+        except RuntimeError as e:
+            out.append((None, None, str(e)))
+    return out
+
+
+@needs_ref
+@pytest.mark.parametrize("name", sorted(EDGE_LS))
+def test_hostlogic_edge_cases_match_reference(name):
+    """Same success flag and iteration counters (+-1) as the reference, same solution (<= 1e-8) - or the same exception text -
+    for restarts, iteration limits, absolute-tolerance exits and the NS solver's inner limits."""
+    g = golden("pipe_4_4_6.npz")
+    case = P.pipe_case(4, 4, 6)
+    ls = EDGE_LS[name]
+    (Xr, oref, er), (X, o, eh) = _both(case, g["R"], g["Val"], ls)
+    assert er == eh, (er, eh)
+    if er is not None:
+        assert er.startswith("FSILS:")
+        return
+    assert bool(o["suc"]) == bool(oref["suc"])
+    assert abs(int(o["itr"]) - int(oref["itr"])) <= 1
+    if ls[0] == B.LS_NS:
+        assert abs(int(o["GM_itr"]) - int(oref["GM_itr"])) <= 2 and abs(int(o["CG_itr"]) - int(oref["CG_itr"])) <= 3
+    scale = max(np.linalg.norm(Xr), 1e-300)
+    assert np.linalg.norm(X - Xr) / scale < 1e-8
+    assert np.isfinite(X).all()
+
+
+@needs_ref
+@pytest.mark.parametrize("ls", ["NS", "GMRES", "CG", "BICGS"])
+def test_hostlogic_zero_right_hand_side(ls):
+    """R = 0: whatever the reference does (zero vector without iterating, NaNs from the zero norm, or 'Singular matrix detected'
+    from the NS solver's Gram system) the product's control flow does too."""
+    g = golden("pipe_4_4_6.npz")
+    case = P.pipe_case(4, 4, 6)
+    R0 = np.zeros_like(g["R"])
+    (Xr, oref, er), (X, o, eh) = _both(case, R0, g["Val"], P.LS_SETTINGS[ls])
+    assert er == eh, (er, eh)
+    if er is not None:
+        return
+    assert np.array_equal(np.isnan(X), np.isnan(Xr))
+    assert np.array_equal(np.nan_to_num(X), np.nan_to_num(Xr))
+    assert int(o["itr"]) == int(oref["itr"])
+
+
+@needs_ref
+@pytest.mark.parametrize("elem", ["tet", "hex"])
+@pytest.mark.parametrize("ls", ["BICGS_STRUCT", "GMRES_STRUCT", "GMRES_STRUCT_LOOSE", "CG_MESH"])
+def test_hostlogic_dof3_systems_match_reference(elem, ls):
+    """The 3-dof block systems (struct / mesh equation: spar_mul_vv with dof 3, Dirichlet faces only) through the product's
+    control flow against fsils_solve: same counters, solution <= 1e-8."""
+    from oracle import refcase
+    kind = "mesh" if ls == "CG_MESH" else "struct"
+    case = P.block_case(3, elem=elem, kind=kind)
+    R, Val, rowPtr, colPtr, *_ = refcase.reference_assemble_solid(case)
+    m = case["mesh"]
+    part = dict(gnNo=m.nNo, gNodes=np.arange(m.nNo), rowPtr=rowPtr, colPtr=colPtr,
+                faces=[dict(nodes=f["nodes"], dof=f["dof"], bGrp=f["bGrp"], val=f["val"]) for f in case["faces"]])
+    from oracle import ref
+    rr = ref.RefRanks([part])
+    Xr, _, oref = rr.solve(3, _ls_vec(ls), ref.PREC_FSILS, [R], [Val], case["incL"], case["res"])
+    rr.close()
+    X, V, o = hl_solve(rowPtr, colPtr, 3, R, Val, _ls_vec(ls), 701, case["faces"], case["incL"], case["res"])
+    assert bool(o["suc"]) == bool(oref[0]["suc"])
+    assert abs(int(o["itr"]) - int(oref[0]["itr"])) <= 1
+    assert rel_l2(X, Xr[0]) < 1e-8
