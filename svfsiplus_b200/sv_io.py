@@ -214,3 +214,47 @@ def history_line(sym, cTS, itr, *, saved=False, elapsed, since_last, eq_iNorm, e
     buf = C.create_string_buffer(1024)
     lib().b200io_history_line(C.byref(h), buf, len(buf))
     return buf.value.decode()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# result comparison with the reference's own acceptance criterion
+# ---------------------------------------------------------------------------------------------------------------------------
+# per-field relative tolerances of the reference's test harness (tests/conftest.py:18-35)
+RTOL = {
+    "Action_potential": 1.0e-10, "Cauchy_stress": 1.0e-4, "Concentration": 1.0e-10, "Def_grad": 1.0e-10, "Divergence": 1.0e-9,
+    "Displacement": 1.0e-10, "Jacobian": 1.0e-10, "Pressure": 1.0e-6, "Stress": 1.0e-4, "Strain": 1.0e-10, "Temperature": 1.0e-10,
+    "Traction": 1.0e-6, "Velocity": 1.0e-7, "VonMises_stress": 1.0e-3, "Vorticity": 1.0e-7, "WSS": 1.0e-8,
+}
+
+
+def compare_results(result_vtu, reference_vtu, fields, rtol=None):
+    """run_with_reference's check (tests/conftest.py:150-200) on two result files read with the VTK-free reader: every point-data
+    field must satisfy |a - b| <= rtol + rtol |b| entry by entry (rtol doubles as the absolute floor, as in the reference).
+    A 2-D result against a 3-D reference drops the reference's zero third component.  Returns a list of failure messages
+    (empty = pass); raises ValueError for a missing field or a field without a tolerance, like the reference."""
+    res, ref = read_vtk(result_vtu), read_vtk(reference_vtu)
+    tol = dict(RTOL, **(rtol or {}))
+    msgs = []
+    for f in fields:
+        if f not in res["point_data"]:
+            raise ValueError("Field " + f + " not in simulation result")
+        if f not in ref["point_data"]:
+            raise ValueError("Field " + f + " not in reference result")
+        if f not in tol:
+            raise ValueError("No tolerance defined for field " + f)
+        a, b = np.asarray(res["point_data"][f], np.float64), np.asarray(ref["point_data"][f], np.float64)
+        if a.ndim == 2 and b.ndim == 2 and a.shape[1] == 2 and b.shape[1] == 3:
+            assert not np.any(b[:, 2])
+            b = b[:, :2]
+        if a.shape != b.shape:
+            msgs.append(f"Test failed in field {f}. Shapes differ: {a.shape} vs {b.shape}")
+            continue
+        r = tol[f]
+        a_fl, b_fl = a.ravel(), b.ravel()
+        rel_diff = np.abs(a_fl - b_fl) - r - r * np.abs(b_fl)
+        close = rel_diff <= 0.0
+        if not np.all(close):
+            i = int(rel_diff.argmax())
+            msgs.append(f"Test failed in field {f}. Results differ by more than rtol={r} in {1 - close.sum() / close.size:.1%} of results. "
+                        f"Max. rel. difference is {rel_diff[i]:.1e} (abs. {abs(a_fl[i] - b_fl[i]):.1e})")
+    return msgs

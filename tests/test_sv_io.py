@@ -394,3 +394,26 @@ def test_history_line_is_character_identical_to_the_reference(tmp_path, case):
     kw = {k: v for k, v in case.items() if k not in ("nEq", "sym", "cTS", "itr")}
     mine = IO.history_header(case["nEq"]) + IO.history_line(case["sym"], case["cTS"], case["itr"], elapsed=elapsed, since_last=elapsed, **kw)
     assert mine == text
+
+
+def test_compare_results_applies_the_reference_acceptance_criterion(tmp_path):
+    """compare_results = run_with_reference's field check (reference tests/conftest.py:150-200) on files read without VTK."""
+    m, pd, cd = _mesh("tet")
+    ref = tmp_path / "result_002.vtu"
+    IO.write_vtk(ref, m.x, m.ien, 10, pd, cd)
+    # within tolerance: Velocity 1e-7 relative, Pressure 1e-6
+    ok = dict(pd, Velocity=pd["Velocity"] * (1 + 5e-8), Pressure=pd["Pressure"] * (1 - 5e-7))
+    res = tmp_path / "mine.vtu"
+    IO.write_vtk(res, m.x, m.ien, 10, ok, cd, mode=IO.BINARY)
+    assert IO.compare_results(res, ref, ["Velocity", "Pressure"]) == []
+    # one entry off by 1e-5 relative: reported with its field
+    bad = dict(ok)
+    bad["Velocity"] = ok["Velocity"].copy()
+    bad["Velocity"][3, 1] *= 1 + 1e-5
+    IO.write_vtk(res, m.x, m.ien, 10, bad, cd)
+    msgs = IO.compare_results(res, ref, ["Velocity", "Pressure"])
+    assert len(msgs) == 1 and "Velocity" in msgs[0] and "rtol=1e-07" in msgs[0]
+    with pytest.raises(ValueError, match="not in simulation result"):
+        IO.compare_results(res, ref, ["WSS"])
+    with pytest.raises(ValueError, match="No tolerance"):
+        IO.compare_results(res, ref, ["GlobalNodeID"])
