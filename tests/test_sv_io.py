@@ -417,3 +417,25 @@ def test_compare_results_applies_the_reference_acceptance_criterion(tmp_path):
         IO.compare_results(res, ref, ["WSS"])
     with pytest.raises(ValueError, match="No tolerance"):
         IO.compare_results(res, ref, ["GlobalNodeID"])
+
+
+def test_headers_are_plain_c_and_a_c_client_links(tmp_path):
+    """The drop-in boundary is a C ABI: both headers compile as C99 (-pedantic), and a C program using the I/O library builds,
+    links and round-trips a mesh and a restart record."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    inc = os.path.join(ROOT, "include")
+    for h in ("svb200.h", "svb200_io.h"):
+        src = tmp_path / f"use_{h}.c"
+        src.write_text(f'#include "{h}"\nint main(void) {{ return 0; }}\n')
+        subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I" + inc, "-c", str(src), "-o", str(tmp_path / "t.o")], check=True)
+    exe = tmp_path / "io_roundtrip"
+    libdir = os.path.join(ROOT, "svfsiplus_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-I" + inc, os.path.join(ROOT, "examples", "io_roundtrip.c"), "-L" + libdir, "-lsvb200io",
+                    "-Wl,-rpath," + libdir, "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe), str(tmp_path)], check=True, capture_output=True, text=True).stdout
+    assert "io_roundtrip ok" in out
+    r = IO.read_vtk(tmp_path / "one_tet.vtu")
+    assert r["nNo"] == 4 and np.array_equal(r["point_data"]["Velocity"], np.arange(1.0, 13.0).reshape(4, 3))
