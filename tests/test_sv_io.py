@@ -439,3 +439,100 @@ def test_headers_are_plain_c_and_a_c_client_links(tmp_path):
     assert "io_roundtrip ok" in out
     r = IO.read_vtk(tmp_path / "one_tet.vtu")
     assert r["nNo"] == 4 and np.array_equal(r["point_data"]["Velocity"], np.arange(1.0, 13.0).reshape(4, 3))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the reference's VtkData classes re-implemented on the I/O library (host/VtkDataB200.cpp), driven through the reference's own
+# header and containers
+# ---------------------------------------------------------------------------------------------------------------------------
+_VD = None
+
+
+def _vd():
+    global _VD
+    import ctypes as C
+    path = os.path.join(ROOT, "oracle", "_ref", "libvtkdata_b200.so")
+    if _VD is None:
+        if not os.path.exists(path):
+            pytest.skip("oracle/_ref/libvtkdata_b200.so not built (needs the reference headers)")
+        L = C.CDLL(path)
+        L.vd_last_error.restype = C.c_char_p
+        L.vd_write.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_char_p, C.c_void_p]
+        L.vd_read.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int] + [C.c_void_p] * 5
+        _VD = L
+    return _VD
+
+
+def _ptr(a):
+    import ctypes as C
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["tet", "hex", "tet10"])
+def test_reference_vtkdata_classes_on_the_io_library_volume_mesh(tmp_path, kind):
+    """VtkData::create_writer(...)->set_points / set_connectivity / set_point_data / set_element_data / write, then
+    VtkData::create_reader(...)->num_points / num_elems / np_elem / get_points / get_connectivity / copy_point_data /
+    get_point_data / has_point_data: the reference's class interface (VtkData.h) with its Array / Vector containers."""
+    import ctypes as C
+    L = _vd()
+    m = M.block_mesh(2, kind)
+    rng = np.random.default_rng(1)
+    vel = np.ascontiguousarray(rng.standard_normal((m.nNo, 3)))
+    gnid = np.arange(1, m.nNo + 1, dtype=np.int32)
+    dom = rng.integers(1, 4, m.nEl).astype(np.int32)
+    path = str(tmp_path / "mesh-complete.mesh.vtu").encode()
+    ien = np.ascontiguousarray(m.ien, np.int32)
+    assert L.vd_write(path, 3, m.nNo, _ptr(m.x), ien.shape[1], m.nEl, _ptr(ien), b"Velocity", 3, _ptr(vel), _ptr(gnid), b"Domain_ID", _ptr(dom)) == 0, \
+        L.vd_last_error()
+    # the file is an ordinary VTU: the library's own reader and the right VTK cell type
+    r = IO.read_vtk(path.decode())
+    assert (r["types"] == {"tet": 10, "hex": 12, "tet10": 24}[kind]).all()
+    assert np.array_equal(r["ien"], m.ien) and np.array_equal(r["x"], m.x)
+    assert np.array_equal(r["point_data"]["Velocity"], vel) and np.array_equal(r["cell_data"]["Domain_ID"], dom)
+    # and it reads back through the reference's class interface
+    sizes = np.zeros(3, np.int32)
+    assert L.vd_read(path, _ptr(sizes), None, None, b"Velocity", 3, None, None, None, None, None) == 0
+    assert sizes.tolist() == [m.nNo, m.nEl, m.ien.shape[1]]
+    x = np.zeros((m.nNo, 3)); conn = np.zeros((m.nEl, sizes[2]), np.int32)
+    fc = np.zeros((m.nNo, 3)); fg = np.zeros((3, m.nNo)); ids = np.zeros(m.nNo, np.int32)
+    hf, hm = C.c_int(), C.c_int()
+    assert L.vd_read(path, _ptr(sizes), _ptr(x), _ptr(conn), b"Velocity", 3, _ptr(fc), _ptr(fg), _ptr(ids), C.byref(hf), C.byref(hm)) == 0, L.vd_last_error()
+    assert np.array_equal(x, m.x) and np.array_equal(conn, m.ien)
+    assert np.array_equal(fc, vel)                      # copy_point_data: Array(comp, point) = node-major memory
+    assert np.array_equal(fg.T, vel)                    # get_point_data: Array(point, comp)
+    assert np.array_equal(ids, gnid) and hf.value == 1 and hm.value == 0
+
+
+@needs_ref
+def test_reference_vtkdata_classes_on_the_io_library_face_and_errors(tmp_path):
+    import ctypes as C
+    L = _vd()
+    m = M.block_mesh(2, "hex")
+    nodes = m.faces["Z0"]["nodes"]
+    on = np.zeros(m.nNo, bool); on[nodes] = True
+    IENb, gE = M.face_elements(m, on)
+    loc = -np.ones(m.nNo, np.int64); loc[nodes] = np.arange(len(nodes))
+    quad = np.ascontiguousarray(loc[IENb], np.int32)
+    xf = np.ascontiguousarray(m.x[nodes])
+    gn = (nodes + 1).astype(np.int32)
+    path = str(tmp_path / "Z0.vtp").encode()
+    assert L.vd_write(path, 3, len(nodes), _ptr(xf), 4, len(quad), _ptr(quad), None, 0, None, _ptr(gn), b"GlobalElementID", _ptr((gE + 1).astype(np.int32))) == 0, \
+        L.vd_last_error()
+    r = IO.read_vtk(path.decode())
+    assert r["polydata"] and (r["types"] == 9).all() and np.array_equal(r["ien"], quad)
+    assert np.array_equal(r["point_data"]["GlobalNodeID"], gn) and np.array_equal(r["cell_data"]["GlobalElementID"], gE + 1)
+    sizes = np.zeros(3, np.int32)
+    x = np.zeros((len(nodes), 3)); conn = np.zeros((len(quad), 4), np.int32)
+    fc = np.zeros((len(nodes), 1)); fg = np.zeros((1, len(nodes))); ids = np.zeros(len(nodes), np.int32)
+    hf, hm = C.c_int(), C.c_int()
+    assert L.vd_read(path, _ptr(sizes), _ptr(x), _ptr(conn), b"GlobalNodeID", 1, _ptr(fc), _ptr(fg), _ptr(ids), C.byref(hf), C.byref(hm)) == 0, L.vd_last_error()
+    assert sizes.tolist() == [len(nodes), len(quad), 4] and np.array_equal(conn, quad) and np.array_equal(ids, gn)
+    assert np.array_equal(fc[:, 0], gn.astype(float))    # an integer array read into an Array<double>
+    # the reference's own message for a node id outside the points
+    bad = quad.copy(); bad[1, 2] = 999
+    assert L.vd_write(str(tmp_path / "bad.vtu").encode(), 3, len(nodes), _ptr(xf), 4, len(bad), _ptr(bad), None, 0, None, None, None, None) == 1
+    assert L.vd_last_error().decode() == "[VtkVtuData.set_connectivity] Element 2 has the non-valid node ID 999."
+    assert L.vd_read(str(tmp_path / "missing.vtu").encode(), _ptr(sizes), None, None, b"x", 1, None, None, None, None, None) == 1
+    assert "cannot open" in L.vd_last_error().decode()
