@@ -12,7 +12,8 @@
 //   * set_point_data / set_element_data(name, Array(comp, n)) (:183-226, :391-485); VtkVtuData::set_point_data(Vector<int>) throws as
 //     in the reference (:480-485), VtkVtpData's stores one component
 //   * create_reader / create_writer choose the class from the file extension (:520-545); write() writes file_name
-// Differences, on purpose: arrays of any numeric type are accepted where the reference only down-casts vtkDoubleArray / vtkIntArray
+// Differences, on purpose: a per-element Vector<int> handed to set_point_data (write_vtp's GlobalElementID) is stored as cell data;
+// arrays of any numeric type are accepted where the reference only down-casts vtkDoubleArray / vtkIntArray
 // (a Float32 field or an Int64 GlobalNodeID reads instead of being silently skipped); files are written appended-raw + zlib.
 #include "VtkData.h"
 
@@ -139,6 +140,10 @@ struct Impl {
   void add(int where, const std::string& name, const Vector<int>& data)
   {
     reset_writer();
+    // write_vtp hands the face's GlobalElementID (one value per ELEMENT) to set_point_data (vtk_xml.cpp:846-848); VTK stores such an
+    // array as it is and the reference's own read_vtp then finds no element ids in the file.  An array that has the length of the
+    // cells and not of the points is stored where it belongs, as cell data - the file then reads back through read_vtp.
+    if (where == B200IO_POINT_DATA && data.size() != b200io_vtk_num_points(h) && data.size() == b200io_vtk_num_cells(h)) where = B200IO_CELL_DATA;
     ck(b200io_vtk_add_array_i32(h, where, name.c_str(), 1, data.size(), data.data()), "set data");
   }
   void write(const std::string& file_name) const

@@ -536,3 +536,142 @@ def test_reference_vtkdata_classes_on_the_io_library_face_and_errors(tmp_path):
     assert L.vd_last_error().decode() == "[VtkVtuData.set_connectivity] Element 2 has the non-valid node ID 999."
     assert L.vd_read(str(tmp_path / "missing.vtu").encode(), _ptr(sizes), None, None, b"x", 1, None, None, None, None, None) == 1
     assert "cannot open" in L.vd_last_error().decode()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the reference's own, unmodified vtk_xml.cpp running on the two VTK-free replacements (VtkDataB200.cpp, vtk_xml_parser_b200.cpp)
+# ---------------------------------------------------------------------------------------------------------------------------
+_VX = None
+
+
+def _vx():
+    global _VX
+    import ctypes as C
+    path = os.path.join(ROOT, "oracle", "_ref", "libvtkxml_b200.so")
+    if _VX is None:
+        if not os.path.exists(path):
+            pytest.skip("oracle/_ref/libvtkxml_b200.so not built (needs the reference sources)")
+        L = C.CDLL(path)
+        L.vx_last_error.restype = C.c_char_p
+        vp, ci, cs = C.c_void_p, C.c_int, C.c_char_p
+        L.vx_read_vtu.argtypes = [cs, vp, vp, vp, vp, vp]
+        L.vx_read_vtp.argtypes = [cs, vp, vp, vp, vp, vp, vp]
+        L.vx_write_vtu.argtypes = [cs, ci, vp, ci, ci, vp]
+        L.vx_write_vtp.argtypes = [cs, ci, vp, ci, ci, vp, vp, vp]
+        L.vx_read_vtu_pdata.argtypes = [cs, cs, ci, ci, vp]
+        L.vx_load_fibers.argtypes = [cs, cs, ci, ci, ci, vp]
+        L.vx_load_time_field.argtypes = [cs, cs, vp, vp, ci]
+        _VX = L
+    return _VX
+
+
+HEX_FACES = [[0, 3, 2, 1], [4, 5, 6, 7], [0, 1, 5, 4], [1, 2, 6, 5], [2, 3, 7, 6], [3, 0, 4, 7]]
+TET_FACES = [[0, 1, 2], [0, 1, 3], [1, 2, 3], [2, 0, 3]]
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["tet", "hex", "tet10"])
+def test_reference_read_vtu_runs_on_the_vtk_free_replacements(tmp_path, kind):
+    """vtk_xml::read_vtu (unmodified reference source) -> VtkData::create_reader + vtk_xml_parser::load_vtu, both VTK-free:
+    gnNo, x, gnEl, eNoN, gIEN, gN (GlobalNodeID as stored) and the face-node table of the cell type in mesh.ordering."""
+    L = _vx()
+    m = M.block_mesh(2, kind)
+    gn = np.arange(1, m.nNo + 1, dtype=np.int32)
+    path = tmp_path / "mesh.vtu"
+    vt = {"tet": 10, "hex": 12, "tet10": 24}[kind]
+    IO.write_vtk(path, m.x, m.ien, vt, {"GlobalNodeID": gn}, {"GlobalElementID": np.arange(1, m.nEl + 1, dtype=np.int32)}, mode=IO.APPENDED_BASE64,
+                 header64=False)
+    sizes = np.zeros(6, np.int32)
+    assert L.vx_read_vtu(str(path).encode(), _ptr(sizes), None, None, None, None) == 0, L.vx_last_error()
+    nface, flen = {"tet": (4, 3), "hex": (6, 4), "tet10": (4, 6)}[kind]
+    assert sizes.tolist() == [m.nNo, m.nEl, m.ien.shape[1], m.nNo, nface, flen]
+    x = np.zeros((m.nNo, 3)); ien = np.zeros((m.nEl, sizes[2]), np.int32); gN = np.zeros(m.nNo, np.int32); order = np.zeros((nface, flen), np.int32)
+    assert L.vx_read_vtu(str(path).encode(), _ptr(sizes), _ptr(x), _ptr(ien), _ptr(gN), _ptr(order)) == 0, L.vx_last_error()
+    assert np.array_equal(x, m.x) and np.array_equal(ien, m.ien) and np.array_equal(gN, gn)
+    if kind == "hex":
+        assert order.tolist() == HEX_FACES
+    if kind == "tet":
+        assert order.tolist() == TET_FACES
+    # every row of the table is a face of the element: its corner nodes lie in one plane of the reference block element
+    assert len({tuple(sorted(r)) for r in order.tolist()}) == nface
+
+
+@needs_ref
+def test_reference_read_vtp_write_vtp_write_vtu_run_on_the_vtk_free_replacements(tmp_path):
+    L = _vx()
+    m = M.block_mesh(2, "tet")
+    nodes = m.faces["X0"]["nodes"]
+    on = np.zeros(m.nNo, bool); on[nodes] = True
+    IENb, gE = M.face_elements(m, on)
+    loc = -np.ones(m.nNo, np.int64); loc[nodes] = np.arange(len(nodes))
+    tri = np.ascontiguousarray(loc[IENb], np.int32)
+    xf = np.ascontiguousarray(m.x[nodes])
+    # write_vtp (reference) -> file -> read_vtp (reference): GlobalNodeID / GlobalElementID go out as given and come back minus one
+    path = tmp_path / "X0.vtp"
+    gn1 = (nodes + 1).astype(np.int32); ge1 = (gE + 1).astype(np.int32)
+    assert L.vx_write_vtp(str(path).encode(), len(nodes), _ptr(xf), 3, len(tri), _ptr(tri), _ptr(gn1), _ptr(ge1)) == 0, L.vx_last_error()
+    r = IO.read_vtk(path)
+    assert r["polydata"] and np.array_equal(r["ien"], tri) and np.array_equal(r["point_data"]["GlobalNodeID"], gn1)
+    # the reference's write_vtp hands GlobalElementID (per element) to set_point_data (vtk_xml.cpp:846-848); the replacement stores an
+    # array of the cells' length as cell data, so the file reads back through the reference's own read_vtp
+    assert np.array_equal(r["cell_data"]["GlobalElementID"], ge1)
+    face_file = path
+    sizes = np.zeros(5, np.int32)
+    assert L.vx_read_vtp(str(face_file).encode(), _ptr(sizes), None, None, None, None, None) == 0, L.vx_last_error()
+    assert sizes.tolist() == [len(nodes), len(tri), 3, len(nodes), len(tri)]
+    x = np.zeros((len(nodes), 3)); ien = np.zeros((len(tri), 3), np.int32); gN = np.zeros(len(nodes), np.int32)
+    gEo = np.zeros(len(tri), np.int32); gebc = np.zeros((len(tri), 4), np.int32)
+    assert L.vx_read_vtp(str(face_file).encode(), _ptr(sizes), _ptr(x), _ptr(ien), _ptr(gN), _ptr(gEo), _ptr(gebc)) == 0, L.vx_last_error()
+    assert np.array_equal(x, xf) and np.array_equal(ien, tri)
+    assert np.array_equal(gN, nodes) and np.array_equal(gEo, gE)                 # 1-based in the file, 0-based in the solver
+    assert np.array_equal(gebc[:, 0], gE) and np.array_equal(gebc[:, 1:], tri)   # face.gebc = [gE; IEN]
+    # a face file without element ids: the reference's message
+    IO.write_vtk(face_file, xf, tri, 5, {"GlobalNodeID": gn1}, {}, polydata=True)
+    assert L.vx_read_vtp(str(face_file).encode(), _ptr(sizes), None, None, None, None, None) == 1
+    assert L.vx_last_error().decode() == "No 'GlobalElementID' data of type Int32 found in VTK mesh."
+    assert L.vx_read_vtp(str(tmp_path / "nope.vtp").encode(), _ptr(sizes), None, None, None, None, None) == 1
+    assert "can't be read" in L.vx_last_error().decode()
+    # write_vtu (reference) -> an ordinary VTU
+    vol = tmp_path / "vol.vtu"
+    ien_v = np.ascontiguousarray(m.ien, np.int32)
+    assert L.vx_write_vtu(str(vol).encode(), m.nNo, _ptr(m.x), 4, m.nEl, _ptr(ien_v)) == 0, L.vx_last_error()
+    r = IO.read_vtk(vol)
+    assert (r["types"] == 10).all() and np.array_equal(r["ien"], m.ien) and np.array_equal(r["x"], m.x)
+
+
+@needs_ref
+def test_reference_point_data_fibre_and_time_field_readers_on_the_replacements(tmp_path):
+    L = _vx()
+    m = M.block_mesh(2, "tet")
+    rng = np.random.default_rng(8)
+    pS0 = rng.standard_normal((m.nNo, 6))
+    fib = rng.standard_normal((m.nEl, 3)); sheet = rng.standard_normal((m.nEl, 3))
+    steps = {f"Velocity_{k:05d}": rng.standard_normal((m.nNo, 3)) for k in (200, 5, 40)}
+    path = tmp_path / "data.vtu"
+    IO.write_vtk(path, m.x, m.ien, 10, dict({"Stress": pS0, "Pressure": rng.standard_normal(m.nNo)}, **steps), {"FIB_DIR": fib, "SHEET": sheet})
+    # read_vtu_pdata: the prestress field into an (m, gnNo) array
+    out = np.zeros((m.nNo, 6))
+    assert L.vx_read_vtu_pdata(str(path).encode(), b"Stress", 6, m.nNo, _ptr(out)) == 0, L.vx_last_error()
+    assert np.array_equal(out, pS0)
+    assert L.vx_read_vtu_pdata(str(path).encode(), b"Nope", 6, m.nNo, _ptr(out)) == 1
+    assert "No PointData DataArray named 'Nope'" in L.vx_last_error().decode()
+    assert L.vx_read_vtu_pdata(str(path).encode(), b"Stress", 6, m.nNo + 1, _ptr(out)) == 1
+    assert "is not equal to the number of nodes" in L.vx_last_error().decode()
+    # load_fiber_direction_vtu: two families into rows 0..2 and 3..5 of mesh.fN
+    fN = np.zeros((m.nEl, 6))
+    assert L.vx_load_fibers(str(path).encode(), b"FIB_DIR", 0, 2, m.nEl, _ptr(fN)) == 0, L.vx_last_error()
+    assert np.array_equal(fN[:, :3], fib) and not fN[:, 3:].any()
+    fN2 = np.zeros((m.nEl, 6))
+    assert L.vx_load_fibers(str(path).encode(), b"SHEET", 1, 2, m.nEl, _ptr(fN2)) == 0
+    assert np.array_equal(fN2[:, 3:], sheet)
+    assert L.vx_load_fibers(str(path).encode(), b"FIB_DIR", 0, 2, m.nEl + 3, _ptr(fN)) == 1
+    assert "is not equal to the number of elements" in L.vx_last_error().decode()
+    # load_time_varying_field_vtu: every "Velocity*" array, ordered by its trailing number
+    dims = np.zeros(3, np.int32)
+    Ys = np.zeros((3, m.nNo, 3))                                   # memory order of Array3(ncomp, nNo, nsteps): [step][node][comp]
+    assert L.vx_load_time_field(str(path).encode(), b"Velocity", _ptr(dims), _ptr(Ys), Ys.size) == 0, L.vx_last_error()
+    assert dims.tolist() == [3, m.nNo, 3]
+    for i, k in enumerate((5, 40, 200)):
+        assert np.array_equal(Ys[i], steps[f"Velocity_{k:05d}"])
+    assert L.vx_load_time_field(str(path).encode(), b"Temperature", _ptr(dims), None, 0) == 1
+    assert "No 'Temperature' data found" in L.vx_last_error().decode()
