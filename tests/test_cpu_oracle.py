@@ -257,3 +257,22 @@ def test_hostlogic_dof3_systems_match_reference(elem, ls):
     assert bool(o["suc"]) == bool(oref[0]["suc"])
     assert abs(int(o["itr"]) - int(oref[0]["itr"])) <= 1
     assert rel_l2(X, Xr[0]) < 1e-8
+
+
+def test_c_client_of_the_hot_path_builds_and_refuses_to_run_without_a_device(tmp_path):
+    """examples/newton_step.c - the C ABI's call sequence for one Newton iteration in plain C99 - compiles and links against
+    libsvb200.so; on a box without a GPU it reports that and exits with status 3 (no CPU fallback), with one it solves."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    libdir = os.path.join(ROOT, "svfsiplus_b200")
+    exe = tmp_path / "newton_step"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "newton_step.c"),
+                    "-L" + libdir, "-lsvb200", "-Wl,-rpath," + libdir, "-lm", "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    from svfsiplus_b200 import backend as B
+    if B.lib().b200_device_count() > 0:
+        assert r.returncode == 0 and "GMRES:" in r.stdout, r.stdout + r.stderr
+    else:
+        assert r.returncode == 3 and "no CUDA device" in r.stderr
