@@ -6,6 +6,7 @@
 #include "Simulation.h"
 #include "vtk_xml.h"
 #include "vtk_xml_parser.h"
+#include "Parameters.h"
 
 #include <cstring>
 #include <stdexcept>
@@ -138,6 +139,35 @@ int vx_load_time_field(const char* path, const char* field, int* dims3, double* 
     dims3[0] = mesh.Ys.nrows(); dims3[1] = mesh.Ys.ncols(); dims3[2] = mesh.Ys.nslices();
     const size_t n = size_t(dims3[0])*dims3[1]*dims3[2];
     if (Ys && n <= size_t(cap)) std::memcpy(Ys, mesh.Ys.data(), sizeof(double)*n);
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// Parameters::read_xml (Code/Source/solver/Parameters.cpp:147): the reference's own parser on a solver.xml.  out = {time steps,
+// meshes, faces of mesh 0, equations, BCs of equation 0, LS max_iterations, NS_GM max, NS_CG max, Krylov dimension};
+// dout = {dt, density, Newton tolerance, LS tolerance, LS absolute tolerance}; ls_type / la_type: the <LS type> and <Linear_algebra type>.
+int vx_parse_solver_xml(const char* path, int* out, double* dout, char* ls_type, char* la_type, int cap)
+{
+  try {
+    Parameters params;
+    params.read_xml(path);
+    out[0] = params.general_simulation_parameters.number_of_time_steps();
+    out[1] = int(params.mesh_parameters.size());
+    out[2] = params.mesh_parameters.empty() ? 0 : int(params.mesh_parameters[0]->face_parameters.size());
+    out[3] = int(params.equation_parameters.size());
+    auto* eq = params.equation_parameters.at(0);
+    out[4] = int(eq->boundary_conditions.size());
+    out[5] = eq->linear_solver.max_iterations();
+    out[6] = eq->linear_solver.ns_gm_max_iterations();
+    out[7] = eq->linear_solver.ns_cg_max_iterations();
+    out[8] = eq->linear_solver.krylov_space_dimension();
+    dout[0] = params.general_simulation_parameters.time_step_size();
+    dout[1] = eq->default_domain ? eq->default_domain->density() : 0.0;      // <Density> of the equation (its default domain)
+    dout[2] = eq->tolerance();
+    dout[3] = eq->linear_solver.tolerance();
+    dout[4] = eq->linear_solver.absolute_tolerance();
+    snprintf(ls_type, size_t(cap), "%s", eq->linear_solver.type().c_str());
+    snprintf(la_type, size_t(cap), "%s", eq->linear_solver.linear_algebra.type().c_str());
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return 1; }
 }

@@ -675,3 +675,69 @@ def test_reference_point_data_fibre_and_time_field_readers_on_the_replacements(t
         assert np.array_equal(Ys[i], steps[f"Velocity_{k:05d}"])
     assert L.vx_load_time_field(str(path).encode(), b"Temperature", _ptr(dims), None, 0) == 1
     assert "No 'Temperature' data found" in L.vx_last_error().decode()
+
+
+@needs_ref
+def test_exported_case_directory_loads_through_the_reference_readers(tmp_path):
+    """tools/export_case.py writes the synthetic pipe in the reference's case layout; the reference's own read_vtu / read_vtp
+    (unmodified vtk_xml.cpp, on the VTK-free replacements) load every file: sizes, connectivity, 0-based ids, parent elements."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("export_case", os.path.join(ROOT, "tools", "export_case.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    L = _vx()
+    out = tmp_path / "case"
+    info = ex.export_pipe(str(out), (4, 4, 6))
+    m = M.pipe_mesh(4, 4, 6)
+    assert info["nNo"] == m.nNo and info["nEl"] == m.nEl
+    sizes = np.zeros(6, np.int32)
+    vol = str(out / "mesh" / "mesh-complete.mesh.vtu").encode()
+    assert L.vx_read_vtu(vol, _ptr(sizes), None, None, None, None) == 0, L.vx_last_error()
+    assert sizes[:4].tolist() == [m.nNo, m.nEl, 4, m.nNo]
+    x = np.zeros((m.nNo, 3)); ien = np.zeros((m.nEl, 4), np.int32); gN = np.zeros(m.nNo, np.int32); order = np.zeros((4, 3), np.int32)
+    assert L.vx_read_vtu(vol, _ptr(sizes), _ptr(x), _ptr(ien), _ptr(gN), _ptr(order)) == 0
+    assert np.array_equal(x, m.x) and np.array_equal(ien, m.ien)
+    covered = np.zeros(m.nNo, int)
+    for name, key in ex.FACES.items():
+        fs = np.zeros(5, np.int32)
+        path = str(out / "mesh" / "mesh-surfaces" / (name + ".vtp")).encode()
+        assert L.vx_read_vtp(path, _ptr(fs), None, None, None, None, None) == 0, L.vx_last_error()
+        nn, ne = info["faces"][name]
+        assert fs.tolist() == [nn, ne, 3, nn, ne]
+        fx = np.zeros((nn, 3)); fien = np.zeros((ne, 3), np.int32); fgN = np.zeros(nn, np.int32); fgE = np.zeros(ne, np.int32); gebc = np.zeros((ne, 4), np.int32)
+        assert L.vx_read_vtp(path, _ptr(fs), _ptr(fx), _ptr(fien), _ptr(fgN), _ptr(fgE), _ptr(gebc)) == 0
+        assert np.array_equal(np.sort(fgN), np.sort(m.faces[key]["nodes"]))         # 0-based global node ids of the face
+        assert np.array_equal(fx, m.x[fgN])
+        # every face triangle is a face of its parent element
+        for e in range(ne):
+            assert set(fgN[fien[e]].tolist()) <= set(m.ien[fgE[e]].tolist())
+        covered[fgN] += 1
+    assert (covered[np.unique(np.concatenate([m.faces[k]["nodes"] for k in ex.FACES.values()]))] >= 1).all()
+    assert (out / "solver.xml").read_text().count("<Add_face") == 3 and (out / "lumen_inlet.flow").read_text().startswith("33")
+    # the generated solver.xml goes through the reference's own parser (Parameters::read_xml) with the case's parameters.  The
+    # parser is run from a small C driver in its own process: inside the Python process it reads uninitialised stack memory
+    # and crashes (with the reference's own solver.xml as well), from a C main it works.
+    import shutil
+    import subprocess
+    if shutil.which("gcc"):
+        drv = tmp_path / "parse.c"
+        drv.write_text('''#include <stdio.h>
+int vx_parse_solver_xml(const char*, int*, double*, char*, char*, int);
+const char* vx_last_error(void);
+int main(int argc, char** argv) { int iv[9]; double dv[5]; char a[64], b[64];
+  if (vx_parse_solver_xml(argv[1], iv, dv, a, b, 64) != 0) { printf("ERR %s\\n", vx_last_error()); return 1; }
+  for (int i = 0; i < 9; i++) printf("%d ", iv[i]);
+  for (int i = 0; i < 5; i++) printf("%.17g ", dv[i]);
+  printf("%s %s\\n", a, b); return 0; }
+''')
+        refdir = os.path.join(ROOT, "oracle", "_ref")
+        exe = tmp_path / "parse"
+        subprocess.run(["gcc", "-std=c99", str(drv), "-L" + refdir, "-lvtkxml_b200", "-Wl,-rpath," + refdir,
+                        "-Wl,-rpath," + os.path.join(ROOT, "svfsiplus_b200"), "-o", str(exe)], check=True)
+        for xml in (out / "solver.xml", "/root/reference/tests/cases/fluid/pipe_RCR_3d/solver.xml"):
+            if not os.path.exists(xml):
+                continue
+            tok = subprocess.run([str(exe), str(xml)], check=True, capture_output=True, text=True).stdout.split()
+            assert [int(t) for t in tok[:9]] == [2, 1, 3, 1, 3, 15, 10, 300, 250]
+            assert [float(t) for t in tok[9:14]] == [0.005, 1.06, 1e-11, 1e-3, 1e-17]
+            assert tok[14:] == ["NS", "fsils"]

@@ -1,0 +1,129 @@
+"""Write the synthetic pipe of SURVEY.md 8(d) as a case directory in the layout of the reference's tests/cases/fluid/pipe_RCR_3d
+(mesh/mesh-complete.mesh.vtu, mesh/mesh-surfaces/lumen_{inlet,outlet,wall}.vtp, solver.xml, lumen_inlet.flow), with the VTK-free
+writer (svfsiplus_b200/sv_io.py -> libsvb200io.so).  A maintainer who has the real `svmultiphysics` binary can then run the SAME
+workload the bench times (P10: --dims 96 96 181) through the reference with MPI and through the B200 backend:
+
+    python tools/export_case.py --dims 96 96 181 --out /tmp/pipe_p10        # ~10 M tets, a few hundred MB
+    cd /tmp/pipe_p10 && mpiexec -n 16 svmultiphysics solver.xml              # reference, FSILS
+    sed -i 's/type="fsils"/type="b200"/' solver.xml && svmultiphysics solver.xml   # this backend
+
+Node and element ids are 1-based in the files (GlobalNodeID point data, GlobalElementID cell data), as the reference's loaders
+expect (vtk_xml_parser.cpp: faces subtract one).  The solver parameters are those of the reference case (rho 1.06, mu 0.04, dt 0.005,
+rho_inf 0.5, LS NS 1e-3 / GM 1e-3 x 10 / CG 1e-3 x 300, Krylov 250, RCR outlet C 1.5e-5, Rd 1212, Rp 121, backflow 0.2); the inflow
+is a smooth synthetic pulse (one period, 33 samples, 16 Fourier modes), not the reference's measured waveform.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from svfsiplus_b200 import mesh as M      # noqa: E402
+from svfsiplus_b200 import sv_io as IO    # noqa: E402
+
+FACES = {"lumen_inlet": "inlet", "lumen_outlet": "outlet", "lumen_wall": "wall"}
+
+SOLVER_XML = """<?xml version="1.0" encoding="UTF-8" ?>
+<svMultiPhysicsFile version="0.1">
+<GeneralSimulationParameters>
+  <Continue_previous_simulation> false </Continue_previous_simulation>
+  <Number_of_spatial_dimensions> 3 </Number_of_spatial_dimensions>
+  <Number_of_time_steps> {steps} </Number_of_time_steps>
+  <Time_step_size> 0.005 </Time_step_size>
+  <Spectral_radius_of_infinite_time_step> 0.50 </Spectral_radius_of_infinite_time_step>
+  <Searched_file_name_to_trigger_stop> STOP_SIM </Searched_file_name_to_trigger_stop>
+  <Save_results_to_VTK_format> 1 </Save_results_to_VTK_format>
+  <Name_prefix_of_saved_VTK_files> result </Name_prefix_of_saved_VTK_files>
+  <Increment_in_saving_VTK_files> {steps} </Increment_in_saving_VTK_files>
+  <Start_saving_after_time_step> 1 </Start_saving_after_time_step>
+  <Increment_in_saving_restart_files> 100 </Increment_in_saving_restart_files>
+  <Convert_BIN_to_VTK_format> 0 </Convert_BIN_to_VTK_format>
+  <Verbose> 1 </Verbose>
+  <Warning> 0 </Warning>
+  <Debug> 0 </Debug>
+</GeneralSimulationParameters>
+<Add_mesh name="msh" >
+  <Mesh_file_path> mesh/mesh-complete.mesh.vtu </Mesh_file_path>
+{faces}</Add_mesh>
+<Add_equation type="fluid" >
+  <Coupled> true </Coupled>
+  <Min_iterations> 3 </Min_iterations>
+  <Max_iterations> 5 </Max_iterations>
+  <Tolerance> 1e-11 </Tolerance>
+  <Backflow_stabilization_coefficient> 0.2 </Backflow_stabilization_coefficient>
+  <Density> 1.06 </Density>
+  <Viscosity model="Constant" > <Value> 0.04 </Value> </Viscosity>
+  <Output type="Spatial" > <Velocity> true </Velocity> <Pressure> true </Pressure> </Output>
+  <LS type="NS" >
+    <Linear_algebra type="fsils" > <Preconditioner> fsils </Preconditioner> </Linear_algebra>
+    <Max_iterations> 15 </Max_iterations>
+    <NS_GM_max_iterations> 10 </NS_GM_max_iterations>
+    <NS_CG_max_iterations> 300 </NS_CG_max_iterations>
+    <Tolerance> 1e-3 </Tolerance>
+    <NS_GM_tolerance> 1e-3 </NS_GM_tolerance>
+    <NS_CG_tolerance> 1e-3 </NS_CG_tolerance>
+    <Absolute_tolerance> 1e-17 </Absolute_tolerance>
+    <Krylov_space_dimension> 250 </Krylov_space_dimension>
+  </LS>
+  <Add_BC name="lumen_inlet" >
+    <Type> Dir </Type> <Time_dependence> Unsteady </Time_dependence>
+    <Temporal_values_file_path> lumen_inlet.flow </Temporal_values_file_path>
+    <Profile> Parabolic </Profile> <Impose_flux> true </Impose_flux>
+  </Add_BC>
+  <Add_BC name="lumen_outlet" >
+    <Type> Neu </Type> <Time_dependence> RCR </Time_dependence>
+    <RCR_values>
+      <Capacitance> 1.5e-5 </Capacitance> <Distal_resistance> 1212 </Distal_resistance> <Proximal_resistance> 121 </Proximal_resistance>
+      <Distal_pressure> 0 </Distal_pressure> <Initial_pressure> 0 </Initial_pressure>
+    </RCR_values>
+  </Add_BC>
+  <Add_BC name="lumen_wall" > <Type> Dir </Type> <Time_dependence> Steady </Time_dependence> <Value> 0.0 </Value> </Add_BC>
+</Add_equation>
+</svMultiPhysicsFile>
+"""
+
+
+def export_pipe(out, dims, steps=2, mode=IO.APPENDED_RAW):
+    """Returns dict(nNo, nEl, faces={name: (n_nodes, n_elems)})."""
+    nx, ny, nz = dims
+    m = M.pipe_mesh(nx, ny, nz)
+    os.makedirs(os.path.join(out, "mesh", "mesh-surfaces"), exist_ok=True)
+    IO.write_vtk(os.path.join(out, "mesh", "mesh-complete.mesh.vtu"), m.x, m.ien, IO.VTK_TYPE["TET4"],
+                 {"GlobalNodeID": np.arange(1, m.nNo + 1, dtype=np.int32)}, {"GlobalElementID": np.arange(1, m.nEl + 1, dtype=np.int32)}, mode=mode)
+    info = dict(nNo=m.nNo, nEl=m.nEl, faces={})
+    xml_faces = ""
+    for name, key in FACES.items():
+        nodes = np.asarray(m.faces[key]["nodes"])
+        on = np.zeros(m.nNo, bool)
+        on[nodes] = True
+        IENb, gE = M.face_elements(m, on)
+        loc = np.full(m.nNo, -1, np.int64)
+        loc[nodes] = np.arange(len(nodes))
+        IO.write_vtk(os.path.join(out, "mesh", "mesh-surfaces", name + ".vtp"), m.x[nodes], loc[IENb].astype(np.int32), IO.VTK_TYPE["TRI3"],
+                     {"GlobalNodeID": (nodes + 1).astype(np.int32)}, {"GlobalElementID": (gE + 1).astype(np.int32)}, polydata=True, mode=mode)
+        info["faces"][name] = (len(nodes), len(gE))
+        xml_faces += f'  <Add_face name="{name}"> <Face_file_path> mesh/mesh-surfaces/{name}.vtp </Face_file_path> </Add_face>\n'
+    with open(os.path.join(out, "solver.xml"), "w") as f:
+        f.write(SOLVER_XML.format(steps=steps, faces=xml_faces))
+    # one smooth pulse per second, peak inflow 50 mL/s (negative = into the domain, like the reference case)
+    t = np.linspace(0.0, 1.0, 33)
+    q = -50.0 * np.sin(np.pi * t) ** 2
+    with open(os.path.join(out, "lumen_inlet.flow"), "w") as f:
+        f.write("33    16\n")
+        for ti, qi in zip(t, q):
+            f.write(f"{ti:.6f}    {qi:.6f}\n")
+    return info
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("--dims", type=int, nargs=3, default=[24, 24, 48], help="pipe hex counts nx ny nz (P10 = 96 96 181)")
+    ap.add_argument("--out", required=True)
+    ap.add_argument("--steps", type=int, default=2)
+    a = ap.parse_args()
+    print(export_pipe(a.out, tuple(a.dims), a.steps))
