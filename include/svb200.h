@@ -67,7 +67,7 @@ typedef struct {
                         for stM.Tf at this time, and Tfa*Tf.eta_s (mat_models_carray.h:222-225); laws 0, 3, 4, 5, needs fibres */
   double kap;        /* isoType 5 (Holzapfel-Gasser-Ogden): fibre dispersion stM.kap; C10, aff, bff, ass, bss as in the XML */
   int viscType;      /* solid viscosity (dmn.solid_visc, mat_models_carray.h:1383-1590): 0 none, 1 Newtonian, 2 pseudo-potential;
-                        struct equations (b200_assemble_struct, b200_assemble_struct_dmn), not the FSI equation */
+                        struct equations (b200_assemble_struct, b200_assemble_struct_dmn) and the struct domains of the FSI equation */
   double visc_mu;
 } b200_struct_props;
 

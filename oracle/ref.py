@@ -412,7 +412,7 @@ class RefAssembly:
         return R, Val, t
 
 
-    def fsi(self, elem_dmn, Ag, Yg, Dg, Bf, *, dt, am, af, gam, beta, fluid, solid):
+    def fsi(self, elem_dmn, Ag, Yg, Dg, Bf, *, dt, am, af, gam, beta, fluid, solid, pS0=None):
         """construct_fsi (S/fsi.cpp:42) with domain 0 = fluid, 1 = struct.  fluid: dict(rho, mu, f, viscType...);
         solid: dict(rho, dmp, f, iso, vol, C10, C01, Kpen).  Returns R (nNo,4), Val (nnz,16), seconds."""
         Ag = _c(Ag, np.float64); Yg = _c(Yg, np.float64); Dg = _c(Dg, np.float64); Bf = _c(Bf, np.float64)
@@ -425,6 +425,10 @@ class RefAssembly:
                          solid.get("C01", 0.0), solid.get("Kpen", 0.0), 0.0, 0.0] + [0.0] * 8 + [100.0, 0.0, 0.0, 0.0], np.float64)
         R = np.empty((self.nNo, 4))
         Val = np.empty((self.nnz, 16))
+        # wall viscosity (solid["visc"], solid["visc_mu"]) and prestress (com_mod.pS0; construct_fsi never accumulates pSn / pSa)
+        lib().ref_asm_set_visc(self.h, {None: 0, "newt": 1, "pot": 2}[solid.get("visc")], float(solid.get("visc_mu", 0.0)))
+        pS0 = None if pS0 is None else _c(pS0, np.float64)
+        lib().ref_asm_set_prestress(self.h, None if pS0 is None else _p(pS0), 0)
         t = lib().ref_asm_fsi(self.h, Ag.shape[1], dt, am, af, gam, beta, _p(fpar), _p(spar), _p(ed), _p(Ag), _p(Yg), _p(Dg),
                               _p(Bf), _p(R), _p(Val))
         if t < 0:

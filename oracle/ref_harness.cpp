@@ -520,6 +520,12 @@ double ref_asm_fsi(void* h, int tDof, double dt, double am, double af, double ga
                       : (vol == 2) ? ConstitutiveModelType::stVol_ST91
                       : (vol == 3) ? ConstitutiveModelType::stVol_M94 : ConstitutiveModelType::stIso_NA;
       dmn.stM.C10 = spar[12]; dmn.stM.C01 = spar[13]; dmn.stM.Kpen = spar[14];
+      // wall viscosity / prestress of the next call (ref_asm_set_visc / ref_asm_set_prestress); construct_fsi reads com_mod.pS0 only
+      dmn.solid_visc.viscType = (ctx->visc_model == 1) ? SolidViscosityModelType::viscType_Newtonian
+                              : (ctx->visc_model == 2) ? SolidViscosityModelType::viscType_Potential : SolidViscosityModelType::viscType_NA;
+      dmn.solid_visc.mu = ctx->visc_mu;
+      if (ctx->pS0.empty()) com_mod.pS0.clear();
+      else { com_mod.pS0.resize(6, com_mod.tnNo); std::memcpy(com_mod.pS0.data(), ctx->pS0.data(), sizeof(double)*6*size_t(com_mod.tnNo)); }
     }
     msh.eId.resize(msh.nEl);
     for (int e = 0; e < msh.nEl; e++) msh.eId(e) = 1 << elem_dmn[e];

@@ -75,7 +75,7 @@ def reference_assemble_fsi(case):
     ra = ref.RefAssembly(m.x, m.ien)
     t = case["time"]
     R, Val, secs = ra.fsi(case["elem_dmn"], case["Ag"], case["Yg"], case["Dg"], case["Bf"], dt=t["dt"], am=t["am"], af=t["af"],
-                          gam=t["gam"], beta=t["beta"], fluid=case["fluid"], solid=case["solid"])
+                          gam=t["gam"], beta=t["beta"], fluid=case["fluid"], solid=case["solid"], pS0=case.get("pS0"))
     ra.close()
     return R, Val, secs
 

@@ -270,8 +270,9 @@ void finish_assembly(b200_handle* h, int dof, double t0, const char* who)
   }
 }
 
+// with_pst: pass the pstEq staging (construct_dsolid accumulates pSn / pSa; construct_fsi reads pS0 but does not, fsi.cpp:147-225)
 template <int ENON, int NG, int EPB, int APT, int ODOF, bool VISC = false>
-void launch_solid(b200_handle* h, const SolidConsts& c, int nList, const int* d_elist)
+void launch_solid(b200_handle* h, const SolidConsts& c, int nList, const int* d_elist, bool with_pst = true)
 {
   auto& ops = *h->ops;
   if (nList == 0) return;
@@ -281,7 +282,7 @@ void launch_solid(b200_handle* h, const SolidConsts& c, int nList, const int* d_
   CU_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   kern<<<(nList + EPB - 1)/EPB, EPB*NG, smem, ops.st>>>(nList, d_elist, c, h->d_tab, h->d_ien, h->d_rslot, h->d_kslot, h->d_x,
                                                         h->d_Ag, h->d_Yg, h->d_Dg, h->d_Do, h->d_Bf, h->d_fN, h->stageR, h->stageK, h->d_err,
-                                                        VISC ? h->d_pS0 : nullptr, (VISC && h->pstEq && c.kind == 0) ? h->stageP : nullptr);
+                                                        VISC ? h->d_pS0 : nullptr, (VISC && with_pst && h->pstEq && c.kind == 0) ? h->stageP : nullptr);
   CU_CHECK(cudaGetLastError());
   ops.post();
 }
@@ -967,8 +968,13 @@ int b200_assemble_fsi(b200_handle* h, int nDmn, const int* dmn_kind, const b200_
         } else if (dmn_kind[d] == 1) {
           if (solid[d].tDof != h->tDof) throw std::runtime_error("assemble_fsi: tDof differs from the uploaded state");
           const SolidConsts c = struct_consts(&solid[d]);
-          if (c.viscType != 0 || h->d_pS0 || h->pstEq) throw std::runtime_error("assemble_fsi: solid viscosity and prestress have a device kernel for struct equations only, not inside the FSI equation");
-          if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 4>(h, c, n, h->d_dmn_elems[d]);
+          if (c.viscType != 0 || h->d_pS0) {
+            // wall with solid viscosity and / or prestress (construct_fsi reads com_mod.pS0, fsi.cpp:147-148; it never accumulates pSn / pSa)
+            if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 4, true>(h, c, n, h->d_dmn_elems[d], false);
+            else if (h->eNoN == 8) launch_solid<8, 8, 16, 2, 4, true>(h, c, n, h->d_dmn_elems[d], false);
+            else launch_solid<10, 15, 8, 2, 4, true>(h, c, n, h->d_dmn_elems[d], false);
+          }
+          else if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 4>(h, c, n, h->d_dmn_elems[d]);
           else if (h->eNoN == 8) launch_solid<8, 8, 16, 2, 4>(h, c, n, h->d_dmn_elems[d]);
           else launch_solid<10, 15, 8, 2, 4>(h, c, n, h->d_dmn_elems[d]);
         } else {

@@ -256,7 +256,7 @@ bool B200LinearAlgebra::fill_struct_props(ComMod& com_mod, const eqType& eq, con
     default: return false;
   }
   sp.visc_mu = dmn.solid_visc.mu;
-  if (sp.viscType != 0 && eq.phys != EquationType::phys_struct) return false;      // not inside the FSI equation
+  if (sp.viscType != 0 && eq.phys != EquationType::phys_struct && eq.phys != EquationType::phys_FSI) return false;
   fibre_stress(com_mod, stM.Tf, sp.Tfa, sp.Tsa);
   if (sp.Tfa != 0.0 && stM.isoType != ConstitutiveModelType::stIso_nHook && stM.isoType != ConstitutiveModelType::stIso_HO &&
       stM.isoType != ConstitutiveModelType::stIso_MR && stM.isoType != ConstitutiveModelType::stIso_HGO &&
@@ -298,7 +298,9 @@ bool B200LinearAlgebra::assemble_fsi_mesh(ComMod& com_mod, const mshType& lM, co
   using namespace consts;
   auto& eq = com_mod.eq[com_mod.cEq];
   if ((lM.eType != ElementType::TET4 && lM.eType != ElementType::HEX8 && lM.eType != ElementType::TET10) || com_mod.dof != 4 || !com_mod.mvMsh) return false;
-  if (com_mod.pS0.size() != 0 || com_mod.pstEq) return false;
+  // the wall's prestress is read by construct_fsi (fsi.cpp:147-148) and never accumulated there; a prestress EQUATION is a struct run
+  if (com_mod.pstEq) return false;
+  if (com_mod.pS0.size() != 0 && (com_mod.pS0.nrows() != 6 || com_mod.pS0.ncols() != com_mod.tnNo)) return false;
   if (cep_mod && (cep_mod->cem.cpld || cep_mod->cem.aStress || cep_mod->cem.aStrain)) return false;
   const int nDmn = eq.nDmn;
   std::vector<int> kinds(nDmn, -1);
@@ -328,6 +330,10 @@ bool B200LinearAlgebra::assemble_fsi_mesh(ComMod& com_mod, const mshType& lM, co
   const bool have_do = com_mod.Do.size() != 0 && com_mod.Do.nrows() == com_mod.tDof;
   check(b200_disp_set(h_, com_mod.tDof, Dg.data(), have_do ? com_mod.Do.data() : nullptr), "b200_disp_set");
   do_uploaded_ = have_do;
+  if (com_mod.pS0.size() != 0 || prestress_on_device_) {
+    check(b200_prestress_set(h_, com_mod.pS0.size() != 0 ? com_mod.pS0.data() : nullptr, 0), "b200_prestress_set");
+    prestress_on_device_ = com_mod.pS0.size() != 0;
+  }
   check(b200_assemble_fsi(h_, nDmn, kinds.data(), fl.data(), st.data()), "b200_assemble_fsi");
   any_device_contribution_ = true;
   return true;

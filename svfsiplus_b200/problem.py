@@ -302,6 +302,8 @@ def assemble_fsi(be: B.Backend, case, upload=True):
         be.state_set(7, case["Ag"], case["Yg"], case["Bf"])
         be.disp_set(7, case["Dg"])
         be.mesh_domains(2, case["elem_dmn"])
+        if case.get("pS0") is not None:
+            be.prestress_set(case["pS0"], False)              # the wall's prestress: read, never accumulated (fsi.cpp:147-148)
     be.zero(4)
     fp = B.fluid_props(tDof=7, mvMsh=True, dt=t["dt"], am=t["am"], af=t["af"], gam=t["gam"], **case["fluid"])
     sp = B.struct_props(tDof=7, s=0, dt=t["dt"], am=t["am"], af=t["af"], gam=t["gam"], beta=t["beta"], **case["solid"])

@@ -45,6 +45,13 @@ def main():
             R, Val, *_ = refcase.reference_assemble_solid(c)
             tag = f"{elem}_struct_pst_{visc}"
             out[f"R_{tag}"], out[f"Val_{tag}"], out[f"pSn_{tag}"], out[f"pSa_{tag}"] = R, Val, c["_ref_pSn"], c["_ref_pSa"]
+    # FSI with a prestressed, viscous wall (construct_fsi reads com_mod.pS0; dmn.solid_visc of the struct domain)
+    for tag, c in (("tet", P.fsi_case(4, 4, 4)), ("hex", P.fsi_block_case(3, elem="hex")), ("tet10", P.fsi_block_case(2, elem="tet10"))):
+        rng = np.random.default_rng(77)
+        c["solid"] = dict(c["solid"], visc="pot", visc_mu=200.0)
+        c["pS0"] = 1.0e4 * rng.standard_normal((c["mesh"].nNo, 6))
+        R, Val, _ = refcase.reference_assemble_fsi(c)
+        out[f"R_{tag}_fsi_wall"], out[f"Val_{tag}_fsi_wall"] = R, Val
     # ... and in ustruct_3d_m (Siso + Svis, Kvis_u in Ku, af Kvis_v)
     for elem, n in (("tet", 3), ("hex", 3), ("tet10", 2)):
         for visc in ("newt", "pot"):

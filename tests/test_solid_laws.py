@@ -102,6 +102,12 @@ def test_oracle_reproduces_late_addition_fixtures():
         R, Val, Kd, _ = refcase.reference_assemble_ustruct(c)
         assert np.array_equal(R, g[f"R_{elem}_ustruct_HO_ma"]) and np.array_equal(Val, g[f"Val_{elem}_ustruct_HO_ma"])
         assert np.array_equal(Kd, g[f"Kd_{elem}_ustruct_HO_ma"])
+    for tag, c in (("tet", P.fsi_case(4, 4, 4)), ("hex", P.fsi_block_case(3, elem="hex")), ("tet10", P.fsi_block_case(2, elem="tet10"))):
+        rng = np.random.default_rng(77)
+        c["solid"] = dict(c["solid"], visc="pot", visc_mu=200.0)
+        c["pS0"] = 1.0e4 * rng.standard_normal((c["mesh"].nNo, 6))
+        R, Val, _ = refcase.reference_assemble_fsi(c)
+        assert np.array_equal(R, g[f"R_{tag}_fsi_wall"]) and np.array_equal(Val, g[f"Val_{tag}_fsi_wall"])
     for elem, n in (("tet", 3), ("hex", 3), ("tet10", 2)):
         for visc in ("newt", "pot"):
             c = P.block_case(n, elem=elem, kind="struct", iso="nHook", vol="ST91", visc=visc, visc_mu=5.0e4)

@@ -100,3 +100,25 @@ def test_struct_prestress_matches_golden(elem, n, visc):
     with pytest.raises(RuntimeError, match="prestress_get"):
         be.prestress_get()
     be.close()
+
+
+# ---- written after the round's last GPU second was spent: CPU-pinned goldens, device run pending -----------------------------------
+_PENDING = pytest.mark.xfail(reason="added in round 1 after the GPU budget was spent: golden from the compiled reference, not yet run on a B200",
+                             strict=False)
+
+
+@_PENDING
+@pytest.mark.parametrize("tag", ["tet", "hex", "tet10"])
+def test_fsi_with_prestressed_viscous_wall_matches_golden(tag):
+    """construct_fsi with com_mod.pS0 (read, never accumulated: fsi.cpp:147-148, 225) and dmn.solid_visc on the struct domain: the
+    extended struct element writing into the dof-4 blocks."""
+    g = golden("late_additions.npz")
+    case = {"tet": lambda: P.fsi_case(4, 4, 4), "hex": lambda: P.fsi_block_case(3, elem="hex"), "tet10": lambda: P.fsi_block_case(2, elem="tet10")}[tag]()
+    rng = np.random.default_rng(77)
+    case["solid"] = dict(case["solid"], visc="pot", visc_mu=200.0)
+    case["pS0"] = 1.0e4 * rng.standard_normal((case["mesh"].nNo, 6))
+    be = P.setup_backend(case)
+    P.assemble_fsi(be, case)
+    assert rel_inf(be.get_R(), g[f"R_{tag}_fsi_wall"]) < TOL_ASM
+    assert rel_inf(be.get_Val(), g[f"Val_{tag}_fsi_wall"]) < TOL_ASM
+    be.close()
