@@ -7,6 +7,9 @@
 #include "vtk_xml.h"
 #include "vtk_xml_parser.h"
 #include "Parameters.h"
+#include "read_msh.h"
+
+#include <unistd.h>
 
 #include <cstring>
 #include <stdexcept>
@@ -168,6 +171,30 @@ int vx_parse_solver_xml(const char* path, int* out, double* dout, char* ls_type,
     dout[4] = eq->linear_solver.absolute_tolerance();
     snprintf(ls_type, size_t(cap), "%s", eq->linear_solver.type().c_str());
     snprintf(la_type, size_t(cap), "%s", eq->linear_solver.linear_algebra.type().c_str());
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// The reference's mesh ingestion on a case directory: Simulation::read_parameters + set_module_parameters + read_msh_ns::read_msh
+// (Code/Source/solver/read_files.cpp:1649-1652, read_msh.cpp:1077: read_sv -> read_vtu / read_vtp for the mesh and every face, face /
+// element matching, check_ien, global coordinates) - all unmodified reference code, running on the VTK-free replacements.
+// sizes = {nsd, nMsh, gtnNo, gnEl, eNoN, nFa}; face_sizes = nFa x {nNo, nEl, eNoN}.  x (3 x gtnNo) and gIEN (eNoN x gnEl) may be null.
+int vx_read_case(const char* dir, const char* xml, int* sizes, int* face_sizes, int max_faces, double* x, int* gIEN)
+{
+  try {
+    if (chdir(dir) != 0) throw std::runtime_error(std::string("cannot enter '") + dir + "'");
+    Simulation sim;
+    sim.read_parameters(xml);
+    sim.set_module_parameters();
+    read_msh_ns::read_msh(&sim);
+    auto& com_mod = sim.com_mod;
+    auto& msh = com_mod.msh.at(0);
+    sizes[0] = com_mod.nsd; sizes[1] = com_mod.nMsh; sizes[2] = com_mod.gtnNo; sizes[3] = msh.gnEl; sizes[4] = msh.eNoN; sizes[5] = msh.nFa;
+    for (int i = 0; i < msh.nFa && i < max_faces; i++) {
+      face_sizes[3*i] = msh.fa[i].nNo; face_sizes[3*i + 1] = msh.fa[i].nEl; face_sizes[3*i + 2] = msh.fa[i].eNoN;
+    }
+    if (x) std::memcpy(x, com_mod.x.data(), sizeof(double)*size_t(com_mod.nsd)*com_mod.gtnNo);
+    if (gIEN) std::memcpy(gIEN, msh.gIEN.data(), sizeof(int)*size_t(msh.eNoN)*msh.gnEl);
     return 0;
   } catch (const std::exception& e) { g_err = e.what(); return 1; }
 }

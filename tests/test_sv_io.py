@@ -741,3 +741,34 @@ int main(int argc, char** argv) { int iv[9]; double dv[5]; char a[64], b[64];
             assert [int(t) for t in tok[:9]] == [2, 1, 3, 1, 3, 15, 10, 300, 250]
             assert [float(t) for t in tok[9:14]] == [0.005, 1.06, 1e-11, 1e-3, 1e-17]
             assert tok[14:] == ["NS", "fsils"]
+        # ... and the whole directory goes through the reference's mesh ingestion: Simulation::read_parameters + read_msh (read_sv ->
+        # read_vtu / read_vtp per file, face-to-element matching, check_ien), unmodified reference code on the VTK-free replacements
+        drv2 = tmp_path / "read_case.c"
+        drv2.write_text('''#include <stdio.h>
+#include <stdlib.h>
+int vx_read_case(const char*, const char*, int*, int*, int, double*, int*);
+const char* vx_last_error(void);
+int main(int argc, char** argv) { int s[6] = {0}, f[30] = {0};
+  if (vx_read_case(argv[1], "solver.xml", s, f, 10, 0, 0) != 0) { printf("ERR %s\\n", vx_last_error()); return 1; }
+  double* x = malloc(sizeof(double)*3*s[2]); int* ien = malloc(sizeof(int)*s[4]*s[3]);
+  if (vx_read_case(argv[1], "solver.xml", s, f, 10, x, ien) != 0) { printf("ERR %s\\n", vx_last_error()); return 1; }
+  for (int i = 0; i < 6; i++) printf("%d ", s[i]);
+  for (int i = 0; i < 3*s[5]; i++) printf("%d ", f[i]);
+  printf("\\n");
+  FILE* o = fopen(argv[2], "wb"); fwrite(x, sizeof(double), 3*s[2], o); fwrite(ien, sizeof(int), s[4]*s[3], o); fclose(o);
+  return 0; }
+''')
+        exe2 = tmp_path / "read_case"
+        subprocess.run(["gcc", "-std=c99", str(drv2), "-L" + refdir, "-lvtkxml_b200", "-Wl,-rpath," + refdir,
+                        "-Wl,-rpath," + os.path.join(ROOT, "svfsiplus_b200"), "-o", str(exe2)], check=True)
+        dump = tmp_path / "case.bin"
+        tok = subprocess.run([str(exe2), str(out), str(dump)], check=True, capture_output=True, text=True).stdout.split()
+        assert "ERR" not in tok
+        vals = [int(t) for t in tok]
+        assert vals[:6] == [3, 1, m.nNo, m.nEl, 4, 3]
+        assert vals[6:] == [v for name in ex.FACES for v in (*info["faces"][name], 3)]
+        raw = dump.read_bytes()
+        xr = np.frombuffer(raw[:m.nNo * 24], np.float64).reshape(m.nNo, 3)
+        ir = np.frombuffer(raw[m.nNo * 24:], np.int32).reshape(m.nEl, 4)
+        assert np.array_equal(xr, m.x)
+        assert np.array_equal(np.sort(ir, axis=1), np.sort(m.ien, axis=1))          # check_ien may reorder the nodes of an element
