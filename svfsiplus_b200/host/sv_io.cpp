@@ -525,9 +525,19 @@ struct Writer {
   {
     const TypeInfo& ti = type_info(a.type);
     char buf[512];
-    snprintf(buf, sizeof(buf), "%s<DataArray type=\"%s\" Name=\"%s\" NumberOfComponents=\"%d\" format=\"%s\"", indent, ti.name, a.name.c_str(), a.ncomp,
-             mode == B200IO_ASCII ? "ascii" : mode == B200IO_BINARY ? "binary" : "appended");
-    xml += buf;
+    std::string esc;                        // attribute value: the five XML entities
+    for (char ch : a.name) {
+      switch (ch) {
+        case '&': esc += "&amp;"; break;
+        case '<': esc += "&lt;"; break;
+        case '>': esc += "&gt;"; break;
+        case '"': esc += "&quot;"; break;
+        case '\'': esc += "&apos;"; break;
+        default: esc.push_back(ch);
+      }
+    }
+    xml += std::string(indent) + "<DataArray type=\"" + ti.name + "\" Name=\"" + esc + "\" NumberOfComponents=\"" + std::to_string(a.ncomp) +
+           "\" format=\"" + (mode == B200IO_ASCII ? "ascii" : mode == B200IO_BINARY ? "binary" : "appended") + "\"";
     if (mode == B200IO_ASCII) {
       xml += ">\n";
       const size_t n = a.count();

@@ -772,3 +772,51 @@ int main(int argc, char** argv) { int s[6] = {0}, f[30] = {0};
         ir = np.frombuffer(raw[m.nNo * 24:], np.int32).reshape(m.nEl, 4)
         assert np.array_equal(xr, m.x)
         assert np.array_equal(np.sort(ir, axis=1), np.sort(m.ien, axis=1))          # check_ien may reorder the nodes of an element
+
+
+@pytest.mark.parametrize("mode", [IO.ASCII, IO.BINARY, IO.APPENDED_RAW, IO.APPENDED_BASE64])
+def test_edge_cases_empty_cells_special_names_single_point(tmp_path, mode):
+    """a point cloud without cells, array names that need XML escaping, a one-element mesh, constant and extreme values"""
+    path = tmp_path / "edge.vtu"
+    x = np.array([[0.0, 0.0, 0.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]])
+    pd = {'p<0> & "q"': np.array([1e-310, -0.0, 1.7976931348623157e308, 5e-324]),          # subnormals, signed zero, the largest double
+          "ids": np.array([-2147483648, 0, 7, 2147483647], dtype=np.int32)}
+    IO.write_vtk(path, x, np.zeros((0, 4), np.int32), 10, pd, {}, mode=mode)
+    r = IO.read_vtk(path)
+    assert r["nNo"] == 4 and r["nEl"] == 0 and r["eNoN"] == -1
+    assert list(r["point_data"]) == list(pd)
+    got = r["point_data"]['p<0> & "q"']
+    assert np.array_equal(got.view(np.uint64), pd['p<0> & "q"'].view(np.uint64))             # bit for bit, the sign of zero included
+    assert np.array_equal(r["point_data"]["ids"], pd["ids"])
+    ET.parse(path) if mode in (IO.ASCII, IO.BINARY, IO.APPENDED_BASE64) else None            # well-formed XML (raw appended data is not XML)
+    IO.write_vtk(path, x, np.array([[0, 1, 2, 3]], np.int32), 10, {}, {"one": np.array([3.5])}, mode=mode, compress=False)
+    r = IO.read_vtk(path)
+    assert r["nEl"] == 1 and r["ien"].tolist() == [[0, 1, 2, 3]] and r["cell_data"]["one"].tolist() == [3.5]
+
+
+def test_random_meshes_round_trip_property():
+    """hypothesis: any point count, element size, connectivity, field shapes and data mode survive write -> read bit for bit"""
+    import tempfile
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.integers(1, 40), st.sampled_from([2, 3, 4, 6, 8, 10]), st.integers(0, 30), st.integers(1, 9), st.sampled_from([0, 1, 2, 3]),
+           st.booleans(), st.booleans(), st.integers(0, 2**31 - 1))
+    def prop(nNo, eNoN, nEl, ncomp, mode, compress, h64, seed):
+        rng = np.random.default_rng(seed)
+        x = rng.standard_normal((nNo, 3)) * 10.0 ** rng.integers(-6, 6)
+        ien = rng.integers(0, nNo, (nEl, eNoN)).astype(np.int32)
+        pd = {"f": rng.standard_normal((nNo, ncomp)) if ncomp > 1 else rng.standard_normal(nNo), "i": rng.integers(-5, 5, nNo).astype(np.int32)}
+        cd = {"c": rng.standard_normal((nEl, ncomp)) if ncomp > 1 else rng.standard_normal(nEl)}
+        vt = {2: 3, 3: 5, 4: 10, 6: 13, 8: 12, 10: 24}[eNoN]
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "m.vtu")
+            IO.write_vtk(path, x, ien, vt, pd, cd, mode=mode, compress=compress, header64=h64)
+            r = IO.read_vtk(path)
+        assert np.array_equal(r["x"], x) and r["nEl"] == nEl
+        if nEl:
+            assert np.array_equal(r["ien"], ien) and (r["types"] == vt).all()
+        assert np.array_equal(r["point_data"]["f"], pd["f"]) and np.array_equal(r["point_data"]["i"], pd["i"])
+        assert np.array_equal(r["cell_data"]["c"].reshape(cd["c"].shape), cd["c"])
+
+    prop()
