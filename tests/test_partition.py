@@ -219,3 +219,27 @@ def test_rcb_partition_layout_equals_reference_fsils_lhs_create():
         for (_, pa), (_, pb) in zip(lay["reqs"], info["reqs"]):
             assert (pa == pb).all()
     rr.close()
+
+
+@needs_ref
+@pytest.mark.parametrize("nparts,seed", [(2, 11), (5, 12), (6, 13)])
+def test_native_layout_equals_reference_on_random_partitions(nparts, seed):
+    """Random element -> rank maps (ragged part sizes, nodes with many owners, possibly ranks that share nothing) through split_case
+    and the native layout, integer for integer against fsils_lhs_create on threads-as-ranks."""
+    from oracle import ref
+    rng = np.random.default_rng(seed)
+    case = P.pipe_case(3, 3, 7)
+    m = case["mesh"]
+    part = rng.integers(0, nparts, m.nEl).astype(np.int32)
+    part[:nparts] = np.arange(nparts)                          # no empty rank
+    parts = PT.split_case(case, nparts, part)
+    rr = ref.RefRanks([dict(gnNo=p["gnNo"], gNodes=p["gNodes"], rowPtr=p["rowPtr"], colPtr=p["colPtr"], faces=[]) for p in parts])
+    allg = [p["gNodes"] for p in parts]
+    for r in range(nparts):
+        info = rr.info(r)
+        lay = PT.lhs_layout(r, allg, parts[r]["gnNo"])
+        assert lay["mynNo"] == info["mynNo"] and lay["shnNo"] == info["shnNo"] and (lay["map"] == info["map"]).all()
+        assert [q[0] for q in lay["reqs"]] == [q[0] for q in info["reqs"]]
+        for (_, pa), (_, pb) in zip(lay["reqs"], info["reqs"]):
+            assert (pa == pb).all()
+    rr.close()
