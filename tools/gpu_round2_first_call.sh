@@ -17,3 +17,9 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_as
 bash tools/ncu_export.sh gpurun_out/r02a_solid_ext
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks_throttle_reasons.active --format=csv > gpurun_out/r02a_smi.txt
 tail -4 gpurun_out/r02a_pytest.log; tail -2 gpurun_out/r02a_smoke.log; head -c 700 gpurun_out/r02a_bench.json; echo; head -c 300 gpurun_out/r02a_bench_ref.json
+
+# Second call (two GPUs, ~6 minutes): where the N = 2 line loses its 28 % - kernel classes incl. "halo" and the all-reduce share are in
+# the bench line's kernel_shares / kernels objects, NVLS use in the NCCL log.
+#   gpurun --gpus 2 --timeout 600 -- 'NCCL_DEBUG=INFO python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+#       --master-port 29533 bench.py --gpus 2 --steps 2 --warmup 3 > gpurun_out/r02b_bench_n2.json 2> gpurun_out/r02b_bench_n2.err; \
+#       python -m pytest tests/test_multigpu.py -m gpu -q > gpurun_out/r02b_multigpu.log 2>&1; tail -3 gpurun_out/r02b_multigpu.log'
