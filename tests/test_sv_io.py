@@ -820,3 +820,42 @@ def test_random_meshes_round_trip_property():
         assert np.array_equal(r["cell_data"]["c"].reshape(cd["c"].shape), cd["c"])
 
     prop()
+
+
+def test_restart_round_trip_property():
+    """hypothesis: any sizes / flag combination / rank layout: what one rank writes at its record offset reads back bit for bit,
+    the record length formula covers the record, and neighbouring records do not overlap (without the reference's trailing Dn)."""
+    import tempfile
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=50, deadline=None)
+    @given(st.integers(1, 30), st.integers(1, 8), st.integers(1, 4), st.integers(0, 5), st.booleans(), st.booleans(), st.booleans(),
+           st.integers(1, 4), st.integers(0, 2**31 - 1))
+    def prop(tnNo, tDof, nEq, nXn, dFlag, sst, pst, nranks, seed):
+        rng = np.random.default_rng(seed)
+        sst, pst = sst and dFlag, pst and dFlag                      # Ad / pS0 only exist with a displacement field
+        recs = []
+        for r in range(nranks):
+            kw = dict(stamp=[nranks, nEq, 1, tnNo, nXn, tDof, int(dFlag)], cTS=int(rng.integers(0, 5000)), time=float(rng.random()), cpu_time=float(rng.random()),
+                      iNorm=rng.random(nEq), xn=rng.standard_normal(nXn), Yn=rng.standard_normal((tnNo, tDof)), An=rng.standard_normal((tnNo, tDof)))
+            if dFlag:
+                kw["Dn"] = rng.standard_normal((tnNo, tDof))
+            if sst:
+                kw["Ad"] = rng.standard_normal((tnNo, 3))
+            if pst:
+                kw["pS0"] = rng.standard_normal((tnNo, 6))
+            recs.append(kw)
+        recLn = max(IO.restart_record_bytes(**k) for k in recs)
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "st.bin")
+            for r in rng.permutation(nranks):
+                IO.write_restart(path, int(r), recLn, create=not os.path.exists(path), trailing_Dn=False, **recs[int(r)])
+            assert os.path.getsize(path) <= nranks * recLn
+            for r, kw in enumerate(recs):
+                got = IO.read_restart(path, r, recLn, nEq=nEq, nXn=nXn, tDof=tDof, tnNo=tnNo, dFlag=dFlag, nsd=3 if sst else 0, nsymd=6 if pst else 0)
+                assert got["cTS"] == kw["cTS"] and got["time"] == kw["time"] and got["stamp"] == kw["stamp"]
+                for k in ("iNorm", "xn", "Yn", "An", "Dn", "Ad", "pS0"):
+                    if k in kw:
+                        assert np.array_equal(got[k], kw[k]), k
+
+    prop()
