@@ -258,3 +258,22 @@ def compare_results(result_vtu, reference_vtu, fields, rtol=None):
             msgs.append(f"Test failed in field {f}. Results differ by more than rtol={r} in {1 - close.sum() / close.size:.1%} of results. "
                         f"Max. rel. difference is {rel_diff[i]:.1e} (abs. {abs(a_fl[i] - b_fl[i]):.1e})")
     return msgs
+
+
+def result_name(save_name, cTS):
+    """write_vtus' file name (vtk_xml.cpp:1344-1352): <saveName>_<cTS, three digits up to 1000>.vtu"""
+    return f"{save_name}_{cTS}.vtu" if cTS > 1000 else f"{save_name}_{cTS:03d}.vtu"
+
+
+def write_results(save_name, cTS, x, ien, vtk_type, fields, domain_id=None, proc_id=None, **kw):
+    """The file write_vtus leaves for one mesh (vtk_xml.cpp:913-1470): the named nodal output fields as point data, in the order
+    given (a dict name -> (nNo,) or (nNo, ncomp); the reference's names are Velocity, Pressure, Displacement, WSS, ...), Domain_ID /
+    Proc_ID as cell data when given.  Returns the path; compare two such files with compare_results."""
+    path = result_name(save_name, cTS)
+    cd = {}
+    if domain_id is not None:
+        cd["Domain_ID"] = np.asarray(domain_id, np.int32)
+    if proc_id is not None:
+        cd["Proc_ID"] = np.asarray(proc_id, np.int32)
+    write_vtk(path, x, ien, vtk_type, {k: np.asarray(v, np.float64) for k, v in fields.items()}, cd, **kw)
+    return path

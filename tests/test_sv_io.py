@@ -859,3 +859,16 @@ def test_restart_round_trip_property():
                         assert np.array_equal(got[k], kw[k]), k
 
     prop()
+
+
+def test_result_files_named_and_compared_like_the_reference(tmp_path):
+    """write_results: write_vtus' naming and layout; two runs' files compare with the reference harness's criterion"""
+    m, pd, cd = _mesh("tet")
+    Y = np.random.default_rng(2).standard_normal((m.nNo, 4))
+    a = IO.write_results(str(tmp_path / "result"), 2, m.x, m.ien, 10, {"Velocity": Y[:, :3], "Pressure": Y[:, 3]}, domain_id=cd["Domain_ID"])
+    assert a.endswith("result_002.vtu") and IO.result_name("r", 1500) == "r_1500.vtu" and IO.result_name("r", 1000) == "r_1000.vtu"
+    r = IO.read_vtk(a)
+    assert list(r["point_data"]) == ["Velocity", "Pressure"] and np.array_equal(r["cell_data"]["Domain_ID"], cd["Domain_ID"])
+    os.makedirs(tmp_path / "other")
+    b = IO.write_results(str(tmp_path / "other" / "result"), 2, m.x, m.ien, 10, {"Velocity": Y[:, :3] * (1 + 1e-9), "Pressure": Y[:, 3]})
+    assert IO.compare_results(b, a, ["Velocity", "Pressure"]) == []
