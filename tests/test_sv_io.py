@@ -872,3 +872,55 @@ def test_result_files_named_and_compared_like_the_reference(tmp_path):
     os.makedirs(tmp_path / "other")
     b = IO.write_results(str(tmp_path / "other" / "result"), 2, m.x, m.ien, 10, {"Velocity": Y[:, :3] * (1 + 1e-9), "Pressure": Y[:, 3]})
     assert IO.compare_results(b, a, ["Velocity", "Pressure"]) == []
+
+
+READ_CASE_C = r'''#include <stdio.h>
+#include <stdlib.h>
+int vx_read_case(const char*, const char*, int*, int*, int, double*, int*);
+const char* vx_last_error(void);
+int main(int argc, char** argv) { int s[6] = {0}, f[30] = {0};
+  if (vx_read_case(argv[1], "solver.xml", s, f, 10, 0, 0) != 0) { printf("ERR %s\n", vx_last_error()); return 1; }
+  double* x = malloc(sizeof(double)*3*s[2]); int* ien = malloc(sizeof(int)*s[4]*s[3]);
+  if (vx_read_case(argv[1], "solver.xml", s, f, 10, x, ien) != 0) { printf("ERR %s\n", vx_last_error()); return 1; }
+  for (int i = 0; i < 6; i++) printf("%d ", s[i]);
+  for (int i = 0; i < 3*s[5]; i++) printf("%d ", f[i]);
+  printf("\n");
+  FILE* o = fopen(argv[2], "wb"); fwrite(x, sizeof(double), 3*s[2], o); fwrite(ien, sizeof(int), s[4]*s[3], o); fclose(o);
+  return 0; }
+'''
+
+
+@needs_ref
+@pytest.mark.parametrize("elem", ["hex", "tet", "tet10"])
+def test_exported_solid_block_goes_through_the_reference_mesh_ingestion(tmp_path, elem):
+    """tools/export_case.py --block: HEX8 / QUD4, TET4 / TRI3 and TET10 / TRI6 case directories through the reference's
+    Simulation::read_parameters + read_msh (unmodified read_msh.cpp / load_msh.cpp / vtk_xml.cpp on the VTK-free replacements).
+    check_ien leaves the generator's element node order as it is: the reference's ordering conventions are the generator's."""
+    import importlib.util
+    import shutil
+    import subprocess
+    _vx()
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    spec = importlib.util.spec_from_file_location("export_case", os.path.join(ROOT, "tools", "export_case.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    out = tmp_path / "case"
+    info = ex.export_block(str(out), 3, elem)
+    m = M.block_mesh(3, elem)
+    drv = tmp_path / "read_case.c"
+    drv.write_text(READ_CASE_C)
+    refdir = os.path.join(ROOT, "oracle", "_ref")
+    exe = tmp_path / "read_case"
+    subprocess.run(["gcc", "-std=c99", str(drv), "-L" + refdir, "-lvtkxml_b200", "-Wl,-rpath," + refdir,
+                    "-Wl,-rpath," + os.path.join(ROOT, "svfsiplus_b200"), "-o", str(exe)], check=True)
+    dump = tmp_path / "case.bin"
+    r = subprocess.run([str(exe), str(out), str(dump)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    vals = [int(t) for t in r.stdout.split()]
+    assert vals[:6] == [3, 1, m.nNo, m.nEl, m.ien.shape[1], 6]
+    assert vals[6:] == [v for name in ("X0", "X1", "Y0", "Y1", "Z0", "Z1") for v in info["faces"][name]]
+    raw = dump.read_bytes()
+    xr = np.frombuffer(raw[:m.nNo * 24], np.float64).reshape(m.nNo, 3)
+    ir = np.frombuffer(raw[m.nNo * 24:], np.int32).reshape(m.nEl, m.ien.shape[1])
+    assert np.array_equal(xr, m.x) and np.array_equal(ir, m.ien)

@@ -120,10 +120,82 @@ def export_pipe(out, dims, steps=2, mode=IO.APPENDED_RAW):
     return info
 
 
+BLOCK_XML = """<?xml version="1.0" encoding="UTF-8" ?>
+<svMultiPhysicsFile version="0.1">
+<GeneralSimulationParameters>
+  <Continue_previous_simulation> false </Continue_previous_simulation>
+  <Number_of_spatial_dimensions> 3 </Number_of_spatial_dimensions>
+  <Number_of_time_steps> {steps} </Number_of_time_steps>
+  <Time_step_size> 1e-4 </Time_step_size>
+  <Spectral_radius_of_infinite_time_step> 0.50 </Spectral_radius_of_infinite_time_step>
+  <Save_results_to_VTK_format> 1 </Save_results_to_VTK_format>
+  <Name_prefix_of_saved_VTK_files> result </Name_prefix_of_saved_VTK_files>
+  <Increment_in_saving_VTK_files> {steps} </Increment_in_saving_VTK_files>
+  <Start_saving_after_time_step> 1 </Start_saving_after_time_step>
+  <Increment_in_saving_restart_files> 100 </Increment_in_saving_restart_files>
+  <Verbose> 1 </Verbose>
+</GeneralSimulationParameters>
+<Add_mesh name="msh" >
+  <Mesh_file_path> mesh/mesh-complete.mesh.vtu </Mesh_file_path>
+{faces}</Add_mesh>
+<Add_equation type="struct" >
+  <Coupled> true </Coupled>
+  <Min_iterations> 1 </Min_iterations>
+  <Max_iterations> 3 </Max_iterations>
+  <Tolerance> 1e-9 </Tolerance>
+  <Constitutive_model type="nHK"> </Constitutive_model>
+  <Density> 1000.0 </Density>
+  <Elasticity_modulus> 240.56596E6 </Elasticity_modulus>
+  <Poisson_ratio> 0.5 </Poisson_ratio>
+  <Dilational_penalty_model> ST91 </Dilational_penalty_model>
+  <Penalty_parameter> 4.0E9 </Penalty_parameter>
+  <Output type="Spatial" > <Displacement> true </Displacement> <Velocity> true </Velocity> </Output>
+  <LS type="BICG" >
+    <Linear_algebra type="fsils" > <Preconditioner> fsils </Preconditioner> </Linear_algebra>
+    <Tolerance> 1e-12 </Tolerance>
+    <Max_iterations> 600 </Max_iterations>
+  </LS>
+  <Add_BC name="X0" > <Type> Dir </Type> <Value> 0.0 </Value> <Effective_direction> (0, 0, 1) </Effective_direction> </Add_BC>
+  <Add_BC name="Y0" > <Type> Dir </Type> <Value> 0.0 </Value> <Effective_direction> (0, 1, 0) </Effective_direction> </Add_BC>
+  <Add_BC name="Z0" > <Type> Dir </Type> <Value> 0.0 </Value> <Effective_direction> (1, 0, 0) </Effective_direction> </Add_BC>
+</Add_equation>
+</svMultiPhysicsFile>
+"""
+
+
+def export_block(out, n, elem="hex", steps=1, mode=IO.APPENDED_RAW):
+    """The solid block of SURVEY 8(d) (n^3 HEX8, its 6-tet split, or the quadratic split) in the layout of the reference's
+    tests/cases/struct/block_compression: volume mesh, the six faces X0..Z1 (QUD4 / TRI3 / TRI6), a struct solver.xml."""
+    m = M.block_mesh(n, elem)
+    os.makedirs(os.path.join(out, "mesh", "mesh-surfaces"), exist_ok=True)
+    vt = {"hex": "HEX8", "tet": "TET4", "tet10": "TET10"}[elem]
+    ft = {"hex": "QUD4", "tet": "TRI3", "tet10": "TRI6"}[elem]
+    IO.write_vtk(os.path.join(out, "mesh", "mesh-complete.mesh.vtu"), m.x, m.ien, IO.VTK_TYPE[vt],
+                 {"GlobalNodeID": np.arange(1, m.nNo + 1, dtype=np.int32)}, {"GlobalElementID": np.arange(1, m.nEl + 1, dtype=np.int32)}, mode=mode)
+    info = dict(nNo=m.nNo, nEl=m.nEl, eNoN=m.ien.shape[1], faces={})
+    xml_faces = ""
+    for name in ("X0", "X1", "Y0", "Y1", "Z0", "Z1"):
+        nodes = np.asarray(m.faces[name]["nodes"])
+        on = np.zeros(m.nNo, bool)
+        on[nodes] = True
+        IENb, gE = M.face_elements(m, on)
+        loc = np.full(m.nNo, -1, np.int64)
+        loc[nodes] = np.arange(len(nodes))
+        IO.write_vtk(os.path.join(out, "mesh", "mesh-surfaces", name + ".vtp"), m.x[nodes], loc[IENb].astype(np.int32), IO.VTK_TYPE[ft],
+                     {"GlobalNodeID": (nodes + 1).astype(np.int32)}, {"GlobalElementID": (gE + 1).astype(np.int32)}, polydata=True, mode=mode)
+        info["faces"][name] = (len(nodes), len(gE), IENb.shape[1])
+        xml_faces += f'  <Add_face name="{name}"> <Face_file_path> mesh/mesh-surfaces/{name}.vtp </Face_file_path> </Add_face>\n'
+    with open(os.path.join(out, "solver.xml"), "w") as f:
+        f.write(BLOCK_XML.format(steps=steps, faces=xml_faces))
+    return info
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--dims", type=int, nargs=3, default=[24, 24, 48], help="pipe hex counts nx ny nz (P10 = 96 96 181)")
     ap.add_argument("--out", required=True)
     ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--block", type=int, default=0, help="write the solid block with this many elements per edge instead of the pipe")
+    ap.add_argument("--elem", default="hex", choices=["hex", "tet", "tet10"])
     a = ap.parse_args()
-    print(export_pipe(a.out, tuple(a.dims), a.steps))
+    print(export_block(a.out, a.block, a.elem, a.steps) if a.block else export_pipe(a.out, tuple(a.dims), a.steps))
