@@ -52,6 +52,24 @@ int MPI_Recv(void* b, int n, MPI_Datatype t, int src, int tag, MPI_Comm c, MPI_S
 int MPI_Isend(const void* b, int n, MPI_Datatype t, int dst, int tag, MPI_Comm c, MPI_Request* rq);
 int MPI_Irecv(void* b, int n, MPI_Datatype t, int src, int tag, MPI_Comm c, MPI_Request* rq);
 int MPI_Wait(MPI_Request* rq, MPI_Status* st);
+int MPI_Reduce(const void* s, void* r, int n, MPI_Datatype t, MPI_Op op, int root, MPI_Comm c);
+int MPI_Gather(const void* s, int sn, MPI_Datatype st, void* r, int rn, MPI_Datatype rt, int root, MPI_Comm c);
+int MPI_Scatterv(const void* s, const int* sc, const int* disp, MPI_Datatype st, void* r, int rn, MPI_Datatype rt, int root, MPI_Comm c);
+
+/* MPI-IO: the reference only uses it for its partition cache file (distribute.cpp:1649-1653, 1724-1728: partitioning.bin).  The
+ * stand-in never finds such a file and never writes one, so every run partitions afresh. */
+typedef struct { int unused; } MPI_File;
+typedef long long MPI_Offset;
+typedef int MPI_Info;
+#define MPI_INFO_NULL 0
+#define MPI_MODE_RDONLY 2
+#define MPI_MODE_WRONLY 8
+#define MPI_MODE_CREATE 1
+int MPI_File_open(MPI_Comm c, const char* name, int mode, MPI_Info info, MPI_File* f);
+int MPI_File_set_view(MPI_File f, MPI_Offset disp, MPI_Datatype et, MPI_Datatype ft, const char* rep, MPI_Info info);
+int MPI_File_read(MPI_File f, void* buf, int n, MPI_Datatype t, MPI_Status* st);
+int MPI_File_write(MPI_File f, const void* buf, int n, MPI_Datatype t, MPI_Status* st);
+int MPI_File_close(MPI_File* f);
 
 /* stub control (called by the harness, not by the reference) */
 void mpistub_set_world(int size);      /* before spawning rank threads */

@@ -226,4 +226,39 @@ int MPI_Wait(MPI_Request* rq, MPI_Status*)
   return 0;
 }
 
+int MPI_Reduce(const void* s, void* r, int n, MPI_Datatype t, MPI_Op op, int root, MPI_Comm c)
+{
+  // every rank gets the result; the root is the one that reads it
+  (void)root;
+  return MPI_Allreduce(s, r, n, t, op, c);
+}
+
+int MPI_Gather(const void* s, int sn, MPI_Datatype st, void* r, int rn, MPI_Datatype rt, int root, MPI_Comm c)
+{
+  (void)root;
+  return MPI_Allgather(s, sn, st, r, rn, rt, c);
+}
+
+int MPI_Scatterv(const void* s, const int* sc, const int* disp, MPI_Datatype st, void* r, int rn, MPI_Datatype rt, int root, MPI_Comm)
+{
+  const size_t sz = tsize(st);
+  if (g_size == 1) { std::memcpy(r, static_cast<const char*>(s) + size_t(disp[0])*sz, size_t(sc[0])*sz); return 0; }
+  // the root publishes its buffer and layout; every rank copies its own piece
+  static const int* s_sc = nullptr;
+  static const int* s_disp = nullptr;
+  if (t_rank == root) { g_slots[root] = s; s_sc = sc; s_disp = disp; }
+  barrier();
+  std::memcpy(r, static_cast<const char*>(g_slots[root]) + size_t(s_disp[t_rank])*sz, size_t(s_sc[t_rank])*sz);
+  barrier();
+  (void)rn; (void)rt;
+  return 0;
+}
+
+// MPI-IO: only the reference's partition cache file uses it; never found, never written (every run partitions afresh)
+int MPI_File_open(MPI_Comm, const char*, int, MPI_Info, MPI_File* f) { f->unused = 0; return 1; }
+int MPI_File_set_view(MPI_File, MPI_Offset, MPI_Datatype, MPI_Datatype, const char*, MPI_Info) { return 0; }
+int MPI_File_read(MPI_File, void*, int, MPI_Datatype, MPI_Status*) { return 1; }
+int MPI_File_write(MPI_File, const void*, int, MPI_Datatype, MPI_Status*) { return 0; }
+int MPI_File_close(MPI_File*) { return 0; }
+
 } // extern "C"

@@ -13,6 +13,7 @@
 #include <stdexcept>
 #include <vector>
 
+#ifndef ORACLE_FULL_REFERENCE      // the full-reference build (libsvfull.so) links the real cep.cpp / cep_ion.cpp
 namespace cep {
 void b_cep(ComMod&, const int, const double, const Vector<double>&, const double, Array<double>&)
 { throw std::runtime_error("[oracle] cep::b_cep is outside the hot path"); }
@@ -24,6 +25,8 @@ namespace cep_ion {
 void cep_integ(Simulation*, const int, const int, const Array<double>&)
 { throw std::runtime_error("[oracle] cep_ion::cep_integ is outside the hot path"); }
 }
+
+#endif
 
 extern "C" {
 

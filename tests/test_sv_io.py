@@ -925,3 +925,77 @@ def test_exported_solid_block_goes_through_the_reference_mesh_ingestion(tmp_path
     xr = np.frombuffer(raw[:m.nNo * 24], np.float64).reshape(m.nNo, 3)
     ir = np.frombuffer(raw[m.nNo * 24:], np.int32).reshape(m.nEl, m.ien.shape[1])
     assert np.array_equal(xr, m.x) and np.array_equal(ir, m.ien)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# the COMPLETE reference solver (oracle/_ref/svmultiphysics_ref: the reference's own main() and every solver source, with the two
+# VTK-bound files replaced by the product's VTK-free ones) on exported case directories
+# ---------------------------------------------------------------------------------------------------------------------------
+def _full_reference():
+    exe = os.path.join(ROOT, "oracle", "_ref", "svmultiphysics_ref")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/svmultiphysics_ref not built (needs the reference sources)")
+    return exe
+
+
+def _export_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("export_case", os.path.join(ROOT, "tools", "export_case.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    return ex
+
+
+@needs_ref
+def test_complete_reference_solver_runs_the_exported_pipe_and_its_files_read_back(tmp_path):
+    """read_files -> distribute -> initialize -> two time steps of Newton iterations (NS solver, unsteady parabolic inflow, RCR outlet)
+    -> write_vtus / write_restart / histor.dat: the whole reference, unmodified, reading the exported case and writing its results
+    through the VTK-free classes.  Its result file and restart record read back with the product's readers and agree with each other."""
+    import subprocess
+    exe = _full_reference()
+    out = tmp_path / "case"
+    info = _export_module().export_pipe(str(out), (4, 4, 6), steps=2)
+    r = subprocess.run([exe, "solver.xml"], cwd=out, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res = out / "1-procs"
+    hist = (res / "histor.dat").read_text()
+    assert hist.startswith(IO.history_header(1))                       # the header block, character for character
+    lines = hist[len(IO.history_header(1)):].splitlines()
+    assert len(lines) == 10 and all(l.startswith(" NS ") for l in lines) and lines[-1].split()[1] == "2-5s"
+    vt = IO.read_vtk(res / "result_002.vtu")
+    assert vt["nNo"] == info["nNo"] and vt["nEl"] == info["nEl"] and list(vt["point_data"]) == ["Velocity", "Pressure"]
+    assert np.isfinite(vt["point_data"]["Velocity"]).all() and np.abs(vt["point_data"]["Velocity"]).max() > 0
+    # the restart record of the same step: stamp = {procs, equations, meshes, nodes, coupled unknowns, tDof, dFlag}
+    kw = dict(nEq=1, nXn=1, tDof=4, tnNo=info["nNo"])
+    recLn = IO.restart_record_bytes(stamp=[0] * 7, cTS=0, time=0.0, cpu_time=0.0, iNorm=np.zeros(1), xn=np.zeros(1),
+                                    Yn=np.zeros((info["nNo"], 4)), An=np.zeros((info["nNo"], 4)))
+    assert os.path.getsize(res / "stFile_002.bin") == recLn
+    rs = IO.read_restart(res / "stFile_last.bin", 0, recLn, **kw)
+    assert rs["stamp"] == [1, 1, 1, info["nNo"], 1, 4, 0] and rs["cTS"] == 2 and abs(rs["time"] - 0.01) < 1e-15
+    assert np.array_equal(rs["Yn"][:, :3], vt["point_data"]["Velocity"]) and np.array_equal(rs["Yn"][:, 3], vt["point_data"]["Pressure"])
+
+
+@needs_ref
+@pytest.mark.parametrize("elem", ["hex", "tet"])
+def test_complete_reference_solver_runs_the_exported_solid_block(tmp_path, elem):
+    """struct equation (neo-Hookean, ST91, BICG) with a traction on Z1: Newton converges, Displacement / Velocity come out through
+    the VTK-free writer, and the restart record (dFlag: Yn, An, Dn + the reference's trailing second Dn) holds the same displacement."""
+    import subprocess
+    exe = _full_reference()
+    out = tmp_path / "case"
+    info = _export_module().export_block(str(out), 3, elem, steps=2)
+    r = subprocess.run([exe, "solver.xml"], cwd=out, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    res = out / "1-procs"
+    vt = IO.read_vtk(res / "result_002.vtu")
+    assert list(vt["point_data"]) == ["Displacement", "Velocity"] and np.abs(vt["point_data"]["Displacement"]).max() > 1e-6
+    nNo = info["nNo"]
+    z = np.zeros((nNo, 3))
+    recLn = IO.restart_record_bytes(stamp=[0] * 7, cTS=0, time=0.0, cpu_time=0.0, iNorm=np.zeros(1), xn=np.zeros(0), Yn=z, An=z, Dn=z)
+    assert os.path.getsize(res / "stFile_002.bin") == recLn + nNo * 3 * 8          # the trailing second copy of Dn
+    rs = IO.read_restart(res / "stFile_002.bin", 0, recLn, nEq=1, nXn=0, tDof=3, tnNo=nNo, dFlag=True)
+    assert rs["stamp"] == [1, 1, 1, nNo, 0, 3, 1] and rs["cTS"] == 2
+    assert np.array_equal(rs["Dn"], vt["point_data"]["Displacement"]) and np.array_equal(rs["Yn"], vt["point_data"]["Velocity"])
+    # the last Newton line of each step reports convergence well below the tolerance of 1e-9
+    last = [l for l in (res / "histor.dat").read_text().splitlines() if l.startswith(" ST 2-")][-1]
+    assert float(last.split("[")[1].split()[1]) < 1e-9

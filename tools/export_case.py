@@ -158,6 +158,7 @@ BLOCK_XML = """<?xml version="1.0" encoding="UTF-8" ?>
   <Add_BC name="X0" > <Type> Dir </Type> <Value> 0.0 </Value> <Effective_direction> (0, 0, 1) </Effective_direction> </Add_BC>
   <Add_BC name="Y0" > <Type> Dir </Type> <Value> 0.0 </Value> <Effective_direction> (0, 1, 0) </Effective_direction> </Add_BC>
   <Add_BC name="Z0" > <Type> Dir </Type> <Value> 0.0 </Value> <Effective_direction> (1, 0, 0) </Effective_direction> </Add_BC>
+  <Add_BC name="Z1" > <Type> Neu </Type> <Time_dependence> Steady </Time_dependence> <Value> 5.0e6 </Value> </Add_BC>
 </Add_equation>
 </svMultiPhysicsFile>
 """
