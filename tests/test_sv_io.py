@@ -999,3 +999,20 @@ def test_complete_reference_solver_runs_the_exported_solid_block(tmp_path, elem)
     # the last Newton line of each step reports convergence well below the tolerance of 1e-9
     last = [l for l in (res / "histor.dat").read_text().splitlines() if l.startswith(" ST 2-")][-1]
     assert float(last.split("[")[1].split()[1]) < 1e-9
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["pipe_4_4_6", "block_hex_3", "block_tet_3"])
+def test_complete_reference_reproduces_its_golden_runs(tmp_path, name):
+    """tests/golden/full_reference_runs.npz (make_golden_full_reference.py): two time steps of the exported cases through the complete
+    reference solver give the same nodal fields today, bit for bit - the fixtures an end-to-end run of the product has to meet."""
+    import importlib.util
+    _full_reference()
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(ROOT, "tests", "golden", "make_golden_full_reference.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "full_reference_runs.npz"))
+    got = mk.run_case(name, str(tmp_path))
+    assert got and all(k in g.files for k in got)
+    for k, v in got.items():
+        assert np.array_equal(v, g[k]), k
