@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of round 2 (one B200, ~12 minutes): everything that could not be re-measured after the last session of round 1.
 #   gpurun --timeout 900 -- 'bash tools/gpu_round2_first_call.sh'
-#   1. full GPU suite with the pending marks lifted (--runxfail): the three FSI-wall tests of tests/test_zz_late_additions.py and the
+#   1. full GPU suite with the pending marks lifted (--runxfail): the six pending tests of tests/test_zz_late_additions.py (FSI wall, result-file comparison, solid block end to end) and the
 #      three P10-size property tests are the ones that have not run since the last additions
 #   2. smoke(), the bench line (own arm + reference arm)
 #   3. event timings + one ncu capture of the extended struct / ustruct element (VISC = true instantiations: 252 registers; the
