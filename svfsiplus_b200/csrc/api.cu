@@ -967,9 +967,12 @@ int b200_assemble_fsi(b200_handle* h, int nDmn, const int* dmn_kind, const b200_
           launch_fluid(h, c, n, h->d_dmn_elems[d], h->d_Dg);
         } else if (dmn_kind[d] == 1) {
           if (solid[d].tDof != h->tDof) throw std::runtime_error("assemble_fsi: tDof differs from the uploaded state");
-          const SolidConsts c = struct_consts(&solid[d]);
-          if (c.viscType != 0 || h->d_pS0) {
-            // wall with solid viscosity and / or prestress (construct_fsi reads com_mod.pS0, fsi.cpp:147-148; it never accumulates pSn / pSa)
+          SolidConsts c = struct_consts(&solid[d]);
+          // construct_fsi calls the non-carray struct_3d (fsi.cpp:225), which hard-codes `double mu = 0.0` (sv_struct.cpp:878): the wall's
+          // solid viscosity model is IGNORED inside the FSI equation.  Reproduced on purpose - the reference is the specification.
+          c.viscType = 0; c.visc_mu = 0.0;
+          if (h->d_pS0) {
+            // prestressed wall (construct_fsi reads com_mod.pS0, fsi.cpp:147-148; it never accumulates pSn / pSa)
             if (h->eNoN == 4) launch_solid<4, 4, 32, 1, 4, true>(h, c, n, h->d_dmn_elems[d], false);
             else if (h->eNoN == 8) launch_solid<8, 8, 16, 2, 4, true>(h, c, n, h->d_dmn_elems[d], false);
             else launch_solid<10, 15, 8, 2, 4, true>(h, c, n, h->d_dmn_elems[d], false);

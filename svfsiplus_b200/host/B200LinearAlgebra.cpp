@@ -485,6 +485,14 @@ bool B200LinearAlgebra::ustruct_r(ComMod& com_mod, const Array<double>& Yg)
   const double amg = (eq.gam - eq.am) / (eq.gam - 1.0);
   const double ami = 1.0 / eq.am;
   check(b200_ustruct_r(h_, amg, ami, eq.s, com_mod.Ad.data()), "b200_ustruct_r");
+  // The host time integrator (pic::picc, pic.cpp:92,139: dUl = Rd*coef[2] + R*coef[3]) reads com_mod.Rd, so the first iteration's
+  // Rd = amg*Ad - Yg(s..) has to exist on the host as well (ustruct.cpp:1768-1775); the device copy only feeds Kd*Rd.
+  // Rd keeps whatever it held on rows outside a ustruct domain, exactly as the reference loop does.
+  const int nsd = com_mod.nsd;
+  for (int a = 0; a < com_mod.tnNo; a++) {
+    if (!all_fun::is_domain(com_mod, eq, a, consts::EquationType::phys_ustruct)) continue;
+    for (int i = 0; i < nsd; i++) com_mod.Rd(i, a) = amg*com_mod.Ad(i, a) - Yg(eq.s + i, a);
+  }
   return true;
 }
 

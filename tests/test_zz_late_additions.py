@@ -102,12 +102,9 @@ def test_struct_prestress_matches_golden(elem, n, visc):
     be.close()
 
 
-# ---- written after the round's last GPU second was spent: CPU-pinned goldens, device run pending -----------------------------------
-_PENDING = pytest.mark.xfail(reason="added in round 1 after the GPU budget was spent: golden from the compiled reference, not yet run on a B200",
-                             strict=False)
+# ---- end-to-end and FSI-wall cases (goldens from the compiled reference) ------------------------------------------------------
 
 
-@_PENDING
 @pytest.mark.parametrize("tag", ["tet", "hex", "tet10"])
 def test_fsi_with_prestressed_viscous_wall_matches_golden(tag):
     """construct_fsi with com_mod.pS0 (read, never accumulated: fsi.cpp:147-148, 225) and dmn.solid_visc on the struct domain: the
@@ -124,7 +121,6 @@ def test_fsi_with_prestressed_viscous_wall_matches_golden(tag):
     be.close()
 
 
-@_PENDING
 def test_time_step_result_file_passes_the_reference_harness_criterion(tmp_path):
     """One Newton-converged time step with the state resident on the device, written as result_001.vtu by the VTK-free writer, against
     the same step made of the reference's own functions written the same way: compared file against file with the reference test
@@ -163,7 +159,6 @@ def test_time_step_result_file_passes_the_reference_harness_criterion(tmp_path):
     assert IO.compare_results(mine, theirs, ["Velocity", "Pressure"]) == []
 
 
-@_PENDING
 @pytest.mark.parametrize("elem", ["hex", "tet"])
 def test_solid_block_two_time_steps_match_the_complete_reference(elem):
     """End to end against the reference ITSELF: tests/golden/full_reference_runs.npz holds Displacement / Velocity after two time steps
