@@ -32,6 +32,8 @@ sys.path.insert(0, ROOT)
 METRIC = "NS Newton-iters/s, 10M-tet pipe (assembly+GMRES)"
 UNIT = "Newton-iters/s"
 P10 = (96, 96, 181)
+# LS NS with fixed iteration counts (see `fixed_work` in run_gpu); 796 = LS_NS (the reference's code, liner_solver/fils_struct.hpp)
+FIXED_WORK_LS = (796, (0.0, 0.0, 2, 250), (0.0, 0.0, 1, 50), (0.0, 0.0, 200, 0))
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at P10 on one GPU, from the `ncu --set full` capture
@@ -99,6 +101,27 @@ def _dist():
     return rank, world, local
 
 
+def workload_dims(args, world):
+    """The pipe the line is quoted on: P10 (configs[1]) on one GPU, the same pipe refined to N x the tets on N GPUs
+    (configs[2] at N = 8)."""
+    if world > 1:
+        from svfsiplus_b200 import partition as PT
+        return PT.weak_dims(tuple(args.dims), world)
+    return tuple(args.dims)
+
+
+def make_config(args, world):
+    """`config` is the SAME object in both arms (the reference arm times a bounded sample of this workload and says so in
+    cpu_baseline.sample; run-dependent numbers such as Krylov counts live under `run`, not here)."""
+    dims = workload_dims(args, world)
+    ntet = 6 * dims[0] * dims[1] * dims[2]
+    return {"workload": f"pipe {dims[0]}x{dims[1]}x{dims[2]} = {ntet} TET4, NS VMS P1-P1, one Newton iteration "
+                        f"(ls_alloc + construct_fluid + fsils_solve LS {args.ls}, pipe_RCR_3d solver.xml parameters)",
+            "ls": args.ls, "parallelism": f"dd{world}",
+            "l2": "inputs larger than L2 (Val 3.2 GB vs 126 MB L2): no flush between iterations",
+            "value_note": "N>1: Newton-iters/s x (total tets / 10,008,576), i.e. 10M-tet-equivalent iterations/s"}
+
+
 def _ref_ranks(args, dims):
     """Ranks (= host threads) of the reference arm: its parallelism is MPI ranks; no MPI runtime exists on the box,
     so the ranks are threads of the in-process MPI stand-in (oracle/mpi_stub).  At least two hex layers per rank."""
@@ -111,11 +134,17 @@ def _ref_ranks(args, dims):
     return max(1, min(ncpu, 16, dims[2] // 2))
 
 
+_REF_CASES = {}
+
+
 def _reference_sample(args, ls_name):
-    from oracle import ref, refcase
+    """One Newton-iteration hot path of the compiled reference on the bounded sample --ref-dims (the case is built once)."""
+    from oracle import refcase
     from svfsiplus_b200 import problem as P
     dims = tuple(args.ref_dims)
-    case = P.pipe_case(*dims)
+    if dims not in _REF_CASES:
+        _REF_CASES[dims] = P.pipe_case(*dims)
+    case = _REF_CASES[dims]
     ntet = case["mesh"].nEl
     scale = ntet / float(6 * P10[0] * P10[1] * P10[2])
     nr = _ref_ranks(args, dims)
@@ -127,7 +156,8 @@ def _sample_text(dims, ntet, scale, nr, r, ls_name):
     return (f"pipe {dims[0]}x{dims[1]}x{dims[2]} = {ntet} tets ({100*scale:.2f}% of P10) on {nr} rank(s) = host threads of the "
             f"in-process MPI stand-in: construct_fluid ({r['asm_s']:.2f} s, slowest rank) + commu + fsils_solve {ls_name} "
             f"({r['solve_s']:.2f} s, itr {r['itr']}/{r['GM_itr']}/{r['CG_itr']}); iters/s scaled by the tet ratio to the 10M-tet unit "
-            f"(optimistic for the CPU: Krylov counts grow with refinement)")
+            f"(EXTRAPOLATED, optimistic for the CPU: Krylov counts grow with refinement; the measured same-size ratio is the GPU "
+            f"line's `same_config` object)")
 
 
 def run_reference(args):
@@ -149,10 +179,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"P10 pipe 96x96x181 (10,008,576 TET4), NS VMS, LS {args.ls}; reference timed on a bounded sample",
-                   "sample_dims": list(dims), "ls": args.ls, "krylov_itr": r["itr"], "gm_itr": r["GM_itr"], "cg_itr": r["CG_itr"]},
+        "config": make_config(args, max(1, args.gpus)),
+        "run": {"sample_dims": list(dims), "sample_tets": int(ntet), "extrapolated": True, "same_config": False,
+                "sample_iters_per_s": 1.0 / (ms * 1e-3),
+                "krylov_itr": r["itr"], "gm_itr": r["GM_itr"], "cg_itr": r["CG_itr"]},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nr, "kind": "reference" if ref.available() else "port",
-                         "sample": _sample_text(dims, ntet, scale, nr, r, args.ls)},
+                         "sample": _sample_text(dims, ntet, scale, nr, r, args.ls), "extrapolated": True},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -167,8 +199,10 @@ def cpu_baseline_leg(args, ls_name):
             return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "oracle/_ref not present"}
         case, dims, ntet, scale, nr, r = _reference_sample(args, ls_name)
         return {"value": (1.0 / r["wall_s"]) * scale, "unit": UNIT, "cores": nr, "kind": "reference",
-                "sample": _sample_text(dims, ntet, scale, nr, r, ls_name),
-                "assembly_us_per_tet_per_rank": 1e6 * r["asm_s"] * nr / ntet}
+                "sample": _sample_text(dims, ntet, scale, nr, r, ls_name), "extrapolated": True,
+                "assembly_us_per_tet_per_rank": 1e6 * r["asm_s"] * nr / ntet,
+                "_sample": {"dims": list(dims), "tets": int(ntet), "iters_per_s": 1.0 / r["wall_s"], "wall_s": r["wall_s"],
+                            "krylov_itr": int(r["itr"]), "gm_itr": int(r["GM_itr"]), "cg_itr": int(r["CG_itr"])}}
     except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU line
         return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
 
@@ -184,42 +218,53 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
 
-    if world > 1:
-        from svfsiplus_b200 import partition as PT
-        dims = PT.weak_dims(tuple(args.dims), world)      # default --dims = P10 -> configs[2] at N = 8
-        case, be = PT.setup_distributed_case(dims, rank, world, local, dist)
-    else:
-        dims = tuple(args.dims)
-        from svfsiplus_b200 import backend as B
-        be = B.Backend(local)
-        case = P.pipe_case(*dims, pattern=lambda n, ien: be.pattern(n, [ien]))       # lhsa on the device (b200_pattern_*)
-        be = P.setup_backend(case, device=local, be=be)
+    from svfsiplus_b200 import partition as PT
+    dims = workload_dims(args, world)                     # default --dims = P10 -> configs[2] at N = 8
+
+    def build(dims_):
+        # the pipe is composed of 8 generation blocks whatever N is (partition.local_slab_case): 1, 2, 4 and 8 ranks hold the SAME
+        # global mesh and state, so the strong-scaling object and the one-GPU line solve identical systems
+        return PT.setup_distributed_case(dims_, rank, world, local, dist)
+
+    case, be = build(dims)
     nNo_local = be.nNo
     tDof = case["Ag"].shape[1]
     ntet_total = 6 * dims[0] * dims[1] * dims[2]
+    transport = be.comm_transport()
 
     # pinned host buffers for the end-to-end leg
-    pin = {k: torch.from_numpy(np.ascontiguousarray(case[k])).pin_memory() for k in ("Ag", "Yg", "Bf")}
-    out_pin = torch.empty((nNo_local, 4), dtype=torch.float64).pin_memory()
-    ls_type, RI, GM, CG = P.LS_SETTINGS[args.ls]
+    def pinned(c, b):
+        pin_ = {k: torch.from_numpy(np.ascontiguousarray(c[k])).pin_memory() for k in ("Ag", "Yg", "Bf")}
+        return pin_, torch.empty((b.nNo, 4), dtype=torch.float64).pin_memory()
+
+    pin, out_pin = pinned(case, be)
+    LS = P.LS_SETTINGS[args.ls]
     props = B.fluid_props(tDof=tDof, **case["props"])
 
-    def step_resident():
-        be.zero(4)
-        be.assemble_fluid(props)
-        if world > 1:
-            be.commu_R()
-        _, info = be.solve(ls_type, B.PREC_FSILS, RI, GM, CG, case["incL"], case["res"], fetch=False)
-        return info
+    def make_steps(be_, case_, pin_, out_pin_, ls):
+        ls_type, RI, GM, CG = ls
+        props_ = B.fluid_props(tDof=case_["Ag"].shape[1], **case_["props"])
+        tD = case_["Ag"].shape[1]
 
-    def step_e2e():
-        be.state_set(tDof, pin["Ag"].data_ptr(), pin["Yg"].data_ptr(), pin["Bf"].data_ptr())
-        be.zero(4)
-        be.assemble_fluid(props)
-        if world > 1:
-            be.commu_R()
-        _, info = be.solve(ls_type, B.PREC_FSILS, RI, GM, CG, case["incL"], case["res"], out=out_pin.data_ptr(), fetch=True)
-        return info
+        def resident():
+            be_.zero(4)
+            be_.assemble_fluid(props_)
+            if world > 1:
+                be_.commu_R()
+            _, info_ = be_.solve(ls_type, B.PREC_FSILS, RI, GM, CG, case_["incL"], case_["res"], fetch=False)
+            return info_
+
+        def e2e():
+            be_.state_set(tD, pin_["Ag"].data_ptr(), pin_["Yg"].data_ptr(), pin_["Bf"].data_ptr())
+            be_.zero(4)
+            be_.assemble_fluid(props_)
+            if world > 1:
+                be_.commu_R()
+            _, info_ = be_.solve(ls_type, B.PREC_FSILS, RI, GM, CG, case_["incL"], case_["res"], out=out_pin_.data_ptr(), fetch=True)
+            return info_
+        return resident, e2e
+
+    step_resident, step_e2e = make_steps(be, case, pin, out_pin, LS)
 
     def barrier():
         torch.cuda.synchronize()
@@ -284,11 +329,98 @@ def run_gpu(args):
     e2e_ms = maxreduce(e2e_ms) / args.steps
     clocks = sampler.stop() if rank == 0 else None
 
+    def global_norms(xpin, case_):
+        """||X(:, j)|| over the global nodes, every node counted once (an interface plane belongs to the lower rank), and the
+        solution at the golden file's probe nodes (zeros where another rank owns the node; summed over ranks)."""
+        X = xpin.numpy()
+        nx_, ny_, _ = case_["mesh"].shape
+        plane_ = (nx_ + 1) * (ny_ + 1)
+        own = X.shape[0] - (plane_ if rank < world - 1 else 0)
+        v = torch.tensor((X[:own] ** 2).sum(axis=0), dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(v)
+        return [float(t) for t in v.sqrt().cpu()]
+
+    x_norm = global_norms(out_pin, case)
+
     # stand-alone block SpMV (the north-star kernel): CUDA events over 50 back-to-back launches.  Collective
     # for N > 1 (assembly is followed by commu(R), every product by its overlap add): ALL ranks run it.
     P.assemble(be, case, upload=False)
     spmv_ms, spmv_bytes = be.op_bench("spmv_vv4", reps=50)
     barrier()
+
+    def timed(fn, n):
+        barrier()
+        be_timer.timer_start()
+        inf = None
+        for _ in range(n):
+            inf = fn()
+        ms = be_timer.timer_stop()
+        barrier()
+        return maxreduce(ms) / n, inf
+
+    def counts(inf):
+        return {"krylov_itr": inf["RI"]["itr"], "gm_itr": inf["GM"]["itr"], "cg_itr": inf["CG"]["itr"], "suc": inf["RI"]["suc"]}
+
+    # (1) fixed work: the SAME partitioned mesh, LS NS with every tolerance 0 and fixed iteration limits, so every N does
+    # identical Krylov work per node (2 outer iterations x [2 x 50 GMRES + 200 Schur-CG]); the ratio of this number between
+    # N and 1 is pure kernel + communication cost, free of the refinement-driven growth of the iteration counts.
+    be_timer = be
+    fw_steps = max(2, min(args.steps, 5))
+    fw_res, _ = make_steps(be, case, pin, out_pin, FIXED_WORK_LS)
+    fw_res()
+    fw_ms, fw_info = timed(fw_res, fw_steps)
+    fw_inner = int(fw_info["GM"]["itr"]) + int(fw_info["CG"]["itr"])
+    fixed_work = {"ls": "NS, relTol = absTol = 0, RI mItr 2, GM 1 x 50, CG 200 (fixed iteration counts)", "steps": fw_steps,
+                  "ms_per_step": fw_ms, **counts(fw_info), "tets": ntet_total,
+                  "work_rate": ntet_total * fw_inner / (fw_ms * 1e-3), "work_rate_per_gpu": ntet_total * fw_inner / (fw_ms * 1e-3) / world,
+                  "unit": "tet x inner Krylov iterations / s", "scaling": "weak (same per-GPU mesh as the headline line)"}
+    be.close()
+
+    # (2) strong scaling: the 10M-tet pipe itself split over the N ranks (the metric reads "10M-tet pipe @1-8 B200")
+    strong = None
+    if world > 1:
+        sdims = tuple(args.dims)
+        case_s, be_s = build(sdims)
+        pin_s, out_s = pinned(case_s, be_s)
+        be_timer = be_s
+        s_res, s_e2e = make_steps(be_s, case_s, pin_s, out_s, LS)
+        be_s.state_set(case_s["Ag"].shape[1], pin_s["Ag"].data_ptr(), pin_s["Yg"].data_ptr(), pin_s["Bf"].data_ptr())
+        for _ in range(max(3, min(args.warmup, 3))):
+            s_res()
+        s_steps = max(2, min(args.steps, 5))
+        s_ms, s_info = timed(s_res, s_steps)
+        s_e2e()
+        s_e2e_ms, _ = timed(s_e2e, s_steps)
+        fw_s, _ = make_steps(be_s, case_s, pin_s, out_s, FIXED_WORK_LS)
+        fw_s()
+        s_fw_ms, s_fw_info = timed(fw_s, s_steps)
+        s_xnorm = global_norms(out_s, case_s)
+        strong = {"dims": list(sdims), "X_norm": s_xnorm, "tets": 6 * sdims[0] * sdims[1] * sdims[2], "steps": s_steps, "ms_per_step": s_ms,
+                  "value": 1e3 / s_ms, "e2e_value": 1e3 / s_e2e_ms, "unit": UNIT, **counts(s_info),
+                  "fixed_work_ms_per_step": s_fw_ms, "fixed_work_inner": int(s_fw_info["GM"]["itr"]) + int(s_fw_info["CG"]["itr"]),
+                  "note": "rank-local slabs are jittered per rank (partition.local_slab_case), so counts may differ by a few from "
+                          "the one-GPU P10 line"}
+        be_s.close()
+
+    # (3) same-config measurement against the reference (N = 1): the bounded sample the reference arm times, on the GPU
+    same_gpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sd = tuple(args.ref_dims)
+        case_c = P.pipe_case(*sd)
+        be_c = P.setup_backend(case_c, device=local)
+        pin_c, out_c = pinned(case_c, be_c)
+        be_timer = be_c
+        c_res, c_e2e = make_steps(be_c, case_c, pin_c, out_c, LS)
+        be_c.state_set(case_c["Ag"].shape[1], pin_c["Ag"].data_ptr(), pin_c["Yg"].data_ptr(), pin_c["Bf"].data_ptr())
+        for _ in range(3):
+            c_res()
+        c_ms, c_info = timed(c_res, max(args.steps, 5))
+        c_e2e()
+        c_e2e_ms, _ = timed(c_e2e, max(args.steps, 5))
+        same_gpu = {"dims": list(sd), "tets": int(case_c["mesh"].nEl), "gpu_ms_per_step": c_ms, "gpu_value": 1e3 / c_ms,
+                    "gpu_e2e_value": 1e3 / c_e2e_ms, "gpu_counts": counts(c_info)}
+        be_c.close()
 
     if rank != 0:
         if world > 1:
@@ -314,13 +446,10 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"pipe {dims[0]}x{dims[1]}x{dims[2]} = {ntet_total} TET4, NS VMS P1-P1, one Newton iteration "
-                               f"(ls_alloc + construct_fluid + fsils_solve LS {args.ls}, pipe_RCR_3d solver.xml parameters)",
-                   "ls": args.ls, "nNo": int(nNo), "nnz_blocks": int(nnz), "parallelism": f"dd{world}",
-                   "l2": "inputs larger than L2 (Val 3.2 GB vs 126 MB L2): no flush between iterations",
-                   "krylov_itr": info["RI"]["itr"], "gm_itr": info["GM"]["itr"], "cg_itr": info["CG"]["itr"],
-                   "suc": info["RI"]["suc"], "wall_ms_per_step": wall_ms / args.steps,
-                   "value_note": "N>1: Newton-iters/s x (total tets / 10,008,576), i.e. 10M-tet-equivalent iterations/s"},
+        "config": make_config(args, world),
+        "run": {"nNo": int(nNo), "nnz_blocks": int(nnz), "krylov_itr": info["RI"]["itr"], "gm_itr": info["GM"]["itr"],
+                "cg_itr": info["CG"]["itr"], "suc": info["RI"]["suc"], "wall_ms_per_step": wall_ms / args.steps,
+                "transport": transport, "X_norm": x_norm},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int((2 * tDof + 3) * nNo_local * 8),
                 "d2h_bytes_per_step": int(4 * nNo_local * 8), "ms_per_step": e2e_ms},
         "gpu_launches": int(launches),
@@ -346,17 +475,48 @@ def run_gpu(args):
                                     "inner_iterations_per_step": inner, "per_gpu": ntet_total * inner / (ms_per_step * 1e-3) / world}
     except Exception:                      # never let a reporting extra cost the bench line
         pass
+    line["fixed_work"] = fixed_work
+    if strong is not None:
+        line["strong"] = strong
+    # benchmark-size parity: counts and solution norms of the compiled reference on the same P10 system (tests/golden/p10_ns_counts.json,
+    # generated offline by tests/golden/make_golden_p10.py); a plain file read, nothing of oracle/ is executed here
+    try:
+        gp = os.path.join(ROOT, "tests", "golden", "p10_ns_counts.json")
+        if os.path.exists(gp) and args.ls == "NS":
+            g = json.load(open(gp))
+
+            def chk(cnt, xn):
+                return {"reference": {k: g[k] for k in ("itr", "GM_itr", "CG_itr")},
+                        "counts_within_1": bool(abs(cnt["krylov_itr"] - g["itr"]) <= 1),
+                        "inner_counts_rel": [abs(cnt["gm_itr"] - g["GM_itr"]) / max(g["GM_itr"], 1), abs(cnt["cg_itr"] - g["CG_itr"]) / max(g["CG_itr"], 1)],
+                        "X_norm_rel": [abs(a - b) / b for a, b in zip(xn, g["X_norm"])]}
+            if world == 1 and list(dims) == g["dims"]:
+                line["golden_p10"] = chk({"krylov_itr": info["RI"]["itr"], "gm_itr": info["GM"]["itr"], "cg_itr": info["CG"]["itr"]}, x_norm)
+            if strong is not None and strong["dims"] == g["dims"]:
+                strong["golden_p10"] = chk(strong, strong["X_norm"])
+    except Exception as e:
+        line["golden_p10"] = {"error": str(e)}
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_leg(args, args.ls)
+        cb = cpu_baseline_leg(args, args.ls)
+        smp = cb.pop("_sample", None)
+        line["cpu_baseline"] = cb
+        if smp and same_gpu:
+            # the one ratio in this record that is a MEASUREMENT on identical inputs (same mesh, same <LS> block, both arms
+            # converge their own Krylov loops); the P10 ratio the driver computes from `value` is an extrapolation of this sample
+            line["same_config"] = {**same_gpu, "ref_value": smp["iters_per_s"], "ref_wall_s": smp["wall_s"], "ref_cores": cb["cores"],
+                                   "ref_counts": {"krylov_itr": smp["krylov_itr"], "gm_itr": smp["gm_itr"], "cg_itr": smp["cg_itr"]},
+                                   "unit": "Newton-iters/s on this mesh", "ratio": same_gpu["gpu_value"] * smp["wall_s"],
+                                   "e2e_ratio": same_gpu["gpu_e2e_value"] * smp["wall_s"]}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
-    # NCCL prints a "NCCL version ..." banner to STDOUT at NCCL_DEBUG=VERSION/WARN; stdout must carry one JSON line
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
-        os.environ["NCCL_DEBUG"] = "NONE"
+    # NCCL prints its banner / log to STDOUT; stdout must carry one JSON line, so the log is routed to stderr (nothing is
+    # suppressed: NCCL_DEBUG keeps whatever level the caller asked for)
+    if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -364,7 +524,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--ls", default="NS", choices=["NS", "GMRES", "BICGS"])
     ap.add_argument("--dims", type=int, nargs=3, default=list(P10), help="pipe hex counts nx ny nz (default P10)")
-    ap.add_argument("--ref-dims", type=int, nargs=3, default=[24, 24, 48], help="bounded CPU sample of the workload")
+    ap.add_argument("--ref-dims", type=int, nargs=3, default=[32, 32, 64], help="bounded CPU sample of the workload")
     ap.add_argument("--ref-ranks", type=int, default=0, help="ranks (threads) of the reference arm; 0 = min(host cores, 16, layers/2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--prof-steps", type=int, default=1, help="extra steps run with per-kernel CUDA events (shares, roofline)")

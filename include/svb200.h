@@ -112,6 +112,12 @@ int  b200_elem_tables(int eNoN, double qmTET4, double* w, double* N, double* Nxi
 /* uid: 128 bytes produced on rank 0 and distributed by the caller (MPI_Bcast / torch.distributed). */
 int b200_comm_unique_id(void* uid128);
 int b200_comm_init(b200_handle* h, int rank, int nranks, const void* uid128);
+/* Which transport carries the overlap-node adds (fsils_commuv, liner_solver/in_commu.cpp:111) and the Krylov all-reduces
+ * (liner_solver/dot.cpp, norm.cpp, bcast.cpp:51) after b200_lhs_create: "p2p: ..." = the library's own kernels over
+ * peer-mapped windows (CUDA IPC, NVLink stores + epoch flags), "nccl: <why not p2p>" = ncclSend/Recv + ncclAllReduce,
+ * "none: single rank".  With more than one rank b200_lhs_create is COLLECTIVE (every rank calls it, also ranks without
+ * neighbours).  SVB200_P2P=0 in the environment selects the NCCL path.  The string is owned by the handle. */
+const char* b200_comm_transport(b200_handle* h);
 
 /* ---- structure (replaces fsils_lhs_create liner_solver/lhs.cpp:57; consumes its result) ---- */
 /* rowPtr(nNo+1)/colPtr(nnz): the assembly-order CSR of lhsa (solver/lhsa.cpp:153).  map(nNo):
@@ -143,6 +149,11 @@ void b200_lhs_layout_free(b200_layout* lay);
  * ParMETIS call (solver/distribute.cpp:1683-1700) on meshes that are not generated slab by slab.  Balanced to one element,
  * deterministic, parts numbered along the cuts.  Host-side, no device. */
 int b200_partition_rcb(int nEl, const double* centroids, int nParts, int* part /* nEl */);
+/* The reference's own partition criterion: k-way partition of the mesh's DUAL graph, two elements being neighbours when they share
+ * `ncommon` nodes (solver/distribute.cpp:1683-1706 passes eNoNb, the node count of a boundary element, to ParMETIS_V3_PartMeshKway
+ * through split_).  IEN(eNoN,nEl) 0-based, element-major.  Serial METIS 5 (libmetis_static.a of the CUDA toolkit), host side, set-up
+ * only; edgecut (may be NULL) = number of element faces between parts.  Fails when the library was not present at build time. */
+int b200_partition_metis(int nEl, int eNoN, int nNo, const int* IEN, int ncommon, int nParts, int* part /* nEl */, long long* edgecut);
 
 /* ---- prestress (com_mod.pS0 / pSn / pSa of the struct equation; solver/sv_struct.cpp:262-345, 646-700) ------------------ */
 /* b200_prestress_set uploads the nodal prestress pS0(6,nNo) (rows 00 11 22 01 12 20, assembly node order; NULL: none) that

@@ -94,7 +94,7 @@ ISO_TYPES = {"nHook": 0, "StVK": 1, "mStVK": 2, "HO": 3, "MR": 4, "HGO": 5, "Guc
 VOL_TYPES = {None: 0, "Quad": 1, "ST91": 2, "M94": 3}
 
 EXPORTS = [
-    "b200_create", "b200_destroy", "b200_last_error", "b200_device_count", "b200_elem_tables", "b200_comm_unique_id", "b200_comm_init",
+    "b200_create", "b200_destroy", "b200_last_error", "b200_device_count", "b200_elem_tables", "b200_comm_unique_id", "b200_comm_init", "b200_comm_transport",
     "b200_lhs_create", "b200_face_set", "b200_mesh_set", "b200_zero", "b200_state_set", "b200_assemble_fluid",
     "b200_disp_set", "b200_assemble_struct", "b200_assemble_lelas", "b200_mesh_domains", "b200_mesh_fibers", "b200_assemble_fsi",
     "b200_assemble_ustruct", "b200_ustruct_r", "b200_get_Kd",
@@ -106,7 +106,7 @@ EXPORTS = [
     "b200_assemble_fluid_dmn", "b200_assemble_struct_dmn",
     "b200_assemble_bfolw", "b200_face_integ", "b200_face_normal_update", "b200_face_get_val", "b200_pattern_begin", "b200_pattern_add_mesh", "b200_pattern_finish", "b200_pattern_get",
     "b200_lhs_layout_create", "b200_lhs_layout_sizes", "b200_lhs_layout_map", "b200_lhs_layout_req", "b200_lhs_layout_free",
-    "b200_partition_rcb", "b200_prestress_set", "b200_prestress_get",
+    "b200_partition_rcb", "b200_partition_metis", "b200_prestress_set", "b200_prestress_get",
 ]
 
 KERNEL_CLASSES = ["spmv_vv4", "spmv_vv3", "spmv_ss", "spmv_sv", "spmv_vs", "multi_dot", "cgs_update_scale", "blas1",
@@ -132,6 +132,8 @@ def lib():
         L.b200_elem_tables.argtypes = [ci, cd, vp, vp, vp]
         L.b200_comm_unique_id.argtypes = [vp]
         L.b200_comm_init.argtypes = [vp, ci, ci, vp]
+        L.b200_comm_transport.argtypes = [vp]
+        L.b200_comm_transport.restype = C.c_char_p
         L.b200_lhs_create.argtypes = [vp, ci, ci, ci, ci, vp, vp, vp, ci, vp, vp, vp, ci]
         L.b200_lhs_layout_create.argtypes = [ci, ci, ci, vp, vp, C.POINTER(vp)]
         L.b200_lhs_layout_sizes.argtypes = [vp, vp, vp, vp, vp]
@@ -294,6 +296,19 @@ def partition_rcb(centroids, nparts: int) -> np.ndarray:
     return part
 
 
+def partition_metis(ien, nNo: int, nparts: int, ncommon: int):
+    """Element -> rank map by METIS' k-way partition of the dual graph (b200_partition_metis; the reference's criterion,
+    distribute.cpp:1683-1706: ncommon = nodes of a boundary element).  Returns (part, edgecut)."""
+    ien = _c(ien, np.int32)
+    part = np.zeros(ien.shape[0], np.int32)
+    cut = C.c_longlong(0)
+    L = lib()
+    L.b200_partition_metis.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_longlong)]
+    if L.b200_partition_metis(ien.shape[0], ien.shape[1], int(nNo), _p(ien), int(ncommon), int(nparts), _p(part), C.byref(cut)) != 0:
+        raise RuntimeError("b200_partition_metis: " + L.b200_last_error(None).decode())
+    return part, int(cut.value)
+
+
 def lhs_layout(rank: int, all_gnodes, gnNo: int):
     """fsils_lhs_create's renumbering and overlap lists through the C ABI (b200_lhs_layout_*, csrc/lhs_layout.hpp; host side,
     needs no device): dict(map, mynNo, shnNo, reqs=[(peer, solver ids)]) for `rank` from every rank's global node list."""
@@ -355,6 +370,10 @@ class Backend:
     def comm_init(self, rank, nranks, uid):
         uid = _c(uid, np.uint8)
         self._ck(self.L.b200_comm_init(self.h, rank, nranks, _p(uid)), "b200_comm_init")
+
+    def comm_transport(self):
+        """'p2p: ...' (own kernels over peer-mapped windows), 'nccl: <why not p2p>' or 'none: single rank'."""
+        return self.L.b200_comm_transport(self.h).decode()
 
     # -- structure -----------------------------------------------------------------------------
     def lhs_create(self, gnNo, rowPtr, colPtr, map=None, mynNo=None, reqs=(), nFaces=0):

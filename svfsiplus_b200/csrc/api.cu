@@ -31,6 +31,7 @@ struct b200_handle {
   int device = 0;
   std::unique_ptr<CudaOps> ops;
   std::string err;
+  std::string transport;
 
   // assembly-order structure kept for layout conversions and staged-element scatter
   int nNo = 0, nnz = 0, dof = 0;
@@ -645,7 +646,22 @@ int b200_lhs_create(b200_handle* h, int gnNo, int nNo, int mynNo, int nnz, const
       ops.ovA = a; ops.ovB = b; ops.overlap_ok = ok && (b > a);
     }
     CU_CHECK(cudaStreamSynchronize(ops.st));
+    // peer-mapped transport for the overlap adds and the Krylov all-reduces (collective: like fsils_lhs_create itself,
+    // which gathers every rank's node list, lhs.cpp:156)
+    if (ops.nranks > 1) {
+      std::vector<std::vector<int>> lists(nReq);
+      size_t o = 0;
+      for (int i = 0; i < nReq; i++) { lists[i].assign(req_ptr + o, req_ptr + o + req_n[i]); o += size_t(req_n[i]); }
+      ops.peer_setup(lists);
+    }
   });
+}
+
+const char* b200_comm_transport(b200_handle* h)
+{
+  if (!h) return "";
+  h->transport = std::string(h->ops->p2p ? "p2p: " : (h->ops->nranks > 1 ? "nccl: " : "none: ")) + h->ops->p2p_why;
+  return h->transport.c_str();
 }
 
 int b200_face_set(b200_handle* h, int faIn, int nNo, int dof, int bGrp, const int* glob, const double* val, int shared)
@@ -1264,6 +1280,21 @@ int b200_partition_rcb(int nEl, const double* centroids, int nParts, int* part)
 {
   try {
     svb200::partition_rcb(nEl, centroids, nParts, part);
+    return 0;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return 1;
+  }
+}
+
+/* host/partition_metis.cpp (throws std::runtime_error) */
+long long svb200_partition_metis_impl(int nEl, int eNoN, int nNo, const int* IEN, int ncommon, int nparts, int* part);
+
+int b200_partition_metis(int nEl, int eNoN, int nNo, const int* IEN, int ncommon, int nParts, int* part, long long* edgecut)
+{
+  try {
+    const long long cut = svb200_partition_metis_impl(nEl, eNoN, nNo, IEN, ncommon, nParts, part);
+    if (edgecut) *edgecut = cut;
     return 0;
   } catch (const std::exception& e) {
     g_create_error = e.what();
@@ -1952,6 +1983,7 @@ int b200_solve(b200_handle* h, int ls_type, int prec, const b200_tol* RI, const 
       }
     }
     CU_CHECK(cudaStreamSynchronize(ops.st));
+    ops.peer_check();
     if (out) {
       auto cp = [](b200_sub_out& o, const SubLs& s) { o.suc = s.suc; o.itr = s.itr; o.iNorm = s.iNorm; o.fNorm = s.fNorm; o.dB = s.dB; o.callD = s.callD; };
       cp(out->RI, ls.RI); cp(out->GM, ls.GM); cp(out->CG, ls.CG);

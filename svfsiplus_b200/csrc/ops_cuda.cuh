@@ -14,6 +14,7 @@
 
 #include "kernels.cuh"
 #include "krylov.hpp"
+#include "peer_comm.cuh"
 
 namespace svb200 {
 
@@ -34,12 +35,13 @@ struct Nccl {
   int (*CommInitRank)(Comm*, int, UniqueId, int) = nullptr;
   int (*CommDestroy)(Comm) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, Comm, cudaStream_t) = nullptr;
   int (*Send)(const void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
   int (*Recv)(void*, size_t, int, int, Comm, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
-  static constexpr int kFloat64 = 8, kSum = 0, kInt32 = 2, kMax = 2;
+  static constexpr int kFloat64 = 8, kSum = 0, kInt32 = 2, kMax = 2, kInt8 = 0, kMin = 3;
 
   void load()
   {
@@ -52,6 +54,7 @@ struct Nccl {
     CommInitRank = reinterpret_cast<decltype(CommInitRank)>(sym("ncclCommInitRank"));
     CommDestroy = reinterpret_cast<decltype(CommDestroy)>(sym("ncclCommDestroy"));
     AllReduce = reinterpret_cast<decltype(AllReduce)>(sym("ncclAllReduce"));
+    AllGather = reinterpret_cast<decltype(AllGather)>(sym("ncclAllGather"));
     Send = reinterpret_cast<decltype(Send)>(sym("ncclSend"));
     Recv = reinterpret_cast<decltype(Recv)>(sym("ncclRecv"));
     GroupStart = reinterpret_cast<decltype(GroupStart)>(sym("ncclGroupStart"));
@@ -152,6 +155,21 @@ class CudaOps {
   Nccl::Comm comm = nullptr;
   int rank = 0, nranks = 1;
 
+  // peer-mapped transport (peer_comm.cuh): set up collectively by peer_setup() at the end of b200_lhs_create; when it is
+  // not available (no CUDA IPC between the ranks, SVB200_P2P=0) the NCCL send/recv + all-reduce path below is used.
+  bool p2p = false;
+  std::string p2p_why = "single rank";
+  char* win = nullptr;                       // own window
+  size_t win_bytes = 0;
+  std::vector<char*> peer_win;               // every rank's window as mapped in this process
+  PeerRedArgs red_args{};
+  PeerState* peer_state = nullptr;
+  PeerHaloReq* d_peer_reqs = nullptr;
+  int* d_halo_ptr_all = nullptr;             // concatenated overlap lists
+  int halo_tot = 0;
+  int* d_hn_node = nullptr; int* d_hn_ptr = nullptr; int2* d_hn_src = nullptr;
+  int halo_nh = 0;
+
   // reductions
   static constexpr int kMaxSlots = 1024;
   double* red_d = nullptr;
@@ -195,6 +213,7 @@ class CudaOps {
   }
   ~CudaOps()
   {
+    peer_teardown();
     for (auto& c : chunks) cudaFree(c.p);
     for (auto& sp : spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto& f : faces) { cudaFree(f.glob); cudaFree(f.val); cudaFree(f.valM); }
@@ -315,10 +334,20 @@ class CudaOps {
       done += m;
     }
   }
-  void reduce_begin(int nslots)
+  // all-reduce of n doubles at device pointer v (MPI_Allreduce of dot.cpp / norm.cpp / bcast.cpp:51-58)
+  void allreduce(double* v, int n, bool is_max = false)
   {
-    if (nranks > 1) nccl.check(nccl.AllReduce(red_d, red_d, size_t(nslots), Nccl::kFloat64, Nccl::kSum, comm, st), "AllReduce");
+    if (nranks == 1) return;
+    if (p2p) {
+      if (n > kPeerSlots) throw std::runtime_error("allreduce: more slots than the peer mailbox holds");
+      if (is_max) k_peer_allreduce<1><<<1, 256, 0, st>>>(red_args, peer_state, v, n);
+      else k_peer_allreduce<0><<<1, 256, 0, st>>>(red_args, peer_state, v, n);
+      post();
+      return;
+    }
+    nccl.check(nccl.AllReduce(v, v, size_t(n), Nccl::kFloat64, is_max ? Nccl::kMax : Nccl::kSum, comm, st), "AllReduce");
   }
+  void reduce_begin(int nslots) { allreduce(red_d, nslots); }
   void reduce_fetch(int nslots, double* out)
   {
     CU_CHECK(cudaMemcpyAsync(red_h, red_d, sizeof(double)*nslots, cudaMemcpyDeviceToHost, st));
@@ -357,6 +386,16 @@ class CudaOps {
   {
     if (nranks == 1 || reqs.empty()) { launch(0, nNo_); return; }
     if (!overlap_ok) { launch(0, nNo_); halo_add(dof, out, ld); return; }
+    if (p2p) {
+      // one stream, no library call: boundary rows -> push into the neighbours' windows -> interior rows (the NVLink
+      // stores fly meanwhile) -> acquire the neighbours' flags and add
+      if (ovA > 0) launch(0, ovA);
+      if (ovB < nNo_) launch(ovB, nNo_);
+      halo_push(dof, out, ld ? ld : dof);
+      if (ovB > ovA) launch(ovA, ovB);
+      halo_wait_add(dof, out, ld ? ld : dof);
+      return;
+    }
     if (ovA > 0) launch(0, ovA);
     if (ovB < nNo_) launch(ovB, nNo_);
     CU_CHECK(cudaEventRecord(ev_b, st));
@@ -440,14 +479,184 @@ class CudaOps {
       post();
     }
   }
+  void halo_push(int dof, const double* V, int ld)
+  {
+    if (dof > halo_dof_cap) throw std::runtime_error("halo buffers too small for dof");
+    const int g = std::max(1, std::min(kSmCount, (halo_tot*dof + 255)/256));
+    k_halo_push<<<g, 256, 0, st>>>(int(reqs.size()), d_peer_reqs, d_halo_ptr_all, halo_tot, dof, halo_dof_cap, ld, V, peer_state);
+    post();
+  }
+  void halo_wait_add(int dof, double* V, int ld)
+  {
+    const int g = std::max(1, std::min(kSmCount, (halo_nh*dof + 255)/256));
+    k_halo_wait_add<<<g, 256, 0, st>>>(int(reqs.size()), d_peer_reqs, halo_nh, d_hn_node, d_hn_ptr, d_hn_src, dof, halo_dof_cap, ld, V, peer_state);
+    post();
+  }
   void halo_add(int dof, double* V, int ld = 0)
   {
     if (nranks == 1 || reqs.empty()) return;
     if (ld == 0) ld = dof;
     double hb = 0; for (auto& r : reqs) hb += 32.0*r.n*dof;
-    Scope sc(*this, KC_HALO, hb, int(reqs.size())*2);
+    Scope sc(*this, KC_HALO, hb, p2p ? 2 : int(reqs.size())*2);
+    if (p2p) { halo_push(dof, V, ld); halo_wait_add(dof, V, ld); return; }
     halo_exchange(dof, V, ld, st);
     halo_accumulate(dof, V, ld);
+  }
+
+  // ---- peer-mapped transport: collective set-up (every rank of the communicator calls it, also ranks without neighbours) ----
+  struct PeerRec {                          // what every rank publishes (gathered with ncclAllGather)
+    cudaIpcMemHandle_t handle;
+    long long halo_off[kPeerMaxRanks];      // byte offset in MY window where rank p's values arrive, -1: no exchange with p
+    int req_idx[kPeerMaxRanks];             // my request index for rank p (= my flag slot for it)
+    int req_n[kPeerMaxRanks];
+    int ok;                                 // 0: this rank cannot use the peer transport
+    int pad;
+  };
+  void peer_teardown()
+  {
+    for (int p = 0; p < int(peer_win.size()); p++)
+      if (peer_win[p] && p != rank) cudaIpcCloseMemHandle(peer_win[p]);
+    peer_win.clear();
+    cudaFree(win); win = nullptr; win_bytes = 0;
+    cudaFree(peer_state); peer_state = nullptr;
+    cudaFree(d_peer_reqs); d_peer_reqs = nullptr;
+    cudaFree(d_halo_ptr_all); d_halo_ptr_all = nullptr;
+    cudaFree(d_hn_node); cudaFree(d_hn_ptr); cudaFree(d_hn_src);
+    d_hn_node = nullptr; d_hn_ptr = nullptr; d_hn_src = nullptr;
+    p2p = false;
+  }
+  // host_lists[i]: the overlap list of request i (solver row ids)
+  void peer_setup(const std::vector<std::vector<int>>& host_lists)
+  {
+    peer_teardown();
+    if (nranks == 1) { p2p_why = "single rank"; return; }
+    const char* env = getenv("SVB200_P2P");
+    PeerRec me;
+    std::memset(&me, 0, sizeof(me));
+    me.ok = 1;
+    std::string why;
+    if (env && std::string(env) == "0") { me.ok = 0; why = "disabled by SVB200_P2P=0"; }
+    if (nranks > kPeerMaxRanks || int(reqs.size()) > kPeerMaxReq) { me.ok = 0; why = "more ranks / neighbours than the window holds"; }
+    for (int p = 0; p < kPeerMaxRanks; p++) { me.halo_off[p] = -1; me.req_idx[p] = -1; }
+    size_t bytes = PeerLayout::halo_data_off;
+    for (int i = 0; i < int(reqs.size()) && me.ok; i++) {
+      const int p = reqs[i].peer;
+      if (p < 0 || p >= nranks || p == rank || me.req_idx[p] >= 0) { me.ok = 0; why = "overlap lists are not one per neighbour rank"; break; }
+      me.halo_off[p] = (long long)bytes;
+      me.req_idx[p] = i;
+      me.req_n[p] = reqs[i].n;
+      bytes += ((sizeof(double)*2*size_t(std::max(1, reqs[i].n))*halo_dof_cap + 255)/256)*256;
+    }
+    if (me.ok) {
+      if (cudaMalloc(&win, bytes) != cudaSuccess) { me.ok = 0; why = "window allocation failed"; win = nullptr; cudaGetLastError(); }
+      else {
+        win_bytes = bytes;
+        CU_CHECK(cudaMemset(win, 0, bytes));
+        CU_CHECK(cudaDeviceSynchronize());
+        if (cudaIpcGetMemHandle(&me.handle, win) != cudaSuccess) { me.ok = 0; why = "cudaIpcGetMemHandle failed"; cudaGetLastError(); }
+      }
+    }
+    // gather everybody's record
+    PeerRec* d_rec = nullptr;
+    CU_CHECK(cudaMalloc(&d_rec, sizeof(PeerRec)*(nranks + 1)));
+    CU_CHECK(cudaMemcpyAsync(d_rec + nranks, &me, sizeof(PeerRec), cudaMemcpyHostToDevice, st));
+    nccl.check(nccl.AllGather(d_rec + nranks, d_rec, sizeof(PeerRec), Nccl::kInt8, comm, st), "AllGather");
+    std::vector<PeerRec> rec(nranks);
+    CU_CHECK(cudaMemcpyAsync(rec.data(), d_rec, sizeof(PeerRec)*nranks, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    int ok = 1;
+    for (int p = 0; p < nranks; p++) if (!rec[p].ok) ok = 0;
+    // the two sides of every exchange must agree
+    if (ok) {
+      for (int i = 0; i < int(reqs.size()); i++) {
+        const int p = reqs[i].peer;
+        if (rec[p].req_idx[rank] < 0 || rec[p].req_n[rank] != reqs[i].n) { ok = 0; why = "a neighbour's overlap list does not match ours"; }
+      }
+    }
+    // map the other ranks' windows
+    peer_win.assign(nranks, nullptr);
+    if (ok) {
+      peer_win[rank] = win;
+      for (int p = 0; p < nranks && ok; p++) {
+        if (p == rank) continue;
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, rec[p].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          ok = 0; why = std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(cudaGetLastError());
+        } else peer_win[p] = static_cast<char*>(q);
+      }
+    }
+    // every rank must take the same decision
+    {
+      int* d_ok = reinterpret_cast<int*>(d_rec);
+      CU_CHECK(cudaMemcpyAsync(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
+      nccl.check(nccl.AllReduce(d_ok, d_ok, 1, Nccl::kInt32, Nccl::kMin, comm, st), "AllReduce");
+      int all_ok = 0;
+      CU_CHECK(cudaMemcpyAsync(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CU_CHECK(cudaStreamSynchronize(st));
+      if (ok && !all_ok) why = "another rank could not set the peer transport up";
+      ok = all_ok;
+    }
+    cudaFree(d_rec);
+    if (!ok) {
+      const std::string keep = why.empty() ? std::string("another rank could not set the peer transport up") : why;
+      peer_teardown();
+      p2p_why = keep;
+      return;
+    }
+    // device tables
+    CU_CHECK(cudaMalloc(&peer_state, sizeof(PeerState)));
+    CU_CHECK(cudaMemset(peer_state, 0, sizeof(PeerState)));
+    std::memset(&red_args, 0, sizeof(red_args));
+    red_args.rank = rank; red_args.nranks = nranks;
+    for (int p = 0; p < nranks; p++) red_args.win[p] = peer_win[p];
+    std::vector<PeerHaloReq> hr(reqs.size());
+    std::vector<int> all;
+    for (int i = 0; i < int(reqs.size()); i++) {
+      const int p = reqs[i].peer;
+      hr[i].off = int(all.size());
+      hr[i].n = reqs[i].n;
+      hr[i].rdata = reinterpret_cast<double*>(peer_win[p] + rec[p].halo_off[rank]);
+      hr[i].rflag = reinterpret_cast<unsigned long long*>(peer_win[p] + PeerLayout::halo_flag_off) + rec[p].req_idx[rank];
+      hr[i].ldata = reinterpret_cast<const double*>(win + me.halo_off[p]);
+      hr[i].lflag = reinterpret_cast<const unsigned long long*>(win + PeerLayout::halo_flag_off) + i;
+      all.insert(all.end(), host_lists[i].begin(), host_lists[i].end());
+    }
+    halo_tot = int(all.size());
+    // node-centric source lists: every distinct overlap row with its (request, position) sources in request order
+    std::vector<int> cnt(size_t(nNo_) + 1, 0);
+    for (int v : all) cnt[v + 1]++;
+    std::vector<int> hn_node, hn_ptr(1, 0), slot(nNo_, -1);
+    for (int r = 0; r < nNo_; r++) if (cnt[r + 1]) { slot[r] = int(hn_node.size()); hn_node.push_back(r); hn_ptr.push_back(hn_ptr.back() + cnt[r + 1]); }
+    std::vector<int2> hn_src(all.size());
+    std::vector<int> fill(hn_node.size(), 0);
+    for (int i = 0; i < int(reqs.size()); i++)
+      for (int j = 0; j < reqs[i].n; j++) {
+        const int k = slot[host_lists[i][j]];
+        hn_src[hn_ptr[k] + fill[k]++] = make_int2(i, j);
+      }
+    halo_nh = int(hn_node.size());
+    auto up = [&](const void* src, size_t nbytes) { void* d = nullptr; CU_CHECK(cudaMalloc(&d, std::max<size_t>(nbytes, 16))); if (nbytes) CU_CHECK(cudaMemcpyAsync(d, src, nbytes, cudaMemcpyHostToDevice, st)); return d; };
+    d_peer_reqs = static_cast<PeerHaloReq*>(up(hr.data(), sizeof(PeerHaloReq)*hr.size()));
+    d_halo_ptr_all = static_cast<int*>(up(all.data(), sizeof(int)*all.size()));
+    d_hn_node = static_cast<int*>(up(hn_node.data(), sizeof(int)*hn_node.size()));
+    d_hn_ptr = static_cast<int*>(up(hn_ptr.data(), sizeof(int)*hn_ptr.size()));
+    d_hn_src = static_cast<int2*>(up(hn_src.data(), sizeof(int2)*hn_src.size()));
+    CU_CHECK(cudaStreamSynchronize(st));
+    p2p = true;
+    p2p_why = "peer-mapped windows (CUDA IPC over NVLink)";
+  }
+  // raises when a wait of the peer transport timed out (a rank died or the launch order diverged)
+  void peer_check()
+  {
+    if (!p2p) return;
+    PeerState s;
+    CU_CHECK(cudaMemcpyAsync(&s, peer_state, sizeof(PeerState), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    if (s.error) {
+      CU_CHECK(cudaMemsetAsync(&peer_state->error, 0, sizeof(int), st));
+      throw std::runtime_error(s.error == 1 ? "overlap-node exchange timed out waiting for a neighbour rank"
+                                            : "all-reduce timed out waiting for another rank");
+    }
   }
 
   // ---- faces ----------------------------------------------------------------------------------------
@@ -485,8 +694,7 @@ class CudaOps {
     // only when every coupled face is shared; otherwise reduce face by face.
     if (nranks > 1) {
       for (int k = 0; k < nslot; k++) {
-        if (faces[which[k]].shared)
-          nccl.check(nccl.AllReduce(red_d + k, red_d + k, 1, Nccl::kFloat64, Nccl::kSum, comm, st), "AllReduce");
+        if (faces[which[k]].shared) allreduce(red_d + k, 1);
       }
     }
     std::vector<double> v(nslot);
@@ -507,7 +715,7 @@ class CudaOps {
       const int lim = fa.shared ? mynNo_ : nNo_;
       double* S = red_d + (kMaxSlots - 1);
       face_dot(fa, m, ld, lim, X, S);
-      if (fa.shared && nranks > 1) nccl.check(nccl.AllReduce(S, S, 1, Nccl::kFloat64, Nccl::kSum, comm, st), "AllReduce");
+      if (fa.shared && nranks > 1) allreduce(S, 1);
       if (fa.nNo > 0) {
         k_face_axpy<<<grid_for(size_t(fa.nNo)*m, 256, 1), 256, 0, st>>>(fa.nNo, m, fa.dof, ld, fa.glob, fa.valM, coef, S, Y);
         post();
@@ -609,7 +817,7 @@ class CudaOps {
       if (nranks > 1) {
         // MPI_Allgather of the flags + any() (:529-534)
         fill(1, flag ? 1.0 : 0.0, red_d);
-        nccl.check(nccl.AllReduce(red_d, red_d, 1, Nccl::kFloat64, Nccl::kMax, comm, st), "AllReduce");
+        allreduce(red_d, 1, true);
         double f;
         reduce_fetch(1, &f);
         flag = f > 0.5;
@@ -705,7 +913,7 @@ class CudaOps {
           Scope sc(*this, KC_BLAS1, 48.0*double(n));
           k_cg_update<<<g, kRedThreads, 0, st>>>(n, nOwn, cg_d, red_d, P, SP, X, R, partial_d, counter_d, red_d + 1); post();
         }
-        if (nranks > 1) nccl.check(nccl.AllReduce(red_d + 1, red_d + 1, 1, Nccl::kFloat64, Nccl::kSum, comm, st), "AllReduce");
+        allreduce(red_d + 1, 1);
         {
           Scope sc(*this, KC_BLAS1, 24.0*double(n));
           k_cg_pupdate<<<grid_for(n, 256), 256, 0, st>>>(n, cg_d, red_d + 1, R, P); post();

@@ -41,6 +41,14 @@ def element_partition_rcb(mesh: M.Mesh, nparts: int) -> np.ndarray:
     return B.partition_rcb(mesh.x[mesh.ien].mean(axis=1), nparts)
 
 
+def element_partition_metis(mesh: M.Mesh, nparts: int) -> np.ndarray:
+    """part[e] by the reference's own criterion (distribute.cpp:1683-1706 -> split_ -> ParMETIS_V3_PartMeshKway with
+    ncommonnodes = eNoNb): METIS k-way partition of the dual graph, elements adjacent across a shared face."""
+    from . import backend as B
+    eNoNb = {4: 3, 8: 4, 10: 6}[mesh.ien.shape[1]]            # TET4 -> TRI3, HEX8 -> QUD4, TET10 -> TRI6 (consts.cpp element_type_to_elem_nonb)
+    return B.partition_metis(mesh.ien, mesh.nNo, nparts, eNoNb)[0]
+
+
 def element_partition(mesh: M.Mesh, nparts: int) -> np.ndarray:
     """part[e] for the generator's element order (6 tets per hex, hexes x-fastest then y then z)."""
     nx, ny, nz = mesh.shape
@@ -203,30 +211,25 @@ def weak_dims(base_dims, world):
     return (int(round(nx * f)), int(round(ny * f)), int(round(nz * f)))
 
 
-def local_slab_case(dims, rank, world, *, radius=1.0, length=10.0, pattern=None):
-    """The rank's z-slab of the global pipe `dims`, generated without ever building the global mesh.
+def generation_blocks(world: int) -> int:
+    """Number of independently generated z-blocks the synthetic pipe is composed of.  It does NOT depend on how many ranks
+    own them when the rank count divides 8, so the global mesh and state are bit-identical for 1, 2, 4 and 8 GPUs
+    (strong-scaling runs and the single-GPU line solve the same system)."""
+    return 8 if 8 % world == 0 else world
 
-    Node (i,j,k) has global id k*(nx+1)*(ny+1) + j*(nx+1) + i.  The global pipe's jitter is not
-    reproduced (it would need the global random stream): the slab is jittered on its own with a
-    rank-dependent seed and the two interface planes are left unjittered so that neighbours agree.
-    Returns a per-rank case like split_case's plus `all_gnodes` (analytic, no communication needed).
-    pattern: optional callable (nNo, ien) -> (rowPtr, colPtr), e.g. the device-side lhsa (Backend.pattern); the host
-    construction (numpy) takes ~30 s at 10 M tets.
-    """
-    from . import backend as B
+
+def _pipe_block(dims, b, blocks, radius, length):
+    """Generation block b of the global pipe: its hex layers, jittered on its own with a block-dependent seed; the two
+    interface planes are left unjittered and carry state from a plane-keyed stream, so neighbouring blocks agree bit for bit."""
     nx, ny, nz = dims
-    ranges = slab_ranges(nz, world)
-    k0, k1 = ranges[rank]
+    k0, k1 = slab_ranges(nz, blocks)[b]
     plane = (nx + 1) * (ny + 1)
     dz = length / nz
-    m = M.pipe_mesh(nx, ny, k1 - k0, radius=radius, length=(k1 - k0) * dz, jitter=0.1, seed=1234 + rank)
+    m = M.pipe_mesh(nx, ny, k1 - k0, radius=radius, length=(k1 - k0) * dz, jitter=0.1, seed=1234 + b)
     m.x[:, 2] += k0 * dz
-    m.shape = (nx, ny, nz)
-    gN = (np.arange(m.nNo, dtype=np.int64) + k0 * plane).astype(np.int32)
-    rowPtr, colPtr = pattern(m.nNo, m.ien) if pattern else M.csr_pattern(m.ien, m.nNo)
-    am, af, gam = M.gen_alpha(0.5)
-    Ag, Yg, Bf = M.pipe_state(m, radius=radius, length=length, seed_y=2024 + rank, seed_a=2025 + rank)
-    # interface planes must carry identical state on both owners: take them from a plane-keyed stream
+    m.x[:plane, 2] = k0 * dz                      # the same expression on both owners of an interface plane
+    m.x[m.nNo - plane:, 2] = k1 * dz
+    Ag, Yg, Bf = M.pipe_state(m, radius=radius, length=length, seed_y=2024 + b, seed_a=2025 + b)
     for kk, sl in ((k0, slice(0, plane)), (k1, slice(m.nNo - plane, m.nNo))):
         if 0 < kk < nz:
             rng = np.random.default_rng(777000 + kk)
@@ -236,23 +239,69 @@ def local_slab_case(dims, rank, world, *, radius=1.0, length=10.0, pattern=None)
             Yg[sl, :3] += 0.2 * rng.standard_normal((plane, 3))
             Yg[sl, 3] = 100.0 * (1.0 - m.x[sl, 2] / length) + rng.standard_normal(plane)
             Ag[sl, :4] = 10.0 * rng.standard_normal((plane, 4))
+    return m, Ag, Yg, Bf, k0, k1
+
+
+def local_slab_case(dims, rank, world, *, radius=1.0, length=10.0, pattern=None, blocks=None):
+    """The rank's z-slab of the global pipe `dims`, generated without ever building the global mesh.
+
+    Node (i,j,k) has global id k*(nx+1)*(ny+1) + j*(nx+1) + i.  The pipe is composed of `blocks` generation blocks
+    (generation_blocks: 8 for 1, 2, 4, 8 ranks) of whole hex layers; a rank owns blocks/world consecutive ones and merges
+    them (shared interface planes are identical by construction).  world = 1 therefore yields the SAME global mesh and
+    state that 2, 4 or 8 ranks hold in pieces.
+    Returns a per-rank case like split_case's plus `all_gnodes` (analytic, no communication needed).
+    pattern: optional callable (nNo, ien) -> (rowPtr, colPtr), e.g. the device-side lhsa (Backend.pattern); the host
+    construction (numpy) takes ~30 s at 10 M tets.
+    """
+    from . import backend as B
+    nx, ny, nz = dims
+    if blocks is None:
+        blocks = generation_blocks(world)
+    if blocks % world != 0 or blocks > nz:
+        raise ValueError("blocks must be a multiple of the rank count and at most nz")
+    per = blocks // world
+    plane = (nx + 1) * (ny + 1)
+    xs, iens, As, Ys, Bs = [], [], [], [], []
+    off = 0
+    K0 = K1 = None
+    out_tris = None
+    for b in range(rank * per, (rank + 1) * per):
+        mb, Ag_b, Yg_b, Bf_b, k0, k1 = _pipe_block(dims, b, blocks, radius, length)
+        first = K0 is None
+        if first:
+            K0 = k0
+        K1 = k1
+        skip = 0 if first else plane                  # the shared plane comes from the lower block
+        xs.append(mb.x[skip:]); As.append(Ag_b[skip:]); Ys.append(Yg_b[skip:]); Bs.append(Bf_b[skip:])
+        iens.append(mb.ien + np.int32(off - skip))
+        out_tris = mb.faces["outlet"]["tris"] + np.int32(off - skip)
+        off += mb.nNo - skip
+    x = np.ascontiguousarray(np.concatenate(xs)); ien = np.ascontiguousarray(np.concatenate(iens).astype(np.int32))
+    Ag = np.ascontiguousarray(np.concatenate(As)); Yg = np.ascontiguousarray(np.concatenate(Ys)); Bf = np.ascontiguousarray(np.concatenate(Bs))
+    del xs, iens, As, Ys, Bs
+    nNo = x.shape[0]
+    assert nNo == plane * (K1 - K0 + 1)
+    nid = np.arange(nNo, dtype=np.int32)
+    I = nid % (nx + 1); J = (nid // (nx + 1)) % (ny + 1)
+    wall = nid[(I == 0) | (I == nx) | (J == 0) | (J == ny)]
+    m = M.Mesh(x=x, ien=ien, faces={}, shape=(nx, ny, nz))
+    gN = (np.arange(nNo, dtype=np.int64) + K0 * plane).astype(np.int32)
+    rowPtr, colPtr = pattern(nNo, ien) if pattern else M.csr_pattern(ien, nNo)
+    am, af, gam = M.gen_alpha(0.5)
     dt = 0.005
     props = dict(dt=dt, am=am, af=af, gam=gam, rho=1.06, mu=0.04)
-    nid = np.arange(m.nNo, dtype=np.int32)
-    wall = m.faces["wall"]["nodes"]
-    inlet = m.faces["inlet"]["nodes"] if rank == 0 else np.zeros(0, np.int32)
-    outlet = m.faces["outlet"]["nodes"] if rank == world - 1 else np.zeros(0, np.int32)
-    out_val = (M.face_normal_integral(m.x, m.faces["outlet"]["tris"], outlet) if rank == world - 1
-               else np.zeros((0, 3)))
+    inlet = nid[:plane] if K0 == 0 else np.zeros(0, np.int32)
+    outlet = nid[nNo - plane:] if K1 == nz else np.zeros(0, np.int32)
+    out_val = (M.face_normal_integral(x, out_tris, outlet) if K1 == nz else np.zeros((0, 3)))
     faces = [dict(name="lumen_inlet", nodes=inlet, dof=3, bGrp=B.BC_DIR, val=np.zeros((len(inlet), 3))),
              dict(name="lumen_wall", nodes=wall, dof=3, bGrp=B.BC_DIR, val=np.zeros((len(wall), 3))),
              dict(name="lumen_outlet", nodes=outlet, dof=3, bGrp=B.BC_NEU, val=out_val)]
     res = np.array([0.0, 0.0, gam * dt * (121.0 + 1212.0)])
-    all_gnodes = [np.arange(a * plane, (b + 1) * plane, dtype=np.int32) for a, b in ranges]
+    br = slab_ranges(nz, blocks)
+    all_gnodes = [np.arange(br[r * per][0] * plane, (br[(r + 1) * per - 1][1] + 1) * plane, dtype=np.int32) for r in range(world)]
     part = dict(mesh=m, gNodes=gN, gnNo=plane * (nz + 1), rowPtr=rowPtr, colPtr=colPtr, Ag=Ag, Yg=Yg, Bf=Bf,
                 props=props, faces=faces, res=res, incL=np.array([1, 1, 1], np.int32), rank=rank, nranks=world,
                 face_shared=[False, world > 1, False])
-    _ = nid
     return part, all_gnodes
 
 

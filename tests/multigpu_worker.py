@@ -26,13 +26,19 @@ from svfsiplus_b200 import problem as P  # noqa: E402
 def main():
     dims = tuple(int(v) for v in sys.argv[1:4])
     ls_name = sys.argv[4]
+    partition = sys.argv[5] if len(sys.argv) > 5 else "slab"      # slab | rcb (irregular: more neighbours per rank, unbalanced halos)
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank, world = dist.get_rank(), dist.get_world_size()
 
     case = P.pipe_case(*dims)
-    parts = PT.split_case(case, world)
+    if partition == "rcb":
+        parts = PT.split_case(case, world, PT.element_partition_rcb(case["mesh"], world))
+    elif partition == "metis":
+        parts = PT.split_case(case, world, PT.element_partition_metis(case["mesh"], world))
+    else:
+        parts = PT.split_case(case, world)
     shared = PT.face_shared_flags(parts)
     part = parts[rank]
     part["face_shared"] = shared
@@ -43,6 +49,7 @@ def main():
     dist.broadcast(t, src=0)
     be = PT.setup_rank_backend(part, layout, local, t.cpu().numpy())
 
+    transport = be.comm_transport()
     be.state_set(part["Ag"].shape[1], part["Ag"], part["Yg"], part["Bf"])
     be.zero(4)
     be.assemble_fluid(B.fluid_props(tDof=part["Ag"].shape[1], **part["props"]))
@@ -54,7 +61,8 @@ def main():
 
     # gather to rank 0
     objs = [None] * world
-    dist.all_gather_object(objs, dict(g=part["gNodes"], X=X, R=Rsum, Rloc=Rloc, Vloc=Vloc, info=info))
+    dist.all_gather_object(objs, dict(g=part["gNodes"], X=X, R=Rsum, Rloc=Rloc, Vloc=Vloc, info=info, transport=transport,
+                                      nreq=len(layout["reqs"])))
     ok = True
     report = {}
     if rank == 0:
@@ -63,11 +71,23 @@ def main():
         for o in objs:
             Xg[o["g"]] = o["X"]; Rg[o["g"]] = o["R"]
         report["itr"] = [o["info"]["RI"]["itr"] for o in objs]
+        report["gm_itr"] = [o["info"]["GM"]["itr"] for o in objs]
+        report["cg_itr"] = [o["info"]["CG"]["itr"] for o in objs]
+        report["transport"] = [o["transport"] for o in objs]
+        report["neighbours"] = [o["nreq"] for o in objs]
+        report["X_max"] = float(np.abs(Xg).max())
         report["suc"] = [o["info"]["RI"]["suc"] for o in objs]
         # overlap nodes hold identical values on both owners
         for o in objs:
             report.setdefault("overlap_X", []).append(float(np.abs(Xg[o["g"]] - o["X"]).max()))
+        # the same global system on ONE GPU (rank 0's device): partition-independence of the product itself
+        be1 = P.setup_backend(case, device=local)
+        X1, info1 = P.newton_linear_step(be1, case, ls=ls_name)
+        be1.close()
+        report["X_vs_1gpu"] = float(np.linalg.norm(Xg - X1) / np.linalg.norm(X1))
+        report["itr_1gpu"] = [int(info1["RI"]["itr"]), int(info1["GM"]["itr"]), int(info1["CG"]["itr"])]
         from oracle import ref, refcase
+        report["oracle"] = bool(ref.available())
         if ref.available():
             Rr, Vr, Xr, oref = refcase.reference_step(case, ls_name)
             report["R_vs_1rank"] = float(np.abs(Rg - Rr).max() / np.abs(Rr).max())

@@ -323,3 +323,71 @@ def test_time_step_matches_reference(ls):
     assert rel_l2(Yg[:, 3], Yr[:, 3]) < TOL_SOL                      # pressure
     assert rel_l2(Ag, Ar) < TOL_SOL
     be.close()
+
+
+def test_time_step_matches_reference_coupled_outlet():
+    """The same bar with the resistance (RCR) outlet COUPLED (res != 0: add_bc_mul ADD + PRE inside every Krylov loop),
+    on 12 x 12 x 24: nodal velocity / pressure after a Newton-converged time step within 1e-8 rel. L2."""
+    if not _ref_available():
+        pytest.skip("oracle/_ref not present on this box")
+    from oracle import refcase
+    case = P.pipe_case(12, 12, 24, coupled=True)
+    assert np.any(np.asarray(case["res"]) != 0.0)
+    be = P.setup_backend(case)
+
+    def gpu_step(c):
+        X, info = P.newton_linear_step(be, c, ls="NS")
+        return X, info["RI"]["iNorm"]
+
+    def ref_step(c):
+        R, Val, X, o = refcase.reference_step(c, "NS")
+        return X, o["iNorm"]
+
+    Ag, Yg, ng = _time_step(case, gpu_step, n_newton=9)
+    Ar, Yr, nr = _time_step(case, ref_step, n_newton=9)
+    assert nr[-1] < 1e-9 * nr[0] and ng[-1] < 1e-9 * ng[0]
+    assert rel_l2(Yg[:, :3], Yr[:, :3]) < TOL_SOL
+    assert rel_l2(Yg[:, 3], Yr[:, 3]) < TOL_SOL
+    assert rel_l2(Ag, Ar) < TOL_SOL
+    be.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# the BENCHMARK size against the compiled reference: tests/golden/p10_ns_counts.json is one Newton-iteration hot path
+# of oracle/_ref on the same 10,008,576-tet system (generated offline by tests/golden/make_golden_p10.py, 8 ranks,
+# 330 s); the device has to reproduce its iteration counts, norms and solution
+# ---------------------------------------------------------------------------------------------------
+def test_benchmark_size_matches_reference_golden():
+    import json
+    import os
+    from util import ROOT
+    from svfsiplus_b200 import partition as PT
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "p10_ns_counts.json")))
+    dims = tuple(g["dims"])
+    part, be = PT.setup_distributed_case(dims, 0, 1, 0)
+    assert be.nNo == g["gnNo"]
+    tDof = part["Ag"].shape[1]
+    be.state_set(tDof, part["Ag"], part["Yg"], part["Bf"])
+    be.zero(4)
+    be.assemble_fluid(B.fluid_props(tDof=tDof, **part["props"]))
+    R = be.get_R()
+    # assembled residual: norms to 1e-12, probe nodes entry by entry
+    for j in range(4):
+        assert abs(np.linalg.norm(R[:, j]) - g["R_norm"][j]) <= 1e-12 * g["R_norm"][j]
+    pr = np.asarray(g["probe_nodes"])
+    assert rel_inf(R[pr], np.asarray(g["R_probe"])) < TOL_ASM
+    ls_type, RI, GM, CG = P.LS_SETTINGS["NS"]
+    X, info = be.solve(ls_type, B.PREC_FSILS, RI, GM, CG, part["incL"], part["res"])
+    print("P10 counts gpu", info["RI"]["itr"], info["GM"]["itr"], info["CG"]["itr"], "ref", g["itr"], g["GM_itr"], g["CG_itr"],
+          "iNorm", info["RI"]["iNorm"], g["iNorm"], "fNorm", info["RI"]["fNorm"], g["fNorm"])
+    assert info["RI"]["suc"] == g["suc"]
+    assert abs(info["RI"]["itr"] - g["itr"]) <= 1                       # outer (Newton-level linear) iterations: +-1
+    # inner totals are sums over 2 x itr GMRES calls and itr CG calls, each within +-1 of the reference's
+    assert abs(info["GM"]["itr"] - g["GM_itr"]) <= 2 * (g["itr"] + 1)
+    assert abs(info["CG"]["itr"] - g["CG_itr"]) <= (g["itr"] + 1)
+    assert abs(info["RI"]["iNorm"] - g["iNorm"]) <= 1e-8 * g["iNorm"]
+    # the solution of a 1e-3 linear solve: same Krylov spaces, compared well below the solve tolerance
+    for j in range(4):
+        assert abs(np.linalg.norm(X[:, j]) - g["X_norm"][j]) <= 1e-6 * g["X_norm"][j]
+    assert rel_l2(X[pr], np.asarray(g["X_probe"])) < 1e-5
+    be.close()

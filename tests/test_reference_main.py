@@ -1,0 +1,112 @@
+"""The plug-in INSIDE the reference's own main() (`-m gpu`).
+
+oracle/_ref/svmultiphysics_b200 is the complete reference solver (its own main(), read_files, distribute, initialize, the time
+loop, set_bc / RCR coupling, picc, output) with the B200 backend registered exactly as INTEGRATION.md items 1-5 describe
+(oracle/patch_reference.py applies the edits to copies of consts.h, LinearAlgebra.cpp, eq_assem.cpp, main.cpp, set_bc.cpp at build
+time; nothing else differs from oracle/_ref/svmultiphysics_ref).  Each case directory is run twice from a real solver.xml:
+
+    <Linear_algebra type="fsils">                               the reference's own backend
+    <Linear_algebra type="b200"> <Assembly> b200 </Assembly>    whole-mesh assembly + FSILS-equivalent solve on the GPU
+
+and the result files are compared with the reference's own acceptance criterion (tests/conftest.py RTOL table, restated in
+sv_io.compare_results), the Newton / Krylov counts of histor.dat within +-1 (north_star).
+"""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import ROOT
+from svfsiplus_b200 import sv_io as IO
+
+pytestmark = pytest.mark.gpu
+
+EXE_REF = os.path.join(ROOT, "oracle", "_ref", "svmultiphysics_ref")
+EXE_B200 = os.path.join(ROOT, "oracle", "_ref", "svmultiphysics_b200")
+
+
+def _need():
+    if not (os.path.exists(EXE_REF) and os.path.exists(EXE_B200)):
+        pytest.skip("oracle/_ref/svmultiphysics_ref / svmultiphysics_b200 not built (make -C oracle full b200 needs the reference sources)")
+
+
+def _export():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("export_case", os.path.join(ROOT, "tools", "export_case.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    return ex
+
+
+def _run(exe, cwd):
+    r = subprocess.run([exe, "solver.xml"], cwd=cwd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return r.stdout
+
+
+_LINE = re.compile(r"^\s*(\S+)\s+(\d+)-(\d+)(s?)\s+\S+\s+\[(\S+)\s+(\S+)\s+(\S+)\s+(\S+)\]\s+\[(\d+)\s+(\S+)\s+(\S+)\]")
+
+
+def history(path):
+    """histor.dat lines (output.cpp:46-180): (eq, time step, Newton iteration, converged, Ri/R1, Ri/R0, lsIt)."""
+    out = []
+    for l in open(path).read().splitlines():
+        m = _LINE.match(l)
+        if m:
+            out.append(dict(eq=m.group(1), ts=int(m.group(2)), it=int(m.group(3)), conv=m.group(4) == "s",
+                            ri_r1=float(m.group(6)), ri_r0=float(m.group(7)), lsit=int(m.group(9))))
+    return out
+
+
+def _compare(tmp_path, make, fields, steps, rtol=None, lsit_slack=1):
+    _need()
+    ex = _export()
+    a, b = tmp_path / "fsils", tmp_path / "b200"
+    make(ex, str(a), "fsils")
+    make(ex, str(b), "b200")
+    _run(EXE_REF, a)
+    log = _run(EXE_B200, b)
+    name = IO.result_name("result", steps)
+    msgs = IO.compare_results(b / "1-procs" / name, a / "1-procs" / name, fields, rtol=rtol)
+    assert msgs == [], msgs
+    ha, hb = history(a / "1-procs" / "histor.dat"), history(b / "1-procs" / "histor.dat")
+    assert len(ha) == len(hb) and len(ha) >= steps          # same number of Newton iterations in every time step
+    for x, y in zip(ha, hb):
+        assert (x["eq"], x["ts"], x["it"], x["conv"]) == (y["eq"], y["ts"], y["it"], y["conv"])
+        assert abs(x["lsit"] - y["lsit"]) <= lsit_slack, (x, y)
+    return ha, hb, log
+
+
+def test_pipe_with_unsteady_inflow_and_rcr_outlet_through_solver_xml(tmp_path):
+    """Fluid equation, NS solver, parabolic unsteady inflow with imposed flux, RCR outlet: everything the harness tests bypass
+    (Parameters.cpp instantiating the backend at parse time, set_bc_cpl / RCR integration feeding `res`, incL, Neumann face through
+    set_bc_neu_l -> assemble_face, picc and output_result reading eq.FSILS.RI) runs as reference code around the backend."""
+    steps = 2
+    ha, hb, _ = _compare(tmp_path, lambda ex, out, la: ex.export_pipe(out, (8, 8, 16), steps=steps, linear_algebra=la),
+                         ["Velocity", "Pressure"], steps)
+    assert hb[-1]["conv"] and hb[-1]["ri_r1"] < 1e-9
+
+
+@pytest.mark.parametrize("elem", ["hex", "tet"])
+def test_solid_block_through_solver_xml(tmp_path, elem):
+    """struct equation (neo-Hookean, ST91, BICG 1e-12) with a traction face, two time steps."""
+    steps = 2
+    _compare(tmp_path, lambda ex, out, la: ex.export_block(out, 4, elem, steps=steps, linear_algebra=la),
+             ["Displacement", "Velocity"], steps, lsit_slack=3)
+
+
+def test_solve_only_mode_through_solver_xml(tmp_path):
+    """<Linear_algebra type="b200"> without <Assembly>: the reference assembles on the host, the GPU solves."""
+    _need()
+    ex = _export()
+    a, b = tmp_path / "fsils", tmp_path / "b200"
+    ex.export_pipe(str(a), (6, 6, 10), steps=1, linear_algebra="fsils")
+    ex.export_pipe(str(b), (6, 6, 10), steps=1, linear_algebra="b200_solve_only")
+    _run(EXE_REF, a)
+    _run(EXE_B200, b)
+    assert IO.compare_results(b / "1-procs" / "result_001.vtu", a / "1-procs" / "result_001.vtu", ["Velocity", "Pressure"]) == []
+    ha, hb = history(a / "1-procs" / "histor.dat"), history(b / "1-procs" / "histor.dat")
+    assert [(x["it"], x["conv"]) for x in ha] == [(x["it"], x["conv"]) for x in hb]
+    assert all(abs(x["lsit"] - y["lsit"]) <= 1 for x, y in zip(ha, hb))

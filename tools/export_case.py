@@ -60,7 +60,7 @@ SOLVER_XML = """<?xml version="1.0" encoding="UTF-8" ?>
   <Viscosity model="Constant" > <Value> 0.04 </Value> </Viscosity>
   <Output type="Spatial" > <Velocity> true </Velocity> <Pressure> true </Pressure> </Output>
   <LS type="NS" >
-    <Linear_algebra type="fsils" > <Preconditioner> fsils </Preconditioner> </Linear_algebra>
+    {linear_algebra}
     <Max_iterations> 15 </Max_iterations>
     <NS_GM_max_iterations> 10 </NS_GM_max_iterations>
     <NS_CG_max_iterations> 300 </NS_CG_max_iterations>
@@ -88,7 +88,16 @@ SOLVER_XML = """<?xml version="1.0" encoding="UTF-8" ?>
 """
 
 
-def export_pipe(out, dims, steps=2, mode=IO.APPENDED_RAW):
+LINEAR_ALGEBRA = {
+    # the reference's own backend
+    "fsils": '<Linear_algebra type="fsils" > <Preconditioner> fsils </Preconditioner> </Linear_algebra>',
+    # this repository's backend: whole-mesh assembly + solve on the GPU / host assembly + GPU solve
+    "b200": '<Linear_algebra type="b200" > <Preconditioner> fsils </Preconditioner> <Assembly> b200 </Assembly> </Linear_algebra>',
+    "b200_solve_only": '<Linear_algebra type="b200" > <Preconditioner> fsils </Preconditioner> </Linear_algebra>',
+}
+
+
+def export_pipe(out, dims, steps=2, mode=IO.APPENDED_RAW, linear_algebra="fsils"):
     """Returns dict(nNo, nEl, faces={name: (n_nodes, n_elems)})."""
     nx, ny, nz = dims
     m = M.pipe_mesh(nx, ny, nz)
@@ -109,7 +118,7 @@ def export_pipe(out, dims, steps=2, mode=IO.APPENDED_RAW):
         info["faces"][name] = (len(nodes), len(gE))
         xml_faces += f'  <Add_face name="{name}"> <Face_file_path> mesh/mesh-surfaces/{name}.vtp </Face_file_path> </Add_face>\n'
     with open(os.path.join(out, "solver.xml"), "w") as f:
-        f.write(SOLVER_XML.format(steps=steps, faces=xml_faces))
+        f.write(SOLVER_XML.format(steps=steps, faces=xml_faces, linear_algebra=LINEAR_ALGEBRA[linear_algebra]))
     # one smooth pulse per second, peak inflow 50 mL/s (negative = into the domain, like the reference case)
     t = np.linspace(0.0, 1.0, 33)
     q = -50.0 * np.sin(np.pi * t) ** 2
@@ -151,7 +160,7 @@ BLOCK_XML = """<?xml version="1.0" encoding="UTF-8" ?>
   <Penalty_parameter> 4.0E9 </Penalty_parameter>
   <Output type="Spatial" > <Displacement> true </Displacement> <Velocity> true </Velocity> </Output>
   <LS type="BICG" >
-    <Linear_algebra type="fsils" > <Preconditioner> fsils </Preconditioner> </Linear_algebra>
+    {linear_algebra}
     <Tolerance> 1e-12 </Tolerance>
     <Max_iterations> 600 </Max_iterations>
   </LS>
@@ -164,7 +173,7 @@ BLOCK_XML = """<?xml version="1.0" encoding="UTF-8" ?>
 """
 
 
-def export_block(out, n, elem="hex", steps=1, mode=IO.APPENDED_RAW):
+def export_block(out, n, elem="hex", steps=1, mode=IO.APPENDED_RAW, linear_algebra="fsils"):
     """The solid block of SURVEY 8(d) (n^3 HEX8, its 6-tet split, or the quadratic split) in the layout of the reference's
     tests/cases/struct/block_compression: volume mesh, the six faces X0..Z1 (QUD4 / TRI3 / TRI6), a struct solver.xml."""
     m = M.block_mesh(n, elem)
@@ -187,7 +196,7 @@ def export_block(out, n, elem="hex", steps=1, mode=IO.APPENDED_RAW):
         info["faces"][name] = (len(nodes), len(gE), IENb.shape[1])
         xml_faces += f'  <Add_face name="{name}"> <Face_file_path> mesh/mesh-surfaces/{name}.vtp </Face_file_path> </Add_face>\n'
     with open(os.path.join(out, "solver.xml"), "w") as f:
-        f.write(BLOCK_XML.format(steps=steps, faces=xml_faces))
+        f.write(BLOCK_XML.format(steps=steps, faces=xml_faces, linear_algebra=LINEAR_ALGEBRA[linear_algebra]))
     return info
 
 
@@ -198,5 +207,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--block", type=int, default=0, help="write the solid block with this many elements per edge instead of the pipe")
     ap.add_argument("--elem", default="hex", choices=["hex", "tet", "tet10"])
+    ap.add_argument("--linear-algebra", default="fsils", choices=sorted(LINEAR_ALGEBRA))
     a = ap.parse_args()
-    print(export_block(a.out, a.block, a.elem, a.steps) if a.block else export_pipe(a.out, tuple(a.dims), a.steps))
+    print(export_block(a.out, a.block, a.elem, a.steps, linear_algebra=a.linear_algebra) if a.block
+          else export_pipe(a.out, tuple(a.dims), a.steps, linear_algebra=a.linear_algebra))
