@@ -308,6 +308,11 @@ int b200_spmv(b200_handle* h, int dof, const double* x, double* y);
 int b200_op_bench(b200_handle* h, int op, int k, int reps, double* ms_per_launch, double* bytes_per_launch);
 /* Kernel-launch counter (all kernels this handle launched since creation). */
 long long b200_launch_count(b200_handle* h);
+/* Kernel-variant knobs for A/B measurements and the parity tests of every variant (all variants compute the same products; they
+ * differ in how the matrix stream reaches the lanes): "vv3" 0 lane = component / 1 lanes stride over the row's blocks / 2 TMA-staged
+ * row tiles; "schur_gp", "schur_sp" 0 / 1 (two / four entries in flight) / 2 TMA-staged; "narrow" (spmv_ss/sv/vs) 0 / 2;
+ * "cg_batch" iterations enqueued per host poll of the device-resident CG loops. */
+int b200_tune(b200_handle* h, const char* name, int value);
 /* Live kernel timing inside a step.  b200_profile(h,1) resets the counters and makes every kernel
  * class record CUDA-event pairs on the launch stream; b200_profile_read synchronises and returns,
  * per class, the summed device milliseconds, the ALGORITHMIC bytes (SURVEY.md par. 8d formulas) and the

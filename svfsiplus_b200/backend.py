@@ -99,7 +99,7 @@ EXPORTS = [
     "b200_disp_set", "b200_assemble_struct", "b200_assemble_lelas", "b200_mesh_domains", "b200_mesh_fibers", "b200_assemble_fsi",
     "b200_assemble_ustruct", "b200_ustruct_r", "b200_get_Kd",
     "b200_assemble_elem", "b200_get_R", "b200_set_R", "b200_add_R", "b200_get_Val", "b200_set_Val", "b200_commu_R", "b200_solve",
-    "b200_spmv", "b200_op_bench", "b200_launch_count", "b200_last_timings", "b200_profile", "b200_profile_read",
+    "b200_spmv", "b200_op_bench", "b200_launch_count", "b200_tune", "b200_last_timings", "b200_profile", "b200_profile_read",
     "b200_timer",
     "b200_pic_init", "b200_pic_set", "b200_pic_get", "b200_pic_scatter", "b200_picp", "b200_pici", "b200_picc",
     "b200_pic_copy_rows", "b200_pic_advance", "b200_face_mesh_set", "b200_assemble_bneu",
@@ -622,6 +622,11 @@ class Backend:
         ms = C.c_double(0); by = C.c_double(0)
         self._ck(self.L.b200_op_bench(self.h, op, k, reps, C.byref(ms), C.byref(by)), "b200_op_bench")
         return ms.value, by.value
+
+    def tune(self, name, value):
+        """Kernel-variant knob (b200_tune): 'vv3', 'schur_gp', 'schur_sp', 'narrow', 'cg_batch'."""
+        self.L.b200_tune.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        self._ck(self.L.b200_tune(self.h, name.encode(), int(value)), "b200_tune")
 
     def profile(self, enable=True):
         self._ck(self.L.b200_profile(self.h, int(enable)), "b200_profile")

@@ -607,6 +607,7 @@ int b200_lhs_create(b200_handle* h, int gnNo, int nNo, int mynNo, int nnz, const
     cudaFree(ops.rowPtr); cudaFree(ops.col); cudaFree(ops.diag); cudaFree(ops.tpos);
     cudaFree(h->d_rowPtrA); cudaFree(h->d_colA); cudaFree(h->d_map);
     ops.rowPtr = upload(rpS.data(), rpS.size(), ops.st);
+    colS.resize(colS.size() + 4, 0);                     // slack: the tiled SpMV's bulk copies round their size up to 16 bytes
     ops.col = upload(colS.data(), colS.size(), ops.st);
     ops.diag = upload(diag.data(), diag.size(), ops.st);
     ops.tpos = upload(tpos.data(), tpos.size(), ops.st);
@@ -646,6 +647,7 @@ int b200_lhs_create(b200_handle* h, int gnNo, int nNo, int mynNo, int nnz, const
       ops.ovA = a; ops.ovB = b; ops.overlap_ok = ok && (b > a);
     }
     CU_CHECK(cudaStreamSynchronize(ops.st));
+    ops.build_tiles(rpS);
     // peer-mapped transport for the overlap adds and the Krylov all-reduces (collective: like fsils_lhs_create itself,
     // which gathers every rank's node list, lhs.cpp:156)
     if (ops.nranks > 1) {
@@ -2051,13 +2053,15 @@ int b200_op_bench(b200_handle* h, int op, int k, int reps, double* ms_per_launch
       switch (op) {
         case KC_SPMV_VV4: ops.spmv_vv(4, h->Val, x, y); bytes = ops.bytes_vv(4); break;
         case KC_SPMV_VV3: { const int v0 = ops.variant_vv3; ops.variant_vv3 = k; ops.spmv_vv(3, mK, x, y); ops.variant_vv3 = v0; bytes = ops.bytes_vv(3); break; }
-        case KC_SPMV_SS:  ops.spmv_ss(mL, x, y); bytes = ops.bytes_ss(); break;
+        case KC_SPMV_SS:  { const int v0 = ops.variant_narrow; ops.variant_narrow = k; ops.spmv_ss(mL, x, y); ops.variant_narrow = v0; bytes = ops.bytes_ss(); break; }
         case KC_SPMV_SV:  // pass 1 of the fused Schur operator
+          if (k == 2) { int t0, t1; if (!ops.tiles_for(0, h->nNo, t0, t1)) throw std::runtime_error("op_bench: no row tiles"); ops.launch_tiled(t0, t1, mG, TileGP{x, x, ops.V4}); bytes = ops.bytes_schur_gp(); break; }
           if (k == 1) k_schur_gp4<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(nullptr, h->nNo, ops.rowPtr, ops.col, mG, x, x, ops.V4);
           else k_schur_gp<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(nullptr, h->nNo, ops.rowPtr, ops.col, mG, x, x, ops.V4);
           ops.post();
           bytes = ops.bytes_schur_gp(); break;
         case KC_SPMV_VS:  // pass 2 of the fused Schur operator
+          if (k == 2) { int t0, t1; if (!ops.tiles_for(0, h->nNo, t0, t1)) throw std::runtime_error("op_bench: no row tiles"); ops.launch_tiled(t0, t1, ops.GtL, TileSP{ops.V4, y}); bytes = ops.bytes_schur_sp(); break; }
           if (k == 1) k_schur_sp4<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(nullptr, h->nNo, ops.rowPtr, ops.col, ops.GtL, ops.V4, y);
           else k_schur_sp<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(nullptr, h->nNo, ops.rowPtr, ops.col, ops.GtL, ops.V4, y);
           ops.post();
@@ -2097,6 +2101,20 @@ int b200_op_bench(b200_handle* h, int op, int k, int reps, double* ms_per_launch
 }
 
 long long b200_launch_count(b200_handle* h) { return h ? h->ops->launches : 0; }
+
+int b200_tune(b200_handle* h, const char* name, int value)
+{
+  return guarded(h, [&] {
+    auto& ops = *h->ops;
+    const std::string n = name ? name : "";
+    if (n == "vv3") ops.variant_vv3 = value;
+    else if (n == "schur_gp") ops.variant_gp = value;
+    else if (n == "schur_sp") ops.variant_sp = value;
+    else if (n == "narrow") ops.variant_narrow = value;
+    else if (n == "cg_batch") ops.cg_batch = std::max(1, value);
+    else throw std::runtime_error("tune: unknown knob '" + n + "' (vv3, schur_gp, schur_sp, narrow, cg_batch)");
+  });
+}
 
 int b200_profile(b200_handle* h, int enable)
 {

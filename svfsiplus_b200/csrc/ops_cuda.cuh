@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "krylov.hpp"
 #include "peer_comm.cuh"
+#include "spmv_tiled.cuh"
 
 namespace svb200 {
 
@@ -143,6 +144,60 @@ class CudaOps {
   std::vector<HaloReq> reqs;
   int halo_dof_cap = 0;
 
+  // row tiles of the TMA-staged SpMV kernels (spmv_tiled.cuh): tile t = rows [tile_row[t], tile_row[t+1]); tiles never straddle
+  // ovA / ovB, tile_at[] = first tile of the row ranges [0, ovA), [ovA, ovB), [ovB, nNo) and the end
+  int* tile_row = nullptr;
+  int tile_at[4] = {0, 0, 0, 0};
+  bool tiles_ok = false;
+  void build_tiles(const std::vector<int>& rp)          // rp: host copy of rowPtr (solver ordering)
+  {
+    cudaFree(tile_row); tile_row = nullptr; tiles_ok = false;
+    const int cuts[4] = {0, overlap_ok ? ovA : 0, overlap_ok ? ovB : nNo_, nNo_};
+    std::vector<int> tr;
+    for (int sgm = 0; sgm < 3; sgm++) {
+      tile_at[sgm] = int(tr.size());
+      int r = cuts[sgm];
+      while (r < cuts[sgm+1]) {
+        tr.push_back(r);
+        const int p0 = rp[r] & ~3;
+        int q = r;
+        while (q < cuts[sgm+1] && q - r < kTileRows && rp[q+1] - p0 <= kTileCap - 4) q++;
+        if (q == r) return;                              // a single row longer than a tile: keep the per-lane kernels
+        r = q;
+      }
+    }
+    tile_at[3] = int(tr.size());
+    tr.push_back(nNo_);
+    CU_CHECK(cudaMalloc(&tile_row, sizeof(int)*tr.size()));
+    CU_CHECK(cudaMemcpyAsync(tile_row, tr.data(), sizeof(int)*tr.size(), cudaMemcpyHostToDevice, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    tiles_ok = true;
+  }
+  // tile range of a row range handed out by rows_then_halo (always one of the three segments or the whole matrix)
+  bool tiles_for(int r0, int r1, int& t0, int& t1) const
+  {
+    if (!tiles_ok) return false;
+    if (r0 == 0 && r1 == nNo_) { t0 = tile_at[0]; t1 = tile_at[3]; return true; }
+    if (!overlap_ok) return false;
+    if (r0 == 0 && r1 == ovA) { t0 = tile_at[0]; t1 = tile_at[1]; return true; }
+    if (r0 == ovA && r1 == ovB) { t0 = tile_at[1]; t1 = tile_at[2]; return true; }
+    if (r0 == ovB && r1 == nNo_) { t0 = tile_at[2]; t1 = tile_at[3]; return true; }
+    return false;
+  }
+  unsigned tiled_attr_mask = 0;        // shapes whose kernel already carries the dynamic shared memory attribute on this device
+  template <class S>
+  void launch_tiled(int t0, int t1, const double* K, const S& shape)
+  {
+    if (!((tiled_attr_mask >> S::ID) & 1u)) {
+      CU_CHECK(cudaFuncSetAttribute(k_spmv_tiled<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(tile_smem_bytes<S>())));
+      tiled_attr_mask |= (1u << S::ID);
+    }
+    if (t1 <= t0) return;
+    const int g = std::min(t1 - t0, kSmCount);
+    k_spmv_tiled<S><<<g, kTileThreads, tile_smem_bytes<S>(), st>>>(skip_flag, t0, t1, tile_row, rowPtr, col, K, shape);
+    post();
+  }
+
   // overlap of the halo exchange with the interior rows: in the FSILS ordering the rows that appear in an
   // overlap list are [0, ovA) (shared with lower ranks) and [ovB, nNo) (shared with higher ranks)
   cudaStream_t st2 = nullptr;          // communication stream (highest priority)
@@ -218,7 +273,7 @@ class CudaOps {
     for (auto& sp : spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
     for (auto& f : faces) { cudaFree(f.glob); cudaFree(f.val); cudaFree(f.valM); }
     for (auto& r : reqs) { cudaFree(r.ptr); cudaFree(r.sbuf); cudaFree(r.rbuf); }
-    cudaFree(rowPtr); cudaFree(col); cudaFree(diag); cudaFree(tpos);
+    cudaFree(rowPtr); cudaFree(col); cudaFree(diag); cudaFree(tpos); cudaFree(tile_row);
     cudaFree(cg_d); cudaFreeHost(cg_h);
     if (cg_ev[0]) cudaEventDestroy(cg_ev[0]);
     if (cg_ev[1]) cudaEventDestroy(cg_ev[1]);
@@ -246,7 +301,7 @@ class CudaOps {
   }
   double* vec(size_t n)
   {
-    const size_t bytes = ((n*sizeof(double) + 255)/256)*256;
+    const size_t bytes = ((n*sizeof(double) + 16 + 255)/256)*256;     // +16: the tiled SpMV's bulk copies round their size up to 16 bytes
     for (int c = cur_chunk; c < int(chunks.size()); c++) {
       if (c > cur_chunk && chunks[c].top != 0) continue;
       if (chunks[c].cap - chunks[c].top >= bytes) {
@@ -374,8 +429,9 @@ class CudaOps {
 
   // entries in flight per lane in the two Schur passes (A/B on B200, profiles/r01_tour_b.jsonl): pass 1 is
   // fastest with two (0.151 vs 0.163 ms at P10), pass 2 with four (0.193 vs 0.217 ms)
-  int variant_gp = 0, variant_sp = 1;
-  int variant_vv3 = 0;       // 0: lane = component, 1: lanes stride over the row's blocks (A/B by op_bench)
+  int variant_gp = 0, variant_sp = 1;   // 2: TMA-staged row tiles (spmv_tiled.cuh)
+  int variant_vv3 = 0;       // 0: lane = component, 1: lanes stride over the row's blocks, 2: TMA-staged row tiles (A/B by op_bench)
+  int variant_narrow = 0;    // spmv_ss / sv / vs: 0 per-lane loads, 2 TMA-staged row tiles
 
   // ---- SpMV (+ overlap-node add) --------------------------------------------------------------------
   // Every product is launched on row ranges: launch(r0, r1) computes rows [r0, r1).  With more than one rank the
@@ -415,6 +471,8 @@ class CudaOps {
       const int n = r1 - r0, g = grid_rows(n);
       const int* rp = rowPtr + r0;
       double* out = KU + size_t(r0)*dof;
+      int t0, t1;
+      if (dof == 3 && variant_vv3 == 2 && tiles_for(r0, r1, t0, t1)) { launch_tiled(t0, t1, K, TileVV3{U, KU}); return; }
       switch (dof) {
         case 4: k_spmv_vv4<<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out); break;
         case 3: if (variant_vv3 == 1) k_spmv_vv3s<<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out);
@@ -430,6 +488,8 @@ class CudaOps {
   {
     Scope sc(*this, KC_SPMV_SS, bytes_ss());
     rows_then_halo(1, KU, 1, [&](int r0, int r1) {
+      int t0, t1;
+      if (variant_narrow == 2 && tiles_for(r0, r1, t0, t1)) { launch_tiled(t0, t1, K, TileSS{U, KU}); return; }
       k_spmv_ss<<<grid_rows(r1 - r0), 256, 0, st>>>(skip_flag, r1 - r0, rowPtr + r0, col, K, U, KU + r0);
       post();
     });
@@ -440,6 +500,8 @@ class CudaOps {
     Scope sc(*this, KC_SPMV_SV, bytes_svs(dof));
     rows_then_halo(dof, KU, dof, [&](int r0, int r1) {
       const int n = r1 - r0, g = grid_rows(n);
+      int t0, t1;
+      if (dof == 3 && variant_narrow == 2 && tiles_for(r0, r1, t0, t1)) { launch_tiled(t0, t1, K, TileSV3{U, KU}); return; }
       if (dof == 3) k_spmv_sv<3><<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, K, U, KU + size_t(r0)*3);
       else k_spmv_sv<2><<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, K, U, KU + size_t(r0)*2);
       post();
@@ -451,6 +513,8 @@ class CudaOps {
     Scope sc(*this, KC_SPMV_VS, bytes_svs(dof));
     rows_then_halo(1, KU, 1, [&](int r0, int r1) {
       const int n = r1 - r0, g = grid_rows(n);
+      int t0, t1;
+      if (dof == 3 && variant_narrow == 2 && tiles_for(r0, r1, t0, t1)) { launch_tiled(t0, t1, K, TileVS3{U, KU}); return; }
       if (dof == 3) k_spmv_vs<3><<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, K, U, KU + r0);
       else k_spmv_vs<2><<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, K, U, KU + r0);
       post();
@@ -862,6 +926,8 @@ class CudaOps {
         Scope sc(*this, KC_SPMV_SV, bytes_schur_gp());
         rows_then_halo(3, V4, 4, [&](int r0, int r1) {
           const int n = r1 - r0, g = grid_rows(n);
+          int t0, t1;
+          if (variant_gp == 2 && tiles_for(r0, r1, t0, t1)) { launch_tiled(t0, t1, G, TileGP{P, P, V4}); return; }
           if (variant_gp == 1) k_schur_gp4<<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, G, P, P + r0, V4 + size_t(r0)*4);
           else k_schur_gp<<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, G, P, P + r0, V4 + size_t(r0)*4);
           post();
@@ -872,6 +938,8 @@ class CudaOps {
         Scope sc(*this, KC_SPMV_VS, bytes_schur_sp());
         rows_then_halo(1, SP, 1, [&](int r0, int r1) {
           const int n = r1 - r0, g = grid_rows(n);
+          int t0, t1;
+          if (variant_sp == 2 && tiles_for(r0, r1, t0, t1)) { launch_tiled(t0, t1, GtL, TileSP{V4, SP}); return; }
           if (variant_sp == 1) k_schur_sp4<<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, GtL, V4, SP + r0);
           else k_schur_sp<<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, GtL, V4, SP + r0);
           post();

@@ -391,3 +391,31 @@ def test_benchmark_size_matches_reference_golden():
         assert abs(np.linalg.norm(X[:, j]) - g["X_norm"][j]) <= 1e-6 * g["X_norm"][j]
     assert rel_l2(X[pr], np.asarray(g["X_probe"])) < 1e-5
     be.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# every SpMV variant computes the same products: TMA-staged row tiles (spmv_tiled.cuh) against the per-lane kernels
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dims", [(8, 8, 16), (24, 24, 48)])
+def test_tma_staged_spmv_variants_match_per_lane_kernels(dims):
+    case = P.pipe_case(*dims)
+    be = P.setup_backend(case)
+    tight = (B.LS_NS, (1e-9, 1e-30, 10, 200), (1e-6, 1e-30, 5, 200), (1e-6, 1e-30, 500, 0))
+    X0, i0 = P.newton_linear_step(be, case, ls=tight)
+    for knobs in (dict(vv3=2), dict(schur_gp=2), dict(schur_sp=2), dict(narrow=2), dict(vv3=2, schur_gp=2, schur_sp=2, narrow=2)):
+        for k, v in knobs.items():
+            be.tune(k, v)
+        X1, i1 = P.newton_linear_step(be, case, ls=tight)
+        assert i1["RI"]["suc"] == i0["RI"]["suc"]
+        assert abs(i1["RI"]["itr"] - i0["RI"]["itr"]) <= 1
+        assert rel_l2(X1, X0) < 1e-6, (knobs, rel_l2(X1, X0))
+        for k in knobs:
+            be.tune(k, {"vv3": 0, "schur_gp": 0, "schur_sp": 1, "narrow": 0}[k])
+    if _ref_available():
+        from oracle import refcase
+        for k, v in dict(vv3=2, schur_gp=2, schur_sp=2, narrow=2).items():
+            be.tune(k, v)
+        X2, i2 = P.newton_linear_step(be, case, ls="NS")
+        Rr, Vr, Xr, oref = refcase.reference_step(case, "NS")
+        assert rel_l2(X2, Xr) < TOL_SOL_LOOSE and abs(i2["RI"]["itr"] - int(oref["itr"])) <= 1
+    be.close()

@@ -243,3 +243,73 @@ def test_native_layout_equals_reference_on_random_partitions(nparts, seed):
         for (_, pa), (_, pb) in zip(lay["reqs"], info["reqs"]):
             assert (pa == pb).all()
     rr.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's own partition criterion (METIS dual graph) and the block-composed benchmark pipe
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nparts", [2, 3, 4, 8])
+def test_metis_dual_graph_partition_is_valid_and_balanced(nparts):
+    """b200_partition_metis (distribute.cpp:1683-1706: ncommonnodes = eNoNb): every element gets a part, parts are balanced
+    within METIS' default 3 % tolerance (+ slack for tiny meshes), the edge cut is far below a random assignment's, and the
+    FSILS layout (b200_lhs_layout_*) of the resulting irregular partition is consistent between neighbours."""
+    from svfsiplus_b200 import backend as B
+    from svfsiplus_b200 import mesh as M
+    m = M.pipe_mesh(12, 12, 24)
+    part, cut = B.partition_metis(m.ien, m.nNo, nparts, 3)
+    assert part.min() == 0 and part.max() == nparts - 1
+    cnt = np.bincount(part, minlength=nparts)
+    assert cnt.max() <= 1.06 * cnt.mean()
+    # faces between parts, counted independently: tets sharing 3 nodes
+    from collections import defaultdict
+    faces = defaultdict(list)
+    for e, el in enumerate(m.ien):
+        for tri in ((0, 1, 2), (0, 1, 3), (0, 2, 3), (1, 2, 3)):
+            faces[tuple(sorted(el[list(tri)]))].append(e)
+    mycut = sum(1 for v in faces.values() if len(v) == 2 and part[v[0]] != part[v[1]])
+    assert mycut == cut
+    inner = sum(1 for v in faces.values() if len(v) == 2)
+    assert cut < 0.25 * inner * (1.0 - 1.0 / nparts)
+    case = dict(mesh=m, Ag=np.zeros((m.nNo, 4)), Yg=np.zeros((m.nNo, 4)), Bf=np.zeros((m.nNo, 3)), props={}, faces=[], res=None, incL=None)
+    parts = PT.split_case(case, nparts, part)
+    lays = [PT.lhs_layout(r, [p["gNodes"] for p in parts], m.nNo) for r in range(nparts)]
+    for r, lay in enumerate(lays):
+        for peer, lst in lay["reqs"]:
+            back = dict(lays[peer]["reqs"])[r]
+            inv_r = np.empty(len(lay["map"]), np.int64); inv_r[lay["map"]] = np.arange(len(lay["map"]))
+            inv_p = np.empty(len(lays[peer]["map"]), np.int64); inv_p[lays[peer]["map"]] = np.arange(len(lays[peer]["map"]))
+            # the i-th entry of both lists is the same global node (fsils_commuv pairs them by position)
+            assert np.array_equal(parts[r]["gNodes"][inv_r[lst]], parts[peer]["gNodes"][inv_p[back]])
+
+
+def test_metis_partition_errors():
+    from svfsiplus_b200 import backend as B
+    with pytest.raises(RuntimeError, match="out of range"):
+        B.partition_metis(np.array([[0, 1, 2, 9]], np.int32), 4, 2, 3)
+
+
+def test_block_composed_pipe_is_identical_for_every_rank_count():
+    """bench.py's workload (partition.local_slab_case): the pipe is composed of 8 generation blocks, so the pieces 2, 4 and 8 ranks
+    hold are bit-identical restrictions of the mesh and state one rank holds - strong-scaling runs solve the same system."""
+    dims = (6, 6, 20)
+    p1, g1 = PT.local_slab_case(dims, 0, 1)
+    assert len(g1) == 1 and p1["mesh"].nNo == 7 * 7 * 21 and p1["mesh"].nEl == 6 * 6 * 6 * 20
+    from svfsiplus_b200 import mesh as M
+    assert (M.tet_volumes(p1["mesh"].x, p1["mesh"].ien) > 0).all()
+    for w in (2, 4, 8):
+        els = 0
+        for r in range(w):
+            pr, ag = PT.local_slab_case(dims, r, w)
+            g = pr["gNodes"]
+            assert np.array_equal(np.asarray(ag[r]), g)
+            for k in ("Ag", "Yg", "Bf"):
+                assert np.array_equal(pr[k], p1[k][g])
+            assert np.array_equal(pr["mesh"].x, p1["mesh"].x[g])
+            gi = g[pr["mesh"].ien]
+            assert np.array_equal(gi, p1["mesh"].ien[els:els + len(gi)])
+            els += len(gi)
+            for f, f1 in zip(pr["faces"], p1["faces"]):
+                assert set(g[f["nodes"]]) <= set(f1["nodes"])
+            if len(pr["faces"][2]["nodes"]):
+                assert np.array_equal(pr["faces"][2]["val"], p1["faces"][2]["val"])
+        assert els == p1["mesh"].nEl

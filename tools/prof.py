@@ -30,7 +30,7 @@ def peak():
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["tour", "step", "asm", "solid", "fluidgen"])
+    ap.add_argument("mode", choices=["tour", "tiled", "step", "asm", "solid", "fluidgen"])
     ap.add_argument("--dims", type=int, nargs=3, default=[96, 96, 181])
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--ls", default="NS")
@@ -84,6 +84,15 @@ def main():
                               ns_per_tet=1e6 * ms / case["mesh"].nEl)))
         return
     P.assemble(be, case)
+    if a.mode == "tiled":
+        # A/B of the TMA-staged row-tile kernels (k = 2) against the per-lane kernels on the same data
+        plan = [("spmv_vv3", 0), ("spmv_vv3", 1), ("spmv_vv3", 2), ("spmv_sv", 0), ("spmv_sv", 2), ("spmv_vs", 1), ("spmv_vs", 2),
+                ("spmv_ss", 0), ("spmv_ss", 2)]
+        for name, k in plan:
+            ms, by = be.op_bench(name, k=k, reps=a.reps)
+            print(json.dumps(dict(kernel=name, k=k, ms=ms, MB=by / 1e6, GBps=by / 1e6 / ms, frac=by / 1e6 / ms / pk)), flush=True)
+        be.close()
+        return
     if a.mode == "tour":
         plan = [("spmv_vv4", 0), ("spmv_vv3", 0), ("spmv_vv3", 1), ("spmv_ss", 0), ("spmv_sv", 0), ("spmv_sv", 1), ("spmv_vs", 0), ("spmv_vs", 1), ("multi_dot", 8),
                 ("multi_dot", 64), ("cgs_update_scale", 8), ("cgs_update_scale", 64), ("blas1", 0), ("scale_val", 0), ("depart", 0)]
