@@ -512,6 +512,168 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------------------------------
+# the other GPU configurations of BASELINE.json: configs[3] (struct / ustruct hyperelastic block compression) and configs[4]
+# (FSI pipe: fluid + struct domains in one block system).  One GPU; under torchrun every rank runs an independent replica
+# ("replicas only": these lines have no partitioned variant yet) and the value is the sum.
+# ---------------------------------------------------------------------------------------------------------------------------
+WORKLOADS = {
+    # name: (description, default size)
+    "struct_block": ("struct equation, neo-Hookean ST91 block compression (tests/cases/struct/block_compression/solver.xml: "
+                     "BICG 1e-12 / 600), HEX8 n^3", 160),
+    "ustruct_block": ("ustruct equation, P1-P1 VMS neo-Hookean block compression (tests/cases/ustruct/block_compression/P1P1_VMS/"
+                      "solver.xml: GMRES), TET4 6 n^3, with ustruct_r", 100),
+    "fsi_pipe": ("FSI equation of tests/cases/fsi/pipe_3d scaled up: fluid lumen on the ALE configuration + neo-Hookean wall in one "
+                 "dof-4 block system (GMRES 1e-12 / 100 x 50), TET4 pipe", 0),
+}
+
+
+def run_gpu_workload(args):
+    import torch
+    from svfsiplus_b200 import backend as B
+    from svfsiplus_b200 import problem as P
+
+    rank, world, local = _dist()
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    be = B.Backend(local)
+    pat = lambda n, ien: be.pattern(n, [ien])                         # lhsa on the device (b200_pattern_*)
+    wl = args.workload
+    n = args.size if args.size > 0 else WORKLOADS[wl][1]
+    t_setup = time.perf_counter()
+    if wl == "struct_block":
+        case = P.block_case(n, elem="hex", kind="struct", pattern=pat)
+        ls_name, dof = "BICGS_STRUCT", 3
+        asm = lambda up: P.assemble_solid(be, case, upload=up)
+        ref_step = lambda c: __import__("oracle.refcase", fromlist=["x"]).reference_solid_step(c, ls_name)
+        small = lambda: P.block_case(args.ref_size or 20, elem="hex", kind="struct")
+        size_txt = f"{n}^3 HEX8"
+    elif wl == "ustruct_block":
+        case = P.ustruct_case(n, elem="tet", pattern=pat)
+        ls_name, dof = "GMRES_USTRUCT", 4
+        asm = lambda up: P.assemble_ustruct(be, case, upload=up, with_r=True)
+        ref_step = lambda c: __import__("oracle.refcase", fromlist=["x"]).reference_ustruct_step(c, ls_name)
+        small = lambda: P.ustruct_case(args.ref_size or 14, elem="tet")
+        size_txt = f"6 x {n}^3 TET4"
+    else:
+        dims = tuple(args.dims)
+        case = P.fsi_case(*dims, pattern=pat)
+        ls_name, dof = "GMRES_FSI", 4
+        asm = lambda up: P.assemble_fsi(be, case, upload=up)
+        ref_step = lambda c: __import__("oracle.refcase", fromlist=["x"]).reference_fsi_step(c, ls_name)
+        small = lambda: P.fsi_case(12, 12, 24)
+        size_txt = f"pipe {dims[0]}x{dims[1]}x{dims[2]} TET4"
+    be = P.setup_backend(case, device=local, be=be)
+    nEl, nNo = int(case["mesh"].nEl), int(be.nNo)
+    t_setup = time.perf_counter() - t_setup
+    ls_type, RI, GM, CG = P.LS_SETTINGS[ls_name]
+    # pinned host copies of the per-step inputs for the end-to-end leg (the case dict then points at pinned memory)
+    h2d = 0
+    for k in ("Ag", "Yg", "Dg", "Bf", "Ad"):
+        if k in case and case[k] is not None:
+            t = torch.from_numpy(np.ascontiguousarray(case[k])).pin_memory()
+            case[k] = t.numpy()
+            case["_pin_" + k] = t
+            h2d += t.numel() * 8
+    out_pin = torch.empty((nNo, dof), dtype=torch.float64).pin_memory()
+
+    def step(upload):
+        asm(upload)
+        _, inf = be.solve(ls_type, B.PREC_FSILS, RI, GM, CG, case["incL"], case["res"], out=out_pin.data_ptr() if upload else None,
+                          fetch=upload)
+        return inf
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, nsteps):
+        barrier()
+        be.timer_start()
+        inf = None
+        for _ in range(nsteps):
+            inf = fn()
+        ms = be.timer_stop()
+        barrier()
+        return ms / nsteps, inf
+
+    step(True)
+    for _ in range(max(args.warmup - 1, 2)):
+        step(False)
+    be.profile(True)
+    prof_ms, _ = timed(lambda: step(False), 1)
+    prof = be.profile_read()
+    be.profile(False)
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    be.profile(2 + B.KERNEL_CLASSES.index(dom))
+    l0 = be.launch_count()
+    ms_per_step, info = timed(lambda: step(False), args.steps)
+    launches = be.launch_count() - l0
+    dom_live = be.profile_read()[dom]
+    be.profile(False)
+    e2e_ms, _ = timed(lambda: step(True), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    # assembly alone (whole-mesh element kernel + ordered sums), resident inputs
+    asm_ms, _ = timed(lambda: asm(False), max(3, args.steps))
+    if world > 1:
+        t = torch.tensor([ms_per_step, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = _peaks()
+    achieved = (dom_live["bytes"] / 1e9) / (dom_live["ms"] * 1e-3) if dom_live["ms"] > 0 else 0.0
+    line = {
+        "metric": f"Newton-iters/s, {wl}", "value": world * 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{wl}: {WORKLOADS[wl][0]}; {size_txt} = {nEl} elements, one Newton iteration (ls_alloc + whole-mesh "
+                               f"assembly + fsils_solve LS {ls_name})", "ls": ls_name,
+                   "parallelism": "replicas only" if world > 1 else "dd1",
+                   "l2": "inputs larger than L2 (Val >> 126 MB): no flush between iterations"},
+        "run": {"nEl": nEl, "nNo": nNo, "nnz_blocks": int(be.nnz), "dof": dof, "krylov_itr": info["RI"]["itr"], "suc": info["RI"]["suc"],
+                "iNorm": info["RI"]["iNorm"], "fNorm": info["RI"]["fNorm"], "setup_s": t_setup},
+        "e2e": {"value": world * 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(nNo * dof * 8),
+                "ms_per_step": e2e_ms},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "share_of_step": dom_live["ms"] / (ms_per_step * args.steps),
+                     "launches": dom_live["launches"], "bytes_per_launch": dom_live["bytes"] / max(dom_live["launches"], 1)},
+        "kernel_shares": {k: round(v["ms"] / prof_ms, 4) for k, v in prof.items() if v["ms"] > 0},
+        "kernels": {k: {"ms_per_launch": v["ms"] / max(v["launches"], 1), "launches_per_step": v["launches"],
+                        "GBps": (v["bytes"] / 1e9) / (v["ms"] * 1e-3) if v["ms"] > 0 else None} for k, v in prof.items() if v["launches"] > 0},
+        "assembly": {"ms": asm_ms, "ns_per_element": 1e6 * asm_ms / nEl, "share_of_step": asm_ms / ms_per_step},
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import ref
+            if ref.available():
+                c = small()
+                t0 = time.perf_counter()
+                out = ref_step(c)
+                w = time.perf_counter() - t0
+                sc = c["mesh"].nEl / float(nEl)
+                line["cpu_baseline"] = {"value": sc / w, "unit": UNIT, "cores": 1, "kind": "reference", "extrapolated": True,
+                                        "sample": f"{c['name']}: {c['mesh'].nEl} elements ({100 * sc:.3f}% of the workload), the compiled "
+                                                  f"reference's construct_* + fsils_solve {ls_name} on one core, {w:.2f} s, itr "
+                                                  f"{int(out[-1]['itr'])}; iters/s scaled by the element ratio (optimistic for the CPU)"}
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     # NCCL prints its banner / log to STDOUT; stdout must carry one JSON line, so the log is routed to stderr (nothing is
     # suppressed: NCCL_DEBUG keeps whatever level the caller asked for)
@@ -527,9 +689,21 @@ def main():
     ap.add_argument("--ref-dims", type=int, nargs=3, default=[32, 32, 64], help="bounded CPU sample of the workload")
     ap.add_argument("--ref-ranks", type=int, default=0, help="ranks (threads) of the reference arm; 0 = min(host cores, 16, layers/2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="ns_pipe", choices=["ns_pipe"] + sorted(WORKLOADS),
+                    help="ns_pipe = the headline metric (configs[1]/[2]); the others are BASELINE.json configs[3] and configs[4]")
+    ap.add_argument("--size", type=int, default=0, help="elements per edge of the block workloads (default: the workload's own)")
+    ap.add_argument("--ref-size", type=int, default=0, help="elements per edge of the CPU sample of the block workloads")
     ap.add_argument("--prof-steps", type=int, default=1, help="extra steps run with per-kernel CUDA events (shares, roofline)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload != "ns_pipe":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference arm is implemented for the headline workload ns_pipe only; "
+                              "the other workloads carry their CPU sample in cpu_baseline"}))
+            return
+        if args.workload == "fsi_pipe" and args.dims == list(P10):
+            args.dims = [64, 64, 128]
+        run_gpu_workload(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)

@@ -135,9 +135,10 @@ def newton_linear_step(be: B.Backend, case, ls="NS", want_system=False, upload=T
 # solid block (tests/cases/struct/block_compression/solver.xml: neo-Hookean, E 240.56596e6, nu 0.5, ST91
 # penalty 4e9, density 1000, dt 1e-4, rho_inf 0.5; X0/Y0/Z0 Dirichlet in one direction each)
 # ---------------------------------------------------------------------------------------------------
-def block_case(n, elem="hex", kind="struct", iso="nHook", vol="ST91", jitter=0.1, visc=None, visc_mu=0.0, prestress=False):
+def block_case(n, elem="hex", kind="struct", iso="nHook", vol="ST91", jitter=0.1, visc=None, visc_mu=0.0, prestress=False, pattern=None):
+    """pattern: optional callable (nNo, ien) -> (rowPtr, colPtr), e.g. the device-side lhsa (Backend.pattern)."""
     m = M.block_mesh(n, elem=elem, jitter=jitter)
-    rowPtr, colPtr = M.csr_pattern(m.ien, m.nNo)
+    rowPtr, colPtr = pattern(m.nNo, m.ien) if pattern else M.csr_pattern(m.ien, m.nNo)
     am, af, gam, beta = M.gen_alpha2(0.5)
     Ag, Yg, Dg, Bf = M.block_state(m)
     E, nu = 240.56596e6, 0.5
@@ -236,9 +237,9 @@ def solid_linear_step(be: B.Backend, case, ls="BICGS_STRUCT", want_system=False,
 # FSI pipe (tests/cases/fsi/pipe_3d/solver.xml): lumen = fluid domain, outer shell of the same structured
 # pipe = struct domain (neo-Hookean wall), one dof-4 matrix, tDof = 7 (FSI unknowns 0..3, mesh 4..6)
 # ---------------------------------------------------------------------------------------------------
-def fsi_case(nx, ny, nz, *, wall_from=0.8, radius=1.0, length=10.0):
+def fsi_case(nx, ny, nz, *, wall_from=0.8, radius=1.0, length=10.0, pattern=None):
     m = M.pipe_mesh(nx, ny, nz, radius=radius, length=length)
-    rowPtr, colPtr = M.csr_pattern(m.ien, m.nNo)
+    rowPtr, colPtr = pattern(m.nNo, m.ien) if pattern else M.csr_pattern(m.ien, m.nNo)
     am, af, gam = M.gen_alpha(0.5)                 # FSI is a first-order equation (initialize.cpp:424-433)
     beta = 0.25 * (1.0 + am - af) ** 2
     dt = 1e-4
@@ -324,9 +325,9 @@ def fsi_linear_step(be: B.Backend, case, ls="GMRES_FSI", want_system=False):
 # ustruct block (tests/cases/ustruct/block_compression/P1P1_VMS/solver.xml: neo-Hookean, E 240.56596e6,
 # nu 0.4999999, ST91, density 1e-3, stabilisation coefficients 1e-3, first-order generalised-alpha)
 # ---------------------------------------------------------------------------------------------------
-def ustruct_case(n, elem="tet", vol="ST91", iso="nHook", visc=None, visc_mu=0.0):
+def ustruct_case(n, elem="tet", vol="ST91", iso="nHook", visc=None, visc_mu=0.0, pattern=None):
     m = M.block_mesh(n, elem=elem)
-    rowPtr, colPtr = M.csr_pattern(m.ien, m.nNo)
+    rowPtr, colPtr = pattern(m.nNo, m.ien) if pattern else M.csr_pattern(m.ien, m.nNo)
     am, af, gam = M.gen_alpha(0.5)
     E, nu = 240.56596e6, 0.4999999
     mu = 0.5 * E / (1.0 + nu)

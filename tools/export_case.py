@@ -173,7 +173,61 @@ BLOCK_XML = """<?xml version="1.0" encoding="UTF-8" ?>
 """
 
 
-def export_block(out, n, elem="hex", steps=1, mode=IO.APPENDED_RAW, linear_algebra="fsils"):
+USTRUCT_XML = """<?xml version="1.0" encoding="UTF-8" ?>
+<svMultiPhysicsFile version="0.1">
+<GeneralSimulationParameters>
+  <Continue_previous_simulation> 0 </Continue_previous_simulation>
+  <Number_of_spatial_dimensions> 3 </Number_of_spatial_dimensions>
+  <Number_of_time_steps> {steps} </Number_of_time_steps>
+  <Time_step_size> 0.01 </Time_step_size>
+  <Spectral_radius_of_infinite_time_step> 0.50 </Spectral_radius_of_infinite_time_step>
+  <Searched_file_name_to_trigger_stop> STOP_SIM </Searched_file_name_to_trigger_stop>
+  <Save_results_to_VTK_format> 1 </Save_results_to_VTK_format>
+  <Name_prefix_of_saved_VTK_files> result </Name_prefix_of_saved_VTK_files>
+  <Increment_in_saving_VTK_files> {steps} </Increment_in_saving_VTK_files>
+  <Start_saving_after_time_step> 1 </Start_saving_after_time_step>
+  <Increment_in_saving_restart_files> 100 </Increment_in_saving_restart_files>
+  <Convert_BIN_to_VTK_format> 0 </Convert_BIN_to_VTK_format>
+  <Verbose> 1 </Verbose>
+  <Warning> 0 </Warning>
+  <Debug> 0 </Debug>
+</GeneralSimulationParameters>
+<Add_mesh name="msh" >
+  <Mesh_file_path> mesh/mesh-complete.mesh.vtu </Mesh_file_path>
+{faces}</Add_mesh>
+<Add_equation type="ustruct" >
+  <Coupled> true </Coupled>
+  <Min_iterations> 3 </Min_iterations>
+  <Max_iterations> 5 </Max_iterations>
+  <Tolerance> 1e-12 </Tolerance>
+  <Constitutive_model type="nHK"> </Constitutive_model>
+  <Density> 1e-3 </Density>
+  <Elasticity_modulus> 240.56596e6 </Elasticity_modulus>
+  <Poisson_ratio> 0.4999999 </Poisson_ratio>
+  <Dilational_penalty_model> ST91 </Dilational_penalty_model>
+  <Momentum_stabilization_coefficient> 1e-3 </Momentum_stabilization_coefficient>
+  <Continuity_stabilization_coefficient> 1e-3 </Continuity_stabilization_coefficient>
+  <Output type="Spatial" > <Displacement> true </Displacement> <Velocity> true </Velocity> <Pressure> true </Pressure> </Output>
+  <LS type="GMRES" >
+    {linear_algebra}
+    <Tolerance> 1e-12 </Tolerance>
+    <Max_iterations> 100 </Max_iterations>
+    <Krylov_space_dimension> 300 </Krylov_space_dimension>
+  </LS>
+  <Add_BC name="X0" > <Type> Dir </Type> <Value> 0.0 </Value> <Effective_direction> (1, 0, 0) </Effective_direction>
+    <Impose_on_state_variable_integral> true </Impose_on_state_variable_integral> </Add_BC>
+  <Add_BC name="Y0" > <Type> Dir </Type> <Value> 0.0 </Value> <Effective_direction> (0, 1, 0) </Effective_direction>
+    <Impose_on_state_variable_integral> true </Impose_on_state_variable_integral> </Add_BC>
+  <Add_BC name="Z0" > <Type> Dir </Type> <Value> 0.0 </Value> <Effective_direction> (0, 0, 1) </Effective_direction>
+    <Impose_on_state_variable_integral> true </Impose_on_state_variable_integral> </Add_BC>
+  <Add_BC name="Z1" > <Type> Neu </Type> <Time_dependence> Steady </Time_dependence> <Value> 5.0e6 </Value>
+    <Follower_pressure_load> {follower} </Follower_pressure_load> </Add_BC>
+</Add_equation>
+</svMultiPhysicsFile>
+"""
+
+
+def export_block(out, n, elem="hex", steps=1, mode=IO.APPENDED_RAW, linear_algebra="fsils", phys="struct", follower=True):
     """The solid block of SURVEY 8(d) (n^3 HEX8, its 6-tet split, or the quadratic split) in the layout of the reference's
     tests/cases/struct/block_compression: volume mesh, the six faces X0..Z1 (QUD4 / TRI3 / TRI6), a struct solver.xml."""
     m = M.block_mesh(n, elem)
@@ -196,7 +250,11 @@ def export_block(out, n, elem="hex", steps=1, mode=IO.APPENDED_RAW, linear_algeb
         info["faces"][name] = (len(nodes), len(gE), IENb.shape[1])
         xml_faces += f'  <Add_face name="{name}"> <Face_file_path> mesh/mesh-surfaces/{name}.vtp </Face_file_path> </Add_face>\n'
     with open(os.path.join(out, "solver.xml"), "w") as f:
-        f.write(BLOCK_XML.format(steps=steps, faces=xml_faces, linear_algebra=LINEAR_ALGEBRA[linear_algebra]))
+        if phys == "ustruct":        # tests/cases/ustruct/block_compression/P1P1_VMS/solver.xml (steady load instead of the ramp file)
+            f.write(USTRUCT_XML.format(steps=steps, faces=xml_faces, linear_algebra=LINEAR_ALGEBRA[linear_algebra],
+                                       follower="true" if follower else "false"))
+        else:
+            f.write(BLOCK_XML.format(steps=steps, faces=xml_faces, linear_algebra=LINEAR_ALGEBRA[linear_algebra]))
     return info
 
 
