@@ -81,8 +81,11 @@ __device__ __forceinline__ double ld_peer_written(const double* p)
   asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long epoch)
+// once a wait has timed out (ps->error set) later waits do not spin again: the solve finishes quickly with garbage and the host
+// raises the error (CudaOps::peer_check) instead of the GPU sitting in 4-second waits for the rest of the solve
+__device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long epoch, const PeerState* ps)
 {
+  if (*reinterpret_cast<const volatile int*>(&ps->error) != 0) return false;
   const long long t0 = clock64();
   while (ld_acquire_sys(flag) < epoch) {
     if (clock64() - t0 > kSpinLimit) return false;
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(PeerRedArgs a, PeerState
     st_release_sys(reinterpret_cast<unsigned long long*>(a.win[p] + PeerLayout::red_flag_off) + par*kPeerMaxRanks + a.rank, epoch);
     // 2. wait for rank p's partials to arrive in OUR mailbox
     const unsigned long long* f = reinterpret_cast<const unsigned long long*>(a.win[a.rank] + PeerLayout::red_flag_off) + par*kPeerMaxRanks + p;
-    if (!spin_until(f, epoch)) s_ok = 0;
+    if (!spin_until(f, epoch, ps)) s_ok = 0;
   }
   __syncthreads();
   // 3. rank-ordered reduction: bit-identical on every rank
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(256) k_halo_wait_add(int nreq, const PeerHaloR
   if (threadIdx.x == 0) s_ok = 1;
   __syncthreads();
   if (threadIdx.x < nreq) {
-    if (!spin_until(reqs[threadIdx.x].lflag + par*kPeerMaxReq, epoch)) s_ok = 0;
+    if (!spin_until(reqs[threadIdx.x].lflag + par*kPeerMaxReq, epoch, ps)) s_ok = 0;
   }
   __syncthreads();
   const int total = nh*dof;
