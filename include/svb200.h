@@ -304,7 +304,10 @@ int b200_spmv(b200_handle* h, int dof, const double* x, double* y);
  * b200_profile_read) on device-resident data with CUDA events on the launch stream, after 3 warm-up
  * launches (none when reps == 1, for profiler captures); returns mean milliseconds and the ALGORITHMIC bytes per launch.  Needs an assembled dof-4
  * system.  NS shapes (1-4, 9) run on the departed matrix; 3 / 4 are the two passes of the fused Schur
- * operator; k = number of basis vectors for multi_dot (5) and cgs_update_scale (6) on dof-3 vectors. */
+ * operator; k = number of basis vectors for multi_dot (5) and cgs_update_scale (6) on dof-3 vectors; for the SpMV shapes k selects
+ * the kernel variant (see b200_tune).  op 100 = the FP64 FMA peak micro-kernel (needs no system): k x 1024 dependent DFMAs in 8
+ * independent chains per thread, `bytes_per_launch` then returns the FLOPs of one launch - the roofline denominator of the element
+ * kernels. */
 int b200_op_bench(b200_handle* h, int op, int k, int reps, double* ms_per_launch, double* bytes_per_launch);
 /* Kernel-launch counter (all kernels this handle launched since creation). */
 long long b200_launch_count(b200_handle* h);

@@ -623,6 +623,11 @@ class Backend:
         self._ck(self.L.b200_op_bench(self.h, op, k, reps, C.byref(ms), C.byref(by)), "b200_op_bench")
         return ms.value, by.value
 
+    def fp64_peak(self, k=16, reps=5):
+        """FP64 FMA peak of the device in TFLOP/s (k_fma_peak: 8 independent DFMA chains per thread, 148 x 8 CTAs)."""
+        ms, flops = self.op_bench(100, k=k, reps=reps)
+        return flops / (ms * 1e-3) / 1e12
+
     def tune(self, name, value):
         """Kernel-variant knob (b200_tune): 'vv3', 'schur_gp', 'schur_sp', 'narrow', 'cg_batch'."""
         self.L.b200_tune.argtypes = [C.c_void_p, C.c_char_p, C.c_int]

@@ -2019,8 +2019,28 @@ int b200_op_bench(b200_handle* h, int op, int k, int reps, double* ms_per_launch
 {
   return guarded(h, [&] {
     auto& ops = *h->ops;
-    if (!h->Val || h->dof != 4) throw std::runtime_error("op_bench: needs an assembled dof-4 system on the device");
     if (reps < 1) throw std::runtime_error("op_bench: reps must be positive");
+    if (op == 100) {
+      // FP64 FMA peak of this GPU (no matrix needed): `bytes_per_launch` returns the FLOPs of one launch
+      const int iters = std::max(1, k) * 1024, blocks = kSmCount*8;
+      auto mk0 = ops.mark();
+      double* out = ops.vec(size_t(blocks)*256);
+      cudaEvent_t e0, e1;
+      CU_CHECK(cudaEventCreate(&e0)); CU_CHECK(cudaEventCreate(&e1));
+      k_fma_peak<<<blocks, 256, 0, ops.st>>>(iters, 0.999999, 1e-9, out); ops.post();
+      CU_CHECK(cudaEventRecord(e0, ops.st));
+      for (int i = 0; i < reps; i++) { k_fma_peak<<<blocks, 256, 0, ops.st>>>(iters, 0.999999, 1e-9, out); ops.post(); }
+      CU_CHECK(cudaEventRecord(e1, ops.st));
+      CU_CHECK(cudaEventSynchronize(e1));
+      float ms = 0;
+      CU_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+      if (ms_per_launch) *ms_per_launch = double(ms)/reps;
+      if (bytes_per_launch) *bytes_per_launch = double(blocks)*256.0*double(iters)*16.0;
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+      ops.release(mk0);
+      return;
+    }
+    if (!h->Val || h->dof != 4) throw std::runtime_error("op_bench: needs an assembled dof-4 system on the device");
     flush_staged(h);
     const size_t nNo = size_t(h->nNo), nnz = size_t(h->nnz);
     auto mk = ops.mark();

@@ -58,6 +58,20 @@ __device__ __forceinline__ double ld_stream(const double* p)
   asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
   return v;
 }
+// scalar forms of the two cache policies of the dof-4 kernel: matrix entries are read once per product (evict first),
+// gathered vector entries are re-used by ~15 rows and by the next kernel of the Krylov step (evict last)
+__device__ __forceinline__ double ld_stream_ef(const double* p)
+{
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_keep(const double* p)
+{
+  double v;
+  asm volatile("ld.global.nc.L2::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ int ld_stream_i(const int* p)
 {
   int v;
@@ -114,7 +128,7 @@ k_spmv_vv4(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr
 
 // Generic small-dof variant (dof 1..3; mK of the NS solver is dof 3: 72-byte blocks).  4 lanes per
 // row, lane i < DOF owns component i.
-template <int DOF>
+template <int DOF, bool HINT = false>
 __global__ void __launch_bounds__(256)
 k_spmv_vv(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
           const double* __restrict__ K, const double* __restrict__ U, double* __restrict__ KU)
@@ -130,12 +144,12 @@ k_spmv_vv(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr,
       double acc = 0.0;
 #pragma unroll 4
       for (int p = s; p < e; p++) {
-        const int c = __ldg(col + p);
+        const int c = HINT ? ld_stream_i(col + p) : __ldg(col + p);
         const double* k = K + (size_t(p)*DOF*DOF + lane4*DOF);
         const double* u = U + size_t(c)*DOF;
         double t = acc;
 #pragma unroll
-        for (int j = 0; j < DOF; j++) t = t + __ldg(k + j)*__ldg(u + j);
+        for (int j = 0; j < DOF; j++) t = t + (HINT ? ld_stream_ef(k + j)*ld_keep(u + j) : __ldg(k + j)*__ldg(u + j));
         acc = t;
       }
       KU[size_t(row)*DOF + lane4] = acc;
@@ -172,6 +186,45 @@ k_spmv_vv3s(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPt
         a2 = a2 + (__ldg(k + 6)*u0 + __ldg(k + 7)*u1 + __ldg(k + 8)*u2);
       }
     }
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 2); a1 += __shfl_xor_sync(0xffffffffu, a1, 2); a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
+    if (row < nNo && lane4 < 3) KU[size_t(row)*3 + lane4] = (lane4 == 0) ? a0 : (lane4 == 1) ? a1 : a2;
+  }
+}
+
+// dof-3 variant with COLUMN-owner lanes: lane i < 3 of the quad loads the three words 3*jj + i (jj = 0..2) of every 3x3 block,
+// i.e. each load instruction of a quad reads 24 CONSECUTIVE bytes (one or two sectors) instead of three words 24 bytes apart, and
+// the lane needs only ONE gathered vector entry u_i per block (the quad's gather is again 24 consecutive bytes).  Lane i
+// accumulates the column-i contributions to the three outputs over the whole row; the quad adds the three partial 3-vectors once
+// per row in a fixed order.  L1 sector requests per block drop from ~11 (profiles/r01_tour_c_ncu_raw.csv) to ~6; the sum is
+// re-associated (columns outer, blocks inner), a rounding-level difference like the strided variants.
+__global__ void __launch_bounds__(256)
+k_spmv_vv3c(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
+            const double* __restrict__ K, const double* __restrict__ U, double* __restrict__ KU)
+{
+  if (skip && *skip) return;
+  const int lane4 = threadIdx.x & 3;
+  const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
+  const int ngroups = (gridDim.x*blockDim.x) >> 2;
+  const int nrounds = (nNo + ngroups - 1)/ngroups;
+  const int li = lane4 < 3 ? lane4 : 0;          // lane 3 idles on a duplicate of lane 0's addresses (its sums are discarded)
+  for (int r = 0; r < nrounds; r++) {
+    const int row = group + r*ngroups;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    if (row < nNo) {
+      const int s = __ldg(rowPtr + row);
+      const int e = __ldg(rowPtr + row + 1);
+#pragma unroll 4
+      for (int p = s; p < e; p++) {
+        const int c = ld_stream_i(col + p);
+        const double* k = K + size_t(p)*9 + li;
+        const double u = ld_keep(U + size_t(c)*3 + li);
+        a0 = fma(ld_stream_ef(k), u, a0);
+        a1 = fma(ld_stream_ef(k + 3), u, a1);
+        a2 = fma(ld_stream_ef(k + 6), u, a2);
+      }
+    }
+    if (lane4 == 3) { a0 = 0.0; a1 = 0.0; a2 = 0.0; }
     a0 += __shfl_xor_sync(0xffffffffu, a0, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
     a0 += __shfl_xor_sync(0xffffffffu, a0, 2); a1 += __shfl_xor_sync(0xffffffffu, a1, 2); a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
     if (row < nNo && lane4 < 3) KU[size_t(row)*3 + lane4] = (lane4 == 0) ? a0 : (lane4 == 1) ? a1 : a2;
@@ -1020,6 +1073,19 @@ __global__ void k_halo_add(int n, int dof, int ld, const int* __restrict__ ptr, 
     const int j = t / dof, l = t % dof;
     V[size_t(ptr[j])*ld + l] += buf[t];
   }
+}
+
+// ---- FP64 pipe peak: the roofline denominator of the element kernels (BASELINE.md par. 2) ---------------------------------
+// 8 independent DFMA chains per thread, `iters` x 8 x 2 flops each; the result is stored so that nothing is optimised away.
+__global__ void __launch_bounds__(256) k_fma_peak(int iters, double a, double b, double* __restrict__ out)
+{
+  double x0 = threadIdx.x*1e-3, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+#pragma unroll 4
+  for (int i = 0; i < iters; i++) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[size_t(blockIdx.x)*blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
 // ---- staged element scatter (LinearAlgebra::assemble path; lhsa.cpp:97-142) -----------------------

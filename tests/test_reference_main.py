@@ -119,8 +119,10 @@ def test_ustruct_block_through_solver_xml(tmp_path, follower):
     pic::picc reads com_mod.Rd (pic.cpp:92,139) - which the plug-in therefore has to fill on the first Newton iteration.  With
     `follower` the Z1 load is a follower pressure load (set_bc_neu_l -> assemble_follower_face)."""
     steps = 2
-    # GMRES at 1e-12 with restarts of 300 on this system takes 150-500 iterations per Newton step in the reference itself; the totals
-    # are rounding-sensitive, so the linear iteration counts are compared at 5 % and the parity statement is the result file
+    # The reference case asks GMRES for 1e-12 on this system, which it cannot reach before rounding takes over: the reference ITSELF
+    # then needs 242 / 238 / 477 iterations for the first three Newton steps in the build container and 316 / ... on the GPU box's
+    # CPU - counts in that regime are not reproducible between two machines, let alone two implementations.  The exported case
+    # therefore asks for 1e-6 (Newton still converges quadratically to 1e-14), where the counts are stable, and compares them at 3 %.
     _need()
     ex = _export()
     a, b = tmp_path / "fsils", tmp_path / "b200"
@@ -134,4 +136,4 @@ def test_ustruct_block_through_solver_xml(tmp_path, follower):
     ha, hb = history(a / "1-procs" / "histor.dat"), history(b / "1-procs" / "histor.dat")
     assert [(x["ts"], x["it"], x["conv"]) for x in ha] == [(x["ts"], x["it"], x["conv"]) for x in hb]
     for x, y in zip(ha, hb):
-        assert abs(x["lsit"] - y["lsit"]) <= max(2, 0.05 * x["lsit"]), (x, y)
+        assert abs(x["lsit"] - y["lsit"]) <= max(2, 0.03 * x["lsit"]), (x, y)

@@ -210,7 +210,7 @@ USTRUCT_XML = """<?xml version="1.0" encoding="UTF-8" ?>
   <Output type="Spatial" > <Displacement> true </Displacement> <Velocity> true </Velocity> <Pressure> true </Pressure> </Output>
   <LS type="GMRES" >
     {linear_algebra}
-    <Tolerance> 1e-12 </Tolerance>
+    <Tolerance> {ls_tol} </Tolerance>
     <Max_iterations> 100 </Max_iterations>
     <Krylov_space_dimension> 300 </Krylov_space_dimension>
   </LS>
@@ -227,7 +227,7 @@ USTRUCT_XML = """<?xml version="1.0" encoding="UTF-8" ?>
 """
 
 
-def export_block(out, n, elem="hex", steps=1, mode=IO.APPENDED_RAW, linear_algebra="fsils", phys="struct", follower=True):
+def export_block(out, n, elem="hex", steps=1, mode=IO.APPENDED_RAW, linear_algebra="fsils", phys="struct", follower=True, ls_tol="1e-6"):
     """The solid block of SURVEY 8(d) (n^3 HEX8, its 6-tet split, or the quadratic split) in the layout of the reference's
     tests/cases/struct/block_compression: volume mesh, the six faces X0..Z1 (QUD4 / TRI3 / TRI6), a struct solver.xml."""
     m = M.block_mesh(n, elem)
@@ -252,7 +252,7 @@ def export_block(out, n, elem="hex", steps=1, mode=IO.APPENDED_RAW, linear_algeb
     with open(os.path.join(out, "solver.xml"), "w") as f:
         if phys == "ustruct":        # tests/cases/ustruct/block_compression/P1P1_VMS/solver.xml (steady load instead of the ramp file)
             f.write(USTRUCT_XML.format(steps=steps, faces=xml_faces, linear_algebra=LINEAR_ALGEBRA[linear_algebra],
-                                       follower="true" if follower else "false"))
+                                       follower="true" if follower else "false", ls_tol=ls_tol))
         else:
             f.write(BLOCK_XML.format(steps=steps, faces=xml_faces, linear_algebra=LINEAR_ALGEBRA[linear_algebra]))
     return info
