@@ -59,17 +59,30 @@ __device__ __forceinline__ double ld_stream(const double* p)
   return v;
 }
 // scalar forms of the two cache policies of the dof-4 kernel: matrix entries are read once per product (evict first),
-// gathered vector entries are re-used by ~15 rows and by the next kernel of the Krylov step (evict last)
-__device__ __forceinline__ double ld_stream_ef(const double* p)
+// gathered vector entries are re-used by ~15 rows and by the next kernel of the Krylov step (evict last).  Below 256 bits the
+// L2 eviction priority cannot be named in the instruction: it is passed as a cache-policy operand (createpolicy).
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ double ld_hint(const double* p, uint64_t pol)
 {
   double v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
   return v;
 }
-__device__ __forceinline__ double ld_keep(const double* p)
+__device__ __forceinline__ double ld_hint_na(const double* p, uint64_t pol)      // + no L1 allocation (streamed once)
 {
   double v;
-  asm volatile("ld.global.nc.L2::evict_last.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
   return v;
 }
 __device__ __forceinline__ int ld_stream_i(const int* p)
@@ -137,6 +150,7 @@ k_spmv_vv(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr,
   const int lane4 = threadIdx.x & 3;
   const int group = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
   const int ngroups = (gridDim.x*blockDim.x) >> 2;
+  const uint64_t pol_k = HINT ? l2_policy_evict_first() : 0, pol_u = HINT ? l2_policy_evict_last() : 0;
   for (int row = group; row < nNo; row += ngroups) {
     const int s = __ldg(rowPtr + row);
     const int e = __ldg(rowPtr + row + 1);
@@ -149,7 +163,7 @@ k_spmv_vv(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr,
         const double* u = U + size_t(c)*DOF;
         double t = acc;
 #pragma unroll
-        for (int j = 0; j < DOF; j++) t = t + (HINT ? ld_stream_ef(k + j)*ld_keep(u + j) : __ldg(k + j)*__ldg(u + j));
+        for (int j = 0; j < DOF; j++) t = t + (HINT ? ld_hint_na(k + j, pol_k)*ld_hint(u + j, pol_u) : __ldg(k + j)*__ldg(u + j));
         acc = t;
       }
       KU[size_t(row)*DOF + lane4] = acc;
@@ -208,6 +222,7 @@ k_spmv_vv3c(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPt
   const int ngroups = (gridDim.x*blockDim.x) >> 2;
   const int nrounds = (nNo + ngroups - 1)/ngroups;
   const int li = lane4 < 3 ? lane4 : 0;          // lane 3 idles on a duplicate of lane 0's addresses (its sums are discarded)
+  const uint64_t pol_k = l2_policy_evict_first(), pol_u = l2_policy_evict_last();
   for (int r = 0; r < nrounds; r++) {
     const int row = group + r*ngroups;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
@@ -218,10 +233,10 @@ k_spmv_vv3c(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPt
       for (int p = s; p < e; p++) {
         const int c = ld_stream_i(col + p);
         const double* k = K + size_t(p)*9 + li;
-        const double u = ld_keep(U + size_t(c)*3 + li);
-        a0 = fma(ld_stream_ef(k), u, a0);
-        a1 = fma(ld_stream_ef(k + 3), u, a1);
-        a2 = fma(ld_stream_ef(k + 6), u, a2);
+        const double u = ld_hint(U + size_t(c)*3 + li, pol_u);
+        a0 = fma(ld_hint_na(k, pol_k), u, a0);
+        a1 = fma(ld_hint_na(k + 3, pol_k), u, a1);
+        a2 = fma(ld_hint_na(k + 6, pol_k), u, a2);
       }
     }
     if (lane4 == 3) { a0 = 0.0; a1 = 0.0; a2 = 0.0; }
