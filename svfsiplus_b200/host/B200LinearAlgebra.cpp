@@ -10,6 +10,8 @@
 #include "fft.h"
 #include "utils.h"
 
+#include <cstdlib>
+#include <iostream>
 #include <stdexcept>
 #include <vector>
 
@@ -26,9 +28,17 @@ B200LinearAlgebra::B200LinearAlgebra()
   preconditioner_type = consts::PreconditionerType::PREC_FSILS;
 }
 
+// The reference never deletes eq.linear_algebra, so the totals are printed when the process exits (or by the destructor when an
+// owner does delete the object).
+namespace {
+std::vector<B200LinearAlgebra*>& live_instances() { static std::vector<B200LinearAlgebra*> v; return v; }
+void report_at_exit() { for (auto* p : live_instances()) if (p) p->report(); }
+}
+
 B200LinearAlgebra::~B200LinearAlgebra()
 {
-  if (h_) b200_destroy(h_);
+  for (auto& p : live_instances()) if (p == this) p = nullptr;
+  if (h_) { report(); b200_destroy(h_); }
 }
 
 void B200LinearAlgebra::check(int rc, const char* what)
@@ -90,6 +100,8 @@ void B200LinearAlgebra::initialize(ComMod& com_mod, eqType& lEq)
   if (b200_create(&h_, device_) != 0) {
     throw std::runtime_error(std::string("[B200LinearAlgebra] ") + b200_last_error(nullptr));
   }
+  if (live_instances().empty()) std::atexit(report_at_exit);
+  live_instances().push_back(this);
   // multi-rank: rank 0 creates the NCCL id, the solver's own communicator distributes it
   const int nranks = com_mod.cm.np();
   if (nranks > 1) {
@@ -165,7 +177,38 @@ void B200LinearAlgebra::upload_mesh(ComMod& com_mod, const mshType& lM)
   mesh_uploaded_ = &lM;
 }
 
+// Where the work ran: every routing decision of the three assembly hooks is counted, the first host fall-back of each kind is
+// announced once on stdout (a user must be able to tell a device-assembly run from a host-assembly run), and the destructor
+// prints the totals.
+void B200LinearAlgebra::note(int which, bool on_device, const std::string& what)
+{
+  (on_device ? stats_.device : stats_.host)[which]++;
+  if (!on_device && device_assembly_ && !(stats_.announced & (1u << which))) {
+    stats_.announced |= (1u << which);
+    std::cout << "[B200LinearAlgebra] " << what << ": no device kernel for this physics / element type / option -> the reference's "
+                 "host path runs for it (assembly on the host, solve on the GPU)" << std::endl;
+  }
+}
+
+void B200LinearAlgebra::report() const
+{
+  static const char* names[3] = {"whole-mesh assemblies", "Neumann faces", "follower-load faces"};
+  std::cout << "[B200LinearAlgebra] solves on the GPU: " << stats_.solves;
+  for (int i = 0; i < 3; i++)
+    if (stats_.device[i] + stats_.host[i] > 0)
+      std::cout << "; " << names[i] << ": " << stats_.device[i] << " on the GPU, " << stats_.host[i] << " on the host";
+  std::cout << std::endl;
+}
+
 bool B200LinearAlgebra::assemble_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag,
+    const Array<double>& Yg, const Array<double>& Dg, const CepMod* cep_mod)
+{
+  const bool ok = assemble_mesh_impl(com_mod, lM, Ag, Yg, Dg, cep_mod);
+  if (device_assembly_) note(0, ok, "equation " + com_mod.eq[com_mod.cEq].sym + ", mesh " + lM.name);
+  return ok;
+}
+
+bool B200LinearAlgebra::assemble_mesh_impl(ComMod& com_mod, const mshType& lM, const Array<double>& Ag,
     const Array<double>& Yg, const Array<double>& Dg, const CepMod* cep_mod)
 {
   using namespace consts;
@@ -346,6 +389,13 @@ bool B200LinearAlgebra::assemble_fsi_mesh(ComMod& com_mod, const mshType& lM, co
 /// use the Do that assemble_mesh uploaded with this iteration's state.
 bool B200LinearAlgebra::assemble_face(ComMod& com_mod, const faceType& lFa, const Vector<double>& hg, const Array<double>& Yg)
 {
+  const bool ok = assemble_face_impl(com_mod, lFa, hg, Yg);
+  if (device_assembly_) note(1, ok, "equation " + com_mod.eq[com_mod.cEq].sym + ", Neumann face " + lFa.name);
+  return ok;
+}
+
+bool B200LinearAlgebra::assemble_face_impl(ComMod& com_mod, const faceType& lFa, const Vector<double>& hg, const Array<double>& Yg)
+{
   using namespace consts;
   if (!device_assembly_ || !any_device_contribution_ || com_mod.nsd != 3) return false;
   auto& eq = com_mod.eq[com_mod.cEq];
@@ -388,6 +438,13 @@ bool B200LinearAlgebra::assemble_face(ComMod& com_mod, const faceType& lFa, cons
 
 /// Follower pressure load on the device (b_neu_folw_p, eq_assem.cpp:186) for a single-domain struct or ustruct equation.
 bool B200LinearAlgebra::assemble_follower_face(ComMod& com_mod, const faceType& lFa, const Vector<double>& hg, const Array<double>& Dg)
+{
+  const bool ok = assemble_follower_face_impl(com_mod, lFa, hg, Dg);
+  if (device_assembly_) note(2, ok, "equation " + com_mod.eq[com_mod.cEq].sym + ", follower-load face " + lFa.name);
+  return ok;
+}
+
+bool B200LinearAlgebra::assemble_follower_face_impl(ComMod& com_mod, const faceType& lFa, const Vector<double>& hg, const Array<double>& Dg)
 {
   using namespace consts;
   if (!device_assembly_ || !any_device_contribution_ || com_mod.nsd != 3 || com_mod.mvMsh) return false;
@@ -604,6 +661,7 @@ bool B200LinearAlgebra::assemble_domains_mesh(ComMod& com_mod, const mshType& lM
 /// the solution, like FsilsLinearAlgebra::solve.
 void B200LinearAlgebra::solve(ComMod& com_mod, eqType& lEq, const Vector<int>& incL, const Vector<double>& res)
 {
+  stats_.solves++;
   const int dof = com_mod.dof;
   auto& ls = lEq.FSILS;
   if (device_assembly_) {

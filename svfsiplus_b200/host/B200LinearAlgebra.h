@@ -69,11 +69,23 @@ class B200LinearAlgebra : public virtual LinearAlgebra {
     /// fsils_bc_update counterpart: re-upload the face vectors (moving meshes, follower loads).
     void update_faces(ComMod& com_mod);
 
+    /// Where the work ran so far (also printed by the destructor): counts of the three assembly hooks that ran on the device and
+    /// that fell back to the reference's host path, and of the solves.
+    struct Stats { long solves = 0; long device[3] = {0, 0, 0}; long host[3] = {0, 0, 0}; unsigned announced = 0; };
+    const Stats& stats() const { return stats_; }
+    void report() const;
+
     bool device_assembly() const { return device_assembly_; }
     void set_device(int device) { device_ = device; }
 
   private:
     void check(int rc, const char* what);
+    void note(int which, bool on_device, const std::string& what);
+    bool assemble_mesh_impl(ComMod& com_mod, const mshType& lM, const Array<double>& Ag, const Array<double>& Yg,
+        const Array<double>& Dg, const CepMod* cep_mod);
+    bool assemble_face_impl(ComMod& com_mod, const faceType& lFa, const Vector<double>& hg, const Array<double>& Yg);
+    bool assemble_follower_face_impl(ComMod& com_mod, const faceType& lFa, const Vector<double>& hg, const Array<double>& Dg);
+    Stats stats_;
     void upload_structure(ComMod& com_mod);
     void upload_mesh(ComMod& com_mod, const mshType& lM);
     bool assemble_fluid_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag, const Array<double>& Yg);

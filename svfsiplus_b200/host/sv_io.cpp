@@ -180,8 +180,16 @@ void inflate_block(const unsigned char* src, size_t csize, unsigned char* dst, s
 struct ByteSource {
   const unsigned char* raw = nullptr; size_t raw_n = 0, raw_pos = 0;
   B64Reader* b64 = nullptr; std::vector<unsigned char> buf; size_t buf_pos = 0;
+  // upper bound of the bytes this source can still deliver (header fields of a corrupt file must not drive an allocation)
+  size_t available() const
+  {
+    if (raw) return raw_n - raw_pos;
+    return (buf.size() - buf_pos) + (size_t(b64->end - b64->p)/4 + 1)*3;
+  }
   void take(size_t n, std::vector<unsigned char>& out)
   {
+    if (n > available()) throw std::runtime_error(raw ? "appended data: block runs past the end of the file"
+                                                      : "base64 data: block is shorter than its header says");
     out.resize(n);
     if (raw) {
       if (raw_pos + n > raw_n) throw std::runtime_error("appended data: block runs past the end of the file");
@@ -207,9 +215,14 @@ std::vector<unsigned char> read_block(ByteSource& src, int hsize, bool compresse
   src.take(3*size_t(hsize), h);
   const uint64_t nb = header_word(h.data(), hsize), us = header_word(h.data() + hsize, hsize), ps = header_word(h.data() + 2*hsize, hsize);
   if (nb == 0) return out;
+  // header sanity before anything is sized from it: the last block is a partial block (ps <= us), the block table must fit in
+  // what is left of the input, and zlib cannot expand a block by more than ~1032 : 1
+  if (us == 0 || ps > us) throw std::runtime_error("compressed data: inconsistent block header (partial block larger than the block size)");
+  if (nb > src.available()/size_t(hsize)) throw std::runtime_error("compressed data: block table runs past the end of the input");
   std::vector<unsigned char> cs;
   src.take(size_t(nb)*hsize, cs);
   const size_t total = size_t(nb - 1)*us + (ps ? ps : us);
+  if (total/1100 > src.available()) throw std::runtime_error("compressed data: header announces more data than the input can hold");
   out.resize(total);
   size_t off = 0;
   std::vector<unsigned char> blk;

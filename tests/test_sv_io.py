@@ -304,6 +304,25 @@ def test_errors_are_reported_not_swallowed(tmp_path):
         IO.write_vtk(bad, m.x[:5], m.ien, 10)
     with pytest.raises(IO.IoError, match="tuple count"):
         IO.write_vtk(bad, m.x, m.ien, 10, {"P": np.zeros(3)})
+    # corrupt compressed-block headers must be rejected before they size an allocation: a block count / block size of 2^40, a
+    # partial block larger than the block size
+    import base64
+    import struct
+    IO.write_vtk(good, m.x, m.ien, 10, pd, cd, mode=IO.BINARY, compress=True, header64=True)
+    txt = good.read_text()
+    i = txt.index("format=\"binary\">") + len("format=\"binary\">")
+    j = txt.index("</DataArray>", i)
+    payload = txt[i:j].strip()
+    hdr = bytearray(base64.b64decode(payload[:32]))           # 24 bytes: nb, us, ps
+    for field, value, msg in ((0, 1 << 40, "block table|shorter than its header"), (1, 1 << 40, "more data than the input|shorter"),
+                              (2, (1 << 20), "partial block larger")):
+        h = bytearray(hdr)
+        struct.pack_into("<Q", h, 8 * field, value)
+        if field == 1:
+            struct.pack_into("<Q", h, 16, 0)                    # no partial block: the (only) block then has the announced 2^40 bytes
+        bad.write_text(txt[:i] + base64.b64encode(bytes(h)).decode() + payload[32:] + txt[j:])
+        with pytest.raises(IO.IoError, match=msg):
+            IO.read_vtk(bad)
 
 
 def test_library_exports_every_declared_symbol():
