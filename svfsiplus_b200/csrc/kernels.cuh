@@ -158,12 +158,12 @@ k_spmv_vv(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr,
       double acc = 0.0;
 #pragma unroll 4
       for (int p = s; p < e; p++) {
-        const int c = HINT ? ld_stream_i(col + p) : __ldg(col + p);
+        const int c = __ldg(col + p);
         const double* k = K + (size_t(p)*DOF*DOF + lane4*DOF);
         const double* u = U + size_t(c)*DOF;
         double t = acc;
 #pragma unroll
-        for (int j = 0; j < DOF; j++) t = t + (HINT ? ld_hint_na(k + j, pol_k)*ld_hint(u + j, pol_u) : __ldg(k + j)*__ldg(u + j));
+        for (int j = 0; j < DOF; j++) t = t + (HINT ? __ldg(k + j)*ld_hint(u + j, pol_u) : __ldg(k + j)*__ldg(u + j));
         acc = t;
       }
       KU[size_t(row)*DOF + lane4] = acc;
@@ -212,6 +212,7 @@ k_spmv_vv3s(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPt
 // accumulates the column-i contributions to the three outputs over the whole row; the quad adds the three partial 3-vectors once
 // per row in a fixed order.  L1 sector requests per block drop from ~11 (profiles/r01_tour_c_ncu_raw.csv) to ~6; the sum is
 // re-associated (columns outer, blocks inner), a rounding-level difference like the strided variants.
+template <bool HINT>
 __global__ void __launch_bounds__(256)
 k_spmv_vv3c(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
             const double* __restrict__ K, const double* __restrict__ U, double* __restrict__ KU)
@@ -222,7 +223,7 @@ k_spmv_vv3c(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPt
   const int ngroups = (gridDim.x*blockDim.x) >> 2;
   const int nrounds = (nNo + ngroups - 1)/ngroups;
   const int li = lane4 < 3 ? lane4 : 0;          // lane 3 idles on a duplicate of lane 0's addresses (its sums are discarded)
-  const uint64_t pol_k = l2_policy_evict_first(), pol_u = l2_policy_evict_last();
+  const uint64_t pol_u = HINT ? l2_policy_evict_last() : 0;
   for (int r = 0; r < nrounds; r++) {
     const int row = group + r*ngroups;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
@@ -231,12 +232,14 @@ k_spmv_vv3c(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPt
       const int e = __ldg(rowPtr + row + 1);
 #pragma unroll 4
       for (int p = s; p < e; p++) {
-        const int c = ld_stream_i(col + p);
+        // (the three words of a lane share sectors with its neighbours' words of the NEXT instruction: they must allocate in L1 -
+        // with L1::no_allocate every instruction refetches its sectors from L2 and the kernel drops to 0.60 of the HBM peak)
+        const int c = __ldg(col + p);
         const double* k = K + size_t(p)*9 + li;
-        const double u = ld_hint(U + size_t(c)*3 + li, pol_u);
-        a0 = fma(ld_hint_na(k, pol_k), u, a0);
-        a1 = fma(ld_hint_na(k + 3, pol_k), u, a1);
-        a2 = fma(ld_hint_na(k + 6, pol_k), u, a2);
+        const double u = HINT ? ld_hint(U + size_t(c)*3 + li, pol_u) : __ldg(U + size_t(c)*3 + li);
+        a0 = fma(__ldg(k), u, a0);
+        a1 = fma(__ldg(k + 3), u, a1);
+        a2 = fma(__ldg(k + 6), u, a2);
       }
     }
     if (lane4 == 3) { a0 = 0.0; a1 = 0.0; a2 = 0.0; }

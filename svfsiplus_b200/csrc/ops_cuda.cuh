@@ -430,7 +430,7 @@ class CudaOps {
   // entries in flight per lane in the two Schur passes (A/B on B200, profiles/r01_tour_b.jsonl): pass 1 is
   // fastest with two (0.151 vs 0.163 ms at P10), pass 2 with four (0.193 vs 0.217 ms)
   int variant_gp = 0, variant_sp = 1;   // 2: TMA-staged row tiles (spmv_tiled.cuh)
-  int variant_vv3 = 0;       // 0: lane = component, 1: lanes stride over the row's blocks, 2: TMA-staged row tiles, 3: as 0 with L2 evict-first / evict-last hints, 4: column-owner lanes (A/B by op_bench)
+  int variant_vv3 = 0;       // 0: lane = component, 1: lanes stride over the row's blocks, 2: TMA-staged row tiles, 3: as 0 with an L2 evict-last policy on the gathered vector, 4 / 5: column-owner lanes with / without that policy (A/B by op_bench)
   int variant_narrow = 0;    // spmv_ss / sv / vs: 0 per-lane loads, 2 TMA-staged row tiles
 
   // ---- SpMV (+ overlap-node add) --------------------------------------------------------------------
@@ -476,7 +476,8 @@ class CudaOps {
       switch (dof) {
         case 4: k_spmv_vv4<<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out); break;
         case 3: if (variant_vv3 == 1) k_spmv_vv3s<<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out);
-                else if (variant_vv3 == 4) k_spmv_vv3c<<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out);
+                else if (variant_vv3 == 4) k_spmv_vv3c<true><<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out);
+                else if (variant_vv3 == 5) k_spmv_vv3c<false><<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out);
                 else if (variant_vv3 == 3) k_spmv_vv<3, true><<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out);
                 else k_spmv_vv<3><<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out);
                 break;

