@@ -152,8 +152,12 @@ def _reference_sample(args, ls_name):
     return case, dims, ntet, scale, nr, r
 
 
+def _ref_build():
+    return "-O3 build (oracle/_ref/o3)" if "o3" in os.environ.get("SVREF_LIB", "") else "-O2 build"
+
+
 def _sample_text(dims, ntet, scale, nr, r, ls_name):
-    return (f"pipe {dims[0]}x{dims[1]}x{dims[2]} = {ntet} tets ({100*scale:.2f}% of P10) on {nr} rank(s) = host threads of the "
+    return (f"compiled reference, {_ref_build()}; pipe {dims[0]}x{dims[1]}x{dims[2]} = {ntet} tets ({100*scale:.2f}% of P10) on {nr} rank(s) = host threads of the "
             f"in-process MPI stand-in: construct_fluid ({r['asm_s']:.2f} s, slowest rank) + commu + fsils_solve {ls_name} "
             f"({r['solve_s']:.2f} s, itr {r['itr']}/{r['GM_itr']}/{r['CG_itr']}); iters/s scaled by the tet ratio to the 10M-tet unit "
             f"(EXTRAPOLATED, optimistic for the CPU: Krylov counts grow with refinement; the measured same-size ratio is the GPU "
@@ -679,6 +683,11 @@ def main():
     # suppressed: NCCL_DEBUG keeps whatever level the caller asked for)
     if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
         os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
+    # timing legs of the reference use its -O3 build when it exists (oracle/Makefile target o3; the parity tests keep the default
+    # -O2 library) - the faster of the two, i.e. the conservative denominator
+    o3 = os.path.join(ROOT, "oracle", "_ref", "o3", "libsvref.so")
+    if os.path.exists(o3) and not os.environ.get("SVREF_LIB"):
+        os.environ["SVREF_LIB"] = o3
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

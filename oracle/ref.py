@@ -13,7 +13,10 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_ref", "libsvref.so")
+# SVREF_LIB selects another build of the same sources (bench.py's -O3 timing leg: oracle/_ref/o3/libsvref.so); the parity tests
+# always use the default -O2 build
+LIB_PATH = os.environ.get("SVREF_LIB") or os.path.join(_HERE, "_ref", "libsvref.so")
+O3_LIB_PATH = os.path.join(_HERE, "_ref", "o3", "libsvref.so")
 
 LS_CG, LS_GMRES, LS_NS, LS_BICGS = 798, 797, 796, 795      # L/fils_struct.hpp:70-76
 PREC_FSILS, PREC_RCS = 701, 709                              # S/consts.h:426
