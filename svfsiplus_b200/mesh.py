@@ -70,6 +70,16 @@ def tet_volumes(x: np.ndarray, ien: np.ndarray) -> np.ndarray:
     return np.einsum("ij,ij->i", a, np.cross(b, c)) / 6.0
 
 
+def node_hmin(x: np.ndarray, ien: np.ndarray) -> np.ndarray:
+    """Local spacing per node: the shortest edge of any incident tet (TET4 connectivity)."""
+    hmin = np.full(x.shape[0], np.inf)
+    for a, b in itertools.combinations(range(4), 2):
+        d = np.linalg.norm(x[ien[:, a]] - x[ien[:, b]], axis=1)
+        np.minimum.at(hmin, ien[:, a], d)
+        np.minimum.at(hmin, ien[:, b], d)
+    return hmin
+
+
 def pipe_mesh(nx: int, ny: int, nz: int, radius: float = 1.0, length: float = 10.0,
               jitter: float = 0.1, seed: int = 1234) -> Mesh:
     """Cylinder of TET4: nx*ny*nz hexes -> 6*nx*ny*nz tets, (nx+1)(ny+1)(nz+1) nodes.

@@ -251,7 +251,11 @@ def fsi_case(nx, ny, nz, *, wall_from=0.8, radius=1.0, length=10.0, pattern=None
     rng = np.random.default_rng(99)
     Ag = np.zeros((n, 7)); Yg = np.zeros((n, 7)); Dg = np.zeros((n, 7))
     Ag[:, :4] = A4; Yg[:, :4] = Y4
+    # displacement noise relative to the LOCAL spacing (the disc map's cells near the square's corners are far smaller than
+    # 2R/nx on fine meshes; a global amplitude inverts them).  Small meshes keep the global amplitude their goldens were made with.
     h = 2.0 * radius / nx
+    if nx * ny * nz > 20000:
+        h = np.minimum(M.node_hmin(m.x, m.ien), h)[:, None]
     Dg[:, 0:3] = 0.02 * h * rng.standard_normal((n, 3))         # solid displacement (used in the wall)
     Dg[:, 4:7] = 0.05 * h * rng.standard_normal((n, 3))         # mesh displacement (used in the lumen)
     Yg[:, 4:7] = 0.5 * rng.standard_normal((n, 3))              # mesh velocity
