@@ -4,12 +4,16 @@ solve) on the synthetic 10M-tet pipe (P10), one process per GPU.
 
     python bench.py --gpus 1 --steps K --warmup W            # this framework (CUDA, sm_100a)
     python bench.py --impl reference --steps K --warmup W    # the reference's own CPU code (oracle/_ref)
+    python bench.py --workload struct_block|ustruct_block|fsi_pipe      # BASELINE.json configs[3] / configs[4]
 
 A "step" is one Newton iteration's hot path: ls_alloc (zero R/Val) + construct_fluid over the whole
 mesh + fsils_solve with the <LS> block of tests/cases/fluid/pipe_RCR_3d/solver.xml.
-  value : Newton iterations / s, inputs (Ag, Yg, Bf) resident in HBM when the timed region starts
+  value : Newton iterations / s of the 10M-tet pipe on N GPUs (N > 1: the same mesh split over the ranks - BASELINE's metric reads
+          "10M-tet pipe @1-8 B200", scaling "strong"), inputs (Ag, Yg, Bf) resident in HBM when the timed region starts
   e2e   : the same metric through the C ABI with HOST buffers: every step copies Ag/Yg/Bf host->device
           from pinned memory and the solution device->host inside the timed region
+  weak  : (N > 1) the pipe refined to N x the tets (configs[2]; 80 M at N = 8), 10M-tet-equivalent iterations/s
+  fixed_work, same_config, golden_p10: see DESIGN.md section 6
 Timing: CUDA events on the library's launch stream (b200_timer), barrier + device synchronize on both
 sides, max over ranks.  The matrix (3.2 GB at P10) is far larger than L2 (126 MB), so no L2 flush is
 needed between iterations (stated in config.l2).
@@ -102,11 +106,9 @@ def _dist():
 
 
 def workload_dims(args, world):
-    """The pipe the line is quoted on: P10 (configs[1]) on one GPU, the same pipe refined to N x the tets on N GPUs
-    (configs[2] at N = 8)."""
-    if world > 1:
-        from svfsiplus_b200 import partition as PT
-        return PT.weak_dims(tuple(args.dims), world)
+    """The pipe the line is quoted on: the 10M-tet pipe P10 (BASELINE.json: "10M-tet pipe (assembly+GMRES) @1-8 B200") whatever N
+    is - N GPUs split the SAME mesh (strong scaling).  The refined pipes of configs[2] (N x the tets on N GPUs) are timed in the
+    same run and reported in the `weak` object."""
     return tuple(args.dims)
 
 
@@ -119,7 +121,8 @@ def make_config(args, world):
                         f"(ls_alloc + construct_fluid + fsils_solve LS {args.ls}, pipe_RCR_3d solver.xml parameters)",
             "ls": args.ls, "parallelism": f"dd{world}",
             "l2": "inputs larger than L2 (Val 3.2 GB vs 126 MB L2): no flush between iterations",
-            "value_note": "N>1: Newton-iters/s x (total tets / 10,008,576), i.e. 10M-tet-equivalent iterations/s"}
+            "value_note": "Newton iterations per second of THIS mesh on N GPUs (strong scaling); the `weak` object holds the pipe "
+                          "refined to N x the tets, in 10M-tet-equivalent iterations/s"}
 
 
 def _ref_ranks(args, dims):
@@ -181,7 +184,7 @@ def run_reference(args):
     value = (1.0 / (ms * 1e-3)) * scale
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": make_config(args, max(1, args.gpus)),
         "run": {"sample_dims": list(dims), "sample_tets": int(ntet), "extrapolated": True, "same_config": False,
@@ -378,33 +381,37 @@ def run_gpu(args):
     fixed_work = {"ls": "NS, relTol = absTol = 0, RI mItr 2, GM 1 x 50, CG 200 (fixed iteration counts)", "steps": fw_steps,
                   "ms_per_step": fw_ms, **counts(fw_info), "tets": ntet_total,
                   "work_rate": ntet_total * fw_inner / (fw_ms * 1e-3), "work_rate_per_gpu": ntet_total * fw_inner / (fw_ms * 1e-3) / world,
-                  "unit": "tet x inner Krylov iterations / s", "scaling": "weak (same per-GPU mesh as the headline line)"}
+                  "unit": "tet x inner Krylov iterations / s", "scaling": "strong (the headline mesh split over N ranks); the weak object carries its own fixed-work time"}
     be.close()
 
-    # (2) strong scaling: the 10M-tet pipe itself split over the N ranks (the metric reads "10M-tet pipe @1-8 B200")
-    strong = None
-    if world > 1:
-        sdims = tuple(args.dims)
-        case_s, be_s = build(sdims)
+    # (2) weak scaling (BASELINE.json configs[2]): the same pipe refined to N x the tets (192 x 192 x 362 = 80 M at N = 8), each rank
+    # its z-slab; value in 10M-tet-equivalent iterations/s.  Krylov counts grow with refinement (the reference algorithm has no
+    # multilevel preconditioner), which this number contains together with the communication cost; `fixed_work` separates them.
+    weak = None
+    if world > 1 and not args.no_weak:
+        wdims = PT.weak_dims(tuple(args.dims), world)
+        case_s, be_s = build(wdims)
         pin_s, out_s = pinned(case_s, be_s)
         be_timer = be_s
         s_res, s_e2e = make_steps(be_s, case_s, pin_s, out_s, LS)
         be_s.state_set(case_s["Ag"].shape[1], pin_s["Ag"].data_ptr(), pin_s["Yg"].data_ptr(), pin_s["Bf"].data_ptr())
-        for _ in range(max(3, min(args.warmup, 3))):
+        for _ in range(2):
             s_res()
-        s_steps = max(2, min(args.steps, 5))
+        s_steps = max(2, min(args.steps, 3))
         s_ms, s_info = timed(s_res, s_steps)
         s_e2e()
         s_e2e_ms, _ = timed(s_e2e, s_steps)
         fw_s, _ = make_steps(be_s, case_s, pin_s, out_s, FIXED_WORK_LS)
         fw_s()
         s_fw_ms, s_fw_info = timed(fw_s, s_steps)
-        s_xnorm = global_norms(out_s, case_s)
-        strong = {"dims": list(sdims), "X_norm": s_xnorm, "tets": 6 * sdims[0] * sdims[1] * sdims[2], "steps": s_steps, "ms_per_step": s_ms,
-                  "value": 1e3 / s_ms, "e2e_value": 1e3 / s_e2e_ms, "unit": UNIT, **counts(s_info),
-                  "fixed_work_ms_per_step": s_fw_ms, "fixed_work_inner": int(s_fw_info["GM"]["itr"]) + int(s_fw_info["CG"]["itr"]),
-                  "note": "rank-local slabs are jittered per rank (partition.local_slab_case), so counts may differ by a few from "
-                          "the one-GPU P10 line"}
+        wtets = 6 * wdims[0] * wdims[1] * wdims[2]
+        wscale = wtets / float(6 * P10[0] * P10[1] * P10[2])
+        w_inner = int(s_fw_info["GM"]["itr"]) + int(s_fw_info["CG"]["itr"])
+        weak = {"dims": list(wdims), "tets": wtets, "steps": s_steps, "ms_per_step": s_ms, "value": (1e3 / s_ms) * wscale,
+                "e2e_value": (1e3 / s_e2e_ms) * wscale, "unit": UNIT + " x (tets / 10,008,576)", **counts(s_info),
+                "fixed_work_ms_per_step": s_fw_ms, "fixed_work_inner": w_inner,
+                "fixed_work_rate_per_gpu": wtets * w_inner / (s_fw_ms * 1e-3) / world,
+                "krylov_work_rate_per_gpu": wtets * (int(s_info["GM"]["itr"]) + int(s_info["CG"]["itr"])) / (s_ms * 1e-3) / world}
         be_s.close()
 
     # (3) same-config measurement against the reference (N = 1): the bounded sample the reference arm times, on the GPU
@@ -443,12 +450,11 @@ def run_gpu(args):
     nnz, nNo = be.nnz, be.nNo
     spmv_gbs = spmv_bytes / 1e9 / (spmv_ms * 1e-3)
 
-    scale = ntet_total / float(6 * P10[0] * P10[1] * P10[2])
-    value = (1e3 / ms_per_step) * (scale if world > 1 else 1.0)
-    e2e_value = (1e3 / e2e_ms) * (scale if world > 1 else 1.0)
+    value = 1e3 / ms_per_step
+    e2e_value = 1e3 / e2e_ms
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": make_config(args, world),
         "run": {"nNo": int(nNo), "nnz_blocks": int(nnz), "krylov_itr": info["RI"]["itr"], "gm_itr": info["GM"]["itr"],
@@ -480,8 +486,8 @@ def run_gpu(args):
     except Exception:                      # never let a reporting extra cost the bench line
         pass
     line["fixed_work"] = fixed_work
-    if strong is not None:
-        line["strong"] = strong
+    if weak is not None:
+        line["weak"] = weak
     # benchmark-size parity: counts and solution norms of the compiled reference on the same P10 system (tests/golden/p10_ns_counts.json,
     # generated offline by tests/golden/make_golden_p10.py); a plain file read, nothing of oracle/ is executed here
     try:
@@ -494,10 +500,8 @@ def run_gpu(args):
                         "counts_within_1": bool(abs(cnt["krylov_itr"] - g["itr"]) <= 1),
                         "inner_counts_rel": [abs(cnt["gm_itr"] - g["GM_itr"]) / max(g["GM_itr"], 1), abs(cnt["cg_itr"] - g["CG_itr"]) / max(g["CG_itr"], 1)],
                         "X_norm_rel": [abs(a - b) / b for a, b in zip(xn, g["X_norm"])]}
-            if world == 1 and list(dims) == g["dims"]:
+            if list(dims) == g["dims"]:            # every N solves the same global system: same counts, same solution norms
                 line["golden_p10"] = chk({"krylov_itr": info["RI"]["itr"], "gm_itr": info["GM"]["itr"], "cg_itr": info["CG"]["itr"]}, x_norm)
-            if strong is not None and strong["dims"] == g["dims"]:
-                strong["golden_p10"] = chk(strong, strong["X_norm"])
     except Exception as e:
         line["golden_p10"] = {"error": str(e)}
     if world == 1 and not args.no_cpu_baseline:
@@ -698,6 +702,7 @@ def main():
     ap.add_argument("--ref-dims", type=int, nargs=3, default=[32, 32, 64], help="bounded CPU sample of the workload")
     ap.add_argument("--ref-ranks", type=int, default=0, help="ranks (threads) of the reference arm; 0 = min(host cores, 16, layers/2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the refined (weak-scaling) pipe of configs[2]")
     ap.add_argument("--workload", default="ns_pipe", choices=["ns_pipe"] + sorted(WORKLOADS),
                     help="ns_pipe = the headline metric (configs[1]/[2]); the others are BASELINE.json configs[3] and configs[4]")
     ap.add_argument("--size", type=int, default=0, help="elements per edge of the block workloads (default: the workload's own)")
