@@ -45,6 +45,28 @@
 #include "output.h"
 #ifdef WITH_B200_DROPIN
 #include "B200LinearAlgebra.h"
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+// test infrastructure: a native backtrace on SIGSEGV / SIGABRT (the Python fault handler only shows the ctypes call)
+static void dropin_crash_handler(int sig)
+{
+  void* frames[64];
+  const int n = backtrace(frames, 64);
+  const char msg[] = "[dropin harness] fatal signal, native backtrace:\n";
+  (void)!write(2, msg, sizeof(msg) - 1);
+  backtrace_symbols_fd(frames, n, 2);
+  signal(sig, SIG_DFL);
+  raise(sig);
+}
+static void dropin_install_crash_handler()
+{
+  static bool done = false;
+  if (done) return;
+  done = true;
+  signal(SIGSEGV, dropin_crash_handler);
+  signal(SIGABRT, dropin_crash_handler);
+}
 #endif
 
 #include "mpi.h"
@@ -863,6 +885,7 @@ void dropin_newton_iteration(AsmCtx* ctx, int dof, int mode, int tDof, const dou
                              const std::function<void(B200LinearAlgebra*, Array<double>&)>& after_assembly = nullptr)
 {
   using namespace consts;
+  dropin_install_crash_handler();
   auto& com_mod = ctx->sim->com_mod;
   const int nNo = com_mod.tnNo;
   auto& eq = com_mod.eq[0];
