@@ -10,8 +10,8 @@
 #include "fft.h"
 #include "utils.h"
 
+#include <cstdio>
 #include <cstdlib>
-#include <iostream>
 #include <stdexcept>
 #include <vector>
 
@@ -185,19 +185,23 @@ void B200LinearAlgebra::note(int which, bool on_device, const std::string& what)
   (on_device ? stats_.device : stats_.host)[which]++;
   if (!on_device && device_assembly_ && !(stats_.announced & (1u << which))) {
     stats_.announced |= (1u << which);
-    std::cout << "[B200LinearAlgebra] " << what << ": no device kernel for this physics / element type / option -> the reference's "
-                 "host path runs for it (assembly on the host, solve on the GPU)" << std::endl;
+    // (stdio, not iostream: in a build that links libstdc++ statically into a dlopen'ed library - the test harness does - that
+    // library's own std::cout has no locale facets and formatted output of numbers crashes)
+    std::printf("[B200LinearAlgebra] %s: no device kernel for this physics / element type / option -> the reference's host path "
+                "runs for it (assembly on the host, solve on the GPU)\n", what.c_str());
+    std::fflush(stdout);
   }
 }
 
 void B200LinearAlgebra::report() const
 {
   static const char* names[3] = {"whole-mesh assemblies", "Neumann faces", "follower-load faces"};
-  std::cout << "[B200LinearAlgebra] solves on the GPU: " << stats_.solves;
+  std::printf("[B200LinearAlgebra] solves on the GPU: %ld", stats_.solves);
   for (int i = 0; i < 3; i++)
     if (stats_.device[i] + stats_.host[i] > 0)
-      std::cout << "; " << names[i] << ": " << stats_.device[i] << " on the GPU, " << stats_.host[i] << " on the host";
-  std::cout << std::endl;
+      std::printf("; %s: %ld on the GPU, %ld on the host", names[i], stats_.device[i], stats_.host[i]);
+  std::printf("\n");
+  std::fflush(stdout);
 }
 
 bool B200LinearAlgebra::assemble_mesh(ComMod& com_mod, const mshType& lM, const Array<double>& Ag,
