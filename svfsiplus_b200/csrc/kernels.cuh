@@ -212,8 +212,8 @@ k_spmv_vv3s(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPt
 // accumulates the column-i contributions to the three outputs over the whole row; the quad adds the three partial 3-vectors once
 // per row in a fixed order.  L1 sector requests per block drop from ~11 (profiles/r01_tour_c_ncu_raw.csv) to ~6; the sum is
 // re-associated (columns outer, blocks inner), a rounding-level difference like the strided variants.
-template <bool HINT>
-__global__ void __launch_bounds__(256)
+template <bool HINT, int MINB = 6>
+__global__ void __launch_bounds__(256, MINB)
 k_spmv_vv3c(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPtr, const int* __restrict__ col,
             const double* __restrict__ K, const double* __restrict__ U, double* __restrict__ KU)
 {

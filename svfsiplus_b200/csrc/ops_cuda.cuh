@@ -478,6 +478,7 @@ class CudaOps {
         case 3: if (variant_vv3 == 1) k_spmv_vv3s<<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out);
                 else if (variant_vv3 == 4) k_spmv_vv3c<true><<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out);
                 else if (variant_vv3 == 5) k_spmv_vv3c<false><<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out);
+                else if (variant_vv3 == 6) k_spmv_vv3c<true, 8><<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out);   // <= 32 registers: 64 warps per SM
                 else if (variant_vv3 == 3) k_spmv_vv<3, true><<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out);
                 else k_spmv_vv<3><<<g, 256, 0, st>>>(skip_flag, n, rp, col, K, U, out);
                 break;
