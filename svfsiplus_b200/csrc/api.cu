@@ -2132,7 +2132,8 @@ int b200_tune(b200_handle* h, const char* name, int value)
     else if (n == "schur_sp") ops.variant_sp = value;
     else if (n == "narrow") ops.variant_narrow = value;
     else if (n == "cg_batch") ops.cg_batch = std::max(1, value);
-    else throw std::runtime_error("tune: unknown knob '" + n + "' (vv3, schur_gp, schur_sp, narrow, cg_batch)");
+    else if (n == "fused") ops.variant_fused = value;
+    else throw std::runtime_error("tune: unknown knob '" + n + "' (vv3, schur_gp, schur_sp, narrow, cg_batch, fused)");
   });
 }
 

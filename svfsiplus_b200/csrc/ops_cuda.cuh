@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -16,6 +17,7 @@
 #include "krylov.hpp"
 #include "peer_comm.cuh"
 #include "spmv_tiled.cuh"
+#include "fused_halo.cuh"
 
 namespace svb200 {
 
@@ -255,6 +257,7 @@ class CudaOps {
       CU_CHECK(cudaEventCreateWithFlags(&ev_b, cudaEventDisableTiming));
       CU_CHECK(cudaEventCreateWithFlags(&ev_c, cudaEventDisableTiming));
     }
+    if (const char* e = getenv("SVB200_FUSED")) variant_fused = std::atoi(e);      // A/B of the fused product + exchange kernel
     CU_CHECK(cudaMalloc(&red_d, sizeof(double)*kMaxSlots));
     CU_CHECK(cudaMallocHost(&red_h, sizeof(double)*kMaxSlots));
     CU_CHECK(cudaMalloc(&partial_d, sizeof(double)*kRedBlocks*kMaxDots));
@@ -447,9 +450,9 @@ class CudaOps {
       // stores fly meanwhile) -> acquire the neighbours' flags and add
       if (ovA > 0) launch(0, ovA);
       if (ovB < nNo_) launch(ovB, nNo_);
-      halo_push(dof, out, ld ? ld : dof);
+      { Scope hs(*this, KC_HALO, 0.0, 1); halo_push(dof, out, ld ? ld : dof); }          // profiled separately: push ...
       if (ovB > ovA) launch(ovA, ovB);
-      halo_wait_add(dof, out, ld ? ld : dof);
+      { Scope hs(*this, KC_HALO, 0.0, 1); halo_wait_add(dof, out, ld ? ld : dof); }      // ... and wait + add (incl. the wait for the neighbour)
       return;
     }
     if (ovA > 0) launch(0, ovA);
@@ -463,10 +466,36 @@ class CudaOps {
     halo_accumulate(dof, out, ld ? ld : dof);
   }
 
+  // ---- fused product + overlap exchange (fused_halo.cuh): one cooperative launch instead of four -------------------------------
+  int variant_fused = 1;               // b200_tune("fused", 0) selects the unfused peer path (A/B, parity tests)
+  int fused_grid[4] = {0, 0, 0, 0};    // resident CTAs per shape (occupancy x SMs), filled at first use
+  bool use_fused() const { return variant_fused != 0 && nranks > 1 && p2p && overlap_ok && !reqs.empty(); }
+  template <class Rows>
+  void launch_fused(int shape_id, const Rows& rows, int dof, double* out, int ld)
+  {
+    if (dof > halo_dof_cap) throw std::runtime_error("halo buffers too small for dof");
+    if (fused_grid[shape_id] == 0) {
+      int per_sm = 0;
+      CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_rows_halo<Rows>, 256, 0));
+      if (per_sm < 1) throw std::runtime_error("fused halo kernel cannot be resident");
+      fused_grid[shape_id] = per_sm*kSmCount;
+    }
+    FusedHaloArgs f;
+    f.skip = skip_flag; f.nNo = nNo_; f.ovA = ovA; f.ovB = ovB; f.dof = dof; f.ld = ld; f.dofcap = halo_dof_cap; f.out = out;
+    f.nreq = int(reqs.size()); f.reqs = d_peer_reqs; f.ptr_all = d_halo_ptr_all; f.halo_tot = halo_tot;
+    f.nh = halo_nh; f.hn_node = d_hn_node; f.hn_ptr = d_hn_ptr; f.hn_src = d_hn_src; f.ps = peer_state;
+    Rows r = rows;
+    void* args[] = {&r, &f};
+    CU_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_rows_halo<Rows>), dim3(fused_grid[shape_id]), dim3(256), args, 0, st));
+    post();
+  }
+
   void spmv_vv(int dof, const double* K, const double* U, double* KU)
   {
     if (dof < 1 || dof > 4) throw std::runtime_error("spmv_vv: dof > 4 is not a supported FSILS path");
     Scope sc(*this, dof == 4 ? KC_SPMV_VV4 : KC_SPMV_VV3, bytes_vv(dof));
+    if (use_fused() && dof == 4) { launch_fused(1, RowsVV4{rowPtr, col, K, U, KU}, 4, KU, 4); return; }
+    if (use_fused() && dof == 3 && variant_vv3 == 4) { launch_fused(0, RowsVV3{rowPtr, col, K, U, KU}, 3, KU, 3); return; }
     rows_then_halo(dof, KU, dof, [&](int r0, int r1) {
       const int n = r1 - r0, g = grid_rows(n);
       const int* rp = rowPtr + r0;
@@ -926,7 +955,10 @@ class CudaOps {
                 double* SP, bool coupled)
   {
     if (nsd == 3 && Gt == packed_Gt && GtL) {
-      {
+      if (use_fused() && variant_gp == 0) {
+        Scope sc(*this, KC_SPMV_SV, bytes_schur_gp());
+        launch_fused(2, RowsGP{rowPtr, col, G, P, V4}, 3, V4, 4);
+      } else {
         Scope sc(*this, KC_SPMV_SV, bytes_schur_gp());
         rows_then_halo(3, V4, 4, [&](int r0, int r1) {
           const int n = r1 - r0, g = grid_rows(n);
@@ -938,7 +970,10 @@ class CudaOps {
         });
       }
       if (coupled) add_bc_mul(BCOP_PRE, 3, V4, V4, 4);
-      {
+      if (use_fused() && variant_sp == 1) {
+        Scope sc(*this, KC_SPMV_VS, bytes_schur_sp());
+        launch_fused(3, RowsSP{rowPtr, col, GtL, V4, SP}, 1, SP, 1);
+      } else {
         Scope sc(*this, KC_SPMV_VS, bytes_schur_sp());
         rows_then_halo(1, SP, 1, [&](int r0, int r1) {
           const int n = r1 - r0, g = grid_rows(n);

