@@ -3,7 +3,7 @@
 // (liner_solver/spar_mul.cpp, in_commu.cpp:111-170) without a second launch.
 //
 //   phase A   boundary rows [0, ovA) and [ovB, nNo) (the rows that appear in an overlap list), spread over the whole grid
-//   barrier   grid-wide arrive/wait on a device counter (the grid is launched cooperatively: every CTA is resident)
+//   barrier   grid-wide arrive/wait on a device counter (the grid never exceeds what is resident: occupancy x SMs)
 //   push      every CTA packs its slice of the overlap lists straight into the neighbours' windows (NVLink stores); the last CTA
 //             to finish release-stores the epoch flags
 //   phase B   interior rows [ovA, ovB) - the exchange is in flight meanwhile
@@ -14,8 +14,6 @@
 // The row bodies are the same arithmetic as the stand-alone kernels of kernels.cuh (k_spmv_vv3c, k_spmv_vv4, k_schur_gp,
 // k_schur_sp4), restated as device functions on global row indices.
 #pragma once
-
-#include <cooperative_groups.h>
 
 #include "kernels.cuh"
 #include "peer_comm.cuh"
@@ -120,15 +118,23 @@ struct RowsSP {             // pass 2 of the Schur operator (k_schur_sp): SP(i) 
       double aL = 0.0, aD = 0.0;
       if (row < r1) {
         const int s = __ldg(rowPtr + row), e = __ldg(rowPtr + row + 1);
-#pragma unroll 4
-        for (int p = s + lane4; p < e; p += 4) {
-          const int c = ld_stream_i(col + p);
-          const d4 k = ld256_stream(GtL + size_t(p)*4);
-          // V4 rows of the overlap nodes were completed by THIS kernel's add phase of the previous product or by an earlier kernel:
-          // plain cached loads are fine (pass 2 never runs in the same launch as the pass 1 that wrote V4)
-          const d4 v = ld256_keep(V4 + size_t(c)*4);
-          aL = fma(k.w, v.w, aL);
-          aD = aD + (k.x*v.x + k.y*v.y + k.z*v.z);
+        // four entries in flight per lane (k_schur_sp4); V4 was completed by an earlier launch, cached loads are fine
+        for (int base = s + lane4; base < e; base += 16) {
+          int c[4];
+          d4 k[4], v[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) { const int p = base + 4*q; c[q] = (p < e) ? ld_stream_i(col + p) : -1; }
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const int p = base + 4*q;
+            if (c[q] >= 0) { k[q] = ld256_stream(GtL + size_t(p)*4); v[q] = ld256_keep(V4 + size_t(c[q])*4); }
+            else { k[q].x = k[q].y = k[q].z = k[q].w = 0.0; v[q] = k[q]; }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            aL = fma(k[q].w, v[q].w, aL);
+            aD = aD + (k[q].x*v[q].x + k[q].y*v[q].y + k[q].z*v[q].z);
+          }
         }
       }
       aL += __shfl_xor_sync(0xffffffffu, aL, 1); aD += __shfl_xor_sync(0xffffffffu, aD, 1);
@@ -151,8 +157,6 @@ struct FusedHaloArgs {
 template <class Rows>
 __global__ void __launch_bounds__(256) k_rows_halo(Rows rows, FusedHaloArgs f)
 {
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
   const bool skip = f.skip && *f.skip;                      // compute may be skipped, the exchange never is (peer_comm.cuh)
   const int lane4 = threadIdx.x & 3;
   const int gq = (blockIdx.x*blockDim.x + threadIdx.x) >> 2;
@@ -165,7 +169,19 @@ __global__ void __launch_bounds__(256) k_rows_halo(Rows rows, FusedHaloArgs f)
     if (f.ovA > 0) rows.run(0, f.ovA, gq, nq, lane4);
     if (f.ovB < f.nNo) rows.run(f.ovB, f.nNo, gq, nq, lane4);
   }
-  grid.sync();
+  // grid-wide barrier: every CTA of this launch is resident (the grid is sized by the occupancy calculator and the stream runs one
+  // kernel at a time), arrivals are counted on a device counter that the last CTA of the launch resets
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&f.ps->bar_count, 1u);
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(&f.ps->bar_count) < gridDim.x) {
+      if (clock64() - t0 > kSpinLimit) { f.ps->error = 3; break; }       // not every CTA resident: reported by peer_check, no hang
+      __nanosleep(32);
+    }
+  }
+  __syncthreads();
 
   // push: this CTA's slice of the overlap lists into the neighbours' windows
   {
@@ -217,7 +233,7 @@ __global__ void __launch_bounds__(256) k_rows_halo(Rows rows, FusedHaloArgs f)
     if (threadIdx.x == 0) {
       if (!s_ok) f.ps->error = 1;
       __threadfence();
-      if (atomicAdd(&f.ps->wait_count, 1u) == gridDim.x - 1) { f.ps->wait_count = 0; f.ps->halo_epoch = epoch; }
+      if (atomicAdd(&f.ps->wait_count, 1u) == gridDim.x - 1) { f.ps->wait_count = 0; f.ps->bar_count = 0; f.ps->halo_epoch = epoch; }
     }
   }
 }

@@ -466,7 +466,7 @@ class CudaOps {
     halo_accumulate(dof, out, ld ? ld : dof);
   }
 
-  // ---- fused product + overlap exchange (fused_halo.cuh): one cooperative launch instead of four -------------------------------
+  // ---- fused product + overlap exchange (fused_halo.cuh): one launch instead of four -------------------------------
   int variant_fused = 1;               // b200_tune("fused", 0) selects the unfused peer path (A/B, parity tests)
   int fused_grid[4] = {0, 0, 0, 0};    // resident CTAs per shape (occupancy x SMs), filled at first use
   bool use_fused() const { return variant_fused != 0 && nranks > 1 && p2p && overlap_ok && !reqs.empty(); }
@@ -484,9 +484,7 @@ class CudaOps {
     f.skip = skip_flag; f.nNo = nNo_; f.ovA = ovA; f.ovB = ovB; f.dof = dof; f.ld = ld; f.dofcap = halo_dof_cap; f.out = out;
     f.nreq = int(reqs.size()); f.reqs = d_peer_reqs; f.ptr_all = d_halo_ptr_all; f.halo_tot = halo_tot;
     f.nh = halo_nh; f.hn_node = d_hn_node; f.hn_ptr = d_hn_ptr; f.hn_src = d_hn_src; f.ps = peer_state;
-    Rows r = rows;
-    void* args[] = {&r, &f};
-    CU_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_rows_halo<Rows>), dim3(fused_grid[shape_id]), dim3(256), args, 0, st));
+    k_rows_halo<Rows><<<fused_grid[shape_id], 256, 0, st>>>(rows, f);
     post();
   }
 
@@ -752,7 +750,8 @@ class CudaOps {
     if (s.error) {
       CU_CHECK(cudaMemsetAsync(&peer_state->error, 0, sizeof(int), st));
       throw std::runtime_error(s.error == 1 ? "overlap-node exchange timed out waiting for a neighbour rank"
-                                            : "all-reduce timed out waiting for another rank");
+                               : s.error == 2 ? "all-reduce timed out waiting for another rank"
+                                              : "fused product + exchange kernel: grid barrier timed out (not every CTA resident)");
     }
   }
 

@@ -36,7 +36,7 @@ struct PeerState {                 // device memory, one per CudaOps
   unsigned int push_count;         // CTA counters of the two halo kernels
   unsigned int wait_count;
   int error;                       // 1: halo wait timed out, 2: all-reduce wait timed out
-  int pad;
+  unsigned int bar_count;          // grid barrier of the fused product + exchange kernel (fused_halo.cuh)
 };
 
 // Layout of a rank's window (all offsets in bytes, 256-byte aligned):
@@ -68,6 +68,12 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 {
   asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p)
+{
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
 {
   unsigned long long v;
@@ -95,11 +101,14 @@ __device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsig
 }
 
 // ---- all-reduce of n <= kPeerSlots doubles at `v` (sum or max), one CTA -------------------------------------------------
+// The body is a device function so that the LAST CTA of a reduction kernel (k_multi_dot, k_cg_update) can run it as its
+// epilogue: local reduction + all-reduce in one launch.  Every thread of the CTA must call it.
 template <int OP>   // 0 sum, 1 max
-__global__ void __launch_bounds__(256) k_peer_allreduce(PeerRedArgs a, PeerState* ps, double* __restrict__ v, int n)
+__device__ __forceinline__ void peer_allreduce_body(const PeerRedArgs& a, PeerState* ps, double* __restrict__ v, int n)
 {
   __shared__ unsigned long long s_epoch;
   __shared__ int s_ok;
+  __syncthreads();
   if (threadIdx.x == 0) { s_epoch = ps->red_epoch + 1; s_ok = 1; }
   __syncthreads();
   const unsigned long long epoch = s_epoch;
@@ -108,7 +117,7 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(PeerRedArgs a, PeerState
   // 1. own partials into every rank's mailbox (including our own: the sum below then treats all ranks alike)
   for (int t = threadIdx.x; t < n*a.nranks; t += blockDim.x) {
     const int p = t / n, i = t - p*n;
-    reinterpret_cast<double*>(a.win[p] + mail)[i] = v[i];
+    reinterpret_cast<double*>(a.win[p] + mail)[i] = __ldcg(v + i);
   }
   __threadfence_system();
   __syncthreads();
@@ -131,6 +140,12 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(PeerRedArgs a, PeerState
     v[i] = s;
   }
   if (threadIdx.x == 0) { ps->red_epoch = epoch; if (!s_ok) ps->error = 2; }
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256) k_peer_allreduce(PeerRedArgs a, PeerState* ps, double* __restrict__ v, int n)
+{
+  peer_allreduce_body<OP>(a, ps, v, n);
 }
 
 // ---- halo push: pack the overlap rows of V straight into the neighbours' windows -----------------------------------------

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round 2, GPU call 9 (TWO B200s): the fused product + exchange kernel: parity on all three transports, N = 2 bench fused vs unfused.
+# Round 2, GPU call 10 (TWO B200s): the fused product + exchange kernel: parity on all three transports, N = 2 bench fused vs unfused.
 mkdir -p gpurun_out
 ( time timeout 1200 python -m pytest tests/test_multigpu.py -m gpu -q --timeout 900 -p no:cacheprovider ) > gpurun_out/r02i_pytest.log 2>&1
 echo "pytest rc $?" >> gpurun_out/r02i_pytest.log
