@@ -316,7 +316,8 @@ long long b200_launch_count(b200_handle* h);
  * row tiles; "schur_gp", "schur_sp" 0 / 1 (two / four entries in flight) / 2 TMA-staged; "narrow" (spmv_ss/sv/vs) 0 / 2;
  * "cg_batch" iterations enqueued per host poll of the device-resident CG loops; "fused" 1 (default) / 0: with the peer transport, the
  * partitioned block products run as ONE cooperative kernel each (rows + overlap exchange + ordered add, csrc/fused_halo.cuh) or as the
- * four launches boundary rows / push / interior rows / wait-add. */
+ * four launches boundary rows / push / interior rows / wait-add; "gmres_device" 1 (default) / 0: the Arnoldi loops keep their Givens
+ * bookkeeping and convergence test on the device (the host polls one batch behind) or fetch the reduced dots every iteration. */
 int b200_tune(b200_handle* h, const char* name, int value);
 /* Live kernel timing inside a step.  b200_profile(h,1) resets the counters and makes every kernel
  * class record CUDA-event pairs on the launch stream; b200_profile_read synchronises and returns,

@@ -2133,7 +2133,9 @@ int b200_tune(b200_handle* h, const char* name, int value)
     else if (n == "narrow") ops.variant_narrow = value;
     else if (n == "cg_batch") ops.cg_batch = std::max(1, value);
     else if (n == "fused") ops.variant_fused = value;
-    else throw std::runtime_error("tune: unknown knob '" + n + "' (vv3, schur_gp, schur_sp, narrow, cg_batch, fused)");
+    else if (n == "gmres_device") ops.variant_gmres_device = value;
+    else if (n == "face_fused") ops.variant_face_fused = value;
+    else throw std::runtime_error("tune: unknown knob '" + n + "' (vv3, schur_gp, schur_sp, narrow, cg_batch, fused, gmres_device, face_fused)");
   });
 }
 

@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "peer_comm.cuh"
+
 namespace svb200 {
 
 constexpr int kSmCount = 148;           // B200: 2 dies x 74 SMs; grids are sized in multiples of this
@@ -491,7 +493,8 @@ k_schur_sp4(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPt
 // =================================================================================================
 __global__ void __launch_bounds__(kRedThreads)
 k_multi_dot(const int* __restrict__ skip, size_t n, const double* __restrict__ base, size_t stride, const double* __restrict__ w, int cnt,
-            double* __restrict__ partial, unsigned int* __restrict__ counter, double* __restrict__ red, int slot0)
+            double* __restrict__ partial, unsigned int* __restrict__ counter, double* __restrict__ red, int slot0,
+            PeerRedArgs pa = PeerRedArgs(), PeerState* ps = nullptr)      // ps != null: the last CTA also all-reduces red[slot0 .. slot0+cnt)
 {
   if (skip && *skip) return;
   __shared__ double sm[kRedThreads/32][kDotJB];
@@ -558,6 +561,7 @@ k_multi_dot(const int* __restrict__ skip, size_t n, const double* __restrict__ b
       if (lane == 0) red[slot0 + j] = v;
     }
     if (threadIdx.x == 0) *counter = 0u;
+    if (ps) peer_allreduce_body<0>(pa, ps, red + slot0, cnt);        // (starts with a __syncthreads: red[] is complete)
   }
 }
 
@@ -667,6 +671,38 @@ __global__ void k_bicg_p(size_t n, double* __restrict__ P, const double* __restr
 // kernel of the remaining (already enqueued) iterations returns at once.
 struct CgState { double err, errO, eps; int done, suc, last_i, pad; };
 
+// ---- device-resident Arnoldi bookkeeping (Hessenberg::finish_column of krylov.hpp, liner_solver/gmres.cpp:556-612) -------------
+// One thread: column i of the Hessenberg matrix from the reduced dots, the Pythagorean norm, the Givens rotations and the residual
+// estimate; sets `done` when |err(i+1)| < eps.  Every product and sum is rounded separately (__dmul_rn / __dadd_rn: no FMA
+// contraction), so the numbers are bit-identical to the host version the serial test policy runs against the compiled reference.
+// `done` must stay the FIRST int after the doubles: the skip pointer of the heavy kernels points at it.
+struct GmresState { double eps, err0; int done, suc, last_i, pad; };
+__global__ void k_gmres_givens(GmresState* st, int i, int sD, const double* __restrict__ red, double* __restrict__ h,
+                               double* __restrict__ c, double* __restrict__ s, double* __restrict__ err)
+{
+  if (st->done) return;
+  double* col = h + size_t(i)*(sD + 1);
+  for (int j = 0; j <= i + 1; j++) col[j] = red[j];
+  if (i == 0) err[0] = st->err0;
+  double hh = col[i+1];
+  for (int j = 0; j <= i; j++) hh = __dsub_rn(hh, __dmul_rn(col[j], col[j]));
+  col[i+1] = sqrt(fabs(hh));
+  for (int j = 0; j <= i - 1; j++) {
+    const double tmp = __dadd_rn(__dmul_rn(c[j], col[j]), __dmul_rn(s[j], col[j+1]));
+    col[j+1] = __dadd_rn(__dmul_rn(-s[j], col[j]), __dmul_rn(c[j], col[j+1]));
+    col[j] = tmp;
+  }
+  const double tmp = sqrt(__dadd_rn(__dmul_rn(col[i], col[i]), __dmul_rn(col[i+1], col[i+1])));
+  c[i] = col[i] / tmp;
+  s[i] = col[i+1] / tmp;
+  col[i] = tmp;
+  col[i+1] = 0.0;
+  err[i+1] = __dmul_rn(-s[i], err[i]);
+  err[i] = __dmul_rn(c[i], err[i]);
+  st->last_i = i;
+  if (fabs(err[i+1]) < st->eps) { st->done = 1; st->suc = 1; }
+}
+
 // top of iteration i:  last_i = i; if (err < eps) { suc; break; }  errO = err;
 __global__ void k_cg_head(CgState* st, int i)
 {
@@ -680,7 +716,8 @@ __global__ void k_cg_head(CgState* st, int i)
 __global__ void __launch_bounds__(kRedThreads)
 k_cg_update(size_t n, size_t nOwn, const CgState* __restrict__ st, const double* __restrict__ red_dot,
             const double* __restrict__ P, const double* __restrict__ SP, double* __restrict__ X, double* __restrict__ R,
-            double* __restrict__ partial, unsigned int* __restrict__ counter, double* __restrict__ red_out)
+            double* __restrict__ partial, unsigned int* __restrict__ counter, double* __restrict__ red_out,
+            PeerRedArgs pa = PeerRedArgs(), PeerState* ps = nullptr)      // ps != null: the last CTA also all-reduces red_out[0]
 {
   if (st->done) return;
   __shared__ double sm[kRedThreads/32];
@@ -718,6 +755,7 @@ k_cg_update(size_t n, size_t nOwn, const CgState* __restrict__ st, const double*
     for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
     if (lane == 0) { red_out[0] = v; *counter = 0u; }
   }
+  if (last && ps) peer_allreduce_body<0>(pa, ps, red_out, 1);
 }
 // err = (sqrt(red))^2;  P = (err/errO) * (P + (errO/err) R);  state.err = err   (cgrad.cpp:222-227)
 __global__ void __launch_bounds__(256)
@@ -1071,6 +1109,40 @@ __global__ void k_face_axpy(int fnNo, int m, int fdof, int dof, const int* __res
   for (int t = blockIdx.x*blockDim.x + threadIdx.x; t < n; t += gridDim.x*blockDim.x) {
     const int a = t / m, i = t % m;
     Y[size_t(glob[a])*dof + i] += valM[size_t(a)*fdof + i]*s;
+  }
+}
+
+// both stages in ONE single-CTA launch for a face that lives on one rank (no all-reduce between the stages): S = v^T X over the
+// face, then Y += coef S v.  X may alias Y: every thread finishes reading before anyone writes.  Fixed-shape reduction
+// (thread-strided serial sums, shuffle tree, warp sums in order) -> deterministic.
+__global__ void __launch_bounds__(1024)
+k_face_rank1(int fnNo, int m, int fdof, int ld, int lim, const int* __restrict__ glob, const double* __restrict__ valM,
+             const double* X, double coef, double* Y)
+{
+  const int n = fnNo*m;
+  double acc = 0.0;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    const int a = t / m, i = t % m;
+    const int Ac = glob[a];
+    if (Ac < lim) acc = fma(valM[size_t(a)*fdof + i], X[size_t(Ac)*ld + i], acc);
+  }
+  __shared__ double sm[32];
+  __shared__ double S;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if (lane == 0) sm[wid] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int k = 0; k < int(blockDim.x >> 5); k++) v += sm[k];
+    S = coef*v;
+  }
+  __syncthreads();
+  const double s = S;
+  for (int t = threadIdx.x; t < n; t += blockDim.x) {
+    const int a = t / m, i = t % m;
+    Y[size_t(glob[a])*ld + i] += valM[size_t(a)*fdof + i]*s;
   }
 }
 

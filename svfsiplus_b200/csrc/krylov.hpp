@@ -148,6 +148,11 @@ struct Hessenberg {
 template <class T, class = void> struct has_cg_device : std::false_type {};
 template <class T> struct has_cg_device<T, std::void_t<decltype(&T::cg_batch)>> : std::true_type {};
 
+template <class T, class = void> struct has_gmres_device : std::false_type {};
+template <class T> struct has_gmres_device<T, std::void_t<decltype(&T::gmres_device_ok)>> : std::true_type {};
+template <class T, class = void> struct has_dots_reduce : std::false_type {};
+template <class T> struct has_dots_reduce<T, std::void_t<decltype(&T::dots_reduce)>> : std::true_type {};
+
 template <class Ops> inline bool any_coupled(Ops& ops)
 {
   for (int f = 0; f < ops.n_faces(); f++) if (ops.face_coupled(f)) return true;
@@ -157,12 +162,30 @@ template <class Ops> inline bool any_coupled(Ops& ops)
 // One Arnoldi step shared by both GMRES flavours: w = u[i+1] already holds K u[i] (+bc terms).
 // Queues the (i+2) local dots, reduces them, queues the Gram-Schmidt update + normalisation (which
 // reads the reduced dots on the device) and returns the reduced column on the host.
+// the device part of an Arnoldi step alone (dots + all-reduce + Gram-Schmidt update), for the device-resident loop
+template <class Ops>
+inline void arnoldi_enqueue(Ops& ops, int dof, double* u, size_t stride, int i)
+{
+  double* w = u + size_t(i+1)*stride;
+  if constexpr (has_dots_reduce<Ops>::value) {
+    ops.dots_reduce(dof, i+2, u, stride, w, 0);
+  } else {
+    ops.dots_local(dof, i+2, u, stride, w, 0);
+    ops.reduce_begin(i+2);
+  }
+  ops.cgs_update_scale(dof, i+1, u, stride, w, 0);
+}
+
 template <class Ops>
 inline void arnoldi_orthogonalise(Ops& ops, int dof, double* u, size_t stride, int i, Hessenberg& hs)
 {
   double* w = u + size_t(i+1)*stride;
-  ops.dots_local(dof, i+2, u, stride, w, 0);
-  ops.reduce_begin(i+2);
+  if constexpr (has_dots_reduce<Ops>::value) {
+    ops.dots_reduce(dof, i+2, u, stride, w, 0);        // local dots + all-reduce in one launch where the policy can
+  } else {
+    ops.dots_local(dof, i+2, u, stride, w, 0);
+    ops.reduce_begin(i+2);
+  }
   ops.cgs_update_scale(dof, i+1, u, stride, w, 0);     // consumes the reduced slots on the device
   ops.reduce_fetch(i+2, &hs.H(0,i));
 }
@@ -214,6 +237,23 @@ void gmres_v(Ops& ops, SubLs& ls, int dof, const double* Val, double* R)
     hs.err[0] = ops.norm(dof, u0);
     ops.divs(n, hs.err[0], u0);                 // u0 = u0 / err0 (a true division, like the reference)
 
+    bool on_device = false;
+    if constexpr (has_gmres_device<Ops>::value) on_device = ops.gmres_device_ok();
+    if constexpr (has_gmres_device<Ops>::value) {
+      if (on_device) {
+        bool suc = false;
+        last_i = ops.gmres_device_cycle(ls.sD, eps, hs.err[0], [&](int i) {
+          double* ui = u + size_t(i)*n;
+          double* ui1 = u + size_t(i+1)*n;
+          ops.spmv_vv(dof, Val, ui, ui1);
+          ops.add_bc_mul(BCOP_ADD, dof, ui, ui1);
+          arnoldi_enqueue(ops, dof, u, n, i);
+        }, hs, suc);
+        ls.itr += last_i + 1;
+        if (suc) ls.suc = true;
+      }
+    }
+    if (!on_device)
     for (int i = 0; i < ls.sD; i++) {
       ls.itr++;
       last_i = i;
@@ -288,6 +328,24 @@ void gmres_inner(Ops& ops, SubLs& ls, int dof, const double* Val, const double* 
     ls.dB = ls.fNorm;
     ops.divs(n, hs.err[0], u0);
 
+    bool on_device = false;
+    if constexpr (has_gmres_device<Ops>::value) on_device = ops.gmres_device_ok();
+    if constexpr (has_gmres_device<Ops>::value) {
+      if (on_device) {
+        bool suc = false;
+        last_i = ops.gmres_device_cycle(ls.sD, eps, hs.err[0], [&](int i) {
+          double* ui = u + size_t(i)*n;
+          double* ui1 = u + size_t(i+1)*n;
+          ops.spmv_vv(dof, Val, ui, ui1);
+          ops.add_bc_mul(BCOP_ADD, dof, ui, ui1);
+          if (coupled) ops.add_bc_mul(BCOP_PRE, dof, ui1, ui1);
+          arnoldi_enqueue(ops, dof, u, n, i);
+        }, hs, suc);
+        ls.itr += last_i + 1;
+        if (suc) ls.suc = true;
+      }
+    }
+    if (!on_device)
     for (int i = 0; i < ls.sD; i++) {
       last_i = i;
       double* ui = u + size_t(i)*n;

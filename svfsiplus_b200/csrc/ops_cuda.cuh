@@ -239,6 +239,16 @@ class CudaOps {
   cudaEvent_t cg_ev[2] = {nullptr, nullptr};
   int cg_batch = 8;
   const int* skip_flag = nullptr;      // != null inside a device-resident loop: heavy kernels return at once when set
+  // device-resident Arnoldi loop (gmres_device_cycle)
+  GmresState* gm_d = nullptr;
+  GmresState* gm_h = nullptr;          // pinned: [0..1] polling slots, [2] initial / final state
+  cudaEvent_t gm_ev[2] = {nullptr, nullptr};
+  double* gm_arr = nullptr;            // h((sD+1) x sD), c(sD), s(sD), err(sD+1)
+  double* gm_host = nullptr;           // pinned copy of h and err for the back substitution
+  int gm_sD = 0;
+  int gm_batch = 8;
+  int variant_face_fused = 1;          // b200_tune("face_fused", 0): the two-launch resistance-face update
+  int variant_gmres_device = 1;        // b200_tune("gmres_device", 0): host-driven Arnoldi loop (one D2H sync per iteration)
 
   // arena
   struct Chunk { char* p; size_t cap, top; };
@@ -278,6 +288,9 @@ class CudaOps {
     for (auto& r : reqs) { cudaFree(r.ptr); cudaFree(r.sbuf); cudaFree(r.rbuf); }
     cudaFree(rowPtr); cudaFree(col); cudaFree(diag); cudaFree(tpos); cudaFree(tile_row);
     cudaFree(cg_d); cudaFreeHost(cg_h);
+    cudaFree(gm_d); cudaFreeHost(gm_h); cudaFree(gm_arr); cudaFreeHost(gm_host);
+    if (gm_ev[0]) cudaEventDestroy(gm_ev[0]);
+    if (gm_ev[1]) cudaEventDestroy(gm_ev[1]);
     if (cg_ev[0]) cudaEventDestroy(cg_ev[0]);
     if (cg_ev[1]) cudaEventDestroy(cg_ev[1]);
     cudaFree(red_d); cudaFreeHost(red_h); cudaFree(partial_d); cudaFree(counter_d); cudaFree(face_partial_d);
@@ -406,6 +419,19 @@ class CudaOps {
     nccl.check(nccl.AllReduce(v, v, size_t(n), Nccl::kFloat64, is_max ? Nccl::kMax : Nccl::kSum, comm, st), "AllReduce");
   }
   void reduce_begin(int nslots) { allreduce(red_d, nslots); }
+  // dots_local + the all-reduce of the same slots in ONE launch: the last CTA of the reduction kernel runs the all-reduce as its
+  // epilogue (peer transport, one launch of <= kMaxDots dots); otherwise the two separate steps
+  bool fuse_reduce() const { return variant_fused != 0 && nranks > 1 && p2p; }
+  void dots_reduce(int dof, int count, const double* base, size_t stride, const double* w, int slot0)
+  {
+    if (!fuse_reduce() || count > kMaxDots) { dots_local(dof, count, base, stride, w, slot0); allreduce(red_d + slot0, count); return; }
+    if (slot0 + count > kMaxSlots) throw std::runtime_error("reduction slot overflow");
+    const size_t n = size_t(dof)*mynNo_;
+    Scope sc(*this, KC_MULTI_DOT, 8.0*double(n)*(count + 1));
+    const int g = int(std::min<size_t>(size_t(kRedBlocks), (n + 1023)/1024 + 1));
+    k_multi_dot<<<g, kRedThreads, 0, st>>>(skip_flag, n, base, stride, w, count, partial_d, counter_d, red_d, slot0, red_args, peer_state);
+    post();
+  }
   void reduce_fetch(int nslots, double* out)
   {
     CU_CHECK(cudaMemcpyAsync(red_h, red_d, sizeof(double)*nslots, cudaMemcpyDeviceToHost, st));
@@ -809,6 +835,15 @@ class CudaOps {
       const double coef = (op == BCOP_ADD) ? fa.res : -fa.res/(1.0 + fa.res*fa.nS);
       const int m = std::min(fa.dof, dof);
       const int lim = fa.shared ? mynNo_ : nNo_;
+      if (!(fa.shared && nranks > 1)) {
+        // the face lives on this rank alone: ranks that hold none of it have nothing to do, the owner does both stages in one launch
+        if (fa.nNo == 0) continue;
+        if (variant_face_fused && size_t(fa.nNo)*m <= 131072) {
+          k_face_rank1<<<1, 1024, 0, st>>>(fa.nNo, m, fa.dof, ld, lim, fa.glob, fa.valM, X, coef, Y);
+          post();
+          continue;
+        }
+      }
       double* S = red_d + (kMaxSlots - 1);
       face_dot(fa, m, ld, lim, X, S);
       if (fa.shared && nranks > 1) allreduce(S, 1);
@@ -1013,13 +1048,14 @@ class CudaOps {
       for (int k = 0; k < nb; k++) {
         k_cg_head<<<1, 1, 0, st>>>(cg_d, enq + k); post();
         apply(P, SP);
-        dots_local(dof, 1, P, 0, SP, 0);
-        reduce_begin(1);
+        dots_reduce(dof, 1, P, 0, SP, 0);
         {
           Scope sc(*this, KC_BLAS1, 48.0*double(n));
-          k_cg_update<<<g, kRedThreads, 0, st>>>(n, nOwn, cg_d, red_d, P, SP, X, R, partial_d, counter_d, red_d + 1); post();
+          if (fuse_reduce()) k_cg_update<<<g, kRedThreads, 0, st>>>(n, nOwn, cg_d, red_d, P, SP, X, R, partial_d, counter_d, red_d + 1, red_args, peer_state);
+          else k_cg_update<<<g, kRedThreads, 0, st>>>(n, nOwn, cg_d, red_d, P, SP, X, R, partial_d, counter_d, red_d + 1);
+          post();
         }
-        allreduce(red_d + 1, 1);
+        if (!fuse_reduce()) allreduce(red_d + 1, 1);
         {
           Scope sc(*this, KC_BLAS1, 24.0*double(n));
           k_cg_pupdate<<<grid_for(n, 256), 256, 0, st>>>(n, cg_d, red_d + 1, R, P); post();
@@ -1045,6 +1081,71 @@ class CudaOps {
     last_i = cg_h[2].last_i;
     err = cg_h[2].err;
     errO = cg_h[2].errO;
+  }
+
+  // ---- device-resident Arnoldi loop ---------------------------------------------------------------------------------------------
+  // One restart cycle of gmres / gmres_v (krylov.hpp) without a host round trip per iteration: `step(i)` enqueues the product, the
+  // resistance-face terms, the dots (+ all-reduce) and the Gram-Schmidt update of iteration i; k_gmres_givens then does the Givens
+  // bookkeeping and the convergence test on the device.  The host enqueues iterations in batches and polls the state one batch
+  // behind (as the CG loops do); iterations enqueued past convergence return at once (skip flag).  On return hs holds the columns
+  // 0..last_i of the Hessenberg matrix and the residual estimates, as the host loop would have left them.
+  bool gmres_device_ok() const { return variant_gmres_device != 0; }
+  template <class Step>
+  int gmres_device_cycle(int sD, double eps, double err0, Step&& step, Hessenberg& hs, bool& suc)
+  {
+    if (sD > gm_sD || !gm_d) {
+      if (!gm_d) {
+        CU_CHECK(cudaMalloc(&gm_d, sizeof(GmresState)));
+        CU_CHECK(cudaMallocHost(&gm_h, 3*sizeof(GmresState)));
+        CU_CHECK(cudaEventCreateWithFlags(&gm_ev[0], cudaEventDisableTiming));
+        CU_CHECK(cudaEventCreateWithFlags(&gm_ev[1], cudaEventDisableTiming));
+      }
+      cudaFree(gm_arr); cudaFreeHost(gm_host);
+      const size_t nd = size_t(sD + 1)*sD + 3*size_t(sD) + 2;
+      CU_CHECK(cudaMalloc(&gm_arr, sizeof(double)*nd));
+      CU_CHECK(cudaMallocHost(&gm_host, sizeof(double)*nd));
+      gm_sD = sD;
+    }
+    double* d_h = gm_arr;
+    double* d_c = d_h + size_t(gm_sD + 1)*gm_sD;
+    double* d_s = d_c + gm_sD;
+    double* d_err = d_s + gm_sD;
+    GmresState init;
+    init.eps = eps; init.err0 = err0; init.done = 0; init.suc = 0; init.last_i = 0; init.pad = 0;
+    gm_h[2] = init;
+    CU_CHECK(cudaMemcpyAsync(gm_d, &gm_h[2], sizeof(GmresState), cudaMemcpyHostToDevice, st));
+    const int* outer_skip = skip_flag;
+    skip_flag = &gm_d->done;
+    int enq = 0, slot = 0, pending = -1;
+    bool stop = (sD <= 0);
+    while (!stop) {
+      const int nb = std::min(gm_batch, sD - enq);
+      for (int k = 0; k < nb; k++) {
+        step(enq + k);
+        k_gmres_givens<<<1, 1, 0, st>>>(gm_d, enq + k, sD, red_d, d_h, d_c, d_s, d_err); post();
+      }
+      enq += nb;
+      CU_CHECK(cudaMemcpyAsync(&gm_h[slot], gm_d, sizeof(GmresState), cudaMemcpyDeviceToHost, st));
+      CU_CHECK(cudaEventRecord(gm_ev[slot], st));
+      if (pending >= 0) {
+        CU_CHECK(cudaEventSynchronize(gm_ev[pending]));
+        if (gm_h[pending].done) stop = true;
+      }
+      pending = slot; slot ^= 1;
+      if (enq >= sD) stop = true;
+    }
+    skip_flag = outer_skip;
+    CU_CHECK(cudaMemcpyAsync(&gm_h[2], gm_d, sizeof(GmresState), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    const int last_i = gm_h[2].last_i;
+    suc = gm_h[2].suc != 0;
+    // the columns the back substitution needs + the residual estimates
+    CU_CHECK(cudaMemcpyAsync(gm_host, d_h, sizeof(double)*size_t(last_i + 1)*(sD + 1), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaMemcpyAsync(gm_host + size_t(sD + 1)*sD, d_err, sizeof(double)*(last_i + 2), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    std::memcpy(hs.h.data(), gm_host, sizeof(double)*size_t(last_i + 1)*(sD + 1));
+    std::memcpy(hs.err.data(), gm_host + size_t(sD + 1)*sD, sizeof(double)*(last_i + 2));
+    return last_i;
   }
 
   void split_mc(int dof, const double* Ri, double* Rm, double* Rc)
