@@ -570,8 +570,9 @@ k_multi_dot(const int* __restrict__ skip, size_t n, const double* __restrict__ b
 // (omp_sum_v / omp_mul_v calls at liner_solver/gmres.cpp:561-569; same left-to-right order.)
 __global__ void __launch_bounds__(256)
 k_cgs_update_scale(size_t n, int k, const double* __restrict__ base, size_t stride, double* __restrict__ w,
-                   const double* __restrict__ red, int slot0)
+                   const double* __restrict__ red, int slot0, const int* __restrict__ skip = nullptr)
 {
+  if (skip && *skip) return;
   extern __shared__ double hs[];     // k+1 coefficients
   for (int j = threadIdx.x; j <= k; j += blockDim.x) hs[j] = red[slot0 + j];
   __syncthreads();
@@ -677,30 +678,43 @@ struct CgState { double err, errO, eps; int done, suc, last_i, pad; };
 // contraction), so the numbers are bit-identical to the host version the serial test policy runs against the compiled reference.
 // `done` must stay the FIRST int after the doubles: the skip pointer of the heavy kernels points at it.
 struct GmresState { double eps, err0; int done, suc, last_i, pad; };
-__global__ void k_gmres_givens(GmresState* st, int i, int sD, const double* __restrict__ red, double* __restrict__ h,
-                               double* __restrict__ c, double* __restrict__ s, double* __restrict__ err)
+constexpr int kGivensMax = 1024;          // Krylov dimensions up to this keep the column in shared memory
+__global__ void __launch_bounds__(256)
+k_gmres_givens(GmresState* st, int i, int sD, const double* __restrict__ red, double* __restrict__ h,
+               double* __restrict__ c, double* __restrict__ s, double* __restrict__ err)
 {
   if (st->done) return;
-  double* col = h + size_t(i)*(sD + 1);
-  for (int j = 0; j <= i + 1; j++) col[j] = red[j];
-  if (i == 0) err[0] = st->err0;
-  double hh = col[i+1];
-  for (int j = 0; j <= i; j++) hh = __dsub_rn(hh, __dmul_rn(col[j], col[j]));
-  col[i+1] = sqrt(fabs(hh));
-  for (int j = 0; j <= i - 1; j++) {
-    const double tmp = __dadd_rn(__dmul_rn(c[j], col[j]), __dmul_rn(s[j], col[j+1]));
-    col[j+1] = __dadd_rn(__dmul_rn(-s[j], col[j]), __dmul_rn(c[j], col[j+1]));
-    col[j] = tmp;
+  // the column and the rotations are staged in shared memory by the whole CTA (coalesced), the inherently sequential recurrences
+  // run on one thread out of shared memory (a single thread walking global memory costs ~1 us per dependent access)
+  __shared__ double sc[kGivensMax + 2], cc[kGivensMax], ss[kGivensMax];
+  for (int j = threadIdx.x; j <= i + 1; j += blockDim.x) sc[j] = red[j];
+  for (int j = threadIdx.x; j < i; j += blockDim.x) { cc[j] = c[j]; ss[j] = s[j]; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double hh = sc[i+1];
+    for (int j = 0; j <= i; j++) hh = __dsub_rn(hh, __dmul_rn(sc[j], sc[j]));
+    sc[i+1] = sqrt(fabs(hh));
+    for (int j = 0; j <= i - 1; j++) {
+      const double tmp = __dadd_rn(__dmul_rn(cc[j], sc[j]), __dmul_rn(ss[j], sc[j+1]));
+      sc[j+1] = __dadd_rn(__dmul_rn(-ss[j], sc[j]), __dmul_rn(cc[j], sc[j+1]));
+      sc[j] = tmp;
+    }
+    const double tmp = sqrt(__dadd_rn(__dmul_rn(sc[i], sc[i]), __dmul_rn(sc[i+1], sc[i+1])));
+    const double ci = sc[i] / tmp, si = sc[i+1] / tmp;
+    c[i] = ci;
+    s[i] = si;
+    sc[i] = tmp;
+    sc[i+1] = 0.0;
+    const double e0 = (i == 0) ? st->err0 : err[i];
+    const double e1 = __dmul_rn(-si, e0);
+    err[i+1] = e1;
+    err[i] = __dmul_rn(ci, e0);
+    st->last_i = i;
+    if (fabs(e1) < st->eps) { st->done = 1; st->suc = 1; }
   }
-  const double tmp = sqrt(__dadd_rn(__dmul_rn(col[i], col[i]), __dmul_rn(col[i+1], col[i+1])));
-  c[i] = col[i] / tmp;
-  s[i] = col[i+1] / tmp;
-  col[i] = tmp;
-  col[i+1] = 0.0;
-  err[i+1] = __dmul_rn(-s[i], err[i]);
-  err[i] = __dmul_rn(c[i], err[i]);
-  st->last_i = i;
-  if (fabs(err[i+1]) < st->eps) { st->done = 1; st->suc = 1; }
+  __syncthreads();
+  double* col = h + size_t(i)*(sD + 1);
+  for (int j = threadIdx.x; j <= i + 1; j += blockDim.x) col[j] = sc[j];
 }
 
 // top of iteration i:  last_i = i; if (err < eps) { suc; break; }  errO = err;

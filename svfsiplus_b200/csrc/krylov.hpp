@@ -238,7 +238,7 @@ void gmres_v(Ops& ops, SubLs& ls, int dof, const double* Val, double* R)
     ops.divs(n, hs.err[0], u0);                 // u0 = u0 / err0 (a true division, like the reference)
 
     bool on_device = false;
-    if constexpr (has_gmres_device<Ops>::value) on_device = ops.gmres_device_ok();
+    if constexpr (has_gmres_device<Ops>::value) on_device = ops.gmres_device_ok() && ls.sD <= Ops::kGivensMaxHost;
     if constexpr (has_gmres_device<Ops>::value) {
       if (on_device) {
         bool suc = false;
@@ -329,7 +329,7 @@ void gmres_inner(Ops& ops, SubLs& ls, int dof, const double* Val, const double* 
     ops.divs(n, hs.err[0], u0);
 
     bool on_device = false;
-    if constexpr (has_gmres_device<Ops>::value) on_device = ops.gmres_device_ok();
+    if constexpr (has_gmres_device<Ops>::value) on_device = ops.gmres_device_ok() && ls.sD <= Ops::kGivensMaxHost;
     if constexpr (has_gmres_device<Ops>::value) {
       if (on_device) {
         bool suc = false;

@@ -452,7 +452,7 @@ class CudaOps {
   {
     const size_t n = size_t(dof)*nNo_;
     Scope sc(*this, KC_CGS_UPDATE, 8.0*double(n)*(k + 2));
-    k_cgs_update_scale<<<grid_for(n, 256), 256, sizeof(double)*(k+1), st>>>(n, k, base, stride, w, red_d, slot0);
+    k_cgs_update_scale<<<grid_for(n, 256), 256, sizeof(double)*(k+1), st>>>(n, k, base, stride, w, red_d, slot0, skip_flag);
     post();
   }
 
@@ -1090,6 +1090,7 @@ class CudaOps {
   // behind (as the CG loops do); iterations enqueued past convergence return at once (skip flag).  On return hs holds the columns
   // 0..last_i of the Hessenberg matrix and the residual estimates, as the host loop would have left them.
   bool gmres_device_ok() const { return variant_gmres_device != 0; }
+  static constexpr int kGivensMaxHost = kGivensMax;
   template <class Step>
   int gmres_device_cycle(int sD, double eps, double err0, Step&& step, Hessenberg& hs, bool& suc)
   {
@@ -1122,7 +1123,7 @@ class CudaOps {
       const int nb = std::min(gm_batch, sD - enq);
       for (int k = 0; k < nb; k++) {
         step(enq + k);
-        k_gmres_givens<<<1, 1, 0, st>>>(gm_d, enq + k, sD, red_d, d_h, d_c, d_s, d_err); post();
+        k_gmres_givens<<<1, 256, 0, st>>>(gm_d, enq + k, sD, red_d, d_h, d_c, d_s, d_err); post();
       }
       enq += nb;
       CU_CHECK(cudaMemcpyAsync(&gm_h[slot], gm_d, sizeof(GmresState), cudaMemcpyDeviceToHost, st));
