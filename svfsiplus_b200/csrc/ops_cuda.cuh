@@ -268,6 +268,9 @@ class CudaOps {
       CU_CHECK(cudaEventCreateWithFlags(&ev_c, cudaEventDisableTiming));
     }
     if (const char* e = getenv("SVB200_FUSED")) variant_fused = std::atoi(e);      // A/B of the fused product + exchange kernel
+    if (const char* e = getenv("SVB200_GMRES_DEVICE")) variant_gmres_device = std::atoi(e);
+    if (const char* e = getenv("SVB200_FACE_FUSED")) variant_face_fused = std::atoi(e);
+    if (const char* e = getenv("SVB200_GM_BATCH")) gm_batch = std::max(1, std::atoi(e));
     CU_CHECK(cudaMalloc(&red_d, sizeof(double)*kMaxSlots));
     CU_CHECK(cudaMallocHost(&red_h, sizeof(double)*kMaxSlots));
     CU_CHECK(cudaMalloc(&partial_d, sizeof(double)*kRedBlocks*kMaxDots));
