@@ -247,7 +247,9 @@ class CudaOps {
   double* gm_host = nullptr;           // pinned copy of h and err for the back substitution
   int gm_sD = 0;
   int gm_batch = 8;
-  int variant_face_fused = 1;          // b200_tune("face_fused", 0): the two-launch resistance-face update
+  int variant_face_fused = 0;          // b200_tune("face_fused", 1): single-CTA one-launch resistance-face update.  Measured SLOWER at P10
+                                       // (1 665 vs 1 593 ms per Newton iteration, profiles/r02_ab_device_loop.txt): one CTA walking
+                                       // the 28 k face values costs ~40 us against two multi-CTA launches of ~5 us
   int variant_gmres_device = 1;        // b200_tune("gmres_device", 0): host-driven Arnoldi loop (one D2H sync per iteration)
 
   // arena
