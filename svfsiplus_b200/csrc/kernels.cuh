@@ -494,7 +494,8 @@ k_schur_sp4(const int* __restrict__ skip, int nNo, const int* __restrict__ rowPt
 __global__ void __launch_bounds__(kRedThreads)
 k_multi_dot(const int* __restrict__ skip, size_t n, const double* __restrict__ base, size_t stride, const double* __restrict__ w, int cnt,
             double* __restrict__ partial, unsigned int* __restrict__ counter, double* __restrict__ red, int slot0,
-            PeerRedArgs pa = PeerRedArgs(), PeerState* ps = nullptr)      // ps != null: the last CTA also all-reduces red[slot0 .. slot0+cnt)
+            PeerRedArgs pa = PeerRedArgs(), PeerState* ps = nullptr,      // ps != null: the last CTA also all-reduces red[slot0 .. slot0+cnt)
+            int defer_tail = 0)        // 1: only write the per-CTA partials, TRANSPOSED (partial[j*gridDim + cta]); k_multi_dot_final adds them
 {
   if (skip && *skip) return;
   __shared__ double sm[kRedThreads/32][kDotJB];
@@ -539,10 +540,12 @@ k_multi_dot(const int* __restrict__ skip, size_t n, const double* __restrict__ b
       double v = 0.0;
 #pragma unroll
       for (int k = 0; k < kRedThreads/32; k++) v += sm[k][threadIdx.x];
-      partial[size_t(blockIdx.x)*cnt + j0 + threadIdx.x] = v;
+      if (defer_tail) partial[size_t(j0 + threadIdx.x)*gridDim.x + blockIdx.x] = v;
+      else partial[size_t(blockIdx.x)*cnt + j0 + threadIdx.x] = v;
     }
     __syncthreads();
   }
+  if (defer_tail) return;
   __threadfence();
   if (threadIdx.x == 0) {
     unsigned int t = atomicAdd(counter, 1u);
@@ -562,6 +565,44 @@ k_multi_dot(const int* __restrict__ skip, size_t n, const double* __restrict__ b
     }
     if (threadIdx.x == 0) *counter = 0u;
     if (ps) peer_allreduce_body<0>(pa, ps, red + slot0, cnt);        // (starts with a __syncthreads: red[] is complete)
+  }
+}
+
+// Second stage of k_multi_dot for many dots: with one CTA doing the ordered sum of G partials for cnt columns (the in-kernel tail)
+// the tail costs ~0.3 us per column - 30+ us at a basis depth of 100, more than the first stage itself once the vectors are split
+// over 8 GPUs.  Here one WARP per column, spread over ceil(cnt/8) CTAs, reads the transposed partials with coalesced loads and adds
+// them in exactly the order of the in-kernel tail (lane-strided serial sums in CTA order, fixed shuffle tree): bit-identical results.
+// The last CTA to finish runs the all-reduce epilogue.
+__global__ void __launch_bounds__(kRedThreads)
+k_multi_dot_final(const int* __restrict__ skip, int G, int cnt, const double* __restrict__ partialT, unsigned int* __restrict__ counter,
+                  double* __restrict__ red, int slot0, PeerRedArgs pa = PeerRedArgs(), PeerState* ps = nullptr)
+{
+  if (skip && *skip) return;
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int j = blockIdx.x*(kRedThreads/32) + wid;
+  if (j < cnt) {
+    const double* col = partialT + size_t(j)*G;
+    double v = 0.0;
+    int b = lane;
+    for (; b + 96 < G; b += 128) {
+      const double p0 = __ldcg(col + b), p1 = __ldcg(col + b + 32), p2 = __ldcg(col + b + 64), p3 = __ldcg(col + b + 96);
+      v += p0; v += p1; v += p2; v += p3;
+    }
+    for (; b < G; b += 32) v += __ldcg(col + b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[slot0 + j] = v;
+  }
+  if (!ps) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last) {
+    if (threadIdx.x == 0) *counter = 0u;
+    __threadfence();
+    peer_allreduce_body<0>(pa, ps, red + slot0, cnt);
   }
 }
 

@@ -229,6 +229,7 @@ class CudaOps {
 
   // reductions
   static constexpr int kMaxSlots = 1024;
+  static constexpr int kDotsTwoStage = 12;   // from this many dots per launch the ordered sum of the partials runs as its own kernel (warp per dot)
   double* red_d = nullptr;
   double* red_h = nullptr;        // pinned
   double* partial_d = nullptr;
@@ -405,8 +406,16 @@ class CudaOps {
       Scope sc(*this, KC_MULTI_DOT, 8.0*double(n)*(m + 1));
       // enough CTAs to fill the machine, never more than one per 1024 entries (tiny systems)
       const int g = int(std::min<size_t>(size_t(kRedBlocks), (n + 1023)/1024 + 1));
-      k_multi_dot<<<g, kRedThreads, 0, st>>>(skip_flag, n, base + size_t(done)*stride, stride, w, m, partial_d, counter_d, red_d, slot0 + done);
-      post();
+      if (m >= kDotsTwoStage) {
+        k_multi_dot<<<g, kRedThreads, 0, st>>>(skip_flag, n, base + size_t(done)*stride, stride, w, m, partial_d, counter_d, red_d, slot0 + done,
+                                               PeerRedArgs(), nullptr, 1);
+        post();
+        k_multi_dot_final<<<(m + kRedThreads/32 - 1)/(kRedThreads/32), kRedThreads, 0, st>>>(skip_flag, g, m, partial_d, counter_d, red_d, slot0 + done);
+        post();
+      } else {
+        k_multi_dot<<<g, kRedThreads, 0, st>>>(skip_flag, n, base + size_t(done)*stride, stride, w, m, partial_d, counter_d, red_d, slot0 + done);
+        post();
+      }
       done += m;
     }
   }
@@ -434,8 +443,16 @@ class CudaOps {
     const size_t n = size_t(dof)*mynNo_;
     Scope sc(*this, KC_MULTI_DOT, 8.0*double(n)*(count + 1));
     const int g = int(std::min<size_t>(size_t(kRedBlocks), (n + 1023)/1024 + 1));
-    k_multi_dot<<<g, kRedThreads, 0, st>>>(skip_flag, n, base, stride, w, count, partial_d, counter_d, red_d, slot0, red_args, peer_state);
-    post();
+    if (count >= kDotsTwoStage) {
+      k_multi_dot<<<g, kRedThreads, 0, st>>>(skip_flag, n, base, stride, w, count, partial_d, counter_d, red_d, slot0, PeerRedArgs(), nullptr, 1);
+      post();
+      k_multi_dot_final<<<(count + kRedThreads/32 - 1)/(kRedThreads/32), kRedThreads, 0, st>>>(skip_flag, g, count, partial_d, counter_d, red_d, slot0,
+                                                                                                 red_args, peer_state);
+      post();
+    } else {
+      k_multi_dot<<<g, kRedThreads, 0, st>>>(skip_flag, n, base, stride, w, count, partial_d, counter_d, red_d, slot0, red_args, peer_state);
+      post();
+    }
   }
   void reduce_fetch(int nslots, double* out)
   {
