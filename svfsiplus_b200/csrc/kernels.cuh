@@ -606,14 +606,70 @@ k_multi_dot_final(const int* __restrict__ skip, int G, int cnt, const double* __
   }
 }
 
+// ---- device-resident Arnoldi bookkeeping (Hessenberg::finish_column of krylov.hpp, liner_solver/gmres.cpp:556-612) -------------
+// One thread: column i of the Hessenberg matrix from the reduced dots, the Pythagorean norm, the Givens rotations and the residual
+// estimate; sets `done` when |err(i+1)| < eps.  Every product and sum is rounded separately (__dmul_rn / __dadd_rn: no FMA
+// contraction), so the numbers are bit-identical to the host version the serial test policy runs against the compiled reference.
+// `done` must stay the FIRST int after the doubles: the skip pointer of the heavy kernels points at it.
+struct GmresState { double eps, err0; int done, suc, last_i, pad; };
+constexpr int kGivensMax = 1024;          // Krylov dimensions up to this keep the column in shared memory
+__device__ __forceinline__ void gmres_givens_body(GmresState* st, int i, int sD, const double* __restrict__ red, double* __restrict__ h,
+                                                  double* __restrict__ c, double* __restrict__ s, double* __restrict__ err)
+{
+  if (st->done) return;
+  // the column and the rotations are staged in shared memory by the whole CTA (coalesced), the inherently sequential recurrences
+  // run on one thread out of shared memory (a single thread walking global memory costs ~1 us per dependent access)
+  __shared__ double sc[kGivensMax + 2], cc[kGivensMax], ss[kGivensMax];
+  for (int j = threadIdx.x; j <= i + 1; j += blockDim.x) sc[j] = red[j];
+  for (int j = threadIdx.x; j < i; j += blockDim.x) { cc[j] = c[j]; ss[j] = s[j]; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double hh = sc[i+1];
+    for (int j = 0; j <= i; j++) hh = __dsub_rn(hh, __dmul_rn(sc[j], sc[j]));
+    sc[i+1] = sqrt(fabs(hh));
+    for (int j = 0; j <= i - 1; j++) {
+      const double tmp = __dadd_rn(__dmul_rn(cc[j], sc[j]), __dmul_rn(ss[j], sc[j+1]));
+      sc[j+1] = __dadd_rn(__dmul_rn(-ss[j], sc[j]), __dmul_rn(cc[j], sc[j+1]));
+      sc[j] = tmp;
+    }
+    const double tmp = sqrt(__dadd_rn(__dmul_rn(sc[i], sc[i]), __dmul_rn(sc[i+1], sc[i+1])));
+    const double ci = sc[i] / tmp, si = sc[i+1] / tmp;
+    c[i] = ci;
+    s[i] = si;
+    sc[i] = tmp;
+    sc[i+1] = 0.0;
+    const double e0 = (i == 0) ? st->err0 : err[i];
+    const double e1 = __dmul_rn(-si, e0);
+    err[i+1] = e1;
+    err[i] = __dmul_rn(ci, e0);
+    st->last_i = i;
+    if (fabs(e1) < st->eps) { st->done = 1; st->suc = 1; }
+  }
+  __syncthreads();
+  double* col = h + size_t(i)*(sD + 1);
+  for (int j = threadIdx.x; j <= i + 1; j += blockDim.x) col[j] = sc[j];
+}
+__global__ void __launch_bounds__(256)
+k_gmres_givens(GmresState* st, int i, int sD, const double* __restrict__ red, double* __restrict__ h,
+               double* __restrict__ c, double* __restrict__ s, double* __restrict__ err)
+{
+  gmres_givens_body(st, i, sD, red, h, c, s, err);
+}
+// arguments of the Givens bookkeeping when it rides on the Gram-Schmidt update kernel as one extra CTA (st == null: not riding)
+struct GivensRide { GmresState* st; int i, sD; double* h; double* c; double* s; double* err; };
+
 // K4  classical Gram-Schmidt update + normalisation in one pass
 //   w <- (w - sum_{j<k} h_j u_j) * 1/sqrt|h_k - sum_j h_j^2|,  h = red[slot0 ..]  (already reduced)
 // (omp_sum_v / omp_mul_v calls at liner_solver/gmres.cpp:561-569; same left-to-right order.)
 __global__ void __launch_bounds__(256)
 k_cgs_update_scale(size_t n, int k, const double* __restrict__ base, size_t stride, double* __restrict__ w,
-                   const double* __restrict__ red, int slot0, const int* __restrict__ skip = nullptr)
+                   const double* __restrict__ red, int slot0, const int* __restrict__ skip = nullptr, GivensRide gr = GivensRide())
 {
   if (skip && *skip) return;
+  // device-resident Arnoldi loop: the LAST CTA of the grid is an extra one that does the Givens bookkeeping of this step (it reads the
+  // same reduced dots) while the others update the vector
+  const unsigned int nblk = gr.st ? gridDim.x - 1 : gridDim.x;
+  if (gr.st && blockIdx.x == nblk) { gmres_givens_body(gr.st, gr.i, gr.sD, red + slot0, gr.h, gr.c, gr.s, gr.err); return; }
   extern __shared__ double hs[];     // k+1 coefficients
   for (int j = threadIdx.x; j <= k; j += blockDim.x) hs[j] = red[slot0 + j];
   __syncthreads();
@@ -626,7 +682,7 @@ k_cgs_update_scale(size_t n, int k, const double* __restrict__ base, size_t stri
   __syncthreads();
   const double sc = inv;
   const size_t tid = size_t(blockIdx.x)*blockDim.x + threadIdx.x;
-  const size_t nth = size_t(gridDim.x)*blockDim.x;
+  const size_t nth = size_t(nblk)*blockDim.x;
   for (size_t idx = tid; idx < n; idx += nth) {
     double v = w[idx];
     int j = 0;
@@ -713,50 +769,7 @@ __global__ void k_bicg_p(size_t n, double* __restrict__ P, const double* __restr
 // kernel of the remaining (already enqueued) iterations returns at once.
 struct CgState { double err, errO, eps; int done, suc, last_i, pad; };
 
-// ---- device-resident Arnoldi bookkeeping (Hessenberg::finish_column of krylov.hpp, liner_solver/gmres.cpp:556-612) -------------
-// One thread: column i of the Hessenberg matrix from the reduced dots, the Pythagorean norm, the Givens rotations and the residual
-// estimate; sets `done` when |err(i+1)| < eps.  Every product and sum is rounded separately (__dmul_rn / __dadd_rn: no FMA
-// contraction), so the numbers are bit-identical to the host version the serial test policy runs against the compiled reference.
-// `done` must stay the FIRST int after the doubles: the skip pointer of the heavy kernels points at it.
-struct GmresState { double eps, err0; int done, suc, last_i, pad; };
-constexpr int kGivensMax = 1024;          // Krylov dimensions up to this keep the column in shared memory
-__global__ void __launch_bounds__(256)
-k_gmres_givens(GmresState* st, int i, int sD, const double* __restrict__ red, double* __restrict__ h,
-               double* __restrict__ c, double* __restrict__ s, double* __restrict__ err)
-{
-  if (st->done) return;
-  // the column and the rotations are staged in shared memory by the whole CTA (coalesced), the inherently sequential recurrences
-  // run on one thread out of shared memory (a single thread walking global memory costs ~1 us per dependent access)
-  __shared__ double sc[kGivensMax + 2], cc[kGivensMax], ss[kGivensMax];
-  for (int j = threadIdx.x; j <= i + 1; j += blockDim.x) sc[j] = red[j];
-  for (int j = threadIdx.x; j < i; j += blockDim.x) { cc[j] = c[j]; ss[j] = s[j]; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double hh = sc[i+1];
-    for (int j = 0; j <= i; j++) hh = __dsub_rn(hh, __dmul_rn(sc[j], sc[j]));
-    sc[i+1] = sqrt(fabs(hh));
-    for (int j = 0; j <= i - 1; j++) {
-      const double tmp = __dadd_rn(__dmul_rn(cc[j], sc[j]), __dmul_rn(ss[j], sc[j+1]));
-      sc[j+1] = __dadd_rn(__dmul_rn(-ss[j], sc[j]), __dmul_rn(cc[j], sc[j+1]));
-      sc[j] = tmp;
-    }
-    const double tmp = sqrt(__dadd_rn(__dmul_rn(sc[i], sc[i]), __dmul_rn(sc[i+1], sc[i+1])));
-    const double ci = sc[i] / tmp, si = sc[i+1] / tmp;
-    c[i] = ci;
-    s[i] = si;
-    sc[i] = tmp;
-    sc[i+1] = 0.0;
-    const double e0 = (i == 0) ? st->err0 : err[i];
-    const double e1 = __dmul_rn(-si, e0);
-    err[i+1] = e1;
-    err[i] = __dmul_rn(ci, e0);
-    st->last_i = i;
-    if (fabs(e1) < st->eps) { st->done = 1; st->suc = 1; }
-  }
-  __syncthreads();
-  double* col = h + size_t(i)*(sD + 1);
-  for (int j = threadIdx.x; j <= i + 1; j += blockDim.x) col[j] = sc[j];
-}
+
 
 // top of iteration i:  last_i = i; if (err < eps) { suc; break; }  errO = err;
 __global__ void k_cg_head(CgState* st, int i)
@@ -1164,6 +1177,54 @@ __global__ void k_face_axpy(int fnNo, int m, int fdof, int dof, const int* __res
   for (int t = blockIdx.x*blockDim.x + threadIdx.x; t < n; t += gridDim.x*blockDim.x) {
     const int a = t / m, i = t % m;
     Y[size_t(glob[a])*dof + i] += valM[size_t(a)*fdof + i]*s;
+  }
+}
+
+// both stages in one MULTI-CTA launch for a face that lives on one rank: the chunked partial sums of k_face_dot, a grid barrier (at
+// most kFaceBlocks CTAs: always resident), every CTA adds the partials in CTA order (the same S as k_face_dot's last CTA, bit for
+// bit) and updates its share of Y.  X may alias Y: nobody writes before everybody has passed the barrier.
+// counter[0]: arrivals, counter[1]: finished CTAs (the last one resets both).
+__global__ void __launch_bounds__(256)
+k_face_rank1_grid(int fnNo, int m, int fdof, int ld, int lim, const int* __restrict__ glob, const double* __restrict__ valM,
+                  const double* X, double coef, double* Y, double* __restrict__ partial, unsigned int* __restrict__ counter)
+{
+  const int n = fnNo*m;
+  const int chunk = (n + gridDim.x - 1)/gridDim.x;
+  const int beg = blockIdx.x*chunk;
+  const int end = min(n, beg + chunk);
+  double acc = 0.0;
+  for (int t = beg + threadIdx.x; t < end; t += blockDim.x) {
+    const int a = t / m, i = t % m;
+    const int Ac = glob[a];
+    if (Ac < lim) acc = fma(valM[size_t(a)*fdof + i], X[size_t(Ac)*ld + i], acc);
+  }
+  __shared__ double sm[8];
+  __shared__ double S;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if (lane == 0) sm[wid] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+    for (int k = 0; k < 8; k++) v += sm[k];
+    partial[blockIdx.x] = v;
+    __threadfence();
+    atomicAdd(&counter[0], 1u);
+    { const long long t0 = clock64(); while (ld_acquire_gpu(&counter[0]) < gridDim.x) { if (clock64() - t0 > kSpinLimit) break; } }
+    double sum = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; b++) sum += __ldcg(partial + b);
+    S = coef*sum;
+  }
+  __syncthreads();
+  const double s = S;
+  for (int t = beg + threadIdx.x; t < end; t += blockDim.x) {
+    const int a = t / m, i = t % m;
+    Y[size_t(glob[a])*ld + i] += valM[size_t(a)*fdof + i]*s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(&counter[1], 1u) == gridDim.x - 1) { counter[0] = 0u; counter[1] = 0u; }
   }
 }
 

@@ -233,7 +233,7 @@ class CudaOps {
   double* red_d = nullptr;
   double* red_h = nullptr;        // pinned
   double* partial_d = nullptr;
-  unsigned int* counter_d = nullptr;   // [0] multi-dot, [1] face dot
+  unsigned int* counter_d = nullptr;   // [0] multi-dot, [1] face dot, [2..3] one-launch face update (arrivals, finished)
   double* face_partial_d = nullptr;
   CgState* cg_d = nullptr;             // device-resident CG scalars
   CgState* cg_h = nullptr;             // pinned: [0..1] polling slots, [2] initial / final state
@@ -248,9 +248,11 @@ class CudaOps {
   double* gm_host = nullptr;           // pinned copy of h and err for the back substitution
   int gm_sD = 0;
   int gm_batch = 8;
-  int variant_face_fused = 0;          // b200_tune("face_fused", 1): single-CTA one-launch resistance-face update.  Measured SLOWER at P10
+  int variant_face_fused = 2;          // 2 (default): one multi-CTA launch with a grid barrier (same sums, bit for bit, as the two
+                                       // launches of 0); 1: single-CTA one-launch form, measured SLOWER at P10
                                        // (1 665 vs 1 593 ms per Newton iteration, profiles/r02_ab_device_loop.txt): one CTA walking
                                        // the 28 k face values costs ~40 us against two multi-CTA launches of ~5 us
+  GivensRide givens_ride{};            // set by gmres_device_cycle: the next cgs_update_scale launch carries the Givens CTA
   int variant_gmres_device = 1;        // b200_tune("gmres_device", 0): host-driven Arnoldi loop (one D2H sync per iteration)
 
   // arena
@@ -277,8 +279,8 @@ class CudaOps {
     CU_CHECK(cudaMalloc(&red_d, sizeof(double)*kMaxSlots));
     CU_CHECK(cudaMallocHost(&red_h, sizeof(double)*kMaxSlots));
     CU_CHECK(cudaMalloc(&partial_d, sizeof(double)*kRedBlocks*kMaxDots));
-    CU_CHECK(cudaMalloc(&counter_d, 2*sizeof(unsigned int)));
-    CU_CHECK(cudaMemset(counter_d, 0, 2*sizeof(unsigned int)));
+    CU_CHECK(cudaMalloc(&counter_d, 4*sizeof(unsigned int)));
+    CU_CHECK(cudaMemset(counter_d, 0, 4*sizeof(unsigned int)));
     CU_CHECK(cudaMalloc(&face_partial_d, sizeof(double)*kFaceBlocks));
     CU_CHECK(cudaMalloc(&cg_d, sizeof(CgState)));
     CU_CHECK(cudaMallocHost(&cg_h, 3*sizeof(CgState)));
@@ -474,7 +476,13 @@ class CudaOps {
   {
     const size_t n = size_t(dof)*nNo_;
     Scope sc(*this, KC_CGS_UPDATE, 8.0*double(n)*(k + 2));
-    k_cgs_update_scale<<<grid_for(n, 256), 256, sizeof(double)*(k+1), st>>>(n, k, base, stride, w, red_d, slot0, skip_flag);
+    if (givens_ride.st) {
+      // (static shared memory of the riding Givens CTA + the dynamic coefficient array stay below 48 KB)
+      k_cgs_update_scale<<<grid_for(n, 256) + 1, 256, sizeof(double)*(k+1), st>>>(n, k, base, stride, w, red_d, slot0, skip_flag, givens_ride);
+      givens_ride.st = nullptr;
+    } else {
+      k_cgs_update_scale<<<grid_for(n, 256), 256, sizeof(double)*(k+1), st>>>(n, k, base, stride, w, red_d, slot0, skip_flag);
+    }
     post();
   }
 
@@ -860,7 +868,14 @@ class CudaOps {
       if (!(fa.shared && nranks > 1)) {
         // the face lives on this rank alone: ranks that hold none of it have nothing to do, the owner does both stages in one launch
         if (fa.nNo == 0) continue;
-        if (variant_face_fused && size_t(fa.nNo)*m <= 131072) {
+        if (variant_face_fused == 2) {             // one multi-CTA launch: same partial sums and order as the two-launch path
+          const int n = fa.nNo*m;
+          const int g = std::max(1, std::min(kFaceBlocks, (n + 511)/512));
+          k_face_rank1_grid<<<g, 256, 0, st>>>(fa.nNo, m, fa.dof, ld, lim, fa.glob, fa.valM, X, coef, Y, face_partial_d, counter_d + 2);
+          post();
+          continue;
+        }
+        if (variant_face_fused == 1 && size_t(fa.nNo)*m <= 131072) {
           k_face_rank1<<<1, 1024, 0, st>>>(fa.nNo, m, fa.dof, ld, lim, fa.glob, fa.valM, X, coef, Y);
           post();
           continue;
@@ -1144,8 +1159,13 @@ class CudaOps {
     while (!stop) {
       const int nb = std::min(gm_batch, sD - enq);
       for (int k = 0; k < nb; k++) {
+        // the Givens bookkeeping of this step rides on the step's Gram-Schmidt update kernel as one extra CTA
+        givens_ride = GivensRide{gm_d, enq + k, sD, d_h, d_c, d_s, d_err};
         step(enq + k);
-        k_gmres_givens<<<1, 256, 0, st>>>(gm_d, enq + k, sD, red_d, d_h, d_c, d_s, d_err); post();
+        if (givens_ride.st) {                    // the step did not launch an update kernel (cannot happen today): stand-alone launch
+          givens_ride.st = nullptr;
+          k_gmres_givens<<<1, 256, 0, st>>>(gm_d, enq + k, sD, red_d, d_h, d_c, d_s, d_err); post();
+        }
       }
       enq += nb;
       CU_CHECK(cudaMemcpyAsync(&gm_h[slot], gm_d, sizeof(GmresState), cudaMemcpyDeviceToHost, st));
