@@ -655,21 +655,18 @@ k_gmres_givens(GmresState* st, int i, int sD, const double* __restrict__ red, do
 {
   gmres_givens_body(st, i, sD, red, h, c, s, err);
 }
-// arguments of the Givens bookkeeping when it rides on the Gram-Schmidt update kernel as one extra CTA (st == null: not riding)
-struct GivensRide { GmresState* st; int i, sD; double* h; double* c; double* s; double* err; };
+
 
 // K4  classical Gram-Schmidt update + normalisation in one pass
 //   w <- (w - sum_{j<k} h_j u_j) * 1/sqrt|h_k - sum_j h_j^2|,  h = red[slot0 ..]  (already reduced)
 // (omp_sum_v / omp_mul_v calls at liner_solver/gmres.cpp:561-569; same left-to-right order.)
 __global__ void __launch_bounds__(256)
 k_cgs_update_scale(size_t n, int k, const double* __restrict__ base, size_t stride, double* __restrict__ w,
-                   const double* __restrict__ red, int slot0, const int* __restrict__ skip = nullptr, GivensRide gr = GivensRide())
+                   const double* __restrict__ red, int slot0, const int* __restrict__ skip = nullptr)
 {
   if (skip && *skip) return;
-  // device-resident Arnoldi loop: the LAST CTA of the grid is an extra one that does the Givens bookkeeping of this step (it reads the
-  // same reduced dots) while the others update the vector
-  const unsigned int nblk = gr.st ? gridDim.x - 1 : gridDim.x;
-  if (gr.st && blockIdx.x == nblk) { gmres_givens_body(gr.st, gr.i, gr.sD, red + slot0, gr.h, gr.c, gr.s, gr.err); return; }
+  // (the Givens bookkeeping of the device-resident Arnoldi loop once rode on this kernel as an extra CTA: its 24 KB of static shared
+  // memory cost the streaming update 50 % of its bandwidth - it is a kernel of its own again, k_gmres_givens)
   extern __shared__ double hs[];     // k+1 coefficients
   for (int j = threadIdx.x; j <= k; j += blockDim.x) hs[j] = red[slot0 + j];
   __syncthreads();
@@ -682,7 +679,7 @@ k_cgs_update_scale(size_t n, int k, const double* __restrict__ base, size_t stri
   __syncthreads();
   const double sc = inv;
   const size_t tid = size_t(blockIdx.x)*blockDim.x + threadIdx.x;
-  const size_t nth = size_t(nblk)*blockDim.x;
+  const size_t nth = size_t(gridDim.x)*blockDim.x;
   for (size_t idx = tid; idx < n; idx += nth) {
     double v = w[idx];
     int j = 0;

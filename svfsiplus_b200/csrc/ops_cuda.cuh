@@ -252,7 +252,6 @@ class CudaOps {
                                        // launches of 0); 1: single-CTA one-launch form, measured SLOWER at P10
                                        // (1 665 vs 1 593 ms per Newton iteration, profiles/r02_ab_device_loop.txt): one CTA walking
                                        // the 28 k face values costs ~40 us against two multi-CTA launches of ~5 us
-  GivensRide givens_ride{};            // set by gmres_device_cycle: the next cgs_update_scale launch carries the Givens CTA
   int variant_gmres_device = 1;        // b200_tune("gmres_device", 0): host-driven Arnoldi loop (one D2H sync per iteration)
 
   // arena
@@ -476,13 +475,7 @@ class CudaOps {
   {
     const size_t n = size_t(dof)*nNo_;
     Scope sc(*this, KC_CGS_UPDATE, 8.0*double(n)*(k + 2));
-    if (givens_ride.st) {
-      // (static shared memory of the riding Givens CTA + the dynamic coefficient array stay below 48 KB)
-      k_cgs_update_scale<<<grid_for(n, 256) + 1, 256, sizeof(double)*(k+1), st>>>(n, k, base, stride, w, red_d, slot0, skip_flag, givens_ride);
-      givens_ride.st = nullptr;
-    } else {
-      k_cgs_update_scale<<<grid_for(n, 256), 256, sizeof(double)*(k+1), st>>>(n, k, base, stride, w, red_d, slot0, skip_flag);
-    }
+    k_cgs_update_scale<<<grid_for(n, 256), 256, sizeof(double)*(k+1), st>>>(n, k, base, stride, w, red_d, slot0, skip_flag);
     post();
   }
 
@@ -1159,13 +1152,11 @@ class CudaOps {
     while (!stop) {
       const int nb = std::min(gm_batch, sD - enq);
       for (int k = 0; k < nb; k++) {
-        // the Givens bookkeeping of this step rides on the step's Gram-Schmidt update kernel as one extra CTA
-        givens_ride = GivensRide{gm_d, enq + k, sD, d_h, d_c, d_s, d_err};
+        // (letting the Givens bookkeeping ride on the Gram-Schmidt update kernel as an extra CTA was measured and rejected: the 24 KB
+        // of static shared memory it brings into that kernel cost the streaming update 50 % of its bandwidth, 0.39 vs 0.26 ms per
+        // launch at P10; profiles/r02_bench_n1_givens_ride.json)
         step(enq + k);
-        if (givens_ride.st) {                    // the step did not launch an update kernel (cannot happen today): stand-alone launch
-          givens_ride.st = nullptr;
-          k_gmres_givens<<<1, 256, 0, st>>>(gm_d, enq + k, sD, red_d, d_h, d_c, d_s, d_err); post();
-        }
+        k_gmres_givens<<<1, 256, 0, st>>>(gm_d, enq + k, sD, red_d, d_h, d_c, d_s, d_err); post();
       }
       enq += nb;
       CU_CHECK(cudaMemcpyAsync(&gm_h[slot], gm_d, sizeof(GmresState), cudaMemcpyDeviceToHost, st));
