@@ -40,9 +40,11 @@ P10 = (96, 96, 181)
 FIXED_WORK_LS = (796, (0.0, 0.0, 2, 250), (0.0, 0.0, 1, 50), (0.0, 0.0, 200, 0))
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at P10 on one GPU, from the `ncu --set full` capture
-# profiles/r01_tour_c_ncu_raw.csv (same kernels, same data set-up as the bench)
-NCU_TRAFFIC_P10 = {"spmv_vv4": 3.5201e9 + 0.0319e9, "spmv_vv3": 2.0842e9 + 0.0425e9, "spmv_sv": 0.7326e9 + 0.0516e9,
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at P10 on one GPU, from `ncu --set full` captures of the same kernels on the
+# same data set-up as the bench: profiles/r01_tour_c_ncu_raw.csv (round 1) and profiles/r02_vv3_variants_ncu_raw.csv (the column-owner
+# dof-3 kernel that is the default since round 2).  The Arnoldi kernels' traffic depends on the basis depth of the launch, so there is
+# no single per-launch figure for them (null; at a depth of 64 ncu reads 2.68 GB against 2.71 GB algorithmic).
+NCU_TRAFFIC_P10 = {"spmv_vv4": 3.5201e9 + 0.0319e9, "spmv_vv3": 2.0080e9 + 0.0430e9, "spmv_sv": 0.7326e9 + 0.0516e9,
                    "spmv_vs": 1.0476e9 + 0.0084e9, "multi_dot": None, "cgs_update_scale": None}
 
 
@@ -466,7 +468,7 @@ def run_gpu(args):
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak,
                      "traffic": (NCU_TRAFFIC_P10.get(dom) if (world == 1 and tuple(dims) == P10) else None),
-                     "traffic_source": "ncu --set full, profiles/r01_tour_c_ncu_raw.csv (per launch)", "peak_source": peak_src,
+                     "traffic_source": "ncu --set full, profiles/r01_tour_c_ncu_raw.csv / r02_vv3_variants_ncu_raw.csv (per launch; null for kernels whose traffic depends on the basis depth)", "peak_source": peak_src,
                      "share_of_step": d["ms"] / dev_ms, "launches": d["launches"],
                      "bytes_per_launch": d["bytes"] / max(d["launches"], 1)},
         "kernel_shares": shares, "kernels": per_class, "kernel_time_frac_of_step": tot_k / prof_ms, "profiled_ms_per_step": prof_ms / args.prof_steps,
