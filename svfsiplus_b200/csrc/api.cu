@@ -2048,7 +2048,10 @@ int b200_op_bench(b200_handle* h, int op, int k, int reps, double* ms_per_launch
     const bool ns_shape = (op == KC_SPMV_VV3 || op == KC_SPMV_SS || op == KC_SPMV_SV || op == KC_SPMV_VS || op == KC_DEPART);
     if (ns_shape) {
       Gt = ops.vec(3*nnz); mK = ops.vec(9*nnz); mG = ops.vec(3*nnz); mD = ops.vec(3*nnz); mL = ops.vec(nnz);
+      const int vg = ops.variant_gp;
+      if (op == KC_SPMV_SV && k == 3) ops.variant_gp = 3;       // depart then also writes the component-wise copy of G
       ops.depart(3, h->Val, Gt, mK, mG, mD, mL);
+      ops.variant_gp = vg;
     }
     const int kk = std::max(1, k);
     const size_t n4 = 4*nNo, n3 = 3*nNo;
@@ -2076,6 +2079,11 @@ int b200_op_bench(b200_handle* h, int op, int k, int reps, double* ms_per_launch
         case KC_SPMV_SS:  { const int v0 = ops.variant_narrow; ops.variant_narrow = k; ops.spmv_ss(mL, x, y); ops.variant_narrow = v0; bytes = ops.bytes_ss(); break; }
         case KC_SPMV_SV:  // pass 1 of the fused Schur operator
           if (k == 2) { int t0, t1; if (!ops.tiles_for(0, h->nNo, t0, t1)) throw std::runtime_error("op_bench: no row tiles"); ops.launch_tiled(t0, t1, mG, TileGP{x, x, ops.V4}); bytes = ops.bytes_schur_gp(); break; }
+          if (k == 3) {
+            if (!ops.Gs) throw std::runtime_error("op_bench: no component-wise copy of G (tune schur_gp = 3 before)");
+            k_schur_gp_soa<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(nullptr, h->nNo, ops.rowPtr, ops.col, ops.Gs, size_t(h->nnz), x, x, ops.V4);
+            ops.post(); bytes = ops.bytes_schur_gp(); break;
+          }
           if (k == 1) k_schur_gp4<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(nullptr, h->nNo, ops.rowPtr, ops.col, mG, x, x, ops.V4);
           else k_schur_gp<<<CudaOps::grid_rows(h->nNo), 256, 0, ops.st>>>(nullptr, h->nNo, ops.rowPtr, ops.col, mG, x, x, ops.V4);
           ops.post();

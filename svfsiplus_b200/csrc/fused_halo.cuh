@@ -79,8 +79,9 @@ struct RowsVV4 {            // dof-4 block rows (k_spmv_vv4)
   }
 };
 
-struct RowsGP {             // pass 1 of the Schur operator (k_schur_gp): V4(i) = [sum_j G(:,j) P(col_j), P(i)]
+struct RowsGP {             // pass 1 of the Schur operator (k_schur_gp / k_schur_gp_soa): V4(i) = [sum_j G(:,j) P(col_j), P(i)]
   const int* rowPtr; const int* col; const double* G; const double* P; double* V4;
+  size_t soa = 0;             // 0: G(3,nnz) entry-wise; else G is the component-wise copy with this component stride (= nnz)
   __device__ __forceinline__ void run(int r0, int r1, int gq, int nq, int lane4) const
   {
     const int n = r1 - r0, nrounds = (n + nq - 1)/nq;
@@ -92,10 +93,11 @@ struct RowsGP {             // pass 1 of the Schur operator (k_schur_gp): V4(i) 
 #pragma unroll 2
         for (int p = s + lane4; p < e; p += 4) {
           const double u = __ldg(P + __ldg(col + p));
-          const double* g = G + size_t(p)*3;
+          const double* g = soa ? G + p : G + size_t(p)*3;
+          const size_t st = soa ? soa : 1;
           a0 = fma(__ldg(g), u, a0);
-          a1 = fma(__ldg(g + 1), u, a1);
-          a2 = fma(__ldg(g + 2), u, a2);
+          a1 = fma(__ldg(g + st), u, a1);
+          a2 = fma(__ldg(g + 2*st), u, a2);
         }
       }
       a0 += __shfl_xor_sync(0xffffffffu, a0, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a2 += __shfl_xor_sync(0xffffffffu, a2, 1);

@@ -273,6 +273,7 @@ class CudaOps {
     }
     if (const char* e = getenv("SVB200_FUSED")) variant_fused = std::atoi(e);      // A/B of the fused product + exchange kernel
     if (const char* e = getenv("SVB200_GMRES_DEVICE")) variant_gmres_device = std::atoi(e);
+    if (const char* e = getenv("SVB200_SCHUR_GP")) variant_gp = std::atoi(e);
     if (const char* e = getenv("SVB200_FACE_FUSED")) variant_face_fused = std::atoi(e);
     if (const char* e = getenv("SVB200_GM_BATCH")) gm_batch = std::max(1, std::atoi(e));
     CU_CHECK(cudaMalloc(&red_d, sizeof(double)*kMaxSlots));
@@ -481,7 +482,7 @@ class CudaOps {
 
   // entries in flight per lane in the two Schur passes (A/B on B200, profiles/r01_tour_b.jsonl): pass 1 is
   // fastest with two (0.151 vs 0.163 ms at P10), pass 2 with four (0.193 vs 0.217 ms)
-  int variant_gp = 0, variant_sp = 1;   // 2: TMA-staged row tiles (spmv_tiled.cuh)
+  int variant_gp = 0, variant_sp = 1;   // 2: TMA-staged row tiles (spmv_tiled.cuh); variant_gp 3: component-wise copy of G (k_schur_gp_soa)
   int variant_vv3 = 4;       // (default 4: 0.853 vs 0.813 of the HBM peak at P10, profiles/r02_vv3_variants_d.jsonl)  0: lane = component, 1: lanes stride over the row's blocks, 2: TMA-staged row tiles, 3: as 0 with an L2 evict-last policy on the gathered vector, 4 / 5: column-owner lanes with / without that policy (A/B by op_bench)
   int variant_narrow = 0;    // spmv_ss / sv / vs: 0 per-lane loads, 2 TMA-staged row tiles
 
@@ -994,18 +995,21 @@ class CudaOps {
   const double* packed_Gt = nullptr;
   double* GtL = nullptr;
   double* V4 = nullptr;
+  double* Gs = nullptr;       // component-wise copy of mG (variant_gp == 3)
 
   void depart(int nsd, const double* Val, double* Gt, double* mK, double* mG, double* mD, double* mL)
   {
     const size_t nz = size_t(nnz_);
     packed_Gt = nullptr; GtL = nullptr; V4 = nullptr;
+    Gs = nullptr;
     if (nsd == 3) {
       GtL = vec(4*nz);
       V4 = vec(4*size_t(nNo_));
       packed_Gt = Gt;
+      if (variant_gp == 3) Gs = vec(3*nz);             // component-wise copy of mG for pass 1
     }
     Scope sc(*this, KC_DEPART, double(nnz_)*(8.0*(nsd+1)*(nsd+1)*2 + 8.0*nsd + 4.0 + (nsd == 3 ? 32.0 : 0.0)));
-    if (nsd == 3) k_depart3<<<grid_for(nz, 256, 1), 256, 0, st>>>(nz, tpos, Val, Gt, mK, mG, mD, mL, GtL);
+    if (nsd == 3) k_depart3<<<grid_for(nz, 256, 1), 256, 0, st>>>(nz, tpos, Val, Gt, mK, mG, mD, mL, GtL, Gs);
     else if (nsd == 2) k_depart_generic<2><<<grid_for(nz, 256, 1), 256, 0, st>>>(nz, tpos, Val, Gt, mK, mG, mD, mL);
     else throw std::runtime_error("FSILS: Not defined nsd for DEPART");
     post();
@@ -1019,16 +1023,18 @@ class CudaOps {
                 double* SP, bool coupled)
   {
     if (nsd == 3 && Gt == packed_Gt && GtL) {
-      if (use_fused() && variant_gp == 0) {
+      if (use_fused() && (variant_gp == 0 || (variant_gp == 3 && Gs))) {
         Scope sc(*this, KC_SPMV_SV, bytes_schur_gp());
-        launch_fused(2, RowsGP{rowPtr, col, G, P, V4}, 3, V4, 4);
+        if (variant_gp == 3) launch_fused(2, RowsGP{rowPtr, col, Gs, P, V4, size_t(nnz_)}, 3, V4, 4);
+        else launch_fused(2, RowsGP{rowPtr, col, G, P, V4}, 3, V4, 4);
       } else {
         Scope sc(*this, KC_SPMV_SV, bytes_schur_gp());
         rows_then_halo(3, V4, 4, [&](int r0, int r1) {
           const int n = r1 - r0, g = grid_rows(n);
           int t0, t1;
           if (variant_gp == 2 && tiles_for(r0, r1, t0, t1)) { launch_tiled(t0, t1, G, TileGP{P, P, V4}); return; }
-          if (variant_gp == 1) k_schur_gp4<<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, G, P, P + r0, V4 + size_t(r0)*4);
+          if (variant_gp == 3 && Gs) k_schur_gp_soa<<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, Gs, size_t(nnz_), P, P + r0, V4 + size_t(r0)*4);
+          else if (variant_gp == 1) k_schur_gp4<<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, G, P, P + r0, V4 + size_t(r0)*4);
           else k_schur_gp<<<g, 256, 0, st>>>(skip_flag, n, rowPtr + r0, col, G, P, P + r0, V4 + size_t(r0)*4);
           post();
         });

@@ -86,7 +86,7 @@ def main():
     P.assemble(be, case)
     if a.mode == "tiled":
         # A/B of the TMA-staged row-tile kernels (k = 2) against the per-lane kernels on the same data
-        plan = [("spmv_vv3", 0), ("spmv_vv3", 1), ("spmv_vv3", 2), ("spmv_vv3", 3), ("spmv_vv3", 4), ("spmv_vv3", 5), ("spmv_vv3", 6), ("spmv_sv", 0), ("spmv_sv", 2), ("spmv_vs", 1), ("spmv_vs", 2),
+        plan = [("spmv_vv3", 0), ("spmv_vv3", 1), ("spmv_vv3", 2), ("spmv_vv3", 3), ("spmv_vv3", 4), ("spmv_vv3", 5), ("spmv_vv3", 6), ("spmv_sv", 0), ("spmv_sv", 3), ("spmv_sv", 2), ("spmv_vs", 1), ("spmv_vs", 2),
                 ("spmv_ss", 0), ("spmv_ss", 2)]
         for name, k in plan:
             ms, by = be.op_bench(name, k=k, reps=a.reps)
