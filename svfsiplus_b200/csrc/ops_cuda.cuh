@@ -482,7 +482,8 @@ class CudaOps {
 
   // entries in flight per lane in the two Schur passes (A/B on B200, profiles/r01_tour_b.jsonl): pass 1 is
   // fastest with two (0.151 vs 0.163 ms at P10), pass 2 with four (0.193 vs 0.217 ms)
-  int variant_gp = 0, variant_sp = 1;   // 2: TMA-staged row tiles (spmv_tiled.cuh); variant_gp 3: component-wise copy of G (k_schur_gp_soa)
+  int variant_gp = 3, variant_sp = 1;   // 2: TMA-staged row tiles (spmv_tiled.cuh); variant_gp 3 (default): component-wise copy of G
+                                        // (k_schur_gp_soa: 0.843 vs 0.785 of the HBM peak stand-alone, same sums bit for bit; profiles/r02_schur_gp_soa.txt)
   int variant_vv3 = 4;       // (default 4: 0.853 vs 0.813 of the HBM peak at P10, profiles/r02_vv3_variants_d.jsonl)  0: lane = component, 1: lanes stride over the row's blocks, 2: TMA-staged row tiles, 3: as 0 with an L2 evict-last policy on the gathered vector, 4 / 5: column-owner lanes with / without that policy (A/B by op_bench)
   int variant_narrow = 0;    // spmv_ss / sv / vs: 0 per-lane loads, 2 TMA-staged row tiles
 
