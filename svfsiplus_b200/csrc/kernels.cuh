@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #include "peer_comm.cuh"
+#include "krylov.hpp"
 
 namespace svb200 {
 
@@ -660,26 +661,15 @@ __device__ __forceinline__ void gmres_givens_body(GmresState* st, int i, int sD,
   for (int j = threadIdx.x; j < i; j += blockDim.x) { cc[j] = c[j]; ss[j] = s[j]; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    double hh = sc[i+1];
-    for (int j = 0; j <= i; j++) hh = __dsub_rn(hh, __dmul_rn(sc[j], sc[j]));
-    sc[i+1] = sqrt(fabs(hh));
-    for (int j = 0; j <= i - 1; j++) {
-      const double tmp = __dadd_rn(__dmul_rn(cc[j], sc[j]), __dmul_rn(ss[j], sc[j+1]));
-      sc[j+1] = __dadd_rn(__dmul_rn(-ss[j], sc[j]), __dmul_rn(cc[j], sc[j+1]));
-      sc[j] = tmp;
-    }
-    const double tmp = sqrt(__dadd_rn(__dmul_rn(sc[i], sc[i]), __dmul_rn(sc[i+1], sc[i+1])));
-    const double ci = sc[i] / tmp, si = sc[i+1] / tmp;
-    c[i] = ci;
-    s[i] = si;
-    sc[i] = tmp;
-    sc[i+1] = 0.0;
-    const double e0 = (i == 0) ? st->err0 : err[i];
-    const double e1 = __dmul_rn(-si, e0);
-    err[i+1] = e1;
-    err[i] = __dmul_rn(ci, e0);
+    // the recurrences themselves: krylov.hpp's givens_finish_column, the function the host loop runs (one source for both)
+    double e_i = (i == 0) ? st->err0 : err[i], e_i1 = 0.0;
+    const double e1 = givens_finish_column(sc, cc, ss, e_i, e_i1, i);
+    c[i] = cc[i];
+    s[i] = ss[i];
+    err[i] = e_i;
+    err[i+1] = e_i1;
     st->last_i = i;
-    if (fabs(e1) < st->eps) { st->done = 1; st->suc = 1; }
+    if (e1 < st->eps) { st->done = 1; st->suc = 1; }
   }
   __syncthreads();
   double* col = h + size_t(i)*(sD + 1);

@@ -103,6 +103,54 @@ inline bool ge_solve(int nV, int N, const std::vector<double>& A, std::vector<do
 }
 
 // ---------------------------------------------------------------------------------------------
+// One column of the Arnoldi bookkeeping, written ONCE for the host (Hessenberg::finish_column below, which the serial test policy
+// runs against the compiled reference) and for the device (k_gmres_givens of the device-resident loop): `col` = column i of the
+// Hessenberg matrix holding the reduced dots <u_j, w>, j = 0..i+1 (entry i+1 = <w,w>); c, s: the rotations so far; err_i, err_i1:
+// the residual estimates err(i), err(i+1).  Every product and sum is rounded separately on both sides (the device spells it __dmul_rn / __dadd_rn so
+// that nvcc cannot contract them into FMAs; the host build has no FMA contraction), so the two give the same bits.
+// Returns |err(i+1)|.
+// ---------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+#define SVB_KR_HD __host__ __device__ __forceinline__
+#else
+#define SVB_KR_HD inline
+#endif
+SVB_KR_HD double kr_mul(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(a, b);
+#else
+  return a*b;
+#endif
+}
+SVB_KR_HD double kr_add(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+  return __dadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+SVB_KR_HD double givens_finish_column(double* col, double* c, double* s, double& err_i, double& err_i1, int i)
+{
+  for (int j = 0; j <= i; j++) col[i+1] = kr_add(col[i+1], -kr_mul(col[j], col[j]));
+  col[i+1] = sqrt(fabs(col[i+1]));
+  for (int j = 0; j <= i-1; j++) {
+    const double tmp = kr_add(kr_mul(c[j], col[j]), kr_mul(s[j], col[j+1]));
+    col[j+1] = kr_add(kr_mul(-s[j], col[j]), kr_mul(c[j], col[j+1]));
+    col[j] = tmp;
+  }
+  const double tmp = sqrt(kr_add(kr_mul(col[i], col[i]), kr_mul(col[i+1], col[i+1])));
+  c[i] = col[i] / tmp;
+  s[i] = col[i+1] / tmp;
+  col[i] = tmp;
+  col[i+1] = 0.0;
+  err_i1 = kr_mul(-s[i], err_i);
+  err_i = kr_mul(c[i], err_i);
+  return fabs(err_i1);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Arnoldi / Givens bookkeeping shared by gmres_v and the NS solver's inner gmres
 // (liner_solver/gmres.cpp:550-612 and :202-262).  h is (sD+1) x sD column-major.
 // ---------------------------------------------------------------------------------------------
@@ -115,24 +163,7 @@ struct Hessenberg {
   // Column i has been filled with the reduced dots <u_j, w>, j = 0..i+1 (entry i+1 = <w,w>).
   // Performs the Pythagorean norm, Givens rotations and the residual-estimate update; returns
   // |err(i+1)|.
-  double finish_column(int i)
-  {
-    for (int j = 0; j <= i; j++) H(i+1,i) = H(i+1,i) - H(j,i)*H(j,i);
-    H(i+1,i) = std::sqrt(std::fabs(H(i+1,i)));
-    for (int j = 0; j <= i-1; j++) {
-      double tmp = c[j]*H(j,i) + s[j]*H(j+1,i);
-      H(j+1,i) = -s[j]*H(j,i) + c[j]*H(j+1,i);
-      H(j,i) = tmp;
-    }
-    double tmp = std::sqrt(H(i,i)*H(i,i) + H(i+1,i)*H(i+1,i));
-    c[i] = H(i,i) / tmp;
-    s[i] = H(i+1,i) / tmp;
-    H(i,i) = tmp;
-    H(i+1,i) = 0.0;
-    err[i+1] = -s[i]*err[i];
-    err[i] = c[i]*err[i];
-    return std::fabs(err[i+1]);
-  }
+  double finish_column(int i) { return givens_finish_column(&H(0,i), c.data(), s.data(), err[i], err[i+1], i); }
 
   void back_substitute(int last_i)
   {
