@@ -154,4 +154,53 @@ inline void partition_rcb(int nEl, const double* centroids, int nParts, int* par
   detail::rcb(centroids, idx.data(), nEl, 0, nParts, part);
 }
 
+
+// ---- host-side tables of the device transport and of the row-tile kernels (pure functions: tests/hostlogic drives them on the CPU) ----
+
+// Node-centric source lists of the overlap add (fsils_commuv adds the received values request by request, in_commu.cpp:150-168): for
+// every distinct overlap row, its (request, position) sources in REQUEST order.  lists[i] = solver rows of request i.
+struct HaloSources { std::vector<int> node, ptr; std::vector<int> src_req, src_pos; };
+inline HaloSources halo_source_lists(int nNo, const std::vector<std::vector<int>>& lists)
+{
+  HaloSources h;
+  std::vector<int> cnt(size_t(nNo) + 1, 0);
+  size_t total = 0;
+  for (const auto& l : lists) for (int v : l) { if (v < 0 || v >= nNo) throw std::runtime_error("overlap list entry out of range"); cnt[v + 1]++; total++; }
+  std::vector<int> slot(nNo, -1);
+  h.ptr.push_back(0);
+  for (int r = 0; r < nNo; r++) if (cnt[r + 1]) { slot[r] = int(h.node.size()); h.node.push_back(r); h.ptr.push_back(h.ptr.back() + cnt[r + 1]); }
+  h.src_req.assign(total, 0); h.src_pos.assign(total, 0);
+  std::vector<int> fill(h.node.size(), 0);
+  for (int i = 0; i < int(lists.size()); i++)
+    for (int j = 0; j < int(lists[i].size()); j++) {
+      const int k = slot[lists[i][j]];
+      const int e = h.ptr[k] + fill[k]++;
+      h.src_req[e] = i; h.src_pos[e] = j;
+    }
+  return h;
+}
+
+// Row tiles of the TMA-staged SpMV kernels: consecutive rows, at most max_rows rows and cap - 4 entries counted from the tile's first
+// entry rounded down to a multiple of 4 (the bulk copies are 16-byte aligned), never across cuts[1] / cuts[2].  Returns the tile start
+// rows + the end row, tile_at[4] = first tile of each of the three segments and the tile count; empty when a single row exceeds a tile.
+inline std::vector<int> row_tiles(const std::vector<int>& rowPtr, const int cuts[4], int max_rows, int cap, int tile_at[4])
+{
+  std::vector<int> tr;
+  for (int sgm = 0; sgm < 3; sgm++) {
+    tile_at[sgm] = int(tr.size());
+    int r = cuts[sgm];
+    while (r < cuts[sgm+1]) {
+      tr.push_back(r);
+      const int p0 = rowPtr[r] & ~3;
+      int q = r;
+      while (q < cuts[sgm+1] && q - r < max_rows && rowPtr[q+1] - p0 <= cap - 4) q++;
+      if (q == r) return std::vector<int>();
+      r = q;
+    }
+  }
+  tile_at[3] = int(tr.size());
+  tr.push_back(cuts[3]);
+  return tr;
+}
+
 } // namespace svb200

@@ -15,6 +15,7 @@
 
 #include "kernels.cuh"
 #include "krylov.hpp"
+#include "lhs_layout.hpp"
 #include "peer_comm.cuh"
 #include "spmv_tiled.cuh"
 #include "fused_halo.cuh"
@@ -155,21 +156,8 @@ class CudaOps {
   {
     cudaFree(tile_row); tile_row = nullptr; tiles_ok = false;
     const int cuts[4] = {0, overlap_ok ? ovA : 0, overlap_ok ? ovB : nNo_, nNo_};
-    std::vector<int> tr;
-    for (int sgm = 0; sgm < 3; sgm++) {
-      tile_at[sgm] = int(tr.size());
-      int r = cuts[sgm];
-      while (r < cuts[sgm+1]) {
-        tr.push_back(r);
-        const int p0 = rp[r] & ~3;
-        int q = r;
-        while (q < cuts[sgm+1] && q - r < kTileRows && rp[q+1] - p0 <= kTileCap - 4) q++;
-        if (q == r) return;                              // a single row longer than a tile: keep the per-lane kernels
-        r = q;
-      }
-    }
-    tile_at[3] = int(tr.size());
-    tr.push_back(nNo_);
+    const std::vector<int> tr = row_tiles(rp, cuts, kTileRows, kTileCap, tile_at);     // lhs_layout.hpp (pure host, CPU-tested)
+    if (tr.empty()) return;                              // a single row longer than a tile: keep the per-lane kernels
     CU_CHECK(cudaMalloc(&tile_row, sizeof(int)*tr.size()));
     CU_CHECK(cudaMemcpyAsync(tile_row, tr.data(), sizeof(int)*tr.size(), cudaMemcpyHostToDevice, st));
     CU_CHECK(cudaStreamSynchronize(st));
@@ -769,17 +757,11 @@ class CudaOps {
     }
     halo_tot = int(all.size());
     // node-centric source lists: every distinct overlap row with its (request, position) sources in request order
-    std::vector<int> cnt(size_t(nNo_) + 1, 0);
-    for (int v : all) cnt[v + 1]++;
-    std::vector<int> hn_node, hn_ptr(1, 0), slot(nNo_, -1);
-    for (int r = 0; r < nNo_; r++) if (cnt[r + 1]) { slot[r] = int(hn_node.size()); hn_node.push_back(r); hn_ptr.push_back(hn_ptr.back() + cnt[r + 1]); }
-    std::vector<int2> hn_src(all.size());
-    std::vector<int> fill(hn_node.size(), 0);
-    for (int i = 0; i < int(reqs.size()); i++)
-      for (int j = 0; j < reqs[i].n; j++) {
-        const int k = slot[host_lists[i][j]];
-        hn_src[hn_ptr[k] + fill[k]++] = make_int2(i, j);
-      }
+    const HaloSources hsrc = halo_source_lists(nNo_, host_lists);                       // lhs_layout.hpp (pure host, CPU-tested)
+    const std::vector<int>& hn_node = hsrc.node;
+    const std::vector<int>& hn_ptr = hsrc.ptr;
+    std::vector<int2> hn_src(hsrc.src_req.size());
+    for (size_t e = 0; e < hn_src.size(); e++) hn_src[e] = make_int2(hsrc.src_req[e], hsrc.src_pos[e]);
     halo_nh = int(hn_node.size());
     auto up = [&](const void* src, size_t nbytes) { void* d = nullptr; CU_CHECK(cudaMalloc(&d, std::max<size_t>(nbytes, 16))); if (nbytes) CU_CHECK(cudaMemcpyAsync(d, src, nbytes, cudaMemcpyHostToDevice, st)); return d; };
     d_peer_reqs = static_cast<PeerHaloReq*>(up(hr.data(), sizeof(PeerHaloReq)*hr.size()));

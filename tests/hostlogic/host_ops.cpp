@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "krylov.hpp"
+#include "lhs_layout.hpp"
 
 namespace {
 
@@ -197,6 +198,33 @@ std::string g_err;
 extern "C" {
 
 const char* hl_last_error() { return g_err.c_str(); }
+
+// svfsiplus_b200/csrc/lhs_layout.hpp: the host-side tables of the device transport and of the row-tile kernels
+// lists: nReq lists concatenated (req_n[i] entries each).  Outputs sized by the caller: node / ptr (<= nNo + 1), src_req / src_pos (total).
+int hl_halo_sources(int nNo, int nReq, const int* req_n, const int* req_ptr, int* nh, int* node, int* ptr, int* src_req, int* src_pos)
+{
+  try {
+    std::vector<std::vector<int>> lists(nReq);
+    size_t o = 0;
+    for (int i = 0; i < nReq; i++) { lists[i].assign(req_ptr + o, req_ptr + o + req_n[i]); o += size_t(req_n[i]); }
+    const svb200::HaloSources h = svb200::halo_source_lists(nNo, lists);
+    *nh = int(h.node.size());
+    std::copy(h.node.begin(), h.node.end(), node);
+    std::copy(h.ptr.begin(), h.ptr.end(), ptr);
+    std::copy(h.src_req.begin(), h.src_req.end(), src_req);
+    std::copy(h.src_pos.begin(), h.src_pos.end(), src_pos);
+    return 0;
+  } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+// returns the number of tiles (0: a row does not fit); tile_row must hold nNo + 1 ints
+int hl_row_tiles(int nNo, const int* rowPtr, int ovA, int ovB, int max_rows, int cap, int* tile_row, int* tile_at)
+{
+  const int cuts[4] = {0, ovA, ovB, nNo};
+  const std::vector<int> rp(rowPtr, rowPtr + nNo + 1);
+  const std::vector<int> tr = svb200::row_tiles(rp, cuts, max_rows, cap, tile_at);
+  std::copy(tr.begin(), tr.end(), tile_row);
+  return tr.empty() ? 0 : int(tr.size()) - 1;
+}
 
 // Single-rank solve with the product's krylov.hpp driven by the serial host policy.
 // faces: arrays of length nFaces; glob/val concatenated.  ls = 12 doubles as in oracle/ref.py.

@@ -313,3 +313,82 @@ def test_block_composed_pipe_is_identical_for_every_rank_count():
             if len(pr["faces"][2]["nodes"]):
                 assert np.array_equal(pr["faces"][2]["val"], p1["faces"][2]["val"])
         assert els == p1["mesh"].nEl
+
+
+# ---------------------------------------------------------------------------------------------------
+# host-side tables of the device transport and of the row-tile kernels (csrc/lhs_layout.hpp, through tests/hostlogic)
+# ---------------------------------------------------------------------------------------------------
+def _hl():
+    from util import hostlogic
+    return hostlogic()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_halo_source_lists_keep_request_order(seed):
+    """fsils_commuv adds the received values request by request (in_commu.cpp:150-168); the device adds per overlap row, so every
+    row's sources must be listed in request order, each (request, position) exactly once."""
+    import ctypes as C
+    rng = np.random.default_rng(seed)
+    nNo, nReq = 200, 4
+    lists = [rng.choice(nNo, size=rng.integers(5, 60), replace=False).astype(np.int32) for _ in range(nReq)]
+    lists[2] = np.concatenate([lists[2], lists[0][:7]]).astype(np.int32)           # rows shared by two and three requests
+    lists[3] = np.unique(np.concatenate([lists[3], lists[0][:4], lists[1][:5]])).astype(np.int32)
+    lists[2] = np.array(list(dict.fromkeys(lists[2].tolist())), np.int32)
+    req_n = np.array([len(l) for l in lists], np.int32)
+    cat = np.concatenate(lists).astype(np.int32)
+    tot = int(req_n.sum())
+    nh = C.c_int(0)
+    node = np.zeros(nNo + 1, np.int32); ptr = np.zeros(nNo + 2, np.int32); sr = np.zeros(tot, np.int32); sp = np.zeros(tot, np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert _hl().hl_halo_sources(nNo, nReq, p(req_n), p(cat), C.byref(nh), p(node), p(ptr), p(sr), p(sp)) == 0
+    n = nh.value
+    assert list(node[:n]) == sorted(set(cat.tolist())) and ptr[n] == tot
+    seen = set()
+    for k in range(n):
+        reqs = sr[ptr[k]:ptr[k+1]]
+        assert list(reqs) == sorted(reqs) and len(set(reqs.tolist())) == len(reqs)      # request order, one source per request
+        for e in range(ptr[k], ptr[k+1]):
+            assert lists[sr[e]][sp[e]] == node[k]
+            seen.add((int(sr[e]), int(sp[e])))
+    assert len(seen) == tot
+    # emulate the exchange: every overlap row gets the sum of its sources added in request order = what the request loop does
+    V = rng.standard_normal(nNo)
+    rbuf = [rng.standard_normal(len(l)) for l in lists]
+    ref = V.copy()
+    for i, l in enumerate(lists):
+        for j, r in enumerate(l):
+            ref[r] += rbuf[i][j]
+    got = V.copy()
+    for k in range(n):
+        s = got[node[k]]
+        for e in range(ptr[k], ptr[k+1]):
+            s += rbuf[sr[e]][sp[e]]
+        got[node[k]] = s
+    assert np.array_equal(got, ref)                                                    # bit for bit: same order of additions
+    bad = np.array([nNo], np.int32)
+    assert _hl().hl_halo_sources(nNo, 1, p(np.array([1], np.int32)), p(bad), C.byref(nh), p(node), p(ptr), p(sr), p(sp)) == 1
+
+
+def test_row_tiles_cover_the_rows_and_respect_caps_and_cuts():
+    import ctypes as C
+    from svfsiplus_b200 import mesh as M
+    m = M.pipe_mesh(8, 8, 16)
+    rowPtr, _ = M.csr_pattern(m.ien, m.nNo)
+    rowPtr = np.ascontiguousarray(rowPtr, np.int32)
+    nNo = m.nNo
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    for ovA, ovB, max_rows, cap in ((0, nNo, 128, 1152), (81, nNo - 81, 128, 1152), (81, nNo - 81, 16, 200), (0, nNo, 128, 64)):
+        tr = np.zeros(nNo + 1, np.int32); at = np.zeros(4, np.int32)
+        nt = _hl().hl_row_tiles(nNo, p(rowPtr), ovA, ovB, max_rows, cap, p(tr), p(at))
+        assert nt > 0
+        t = tr[:nt + 1]
+        assert t[0] == 0 and t[-1] == nNo and (np.diff(t) > 0).all() and (np.diff(t) <= max_rows).all()
+        for a, b in zip(t[:-1], t[1:]):
+            assert rowPtr[b] - (rowPtr[a] & ~3) <= cap - 4
+            assert not (a < ovA < b) and not (a < ovB < b)                             # tiles never straddle the segment cuts
+        assert t[at[0]] == 0 and at[3] == nt
+        if ovA > 0:
+            assert t[at[1]] == ovA and t[at[2]] == ovB
+    # a row that does not fit into a tile: no tiles (the per-lane kernels are used)
+    tr = np.zeros(nNo + 1, np.int32); at = np.zeros(4, np.int32)
+    assert _hl().hl_row_tiles(nNo, p(rowPtr), 0, nNo, 128, 12, p(tr), p(at)) == 0
