@@ -490,11 +490,11 @@ def run_gpu(args):
     line["fixed_work"] = fixed_work
     if weak is not None:
         line["weak"] = weak
-    # benchmark-size parity: counts and solution norms of the compiled reference on the same P10 system (tests/golden/p10_ns_counts.json,
+    # benchmark-size parity: counts and solution norms of the compiled reference on the same P10 system (tests/golden/p10_<ls>_counts.json,
     # generated offline by tests/golden/make_golden_p10.py); a plain file read, nothing of oracle/ is executed here
     try:
-        gp = os.path.join(ROOT, "tests", "golden", "p10_ns_counts.json")
-        if os.path.exists(gp) and args.ls == "NS":
+        gp = os.path.join(ROOT, "tests", "golden", f"p10_{args.ls.lower()}_counts.json")       # NS (headline) or the plain GMRES variant
+        if os.path.exists(gp):
             g = json.load(open(gp))
 
             def chk(cnt, xn):

@@ -70,9 +70,12 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--dims", type=int, nargs=3, default=[96, 96, 181])
     ap.add_argument("--ranks", type=int, default=8)
-    ap.add_argument("--out", default=os.path.join(ROOT, "tests", "golden", "p10_ns_counts.json"))
+    ap.add_argument("--ls", default="NS", choices=["NS", "GMRES"], help="<LS> block: NS (pipe_RCR_3d) or the plain GMRES variant of SURVEY 8(d)")
+    ap.add_argument("--out", default=None)
     a = ap.parse_args()
-    res = run(tuple(a.dims), a.ranks)
+    if a.out is None:
+        a.out = os.path.join(ROOT, "tests", "golden", f"p10_{a.ls.lower()}_counts.json")
+    res = run(tuple(a.dims), a.ranks, a.ls)
     with open(a.out, "w") as f:
         json.dump(res, f, indent=1)
     print({k: res[k] for k in ("itr", "GM_itr", "CG_itr", "iNorm", "fNorm", "reference_solve_s")})
