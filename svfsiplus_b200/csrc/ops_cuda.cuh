@@ -132,6 +132,20 @@ class CudaOps {
     span_used = 0;
     for (int c = 0; c < KC_COUNT; c++) { cls_ms[c] = 0; cls_bytes[c] = 0; cls_launches[c] = 0; }
   }
+  // Device-resident loops enqueue iterations past convergence that return at once (skip flag): their algorithmic bytes and launch
+  // counts must not be credited to the kernel classes.  The loops snapshot the counters around every enqueued iteration and take the
+  // skipped iterations' share back once the device has said where it stopped.
+  struct ProfCount { double bytes[KC_COUNT]; long long launches[KC_COUNT]; };
+  ProfCount prof_snapshot() const
+  {
+    ProfCount p;
+    for (int c = 0; c < KC_COUNT; c++) { p.bytes[c] = cls_bytes[c]; p.launches[c] = cls_launches[c]; }
+    return p;
+  }
+  void prof_uncredit(const ProfCount& before, const ProfCount& after)
+  {
+    for (int c = 0; c < KC_COUNT; c++) { cls_bytes[c] -= after.bytes[c] - before.bytes[c]; cls_launches[c] -= after.launches[c] - before.launches[c]; }
+  }
   // algorithmic bytes (SURVEY.md par. 8d)
   double bytes_vv(int d) const { return double(nnz_)*(8.0*d*d + 4.0) + double(nNo_)*(16.0*d + 8.0); }
   double bytes_ss() const { return double(nnz_)*12.0 + double(nNo_)*24.0; }
@@ -1062,9 +1076,11 @@ class CudaOps {
     int enq = 0, slot = 0, pending = -1;
     bool stop = (ls.mItr <= 0);
     skip_flag = &cg_d->done;
+    std::vector<ProfCount> marks;                 // counters before iteration i (profiling only)
     while (!stop) {
       const int nb = std::min(cg_batch, ls.mItr - enq);
       for (int k = 0; k < nb; k++) {
+        if (profiling) marks.push_back(prof_snapshot());
         k_cg_head<<<1, 1, 0, st>>>(cg_d, enq + k); post();
         apply(P, SP);
         dots_reduce(dof, 1, P, 0, SP, 0);
@@ -1098,6 +1114,11 @@ class CudaOps {
     CU_CHECK(cudaStreamSynchronize(st));
     ls.suc = cg_h[2].suc != 0;
     last_i = cg_h[2].last_i;
+    {
+      // bodies ran for the iterations before the one whose head found convergence (all enqueued ones when it never did)
+      const int executed = ls.suc ? last_i : last_i + 1;
+      if (profiling && int(marks.size()) > executed) prof_uncredit(marks[executed], prof_snapshot());
+    }
     err = cg_h[2].err;
     errO = cg_h[2].errO;
   }
@@ -1138,9 +1159,11 @@ class CudaOps {
     skip_flag = &gm_d->done;
     int enq = 0, slot = 0, pending = -1;
     bool stop = (sD <= 0);
+    std::vector<ProfCount> marks;                 // counters before iteration i (profiling only) + one after the last
     while (!stop) {
       const int nb = std::min(gm_batch, sD - enq);
       for (int k = 0; k < nb; k++) {
+        if (profiling) marks.push_back(prof_snapshot());
         // (letting the Givens bookkeeping ride on the Gram-Schmidt update kernel as an extra CTA was measured and rejected: the 24 KB
         // of static shared memory it brings into that kernel cost the streaming update 50 % of its bandwidth, 0.39 vs 0.26 ms per
         // launch at P10; profiles/r02_bench_n1_givens_ride.json)
@@ -1162,6 +1185,7 @@ class CudaOps {
     CU_CHECK(cudaStreamSynchronize(st));
     const int last_i = gm_h[2].last_i;
     suc = gm_h[2].suc != 0;
+    if (profiling && int(marks.size()) > last_i + 1) prof_uncredit(marks[last_i + 1], prof_snapshot());    // iterations > last_i were skipped
     // the columns the back substitution needs + the residual estimates
     CU_CHECK(cudaMemcpyAsync(gm_host, d_h, sizeof(double)*size_t(last_i + 1)*(sD + 1), cudaMemcpyDeviceToHost, st));
     CU_CHECK(cudaMemcpyAsync(gm_host + size_t(sD + 1)*sD, d_err, sizeof(double)*(last_i + 2), cudaMemcpyDeviceToHost, st));
