@@ -231,6 +231,9 @@ class CudaOps {
 
   // reductions
   static constexpr int kMaxSlots = 1024;
+  static constexpr size_t kDotsTwoStageMaxN = size_t(1) << 21;   // ... and only for vectors up to 2 M entries per rank: on longer ones the
+                                                                 // first stage hides the in-kernel tail and the extra launch costs more (P10, one GPU:
+                                                                 // 0.137 vs 0.133 ms per launch; 8 GPUs: 47.9 vs 52.8 us)
   static constexpr int kDotsTwoStage = 12;   // from this many dots per launch the ordered sum of the partials runs as its own kernel (warp per dot)
   double* red_d = nullptr;
   double* red_h = nullptr;        // pinned
@@ -410,7 +413,7 @@ class CudaOps {
       Scope sc(*this, KC_MULTI_DOT, 8.0*double(n)*(m + 1));
       // enough CTAs to fill the machine, never more than one per 1024 entries (tiny systems)
       const int g = int(std::min<size_t>(size_t(kRedBlocks), (n + 1023)/1024 + 1));
-      if (m >= kDotsTwoStage) {
+      if (m >= kDotsTwoStage && n <= kDotsTwoStageMaxN) {
         k_multi_dot<<<g, kRedThreads, 0, st>>>(skip_flag, n, base + size_t(done)*stride, stride, w, m, partial_d, counter_d, red_d, slot0 + done,
                                                PeerRedArgs(), nullptr, 1);
         post();
@@ -447,7 +450,7 @@ class CudaOps {
     const size_t n = size_t(dof)*mynNo_;
     Scope sc(*this, KC_MULTI_DOT, 8.0*double(n)*(count + 1));
     const int g = int(std::min<size_t>(size_t(kRedBlocks), (n + 1023)/1024 + 1));
-    if (count >= kDotsTwoStage) {
+    if (count >= kDotsTwoStage && n <= kDotsTwoStageMaxN) {
       k_multi_dot<<<g, kRedThreads, 0, st>>>(skip_flag, n, base, stride, w, count, partial_d, counter_d, red_d, slot0, PeerRedArgs(), nullptr, 1);
       post();
       k_multi_dot_final<<<(count + kRedThreads/32 - 1)/(kRedThreads/32), kRedThreads, 0, st>>>(skip_flag, g, count, partial_d, counter_d, red_d, slot0,
